@@ -1,0 +1,343 @@
+/*
+ * lrk.h — C-ABI of the B200 radiance kernel library (libb200pt.so).
+ *
+ * This is the drop-in boundary below LuisaRender's integrator interface
+ * (SURVEY.md §8b).  The reference's Integrator/Surface/Light/Sampler classes are
+ * DSL-staging objects (they record an AST, they are not callable at run time), so
+ * the run-time boundary sits one level lower: the host (scene parsing, flattening,
+ * BVH build, film I/O — include/lrh.h) hands a flattened, POD scene to this
+ * library, which owns all device memory and runs the per-sample radiance loop in
+ * hand-written sm_100a CUDA.
+ *
+ * What each entry point replaces in the reference (paths relative to /root/reference):
+ *   lrk_create          <- Context::create_device + Device::create_stream      src/apps/cli.cpp:167-181
+ *   lrk_upload_scene    <- Pipeline::create (Geometry::build, register_surface/light,
+ *                          Integrator::build)                                    src/base/pipeline.cpp:44-99
+ *   lrk_set_shard       <- (none: the reference is single device)               SURVEY.md §8e
+ *   lrk_film_clear      <- Film::Instance::prepare / clear                      src/films/color.cpp:132-144
+ *   lrk_render          <- ProgressiveIntegrator::Instance::_render_one_camera  src/integrators/wave_path.cpp:220-567
+ *   lrk_download_film   <- Film::Instance::download (convert_image + copy)      src/films/color.cpp:87-105
+ *   lrk_download_film_raw / lrk_film_device_ptr
+ *                       <- the raw (sum rgb, sum weight) float4 film buffer     src/films/color.cpp:107-130
+ *   lrk_trace           <- Geometry::trace_closest / trace_any                  src/base/geometry.cpp:218-279
+ *   lrk_get_stats       <- "Rendering finished in {} ms." + device counters     src/integrators/wave_path.cpp:565-566
+ *   lrk_last_error      <- LUISA_ERROR (log + abort)                            src/compute/include/luisa/core/logging.h:63
+ *
+ * Conventions: every function is extern "C", takes plain pointers and sizes, never
+ * throws; returns 0 on success or a negative lrk_status.  All host arrays passed to
+ * lrk_upload_scene are copied; the caller keeps ownership.  One lrk_ctx per GPU; calls
+ * on one ctx must come from one thread at a time.
+ */
+#ifndef LRK_H
+#define LRK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LRK_ABI_VERSION 1u
+
+typedef enum lrk_status {
+    LRK_OK = 0,
+    LRK_ERR_INVALID_ARGUMENT = -1,
+    LRK_ERR_NO_DEVICE = -2,
+    LRK_ERR_CUDA = -3,
+    LRK_ERR_NO_SCENE = -4,
+    LRK_ERR_UNSUPPORTED = -5,
+    LRK_ERR_OUT_OF_MEMORY = -6
+} lrk_status;
+
+/* ---- geometry records (layouts follow SURVEY.md App. B) ---------------------------- */
+
+/* Vertex, 32 B: src/util/vertex.h:37-56 */
+typedef struct lrk_vertex {
+    float p[3];
+    float n[3];
+    float uv[2];
+} lrk_vertex;
+
+/* Triangle, 12 B: src/compute/include/luisa/runtime/rtx/triangle.h:7-11 */
+typedef struct lrk_triangle {
+    uint32_t i0, i1, i2;
+} lrk_triangle;
+
+/* AliasEntry, 8 B: src/util/sampling.h:29-32 */
+typedef struct lrk_alias_entry {
+    float prob;
+    uint32_t alias;
+} lrk_alias_entry;
+
+/* Ray, 32 B: src/compute/include/luisa/runtime/rtx/ray.h:10-16 */
+typedef struct lrk_ray {
+    float o[3];
+    float tmin;
+    float d[3];
+    float tmax;
+} lrk_ray;
+
+/* Hit, 16 B: src/base/geometry.h:16-27; miss <=> inst == ~0u */
+typedef struct lrk_hit {
+    uint32_t inst;
+    uint32_t prim;
+    float bary[2];
+} lrk_hit;
+
+/* One unique mesh (= one BLAS).  Mirrors the four bindless slots of
+ * src/base/geometry.cpp:68-84: vertices, triangles, alias table, pdf. Offsets index the
+ * scene-global arrays of lrk_scene_desc. */
+typedef struct lrk_mesh {
+    uint32_t vertex_offset;
+    uint32_t vertex_count;
+    uint32_t triangle_offset; /* also the offset into alias[] and pdf[] */
+    uint32_t triangle_count;
+    uint32_t bvh_root;        /* index of this BLAS's root node in bvh_nodes[] */
+    uint32_t tri_slot_offset; /* first BVH-ordered triangle slot of this mesh in tri_verts[] */
+    uint32_t reserved[2];
+} lrk_mesh;
+
+/* BVH2 node, 64 B: both children's boxes + two child references.
+ * ref: bit31 = leaf.  BLAS leaf: bits 28..30 = triangle count - 1, bits 0..27 = first
+ * triangle slot (scene-global, indexes tri_verts[3*slot .. 3*slot+2]).  TLAS leaf:
+ * bits 0..30 = instance index.  An unused child has an inverted box (lo=+inf, hi=-inf)
+ * and ref LRK_BVH_EMPTY. */
+typedef struct lrk_bvh_node {
+    float lo0[3], hi0[3];
+    float lo1[3], hi1[3];
+    uint32_t ref0, ref1;
+    uint32_t parent; /* index of the parent node (root: ~0u) */
+    uint32_t reserved;
+} lrk_bvh_node;
+
+#define LRK_BVH_LEAF 0x80000000u
+#define LRK_BVH_EMPTY 0xffffffffu
+#define LRK_BVH_MAX_LEAF_TRIS 4u
+
+/* One TLAS instance = one mesh leaf of the flattened shape graph
+ * (src/base/geometry.cpp:29-163).  `handle` is exactly Shape::Handle::encode
+ * (src/base/shape.cpp:46-70) with buffer_base = 4 * mesh index. */
+typedef struct lrk_instance {
+    uint32_t handle[4];
+    float object_to_world[12]; /* row-major 3x4 */
+    float world_to_object[12]; /* row-major 3x4 */
+    uint32_t mesh;
+    uint32_t visible; /* src/base/geometry.cpp:130-131: invisible instances are skipped by all rays */
+    uint32_t reserved[2];
+} lrk_instance;
+
+/* Shape property flags: src/base/shape.h:34-39 */
+#define LRK_SHAPE_HAS_VERTEX_NORMAL 1u
+#define LRK_SHAPE_HAS_VERTEX_UV 2u
+#define LRK_SHAPE_HAS_SURFACE 4u
+#define LRK_SHAPE_HAS_LIGHT 8u
+#define LRK_SHAPE_HAS_MEDIUM 16u
+#define LRK_SHAPE_MAYBE_NON_OPAQUE 32u
+
+/* ---- materials, lights ---------------------------------------------------------------- */
+
+#define LRK_SURFACE_MATTE 0u  /* src/surfaces/matte.cpp */
+#define LRK_SURFACE_DISNEY 1u /* src/surfaces/disney.cpp (opaque, non-thin closure "disney") */
+
+/* Disney lobe bits: src/surfaces/disney.cpp:326-333 */
+#define LRK_DISNEY_LOBE_DIFFUSE 1u
+#define LRK_DISNEY_LOBE_RETRO 2u
+#define LRK_DISNEY_LOBE_FAKE_SS 4u
+#define LRK_DISNEY_LOBE_SHEEN 8u
+#define LRK_DISNEY_LOBE_CLEARCOAT 16u
+#define LRK_DISNEY_LOBE_SPECULAR 32u
+#define LRK_DISNEY_LOBE_DIFF_TRANS 64u
+#define LRK_DISNEY_LOBE_SPEC_TRANS 128u
+
+/* One surface node (tag = index), constants already decoded the way the reference's
+ * constant textures + sRGB spectrum decode them (src/base/texture.cpp:15-80,
+ * src/spectra/srgb.cpp:34-40).
+ *   MATTE : p[0..2] = Kd, p[3] = sigma in degrees (saturate(v)*90, 0 if absent)
+ *   DISNEY: p[0..2] = color, p[3] = color_lum, p[4] = metallic, p[5] = eta, p[6] = roughness
+ *           (already remapped to alpha when remap_roughness), p[7] = specular_tint,
+ *           p[8] = anisotropic, p[9] = sheen, p[10] = sheen_tint, p[11] = clearcoat,
+ *           p[12] = clearcoat_gloss, p[13] = specular_trans, p[14] = flatness,
+ *           p[15] = diffuse_trans; lobes = union of enabled lobes over ALL disney surface
+ *           nodes of the scene (the reference ORs them into one shared closure,
+ *           src/surfaces/disney.cpp:869,994-995). */
+typedef struct lrk_surface {
+    uint32_t type;
+    uint32_t lobes;
+    uint32_t reserved[2];
+    float p[16];
+} lrk_surface;
+
+/* One light node (tag = index): src/lights/diffuse.cpp:23-26. emission is the decoded
+ * illuminant (max(rgb,0)), L = emission * scale. */
+typedef struct lrk_light {
+    float emission[3];
+    float scale;
+    uint32_t two_sided;
+    uint32_t reserved[3];
+} lrk_light;
+
+/* Light::Handle, 8 B: src/base/light.h:26-29 */
+typedef struct lrk_light_handle {
+    uint32_t instance_id;
+    uint32_t light_tag;
+} lrk_light_handle;
+
+/* ---- camera, film, integrator ------------------------------------------------------- */
+
+#define LRK_FILTER_LUT_SIZE 64u /* src/base/filter.h:18 */
+
+typedef struct lrk_camera {
+    float camera_to_world[12]; /* row-major 3x4 */
+    uint32_t resolution[2];
+    float tan_half_fov;     /* src/cameras/pinhole.cpp:56-57 */
+    float filter_radius;    /* src/base/filter.cpp:13 */
+    float filter_shift[2];
+    uint32_t spp;           /* src/base/camera.cpp:28 */
+    uint32_t reserved;
+    float filter_lut[LRK_FILTER_LUT_SIZE];              /* src/base/filter.cpp:24-48 */
+    float filter_pdf[LRK_FILTER_LUT_SIZE];              /* 63 used */
+    float filter_alias_probs[LRK_FILTER_LUT_SIZE];      /* 63 used */
+    uint32_t filter_alias_indices[LRK_FILTER_LUT_SIZE]; /* 63 used */
+} lrk_camera;
+
+typedef struct lrk_film {
+    float scale[3]; /* 2^exposure, src/films/color.cpp:38-40 */
+    float clamp;    /* src/films/color.cpp:41 */
+} lrk_film;
+
+#define LRK_INTEGRATOR_PATH 0u       /* src/integrators/wave_path.cpp (== mega_path.cpp estimator) */
+#define LRK_INTEGRATOR_VOLUME_PATH 1u /* src/integrators/mega_vpt_naive.cpp (config C4) */
+
+typedef struct lrk_integrator {
+    uint32_t type;
+    uint32_t max_depth;        /* src/integrators/wave_path.cpp:43 */
+    uint32_t rr_depth;         /* :44 */
+    float rr_threshold;        /* :45 */
+    uint32_t samples_per_pass; /* :46 (a hint: the pass size is chosen by the library) */
+    uint32_t sampler_seed;     /* src/base/sampler.cpp:11 */
+    uint32_t reserved[2];
+} lrk_integrator;
+
+/* Homogeneous environment medium (config C4): src/media/homogeneous.cpp */
+typedef struct lrk_medium {
+    uint32_t present;
+    uint32_t priority;
+    float eta;
+    float g; /* Henyey-Greenstein */
+    float sigma_a[3];
+    float sigma_s[3];
+    float le[3];
+    float reserved[3];
+} lrk_medium;
+
+typedef struct lrk_scene_desc {
+    uint32_t abi_version; /* LRK_ABI_VERSION */
+    uint32_t reserved0;
+
+    const lrk_vertex *vertices;
+    uint64_t vertex_count;
+    const lrk_triangle *triangles;
+    const lrk_alias_entry *alias;
+    const float *pdf;
+    uint64_t triangle_count;
+
+    const lrk_mesh *meshes;
+    uint32_t mesh_count;
+    uint32_t instance_count;
+    const lrk_instance *instances;
+
+    const lrk_bvh_node *bvh_nodes;
+    uint64_t bvh_node_count;
+    uint32_t tlas_root;
+    uint32_t reserved1;
+    const float *tri_verts; /* 12 floats per BVH-ordered slot: v0.xyz, as_float(prim id), v1.xyz, 0, v2.xyz, 0 */
+    uint64_t tri_slot_count;
+
+    const lrk_surface *surfaces;
+    uint32_t surface_count;
+    uint32_t light_count; /* number of distinct light NODES */
+    const lrk_light *lights;
+    const lrk_light_handle *light_handles; /* first light_count per-instance handles (src/lightsamplers/uniform.cpp:34-38) */
+
+    lrk_camera camera;
+    lrk_film film;
+    lrk_integrator integrator;
+    lrk_medium environment_medium;
+} lrk_scene_desc;
+
+/* ---- device control ----------------------------------------------------------------- */
+
+typedef struct lrk_device_cfg {
+    int32_t device_index;      /* -1: current device */
+    uint32_t reserved;
+    uint64_t max_paths_per_pass; /* 0: default (8 Mi) */
+} lrk_device_cfg;
+
+typedef struct lrk_stats {
+    double render_ms;        /* device time of all lrk_render calls since the last lrk_film_clear */
+    uint64_t samples;        /* camera samples started */
+    uint64_t closest_rays;   /* rays traced by the closest-hit kernel */
+    uint64_t shadow_rays;    /* rays traced by the any-hit kernel */
+    uint64_t kernel_launches;
+    uint64_t passes;
+    /* filled only when counting is enabled (lrk_set_option("count_traversal", 1)) */
+    uint64_t nodes_visited;  /* N_int   */
+    uint64_t tris_tested;    /* N_tri */
+    uint64_t xforms;         /* N_xform */
+    double trace_closest_ms; /* CUDA-event time of the closest-hit kernel launches (when "time_kernels" = 1) */
+    double trace_shadow_ms;
+    double shade_ms;
+    double other_ms;
+} lrk_stats;
+
+typedef struct lrk_ctx lrk_ctx;
+
+int lrk_abi_version(void);
+int lrk_create(const lrk_device_cfg *cfg, lrk_ctx **out);
+void lrk_destroy(lrk_ctx *ctx);
+const char *lrk_last_error(const lrk_ctx *ctx);
+
+int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *scene);
+
+/* Pixel-tile sharding for multi-GPU: this ctx renders the tiles with
+ * tile_id % world == rank, tiles are tile_size x tile_size pixels in row-major tile order. */
+int lrk_set_shard(lrk_ctx *ctx, uint32_t rank, uint32_t world, uint32_t tile_size);
+
+/* Options: "count_traversal" (0/1), "time_kernels" (0/1), "sort_by_surface" (0/1),
+ * "use_graph" (0/1). Unknown name -> LRK_ERR_INVALID_ARGUMENT. */
+int lrk_set_option(lrk_ctx *ctx, const char *name, int64_t value);
+
+int lrk_film_clear(lrk_ctx *ctx);
+
+/* Render sample indices [spp_begin, spp_end) of every pixel of this ctx's shard and add
+ * them to the film.  Asynchronous work is synchronised before returning. */
+int lrk_render(lrk_ctx *ctx, uint32_t spp_begin, uint32_t spp_end);
+
+/* rgba = (sum_rgb / max(sum_w, 1)) * scale, a = 1 : W*H float4 (src/films/color.cpp:87-93) */
+int lrk_download_film(lrk_ctx *ctx, float *rgba);
+/* raw (sum r, sum g, sum b, sum w) : W*H float4 */
+int lrk_download_film_raw(lrk_ctx *ctx, float *rgba);
+/* device pointer of the raw film buffer (for the NCCL reduce of config C5) and its size */
+int lrk_film_device_ptr(lrk_ctx *ctx, void **ptr, uint64_t *bytes);
+/* overwrite the raw film with the (reduced) content of a device buffer of the same size */
+int lrk_film_normalize_to_host(lrk_ctx *ctx, const void *device_raw, float *rgba);
+
+/* Stand-alone ray queries against the uploaded scene (parity tests of rows a5/a7):
+ * n rays in host memory -> n hits (any_hit == 0) or n occlusion flags in hits[i].inst
+ * (0 = free, 1 = occluded; any_hit != 0). */
+int lrk_trace(lrk_ctx *ctx, const lrk_ray *rays, uint64_t n, int any_hit, lrk_hit *hits);
+
+/* Device-resident variant used by bench.py for the roofline measurement: traces the
+ * same n device rays `repeat` times and returns the average kernel time in ms. */
+int lrk_trace_device(lrk_ctx *ctx, const void *d_rays, uint64_t n, int any_hit, void *d_hits,
+                     uint32_t repeat, float *avg_ms);
+
+int lrk_get_stats(lrk_ctx *ctx, lrk_stats *stats);
+
+/* the CUDA stream all work of this ctx is launched on (cudaStream_t as void*) */
+void *lrk_stream(lrk_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LRK_H */

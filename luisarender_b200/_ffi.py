@@ -1,0 +1,191 @@
+"""ctypes mirror of include/lrk.h and include/lrh.h, and loaders for the in-tree shared libraries.
+
+The product is the two native libraries; Python only binds them for tests and bench.py.  The loaders
+fail loudly when a library is missing — there is no Python/CPU fallback for the radiance path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+REPO_DIR = PKG_DIR.parent
+LIB_DIR = PKG_DIR / "lib"
+
+LRK_ABI_VERSION = 1
+LRK_FILTER_LUT_SIZE = 64
+
+u32, u64, i32, i64, f32, f64 = C.c_uint32, C.c_uint64, C.c_int32, C.c_int64, C.c_float, C.c_double
+
+
+class Vertex(C.Structure):
+    _fields_ = [("p", f32 * 3), ("n", f32 * 3), ("uv", f32 * 2)]
+
+
+class Triangle(C.Structure):
+    _fields_ = [("i0", u32), ("i1", u32), ("i2", u32)]
+
+
+class AliasEntry(C.Structure):
+    _fields_ = [("prob", f32), ("alias", u32)]
+
+
+class Ray(C.Structure):
+    _fields_ = [("o", f32 * 3), ("tmin", f32), ("d", f32 * 3), ("tmax", f32)]
+
+
+class Hit(C.Structure):
+    _fields_ = [("inst", u32), ("prim", u32), ("bary", f32 * 2)]
+
+
+class Mesh(C.Structure):
+    _fields_ = [("vertex_offset", u32), ("vertex_count", u32), ("triangle_offset", u32), ("triangle_count", u32),
+                ("bvh_root", u32), ("tri_slot_offset", u32), ("reserved", u32 * 2)]
+
+
+class BvhNode(C.Structure):
+    _fields_ = [("lo0", f32 * 3), ("hi0", f32 * 3), ("lo1", f32 * 3), ("hi1", f32 * 3),
+                ("ref0", u32), ("ref1", u32), ("parent", u32), ("reserved", u32)]
+
+
+class Instance(C.Structure):
+    _fields_ = [("handle", u32 * 4), ("object_to_world", f32 * 12), ("world_to_object", f32 * 12),
+                ("mesh", u32), ("visible", u32), ("reserved", u32 * 2)]
+
+
+class Surface(C.Structure):
+    _fields_ = [("type", u32), ("lobes", u32), ("reserved", u32 * 2), ("p", f32 * 16)]
+
+
+class Light(C.Structure):
+    _fields_ = [("emission", f32 * 3), ("scale", f32), ("two_sided", u32), ("reserved", u32 * 3)]
+
+
+class LightHandle(C.Structure):
+    _fields_ = [("instance_id", u32), ("light_tag", u32)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("camera_to_world", f32 * 12), ("resolution", u32 * 2), ("tan_half_fov", f32),
+                ("filter_radius", f32), ("filter_shift", f32 * 2), ("spp", u32), ("reserved", u32),
+                ("filter_lut", f32 * 64), ("filter_pdf", f32 * 64), ("filter_alias_probs", f32 * 64),
+                ("filter_alias_indices", u32 * 64)]
+
+
+class Film(C.Structure):
+    _fields_ = [("scale", f32 * 3), ("clamp", f32)]
+
+
+class Integrator(C.Structure):
+    _fields_ = [("type", u32), ("max_depth", u32), ("rr_depth", u32), ("rr_threshold", f32),
+                ("samples_per_pass", u32), ("sampler_seed", u32), ("reserved", u32 * 2)]
+
+
+class Medium(C.Structure):
+    _fields_ = [("present", u32), ("priority", u32), ("eta", f32), ("g", f32), ("sigma_a", f32 * 3),
+                ("sigma_s", f32 * 3), ("le", f32 * 3), ("reserved", f32 * 3)]
+
+
+class SceneDesc(C.Structure):
+    _fields_ = [
+        ("abi_version", u32), ("reserved0", u32),
+        ("vertices", C.POINTER(Vertex)), ("vertex_count", u64),
+        ("triangles", C.POINTER(Triangle)), ("alias", C.POINTER(AliasEntry)), ("pdf", C.POINTER(f32)),
+        ("triangle_count", u64),
+        ("meshes", C.POINTER(Mesh)), ("mesh_count", u32), ("instance_count", u32),
+        ("instances", C.POINTER(Instance)),
+        ("bvh_nodes", C.POINTER(BvhNode)), ("bvh_node_count", u64), ("tlas_root", u32), ("reserved1", u32),
+        ("tri_verts", C.POINTER(f32)), ("tri_slot_count", u64),
+        ("surfaces", C.POINTER(Surface)), ("surface_count", u32), ("light_count", u32),
+        ("lights", C.POINTER(Light)), ("light_handles", C.POINTER(LightHandle)),
+        ("camera", Camera), ("film", Film), ("integrator", Integrator), ("environment_medium", Medium),
+    ]
+
+
+class DeviceCfg(C.Structure):
+    _fields_ = [("device_index", i32), ("reserved", u32), ("max_paths_per_pass", u64)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("render_ms", f64), ("samples", u64), ("closest_rays", u64), ("shadow_rays", u64),
+                ("kernel_launches", u64), ("passes", u64), ("nodes_visited", u64), ("tris_tested", u64),
+                ("xforms", u64), ("trace_closest_ms", f64), ("trace_shadow_ms", f64), ("shade_ms", f64),
+                ("other_ms", f64)]
+
+
+class SceneInfo(C.Structure):
+    _fields_ = [("unique_triangles", u64), ("instanced_triangles", u64), ("vertices", u64), ("bvh_nodes", u64),
+                ("meshes", u32), ("instances", u32), ("surfaces", u32), ("lights", u32), ("cameras", u32),
+                ("reserved", u32), ("bvh_build_ms", f64), ("world_min", f32 * 3), ("world_max", f32 * 3)]
+
+
+LRK_SYMBOLS = [
+    "lrk_abi_version", "lrk_create", "lrk_destroy", "lrk_last_error", "lrk_upload_scene", "lrk_set_shard",
+    "lrk_set_option", "lrk_film_clear", "lrk_render", "lrk_download_film", "lrk_download_film_raw",
+    "lrk_film_device_ptr", "lrk_film_normalize_to_host", "lrk_trace", "lrk_trace_device", "lrk_get_stats",
+    "lrk_stream",
+]
+LRH_SYMBOLS = [
+    "lrh_last_error", "lrh_scene_load", "lrh_scene_load_source", "lrh_scene_destroy", "lrh_scene_get_info",
+    "lrh_scene_get_desc", "lrh_scene_camera_file", "lrh_save_image", "lrh_plugin_count", "lrh_plugin_name",
+]
+
+_libs: dict[str, C.CDLL] = {}
+
+
+def _load(name: str) -> C.CDLL:
+    if name not in _libs:
+        path = LIB_DIR / name
+        if not path.exists():
+            raise RuntimeError(
+                f"native library {path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                f"(there is no Python fallback)")
+        _libs[name] = C.CDLL(str(path), mode=C.RTLD_GLOBAL if hasattr(C, "RTLD_GLOBAL") else os.RTLD_NOW)
+    return _libs[name]
+
+
+def host_lib() -> C.CDLL:
+    lib = _load("libluisa_render_host.so")
+    if not getattr(lib, "_lrh_typed", False):
+        lib.lrh_last_error.restype = C.c_char_p
+        lib.lrh_scene_load.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), u32, C.POINTER(C.c_void_p)]
+        lib.lrh_scene_load_source.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), u32, C.POINTER(C.c_void_p)]
+        lib.lrh_scene_destroy.argtypes = [C.c_void_p]
+        lib.lrh_scene_destroy.restype = None
+        lib.lrh_scene_get_info.argtypes = [C.c_void_p, C.POINTER(SceneInfo)]
+        lib.lrh_scene_get_desc.argtypes = [C.c_void_p, u32, C.POINTER(SceneDesc)]
+        lib.lrh_scene_camera_file.argtypes = [C.c_void_p, u32]
+        lib.lrh_scene_camera_file.restype = C.c_char_p
+        lib.lrh_save_image.argtypes = [C.c_char_p, C.c_void_p, u32, u32]
+        lib.lrh_plugin_count.restype = u32
+        lib.lrh_plugin_name.argtypes = [u32]
+        lib.lrh_plugin_name.restype = C.c_char_p
+        lib._lrh_typed = True
+    return lib
+
+
+def device_lib() -> C.CDLL:
+    lib = _load("libb200pt.so")
+    if not getattr(lib, "_lrk_typed", False):
+        lib.lrk_create.argtypes = [C.POINTER(DeviceCfg), C.POINTER(C.c_void_p)]
+        lib.lrk_destroy.argtypes = [C.c_void_p]
+        lib.lrk_destroy.restype = None
+        lib.lrk_last_error.argtypes = [C.c_void_p]
+        lib.lrk_last_error.restype = C.c_char_p
+        lib.lrk_upload_scene.argtypes = [C.c_void_p, C.POINTER(SceneDesc)]
+        lib.lrk_set_shard.argtypes = [C.c_void_p, u32, u32, u32]
+        lib.lrk_set_option.argtypes = [C.c_void_p, C.c_char_p, i64]
+        lib.lrk_film_clear.argtypes = [C.c_void_p]
+        lib.lrk_render.argtypes = [C.c_void_p, u32, u32]
+        lib.lrk_download_film.argtypes = [C.c_void_p, C.c_void_p]
+        lib.lrk_download_film_raw.argtypes = [C.c_void_p, C.c_void_p]
+        lib.lrk_film_device_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(u64)]
+        lib.lrk_film_normalize_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.lrk_trace.argtypes = [C.c_void_p, C.c_void_p, u64, C.c_int, C.c_void_p]
+        lib.lrk_trace_device.argtypes = [C.c_void_p, C.c_void_p, u64, C.c_int, C.c_void_p, u32, C.POINTER(f32)]
+        lib.lrk_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        lib.lrk_stream.argtypes = [C.c_void_p]
+        lib.lrk_stream.restype = C.c_void_p
+        lib._lrk_typed = True
+    return lib

@@ -1,0 +1,375 @@
+#include "flatten.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <unordered_map>
+
+#include "bvh.h"
+
+namespace lrh {
+
+lrk_scene_desc FlatScene::desc(uint32_t camera_index) const {
+    if (camera_index >= cameras.size()) throw Error("Camera index out of range.");
+    lrk_scene_desc d{};
+    d.abi_version = LRK_ABI_VERSION;
+    d.vertices = vertices.data();
+    d.vertex_count = vertices.size();
+    d.triangles = triangles.data();
+    d.alias = alias.data();
+    d.pdf = pdf.data();
+    d.triangle_count = triangles.size();
+    d.meshes = meshes.data();
+    d.mesh_count = static_cast<uint32_t>(meshes.size());
+    d.instances = instances.data();
+    d.instance_count = static_cast<uint32_t>(instances.size());
+    d.bvh_nodes = bvh_nodes.data();
+    d.bvh_node_count = bvh_nodes.size();
+    d.tlas_root = tlas_root;
+    d.tri_verts = tri_verts.data();
+    d.tri_slot_count = tri_verts.size() / 12u;
+    d.surfaces = surfaces.data();
+    d.surface_count = static_cast<uint32_t>(surfaces.size());
+    d.lights = lights.data();
+    d.light_count = static_cast<uint32_t>(lights.size());
+    d.light_handles = light_handles.data();
+    d.camera = cameras[camera_index].camera;
+    d.film = cameras[camera_index].film;
+    d.integrator = integrator;
+    d.environment_medium = environment_medium;
+    return d;
+}
+
+namespace {
+
+uint64_t fnv1a(const void *data, size_t bytes, uint64_t h = 1469598103934665603ull) {
+    auto p = static_cast<const unsigned char *>(data);
+    for (size_t i = 0; i < bytes; i++) {
+        h ^= p[i];
+        h *= 1099511628211ull;
+    }
+    return h;
+}
+
+// Shape::Handle::encode, src/base/shape.cpp:46-70
+void encode_handle(uint32_t out[4], uint32_t buffer_base, uint32_t flags, uint32_t surface_tag, uint32_t light_tag,
+                   uint32_t medium_tag, uint32_t tri_count, float shadow_terminator, float intersection_offset) {
+    if (buffer_base > (1u << 22u) - 1u) throw Error("Invalid geometry buffer base.");
+    if (surface_tag > 4095u) throw Error("Invalid surface tag (more than 4096 surfaces).");
+    if (light_tag > 4095u) throw Error("Invalid light tag (more than 4096 lights).");
+    if (medium_tag > 255u) throw Error("Invalid medium tag (more than 256 media).");
+    auto fixed = [](float x) {
+        x = std::min(std::max(x, 0.f), 1.f);
+        constexpr float scale = 1.f / 65536.f;
+        return static_cast<uint32_t>(std::min(std::max(std::round(x / scale), 0.f), 65535.f));
+    };
+    out[0] = (buffer_base << 10u) | flags;
+    out[1] = (surface_tag << 12u) | light_tag | (medium_tag << 24u);
+    out[2] = tri_count;
+    out[3] = (fixed(shadow_terminator) << 16u) | fixed(intersection_offset);
+}
+
+struct Flattener {
+    const Scene &scene;
+    FlatScene &out;
+    std::unordered_map<const Shape *, uint32_t> shape_mesh;
+    std::multimap<uint64_t, uint32_t> mesh_by_hash;
+    std::unordered_map<const Surface *, uint32_t> surface_tags;
+    std::unordered_map<const Light *, uint32_t> light_tags;
+    std::vector<const Surface *> surface_nodes;
+    std::vector<const Light *> light_nodes;
+    std::vector<float4x4> xform_stack;
+    std::vector<Aabb> mesh_bounds;
+
+    uint32_t register_mesh(const Shape *shape) {
+        if (auto it = shape_mesh.find(shape); it != shape_mesh.end()) return it->second;
+        auto &v = shape->vertices();
+        auto &t = shape->triangles();
+        if (v.empty() || t.empty()) throw Error("Empty mesh.");
+        auto h = fnv1a(v.data(), v.size() * sizeof(lrk_vertex));
+        h = fnv1a(t.data(), t.size() * sizeof(lrk_triangle), h);
+        auto range = mesh_by_hash.equal_range(h);
+        for (auto it = range.first; it != range.second; ++it) {
+            auto &m = out.meshes[it->second];
+            if (m.vertex_count == v.size() && m.triangle_count == t.size() &&
+                std::memcmp(&out.vertices[m.vertex_offset], v.data(), v.size() * sizeof(lrk_vertex)) == 0 &&
+                std::memcmp(&out.triangles[m.triangle_offset], t.data(), t.size() * sizeof(lrk_triangle)) == 0) {
+                shape_mesh.emplace(shape, it->second);
+                return it->second;
+            }
+        }
+        lrk_mesh m{};
+        m.vertex_offset = static_cast<uint32_t>(out.vertices.size());
+        m.vertex_count = static_cast<uint32_t>(v.size());
+        m.triangle_offset = static_cast<uint32_t>(out.triangles.size());
+        m.triangle_count = static_cast<uint32_t>(t.size());
+        out.vertices.insert(out.vertices.end(), v.begin(), v.end());
+        out.triangles.insert(out.triangles.end(), t.begin(), t.end());
+        // per-mesh area alias table (src/base/geometry.cpp:71-80)
+        std::vector<float> areas(t.size());
+        std::vector<Aabb> tri_bounds(t.size());
+        Aabb mb;
+        auto pos = [&](uint32_t i) { return float3{v[i].p[0], v[i].p[1], v[i].p[2]}; };
+        for (size_t i = 0; i < t.size(); i++) {
+            if (t[i].i0 >= v.size() || t[i].i1 >= v.size() || t[i].i2 >= v.size()) throw Error("Triangle index out of range.");
+            auto p0 = pos(t[i].i0), p1 = pos(t[i].i1), p2 = pos(t[i].i2);
+            areas[i] = std::abs(length(cross(p1 - p0, p2 - p0)));
+            tri_bounds[i].grow(p0); tri_bounds[i].grow(p1); tri_bounds[i].grow(p2);
+            mb.grow(tri_bounds[i]);
+        }
+        std::vector<lrk_alias_entry> table;
+        std::vector<float> pdf;
+        create_alias_table(areas.data(), areas.size(), table, pdf);
+        out.alias.insert(out.alias.end(), table.begin(), table.end());
+        out.pdf.insert(out.pdf.end(), pdf.begin(), pdf.end());
+        // BLAS
+        auto bvh = build_bvh(tri_bounds.data(), static_cast<uint32_t>(t.size()), LRK_BVH_MAX_LEAF_TRIS, false);
+        auto node_base = static_cast<uint32_t>(out.bvh_nodes.size());
+        auto slot_base = static_cast<uint32_t>(out.tri_verts.size() / 12u);
+        if (static_cast<uint64_t>(slot_base) + t.size() >= (1ull << 28)) throw Error("Too many triangles for the BVH leaf encoding.");
+        m.bvh_root = node_base;
+        m.tri_slot_offset = slot_base;
+        auto rebase = [&](uint32_t ref) {
+            if (ref == LRK_BVH_EMPTY) return ref;
+            if (ref & LRK_BVH_LEAF) return (ref & 0xf0000000u) | ((ref & 0x0fffffffu) + slot_base);
+            return ref + node_base;
+        };
+        for (auto n : bvh.nodes) {
+            n.ref0 = rebase(n.ref0);
+            n.ref1 = rebase(n.ref1);
+            n.parent = n.parent == LRK_BVH_EMPTY ? LRK_BVH_EMPTY : n.parent + node_base;
+            out.bvh_nodes.push_back(n);
+        }
+        out.tri_verts.reserve(out.tri_verts.size() + t.size() * 12u);
+        for (auto prim : bvh.prim_order) {
+            auto p0 = pos(t[prim].i0), p1 = pos(t[prim].i1), p2 = pos(t[prim].i2);
+            float id_bits;
+            std::memcpy(&id_bits, &prim, 4);
+            float rec[12]{p0.x, p0.y, p0.z, id_bits, p1.x, p1.y, p1.z, 0.f, p2.x, p2.y, p2.z, 0.f};
+            out.tri_verts.insert(out.tri_verts.end(), rec, rec + 12);
+        }
+        auto index = static_cast<uint32_t>(out.meshes.size());
+        out.meshes.push_back(m);
+        mesh_bounds.push_back(mb);
+        mesh_by_hash.emplace(h, index);
+        shape_mesh.emplace(shape, index);
+        return index;
+    }
+
+    uint32_t register_surface(const Surface *s) {
+        if (auto it = surface_tags.find(s); it != surface_tags.end()) return it->second;
+        auto tag = static_cast<uint32_t>(surface_nodes.size());
+        surface_nodes.push_back(s);
+        surface_tags.emplace(s, tag);
+        return tag;
+    }
+    uint32_t register_light(const Light *l) {
+        if (auto it = light_tags.find(l); it != light_tags.end()) return it->second;
+        auto tag = static_cast<uint32_t>(light_nodes.size());
+        light_nodes.push_back(l);
+        light_tags.emplace(l, tag);
+        return tag;
+    }
+
+    // TransformTree::Node::matrix (src/base/transform.cpp:18-24): innermost first, parents applied on the left
+    float4x4 chain_matrix(const Transform *leaf) const {
+        std::vector<float4x4> chain = xform_stack;
+        if (leaf != nullptr && !leaf->is_identity()) chain.push_back(leaf->matrix());
+        if (chain.empty()) return float4x4::identity();
+        auto m = chain.back();
+        for (auto i = chain.size() - 1u; i-- > 0u;) m = chain[i] * m;
+        return m;
+    }
+
+    // Geometry::_process_shape (src/base/geometry.cpp:29-163)
+    void process(const Shape *shape, const Surface *ov_surface, const Light *ov_light, const Medium *ov_medium, bool ov_visible) {
+        auto surface = ov_surface == nullptr ? shape->surface : ov_surface;
+        auto light = ov_light == nullptr ? shape->light : ov_light;
+        auto medium = ov_medium == nullptr ? shape->medium : ov_medium;
+        auto visible = ov_visible && shape->visible;
+        if (shape->is_mesh()) {
+            auto mesh_index = register_mesh(shape);
+            auto &mesh = out.meshes[mesh_index];
+            auto instance_id = static_cast<uint32_t>(out.instances.size());
+            auto o2w = chain_matrix(shape->transform);
+            auto &v = shape->vertices();
+            for (auto &vert : v) {
+                auto p = transform_point(o2w, {vert.p[0], vert.p[1], vert.p[2]});
+                for (int a = 0; a < 3; a++) {
+                    out.world_max[a] = std::max(out.world_max[a], p[a]);
+                    out.world_min[a] = std::min(out.world_min[a], p[a]);
+                }
+            }
+            uint32_t surface_tag = 0u, light_tag = 0u, medium_tag = 0u;
+            auto properties = shape->vertex_properties();
+            if (surface != nullptr && !surface->is_null()) {
+                surface_tag = register_surface(surface);
+                properties |= LRK_SHAPE_HAS_SURFACE;
+            }
+            if (light != nullptr && !light->is_null()) {
+                light_tag = register_light(light);
+                properties |= LRK_SHAPE_HAS_LIGHT;
+            }
+            if (medium != nullptr && !medium->is_null()) {
+                throw Error("Per-shape media are not supported (only environment_medium). [" + shape->desc()->location() + "]");
+            }
+            auto fixed16 = [](float x) {
+                return static_cast<float>(static_cast<uint16_t>(std::min(std::max(std::round(x * 65535.f), 0.f), 65535.f))) / 65535.f;
+            };
+            auto has_normal = (shape->vertex_properties() & LRK_SHAPE_HAS_VERTEX_NORMAL) != 0u;
+            lrk_instance inst{};
+            encode_handle(inst.handle, mesh_index * 4u, properties, surface_tag, light_tag, medium_tag, mesh.triangle_count,
+                          fixed16(has_normal ? shape->shadow_terminator : 0.f), fixed16(shape->intersection_offset));
+            to_rows_3x4(o2w, inst.object_to_world);
+            if (!inverse_affine_rows(o2w, inst.world_to_object))
+                throw Error("Singular instance transform. [" + shape->desc()->location() + "]");
+            inst.mesh = mesh_index;
+            inst.visible = visible ? 1u : 0u;
+            out.instances.push_back(inst);
+            if (properties & LRK_SHAPE_HAS_LIGHT) out.light_handles.push_back({instance_id, light_tag});
+            out.total_instanced_triangles += mesh.triangle_count;
+        } else {
+            bool pushed = shape->transform != nullptr && !shape->transform->is_identity();
+            if (pushed) xform_stack.push_back(shape->transform->matrix());
+            for (auto child : shape->children()) process(child, surface, light, medium, visible);
+            if (pushed) xform_stack.pop_back();
+        }
+    }
+
+    void build_tlas() {
+        std::vector<Aabb> bounds;
+        std::vector<uint32_t> ids;
+        for (uint32_t i = 0; i < out.instances.size(); i++) {
+            auto &inst = out.instances[i];
+            if (!inst.visible) continue;// invisible instances are skipped by all rays (src/base/geometry.cpp:130-131)
+            auto &mesh = out.meshes[inst.mesh];
+            Aabb b;
+            const float *m = inst.object_to_world;
+            for (uint32_t k = 0; k < mesh.vertex_count; k++) {
+                auto &v = out.vertices[mesh.vertex_offset + k];
+                float3 p{m[0] * v.p[0] + m[1] * v.p[1] + m[2] * v.p[2] + m[3],
+                         m[4] * v.p[0] + m[5] * v.p[1] + m[6] * v.p[2] + m[7],
+                         m[8] * v.p[0] + m[9] * v.p[1] + m[10] * v.p[2] + m[11]};
+                b.grow(p);
+            }
+            // pad by a few ulps: object-space intersection rounds differently from this world-space box
+            for (int a = 0; a < 3; a++) {
+                auto e = 4e-7f * std::max(std::abs(b.lo[a]), std::abs(b.hi[a])) + 1e-30f;
+                b.lo[a] -= e;
+                b.hi[a] += e;
+            }
+            bounds.push_back(b);
+            ids.push_back(i);
+        }
+        auto bvh = build_bvh(bounds.data(), static_cast<uint32_t>(bounds.size()), 1u, true);
+        auto node_base = static_cast<uint32_t>(out.bvh_nodes.size());
+        out.tlas_root = node_base;
+        auto rebase = [&](uint32_t ref) {
+            if (ref == LRK_BVH_EMPTY) return ref;
+            if (ref & LRK_BVH_LEAF) return LRK_BVH_LEAF | ids[ref & 0x7fffffffu];
+            return ref + node_base;
+        };
+        for (auto n : bvh.nodes) {
+            n.ref0 = rebase(n.ref0);
+            n.ref1 = rebase(n.ref1);
+            n.parent = n.parent == LRK_BVH_EMPTY ? LRK_BVH_EMPTY : n.parent + node_base;
+            out.bvh_nodes.push_back(n);
+        }
+    }
+};
+
+FlatCamera flatten_camera(const Camera *cam) {
+    FlatCamera fc{};
+    auto &c = fc.camera;
+    to_rows_3x4(cam->camera_to_world, c.camera_to_world);
+    c.resolution[0] = cam->film->resolution[0];
+    c.resolution[1] = cam->film->resolution[1];
+    c.tan_half_fov = cam->tan_half_fov();
+    c.filter_radius = cam->filter->radius;
+    c.filter_shift[0] = cam->filter->shift[0];
+    c.filter_shift[1] = cam->filter->shift[1];
+    c.spp = cam->spp;
+    // Filter::Instance::Instance, src/base/filter.cpp:24-48
+    constexpr uint32_t n = LRK_FILTER_LUT_SIZE - 1u;
+    constexpr float inv_n = 1.0f / static_cast<float>(n);
+    float abs_f[n];
+    auto filter = cam->filter;
+    c.filter_lut[0] = filter->evaluate(-filter->radius);
+    auto integral = 0.0f;
+    for (uint32_t i = 0; i < n; i++) {
+        auto x = static_cast<float>(i + 1u) * inv_n * 2.0f - 1.0f;
+        c.filter_lut[i + 1u] = filter->evaluate(x * filter->radius);
+        auto f_mid = 0.5f * (c.filter_lut[i] + c.filter_lut[i + 1u]);
+        integral += f_mid;
+        abs_f[i] = std::abs(f_mid);
+    }
+    auto inv_integral = 1.0f / integral;
+    for (auto &f : c.filter_lut) f *= inv_integral;
+    std::vector<lrk_alias_entry> table;
+    std::vector<float> pdf;
+    create_alias_table(abs_f, n, table, pdf);
+    for (uint32_t i = 0; i < n; i++) {
+        c.filter_pdf[i] = pdf[i];
+        c.filter_alias_probs[i] = table[i].prob;
+        c.filter_alias_indices[i] = table[i].alias;
+    }
+    for (int i = 0; i < 3; i++) fc.film.scale[i] = cam->film->scale[i];
+    fc.film.clamp = cam->film->clamp;
+    fc.file = cam->file;
+    return fc;
+}
+
+}// namespace
+
+std::unique_ptr<FlatScene> flatten_scene(const Scene &scene) {
+    auto out = std::make_unique<FlatScene>();
+    for (int a = 0; a < 3; a++) {
+        out->world_max[a] = -std::numeric_limits<float>::max();
+        out->world_min[a] = std::numeric_limits<float>::max();
+    }
+    auto t0 = std::chrono::steady_clock::now();
+    Flattener f{scene, *out};
+    for (auto shape : scene.shapes()) f.process(shape, nullptr, nullptr, nullptr, true);
+    if (out->instances.empty()) throw Error("The scene has no geometry.");
+    f.build_tlas();
+    out->bvh_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+
+    // surfaces; Disney lobes are OR-ed over all disney nodes (one shared closure, src/surfaces/disney.cpp:869,994)
+    uint32_t disney_lobes = 0u;
+    for (auto s : f.surface_nodes) {
+        out->surfaces.push_back(s->flatten());
+        if (out->surfaces.back().type == LRK_SURFACE_DISNEY) disney_lobes |= out->surfaces.back().lobes;
+    }
+    for (auto &s : out->surfaces)
+        if (s.type == LRK_SURFACE_DISNEY) s.lobes = disney_lobes;
+    for (auto l : f.light_nodes) out->lights.push_back(l->flatten());
+
+    for (auto cam : scene.cameras()) out->cameras.push_back(flatten_camera(cam));
+    if (out->cameras.empty()) throw Error("The scene has no camera.");
+
+    auto integ = scene.integrator();
+    out->integrator.type = integ->kind;
+    out->integrator.max_depth = integ->max_depth;
+    out->integrator.rr_depth = integ->rr_depth;
+    out->integrator.rr_threshold = integ->rr_threshold;
+    out->integrator.samples_per_pass = integ->samples_per_pass;
+    out->integrator.sampler_seed = integ->sampler->seed;
+
+    if (auto m = scene.environment_medium(); m != nullptr && !m->is_null() && !m->is_vacuum()) {
+        auto &em = out->environment_medium;
+        em.present = 1u;
+        em.priority = m->priority;
+        em.eta = m->eta;
+        em.g = m->phase ? m->phase->g : 0.f;
+        for (int i = 0; i < 3; i++) {
+            em.sigma_a[i] = m->sigma_a[i];
+            em.sigma_s[i] = m->sigma_s[i];
+            em.le[i] = m->le[i];
+        }
+    }
+    return out;
+}
+
+}// namespace lrh

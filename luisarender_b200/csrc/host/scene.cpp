@@ -1,0 +1,799 @@
+#include "scene.h"
+
+#include <algorithm>
+#include <cmath>
+
+namespace lrh {
+
+// ---------------------------------------------------------------- plugin registry
+
+namespace {
+struct Registry {
+    std::mutex mutex;
+    std::unordered_map<std::string, Plugin> plugins;
+};
+Registry &registry() {
+    static Registry r;
+    return r;
+}
+}// namespace
+
+void register_plugin(const std::string &key, Plugin plugin) {
+    auto &r = registry();
+    std::scoped_lock lock{r.mutex};
+    r.plugins[key] = plugin;
+}
+
+const Plugin *find_plugin(const std::string &key) {
+    auto &r = registry();
+    std::scoped_lock lock{r.mutex};
+    auto it = r.plugins.find(key);
+    return it == r.plugins.end() ? nullptr : &it->second;
+}
+
+std::vector<std::string> registered_plugins() {
+    auto &r = registry();
+    std::scoped_lock lock{r.mutex};
+    std::vector<std::string> keys;
+    for (auto &kv : r.plugins) keys.push_back(kv.first);
+    std::sort(keys.begin(), keys.end());
+    return keys;
+}
+
+// same shape as LUISA_RENDER_MAKE_SCENE_NODE_PLUGIN (src/base/scene_node.h:58-67)
+#define LRH_PLUGIN(key, cls)                                                                          \
+    namespace {                                                                                       \
+    SceneNode *create_##cls(Scene *scene, const NodeDesc *desc) { return new cls{scene, desc}; }      \
+    void destroy_##cls(SceneNode *node) { delete node; }                                              \
+    struct Register_##cls {                                                                           \
+        Register_##cls() { register_plugin(key, Plugin{create_##cls, destroy_##cls}); }               \
+    } register_##cls##_instance;                                                                      \
+    }
+
+// ---------------------------------------------------------------- Scene
+
+Scene::~Scene() {
+    for (auto it = _internal_nodes.rbegin(); it != _internal_nodes.rend(); ++it) it->destroy(it->node);
+    for (auto &kv : _nodes) kv.second.destroy(kv.second.node);
+}
+
+const NodeDesc *Scene::shared_default(Tag tag, const std::string &impl) {
+    std::string key{tag_description(tag)};
+    key.append("-").append(impl);
+    for (auto &c : key) c = static_cast<char>(std::tolower(static_cast<unsigned char>(c)));
+    std::scoped_lock lock{_mutex};
+    if (auto it = _default_lookup.find(key); it != _default_lookup.end()) return it->second;
+    auto d = std::make_unique<NodeDesc>("__shared_default_" + key, tag);
+    d->define(tag, impl, "shared default", {});
+    auto p = _default_descs.emplace_back(std::move(d)).get();
+    _default_lookup.emplace(key, p);
+    return p;
+}
+
+SceneNode *Scene::load_node(Tag tag, const NodeDesc *desc) {
+    if (desc == nullptr) return nullptr;
+    if (!desc->is_defined()) {
+        throw Error("Undefined scene description node '" + desc->identifier() + "' (type = " +
+                    std::string{tag_description(desc->tag())} + "::" + desc->impl_type() + ").");
+    }
+    std::string key{tag_description(tag)};
+    key.append("-").append(desc->impl_type());
+    auto plugin = find_plugin(key);
+    if (plugin == nullptr) {
+        throw Error("Failed to load plugin 'luisa-render-" + key + "' for scene node '" + desc->identifier() +
+                    "' (not implemented in this build). [" + desc->location() + "]");
+    }
+    std::scoped_lock lock{_mutex};
+    if (desc->is_internal()) {
+        auto node = plugin->create(this, desc);
+        _internal_nodes.push_back({node, plugin->destroy});
+        return node;
+    }
+    if (desc->tag() != tag) {
+        throw Error("Invalid tag " + std::string{tag_description(desc->tag())} + " of scene description node '" +
+                    desc->identifier() + "' (expected " + std::string{tag_description(tag)} + "). [" + desc->location() + "]");
+    }
+    if (auto it = _nodes.find(desc->identifier()); it != _nodes.end()) {
+        auto node = it->second.node;
+        if (node->tag() != tag || node->impl_type() != desc->impl_type()) {
+            throw Error("Scene node `" + desc->identifier() + "` is already in the graph with another type. [" +
+                        desc->location() + "]");
+        }
+        return node;
+    }
+    auto node = plugin->create(this, desc);
+    _nodes.emplace(desc->identifier(), Handle{node, plugin->destroy});
+    return node;
+}
+
+std::unique_ptr<Scene> Scene::create(const SceneDesc *desc) {
+    auto root = desc->root();
+    if (!root->is_defined()) throw Error("Root node is not defined in the scene description.");
+    std::unique_ptr<Scene> scene{new Scene};
+    // order of loading follows src/base/scene.cpp:201-233
+    scene->_shadow_terminator = root->f("shadow_terminator", 0.f);
+    scene->_intersection_offset = root->f("intersection_offset", 0.f);
+    auto spectrum_desc = root->node("spectrum");
+    if (!spectrum_desc) spectrum_desc = scene->shared_default(Tag::SPECTRUM, "sRGB");
+    scene->_spectrum = scene->load<Spectrum>(Tag::SPECTRUM, spectrum_desc);
+    scene->_integrator = scene->load<Integrator>(Tag::INTEGRATOR, root->required_node("integrator"));
+    if (auto env = root->node("environment")) scene->load_node(Tag::ENVIRONMENT, env);// no env plugin -> hard error
+    scene->_environment_medium = scene->load_medium(root->node("environment_medium"));
+    for (auto c : root->required_nodes("cameras")) scene->_cameras.push_back(scene->load<Camera>(Tag::CAMERA, c));
+    for (auto s : root->required_nodes("shapes")) scene->_shapes.push_back(scene->load_shape(s));
+    return scene;
+}
+
+// ---------------------------------------------------------------- base-class constructors
+
+static float4x4 view_matrix(float3 origin, float3 front, float3 up) {
+    // src/transforms/view.cpp:27-48
+    auto w = normalize(-front);
+    auto u = normalize(cross(up, w));
+    auto v = normalize(cross(w, u));
+    float4x4 m;
+    m.c[0] = {u.x, u.y, u.z, 0.f};
+    m.c[1] = {v.x, v.y, v.z, 0.f};
+    m.c[2] = {w.x, w.y, w.z, 0.f};
+    m.c[3] = {origin.x, origin.y, origin.z, 1.f};
+    return m;
+}
+
+Filter::Filter(const Scene *s, const NodeDesc *d) : SceneNode{s, d, Tag::FILTER} {
+    // src/base/filter.cpp:11-17
+    radius = std::max(d->f("radius", .5f), 1e-3f);
+    if (!d->fN("shift", 2, shift)) shift[0] = shift[1] = d->f("shift", 0.f);
+}
+
+Sampler::Sampler(const Scene *s, const NodeDesc *d)
+    : SceneNode{s, d, Tag::SAMPLER}, seed{d->u("seed", 19980810u)} {}// src/base/sampler.cpp:11
+
+Integrator::Integrator(Scene *s, const NodeDesc *d) : SceneNode{s, d, Tag::INTEGRATOR} {
+    // src/base/integrator.cpp:13-18
+    auto sd = d->node("sampler");
+    if (!sd) sd = s->shared_default(Tag::SAMPLER, "independent");
+    sampler = s->load_sampler(sd);
+    auto ld = d->node("light_sampler");
+    if (!ld) ld = s->shared_default(Tag::LIGHT_SAMPLER, "uniform");
+    light_sampler = s->load_light_sampler(ld);
+}
+
+Camera::Camera(Scene *s, const NodeDesc *d) : SceneNode{s, d, Tag::CAMERA} {
+    // src/base/camera.cpp:16-50,137-147
+    film = s->load_film(d->required_node("film"));
+    auto fd = d->node("filter");
+    if (!fd) fd = s->shared_default(Tag::FILTER, "Box");
+    filter = s->load_filter(fd);
+    transform = s->load_transform(d->node("transform"));
+    camera_to_world = transform ? transform->matrix() : float4x4::identity();
+    if (transform == nullptr) {
+        // compatibility with older scene files: position / front | look_at / up (src/base/camera.cpp:30-50)
+        float p[3]{0.f, 0.f, 0.f}, f[3], up[3]{0.f, 1.f, 0.f};
+        d->fN("position", 3, p);
+        if (!d->fN("front", 3, f)) {
+            float la[3]{p[0], p[1], p[2] - 1.f};
+            d->fN("look_at", 3, la);
+            auto n = normalize(float3{la[0] - p[0], la[1] - p[1], la[2] - p[2]});
+            f[0] = n.x; f[1] = n.y; f[2] = n.z;
+        }
+        d->fN("up", 3, up);
+        bool is_default = p[0] == 0.f && p[1] == 0.f && p[2] == 0.f && f[0] == 0.f && f[1] == 0.f && f[2] == -1.f &&
+                          up[0] == 0.f && up[1] == 1.f && up[2] == 0.f;
+        if (!is_default) camera_to_world = view_matrix({p[0], p[1], p[2]}, {f[0], f[1], f[2]}, {up[0], up[1], up[2]});
+    }
+    spp = d->u("spp", 1024u);
+    float span[2];
+    if (!d->fN("shutter_span", 2, span)) span[0] = span[1] = d->f("shutter_span", 0.f);
+    if (span[0] != span[1]) throw Error("Motion blur (shutter_span) is not supported. [" + d->location() + "]");
+    if (auto f = d->string("file")) {
+        std::filesystem::path p{*f};
+        file = p.is_absolute() ? p : d->source_dir() / p;
+    } else {
+        file = (d->source_dir().empty() ? std::filesystem::current_path() : d->source_dir()) / "render.exr";
+    }
+}
+
+Shape::Shape(Scene *s, const NodeDesc *d) : SceneNode{s, d, Tag::SHAPE} {
+    // src/base/shape.cpp:15-20
+    surface = s->load_surface(d->node("surface"));
+    light = s->load_light(d->node("light"));
+    transform = s->load_transform(d->node("transform"));
+    medium = s->load_medium(d->node("medium"));
+}
+
+const std::vector<lrk_vertex> &Shape::vertices() const {
+    static const std::vector<lrk_vertex> empty;
+    return empty;
+}
+const std::vector<lrk_triangle> &Shape::triangles() const {
+    static const std::vector<lrk_triangle> empty;
+    return empty;
+}
+
+// ---------------------------------------------------------------- textures / spectrum
+
+namespace {
+
+struct ConstantTexture final : Texture {
+    // src/textures/constant.cpp:24-47
+    float4 v{};
+    uint32_t n{0};
+    bool black{false};
+    ConstantTexture(Scene *s, const NodeDesc *d) : Texture{s, d, Tag::TEXTURE} {
+        auto scale = d->f("scale", 1.f);
+        auto values = d->float_list("v");
+        if (values.empty()) values.push_back(0.f);
+        if (values.size() > 4) values.resize(4);
+        n = static_cast<uint32_t>(values.size());
+        for (uint32_t i = 0; i < n; i++) v[i] = scale * values[i];
+        black = v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f;
+    }
+    bool is_black() const override { return black; }
+    bool is_constant() const override { return true; }
+    uint32_t channels() const override { return n; }
+    float4 value() const override { return v; }
+};
+
+struct SRGBSpectrum final : Spectrum {
+    SRGBSpectrum(Scene *s, const NodeDesc *d) : Spectrum{s, d, Tag::SPECTRUM} {}
+};
+
+// src/base/texture.cpp:15-19
+float3 extend_color_to_rgb(float4 c, uint32_t n) {
+    if (n == 1u) return {c.x, c.x, c.x};
+    if (n == 2u) return {c.x, c.y, 1.f};
+    return {c.x, c.y, c.z};
+}
+float saturate(float x) { return std::min(std::max(x, 0.f), 1.f); }
+// albedo decode with the sRGB spectrum: src/spectra/srgb.cpp:18,34-40; returns luminance strength
+float3 decode_albedo(const Texture *t, float *strength) {
+    float3 rgb{1.f, 1.f, 1.f};
+    if (t != nullptr) {
+        auto c = extend_color_to_rgb(t->value(), t->channels());
+        rgb = {saturate(c.x), saturate(c.y), saturate(c.z)};
+    }
+    // src/util/colorspace.h:21-25
+    if (strength) *strength = 0.212671f * rgb.x + 0.715160f * rgb.y + 0.072169f * rgb.z;
+    return rgb;
+}
+const Texture *constant_or_null(Scene *s, const NodeDesc *d, const char *name) {
+    auto t = s->load_texture(d->node(name));
+    if (t && !t->is_constant()) throw Error("Only constant textures are supported ('" + std::string{name} + "').");
+    return t;
+}
+void reject_wrappers(const NodeDesc *d) {
+    // NormalMapWrapper<OpacitySurfaceWrapper<...>> (src/base/surface.h:160-330) is out of scope
+    for (auto name : {"normal_map", "alpha", "opacity"}) {
+        if (d->has_property(name))
+            throw Error("Surface property '" + std::string{name} + "' (opacity / normal-map wrappers) is not supported. [" + d->location() + "]");
+    }
+}
+
+}// namespace
+LRH_PLUGIN("texture-constant", ConstantTexture)
+LRH_PLUGIN("spectrum-srgb", SRGBSpectrum)
+
+// ---------------------------------------------------------------- transforms
+
+namespace {
+
+struct IdentityTransform final : Transform {
+    IdentityTransform(Scene *s, const NodeDesc *d) : Transform{s, d, Tag::TRANSFORM} {}
+    float4x4 matrix() const override { return float4x4::identity(); }
+};
+
+struct MatrixTransform final : Transform {
+    // src/transforms/matrix.cpp:17-43 : row-major list of 16
+    float4x4 m{float4x4::identity()};
+    MatrixTransform(Scene *s, const NodeDesc *d) : Transform{s, d, Tag::TRANSFORM} {
+        auto v = d->float_list("m");
+        if (v.size() == 16u) {
+            v[12] = 0.f; v[13] = 0.f; v[14] = 0.f; v[15] = 1.f;
+            for (int row = 0; row < 4; row++)
+                for (int col = 0; col < 4; col++) m.c[col][row] = v[row * 4 + col];
+        } else if (!v.empty()) {
+            throw Error("Invalid matrix entries. [" + d->location() + "]");
+        }
+    }
+    float4x4 matrix() const override { return m; }
+};
+
+float4x4 translation(float3 v) {
+    auto m = float4x4::identity();
+    m.c[3] = {v.x, v.y, v.z, 1.f};
+    return m;
+}
+float4x4 scaling(float3 s) {
+    auto m = float4x4::identity();
+    m.c[0].x = s.x; m.c[1].y = s.y; m.c[2].z = s.z;
+    return m;
+}
+// src/compute/include/luisa/core/mathematics.h:470-481
+float4x4 rotation(float3 axis, float angle) {
+    if (angle == 0.0f) return float4x4::identity();
+    auto c = std::cos(angle);
+    auto s = std::sin(angle);
+    auto a = normalize(axis);
+    auto t = (1.0f - c) * a;
+    float4x4 m;
+    m.c[0] = {c + t.x * a.x, t.x * a.y + s * a.z, t.x * a.z - s * a.y, 0.0f};
+    m.c[1] = {t.y * a.x - s * a.z, c + t.y * a.y, t.y * a.z + s * a.x, 0.0f};
+    m.c[2] = {t.z * a.x + s * a.y, t.z * a.y - s * a.x, c + t.z * a.z, 0.0f};
+    m.c[3] = {0.0f, 0.0f, 0.0f, 1.0f};
+    return m;
+}
+
+struct SRTTransform final : Transform {
+    // src/transforms/srt.cpp:18-28
+    float4x4 m;
+    SRTTransform(Scene *s, const NodeDesc *d) : Transform{s, d, Tag::TRANSFORM} {
+        float sc[3], rot[4], tr[3];
+        if (!d->fN("scale", 3, sc)) sc[0] = sc[1] = sc[2] = d->f("scale", 1.f);
+        if (!d->fN("rotate", 4, rot)) { rot[0] = 0.f; rot[1] = 0.f; rot[2] = 1.f; rot[3] = 0.f; }
+        if (!d->fN("translate", 3, tr)) tr[0] = tr[1] = tr[2] = 0.f;
+        m = translation({tr[0], tr[1], tr[2]}) *
+            rotation(normalize(float3{rot[0], rot[1], rot[2]}), radians(rot[3])) *
+            scaling({sc[0], sc[1], sc[2]});
+    }
+    float4x4 matrix() const override { return m; }
+};
+
+struct ViewTransform final : Transform {
+    float4x4 m;
+    ViewTransform(Scene *s, const NodeDesc *d) : Transform{s, d, Tag::TRANSFORM} {
+        float o[3], f[3], up[3];
+        if (!d->fN("origin", 3, o) && !d->fN("position", 3, o)) o[0] = o[1] = o[2] = 0.f;
+        if (!d->fN("front", 3, f)) { f[0] = 0.f; f[1] = 0.f; f[2] = -1.f; }
+        if (!d->fN("up", 3, up)) { up[0] = 0.f; up[1] = 1.f; up[2] = 0.f; }
+        m = view_matrix({o[0], o[1], o[2]}, {f[0], f[1], f[2]}, {up[0], up[1], up[2]});
+    }
+    float4x4 matrix() const override { return m; }
+};
+
+struct StackTransform final : Transform {
+    // src/transforms/stack.cpp:24-37 : later entries are applied after earlier ones
+    float4x4 m{float4x4::identity()};
+    bool identity{true};
+    StackTransform(Scene *s, const NodeDesc *d) : Transform{s, d, Tag::TRANSFORM} {
+        for (auto c : d->nodes("transforms")) {
+            auto t = s->load_transform(c);
+            identity = identity && t->is_identity();
+            m = t->matrix() * m;
+        }
+    }
+    float4x4 matrix() const override { return m; }
+    bool is_identity() const override { return identity; }
+};
+
+}// namespace
+LRH_PLUGIN("transform-identity", IdentityTransform)
+LRH_PLUGIN("transform-matrix", MatrixTransform)
+LRH_PLUGIN("transform-srt", SRTTransform)
+LRH_PLUGIN("transform-view", ViewTransform)
+LRH_PLUGIN("transform-stack", StackTransform)
+
+// ---------------------------------------------------------------- filters
+
+namespace {
+struct BoxFilter final : Filter {
+    BoxFilter(Scene *s, const NodeDesc *d) : Filter{s, d} {}
+    float evaluate(float) const override { return 1.0f; }
+};
+struct TriangleFilter final : Filter {
+    TriangleFilter(Scene *s, const NodeDesc *d) : Filter{s, d} {}
+    float evaluate(float x) const override { return std::max(1.0f - std::abs(x / radius), 0.0f); }
+};
+struct GaussianFilter final : Filter {
+    // src/filters/gaussian.cpp:16-37
+    float sigma;
+    GaussianFilter(Scene *s, const NodeDesc *d) : Filter{s, d}, sigma{d->f("sigma", 0.f)} {
+        if (sigma <= 0.f) sigma = radius / 3.f;
+    }
+    float G(float x) const {
+        auto s2 = 2.0f * sigma * sigma;
+        return 1.0f / std::sqrt(kPi * s2) * std::exp(-x * x / s2);
+    }
+    float evaluate(float x) const override { return G(x) - G(radius); }
+};
+struct MitchellFilter final : Filter {
+    // src/filters/mitchell.cpp:17-38
+    float B, C;
+    MitchellFilter(Scene *s, const NodeDesc *d) : Filter{s, d}, B{d->f("b", 1.0f / 3.0f)}, C{d->f("c", 1.0f / 3.0f)} {}
+    float evaluate(float x) const override {
+        x = 2.f * std::abs(x / radius);
+        if (x <= 1.0f)
+            return ((12.0f - 9.0f * B - 6.0f * C) * x * x * x + (-18.0f + 12.0f * B + 6.0f * C) * x * x + (6.0f - 2.0f * B)) * (1.f / 6.f);
+        if (x <= 2.0f)
+            return ((-B - 6.0f * C) * x * x * x + (6.0f * B + 30.0f * C) * x * x + (-12.0f * B - 48.0f * C) * x + (8.0f * B + 24.0f * C)) * (1.0f / 6.0f);
+        return 0.0f;
+    }
+};
+struct LanczosSincFilter final : Filter {
+    // src/filters/lanczos_sinc.cpp:16-31
+    float tau;
+    LanczosSincFilter(Scene *s, const NodeDesc *d) : Filter{s, d}, tau{d->f("tau", 3.0f)} {}
+    static float sinc(float x) {
+        x = kPi * x;
+        return 1.0f + x * x == 1.0f ? 1.0f : std::sin(x) / x;
+    }
+    float evaluate(float x) const override {
+        x = x / radius;
+        if (std::abs(x) > 1.0f) return 0.0f;
+        return sinc(x) * sinc(x / tau);
+    }
+};
+}// namespace
+LRH_PLUGIN("filter-box", BoxFilter)
+LRH_PLUGIN("filter-triangle", TriangleFilter)
+LRH_PLUGIN("filter-gaussian", GaussianFilter)
+LRH_PLUGIN("filter-mitchell", MitchellFilter)
+LRH_PLUGIN("filter-lanczossinc", LanczosSincFilter)
+
+// ---------------------------------------------------------------- film / sampler / light sampler / integrators
+
+namespace {
+
+struct ColorFilm final : Film {
+    // src/films/color.cpp:26-42
+    ColorFilm(Scene *s, const NodeDesc *d) : Film{s, d, Tag::FILM} {
+        auto r = d->uint_list("resolution");
+        if (r.size() >= 2) { resolution[0] = r[0]; resolution[1] = r[1]; }
+        else { resolution[0] = resolution[1] = d->u("resolution", 1024u); }
+        float e[3];
+        if (!d->fN("exposure", 3, e)) e[0] = e[1] = e[2] = d->f("exposure", 0.f);
+        for (int i = 0; i < 3; i++) scale[i] = std::pow(2.0f, e[i]);
+        clamp = std::max(1.f, d->f("clamp", 256.f));
+        if (resolution[0] == 0 || resolution[1] == 0) throw Error("Invalid film resolution. [" + d->location() + "]");
+    }
+};
+
+struct IndependentSampler final : Sampler {
+    IndependentSampler(Scene *s, const NodeDesc *d) : Sampler{s, d} {}
+};
+
+struct UniformLightSampler final : LightSampler {
+    UniformLightSampler(Scene *s, const NodeDesc *d) : LightSampler{s, d, Tag::LIGHT_SAMPLER} {
+        environment_weight = d->f("environment_weight", .5f);// src/lightsamplers/uniform.cpp:17-19
+    }
+};
+
+// wavepath / wavepath_v2 / megapath share one estimator; parameters and defaults from
+// src/integrators/wave_path.cpp:41-46 (identical in mega_path.cpp:22-29 and wave_path_v2.cpp:60-72).
+struct PathIntegrator final : Integrator {
+    PathIntegrator(Scene *s, const NodeDesc *d) : Integrator{s, d} {
+        kind = LRK_INTEGRATOR_PATH;
+        max_depth = std::max(d->u("depth", 10u), 1u);
+        rr_depth = d->u("rr_depth", 0u);
+        rr_threshold = std::max(d->f("rr_threshold", 0.95f), 0.05f);
+        samples_per_pass = std::max(d->u("samples_per_pass", 16u), 1u);
+    }
+};
+
+// src/integrators/mega_vpt_naive.cpp:33-42
+struct VolumePathIntegrator final : Integrator {
+    VolumePathIntegrator(Scene *s, const NodeDesc *d) : Integrator{s, d} {
+        kind = LRK_INTEGRATOR_VOLUME_PATH;
+        max_depth = std::max(d->u("depth", 10u), 1u);
+        rr_depth = d->u("rr_depth", 0u);
+        rr_threshold = std::max(d->f("rr_threshold", 0.95f), 0.05f);
+        samples_per_pass = std::max(d->u("samples_per_pass", 16u), 1u);
+    }
+};
+
+}// namespace
+LRH_PLUGIN("film-color", ColorFilm)
+LRH_PLUGIN("sampler-independent", IndependentSampler)
+LRH_PLUGIN("lightsampler-uniform", UniformLightSampler)
+LRH_PLUGIN("integrator-wavepath", PathIntegrator)
+namespace {
+SceneNode *create_path_alias(Scene *scene, const NodeDesc *desc) { return new PathIntegrator{scene, desc}; }
+void destroy_path_alias(SceneNode *n) { delete n; }
+struct RegisterPathAliases {
+    RegisterPathAliases() {
+        register_plugin("integrator-wavepath_v2", Plugin{create_path_alias, destroy_path_alias});
+        register_plugin("integrator-megapath", Plugin{create_path_alias, destroy_path_alias});
+    }
+} register_path_aliases_instance;
+}// namespace
+LRH_PLUGIN("integrator-megavptnaive", VolumePathIntegrator)
+
+// ---------------------------------------------------------------- media
+
+namespace {
+
+struct HenyeyGreenstein final : PhaseFunction {
+    HenyeyGreenstein(Scene *s, const NodeDesc *d) : PhaseFunction{s, d, Tag::PHASE_FUNCTION} {
+        g = std::min(std::max(d->f("g", 0.f), -1.f), 1.f);// src/phasefunctions/henyey_greenstein.cpp:66-68
+    }
+};
+
+struct HomogeneousMedium final : Medium {
+    // src/media/homogeneous.cpp:188-199
+    HomogeneousMedium(Scene *s, const NodeDesc *d) : Medium{s, d, Tag::MEDIUM} {
+        priority = d->u("priority", 0u);
+        eta = d->f("eta", 1.f);
+        auto sa = constant_or_null(s, d, "sigma_a");
+        auto ss = constant_or_null(s, d, "sigma_s");
+        auto le_t = constant_or_null(s, d, "Le");
+        phase = s->load_phase_function(d->node("phasefunction"));
+        if (!sa) throw Error("sigma_a must be specified as constant. [" + d->location() + "]");
+        if (!ss) throw Error("sigma_s must be specified as constant. [" + d->location() + "]");
+        if (!phase) throw Error("Phase function must be specified. [" + d->location() + "]");
+        auto a = extend_color_to_rgb(sa->value(), sa->channels());
+        auto sc = extend_color_to_rgb(ss->value(), ss->channels());
+        for (int i = 0; i < 3; i++) { sigma_a[i] = a[i]; sigma_s[i] = sc[i]; }
+        if (le_t) {
+            auto e = extend_color_to_rgb(le_t->value(), le_t->channels());
+            for (int i = 0; i < 3; i++) le[i] = std::max(e[i], 0.f);
+        }
+    }
+};
+struct NullMedium final : Medium {
+    NullMedium(Scene *s, const NodeDesc *d) : Medium{s, d, Tag::MEDIUM} {}
+    bool is_null() const override { return true; }
+};
+struct VacuumMedium final : Medium {
+    VacuumMedium(Scene *s, const NodeDesc *d) : Medium{s, d, Tag::MEDIUM} { priority = d->u("priority", 0u); }
+    bool is_vacuum() const override { return true; }
+};
+
+}// namespace
+LRH_PLUGIN("phasefunction-henyeygreenstein", HenyeyGreenstein)
+LRH_PLUGIN("medium-homogeneous", HomogeneousMedium)
+LRH_PLUGIN("medium-null", NullMedium)
+LRH_PLUGIN("medium-vacuum", VacuumMedium)
+
+// ---------------------------------------------------------------- surfaces / lights
+
+namespace {
+
+struct MatteSurface final : Surface {
+    // src/surfaces/matte.cpp:22-27,119-134
+    const Texture *kd;
+    const Texture *sigma;
+    MatteSurface(Scene *s, const NodeDesc *d) : Surface{s, d, Tag::SURFACE} {
+        reject_wrappers(d);
+        kd = constant_or_null(s, d, "Kd");
+        sigma = constant_or_null(s, d, "sigma");
+    }
+    lrk_surface flatten() const override {
+        lrk_surface out{};
+        out.type = LRK_SURFACE_MATTE;
+        auto c = decode_albedo(kd, nullptr);
+        out.p[0] = c.x; out.p[1] = c.y; out.p[2] = c.z;
+        out.p[3] = (sigma && !sigma->is_black()) ? saturate(sigma->value().x) * 90.f : 0.f;
+        return out;
+    }
+};
+
+struct DisneySurface final : Surface {
+    // src/surfaces/disney.cpp:36-58,932-998
+    const Texture *color, *metallic, *eta, *roughness, *specular_tint, *anisotropic, *sheen, *sheen_tint,
+        *clearcoat, *clearcoat_gloss, *specular_trans, *flatness, *diffuse_trans;
+    bool thin, remap_roughness;
+    DisneySurface(Scene *s, const NodeDesc *d) : Surface{s, d, Tag::SURFACE} {
+        reject_wrappers(d);
+        color = constant_or_null(s, d, d->has_property("color") ? "color" : "Kd");
+        thin = d->b("thin", false);
+        remap_roughness = d->b("remap_roughness", true);
+        metallic = constant_or_null(s, d, "metallic");
+        eta = constant_or_null(s, d, "eta");
+        roughness = constant_or_null(s, d, "roughness");
+        specular_tint = constant_or_null(s, d, "specular_tint");
+        anisotropic = constant_or_null(s, d, "anisotropic");
+        sheen = constant_or_null(s, d, "sheen");
+        sheen_tint = constant_or_null(s, d, "sheen_tint");
+        clearcoat = constant_or_null(s, d, "clearcoat");
+        clearcoat_gloss = constant_or_null(s, d, "clearcoat_gloss");
+        specular_trans = constant_or_null(s, d, "specular_trans");
+        flatness = constant_or_null(s, d, "flatness");
+        diffuse_trans = constant_or_null(s, d, "diffuse_trans");
+        if (thin) throw Error("Thin Disney surfaces are not supported. [" + d->location() + "]");
+        if (specular_trans && !specular_trans->is_black())
+            throw Error("Transmissive Disney surfaces (specular_trans != 0) are not supported. [" + d->location() + "]");
+    }
+    uint32_t lobes() const {
+        // src/surfaces/disney.cpp:966-990
+        uint32_t l = 0u;
+        if (!color || !color->is_black()) {
+            l |= LRK_DISNEY_LOBE_DIFFUSE | LRK_DISNEY_LOBE_RETRO;
+            if (sheen && !sheen->is_black()) l |= LRK_DISNEY_LOBE_SHEEN;
+            if (flatness && !flatness->is_black()) l |= LRK_DISNEY_LOBE_FAKE_SS;
+        }
+        l |= LRK_DISNEY_LOBE_SPECULAR;
+        if (clearcoat && !clearcoat->is_black()) l |= LRK_DISNEY_LOBE_CLEARCOAT;
+        return l;
+    }
+    lrk_surface flatten() const override {
+        lrk_surface out{};
+        out.type = LRK_SURFACE_DISNEY;
+        out.lobes = lobes();
+        float lum;
+        auto c = decode_albedo(color, &lum);
+        auto x = [](const Texture *t, float dflt) { return t ? t->value().x : dflt; };
+        out.p[0] = c.x; out.p[1] = c.y; out.p[2] = c.z; out.p[3] = lum;
+        out.p[4] = x(metallic, 0.f);
+        out.p[5] = x(eta, 1.5f);
+        auto r = x(roughness, .5f);
+        if (remap_roughness) r = std::max(r * r, 1e-4f);// roughness_to_alpha, src/util/scattering.cpp:137-139
+        out.p[6] = r;
+        out.p[7] = x(specular_tint, 0.f);
+        out.p[8] = x(anisotropic, 0.f);
+        out.p[9] = x(sheen, 0.f);
+        out.p[10] = x(sheen_tint, 0.f);
+        out.p[11] = x(clearcoat, 0.f);
+        out.p[12] = x(clearcoat_gloss, 1.f);
+        out.p[13] = x(specular_trans, 0.f);
+        out.p[14] = x(flatness, 0.f);
+        out.p[15] = 0.f;// diffuse_trans is only built for thin surfaces (src/surfaces/disney.cpp:1017)
+        return out;
+    }
+};
+
+struct NullSurface final : Surface {
+    NullSurface(Scene *s, const NodeDesc *d) : Surface{s, d, Tag::SURFACE} {}
+    bool is_null() const override { return true; }
+    lrk_surface flatten() const override { throw Error("NullSurface cannot be instantiated."); }
+};
+
+struct DiffuseLight final : Light {
+    // src/lights/diffuse.cpp:21-30
+    const Texture *emission;
+    float scale;
+    bool two_sided;
+    DiffuseLight(Scene *s, const NodeDesc *d) : Light{s, d, Tag::LIGHT} {
+        auto e = d->node("emission");
+        if (!e) e = s->shared_default(Tag::TEXTURE, "Constant");
+        emission = s->load_texture(e);
+        if (!emission->is_constant()) throw Error("Only constant emission textures are supported.");
+        scale = std::max(d->f("scale", 1.0f), 0.0f);
+        two_sided = d->b("two_sided", false);
+    }
+    bool is_null() const override { return scale == 0.0f || emission->is_black(); }
+    lrk_light flatten() const override {
+        lrk_light out{};
+        auto c = extend_color_to_rgb(emission->value(), emission->channels());
+        out.emission[0] = std::max(c.x, 0.f);
+        out.emission[1] = std::max(c.y, 0.f);
+        out.emission[2] = std::max(c.z, 0.f);
+        out.scale = scale;
+        out.two_sided = two_sided ? 1u : 0u;
+        return out;
+    }
+};
+
+struct NullLight final : Light {
+    NullLight(Scene *s, const NodeDesc *d) : Light{s, d, Tag::LIGHT} {}
+    bool is_null() const override { return true; }
+    lrk_light flatten() const override { throw Error("NullLight cannot be instantiated."); }
+};
+
+}// namespace
+LRH_PLUGIN("surface-matte", MatteSurface)
+LRH_PLUGIN("surface-disney", DisneySurface)
+LRH_PLUGIN("surface-null", NullSurface)
+LRH_PLUGIN("light-diffuse", DiffuseLight)
+LRH_PLUGIN("light-null", NullLight)
+
+// ---------------------------------------------------------------- cameras
+
+namespace {
+
+struct PinholeCamera final : Camera {
+    // src/cameras/pinhole.cpp:33-37
+    float fov;
+    PinholeCamera(Scene *s, const NodeDesc *d) : Camera{s, d} {
+        fov = radians(std::min(std::max(d->f("fov", 35.0f), 1e-3f), 180.f - 1e-3f));
+    }
+    float tan_half_fov() const override { return std::tan(fov * 0.5f); }
+};
+
+}// namespace
+LRH_PLUGIN("camera-pinhole", PinholeCamera)
+
+// ---------------------------------------------------------------- shapes
+
+namespace {
+
+// VisibilityShapeWrapper / ShadowTerminatorShapeWrapper / IntersectionOffsetShapeWrapper: src/base/shape.h:66-115
+void read_mesh_wrappers(Shape *shape, Scene *s, const NodeDesc *d) {
+    shape->visible = d->b("visible", true);
+    shape->shadow_terminator = std::min(std::max(d->f("shadow_terminator", s->shadow_terminator_factor()), 0.f), 1.f);
+    shape->intersection_offset = std::min(std::max(d->f("intersection_offset", s->intersection_offset_factor()), 0.f), 1.f);
+}
+
+struct InlineMesh final : Shape {
+    // src/shapes/inline_mesh.cpp:21-71
+    std::vector<lrk_vertex> verts;
+    std::vector<lrk_triangle> tris;
+    uint32_t props{0};
+    InlineMesh(Scene *s, const NodeDesc *d) : Shape{s, d} {
+        read_mesh_wrappers(this, s, d);
+        if (!d->has_property("indices") || !d->has_property("positions"))
+            throw Error("No valid values given for property 'indices'/'positions' in scene description node '" +
+                        d->identifier() + "'. [" + d->location() + "]");
+        auto indices = d->uint_list("indices");
+        auto positions = d->float_list("positions");
+        auto normals = d->float_list("normals");
+        auto uvs = d->float_list("uvs");
+        if (indices.size() % 3u != 0u || positions.size() % 3u != 0u || normals.size() % 3u != 0u || uvs.size() % 2u != 0u ||
+            (!normals.empty() && normals.size() != positions.size()) ||
+            (!uvs.empty() && uvs.size() / 2u != positions.size() / 3u)) {
+            throw Error("Invalid vertex or triangle count. [" + d->location() + "]");
+        }
+        props = (!uvs.empty() ? LRK_SHAPE_HAS_VERTEX_UV : 0u) | (!normals.empty() ? LRK_SHAPE_HAS_VERTEX_NORMAL : 0u);
+        auto nv = positions.size() / 3u;
+        tris.resize(indices.size() / 3u);
+        for (size_t i = 0; i < tris.size(); i++) {
+            tris[i] = {indices[i * 3], indices[i * 3 + 1], indices[i * 3 + 2]};
+            if (tris[i].i0 >= nv || tris[i].i1 >= nv || tris[i].i2 >= nv)
+                throw Error("Triangle index out of range. [" + d->location() + "]");
+        }
+        verts.resize(nv);
+        for (size_t i = 0; i < nv; i++) {
+            auto &v = verts[i];
+            v.p[0] = positions[i * 3]; v.p[1] = positions[i * 3 + 1]; v.p[2] = positions[i * 3 + 2];
+            if (normals.empty()) { v.n[0] = 0.f; v.n[1] = 0.f; v.n[2] = 1.f; }
+            else { v.n[0] = normals[i * 3]; v.n[1] = normals[i * 3 + 1]; v.n[2] = normals[i * 3 + 2]; }
+            if (uvs.empty()) { v.uv[0] = v.uv[1] = 0.f; }
+            else { v.uv[0] = uvs[i * 2]; v.uv[1] = uvs[i * 2 + 1]; }
+        }
+        if (verts.empty() || tris.empty()) throw Error("Empty mesh. [" + d->location() + "]");
+    }
+    bool is_mesh() const override { return true; }
+    uint32_t vertex_properties() const override { return props; }
+    const std::vector<lrk_vertex> &vertices() const override { return verts; }
+    const std::vector<lrk_triangle> &triangles() const override { return tris; }
+};
+
+struct SphereShape final : Shape {
+    // src/shapes/sphere.cpp:103-118 ; geometry cached per subdivision level like the reference (:88-100)
+    struct Geometry {
+        std::vector<lrk_vertex> v;
+        std::vector<lrk_triangle> t;
+    };
+    const Geometry *geom;
+    SphereShape(Scene *s, const NodeDesc *d) : Shape{s, d} {
+        read_mesh_wrappers(this, s, d);
+        auto level = std::min(d->u("subdivision", 0u), 8u);
+        static std::mutex mutex;
+        static std::unique_ptr<Geometry> cache[9];
+        std::scoped_lock lock{mutex};
+        if (!cache[level]) {
+            auto g = std::make_unique<Geometry>();
+            make_sphere(level, g->v, g->t);
+            cache[level] = std::move(g);
+        }
+        geom = cache[level].get();
+    }
+    bool is_mesh() const override { return true; }
+    uint32_t vertex_properties() const override { return LRK_SHAPE_HAS_VERTEX_NORMAL | LRK_SHAPE_HAS_VERTEX_UV; }
+    const std::vector<lrk_vertex> &vertices() const override { return geom->v; }
+    const std::vector<lrk_triangle> &triangles() const override { return geom->t; }
+};
+
+struct InstanceShape final : Shape {
+    const Shape *child;
+    InstanceShape(Scene *s, const NodeDesc *d) : Shape{s, d} {
+        visible = d->b("visible", true);
+        child = s->load_shape(d->required_node("shape"));
+    }
+    std::vector<const Shape *> children() const override { return {child}; }
+};
+
+struct GroupShape final : Shape {
+    std::vector<const Shape *> kids;
+    GroupShape(Scene *s, const NodeDesc *d) : Shape{s, d} {
+        visible = d->b("visible", true);
+        for (auto c : d->required_nodes("shapes")) kids.push_back(s->load_shape(c));
+    }
+    std::vector<const Shape *> children() const override { return kids; }
+};
+
+}// namespace
+LRH_PLUGIN("shape-inlinemesh", InlineMesh)
+LRH_PLUGIN("shape-sphere", SphereShape)
+LRH_PLUGIN("shape-instance", InstanceShape)
+LRH_PLUGIN("shape-group", GroupShape)
+
+}// namespace lrh

@@ -1,0 +1,196 @@
+"""Synthetic scene generators (SURVEY.md §8d "Synthetic inputs").
+
+Both scenes are emitted as LuisaRender scene-description text (.luisa grammar,
+/root/reference/src/sdl/scene_parser.cpp:72-451) so the *same file* would load in the reference.
+
+* ``cornell_box``  — configs C1/C2: the 16 quads (32 triangles) of the Cornell box fixture embedded in
+  the LuisaCompute path-tracing demo (src/compute/src/tests/common/cornell_box.h:17-145, minus the two
+  never-visible "Bottom Face" quads), colours / camera / emission from
+  src/compute/src/tests/test_path_tracing.cpp:104-113,159-160,192.
+* ``instanced_spheres`` — configs C3-C5: one level-7 icosphere (327 680 triangles) instanced 4x
+  (1 310 720 triangles) + 60 level-3 spheres + a ground quad, 8 Disney surfaces, 2 one-sided quad area
+  lights; all random numbers from ``numpy.random.default_rng(seed)``.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# quads as (name, [4 vertices]); triangulated (0,1,2),(0,2,3)
+_CORNELL_QUADS = {
+    "floor": [[(-1.01, 0.00, 0.99), (1.00, 0.00, 0.99), (1.00, 0.00, -1.04), (-0.99, 0.00, -1.04)]],
+    "ceiling": [[(-1.02, 1.99, 0.99), (-1.02, 1.99, -1.04), (1.00, 1.99, -1.04), (1.00, 1.99, 0.99)]],
+    "back_wall": [[(-0.99, 0.00, -1.04), (1.00, 0.00, -1.04), (1.00, 1.99, -1.04), (-1.02, 1.99, -1.04)]],
+    "right_wall": [[(1.00, 0.00, -1.04), (1.00, 0.00, 0.99), (1.00, 1.99, 0.99), (1.00, 1.99, -1.04)]],
+    "left_wall": [[(-1.01, 0.00, 0.99), (-0.99, 0.00, -1.04), (-1.02, 1.99, -1.04), (-1.02, 1.99, 0.99)]],
+    "short_box": [
+        [(0.53, 0.60, 0.75), (0.70, 0.60, 0.17), (0.13, 0.60, 0.00), (-0.05, 0.60, 0.57)],
+        [(-0.05, 0.00, 0.57), (-0.05, 0.60, 0.57), (0.13, 0.60, 0.00), (0.13, 0.00, 0.00)],
+        [(0.53, 0.00, 0.75), (0.53, 0.60, 0.75), (-0.05, 0.60, 0.57), (-0.05, 0.00, 0.57)],
+        [(0.70, 0.00, 0.17), (0.70, 0.60, 0.17), (0.53, 0.60, 0.75), (0.53, 0.00, 0.75)],
+        [(0.13, 0.00, 0.00), (0.13, 0.60, 0.00), (0.70, 0.60, 0.17), (0.70, 0.00, 0.17)],
+    ],
+    "tall_box": [
+        [(-0.53, 1.20, 0.09), (0.04, 1.20, -0.09), (-0.14, 1.20, -0.67), (-0.71, 1.20, -0.49)],
+        [(-0.53, 0.00, 0.09), (-0.53, 1.20, 0.09), (-0.71, 1.20, -0.49), (-0.71, 0.00, -0.49)],
+        [(-0.71, 0.00, -0.49), (-0.71, 1.20, -0.49), (-0.14, 1.20, -0.67), (-0.14, 0.00, -0.67)],
+        [(-0.14, 0.00, -0.67), (-0.14, 1.20, -0.67), (0.04, 1.20, -0.09), (0.04, 0.00, -0.09)],
+        [(0.04, 0.00, -0.09), (0.04, 1.20, -0.09), (-0.53, 1.20, 0.09), (-0.53, 0.00, 0.09)],
+    ],
+    "light": [[(-0.24, 1.98, 0.16), (-0.24, 1.98, -0.22), (0.23, 1.98, -0.22), (0.23, 1.98, 0.16)]],
+}
+
+_CORNELL_COLORS = {
+    "white": (0.725, 0.710, 0.680),
+    "green": (0.140, 0.450, 0.091),
+    "red": (0.630, 0.065, 0.050),
+}
+
+_CORNELL_SURFACE_OF = {
+    "floor": "white", "ceiling": "white", "back_wall": "white", "right_wall": "green",
+    "left_wall": "red", "short_box": "white", "tall_box": "white",
+}
+
+
+def _fmt(x: float) -> str:
+    return repr(float(x))
+
+
+def _mesh_props(quads) -> tuple[str, str]:
+    positions, indices = [], []
+    for q in quads:
+        base = len(positions) // 3
+        for v in q:
+            positions.extend(v)
+        indices.extend([base, base + 1, base + 2, base, base + 2, base + 3])
+    return ", ".join(_fmt(p) for p in positions), ", ".join(str(i) for i in indices)
+
+
+def cornell_box(resolution=(512, 512), spp=16, depth=10, rr_depth=0, rr_threshold=0.95,
+                integrator="WavePath", seed=19980810, output="cornell.exr", surface="Matte") -> str:
+    """Configs C1 (512x512 @16) and C2 (1024x1024 @4096). ``surface`` may be "Matte" or "Disney"
+    (the latter is only used by tests to exercise the Disney closure on simple geometry)."""
+    out = []
+    for name, rgb in _CORNELL_COLORS.items():
+        key = "Kd" if surface == "Matte" else "color"
+        out.append(f"Surface {name} : {surface} {{ {key} : Constant {{ v {{ {_fmt(rgb[0])}, {_fmt(rgb[1])}, {_fmt(rgb[2])} }} }} }}")
+    out.append("Light area_light : Diffuse { emission : Constant { v { 17.0, 12.0, 4.0 } } }")
+    shape_names = []
+    for name, quads in _CORNELL_QUADS.items():
+        positions, indices = _mesh_props(quads)
+        binding = "light { @area_light }" if name == "light" else f"surface {{ @{_CORNELL_SURFACE_OF[name]} }}"
+        out.append(f"Shape {name} : InlineMesh {{\n  positions {{ {positions} }}\n  indices {{ {indices} }}\n  {binding}\n}}")
+        shape_names.append(f"@{name}")
+    out.append(f"""Camera camera : Pinhole {{
+  position {{ -0.01, 0.995, 5.0 }}
+  front {{ 0.0, 0.0, -1.0 }}
+  up {{ 0.0, 1.0, 0.0 }}
+  fov {{ 27.8 }}
+  spp {{ {int(spp)} }}
+  film : Color {{ resolution {{ {int(resolution[0])}, {int(resolution[1])} }} }}
+  filter : Box {{ radius {{ 0.5 }} }}
+  file {{ "{output}" }}
+}}""")
+    out.append(f"""render {{
+  integrator : {integrator} {{
+    depth {{ {int(depth)} }}
+    rr_depth {{ {int(rr_depth)} }}
+    rr_threshold {{ {_fmt(rr_threshold)} }}
+    sampler : Independent {{ seed {{ {int(seed)} }} }}
+  }}
+  cameras {{ @camera }}
+  shapes {{ {", ".join(shape_names)} }}
+}}""")
+    return "\n".join(out) + "\n"
+
+
+def instanced_spheres(resolution=(1920, 1080), spp=1024, seed=1, depth=10, rr_depth=0, rr_threshold=0.95,
+                      big_subdivision=7, big_count=4, small_subdivision=3, small_count=60, medium=False,
+                      integrator=None, sampler_seed=19980810, output="spheres.exr") -> str:
+    """Configs C3 (1920x1080 @1024), C4 (+ homogeneous medium, depth 8, 3840x2160 @4096) and C5.
+    4 x 327 680 + 60 x 1 280 + 2 (ground) + 4 (lights) = 1 387 526 instanced triangles."""
+    rng = np.random.default_rng(seed)
+    out = []
+    # 8 Disney surfaces, parameters ~ U[0,1]
+    for i in range(8):
+        color = rng.uniform(0.0, 1.0, 3)
+        metallic, roughness, specular_tint, clearcoat, sheen = rng.uniform(0.0, 1.0, 5)
+        out.append(
+            f"Surface disney_{i} : Disney {{\n"
+            f"  color : Constant {{ v {{ {_fmt(color[0])}, {_fmt(color[1])}, {_fmt(color[2])} }} }}\n"
+            f"  metallic : Constant {{ v {{ {_fmt(metallic)} }} }}\n"
+            f"  roughness : Constant {{ v {{ {_fmt(roughness)} }} }}\n"
+            f"  specular_tint : Constant {{ v {{ {_fmt(specular_tint)} }} }}\n"
+            f"  clearcoat : Constant {{ v {{ {_fmt(clearcoat)} }} }}\n"
+            f"  sheen : Constant {{ v {{ {_fmt(sheen)} }} }}\n"
+            f"}}")
+    out.append("Surface ground_surface : Disney { color : Constant { v { 0.6, 0.6, 0.6 } } roughness : Constant { v { 0.8 } } }")
+    # each light shape has its own Light node (the uniform light sampler counts light NODES,
+    # src/lightsamplers/uniform.cpp:34-38)
+    out.append("Light light_a : Diffuse { emission : Constant { v { 20.0, 20.0, 20.0 } } two_sided { false } }")
+    out.append("Light light_b : Diffuse { emission : Constant { v { 20.0, 20.0, 20.0 } } two_sided { false } }")
+    out.append(f"Shape big_sphere : Sphere {{ subdivision {{ {int(big_subdivision)} }} }}")
+    out.append(f"Shape small_sphere : Sphere {{ subdivision {{ {int(small_subdivision)} }} }}")
+    shapes = []
+    # ground quad (y = 0), facing up
+    g = 12.0
+    pos, idx = _mesh_props([[(-g, 0.0, g), (g, 0.0, g), (g, 0.0, -g), (-g, 0.0, -g)]])
+    out.append(f"Shape ground : InlineMesh {{ positions {{ {pos} }} indices {{ {idx} }} surface {{ @ground_surface }} }}")
+    shapes.append("@ground")
+    # two one-sided quad lights above the scene, facing down
+    for name, (cx, cz) in (("a", (-3.0, 1.0)), ("b", (3.5, -2.0))):
+        h, s = 9.0, 1.5
+        pos, idx = _mesh_props([[(cx - s, h, cz + s), (cx - s, h, cz - s), (cx + s, h, cz - s), (cx + s, h, cz + s)]])
+        out.append(f"Shape light_shape_{name} : InlineMesh {{ positions {{ {pos} }} indices {{ {idx} }} light {{ @light_{name} }} }}")
+        shapes.append(f"@light_shape_{name}")
+
+    def add_instance(name, base, scale_range, surface_index):
+        p = rng.uniform(-4.0, 4.0, 3)
+        s = rng.uniform(*scale_range)
+        p[1] = abs(p[1]) + s  # keep spheres above the ground plane
+        axis = rng.normal(size=3)
+        axis /= np.linalg.norm(axis)
+        angle = rng.uniform(0.0, 360.0)
+        out.append(
+            f"Shape {name} : Instance {{\n"
+            f"  shape {{ @{base} }}\n"
+            f"  surface {{ @disney_{surface_index} }}\n"
+            f"  transform : SRT {{ scale {{ {_fmt(s)} }} rotate {{ {_fmt(axis[0])}, {_fmt(axis[1])}, {_fmt(axis[2])}, {_fmt(angle)} }} "
+            f"translate {{ {_fmt(p[0])}, {_fmt(p[1])}, {_fmt(p[2])} }} }}\n"
+            f"}}")
+        shapes.append(f"@{name}")
+
+    for i in range(big_count):
+        add_instance(f"big_{i}", "big_sphere", (0.7, 1.0), i % 8)
+    for i in range(small_count):
+        add_instance(f"small_{i}", "small_sphere", (0.2, 0.5), int(rng.integers(0, 8)))
+
+    out.append(f"""Camera camera : Pinhole {{
+  position {{ 0.0, 3.0, 12.0 }}
+  look_at {{ 0.0, 1.5, 0.0 }}
+  up {{ 0.0, 1.0, 0.0 }}
+  fov {{ 45.0 }}
+  spp {{ {int(spp)} }}
+  film : Color {{ resolution {{ {int(resolution[0])}, {int(resolution[1])} }} }}
+  filter : Box {{ radius {{ 0.5 }} }}
+  file {{ "{output}" }}
+}}""")
+    if integrator is None:
+        integrator = "MegaVPTNaive" if medium else "WavePath"
+    medium_line = ""
+    if medium:
+        medium_line = ("  environment_medium : Homogeneous {\n"
+                       "    sigma_a : Constant { v { 0.01, 0.01, 0.01 } }\n"
+                       "    sigma_s : Constant { v { 0.05, 0.05, 0.05 } }\n"
+                       "    phasefunction : HenyeyGreenstein { g { 0.3 } }\n"
+                       "  }\n")
+    out.append(f"""render {{
+  integrator : {integrator} {{
+    depth {{ {int(depth)} }}
+    rr_depth {{ {int(rr_depth)} }}
+    rr_threshold {{ {_fmt(rr_threshold)} }}
+    sampler : Independent {{ seed {{ {int(sampler_seed)} }} }}
+  }}
+{medium_line}  cameras {{ @camera }}
+  shapes {{ {", ".join(shapes)} }}
+}}""")
+    return "\n".join(out) + "\n"
