@@ -1,0 +1,1262 @@
+// CPU oracle — TEST INFRASTRUCTURE ONLY (see oracle.h).  Scalar fp32 restatement of the reference's
+// per-sample path-tracing estimator; every function cites the reference file:line it follows
+// (paths relative to /root/reference).  Compiled with -ffp-contract=off so that a*b+c never fuses
+// unless fmaf() is written explicitly (only in the BVH traversal, which has no reference arithmetic:
+// the reference delegates traversal to Embree / OptiX).
+//
+// PARITY UNPINNED: the reference holds no golden vectors for this path and cannot be built here.
+#include "oracle.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <thread>
+#include <vector>
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// small vector algebra (component-wise, evaluation order = LuisaCompute's device math,
+// src/compute/src/backends/cuda/cuda_builtin/cuda_device_math.h)
+// ------------------------------------------------------------------------------------------------
+struct V3 {
+    float x, y, z;
+};
+inline V3 v3(float x, float y, float z) { return {x, y, z}; }
+inline V3 v3(float s) { return {s, s, s}; }
+inline V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline V3 operator*(V3 a, V3 b) { return {a.x * b.x, a.y * b.y, a.z * b.z}; }
+inline V3 operator*(V3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+inline V3 operator*(float s, V3 a) { return {s * a.x, s * a.y, s * a.z}; }
+inline V3 operator+(V3 a, float s) { return {a.x + s, a.y + s, a.z + s}; }
+inline V3 operator-(V3 a) { return {-a.x, -a.y, -a.z}; }
+inline float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }// :lc_dot
+inline V3 cross(V3 a, V3 b) { return {a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y}; }
+inline float length(V3 a) { return std::sqrt(dot(a, a)); }
+// the CUDA backend uses v * rsqrt(dot) (cuda_device_math.h:3509), the CPU backend a true sqrt; the
+// oracle and the sm_100a kernels both use the IEEE form v * (1 / sqrt(dot)).
+inline V3 normalize(V3 a) { return a * (1.0f / std::sqrt(dot(a, a))); }
+inline float sqr(float x) { return x * x; }
+inline float saturate(float x) { return std::fmin(std::fmax(x, 0.f), 1.f); }// lc_clamp = min(max(v,lo),hi)
+inline float clampf(float x, float lo, float hi) { return std::fmin(std::fmax(x, lo), hi); }
+inline float lerp(float a, float b, float t) { return t * (b - a) + a; }// cuda_device_math.h:3353
+inline V3 lerp(V3 a, V3 b, float t) { return t * (b - a) + a; }// src/util/spec.h:272
+inline float sign(float x) { return std::copysign(1.0f, x); }// src/compute/include/luisa/dsl/builtin.h:1542-1543
+inline V3 reflect(V3 v, V3 n) { return v - 2.0f * dot(v, n) * n; }// cuda_device_math.h:3680-3682
+inline V3 face_forward(V3 v, V3 n) { return dot(v, n) < 0.f ? -v : v; }// src/util/scattering.cpp:79-81
+inline float max3(V3 a) { return std::fmax(std::fmax(std::fmax(0.f, a.x), a.y), a.z); }// SampledSpectrum::max, src/util/spec.h:125-129
+
+constexpr float kPi = 3.14159265358979323846264338327950288f;
+constexpr float kPiOverTwo = 1.57079632679489661923132169163975144f;
+constexpr float kPiOverFour = 0.785398163397448309615660845819875721f;
+constexpr float kInvPi = 0.318309886183790671537767526745028724f;
+constexpr float kOneMinusEpsilon = 0x1.fffffep-1f;
+
+// ------------------------------------------------------------------------------------------------
+// RNG: src/util/rng.cpp:53-68 (xxhash32 of a uint4), :128-140 (lcg), src/samplers/independent.cpp:57-82
+// ------------------------------------------------------------------------------------------------
+inline uint32_t rotl(uint32_t x, uint32_t r) { return (x << r) | (x >> (32u - r)); }
+
+uint32_t xxhash32_uint4(uint32_t px, uint32_t py, uint32_t pz, uint32_t pw) {
+    constexpr uint32_t PRIME32_2 = 2246822519u, PRIME32_3 = 3266489917u;
+    constexpr uint32_t PRIME32_4 = 668265263u, PRIME32_5 = 374761393u;
+    uint32_t h32 = pw + PRIME32_5 + px * PRIME32_3;
+    h32 = PRIME32_4 * rotl(h32, 17u);
+    h32 += py * PRIME32_3;
+    h32 = PRIME32_4 * rotl(h32, 17u);
+    h32 += pz * PRIME32_3;
+    h32 = PRIME32_4 * rotl(h32, 17u);
+    h32 = PRIME32_2 * (h32 ^ (h32 >> 15u));
+    h32 = PRIME32_3 * (h32 ^ (h32 >> 13u));
+    return h32 ^ (h32 >> 16u);
+}
+
+inline float lcg(uint32_t &state) {
+    state = 1664525u * state + 1013904223u;
+    return std::fmin(kOneMinusEpsilon, static_cast<float>(state) * 0x1p-32f);
+}
+
+struct Sampler {
+    uint32_t state;
+    void start(uint32_t px, uint32_t py, uint32_t seed, uint32_t index) { state = xxhash32_uint4(px, py, seed, index); }
+    float generate_1d() { return lcg(state); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// warps: src/util/sampling.cpp:13-31 (concentric disk, cosine hemisphere), :89-98 (triangle),
+// src/util/sampling.h:38-70 (alias table), sampling.cpp:133-155 (balance heuristic)
+// ------------------------------------------------------------------------------------------------
+inline void sample_uniform_disk_concentric(float ux, float uy, float &dx, float &dy) {
+    float x = ux * 2.0f - 1.0f, y = uy * 2.0f - 1.0f;
+    bool p = std::fabs(x) > std::fabs(y);
+    float r = p ? x : y;
+    float theta = p ? kPiOverFour * (y / x) : kPiOverTwo - kPiOverFour * (x / y);
+    dx = r * std::cos(theta);
+    dy = r * std::sin(theta);
+}
+inline V3 sample_cosine_hemisphere(float ux, float uy) {
+    float dx, dy;
+    sample_uniform_disk_concentric(ux, uy, dx, dy);
+    float z = std::sqrt(std::fmax(1.0f - dx * dx - dy * dy, 0.0f));
+    return {dx, dy, z};
+}
+inline V3 sample_uniform_triangle(float ux, float uy) {
+    float a, b;
+    if (ux < uy) { a = 0.5f * ux; b = -0.5f * ux + uy; }
+    else { a = -0.5f * uy + ux; b = 0.5f * uy; }
+    return {a, b, 1.0f - a - b};
+}
+inline float balance_heuristic(float f_pdf, float g_pdf) {
+    float sum_f = 1.0f * f_pdf;// nf = 1
+    float sum = sum_f + 1.0f * g_pdf;
+    return sum == 0.0f ? 0.0f : sum_f / sum;
+}
+template<typename ProbAt, typename AliasAt>
+inline void sample_alias_table(ProbAt prob_at, AliasAt alias_at, uint32_t n, float u_in, uint32_t &index, float &uu) {
+    float u = u_in * static_cast<float>(n);
+    // cast<uint>(u) then clamp to [0, n-1]
+    uint32_t i = static_cast<uint32_t>(u);
+    i = std::min(std::max(i, 0u), n - 1u);
+    float u_remapped = u - std::floor(u);// fract
+    float prob = prob_at(i);
+    bool keep = u_remapped < prob;
+    index = keep ? i : alias_at(i);
+    uu = keep ? u_remapped / prob : (u_remapped - prob) / (1.0f - prob);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Frame: src/util/frame.cpp:21-42
+// ------------------------------------------------------------------------------------------------
+struct Frame {
+    V3 s, t, n;
+    static Frame make(V3 n) {
+        float sgn = sign(n.z);
+        float a = -1.f / (sgn + n.z);
+        float b = n.x * n.y * a;
+        V3 s = v3(1.f + sgn * sqr(n.x) * a, sgn * b, -sgn * n.x);
+        V3 t = v3(b, sgn + sqr(n.y) * a, -n.y);
+        return {normalize(s), normalize(t), n};
+    }
+    static Frame make(V3 n, V3 s) {
+        V3 ss = normalize(s - n * dot(n, s));
+        V3 tt = normalize(cross(n, ss));
+        return {ss, tt, n};
+    }
+    V3 local_to_world(V3 d) const { return normalize(d.x * s + d.y * t + d.z * n); }
+    V3 world_to_local(V3 d) const { return normalize(v3(dot(d, s), dot(d, t), dot(d, n))); }
+};
+
+// local-frame trigonometry: src/util/frame.h:50-71
+inline float cos_theta(V3 w) { return w.z; }
+inline float cos2_theta(V3 w) { return sqr(w.z); }
+inline float abs_cos_theta(V3 w) { return std::fabs(w.z); }
+inline float sin2_theta(V3 w) { return saturate(1.0f - cos2_theta(w)); }
+inline float sin_theta(V3 w) { return std::sqrt(sin2_theta(w)); }
+inline float tan_theta(V3 w) { return sin_theta(w) / cos_theta(w); }
+inline float tan2_theta(V3 w) { return sin2_theta(w) / cos2_theta(w); }
+inline float cos_phi(V3 w) {
+    float s = sin_theta(w);
+    return s == 0.0f ? 1.0f : clampf(w.x / s, -1.0f, 1.0f);
+}
+inline float sin_phi(V3 w) {
+    float s = sin_theta(w);
+    return s == 0.0f ? 0.0f : clampf(w.y / s, -1.0f, 1.0f);
+}
+inline float cos2_phi(V3 w) { return sqr(cos_phi(w)); }
+inline float sin2_phi(V3 w) { return sqr(sin_phi(w)); }
+inline bool same_hemisphere(V3 w, V3 wp) { return w.z * wp.z > 0.0f; }
+inline float abs_dot(V3 a, V3 b) { return std::fabs(dot(a, b)); }
+
+// ------------------------------------------------------------------------------------------------
+// Shape::Handle::decode: src/base/shape.cpp:72-93
+// ------------------------------------------------------------------------------------------------
+struct ShapeHandle {
+    uint32_t buffer_base, flags, surface_tag, light_tag, medium_tag, tri_count;
+    float shadow_terminator, intersection_offset;
+    bool has_vertex_normal() const { return flags & LRK_SHAPE_HAS_VERTEX_NORMAL; }
+    bool has_vertex_uv() const { return flags & LRK_SHAPE_HAS_VERTEX_UV; }
+    bool has_surface() const { return flags & LRK_SHAPE_HAS_SURFACE; }
+    bool has_light() const { return flags & LRK_SHAPE_HAS_LIGHT; }
+};
+ShapeHandle decode_handle(const uint32_t c[4]) {
+    ShapeHandle h;
+    h.buffer_base = c[0] >> 10u;
+    h.flags = c[0] & 1023u;
+    h.surface_tag = (c[1] >> 12u) & 4095u;
+    h.light_tag = c[1] & 4095u;
+    h.medium_tag = (c[1] >> 24u) & 255u;
+    h.tri_count = c[2];
+    auto fixed = [](uint32_t x) { return static_cast<float>(x & 0xffffu) * (1.0f / 65536.f); };
+    h.shadow_terminator = fixed(c[3] >> 16u);
+    float off = fixed(c[3] & 0xffffu);
+    h.intersection_offset = clampf(off * 255.f + 1.f, 1.f, 256.f);
+    return h;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Interaction and hit reconstruction: src/base/geometry.cpp:281-389, src/base/interaction.{h,cpp}
+// ------------------------------------------------------------------------------------------------
+struct Interaction {
+    ShapeHandle shape{};
+    V3 pg{}, ng{}, ps{};
+    float u{}, v{};
+    Frame shading{};
+    uint32_t inst{~0u}, prim{~0u};
+    float prim_area{};
+    bool back_facing{};
+    bool valid() const { return inst != ~0u; }
+};
+
+// src/compute/src/dsl/rtx/ray.cpp:16-23 — integer-ULP offset along n
+V3 offset_ray_origin(V3 p, V3 n) {
+    constexpr float origin = 1.0f / 32.0f;
+    constexpr float float_scale = 1.0f / 65536.0f;
+    constexpr float int_scale = 256.0f;
+    auto one = [&](float pc, float nc) {
+        int32_t of_i = static_cast<int32_t>(int_scale * nc);
+        int32_t bits;
+        std::memcpy(&bits, &pc, 4);
+        bits += pc < 0.0f ? -of_i : of_i;
+        float p_i;
+        std::memcpy(&p_i, &bits, 4);
+        return std::fabs(pc) < origin ? pc + float_scale * nc : p_i;
+    };
+    return {one(p.x, n.x), one(p.y, n.y), one(p.z, n.z)};
+}
+
+// src/base/interaction.cpp:13-30
+V3 p_robust(const Interaction &it, V3 w) {
+    bool front = dot(it.shading.n, w) > 0.f;
+    V3 n = front ? it.ng : -it.ng;
+    return offset_ray_origin(it.pg, it.shape.intersection_offset * n);
+}
+lrk_ray make_ray(V3 o, V3 d, float tmin, float tmax) { return {{o.x, o.y, o.z}, tmin, {d.x, d.y, d.z}, tmax}; }
+lrk_ray spawn_ray(const Interaction &it, V3 wi) {
+    return make_ray(p_robust(it, wi), wi, 0.f, std::numeric_limits<float>::max());
+}
+lrk_ray spawn_ray_to(const Interaction &it, V3 p) {
+    V3 p_from = p_robust(it, p - it.pg);
+    V3 L = p - p_from;
+    float d = length(L);
+    return make_ray(p_from, L * (1.f / d), 0.f, d * .9999f);
+}
+
+struct Mat34 {// row-major 3x4; columns c0..c2 are the 3x3 part, c3 the translation
+    const float *m;
+    V3 col(int j) const { return {m[j], m[4 + j], m[8 + j]}; }
+};
+// float3x3 * float3 = v.x*m[0] + v.y*m[1] + v.z*m[2] (cuda_device_math.h:2746)
+inline V3 mul3(const Mat34 &m, V3 v) { return v.x * m.col(0) + v.y * m.col(1) + v.z * m.col(2); }
+
+inline V3 vertex_p(const lrk_vertex &v) { return {v.p[0], v.p[1], v.p[2]}; }
+inline V3 vertex_n(const lrk_vertex &v) { return {v.n[0], v.n[1], v.n[2]}; }
+
+// Geometry::shading_point, src/base/geometry.cpp:345-389, then the Interaction constructor
+// (src/base/interaction.h:97-101): shading frame = Frame::make(ns, dpdu)
+Interaction make_interaction(const lrk_scene_desc &sc, uint32_t inst_id, uint32_t prim_id, V3 bary, bool use_wo, V3 wo,
+                             V3 p_from_for_back_facing) {
+    Interaction it;
+    const auto &inst = sc.instances[inst_id];
+    it.shape = decode_handle(inst.handle);
+    const auto &mesh = sc.meshes[it.shape.buffer_base >> 2u];
+    const auto &tri = sc.triangles[mesh.triangle_offset + prim_id];
+    const auto &v0 = sc.vertices[mesh.vertex_offset + tri.i0];
+    const auto &v1 = sc.vertices[mesh.vertex_offset + tri.i1];
+    const auto &v2 = sc.vertices[mesh.vertex_offset + tri.i2];
+    Mat34 m{inst.object_to_world};
+    V3 t = m.col(3);
+    V3 p0 = vertex_p(v0), p1 = vertex_p(v1), p2 = vertex_p(v2);
+    V3 ns_local = bary.x * vertex_n(v0) + bary.y * vertex_n(v1) + bary.z * vertex_n(v2);
+    float duv0x = v1.uv[0] - v0.uv[0], duv0y = v1.uv[1] - v0.uv[1];
+    float duv1x = v2.uv[0] - v0.uv[0], duv1y = v2.uv[1] - v0.uv[1];
+    float det = duv0x * duv1y - duv0y * duv1x;
+    float inv_det = 1.f / det;
+    V3 dp0 = p1 - p0, dp1 = p2 - p0;
+    V3 dpdu_local = (dp0 * duv1y - dp1 * duv0y) * inv_det;
+    V3 p = mul3(m, bary.x * p0 + bary.y * p1 + bary.z * p2) + t;
+    V3 c = cross(mul3(m, dp0), mul3(m, dp1));
+    float area = length(c) * .5f;
+    V3 ng = normalize(c);
+    Frame fallback = Frame::make(ng);
+    V3 dpdu = det == 0.f ? fallback.s : mul3(m, dpdu_local);
+    // mn = transpose(inverse(m)), GLM-style inverse (cuda_device_math.h:3615-3630)
+    V3 m0 = m.col(0), m1 = m.col(1), m2 = m.col(2);
+    float one_over_det = 1.0f / (m0.x * (m1.y * m2.z - m2.y * m1.z) - m1.x * (m0.y * m2.z - m2.y * m0.z) +
+                                 m2.x * (m0.y * m1.z - m1.y * m0.z));
+    V3 i0 = v3((m1.y * m2.z - m2.y * m1.z) * one_over_det, (m2.y * m0.z - m0.y * m2.z) * one_over_det,
+               (m0.y * m1.z - m1.y * m0.z) * one_over_det);
+    V3 i1 = v3((m2.x * m1.z - m1.x * m2.z) * one_over_det, (m0.x * m2.z - m2.x * m0.z) * one_over_det,
+               (m1.x * m0.z - m0.x * m1.z) * one_over_det);
+    V3 i2 = v3((m1.x * m2.y - m2.x * m1.y) * one_over_det, (m2.x * m0.y - m0.x * m2.y) * one_over_det,
+               (m0.x * m1.y - m1.x * m0.y) * one_over_det);
+    // transpose: columns of mn are the rows of the inverse
+    V3 mn0 = v3(i0.x, i1.x, i2.x), mn1 = v3(i0.y, i1.y, i2.y), mn2 = v3(i0.z, i1.z, i2.z);
+    V3 ns = it.shape.has_vertex_normal() ? normalize(ns_local.x * mn0 + ns_local.y * mn1 + ns_local.z * mn2) : ng;
+    if (it.shape.has_vertex_uv()) {
+        it.u = bary.x * v0.uv[0] + bary.y * v1.uv[0] + bary.z * v2.uv[0];
+        it.v = bary.x * v0.uv[1] + bary.y * v1.uv[1] + bary.z * v2.uv[1];
+    } else {
+        it.u = bary.y;
+        it.v = bary.z;
+    }
+    it.pg = p;
+    it.ps = p;
+    it.ng = ng;
+    it.prim_area = area;
+    it.shading = Frame::make(face_forward(ns, ng), dpdu);
+    it.inst = inst_id;
+    it.prim = prim_id;
+    // geometry.cpp:290 (hit): dot(wo, ng) < 0 ; uniform.cpp:121 (sampled light point): dot(ng, p_from - p) < 0
+    it.back_facing = use_wo ? dot(wo, ng) < 0.0f : dot(ng, p_from_for_back_facing - p) < 0.f;
+    return it;
+}
+
+Interaction interaction_from_hit(const lrk_scene_desc &sc, const lrk_ray &ray, const lrk_hit &hit) {
+    if (hit.inst == ~0u) return {};
+    V3 bary = v3(1.f - hit.bary[0] - hit.bary[1], hit.bary[0], hit.bary[1]);
+    V3 wo = -v3(ray.d[0], ray.d[1], ray.d[2]);
+    return make_interaction(sc, hit.inst, hit.prim, bary, true, wo, v3(0.f));
+}
+
+// ------------------------------------------------------------------------------------------------
+// BVH traversal.  No reference arithmetic exists for this (Embree / OptiX); these rules are OURS and the
+// sm_100a kernel follows exactly the same ones (luisarender_b200/csrc/device/traverse.cuh):
+//   * slab test in the fused form t = fma(plane, inv_d, -o*inv_d), |d| clamped to >= 1e-30 before 1/d,
+//     child hit <=> max(tnear, tmin) <= min(tfar, t_best);
+//   * both children hit -> visit the one with the smaller entry distance first (ties: child 0);
+//   * Moeller-Trumbore in object space with explicit fma dot/cross, accept tmin < t < t_best,
+//     u >= 0, v >= 0, u + v <= 1, det != 0;
+//   * instances: ray transformed with world_to_object (fma chains), direction NOT renormalised (t is shared).
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kSentinelDone = 0xfffffffdu;
+constexpr uint32_t kSentinelExit = 0xfffffffeu;
+
+struct TraceCounters {
+    uint64_t nodes{0}, tris{0}, xforms{0};
+};
+
+inline float fdot(V3 a, V3 b) { return std::fmaf(a.x, b.x, std::fmaf(a.y, b.y, a.z * b.z)); }
+inline V3 fcross(V3 a, V3 b) {
+    return {std::fmaf(a.y, b.z, -(a.z * b.y)), std::fmaf(a.z, b.x, -(a.x * b.z)), std::fmaf(a.x, b.y, -(a.y * b.x))};
+}
+inline float safe_rcp(float d) {
+    float a = std::fabs(d) < 1e-30f ? std::copysign(1e-30f, d) : d;
+    return 1.0f / a;
+}
+
+struct RaySetup {
+    V3 o, d, inv, ood;
+    void set(V3 oo, V3 dd) {
+        o = oo;
+        d = dd;
+        inv = v3(safe_rcp(dd.x), safe_rcp(dd.y), safe_rcp(dd.z));
+        ood = v3(oo.x * inv.x, oo.y * inv.y, oo.z * inv.z);
+    }
+};
+
+inline bool slab(const float lo[3], const float hi[3], const RaySetup &r, float tmin, float tbest, float &tnear) {
+    float t0x = std::fmaf(lo[0], r.inv.x, -r.ood.x), t1x = std::fmaf(hi[0], r.inv.x, -r.ood.x);
+    float t0y = std::fmaf(lo[1], r.inv.y, -r.ood.y), t1y = std::fmaf(hi[1], r.inv.y, -r.ood.y);
+    float t0z = std::fmaf(lo[2], r.inv.z, -r.ood.z), t1z = std::fmaf(hi[2], r.inv.z, -r.ood.z);
+    float tn = std::fmax(std::fmax(std::fmin(t0x, t1x), std::fmin(t0y, t1y)), std::fmax(std::fmin(t0z, t1z), tmin));
+    float tf = std::fmin(std::fmin(std::fmax(t0x, t1x), std::fmax(t0y, t1y)), std::fmin(std::fmax(t0z, t1z), tbest));
+    tnear = tn;
+    return tn <= tf;
+}
+
+lrk_hit trace_bvh(const lrk_scene_desc &sc, const lrk_ray &ray, bool any_hit, TraceCounters *cnt) {
+    lrk_hit best{~0u, ~0u, {0.f, 0.f}};
+    float tbest = ray.tmax;
+    const float tmin = ray.tmin;
+    RaySetup world, cur;
+    world.set(v3(ray.o[0], ray.o[1], ray.o[2]), v3(ray.d[0], ray.d[1], ray.d[2]));
+    cur = world;
+    uint32_t stack[128];
+    int sp = 0;
+    stack[sp++] = kSentinelDone;
+    uint32_t node = sc.tlas_root;
+    bool in_blas = false;
+    uint32_t cur_inst = ~0u;
+    for (;;) {
+        while (!(node & LRK_BVH_LEAF)) {
+            const auto &n = sc.bvh_nodes[node];
+            if (cnt) cnt->nodes++;
+            float tn0, tn1;
+            bool h0 = slab(n.lo0, n.hi0, cur, tmin, tbest, tn0);
+            bool h1 = slab(n.lo1, n.hi1, cur, tmin, tbest, tn1);
+            if (h0 && h1) {
+                bool first0 = tn0 <= tn1;
+                stack[sp++] = first0 ? n.ref1 : n.ref0;
+                node = first0 ? n.ref0 : n.ref1;
+            } else if (h0) {
+                node = n.ref0;
+            } else if (h1) {
+                node = n.ref1;
+            } else {
+                node = stack[--sp];
+            }
+        }
+        if (node == kSentinelDone) break;
+        if (node == kSentinelExit) {
+            cur = world;
+            in_blas = false;
+            node = stack[--sp];
+            continue;
+        }
+        if (node == LRK_BVH_EMPTY) {
+            node = stack[--sp];
+            continue;
+        }
+        if (in_blas) {
+            uint32_t first = node & 0x0fffffffu;
+            uint32_t count = ((node >> 28u) & 7u) + 1u;
+            for (uint32_t k = 0; k < count; k++) {
+                const float *tv = sc.tri_verts + static_cast<size_t>(first + k) * 12u;
+                if (cnt) cnt->tris++;
+                V3 p0 = v3(tv[0], tv[1], tv[2]), p1 = v3(tv[4], tv[5], tv[6]), p2 = v3(tv[8], tv[9], tv[10]);
+                V3 e1 = p1 - p0, e2 = p2 - p0;
+                V3 pvec = fcross(cur.d, e2);
+                float det = fdot(e1, pvec);
+                if (!(det != 0.0f)) continue;
+                float inv_det = 1.0f / det;
+                V3 tvec = cur.o - p0;
+                float u = fdot(tvec, pvec) * inv_det;
+                if (!(u >= 0.0f && u <= 1.0f)) continue;
+                V3 qvec = fcross(tvec, e1);
+                float v = fdot(cur.d, qvec) * inv_det;
+                if (!(v >= 0.0f && u + v <= 1.0f)) continue;
+                float t = fdot(e2, qvec) * inv_det;
+                if (!(t > tmin && t < tbest)) continue;
+                tbest = t;
+                uint32_t prim;
+                std::memcpy(&prim, &tv[3], 4);
+                best = {cur_inst, prim, {u, v}};
+                if (any_hit) return best;
+            }
+            node = stack[--sp];
+        } else {
+            cur_inst = node & 0x7fffffffu;
+            if (cnt) cnt->xforms++;
+            const auto &inst = sc.instances[cur_inst];
+            const float *w = inst.world_to_object;
+            V3 o = world.o, d = world.d;
+            V3 oo = v3(std::fmaf(w[0], o.x, std::fmaf(w[1], o.y, std::fmaf(w[2], o.z, w[3]))),
+                       std::fmaf(w[4], o.x, std::fmaf(w[5], o.y, std::fmaf(w[6], o.z, w[7]))),
+                       std::fmaf(w[8], o.x, std::fmaf(w[9], o.y, std::fmaf(w[10], o.z, w[11]))));
+            V3 dd = v3(std::fmaf(w[0], d.x, std::fmaf(w[1], d.y, w[2] * d.z)),
+                       std::fmaf(w[4], d.x, std::fmaf(w[5], d.y, w[6] * d.z)),
+                       std::fmaf(w[8], d.x, std::fmaf(w[9], d.y, w[10] * d.z)));
+            cur.set(oo, dd);
+            stack[sp++] = kSentinelExit;
+            in_blas = true;
+            node = sc.meshes[inst.mesh].bvh_root;
+        }
+    }
+    return best;
+}
+
+lrk_hit trace_brute(const lrk_scene_desc &sc, const lrk_ray &ray, bool any_hit) {
+    lrk_hit best{~0u, ~0u, {0.f, 0.f}};
+    float tbest = ray.tmax;
+    V3 o = v3(ray.o[0], ray.o[1], ray.o[2]), d = v3(ray.d[0], ray.d[1], ray.d[2]);
+    for (uint32_t i = 0; i < sc.instance_count; i++) {
+        const auto &inst = sc.instances[i];
+        if (!inst.visible) continue;
+        const float *w = inst.world_to_object;
+        V3 oo = v3(std::fmaf(w[0], o.x, std::fmaf(w[1], o.y, std::fmaf(w[2], o.z, w[3]))),
+                   std::fmaf(w[4], o.x, std::fmaf(w[5], o.y, std::fmaf(w[6], o.z, w[7]))),
+                   std::fmaf(w[8], o.x, std::fmaf(w[9], o.y, std::fmaf(w[10], o.z, w[11]))));
+        V3 dd = v3(std::fmaf(w[0], d.x, std::fmaf(w[1], d.y, w[2] * d.z)),
+                   std::fmaf(w[4], d.x, std::fmaf(w[5], d.y, w[6] * d.z)),
+                   std::fmaf(w[8], d.x, std::fmaf(w[9], d.y, w[10] * d.z)));
+        const auto &mesh = sc.meshes[inst.mesh];
+        for (uint32_t k = 0; k < mesh.triangle_count; k++) {
+            const auto &tri = sc.triangles[mesh.triangle_offset + k];
+            V3 p0 = vertex_p(sc.vertices[mesh.vertex_offset + tri.i0]);
+            V3 p1 = vertex_p(sc.vertices[mesh.vertex_offset + tri.i1]);
+            V3 p2 = vertex_p(sc.vertices[mesh.vertex_offset + tri.i2]);
+            V3 e1 = p1 - p0, e2 = p2 - p0;
+            V3 pvec = fcross(dd, e2);
+            float det = fdot(e1, pvec);
+            if (!(det != 0.0f)) continue;
+            float inv_det = 1.0f / det;
+            V3 tvec = oo - p0;
+            float u = fdot(tvec, pvec) * inv_det;
+            if (!(u >= 0.0f && u <= 1.0f)) continue;
+            V3 qvec = fcross(tvec, e1);
+            float v = fdot(dd, qvec) * inv_det;
+            if (!(v >= 0.0f && u + v <= 1.0f)) continue;
+            float t = fdot(e2, qvec) * inv_det;
+            if (!(t > ray.tmin && t < tbest)) continue;
+            tbest = t;
+            best = {i, k, {u, v}};
+            if (any_hit) return best;
+        }
+    }
+    return best;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Camera: src/base/filter.cpp:50-64, src/base/camera.cpp:212-224, src/cameras/pinhole.cpp:60-67
+// ------------------------------------------------------------------------------------------------
+void sample_filter(const lrk_camera &cam, float ux, float uy, float &ox, float &oy, float &weight) {
+    constexpr uint32_t n = LRK_FILTER_LUT_SIZE - 1u;
+    uint32_t iy, ix;
+    float fy, fx;
+    auto prob = [&](uint32_t i) { return cam.filter_alias_probs[i]; };
+    auto alias = [&](uint32_t i) { return cam.filter_alias_indices[i]; };
+    sample_alias_table(prob, alias, n, ux, iy, fy);
+    sample_alias_table(prob, alias, n, uy, ix, fx);
+    float pdf = cam.filter_pdf[iy] * cam.filter_pdf[ix];
+    float f = lerp(cam.filter_lut[ix], cam.filter_lut[ix + 1u], fx) * lerp(cam.filter_lut[iy], cam.filter_lut[iy + 1u], fy);
+    float px = static_cast<float>(ix) + fx, py = static_cast<float>(iy) + fy;
+    constexpr float inv_size = 1.0f / static_cast<float>(LRK_FILTER_LUT_SIZE);
+    ox = (px * inv_size * 2.0f - 1.0f) * cam.filter_radius + cam.filter_shift[0];
+    oy = (py * inv_size * 2.0f - 1.0f) * cam.filter_radius + cam.filter_shift[1];
+    weight = f / pdf;
+}
+
+lrk_ray generate_camera_ray(const lrk_camera &cam, uint32_t px, uint32_t py, float ux, float uy, float &weight) {
+    float ox, oy, fw;
+    sample_filter(cam, ux, uy, ox, oy, fw);
+    float pixel_x = static_cast<float>(px) + .5f + ox;
+    float pixel_y = static_cast<float>(py) + .5f + oy;
+    float rx = static_cast<float>(cam.resolution[0]), ry = static_cast<float>(cam.resolution[1]);
+    float k = cam.tan_half_fov / ry;
+    float p_x = (pixel_x * 2.0f - rx) * k;
+    float p_y = (pixel_y * 2.0f - ry) * k;
+    V3 direction = normalize(v3(p_x, -p_y, -1.f));
+    weight = 1.f * fw;
+    Mat34 c2w{cam.camera_to_world};
+    // c2w * (0,0,0,1) = 0*c0 + 0*c1 + 0*c2 + 1*c3 (cuda_device_math.h:2754)
+    V3 o = 0.f * c2w.col(0) + 0.f * c2w.col(1) + 0.f * c2w.col(2) + 1.f * c2w.col(3);
+    V3 d = normalize(mul3(c2w, direction));
+    return make_ray(o, d, 0.f, std::numeric_limits<float>::max());
+}
+
+// ------------------------------------------------------------------------------------------------
+// Lights: src/lights/diffuse.cpp:67-88, src/lightsamplers/uniform.cpp:50-65,78-137,
+// src/base/light_sampler.cpp:57-78,116-119
+// ------------------------------------------------------------------------------------------------
+struct LightEval {
+    V3 L{0.f, 0.f, 0.f};
+    float pdf{0.f};
+};
+
+LightEval diffuse_light_evaluate(const lrk_scene_desc &sc, const Interaction &it_light, V3 p_from) {
+    const auto &light = sc.lights[it_light.shape.light_tag];
+    const auto &mesh = sc.meshes[it_light.shape.buffer_base >> 2u];
+    float pdf_triangle = sc.pdf[mesh.triangle_offset + it_light.prim];
+    float pdf_area = pdf_triangle / it_light.prim_area;
+    float cos_wo = abs_dot(normalize(p_from - it_light.pg), it_light.ng);
+    V3 L = v3(light.emission[0], light.emission[1], light.emission[2]) * light.scale;
+    V3 diff = it_light.pg - p_from;
+    float pdf = dot(diff, diff) * pdf_area * (1.0f / cos_wo);
+    bool invalid = std::fabs(cos_wo) < 1e-6f || (!light.two_sided && it_light.back_facing);
+    LightEval e;
+    e.L = invalid ? v3(0.f) : L;
+    e.pdf = invalid ? 0.0f : pdf;
+    return e;
+}
+
+LightEval evaluate_hit(const lrk_scene_desc &sc, const Interaction &it, V3 p_from) {
+    LightEval e = diffuse_light_evaluate(sc, it, p_from);
+    float n = static_cast<float>(sc.light_count);
+    e.pdf *= (1.f - 0.f) / n;// env_prob = 0 (no environment)
+    return e;
+}
+
+struct LightSample {
+    LightEval eval;
+    lrk_ray shadow_ray{};
+};
+
+LightSample sample_light(const lrk_scene_desc &sc, const Interaction &it_from, float u_sel, float u0, float u1) {
+    LightSample s;
+    if (sc.light_count == 0u) return s;
+    float n = static_cast<float>(sc.light_count);
+    uint32_t tag = static_cast<uint32_t>(clampf(u_sel * n, 0.f, n - 1.f));
+    float sel_prob = 1.f / n;
+    const auto &handle = sc.light_handles[tag];
+    ShapeHandle light_inst = decode_handle(sc.instances[handle.instance_id].handle);
+    const auto &mesh = sc.meshes[light_inst.buffer_base >> 2u];
+    uint32_t triangle_id;
+    float ux;
+    sample_alias_table([&](uint32_t i) { return sc.alias[mesh.triangle_offset + i].prob; },
+                       [&](uint32_t i) { return sc.alias[mesh.triangle_offset + i].alias; },
+                       light_inst.tri_count, u0, triangle_id, ux);
+    V3 uvw = sample_uniform_triangle(ux, u1);
+    Interaction it_light = make_interaction(sc, handle.instance_id, triangle_id, uvw, false, v3(0.f), it_from.pg);
+    s.eval = diffuse_light_evaluate(sc, it_light, it_from.ps);
+    s.eval.pdf *= sel_prob;
+    s.shadow_ray = spawn_ray_to(it_from, it_light.pg);
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Surfaces.  Validation wrapper: src/base/surface.cpp:35-68.
+// ------------------------------------------------------------------------------------------------
+struct SurfEval {
+    V3 f{0.f, 0.f, 0.f};
+    float pdf{0.f};
+};
+struct SurfSample {
+    SurfEval eval;
+    V3 wi{0.f, 0.f, 1.f};
+};
+
+inline bool validate_surface_sides(V3 ng, V3 ns, V3 wo, V3 wi) {
+    float flip = sign(dot(ng, ns));
+    return sign(flip * dot(wo, ns)) == sign(dot(wo, ng)) && sign(flip * dot(wi, ns)) == sign(dot(wi, ng));
+}
+
+// --- Matte / Oren-Nayar: src/surfaces/matte.cpp:78-134, src/util/scattering.cpp:247-264,370-400
+struct OrenNayar {
+    V3 r;
+    float a, b;
+    OrenNayar(V3 R, float sigma) : r{R} {
+        float sigma2 = sqr(sigma * (kPi / 180.0f));// DSL radians(): x * (pi/180), builtin.h:1523-1525
+        a = 1.f - (sigma2 / (2.f * sigma2 + 0.66f));
+        b = 0.45f * sigma2 / (sigma2 + 0.09f);
+    }
+    V3 evaluate(V3 wo, V3 wi) const {
+        float s = same_hemisphere(wo, wi) ? kInvPi : 0.f;
+        float sinThetaI = sin_theta(wi), sinThetaO = sin_theta(wo);
+        float sinPhiI = sin_phi(wi), cosPhiI = cos_phi(wi);
+        float sinPhiO = sin_phi(wo), cosPhiO = cos_phi(wo);
+        float dCos = cosPhiI * cosPhiO + sinPhiI * sinPhiO;
+        float maxCos = (sinThetaI > 1e-4f && sinThetaO > 1e-4f) ? std::fmax(0.f, dCos) : 0.f;
+        float absCosThetaI = abs_cos_theta(wi), absCosThetaO = abs_cos_theta(wo);
+        float sinAlpha = absCosThetaI > absCosThetaO ? sinThetaO : sinThetaI;
+        float tanBeta = absCosThetaI > absCosThetaO ? sinThetaI / absCosThetaI : sinThetaO / absCosThetaO;
+        float scale = a + b * maxCos * sinAlpha * tanBeta;
+        return s * scale * r;
+    }
+};
+inline float lambert_pdf(V3 wo, V3 wi) { return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * kInvPi : 0.f; }
+
+SurfEval matte_evaluate(const lrk_surface &s, const Interaction &it, V3 wo, V3 wi) {
+    OrenNayar refl{v3(s.p[0], s.p[1], s.p[2]), s.p[3]};
+    V3 wo_local = it.shading.world_to_local(wo);
+    V3 wi_local = it.shading.world_to_local(wi);
+    SurfEval e;
+    e.f = refl.evaluate(wo_local, wi_local) * abs_cos_theta(wi_local);
+    e.pdf = lambert_pdf(wo_local, wi_local);
+    return e;
+}
+SurfSample matte_sample(const lrk_surface &s, const Interaction &it, V3 wo, float, float u0, float u1) {
+    OrenNayar refl{v3(s.p[0], s.p[1], s.p[2]), s.p[3]};
+    V3 wo_local = it.shading.world_to_local(wo);
+    V3 wi_local = sample_cosine_hemisphere(u0, u1);
+    wi_local.z *= sign(cos_theta(wo_local));
+    float pdf = lambert_pdf(wo_local, wi_local);// valid == true
+    V3 f = refl.evaluate(wo_local, wi_local);
+    SurfSample out;
+    out.wi = it.shading.local_to_world(wi_local);
+    out.eval.f = f * abs_cos_theta(wi_local);
+    out.eval.pdf = pdf;
+    return out;
+}
+
+// --- microfacet machinery: src/util/scattering.cpp:30-52,117-237,286-320
+float fresnel_dielectric(float cosThetaI_in, float etaI_in, float etaT_in) {
+    float cosThetaI = clampf(cosThetaI_in, -1.f, 1.f);
+    bool entering = cosThetaI > 0.f;
+    float etaI = entering ? etaI_in : etaT_in;
+    float etaT = entering ? etaT_in : etaI_in;
+    cosThetaI = std::fabs(cosThetaI);
+    float sinThetaI = std::sqrt(std::fmax(0.f, 1.f - sqr(cosThetaI)));
+    float sinThetaT = etaI / etaT * sinThetaI;
+    float cosThetaT = std::sqrt(std::fmax(0.f, 1.f - sqr(sinThetaT)));
+    float Rparl = (etaT * cosThetaI - etaI * cosThetaT) / (etaT * cosThetaI + etaI * cosThetaT);
+    float Rperp = (etaI * cosThetaI - etaT * cosThetaT) / (etaI * cosThetaI + etaT * cosThetaT);
+    float fr = (Rparl * Rparl + Rperp * Rperp) * .5f;
+    return sinThetaT < 1.f ? fr : 1.f;
+}
+
+struct TrowbridgeReitz {
+    float ax, ay;
+    TrowbridgeReitz(float x, float y) : ax{std::fmax(x, 1e-4f)}, ay{std::fmax(y, 1e-4f)} {}// scattering.cpp:131-132
+    float D(V3 wh) const {
+        float tan2Theta = tan2_theta(wh);
+        float cos4Theta = sqr(cos2_theta(wh));
+        float e = tan2Theta * (sqr(cos_phi(wh) / ax) + sqr(sin_phi(wh) / ay));
+        float d = 1.0f / (kPi * ax * ay * cos4Theta * sqr(1.f + e));
+        return std::isinf(tan2Theta) ? 0.f : d;
+    }
+    float Lambda(V3 w) const {
+        float tanTheta = std::fabs(tan_theta(w));
+        float alpha2 = cos2_phi(w) * sqr(ax) + sin2_phi(w) * sqr(ay);
+        float alpha2Tan2Theta = alpha2 * sqr(tanTheta);
+        float L = (-1.f + std::sqrt(1.f + alpha2Tan2Theta)) * .5f;
+        return std::isinf(tanTheta) ? 0.f : L;
+    }
+    float G1(V3 w) const { return 1.0f / (1.0f + Lambda(w)); }
+    float G(V3 wo, V3 wi) const { return 1.0f / (1.0f + Lambda(wo) + Lambda(wi)); }
+    float pdf(V3 wo, V3 wh) const { return D(wh) * G1(wo) * abs_dot(wo, wh) / abs_cos_theta(wo); }
+    static void sample11(float cosTheta, float U1, float U2, float &slope_x, float &slope_y) {
+        if (cosTheta <= .9999f) {
+            float sinTheta = std::sqrt(std::fmax(0.f, 1.f - sqr(cosTheta)));
+            float tanTheta = sinTheta / cosTheta;
+            float a = 1.f / tanTheta;
+            float G1 = 2.f / (1.f + std::sqrt(1.f + 1.f / sqr(a)));
+            float A = 2.f * U1 / G1 - 1.f;
+            float tmp = std::fmin(1.f / (sqr(A) - 1.f), 1e10f);
+            float B = tanTheta;
+            float D = std::sqrt(std::fmax(sqr(B * tmp) - (sqr(A) - sqr(B)) * tmp, 0.f));
+            float slope_x_1 = B * tmp - D;
+            float slope_x_2 = B * tmp + D;
+            slope_x = (A < 0.f || slope_x_2 * tanTheta > 1.f) ? slope_x_1 : slope_x_2;
+            float S = U2 > .5f ? 1.f : -1.f;
+            float V = U2 > .5f ? 2.f * (U2 - .5f) : 2.f * (.5f - U2);
+            float z = (V * (V * (V * 0.27385f - 0.73369f) + 0.46341f)) /
+                      (V * (V * (V * 0.093073f + 0.309420f) - 1.000000f) + 0.597999f);
+            slope_y = S * z * std::sqrt(1.f + sqr(slope_x));
+        } else {
+            float r = std::sqrt(U1 / (1.f - U1));
+            float phi = (2.f * kPi) * U2;
+            slope_x = r * std::cos(phi);
+            slope_y = r * std::sin(phi);
+        }
+    }
+    V3 sample_wh(V3 wo, float u0, float u1) const {
+        float s = sign(cos_theta(wo));
+        V3 wi = s * wo;
+        V3 wiStretched = normalize(v3(ax * wi.x, ay * wi.y, wi.z));
+        float sx, sy;
+        sample11(cos_theta(wiStretched), u0, u1, sx, sy);
+        float cp = cos_phi(wiStretched), sp = sin_phi(wiStretched);
+        float rx = cp * sx - sp * sy;
+        float ry = sp * sx + cp * sy;
+        rx = ax * rx;
+        ry = ay * ry;
+        V3 wh = normalize(v3(-rx, -ry, 1.f));
+        return s * wh;
+    }
+};
+
+// --- Disney: src/surfaces/disney.cpp:95-303 (lobes), :376-478 (closure set-up), :481-587 (evaluate / sample)
+inline float SchlickWeight(float cosTheta) {
+    float m = saturate(1.f - cosTheta);
+    return sqr(sqr(m)) * m;
+}
+inline float FrSchlick(float R0, float cosTheta) { return lerp(R0, 1.f, SchlickWeight(cosTheta)); }
+inline float SchlickR0FromEta(float eta) { return sqr((eta - 1.f) / (eta + 1.f)); }
+inline float GTR1(float cosTheta, float alpha) {
+    float alpha2 = sqr(alpha);
+    float denom = kPi * std::log(alpha2) * (1.f + (alpha2 - 1.f) * sqr(cosTheta));
+    return (alpha2 - 1.f) / denom;
+}
+inline float smithG_GGX(float cosTheta, float alpha) {
+    float alpha2 = sqr(alpha);
+    float cosTheta2 = sqr(cosTheta);
+    return 1.f / (cosTheta + std::sqrt(alpha2 + cosTheta2 - alpha2 * cosTheta2));
+}
+inline bool any_nonzero(V3 w) { return w.x != 0.f || w.y != 0.f || w.z != 0.f; }
+
+struct DisneyClosure {
+    // context
+    V3 color;
+    float color_lum, metallic, eta_t, roughness, specular_tint, anisotropic, sheen, sheen_tint, clearcoat,
+        clearcoat_gloss, specular_trans, flatness;
+    uint32_t lobes;
+    // derived
+    bool has_diffuse{false}, has_fake_ss{false}, has_sheen{false}, has_clearcoat{false};
+    V3 Cdiff{}, Css{}, Csheen{}, Cspec0{};
+    float fresnel_eta{}, gloss{};
+    TrowbridgeReitz distrib{1.f, 1.f};
+    float w[3]{0.f, 0.f, 0.f};
+    bool enabled[3]{false, false, false};
+
+    explicit DisneyClosure(const lrk_surface &s) {
+        color = v3(s.p[0], s.p[1], s.p[2]);
+        color_lum = s.p[3]; metallic = s.p[4]; eta_t = s.p[5]; roughness = s.p[6]; specular_tint = s.p[7];
+        anisotropic = s.p[8]; sheen = s.p[9]; sheen_tint = s.p[10]; clearcoat = s.p[11]; clearcoat_gloss = s.p[12];
+        specular_trans = s.p[13]; flatness = s.p[14];
+        lobes = s.lobes;
+        const float eta_i = 1.f;
+        float diffuse_weight = (1.f - metallic) * (1.f - specular_trans);
+        float tint_weight = color_lum > 0.f ? 1.f / color_lum : 1.f;
+        V3 tc = color * tint_weight;
+        V3 tint = v3(saturate(tc.x), saturate(tc.y), saturate(tc.z));
+        float tint_lum = color_lum * tint_weight;
+        float diffuse_like_sampling_weight = diffuse_weight * color_lum;
+        if ((lobes & LRK_DISNEY_LOBE_DIFFUSE) || (lobes & LRK_DISNEY_LOBE_RETRO)) {
+            float Cdiff_weight = diffuse_weight * (1.f - flatness);
+            Cdiff = color * Cdiff_weight;
+            has_diffuse = true;
+            enabled[0] = true;
+        }
+        if (lobes & LRK_DISNEY_LOBE_FAKE_SS) {
+            float Css_weight = diffuse_weight * flatness;
+            Css = Css_weight * color;
+            has_fake_ss = true;
+            enabled[0] = true;
+        }
+        if (lobes & LRK_DISNEY_LOBE_SHEEN) {
+            float Csheen_weight = diffuse_weight * sheen;
+            Csheen = Csheen_weight * lerp(v3(1.f), tint, sheen_tint);
+            has_sheen = true;
+            float sheen_lum = Csheen_weight * lerp(1.f, tint_lum, sheen_tint);
+            diffuse_like_sampling_weight += sheen_lum * .1f;
+            enabled[0] = true;
+        }
+        w[0] = saturate(diffuse_like_sampling_weight);
+        float eta = eta_t / eta_i;
+        float SchlickR0 = SchlickR0FromEta(eta);
+        Cspec0 = lerp(lerp(v3(1.f), tint, specular_tint) * SchlickR0, color, metallic);
+        fresnel_eta = eta;
+        float aspect = std::sqrt(1.f - anisotropic * .9f);
+        distrib = TrowbridgeReitz{std::fmax(0.001f, roughness / aspect), std::fmax(0.001f, roughness * aspect)};
+        float Cspec0_lum = lerp(lerp(1.f, tint_lum, specular_tint) * SchlickR0, color_lum, metallic);
+        w[1] = saturate(Cspec0_lum);
+        enabled[1] = true;
+        if (lobes & LRK_DISNEY_LOBE_CLEARCOAT) {
+            gloss = lerp(.1f, .001f, clearcoat_gloss);
+            has_clearcoat = true;
+            w[2] = saturate(clearcoat * FrSchlick(.04f, 1.f));
+            enabled[2] = true;
+        }
+        float sum_weights = 0.f;
+        for (int i = 0; i < 3; i++) if (enabled[i]) sum_weights += w[i];
+        float inv_sum_weights = sum_weights == 0.f ? 0.f : 1.f / sum_weights;
+        for (int i = 0; i < 3; i++) if (enabled[i]) w[i] *= inv_sum_weights;
+    }
+
+    V3 disney_fresnel(float cosI_in) const {// DisneyFresnel::evaluate, two_sided = true (opaque closure)
+        float cosI = std::fabs(cosI_in);
+        float fr = fresnel_dielectric(cosI, 1.f, fresnel_eta);
+        V3 f0 = v3(FrSchlick(Cspec0.x, cosI), FrSchlick(Cspec0.y, cosI), FrSchlick(Cspec0.z, cosI));
+        return lerp(v3(fr), f0, metallic);
+    }
+    V3 specular_evaluate(V3 wo, V3 wi) const {// MicrofacetReflection::evaluate, R = 1
+        V3 wh = wi + wo;
+        V3 f = v3(0.f);
+        if (same_hemisphere(wo, wi) && any_nonzero(wh)) {
+            wh = normalize(wh);
+            V3 F = disney_fresnel(dot(wi, face_forward(wh, v3(0.f, 0.f, 1.f))));
+            float D = distrib.D(wh);
+            float G = distrib.G(wo, wi);
+            float cos_o = cos_theta(wo), cos_i = cos_theta(wi);
+            f = v3(1.f) * F * std::fabs(0.25f * D * G / (cos_i * cos_o));
+        }
+        return f;
+    }
+    float specular_pdf(V3 wo, V3 wi) const {
+        float p = 0.f;
+        V3 wh = wi + wo;
+        if (same_hemisphere(wo, wi) && any_nonzero(wh)) {
+            wh = normalize(wh);
+            p = distrib.pdf(wo, wh) / (4.f * dot(wo, wh));
+        }
+        return p;
+    }
+    float clearcoat_evaluate(V3 wo, V3 wi) const {
+        V3 wh = wi + wo;
+        bool valid = any_nonzero(wh);
+        wh = normalize(wh);
+        float Dr = GTR1(abs_cos_theta(wh), gloss);
+        float Fr = FrSchlick(.04f, dot(wo, wh));
+        float Gr = smithG_GGX(abs_cos_theta(wo), .25f) * smithG_GGX(abs_cos_theta(wi), .25f);
+        return valid ? clearcoat * Gr * Fr * Dr * .25f : 0.f;
+    }
+    float clearcoat_pdf(V3 wo, V3 wi) const {
+        V3 wh = wi + wo;
+        bool valid = same_hemisphere(wo, wi) && any_nonzero(wh);
+        wh = normalize(wh);
+        float Dr = GTR1(abs_cos_theta(wh), gloss);
+        return valid ? Dr * abs_cos_theta(wh) / (4.f * dot(wo, wh)) : 0.f;
+    }
+    V3 clearcoat_sample_wi(V3 wo, float u0, float u1, bool &valid) const {
+        float alpha2 = gloss * gloss;
+        float cosTheta = std::sqrt(std::fmax(0.f, (1.f - std::pow(alpha2, 1.f - u0)) / (1.f - alpha2)));
+        float sinTheta = std::sqrt(std::fmax(0.f, 1.f - cosTheta * cosTheta));
+        float phi = 2.f * kPi * u1;
+        V3 wh = v3(sinTheta * std::cos(phi), sinTheta * std::sin(phi), cosTheta);
+        wh = same_hemisphere(wo, wh) ? wh : -wh;
+        V3 wi = reflect(-wo, wh);
+        valid = same_hemisphere(wo, wi);
+        return wi;
+    }
+
+    SurfEval evaluate_local(V3 wo, V3 wi) const {
+        V3 f = v3(0.f);
+        float pdf = 0.f;
+        if (same_hemisphere(wo, wi)) {
+            if (has_diffuse) {
+                if (w[0] > 0.f) {
+                    {// DisneyDiffuse
+                        float Fo = SchlickWeight(abs_cos_theta(wo)), Fi = SchlickWeight(abs_cos_theta(wi));
+                        f = f + Cdiff * (kInvPi * (1.f - Fo * .5f) * (1.f - Fi * .5f));
+                    }
+                    {// DisneyRetro
+                        V3 wh = wi + wo;
+                        bool valid = any_nonzero(wh);
+                        wh = normalize(wh);
+                        float cosThetaD = dot(wi, wh);
+                        float Fo = SchlickWeight(abs_cos_theta(wo)), Fi = SchlickWeight(abs_cos_theta(wi));
+                        float Rr = 2.f * roughness * cosThetaD * cosThetaD;
+                        f = f + Cdiff * (valid ? kInvPi * Rr * (Fo + Fi + Fo * Fi * (Rr - 1.f)) : 0.f);
+                    }
+                    if (has_fake_ss) {
+                        V3 wh = wi + wo;
+                        bool valid = any_nonzero(wh);
+                        wh = normalize(wh);
+                        float cosThetaD = dot(wi, wh);
+                        float Fss90 = cosThetaD * cosThetaD * roughness;
+                        float Fo = SchlickWeight(abs_cos_theta(wo)), Fi = SchlickWeight(abs_cos_theta(wi));
+                        float Fss = lerp(1.0f, Fss90, Fo) * lerp(1.0f, Fss90, Fi);
+                        float ss = 1.25f * (Fss * (1.f / (abs_cos_theta(wo) + abs_cos_theta(wi)) - .5f) + .5f);
+                        f = f + Css * (valid ? kInvPi * ss : 0.f);
+                    }
+                    if (has_sheen) {
+                        V3 wh = wi + wo;
+                        bool valid = any_nonzero(wh);
+                        wh = normalize(wh);
+                        float cosThetaD = dot(wi, wh);
+                        f = f + Csheen * (valid ? SchlickWeight(cosThetaD) : 0.f);
+                    }
+                    pdf += w[0] * lambert_pdf(wo, wi);
+                }
+            }
+            if (w[1] > 0.f) {
+                f = f + specular_evaluate(wo, wi);
+                pdf += w[1] * specular_pdf(wo, wi);
+            }
+            if (has_clearcoat) {
+                if (w[2] > 0.f) {
+                    f = f + clearcoat_evaluate(wo, wi);
+                    pdf += w[2] * clearcoat_pdf(wo, wi);
+                }
+            }
+        }
+        SurfEval e;
+        e.f = f * abs_cos_theta(wi);
+        e.pdf = pdf;
+        return e;
+    }
+};
+
+SurfEval disney_evaluate(const lrk_surface &s, const Interaction &it, V3 wo, V3 wi) {
+    DisneyClosure c{s};
+    return c.evaluate_local(it.shading.world_to_local(wo), it.shading.world_to_local(wi));
+}
+SurfSample disney_sample(const lrk_surface &s, const Interaction &it, V3 wo, float u_lobe, float u0, float u1) {
+    DisneyClosure c{s};
+    uint32_t tech = 0u;
+    float sum_weights = 0.f;
+    for (uint32_t i = 0; i < 3u; i++) {
+        if (c.enabled[i]) {
+            tech = u_lobe > sum_weights ? i : tech;
+            sum_weights += c.w[i];
+        }
+    }
+    V3 wo_local = it.shading.world_to_local(wo);
+    V3 wi_local = v3(0.f);
+    bool valid = false;
+    if (tech == 0u) {
+        if (c.has_diffuse) {// BxDF::sample_wi, scattering.cpp:274-278
+            wi_local = sample_cosine_hemisphere(u0, u1);
+            wi_local.z *= sign(cos_theta(wo_local));
+            valid = true;
+        }
+    } else if (tech == 1u) {// MicrofacetReflection::sample_wi
+        V3 wh = c.distrib.sample_wh(wo_local, u0, u1);
+        wi_local = reflect(-wo_local, wh);
+        valid = same_hemisphere(wo_local, wi_local);
+    } else if (tech == 2u) {
+        if (c.has_clearcoat) wi_local = c.clearcoat_sample_wi(wo_local, u0, u1, valid);
+    }
+    SurfSample out;
+    out.wi = it.shading.local_to_world(wi_local);
+    if (valid) out.eval = c.evaluate_local(wo_local, wi_local);
+    return out;
+}
+
+SurfEval surface_evaluate(const lrk_surface &s, const Interaction &it, V3 wo, V3 wi) {
+    SurfEval e = s.type == LRK_SURFACE_MATTE ? matte_evaluate(s, it, wo, wi) : disney_evaluate(s, it, wo, wi);
+    if (!validate_surface_sides(it.ng, it.shading.n, wo, wi)) {
+        e.f = v3(0.f);
+        e.pdf = 0.f;
+    }
+    return e;
+}
+SurfSample surface_sample(const lrk_surface &s, const Interaction &it, V3 wo, float u_lobe, float u0, float u1) {
+    SurfSample r = s.type == LRK_SURFACE_MATTE ? matte_sample(s, it, wo, u_lobe, u0, u1) : disney_sample(s, it, wo, u_lobe, u0, u1);
+    if (!validate_surface_sides(it.ng, it.shading.n, wo, r.wi)) {
+        r.eval.f = v3(0.f);
+        r.eval.pdf = 0.f;
+    }
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The estimator: src/integrators/mega_path.cpp:49-156 (identical, up to kernel boundaries, to
+// src/integrators/wave_path.cpp:254-469).  Draw order is normative.
+// ------------------------------------------------------------------------------------------------
+V3 path_li(const lrk_scene_desc &sc, uint32_t px, uint32_t py, uint32_t sample_index, oracle_counters *cnt) {
+    Sampler sampler;
+    sampler.start(px, py, sc.integrator.sampler_seed, sample_index);
+    float uf0 = sampler.generate_1d(), uf1 = sampler.generate_1d();
+    float camera_weight;
+    lrk_ray ray = generate_camera_ray(sc.camera, px, py, uf0, uf1, camera_weight);
+    V3 beta = v3(camera_weight);
+    V3 Li = v3(0.f);
+    float pdf_bsdf = 1e16f;
+    TraceCounters tc;
+    for (uint32_t depth = 0; depth < sc.integrator.max_depth; depth++) {
+        V3 wo = -v3(ray.d[0], ray.d[1], ray.d[2]);
+        lrk_hit hit = trace_bvh(sc, ray, false, &tc);
+        if (cnt) cnt->closest_rays++;
+        Interaction it = interaction_from_hit(sc, ray, hit);
+        if (!it.valid()) break;// no environment
+        if (sc.light_count != 0u && it.shape.has_light()) {
+            LightEval e = evaluate_hit(sc, it, v3(ray.o[0], ray.o[1], ray.o[2]));
+            Li = Li + beta * e.L * balance_heuristic(pdf_bsdf, e.pdf);
+        }
+        if (!it.shape.has_surface()) break;
+        if (cnt) cnt->path_vertices++;
+        float u_light_selection = sampler.generate_1d();
+        float ul0 = sampler.generate_1d(), ul1 = sampler.generate_1d();
+        float u_lobe = sampler.generate_1d();
+        float ub0 = sampler.generate_1d(), ub1 = sampler.generate_1d();
+        float u_rr = 0.f;
+        if (depth + 1u >= sc.integrator.rr_depth) u_rr = sampler.generate_1d();
+        LightSample ls = sample_light(sc, it, u_light_selection, ul0, ul1);
+        // the shadow ray is traced unconditionally (mega_path.cpp:108)
+        bool occluded = trace_bvh(sc, ls.shadow_ray, true, &tc).inst != ~0u;
+        if (cnt) cnt->shadow_rays++;
+        const lrk_surface &surface = sc.surfaces[it.shape.surface_tag];
+        if (ls.eval.pdf > 0.0f && !occluded) {
+            V3 wi = v3(ls.shadow_ray.d[0], ls.shadow_ray.d[1], ls.shadow_ray.d[2]);
+            SurfEval ev = surface_evaluate(surface, it, wo, wi);
+            float w = balance_heuristic(ls.eval.pdf, ev.pdf) / ls.eval.pdf;
+            Li = Li + w * beta * ev.f * ls.eval.L;
+        }
+        SurfSample ss = surface_sample(surface, it, wo, u_lobe, ub0, ub1);
+        ray = spawn_ray(it, ss.wi);
+        pdf_bsdf = ss.eval.pdf;
+        float w = ss.eval.pdf > 0.f ? 1.f / ss.eval.pdf : 0.f;
+        beta = beta * (w * ss.eval.f);
+        float eta_scale = 1.f;// no transmissive closures
+        // zero_if_any_nan: src/util/spec.cpp:404-407
+        if (std::isnan(beta.x) || std::isnan(beta.y) || std::isnan(beta.z)) beta = v3(0.f);
+        if (beta.x <= 0.f && beta.y <= 0.f && beta.z <= 0.f) break;
+        float q = std::fmax(max3(beta) * eta_scale, .05f);
+        if (depth + 1u >= sc.integrator.rr_depth) {
+            if (q < sc.integrator.rr_threshold && u_rr >= q) break;
+            beta = beta * (q < sc.integrator.rr_threshold ? 1.0f / q : 1.f);
+        }
+    }
+    if (cnt) {
+        cnt->samples++;
+        cnt->nodes_visited += tc.nodes;
+        cnt->tris_tested += tc.tris;
+        cnt->xforms += tc.xforms;
+    }
+    return Li;
+}
+
+// Film accumulation of one sample: src/films/color.cpp:107-130 (effective_spp = 1)
+inline void film_accumulate(float *px4, V3 rgb, float film_clamp) {
+    bool bad = std::isnan(rgb.x) || std::isnan(rgb.y) || std::isnan(rgb.z) || std::isinf(rgb.x) || std::isinf(rgb.y) || std::isinf(rgb.z);
+    if (bad) return;
+    float threshold = film_clamp * std::fmax(1.f, 1.f);
+    float strength = std::fmax(std::fmax(std::fmax(std::fabs(rgb.x), std::fabs(rgb.y)), std::fabs(rgb.z)), 0.f);
+    V3 c = rgb * (threshold / std::fmax(strength, threshold));
+    if (c.x != 0.f || c.y != 0.f || c.z != 0.f) {
+        px4[0] += c.x;
+        px4[1] += c.y;
+        px4[2] += c.z;
+    }
+    px4[3] += 1.f;
+}
+
+}// namespace
+
+// ================================================================================================
+extern "C" {
+
+int oracle_render(const lrk_scene_desc *scene, uint32_t spp_begin, uint32_t spp_end, uint32_t threads, uint32_t rank,
+                  uint32_t world, uint32_t tile_size, float *film_raw, oracle_counters *counters) {
+    if (!scene || !film_raw || scene->abi_version != LRK_ABI_VERSION) return -1;
+    if (scene->integrator.type != LRK_INTEGRATOR_PATH) return -5;
+    const uint32_t W = scene->camera.resolution[0], H = scene->camera.resolution[1];
+    if (threads == 0u) threads = std::max(1u, std::thread::hardware_concurrency());
+    const uint32_t ts = 16u;
+    const uint32_t tiles_x = (W + ts - 1u) / ts, tiles_y = (H + ts - 1u) / ts;
+    std::atomic<uint32_t> next{0u};
+    std::vector<oracle_counters> local(threads);
+    auto owned = [&](uint32_t x, uint32_t y) {
+        if (tile_size == 0u || world <= 1u) return true;
+        uint32_t shard_tiles_x = (W + tile_size - 1u) / tile_size;
+        uint32_t tile_id = (y / tile_size) * shard_tiles_x + (x / tile_size);
+        return tile_id % world == rank;
+    };
+    auto worker = [&](uint32_t tid) {
+        oracle_counters c{};
+        for (;;) {
+            uint32_t t = next.fetch_add(1u);
+            if (t >= tiles_x * tiles_y) break;
+            uint32_t tx = t % tiles_x, ty = t / tiles_x;
+            for (uint32_t y = ty * ts; y < std::min(H, (ty + 1u) * ts); y++) {
+                for (uint32_t x = tx * ts; x < std::min(W, (tx + 1u) * ts); x++) {
+                    if (!owned(x, y)) continue;
+                    float *px4 = film_raw + (static_cast<size_t>(y) * W + x) * 4u;
+                    for (uint32_t s = spp_begin; s < spp_end; s++) {
+                        V3 li = path_li(*scene, x, y, s, &c);
+                        film_accumulate(px4, li * 1.0f, scene->film.clamp);// shutter weight 1
+                    }
+                }
+            }
+        }
+        local[tid] = c;
+    };
+    std::vector<std::thread> pool;
+    for (uint32_t i = 1; i < threads; i++) pool.emplace_back(worker, i);
+    worker(0u);
+    for (auto &t : pool) t.join();
+    if (counters) {
+        for (auto &c : local) {
+            counters->samples += c.samples;
+            counters->closest_rays += c.closest_rays;
+            counters->shadow_rays += c.shadow_rays;
+            counters->nodes_visited += c.nodes_visited;
+            counters->tris_tested += c.tris_tested;
+            counters->xforms += c.xforms;
+            counters->path_vertices += c.path_vertices;
+        }
+    }
+    return 0;
+}
+
+void oracle_convert_film(const lrk_scene_desc *scene, const float *film_raw, float *rgba) {
+    const size_t n = static_cast<size_t>(scene->camera.resolution[0]) * scene->camera.resolution[1];
+    for (size_t i = 0; i < n; i++) {
+        float nrm = std::fmax(film_raw[i * 4 + 3], 1.f);
+        float inv = 1.f / nrm;
+        for (int c = 0; c < 3; c++) rgba[i * 4 + c] = (inv * scene->film.scale[c]) * film_raw[i * 4 + c];
+        rgba[i * 4 + 3] = 1.f;
+    }
+}
+
+void oracle_li(const lrk_scene_desc *scene, uint32_t px, uint32_t py, uint32_t sample_index, float rgb[3]) {
+    V3 li = path_li(*scene, px, py, sample_index, nullptr);
+    rgb[0] = li.x; rgb[1] = li.y; rgb[2] = li.z;
+}
+
+int oracle_trace(const lrk_scene_desc *scene, const lrk_ray *rays, uint64_t n, int any_hit, lrk_hit *hits,
+                 oracle_counters *counters) {
+    if (!scene || !rays || !hits) return -1;
+    TraceCounters tc;
+    for (uint64_t i = 0; i < n; i++) {
+        lrk_hit h = trace_bvh(*scene, rays[i], any_hit != 0, &tc);
+        if (any_hit) h = {h.inst != ~0u ? 1u : 0u, 0u, {0.f, 0.f}};
+        hits[i] = h;
+    }
+    if (counters) {
+        counters->nodes_visited += tc.nodes;
+        counters->tris_tested += tc.tris;
+        counters->xforms += tc.xforms;
+        (any_hit ? counters->shadow_rays : counters->closest_rays) += n;
+    }
+    return 0;
+}
+
+int oracle_trace_brute(const lrk_scene_desc *scene, const lrk_ray *rays, uint64_t n, int any_hit, lrk_hit *hits) {
+    if (!scene || !rays || !hits) return -1;
+    for (uint64_t i = 0; i < n; i++) {
+        lrk_hit h = trace_brute(*scene, rays[i], any_hit != 0);
+        if (any_hit) h = {h.inst != ~0u ? 1u : 0u, 0u, {0.f, 0.f}};
+        hits[i] = h;
+    }
+    return 0;
+}
+
+uint32_t oracle_xxhash32_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return xxhash32_uint4(x, y, z, w); }
+float oracle_lcg(uint32_t *state) { return lcg(*state); }
+
+void oracle_sample_filter(const lrk_scene_desc *scene, const float u[2], float offset[2], float *weight) {
+    sample_filter(scene->camera, u[0], u[1], offset[0], offset[1], *weight);
+}
+
+void oracle_generate_ray(const lrk_scene_desc *scene, uint32_t px, uint32_t py, uint32_t sample_index, lrk_ray *ray,
+                         float weight[3], uint32_t *rng_state) {
+    Sampler s;
+    s.start(px, py, scene->integrator.sampler_seed, sample_index);
+    float u0 = s.generate_1d(), u1 = s.generate_1d();
+    float w;
+    *ray = generate_camera_ray(scene->camera, px, py, u0, u1, w);
+    weight[0] = weight[1] = weight[2] = w;
+    if (rng_state) *rng_state = s.state;
+}
+
+void oracle_offset_ray_origin(const float p[3], const float n[3], float out[3]) {
+    V3 r = offset_ray_origin(v3(p[0], p[1], p[2]), v3(n[0], n[1], n[2]));
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+
+void oracle_decode_handle(const uint32_t handle[4], uint32_t out_u32[6], float out_f32[2]) {
+    ShapeHandle h = decode_handle(handle);
+    out_u32[0] = h.buffer_base; out_u32[1] = h.flags; out_u32[2] = h.surface_tag; out_u32[3] = h.light_tag;
+    out_u32[4] = h.medium_tag; out_u32[5] = h.tri_count;
+    out_f32[0] = h.shadow_terminator; out_f32[1] = h.intersection_offset;
+}
+
+void oracle_sample_cosine_hemisphere(const float u[2], float w[3]) {
+    V3 r = sample_cosine_hemisphere(u[0], u[1]);
+    w[0] = r.x; w[1] = r.y; w[2] = r.z;
+}
+void oracle_sample_uniform_triangle(const float u[2], float uvw[3]) {
+    V3 r = sample_uniform_triangle(u[0], u[1]);
+    uvw[0] = r.x; uvw[1] = r.y; uvw[2] = r.z;
+}
+
+static Interaction synthetic_interaction(const float ng[3], const float ns[3], const float dpdu[3]) {
+    Interaction it;
+    it.ng = v3(ng[0], ng[1], ng[2]);
+    it.shading = Frame::make(face_forward(v3(ns[0], ns[1], ns[2]), it.ng), v3(dpdu[0], dpdu[1], dpdu[2]));
+    it.inst = 0u;
+    it.prim = 0u;
+    it.shape.intersection_offset = 1.f;
+    return it;
+}
+
+void oracle_surface_evaluate(const lrk_surface *surface, const float ng[3], const float ns[3], const float dpdu[3],
+                             const float wo[3], const float wi[3], float f[3], float *pdf) {
+    Interaction it = synthetic_interaction(ng, ns, dpdu);
+    SurfEval e = surface_evaluate(*surface, it, v3(wo[0], wo[1], wo[2]), v3(wi[0], wi[1], wi[2]));
+    f[0] = e.f.x; f[1] = e.f.y; f[2] = e.f.z;
+    *pdf = e.pdf;
+}
+
+void oracle_surface_sample(const lrk_surface *surface, const float ng[3], const float ns[3], const float dpdu[3],
+                           const float wo[3], float u_lobe, const float u[2], float wi[3], float f[3], float *pdf) {
+    Interaction it = synthetic_interaction(ng, ns, dpdu);
+    SurfSample s = surface_sample(*surface, it, v3(wo[0], wo[1], wo[2]), u_lobe, u[0], u[1]);
+    wi[0] = s.wi.x; wi[1] = s.wi.y; wi[2] = s.wi.z;
+    f[0] = s.eval.f.x; f[1] = s.eval.f.y; f[2] = s.eval.f.z;
+    *pdf = s.eval.pdf;
+}
+
+void oracle_interaction(const lrk_scene_desc *scene, const lrk_ray *ray, const lrk_hit *hit, float out[19]) {
+    Interaction it = interaction_from_hit(*scene, *ray, *hit);
+    const float vals[19]{it.pg.x, it.pg.y, it.pg.z, it.ng.x, it.ng.y, it.ng.z, it.shading.n.x, it.shading.n.y, it.shading.n.z,
+                         it.shading.s.x, it.shading.s.y, it.shading.s.z, it.shading.t.x, it.shading.t.y, it.shading.t.z,
+                         it.u, it.v, it.prim_area, it.back_facing ? 1.f : 0.f};
+    std::memcpy(out, vals, sizeof(vals));
+}
+
+void oracle_sample_light(const lrk_scene_desc *scene, const lrk_ray *ray, const lrk_hit *hit, float u_sel,
+                         const float u_light[2], float out[12]) {
+    Interaction it = interaction_from_hit(*scene, *ray, *hit);
+    LightSample s = sample_light(*scene, it, u_sel, u_light[0], u_light[1]);
+    const float vals[12]{s.eval.L.x, s.eval.L.y, s.eval.L.z, s.eval.pdf, s.shadow_ray.o[0], s.shadow_ray.o[1], s.shadow_ray.o[2],
+                         s.shadow_ray.tmin, s.shadow_ray.d[0], s.shadow_ray.d[1], s.shadow_ray.d[2], s.shadow_ray.tmax};
+    std::memcpy(out, vals, sizeof(vals));
+}
+
+}// extern "C"
