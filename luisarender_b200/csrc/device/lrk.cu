@@ -1,0 +1,564 @@
+// C-ABI implementation of include/lrk.h: context, scene upload, the pass scheduler and film I/O.
+// Host-side scheduling replaces the reference's pass/bounce loop (src/integrators/wave_path.cpp:506-561):
+// no host synchronisation inside a pass, queue sizes stay on the device.
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace lrk;
+
+namespace {
+
+struct DeviceArrays {
+    void *vertices{}, *triangles{}, *alias{}, *pdf{}, *meshes{}, *inst_handles{}, *inst_o2w{}, *inst_xform{}, *bvh_nodes{},
+        *tri_verts{}, *surfaces{}, *lights{}, *light_handles{}, *camera{};
+};
+
+enum KernelCategory { CAT_TRACE_CLOSEST = 0, CAT_TRACE_SHADOW = 1, CAT_SHADE = 2, CAT_OTHER = 3, CAT_COUNT = 4 };
+
+struct TimedLaunch {
+    int cat;
+    cudaEvent_t start, stop;
+};
+
+}// namespace
+
+struct lrk_ctx {
+    int device{0};
+    int sm_count{0};
+    cudaStream_t stream{};
+    std::string error;
+    bool has_scene{false};
+    DeviceArrays arrays;
+    DeviceScene scene{};
+    uint32_t spp_hint{0};
+    // sharding
+    uint32_t rank{0}, world{1}, tile_size{32};
+    uint32_t *d_pixel_list{nullptr};
+    uint32_t npix_owned{0};
+    // path state
+    uint64_t max_paths{0}, capacity{0};
+    PathBuffers pb{};
+    std::vector<void *> path_allocs;
+    float4 *d_film{nullptr};
+    float4 *d_film_out{nullptr};
+    // options
+    bool count_traversal{false}, time_kernels{false};
+    // stats
+    lrk_stats stats{};
+    cudaEvent_t ev_begin{}, ev_end{};
+    std::vector<TimedLaunch> timed;
+    std::vector<cudaEvent_t> event_pool;
+    int grid_trace{0}, grid_shade{0}, grid_shadow{0};
+};
+
+namespace {
+
+int fail(lrk_ctx *ctx, int code, const std::string &msg) {
+    if (ctx) ctx->error = msg;
+    return code;
+}
+
+#define LRK_CUDA(call)                                                                                        \
+    do {                                                                                                      \
+        cudaError_t err__ = (call);                                                                           \
+        if (err__ != cudaSuccess) {                                                                           \
+            return fail(ctx, LRK_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(err__));            \
+        }                                                                                                     \
+    } while (0)
+
+template<typename T>
+int upload(lrk_ctx *ctx, void **dst, const T *src, size_t count) {
+    if (*dst) {
+        cudaFree(*dst);
+        *dst = nullptr;
+    }
+    size_t bytes = std::max<size_t>(count * sizeof(T), 16u);
+    LRK_CUDA(cudaMalloc(dst, bytes));
+    if (count) LRK_CUDA(cudaMemcpyAsync(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return LRK_OK;
+}
+
+void free_arrays(DeviceArrays &a) {
+    void **p = reinterpret_cast<void **>(&a);
+    for (size_t i = 0; i < sizeof(DeviceArrays) / sizeof(void *); i++) {
+        if (p[i]) cudaFree(p[i]);
+        p[i] = nullptr;
+    }
+}
+
+void free_paths(lrk_ctx *ctx) {
+    for (auto p : ctx->path_allocs) cudaFree(p);
+    ctx->path_allocs.clear();
+    ctx->capacity = 0;
+}
+
+int alloc_paths(lrk_ctx *ctx, uint64_t capacity) {
+    if (ctx->capacity >= capacity) return LRK_OK;
+    free_paths(ctx);
+    auto alloc = [&](void **p, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMalloc(p, bytes);
+        if (e == cudaSuccess) ctx->path_allocs.push_back(*p);
+        return e;
+    };
+    auto &pb = ctx->pb;
+    for (int k = 0; k < 2; k++) {
+        LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.ray_o[k]), capacity * sizeof(float4)));
+        LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.ray_d[k]), capacity * sizeof(float4)));
+        LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.beta_pdf[k]), capacity * sizeof(float4)));
+        LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.id_rng[k]), capacity * sizeof(uint2)));
+    }
+    LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.hit), capacity * sizeof(uint4)));
+    LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.sray_o), capacity * sizeof(float4)));
+    LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.sray_d), capacity * sizeof(float4)));
+    LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.scontrib), capacity * sizeof(float4)));
+    LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.li), capacity * sizeof(float4)));
+    LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.counts), 2u * kMaxDepthSlots * sizeof(uint32_t)));
+    LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.stats), 8u * sizeof(unsigned long long)));
+    LRK_CUDA(cudaMemsetAsync(pb.stats, 0, 8u * sizeof(unsigned long long), ctx->stream));
+    ctx->capacity = capacity;
+    return LRK_OK;
+}
+
+// Pixel order of a shard: tiles in row-major tile order (tile_id % world == rank), inside a tile 8x4
+// pixel blocks so that a warp's 32 consecutive paths cover a compact screen region.
+int build_pixel_list(lrk_ctx *ctx) {
+    const uint32_t W = ctx->scene.width, H = ctx->scene.height, ts = ctx->tile_size;
+    const uint32_t tiles_x = (W + ts - 1u) / ts, tiles_y = (H + ts - 1u) / ts;
+    std::vector<uint32_t> list;
+    list.reserve(static_cast<size_t>(W) * H / ctx->world + 1024u);
+    for (uint32_t ty = 0; ty < tiles_y; ty++) {
+        for (uint32_t tx = 0; tx < tiles_x; tx++) {
+            uint32_t tile_id = ty * tiles_x + tx;
+            if (tile_id % ctx->world != ctx->rank) continue;
+            uint32_t x0 = tx * ts, y0 = ty * ts;
+            uint32_t x1 = std::min(W, x0 + ts), y1 = std::min(H, y0 + ts);
+            for (uint32_t by = y0; by < y1; by += 4u)
+                for (uint32_t bx = x0; bx < x1; bx += 8u)
+                    for (uint32_t y = by; y < std::min(y1, by + 4u); y++)
+                        for (uint32_t x = bx; x < std::min(x1, bx + 8u); x++) list.push_back(x | (y << 16u));
+        }
+    }
+    if (ctx->d_pixel_list) {
+        cudaFree(ctx->d_pixel_list);
+        ctx->d_pixel_list = nullptr;
+    }
+    ctx->npix_owned = static_cast<uint32_t>(list.size());
+    LRK_CUDA(cudaMalloc(reinterpret_cast<void **>(&ctx->d_pixel_list), std::max<size_t>(list.size(), 4u) * sizeof(uint32_t)));
+    LRK_CUDA(cudaMemcpyAsync(ctx->d_pixel_list, list.data(), list.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    LRK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return LRK_OK;
+}
+
+cudaEvent_t take_event(lrk_ctx *ctx) {
+    if (!ctx->event_pool.empty()) {
+        auto e = ctx->event_pool.back();
+        ctx->event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct ScopedTimer {
+    lrk_ctx *ctx;
+    TimedLaunch t{};
+    bool on;
+    ScopedTimer(lrk_ctx *c, int cat) : ctx{c}, on{c->time_kernels} {
+        if (on) {
+            t.cat = cat;
+            t.start = take_event(ctx);
+            t.stop = take_event(ctx);
+            cudaEventRecord(t.start, ctx->stream);
+        }
+    }
+    ~ScopedTimer() {
+        if (on) {
+            cudaEventRecord(t.stop, ctx->stream);
+            ctx->timed.push_back(t);
+        }
+    }
+};
+
+int blocks_for(lrk_ctx *ctx, uint64_t n, int persistent_grid) {
+    uint64_t need = (n + kBlock - 1u) / kBlock;
+    return static_cast<int>(std::max<uint64_t>(1u, std::min<uint64_t>(need, static_cast<uint64_t>(persistent_grid))));
+}
+
+int render_pass(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint32_t spp_begin, uint32_t spp) {
+    const uint64_t n = static_cast<uint64_t>(npix) * spp;
+    auto &pb = ctx->pb;
+    const auto &sc = ctx->scene;
+    {
+        ScopedTimer t{ctx, CAT_OTHER};
+        generate_rays_kernel<<<static_cast<unsigned>((n + kBlock - 1u) / kBlock), kBlock, 0, ctx->stream>>>(
+            sc, pb, ctx->d_pixel_list, pixel_offset, npix, spp_begin, static_cast<uint32_t>(n));
+    }
+    ctx->stats.kernel_launches++;
+    // upper bound of the live queue at depth d is n; launch persistent-size grids and let kernels read *count
+    for (uint32_t depth = 0; depth < sc.max_depth; depth++) {
+        const int in = depth & 1u;
+        {
+            ScopedTimer t{ctx, CAT_TRACE_CLOSEST};
+            int g = blocks_for(ctx, n, ctx->grid_trace);
+            if (ctx->count_traversal)
+                trace_closest_kernel<true><<<g, kBlock, 0, ctx->stream>>>(sc, pb.ray_o[in], pb.ray_d[in], pb.hit, pb.counts + depth, pb.stats);
+            else
+                trace_closest_kernel<false><<<g, kBlock, 0, ctx->stream>>>(sc, pb.ray_o[in], pb.ray_d[in], pb.hit, pb.counts + depth, pb.stats);
+        }
+        {
+            ScopedTimer t{ctx, CAT_SHADE};
+            shade_kernel<<<blocks_for(ctx, n, ctx->grid_shade), kBlock, 0, ctx->stream>>>(sc, pb, depth);
+        }
+        {
+            ScopedTimer t{ctx, CAT_TRACE_SHADOW};
+            int g = blocks_for(ctx, n, ctx->grid_shadow);
+            if (ctx->count_traversal)
+                trace_shadow_kernel<true><<<g, kBlock, 0, ctx->stream>>>(sc, pb, pb.counts + kMaxDepthSlots + depth);
+            else
+                trace_shadow_kernel<false><<<g, kBlock, 0, ctx->stream>>>(sc, pb, pb.counts + kMaxDepthSlots + depth);
+        }
+        ctx->stats.kernel_launches += 3;
+    }
+    {
+        ScopedTimer t{ctx, CAT_OTHER};
+        accumulate_kernel<<<(npix + kBlock - 1u) / kBlock, kBlock, 0, ctx->stream>>>(sc, pb.li, ctx->d_film, ctx->d_pixel_list, pixel_offset,
+                                                                                  npix, spp, pb.counts, pb.stats);
+    }
+    ctx->stats.kernel_launches++;
+    ctx->stats.passes++;
+    LRK_CUDA(cudaGetLastError());
+    return LRK_OK;
+}
+
+}// namespace
+
+extern "C" {
+
+int lrk_abi_version(void) { return static_cast<int>(LRK_ABI_VERSION); }
+
+int lrk_create(const lrk_device_cfg *cfg, lrk_ctx **out) {
+    if (!out) return LRK_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return LRK_ERR_NO_DEVICE;
+    auto ctx = new lrk_ctx;
+    int dev = cfg ? cfg->device_index : -1;
+    if (dev < 0) {
+        if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    }
+    if (dev >= count || cudaSetDevice(dev) != cudaSuccess) {
+        delete ctx;
+        return LRK_ERR_NO_DEVICE;
+    }
+    ctx->device = dev;
+    cudaDeviceProp prop{};
+    cudaGetDeviceProperties(&prop, dev);
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->max_paths = cfg && cfg->max_paths_per_pass ? cfg->max_paths_per_pass : (8ull << 20);
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return LRK_ERR_CUDA;
+    }
+    cudaEventCreate(&ctx->ev_begin);
+    cudaEventCreate(&ctx->ev_end);
+    auto grid_for = [&](const void *fn) {
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kBlock, 0);
+        return std::max(1, per_sm) * ctx->sm_count;
+    };
+    ctx->grid_trace = grid_for(reinterpret_cast<const void *>(trace_closest_kernel<false>));
+    ctx->grid_shadow = grid_for(reinterpret_cast<const void *>(trace_shadow_kernel<false>));
+    ctx->grid_shade = grid_for(reinterpret_cast<const void *>(shade_kernel));
+    *out = ctx;
+    return LRK_OK;
+}
+
+void lrk_destroy(lrk_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_paths(ctx);
+    free_arrays(ctx->arrays);
+    if (ctx->d_pixel_list) cudaFree(ctx->d_pixel_list);
+    if (ctx->d_film) cudaFree(ctx->d_film);
+    if (ctx->d_film_out) cudaFree(ctx->d_film_out);
+    for (auto &t : ctx->timed) {
+        cudaEventDestroy(t.start);
+        cudaEventDestroy(t.stop);
+    }
+    for (auto e : ctx->event_pool) cudaEventDestroy(e);
+    cudaEventDestroy(ctx->ev_begin);
+    cudaEventDestroy(ctx->ev_end);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *lrk_last_error(const lrk_ctx *ctx) { return ctx ? ctx->error.c_str() : "null context"; }
+
+int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
+    if (!ctx || !s) return LRK_ERR_INVALID_ARGUMENT;
+    if (s->abi_version != LRK_ABI_VERSION) return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_upload_scene: ABI version mismatch");
+    if (s->integrator.type != LRK_INTEGRATOR_PATH)
+        return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: only the surface path integrator is implemented on the device");
+    if (s->environment_medium.present)
+        return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: participating media are not implemented on the device");
+    if (s->integrator.max_depth > kMaxDepthSlots - 1u) return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: max depth > 63");
+    if (s->camera.resolution[0] > 65535u || s->camera.resolution[1] > 65535u)
+        return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: film larger than 65535 pixels per side");
+    if (s->light_count == 0u) return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "No lights in scene. Rendering aborted.");// wave_path.cpp:224-228
+    for (uint32_t i = 0; i < s->surface_count; i++)
+        if (s->surfaces[i].type > LRK_SURFACE_DISNEY) return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: unknown surface type");
+    LRK_CUDA(cudaSetDevice(ctx->device));
+    auto &a = ctx->arrays;
+    int rc;
+    if ((rc = upload(ctx, &a.vertices, s->vertices, s->vertex_count))) return rc;
+    if ((rc = upload(ctx, &a.triangles, s->triangles, s->triangle_count))) return rc;
+    if ((rc = upload(ctx, &a.alias, s->alias, s->triangle_count))) return rc;
+    if ((rc = upload(ctx, &a.pdf, s->pdf, s->triangle_count))) return rc;
+    if ((rc = upload(ctx, &a.meshes, s->meshes, s->mesh_count))) return rc;
+    if ((rc = upload(ctx, &a.bvh_nodes, s->bvh_nodes, s->bvh_node_count))) return rc;
+    if ((rc = upload(ctx, &a.tri_verts, s->tri_verts, s->tri_slot_count * 12u))) return rc;
+    if ((rc = upload(ctx, &a.surfaces, s->surfaces, s->surface_count))) return rc;
+    if ((rc = upload(ctx, &a.lights, s->lights, s->light_count))) return rc;
+    if ((rc = upload(ctx, &a.light_handles, s->light_handles, s->light_count))) return rc;
+    if ((rc = upload(ctx, &a.camera, &s->camera, 1))) return rc;
+    std::vector<uint32_t> handles(static_cast<size_t>(s->instance_count) * 4u);
+    std::vector<float> o2w(static_cast<size_t>(s->instance_count) * 12u), xform(static_cast<size_t>(s->instance_count) * 16u);
+    for (uint32_t i = 0; i < s->instance_count; i++) {
+        const auto &inst = s->instances[i];
+        std::memcpy(&handles[i * 4u], inst.handle, 16);
+        std::memcpy(&o2w[i * 12u], inst.object_to_world, 48);
+        std::memcpy(&xform[i * 16u], inst.world_to_object, 48);
+        uint32_t root = s->meshes[inst.mesh].bvh_root;
+        std::memcpy(&xform[i * 16u + 12u], &root, 4);
+        xform[i * 16u + 13u] = xform[i * 16u + 14u] = xform[i * 16u + 15u] = 0.f;
+    }
+    if ((rc = upload(ctx, &a.inst_handles, handles.data(), handles.size()))) return rc;
+    if ((rc = upload(ctx, &a.inst_o2w, o2w.data(), o2w.size()))) return rc;
+    if ((rc = upload(ctx, &a.inst_xform, xform.data(), xform.size()))) return rc;
+    LRK_CUDA(cudaStreamSynchronize(ctx->stream));
+
+    auto &sc = ctx->scene;
+    sc.vertices = static_cast<const lrk_vertex *>(a.vertices);
+    sc.triangles = static_cast<const lrk_triangle *>(a.triangles);
+    sc.alias = static_cast<const lrk_alias_entry *>(a.alias);
+    sc.pdf = static_cast<const float *>(a.pdf);
+    sc.meshes = static_cast<const lrk_mesh *>(a.meshes);
+    sc.inst_handles = static_cast<const uint4 *>(a.inst_handles);
+    sc.inst_o2w = static_cast<const float4 *>(a.inst_o2w);
+    sc.inst_xform = static_cast<const float4 *>(a.inst_xform);
+    sc.bvh_nodes = static_cast<const float4 *>(a.bvh_nodes);
+    sc.tri_verts = static_cast<const float4 *>(a.tri_verts);
+    sc.surfaces = static_cast<const lrk_surface *>(a.surfaces);
+    sc.lights = static_cast<const lrk_light *>(a.lights);
+    sc.light_handles = static_cast<const lrk_light_handle *>(a.light_handles);
+    sc.camera = static_cast<const lrk_camera *>(a.camera);
+    sc.tlas_root = s->tlas_root;
+    sc.light_count = s->light_count;
+    sc.instance_count = s->instance_count;
+    sc.surface_count = s->surface_count;
+    sc.max_depth = s->integrator.max_depth;
+    sc.rr_depth = s->integrator.rr_depth;
+    sc.rr_threshold = s->integrator.rr_threshold;
+    sc.sampler_seed = s->integrator.sampler_seed;
+    sc.film_clamp = s->film.clamp;
+    for (int i = 0; i < 3; i++) sc.film_scale[i] = s->film.scale[i];
+    sc.width = s->camera.resolution[0];
+    sc.height = s->camera.resolution[1];
+    ctx->spp_hint = s->camera.spp;
+
+    const size_t npix = static_cast<size_t>(sc.width) * sc.height;
+    if (ctx->d_film) cudaFree(ctx->d_film);
+    if (ctx->d_film_out) cudaFree(ctx->d_film_out);
+    ctx->d_film = ctx->d_film_out = nullptr;
+    LRK_CUDA(cudaMalloc(reinterpret_cast<void **>(&ctx->d_film), npix * sizeof(float4)));
+    LRK_CUDA(cudaMalloc(reinterpret_cast<void **>(&ctx->d_film_out), npix * sizeof(float4)));
+    ctx->has_scene = true;
+    if ((rc = build_pixel_list(ctx))) return rc;
+    return lrk_film_clear(ctx);
+}
+
+int lrk_set_shard(lrk_ctx *ctx, uint32_t rank, uint32_t world, uint32_t tile_size) {
+    if (!ctx || world == 0u || rank >= world || tile_size == 0u) return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_set_shard: invalid shard");
+    ctx->rank = rank;
+    ctx->world = world;
+    ctx->tile_size = tile_size;
+    if (ctx->has_scene) {
+        LRK_CUDA(cudaSetDevice(ctx->device));
+        return build_pixel_list(ctx);
+    }
+    return LRK_OK;
+}
+
+int lrk_set_option(lrk_ctx *ctx, const char *name, int64_t value) {
+    if (!ctx || !name) return LRK_ERR_INVALID_ARGUMENT;
+    std::string n{name};
+    if (n == "count_traversal") ctx->count_traversal = value != 0;
+    else if (n == "time_kernels") ctx->time_kernels = value != 0;
+    else if (n == "max_paths_per_pass") ctx->max_paths = value > 0 ? static_cast<uint64_t>(value) : ctx->max_paths;
+    else if (n == "sort_by_surface" || n == "use_graph") { /* accepted; not implemented yet */ }
+    else return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_set_option: unknown option '" + n + "'");
+    return LRK_OK;
+}
+
+int lrk_film_clear(lrk_ctx *ctx) {
+    if (!ctx || !ctx->has_scene) return fail(ctx, LRK_ERR_NO_SCENE, "lrk_film_clear: no scene");
+    LRK_CUDA(cudaSetDevice(ctx->device));
+    const size_t npix = static_cast<size_t>(ctx->scene.width) * ctx->scene.height;
+    LRK_CUDA(cudaMemsetAsync(ctx->d_film, 0, npix * sizeof(float4), ctx->stream));
+    if (ctx->pb.stats) LRK_CUDA(cudaMemsetAsync(ctx->pb.stats, 0, 8u * sizeof(unsigned long long), ctx->stream));
+    LRK_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->stats = lrk_stats{};
+    return LRK_OK;
+}
+
+int lrk_render(lrk_ctx *ctx, uint32_t spp_begin, uint32_t spp_end) {
+    if (!ctx || !ctx->has_scene) return fail(ctx, LRK_ERR_NO_SCENE, "lrk_render: no scene");
+    if (spp_end < spp_begin) return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_render: spp_end < spp_begin");
+    LRK_CUDA(cudaSetDevice(ctx->device));
+    const uint32_t npix = ctx->npix_owned;
+    if (npix == 0u || spp_end == spp_begin) return LRK_OK;
+    const uint64_t max_paths = std::max<uint64_t>(ctx->max_paths, 1024u);
+    const uint32_t total_spp = spp_end - spp_begin;
+    uint32_t chunk_pix = npix, spp_per_pass = 1u;
+    if (npix > max_paths) chunk_pix = static_cast<uint32_t>(max_paths);
+    else spp_per_pass = static_cast<uint32_t>(std::min<uint64_t>(total_spp, max_paths / npix));
+    int rc = alloc_paths(ctx, static_cast<uint64_t>(chunk_pix) * spp_per_pass);
+    if (rc) return rc;
+    LRK_CUDA(cudaEventRecord(ctx->ev_begin, ctx->stream));
+    for (uint32_t s = 0; s < total_spp; s += spp_per_pass) {
+        uint32_t spp = std::min(spp_per_pass, total_spp - s);
+        for (uint32_t p = 0; p < npix; p += chunk_pix) {
+            uint32_t np = std::min(chunk_pix, npix - p);
+            if ((rc = render_pass(ctx, p, np, spp_begin + s, spp))) return rc;
+        }
+    }
+    LRK_CUDA(cudaEventRecord(ctx->ev_end, ctx->stream));
+    LRK_CUDA(cudaStreamSynchronize(ctx->stream));
+    LRK_CUDA(cudaGetLastError());
+    float ms = 0.f;
+    LRK_CUDA(cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
+    ctx->stats.render_ms += ms;
+    ctx->stats.samples += static_cast<uint64_t>(npix) * total_spp;
+    for (auto &t : ctx->timed) {
+        float kms = 0.f;
+        cudaEventElapsedTime(&kms, t.start, t.stop);
+        double *dst = t.cat == CAT_TRACE_CLOSEST ? &ctx->stats.trace_closest_ms :
+                      t.cat == CAT_TRACE_SHADOW  ? &ctx->stats.trace_shadow_ms :
+                      t.cat == CAT_SHADE         ? &ctx->stats.shade_ms :
+                                                   &ctx->stats.other_ms;
+        *dst += kms;
+        ctx->event_pool.push_back(t.start);
+        ctx->event_pool.push_back(t.stop);
+    }
+    ctx->timed.clear();
+    return LRK_OK;
+}
+
+static int convert_and_copy(lrk_ctx *ctx, const float4 *raw, float *rgba) {
+    const uint32_t npix = ctx->scene.width * ctx->scene.height;
+    convert_film_kernel<<<(npix + kBlock - 1u) / kBlock, kBlock, 0, ctx->stream>>>(ctx->scene, raw, ctx->d_film_out, npix);
+    LRK_CUDA(cudaGetLastError());
+    LRK_CUDA(cudaMemcpyAsync(rgba, ctx->d_film_out, static_cast<size_t>(npix) * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    LRK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return LRK_OK;
+}
+
+int lrk_download_film(lrk_ctx *ctx, float *rgba) {
+    if (!ctx || !ctx->has_scene || !rgba) return fail(ctx, LRK_ERR_NO_SCENE, "lrk_download_film: no scene / null buffer");
+    LRK_CUDA(cudaSetDevice(ctx->device));
+    return convert_and_copy(ctx, ctx->d_film, rgba);
+}
+
+int lrk_download_film_raw(lrk_ctx *ctx, float *rgba) {
+    if (!ctx || !ctx->has_scene || !rgba) return fail(ctx, LRK_ERR_NO_SCENE, "lrk_download_film_raw: no scene / null buffer");
+    LRK_CUDA(cudaSetDevice(ctx->device));
+    const size_t npix = static_cast<size_t>(ctx->scene.width) * ctx->scene.height;
+    LRK_CUDA(cudaMemcpyAsync(rgba, ctx->d_film, npix * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    LRK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return LRK_OK;
+}
+
+int lrk_film_device_ptr(lrk_ctx *ctx, void **ptr, uint64_t *bytes) {
+    if (!ctx || !ctx->has_scene || !ptr || !bytes) return fail(ctx, LRK_ERR_NO_SCENE, "lrk_film_device_ptr: no scene");
+    *ptr = ctx->d_film;
+    *bytes = static_cast<uint64_t>(ctx->scene.width) * ctx->scene.height * sizeof(float4);
+    return LRK_OK;
+}
+
+int lrk_film_normalize_to_host(lrk_ctx *ctx, const void *device_raw, float *rgba) {
+    if (!ctx || !ctx->has_scene || !device_raw || !rgba) return fail(ctx, LRK_ERR_NO_SCENE, "lrk_film_normalize_to_host: bad argument");
+    LRK_CUDA(cudaSetDevice(ctx->device));
+    return convert_and_copy(ctx, static_cast<const float4 *>(device_raw), rgba);
+}
+
+int lrk_trace(lrk_ctx *ctx, const lrk_ray *rays, uint64_t n, int any_hit, lrk_hit *hits) {
+    if (!ctx || !ctx->has_scene) return fail(ctx, LRK_ERR_NO_SCENE, "lrk_trace: no scene");
+    if (n == 0u) return LRK_OK;
+    if (!rays || !hits || n > 0xffffffffull) return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_trace: bad argument");
+    LRK_CUDA(cudaSetDevice(ctx->device));
+    float4 *d_rays = nullptr;
+    uint4 *d_hits = nullptr;
+    LRK_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_rays), n * sizeof(lrk_ray)));
+    if (cudaMalloc(reinterpret_cast<void **>(&d_hits), n * sizeof(lrk_hit)) != cudaSuccess) {
+        cudaFree(d_rays);
+        return fail(ctx, LRK_ERR_OUT_OF_MEMORY, "lrk_trace: out of device memory");
+    }
+    cudaMemcpyAsync(d_rays, rays, n * sizeof(lrk_ray), cudaMemcpyHostToDevice, ctx->stream);
+    int g = blocks_for(ctx, n, ctx->grid_trace);
+    if (any_hit) trace_query_kernel<true><<<g, kBlock, 0, ctx->stream>>>(ctx->scene, d_rays, d_hits, static_cast<uint32_t>(n));
+    else trace_query_kernel<false><<<g, kBlock, 0, ctx->stream>>>(ctx->scene, d_rays, d_hits, static_cast<uint32_t>(n));
+    cudaMemcpyAsync(hits, d_hits, n * sizeof(lrk_hit), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaFree(d_rays);
+    cudaFree(d_hits);
+    if (e != cudaSuccess) return fail(ctx, LRK_ERR_CUDA, std::string("lrk_trace: ") + cudaGetErrorString(e));
+    return LRK_OK;
+}
+
+int lrk_trace_device(lrk_ctx *ctx, const void *d_rays, uint64_t n, int any_hit, void *d_hits, uint32_t repeat, float *avg_ms) {
+    if (!ctx || !ctx->has_scene) return fail(ctx, LRK_ERR_NO_SCENE, "lrk_trace_device: no scene");
+    if (!d_rays || !d_hits || n == 0u || n > 0xffffffffull || repeat == 0u) return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_trace_device: bad argument");
+    LRK_CUDA(cudaSetDevice(ctx->device));
+    int g = blocks_for(ctx, n, ctx->grid_trace);
+    LRK_CUDA(cudaEventRecord(ctx->ev_begin, ctx->stream));
+    for (uint32_t r = 0; r < repeat; r++) {
+        if (any_hit) trace_query_kernel<true><<<g, kBlock, 0, ctx->stream>>>(ctx->scene, static_cast<const float4 *>(d_rays), static_cast<uint4 *>(d_hits), static_cast<uint32_t>(n));
+        else trace_query_kernel<false><<<g, kBlock, 0, ctx->stream>>>(ctx->scene, static_cast<const float4 *>(d_rays), static_cast<uint4 *>(d_hits), static_cast<uint32_t>(n));
+    }
+    LRK_CUDA(cudaEventRecord(ctx->ev_end, ctx->stream));
+    LRK_CUDA(cudaStreamSynchronize(ctx->stream));
+    LRK_CUDA(cudaGetLastError());
+    float ms = 0.f;
+    LRK_CUDA(cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
+    if (avg_ms) *avg_ms = ms / static_cast<float>(repeat);
+    return LRK_OK;
+}
+
+int lrk_get_stats(lrk_ctx *ctx, lrk_stats *stats) {
+    if (!ctx || !stats) return LRK_ERR_INVALID_ARGUMENT;
+    LRK_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->pb.stats) {
+        unsigned long long h[8]{};
+        LRK_CUDA(cudaMemcpy(h, ctx->pb.stats, sizeof(h), cudaMemcpyDeviceToHost));
+        ctx->stats.closest_rays = h[0];
+        ctx->stats.shadow_rays = h[1];
+        ctx->stats.nodes_visited = h[2];
+        ctx->stats.tris_tested = h[3];
+        ctx->stats.xforms = h[4];
+    }
+    *stats = ctx->stats;
+    return LRK_OK;
+}
+
+void *lrk_stream(lrk_ctx *ctx) { return ctx ? static_cast<void *>(ctx->stream) : nullptr; }
+
+}// extern "C"

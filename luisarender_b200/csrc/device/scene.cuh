@@ -1,0 +1,43 @@
+// Device-resident scene: the flattened POD arrays of include/lrk.h re-laid for 16-byte loads.
+#pragma once
+#include <cstdint>
+
+#include "../../../include/lrk.h"
+#include "vecmath.cuh"
+
+namespace lrk {
+
+// One traversal instance record, 64 B = 4 x float4 (counted as N_xform in the roofline model):
+//   rows 0..2 : world_to_object 3x4, row 3 : {as_float(blas_root), 0, 0, 0}
+// One shading instance record: handle (uint4, 16 B) + object_to_world 3x4 (3 x float4, 48 B).
+struct DeviceScene {
+    const lrk_vertex *vertices;
+    const lrk_triangle *triangles;
+    const lrk_alias_entry *alias;
+    const float *pdf;
+    const lrk_mesh *meshes;
+    const uint4 *inst_handles;
+    const float4 *inst_o2w;
+    const float4 *inst_xform;
+    const float4 *bvh_nodes;// 4 x float4 per node: {lo0.xyz,hi0.x} {hi0.yz,lo1.xy} {lo1.z,hi1.xyz} {ref0,ref1,parent,-}
+    const float4 *tri_verts;// 3 x float4 per BVH-ordered triangle slot, v0.w = prim id bits
+    const lrk_surface *surfaces;
+    const lrk_light *lights;
+    const lrk_light_handle *light_handles;
+    const lrk_camera *camera;
+    uint32_t tlas_root;
+    uint32_t light_count;
+    uint32_t instance_count;
+    uint32_t surface_count;
+    // integrator
+    uint32_t max_depth;
+    uint32_t rr_depth;
+    float rr_threshold;
+    uint32_t sampler_seed;
+    // film
+    float film_clamp;
+    float film_scale[3];
+    uint32_t width, height;
+};
+
+}// namespace lrk

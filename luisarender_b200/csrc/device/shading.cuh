@@ -1,0 +1,619 @@
+// Device-side hit reconstruction, light sampling and closures for the sm_100a shade kernel.
+// Hand-written restatement of the reference's DSL-staged functions (they only exist as AST
+// recorders there); each block cites the reference file:line it follows (paths relative to the
+// reference tree).  Expression order follows the reference so that the CPU oracle (oracle/oracle.cpp)
+// and this file evaluate the same fp32 expressions.
+#pragma once
+#include "scene.cuh"
+
+namespace lrk {
+
+// ---- warps / sampling: src/util/sampling.cpp:13-31,89-98,133-155 ; src/util/sampling.h:38-70 ------
+__device__ __forceinline__ void sample_uniform_disk_concentric(float ux, float uy, float &dx, float &dy) {
+    float x = ux * 2.0f - 1.0f, y = uy * 2.0f - 1.0f;
+    bool p = fabsf(x) > fabsf(y);
+    float r = p ? x : y;
+    float theta = p ? kPiOverFour * (y / x) : kPiOverTwo - kPiOverFour * (x / y);
+    float s, c;
+    sincosf(theta, &s, &c);
+    dx = r * c;
+    dy = r * s;
+}
+__device__ __forceinline__ V3 sample_cosine_hemisphere(float ux, float uy) {
+    float dx, dy;
+    sample_uniform_disk_concentric(ux, uy, dx, dy);
+    float z = sqrtf(fmaxf(1.0f - dx * dx - dy * dy, 0.0f));
+    return {dx, dy, z};
+}
+__device__ __forceinline__ V3 sample_uniform_triangle(float ux, float uy) {
+    float a, b;
+    if (ux < uy) { a = 0.5f * ux; b = -0.5f * ux + uy; }
+    else { a = -0.5f * uy + ux; b = 0.5f * uy; }
+    return {a, b, 1.0f - a - b};
+}
+__device__ __forceinline__ float balance_heuristic(float f_pdf, float g_pdf) {
+    float sum_f = 1.0f * f_pdf;
+    float sum = sum_f + 1.0f * g_pdf;
+    return sum == 0.0f ? 0.0f : sum_f / sum;
+}
+
+// ---- Frame: src/util/frame.cpp:21-42 ; local trigonometry: src/util/frame.h:50-71 -------------------
+struct Frame {
+    V3 s, t, n;
+    __device__ __forceinline__ static Frame make(V3 n) {
+        float sgn = sign(n.z);
+        float a = -1.f / (sgn + n.z);
+        float b = n.x * n.y * a;
+        V3 s = v3(1.f + sgn * sqr(n.x) * a, sgn * b, -sgn * n.x);
+        V3 t = v3(b, sgn + sqr(n.y) * a, -n.y);
+        return {normalize(s), normalize(t), n};
+    }
+    __device__ __forceinline__ static Frame make(V3 n, V3 s) {
+        V3 ss = normalize(s - n * dot(n, s));
+        V3 tt = normalize(cross(n, ss));
+        return {ss, tt, n};
+    }
+    __device__ __forceinline__ V3 local_to_world(V3 d) const { return normalize(d.x * s + d.y * t + d.z * n); }
+    __device__ __forceinline__ V3 world_to_local(V3 d) const { return normalize(v3(dot(d, s), dot(d, t), dot(d, n))); }
+};
+__device__ __forceinline__ float cos_theta(V3 w) { return w.z; }
+__device__ __forceinline__ float cos2_theta(V3 w) { return sqr(w.z); }
+__device__ __forceinline__ float abs_cos_theta(V3 w) { return fabsf(w.z); }
+__device__ __forceinline__ float sin2_theta(V3 w) { return saturate(1.0f - cos2_theta(w)); }
+__device__ __forceinline__ float sin_theta(V3 w) { return sqrtf(sin2_theta(w)); }
+__device__ __forceinline__ float tan_theta(V3 w) { return sin_theta(w) / cos_theta(w); }
+__device__ __forceinline__ float tan2_theta(V3 w) { return sin2_theta(w) / cos2_theta(w); }
+__device__ __forceinline__ float cos_phi(V3 w) {
+    float s = sin_theta(w);
+    return s == 0.0f ? 1.0f : clampf(w.x / s, -1.0f, 1.0f);
+}
+__device__ __forceinline__ float sin_phi(V3 w) {
+    float s = sin_theta(w);
+    return s == 0.0f ? 0.0f : clampf(w.y / s, -1.0f, 1.0f);
+}
+__device__ __forceinline__ float cos2_phi(V3 w) { return sqr(cos_phi(w)); }
+__device__ __forceinline__ float sin2_phi(V3 w) { return sqr(sin_phi(w)); }
+__device__ __forceinline__ bool same_hemisphere(V3 w, V3 wp) { return w.z * wp.z > 0.0f; }
+__device__ __forceinline__ float abs_dot(V3 a, V3 b) { return fabsf(dot(a, b)); }
+
+// ---- Shape::Handle::decode: src/base/shape.cpp:72-93 ----------------------------------------------
+struct ShapeHandle {
+    uint32_t mesh, flags, surface_tag, light_tag, tri_count;
+    float intersection_offset;
+    __device__ __forceinline__ bool has_vertex_normal() const { return flags & LRK_SHAPE_HAS_VERTEX_NORMAL; }
+    __device__ __forceinline__ bool has_vertex_uv() const { return flags & LRK_SHAPE_HAS_VERTEX_UV; }
+    __device__ __forceinline__ bool has_surface() const { return flags & LRK_SHAPE_HAS_SURFACE; }
+    __device__ __forceinline__ bool has_light() const { return flags & LRK_SHAPE_HAS_LIGHT; }
+};
+__device__ __forceinline__ ShapeHandle decode_handle(uint4 c) {
+    ShapeHandle h;
+    h.mesh = (c.x >> 10u) >> 2u;// buffer_base = 4 * mesh index (include/lrk.h)
+    h.flags = c.x & 1023u;
+    h.surface_tag = (c.y >> 12u) & 4095u;
+    h.light_tag = c.y & 4095u;
+    h.tri_count = c.z;
+    float off = static_cast<float>(c.w & 0xffffu) * (1.0f / 65536.f);
+    h.intersection_offset = clampf(off * 255.f + 1.f, 1.f, 256.f);
+    return h;
+}
+
+// ---- Interaction: src/base/interaction.{h,cpp}, src/base/geometry.cpp:281-389 ----------------------
+struct Interaction {
+    ShapeHandle shape;
+    V3 pg, ng;
+    Frame shading;
+    uint32_t prim;
+    float prim_area;
+    bool back_facing;
+};
+
+// src/compute/src/dsl/rtx/ray.cpp:16-23
+__device__ __forceinline__ float offset_component(float pc, float nc) {
+    constexpr float origin = 1.0f / 32.0f;
+    constexpr float float_scale = 1.0f / 65536.0f;
+    constexpr float int_scale = 256.0f;
+    int32_t of_i = static_cast<int32_t>(int_scale * nc);
+    int32_t bits = __float_as_int(pc) + (pc < 0.0f ? -of_i : of_i);
+    return fabsf(pc) < origin ? pc + float_scale * nc : __int_as_float(bits);
+}
+__device__ __forceinline__ V3 offset_ray_origin(V3 p, V3 n) {
+    return {offset_component(p.x, n.x), offset_component(p.y, n.y), offset_component(p.z, n.z)};
+}
+// src/base/interaction.cpp:13-30
+__device__ __forceinline__ V3 p_robust(const Interaction &it, V3 w) {
+    bool front = dot(it.shading.n, w) > 0.f;
+    V3 n = front ? it.ng : -it.ng;
+    return offset_ray_origin(it.pg, it.shape.intersection_offset * n);
+}
+
+struct Mat34 {// three float4 rows
+    float4 r0, r1, r2;
+    __device__ __forceinline__ V3 col(int j) const {
+        return j == 0 ? v3(r0.x, r1.x, r2.x) : j == 1 ? v3(r0.y, r1.y, r2.y) : j == 2 ? v3(r0.z, r1.z, r2.z) : v3(r0.w, r1.w, r2.w);
+    }
+};
+// float3x3 * float3 = v.x*m[0] + v.y*m[1] + v.z*m[2] (cuda_device_math.h:2746)
+__device__ __forceinline__ V3 mul3(const Mat34 &m, V3 v) { return v.x * m.col(0) + v.y * m.col(1) + v.z * m.col(2); }
+
+__device__ __forceinline__ Mat34 load_o2w(const DeviceScene &sc, uint32_t inst) {
+    const float4 *p = sc.inst_o2w + static_cast<size_t>(inst) * 3u;
+    return {__ldg(p), __ldg(p + 1), __ldg(p + 2)};
+}
+
+// Geometry::shading_point (src/base/geometry.cpp:345-389) + Interaction ctor (src/base/interaction.h:97-101).
+// `back_facing` is filled by the caller (geometry.cpp:290 for hits, uniform.cpp:121 for sampled light points).
+__device__ __forceinline__ Interaction make_interaction(const DeviceScene &sc, uint32_t inst_id, uint32_t prim_id, V3 bary) {
+    Interaction it;
+    it.shape = decode_handle(__ldg(sc.inst_handles + inst_id));
+    const lrk_mesh mesh = sc.meshes[it.shape.mesh];
+    const lrk_triangle tri = sc.triangles[mesh.triangle_offset + prim_id];
+    const float4 *vb = reinterpret_cast<const float4 *>(sc.vertices + mesh.vertex_offset);
+    float4 a0 = __ldg(vb + tri.i0 * 2u), a1 = __ldg(vb + tri.i0 * 2u + 1u);
+    float4 b0 = __ldg(vb + tri.i1 * 2u), b1 = __ldg(vb + tri.i1 * 2u + 1u);
+    float4 c0 = __ldg(vb + tri.i2 * 2u), c1 = __ldg(vb + tri.i2 * 2u + 1u);
+    // Vertex = {px,py,pz,nx | ny,nz,u,v}
+    V3 p0 = v3(a0.x, a0.y, a0.z), p1 = v3(b0.x, b0.y, b0.z), p2 = v3(c0.x, c0.y, c0.z);
+    V3 n0 = v3(a0.w, a1.x, a1.y), n1 = v3(b0.w, b1.x, b1.y), n2 = v3(c0.w, c1.x, c1.y);
+    Mat34 m = load_o2w(sc, inst_id);
+    V3 t = m.col(3);
+    V3 ns_local = bary.x * n0 + bary.y * n1 + bary.z * n2;
+    float duv0x = b1.z - a1.z, duv0y = b1.w - a1.w;
+    float duv1x = c1.z - a1.z, duv1y = c1.w - a1.w;
+    float det = duv0x * duv1y - duv0y * duv1x;
+    float inv_det = 1.f / det;
+    V3 dp0 = p1 - p0, dp1 = p2 - p0;
+    V3 dpdu_local = (dp0 * duv1y - dp1 * duv0y) * inv_det;
+    V3 p = mul3(m, bary.x * p0 + bary.y * p1 + bary.z * p2) + t;
+    V3 c = cross(mul3(m, dp0), mul3(m, dp1));
+    float area = length(c) * .5f;
+    V3 ng = normalize(c);
+    Frame fallback = Frame::make(ng);
+    V3 dpdu = det == 0.f ? fallback.s : mul3(m, dpdu_local);
+    V3 ns = ng;
+    if (it.shape.has_vertex_normal()) {
+        // mn = transpose(inverse(m)), GLM-style inverse (cuda_device_math.h:3615-3630)
+        V3 m0 = m.col(0), m1 = m.col(1), m2 = m.col(2);
+        float one_over_det = 1.0f / (m0.x * (m1.y * m2.z - m2.y * m1.z) - m1.x * (m0.y * m2.z - m2.y * m0.z) +
+                                     m2.x * (m0.y * m1.z - m1.y * m0.z));
+        V3 i0 = v3((m1.y * m2.z - m2.y * m1.z) * one_over_det, (m2.y * m0.z - m0.y * m2.z) * one_over_det,
+                   (m0.y * m1.z - m1.y * m0.z) * one_over_det);
+        V3 i1 = v3((m2.x * m1.z - m1.x * m2.z) * one_over_det, (m0.x * m2.z - m2.x * m0.z) * one_over_det,
+                   (m1.x * m0.z - m0.x * m1.z) * one_over_det);
+        V3 i2 = v3((m1.x * m2.y - m2.x * m1.y) * one_over_det, (m2.x * m0.y - m0.x * m2.y) * one_over_det,
+                   (m0.x * m1.y - m1.x * m0.y) * one_over_det);
+        V3 mn0 = v3(i0.x, i1.x, i2.x), mn1 = v3(i0.y, i1.y, i2.y), mn2 = v3(i0.z, i1.z, i2.z);
+        ns = normalize(ns_local.x * mn0 + ns_local.y * mn1 + ns_local.z * mn2);
+    }
+    it.pg = p;
+    it.ng = ng;
+    it.prim_area = area;
+    it.shading = Frame::make(face_forward(ns, ng), dpdu);
+    it.prim = prim_id;
+    it.back_facing = false;
+    return it;
+}
+
+// ---- lights: src/lights/diffuse.cpp:67-88 ; src/lightsamplers/uniform.cpp:50-65,78-137 ------------------
+struct LightEval {
+    V3 L;
+    float pdf;
+};
+
+__device__ __forceinline__ LightEval diffuse_light_evaluate(const DeviceScene &sc, const Interaction &it_light, V3 p_from) {
+    const lrk_light light = sc.lights[it_light.shape.light_tag];
+    const lrk_mesh mesh = sc.meshes[it_light.shape.mesh];
+    float pdf_triangle = __ldg(sc.pdf + mesh.triangle_offset + it_light.prim);
+    float pdf_area = pdf_triangle / it_light.prim_area;
+    float cos_wo = abs_dot(normalize(p_from - it_light.pg), it_light.ng);
+    V3 L = v3(light.emission[0], light.emission[1], light.emission[2]) * light.scale;
+    V3 diff = it_light.pg - p_from;
+    float pdf = dot(diff, diff) * pdf_area * (1.0f / cos_wo);
+    bool invalid = fabsf(cos_wo) < 1e-6f || (!light.two_sided && it_light.back_facing);
+    LightEval e;
+    e.L = invalid ? v3(0.f) : L;
+    e.pdf = invalid ? 0.0f : pdf;
+    return e;
+}
+
+__device__ __forceinline__ LightEval evaluate_hit(const DeviceScene &sc, const Interaction &it, V3 p_from) {
+    LightEval e = diffuse_light_evaluate(sc, it, p_from);
+    float n = static_cast<float>(sc.light_count);
+    e.pdf *= (1.f - 0.f) / n;
+    return e;
+}
+
+struct LightSample {
+    LightEval eval;
+    float4 ray_o_tmin, ray_d_tmax;
+};
+
+__device__ __forceinline__ LightSample sample_light(const DeviceScene &sc, const Interaction &it_from, float u_sel, float u0, float u1) {
+    LightSample s;
+    float n = static_cast<float>(sc.light_count);
+    uint32_t tag = static_cast<uint32_t>(clampf(u_sel * n, 0.f, n - 1.f));
+    float sel_prob = 1.f / n;
+    const lrk_light_handle handle = sc.light_handles[tag];
+    ShapeHandle light_inst = decode_handle(__ldg(sc.inst_handles + handle.instance_id));
+    const lrk_mesh mesh = sc.meshes[light_inst.mesh];
+    // sample_alias_table: src/util/sampling.h:38-50
+    float u = u0 * static_cast<float>(light_inst.tri_count);
+    uint32_t i = min(max(static_cast<uint32_t>(u), 0u), light_inst.tri_count - 1u);
+    float u_remapped = u - floorf(u);
+    lrk_alias_entry entry = sc.alias[mesh.triangle_offset + i];
+    bool keep = u_remapped < entry.prob;
+    uint32_t triangle_id = keep ? i : entry.alias;
+    float ux = keep ? u_remapped / entry.prob : (u_remapped - entry.prob) / (1.0f - entry.prob);
+    V3 uvw = sample_uniform_triangle(ux, u1);
+    Interaction it_light = make_interaction(sc, handle.instance_id, triangle_id, uvw);
+    it_light.back_facing = dot(it_light.ng, it_from.pg - it_light.pg) < 0.f;
+    s.eval = diffuse_light_evaluate(sc, it_light, it_from.pg);
+    s.eval.pdf *= sel_prob;
+    // Interaction::spawn_ray_to, src/base/interaction.cpp:25-30
+    V3 p_from = p_robust(it_from, it_light.pg - it_from.pg);
+    V3 Lv = it_light.pg - p_from;
+    float d = length(Lv);
+    V3 dir = Lv * (1.f / d);
+    s.ray_o_tmin = make_float4(p_from.x, p_from.y, p_from.z, 0.f);
+    s.ray_d_tmax = make_float4(dir.x, dir.y, dir.z, d * .9999f);
+    return s;
+}
+
+// ---- surfaces ------------------------------------------------------------------------------------------
+struct SurfEval {
+    V3 f;
+    float pdf;
+};
+
+// src/base/surface.cpp:35-43
+__device__ __forceinline__ bool validate_surface_sides(V3 ng, V3 ns, V3 wo, V3 wi) {
+    float flip = sign(dot(ng, ns));
+    return sign(flip * dot(wo, ns)) == sign(dot(wo, ng)) && sign(flip * dot(wi, ns)) == sign(dot(wi, ng));
+}
+__device__ __forceinline__ float lambert_pdf(V3 wo, V3 wi) { return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * kInvPi : 0.f; }
+
+// Matte / Oren-Nayar: src/surfaces/matte.cpp:78-134, src/util/scattering.cpp:247-264,370-400
+struct MatteClosure {
+    V3 r;
+    float a, b;
+    __device__ __forceinline__ void init(const lrk_surface &s) {
+        r = v3(s.p[0], s.p[1], s.p[2]);
+        float sigma2 = sqr(s.p[3] * (kPi / 180.0f));
+        a = 1.f - (sigma2 / (2.f * sigma2 + 0.66f));
+        b = 0.45f * sigma2 / (sigma2 + 0.09f);
+    }
+    __device__ __forceinline__ V3 oren_nayar(V3 wo, V3 wi) const {
+        float s = same_hemisphere(wo, wi) ? kInvPi : 0.f;
+        float sinThetaI = sin_theta(wi), sinThetaO = sin_theta(wo);
+        float sinPhiI = sin_phi(wi), cosPhiI = cos_phi(wi);
+        float sinPhiO = sin_phi(wo), cosPhiO = cos_phi(wo);
+        float dCos = cosPhiI * cosPhiO + sinPhiI * sinPhiO;
+        float maxCos = (sinThetaI > 1e-4f && sinThetaO > 1e-4f) ? fmaxf(0.f, dCos) : 0.f;
+        float absCosThetaI = abs_cos_theta(wi), absCosThetaO = abs_cos_theta(wo);
+        float sinAlpha = absCosThetaI > absCosThetaO ? sinThetaO : sinThetaI;
+        float tanBeta = absCosThetaI > absCosThetaO ? sinThetaI / absCosThetaI : sinThetaO / absCosThetaO;
+        float scale = a + b * maxCos * sinAlpha * tanBeta;
+        return s * scale * r;
+    }
+    __device__ __forceinline__ SurfEval evaluate_local(V3 wo, V3 wi) const {
+        SurfEval e;
+        e.f = oren_nayar(wo, wi) * abs_cos_theta(wi);
+        e.pdf = lambert_pdf(wo, wi);
+        return e;
+    }
+    __device__ __forceinline__ SurfEval sample_local(V3 wo, float, float u0, float u1, V3 &wi) const {
+        wi = sample_cosine_hemisphere(u0, u1);
+        wi.z *= sign(cos_theta(wo));
+        SurfEval e;
+        e.pdf = lambert_pdf(wo, wi);
+        e.f = oren_nayar(wo, wi) * abs_cos_theta(wi);
+        return e;
+    }
+};
+
+// microfacet machinery: src/util/scattering.cpp:30-52,117-237
+__device__ __forceinline__ float fresnel_dielectric(float cosThetaI_in, float etaI_in, float etaT_in) {
+    float cosThetaI = clampf(cosThetaI_in, -1.f, 1.f);
+    bool entering = cosThetaI > 0.f;
+    float etaI = entering ? etaI_in : etaT_in;
+    float etaT = entering ? etaT_in : etaI_in;
+    cosThetaI = fabsf(cosThetaI);
+    float sinThetaI = sqrtf(fmaxf(0.f, 1.f - sqr(cosThetaI)));
+    float sinThetaT = etaI / etaT * sinThetaI;
+    float cosThetaT = sqrtf(fmaxf(0.f, 1.f - sqr(sinThetaT)));
+    float Rparl = (etaT * cosThetaI - etaI * cosThetaT) / (etaT * cosThetaI + etaI * cosThetaT);
+    float Rperp = (etaI * cosThetaI - etaT * cosThetaT) / (etaI * cosThetaI + etaT * cosThetaT);
+    float fr = (Rparl * Rparl + Rperp * Rperp) * .5f;
+    return sinThetaT < 1.f ? fr : 1.f;
+}
+
+struct TrowbridgeReitz {
+    float ax, ay;
+    __device__ __forceinline__ float D(V3 wh) const {
+        float tan2Theta = tan2_theta(wh);
+        float cos4Theta = sqr(cos2_theta(wh));
+        float e = tan2Theta * (sqr(cos_phi(wh) / ax) + sqr(sin_phi(wh) / ay));
+        float d = 1.0f / (kPi * ax * ay * cos4Theta * sqr(1.f + e));
+        return isinf(tan2Theta) ? 0.f : d;
+    }
+    __device__ __forceinline__ float Lambda(V3 w) const {
+        float tanTheta = fabsf(tan_theta(w));
+        float alpha2 = cos2_phi(w) * sqr(ax) + sin2_phi(w) * sqr(ay);
+        float alpha2Tan2Theta = alpha2 * sqr(tanTheta);
+        float L = (-1.f + sqrtf(1.f + alpha2Tan2Theta)) * .5f;
+        return isinf(tanTheta) ? 0.f : L;
+    }
+    __device__ __forceinline__ float G1(V3 w) const { return 1.0f / (1.0f + Lambda(w)); }
+    __device__ __forceinline__ float G(V3 wo, V3 wi) const { return 1.0f / (1.0f + Lambda(wo) + Lambda(wi)); }
+    __device__ __forceinline__ float pdf(V3 wo, V3 wh) const { return D(wh) * G1(wo) * abs_dot(wo, wh) / abs_cos_theta(wo); }
+    __device__ __forceinline__ static void sample11(float cosTheta, float U1, float U2, float &slope_x, float &slope_y) {
+        if (cosTheta <= .9999f) {
+            float sinTheta = sqrtf(fmaxf(0.f, 1.f - sqr(cosTheta)));
+            float tanTheta = sinTheta / cosTheta;
+            float a = 1.f / tanTheta;
+            float G1 = 2.f / (1.f + sqrtf(1.f + 1.f / sqr(a)));
+            float A = 2.f * U1 / G1 - 1.f;
+            float tmp = fminf(1.f / (sqr(A) - 1.f), 1e10f);
+            float B = tanTheta;
+            float D = sqrtf(fmaxf(sqr(B * tmp) - (sqr(A) - sqr(B)) * tmp, 0.f));
+            float slope_x_1 = B * tmp - D;
+            float slope_x_2 = B * tmp + D;
+            slope_x = (A < 0.f || slope_x_2 * tanTheta > 1.f) ? slope_x_1 : slope_x_2;
+            float S = U2 > .5f ? 1.f : -1.f;
+            float V = U2 > .5f ? 2.f * (U2 - .5f) : 2.f * (.5f - U2);
+            float z = (V * (V * (V * 0.27385f - 0.73369f) + 0.46341f)) /
+                      (V * (V * (V * 0.093073f + 0.309420f) - 1.000000f) + 0.597999f);
+            slope_y = S * z * sqrtf(1.f + sqr(slope_x));
+        } else {
+            float r = sqrtf(U1 / (1.f - U1));
+            float phi = (2.f * kPi) * U2;
+            float s, c;
+            sincosf(phi, &s, &c);
+            slope_x = r * c;
+            slope_y = r * s;
+        }
+    }
+    __device__ __forceinline__ V3 sample_wh(V3 wo, float u0, float u1) const {
+        float s = sign(cos_theta(wo));
+        V3 wi = s * wo;
+        V3 wiStretched = normalize(v3(ax * wi.x, ay * wi.y, wi.z));
+        float sx, sy;
+        sample11(cos_theta(wiStretched), u0, u1, sx, sy);
+        float cp = cos_phi(wiStretched), sp = sin_phi(wiStretched);
+        float rx = cp * sx - sp * sy;
+        float ry = sp * sx + cp * sy;
+        rx = ax * rx;
+        ry = ay * ry;
+        V3 wh = normalize(v3(-rx, -ry, 1.f));
+        return s * wh;
+    }
+};
+
+// Disney: src/surfaces/disney.cpp:95-303 (lobes), :376-478 (closure set-up), :481-587 (evaluate / sample)
+__device__ __forceinline__ float SchlickWeight(float cosTheta) {
+    float m = saturate(1.f - cosTheta);
+    return sqr(sqr(m)) * m;
+}
+__device__ __forceinline__ float FrSchlick(float R0, float cosTheta) { return lerp(R0, 1.f, SchlickWeight(cosTheta)); }
+__device__ __forceinline__ float GTR1(float cosTheta, float alpha) {
+    float alpha2 = sqr(alpha);
+    float denom = kPi * logf(alpha2) * (1.f + (alpha2 - 1.f) * sqr(cosTheta));
+    return (alpha2 - 1.f) / denom;
+}
+__device__ __forceinline__ float smithG_GGX(float cosTheta, float alpha) {
+    float alpha2 = sqr(alpha);
+    float cosTheta2 = sqr(cosTheta);
+    return 1.f / (cosTheta + sqrtf(alpha2 + cosTheta2 - alpha2 * cosTheta2));
+}
+
+struct DisneyClosure {
+    V3 Cdiff, Css, Csheen, Cspec0;
+    float metallic, roughness, clearcoat, fresnel_eta, gloss;
+    TrowbridgeReitz distrib;
+    float w0, w1, w2;
+    bool has_diffuse, has_fake_ss, has_sheen, has_clearcoat;
+
+    __device__ __forceinline__ void init(const lrk_surface &s) {
+        V3 color = v3(s.p[0], s.p[1], s.p[2]);
+        float color_lum = s.p[3];
+        metallic = s.p[4];
+        float eta_t = s.p[5];
+        roughness = s.p[6];
+        float specular_tint = s.p[7], anisotropic = s.p[8], sheen = s.p[9], sheen_tint = s.p[10];
+        clearcoat = s.p[11];
+        float clearcoat_gloss = s.p[12], specular_trans = s.p[13], flatness = s.p[14];
+        uint32_t lobes = s.lobes;
+        has_diffuse = has_fake_ss = has_sheen = has_clearcoat = false;
+        Cdiff = Css = Csheen = v3(0.f);
+        w0 = w1 = w2 = 0.f;
+        gloss = 0.f;
+        bool en0 = false, en2 = false;
+        float diffuse_weight = (1.f - metallic) * (1.f - specular_trans);
+        float tint_weight = color_lum > 0.f ? 1.f / color_lum : 1.f;
+        V3 tc = color * tint_weight;
+        V3 tint = v3(saturate(tc.x), saturate(tc.y), saturate(tc.z));
+        float tint_lum = color_lum * tint_weight;
+        float diffuse_like_sampling_weight = diffuse_weight * color_lum;
+        if ((lobes & LRK_DISNEY_LOBE_DIFFUSE) || (lobes & LRK_DISNEY_LOBE_RETRO)) {
+            float Cdiff_weight = diffuse_weight * (1.f - flatness);
+            Cdiff = color * Cdiff_weight;
+            has_diffuse = true;
+            en0 = true;
+        }
+        if (lobes & LRK_DISNEY_LOBE_FAKE_SS) {
+            float Css_weight = diffuse_weight * flatness;
+            Css = Css_weight * color;
+            has_fake_ss = true;
+            en0 = true;
+        }
+        if (lobes & LRK_DISNEY_LOBE_SHEEN) {
+            float Csheen_weight = diffuse_weight * sheen;
+            Csheen = Csheen_weight * lerp(v3(1.f), tint, sheen_tint);
+            has_sheen = true;
+            float sheen_lum = Csheen_weight * lerp(1.f, tint_lum, sheen_tint);
+            diffuse_like_sampling_weight += sheen_lum * .1f;
+            en0 = true;
+        }
+        w0 = saturate(diffuse_like_sampling_weight);
+        float eta = eta_t / 1.f;
+        float SchlickR0 = sqr((eta - 1.f) / (eta + 1.f));
+        Cspec0 = lerp(lerp(v3(1.f), tint, specular_tint) * SchlickR0, color, metallic);
+        fresnel_eta = eta;
+        float aspect = sqrtf(1.f - anisotropic * .9f);
+        distrib.ax = fmaxf(fmaxf(0.001f, roughness / aspect), 1e-4f);
+        distrib.ay = fmaxf(fmaxf(0.001f, roughness * aspect), 1e-4f);
+        float Cspec0_lum = lerp(lerp(1.f, tint_lum, specular_tint) * SchlickR0, color_lum, metallic);
+        w1 = saturate(Cspec0_lum);
+        if (lobes & LRK_DISNEY_LOBE_CLEARCOAT) {
+            gloss = lerp(.1f, .001f, clearcoat_gloss);
+            has_clearcoat = true;
+            w2 = saturate(clearcoat * FrSchlick(.04f, 1.f));
+            en2 = true;
+        }
+        float sum_weights = 0.f;
+        if (en0) sum_weights += w0;
+        sum_weights += w1;
+        if (en2) sum_weights += w2;
+        float inv_sum_weights = sum_weights == 0.f ? 0.f : 1.f / sum_weights;
+        if (en0) w0 *= inv_sum_weights;
+        w1 *= inv_sum_weights;
+        if (en2) w2 *= inv_sum_weights;
+        enabled0 = en0;
+        enabled2 = en2;
+    }
+    bool enabled0, enabled2;
+
+    __device__ __forceinline__ V3 disney_fresnel(float cosI_in) const {
+        float cosI = fabsf(cosI_in);
+        float fr = fresnel_dielectric(cosI, 1.f, fresnel_eta);
+        V3 f0 = v3(FrSchlick(Cspec0.x, cosI), FrSchlick(Cspec0.y, cosI), FrSchlick(Cspec0.z, cosI));
+        return lerp(v3(fr), f0, metallic);
+    }
+    __device__ __forceinline__ V3 specular_evaluate(V3 wo, V3 wi) const {
+        V3 wh = wi + wo;
+        V3 f = v3(0.f);
+        if (same_hemisphere(wo, wi) && any_nonzero(wh)) {
+            wh = normalize(wh);
+            V3 F = disney_fresnel(dot(wi, face_forward(wh, v3(0.f, 0.f, 1.f))));
+            float D = distrib.D(wh);
+            float G = distrib.G(wo, wi);
+            float cos_o = cos_theta(wo), cos_i = cos_theta(wi);
+            f = v3(1.f) * F * fabsf(0.25f * D * G / (cos_i * cos_o));
+        }
+        return f;
+    }
+    __device__ __forceinline__ float specular_pdf(V3 wo, V3 wi) const {
+        float p = 0.f;
+        V3 wh = wi + wo;
+        if (same_hemisphere(wo, wi) && any_nonzero(wh)) {
+            wh = normalize(wh);
+            p = distrib.pdf(wo, wh) / (4.f * dot(wo, wh));
+        }
+        return p;
+    }
+    __device__ __forceinline__ float clearcoat_evaluate(V3 wo, V3 wi) const {
+        V3 wh = wi + wo;
+        bool valid = any_nonzero(wh);
+        wh = normalize(wh);
+        float Dr = GTR1(abs_cos_theta(wh), gloss);
+        float Fr = FrSchlick(.04f, dot(wo, wh));
+        float Gr = smithG_GGX(abs_cos_theta(wo), .25f) * smithG_GGX(abs_cos_theta(wi), .25f);
+        return valid ? clearcoat * Gr * Fr * Dr * .25f : 0.f;
+    }
+    __device__ __forceinline__ float clearcoat_pdf(V3 wo, V3 wi) const {
+        V3 wh = wi + wo;
+        bool valid = same_hemisphere(wo, wi) && any_nonzero(wh);
+        wh = normalize(wh);
+        float Dr = GTR1(abs_cos_theta(wh), gloss);
+        return valid ? Dr * abs_cos_theta(wh) / (4.f * dot(wo, wh)) : 0.f;
+    }
+    __device__ __forceinline__ SurfEval evaluate_local(V3 wo, V3 wi) const {
+        V3 f = v3(0.f);
+        float pdf = 0.f;
+        if (same_hemisphere(wo, wi)) {
+            if (has_diffuse) {
+                if (w0 > 0.f) {
+                    float Fo = SchlickWeight(abs_cos_theta(wo)), Fi = SchlickWeight(abs_cos_theta(wi));
+                    f = f + Cdiff * (kInvPi * (1.f - Fo * .5f) * (1.f - Fi * .5f));
+                    V3 wh = wi + wo;
+                    bool valid = any_nonzero(wh);
+                    wh = normalize(wh);
+                    float cosThetaD = dot(wi, wh);
+                    {// DisneyRetro
+                        float Rr = 2.f * roughness * cosThetaD * cosThetaD;
+                        f = f + Cdiff * (valid ? kInvPi * Rr * (Fo + Fi + Fo * Fi * (Rr - 1.f)) : 0.f);
+                    }
+                    if (has_fake_ss) {
+                        float Fss90 = cosThetaD * cosThetaD * roughness;
+                        float Fss = lerp(1.0f, Fss90, Fo) * lerp(1.0f, Fss90, Fi);
+                        float ss = 1.25f * (Fss * (1.f / (abs_cos_theta(wo) + abs_cos_theta(wi)) - .5f) + .5f);
+                        f = f + Css * (valid ? kInvPi * ss : 0.f);
+                    }
+                    if (has_sheen) f = f + Csheen * (valid ? SchlickWeight(cosThetaD) : 0.f);
+                    pdf += w0 * lambert_pdf(wo, wi);
+                }
+            }
+            if (w1 > 0.f) {
+                f = f + specular_evaluate(wo, wi);
+                pdf += w1 * specular_pdf(wo, wi);
+            }
+            if (has_clearcoat) {
+                if (w2 > 0.f) {
+                    f = f + clearcoat_evaluate(wo, wi);
+                    pdf += w2 * clearcoat_pdf(wo, wi);
+                }
+            }
+        }
+        SurfEval e;
+        e.f = f * abs_cos_theta(wi);
+        e.pdf = pdf;
+        return e;
+    }
+    __device__ __forceinline__ SurfEval sample_local(V3 wo, float u_lobe, float u0, float u1, V3 &wi) const {
+        // technique selection: src/surfaces/disney.cpp:544-551 (strict '>' against the running sum)
+        uint32_t tech = 0u;
+        float sum_weights = 0.f;
+        if (enabled0) {
+            tech = u_lobe > sum_weights ? 0u : tech;
+            sum_weights += w0;
+        }
+        tech = u_lobe > sum_weights ? 1u : tech;
+        sum_weights += w1;
+        if (enabled2) {
+            tech = u_lobe > sum_weights ? 2u : tech;
+            sum_weights += w2;
+        }
+        wi = v3(0.f);
+        bool valid = false;
+        if (tech == 0u) {
+            if (has_diffuse) {
+                wi = sample_cosine_hemisphere(u0, u1);
+                wi.z *= sign(cos_theta(wo));
+                valid = true;
+            }
+        } else if (tech == 1u) {
+            V3 wh = distrib.sample_wh(wo, u0, u1);
+            wi = reflect(-wo, wh);
+            valid = same_hemisphere(wo, wi);
+        } else {
+            if (has_clearcoat) {
+                float alpha2 = gloss * gloss;
+                float cosTheta = sqrtf(fmaxf(0.f, (1.f - powf(alpha2, 1.f - u0)) / (1.f - alpha2)));
+                float sinTheta = sqrtf(fmaxf(0.f, 1.f - cosTheta * cosTheta));
+                float phi = 2.f * kPi * u1;
+                float s, c;
+                sincosf(phi, &s, &c);
+                V3 wh = v3(sinTheta * c, sinTheta * s, cosTheta);
+                wh = same_hemisphere(wo, wh) ? wh : -wh;
+                wi = reflect(-wo, wh);
+                valid = same_hemisphere(wo, wi);
+            }
+        }
+        SurfEval e;
+        e.f = v3(0.f);
+        e.pdf = 0.f;
+        if (valid) e = evaluate_local(wo, wi);
+        return e;
+    }
+};
+
+}// namespace lrk
