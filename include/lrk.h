@@ -281,9 +281,12 @@ typedef struct lrk_stats {
     uint64_t kernel_launches;
     uint64_t passes;
     /* filled only when counting is enabled (lrk_set_option("count_traversal", 1)) */
-    uint64_t nodes_visited;  /* N_int   */
-    uint64_t tris_tested;    /* N_tri */
-    uint64_t xforms;         /* N_xform */
+    uint64_t closest_nodes;  /* N_int of the closest-hit kernel */
+    uint64_t closest_tris;   /* N_tri */
+    uint64_t closest_xforms; /* N_xform */
+    uint64_t shadow_nodes;   /* the same three for the any-hit kernel */
+    uint64_t shadow_tris;
+    uint64_t shadow_xforms;
     double trace_closest_ms; /* CUDA-event time of the closest-hit kernel launches (when "time_kernels" = 1) */
     double trace_shadow_ms;
     double shade_ms;

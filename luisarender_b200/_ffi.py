@@ -109,8 +109,8 @@ class DeviceCfg(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("render_ms", f64), ("samples", u64), ("closest_rays", u64), ("shadow_rays", u64),
-                ("kernel_launches", u64), ("passes", u64), ("nodes_visited", u64), ("tris_tested", u64),
-                ("xforms", u64), ("trace_closest_ms", f64), ("trace_shadow_ms", f64), ("shade_ms", f64),
+                ("kernel_launches", u64), ("passes", u64), ("closest_nodes", u64), ("closest_tris", u64),
+                ("closest_xforms", u64), ("shadow_nodes", u64), ("shadow_tris", u64), ("shadow_xforms", u64), ("trace_closest_ms", f64), ("trace_shadow_ms", f64), ("shade_ms", f64),
                 ("other_ms", f64)]
 
 

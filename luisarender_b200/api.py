@@ -46,6 +46,7 @@ class Scene:
             d = F.SceneDesc()
             if self._lib.lrh_scene_get_desc(self._h, camera, C.byref(d)) != 0:
                 raise RuntimeError(self._lib.lrh_last_error().decode())
+            d._owner = self  # the view points into memory owned by this Scene: keep it alive with the view
             self._descs[camera] = d
         return self._descs[camera]
 

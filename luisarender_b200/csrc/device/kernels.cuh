@@ -35,7 +35,7 @@ struct PathBuffers {
     float4 *scontrib;// rgb + path id bits
     float4 *li;
     uint32_t *counts;
-    unsigned long long *stats;// [0] closest rays, [1] shadow rays, [2] nodes, [3] tris, [4] xforms
+    unsigned long long *stats;// [0] closest rays, [1] shadow rays, [2..4] closest nodes/tris/xforms, [5..7] shadow nodes/tris/xforms
 };
 
 // ---- Camera: src/base/filter.cpp:50-64, src/base/camera.cpp:212-224, src/cameras/pinhole.cpp:60-67 ----
@@ -131,9 +131,9 @@ __global__ void __launch_bounds__(kBlock) trace_shadow_kernel(DeviceScene sc, Pa
         }
     }
     if (COUNT) {
-        atomicAdd(pb.stats + 2, static_cast<unsigned long long>(tc.nodes));
-        atomicAdd(pb.stats + 3, static_cast<unsigned long long>(tc.tris));
-        atomicAdd(pb.stats + 4, static_cast<unsigned long long>(tc.xforms));
+        atomicAdd(pb.stats + 5, static_cast<unsigned long long>(tc.nodes));
+        atomicAdd(pb.stats + 6, static_cast<unsigned long long>(tc.tris));
+        atomicAdd(pb.stats + 7, static_cast<unsigned long long>(tc.xforms));
     }
 }
 

@@ -551,9 +551,12 @@ int lrk_get_stats(lrk_ctx *ctx, lrk_stats *stats) {
         LRK_CUDA(cudaMemcpy(h, ctx->pb.stats, sizeof(h), cudaMemcpyDeviceToHost));
         ctx->stats.closest_rays = h[0];
         ctx->stats.shadow_rays = h[1];
-        ctx->stats.nodes_visited = h[2];
-        ctx->stats.tris_tested = h[3];
-        ctx->stats.xforms = h[4];
+        ctx->stats.closest_nodes = h[2];
+        ctx->stats.closest_tris = h[3];
+        ctx->stats.closest_xforms = h[4];
+        ctx->stats.shadow_nodes = h[5];
+        ctx->stats.shadow_tris = h[6];
+        ctx->stats.shadow_xforms = h[7];
     }
     *stats = ctx->stats;
     return LRK_OK;

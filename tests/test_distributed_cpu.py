@@ -1,0 +1,65 @@
+"""world_size-2 gloo test (CPU) of the N>1 path: tile sharding + the single film reduce.  Each rank renders its
+own tiles (the oracle stands in for the GPU here — only the host-side sharding / reduce logic is under test),
+the raw films are sum-reduced to rank 0 and must equal the single-process film bit for bit."""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+
+REPO = Path(__file__).resolve().parents[1]
+
+WORKER = r"""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.environ["LRB_REPO"])
+import torch
+from luisarender_b200 import scenes, distributed as D
+from luisarender_b200.api import Scene
+from oracle import binding as O
+
+rank, world, _ = D.env_world()
+dist = D.init_process_group("gloo")
+scene = Scene.from_source(scenes.cornell_box(resolution=(64, 48), spp=2), os.environ["LRB_REPO"])
+d = scene.desc()
+part, _ = O.render(d, 0, 2, threads=2, rank=rank, world=world, tile_size=16)
+mask = D.owned_pixel_mask(64, 48, rank, world, 16)
+assert ((part[..., 3] > 0) == mask).all()
+film = torch.from_numpy(part)
+D.reduce_film(film, dst=0)
+dist.barrier()
+if rank == 0:
+    np.save(os.environ["LRB_OUT"], film.numpy())
+dist.destroy_process_group()
+"""
+
+
+def test_two_rank_film_reduce_matches_single_process(tmp_path):
+    from luisarender_b200 import scenes
+    from luisarender_b200.api import Scene
+    from oracle import binding as O
+
+    out = tmp_path / "film.npy"
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, LRB_REPO=str(REPO), LRB_OUT=str(out), OMP_NUM_THREADS="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", str(script)]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    reduced = np.load(out)
+    scene = Scene.from_source(scenes.cornell_box(resolution=(64, 48), spp=2), REPO)
+    full, _ = O.render(scene.desc(), 0, 2)
+    assert np.array_equal(reduced, full)
+
+
+def test_owned_pixel_mask_partitions_the_film():
+    from luisarender_b200.distributed import owned_pixel_mask
+
+    total = np.zeros((70, 100), dtype=np.int32)
+    for rank in range(4):
+        total += owned_pixel_mask(100, 70, rank, 4, 32)
+    assert (total == 1).all()

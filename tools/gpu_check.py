@@ -65,10 +65,11 @@ def timing(name, src, spp, r, count=False):
         r.render(0, spp)
         st = r.stats()
         rays = st["closest_rays"] + st["shadow_rays"]
-        out.update({"nodes_per_ray": round(st["nodes_visited"] / rays, 2), "tris_per_ray": round(st["tris_tested"] / rays, 2),
-                    "xforms_per_ray": round(st["xforms"] / rays, 2)})
-        alg_bytes = 48 * rays + 64 * st["nodes_visited"] + 48 * st["tris_tested"] + 64 * st["xforms"]
-        out["traversal_alg_GBs"] = round(alg_bytes / ((out["trace_closest_ms"] + out["trace_shadow_ms"]) * 1e-3) * 1e-9, 1)
+        for kind in ("closest", "shadow"):
+            nr = max(st[kind + "_rays"], 1)
+            out[kind + "_per_ray"] = [round(st[kind + "_nodes"] / nr, 2), round(st[kind + "_tris"] / nr, 2), round(st[kind + "_xforms"] / nr, 2)]
+            alg = 48 * nr + 64 * st[kind + "_nodes"] + 48 * st[kind + "_tris"] + 64 * st[kind + "_xforms"]
+            out[kind + "_alg_GBs"] = round(alg / (out["trace_" + kind + "_ms"] * 1e-3) * 1e-9, 1)
         r.set_option("count_traversal", 0)
     print(json.dumps(out), flush=True)
     return r.film()
