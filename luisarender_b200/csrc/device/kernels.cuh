@@ -29,7 +29,8 @@ struct PathBuffers {
     float4 *ray_d[2];
     float4 *beta_pdf[2];
     uint2 *id_rng[2];
-    uint4 *hit;
+    uint4 *hit;// {inst, prim, bary} per ray of the current queue (inst == ~0u: escaped)
+    uint32_t *hit_index[3];// per closure kind: indices (into the current ray queue) of the rays that hit such a surface
     float4 *sray_o;
     float4 *sray_d;
     float4 *scontrib;// rgb + path id bits
@@ -55,7 +56,7 @@ __global__ void __launch_bounds__(kBlock) generate_rays_kernel(DeviceScene sc, P
     uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id == 0u) {
         pb.counts[0] = n;
-        for (uint32_t d = 1u; d < 2u * kMaxDepthSlots; d++) pb.counts[d] = 0u;
+        for (uint32_t d = 1u; d < 7u * kMaxDepthSlots; d++) pb.counts[d] = 0u;// sizes + the traversal kernels' fetch cursors
     }
     if (id >= n) return;
     uint32_t k = id % npix;
@@ -96,16 +97,19 @@ __global__ void __launch_bounds__(kBlock) generate_rays_kernel(DeviceScene sc, P
 }
 
 // ---- traversal kernels -------------------------------------------------------------------------------
+// counts[] layout (all zeroed by generate_rays_kernel at the start of a pass), 64 slots (one per depth) each:
+//   [0] path-queue sizes  [1] shadow-queue sizes  [2] closest-hit fetch cursors  [3] shadow fetch cursors
+//   [4],[5],[6] hit-bucket sizes: light-only hits, Matte hits, Disney hits
 template<bool COUNT>
 __global__ void __launch_bounds__(kBlock) trace_closest_kernel(DeviceScene sc, const float4 *__restrict__ ray_o,
                                                                const float4 *__restrict__ ray_d, uint4 *__restrict__ hits,
-                                                               const uint32_t *__restrict__ count, unsigned long long *stats) {
+                                                               const uint32_t *__restrict__ count, uint32_t *cursor,
+                                                               unsigned long long *stats) {
     const uint32_t n = *count;
     TraversalCounters tc{0u, 0u, 0u};
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        float4 o = ray_o[i], d = ray_d[i];
-        hits[i] = trace_ray<false, COUNT>(sc, o, d, tc);
-    }
+    trace_queue<false, COUNT, 1>(sc, ray_o, ray_d, n, cursor, tc, [&](bool finished, uint32_t i, uint4 h) {
+        if (finished) hits[i] = h;
+    });
     if (COUNT) {
         atomicAdd(stats + 2, static_cast<unsigned long long>(tc.nodes));
         atomicAdd(stats + 3, static_cast<unsigned long long>(tc.tris));
@@ -113,14 +117,54 @@ __global__ void __launch_bounds__(kBlock) trace_closest_kernel(DeviceScene sc, c
     }
 }
 
+// Sorted-by-material dispatch, step 1: bucket the hits of this bounce by closure kind (the reference sorts its
+// SURFACE queue by surface tag, wave_path_v2.cpp:891-928,1255-1260, with a one-thread prefix sum; here a near-stable
+// block-aggregated partition).  Escaped rays are dropped, so the shade kernels only ever see real work; every bucket
+// keeps the ray-queue order inside a block chunk, which keeps the shade kernels' gathers coalesced.
+//   kind 0: hit has no surface (emitter only)   kind 1: Matte closure   kind 2: Disney closure
+constexpr uint32_t kHitKinds = 3u;
+__global__ void __launch_bounds__(kBlock) classify_hits_kernel(DeviceScene sc, PathBuffers pb, uint32_t depth) {
+    __shared__ uint32_t s_warp[kHitKinds][kBlock / 32];
+    __shared__ uint32_t s_base[kHitKinds];
+    const uint32_t n = pb.counts[depth];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5u, lane_lt = (1u << lane) - 1u;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        uint32_t kind = ~0u;
+        if (i < n) {
+            const uint32_t inst = pb.hit[i].x;
+            if (inst != ~0u) kind = __ldg(sc.inst_kind + inst);
+        }
+        uint32_t masks[kHitKinds];
+#pragma unroll
+        for (uint32_t k = 0; k < kHitKinds; k++) {
+            masks[k] = __ballot_sync(0xffffffffu, kind == k);
+            if (lane == 0u) s_warp[k][warp] = __popc(masks[k]);
+        }
+        __syncthreads();
+        if (threadIdx.x < kHitKinds) {
+            const uint32_t k = threadIdx.x;
+            uint32_t total = 0u;
+            for (int w = 0; w < kBlock / 32; w++) {
+                uint32_t c = s_warp[k][w];
+                s_warp[k][w] = total;
+                total += c;
+            }
+            s_base[k] = total ? atomicAdd(pb.counts + (4u + k) * kMaxDepthSlots + depth, total) : 0u;
+        }
+        __syncthreads();
+        if (kind != ~0u) pb.hit_index[kind][s_base[kind] + s_warp[kind][warp] + __popc(masks[kind] & lane_lt)] = i;
+        __syncthreads();
+    }
+}
+
 template<bool COUNT>
-__global__ void __launch_bounds__(kBlock) trace_shadow_kernel(DeviceScene sc, PathBuffers pb, const uint32_t *__restrict__ count) {
+__global__ void __launch_bounds__(kBlock) trace_shadow_kernel(DeviceScene sc, PathBuffers pb, const uint32_t *__restrict__ count,
+                                                              uint32_t *cursor) {
     const uint32_t n = *count;
     TraversalCounters tc{0u, 0u, 0u};
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        float4 o = pb.sray_o[i], d = pb.sray_d[i];
-        uint4 h = trace_ray<true, COUNT>(sc, o, d, tc);
-        if (h.x == ~0u) {// unoccluded: add the pending next-event contribution to the path's radiance
+    trace_queue<true, COUNT, 1>(sc, pb.sray_o, pb.sray_d, n, cursor, tc, [&](bool finished, uint32_t i, uint4 h) {
+        if (finished && h.x == ~0u) {// unoccluded: add the pending next-event contribution to the path's radiance
             float4 c = pb.scontrib[i];
             uint32_t path = __float_as_uint(c.w);
             float4 li = pb.li[path];
@@ -129,7 +173,7 @@ __global__ void __launch_bounds__(kBlock) trace_shadow_kernel(DeviceScene sc, Pa
             li.z += c.z;
             pb.li[path] = li;
         }
-    }
+    });
     if (COUNT) {
         atomicAdd(pb.stats + 5, static_cast<unsigned long long>(tc.nodes));
         atomicAdd(pb.stats + 6, static_cast<unsigned long long>(tc.tris));
@@ -137,17 +181,15 @@ __global__ void __launch_bounds__(kBlock) trace_shadow_kernel(DeviceScene sc, Pa
     }
 }
 
-// stand-alone queries (lrk_trace): any-hit result is written as inst = 1 (occluded) / 0 (free)
+// stand-alone queries (lrk_trace) on interleaved lrk_ray records: any-hit result is written as inst = 1 (occluded) / 0 (free)
 template<bool ANY_HIT>
 __global__ void __launch_bounds__(kBlock) trace_query_kernel(DeviceScene sc, const float4 *__restrict__ rays, uint4 *__restrict__ hits,
-                                                             uint32_t n) {
+                                                             uint32_t n, uint32_t *cursor) {
     TraversalCounters tc{0u, 0u, 0u};
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        float4 o = rays[2u * i], d = rays[2u * i + 1u];
-        uint4 h = trace_ray<ANY_HIT, false>(sc, o, d, tc);
+    trace_queue<ANY_HIT, false, 2>(sc, rays, rays + 1, n, cursor, tc, [&](bool finished, uint32_t i, uint4 h) {
         if (ANY_HIT) h = make_uint4(h.x != ~0u ? 1u : 0u, 0u, 0u, 0u);
-        hits[i] = h;
-    }
+        if (finished) hits[i] = h;
+    });
 }
 
 // ---- shade ----------------------------------------------------------------------------------------------
@@ -177,20 +219,23 @@ __device__ __forceinline__ void shade_surface(const Closure &cl, const Interacti
     pdf_bsdf = s.pdf;
 }
 
+// Sorted-by-material dispatch, step 2: one shade kernel per closure kind, each over its own hit bucket.
+template<uint32_t KIND>
 __global__ void __launch_bounds__(kBlock) shade_kernel(DeviceScene sc, PathBuffers pb, uint32_t depth) {
     __shared__ uint32_t s_warp_next[kBlock / 32], s_warp_shadow[kBlock / 32];
     __shared__ uint32_t s_base_next, s_base_shadow;
-    const uint32_t n = pb.counts[depth];
+    const uint32_t n = pb.counts[(4u + KIND) * kMaxDepthSlots + depth];// size of this kind's hit bucket
     const int in = depth & 1u, out = in ^ 1;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5u;
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-        const uint32_t i = base + threadIdx.x;
+        const uint32_t j = base + threadIdx.x;
         bool push_next = false, push_shadow = false;
         float4 nro, nrd, nbeta, sro, srd, scon;
         uint2 nid;
-        if (i < n) {
-            uint4 hit = pb.hit[i];
-            if (hit.x != ~0u) {
+        if (j < n) {
+            const uint32_t i = pb.hit_index[KIND][j];
+            const uint4 hit = pb.hit[i];
+            {
                 float4 ro = pb.ray_o[in][i], rd = pb.ray_d[in][i];
                 float4 bp = pb.beta_pdf[in][i];
                 uint2 ir = pb.id_rng[in][i];
@@ -211,7 +256,7 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(DeviceScene sc, PathBuffe
                     li.z += add.z;
                     pb.li[ir.x] = li;
                 }
-                if (it.shape.has_surface()) {
+                if (KIND != 0u) {// kind 0 = emitter-only hit (no surface): the path ends here (mega_path.cpp:89)
                     // draw order is normative: mega_path.cpp:91-98
                     float u_sel = lcg(state);
                     float ul0 = lcg(state), ul1 = lcg(state);
@@ -228,7 +273,7 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(DeviceScene sc, PathBuffe
                     const lrk_surface *surf = sc.surfaces + it.shape.surface_tag;
                     V3 contrib, wi, f;
                     float pdf;
-                    if (surf->type == LRK_SURFACE_MATTE) {
+                    if (KIND == 1u) {
                         MatteClosure cl;
                         cl.init(*surf);
                         shade_surface(cl, it, wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);

@@ -15,7 +15,7 @@ using namespace lrk;
 namespace {
 
 struct DeviceArrays {
-    void *vertices{}, *triangles{}, *alias{}, *pdf{}, *meshes{}, *inst_handles{}, *inst_o2w{}, *inst_xform{}, *bvh_nodes{},
+    void *vertices{}, *triangles{}, *alias{}, *pdf{}, *meshes{}, *inst_handles{}, *inst_kind{}, *inst_o2w{}, *inst_xform{}, *bvh_nodes{},
         *tri_verts{}, *surfaces{}, *lights{}, *light_handles{}, *camera{};
 };
 
@@ -47,6 +47,7 @@ struct lrk_ctx {
     std::vector<void *> path_allocs;
     float4 *d_film{nullptr};
     float4 *d_film_out{nullptr};
+    uint32_t *d_query_cursor{nullptr};
     // options
     bool count_traversal{false}, time_kernels{false};
     // stats
@@ -54,7 +55,8 @@ struct lrk_ctx {
     cudaEvent_t ev_begin{}, ev_end{};
     std::vector<TimedLaunch> timed;
     std::vector<cudaEvent_t> event_pool;
-    int grid_trace{0}, grid_shade{0}, grid_shadow{0};
+    int grid_trace{0}, grid_shade[3]{0, 0, 0}, grid_shadow{0}, grid_classify{0};
+    bool has_kind[3]{true, false, false};
 };
 
 namespace {
@@ -114,11 +116,12 @@ int alloc_paths(lrk_ctx *ctx, uint64_t capacity) {
         LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.id_rng[k]), capacity * sizeof(uint2)));
     }
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.hit), capacity * sizeof(uint4)));
+    for (int k = 0; k < 3; k++) LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.hit_index[k]), capacity * sizeof(uint32_t)));
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.sray_o), capacity * sizeof(float4)));
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.sray_d), capacity * sizeof(float4)));
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.scontrib), capacity * sizeof(float4)));
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.li), capacity * sizeof(float4)));
-    LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.counts), 2u * kMaxDepthSlots * sizeof(uint32_t)));
+    LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.counts), 7u * kMaxDepthSlots * sizeof(uint32_t)));
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.stats), 8u * sizeof(unsigned long long)));
     LRK_CUDA(cudaMemsetAsync(pb.stats, 0, 8u * sizeof(unsigned long long), ctx->stream));
     ctx->capacity = capacity;
@@ -208,23 +211,30 @@ int render_pass(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint32_t spp
             ScopedTimer t{ctx, CAT_TRACE_CLOSEST};
             int g = blocks_for(ctx, n, ctx->grid_trace);
             if (ctx->count_traversal)
-                trace_closest_kernel<true><<<g, kBlock, 0, ctx->stream>>>(sc, pb.ray_o[in], pb.ray_d[in], pb.hit, pb.counts + depth, pb.stats);
+                trace_closest_kernel<true><<<g, kBlock, 0, ctx->stream>>>(sc, pb.ray_o[in], pb.ray_d[in], pb.hit, pb.counts + depth,
+                                                                          pb.counts + 2u * kMaxDepthSlots + depth, pb.stats);
             else
-                trace_closest_kernel<false><<<g, kBlock, 0, ctx->stream>>>(sc, pb.ray_o[in], pb.ray_d[in], pb.hit, pb.counts + depth, pb.stats);
+                trace_closest_kernel<false><<<g, kBlock, 0, ctx->stream>>>(sc, pb.ray_o[in], pb.ray_d[in], pb.hit, pb.counts + depth,
+                                                                           pb.counts + 2u * kMaxDepthSlots + depth, pb.stats);
         }
         {
             ScopedTimer t{ctx, CAT_SHADE};
-            shade_kernel<<<blocks_for(ctx, n, ctx->grid_shade), kBlock, 0, ctx->stream>>>(sc, pb, depth);
+            classify_hits_kernel<<<blocks_for(ctx, n, ctx->grid_classify), kBlock, 0, ctx->stream>>>(sc, pb, depth);
+            shade_kernel<0u><<<blocks_for(ctx, n, ctx->grid_shade[0]), kBlock, 0, ctx->stream>>>(sc, pb, depth);
+            if (ctx->has_kind[1]) shade_kernel<1u><<<blocks_for(ctx, n, ctx->grid_shade[1]), kBlock, 0, ctx->stream>>>(sc, pb, depth);
+            if (ctx->has_kind[2]) shade_kernel<2u><<<blocks_for(ctx, n, ctx->grid_shade[2]), kBlock, 0, ctx->stream>>>(sc, pb, depth);
         }
         {
             ScopedTimer t{ctx, CAT_TRACE_SHADOW};
             int g = blocks_for(ctx, n, ctx->grid_shadow);
             if (ctx->count_traversal)
-                trace_shadow_kernel<true><<<g, kBlock, 0, ctx->stream>>>(sc, pb, pb.counts + kMaxDepthSlots + depth);
+                trace_shadow_kernel<true><<<g, kBlock, 0, ctx->stream>>>(sc, pb, pb.counts + kMaxDepthSlots + depth,
+                                                                         pb.counts + 3u * kMaxDepthSlots + depth);
             else
-                trace_shadow_kernel<false><<<g, kBlock, 0, ctx->stream>>>(sc, pb, pb.counts + kMaxDepthSlots + depth);
+                trace_shadow_kernel<false><<<g, kBlock, 0, ctx->stream>>>(sc, pb, pb.counts + kMaxDepthSlots + depth,
+                                                                          pb.counts + 3u * kMaxDepthSlots + depth);
         }
-        ctx->stats.kernel_launches += 3;
+        ctx->stats.kernel_launches += 4u + (ctx->has_kind[1] ? 1u : 0u) + (ctx->has_kind[2] ? 1u : 0u);
     }
     {
         ScopedTimer t{ctx, CAT_OTHER};
@@ -261,13 +271,17 @@ int lrk_create(const lrk_device_cfg *cfg, lrk_ctx **out) {
     cudaDeviceProp prop{};
     cudaGetDeviceProperties(&prop, dev);
     ctx->sm_count = prop.multiProcessorCount;
-    ctx->max_paths = cfg && cfg->max_paths_per_pass ? cfg->max_paths_per_pass : (8ull << 20);
+    ctx->max_paths = cfg && cfg->max_paths_per_pass ? cfg->max_paths_per_pass : (136ull << 20);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete ctx;
         return LRK_ERR_CUDA;
     }
     cudaEventCreate(&ctx->ev_begin);
     cudaEventCreate(&ctx->ev_end);
+    if (cudaMalloc(reinterpret_cast<void **>(&ctx->d_query_cursor), 64u * sizeof(uint32_t)) != cudaSuccess) {
+        delete ctx;
+        return LRK_ERR_OUT_OF_MEMORY;
+    }
     auto grid_for = [&](const void *fn) {
         int per_sm = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kBlock, 0);
@@ -275,7 +289,10 @@ int lrk_create(const lrk_device_cfg *cfg, lrk_ctx **out) {
     };
     ctx->grid_trace = grid_for(reinterpret_cast<const void *>(trace_closest_kernel<false>));
     ctx->grid_shadow = grid_for(reinterpret_cast<const void *>(trace_shadow_kernel<false>));
-    ctx->grid_shade = grid_for(reinterpret_cast<const void *>(shade_kernel));
+    ctx->grid_shade[0] = grid_for(reinterpret_cast<const void *>(shade_kernel<0u>));
+    ctx->grid_shade[1] = grid_for(reinterpret_cast<const void *>(shade_kernel<1u>));
+    ctx->grid_shade[2] = grid_for(reinterpret_cast<const void *>(shade_kernel<2u>));
+    ctx->grid_classify = grid_for(reinterpret_cast<const void *>(classify_hits_kernel));
     *out = ctx;
     return LRK_OK;
 }
@@ -289,6 +306,7 @@ void lrk_destroy(lrk_ctx *ctx) {
     if (ctx->d_pixel_list) cudaFree(ctx->d_pixel_list);
     if (ctx->d_film) cudaFree(ctx->d_film);
     if (ctx->d_film_out) cudaFree(ctx->d_film_out);
+    if (ctx->d_query_cursor) cudaFree(ctx->d_query_cursor);
     for (auto &t : ctx->timed) {
         cudaEventDestroy(t.start);
         cudaEventDestroy(t.stop);
@@ -329,11 +347,22 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
     if ((rc = upload(ctx, &a.lights, s->lights, s->light_count))) return rc;
     if ((rc = upload(ctx, &a.light_handles, s->light_handles, s->light_count))) return rc;
     if ((rc = upload(ctx, &a.camera, &s->camera, 1))) return rc;
-    std::vector<uint32_t> handles(static_cast<size_t>(s->instance_count) * 4u);
+    std::vector<uint32_t> handles(static_cast<size_t>(s->instance_count) * 4u), kinds(s->instance_count);
+    ctx->has_kind[1] = ctx->has_kind[2] = false;
     std::vector<float> o2w(static_cast<size_t>(s->instance_count) * 12u), xform(static_cast<size_t>(s->instance_count) * 16u);
     for (uint32_t i = 0; i < s->instance_count; i++) {
         const auto &inst = s->instances[i];
         std::memcpy(&handles[i * 4u], inst.handle, 16);
+        {// closure kind of the instance: the bucket key of the material sort
+            const uint32_t flags = inst.handle[0] & 1023u, surface_tag = (inst.handle[1] >> 12u) & 4095u;
+            uint32_t kind = 0u;
+            if (flags & LRK_SHAPE_HAS_SURFACE) {
+                if (surface_tag >= s->surface_count) return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_upload_scene: surface tag out of range");
+                kind = s->surfaces[surface_tag].type == LRK_SURFACE_MATTE ? 1u : 2u;
+            }
+            kinds[i] = kind;
+            ctx->has_kind[kind] = true;
+        }
         std::memcpy(&o2w[i * 12u], inst.object_to_world, 48);
         std::memcpy(&xform[i * 16u], inst.world_to_object, 48);
         uint32_t root = s->meshes[inst.mesh].bvh_root;
@@ -341,6 +370,7 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
         xform[i * 16u + 13u] = xform[i * 16u + 14u] = xform[i * 16u + 15u] = 0.f;
     }
     if ((rc = upload(ctx, &a.inst_handles, handles.data(), handles.size()))) return rc;
+    if ((rc = upload(ctx, &a.inst_kind, kinds.data(), kinds.size()))) return rc;
     if ((rc = upload(ctx, &a.inst_o2w, o2w.data(), o2w.size()))) return rc;
     if ((rc = upload(ctx, &a.inst_xform, xform.data(), xform.size()))) return rc;
     LRK_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -352,6 +382,7 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
     sc.pdf = static_cast<const float *>(a.pdf);
     sc.meshes = static_cast<const lrk_mesh *>(a.meshes);
     sc.inst_handles = static_cast<const uint4 *>(a.inst_handles);
+    sc.inst_kind = static_cast<const uint32_t *>(a.inst_kind);
     sc.inst_o2w = static_cast<const float4 *>(a.inst_o2w);
     sc.inst_xform = static_cast<const float4 *>(a.inst_xform);
     sc.bvh_nodes = static_cast<const float4 *>(a.bvh_nodes);
@@ -513,8 +544,9 @@ int lrk_trace(lrk_ctx *ctx, const lrk_ray *rays, uint64_t n, int any_hit, lrk_hi
     }
     cudaMemcpyAsync(d_rays, rays, n * sizeof(lrk_ray), cudaMemcpyHostToDevice, ctx->stream);
     int g = blocks_for(ctx, n, ctx->grid_trace);
-    if (any_hit) trace_query_kernel<true><<<g, kBlock, 0, ctx->stream>>>(ctx->scene, d_rays, d_hits, static_cast<uint32_t>(n));
-    else trace_query_kernel<false><<<g, kBlock, 0, ctx->stream>>>(ctx->scene, d_rays, d_hits, static_cast<uint32_t>(n));
+    cudaMemsetAsync(ctx->d_query_cursor, 0, sizeof(uint32_t), ctx->stream);
+    if (any_hit) trace_query_kernel<true><<<g, kBlock, 0, ctx->stream>>>(ctx->scene, d_rays, d_hits, static_cast<uint32_t>(n), ctx->d_query_cursor);
+    else trace_query_kernel<false><<<g, kBlock, 0, ctx->stream>>>(ctx->scene, d_rays, d_hits, static_cast<uint32_t>(n), ctx->d_query_cursor);
     cudaMemcpyAsync(hits, d_hits, n * sizeof(lrk_hit), cudaMemcpyDeviceToHost, ctx->stream);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (e == cudaSuccess) e = cudaGetLastError();
@@ -531,8 +563,9 @@ int lrk_trace_device(lrk_ctx *ctx, const void *d_rays, uint64_t n, int any_hit, 
     int g = blocks_for(ctx, n, ctx->grid_trace);
     LRK_CUDA(cudaEventRecord(ctx->ev_begin, ctx->stream));
     for (uint32_t r = 0; r < repeat; r++) {
-        if (any_hit) trace_query_kernel<true><<<g, kBlock, 0, ctx->stream>>>(ctx->scene, static_cast<const float4 *>(d_rays), static_cast<uint4 *>(d_hits), static_cast<uint32_t>(n));
-        else trace_query_kernel<false><<<g, kBlock, 0, ctx->stream>>>(ctx->scene, static_cast<const float4 *>(d_rays), static_cast<uint4 *>(d_hits), static_cast<uint32_t>(n));
+        LRK_CUDA(cudaMemsetAsync(ctx->d_query_cursor, 0, sizeof(uint32_t), ctx->stream));
+        if (any_hit) trace_query_kernel<true><<<g, kBlock, 0, ctx->stream>>>(ctx->scene, static_cast<const float4 *>(d_rays), static_cast<uint4 *>(d_hits), static_cast<uint32_t>(n), ctx->d_query_cursor);
+        else trace_query_kernel<false><<<g, kBlock, 0, ctx->stream>>>(ctx->scene, static_cast<const float4 *>(d_rays), static_cast<uint4 *>(d_hits), static_cast<uint32_t>(n), ctx->d_query_cursor);
     }
     LRK_CUDA(cudaEventRecord(ctx->ev_end, ctx->stream));
     LRK_CUDA(cudaStreamSynchronize(ctx->stream));
