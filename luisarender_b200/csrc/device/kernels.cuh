@@ -36,6 +36,14 @@ struct PathBuffers {
     float4 *scontrib;// rgb + path id bits
     float4 *li;
     uint32_t *counts;
+    // volume path integrator only (config C4)
+    ulonglong2 *pcg[2]; // per-path PCG32 {state, inc}
+    float *u_rr[2];     // Russian-roulette number of the coming bounce (drawn at the top of the loop, mega_vpt_naive.cpp:256-257)
+    float4 *s1ray_o;    // in-medium direct-light shadow ray of the coming bounce (from the ray origin)
+    float4 *s1ray_d;
+    uint32_t *occl1;    // ... and whether it hit a surface (advances the PCG32 stream by three draws)
+    uint32_t *occl2[2]; // same for the surface NEE shadow ray of the previous bounce
+    uint32_t *s2_target;// queue slot (next bounce) that receives occl2 for each shadow record, ~0u if the path ended
     unsigned long long *stats;// [0] closest rays, [1] shadow rays, [2..4] closest nodes/tris/xforms, [5..7] shadow nodes/tris/xforms
 };
 
@@ -51,22 +59,9 @@ __device__ __forceinline__ void sample_alias_filter(const lrk_camera *cam, float
     uu = keep ? u_remapped / prob : (u_remapped - prob) / (1.0f - prob);
 }
 
-__global__ void __launch_bounds__(kBlock) generate_rays_kernel(DeviceScene sc, PathBuffers pb, const uint32_t *__restrict__ pixel_list,
-                                                               uint32_t pixel_offset, uint32_t npix, uint32_t spp_begin, uint32_t n) {
-    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
-    if (id == 0u) {
-        pb.counts[0] = n;
-        for (uint32_t d = 1u; d < 7u * kMaxDepthSlots; d++) pb.counts[d] = 0u;// sizes + the traversal kernels' fetch cursors
-    }
-    if (id >= n) return;
-    uint32_t k = id % npix;
-    uint32_t s = id / npix;
-    uint32_t pixel = __ldg(pixel_list + pixel_offset + k);
-    uint32_t px = pixel & 0xffffu, py = pixel >> 16u;
-    uint32_t state = xxhash32_uint4(px, py, sc.sampler_seed, spp_begin + s);
-    float ux = lcg(state);
-    float uy = lcg(state);
-    const lrk_camera *cam = sc.camera;
+// Camera ray for pixel (px, py) from the two filter numbers: Filter::Instance::sample + Camera::generate_ray + pinhole
+__device__ __forceinline__ void camera_ray(const lrk_camera *cam, uint32_t px, uint32_t py, float ux, float uy, float4 &ro, float4 &rd,
+                                           float &weight_out) {
     uint32_t iy, ix;
     float fy, fx;
     sample_alias_filter(cam, ux, iy, fy);
@@ -89,8 +84,31 @@ __global__ void __launch_bounds__(kBlock) generate_rays_kernel(DeviceScene sc, P
     V3 c0 = v3(m[0], m[4], m[8]), c1 = v3(m[1], m[5], m[9]), c2 = v3(m[2], m[6], m[10]), c3 = v3(m[3], m[7], m[11]);
     V3 o = 0.f * c0 + 0.f * c1 + 0.f * c2 + 1.f * c3;
     V3 d = normalize(direction.x * c0 + direction.y * c1 + direction.z * c2);
-    pb.ray_o[0][id] = make_float4(o.x, o.y, o.z, 0.f);
-    pb.ray_d[0][id] = make_float4(d.x, d.y, d.z, kFltMax);
+    ro = make_float4(o.x, o.y, o.z, 0.f);
+    rd = make_float4(d.x, d.y, d.z, kFltMax);
+    weight_out = weight;
+}
+
+__global__ void __launch_bounds__(kBlock) generate_rays_kernel(DeviceScene sc, PathBuffers pb, const uint32_t *__restrict__ pixel_list,
+                                                               uint32_t pixel_offset, uint32_t npix, uint32_t spp_begin, uint32_t n) {
+    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id == 0u) {
+        pb.counts[0] = n;
+        for (uint32_t d = 1u; d < 7u * kMaxDepthSlots; d++) pb.counts[d] = 0u;// sizes + the traversal kernels' fetch cursors
+    }
+    if (id >= n) return;
+    uint32_t k = id % npix;
+    uint32_t s = id / npix;
+    uint32_t pixel = __ldg(pixel_list + pixel_offset + k);
+    uint32_t px = pixel & 0xffffu, py = pixel >> 16u;
+    uint32_t state = xxhash32_uint4(px, py, sc.sampler_seed, spp_begin + s);
+    float ux = lcg(state);
+    float uy = lcg(state);
+    float4 ro, rd;
+    float weight;
+    camera_ray(sc.camera, px, py, ux, uy, ro, rd, weight);
+    pb.ray_o[0][id] = ro;
+    pb.ray_d[0][id] = rd;
     pb.beta_pdf[0][id] = make_float4(weight, weight, weight, 1e16f);
     pb.id_rng[0][id] = make_uint2(id, state);
     pb.li[id] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -207,6 +225,34 @@ __device__ __forceinline__ void shade_surface(const Closure &cl, const Interacti
         }
         float w = balance_heuristic(ls.eval.pdf, ev.pdf) / ls.eval.pdf;
         contrib = w * beta * ev.f * ls.eval.L;
+    }
+    V3 wi_local;
+    SurfEval s = cl.sample_local(wo_local, u_lobe, ub0, ub1, wi_local);
+    wi_world = it.shading.local_to_world(wi_local);
+    if (!validate_surface_sides(it.ng, it.shading.n, wo, wi_world)) {
+        s.f = v3(0.f);
+        s.pdf = 0.f;
+    }
+    f_over = s.f;
+    pdf_bsdf = s.pdf;
+}
+
+// surface shading of the volume integrator: same closures, but the direct-light weight is
+// 1 / (pdf_light + pdf_bsdf + pdf_transmittance) with pdf_transmittance = 0 for an unoccluded ray (mega_vpt_naive.cpp:403-407)
+template<typename Closure>
+__device__ __forceinline__ void volume_shade_surface(const Closure &cl, const Interaction &it, V3 wo, const LightSample &ls, V3 beta,
+                                                     float u_lobe, float ub0, float ub1, V3 &contrib, V3 &wi_world, V3 &f_over, float &pdf_bsdf) {
+    V3 wo_local = it.shading.world_to_local(wo);
+    contrib = v3(0.f);
+    if (ls.eval.pdf > 0.0f) {
+        V3 wi = v3(ls.ray_d_tmax.x, ls.ray_d_tmax.y, ls.ray_d_tmax.z);
+        SurfEval ev = cl.evaluate_local(wo_local, it.shading.world_to_local(wi));
+        if (!validate_surface_sides(it.ng, it.shading.n, wo, wi)) {
+            ev.f = v3(0.f);
+            ev.pdf = 0.f;
+        }
+        float w = 1.f / (ls.eval.pdf + ev.pdf + 0.f);
+        contrib = w * beta * ev.f * ls.eval.L * v3(1.f);
     }
     V3 wi_local;
     SurfEval s = cl.sample_local(wo_local, u_lobe, ub0, ub1, wi_local);
@@ -346,6 +392,366 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(DeviceScene sc, PathBuffe
             pb.sray_o[slot] = sro;
             pb.sray_d[slot] = srd;
             pb.scontrib[slot] = scon;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- volume path (config C4): mega_vpt_naive.cpp:170-485 for ONE homogeneous environment medium ------------------------
+// Scope and the reference quirks that are reproduced on purpose are listed next to the oracle's volume_path_li
+// (oracle/oracle.cpp).  For opaque closures every transmittance ray ends at the first surface with f = 0, so both
+// shadow rays of a bounce reduce to any-hit queries whose only side effect on the path is three PCG32 draws when
+// they hit something (homogeneous.cpp:119-125).
+//
+// Wavefront schedule per depth d:   T1 any-hit(s1 rays) -> occl1 | T0 closest(main rays) -> hits |
+//   volume_shade(d): PCG catch-up (occl2 of d-1, occl1 of d), distance sampling, scatter/absorb or surface shading,
+//                    next ray + next bounce's s1 ray + surface NEE shadow record | T2 any-hit(shadow records) -> Li, occl2
+struct PCG32 {// src/util/rng.cpp:142-174
+    unsigned long long state, inc;
+    __device__ __forceinline__ uint32_t uniform_uint() {
+        unsigned long long oldstate = state;
+        state = oldstate * 0x5851f42d4c957f2dull + inc;
+        uint32_t xorshifted = static_cast<uint32_t>(((oldstate >> 18u) ^ oldstate) >> 27u);
+        uint32_t rot = static_cast<uint32_t>(oldstate >> 59u);
+        return (xorshifted >> rot) | (xorshifted << ((~rot + 1u) & 31u));
+    }
+    __device__ __forceinline__ void set_sequence(unsigned long long init_seq) {
+        state = 0ull;
+        inc = (init_seq << 1u) | 1ull;
+        uniform_uint();
+        state = state + 0x853c49e6748fea9bull;
+        uniform_uint();
+    }
+    __device__ __forceinline__ float uniform_float() { return fminf(kOneMinusEpsilon, static_cast<float>(uniform_uint()) * 0x1p-32f); }
+};
+
+__device__ __forceinline__ float comp3(V3 a, uint32_t i) { return i == 0u ? a.x : i == 1u ? a.y : a.z; }
+__device__ __forceinline__ V3 exp3(V3 a) { return {expf(a.x), expf(a.y), expf(a.z)}; }
+
+// shadow ray from a point in the medium towards a sampled light point: LightSampler::sample with
+// Interaction{ray->origin()} (mega_vpt_naive.cpp:270-273): zero offset factor, so the origin is the point itself
+__device__ __forceinline__ void medium_light_shadow_ray(const DeviceScene &sc, V3 p_from, float u_sel, float u0, float u1,
+                                                        float4 &ro, float4 &rd) {
+    float n = static_cast<float>(sc.light_count);
+    uint32_t tag = static_cast<uint32_t>(clampf(u_sel * n, 0.f, n - 1.f));
+    const lrk_light_handle handle = sc.light_handles[tag];
+    ShapeHandle light_inst = decode_handle(__ldg(sc.inst_handles + handle.instance_id));
+    const lrk_mesh mesh = sc.meshes[light_inst.mesh];
+    float u = u0 * static_cast<float>(light_inst.tri_count);
+    uint32_t i = min(max(static_cast<uint32_t>(u), 0u), light_inst.tri_count - 1u);
+    float u_remapped = u - floorf(u);
+    lrk_alias_entry entry = sc.alias[mesh.triangle_offset + i];
+    bool keep = u_remapped < entry.prob;
+    uint32_t triangle_id = keep ? i : entry.alias;
+    float ux = keep ? u_remapped / entry.prob : (u_remapped - entry.prob) / (1.0f - entry.prob);
+    V3 uvw = sample_uniform_triangle(ux, u1);
+    Interaction it_light = make_interaction(sc, handle.instance_id, triangle_id, uvw);
+    V3 Lv = it_light.pg - p_from;
+    float d = length(Lv);
+    V3 dir = Lv * (1.f / d);
+    ro = make_float4(p_from.x, p_from.y, p_from.z, 0.f);
+    rd = make_float4(dir.x, dir.y, dir.z, d * .9999f);
+}
+
+__global__ void __launch_bounds__(kBlock) generate_rays_volume_kernel(DeviceScene sc, PathBuffers pb, const uint32_t *__restrict__ pixel_list,
+                                                                      uint32_t pixel_offset, uint32_t npix, uint32_t spp_begin, uint32_t n) {
+    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id == 0u) {
+        pb.counts[0] = n;
+        for (uint32_t d = 1u; d < 7u * kMaxDepthSlots; d++) pb.counts[d] = 0u;
+    }
+    if (id >= n) return;
+    uint32_t k = id % npix;
+    uint32_t s = id / npix;
+    uint32_t pixel = __ldg(pixel_list + pixel_offset + k);
+    uint32_t px = pixel & 0xffffu, py = pixel >> 16u;
+    uint32_t state = xxhash32_uint4(px, py, sc.sampler_seed, spp_begin + s);
+    float ux = lcg(state);
+    float uy = lcg(state);
+    float4 ro, rd;
+    float weight;
+    camera_ray(sc.camera, px, py, ux, uy, ro, rd, weight);
+    // PCG32 rng(U64(as<UInt2>(generate_2d()))): first float = high word (src/util/u64.h:48,58-59)
+    float s0 = lcg(state), s1 = lcg(state);
+    PCG32 rng;
+    rng.set_sequence((static_cast<unsigned long long>(__float_as_uint(s0)) << 32u) | __float_as_uint(s1));
+    float u_rr = 0.f;
+    if (1u >= sc.rr_depth) u_rr = lcg(state);
+    float u_sel = lcg(state), ul0 = lcg(state), ul1 = lcg(state);
+    float4 so, sd;
+    medium_light_shadow_ray(sc, v3(ro.x, ro.y, ro.z), u_sel, ul0, ul1, so, sd);
+    pb.ray_o[0][id] = ro;
+    pb.ray_d[0][id] = rd;
+    pb.beta_pdf[0][id] = make_float4(weight, weight, weight, 1e16f);
+    pb.id_rng[0][id] = make_uint2(id, state);
+    pb.li[id] = make_float4(0.f, 0.f, 0.f, 0.f);
+    pb.pcg[0][id] = make_ulonglong2(rng.state, rng.inc);
+    pb.u_rr[0][id] = u_rr;
+    pb.s1ray_o[id] = so;
+    pb.s1ray_d[id] = sd;
+    pb.occl2[0][id] = 0u;
+}
+
+// T1 / T2: any-hit queries that record occlusion.  T2 also applies the pending surface NEE contribution.
+template<bool COUNT>
+__global__ void __launch_bounds__(kBlock) trace_medium_shadow_kernel(DeviceScene sc, PathBuffers pb, const uint32_t *__restrict__ count,
+                                                                     uint32_t *cursor) {
+    const uint32_t n = *count;
+    TraversalCounters tc{0u, 0u, 0u};
+    trace_queue<true, COUNT, 1>(sc, pb.s1ray_o, pb.s1ray_d, n, cursor, tc, [&](bool finished, uint32_t i, uint4 h) {
+        if (finished) pb.occl1[i] = h.x != ~0u ? 1u : 0u;
+    });
+    if (COUNT) {
+        atomicAdd(pb.stats + 5, static_cast<unsigned long long>(tc.nodes));
+        atomicAdd(pb.stats + 6, static_cast<unsigned long long>(tc.tris));
+        atomicAdd(pb.stats + 7, static_cast<unsigned long long>(tc.xforms));
+    }
+}
+
+template<bool COUNT>
+__global__ void __launch_bounds__(kBlock) trace_volume_nee_kernel(DeviceScene sc, PathBuffers pb, const uint32_t *__restrict__ count,
+                                                                  uint32_t *cursor, uint32_t *__restrict__ occl_out) {
+    const uint32_t n = *count;
+    TraversalCounters tc{0u, 0u, 0u};
+    trace_queue<true, COUNT, 1>(sc, pb.sray_o, pb.sray_d, n, cursor, tc, [&](bool finished, uint32_t i, uint4 h) {
+        if (!finished) return;
+        const bool occluded = h.x != ~0u;
+        const uint32_t target = pb.s2_target[i];
+        if (target != ~0u) occl_out[target] = occluded ? 1u : 0u;
+        if (!occluded) {
+            float4 c = pb.scontrib[i];
+            if (c.x != 0.f || c.y != 0.f || c.z != 0.f) {
+                uint32_t path = __float_as_uint(c.w);
+                float4 li = pb.li[path];
+                li.x += c.x;
+                li.y += c.y;
+                li.z += c.z;
+                pb.li[path] = li;
+            }
+        }
+    });
+    if (COUNT) {
+        atomicAdd(pb.stats + 5, static_cast<unsigned long long>(tc.nodes));
+        atomicAdd(pb.stats + 6, static_cast<unsigned long long>(tc.tris));
+        atomicAdd(pb.stats + 7, static_cast<unsigned long long>(tc.xforms));
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) volume_shade_kernel(DeviceScene sc, PathBuffers pb, uint32_t depth) {
+    __shared__ uint32_t s_warp_next[kBlock / 32], s_warp_shadow[kBlock / 32];
+    __shared__ uint32_t s_base_next, s_base_shadow;
+    const uint32_t n = pb.counts[depth];
+    const int in = depth & 1u, out = in ^ 1;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5u;
+    const V3 sigma_a = v3(sc.sigma_a[0], sc.sigma_a[1], sc.sigma_a[2]), sigma_s = v3(sc.sigma_s[0], sc.sigma_s[1], sc.sigma_s[2]);
+    const V3 sigma_t = sigma_a + sigma_s;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        bool push_next = false, push_shadow = false;
+        float4 nro, nrd, nbeta, sro, srd, scon, n1o, n1d;
+        uint2 nid;
+        ulonglong2 npcg;
+        float nurr = 0.f;
+        if (i < n) {
+            const uint4 hit = pb.hit[i];
+            float4 ro = pb.ray_o[in][i], rd = pb.ray_d[in][i];
+            float4 bp = pb.beta_pdf[in][i];
+            uint2 ir = pb.id_rng[in][i];
+            ulonglong2 pc = pb.pcg[in][i];
+            const float u_rr = pb.u_rr[in][i];
+            PCG32 rng{pc.x, pc.y};
+            // transmittance rays that hit a surface consumed three draws each: previous bounce's surface NEE, then this
+            // bounce's in-medium direct light (their contribution is f = Tr * bsdf(-d, d) = 0 for opaque closures)
+            if (pb.occl2[in][i] != 0u) { rng.uniform_uint(); rng.uniform_uint(); rng.uniform_uint(); }
+            if (pb.occl1[i] != 0u) { rng.uniform_uint(); rng.uniform_uint(); rng.uniform_uint(); }
+            V3 beta = v3(bp.x, bp.y, bp.z);
+            float pdf_bsdf = bp.w;
+            uint32_t state = ir.y;
+            V3 o = v3(ro.x, ro.y, ro.z), d = v3(rd.x, rd.y, rd.z);
+            const bool valid = hit.x != ~0u;
+            Interaction it;
+            float t_max = kFltMax;
+            if (valid) {
+                float bu = __uint_as_float(hit.z), bv = __uint_as_float(hit.w);
+                it = make_interaction(sc, hit.x, hit.y, v3(1.f - bu - bv, bu, bv));
+                it.back_facing = dot(-d, it.ng) < 0.0f;
+                t_max = length(it.pg - o);
+            }
+            // HomogeneousMediumClosure::sample, homogeneous.cpp:48-118
+            V3 pch;
+            pch.x = rng.uniform_float();
+            pch.y = rng.uniform_float();
+            pch.z = rng.uniform_float();
+            float psum = pch.x + pch.y + pch.z;
+            pch = v3(pch.x / psum, pch.y / psum, pch.z / psum);
+            float u_rescaled = rng.uniform_float() * (pch.x + pch.y + pch.z);
+            uint32_t channel = ~0u;
+            float accum = 0.f;
+#pragma unroll
+            for (uint32_t c = 0; c < 3u; c++) {
+                accum += comp3(pch, c);
+                if (channel == ~0u && u_rescaled <= accum) channel = c;
+            }
+            float u = rng.uniform_float();
+            float st = channel < 3u ? comp3(sigma_t, channel) : __int_as_float(0x7fc00000);
+            float t = -logf(fmaxf(1.f - u, 1.17549435e-38f)) / st;
+            uint32_t event;
+            V3 mf, no = o, nd = d;
+            float mpdf;
+            if (t > t_max) {
+                event = 3u;
+                t = t_max;
+                V3 Tr = exp3(-sigma_t * t);
+                no = o + d * t;
+                mf = Tr;
+                mpdf = (pch * Tr).x + (pch * Tr).y + (pch * Tr).z;
+            } else {
+                float p_absorb = comp3(sigma_a, channel) / st, p_scatter = comp3(sigma_s, channel) / st;
+                float ur = rng.uniform_float() * (p_absorb + p_scatter);
+                if (ur <= p_absorb) {
+                    event = 0u;
+                    mf = v3(0.f);
+                    V3 pp = pch * sigma_t;
+                    mpdf = pp.x + pp.y + pp.z;
+                } else {
+                    event = 1u;
+                    V3 Tr = exp3(-sigma_t * t);
+                    float u0 = rng.uniform_float(), u1 = rng.uniform_float();
+                    float g = sc.medium_g;
+                    float cosTheta = fabsf(g) < 1e-3f ? 1.f - 2.f * u0
+                                                      : -1.f / (2.f * g) * (1.f + sqr(g) - sqr((1.f - sqr(g)) / (1.f + g - 2.f * g * u0)));
+                    float sinTheta = sqrtf(fmaxf(0.f, 1.f - sqr(cosTheta)));
+                    float phi = 2.f * kPi * u1;
+                    float sphi, cphi;
+                    sincosf(phi, &sphi, &cphi);
+                    no = o + d * t;
+                    nd = v3(sinTheta * cphi, cosTheta, sinTheta * sphi);
+                    mf = Tr * sigma_s;
+                    V3 pp = pch * (sigma_t * Tr);
+                    mpdf = pp.x + pp.y + pp.z;
+                }
+            }
+            {
+                float w = mpdf > 0.f ? 1.f / mpdf : 0.f;
+                beta = beta * (mf * w);
+                pdf_bsdf = mpdf;
+            }
+            bool alive = true;
+            V3 next_o = no, next_d = nd;
+            if (event == 3u) {
+                if (!valid) {
+                    alive = false;
+                } else {
+                    if (it.shape.has_light()) {// evaluate_hit from the MOVED ray origin (mega_vpt_naive.cpp:308,319)
+                        LightEval e = evaluate_hit(sc, it, no);
+                        V3 add = beta * e.L * balance_heuristic(pdf_bsdf, e.pdf);
+                        float4 li = pb.li[ir.x];
+                        li.x += add.x;
+                        li.y += add.y;
+                        li.z += add.z;
+                        pb.li[ir.x] = li;
+                    }
+                    if (!it.shape.has_surface()) {
+                        alive = false;
+                    } else {
+                        float u_sel = lcg(state);
+                        float ul0 = lcg(state), ul1 = lcg(state);
+                        float u_lobe = lcg(state);
+                        float ub0 = lcg(state), ub1 = lcg(state);
+                        LightSample ls = sample_light(sc, it, u_sel, ul0, ul1);
+                        const lrk_surface *surf = sc.surfaces + it.shape.surface_tag;
+                        V3 wo = -d;
+                        V3 contrib = v3(0.f), wi, f;
+                        float pdf;
+                        if (sc.medium_priority != 0u && false) {
+                            // true_hit(medium_tag = 0) <=> 0 <= priority: always true (medium_tracker.cpp:19-21)
+                        }
+                        if (surf->type == LRK_SURFACE_MATTE) {
+                            MatteClosure cl;
+                            cl.init(*surf);
+                            volume_shade_surface(cl, it, wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
+                        } else {
+                            DisneyClosure cl;
+                            cl.init(*surf);
+                            volume_shade_surface(cl, it, wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
+                        }
+                        push_shadow = true;// always traced: its occlusion advances the PCG stream of the next bounce
+                        sro = ls.ray_o_tmin;
+                        srd = ls.ray_d_tmax;
+                        scon = make_float4(contrib.x, contrib.y, contrib.z, __uint_as_float(ir.x));
+                        next_o = p_robust(it, wi);
+                        next_d = wi;
+                        float w = pdf > 0.f ? 1.f / pdf : 0.f;
+                        pdf_bsdf = pdf;
+                        beta = beta * (w * f);
+                    }
+                }
+            }
+            if (alive) {
+                if (isnan(beta.x) || isnan(beta.y) || isnan(beta.z)) beta = v3(0.f);
+                alive = !(beta.x <= 0.f && beta.y <= 0.f && beta.z <= 0.f);
+                if (alive) {
+                    float q = fmaxf(max3(beta) * 1.f, .05f);
+                    if (depth + 1u >= sc.rr_depth) {
+                        if (q < sc.rr_threshold && u_rr >= q) alive = false;
+                        beta = beta * (q < sc.rr_threshold ? 1.0f / q : 1.f);
+                    }
+                }
+            }
+            if (alive && depth + 1u < sc.max_depth) {
+                push_next = true;
+                // draws at the top of the next iteration: u_rr, then the in-medium light sample (mega_vpt_naive.cpp:256-273)
+                if (depth + 2u >= sc.rr_depth) nurr = lcg(state);
+                float u_sel = lcg(state), ul0 = lcg(state), ul1 = lcg(state);
+                medium_light_shadow_ray(sc, next_o, u_sel, ul0, ul1, n1o, n1d);
+                nro = make_float4(next_o.x, next_o.y, next_o.z, 0.f);
+                nrd = make_float4(next_d.x, next_d.y, next_d.z, kFltMax);
+                nbeta = make_float4(beta.x, beta.y, beta.z, pdf_bsdf);
+                nid = make_uint2(ir.x, state);
+                npcg = make_ulonglong2(rng.state, rng.inc);
+            }
+            if (push_shadow && !push_next && scon.x == 0.f && scon.y == 0.f && scon.z == 0.f) push_shadow = false;// nothing depends on it
+        }
+        uint32_t m_next = __ballot_sync(0xffffffffu, push_next);
+        uint32_t m_shadow = __ballot_sync(0xffffffffu, push_shadow);
+        if (lane == 0u) {
+            s_warp_next[warp] = __popc(m_next);
+            s_warp_shadow[warp] = __popc(m_shadow);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0u) {
+            uint32_t tn = 0u, ts = 0u;
+            for (int w = 0; w < kBlock / 32; w++) {
+                uint32_t a = s_warp_next[w], b = s_warp_shadow[w];
+                s_warp_next[w] = tn;
+                s_warp_shadow[w] = ts;
+                tn += a;
+                ts += b;
+            }
+            s_base_next = tn ? atomicAdd(pb.counts + depth + 1u, tn) : 0u;
+            s_base_shadow = ts ? atomicAdd(pb.counts + kMaxDepthSlots + depth, ts) : 0u;
+        }
+        __syncthreads();
+        const uint32_t lt = (1u << lane) - 1u;
+        uint32_t next_slot = ~0u;
+        if (push_next) {
+            next_slot = s_base_next + s_warp_next[warp] + __popc(m_next & lt);
+            pb.ray_o[out][next_slot] = nro;
+            pb.ray_d[out][next_slot] = nrd;
+            pb.beta_pdf[out][next_slot] = nbeta;
+            pb.id_rng[out][next_slot] = nid;
+            pb.pcg[out][next_slot] = npcg;
+            pb.u_rr[out][next_slot] = nurr;
+            pb.s1ray_o[next_slot] = n1o;
+            pb.s1ray_d[next_slot] = n1d;
+            pb.occl2[out][next_slot] = 0u;
+        }
+        if (push_shadow) {
+            uint32_t slot = s_base_shadow + s_warp_shadow[warp] + __popc(m_shadow & lt);
+            pb.sray_o[slot] = sro;
+            pb.sray_d[slot] = srd;
+            pb.scontrib[slot] = scon;
+            pb.s2_target[slot] = next_slot;
         }
         __syncthreads();
     }

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "kernels.cuh"
@@ -41,6 +42,9 @@ struct lrk_ctx {
     uint32_t rank{0}, world{1}, tile_size{32};
     uint32_t *d_pixel_list{nullptr};
     uint32_t npix_owned{0};
+    uint32_t pixel_list_key[5]{0, 0, 0, 0, 0};// width, height, rank, world, tile size of the cached list
+    std::unordered_map<void **, size_t> array_bytes;// capacity of each scene array allocation
+    size_t film_pixels{0};
     // path state
     uint64_t max_paths{0}, capacity{0};
     PathBuffers pb{};
@@ -57,6 +61,9 @@ struct lrk_ctx {
     std::vector<cudaEvent_t> event_pool;
     int grid_trace{0}, grid_shade[3]{0, 0, 0}, grid_shadow{0}, grid_classify{0};
     bool has_kind[3]{true, false, false};
+    bool volume{false};
+    uint64_t volume_capacity{0};
+    int grid_vshade{0}, grid_vshadow{0};
 };
 
 namespace {
@@ -74,14 +81,20 @@ int fail(lrk_ctx *ctx, int code, const std::string &msg) {
         }                                                                                                     \
     } while (0)
 
+// Host -> device copy of one scene array.  The allocation is kept across uploads when it is large enough, so
+// re-uploading a scene of the same shape (the end-to-end path of bench.py, animation frames) costs only the copy.
 template<typename T>
 int upload(lrk_ctx *ctx, void **dst, const T *src, size_t count) {
-    if (*dst) {
-        cudaFree(*dst);
-        *dst = nullptr;
-    }
     size_t bytes = std::max<size_t>(count * sizeof(T), 16u);
-    LRK_CUDA(cudaMalloc(dst, bytes));
+    size_t &have = ctx->array_bytes[dst];
+    if (*dst == nullptr || have < bytes) {
+        if (*dst) {
+            cudaFree(*dst);
+            *dst = nullptr;
+        }
+        LRK_CUDA(cudaMalloc(dst, bytes));
+        have = bytes;
+    }
     if (count) LRK_CUDA(cudaMemcpyAsync(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
     return LRK_OK;
 }
@@ -98,10 +111,11 @@ void free_paths(lrk_ctx *ctx) {
     for (auto p : ctx->path_allocs) cudaFree(p);
     ctx->path_allocs.clear();
     ctx->capacity = 0;
+    ctx->volume_capacity = 0;
 }
 
 int alloc_paths(lrk_ctx *ctx, uint64_t capacity) {
-    if (ctx->capacity >= capacity) return LRK_OK;
+    if (ctx->capacity >= capacity && (!ctx->volume || ctx->volume_capacity >= capacity)) return LRK_OK;
     free_paths(ctx);
     auto alloc = [&](void **p, size_t bytes) -> cudaError_t {
         cudaError_t e = cudaMalloc(p, bytes);
@@ -125,6 +139,19 @@ int alloc_paths(lrk_ctx *ctx, uint64_t capacity) {
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.stats), 8u * sizeof(unsigned long long)));
     LRK_CUDA(cudaMemsetAsync(pb.stats, 0, 8u * sizeof(unsigned long long), ctx->stream));
     ctx->capacity = capacity;
+    ctx->volume_capacity = 0;
+    if (ctx->volume) {
+        for (int k = 0; k < 2; k++) {
+            LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.pcg[k]), capacity * sizeof(ulonglong2)));
+            LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.u_rr[k]), capacity * sizeof(float)));
+            LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.occl2[k]), capacity * sizeof(uint32_t)));
+        }
+        LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.s1ray_o), capacity * sizeof(float4)));
+        LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.s1ray_d), capacity * sizeof(float4)));
+        LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.occl1), capacity * sizeof(uint32_t)));
+        LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.s2_target), capacity * sizeof(uint32_t)));
+        ctx->volume_capacity = capacity;
+    }
     return LRK_OK;
 }
 
@@ -132,6 +159,9 @@ int alloc_paths(lrk_ctx *ctx, uint64_t capacity) {
 // pixel blocks so that a warp's 32 consecutive paths cover a compact screen region.
 int build_pixel_list(lrk_ctx *ctx) {
     const uint32_t W = ctx->scene.width, H = ctx->scene.height, ts = ctx->tile_size;
+    const uint32_t key[5]{W, H, ctx->rank, ctx->world, ts};
+    if (ctx->d_pixel_list != nullptr && std::memcmp(key, ctx->pixel_list_key, sizeof(key)) == 0) return LRK_OK;
+    std::memcpy(ctx->pixel_list_key, key, sizeof(key));
     const uint32_t tiles_x = (W + ts - 1u) / ts, tiles_y = (H + ts - 1u) / ts;
     std::vector<uint32_t> list;
     list.reserve(static_cast<size_t>(W) * H / ctx->world + 1024u);
@@ -247,6 +277,65 @@ int render_pass(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint32_t spp
     return LRK_OK;
 }
 
+// One pass of the volume path integrator (config C4); schedule described in kernels.cuh.
+int render_pass_volume(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint32_t spp_begin, uint32_t spp) {
+    const uint64_t n = static_cast<uint64_t>(npix) * spp;
+    auto &pb = ctx->pb;
+    const auto &sc = ctx->scene;
+    {
+        ScopedTimer t{ctx, CAT_OTHER};
+        generate_rays_volume_kernel<<<static_cast<unsigned>((n + kBlock - 1u) / kBlock), kBlock, 0, ctx->stream>>>(
+            sc, pb, ctx->d_pixel_list, pixel_offset, npix, spp_begin, static_cast<uint32_t>(n));
+    }
+    ctx->stats.kernel_launches++;
+    for (uint32_t depth = 0; depth < sc.max_depth; depth++) {
+        const int in = depth & 1u, out = in ^ 1;
+        {
+            ScopedTimer t{ctx, CAT_TRACE_SHADOW};
+            int g = blocks_for(ctx, n, ctx->grid_vshadow);
+            // the in-medium shadow rays share the depth's path-queue size; their cursor lives in the shadow-cursor region + 32
+            if (ctx->count_traversal)
+                trace_medium_shadow_kernel<true><<<g, kBlock, 0, ctx->stream>>>(sc, pb, pb.counts + depth, pb.counts + 3u * kMaxDepthSlots + 32u + depth);
+            else
+                trace_medium_shadow_kernel<false><<<g, kBlock, 0, ctx->stream>>>(sc, pb, pb.counts + depth, pb.counts + 3u * kMaxDepthSlots + 32u + depth);
+        }
+        {
+            ScopedTimer t{ctx, CAT_TRACE_CLOSEST};
+            int g = blocks_for(ctx, n, ctx->grid_trace);
+            if (ctx->count_traversal)
+                trace_closest_kernel<true><<<g, kBlock, 0, ctx->stream>>>(sc, pb.ray_o[in], pb.ray_d[in], pb.hit, pb.counts + depth,
+                                                                          pb.counts + 2u * kMaxDepthSlots + depth, pb.stats);
+            else
+                trace_closest_kernel<false><<<g, kBlock, 0, ctx->stream>>>(sc, pb.ray_o[in], pb.ray_d[in], pb.hit, pb.counts + depth,
+                                                                           pb.counts + 2u * kMaxDepthSlots + depth, pb.stats);
+        }
+        {
+            ScopedTimer t{ctx, CAT_SHADE};
+            volume_shade_kernel<<<blocks_for(ctx, n, ctx->grid_vshade), kBlock, 0, ctx->stream>>>(sc, pb, depth);
+        }
+        {
+            ScopedTimer t{ctx, CAT_TRACE_SHADOW};
+            int g = blocks_for(ctx, n, ctx->grid_vshadow);
+            if (ctx->count_traversal)
+                trace_volume_nee_kernel<true><<<g, kBlock, 0, ctx->stream>>>(sc, pb, pb.counts + kMaxDepthSlots + depth,
+                                                                             pb.counts + 3u * kMaxDepthSlots + depth, pb.occl2[out]);
+            else
+                trace_volume_nee_kernel<false><<<g, kBlock, 0, ctx->stream>>>(sc, pb, pb.counts + kMaxDepthSlots + depth,
+                                                                              pb.counts + 3u * kMaxDepthSlots + depth, pb.occl2[out]);
+        }
+        ctx->stats.kernel_launches += 4;
+    }
+    {
+        ScopedTimer t{ctx, CAT_OTHER};
+        accumulate_kernel<<<(npix + kBlock - 1u) / kBlock, kBlock, 0, ctx->stream>>>(sc, pb.li, ctx->d_film, ctx->d_pixel_list, pixel_offset,
+                                                                                  npix, spp, pb.counts, pb.stats);
+    }
+    ctx->stats.kernel_launches++;
+    ctx->stats.passes++;
+    LRK_CUDA(cudaGetLastError());
+    return LRK_OK;
+}
+
 }// namespace
 
 extern "C" {
@@ -293,6 +382,8 @@ int lrk_create(const lrk_device_cfg *cfg, lrk_ctx **out) {
     ctx->grid_shade[1] = grid_for(reinterpret_cast<const void *>(shade_kernel<1u>));
     ctx->grid_shade[2] = grid_for(reinterpret_cast<const void *>(shade_kernel<2u>));
     ctx->grid_classify = grid_for(reinterpret_cast<const void *>(classify_hits_kernel));
+    ctx->grid_vshade = grid_for(reinterpret_cast<const void *>(volume_shade_kernel));
+    ctx->grid_vshadow = grid_for(reinterpret_cast<const void *>(trace_volume_nee_kernel<false>));
     *out = ctx;
     return LRK_OK;
 }
@@ -323,10 +414,18 @@ const char *lrk_last_error(const lrk_ctx *ctx) { return ctx ? ctx->error.c_str()
 int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
     if (!ctx || !s) return LRK_ERR_INVALID_ARGUMENT;
     if (s->abi_version != LRK_ABI_VERSION) return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_upload_scene: ABI version mismatch");
-    if (s->integrator.type != LRK_INTEGRATOR_PATH)
-        return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: only the surface path integrator is implemented on the device");
-    if (s->environment_medium.present)
-        return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: participating media are not implemented on the device");
+    if (s->integrator.type == LRK_INTEGRATOR_VOLUME_PATH) {
+        // supported volume scope: one homogeneous environment medium with eta = 1, opaque surfaces (see kernels.cuh)
+        if (!s->environment_medium.present)
+            return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: the volume path integrator needs an environment medium");
+        if (s->environment_medium.eta != 1.f)
+            return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: environment media with eta != 1 are not supported");
+        if (s->integrator.max_depth > 31u) return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: volume path depth > 31");
+    } else if (s->integrator.type != LRK_INTEGRATOR_PATH) {
+        return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: unknown integrator type");
+    } else if (s->environment_medium.present) {
+        return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: an environment medium needs the volume path integrator (MegaVPTNaive)");
+    }
     if (s->integrator.max_depth > kMaxDepthSlots - 1u) return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: max depth > 63");
     if (s->camera.resolution[0] > 65535u || s->camera.resolution[1] > 65535u)
         return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: film larger than 65535 pixels per side");
@@ -404,13 +503,24 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
     sc.width = s->camera.resolution[0];
     sc.height = s->camera.resolution[1];
     ctx->spp_hint = s->camera.spp;
+    ctx->volume = s->integrator.type == LRK_INTEGRATOR_VOLUME_PATH;
+    for (int i = 0; i < 3; i++) {
+        sc.sigma_a[i] = s->environment_medium.sigma_a[i];
+        sc.sigma_s[i] = s->environment_medium.sigma_s[i];
+    }
+    sc.medium_g = s->environment_medium.g;
+    sc.medium_priority = s->environment_medium.priority;
 
     const size_t npix = static_cast<size_t>(sc.width) * sc.height;
-    if (ctx->d_film) cudaFree(ctx->d_film);
-    if (ctx->d_film_out) cudaFree(ctx->d_film_out);
-    ctx->d_film = ctx->d_film_out = nullptr;
-    LRK_CUDA(cudaMalloc(reinterpret_cast<void **>(&ctx->d_film), npix * sizeof(float4)));
-    LRK_CUDA(cudaMalloc(reinterpret_cast<void **>(&ctx->d_film_out), npix * sizeof(float4)));
+    if (ctx->film_pixels != npix) {
+        if (ctx->d_film) cudaFree(ctx->d_film);
+        if (ctx->d_film_out) cudaFree(ctx->d_film_out);
+        ctx->d_film = ctx->d_film_out = nullptr;
+        ctx->film_pixels = 0;
+        LRK_CUDA(cudaMalloc(reinterpret_cast<void **>(&ctx->d_film), npix * sizeof(float4)));
+        LRK_CUDA(cudaMalloc(reinterpret_cast<void **>(&ctx->d_film_out), npix * sizeof(float4)));
+        ctx->film_pixels = npix;
+    }
     ctx->has_scene = true;
     if ((rc = build_pixel_list(ctx))) return rc;
     return lrk_film_clear(ctx);
@@ -468,7 +578,8 @@ int lrk_render(lrk_ctx *ctx, uint32_t spp_begin, uint32_t spp_end) {
         uint32_t spp = std::min(spp_per_pass, total_spp - s);
         for (uint32_t p = 0; p < npix; p += chunk_pix) {
             uint32_t np = std::min(chunk_pix, npix - p);
-            if ((rc = render_pass(ctx, p, np, spp_begin + s, spp))) return rc;
+            rc = ctx->volume ? render_pass_volume(ctx, p, np, spp_begin + s, spp) : render_pass(ctx, p, np, spp_begin + s, spp);
+            if (rc) return rc;
         }
     }
     LRK_CUDA(cudaEventRecord(ctx->ev_end, ctx->stream));

@@ -39,6 +39,10 @@ struct DeviceScene {
     float film_clamp;
     float film_scale[3];
     uint32_t width, height;
+    // homogeneous environment medium (volume path integrator only)
+    float sigma_a[3], sigma_s[3];
+    float medium_g;
+    uint32_t medium_priority;
 };
 
 }// namespace lrk

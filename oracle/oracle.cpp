@@ -1060,6 +1060,262 @@ V3 path_li(const lrk_scene_desc &sc, uint32_t px, uint32_t py, uint32_t sample_i
     return Li;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Volumetric estimator (config C4): src/integrators/mega_vpt_naive.cpp:170-485 with
+// VPT_NAIVE_ENABLE_DIRECT_LIGHTING defined (:16) and VPT_NAIVE_ENABLE_MEDIUM_STACK_INIT not (:15).
+// Scope: ONE homogeneous environment medium, no per-shape media, opaque surfaces — so the medium tracker
+// (src/util/medium_tracker.cpp) always holds exactly the environment medium and never becomes vacuum.
+// The reference's quirks are kept on purpose (they define its output):
+//   * `_transmittance` (:96-168) only accumulates medium transmittance up to a surface it HITS; an unoccluded
+//     shadow ray returns f = 1, pdf = 0 — light reaches surfaces unattenuated, and the in-medium direct light
+//     (guarded by pdf > 0, :279) only ever adds f = Tr * bsdf(-d, d) = 0 for opaque closures;
+//   * each surface hit by a transmittance ray draws three numbers from the path's PCG32 stream
+//     (homogeneous.cpp:119-125), which shifts all later medium decisions — so the shadow rays must be traced;
+//   * Henyey-Greenstein returns its sampled direction in a fixed y-up frame, not around wo
+//     (henyey_greenstein.cpp:30-43); the phase value is not part of f/pdf (homogeneous.cpp:88-96);
+//   * after a "hit surface" medium event the ray origin has moved to the surface, and that moved origin is
+//     what `evaluate_hit` gets (mega_vpt_naive.cpp:308,319).
+// ------------------------------------------------------------------------------------------------
+struct PCG32 {// src/util/rng.cpp:142-174, constants src/util/rng.h:36-38
+    uint64_t state, inc;
+    static constexpr uint64_t default_state = 0x853c49e6748fea9bull;
+    static constexpr uint64_t mult = 0x5851f42d4c957f2dull;
+    uint32_t uniform_uint() {
+        uint64_t oldstate = state;
+        state = oldstate * mult + inc;
+        uint32_t xorshifted = static_cast<uint32_t>(((oldstate >> 18u) ^ oldstate) >> 27u);
+        uint32_t rot = static_cast<uint32_t>(oldstate >> 59u);
+        return (xorshifted >> rot) | (xorshifted << ((~rot + 1u) & 31u));
+    }
+    void set_sequence(uint64_t init_seq) {
+        state = 0u;
+        inc = (init_seq << 1u) | 1u;
+        uniform_uint();
+        state = state + default_state;
+        uniform_uint();
+    }
+    float uniform_float() { return std::fmin(kOneMinusEpsilon, static_cast<float>(uniform_uint()) * 0x1p-32f); }
+};
+
+struct MediumSample {
+    V3 f{0.f, 0.f, 0.f};
+    float pdf{0.f};
+    V3 o{}, d{};
+    uint32_t event{~0u};// 0 absorb, 1 scatter, 3 hit surface, ~0 invalid (src/base/medium.h:31-36)
+};
+inline V3 exp3(V3 a) { return {std::exp(a.x), std::exp(a.y), std::exp(a.z)}; }
+inline float sum3(V3 a) { return a.x + a.y + a.z; }
+inline float comp(V3 a, uint32_t i) { return i == 0u ? a.x : i == 1u ? a.y : a.z; }
+
+// HomogeneousMediumClosure::sample, src/media/homogeneous.cpp:48-118
+MediumSample homogeneous_sample(const lrk_medium &m, V3 o, V3 d, float t_max, PCG32 &rng) {
+    V3 sigma_a = v3(m.sigma_a[0], m.sigma_a[1], m.sigma_a[2]), sigma_s = v3(m.sigma_s[0], m.sigma_s[1], m.sigma_s[2]);
+    V3 sigma_t = sigma_a + sigma_s;
+    MediumSample s;
+    V3 pdf_channels;
+    pdf_channels.x = rng.uniform_float();
+    pdf_channels.y = rng.uniform_float();
+    pdf_channels.z = rng.uniform_float();
+    float psum = sum3(pdf_channels);
+    pdf_channels = v3(pdf_channels.x / psum, pdf_channels.y / psum, pdf_channels.z / psum);
+    // sample_discrete(spectrum, u): src/util/sampling.cpp:177-190
+    float u_rescaled = rng.uniform_float() * sum3(pdf_channels);
+    uint32_t channel = ~0u;
+    float accum = 0.f;
+    for (uint32_t i = 0; i < 3u; i++) {
+        accum += comp(pdf_channels, i);
+        if (u_rescaled <= accum) { channel = i; break; }
+    }
+    float u = rng.uniform_float();
+    float st = channel < 3u ? comp(sigma_t, channel) : std::numeric_limits<float>::quiet_NaN();
+    float t = -std::log(std::fmax(1.f - u, std::numeric_limits<float>::min())) / st;
+    if (t > t_max) {
+        s.event = 3u;
+        t = t_max;
+        V3 Tr = exp3(-sigma_t * t);
+        s.o = o + d * t;
+        s.d = d;
+        s.f = Tr;
+        s.pdf = sum3(pdf_channels * Tr);
+    } else {
+        float p_absorb = comp(sigma_a, channel) / st, p_scatter = comp(sigma_s, channel) / st;
+        float ur = rng.uniform_float() * (p_absorb + p_scatter);// sample_discrete(float2, u): sampling.cpp:157-161
+        if (ur <= p_absorb) {
+            s.event = 0u;
+            s.o = o;
+            s.d = d;
+            s.f = v3(0.f);
+            s.pdf = sum3(pdf_channels * sigma_t);
+        } else {
+            s.event = 1u;
+            V3 Tr = exp3(-sigma_t * t);
+            // HenyeyGreenstein::sample_p(wo = -d, u), src/phasefunctions/henyey_greenstein.cpp:28-48
+            float u0 = rng.uniform_float(), u1 = rng.uniform_float();
+            float g = m.g;
+            float cosTheta = std::fabs(g) < 1e-3f ? 1.f - 2.f * u0
+                                                  : -1.f / (2.f * g) * (1.f + sqr(g) - sqr((1.f - sqr(g)) / (1.f + g - 2.f * g * u0)));
+            float sinTheta = std::sqrt(std::fmax(0.f, 1.f - sqr(cosTheta)));
+            float phi = 2.f * kPi * u1;
+            V3 wi = v3(sinTheta * std::cos(phi), cosTheta, sinTheta * std::sin(phi));
+            s.o = o + d * t;
+            s.d = wi;
+            s.f = Tr * sigma_s;
+            s.pdf = sum3(pdf_channels * (sigma_t * Tr));
+        }
+    }
+    return s;
+}
+
+// _transmittance (mega_vpt_naive.cpp:96-168) for the supported scope. Returns f and pdf; draws from rng when a
+// surface is hit.  `occluded_any` reports whether any surface was hit (what the wavefront kernels track).
+struct Transmittance {
+    V3 f{1.f, 1.f, 1.f};
+    float pdf{0.f};
+};
+SurfEval surface_evaluate(const lrk_surface &s, const Interaction &it, V3 wo, V3 wi);// defined above
+Transmittance volume_transmittance(const lrk_scene_desc &sc, PCG32 &rng, lrk_ray origin_ray, TraceCounters *tc, oracle_counters *cnt,
+                                   bool *occluded_any) {
+    const lrk_medium &m = sc.environment_medium;
+    V3 sigma_t = v3(m.sigma_a[0] + m.sigma_s[0], m.sigma_a[1] + m.sigma_s[1], m.sigma_a[2] + m.sigma_s[2]);
+    float t_max = origin_ray.tmax;
+    V3 dir = v3(origin_ray.d[0], origin_ray.d[1], origin_ray.d[2]);
+    lrk_ray ray = origin_ray;
+    V3 light_p = v3(origin_ray.o[0], origin_ray.o[1], origin_ray.o[2]) + dir * t_max;
+    Transmittance T;
+    if (occluded_any) *occluded_any = false;
+    while (T.f.x > 0.f || T.f.y > 0.f || T.f.z > 0.f) {
+        lrk_hit hit = trace_bvh(sc, ray, false, tc);
+        if (cnt) cnt->shadow_rays++;
+        Interaction it = interaction_from_hit(sc, ray, hit);
+        if (!it.valid()) break;
+        if (occluded_any) *occluded_any = true;
+        float t2surface = length(it.pg - v3(ray.o[0], ray.o[1], ray.o[2]));
+        V3 wo = -dir, wi = dir;
+        {// HomogeneousMediumClosure::transmittance, homogeneous.cpp:119-133
+            V3 pc;
+            pc.x = rng.uniform_float();
+            pc.y = rng.uniform_float();
+            pc.z = rng.uniform_float();
+            float ps = sum3(pc);
+            pc = v3(pc.x / ps, pc.y / ps, pc.z / ps);
+            V3 Tr = exp3(-sigma_t * t2surface);
+            T.f = T.f * Tr;
+            T.pdf += sum3(pc * Tr);
+        }
+        if (it.shape.has_surface()) {
+            SurfEval ev = surface_evaluate(sc.surfaces[it.shape.surface_tag], it, wo, wi);
+            T.f = T.f * ev.f;
+            T.pdf += ev.pdf;
+        }
+        ray = spawn_ray_to(it, light_p);
+    }
+    return T;
+}
+
+V3 volume_path_li(const lrk_scene_desc &sc, uint32_t px, uint32_t py, uint32_t sample_index, oracle_counters *cnt) {
+    const lrk_medium &medium = sc.environment_medium;
+    Sampler sampler;
+    sampler.start(px, py, sc.integrator.sampler_seed, sample_index);
+    float uf0 = sampler.generate_1d(), uf1 = sampler.generate_1d();
+    float camera_weight;
+    lrk_ray ray = generate_camera_ray(sc.camera, px, py, uf0, uf1, camera_weight);
+    V3 beta = v3(camera_weight);
+    V3 Li = v3(0.f);
+    // PCG32 rng(U64(as<UInt2>(sampler()->generate_2d()))): x = high word, y = low word (src/util/u64.h:48,58-59)
+    float s0 = sampler.generate_1d(), s1 = sampler.generate_1d();
+    uint32_t hi, lo;
+    std::memcpy(&hi, &s0, 4);
+    std::memcpy(&lo, &s1, 4);
+    PCG32 rng;
+    rng.set_sequence((static_cast<uint64_t>(hi) << 32u) | lo);
+    float pdf_bsdf = 1e16f;
+    const float eta_scale = 1.f;// no refractive interfaces in scope
+    TraceCounters tc;
+    for (uint32_t depth = 0; depth < sc.integrator.max_depth; depth++) {
+        float u_rr = 0.f;
+        if (depth + 1u >= sc.integrator.rr_depth) u_rr = sampler.generate_1d();
+        lrk_hit hit = trace_bvh(sc, ray, false, &tc);
+        if (cnt) cnt->closest_rays++;
+        Interaction it = interaction_from_hit(sc, ray, hit);
+        V3 ro = v3(ray.o[0], ray.o[1], ray.o[2]), rd = v3(ray.d[0], ray.d[1], ray.d[2]);
+        float t_max = it.valid() ? length(it.pg - ro) : std::numeric_limits<float>::max();
+        MediumSample ms;
+        {// the tracker is never vacuum: direct light at the ray origin, then distance sampling
+            float u_sel = sampler.generate_1d();
+            float ul0 = sampler.generate_1d(), ul1 = sampler.generate_1d();
+            Interaction it_medium;// Interaction{ray->origin()}: pg = ng = origin, default frame, zero offset factor
+            it_medium.pg = ro;
+            it_medium.ng = ro;
+            it_medium.ps = v3(0.f);
+            it_medium.shading = Frame{v3(1.f, 0.f, 0.f), v3(0.f, 1.f, 0.f), v3(0.f, 0.f, 1.f)};
+            it_medium.shape.intersection_offset = 0.f;
+            LightSample ls = sample_light(sc, it_medium, u_sel, ul0, ul1);
+            Transmittance T = volume_transmittance(sc, rng, ls.shadow_ray, &tc, cnt, nullptr);
+            if (T.pdf > 0.f) {
+                float w = 1.f / (pdf_bsdf + T.pdf + ls.eval.pdf);
+                Li = Li + w * beta * T.f * ls.eval.L;
+            }
+            ms = homogeneous_sample(medium, ro, rd, t_max, rng);
+            ray = make_ray(ms.o, ms.d, 0.f, std::numeric_limits<float>::max());
+            float w = ms.pdf > 0.f ? 1.f / ms.pdf : 0.f;
+            beta = beta * (ms.f * w);
+            pdf_bsdf = ms.pdf;
+        }
+        if (ms.event == ~0u || ms.event == 3u) {
+            if (!it.valid()) break;
+            if (sc.light_count != 0u && it.shape.has_light()) {
+                LightEval e = evaluate_hit(sc, it, v3(ray.o[0], ray.o[1], ray.o[2]));
+                Li = Li + beta * e.L * balance_heuristic(pdf_bsdf, e.pdf);
+            }
+            if (!it.shape.has_surface()) break;
+            if (cnt) cnt->path_vertices++;
+            float u_light_selection = sampler.generate_1d();
+            float ul0 = sampler.generate_1d(), ul1 = sampler.generate_1d();
+            float u_lobe = sampler.generate_1d();
+            float ub0 = sampler.generate_1d(), ub1 = sampler.generate_1d();
+            LightSample ls = sample_light(sc, it, u_light_selection, ul0, ul1);
+            Transmittance T = volume_transmittance(sc, rng, ls.shadow_ray, &tc, cnt, nullptr);
+            V3 wo = -v3(ray.d[0], ray.d[1], ray.d[2]);
+            const lrk_surface &surface = sc.surfaces[it.shape.surface_tag];
+            // true_hit(medium_tag = 0) is `0 <= priority of the environment medium` (medium_tracker.cpp:19-21)
+            if (!(0u <= medium.priority)) {
+                ray = spawn_ray(it, v3(ray.d[0], ray.d[1], ray.d[2]));
+                pdf_bsdf = 1e16f;
+            } else {
+                if (ls.eval.pdf > 0.0f) {
+                    V3 wi = v3(ls.shadow_ray.d[0], ls.shadow_ray.d[1], ls.shadow_ray.d[2]);
+                    SurfEval ev = surface_evaluate(surface, it, wo, wi);
+                    float w = 1.f / (ls.eval.pdf + ev.pdf + T.pdf);
+                    Li = Li + w * beta * ev.f * ls.eval.L * T.f;
+                }
+                SurfSample ss = surface_sample(surface, it, wo, u_lobe, ub0, ub1);
+                float w = ss.eval.pdf > 0.f ? 1.f / ss.eval.pdf : 0.f;
+                pdf_bsdf = ss.eval.pdf;
+                ray = spawn_ray(it, ss.wi);
+                beta = beta * (w * ss.eval.f);
+            }
+        }
+        if (std::isnan(beta.x) || std::isnan(beta.y) || std::isnan(beta.z)) beta = v3(0.f);
+        if (beta.x <= 0.f && beta.y <= 0.f && beta.z <= 0.f) break;
+        float q = std::fmax(max3(beta) * eta_scale, .05f);
+        if (depth + 1u >= sc.integrator.rr_depth) {
+            if (q < sc.integrator.rr_threshold && u_rr >= q) break;
+            beta = beta * (q < sc.integrator.rr_threshold ? 1.0f / q : 1.f);
+        }
+    }
+    if (cnt) {
+        cnt->samples++;
+        cnt->nodes_visited += tc.nodes;
+        cnt->tris_tested += tc.tris;
+        cnt->xforms += tc.xforms;
+    }
+    return Li;
+}
+
+inline V3 sample_li(const lrk_scene_desc &sc, uint32_t px, uint32_t py, uint32_t s, oracle_counters *cnt) {
+    return sc.integrator.type == LRK_INTEGRATOR_VOLUME_PATH ? volume_path_li(sc, px, py, s, cnt) : path_li(sc, px, py, s, cnt);
+}
+
 // Film accumulation of one sample: src/films/color.cpp:107-130 (effective_spp = 1)
 inline void film_accumulate(float *px4, V3 rgb, float film_clamp) {
     bool bad = std::isnan(rgb.x) || std::isnan(rgb.y) || std::isnan(rgb.z) || std::isinf(rgb.x) || std::isinf(rgb.y) || std::isinf(rgb.z);
@@ -1083,7 +1339,12 @@ extern "C" {
 int oracle_render(const lrk_scene_desc *scene, uint32_t spp_begin, uint32_t spp_end, uint32_t threads, uint32_t rank,
                   uint32_t world, uint32_t tile_size, float *film_raw, oracle_counters *counters) {
     if (!scene || !film_raw || scene->abi_version != LRK_ABI_VERSION) return -1;
-    if (scene->integrator.type != LRK_INTEGRATOR_PATH) return -5;
+    if (scene->integrator.type == LRK_INTEGRATOR_VOLUME_PATH) {
+        // supported volume scope: one homogeneous environment medium with eta = 1 (see volume_path_li)
+        if (!scene->environment_medium.present || scene->environment_medium.eta != 1.f) return -5;
+    } else if (scene->integrator.type != LRK_INTEGRATOR_PATH || scene->environment_medium.present) {
+        return -5;
+    }
     const uint32_t W = scene->camera.resolution[0], H = scene->camera.resolution[1];
     if (threads == 0u) threads = std::max(1u, std::thread::hardware_concurrency());
     const uint32_t ts = 16u;
@@ -1107,7 +1368,7 @@ int oracle_render(const lrk_scene_desc *scene, uint32_t spp_begin, uint32_t spp_
                     if (!owned(x, y)) continue;
                     float *px4 = film_raw + (static_cast<size_t>(y) * W + x) * 4u;
                     for (uint32_t s = spp_begin; s < spp_end; s++) {
-                        V3 li = path_li(*scene, x, y, s, &c);
+                        V3 li = sample_li(*scene, x, y, s, &c);
                         film_accumulate(px4, li * 1.0f, scene->film.clamp);// shutter weight 1
                     }
                 }
@@ -1144,7 +1405,7 @@ void oracle_convert_film(const lrk_scene_desc *scene, const float *film_raw, flo
 }
 
 void oracle_li(const lrk_scene_desc *scene, uint32_t px, uint32_t py, uint32_t sample_index, float rgb[3]) {
-    V3 li = path_li(*scene, px, py, sample_index, nullptr);
+    V3 li = sample_li(*scene, px, py, sample_index, nullptr);
     rgb[0] = li.x; rgb[1] = li.y; rgb[2] = li.z;
 }
 

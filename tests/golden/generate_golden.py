@@ -40,6 +40,9 @@ def golden_scenes():
         "cornell": scenes.cornell_box(resolution=(32, 32), spp=4),
         "cornell_disney": scenes.cornell_box(resolution=(32, 32), spp=4, surface="Disney"),
         "spheres": scenes.instanced_spheres(resolution=(32, 18), spp=2, big_subdivision=3, small_subdivision=2, small_count=10),
+        # config C4 in miniature: homogeneous environment medium + MegaVPTNaive semantics, depth 8
+        "spheres_medium": scenes.instanced_spheres(resolution=(32, 18), spp=4, big_subdivision=3, small_subdivision=2, small_count=10,
+                                                   medium=True, depth=8),
     }
 
 
