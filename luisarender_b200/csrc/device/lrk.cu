@@ -53,7 +53,7 @@ struct lrk_ctx {
     float4 *d_film_out{nullptr};
     uint32_t *d_query_cursor{nullptr};
     // options
-    bool count_traversal{false}, time_kernels{false};
+    bool count_traversal{false}, time_kernels{false}, bin_rays{false};
     // stats
     lrk_stats stats{};
     cudaEvent_t ev_begin{}, ev_end{};
@@ -136,6 +136,9 @@ int alloc_paths(lrk_ctx *ctx, uint64_t capacity) {
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.scontrib), capacity * sizeof(float4)));
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.li), capacity * sizeof(float4)));
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.counts), 7u * kMaxDepthSlots * sizeof(uint32_t)));
+    LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.ray_order), capacity * kRayBins * sizeof(uint32_t)));
+    LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.bin_counts), 2u * kMaxDepthSlots * kRayBins * sizeof(uint32_t)));
+    pb.capacity = static_cast<uint32_t>(capacity);
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.stats), 8u * sizeof(unsigned long long)));
     LRK_CUDA(cudaMemsetAsync(pb.stats, 0, 8u * sizeof(unsigned long long), ctx->stream));
     ctx->capacity = capacity;
@@ -234,18 +237,29 @@ int render_pass(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint32_t spp
             sc, pb, ctx->d_pixel_list, pixel_offset, npix, spp_begin, static_cast<uint32_t>(n));
     }
     ctx->stats.kernel_launches++;
+    const bool bin = ctx->bin_rays;
+    if (bin) LRK_CUDA(cudaMemsetAsync(pb.bin_counts, 0, 2u * kMaxDepthSlots * kRayBins * sizeof(uint32_t), ctx->stream));
     // upper bound of the live queue at depth d is n; launch persistent-size grids and let kernels read *count
     for (uint32_t depth = 0; depth < sc.max_depth; depth++) {
         const int in = depth & 1u;
+        RayOrder closest_order{nullptr, nullptr, 0u}, shadow_order{nullptr, nullptr, 0u};
+        if (bin && depth > 0u) {// camera rays are coherent as generated
+            ScopedTimer t{ctx, CAT_OTHER};
+            uint32_t *bc = pb.bin_counts + static_cast<size_t>(depth) * kRayBins;
+            bin_rays_kernel<<<blocks_for(ctx, n, ctx->grid_classify), kBlock, 0, ctx->stream>>>(pb.ray_d[in], pb.counts + depth, pb.ray_order,
+                                                                                            pb.capacity, bc);
+            closest_order = RayOrder{pb.ray_order, bc, pb.capacity};
+            ctx->stats.kernel_launches++;
+        }
         {
             ScopedTimer t{ctx, CAT_TRACE_CLOSEST};
             int g = blocks_for(ctx, n, ctx->grid_trace);
             if (ctx->count_traversal)
                 trace_closest_kernel<true><<<g, kBlock, 0, ctx->stream>>>(sc, pb.ray_o[in], pb.ray_d[in], pb.hit, pb.counts + depth,
-                                                                          pb.counts + 2u * kMaxDepthSlots + depth, pb.stats);
+                                                                          pb.counts + 2u * kMaxDepthSlots + depth, pb.stats, closest_order);
             else
                 trace_closest_kernel<false><<<g, kBlock, 0, ctx->stream>>>(sc, pb.ray_o[in], pb.ray_d[in], pb.hit, pb.counts + depth,
-                                                                           pb.counts + 2u * kMaxDepthSlots + depth, pb.stats);
+                                                                           pb.counts + 2u * kMaxDepthSlots + depth, pb.stats, closest_order);
         }
         {
             ScopedTimer t{ctx, CAT_SHADE};
@@ -254,15 +268,23 @@ int render_pass(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint32_t spp
             if (ctx->has_kind[1]) shade_kernel<1u><<<blocks_for(ctx, n, ctx->grid_shade[1]), kBlock, 0, ctx->stream>>>(sc, pb, depth);
             if (ctx->has_kind[2]) shade_kernel<2u><<<blocks_for(ctx, n, ctx->grid_shade[2]), kBlock, 0, ctx->stream>>>(sc, pb, depth);
         }
+        if (bin) {
+            ScopedTimer t{ctx, CAT_OTHER};
+            uint32_t *bc = pb.bin_counts + (static_cast<size_t>(kMaxDepthSlots) + depth) * kRayBins;
+            bin_rays_kernel<<<blocks_for(ctx, n, ctx->grid_classify), kBlock, 0, ctx->stream>>>(pb.sray_d, pb.counts + kMaxDepthSlots + depth,
+                                                                                            pb.ray_order, pb.capacity, bc);
+            shadow_order = RayOrder{pb.ray_order, bc, pb.capacity};
+            ctx->stats.kernel_launches++;
+        }
         {
             ScopedTimer t{ctx, CAT_TRACE_SHADOW};
             int g = blocks_for(ctx, n, ctx->grid_shadow);
             if (ctx->count_traversal)
                 trace_shadow_kernel<true><<<g, kBlock, 0, ctx->stream>>>(sc, pb, pb.counts + kMaxDepthSlots + depth,
-                                                                         pb.counts + 3u * kMaxDepthSlots + depth);
+                                                                         pb.counts + 3u * kMaxDepthSlots + depth, shadow_order);
             else
                 trace_shadow_kernel<false><<<g, kBlock, 0, ctx->stream>>>(sc, pb, pb.counts + kMaxDepthSlots + depth,
-                                                                          pb.counts + 3u * kMaxDepthSlots + depth);
+                                                                          pb.counts + 3u * kMaxDepthSlots + depth, shadow_order);
         }
         ctx->stats.kernel_launches += 4u + (ctx->has_kind[1] ? 1u : 0u) + (ctx->has_kind[2] ? 1u : 0u);
     }
@@ -304,10 +326,10 @@ int render_pass_volume(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint3
             int g = blocks_for(ctx, n, ctx->grid_trace);
             if (ctx->count_traversal)
                 trace_closest_kernel<true><<<g, kBlock, 0, ctx->stream>>>(sc, pb.ray_o[in], pb.ray_d[in], pb.hit, pb.counts + depth,
-                                                                          pb.counts + 2u * kMaxDepthSlots + depth, pb.stats);
+                                                                          pb.counts + 2u * kMaxDepthSlots + depth, pb.stats, RayOrder{nullptr, nullptr, 0u});
             else
                 trace_closest_kernel<false><<<g, kBlock, 0, ctx->stream>>>(sc, pb.ray_o[in], pb.ray_d[in], pb.hit, pb.counts + depth,
-                                                                           pb.counts + 2u * kMaxDepthSlots + depth, pb.stats);
+                                                                           pb.counts + 2u * kMaxDepthSlots + depth, pb.stats, RayOrder{nullptr, nullptr, 0u});
         }
         {
             ScopedTimer t{ctx, CAT_SHADE};
@@ -503,6 +525,8 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
     sc.width = s->camera.resolution[0];
     sc.height = s->camera.resolution[1];
     ctx->spp_hint = s->camera.spp;
+    if (sc.refill_below == 0u) sc.refill_below = static_cast<uint32_t>(kRefillBelow);
+    if (sc.inner_min == 0u) sc.inner_min = static_cast<uint32_t>(kInnerMin);
     ctx->volume = s->integrator.type == LRK_INTEGRATOR_VOLUME_PATH;
     for (int i = 0; i < 3; i++) {
         sc.sigma_a[i] = s->environment_medium.sigma_a[i];
@@ -544,7 +568,10 @@ int lrk_set_option(lrk_ctx *ctx, const char *name, int64_t value) {
     if (n == "count_traversal") ctx->count_traversal = value != 0;
     else if (n == "time_kernels") ctx->time_kernels = value != 0;
     else if (n == "max_paths_per_pass") ctx->max_paths = value > 0 ? static_cast<uint64_t>(value) : ctx->max_paths;
-    else if (n == "sort_by_surface" || n == "use_graph") { /* accepted; not implemented yet */ }
+    else if (n == "bin_rays") ctx->bin_rays = value != 0;
+    else if (n == "refill_below") ctx->scene.refill_below = static_cast<uint32_t>(std::min<int64_t>(std::max<int64_t>(value, 1), 32));
+    else if (n == "inner_min") ctx->scene.inner_min = static_cast<uint32_t>(std::min<int64_t>(std::max<int64_t>(value, 1), 32));
+    else if (n == "sort_by_surface" || n == "use_graph") { /* accepted; the material sort is always on, graphs not implemented */ }
     else return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_set_option: unknown option '" + n + "'");
     return LRK_OK;
 }

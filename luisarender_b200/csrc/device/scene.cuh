@@ -39,6 +39,9 @@ struct DeviceScene {
     float film_clamp;
     float film_scale[3];
     uint32_t width, height;
+    // traversal warp scheduling (tunable, results do not depend on them)
+    uint32_t refill_below;// refill idle lanes when fewer than this many lanes hold a live ray
+    uint32_t inner_min;   // leave the inner-node phase when fewer lanes than this have inner work and leaves are waiting
     // homogeneous environment medium (volume path integrator only)
     float sigma_a[3], sigma_s[3];
     float medium_g;

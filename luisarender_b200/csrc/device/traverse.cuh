@@ -28,7 +28,8 @@ namespace lrk {
 constexpr uint32_t kSentinelDone = 0xfffffffdu;
 constexpr uint32_t kSentinelExit = 0xfffffffeu;
 constexpr int kStackSize = 96;
-constexpr int kRefillBelow = 22;// refill when fewer than this many lanes of the warp hold a live ray
+constexpr int kRefillBelow = 16;// refill when fewer than this many lanes of the warp hold a live ray (swept on B200: 13-19 is a plateau)
+constexpr int kInnerMin = 8;   // leave the inner-node phase when fewer lanes than this still descend (swept: 6-10 is a plateau)
 
 struct TraversalCounters {
     uint32_t nodes, tris, xforms;
@@ -64,9 +65,30 @@ __device__ __forceinline__ bool slab(float lox, float loy, float loz, float hix,
 // this launch. `sink(finished, ray_index, hit)` is called by ALL 32 lanes together (warp-convergent) after every
 // traversal step; a lane passes finished = true exactly once per ray, with
 // hit = {inst, prim, bary.u bits, bary.v bits} (miss <=> inst == ~0u; ANY_HIT: first hit found).
+// Optional visiting order: rays binned by direction octant (bin_rays_kernel).  Position p of the launch's cursor is
+// mapped to the p-th entry of the concatenated bins; with `order == nullptr` the queue is visited in storage order.
+constexpr uint32_t kRayBins = 8u;
+struct RayOrder {
+    const uint32_t *order;     // [kRayBins][capacity] ray indices
+    const uint32_t *bin_counts;// [kRayBins]
+    uint32_t capacity;
+};
+__device__ __forceinline__ uint32_t ordered_index(const RayOrder &ro, uint32_t p) {
+    if (ro.order == nullptr) return p;
+    uint32_t start = 0u;
+#pragma unroll
+    for (uint32_t b = 0; b < kRayBins; b++) {
+        const uint32_t c = __ldg(ro.bin_counts + b);
+        if (p < start + c) return __ldg(ro.order + static_cast<size_t>(b) * ro.capacity + (p - start));
+        start += c;
+    }
+    return p;// unreachable when the bins cover [0, n)
+}
+
 template<bool ANY_HIT, bool COUNT, int STRIDE, typename Sink>
 __device__ __forceinline__ void trace_queue(const DeviceScene &sc, const float4 *__restrict__ ray_o, const float4 *__restrict__ ray_d,
-                                            uint32_t n, uint32_t *cursor, TraversalCounters &cnt, Sink &&sink) {
+                                            uint32_t n, uint32_t *cursor, TraversalCounters &cnt, Sink &&sink,
+                                            RayOrder ray_order = RayOrder{nullptr, nullptr, 0u}) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lane_lt = (1u << lane) - 1u;
     uint32_t stack[kStackSize];
@@ -86,8 +108,9 @@ __device__ __forceinline__ void trace_queue(const DeviceScene &sc, const float4 
             uint32_t base = 0u;
             if (lane == 0u) base = atomicAdd(cursor, want);
             base = __shfl_sync(0xffffffffu, base, 0);
-            const uint32_t idx = base + __popc(idle & lane_lt);
-            if (!active && idx < n) {
+            const uint32_t pos = base + __popc(idle & lane_lt);
+            if (!active && pos < n) {
+                const uint32_t idx = ordered_index(ray_order, pos);
                 float4 o = ray_o[static_cast<size_t>(idx) * STRIDE], d = ray_d[static_cast<size_t>(idx) * STRIDE];
                 world_o = v3(o.x, o.y, o.z);
                 world_d = v3(d.x, d.y, d.z);
@@ -109,7 +132,14 @@ __device__ __forceinline__ void trace_queue(const DeviceScene &sc, const float4 
         if (!__any_sync(0xffffffffu, active)) break;
         // ---- traverse until too few lanes are busy (and fresh rays are available) ---------------------------
         for (;;) {
-            while (!(node & LRK_BVH_LEAF)) {
+            // inner phase: step the lanes that stand on an inner node; lanes that have reached a leaf wait, but only while at
+            // least `inner_min` lanes still have inner work (inner_min = 1 is the classic while-while loop, 32 is if-if)
+            for (;;) {
+                const bool inner = !(node & LRK_BVH_LEAF);
+                const uint32_t n_inner = __popc(__ballot_sync(0xffffffffu, inner));
+                if (n_inner == 0u) break;
+                if (n_inner < sc.inner_min && __any_sync(0xffffffffu, active && !inner)) break;
+                if (!inner) continue;
                 const float4 *np = sc.bvh_nodes + static_cast<size_t>(node) * 4u;
                 float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
                 if (COUNT) cnt.nodes++;
@@ -130,7 +160,7 @@ __device__ __forceinline__ void trace_queue(const DeviceScene &sc, const float4 
                 }
             }
             bool finished = false;
-            if (active) {
+            if (active && (node & LRK_BVH_LEAF)) {
                 if (node == kSentinelDone) {
                     finished = true;
                 } else if (node == kSentinelExit) {
@@ -194,7 +224,7 @@ __device__ __forceinline__ void trace_queue(const DeviceScene &sc, const float4 
                 node = kSentinelDone;// idle lanes skip the inner loop
             }
             const uint32_t busy = __popc(__ballot_sync(0xffffffffu, active));
-            if (busy == 0u || (busy < static_cast<uint32_t>(kRefillBelow) && !exhausted)) break;
+            if (busy == 0u || (busy < sc.refill_below && !exhausted)) break;
         }
     }
 }
