@@ -255,63 +255,63 @@ __global__ void __launch_bounds__(kBlock) trace_query_kernel(DeviceScene sc, con
 }
 
 // ---- shade ----------------------------------------------------------------------------------------------
-template<typename Closure>
-__device__ __forceinline__ void shade_surface(const Closure &cl, const Interaction &it, V3 wo, const LightSample &ls, V3 beta,
+// Evaluates the closure for the light sample's direction (NEE term) and for the direction the closure itself samples.
+// Both evaluations run through ONE copy of the closure code (a two-trip loop that is deliberately not unrolled): the Disney
+// closure is several thousand SASS instructions and two inlined copies thrash the instruction cache.
+// VOLUME selects the direct-light weight of the volume integrator: 1 / (pdf_light + pdf_bsdf + pdf_transmittance) with
+// pdf_transmittance = 0 for an unoccluded ray (mega_vpt_naive.cpp:403-407) instead of the balance heuristic (mega_path.cpp:108-113).
+template<bool VOLUME, typename Closure>
+__device__ __forceinline__ void shade_surface(Closure &cl, const Interaction &it, V3 wo, const LightSample &ls, V3 beta,
                                               float u_lobe, float ub0, float ub1, V3 &contrib, V3 &wi_world, V3 &f_over, float &pdf_bsdf) {
     V3 wo_local = it.shading.world_to_local(wo);
-    contrib = v3(0.f);
-    if (ls.eval.pdf > 0.0f) {
-        V3 wi = v3(ls.ray_d_tmax.x, ls.ray_d_tmax.y, ls.ray_d_tmax.z);
-        SurfEval ev = cl.evaluate_local(wo_local, it.shading.world_to_local(wi));
-        if (!validate_surface_sides(it.ng, it.shading.n, wo, wi)) {
-            ev.f = v3(0.f);
-            ev.pdf = 0.f;
+    cl.prepare(wo_local);
+    V3 wi_sampled_local;
+    const bool run_sampled = cl.sample_direction(wo_local, u_lobe, ub0, ub1, wi_sampled_local);
+    wi_world = it.shading.local_to_world(wi_sampled_local);
+    const bool run_light = ls.eval.pdf > 0.0f;
+    V3 wi_w = v3(ls.ray_d_tmax.x, ls.ray_d_tmax.y, ls.ray_d_tmax.z);
+    V3 wi_l = it.shading.world_to_local(wi_w);
+    bool run = run_light;
+    SurfEval e_light;
+    e_light.f = f_over = v3(0.f);
+    e_light.pdf = pdf_bsdf = 0.f;
+#pragma unroll 1
+    for (int k = 0; k < 2; k++) {
+        SurfEval e;
+        e.f = v3(0.f);
+        e.pdf = 0.f;
+        if (run) {
+            e = cl.evaluate_local(wo_local, wi_l);
+            if (!validate_surface_sides(it.ng, it.shading.n, wo, wi_w)) {
+                e.f = v3(0.f);
+                e.pdf = 0.f;
+            }
         }
-        float w = balance_heuristic(ls.eval.pdf, ev.pdf) / ls.eval.pdf;
-        contrib = w * beta * ev.f * ls.eval.L;
-    }
-    V3 wi_local;
-    SurfEval s = cl.sample_local(wo_local, u_lobe, ub0, ub1, wi_local);
-    wi_world = it.shading.local_to_world(wi_local);
-    if (!validate_surface_sides(it.ng, it.shading.n, wo, wi_world)) {
-        s.f = v3(0.f);
-        s.pdf = 0.f;
-    }
-    f_over = s.f;
-    pdf_bsdf = s.pdf;
-}
-
-// surface shading of the volume integrator: same closures, but the direct-light weight is
-// 1 / (pdf_light + pdf_bsdf + pdf_transmittance) with pdf_transmittance = 0 for an unoccluded ray (mega_vpt_naive.cpp:403-407)
-template<typename Closure>
-__device__ __forceinline__ void volume_shade_surface(const Closure &cl, const Interaction &it, V3 wo, const LightSample &ls, V3 beta,
-                                                     float u_lobe, float ub0, float ub1, V3 &contrib, V3 &wi_world, V3 &f_over, float &pdf_bsdf) {
-    V3 wo_local = it.shading.world_to_local(wo);
-    contrib = v3(0.f);
-    if (ls.eval.pdf > 0.0f) {
-        V3 wi = v3(ls.ray_d_tmax.x, ls.ray_d_tmax.y, ls.ray_d_tmax.z);
-        SurfEval ev = cl.evaluate_local(wo_local, it.shading.world_to_local(wi));
-        if (!validate_surface_sides(it.ng, it.shading.n, wo, wi)) {
-            ev.f = v3(0.f);
-            ev.pdf = 0.f;
+        if (k == 0) {
+            e_light = e;
+            wi_w = wi_world;
+            wi_l = wi_sampled_local;
+            run = run_sampled;
+        } else {
+            f_over = e.f;
+            pdf_bsdf = e.pdf;
         }
-        float w = 1.f / (ls.eval.pdf + ev.pdf + 0.f);
-        contrib = w * beta * ev.f * ls.eval.L * v3(1.f);
     }
-    V3 wi_local;
-    SurfEval s = cl.sample_local(wo_local, u_lobe, ub0, ub1, wi_local);
-    wi_world = it.shading.local_to_world(wi_local);
-    if (!validate_surface_sides(it.ng, it.shading.n, wo, wi_world)) {
-        s.f = v3(0.f);
-        s.pdf = 0.f;
+    contrib = v3(0.f);
+    if (run_light) {
+        if (VOLUME) {
+            float w = 1.f / (ls.eval.pdf + e_light.pdf + 0.f);
+            contrib = w * beta * e_light.f * ls.eval.L * v3(1.f);
+        } else {
+            float w = balance_heuristic(ls.eval.pdf, e_light.pdf) / ls.eval.pdf;
+            contrib = w * beta * e_light.f * ls.eval.L;
+        }
     }
-    f_over = s.f;
-    pdf_bsdf = s.pdf;
 }
 
 // Sorted-by-material dispatch, step 2: one shade kernel per closure kind, each over its own hit bucket.
 template<uint32_t KIND>
-__global__ void __launch_bounds__(kBlock) shade_kernel(DeviceScene sc, PathBuffers pb, uint32_t depth) {
+__global__ void __launch_bounds__(kBlock, 2) shade_kernel(DeviceScene sc, PathBuffers pb, uint32_t depth) {
     __shared__ uint32_t s_warp_next[kBlock / 32], s_warp_shadow[kBlock / 32];
     __shared__ uint32_t s_base_next, s_base_shadow;
     const uint32_t n = pb.counts[(4u + KIND) * kMaxDepthSlots + depth];// size of this kind's hit bucket
@@ -366,11 +366,11 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(DeviceScene sc, PathBuffe
                     if (KIND == 1u) {
                         MatteClosure cl;
                         cl.init(*surf);
-                        shade_surface(cl, it, wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
+                        shade_surface<false>(cl, it, wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
                     } else {
                         DisneyClosure cl;
                         cl.init(*surf);
-                        shade_surface(cl, it, wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
+                        shade_surface<false>(cl, it, wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
                     }
                     if (contrib.x != 0.f || contrib.y != 0.f || contrib.z != 0.f) {
                         // a zero (or NaN-free zero) contribution needs no shadow ray; NaNs must reach the film filter
@@ -713,11 +713,11 @@ __global__ void __launch_bounds__(kBlock) volume_shade_kernel(DeviceScene sc, Pa
                         if (surf->type == LRK_SURFACE_MATTE) {
                             MatteClosure cl;
                             cl.init(*surf);
-                            volume_shade_surface(cl, it, wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
+                            shade_surface<true>(cl, it, wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
                         } else {
                             DisneyClosure cl;
                             cl.init(*surf);
-                            volume_shade_surface(cl, it, wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
+                            shade_surface<true>(cl, it, wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
                         }
                         push_shadow = true;// always traced: its occlusion advances the PCG stream of the next bounce
                         sro = ls.ray_o_tmin;

@@ -281,6 +281,7 @@ struct MatteClosure {
         a = 1.f - (sigma2 / (2.f * sigma2 + 0.66f));
         b = 0.45f * sigma2 / (sigma2 + 0.09f);
     }
+    __device__ __forceinline__ void prepare(V3) {}
     __device__ __forceinline__ V3 oren_nayar(V3 wo, V3 wi) const {
         float s = same_hemisphere(wo, wi) ? kInvPi : 0.f;
         float sinThetaI = sin_theta(wi), sinThetaO = sin_theta(wo);
@@ -300,13 +301,11 @@ struct MatteClosure {
         e.pdf = lambert_pdf(wo, wi);
         return e;
     }
-    __device__ __forceinline__ SurfEval sample_local(V3 wo, float, float u0, float u1, V3 &wi) const {
+    // matte.cpp:118-134: cosine-hemisphere direction on wo's side; the sample's f and pdf are evaluate_local at that direction
+    __device__ __forceinline__ bool sample_direction(V3 wo, float, float u0, float u1, V3 &wi) const {
         wi = sample_cosine_hemisphere(u0, u1);
         wi.z *= sign(cos_theta(wo));
-        SurfEval e;
-        e.pdf = lambert_pdf(wo, wi);
-        e.f = oren_nayar(wo, wi) * abs_cos_theta(wi);
-        return e;
+        return true;
     }
 };
 
@@ -481,63 +480,41 @@ struct DisneyClosure {
         enabled2 = en2;
     }
     bool enabled0, enabled2;
+    // values that depend on wo (or on constants) only, shared by the light-direction and the sampled-direction
+    // evaluations of one shading point; every one is the same expression the per-lobe formulas contain
+    // (disney.cpp:95-303), hoisted — not re-associated — so results stay bit-identical to the oracle.
+    float lambda_o, g1_o, schlick_o, ggx_o, gtr1_a2m1, gtr1_pi_log_a2;
 
+    __device__ __forceinline__ void prepare(V3 wo) {
+        lambda_o = distrib.Lambda(wo);
+        g1_o = 1.0f / (1.0f + lambda_o);
+        schlick_o = SchlickWeight(abs_cos_theta(wo));
+        ggx_o = smithG_GGX(abs_cos_theta(wo), .25f);
+        float alpha2 = sqr(gloss);
+        gtr1_a2m1 = alpha2 - 1.f;
+        gtr1_pi_log_a2 = kPi * logf(alpha2);
+    }
     __device__ __forceinline__ V3 disney_fresnel(float cosI_in) const {
         float cosI = fabsf(cosI_in);
         float fr = fresnel_dielectric(cosI, 1.f, fresnel_eta);
         V3 f0 = v3(FrSchlick(Cspec0.x, cosI), FrSchlick(Cspec0.y, cosI), FrSchlick(Cspec0.z, cosI));
         return lerp(v3(fr), f0, metallic);
     }
-    __device__ __forceinline__ V3 specular_evaluate(V3 wo, V3 wi) const {
-        V3 wh = wi + wo;
-        V3 f = v3(0.f);
-        if (same_hemisphere(wo, wi) && any_nonzero(wh)) {
-            wh = normalize(wh);
-            V3 F = disney_fresnel(dot(wi, face_forward(wh, v3(0.f, 0.f, 1.f))));
-            float D = distrib.D(wh);
-            float G = distrib.G(wo, wi);
-            float cos_o = cos_theta(wo), cos_i = cos_theta(wi);
-            f = v3(1.f) * F * fabsf(0.25f * D * G / (cos_i * cos_o));
-        }
-        return f;
-    }
-    __device__ __forceinline__ float specular_pdf(V3 wo, V3 wi) const {
-        float p = 0.f;
-        V3 wh = wi + wo;
-        if (same_hemisphere(wo, wi) && any_nonzero(wh)) {
-            wh = normalize(wh);
-            p = distrib.pdf(wo, wh) / (4.f * dot(wo, wh));
-        }
-        return p;
-    }
-    __device__ __forceinline__ float clearcoat_evaluate(V3 wo, V3 wi) const {
-        V3 wh = wi + wo;
-        bool valid = any_nonzero(wh);
-        wh = normalize(wh);
-        float Dr = GTR1(abs_cos_theta(wh), gloss);
-        float Fr = FrSchlick(.04f, dot(wo, wh));
-        float Gr = smithG_GGX(abs_cos_theta(wo), .25f) * smithG_GGX(abs_cos_theta(wi), .25f);
-        return valid ? clearcoat * Gr * Fr * Dr * .25f : 0.f;
-    }
-    __device__ __forceinline__ float clearcoat_pdf(V3 wo, V3 wi) const {
-        V3 wh = wi + wo;
-        bool valid = same_hemisphere(wo, wi) && any_nonzero(wh);
-        wh = normalize(wh);
-        float Dr = GTR1(abs_cos_theta(wh), gloss);
-        return valid ? Dr * abs_cos_theta(wh) / (4.f * dot(wo, wh)) : 0.f;
-    }
     __device__ __forceinline__ SurfEval evaluate_local(V3 wo, V3 wi) const {
         V3 f = v3(0.f);
         float pdf = 0.f;
         if (same_hemisphere(wo, wi)) {
+            // the half vector every lobe uses (DisneyRetro/FakeSS/Sheen :118-190, MicrofacetReflection scattering.cpp:286-320,
+            // DisneyClearcoat :215-260)
+            V3 whs = wi + wo;
+            bool valid = any_nonzero(whs);
+            V3 wh = normalize(whs);
+            float cosThetaD = dot(wi, wh);
+            float wo_dot_wh = dot(wo, wh);
             if (has_diffuse) {
                 if (w0 > 0.f) {
-                    float Fo = SchlickWeight(abs_cos_theta(wo)), Fi = SchlickWeight(abs_cos_theta(wi));
+                    float Fo = schlick_o, Fi = SchlickWeight(abs_cos_theta(wi));
                     f = f + Cdiff * (kInvPi * (1.f - Fo * .5f) * (1.f - Fi * .5f));
-                    V3 wh = wi + wo;
-                    bool valid = any_nonzero(wh);
-                    wh = normalize(wh);
-                    float cosThetaD = dot(wi, wh);
                     {// DisneyRetro
                         float Rr = 2.f * roughness * cosThetaD * cosThetaD;
                         f = f + Cdiff * (valid ? kInvPi * Rr * (Fo + Fi + Fo * Fi * (Rr - 1.f)) : 0.f);
@@ -553,13 +530,28 @@ struct DisneyClosure {
                 }
             }
             if (w1 > 0.f) {
-                f = f + specular_evaluate(wo, wi);
-                pdf += w1 * specular_pdf(wo, wi);
+                V3 fs = v3(0.f);
+                float ps = 0.f;
+                if (valid) {
+                    // dot(wi, face_forward(wh, +z)) = +-dot(wi, wh) and the Fresnel term takes its absolute value
+                    V3 F = disney_fresnel(cosThetaD);
+                    float D = distrib.D(wh);
+                    float G = 1.0f / (1.0f + lambda_o + distrib.Lambda(wi));
+                    float cos_o = cos_theta(wo), cos_i = cos_theta(wi);
+                    fs = v3(1.f) * F * fabsf(0.25f * D * G / (cos_i * cos_o));
+                    ps = (D * g1_o * fabsf(wo_dot_wh) / abs_cos_theta(wo)) / (4.f * wo_dot_wh);
+                }
+                f = f + fs;
+                pdf += w1 * ps;
             }
             if (has_clearcoat) {
                 if (w2 > 0.f) {
-                    f = f + clearcoat_evaluate(wo, wi);
-                    pdf += w2 * clearcoat_pdf(wo, wi);
+                    float cos_h = abs_cos_theta(wh);
+                    float Dr = gtr1_a2m1 / (gtr1_pi_log_a2 * (1.f + gtr1_a2m1 * sqr(cos_h)));
+                    float Fr = FrSchlick(.04f, wo_dot_wh);
+                    float Gr = ggx_o * smithG_GGX(abs_cos_theta(wi), .25f);
+                    f = f + (valid ? clearcoat * Gr * Fr * Dr * .25f : 0.f);
+                    pdf += w2 * (valid ? Dr * cos_h / (4.f * wo_dot_wh) : 0.f);
                 }
             }
         }
@@ -568,7 +560,7 @@ struct DisneyClosure {
         e.pdf = pdf;
         return e;
     }
-    __device__ __forceinline__ SurfEval sample_local(V3 wo, float u_lobe, float u0, float u1, V3 &wi) const {
+    __device__ __forceinline__ bool sample_direction(V3 wo, float u_lobe, float u0, float u1, V3 &wi) const {
         // technique selection: src/surfaces/disney.cpp:544-551 (strict '>' against the running sum)
         uint32_t tech = 0u;
         float sum_weights = 0.f;
@@ -608,11 +600,7 @@ struct DisneyClosure {
                 valid = same_hemisphere(wo, wi);
             }
         }
-        SurfEval e;
-        e.f = v3(0.f);
-        e.pdf = 0.f;
-        if (valid) e = evaluate_local(wo, wi);
-        return e;
+        return valid;// f and pdf of the sample are evaluate_local(wo, wi) (disney.cpp:583-586)
     }
 };
 
