@@ -22,6 +22,13 @@
 namespace lrk {
 
 constexpr int kBlock = 256;
+#ifndef LRK_SHADE_BLOCK
+#define LRK_SHADE_BLOCK 256
+#endif
+#ifndef LRK_SHADE_MIN_BLOCKS
+#define LRK_SHADE_MIN_BLOCKS 2
+#endif
+constexpr int kShadeBlock = LRK_SHADE_BLOCK;// threads per block of the surface shade kernels (register-bound: see DESIGN.md)
 constexpr uint32_t kMaxDepthSlots = 64u;// counts[0..63]: path queue size per depth, counts[64..127]: shadow queue size
 
 struct PathBuffers {
@@ -311,8 +318,8 @@ __device__ __forceinline__ void shade_surface(Closure &cl, const Interaction &it
 
 // Sorted-by-material dispatch, step 2: one shade kernel per closure kind, each over its own hit bucket.
 template<uint32_t KIND>
-__global__ void __launch_bounds__(kBlock, 2) shade_kernel(DeviceScene sc, PathBuffers pb, uint32_t depth) {
-    __shared__ uint32_t s_warp_next[kBlock / 32], s_warp_shadow[kBlock / 32];
+__global__ void __launch_bounds__(kShadeBlock, LRK_SHADE_MIN_BLOCKS) shade_kernel(DeviceScene sc, PathBuffers pb, uint32_t depth) {
+    __shared__ uint32_t s_warp_next[kShadeBlock / 32], s_warp_shadow[kShadeBlock / 32];
     __shared__ uint32_t s_base_next, s_base_shadow;
     const uint32_t n = pb.counts[(4u + KIND) * kMaxDepthSlots + depth];// size of this kind's hit bucket
     const int in = depth & 1u, out = in ^ 1;
@@ -412,7 +419,7 @@ __global__ void __launch_bounds__(kBlock, 2) shade_kernel(DeviceScene sc, PathBu
         __syncthreads();
         if (threadIdx.x == 0u) {
             uint32_t tn = 0u, ts = 0u;
-            for (int w = 0; w < kBlock / 32; w++) {
+            for (int w = 0; w < kShadeBlock / 32; w++) {
                 uint32_t a = s_warp_next[w], b = s_warp_shadow[w];
                 s_warp_next[w] = tn;
                 s_warp_shadow[w] = ts;
