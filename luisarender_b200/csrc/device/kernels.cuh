@@ -496,8 +496,7 @@ __device__ __forceinline__ void medium_light_shadow_ray(const DeviceScene &sc, V
     uint32_t triangle_id = keep ? i : entry.alias;
     float ux = keep ? u_remapped / entry.prob : (u_remapped - entry.prob) / (1.0f - entry.prob);
     V3 uvw = sample_uniform_triangle(ux, u1);
-    Interaction it_light = make_interaction(sc, handle.instance_id, triangle_id, uvw);
-    V3 Lv = it_light.pg - p_from;
+    V3 Lv = hit_position(sc, handle.instance_id, triangle_id, uvw) - p_from;
     float d = length(Lv);
     V3 dir = Lv * (1.f / d);
     ro = make_float4(p_from.x, p_from.y, p_from.z, 0.f);
@@ -588,7 +587,7 @@ __global__ void __launch_bounds__(kBlock) trace_volume_nee_kernel(DeviceScene sc
     }
 }
 
-__global__ void __launch_bounds__(kBlock) volume_shade_kernel(DeviceScene sc, PathBuffers pb, uint32_t depth) {
+__global__ void __launch_bounds__(kBlock, 2) volume_shade_kernel(DeviceScene sc, PathBuffers pb, uint32_t depth) {
     __shared__ uint32_t s_warp_next[kBlock / 32], s_warp_shadow[kBlock / 32];
     __shared__ uint32_t s_base_next, s_base_shadow;
     const uint32_t n = pb.counts[depth];
@@ -620,14 +619,9 @@ __global__ void __launch_bounds__(kBlock) volume_shade_kernel(DeviceScene sc, Pa
             uint32_t state = ir.y;
             V3 o = v3(ro.x, ro.y, ro.z), d = v3(rd.x, rd.y, rd.z);
             const bool valid = hit.x != ~0u;
-            Interaction it;
+            const float bu = __uint_as_float(hit.z), bv = __uint_as_float(hit.w);
             float t_max = kFltMax;
-            if (valid) {
-                float bu = __uint_as_float(hit.z), bv = __uint_as_float(hit.w);
-                it = make_interaction(sc, hit.x, hit.y, v3(1.f - bu - bv, bu, bv));
-                it.back_facing = dot(-d, it.ng) < 0.0f;
-                t_max = length(it.pg - o);
-            }
+            if (valid) t_max = length(hit_position(sc, hit.x, hit.y, v3(1.f - bu - bv, bu, bv)) - o);// the full interaction: surface events only
             // HomogeneousMediumClosure::sample, homogeneous.cpp:48-118
             V3 pch;
             pch.x = rng.uniform_float();
@@ -693,6 +687,8 @@ __global__ void __launch_bounds__(kBlock) volume_shade_kernel(DeviceScene sc, Pa
                 if (!valid) {
                     alive = false;
                 } else {
+                    Interaction it = make_interaction(sc, hit.x, hit.y, v3(1.f - bu - bv, bu, bv));
+                    it.back_facing = dot(-d, it.ng) < 0.0f;
                     if (it.shape.has_light()) {// evaluate_hit from the MOVED ray origin (mega_vpt_naive.cpp:308,319)
                         LightEval e = evaluate_hit(sc, it, no);
                         V3 add = beta * e.L * balance_heuristic(pdf_bsdf, e.pdf);

