@@ -587,41 +587,92 @@ __global__ void __launch_bounds__(kBlock) trace_volume_nee_kernel(DeviceScene sc
     }
 }
 
-__global__ void __launch_bounds__(kBlock, 2) volume_shade_kernel(DeviceScene sc, PathBuffers pb, uint32_t depth) {
-    __shared__ uint32_t s_warp_next[kBlock / 32], s_warp_shadow[kBlock / 32];
-    __shared__ uint32_t s_base_next, s_base_shadow;
+// What a path carries into the next depth of the volume integrator (the queues of the next wave).
+struct VolumeNext {
+    bool push;
+    float4 ro, rd, beta, s1o, s1d;
+    uint2 id;
+    ulonglong2 pcg;
+    float u_rr;
+};
+
+// End of one loop iteration of mega_vpt_naive.cpp:439-452 (NaN guard, Russian roulette) and, for the survivors, the draws at
+// the top of the next iteration (:256-273): u_rr, then the in-medium light sample whose shadow ray the next wave traces.
+__device__ __forceinline__ void volume_continue(const DeviceScene &sc, uint32_t depth, bool alive, V3 beta, float pdf_bsdf, float u_rr,
+                                                V3 next_o, V3 next_d, uint32_t path_id, uint32_t state, const PCG32 &rng, VolumeNext &nx) {
+    nx.push = false;
+    nx.u_rr = 0.f;
+    if (alive) {
+        if (isnan(beta.x) || isnan(beta.y) || isnan(beta.z)) beta = v3(0.f);
+        alive = !(beta.x <= 0.f && beta.y <= 0.f && beta.z <= 0.f);
+        if (alive) {
+            float q = fmaxf(max3(beta) * 1.f, .05f);
+            if (depth + 1u >= sc.rr_depth) {
+                if (q < sc.rr_threshold && u_rr >= q) alive = false;
+                beta = beta * (q < sc.rr_threshold ? 1.0f / q : 1.f);
+            }
+        }
+    }
+    if (alive && depth + 1u < sc.max_depth) {
+        nx.push = true;
+        if (depth + 2u >= sc.rr_depth) nx.u_rr = lcg(state);
+        float u_sel = lcg(state), ul0 = lcg(state), ul1 = lcg(state);
+        medium_light_shadow_ray(sc, next_o, u_sel, ul0, ul1, nx.s1o, nx.s1d);
+        nx.ro = make_float4(next_o.x, next_o.y, next_o.z, 0.f);
+        nx.rd = make_float4(next_d.x, next_d.y, next_d.z, kFltMax);
+        nx.beta = make_float4(beta.x, beta.y, beta.z, pdf_bsdf);
+        nx.id = make_uint2(path_id, state);
+        nx.pcg = make_ulonglong2(rng.state, rng.inc);
+    }
+}
+
+__device__ __forceinline__ void volume_store_next(const PathBuffers &pb, int out, uint32_t slot, const VolumeNext &nx) {
+    pb.ray_o[out][slot] = nx.ro;
+    pb.ray_d[out][slot] = nx.rd;
+    pb.beta_pdf[out][slot] = nx.beta;
+    pb.id_rng[out][slot] = nx.id;
+    pb.pcg[out][slot] = nx.pcg;
+    pb.u_rr[out][slot] = nx.u_rr;
+    pb.s1ray_o[slot] = nx.s1o;
+    pb.s1ray_d[slot] = nx.s1d;
+    pb.occl2[out][slot] = 0u;
+}
+
+// Volume wave, step 1 (every path of the depth): advance the PCG32 stream by the occlusion results, sample the medium
+// along the ray (homogeneous.cpp:48-118).  Absorption / scattering events finish here; paths that reach their surface hit
+// (event 3) write their updated throughput, pdf, PCG state and the MOVED ray origin back in place and are appended to the
+// hit bucket of their closure kind - the same material sort as the surface integrator - for volume_surface_kernel.
+__global__ void __launch_bounds__(kBlock) volume_medium_kernel(DeviceScene sc, PathBuffers pb, uint32_t depth) {
+    constexpr uint32_t kLists = 1u + kHitKinds;// list 0 = next wave, 1 + k = hit bucket k
+    __shared__ uint32_t s_warp[kLists][kBlock / 32];
+    __shared__ uint32_t s_base[kLists];
     const uint32_t n = pb.counts[depth];
     const int in = depth & 1u, out = in ^ 1;
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5u;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5u, lane_lt = (1u << lane) - 1u;
     const V3 sigma_a = v3(sc.sigma_a[0], sc.sigma_a[1], sc.sigma_a[2]), sigma_s = v3(sc.sigma_s[0], sc.sigma_s[1], sc.sigma_s[2]);
     const V3 sigma_t = sigma_a + sigma_s;
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
         const uint32_t i = base + threadIdx.x;
-        bool push_next = false, push_shadow = false;
-        float4 nro, nrd, nbeta, sro, srd, scon, n1o, n1d;
-        uint2 nid;
-        ulonglong2 npcg;
-        float nurr = 0.f;
+        uint32_t list = ~0u;// which list this item is appended to, if any
+        VolumeNext nx;
+        nx.push = false;
         if (i < n) {
             const uint4 hit = pb.hit[i];
             float4 ro = pb.ray_o[in][i], rd = pb.ray_d[in][i];
             float4 bp = pb.beta_pdf[in][i];
             uint2 ir = pb.id_rng[in][i];
             ulonglong2 pc = pb.pcg[in][i];
-            const float u_rr = pb.u_rr[in][i];
             PCG32 rng{pc.x, pc.y};
             // transmittance rays that hit a surface consumed three draws each: previous bounce's surface NEE, then this
             // bounce's in-medium direct light (their contribution is f = Tr * bsdf(-d, d) = 0 for opaque closures)
             if (pb.occl2[in][i] != 0u) { rng.uniform_uint(); rng.uniform_uint(); rng.uniform_uint(); }
             if (pb.occl1[i] != 0u) { rng.uniform_uint(); rng.uniform_uint(); rng.uniform_uint(); }
             V3 beta = v3(bp.x, bp.y, bp.z);
-            float pdf_bsdf = bp.w;
-            uint32_t state = ir.y;
             V3 o = v3(ro.x, ro.y, ro.z), d = v3(rd.x, rd.y, rd.z);
             const bool valid = hit.x != ~0u;
             const float bu = __uint_as_float(hit.z), bv = __uint_as_float(hit.w);
             float t_max = kFltMax;
-            if (valid) t_max = length(hit_position(sc, hit.x, hit.y, v3(1.f - bu - bv, bu, bv)) - o);// the full interaction: surface events only
+            if (valid) t_max = length(hit_position(sc, hit.x, hit.y, v3(1.f - bu - bv, bu, bv)) - o);
             // HomogeneousMediumClosure::sample, homogeneous.cpp:48-118
             V3 pch;
             pch.x = rng.uniform_float();
@@ -679,87 +730,121 @@ __global__ void __launch_bounds__(kBlock, 2) volume_shade_kernel(DeviceScene sc,
             {
                 float w = mpdf > 0.f ? 1.f / mpdf : 0.f;
                 beta = beta * (mf * w);
-                pdf_bsdf = mpdf;
             }
-            bool alive = true;
-            V3 next_o = no, next_d = nd;
             if (event == 3u) {
-                if (!valid) {
-                    alive = false;
-                } else {
-                    Interaction it = make_interaction(sc, hit.x, hit.y, v3(1.f - bu - bv, bu, bv));
-                    it.back_facing = dot(-d, it.ng) < 0.0f;
-                    if (it.shape.has_light()) {// evaluate_hit from the MOVED ray origin (mega_vpt_naive.cpp:308,319)
-                        LightEval e = evaluate_hit(sc, it, no);
-                        V3 add = beta * e.L * balance_heuristic(pdf_bsdf, e.pdf);
-                        float4 li = pb.li[ir.x];
-                        li.x += add.x;
-                        li.y += add.y;
-                        li.z += add.z;
-                        pb.li[ir.x] = li;
-                    }
-                    if (!it.shape.has_surface()) {
-                        alive = false;
-                    } else {
-                        float u_sel = lcg(state);
-                        float ul0 = lcg(state), ul1 = lcg(state);
-                        float u_lobe = lcg(state);
-                        float ub0 = lcg(state), ub1 = lcg(state);
-                        LightSample ls = sample_light(sc, it, u_sel, ul0, ul1);
-                        const lrk_surface *surf = sc.surfaces + it.shape.surface_tag;
-                        V3 wo = -d;
-                        V3 contrib = v3(0.f), wi, f;
-                        float pdf;
-                        if (sc.medium_priority != 0u && false) {
-                            // true_hit(medium_tag = 0) <=> 0 <= priority: always true (medium_tracker.cpp:19-21)
-                        }
-                        if (surf->type == LRK_SURFACE_MATTE) {
-                            MatteClosure cl;
-                            cl.init(*surf);
-                            shade_surface<true>(cl, it, wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
-                        } else {
-                            DisneyClosure cl;
-                            cl.init(*surf);
-                            shade_surface<true>(cl, it, wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
-                        }
-                        push_shadow = true;// always traced: its occlusion advances the PCG stream of the next bounce
-                        sro = ls.ray_o_tmin;
-                        srd = ls.ray_d_tmax;
-                        scon = make_float4(contrib.x, contrib.y, contrib.z, __uint_as_float(ir.x));
-                        next_o = p_robust(it, wi);
-                        next_d = wi;
-                        float w = pdf > 0.f ? 1.f / pdf : 0.f;
-                        pdf_bsdf = pdf;
-                        beta = beta * (w * f);
-                    }
+                if (valid) {// surface event: handed to volume_surface_kernel<kind>
+                    list = 1u + __ldg(sc.inst_kind + hit.x);
+                    pb.ray_o[in][i] = make_float4(no.x, no.y, no.z, ro.w);
+                    pb.beta_pdf[in][i] = make_float4(beta.x, beta.y, beta.z, mpdf);
+                    pb.pcg[in][i] = make_ulonglong2(rng.state, rng.inc);
                 }
+            } else {
+                volume_continue(sc, depth, true, beta, mpdf, pb.u_rr[in][i], no, nd, ir.x, ir.y, rng, nx);
+                if (nx.push) list = 0u;
             }
-            if (alive) {
-                if (isnan(beta.x) || isnan(beta.y) || isnan(beta.z)) beta = v3(0.f);
-                alive = !(beta.x <= 0.f && beta.y <= 0.f && beta.z <= 0.f);
-                if (alive) {
-                    float q = fmaxf(max3(beta) * 1.f, .05f);
-                    if (depth + 1u >= sc.rr_depth) {
-                        if (q < sc.rr_threshold && u_rr >= q) alive = false;
-                        beta = beta * (q < sc.rr_threshold ? 1.0f / q : 1.f);
-                    }
-                }
-            }
-            if (alive && depth + 1u < sc.max_depth) {
-                push_next = true;
-                // draws at the top of the next iteration: u_rr, then the in-medium light sample (mega_vpt_naive.cpp:256-273)
-                if (depth + 2u >= sc.rr_depth) nurr = lcg(state);
-                float u_sel = lcg(state), ul0 = lcg(state), ul1 = lcg(state);
-                medium_light_shadow_ray(sc, next_o, u_sel, ul0, ul1, n1o, n1d);
-                nro = make_float4(next_o.x, next_o.y, next_o.z, 0.f);
-                nrd = make_float4(next_d.x, next_d.y, next_d.z, kFltMax);
-                nbeta = make_float4(beta.x, beta.y, beta.z, pdf_bsdf);
-                nid = make_uint2(ir.x, state);
-                npcg = make_ulonglong2(rng.state, rng.inc);
-            }
-            if (push_shadow && !push_next && scon.x == 0.f && scon.y == 0.f && scon.z == 0.f) push_shadow = false;// nothing depends on it
         }
-        uint32_t m_next = __ballot_sync(0xffffffffu, push_next);
+        uint32_t masks[kLists];
+#pragma unroll
+        for (uint32_t k = 0; k < kLists; k++) {
+            masks[k] = __ballot_sync(0xffffffffu, list == k);
+            if (lane == 0u) s_warp[k][warp] = __popc(masks[k]);
+        }
+        __syncthreads();
+        if (threadIdx.x < kLists) {
+            const uint32_t k = threadIdx.x;
+            uint32_t total = 0u;
+            for (int w = 0; w < kBlock / 32; w++) {
+                uint32_t c = s_warp[k][w];
+                s_warp[k][w] = total;
+                total += c;
+            }
+            uint32_t *counter = k == 0u ? pb.counts + depth + 1u : pb.counts + (4u + (k - 1u)) * kMaxDepthSlots + depth;
+            s_base[k] = total ? atomicAdd(counter, total) : 0u;
+        }
+        __syncthreads();
+        if (list != ~0u) {
+            uint32_t slot = s_base[list] + s_warp[list][warp];
+#pragma unroll
+            for (uint32_t k = 0; k < kLists; k++)
+                if (list == k) slot += __popc(masks[k] & lane_lt);
+            if (list == 0u) volume_store_next(pb, out, slot, nx);
+            else pb.hit_index[list - 1u][slot] = i;
+        }
+        __syncthreads();
+    }
+}
+
+// Volume wave, step 2 (surface events of one closure kind): emitter hit seen from the moved origin, surface NEE +
+// closure sample (mega_vpt_naive.cpp:300-437), then the common end of the iteration.
+template<uint32_t KIND>
+__global__ void __launch_bounds__(kBlock, 2) volume_surface_kernel(DeviceScene sc, PathBuffers pb, uint32_t depth) {
+    __shared__ uint32_t s_warp_next[kBlock / 32], s_warp_shadow[kBlock / 32];
+    __shared__ uint32_t s_base_next, s_base_shadow;
+    const uint32_t n = pb.counts[(4u + KIND) * kMaxDepthSlots + depth];
+    const int in = depth & 1u, out = in ^ 1;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5u;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const uint32_t j = base + threadIdx.x;
+        bool push_shadow = false;
+        float4 sro, srd, scon;
+        VolumeNext nx;
+        nx.push = false;
+        if (j < n) {
+            const uint32_t i = pb.hit_index[KIND][j];
+            const uint4 hit = pb.hit[i];
+            float4 ro = pb.ray_o[in][i], rd = pb.ray_d[in][i];// ro = the origin moved onto the surface by the medium step
+            float4 bp = pb.beta_pdf[in][i];
+            uint2 ir = pb.id_rng[in][i];
+            ulonglong2 pc = pb.pcg[in][i];
+            PCG32 rng{pc.x, pc.y};
+            V3 beta = v3(bp.x, bp.y, bp.z);
+            float pdf_bsdf = bp.w;
+            uint32_t state = ir.y;
+            V3 no = v3(ro.x, ro.y, ro.z), d = v3(rd.x, rd.y, rd.z);
+            const float bu = __uint_as_float(hit.z), bv = __uint_as_float(hit.w);
+            Interaction it = make_interaction(sc, hit.x, hit.y, v3(1.f - bu - bv, bu, bv));
+            it.back_facing = dot(-d, it.ng) < 0.0f;
+            if (it.shape.has_light()) {// evaluate_hit from the MOVED ray origin (mega_vpt_naive.cpp:308,319)
+                LightEval e = evaluate_hit(sc, it, no);
+                V3 add = beta * e.L * balance_heuristic(pdf_bsdf, e.pdf);
+                float4 li = pb.li[ir.x];
+                li.x += add.x;
+                li.y += add.y;
+                li.z += add.z;
+                pb.li[ir.x] = li;
+            }
+            if (KIND != 0u) {
+                float u_sel = lcg(state);
+                float ul0 = lcg(state), ul1 = lcg(state);
+                float u_lobe = lcg(state);
+                float ub0 = lcg(state), ub1 = lcg(state);
+                LightSample ls = sample_light(sc, it, u_sel, ul0, ul1);
+                const lrk_surface *surf = sc.surfaces + it.shape.surface_tag;
+                V3 wo = -d;
+                V3 contrib = v3(0.f), wi, f;
+                float pdf;
+                // true_hit(medium_tag = 0) <=> 0 <= priority of the environment medium: always true (medium_tracker.cpp:19-21)
+                if (KIND == 1u) {
+                    MatteClosure cl;
+                    cl.init(*surf);
+                    shade_surface<true>(cl, it, wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
+                } else {
+                    DisneyClosure cl;
+                    cl.init(*surf);
+                    shade_surface<true>(cl, it, wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
+                }
+                push_shadow = true;// traced even with a zero contribution: its occlusion advances the PCG stream of the next bounce
+                sro = ls.ray_o_tmin;
+                srd = ls.ray_d_tmax;
+                scon = make_float4(contrib.x, contrib.y, contrib.z, __uint_as_float(ir.x));
+                V3 next_o = p_robust(it, wi);
+                float w = pdf > 0.f ? 1.f / pdf : 0.f;
+                beta = beta * (w * f);
+                volume_continue(sc, depth, true, beta, pdf, pb.u_rr[in][i], next_o, wi, ir.x, state, rng, nx);
+                if (!nx.push && scon.x == 0.f && scon.y == 0.f && scon.z == 0.f) push_shadow = false;// nothing depends on it
+            }
+        }
+        uint32_t m_next = __ballot_sync(0xffffffffu, nx.push);
         uint32_t m_shadow = __ballot_sync(0xffffffffu, push_shadow);
         if (lane == 0u) {
             s_warp_next[warp] = __popc(m_next);
@@ -781,17 +866,9 @@ __global__ void __launch_bounds__(kBlock, 2) volume_shade_kernel(DeviceScene sc,
         __syncthreads();
         const uint32_t lt = (1u << lane) - 1u;
         uint32_t next_slot = ~0u;
-        if (push_next) {
+        if (nx.push) {
             next_slot = s_base_next + s_warp_next[warp] + __popc(m_next & lt);
-            pb.ray_o[out][next_slot] = nro;
-            pb.ray_d[out][next_slot] = nrd;
-            pb.beta_pdf[out][next_slot] = nbeta;
-            pb.id_rng[out][next_slot] = nid;
-            pb.pcg[out][next_slot] = npcg;
-            pb.u_rr[out][next_slot] = nurr;
-            pb.s1ray_o[next_slot] = n1o;
-            pb.s1ray_d[next_slot] = n1d;
-            pb.occl2[out][next_slot] = 0u;
+            volume_store_next(pb, out, next_slot, nx);
         }
         if (push_shadow) {
             uint32_t slot = s_base_shadow + s_warp_shadow[warp] + __popc(m_shadow & lt);

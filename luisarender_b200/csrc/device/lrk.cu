@@ -63,7 +63,7 @@ struct lrk_ctx {
     bool has_kind[3]{true, false, false};
     bool volume{false};
     uint64_t volume_capacity{0};
-    int grid_vshade{0}, grid_vshadow{0};
+    int grid_vshade[3]{0, 0, 0}, grid_vmedium{0}, grid_vshadow{0};
 };
 
 namespace {
@@ -333,7 +333,10 @@ int render_pass_volume(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint3
         }
         {
             ScopedTimer t{ctx, CAT_SHADE};
-            volume_shade_kernel<<<blocks_for(ctx, n, ctx->grid_vshade), kBlock, 0, ctx->stream>>>(sc, pb, depth);
+            volume_medium_kernel<<<blocks_for(ctx, n, ctx->grid_vmedium), kBlock, 0, ctx->stream>>>(sc, pb, depth);
+            volume_surface_kernel<0u><<<blocks_for(ctx, n, ctx->grid_vshade[0]), kBlock, 0, ctx->stream>>>(sc, pb, depth);
+            if (ctx->has_kind[1]) volume_surface_kernel<1u><<<blocks_for(ctx, n, ctx->grid_vshade[1]), kBlock, 0, ctx->stream>>>(sc, pb, depth);
+            if (ctx->has_kind[2]) volume_surface_kernel<2u><<<blocks_for(ctx, n, ctx->grid_vshade[2]), kBlock, 0, ctx->stream>>>(sc, pb, depth);
         }
         {
             ScopedTimer t{ctx, CAT_TRACE_SHADOW};
@@ -345,7 +348,7 @@ int render_pass_volume(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint3
                 trace_volume_nee_kernel<false><<<g, kBlock, 0, ctx->stream>>>(sc, pb, pb.counts + kMaxDepthSlots + depth,
                                                                               pb.counts + 3u * kMaxDepthSlots + depth, pb.occl2[out]);
         }
-        ctx->stats.kernel_launches += 4;
+        ctx->stats.kernel_launches += 5u + (ctx->has_kind[1] ? 1u : 0u) + (ctx->has_kind[2] ? 1u : 0u);
     }
     {
         ScopedTimer t{ctx, CAT_OTHER};
@@ -404,7 +407,10 @@ int lrk_create(const lrk_device_cfg *cfg, lrk_ctx **out) {
     ctx->grid_shade[1] = grid_for(reinterpret_cast<const void *>(shade_kernel<1u>));
     ctx->grid_shade[2] = grid_for(reinterpret_cast<const void *>(shade_kernel<2u>));
     ctx->grid_classify = grid_for(reinterpret_cast<const void *>(classify_hits_kernel));
-    ctx->grid_vshade = grid_for(reinterpret_cast<const void *>(volume_shade_kernel));
+    ctx->grid_vmedium = grid_for(reinterpret_cast<const void *>(volume_medium_kernel));
+    ctx->grid_vshade[0] = grid_for(reinterpret_cast<const void *>(volume_surface_kernel<0u>));
+    ctx->grid_vshade[1] = grid_for(reinterpret_cast<const void *>(volume_surface_kernel<1u>));
+    ctx->grid_vshade[2] = grid_for(reinterpret_cast<const void *>(volume_surface_kernel<2u>));
     ctx->grid_vshadow = grid_for(reinterpret_cast<const void *>(trace_volume_nee_kernel<false>));
     *out = ctx;
     return LRK_OK;
