@@ -6,7 +6,7 @@
 
 Workload (config.workload): BASELINE.json configs[2] — the synthetic 1 387 526-triangle instanced scene, Disney BSDF + NEE,
 1920x1080, Independent sampler seed 19980810, path depth 10 — rendered in *steps* of SPP_PER_STEP samples per pixel (the
-full config is 1024 spp = 64 such steps; step s renders sample indices [s*SPP, (s+1)*SPP)).  One step = one pass of the hot
+full config is 1024 spp = 4 such steps; step s renders sample indices [s*SPP, (s+1)*SPP)).  One step = one pass of the hot
 path over one batch of 1920*1080*SPP camera samples.  For N > 1 the same frame is sharded by interleaved 32x32 pixel tiles
 (strong scaling) and the raw film is sum-reduced to rank 0 once, after the K-th step, inside the timed region (configs[4]).
 
@@ -39,7 +39,7 @@ sys.path.insert(0, str(REPO))
 METRIC = "Msamples/s (wavefront path tracing, 1.39M-triangle instanced scene, Disney + NEE, 1920x1080)"
 UNIT = "Msamples/s"
 WIDTH, HEIGHT = 1920, 1080
-SPP_PER_STEP = 64
+SPP_PER_STEP = 256
 FULL_SPP = 1024
 
 
@@ -57,7 +57,8 @@ def workload_config(n_gpus: int) -> dict:
         "samples_per_step": WIDTH * HEIGHT * SPP_PER_STEP,
         "spp_per_step": SPP_PER_STEP,
         "sharding": "single GPU" if n_gpus == 1 else f"interleaved 32x32 pixel tiles over {n_gpus} GPUs + one NCCL film reduce",
-        "l2_policy": "per-step path state (~25 GB for the 132.7 M paths of one step) is far larger than the 126 MB L2; no explicit flush",
+        "l2_policy": "per-pass path state (~25 GB for the 132.7 M paths of a 64-spp pass, four passes per step on one GPU) is far larger "
+                     "than the 126 MB L2; no explicit flush",
         "host_buffers": "pageable (std::vector) for the e2e upload",
     }
 
@@ -324,7 +325,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
