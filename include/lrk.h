@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define LRK_ABI_VERSION 1u
+#define LRK_ABI_VERSION 2u
 
 typedef enum lrk_status {
     LRK_OK = 0,
@@ -159,13 +159,47 @@ typedef struct lrk_instance {
  *           p[12] = clearcoat_gloss, p[13] = specular_trans, p[14] = flatness,
  *           p[15] = diffuse_trans; lobes = union of enabled lobes over ALL disney surface
  *           nodes of the scene (the reference ORs them into one shared closure,
- *           src/surfaces/disney.cpp:869,994-995). */
+ *           src/surfaces/disney.cpp:869,994-995).
+ *
+ * Image-textured parameters: tex[k] != 0 means parameter slot k is NOT the constant p[k] but is
+ * evaluated per hit from image texture (tex[k] - 1) at the hit's uv, exactly as populate_closure does
+ * (src/surfaces/matte.cpp:117-131, src/surfaces/disney.cpp:932-956):
+ *   colour slots (MATTE 0, DISNEY 0): rgb = saturate(extend_color_to_rgb(v.xyz, channels)) -> p[0..2] (+ luminance ->
+ *   p[3] for DISNEY); MATTE slot 3: saturate(v.x) * 90; DISNEY scalar slots 4..14: v.x, slot 6 additionally remapped
+ *   max(v.x^2, 1e-4) when LRK_SURFACE_REMAP_ROUGHNESS is set in flags. */
+#define LRK_SURFACE_HAS_TEXTURES 1u
+#define LRK_SURFACE_REMAP_ROUGHNESS 2u
 typedef struct lrk_surface {
     uint32_t type;
     uint32_t lobes;
-    uint32_t reserved[2];
+    uint32_t flags;
+    uint32_t reserved;
     float p[16];
+    uint32_t tex[16];
 } lrk_surface;
+
+/* One image texture (src/textures/image.cpp:16-151).  Texels are RGBA float (8/16-bit sources converted with x/255,
+ * x/65535: cpu_texture.h:63), row-major, row 0 first as stored in the file; sampling follows the reference's software
+ * sampler (src/compute/src/rust/luisa_compute_backend_impl/src/cpu/codegen/cpu_texture.h:418-464,489-493), level 0 only
+ * (the reference's evaluate() samples without LOD, image.cpp:165). */
+#define LRK_TEX_ADDRESS_EDGE 0u
+#define LRK_TEX_ADDRESS_REPEAT 1u
+#define LRK_TEX_ADDRESS_MIRROR 2u
+#define LRK_TEX_ADDRESS_ZERO 3u
+#define LRK_TEX_FILTER_POINT 0u
+#define LRK_TEX_FILTER_LINEAR 1u
+#define LRK_TEX_ENCODING_LINEAR 0u
+#define LRK_TEX_ENCODING_SRGB 1u
+#define LRK_TEX_ENCODING_GAMMA 2u
+typedef struct lrk_texture {
+    uint64_t texel_offset; /* index of the first float4 texel in lrk_scene_desc::texels */
+    uint32_t width, height;
+    uint32_t channels; /* channels of the source image (1..4) */
+    uint32_t address, filter, encoding;
+    float scale, gamma;
+    float uv_scale[2], uv_offset[2];
+    uint32_t reserved[2];
+} lrk_texture;
 
 /* One light node (tag = index): src/lights/diffuse.cpp:23-26. emission is the decoded
  * illuminant (max(rgb,0)), L = emission * scale. */
@@ -258,6 +292,12 @@ typedef struct lrk_scene_desc {
     uint32_t light_count; /* number of distinct light NODES */
     const lrk_light *lights;
     const lrk_light_handle *light_handles; /* first light_count per-instance handles (src/lightsamplers/uniform.cpp:34-38) */
+
+    const lrk_texture *textures; /* image textures referenced by lrk_surface::tex (may be NULL when texture_count == 0) */
+    uint32_t texture_count;
+    uint32_t reserved2;
+    const float *texels; /* RGBA float texels of all textures, 4 floats each */
+    uint64_t texel_count;
 
     lrk_camera camera;
     lrk_film film;

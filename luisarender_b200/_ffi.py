@@ -13,7 +13,12 @@ PKG_DIR = Path(__file__).resolve().parent
 REPO_DIR = PKG_DIR.parent
 LIB_DIR = PKG_DIR / "lib"
 
-LRK_ABI_VERSION = 1
+LRK_ABI_VERSION = 2
+TEX_ADDRESS_EDGE, TEX_ADDRESS_REPEAT, TEX_ADDRESS_MIRROR, TEX_ADDRESS_ZERO = 0, 1, 2, 3
+TEX_FILTER_POINT, TEX_FILTER_LINEAR = 0, 1
+TEX_ENCODING_LINEAR, TEX_ENCODING_SRGB, TEX_ENCODING_GAMMA = 0, 1, 2
+SURFACE_HAS_TEXTURES, SURFACE_REMAP_ROUGHNESS = 1, 2
+SHAPE_HAS_VERTEX_NORMAL, SHAPE_HAS_VERTEX_UV, SHAPE_HAS_SURFACE, SHAPE_HAS_LIGHT = 1, 2, 4, 8
 LRK_FILTER_LUT_SIZE = 64
 
 u32, u64, i32, i64, f32, f64 = C.c_uint32, C.c_uint64, C.c_int32, C.c_int64, C.c_float, C.c_double
@@ -55,7 +60,12 @@ class Instance(C.Structure):
 
 
 class Surface(C.Structure):
-    _fields_ = [("type", u32), ("lobes", u32), ("reserved", u32 * 2), ("p", f32 * 16)]
+    _fields_ = [("type", u32), ("lobes", u32), ("flags", u32), ("reserved", u32), ("p", f32 * 16), ("tex", u32 * 16)]
+
+
+class Texture(C.Structure):
+    _fields_ = [("texel_offset", u64), ("width", u32), ("height", u32), ("channels", u32), ("address", u32), ("filter", u32),
+                ("encoding", u32), ("scale", f32), ("gamma", f32), ("uv_scale", f32 * 2), ("uv_offset", f32 * 2), ("reserved", u32 * 2)]
 
 
 class Light(C.Structure):
@@ -99,6 +109,7 @@ class SceneDesc(C.Structure):
         ("tri_verts", C.POINTER(f32)), ("tri_slot_count", u64),
         ("surfaces", C.POINTER(Surface)), ("surface_count", u32), ("light_count", u32),
         ("lights", C.POINTER(Light)), ("light_handles", C.POINTER(LightHandle)),
+        ("textures", C.POINTER(Texture)), ("texture_count", u32), ("reserved2", u32), ("texels", C.POINTER(f32)), ("texel_count", u64),
         ("camera", Camera), ("film", Film), ("integrator", Integrator), ("environment_medium", Medium),
     ]
 

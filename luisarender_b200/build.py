@@ -15,7 +15,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 REPO = PKG.parent
 LIB = PKG / "lib"
-HOST_SRC = ["sdl.cpp", "scene.cpp", "geomutil.cpp", "bvh.cpp", "flatten.cpp", "imageio.cpp", "lrh.cpp"]
+HOST_SRC = ["sdl.cpp", "scene.cpp", "geomutil.cpp", "bvh.cpp", "flatten.cpp", "imageio.cpp", "imageload.cpp", "meshload.cpp", "lrh.cpp"]
 NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # -fmad=false: expressions evaluate as written (see csrc/device/vecmath.cuh); FMAs are explicit fmaf().
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-fmad=false", "--shared", "-Xcompiler", "-fPIC"]
@@ -54,7 +54,7 @@ def build_host(force=False, verbose=False) -> Path:
     if not force and _newer(out, deps):
         return out
     LIB.mkdir(exist_ok=True)
-    _run(["g++", *HOST_FLAGS, "-shared", *[src_dir / s for s in HOST_SRC], "-o", out, "-lpthread"], verbose)
+    _run(["g++", *HOST_FLAGS, "-shared", *[src_dir / s for s in HOST_SRC], "-o", out, "-lpthread", "-lz"], verbose)
     return out
 
 

@@ -262,6 +262,18 @@ __global__ void __launch_bounds__(kBlock) trace_query_kernel(DeviceScene sc, con
 }
 
 // ---- shade ----------------------------------------------------------------------------------------------
+// Closure of the hit's surface node: constants straight from the node, image-textured parameters evaluated at the hit's uv.
+template<typename Closure>
+__device__ __forceinline__ void init_closure(const DeviceScene &sc, Closure &cl, const lrk_surface *node, const Interaction &it) {
+    if (node->flags & LRK_SURFACE_HAS_TEXTURES) {
+        lrk_surface s = *node;
+        resolve_surface_textures(sc, s, it.u, it.v);
+        cl.init(s);
+    } else {
+        cl.init(*node);
+    }
+}
+
 // Evaluates the closure for the light sample's direction (NEE term) and for the direction the closure itself samples.
 // Both evaluations run through ONE copy of the closure code (a two-trip loop that is deliberately not unrolled): the Disney
 // closure is several thousand SASS instructions and two inlined copies thrash the instruction cache.
@@ -372,11 +384,11 @@ __global__ void __launch_bounds__(kShadeBlock, LRK_SHADE_MIN_BLOCKS) shade_kerne
                     float pdf;
                     if (KIND == 1u) {
                         MatteClosure cl;
-                        cl.init(*surf);
+                        init_closure(sc, cl, surf, it);
                         shade_surface<false>(cl, it, wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
                     } else {
                         DisneyClosure cl;
-                        cl.init(*surf);
+                        init_closure(sc, cl, surf, it);
                         shade_surface<false>(cl, it, wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
                     }
                     if (contrib.x != 0.f || contrib.y != 0.f || contrib.z != 0.f) {
@@ -826,11 +838,11 @@ __global__ void __launch_bounds__(kBlock, 2) volume_surface_kernel(DeviceScene s
                 // true_hit(medium_tag = 0) <=> 0 <= priority of the environment medium: always true (medium_tracker.cpp:19-21)
                 if (KIND == 1u) {
                     MatteClosure cl;
-                    cl.init(*surf);
+                    init_closure(sc, cl, surf, it);
                     shade_surface<true>(cl, it, wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
                 } else {
                     DisneyClosure cl;
-                    cl.init(*surf);
+                    init_closure(sc, cl, surf, it);
                     shade_surface<true>(cl, it, wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
                 }
                 push_shadow = true;// traced even with a zero contribution: its occlusion advances the PCG stream of the next bounce

@@ -16,7 +16,7 @@ using namespace lrk;
 namespace {
 
 struct DeviceArrays {
-    void *vertices{}, *triangles{}, *alias{}, *pdf{}, *meshes{}, *inst_handles{}, *inst_kind{}, *inst_o2w{}, *inst_xform{}, *bvh_nodes{},
+    void *vertices{}, *triangles{}, *alias{}, *pdf{}, *meshes{}, *inst_handles{}, *inst_kind{}, *inst_o2w{}, *inst_xform{}, *bvh_nodes{}, *textures{}, *texels{},
         *tri_verts{}, *surfaces{}, *lights{}, *light_handles{}, *camera{};
 };
 
@@ -458,8 +458,17 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
     if (s->camera.resolution[0] > 65535u || s->camera.resolution[1] > 65535u)
         return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: film larger than 65535 pixels per side");
     if (s->light_count == 0u) return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "No lights in scene. Rendering aborted.");// wave_path.cpp:224-228
-    for (uint32_t i = 0; i < s->surface_count; i++)
+    for (uint32_t i = 0; i < s->surface_count; i++) {
         if (s->surfaces[i].type > LRK_SURFACE_DISNEY) return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: unknown surface type");
+        for (uint32_t k = 0; k < 16u; k++)
+            if (s->surfaces[i].tex[k] > s->texture_count) return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_upload_scene: texture id out of range");
+    }
+    for (uint32_t i = 0; i < s->texture_count; i++) {
+        const auto &t = s->textures[i];
+        if (t.width == 0u || t.height == 0u || t.texel_offset + static_cast<uint64_t>(t.width) * t.height > s->texel_count ||
+            t.address > LRK_TEX_ADDRESS_ZERO || t.filter > LRK_TEX_FILTER_LINEAR || t.encoding > LRK_TEX_ENCODING_GAMMA)
+            return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_upload_scene: invalid image texture record");
+    }
     LRK_CUDA(cudaSetDevice(ctx->device));
     auto &a = ctx->arrays;
     int rc;
@@ -471,6 +480,8 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
     if ((rc = upload(ctx, &a.bvh_nodes, s->bvh_nodes, s->bvh_node_count))) return rc;
     if ((rc = upload(ctx, &a.tri_verts, s->tri_verts, s->tri_slot_count * 12u))) return rc;
     if ((rc = upload(ctx, &a.surfaces, s->surfaces, s->surface_count))) return rc;
+    if ((rc = upload(ctx, &a.textures, s->textures, s->texture_count))) return rc;
+    if ((rc = upload(ctx, &a.texels, s->texels, s->texel_count * 4u))) return rc;
     if ((rc = upload(ctx, &a.lights, s->lights, s->light_count))) return rc;
     if ((rc = upload(ctx, &a.light_handles, s->light_handles, s->light_count))) return rc;
     if ((rc = upload(ctx, &a.camera, &s->camera, 1))) return rc;
@@ -515,6 +526,8 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
     sc.bvh_nodes = static_cast<const float4 *>(a.bvh_nodes);
     sc.tri_verts = static_cast<const float4 *>(a.tri_verts);
     sc.surfaces = static_cast<const lrk_surface *>(a.surfaces);
+    sc.textures = static_cast<const lrk_texture *>(a.textures);
+    sc.texels = static_cast<const float4 *>(a.texels);
     sc.lights = static_cast<const lrk_light *>(a.lights);
     sc.light_handles = static_cast<const lrk_light_handle *>(a.light_handles);
     sc.camera = static_cast<const lrk_camera *>(a.camera);

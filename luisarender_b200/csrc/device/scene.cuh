@@ -23,6 +23,8 @@ struct DeviceScene {
     const float4 *bvh_nodes;// 4 x float4 per node: {lo0.xyz,hi0.x} {hi0.yz,lo1.xy} {lo1.z,hi1.xyz} {ref0,ref1,parent,-}
     const float4 *tri_verts;// 3 x float4 per BVH-ordered triangle slot, v0.w = prim id bits
     const lrk_surface *surfaces;
+    const lrk_texture *textures;// image textures referenced by lrk_surface::tex
+    const float4 *texels;       // RGBA float texels of all textures
     const lrk_light *lights;
     const lrk_light_handle *light_handles;
     const lrk_camera *camera;

@@ -101,6 +101,7 @@ __device__ __forceinline__ ShapeHandle decode_handle(uint4 c) {
 struct Interaction {
     ShapeHandle shape;
     V3 pg, ng;
+    float u, v;// interpolated vertex uv (geometry.cpp:372)
     Frame shading;
     uint32_t prim;
     float prim_area;
@@ -164,6 +165,8 @@ __device__ __forceinline__ Interaction make_interaction(const DeviceScene &sc, u
     V3 dp0 = p1 - p0, dp1 = p2 - p0;
     V3 dpdu_local = (dp0 * duv1y - dp1 * duv0y) * inv_det;
     V3 p = mul3(m, bary.x * p0 + bary.y * p1 + bary.z * p2) + t;
+    it.u = bary.x * a1.z + bary.y * b1.z + bary.z * c1.z;
+    it.v = bary.x * a1.w + bary.y * b1.w + bary.z * c1.w;
     V3 c = cross(mul3(m, dp0), mul3(m, dp1));
     float area = length(c) * .5f;
     V3 ng = normalize(c);
@@ -269,6 +272,87 @@ __device__ __forceinline__ LightSample sample_light(const DeviceScene &sc, const
     s.ray_o_tmin = make_float4(p_from.x, p_from.y, p_from.z, 0.f);
     s.ray_d_tmax = make_float4(dir.x, dir.y, dir.z, d * .9999f);
     return s;
+}
+
+// ---- image textures: src/textures/image.cpp:132-166, sampled like the reference's software sampler
+// (src/compute/src/rust/luisa_compute_backend_impl/src/cpu/codegen/cpu_texture.h:418-464,489-493) --------------------
+__device__ __forceinline__ float tex_fract(float x) { return x - floorf(x); }
+__device__ __forceinline__ float tex_coord_point(uint32_t address, float uv, float s) {
+    switch (address) {
+        case LRK_TEX_ADDRESS_EDGE: return clampf(uv, 0.0f, kOneMinusEpsilon) * s;
+        case LRK_TEX_ADDRESS_REPEAT: return tex_fract(uv) * s;
+        case LRK_TEX_ADDRESS_MIRROR: {
+            uv = fmodf(fabsf(uv), 2.0f);
+            uv = uv < 1.f ? uv : 2.f - uv;
+            return fminf(uv, kOneMinusEpsilon) * s;
+        }
+        default: return (uv < 0.f || uv >= 1.f) ? 65536.f : uv * s;// ZERO
+    }
+}
+__device__ __forceinline__ float4 tex_read(const DeviceScene &sc, const lrk_texture &t, uint32_t x, uint32_t y) {
+    if (!(x < t.width & y < t.height)) return make_float4(0.f, 0.f, 0.f, 0.f);
+    return __ldg(sc.texels + t.texel_offset + static_cast<size_t>(y) * t.width + x);
+}
+__device__ __forceinline__ float4 lerp4(float4 a, float4 b, float t) {
+    return make_float4(lerp(a.x, b.x, t), lerp(a.y, b.y, t), lerp(a.z, b.z, t), lerp(a.w, b.w, t));
+}
+__device__ __forceinline__ float4 texture_sample(const DeviceScene &sc, const lrk_texture &t, float u, float v) {
+    const float sx = static_cast<float>(t.width), sy = static_cast<float>(t.height);
+    if (t.filter == LRK_TEX_FILTER_POINT) {
+        float cx = tex_coord_point(t.address, u, sx), cy = tex_coord_point(t.address, v, sy);
+        return tex_read(sc, t, static_cast<uint32_t>(cx), static_cast<uint32_t>(cy));
+    }
+    const float inv_sx = 1.f / sx, inv_sy = 1.f / sy;
+    float ax = tex_coord_point(t.address, u - .5f * inv_sx, sx), bx = tex_coord_point(t.address, u + .5f * inv_sx, sx);
+    float ay = tex_coord_point(t.address, v - .5f * inv_sy, sy), by = tex_coord_point(t.address, v + .5f * inv_sy, sy);
+    float x_min = fminf(ax, bx), x_max = fmaxf(ax, bx), y_min = fminf(ay, by), y_max = fmaxf(ay, by);
+    float tx = tex_fract(x_max), ty = tex_fract(y_max);
+    uint32_t x0 = static_cast<uint32_t>(x_min), y0 = static_cast<uint32_t>(y_min);
+    uint32_t x1 = static_cast<uint32_t>(x_max), y1 = static_cast<uint32_t>(y_max);
+    float4 v00 = tex_read(sc, t, x0, y0), v01 = tex_read(sc, t, x1, y0), v10 = tex_read(sc, t, x0, y1), v11 = tex_read(sc, t, x1, y1);
+    return lerp4(lerp4(v00, v01, tx), lerp4(v10, v11, tx), ty);
+}
+// ImageTextureInstance::evaluate: uv transform, sample, decode (image.cpp:136-166)
+__device__ __forceinline__ float tex_decode(const lrk_texture &t, float x) {
+    if (t.encoding == LRK_TEX_ENCODING_SRGB) {
+        float lin = x <= 0.04045f ? x * (1.0f / 12.92f) : powf((x + 0.055f) * (1.0f / 1.055f), 2.4f);
+        return t.scale * lin;
+    }
+    if (t.encoding == LRK_TEX_ENCODING_GAMMA) return t.scale * powf(x, t.gamma);
+    return t.scale * x;
+}
+// Not inlined on purpose: up to a dozen call sites per closure, executed only for textured materials.
+__device__ __noinline__ float4 texture_evaluate(const DeviceScene &sc, uint32_t tex_id, float u, float v) {
+    const lrk_texture t = sc.textures[tex_id];
+    float4 s = texture_sample(sc, t, u * t.uv_scale[0] + t.uv_offset[0], v * t.uv_scale[1] + t.uv_offset[1]);
+    return make_float4(tex_decode(t, s.x), tex_decode(t, s.y), tex_decode(t, s.z), tex_decode(t, s.w));
+}
+// Surface parameters at a hit: the node's constants with the image-textured slots evaluated at the hit's uv
+// (MatteInstance::populate_closure matte.cpp:117-131, DisneySurfaceInstance::populate_closure disney.cpp:932-956;
+// colours through Texture::Instance::evaluate_albedo_spectrum texture.cpp:20-31 + srgb.cpp:34-40,70-72).
+__device__ __forceinline__ void resolve_surface_textures(const DeviceScene &sc, lrk_surface &s, float u, float v) {
+    if (s.tex[0] != 0u) {
+        float4 val = texture_evaluate(sc, s.tex[0] - 1u, u, v);
+        const uint32_t ch = sc.textures[s.tex[0] - 1u].channels;
+        V3 rgb = ch == 1u ? v3(val.x, val.x, val.x) : ch == 2u ? v3(val.x, val.y, 1.f) : v3(val.x, val.y, val.z);
+        rgb = v3(saturate(rgb.x), saturate(rgb.y), saturate(rgb.z));// encode_srgb_albedo's clamp, decode_albedo's saturate
+        s.p[0] = rgb.x;
+        s.p[1] = rgb.y;
+        s.p[2] = rgb.z;
+        if (s.type == LRK_SURFACE_DISNEY) s.p[3] = 0.212671f * rgb.x + 0.715160f * rgb.y + 0.072169f * rgb.z;
+    }
+    if (s.type == LRK_SURFACE_MATTE) {
+        if (s.tex[3] != 0u) s.p[3] = saturate(texture_evaluate(sc, s.tex[3] - 1u, u, v).x) * 90.f;
+    } else {
+#pragma unroll
+        for (uint32_t k = 4u; k < 15u; k++) {
+            if (s.tex[k] != 0u) {
+                float x = texture_evaluate(sc, s.tex[k] - 1u, u, v).x;
+                if (k == 6u && (s.flags & LRK_SURFACE_REMAP_ROUGHNESS)) x = fmaxf(x * x, 1e-4f);// roughness_to_alpha
+                s.p[k] = x;
+            }
+        }
+    }
 }
 
 // ---- surfaces ------------------------------------------------------------------------------------------

@@ -32,6 +32,10 @@ lrk_scene_desc FlatScene::desc(uint32_t camera_index) const {
     d.tri_slot_count = tri_verts.size() / 12u;
     d.surfaces = surfaces.data();
     d.surface_count = static_cast<uint32_t>(surfaces.size());
+    d.textures = textures.empty() ? nullptr : textures.data();
+    d.texture_count = static_cast<uint32_t>(textures.size());
+    d.texels = texels.empty() ? nullptr : texels.data();
+    d.texel_count = texels.size() / 4u;
     d.lights = lights.data();
     d.light_count = static_cast<uint32_t>(lights.size());
     d.light_handles = light_handles.data();
@@ -338,12 +342,15 @@ std::unique_ptr<FlatScene> flatten_scene(const Scene &scene) {
 
     // surfaces; Disney lobes are OR-ed over all disney nodes (one shared closure, src/surfaces/disney.cpp:869,994)
     uint32_t disney_lobes = 0u;
+    TextureTable texture_table;
     for (auto s : f.surface_nodes) {
-        out->surfaces.push_back(s->flatten());
+        out->surfaces.push_back(s->flatten(texture_table));
         if (out->surfaces.back().type == LRK_SURFACE_DISNEY) disney_lobes |= out->surfaces.back().lobes;
     }
     for (auto &s : out->surfaces)
         if (s.type == LRK_SURFACE_DISNEY) s.lobes = disney_lobes;
+    out->textures = std::move(texture_table.records);
+    out->texels = std::move(texture_table.texels);
     for (auto l : f.light_nodes) out->lights.push_back(l->flatten());
 
     for (auto cam : scene.cameras()) out->cameras.push_back(flatten_camera(cam));

@@ -28,6 +28,8 @@ struct FlatScene {
     std::vector<lrk_bvh_node> bvh_nodes;
     std::vector<float> tri_verts;
     std::vector<lrk_surface> surfaces;
+    std::vector<lrk_texture> textures;// image textures referenced by surfaces (lrk_surface::tex)
+    std::vector<float> texels;        // RGBA float texels of all of them
     std::vector<lrk_light> lights;
     std::vector<lrk_light_handle> light_handles;// all instanced lights; the desc exposes the first lights.size()
     std::vector<FlatCamera> cameras;

@@ -1,0 +1,463 @@
+// Image file readers for the `Image` texture plugin (reference: LoadedImage::load, src/util/imageio.cpp:347-470, which
+// delegates to stb_image / tinyexr — neither is available here, so the decoders below are written against the file
+// format specifications).  What the readers reproduce from the reference is the STORAGE policy, because it decides the
+// texel values the sampler sees:
+//   * 8-bit files  -> BYTE1/2/4  : texel = x / 255        16-bit files -> SHORT1/2/4 : texel = x / 65535
+//   * .hdr         -> HALF4      : RGBE decoded to float, then rounded to binary16 (imageio.cpp:383, 231-245)
+//   * .exr         -> HALF or FLOAT by the file's first channel type; 1, 2 or 4 channels
+//   * 3-channel sources are widened to 4 with alpha = 1 (stbi "desired channels" = 4)
+// Row 0 of the result is the top row of the picture (PFM, stored bottom-up, is flipped).
+#include <zlib.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+
+#include "imageio.h"
+
+namespace lrh {
+
+namespace {
+
+[[noreturn]] void fail(const std::filesystem::path &p, const std::string &why) {
+    throw std::runtime_error("Failed to load image '" + p.string() + "': " + why + ".");
+}
+
+std::vector<uint8_t> read_file(const std::filesystem::path &p) {
+    std::ifstream f{p, std::ios::binary};
+    if (!f) fail(p, "cannot open file");
+    std::vector<uint8_t> data((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    return data;
+}
+
+// binary16 <-> binary32, round-to-nearest-even (what luisa::float_to_half / half_to_float do)
+uint16_t float_to_half(float f) {
+    uint32_t x;
+    std::memcpy(&x, &f, 4);
+    uint32_t sign = (x >> 16u) & 0x8000u;
+    int32_t exp = static_cast<int32_t>((x >> 23u) & 0xffu) - 127 + 15;
+    uint32_t man = x & 0x7fffffu;
+    if (((x >> 23u) & 0xffu) == 0xffu) return static_cast<uint16_t>(sign | 0x7c00u | (man ? 0x200u : 0u));
+    if (exp >= 31) return static_cast<uint16_t>(sign | 0x7c00u);
+    if (exp <= 0) {
+        if (exp < -10) return static_cast<uint16_t>(sign);
+        man |= 0x800000u;
+        uint32_t shift = static_cast<uint32_t>(14 - exp);
+        uint32_t half = man >> shift;
+        uint32_t rem = man & ((1u << shift) - 1u), mid = 1u << (shift - 1u);
+        if (rem > mid || (rem == mid && (half & 1u))) half++;
+        return static_cast<uint16_t>(sign | half);
+    }
+    uint32_t half = (static_cast<uint32_t>(exp) << 10u) | (man >> 13u);
+    uint32_t rem = man & 0x1fffu;
+    if (rem > 0x1000u || (rem == 0x1000u && (half & 1u))) half++;
+    return static_cast<uint16_t>(sign | half);
+}
+float half_to_float(uint16_t h) {
+    uint32_t sign = (h & 0x8000u) << 16u, exp = (h >> 10u) & 0x1fu, man = h & 0x3ffu, x;
+    if (exp == 0u) {
+        if (man == 0u) {
+            x = sign;
+        } else {
+            int e = -1;
+            do {
+                e++;
+                man <<= 1u;
+            } while (!(man & 0x400u));
+            x = sign | (static_cast<uint32_t>(127 - 15 - e) << 23u) | ((man & 0x3ffu) << 13u);
+        }
+    } else if (exp == 31u) {
+        x = sign | 0x7f800000u | (man << 13u);
+    } else {
+        x = sign | ((exp + 127u - 15u) << 23u) | (man << 13u);
+    }
+    float f;
+    std::memcpy(&f, &x, 4);
+    return f;
+}
+
+// widen `nc`-channel interleaved samples to the storage channel count (1, 2 or 4) as RGBA floats
+LoadedImage finish(uint32_t w, uint32_t h, uint32_t nc, const std::vector<float> &samples) {
+    LoadedImage img;
+    img.width = w;
+    img.height = h;
+    img.channels = nc >= 3u ? 4u : nc;
+    img.rgba.assign(static_cast<size_t>(w) * h * 4u, 0.f);
+    for (size_t i = 0; i < static_cast<size_t>(w) * h; i++) {
+        const float *s = samples.data() + i * nc;
+        float *d = img.rgba.data() + i * 4u;
+        if (nc == 1u) {
+            d[0] = s[0];// a 1-channel texel reads back as (x, 0, 0, 1) (cpu_texture.h read_pixel), the consumers use .x / .xxx
+            d[3] = 1.f;
+        } else if (nc == 2u) {
+            d[0] = s[0];
+            d[1] = s[1];
+            d[3] = 1.f;
+        } else {
+            d[0] = s[0];
+            d[1] = s[1];
+            d[2] = s[2];
+            d[3] = nc == 4u ? s[3] : 1.f;
+        }
+    }
+    return img;
+}
+
+// ---- PNG (ISO/IEC 15948): non-interlaced, colour types 0/2/3/4/6, bit depths 1-16 ---------------------------------
+uint32_t be32(const uint8_t *p) { return (uint32_t{p[0]} << 24u) | (uint32_t{p[1]} << 16u) | (uint32_t{p[2]} << 8u) | p[3]; }
+
+LoadedImage load_png(const std::filesystem::path &path, const std::vector<uint8_t> &d) {
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    if (d.size() < 8 || std::memcmp(d.data(), sig, 8) != 0) fail(path, "not a PNG file");
+    uint32_t w = 0, h = 0, depth = 0, ctype = 0, interlace = 0;
+    std::vector<uint8_t> idat, plte, trns;
+    size_t pos = 8;
+    bool end = false;
+    while (!end && pos + 12 <= d.size()) {
+        uint32_t len = be32(&d[pos]);
+        if (pos + 12 + len > d.size()) fail(path, "truncated PNG chunk");
+        std::string type(reinterpret_cast<const char *>(&d[pos + 4]), 4);
+        const uint8_t *body = &d[pos + 8];
+        if (type == "IHDR") {
+            if (len < 13) fail(path, "bad IHDR");
+            w = be32(body);
+            h = be32(body + 4);
+            depth = body[8];
+            ctype = body[9];
+            interlace = body[12];
+        } else if (type == "PLTE") {
+            plte.assign(body, body + len);
+        } else if (type == "tRNS") {
+            trns.assign(body, body + len);
+        } else if (type == "IDAT") {
+            idat.insert(idat.end(), body, body + len);
+        } else if (type == "IEND") {
+            end = true;
+        }
+        pos += 12 + len;
+    }
+    if (w == 0 || h == 0 || idat.empty()) fail(path, "missing IHDR / IDAT");
+    if (interlace != 0) fail(path, "interlaced PNG files are not supported");
+    uint32_t samples_per_pixel = ctype == 0 ? 1u : ctype == 2 ? 3u : ctype == 3 ? 1u : ctype == 4 ? 2u : ctype == 6 ? 4u : 0u;
+    if (samples_per_pixel == 0u || !(depth == 1 || depth == 2 || depth == 4 || depth == 8 || depth == 16)) fail(path, "unsupported PNG colour type / depth");
+    size_t bits_per_pixel = static_cast<size_t>(samples_per_pixel) * depth;
+    size_t stride = (static_cast<size_t>(w) * bits_per_pixel + 7u) / 8u;
+    size_t bpp = std::max<size_t>(1u, bits_per_pixel / 8u);
+    std::vector<uint8_t> raw((stride + 1u) * h);
+    uLongf raw_len = static_cast<uLongf>(raw.size());
+    if (uncompress(raw.data(), &raw_len, idat.data(), static_cast<uLong>(idat.size())) != Z_OK || raw_len != raw.size())
+        fail(path, "zlib inflate failed");
+    // unfilter (PNG spec 9.2)
+    std::vector<uint8_t> pix(stride * h);
+    for (uint32_t y = 0; y < h; y++) {
+        const uint8_t *in = &raw[(stride + 1u) * y];
+        uint8_t ft = in[0];
+        in++;
+        uint8_t *out = &pix[stride * y];
+        const uint8_t *up = y ? &pix[stride * (y - 1u)] : nullptr;
+        for (size_t x = 0; x < stride; x++) {
+            int a = x >= bpp ? out[x - bpp] : 0, b = up ? up[x] : 0, c = (up && x >= bpp) ? up[x - bpp] : 0;
+            int v = in[x];
+            switch (ft) {
+                case 0: break;
+                case 1: v += a; break;
+                case 2: v += b; break;
+                case 3: v += (a + b) / 2; break;
+                case 4: {
+                    int p = a + b - c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c);
+                    v += (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+                    break;
+                }
+                default: fail(path, "bad PNG filter type");
+            }
+            out[x] = static_cast<uint8_t>(v);
+        }
+    }
+    // samples -> floats.  stb_image expands low bit depths and palettes to 8 bits; 16-bit files stay 16-bit.
+    const bool is16 = depth == 16;
+    const float norm = is16 ? 65535.f : 255.f;
+    uint32_t nc = ctype == 3 ? (trns.empty() ? 3u : 4u) : samples_per_pixel;
+    std::vector<float> samples(static_cast<size_t>(w) * h * nc);
+    auto sample_at = [&](uint32_t y, size_t index) -> uint32_t {// index = x * samples_per_pixel + s
+        const uint8_t *row = &pix[stride * y];
+        if (depth == 16) return (uint32_t{row[index * 2u]} << 8u) | row[index * 2u + 1u];
+        if (depth == 8) return row[index];
+        size_t bit = index * depth;
+        uint32_t v = (row[bit / 8u] >> (8u - depth - (bit % 8u))) & ((1u << depth) - 1u);
+        return v;
+    };
+    for (uint32_t y = 0; y < h; y++) {
+        for (uint32_t x = 0; x < w; x++) {
+            float *o = &samples[(static_cast<size_t>(y) * w + x) * nc];
+            if (ctype == 3) {
+                uint32_t idx = sample_at(y, x);
+                if ((idx + 1u) * 3u > plte.size()) fail(path, "palette index out of range");
+                for (int k = 0; k < 3; k++) o[k] = static_cast<float>(plte[idx * 3u + k]) / 255.f;
+                if (nc == 4u) o[3] = (idx < trns.size() ? static_cast<float>(trns[idx]) : 255.f) / 255.f;
+            } else {
+                for (uint32_t s = 0; s < samples_per_pixel; s++) {
+                    uint32_t v = sample_at(y, static_cast<size_t>(x) * samples_per_pixel + s);
+                    if (depth < 8) v = v * 255u / ((1u << depth) - 1u);// stb_image scales 1/2/4-bit grey to 0..255
+                    o[s] = static_cast<float>(v) / norm;
+                }
+            }
+        }
+    }
+    return finish(w, h, nc, samples);
+}
+
+// ---- Netpbm P5/P6 (binary grey / RGB, maxval < 65536) and PFM ---------------------------------------------------
+std::string next_token(const std::vector<uint8_t> &d, size_t &pos) {
+    for (;;) {
+        while (pos < d.size() && std::isspace(d[pos])) pos++;
+        if (pos < d.size() && d[pos] == '#') {
+            while (pos < d.size() && d[pos] != '\n') pos++;
+        } else {
+            break;
+        }
+    }
+    std::string t;
+    while (pos < d.size() && !std::isspace(d[pos])) t.push_back(static_cast<char>(d[pos++]));
+    return t;
+}
+
+LoadedImage load_pnm(const std::filesystem::path &path, const std::vector<uint8_t> &d) {
+    size_t pos = 0;
+    std::string magic = next_token(d, pos);
+    if (magic == "PF" || magic == "Pf") {
+        uint32_t nc = magic == "PF" ? 3u : 1u;
+        uint32_t w = static_cast<uint32_t>(std::stoul(next_token(d, pos))), h = static_cast<uint32_t>(std::stoul(next_token(d, pos)));
+        float scale = std::stof(next_token(d, pos));
+        pos++;// the single whitespace after the scale
+        size_t n = static_cast<size_t>(w) * h * nc;
+        if (pos + n * 4u > d.size()) fail(path, "truncated PFM");
+        std::vector<float> samples(n);
+        for (uint32_t y = 0; y < h; y++) {// stored bottom-up
+            const uint8_t *row = &d[pos + static_cast<size_t>(h - 1u - y) * w * nc * 4u];
+            for (size_t i = 0; i < static_cast<size_t>(w) * nc; i++) {
+                uint8_t b[4] = {row[i * 4u], row[i * 4u + 1u], row[i * 4u + 2u], row[i * 4u + 3u]};
+                if (scale > 0.f) std::swap(b[0], b[3]), std::swap(b[1], b[2]);// positive scale = big endian
+                float f;
+                std::memcpy(&f, b, 4);
+                samples[static_cast<size_t>(y) * w * nc + i] = f;
+            }
+        }
+        return finish(w, h, nc, samples);
+    }
+    if (magic != "P5" && magic != "P6") fail(path, "unsupported Netpbm variant '" + magic + "'");
+    uint32_t nc = magic == "P6" ? 3u : 1u;
+    uint32_t w = static_cast<uint32_t>(std::stoul(next_token(d, pos))), h = static_cast<uint32_t>(std::stoul(next_token(d, pos)));
+    uint32_t maxval = static_cast<uint32_t>(std::stoul(next_token(d, pos)));
+    pos++;
+    size_t n = static_cast<size_t>(w) * h * nc, bytes = maxval > 255u ? 2u : 1u;
+    if (maxval == 0u || maxval > 65535u || pos + n * bytes > d.size()) fail(path, "bad / truncated Netpbm data");
+    std::vector<float> samples(n);
+    for (size_t i = 0; i < n; i++) {
+        uint32_t v = bytes == 2u ? (uint32_t{d[pos + i * 2u]} << 8u) | d[pos + i * 2u + 1u] : d[pos + i];
+        samples[i] = static_cast<float>(v) / static_cast<float>(maxval);
+    }
+    return finish(w, h, nc, samples);
+}
+
+// ---- Radiance RGBE (.hdr): new-style RLE and flat scanlines, -Y h +X w orientation --------------------------------------
+LoadedImage load_hdr(const std::filesystem::path &path, const std::vector<uint8_t> &d) {
+    size_t pos = 0;
+    auto line = [&]() {
+        std::string l;
+        while (pos < d.size() && d[pos] != '\n') l.push_back(static_cast<char>(d[pos++]));
+        pos++;
+        return l;
+    };
+    std::string first = line();
+    if (first.rfind("#?", 0) != 0) fail(path, "not a Radiance HDR file");
+    for (;;) {
+        if (pos >= d.size()) fail(path, "truncated HDR header");
+        std::string l = line();
+        if (l.empty()) break;
+    }
+    std::string res = line();
+    uint32_t w = 0, h = 0;
+    {
+        std::istringstream ss{res};
+        std::string ys, xs;
+        ss >> ys >> h >> xs >> w;
+        if (ys != "-Y" || xs != "+X" || w == 0 || h == 0) fail(path, "unsupported HDR orientation '" + res + "'");
+    }
+    std::vector<uint8_t> scan(static_cast<size_t>(w) * 4u);
+    std::vector<float> samples(static_cast<size_t>(w) * h * 3u);
+    for (uint32_t y = 0; y < h; y++) {
+        if (pos + 4 > d.size()) fail(path, "truncated HDR data");
+        if (w >= 8 && w < 32768 && d[pos] == 2 && d[pos + 1] == 2 && !(d[pos + 2] & 0x80)) {
+            if (((uint32_t{d[pos + 2]} << 8u) | d[pos + 3]) != w) fail(path, "bad HDR scanline width");
+            pos += 4;
+            for (int c = 0; c < 4; c++) {
+                uint32_t x = 0;
+                while (x < w) {
+                    if (pos >= d.size()) fail(path, "truncated HDR RLE data");
+                    uint8_t count = d[pos++];
+                    if (count > 128) {
+                        count -= 128;
+                        if (x + count > w || pos >= d.size()) fail(path, "bad HDR RLE run");
+                        uint8_t v = d[pos++];
+                        for (uint8_t k = 0; k < count; k++) scan[(x++) * 4u + c] = v;
+                    } else {
+                        if (count == 0 || x + count > w || pos + count > d.size()) fail(path, "bad HDR RLE literal");
+                        for (uint8_t k = 0; k < count; k++) scan[(x++) * 4u + c] = d[pos++];
+                    }
+                }
+            }
+        } else {
+            if (pos + static_cast<size_t>(w) * 4u > d.size()) fail(path, "truncated HDR data");
+            std::memcpy(scan.data(), &d[pos], static_cast<size_t>(w) * 4u);
+            pos += static_cast<size_t>(w) * 4u;
+        }
+        for (uint32_t x = 0; x < w; x++) {
+            const uint8_t *p = &scan[x * 4u];
+            float *o = &samples[(static_cast<size_t>(y) * w + x) * 3u];
+            if (p[3] == 0) {
+                o[0] = o[1] = o[2] = 0.f;
+            } else {
+                float f = std::ldexp(1.0f, static_cast<int>(p[3]) - (128 + 8));// stb_image's hdr_convert
+                for (int k = 0; k < 3; k++) o[k] = half_to_float(float_to_half(static_cast<float>(p[k]) * f));// stored as HALF4
+            }
+        }
+    }
+    return finish(w, h, 3u, samples);
+}
+
+// ---- OpenEXR: single-part scan-line files, NO_COMPRESSION / ZIPS / ZIP, HALF / FLOAT channels ---------------------------
+LoadedImage load_exr(const std::filesystem::path &path, const std::vector<uint8_t> &d) {
+    if (d.size() < 8 || be32(d.data()) != 0x762f3101u) fail(path, "not an OpenEXR file");
+    uint32_t version;
+    std::memcpy(&version, &d[4], 4);
+    if (version & 0x1e00u) fail(path, "tiled / multi-part / deep EXR files are not supported");
+    size_t pos = 8;
+    auto cstr = [&]() {
+        std::string s;
+        while (pos < d.size() && d[pos] != 0) s.push_back(static_cast<char>(d[pos++]));
+        pos++;
+        return s;
+    };
+    struct Channel {
+        std::string name;
+        int32_t type;
+    };
+    std::vector<Channel> channels;
+    int32_t compression = -1, dw[4] = {0, 0, -1, -1};
+    for (;;) {
+        std::string name = cstr();
+        if (name.empty()) break;
+        std::string type = cstr();
+        if (pos + 4 > d.size()) fail(path, "truncated EXR header");
+        int32_t size;
+        std::memcpy(&size, &d[pos], 4);
+        pos += 4;
+        size_t start = pos;
+        if (start + static_cast<size_t>(size) > d.size()) fail(path, "truncated EXR attribute");
+        if (name == "channels") {
+            while (pos < start + static_cast<size_t>(size) && d[pos] != 0) {
+                Channel c;
+                c.name = cstr();
+                std::memcpy(&c.type, &d[pos], 4);
+                pos += 16;// pixel type, pLinear + reserved, xSampling, ySampling
+                channels.push_back(c);
+            }
+        } else if (name == "compression") {
+            compression = d[pos];
+        } else if (name == "dataWindow") {
+            std::memcpy(dw, &d[pos], 16);
+        }
+        pos = start + static_cast<size_t>(size);
+    }
+    if (channels.empty() || dw[2] < dw[0] || dw[3] < dw[1]) fail(path, "EXR header without channels / data window");
+    if (compression != 0 && compression != 2 && compression != 3) fail(path, "only uncompressed / ZIPS / ZIP EXR files are supported");
+    for (auto &c : channels)
+        if (c.type != 1 && c.type != 2) fail(path, "only HALF / FLOAT EXR channels are supported");
+    const uint32_t w = static_cast<uint32_t>(dw[2] - dw[0] + 1), h = static_cast<uint32_t>(dw[3] - dw[1] + 1);
+    const uint32_t lines_per_block = compression == 3 ? 16u : 1u;
+    const uint32_t blocks = (h + lines_per_block - 1u) / lines_per_block;
+    if (pos + static_cast<size_t>(blocks) * 8u > d.size()) fail(path, "truncated EXR offset table");
+    std::vector<uint64_t> offsets(blocks);
+    std::memcpy(offsets.data(), &d[pos], static_cast<size_t>(blocks) * 8u);
+    // channel -> output slot: channels are stored alphabetically (A, B, G, R); luminance-only files have "Y"
+    const uint32_t nfile = static_cast<uint32_t>(channels.size());
+    uint32_t nc = nfile == 1u ? 1u : nfile == 2u ? 2u : 4u;
+    auto slot_of = [&](uint32_t i) -> int {
+        const std::string &n = channels[i].name;
+        if (nc == 1u) return 0;
+        if (nc == 2u) return static_cast<int>(i);
+        if (n == "R") return 0;
+        if (n == "G") return 1;
+        if (n == "B") return 2;
+        if (n == "A") return 3;
+        return -1;
+    };
+    size_t line_bytes = 0;
+    for (auto &c : channels) line_bytes += static_cast<size_t>(w) * (c.type == 1 ? 2u : 4u);
+    const bool as_half = channels[0].type == 1;// storage follows the first channel's type (imageio.cpp:355-376)
+    std::vector<float> samples(static_cast<size_t>(w) * h * nc, 0.f);
+    if (nc == 4u)
+        for (size_t i = 0; i < static_cast<size_t>(w) * h; i++) samples[i * 4u + 3u] = 1.f;
+    std::vector<uint8_t> block, tmp;
+    for (uint32_t b = 0; b < blocks; b++) {
+        size_t p = offsets[b];
+        if (p + 8 > d.size()) fail(path, "bad EXR block offset");
+        int32_t y0, data_size;
+        std::memcpy(&y0, &d[p], 4);
+        std::memcpy(&data_size, &d[p + 4], 4);
+        p += 8;
+        if (data_size < 0 || p + static_cast<size_t>(data_size) > d.size()) fail(path, "truncated EXR block");
+        uint32_t lines = std::min(lines_per_block, h - static_cast<uint32_t>(y0 - dw[1]));
+        size_t expect = line_bytes * lines;
+        block.resize(expect);
+        if (compression == 0 || static_cast<size_t>(data_size) == expect) {
+            std::memcpy(block.data(), &d[p], expect);
+        } else {
+            tmp.resize(expect);
+            uLongf out_len = static_cast<uLongf>(expect);
+            if (uncompress(tmp.data(), &out_len, &d[p], static_cast<uLong>(data_size)) != Z_OK || out_len != expect) fail(path, "EXR zlib inflate failed");
+            for (size_t i = 1; i < expect; i++) tmp[i] = static_cast<uint8_t>(tmp[i - 1] + tmp[i] - 128);// predictor
+            size_t half = (expect + 1u) / 2u;// de-interleave
+            for (size_t i = 0; i < expect; i++) block[i] = (i & 1u) ? tmp[half + i / 2u] : tmp[i / 2u];
+        }
+        const uint8_t *q = block.data();
+        for (uint32_t l = 0; l < lines; l++) {
+            uint32_t y = static_cast<uint32_t>(y0 - dw[1]) + l;
+            for (uint32_t c = 0; c < nfile; c++) {
+                int slot = slot_of(c);
+                for (uint32_t x = 0; x < w; x++) {
+                    float v;
+                    if (channels[c].type == 1) {
+                        uint16_t hbits;
+                        std::memcpy(&hbits, q, 2);
+                        q += 2;
+                        v = half_to_float(hbits);
+                    } else {
+                        std::memcpy(&v, q, 4);
+                        q += 4;
+                        if (as_half) v = half_to_float(float_to_half(v));
+                    }
+                    if (slot >= 0) samples[(static_cast<size_t>(y) * w + x) * nc + static_cast<uint32_t>(slot)] = v;
+                }
+            }
+        }
+    }
+    return finish(w, h, nc, samples);
+}
+
+}// namespace
+
+LoadedImage load_image(const std::filesystem::path &path) {
+    auto ext = path.extension().string();
+    for (auto &c : ext) c = static_cast<char>(std::tolower(c));
+    auto data = read_file(path);
+    if (ext == ".png") return load_png(path, data);
+    if (ext == ".ppm" || ext == ".pgm" || ext == ".pnm" || ext == ".pfm") return load_pnm(path, data);
+    if (ext == ".hdr") return load_hdr(path, data);
+    if (ext == ".exr") return load_exr(path, data);
+    fail(path, "unsupported image format '" + ext + "' (supported: .png .ppm .pgm .pfm .hdr .exr)");
+}
+
+}// namespace lrh

@@ -1,5 +1,8 @@
 #include "scene.h"
 
+#include "imageio.h"
+#include "meshload.h"
+
 #include <algorithm>
 #include <cmath>
 
@@ -234,6 +237,72 @@ struct ConstantTexture final : Texture {
     float4 value() const override { return v; }
 };
 
+struct ImageTexture final : Texture {
+    // src/textures/image.cpp:16-131
+    LoadedImage image;
+    lrk_texture rec{};
+    ImageTexture(Scene *s, const NodeDesc *d) : Texture{s, d, Tag::TEXTURE} {
+        auto lower = [](std::string v) {
+            for (auto &c : v) c = static_cast<char>(std::tolower(c));
+            return v;
+        };
+        auto filter = lower(d->s("filter", "bilinear")), address = lower(d->s("address", "repeat"));
+        if (address == "zero") rec.address = LRK_TEX_ADDRESS_ZERO;
+        else if (address == "edge") rec.address = LRK_TEX_ADDRESS_EDGE;
+        else if (address == "mirror") rec.address = LRK_TEX_ADDRESS_MIRROR;
+        else if (address == "repeat") rec.address = LRK_TEX_ADDRESS_REPEAT;
+        else throw Error("Invalid texture address mode '" + address + "'. [" + d->location() + "]");
+        // the reference samples level 0 without LOD for every non-point filter (image.cpp:165, mipmap generation is a TODO
+        // there, :190-200), so bilinear / trilinear / anisotropic all reduce to the bilinear fetch
+        if (filter == "point") rec.filter = LRK_TEX_FILTER_POINT;
+        else if (filter == "bilinear" || filter == "trilinear" || filter == "anisotropic" || filter == "aniso") rec.filter = LRK_TEX_FILTER_LINEAR;
+        else throw Error("Invalid texture filter mode '" + filter + "'. [" + d->location() + "]");
+        auto two = [&](const char *name, float dflt, float out[2]) {
+            auto v = d->float_list(name);
+            if (v.size() >= 2) {
+                out[0] = v[0];
+                out[1] = v[1];
+            } else {
+                out[0] = out[1] = v.empty() ? dflt : v[0];
+            }
+        };
+        two("uv_scale", 1.f, rec.uv_scale);
+        two("uv_offset", 0.f, rec.uv_offset);
+        auto path = d->path("file");
+        auto ext = lower(path.extension().string());
+        auto encoding = lower(d->s("encoding", (ext == ".exr" || ext == ".hdr") ? "linear" : "srgb"));
+        rec.gamma = 1.f;
+        if (encoding == "srgb") {
+            rec.encoding = LRK_TEX_ENCODING_SRGB;
+        } else if (encoding == "gamma") {
+            rec.encoding = LRK_TEX_ENCODING_GAMMA;
+            rec.gamma = d->f("gamma", 1.f);
+        } else {
+            rec.encoding = LRK_TEX_ENCODING_LINEAR;// unknown encodings fall back to linear with a warning in the reference
+        }
+        rec.scale = d->f("scale", 1.f);
+        try {
+            image = load_image(path);
+        } catch (const std::exception &e) {
+            throw Error(std::string{e.what()} + " [" + d->location() + "]");
+        }
+        rec.width = image.width;
+        rec.height = image.height;
+        rec.channels = image.channels;
+    }
+    bool is_black() const override { return rec.scale == 0.f; }
+    bool is_constant() const override { return false; }
+    bool is_image() const override { return true; }
+    uint32_t channels() const override { return image.channels; }
+    float4 value() const override { throw Error("ImageTexture has no constant value."); }
+    void emit(lrk_texture &out, std::vector<float> &texels) const override {
+        auto offset = out.texel_offset;
+        out = rec;
+        out.texel_offset = offset;
+        texels.insert(texels.end(), image.rgba.begin(), image.rgba.end());
+    }
+};
+
 struct SRGBSpectrum final : Spectrum {
     SRGBSpectrum(Scene *s, const NodeDesc *d) : Spectrum{s, d, Tag::SPECTRUM} {}
 };
@@ -261,6 +330,12 @@ const Texture *constant_or_null(Scene *s, const NodeDesc *d, const char *name) {
     if (t && !t->is_constant()) throw Error("Only constant textures are supported ('" + std::string{name} + "').");
     return t;
 }
+// surface parameters: constant or image texture
+const Texture *surface_texture(Scene *s, const NodeDesc *d, const char *name) {
+    auto t = s->load_texture(d->node(name));
+    if (t && !t->is_constant() && !t->is_image()) throw Error("Only constant and image textures are supported ('" + std::string{name} + "').");
+    return t;
+}
 void reject_wrappers(const NodeDesc *d) {
     // NormalMapWrapper<OpacitySurfaceWrapper<...>> (src/base/surface.h:160-330) is out of scope
     for (auto name : {"normal_map", "alpha", "opacity"}) {
@@ -271,6 +346,7 @@ void reject_wrappers(const NodeDesc *d) {
 
 }// namespace
 LRH_PLUGIN("texture-constant", ConstantTexture)
+LRH_PLUGIN("texture-image", ImageTexture)
 LRH_PLUGIN("spectrum-srgb", SRGBSpectrum)
 
 // ---------------------------------------------------------------- transforms
@@ -553,15 +629,23 @@ struct MatteSurface final : Surface {
     const Texture *sigma;
     MatteSurface(Scene *s, const NodeDesc *d) : Surface{s, d, Tag::SURFACE} {
         reject_wrappers(d);
-        kd = constant_or_null(s, d, "Kd");
-        sigma = constant_or_null(s, d, "sigma");
+        kd = surface_texture(s, d, "Kd");
+        sigma = surface_texture(s, d, "sigma");
     }
-    lrk_surface flatten() const override {
+    lrk_surface flatten(TextureTable &textures) const override {
         lrk_surface out{};
         out.type = LRK_SURFACE_MATTE;
-        auto c = decode_albedo(kd, nullptr);
-        out.p[0] = c.x; out.p[1] = c.y; out.p[2] = c.z;
-        out.p[3] = (sigma && !sigma->is_black()) ? saturate(sigma->value().x) * 90.f : 0.f;
+        if (kd && kd->is_image()) {
+            out.tex[0] = textures.slot(kd);
+        } else {
+            auto c = decode_albedo(kd, nullptr);
+            out.p[0] = c.x; out.p[1] = c.y; out.p[2] = c.z;
+        }
+        if (sigma && !sigma->is_black()) {
+            if (sigma->is_image()) out.tex[3] = textures.slot(sigma);
+            else out.p[3] = saturate(sigma->value().x) * 90.f;
+        }
+        if (out.tex[0] || out.tex[3]) out.flags |= LRK_SURFACE_HAS_TEXTURES;
         return out;
     }
 };
@@ -573,20 +657,20 @@ struct DisneySurface final : Surface {
     bool thin, remap_roughness;
     DisneySurface(Scene *s, const NodeDesc *d) : Surface{s, d, Tag::SURFACE} {
         reject_wrappers(d);
-        color = constant_or_null(s, d, d->has_property("color") ? "color" : "Kd");
+        color = surface_texture(s, d, d->has_property("color") ? "color" : "Kd");
         thin = d->b("thin", false);
         remap_roughness = d->b("remap_roughness", true);
-        metallic = constant_or_null(s, d, "metallic");
-        eta = constant_or_null(s, d, "eta");
-        roughness = constant_or_null(s, d, "roughness");
-        specular_tint = constant_or_null(s, d, "specular_tint");
-        anisotropic = constant_or_null(s, d, "anisotropic");
-        sheen = constant_or_null(s, d, "sheen");
-        sheen_tint = constant_or_null(s, d, "sheen_tint");
-        clearcoat = constant_or_null(s, d, "clearcoat");
-        clearcoat_gloss = constant_or_null(s, d, "clearcoat_gloss");
+        metallic = surface_texture(s, d, "metallic");
+        eta = surface_texture(s, d, "eta");
+        roughness = surface_texture(s, d, "roughness");
+        specular_tint = surface_texture(s, d, "specular_tint");
+        anisotropic = surface_texture(s, d, "anisotropic");
+        sheen = surface_texture(s, d, "sheen");
+        sheen_tint = surface_texture(s, d, "sheen_tint");
+        clearcoat = surface_texture(s, d, "clearcoat");
+        clearcoat_gloss = surface_texture(s, d, "clearcoat_gloss");
         specular_trans = constant_or_null(s, d, "specular_trans");
-        flatness = constant_or_null(s, d, "flatness");
+        flatness = surface_texture(s, d, "flatness");
         diffuse_trans = constant_or_null(s, d, "diffuse_trans");
         if (thin) throw Error("Thin Disney surfaces are not supported. [" + d->location() + "]");
         if (specular_trans && !specular_trans->is_black())
@@ -604,27 +688,41 @@ struct DisneySurface final : Surface {
         if (clearcoat && !clearcoat->is_black()) l |= LRK_DISNEY_LOBE_CLEARCOAT;
         return l;
     }
-    lrk_surface flatten() const override {
+    lrk_surface flatten(TextureTable &textures) const override {
         lrk_surface out{};
         out.type = LRK_SURFACE_DISNEY;
         out.lobes = lobes();
-        float lum;
-        auto c = decode_albedo(color, &lum);
-        auto x = [](const Texture *t, float dflt) { return t ? t->value().x : dflt; };
-        out.p[0] = c.x; out.p[1] = c.y; out.p[2] = c.z; out.p[3] = lum;
-        out.p[4] = x(metallic, 0.f);
-        out.p[5] = x(eta, 1.5f);
-        auto r = x(roughness, .5f);
+        if (remap_roughness) out.flags |= LRK_SURFACE_REMAP_ROUGHNESS;
+        // a parameter is either the node's constant (p[k]) or an image texture evaluated per hit (tex[k])
+        auto x = [&](const Texture *t, float dflt, uint32_t slot) {
+            if (t && t->is_image()) {
+                out.tex[slot] = textures.slot(t);
+                out.flags |= LRK_SURFACE_HAS_TEXTURES;
+                return dflt;
+            }
+            return t ? t->value().x : dflt;
+        };
+        if (color && color->is_image()) {
+            out.tex[0] = textures.slot(color);
+            out.flags |= LRK_SURFACE_HAS_TEXTURES;
+        } else {
+            float lum;
+            auto c = decode_albedo(color, &lum);
+            out.p[0] = c.x; out.p[1] = c.y; out.p[2] = c.z; out.p[3] = lum;
+        }
+        out.p[4] = x(metallic, 0.f, 4);
+        out.p[5] = x(eta, 1.5f, 5);
+        auto r = x(roughness, .5f, 6);
         if (remap_roughness) r = std::max(r * r, 1e-4f);// roughness_to_alpha, src/util/scattering.cpp:137-139
         out.p[6] = r;
-        out.p[7] = x(specular_tint, 0.f);
-        out.p[8] = x(anisotropic, 0.f);
-        out.p[9] = x(sheen, 0.f);
-        out.p[10] = x(sheen_tint, 0.f);
-        out.p[11] = x(clearcoat, 0.f);
-        out.p[12] = x(clearcoat_gloss, 1.f);
-        out.p[13] = x(specular_trans, 0.f);
-        out.p[14] = x(flatness, 0.f);
+        out.p[7] = x(specular_tint, 0.f, 7);
+        out.p[8] = x(anisotropic, 0.f, 8);
+        out.p[9] = x(sheen, 0.f, 9);
+        out.p[10] = x(sheen_tint, 0.f, 10);
+        out.p[11] = x(clearcoat, 0.f, 11);
+        out.p[12] = x(clearcoat_gloss, 1.f, 12);
+        out.p[13] = specular_trans ? specular_trans->value().x : 0.f;
+        out.p[14] = x(flatness, 0.f, 14);
         out.p[15] = 0.f;// diffuse_trans is only built for thin surfaces (src/surfaces/disney.cpp:1017)
         return out;
     }
@@ -633,7 +731,7 @@ struct DisneySurface final : Surface {
 struct NullSurface final : Surface {
     NullSurface(Scene *s, const NodeDesc *d) : Surface{s, d, Tag::SURFACE} {}
     bool is_null() const override { return true; }
-    lrk_surface flatten() const override { throw Error("NullSurface cannot be instantiated."); }
+    lrk_surface flatten(TextureTable &) const override { throw Error("NullSurface cannot be instantiated."); }
 };
 
 struct DiffuseLight final : Light {
@@ -746,6 +844,37 @@ struct InlineMesh final : Shape {
     const std::vector<lrk_triangle> &triangles() const override { return tris; }
 };
 
+struct MeshShape final : Shape {
+    // src/shapes/mesh.cpp:148-162 ; files are cached per (path, options) like the reference's lru cache (:32-39)
+    std::shared_ptr<const MeshData> data;
+    MeshShape(Scene *s, const NodeDesc *d) : Shape{s, d} {
+        read_mesh_wrappers(this, s, d);
+        auto path = d->path("file");
+        if (d->u("subdivision", 0u) != 0u)
+            throw Error("Mesh subdivision (Catmull-Clark) is not supported. [" + d->location() + "]");
+        bool flip_uv = d->b("flip_uv", false), drop_normal = d->b("drop_normal", false), drop_uv = d->b("drop_uv", false);
+        std::error_code ec;
+        auto canonical = std::filesystem::weakly_canonical(path, ec);
+        auto key = (ec ? path : canonical).string() + (flip_uv ? "|f" : "|-") + (drop_normal ? "n" : "-") + (drop_uv ? "u" : "-");
+        static std::mutex mutex;
+        static std::unordered_map<std::string, std::shared_ptr<const MeshData>> cache;
+        std::scoped_lock lock{mutex};
+        auto it = cache.find(key);
+        if (it == cache.end()) {
+            try {
+                it = cache.emplace(key, std::make_shared<const MeshData>(load_mesh(path, flip_uv, drop_normal, drop_uv))).first;
+            } catch (const std::exception &e) {
+                throw Error(std::string{e.what()} + " [" + d->location() + "]");
+            }
+        }
+        data = it->second;
+    }
+    bool is_mesh() const override { return true; }
+    uint32_t vertex_properties() const override { return data->properties; }
+    const std::vector<lrk_vertex> &vertices() const override { return data->vertices; }
+    const std::vector<lrk_triangle> &triangles() const override { return data->triangles; }
+};
+
 struct SphereShape final : Shape {
     // src/shapes/sphere.cpp:103-118 ; geometry cached per subdivision level like the reference (:88-100)
     struct Geometry {
@@ -792,6 +921,7 @@ struct GroupShape final : Shape {
 
 }// namespace
 LRH_PLUGIN("shape-inlinemesh", InlineMesh)
+LRH_PLUGIN("shape-mesh", MeshShape)
 LRH_PLUGIN("shape-sphere", SphereShape)
 LRH_PLUGIN("shape-instance", InstanceShape)
 LRH_PLUGIN("shape-group", GroupShape)

@@ -53,7 +53,29 @@ struct Texture : SceneNode {
     virtual bool is_black() const = 0;
     virtual bool is_constant() const = 0;
     virtual uint32_t channels() const = 0;
-    virtual float4 value() const = 0;// constant value (scale applied)
+    virtual float4 value() const = 0;// constant value (scale applied); image textures: not meaningful
+    // image textures (src/textures/image.cpp) append their record + texels to the flattened scene
+    virtual bool is_image() const { return false; }
+    virtual void emit(lrk_texture &, std::vector<float> &) const { throw Error("Texture::emit: not an image texture."); }
+};
+
+// The image textures a flattened scene references: one lrk_texture record + texels per distinct Texture node.
+struct TextureTable {
+    std::vector<lrk_texture> records;
+    std::vector<float> texels;// RGBA
+    std::unordered_map<const Texture *, uint32_t> slots;
+    // value for lrk_surface::tex[k]: 0 for constants / null, index + 1 for image textures
+    uint32_t slot(const Texture *t) {
+        if (t == nullptr || !t->is_image()) return 0u;
+        if (auto it = slots.find(t); it != slots.end()) return it->second;
+        lrk_texture rec{};
+        rec.texel_offset = texels.size() / 4u;
+        t->emit(rec, texels);
+        records.push_back(rec);
+        auto id = static_cast<uint32_t>(records.size());
+        slots.emplace(t, id);
+        return id;
+    }
 };
 
 struct Transform : SceneNode {
@@ -117,7 +139,7 @@ struct Medium : SceneNode {
 struct Surface : SceneNode {
     using SceneNode::SceneNode;
     virtual bool is_null() const { return false; }
-    virtual lrk_surface flatten() const = 0;
+    virtual lrk_surface flatten(TextureTable &textures) const = 0;
 };
 
 struct Light : SceneNode {

@@ -149,6 +149,18 @@ bool NodeDesc::b(std::string_view name, bool dflt) const {
     auto v = boolean(name);
     return v ? *v : dflt;
 }
+
+std::string NodeDesc::s(std::string_view name, const std::string &dflt) const {
+    auto v = string(name);
+    return v ? *v : dflt;
+}
+
+std::filesystem::path NodeDesc::path(std::string_view name) const {
+    auto v = string(name);
+    if (!v) throw Error("No valid values given for property '" + std::string{name} + "' in scene description node '" + _identifier + "'. [" + _location + "]");
+    std::filesystem::path p{*v};
+    return p.is_absolute() ? p : _source_dir / p;
+}
 bool NodeDesc::fN(std::string_view name, int n, float *out) const {
     auto v = numbers(name);
     if (!v || static_cast<int>(v->size()) < n) return false;

@@ -70,6 +70,9 @@ public:
     float f(std::string_view name, float dflt) const;
     uint32_t u(std::string_view name, uint32_t dflt) const;
     bool b(std::string_view name, bool dflt) const;
+    std::string s(std::string_view name, const std::string &dflt) const;
+    // a required file path, relative paths resolved against the directory of the defining file (property_path)
+    std::filesystem::path path(std::string_view name) const;
     // N floats (N<=4); returns false if absent or fewer than N values
     bool fN(std::string_view name, int n, float *out) const;
     std::vector<float> float_list(std::string_view name) const;

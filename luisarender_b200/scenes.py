@@ -194,3 +194,78 @@ def instanced_spheres(resolution=(1920, 1080), spp=1024, seed=1, depth=10, rr_de
   shapes {{ {", ".join(shapes)} }}
 }}""")
     return "\n".join(out) + "\n"
+
+
+def textured_room(resolution=(96, 64), spp=8, depth=6, rr_depth=0, rr_threshold=0.95, seed=19980810,
+                  assets="tests/golden/assets", output="textured.exr", integrator="WavePath") -> str:
+    """SURVEY.md §8 row f1 in one small scene: image-textured Matte and Disney parameters (PNG 8/16-bit, grey, palette; all
+    four address modes, point + bilinear filters, sRGB + linear encodings, uv scale/offset) on an InlineMesh with uvs and
+    on mesh FILES (Wavefront OBJ without normals, binary PLY).  `assets` is relative to the directory the scene is loaded from."""
+    a = assets.rstrip("/")
+    return f"""
+Surface floor_s : Matte {{
+  Kd : Image {{ file {{ "{a}/checker_rgb8.png" }} address {{ "repeat" }} filter {{ "bilinear" }} uv_scale {{ 2.0, 3.0 }} uv_offset {{ 0.25, 0.0 }} }}
+}}
+Surface wall_s : Matte {{
+  Kd : Image {{ file {{ "{a}/ramp_rgba16.png" }} address {{ "edge" }} encoding {{ "linear" }} scale {{ 0.9 }} }}
+  sigma : Image {{ file {{ "{a}/rough_gray8.png" }} encoding {{ "linear" }} filter {{ "point" }} }}
+}}
+Surface cube_s : Disney {{
+  color : Image {{ file {{ "{a}/checker_rgb8.png" }} address {{ "mirror" }} filter {{ "point" }} uv_scale {{ 1.5 }} }}
+  roughness : Image {{ file {{ "{a}/rough_gray8.png" }} encoding {{ "linear" }} address {{ "repeat" }} }}
+  metallic : Constant {{ v {{ 0.2 }} }}
+  clearcoat : Constant {{ v {{ 0.5 }} }}
+}}
+Surface tetra_s : Matte {{
+  Kd : Image {{ file {{ "{a}/palette4.png" }} address {{ "zero" }} encoding {{ "gamma" }} gamma {{ 2.0 }} }}
+}}
+Light area_light : Diffuse {{ emission : Constant {{ v {{ 14.0, 13.0, 11.0 }} }} }}
+Shape floor : InlineMesh {{
+  positions {{ -2.0, 0.0, 2.0,  2.0, 0.0, 2.0,  2.0, 0.0, -2.0,  -2.0, 0.0, -2.0 }}
+  uvs {{ 0.0, 0.0,  1.0, 0.0,  1.0, 1.0,  0.0, 1.0 }}
+  indices {{ 0, 1, 2, 0, 2, 3 }}
+  surface {{ @floor_s }}
+}}
+Shape wall : InlineMesh {{
+  positions {{ -2.0, 0.0, -2.0,  2.0, 0.0, -2.0,  2.0, 2.5, -2.0,  -2.0, 2.5, -2.0 }}
+  uvs {{ -0.2, -0.2,  1.2, -0.2,  1.2, 1.2,  -0.2, 1.2 }}
+  indices {{ 0, 1, 2, 0, 2, 3 }}
+  surface {{ @wall_s }}
+}}
+Shape cube : Mesh {{
+  file {{ "{a}/cube.obj" }}
+  surface {{ @cube_s }}
+  transform : SRT {{ scale {{ 0.8 }} rotate {{ 0.0, 1.0, 0.0, 30.0 }} translate {{ -0.6, 0.4, -0.3 }} }}
+}}
+Shape tetra : Mesh {{
+  file {{ "{a}/tetra_binary.ply" }}
+  flip_uv {{ true }}
+  surface {{ @tetra_s }}
+  transform : SRT {{ scale {{ 1.1 }} translate {{ 0.5, 0.0, -0.2 }} }}
+}}
+Shape lamp : InlineMesh {{
+  positions {{ -0.6, 2.4, 0.4,  -0.6, 2.4, -0.4,  0.6, 2.4, -0.4,  0.6, 2.4, 0.4 }}
+  indices {{ 0, 1, 2, 0, 2, 3 }}
+  light {{ @area_light }}
+}}
+Camera camera : Pinhole {{
+  position {{ 0.0, 1.4, 4.2 }}
+  front {{ 0.0, -0.2, -1.0 }}
+  up {{ 0.0, 1.0, 0.0 }}
+  fov {{ 40.0 }}
+  spp {{ {int(spp)} }}
+  film : Color {{ resolution {{ {int(resolution[0])}, {int(resolution[1])} }} }}
+  filter : Box {{ radius {{ 0.5 }} }}
+  file {{ "{output}" }}
+}}
+render {{
+  integrator : {integrator} {{
+    depth {{ {int(depth)} }}
+    rr_depth {{ {int(rr_depth)} }}
+    rr_threshold {{ {_fmt(rr_threshold)} }}
+    sampler : Independent {{ seed {{ {int(seed)} }} }}
+  }}
+  cameras {{ @camera }}
+  shapes {{ @floor, @wall, @cube, @tetra, @lamp }}
+}}
+"""

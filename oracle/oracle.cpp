@@ -994,6 +994,92 @@ SurfSample surface_sample(const lrk_surface &s, const Interaction &it, V3 wo, fl
 }
 
 // ------------------------------------------------------------------------------------------------
+// Image textures: ImageTextureInstance::evaluate, src/textures/image.cpp:132-166, sampled
+// with the reference's software sampler, src/compute/src/rust/luisa_compute_backend_impl/src/cpu/codegen/
+// cpu_texture.h:418-464 (coordinates / bilinear), :489-493 (point), :63 (unorm conversion, done by the host loader).
+// ------------------------------------------------------------------------------------------------
+struct F4 {
+    float x, y, z, w;
+};
+inline float tex_fract(float x) { return x - std::floor(x); }// device_math.h:3429
+inline float tex_coord_point(uint32_t address, float uv, float s) {
+    constexpr float one_minus_epsilon = 0x1.fffffep-1f;// cpu_texture.h:12
+    switch (address) {
+        case LRK_TEX_ADDRESS_EDGE: return std::fmin(std::fmax(uv, 0.0f), one_minus_epsilon) * s;
+        case LRK_TEX_ADDRESS_REPEAT: return tex_fract(uv) * s;
+        case LRK_TEX_ADDRESS_MIRROR: {
+            uv = std::fmod(std::fabs(uv), 2.0f);
+            uv = uv < 1.f ? uv : 2.f - uv;
+            return std::fmin(uv, one_minus_epsilon) * s;
+        }
+        default: return (uv < 0.f || uv >= 1.f) ? 65536.f : uv * s;// ZERO: lands outside, reads 0
+    }
+}
+inline F4 tex_read(const lrk_scene_desc &sc, const lrk_texture &t, uint32_t x, uint32_t y) {
+    if (!(x < t.width && y < t.height)) return {0.f, 0.f, 0.f, 0.f};// cpu_texture.h:369-372
+    const float *p = sc.texels + 4u * (t.texel_offset + static_cast<uint64_t>(y) * t.width + x);
+    return {p[0], p[1], p[2], p[3]};
+}
+inline F4 lerp4(F4 a, F4 b, float t) { return {lerp(a.x, b.x, t), lerp(a.y, b.y, t), lerp(a.z, b.z, t), lerp(a.w, b.w, t)}; }
+F4 texture_sample(const lrk_scene_desc &sc, const lrk_texture &t, float u, float v) {
+    const float sx = static_cast<float>(t.width), sy = static_cast<float>(t.height);
+    if (t.filter == LRK_TEX_FILTER_POINT) {
+        float cx = tex_coord_point(t.address, u, sx), cy = tex_coord_point(t.address, v, sy);
+        return tex_read(sc, t, static_cast<uint32_t>(cx), static_cast<uint32_t>(cy));
+    }
+    const float inv_sx = 1.f / sx, inv_sy = 1.f / sy;
+    float ax = tex_coord_point(t.address, u - .5f * inv_sx, sx), bx = tex_coord_point(t.address, u + .5f * inv_sx, sx);
+    float ay = tex_coord_point(t.address, v - .5f * inv_sy, sy), by = tex_coord_point(t.address, v + .5f * inv_sy, sy);
+    float x_min = std::fmin(ax, bx), x_max = std::fmax(ax, bx), y_min = std::fmin(ay, by), y_max = std::fmax(ay, by);
+    float tx = tex_fract(x_max), ty = tex_fract(y_max);
+    uint32_t x0 = static_cast<uint32_t>(x_min), y0 = static_cast<uint32_t>(y_min);
+    uint32_t x1 = static_cast<uint32_t>(x_max), y1 = static_cast<uint32_t>(y_max);
+    F4 v00 = tex_read(sc, t, x0, y0), v01 = tex_read(sc, t, x1, y0), v10 = tex_read(sc, t, x0, y1), v11 = tex_read(sc, t, x1, y1);
+    return lerp4(lerp4(v00, v01, tx), lerp4(v10, v11, tx), ty);
+}
+inline float tex_decode(const lrk_texture &t, float x) {// image.cpp:143-158
+    if (t.encoding == LRK_TEX_ENCODING_SRGB) {
+        float lin = x <= 0.04045f ? x * (1.0f / 12.92f) : std::pow((x + 0.055f) * (1.0f / 1.055f), 2.4f);
+        return t.scale * lin;
+    }
+    if (t.encoding == LRK_TEX_ENCODING_GAMMA) return t.scale * std::pow(x, t.gamma);
+    return t.scale * x;
+}
+F4 texture_evaluate(const lrk_scene_desc &sc, uint32_t tex_id, float u, float v) {
+    const lrk_texture &t = sc.textures[tex_id];
+    F4 s = texture_sample(sc, t, u * t.uv_scale[0] + t.uv_offset[0], v * t.uv_scale[1] + t.uv_offset[1]);
+    return {tex_decode(t, s.x), tex_decode(t, s.y), tex_decode(t, s.z), tex_decode(t, s.w)};
+}
+// Surface parameters at a hit (MatteInstance::populate_closure src/surfaces/matte.cpp:117-131,
+// DisneySurfaceInstance::populate_closure src/surfaces/disney.cpp:932-956; colours through
+// Texture::Instance::evaluate_albedo_spectrum src/base/texture.cpp:20-31 and the sRGB spectrum src/spectra/srgb.cpp:34-40,70-72)
+lrk_surface resolve_surface(const lrk_scene_desc &sc, const lrk_surface &node, const Interaction &it) {
+    lrk_surface s = node;
+    if (!(s.flags & LRK_SURFACE_HAS_TEXTURES)) return s;
+    if (s.tex[0] != 0u) {
+        F4 val = texture_evaluate(sc, s.tex[0] - 1u, it.u, it.v);
+        const uint32_t ch = sc.textures[s.tex[0] - 1u].channels;
+        V3 rgb = ch == 1u ? v3(val.x, val.x, val.x) : ch == 2u ? v3(val.x, val.y, 1.f) : v3(val.x, val.y, val.z);// texture.cpp:14-18
+        rgb = v3(saturate(rgb.x), saturate(rgb.y), saturate(rgb.z));
+        s.p[0] = rgb.x;
+        s.p[1] = rgb.y;
+        s.p[2] = rgb.z;
+        if (s.type == LRK_SURFACE_DISNEY) s.p[3] = 0.212671f * rgb.x + 0.715160f * rgb.y + 0.072169f * rgb.z;
+    }
+    if (s.type == LRK_SURFACE_MATTE) {
+        if (s.tex[3] != 0u) s.p[3] = saturate(texture_evaluate(sc, s.tex[3] - 1u, it.u, it.v).x) * 90.f;
+    } else {
+        for (uint32_t k = 4u; k < 15u; k++) {
+            if (s.tex[k] == 0u) continue;
+            float x = texture_evaluate(sc, s.tex[k] - 1u, it.u, it.v).x;
+            if (k == 6u && (s.flags & LRK_SURFACE_REMAP_ROUGHNESS)) x = std::fmax(x * x, 1e-4f);// scattering.cpp:137-139
+            s.p[k] = x;
+        }
+    }
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------------
 // The estimator: src/integrators/mega_path.cpp:49-156 (identical, up to kernel boundaries, to
 // src/integrators/wave_path.cpp:254-469).  Draw order is normative.
 // ------------------------------------------------------------------------------------------------
@@ -1029,7 +1115,7 @@ V3 path_li(const lrk_scene_desc &sc, uint32_t px, uint32_t py, uint32_t sample_i
         // the shadow ray is traced unconditionally (mega_path.cpp:108)
         bool occluded = trace_bvh(sc, ls.shadow_ray, true, &tc).inst != ~0u;
         if (cnt) cnt->shadow_rays++;
-        const lrk_surface &surface = sc.surfaces[it.shape.surface_tag];
+        const lrk_surface surface = resolve_surface(sc, sc.surfaces[it.shape.surface_tag], it);
         if (ls.eval.pdf > 0.0f && !occluded) {
             V3 wi = v3(ls.shadow_ray.d[0], ls.shadow_ray.d[1], ls.shadow_ray.d[2]);
             SurfEval ev = surface_evaluate(surface, it, wo, wi);
@@ -1276,7 +1362,7 @@ V3 volume_path_li(const lrk_scene_desc &sc, uint32_t px, uint32_t py, uint32_t s
             LightSample ls = sample_light(sc, it, u_light_selection, ul0, ul1);
             Transmittance T = volume_transmittance(sc, rng, ls.shadow_ray, &tc, cnt, nullptr);
             V3 wo = -v3(ray.d[0], ray.d[1], ray.d[2]);
-            const lrk_surface &surface = sc.surfaces[it.shape.surface_tag];
+            const lrk_surface surface = resolve_surface(sc, sc.surfaces[it.shape.surface_tag], it);
             // true_hit(medium_tag = 0) is `0 <= priority of the environment medium` (medium_tracker.cpp:19-21)
             if (!(0u <= medium.priority)) {
                 ray = spawn_ray(it, v3(ray.d[0], ray.d[1], ray.d[2]));
@@ -1518,6 +1604,18 @@ void oracle_sample_light(const lrk_scene_desc *scene, const lrk_ray *ray, const 
     const float vals[12]{s.eval.L.x, s.eval.L.y, s.eval.L.z, s.eval.pdf, s.shadow_ray.o[0], s.shadow_ray.o[1], s.shadow_ray.o[2],
                          s.shadow_ray.tmin, s.shadow_ray.d[0], s.shadow_ray.d[1], s.shadow_ray.d[2], s.shadow_ray.tmax};
     std::memcpy(out, vals, sizeof(vals));
+}
+
+void oracle_texture_evaluate(const lrk_scene_desc *scene, uint32_t texture_id, const float uv[2], float out[4]) {
+    F4 v = texture_evaluate(*scene, texture_id, uv[0], uv[1]);
+    out[0] = v.x, out[1] = v.y, out[2] = v.z, out[3] = v.w;
+}
+
+void oracle_resolve_surface(const lrk_scene_desc *scene, uint32_t surface_tag, const float uv[2], lrk_surface *out) {
+    Interaction it;
+    it.u = uv[0];
+    it.v = uv[1];
+    *out = resolve_surface(*scene, scene->surfaces[surface_tag], it);
 }
 
 }// extern "C"

@@ -43,6 +43,8 @@ def golden_scenes():
         # config C4 in miniature: homogeneous environment medium + MegaVPTNaive semantics, depth 8
         "spheres_medium": scenes.instanced_spheres(resolution=(32, 18), spp=4, big_subdivision=3, small_subdivision=2, small_count=10,
                                                    medium=True, depth=8),
+        # image-textured Matte / Disney parameters on an InlineMesh with uvs and on OBJ / PLY mesh files
+        "textured": scenes.textured_room(resolution=(48, 32), spp=4),
     }
 
 

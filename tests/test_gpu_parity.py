@@ -80,7 +80,7 @@ def _image_parity(gpu_raw, cpu_raw):
     return rel, off
 
 
-@pytest.mark.parametrize("name", ["cornell", "cornell_disney", "spheres", "spheres_medium"])
+@pytest.mark.parametrize("name", ["cornell", "cornell_disney", "spheres", "spheres_medium", "textured"])
 def test_render_matches_oracle(name, gpu_renderer):
     import importlib.util
     spec = importlib.util.spec_from_file_location("generate_golden", Path(__file__).resolve().parent / "golden" / "generate_golden.py")
