@@ -166,9 +166,20 @@ typedef struct lrk_instance {
  * (src/surfaces/matte.cpp:117-131, src/surfaces/disney.cpp:932-956):
  *   colour slots (MATTE 0, DISNEY 0): rgb = saturate(extend_color_to_rgb(v.xyz, channels)) -> p[0..2] (+ luminance ->
  *   p[3] for DISNEY); MATTE slot 3: saturate(v.x) * 90; DISNEY scalar slots 4..14: v.x, slot 6 additionally remapped
- *   max(v.x^2, 1e-4) when LRK_SURFACE_REMAP_ROUGHNESS is set in flags. */
+ *   max(v.x^2, 1e-4) when LRK_SURFACE_REMAP_ROUGHNESS is set in flags.
+ *
+ * Wrappers every surface node carries (NormalMapWrapper<OpacitySurfaceWrapper<...>>, src/base/surface.h:160-275):
+ *   opacity   : LRK_SURFACE_MAYBE_NON_OPAQUE set when an `alpha` / `opacity` texture exists whose static value is < 1 (:177-181);
+ *               alpha at a candidate hit = opacity_tex ? image(opacity_tex - 1, uv).x : opacity; the candidate is skipped when
+ *               xxhash32(inst, prim, bary bits) * 2^-32 > alpha (Geometry::_alpha_skip, src/base/geometry.cpp:165-192), in
+ *               closest-hit and any-hit traversal alike (:218-279).  Instances of such surfaces carry
+ *               LRK_SHAPE_MAYBE_NON_OPAQUE in their handle flags (:123-126).
+ *   normal map: LRK_SURFACE_HAS_NORMAL_MAP: n_local = 2 * rgb - 1 (rgb = image(normal_tex - 1, uv) or normal_value), x and y
+ *               scaled by normal_strength when != 1, shading frame rebuilt around clamp_shading_normal (surface.h:236-253). */
 #define LRK_SURFACE_HAS_TEXTURES 1u
 #define LRK_SURFACE_REMAP_ROUGHNESS 2u
+#define LRK_SURFACE_MAYBE_NON_OPAQUE 4u
+#define LRK_SURFACE_HAS_NORMAL_MAP 8u
 typedef struct lrk_surface {
     uint32_t type;
     uint32_t lobes;
@@ -176,6 +187,12 @@ typedef struct lrk_surface {
     uint32_t reserved;
     float p[16];
     uint32_t tex[16];
+    uint32_t opacity_tex; /* 0 = constant `opacity` */
+    float opacity;
+    uint32_t normal_tex; /* 0 = constant `normal_value` */
+    float normal_strength;
+    float normal_value[3];
+    uint32_t reserved2;
 } lrk_surface;
 
 /* One image texture (src/textures/image.cpp:16-151).  Texels are RGBA float (8/16-bit sources converted with x/255,

@@ -17,8 +17,8 @@ LRK_ABI_VERSION = 2
 TEX_ADDRESS_EDGE, TEX_ADDRESS_REPEAT, TEX_ADDRESS_MIRROR, TEX_ADDRESS_ZERO = 0, 1, 2, 3
 TEX_FILTER_POINT, TEX_FILTER_LINEAR = 0, 1
 TEX_ENCODING_LINEAR, TEX_ENCODING_SRGB, TEX_ENCODING_GAMMA = 0, 1, 2
-SURFACE_HAS_TEXTURES, SURFACE_REMAP_ROUGHNESS = 1, 2
-SHAPE_HAS_VERTEX_NORMAL, SHAPE_HAS_VERTEX_UV, SHAPE_HAS_SURFACE, SHAPE_HAS_LIGHT = 1, 2, 4, 8
+SURFACE_HAS_TEXTURES, SURFACE_REMAP_ROUGHNESS, SURFACE_MAYBE_NON_OPAQUE, SURFACE_HAS_NORMAL_MAP = 1, 2, 4, 8
+SHAPE_HAS_VERTEX_NORMAL, SHAPE_HAS_VERTEX_UV, SHAPE_HAS_SURFACE, SHAPE_HAS_LIGHT, SHAPE_MAYBE_NON_OPAQUE = 1, 2, 4, 8, 32
 LRK_FILTER_LUT_SIZE = 64
 
 u32, u64, i32, i64, f32, f64 = C.c_uint32, C.c_uint64, C.c_int32, C.c_int64, C.c_float, C.c_double
@@ -60,7 +60,8 @@ class Instance(C.Structure):
 
 
 class Surface(C.Structure):
-    _fields_ = [("type", u32), ("lobes", u32), ("flags", u32), ("reserved", u32), ("p", f32 * 16), ("tex", u32 * 16)]
+    _fields_ = [("type", u32), ("lobes", u32), ("flags", u32), ("reserved", u32), ("p", f32 * 16), ("tex", u32 * 16),
+                ("opacity_tex", u32), ("opacity", f32), ("normal_tex", u32), ("normal_strength", f32), ("normal_value", f32 * 3), ("reserved2", u32)]
 
 
 class Texture(C.Structure):

@@ -129,14 +129,14 @@ __global__ void __launch_bounds__(kBlock) generate_rays_kernel(DeviceScene sc, P
 // counts[] layout (all zeroed by generate_rays_kernel at the start of a pass), 64 slots (one per depth) each:
 //   [0] path-queue sizes  [1] shadow-queue sizes  [2] closest-hit fetch cursors  [3] shadow fetch cursors
 //   [4],[5],[6] hit-bucket sizes: light-only hits, Matte hits, Disney hits
-template<bool COUNT>
+template<bool COUNT, bool ALPHA = false>
 __global__ void __launch_bounds__(kBlock, 4) trace_closest_kernel(DeviceScene sc, const float4 *__restrict__ ray_o,
                                                                const float4 *__restrict__ ray_d, uint4 *__restrict__ hits,
                                                                const uint32_t *__restrict__ count, uint32_t *cursor,
                                                                unsigned long long *stats, RayOrder order) {
     const uint32_t n = *count;
     TraversalCounters tc{0u, 0u, 0u};
-    trace_queue<false, COUNT, 1>(sc, ray_o, ray_d, n, cursor, tc, [&](bool finished, uint32_t i, uint4 h) {
+    trace_queue<false, COUNT, 1, ALPHA>(sc, ray_o, ray_d, n, cursor, tc, [&](bool finished, uint32_t i, uint4 h) {
         if (finished) hits[i] = h;
     }, order);
     if (COUNT) {
@@ -187,12 +187,12 @@ __global__ void __launch_bounds__(kBlock) classify_hits_kernel(DeviceScene sc, P
     }
 }
 
-template<bool COUNT>
+template<bool COUNT, bool ALPHA = false>
 __global__ void __launch_bounds__(kBlock, 4) trace_shadow_kernel(DeviceScene sc, PathBuffers pb, const uint32_t *__restrict__ count,
                                                               uint32_t *cursor, RayOrder order) {
     const uint32_t n = *count;
     TraversalCounters tc{0u, 0u, 0u};
-    trace_queue<true, COUNT, 1>(sc, pb.sray_o, pb.sray_d, n, cursor, tc, [&](bool finished, uint32_t i, uint4 h) {
+    trace_queue<true, COUNT, 1, ALPHA>(sc, pb.sray_o, pb.sray_d, n, cursor, tc, [&](bool finished, uint32_t i, uint4 h) {
         if (finished && h.x == ~0u) {// unoccluded: add the pending next-event contribution to the path's radiance
             float4 c = pb.scontrib[i];
             uint32_t path = __float_as_uint(c.w);
@@ -251,11 +251,11 @@ __global__ void __launch_bounds__(kBlock) bin_rays_kernel(const float4 *__restri
 }
 
 // stand-alone queries (lrk_trace) on interleaved lrk_ray records: any-hit result is written as inst = 1 (occluded) / 0 (free)
-template<bool ANY_HIT>
+template<bool ANY_HIT, bool ALPHA = false>
 __global__ void __launch_bounds__(kBlock) trace_query_kernel(DeviceScene sc, const float4 *__restrict__ rays, uint4 *__restrict__ hits,
                                                              uint32_t n, uint32_t *cursor) {
     TraversalCounters tc{0u, 0u, 0u};
-    trace_queue<ANY_HIT, false, 2>(sc, rays, rays + 1, n, cursor, tc, [&](bool finished, uint32_t i, uint4 h) {
+    trace_queue<ANY_HIT, false, 2, ALPHA>(sc, rays, rays + 1, n, cursor, tc, [&](bool finished, uint32_t i, uint4 h) {
         if (ANY_HIT) h = make_uint4(h.x != ~0u ? 1u : 0u, 0u, 0u, 0u);
         if (finished) hits[i] = h;
     });
@@ -274,22 +274,28 @@ __device__ __forceinline__ void init_closure(const DeviceScene &sc, Closure &cl,
     }
 }
 
+// The frame the closure works in: the interaction's shading frame, or the normal-mapped one (surface.h:236-253).
+__device__ __forceinline__ Frame closure_frame(const DeviceScene &sc, const lrk_surface *node, const Interaction &it, V3 wo) {
+    if (node->flags & LRK_SURFACE_HAS_NORMAL_MAP) return normal_mapped_frame(sc, node, it, wo);
+    return it.shading;
+}
+
 // Evaluates the closure for the light sample's direction (NEE term) and for the direction the closure itself samples.
 // Both evaluations run through ONE copy of the closure code (a two-trip loop that is deliberately not unrolled): the Disney
 // closure is several thousand SASS instructions and two inlined copies thrash the instruction cache.
 // VOLUME selects the direct-light weight of the volume integrator: 1 / (pdf_light + pdf_bsdf + pdf_transmittance) with
 // pdf_transmittance = 0 for an unoccluded ray (mega_vpt_naive.cpp:403-407) instead of the balance heuristic (mega_path.cpp:108-113).
 template<bool VOLUME, typename Closure>
-__device__ __forceinline__ void shade_surface(Closure &cl, const Interaction &it, V3 wo, const LightSample &ls, V3 beta,
+__device__ __forceinline__ void shade_surface(Closure &cl, const Interaction &it, const Frame &shading, V3 wo, const LightSample &ls, V3 beta,
                                               float u_lobe, float ub0, float ub1, V3 &contrib, V3 &wi_world, V3 &f_over, float &pdf_bsdf) {
-    V3 wo_local = it.shading.world_to_local(wo);
+    V3 wo_local = shading.world_to_local(wo);
     cl.prepare(wo_local);
     V3 wi_sampled_local;
     const bool run_sampled = cl.sample_direction(wo_local, u_lobe, ub0, ub1, wi_sampled_local);
-    wi_world = it.shading.local_to_world(wi_sampled_local);
+    wi_world = shading.local_to_world(wi_sampled_local);
     const bool run_light = ls.eval.pdf > 0.0f;
     V3 wi_w = v3(ls.ray_d_tmax.x, ls.ray_d_tmax.y, ls.ray_d_tmax.z);
-    V3 wi_l = it.shading.world_to_local(wi_w);
+    V3 wi_l = shading.world_to_local(wi_w);
     bool run = run_light;
     SurfEval e_light;
     e_light.f = f_over = v3(0.f);
@@ -301,7 +307,7 @@ __device__ __forceinline__ void shade_surface(Closure &cl, const Interaction &it
         e.pdf = 0.f;
         if (run) {
             e = cl.evaluate_local(wo_local, wi_l);
-            if (!validate_surface_sides(it.ng, it.shading.n, wo, wi_w)) {
+            if (!validate_surface_sides(it.ng, shading.n, wo, wi_w)) {
                 e.f = v3(0.f);
                 e.pdf = 0.f;
             }
@@ -385,11 +391,11 @@ __global__ void __launch_bounds__(kShadeBlock, LRK_SHADE_MIN_BLOCKS) shade_kerne
                     if (KIND == 1u) {
                         MatteClosure cl;
                         init_closure(sc, cl, surf, it);
-                        shade_surface<false>(cl, it, wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
+                        shade_surface<false>(cl, it, closure_frame(sc, surf, it, wo), wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
                     } else {
                         DisneyClosure cl;
                         init_closure(sc, cl, surf, it);
-                        shade_surface<false>(cl, it, wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
+                        shade_surface<false>(cl, it, closure_frame(sc, surf, it, wo), wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
                     }
                     if (contrib.x != 0.f || contrib.y != 0.f || contrib.z != 0.f) {
                         // a zero (or NaN-free zero) contribution needs no shadow ray; NaNs must reach the film filter
@@ -839,11 +845,11 @@ __global__ void __launch_bounds__(kBlock, 2) volume_surface_kernel(DeviceScene s
                 if (KIND == 1u) {
                     MatteClosure cl;
                     init_closure(sc, cl, surf, it);
-                    shade_surface<true>(cl, it, wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
+                    shade_surface<true>(cl, it, closure_frame(sc, surf, it, wo), wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
                 } else {
                     DisneyClosure cl;
                     init_closure(sc, cl, surf, it);
-                    shade_surface<true>(cl, it, wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
+                    shade_surface<true>(cl, it, closure_frame(sc, surf, it, wo), wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
                 }
                 push_shadow = true;// traced even with a zero contribution: its occlusion advances the PCG stream of the next bounce
                 sro = ls.ray_o_tmin;

@@ -44,6 +44,7 @@ struct lrk_ctx {
     uint32_t npix_owned{0};
     uint32_t pixel_list_key[5]{0, 0, 0, 0, 0};// width, height, rank, world, tile size of the cached list
     std::unordered_map<void **, size_t> array_bytes;// capacity of each scene array allocation
+    bool any_non_opaque{false};// some instance carries LRK_SHAPE_MAYBE_NON_OPAQUE: traversal runs its alpha-testing variants
     size_t film_pixels{0};
     // path state
     uint64_t max_paths{0}, capacity{0};
@@ -227,6 +228,12 @@ int blocks_for(lrk_ctx *ctx, uint64_t n, int persistent_grid) {
     return static_cast<int>(std::max<uint64_t>(1u, std::min<uint64_t>(need, static_cast<uint64_t>(persistent_grid))));
 }
 
+void launch_query(lrk_ctx *ctx, int g, bool any_hit, const float4 *d_rays, uint4 *d_hits, uint32_t n) {
+    auto launch = [&](auto kernel) { kernel<<<g, kBlock, 0, ctx->stream>>>(ctx->scene, d_rays, d_hits, n, ctx->d_query_cursor); };
+    if (ctx->any_non_opaque) any_hit ? launch(trace_query_kernel<true, true>) : launch(trace_query_kernel<false, true>);
+    else any_hit ? launch(trace_query_kernel<true, false>) : launch(trace_query_kernel<false, false>);
+}
+
 int render_pass(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint32_t spp_begin, uint32_t spp) {
     const uint64_t n = static_cast<uint64_t>(npix) * spp;
     auto &pb = ctx->pb;
@@ -254,12 +261,13 @@ int render_pass(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint32_t spp
         {
             ScopedTimer t{ctx, CAT_TRACE_CLOSEST};
             int g = blocks_for(ctx, n, ctx->grid_trace);
-            if (ctx->count_traversal)
-                trace_closest_kernel<true><<<g, kBlock, 0, ctx->stream>>>(sc, pb.ray_o[in], pb.ray_d[in], pb.hit, pb.counts + depth,
-                                                                          pb.counts + 2u * kMaxDepthSlots + depth, pb.stats, closest_order);
-            else
-                trace_closest_kernel<false><<<g, kBlock, 0, ctx->stream>>>(sc, pb.ray_o[in], pb.ray_d[in], pb.hit, pb.counts + depth,
-                                                                           pb.counts + 2u * kMaxDepthSlots + depth, pb.stats, closest_order);
+            // four instantiations: traversal counters on/off x stochastic alpha test on/off (scenes with non-opaque surfaces)
+            auto launch = [&](auto kernel) {
+                kernel<<<g, kBlock, 0, ctx->stream>>>(sc, pb.ray_o[in], pb.ray_d[in], pb.hit, pb.counts + depth,
+                                                      pb.counts + 2u * kMaxDepthSlots + depth, pb.stats, closest_order);
+            };
+            if (ctx->any_non_opaque) ctx->count_traversal ? launch(trace_closest_kernel<true, true>) : launch(trace_closest_kernel<false, true>);
+            else ctx->count_traversal ? launch(trace_closest_kernel<true, false>) : launch(trace_closest_kernel<false, false>);
         }
         {
             ScopedTimer t{ctx, CAT_SHADE};
@@ -279,12 +287,11 @@ int render_pass(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint32_t spp
         {
             ScopedTimer t{ctx, CAT_TRACE_SHADOW};
             int g = blocks_for(ctx, n, ctx->grid_shadow);
-            if (ctx->count_traversal)
-                trace_shadow_kernel<true><<<g, kBlock, 0, ctx->stream>>>(sc, pb, pb.counts + kMaxDepthSlots + depth,
-                                                                         pb.counts + 3u * kMaxDepthSlots + depth, shadow_order);
-            else
-                trace_shadow_kernel<false><<<g, kBlock, 0, ctx->stream>>>(sc, pb, pb.counts + kMaxDepthSlots + depth,
-                                                                          pb.counts + 3u * kMaxDepthSlots + depth, shadow_order);
+            auto launch = [&](auto kernel) {
+                kernel<<<g, kBlock, 0, ctx->stream>>>(sc, pb, pb.counts + kMaxDepthSlots + depth, pb.counts + 3u * kMaxDepthSlots + depth, shadow_order);
+            };
+            if (ctx->any_non_opaque) ctx->count_traversal ? launch(trace_shadow_kernel<true, true>) : launch(trace_shadow_kernel<false, true>);
+            else ctx->count_traversal ? launch(trace_shadow_kernel<true, false>) : launch(trace_shadow_kernel<false, false>);
         }
         ctx->stats.kernel_launches += 4u + (ctx->has_kind[1] ? 1u : 0u) + (ctx->has_kind[2] ? 1u : 0u);
     }
@@ -325,11 +332,11 @@ int render_pass_volume(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint3
             ScopedTimer t{ctx, CAT_TRACE_CLOSEST};
             int g = blocks_for(ctx, n, ctx->grid_trace);
             if (ctx->count_traversal)
-                trace_closest_kernel<true><<<g, kBlock, 0, ctx->stream>>>(sc, pb.ray_o[in], pb.ray_d[in], pb.hit, pb.counts + depth,
-                                                                          pb.counts + 2u * kMaxDepthSlots + depth, pb.stats, RayOrder{nullptr, nullptr, 0u});
+                trace_closest_kernel<true, false><<<g, kBlock, 0, ctx->stream>>>(sc, pb.ray_o[in], pb.ray_d[in], pb.hit, pb.counts + depth,
+                                                                                 pb.counts + 2u * kMaxDepthSlots + depth, pb.stats, RayOrder{nullptr, nullptr, 0u});
             else
-                trace_closest_kernel<false><<<g, kBlock, 0, ctx->stream>>>(sc, pb.ray_o[in], pb.ray_d[in], pb.hit, pb.counts + depth,
-                                                                           pb.counts + 2u * kMaxDepthSlots + depth, pb.stats, RayOrder{nullptr, nullptr, 0u});
+                trace_closest_kernel<false, false><<<g, kBlock, 0, ctx->stream>>>(sc, pb.ray_o[in], pb.ray_d[in], pb.hit, pb.counts + depth,
+                                                                                  pb.counts + 2u * kMaxDepthSlots + depth, pb.stats, RayOrder{nullptr, nullptr, 0u});
         }
         {
             ScopedTimer t{ctx, CAT_SHADE};
@@ -401,8 +408,8 @@ int lrk_create(const lrk_device_cfg *cfg, lrk_ctx **out) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kBlock, 0);
         return std::max(1, per_sm) * ctx->sm_count;
     };
-    ctx->grid_trace = grid_for(reinterpret_cast<const void *>(trace_closest_kernel<false>));
-    ctx->grid_shadow = grid_for(reinterpret_cast<const void *>(trace_shadow_kernel<false>));
+    ctx->grid_trace = grid_for(reinterpret_cast<const void *>(trace_closest_kernel<false, false>));
+    ctx->grid_shadow = grid_for(reinterpret_cast<const void *>(trace_shadow_kernel<false, false>));
     ctx->grid_shade[0] = grid_for(reinterpret_cast<const void *>(shade_kernel<0u>));
     ctx->grid_shade[1] = grid_for(reinterpret_cast<const void *>(shade_kernel<1u>));
     ctx->grid_shade[2] = grid_for(reinterpret_cast<const void *>(shade_kernel<2u>));
@@ -462,6 +469,10 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
         if (s->surfaces[i].type > LRK_SURFACE_DISNEY) return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: unknown surface type");
         for (uint32_t k = 0; k < 16u; k++)
             if (s->surfaces[i].tex[k] > s->texture_count) return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_upload_scene: texture id out of range");
+        if (s->surfaces[i].opacity_tex > s->texture_count || s->surfaces[i].normal_tex > s->texture_count)
+            return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_upload_scene: texture id out of range");
+        if ((s->surfaces[i].flags & LRK_SURFACE_MAYBE_NON_OPAQUE) && s->integrator.type == LRK_INTEGRATOR_VOLUME_PATH)
+            return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: non-opaque surfaces are not supported by the volume path integrator");
     }
     for (uint32_t i = 0; i < s->texture_count; i++) {
         const auto &t = s->textures[i];
@@ -487,6 +498,7 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
     if ((rc = upload(ctx, &a.camera, &s->camera, 1))) return rc;
     std::vector<uint32_t> handles(static_cast<size_t>(s->instance_count) * 4u), kinds(s->instance_count);
     ctx->has_kind[1] = ctx->has_kind[2] = false;
+    ctx->any_non_opaque = false;
     std::vector<float> o2w(static_cast<size_t>(s->instance_count) * 12u), xform(static_cast<size_t>(s->instance_count) * 16u);
     for (uint32_t i = 0; i < s->instance_count; i++) {
         const auto &inst = s->instances[i];
@@ -500,6 +512,7 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
             }
             kinds[i] = kind;
             ctx->has_kind[kind] = true;
+            if ((flags & LRK_SHAPE_MAYBE_NON_OPAQUE) && (flags & LRK_SHAPE_HAS_SURFACE)) ctx->any_non_opaque = true;
         }
         std::memcpy(&o2w[i * 12u], inst.object_to_world, 48);
         std::memcpy(&xform[i * 16u], inst.world_to_object, 48);
@@ -702,8 +715,7 @@ int lrk_trace(lrk_ctx *ctx, const lrk_ray *rays, uint64_t n, int any_hit, lrk_hi
     cudaMemcpyAsync(d_rays, rays, n * sizeof(lrk_ray), cudaMemcpyHostToDevice, ctx->stream);
     int g = blocks_for(ctx, n, ctx->grid_trace);
     cudaMemsetAsync(ctx->d_query_cursor, 0, sizeof(uint32_t), ctx->stream);
-    if (any_hit) trace_query_kernel<true><<<g, kBlock, 0, ctx->stream>>>(ctx->scene, d_rays, d_hits, static_cast<uint32_t>(n), ctx->d_query_cursor);
-    else trace_query_kernel<false><<<g, kBlock, 0, ctx->stream>>>(ctx->scene, d_rays, d_hits, static_cast<uint32_t>(n), ctx->d_query_cursor);
+    launch_query(ctx, g, any_hit != 0, d_rays, d_hits, static_cast<uint32_t>(n));
     cudaMemcpyAsync(hits, d_hits, n * sizeof(lrk_hit), cudaMemcpyDeviceToHost, ctx->stream);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (e == cudaSuccess) e = cudaGetLastError();
@@ -721,8 +733,7 @@ int lrk_trace_device(lrk_ctx *ctx, const void *d_rays, uint64_t n, int any_hit, 
     LRK_CUDA(cudaEventRecord(ctx->ev_begin, ctx->stream));
     for (uint32_t r = 0; r < repeat; r++) {
         LRK_CUDA(cudaMemsetAsync(ctx->d_query_cursor, 0, sizeof(uint32_t), ctx->stream));
-        if (any_hit) trace_query_kernel<true><<<g, kBlock, 0, ctx->stream>>>(ctx->scene, static_cast<const float4 *>(d_rays), static_cast<uint4 *>(d_hits), static_cast<uint32_t>(n), ctx->d_query_cursor);
-        else trace_query_kernel<false><<<g, kBlock, 0, ctx->stream>>>(ctx->scene, static_cast<const float4 *>(d_rays), static_cast<uint4 *>(d_hits), static_cast<uint32_t>(n), ctx->d_query_cursor);
+        launch_query(ctx, g, any_hit != 0, static_cast<const float4 *>(d_rays), static_cast<uint4 *>(d_hits), static_cast<uint32_t>(n));
     }
     LRK_CUDA(cudaEventRecord(ctx->ev_end, ctx->stream));
     LRK_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -355,6 +355,47 @@ __device__ __forceinline__ void resolve_surface_textures(const DeviceScene &sc, 
     }
 }
 
+// Geometry::_alpha_skip (src/base/geometry.cpp:165-192): whether a traversal candidate (instance, primitive, barycentrics of
+// the triangle test) is stochastically transparent.  The random number is a hash of the hit, so the decision is the same
+// in every traversal that meets this candidate.
+__device__ __noinline__ bool alpha_skip(const DeviceScene &sc, uint32_t inst_id, uint32_t prim_id, float bu, float bv) {
+    const ShapeHandle shape = decode_handle(__ldg(sc.inst_handles + inst_id));
+    if (!((shape.flags & LRK_SHAPE_MAYBE_NON_OPAQUE) && shape.has_surface())) return false;
+    const lrk_surface *surf = sc.surfaces + shape.surface_tag;
+    if (!(surf->flags & LRK_SURFACE_MAYBE_NON_OPAQUE)) return false;// evaluate_opacity -> nullopt (surface.h:186)
+    const float u = static_cast<float>(xxhash32_uint4(inst_id, prim_id, __float_as_uint(bu), __float_as_uint(bv))) * 0x1p-32f;
+    float alpha = surf->opacity;
+    if (surf->opacity_tex != 0u) {
+        const lrk_mesh mesh = sc.meshes[shape.mesh];
+        const lrk_triangle tri = sc.triangles[mesh.triangle_offset + prim_id];
+        const float4 *vb = reinterpret_cast<const float4 *>(sc.vertices + mesh.vertex_offset);
+        float4 a1 = __ldg(vb + tri.i0 * 2u + 1u), b1 = __ldg(vb + tri.i1 * 2u + 1u), c1 = __ldg(vb + tri.i2 * 2u + 1u);
+        const float b0 = 1.f - bu - bv;
+        float tu = b0 * a1.z + bu * b1.z + bv * c1.z, tv = b0 * a1.w + bu * b1.w + bv * c1.w;// geometry.cpp:372
+        alpha = texture_evaluate(sc, surf->opacity_tex - 1u, tu, tv).x;
+    }
+    return u > alpha;
+}
+
+// clamp_shading_normal, src/util/frame.cpp:49-54
+__device__ __forceinline__ V3 clamp_shading_normal(V3 ns, V3 ng, V3 w) {
+    V3 w_refl = reflect(-w, ns);
+    V3 w_refl_clip = dot(w_refl, ng) * dot(w, ng) > 0.f ? w_refl : normalize(w_refl - ng * dot(w_refl, ng));
+    return normalize(w_refl_clip + w);
+}
+// NormalMapWrapper::populate_closure, src/base/surface.h:236-253: the shading frame the closure sees
+__device__ __forceinline__ Frame normal_mapped_frame(const DeviceScene &sc, const lrk_surface *surf, const Interaction &it, V3 wo) {
+    V3 rgb = v3(surf->normal_value[0], surf->normal_value[1], surf->normal_value[2]);
+    if (surf->normal_tex != 0u) {
+        float4 t = texture_evaluate(sc, surf->normal_tex - 1u, it.u, it.v);
+        rgb = v3(t.x, t.y, t.z);
+    }
+    V3 nl = 2.f * rgb + (-1.f);
+    if (surf->normal_strength != 1.f) nl = nl * v3(surf->normal_strength, surf->normal_strength, 1.f);
+    V3 normal = it.shading.local_to_world(nl);
+    return Frame::make(clamp_shading_normal(normal, it.ng, wo), it.shading.s);
+}
+
 // ---- surfaces ------------------------------------------------------------------------------------------
 struct SurfEval {
     V3 f;

@@ -85,7 +85,9 @@ __device__ __forceinline__ uint32_t ordered_index(const RayOrder &ro, uint32_t p
     return p;// unreachable when the bins cover [0, n)
 }
 
-template<bool ANY_HIT, bool COUNT, int STRIDE, typename Sink>
+// ALPHA: stochastic alpha test of every accepted candidate (scenes with non-opaque surfaces only; alpha_skip is in shading.cuh)
+__device__ bool alpha_skip(const DeviceScene &sc, uint32_t inst_id, uint32_t prim_id, float bu, float bv);
+template<bool ANY_HIT, bool COUNT, int STRIDE, bool ALPHA = false, typename Sink>
 __device__ __forceinline__ void trace_queue(const DeviceScene &sc, const float4 *__restrict__ ray_o, const float4 *__restrict__ ray_d,
                                             uint32_t n, uint32_t *cursor, TraversalCounters &cnt, Sink &&sink,
                                             RayOrder ray_order = RayOrder{nullptr, nullptr, 0u}) {
@@ -190,6 +192,9 @@ __device__ __forceinline__ void trace_queue(const DeviceScene &sc, const float4 
                         if (!(v >= 0.0f && u + v <= 1.0f)) continue;
                         float t = fdot(e2, qvec) * inv_det;
                         if (!(t > tmin && t < tbest)) continue;
+                        if (ALPHA) {// on_surface_candidate: commit only if not skipped (geometry.cpp:248-279)
+                            if (alpha_skip(sc, cur_inst, __float_as_uint(a.w), u, v)) continue;
+                        }
                         tbest = t;
                         best_inst = cur_inst;
                         best_prim = __float_as_uint(a.w);

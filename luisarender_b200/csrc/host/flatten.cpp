@@ -211,6 +211,7 @@ struct Flattener {
             if (surface != nullptr && !surface->is_null()) {
                 surface_tag = register_surface(surface);
                 properties |= LRK_SHAPE_HAS_SURFACE;
+                if (surface->maybe_non_opaque()) properties |= LRK_SHAPE_MAYBE_NON_OPAQUE;// geometry.cpp:123-126
             }
             if (light != nullptr && !light->is_null()) {
                 light_tag = register_light(light);

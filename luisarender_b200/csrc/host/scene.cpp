@@ -336,13 +336,6 @@ const Texture *surface_texture(Scene *s, const NodeDesc *d, const char *name) {
     if (t && !t->is_constant() && !t->is_image()) throw Error("Only constant and image textures are supported ('" + std::string{name} + "').");
     return t;
 }
-void reject_wrappers(const NodeDesc *d) {
-    // NormalMapWrapper<OpacitySurfaceWrapper<...>> (src/base/surface.h:160-330) is out of scope
-    for (auto name : {"normal_map", "alpha", "opacity"}) {
-        if (d->has_property(name))
-            throw Error("Surface property '" + std::string{name} + "' (opacity / normal-map wrappers) is not supported. [" + d->location() + "]");
-    }
-}
 
 }// namespace
 LRH_PLUGIN("texture-constant", ConstantTexture)
@@ -621,6 +614,46 @@ LRH_PLUGIN("medium-vacuum", VacuumMedium)
 
 // ---------------------------------------------------------------- surfaces / lights
 
+Surface::Surface(Scene *scene, const NodeDesc *desc, Tag tag) : SceneNode{scene, desc, tag} {
+    if (desc == nullptr || desc->impl_type() == "null") return;
+    auto load = [&](const char *name) -> const Texture * {
+        auto t = scene->load_texture(desc->node(name));
+        if (t && !t->is_constant() && !t->is_image())
+            throw Error("Only constant and image textures are supported ('" + std::string{name} + "'). [" + desc->location() + "]");
+        return t;
+    };
+    opacity = load(desc->has_property("alpha") ? "alpha" : "opacity");// surface.h:200-206
+    normal_map = load("normal_map");
+    normal_map_strength = desc->f("normal_map_strength", 1.f);
+}
+
+bool Surface::maybe_non_opaque() const {
+    if (opacity == nullptr) return false;
+    return opacity->is_image() ? true : opacity->value().x < 1.f;// evaluate_static().value_or(0).x < 1
+}
+
+void Surface::flatten_wrappers(lrk_surface &out, TextureTable &textures) const {
+    out.opacity = 1.f;
+    out.normal_strength = 1.f;
+    if (maybe_non_opaque()) {
+        out.flags |= LRK_SURFACE_MAYBE_NON_OPAQUE;
+        if (opacity->is_image()) out.opacity_tex = textures.slot(opacity);
+        else out.opacity = opacity->value().x;
+    }
+    if (normal_map != nullptr) {
+        out.flags |= LRK_SURFACE_HAS_NORMAL_MAP;
+        out.normal_strength = normal_map_strength;
+        if (normal_map->is_image()) {
+            out.normal_tex = textures.slot(normal_map);
+        } else {
+            auto v = normal_map->value();
+            out.normal_value[0] = v.x;
+            out.normal_value[1] = v.y;
+            out.normal_value[2] = v.z;
+        }
+    }
+}
+
 namespace {
 
 struct MatteSurface final : Surface {
@@ -628,7 +661,6 @@ struct MatteSurface final : Surface {
     const Texture *kd;
     const Texture *sigma;
     MatteSurface(Scene *s, const NodeDesc *d) : Surface{s, d, Tag::SURFACE} {
-        reject_wrappers(d);
         kd = surface_texture(s, d, "Kd");
         sigma = surface_texture(s, d, "sigma");
     }
@@ -646,6 +678,7 @@ struct MatteSurface final : Surface {
             else out.p[3] = saturate(sigma->value().x) * 90.f;
         }
         if (out.tex[0] || out.tex[3]) out.flags |= LRK_SURFACE_HAS_TEXTURES;
+        flatten_wrappers(out, textures);
         return out;
     }
 };
@@ -656,7 +689,6 @@ struct DisneySurface final : Surface {
         *clearcoat, *clearcoat_gloss, *specular_trans, *flatness, *diffuse_trans;
     bool thin, remap_roughness;
     DisneySurface(Scene *s, const NodeDesc *d) : Surface{s, d, Tag::SURFACE} {
-        reject_wrappers(d);
         color = surface_texture(s, d, d->has_property("color") ? "color" : "Kd");
         thin = d->b("thin", false);
         remap_roughness = d->b("remap_roughness", true);
@@ -724,6 +756,7 @@ struct DisneySurface final : Surface {
         out.p[13] = specular_trans ? specular_trans->value().x : 0.f;
         out.p[14] = x(flatness, 0.f, 14);
         out.p[15] = 0.f;// diffuse_trans is only built for thin surfaces (src/surfaces/disney.cpp:1017)
+        flatten_wrappers(out, textures);
         return out;
     }
 };

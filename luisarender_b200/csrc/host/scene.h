@@ -137,9 +137,18 @@ struct Medium : SceneNode {
 };
 
 struct Surface : SceneNode {
-    using SceneNode::SceneNode;
+    // every surface node is NormalMapWrapper<OpacitySurfaceWrapper<Base>> (src/base/surface.h:160-275, e.g. matte.cpp:136)
+    Surface(Scene *scene, const NodeDesc *desc, Tag tag);
     virtual bool is_null() const { return false; }
     virtual lrk_surface flatten(TextureTable &textures) const = 0;
+    // OpacitySurfaceWrapper::Instance::maybe_non_opaque (surface.h:177-181)
+    bool maybe_non_opaque() const;
+    const Texture *opacity{};
+    const Texture *normal_map{};
+    float normal_map_strength{1.f};
+
+protected:
+    void flatten_wrappers(lrk_surface &out, TextureTable &textures) const;
 };
 
 struct Light : SceneNode {

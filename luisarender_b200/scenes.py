@@ -197,14 +197,33 @@ def instanced_spheres(resolution=(1920, 1080), spp=1024, seed=1, depth=10, rr_de
 
 
 def textured_room(resolution=(96, 64), spp=8, depth=6, rr_depth=0, rr_threshold=0.95, seed=19980810,
-                  assets="tests/golden/assets", output="textured.exr", integrator="WavePath") -> str:
+                  assets="tests/golden/assets", output="textured.exr", integrator="WavePath", wrappers=False) -> str:
     """SURVEY.md §8 row f1 in one small scene: image-textured Matte and Disney parameters (PNG 8/16-bit, grey, palette; all
     four address modes, point + bilinear filters, sRGB + linear encodings, uv scale/offset) on an InlineMesh with uvs and
-    on mesh FILES (Wavefront OBJ without normals, binary PLY).  `assets` is relative to the directory the scene is loaded from."""
+    on mesh FILES (Wavefront OBJ without normals, binary PLY).  `assets` is relative to the directory the scene is loaded from.
+    ``wrappers=True`` adds the surface wrappers of src/base/surface.h:160-275: a normal-mapped floor, a cut-out screen with an
+    alpha texture (stochastic alpha test inside closest-hit and any-hit traversal) and a half-transparent cube (constant opacity)."""
     a = assets.rstrip("/")
+    floor_extra = cube_extra = screen = screen_ref = ""
+    if wrappers:
+        floor_extra = f'normal_map : Image {{ file {{ "{a}/normal_rgb8.png" }} encoding {{ "linear" }} uv_scale {{ 4.0 }} }} normal_map_strength {{ 0.8 }}'
+        cube_extra = "opacity : Constant { v { 0.5 } }"
+        screen = f"""
+Surface screen_s : Matte {{
+  Kd : Constant {{ v {{ 0.8, 0.75, 0.2 }} }}
+  alpha : Image {{ file {{ "{a}/alpha_gray8.png" }} encoding {{ "linear" }} uv_scale {{ 2.0 }} }}
+}}
+Shape screen : InlineMesh {{
+  positions {{ 0.2, 0.0, 1.0,  1.6, 0.0, 0.6,  1.6, 1.3, 0.6,  0.2, 1.3, 1.0 }}
+  uvs {{ 0.0, 0.0,  1.0, 0.0,  1.0, 1.0,  0.0, 1.0 }}
+  indices {{ 0, 1, 2, 0, 2, 3 }}
+  surface {{ @screen_s }}
+}}"""
+        screen_ref = ", @screen"
     return f"""
 Surface floor_s : Matte {{
   Kd : Image {{ file {{ "{a}/checker_rgb8.png" }} address {{ "repeat" }} filter {{ "bilinear" }} uv_scale {{ 2.0, 3.0 }} uv_offset {{ 0.25, 0.0 }} }}
+  {floor_extra}
 }}
 Surface wall_s : Matte {{
   Kd : Image {{ file {{ "{a}/ramp_rgba16.png" }} address {{ "edge" }} encoding {{ "linear" }} scale {{ 0.9 }} }}
@@ -215,6 +234,7 @@ Surface cube_s : Disney {{
   roughness : Image {{ file {{ "{a}/rough_gray8.png" }} encoding {{ "linear" }} address {{ "repeat" }} }}
   metallic : Constant {{ v {{ 0.2 }} }}
   clearcoat : Constant {{ v {{ 0.5 }} }}
+  {cube_extra}
 }}
 Surface tetra_s : Matte {{
   Kd : Image {{ file {{ "{a}/palette4.png" }} address {{ "zero" }} encoding {{ "gamma" }} gamma {{ 2.0 }} }}
@@ -243,6 +263,7 @@ Shape tetra : Mesh {{
   surface {{ @tetra_s }}
   transform : SRT {{ scale {{ 1.1 }} translate {{ 0.5, 0.0, -0.2 }} }}
 }}
+{screen}
 Shape lamp : InlineMesh {{
   positions {{ -0.6, 2.4, 0.4,  -0.6, 2.4, -0.4,  0.6, 2.4, -0.4,  0.6, 2.4, 0.4 }}
   indices {{ 0, 1, 2, 0, 2, 3 }}
@@ -266,6 +287,6 @@ render {{
     sampler : Independent {{ seed {{ {int(seed)} }} }}
   }}
   cameras {{ @camera }}
-  shapes {{ @floor, @wall, @cube, @tetra, @lamp }}
+  shapes {{ @floor, @wall, @cube, @tetra, @lamp{screen_ref} }}
 }}
 """

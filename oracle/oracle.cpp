@@ -367,6 +367,9 @@ inline bool slab(const float lo[3], const float hi[3], const RaySetup &r, float 
     return tn <= tf;
 }
 
+// Geometry::_alpha_skip, src/base/geometry.cpp:165-192 (defined with the texture code below)
+bool alpha_skip(const lrk_scene_desc &sc, uint32_t inst_id, uint32_t prim_id, float bu, float bv);
+
 lrk_hit trace_bvh(const lrk_scene_desc &sc, const lrk_ray &ray, bool any_hit, TraceCounters *cnt) {
     lrk_hit best{~0u, ~0u, {0.f, 0.f}};
     float tbest = ray.tmax;
@@ -430,9 +433,10 @@ lrk_hit trace_bvh(const lrk_scene_desc &sc, const lrk_ray &ray, bool any_hit, Tr
                 if (!(v >= 0.0f && u + v <= 1.0f)) continue;
                 float t = fdot(e2, qvec) * inv_det;
                 if (!(t > tmin && t < tbest)) continue;
-                tbest = t;
                 uint32_t prim;
                 std::memcpy(&prim, &tv[3], 4);
+                if (alpha_skip(sc, cur_inst, prim, u, v)) continue;// candidate not committed (geometry.cpp:248-279)
+                tbest = t;
                 best = {cur_inst, prim, {u, v}};
                 if (any_hit) return best;
             }
@@ -491,6 +495,7 @@ lrk_hit trace_brute(const lrk_scene_desc &sc, const lrk_ray &ray, bool any_hit) 
             if (!(v >= 0.0f && u + v <= 1.0f)) continue;
             float t = fdot(e2, qvec) * inv_det;
             if (!(t > ray.tmin && t < tbest)) continue;
+            if (alpha_skip(sc, i, k, u, v)) continue;
             tbest = t;
             best = {i, k, {u, v}};
             if (any_hit) return best;
@@ -1050,6 +1055,51 @@ F4 texture_evaluate(const lrk_scene_desc &sc, uint32_t tex_id, float u, float v)
     F4 s = texture_sample(sc, t, u * t.uv_scale[0] + t.uv_offset[0], v * t.uv_scale[1] + t.uv_offset[1]);
     return {tex_decode(t, s.x), tex_decode(t, s.y), tex_decode(t, s.z), tex_decode(t, s.w)};
 }
+bool alpha_skip(const lrk_scene_desc &sc, uint32_t inst_id, uint32_t prim_id, float bu, float bv) {
+    const auto &inst = sc.instances[inst_id];
+    ShapeHandle shape = decode_handle(inst.handle);
+    if (!((shape.flags & LRK_SHAPE_MAYBE_NON_OPAQUE) && shape.has_surface())) return false;
+    const lrk_surface &surf = sc.surfaces[shape.surface_tag];
+    if (!(surf.flags & LRK_SURFACE_MAYBE_NON_OPAQUE)) return false;// evaluate_opacity -> nullopt (surface.h:186)
+    uint32_t ub, vb;
+    std::memcpy(&ub, &bu, 4);
+    std::memcpy(&vb, &bv, 4);
+    const float u = static_cast<float>(xxhash32_uint4(inst_id, prim_id, ub, vb)) * 0x1p-32f;
+    float alpha = surf.opacity;
+    if (surf.opacity_tex != 0u) {
+        const lrk_mesh &mesh = sc.meshes[shape.buffer_base / 4u];// buffer_base = mesh index * 4 (shape.cpp:46-70)
+        const lrk_triangle &tri = sc.triangles[mesh.triangle_offset + prim_id];
+        const lrk_vertex &a = sc.vertices[mesh.vertex_offset + tri.i0], &b = sc.vertices[mesh.vertex_offset + tri.i1],
+                         &c = sc.vertices[mesh.vertex_offset + tri.i2];
+        const float b0 = 1.f - bu - bv;
+        float tu = b0 * a.uv[0] + bu * b.uv[0] + bv * c.uv[0], tv = b0 * a.uv[1] + bu * b.uv[1] + bv * c.uv[1];// geometry.cpp:372
+        alpha = texture_evaluate(sc, surf.opacity_tex - 1u, tu, tv).x;
+    }
+    return u > alpha;
+}
+
+// clamp_shading_normal, src/util/frame.cpp:49-54
+V3 clamp_shading_normal(V3 ns, V3 ng, V3 w) {
+    V3 w_refl = reflect(-w, ns);
+    V3 w_refl_clip = dot(w_refl, ng) * dot(w, ng) > 0.f ? w_refl : normalize(w_refl - ng * dot(w_refl, ng));
+    return normalize(w_refl_clip + w);
+}
+// NormalMapWrapper::populate_closure, src/base/surface.h:236-253: the interaction the closure is bound to
+Interaction closure_interaction(const lrk_scene_desc &sc, const lrk_surface &node, const Interaction &it, V3 wo) {
+    if (!(node.flags & LRK_SURFACE_HAS_NORMAL_MAP)) return it;
+    V3 rgb = v3(node.normal_value[0], node.normal_value[1], node.normal_value[2]);
+    if (node.normal_tex != 0u) {
+        F4 t = texture_evaluate(sc, node.normal_tex - 1u, it.u, it.v);
+        rgb = v3(t.x, t.y, t.z);
+    }
+    V3 nl = 2.f * rgb + (-1.f);
+    if (node.normal_strength != 1.f) nl = nl * v3(node.normal_strength, node.normal_strength, 1.f);
+    V3 normal = it.shading.local_to_world(nl);
+    Interaction mapped = it;
+    mapped.shading = Frame::make(clamp_shading_normal(normal, it.ng, wo), it.shading.s);
+    return mapped;
+}
+
 // Surface parameters at a hit (MatteInstance::populate_closure src/surfaces/matte.cpp:117-131,
 // DisneySurfaceInstance::populate_closure src/surfaces/disney.cpp:932-956; colours through
 // Texture::Instance::evaluate_albedo_spectrum src/base/texture.cpp:20-31 and the sRGB spectrum src/spectra/srgb.cpp:34-40,70-72)
@@ -1116,13 +1166,14 @@ V3 path_li(const lrk_scene_desc &sc, uint32_t px, uint32_t py, uint32_t sample_i
         bool occluded = trace_bvh(sc, ls.shadow_ray, true, &tc).inst != ~0u;
         if (cnt) cnt->shadow_rays++;
         const lrk_surface surface = resolve_surface(sc, sc.surfaces[it.shape.surface_tag], it);
+        const Interaction cit = closure_interaction(sc, surface, it, wo);// the closure's (normal-mapped) view of the hit
         if (ls.eval.pdf > 0.0f && !occluded) {
             V3 wi = v3(ls.shadow_ray.d[0], ls.shadow_ray.d[1], ls.shadow_ray.d[2]);
-            SurfEval ev = surface_evaluate(surface, it, wo, wi);
+            SurfEval ev = surface_evaluate(surface, cit, wo, wi);
             float w = balance_heuristic(ls.eval.pdf, ev.pdf) / ls.eval.pdf;
             Li = Li + w * beta * ev.f * ls.eval.L;
         }
-        SurfSample ss = surface_sample(surface, it, wo, u_lobe, ub0, ub1);
+        SurfSample ss = surface_sample(surface, cit, wo, u_lobe, ub0, ub1);
         ray = spawn_ray(it, ss.wi);
         pdf_bsdf = ss.eval.pdf;
         float w = ss.eval.pdf > 0.f ? 1.f / ss.eval.pdf : 0.f;
@@ -1363,6 +1414,7 @@ V3 volume_path_li(const lrk_scene_desc &sc, uint32_t px, uint32_t py, uint32_t s
             Transmittance T = volume_transmittance(sc, rng, ls.shadow_ray, &tc, cnt, nullptr);
             V3 wo = -v3(ray.d[0], ray.d[1], ray.d[2]);
             const lrk_surface surface = resolve_surface(sc, sc.surfaces[it.shape.surface_tag], it);
+            const Interaction cit = closure_interaction(sc, surface, it, wo);
             // true_hit(medium_tag = 0) is `0 <= priority of the environment medium` (medium_tracker.cpp:19-21)
             if (!(0u <= medium.priority)) {
                 ray = spawn_ray(it, v3(ray.d[0], ray.d[1], ray.d[2]));
@@ -1370,11 +1422,11 @@ V3 volume_path_li(const lrk_scene_desc &sc, uint32_t px, uint32_t py, uint32_t s
             } else {
                 if (ls.eval.pdf > 0.0f) {
                     V3 wi = v3(ls.shadow_ray.d[0], ls.shadow_ray.d[1], ls.shadow_ray.d[2]);
-                    SurfEval ev = surface_evaluate(surface, it, wo, wi);
+                    SurfEval ev = surface_evaluate(surface, cit, wo, wi);
                     float w = 1.f / (ls.eval.pdf + ev.pdf + T.pdf);
                     Li = Li + w * beta * ev.f * ls.eval.L * T.f;
                 }
-                SurfSample ss = surface_sample(surface, it, wo, u_lobe, ub0, ub1);
+                SurfSample ss = surface_sample(surface, cit, wo, u_lobe, ub0, ub1);
                 float w = ss.eval.pdf > 0.f ? 1.f / ss.eval.pdf : 0.f;
                 pdf_bsdf = ss.eval.pdf;
                 ray = spawn_ray(it, ss.wi);

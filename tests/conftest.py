@@ -55,6 +55,15 @@ def spheres_small():
 
 
 @pytest.fixture(scope="session")
+def textured_wrappers_small():
+    """Row f1 scene: mesh files, image textures, normal map, alpha-tested and half-transparent surfaces."""
+    from luisarender_b200 import scenes
+    from luisarender_b200.api import Scene
+
+    return Scene.from_source(scenes.textured_room(resolution=(48, 32), spp=4, wrappers=True), REPO)
+
+
+@pytest.fixture(scope="session")
 def gpu_renderer():
     from luisarender_b200.api import Renderer
 

@@ -45,6 +45,8 @@ def golden_scenes():
                                                    medium=True, depth=8),
         # image-textured Matte / Disney parameters on an InlineMesh with uvs and on OBJ / PLY mesh files
         "textured": scenes.textured_room(resolution=(48, 32), spp=4),
+        # + the surface wrappers: normal map, alpha-tested cut-out (stochastic alpha inside traversal), constant opacity
+        "textured_wrappers": scenes.textured_room(resolution=(48, 32), spp=4, wrappers=True),
     }
 
 

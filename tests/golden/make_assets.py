@@ -59,6 +59,21 @@ def ramp_rgba16(w=16, h=8) -> np.ndarray:
     return img
 
 
+def alpha_gray8(n=16) -> np.ndarray:
+    """Cut-out mask: opaque discs on a transparent ground, with a soft rim so that the stochastic test sees fractional alphas."""
+    y, x = np.mgrid[0:n, 0:n]
+    d = np.hypot((x % 8) - 3.5, (y % 8) - 3.5)
+    return np.clip((3.6 - d) * 160, 0, 255).astype(np.uint8)
+
+
+def normal_rgb8(n=32) -> np.ndarray:
+    """Tangent-space normal map of a sine bump field, encoded rgb = (n + 1) / 2."""
+    y, x = np.mgrid[0:n, 0:n]
+    nx, ny = 0.45 * np.cos(x * 2 * np.pi / 8), 0.45 * np.sin(y * 2 * np.pi / 16)
+    nz = np.sqrt(np.maximum(1 - nx * nx - ny * ny, 0))
+    return np.round((np.stack([nx, ny, nz], -1) + 1) * 127.5).astype(np.uint8)
+
+
 CUBE_OBJ = """# unit cube centred at the origin, quads, per-face uvs, no normals (smooth-normal generation is exercised)
 v -0.5 -0.5 -0.5
 v  0.5 -0.5 -0.5
@@ -103,6 +118,8 @@ def main():
     write_png(OUT / "checker_rgb8.png", checker_rgb8())
     write_png(OUT / "rough_gray8.png", rough_gray8())
     write_png(OUT / "ramp_rgba16.png", ramp_rgba16())
+    write_png(OUT / "alpha_gray8.png", alpha_gray8())
+    write_png(OUT / "normal_rgb8.png", normal_rgb8())
     pal = np.array([[255, 0, 0], [0, 255, 0], [0, 0, 255], [255, 255, 0]], np.uint8)
     idx = (np.add.outer(np.arange(8), np.arange(8)) % 4).astype(np.uint8)
     write_png(OUT / "palette4.png", idx, palette=pal)

@@ -36,7 +36,7 @@ def _random_rays(scene, n, seed):
     return rays
 
 
-@pytest.mark.parametrize("fixture", ["cornell_small", "spheres_small"])
+@pytest.mark.parametrize("fixture", ["cornell_small", "spheres_small", "textured_wrappers_small"])
 def test_trace_matches_oracle_bit_exactly(fixture, request, gpu_renderer):
     scene = request.getfixturevalue(fixture)
     d = scene.desc()
@@ -80,7 +80,7 @@ def _image_parity(gpu_raw, cpu_raw):
     return rel, off
 
 
-@pytest.mark.parametrize("name", ["cornell", "cornell_disney", "spheres", "spheres_medium", "textured"])
+@pytest.mark.parametrize("name", ["cornell", "cornell_disney", "spheres", "spheres_medium", "textured", "textured_wrappers"])
 def test_render_matches_oracle(name, gpu_renderer):
     import importlib.util
     spec = importlib.util.spec_from_file_location("generate_golden", Path(__file__).resolve().parent / "golden" / "generate_golden.py")
@@ -106,18 +106,47 @@ def test_render_matches_oracle(name, gpu_renderer):
         err = np.abs(gpu_raw[..., :3] - cpu_raw[..., :3]).max(axis=-1)
         keep = err <= np.quantile(err, 0.99)
         assert np.linalg.norm((gpu_raw[..., :3] - cpu_raw[..., :3])[keep]) / np.linalg.norm(cpu_raw[..., :3][keep]) <= 1e-3
+    elif name == "textured_wrappers":
+        # The stochastic alpha test hashes the candidate's barycentric BITS (geometry.cpp:170), so a bounce direction that
+        # differs by one ulp (CUDA vs glibc sin/cos in the cosine-hemisphere warp) flips the decision for the faces it crosses:
+        # a few per cent of the paths that meet a non-opaque surface after their first bounce take another, equally valid,
+        # branch.  Parity is therefore exact for everything up to the first bounce (test_alpha_first_bounce_is_exact) and
+        # statistical afterwards: <= 4 % of the pixels differ, the rest agree to 1e-3 rel-L2, and the image means agree.
+        assert off <= 4e-2, off
+        err = np.abs(gpu_raw[..., :3] - cpu_raw[..., :3]).max(axis=-1)
+        keep = err <= np.quantile(err, 0.96)
+        assert np.linalg.norm((gpu_raw[..., :3] - cpu_raw[..., :3])[keep]) / np.linalg.norm(cpu_raw[..., :3][keep]) <= 1e-3
+        assert gpu_raw[..., :3].mean() == pytest.approx(cpu_raw[..., :3].mean(), rel=0.03)
     else:
         assert rel <= 1e-3, rel
         assert off <= 5e-3, off
-    assert st["closest_rays"] == cnt["closest_rays"]  # same paths, ray for ray
+    if name != "textured_wrappers":
+        assert st["closest_rays"] == cnt["closest_rays"]  # same paths, ray for ray
     assert st["shadow_rays"] <= cnt["shadow_rays"]    # zero-contribution shadow rays are not traced on the GPU
     # and against the committed golden film row (generated by the oracle, tests/golden/generate_golden.py)
     gold = np.array(GOLD["scenes"][name]["film_row0"], np.float32).reshape(-1, 3)
     row_ok = np.isclose(gpu_raw[0, :, :3], gold, rtol=1e-3, atol=1e-4).all(axis=-1)
-    assert row_ok.all() if name != "spheres_medium" else row_ok.mean() >= 0.9
-    assert st["closest_rays"] == GOLD["scenes"][name]["counters"]["closest_rays"]
+    assert row_ok.all() if name not in ("spheres_medium", "textured_wrappers") else row_ok.mean() >= 0.9
+    if name != "textured_wrappers":
+        assert st["closest_rays"] == GOLD["scenes"][name]["counters"]["closest_rays"]
     # normalised film = (sum / max(w,1)) * 2^exposure (color.cpp:87-93)
     assert np.allclose(gpu_renderer.film(), O.convert_film(d, gpu_raw), rtol=1e-6, atol=1e-7)
+
+
+def test_alpha_first_bounce_is_exact(gpu_renderer):
+    """Alpha-tested and half-transparent surfaces with depth 1 (camera ray, emitter hit, one NEE shadow ray): every ray is
+    generated by exact arithmetic, so closest-hit AND any-hit traversal with the stochastic alpha test must reproduce the
+    oracle exactly; so must the counters."""
+    scene = Scene.from_source(scenes.textured_room(resolution=(64, 40), spp=8, wrappers=True, depth=1), REPO)
+    d = scene.desc()
+    gpu_renderer.upload(d)
+    gpu_renderer.render(0, 8)
+    gpu_raw = gpu_renderer.film(raw=True)
+    st = gpu_renderer.stats()
+    cpu_raw, cnt = O.render(d, 0, 8)
+    rel, off = _image_parity(gpu_raw, cpu_raw)
+    assert rel <= 1e-5 and off == 0.0, (rel, off)
+    assert st["closest_rays"] == cnt["closest_rays"] and np.array_equal(gpu_raw[..., 3], cpu_raw[..., 3])
 
 
 def test_render_is_deterministic_and_independent_of_scheduling(cornell_small, gpu_renderer):

@@ -324,3 +324,70 @@ def test_textured_scene_renders_what_the_textures_say():
     d2 = Scene.from_source(dark, REPO).desc()
     img2 = O.convert_film(d2, O.render(d2, 0, 4)[0])[..., :3]
     assert img2[28:, :, :].max() < img[28:, :, :].mean()
+
+
+# ---- surface wrappers: opacity (stochastic alpha test in traversal) and normal maps (src/base/surface.h:160-275) -------------
+def test_alpha_test_is_a_hash_of_the_hit_and_matches_the_mask_statistics():
+    d = Scene.from_source(scenes.textured_room(wrappers=True), REPO).desc()
+    screen = next(i for i in range(d.instance_count) if d.instances[i].handle[0] & 1023 & F.SHAPE_MAYBE_NON_OPAQUE
+                  and d.surfaces[(d.instances[i].handle[1] >> 12) & 4095].opacity_tex)
+    # rays from the camera side straight at random points of the screen quad
+    rng = np.random.default_rng(5)
+    n = 4000
+    st = rng.uniform(0.02, 0.98, (n, 2)).astype(f32)
+    p = np.array([0.2, 0.0, 1.0], f32) + st[:, :1] * np.array([1.4, 0.0, -0.4], f32) + st[:, 1:] * np.array([0.0, 1.3, 0.0], f32)
+    o = p + np.array([0.3, 0.1, 1.0], f32)
+    dirs = (p - o) / np.linalg.norm(p - o, axis=1, keepdims=True)
+    rays = np.zeros((n, 8), f32)
+    rays[:, :3], rays[:, 4:7], rays[:, 7] = o, dirs, 1e30
+    hits, _ = O.trace(d, rays)
+    on_screen = hits["inst"] == screen
+    # expected hit fraction = mean of the (linear-encoded, bilinear, uv_scale 2) alpha texture over the quad
+    lib = O.lib()
+    tex_id = d.surfaces[(d.instances[screen].handle[1] >> 12) & 4095].opacity_tex - 1
+    alpha = np.zeros(n, f32)
+    out = np.zeros(4, f32)
+    for k in range(n):
+        lib.oracle_texture_evaluate(C.byref(d), tex_id, st[k].ctypes.data_as(C.POINTER(C.c_float)), out.ctypes.data_as(C.POINTER(C.c_float)))
+        alpha[k] = min(max(out[0], 0.0), 1.0)
+    assert 0.2 < alpha.mean() < 0.8
+    assert abs(on_screen.mean() - alpha.mean()) < 0.03
+    assert (alpha[on_screen] > 0).all() and not on_screen[alpha == 0].any()  # fully transparent texels never stop a ray
+    # deterministic (hash of inst, prim, barycentrics), identical in the BVH and the brute-force traversal, and in any-hit mode
+    again, _ = O.trace(d, rays)
+    brute, _ = O.trace(d, rays, brute=True)
+    assert np.array_equal(hits, again) and np.array_equal(hits["inst"], brute["inst"]) and np.array_equal(hits["prim"], brute["prim"])
+    shadow = rays.copy()
+    shadow[:, 7] = np.linalg.norm(p - o, axis=1) * 1.001  # just past the screen: occluded <=> the screen (or the cube) stopped the ray
+    occluded, _ = O.trace(d, shadow, any_hit=True)
+    closest_before = hits["inst"] != 0xFFFFFFFF
+    t_hit_is_screen = on_screen
+    assert (occluded["inst"][t_hit_is_screen] != 0xFFFFFFFF).all()
+    assert closest_before.any()
+
+
+def test_constant_opacity_and_neutral_normal_map():
+    base = scenes.textured_room(resolution=(40, 28), spp=32)
+    d0 = Scene.from_source(base, REPO).desc()
+    img0 = O.convert_film(d0, O.render(d0, 0, 32)[0])[..., :3]
+    # a constant normal map of (0.5, 0.5, 1) decodes to the unperturbed normal: same image up to rounding in the frame rebuild
+    flat = base.replace("Surface floor_s : Matte {", "Surface floor_s : Matte {\n  normal_map : Constant { v { 0.5, 0.5, 1.0 } }")
+    d1 = Scene.from_source(flat, REPO).desc()
+    assert d1.surfaces[0].flags & F.SURFACE_HAS_NORMAL_MAP and d1.surfaces[0].normal_tex == 0
+    img1 = O.convert_film(d1, O.render(d1, 0, 32)[0])[..., :3]
+    assert img1.mean() == pytest.approx(img0.mean(), rel=2e-3)
+    assert np.median(np.abs(img1 - img0)) < 1e-5
+    # a tilted constant normal changes the floor's shading
+    tilted = base.replace("Surface floor_s : Matte {", "Surface floor_s : Matte {\n  normal_map : Constant { v { 0.9, 0.5, 0.8 } }")
+    d2 = Scene.from_source(tilted, REPO).desc()
+    img2 = O.convert_film(d2, O.render(d2, 0, 32)[0])[..., :3]
+    assert np.abs(img2[22:] - img0[22:]).mean() > 0.05 * img0[22:].mean()
+    # opacity 1 is opaque (no flag); opacity 0 makes the cube vanish: the pixels behind it show the wall / floor
+    opaque = Scene.from_source(base.replace("clearcoat : Constant { v { 0.5 } }", "clearcoat : Constant { v { 0.5 } } opacity : Constant { v { 1.0 } }"), REPO).desc()
+    assert not any(opaque.instances[i].handle[0] & 1023 & F.SHAPE_MAYBE_NON_OPAQUE for i in range(opaque.instance_count))
+    gone = Scene.from_source(base.replace("clearcoat : Constant { v { 0.5 } }", "clearcoat : Constant { v { 0.5 } } alpha : Constant { v { 0.0 } }"), REPO).desc()
+    assert gone.surfaces[2].flags & F.SURFACE_MAYBE_NON_OPAQUE and gone.surfaces[2].opacity == 0.0
+    rays = np.array([[0.0, 1.4, 4.2, 0.0, -0.16, -0.25, -0.95, 1e30]], f32)
+    rays[0, 4:7] /= np.linalg.norm(rays[0, 4:7])
+    cube_inst = 2
+    assert O.trace(d0, rays)[0]["inst"][0] == cube_inst and O.trace(gone, rays)[0]["inst"][0] != cube_inst
