@@ -263,9 +263,10 @@ __global__ void __launch_bounds__(kBlock) trace_query_kernel(DeviceScene sc, con
 
 // ---- shade ----------------------------------------------------------------------------------------------
 // Closure of the hit's surface node: constants straight from the node, image-textured parameters evaluated at the hit's uv.
-template<typename Closure>
+// TEXTURED = false is the instantiation for scenes without image-textured parameters / normal maps: the constants-only code.
+template<bool TEXTURED, typename Closure>
 __device__ __forceinline__ void init_closure(const DeviceScene &sc, Closure &cl, const lrk_surface *node, const Interaction &it) {
-    if (node->flags & LRK_SURFACE_HAS_TEXTURES) {
+    if (TEXTURED && (node->flags & LRK_SURFACE_HAS_TEXTURES)) {
         lrk_surface s = *node;
         resolve_surface_textures(sc, s, it.u, it.v);
         cl.init(s);
@@ -275,8 +276,9 @@ __device__ __forceinline__ void init_closure(const DeviceScene &sc, Closure &cl,
 }
 
 // The frame the closure works in: the interaction's shading frame, or the normal-mapped one (surface.h:236-253).
+template<bool TEXTURED>
 __device__ __forceinline__ Frame closure_frame(const DeviceScene &sc, const lrk_surface *node, const Interaction &it, V3 wo) {
-    if (node->flags & LRK_SURFACE_HAS_NORMAL_MAP) return normal_mapped_frame(sc, node, it, wo);
+    if (TEXTURED && (node->flags & LRK_SURFACE_HAS_NORMAL_MAP)) return normal_mapped_frame(sc, node, it, wo);
     return it.shading;
 }
 
@@ -335,7 +337,7 @@ __device__ __forceinline__ void shade_surface(Closure &cl, const Interaction &it
 }
 
 // Sorted-by-material dispatch, step 2: one shade kernel per closure kind, each over its own hit bucket.
-template<uint32_t KIND>
+template<uint32_t KIND, bool TEXTURED = false>
 __global__ void __launch_bounds__(kShadeBlock, LRK_SHADE_MIN_BLOCKS) shade_kernel(DeviceScene sc, PathBuffers pb, uint32_t depth) {
     __shared__ uint32_t s_warp_next[kShadeBlock / 32], s_warp_shadow[kShadeBlock / 32];
     __shared__ uint32_t s_base_next, s_base_shadow;
@@ -390,12 +392,12 @@ __global__ void __launch_bounds__(kShadeBlock, LRK_SHADE_MIN_BLOCKS) shade_kerne
                     float pdf;
                     if (KIND == 1u) {
                         MatteClosure cl;
-                        init_closure(sc, cl, surf, it);
-                        shade_surface<false>(cl, it, closure_frame(sc, surf, it, wo), wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
+                        init_closure<TEXTURED>(sc, cl, surf, it);
+                        shade_surface<false>(cl, it, closure_frame<TEXTURED>(sc, surf, it, wo), wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
                     } else {
                         DisneyClosure cl;
-                        init_closure(sc, cl, surf, it);
-                        shade_surface<false>(cl, it, closure_frame(sc, surf, it, wo), wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
+                        init_closure<TEXTURED>(sc, cl, surf, it);
+                        shade_surface<false>(cl, it, closure_frame<TEXTURED>(sc, surf, it, wo), wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
                     }
                     if (contrib.x != 0.f || contrib.y != 0.f || contrib.z != 0.f) {
                         // a zero (or NaN-free zero) contribution needs no shadow ray; NaNs must reach the film filter
@@ -794,7 +796,7 @@ __global__ void __launch_bounds__(kBlock) volume_medium_kernel(DeviceScene sc, P
 
 // Volume wave, step 2 (surface events of one closure kind): emitter hit seen from the moved origin, surface NEE +
 // closure sample (mega_vpt_naive.cpp:300-437), then the common end of the iteration.
-template<uint32_t KIND>
+template<uint32_t KIND, bool TEXTURED = false>
 __global__ void __launch_bounds__(kBlock, 2) volume_surface_kernel(DeviceScene sc, PathBuffers pb, uint32_t depth) {
     __shared__ uint32_t s_warp_next[kBlock / 32], s_warp_shadow[kBlock / 32];
     __shared__ uint32_t s_base_next, s_base_shadow;
@@ -844,12 +846,12 @@ __global__ void __launch_bounds__(kBlock, 2) volume_surface_kernel(DeviceScene s
                 // true_hit(medium_tag = 0) <=> 0 <= priority of the environment medium: always true (medium_tracker.cpp:19-21)
                 if (KIND == 1u) {
                     MatteClosure cl;
-                    init_closure(sc, cl, surf, it);
-                    shade_surface<true>(cl, it, closure_frame(sc, surf, it, wo), wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
+                    init_closure<TEXTURED>(sc, cl, surf, it);
+                    shade_surface<true>(cl, it, closure_frame<TEXTURED>(sc, surf, it, wo), wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
                 } else {
                     DisneyClosure cl;
-                    init_closure(sc, cl, surf, it);
-                    shade_surface<true>(cl, it, closure_frame(sc, surf, it, wo), wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
+                    init_closure<TEXTURED>(sc, cl, surf, it);
+                    shade_surface<true>(cl, it, closure_frame<TEXTURED>(sc, surf, it, wo), wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
                 }
                 push_shadow = true;// traced even with a zero contribution: its occlusion advances the PCG stream of the next bounce
                 sro = ls.ray_o_tmin;

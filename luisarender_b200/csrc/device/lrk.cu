@@ -44,6 +44,7 @@ struct lrk_ctx {
     uint32_t npix_owned{0};
     uint32_t pixel_list_key[5]{0, 0, 0, 0, 0};// width, height, rank, world, tile size of the cached list
     std::unordered_map<void **, size_t> array_bytes;// capacity of each scene array allocation
+    bool textured{false};// some surface has image-textured parameters or a normal map: the shade kernels' TEXTURED variants run
     bool any_non_opaque{false};// some instance carries LRK_SHAPE_MAYBE_NON_OPAQUE: traversal runs its alpha-testing variants
     size_t film_pixels{0};
     // path state
@@ -341,9 +342,10 @@ int render_pass_volume(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint3
         {
             ScopedTimer t{ctx, CAT_SHADE};
             volume_medium_kernel<<<blocks_for(ctx, n, ctx->grid_vmedium), kBlock, 0, ctx->stream>>>(sc, pb, depth);
-            volume_surface_kernel<0u><<<blocks_for(ctx, n, ctx->grid_vshade[0]), kBlock, 0, ctx->stream>>>(sc, pb, depth);
-            if (ctx->has_kind[1]) volume_surface_kernel<1u><<<blocks_for(ctx, n, ctx->grid_vshade[1]), kBlock, 0, ctx->stream>>>(sc, pb, depth);
-            if (ctx->has_kind[2]) volume_surface_kernel<2u><<<blocks_for(ctx, n, ctx->grid_vshade[2]), kBlock, 0, ctx->stream>>>(sc, pb, depth);
+            auto launch = [&](auto kernel, int kind) { kernel<<<blocks_for(ctx, n, ctx->grid_vshade[kind]), kBlock, 0, ctx->stream>>>(sc, pb, depth); };
+            launch(volume_surface_kernel<0u, false>, 0);
+            if (ctx->has_kind[1]) ctx->textured ? launch(volume_surface_kernel<1u, true>, 1) : launch(volume_surface_kernel<1u, false>, 1);
+            if (ctx->has_kind[2]) ctx->textured ? launch(volume_surface_kernel<2u, true>, 2) : launch(volume_surface_kernel<2u, false>, 2);
         }
         {
             ScopedTimer t{ctx, CAT_TRACE_SHADOW};
@@ -410,14 +412,14 @@ int lrk_create(const lrk_device_cfg *cfg, lrk_ctx **out) {
     };
     ctx->grid_trace = grid_for(reinterpret_cast<const void *>(trace_closest_kernel<false, false>));
     ctx->grid_shadow = grid_for(reinterpret_cast<const void *>(trace_shadow_kernel<false, false>));
-    ctx->grid_shade[0] = grid_for(reinterpret_cast<const void *>(shade_kernel<0u>));
-    ctx->grid_shade[1] = grid_for(reinterpret_cast<const void *>(shade_kernel<1u>));
-    ctx->grid_shade[2] = grid_for(reinterpret_cast<const void *>(shade_kernel<2u>));
+    ctx->grid_shade[0] = grid_for(reinterpret_cast<const void *>(shade_kernel<0u, false>));
+    ctx->grid_shade[1] = grid_for(reinterpret_cast<const void *>(shade_kernel<1u, false>));
+    ctx->grid_shade[2] = grid_for(reinterpret_cast<const void *>(shade_kernel<2u, false>));
     ctx->grid_classify = grid_for(reinterpret_cast<const void *>(classify_hits_kernel));
     ctx->grid_vmedium = grid_for(reinterpret_cast<const void *>(volume_medium_kernel));
-    ctx->grid_vshade[0] = grid_for(reinterpret_cast<const void *>(volume_surface_kernel<0u>));
-    ctx->grid_vshade[1] = grid_for(reinterpret_cast<const void *>(volume_surface_kernel<1u>));
-    ctx->grid_vshade[2] = grid_for(reinterpret_cast<const void *>(volume_surface_kernel<2u>));
+    ctx->grid_vshade[0] = grid_for(reinterpret_cast<const void *>(volume_surface_kernel<0u, false>));
+    ctx->grid_vshade[1] = grid_for(reinterpret_cast<const void *>(volume_surface_kernel<1u, false>));
+    ctx->grid_vshade[2] = grid_for(reinterpret_cast<const void *>(volume_surface_kernel<2u, false>));
     ctx->grid_vshadow = grid_for(reinterpret_cast<const void *>(trace_volume_nee_kernel<false>));
     *out = ctx;
     return LRK_OK;
@@ -474,6 +476,9 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
         if ((s->surfaces[i].flags & LRK_SURFACE_MAYBE_NON_OPAQUE) && s->integrator.type == LRK_INTEGRATOR_VOLUME_PATH)
             return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: non-opaque surfaces are not supported by the volume path integrator");
     }
+    ctx->textured = false;
+    for (uint32_t i = 0; i < s->surface_count; i++)
+        if (s->surfaces[i].flags & (LRK_SURFACE_HAS_TEXTURES | LRK_SURFACE_HAS_NORMAL_MAP)) ctx->textured = true;
     for (uint32_t i = 0; i < s->texture_count; i++) {
         const auto &t = s->textures[i];
         if (t.width == 0u || t.height == 0u || t.texel_offset + static_cast<uint64_t>(t.width) * t.height > s->texel_count ||
