@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define LRK_ABI_VERSION 2u
+#define LRK_ABI_VERSION 3u
 
 typedef enum lrk_status {
     LRK_OK = 0,
@@ -281,6 +281,30 @@ typedef struct lrk_medium {
     float reserved[3];
 } lrk_medium;
 
+/* The environment light: src/environments/spherical.cpp with the uniform light sampler's
+ * environment handling (src/lightsamplers/uniform.cpp:40-47,67-76,78-101,139-146).
+ *   L(w)  = max(rgb, 0) * scale, rgb = emission texture at direction_to_uv(world_to_env * w) (spherical.cpp:51-58,70-75;
+ *           illuminant decode src/spectra/srgb.cpp:48-54) or the constant `emission`
+ *   image emission: importance sampling from a map_width x map_height (2048 x 1024) table built on the host exactly like
+ *           Spherical::build (:140-236): Gaussian-filtered luminance * sin(theta), optional MIS compensation, one alias table
+ *           per row + the marginal one.  alias = [map_height marginal entries][map_height * map_width conditional entries],
+ *           pdf[y * map_width + x] = p(x,y) * pixel_count; directional pdf = pdf / sin(theta) / (2 pi^2) (:77-81)
+ *   constant emission: uniform sphere sampling, pdf = 1 / (4 pi)
+ *   env_prob: probability with which next-event estimation picks the environment (1 when there are no area lights, else
+ *           clamp(environment_weight, 0.01, 0.99), uniform.cpp:40-47); area-light pdfs are scaled by (1 - env_prob). */
+typedef struct lrk_environment {
+    uint32_t present;
+    uint32_t emission_tex; /* 0 = constant emission, else image texture id + 1 */
+    float emission[3];     /* constant emission (already max(rgb, 0)) */
+    float scale;
+    float env_prob;
+    float to_world[9]; /* row-major 3x3: environment -> world (make_float3x3 of the node's transform) */
+    uint32_t map_width, map_height; /* 0 x 0 for constant emission */
+    uint32_t reserved;
+    const lrk_alias_entry *alias; /* map_height + map_height * map_width entries */
+    const float *pdf;             /* map_height * map_width */
+} lrk_environment;
+
 typedef struct lrk_scene_desc {
     uint32_t abi_version; /* LRK_ABI_VERSION */
     uint32_t reserved0;
@@ -320,6 +344,7 @@ typedef struct lrk_scene_desc {
     lrk_film film;
     lrk_integrator integrator;
     lrk_medium environment_medium;
+    lrk_environment environment;
 } lrk_scene_desc;
 
 /* ---- device control ----------------------------------------------------------------- */

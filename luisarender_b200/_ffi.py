@@ -13,7 +13,7 @@ PKG_DIR = Path(__file__).resolve().parent
 REPO_DIR = PKG_DIR.parent
 LIB_DIR = PKG_DIR / "lib"
 
-LRK_ABI_VERSION = 2
+LRK_ABI_VERSION = 3
 TEX_ADDRESS_EDGE, TEX_ADDRESS_REPEAT, TEX_ADDRESS_MIRROR, TEX_ADDRESS_ZERO = 0, 1, 2, 3
 TEX_FILTER_POINT, TEX_FILTER_LINEAR = 0, 1
 TEX_ENCODING_LINEAR, TEX_ENCODING_SRGB, TEX_ENCODING_GAMMA = 0, 1, 2
@@ -98,6 +98,11 @@ class Medium(C.Structure):
                 ("sigma_s", f32 * 3), ("le", f32 * 3), ("reserved", f32 * 3)]
 
 
+class Environment(C.Structure):
+    _fields_ = [("present", u32), ("emission_tex", u32), ("emission", f32 * 3), ("scale", f32), ("env_prob", f32), ("to_world", f32 * 9),
+                ("map_width", u32), ("map_height", u32), ("reserved", u32), ("alias", C.POINTER(AliasEntry)), ("pdf", C.POINTER(f32))]
+
+
 class SceneDesc(C.Structure):
     _fields_ = [
         ("abi_version", u32), ("reserved0", u32),
@@ -112,6 +117,7 @@ class SceneDesc(C.Structure):
         ("lights", C.POINTER(Light)), ("light_handles", C.POINTER(LightHandle)),
         ("textures", C.POINTER(Texture)), ("texture_count", u32), ("reserved2", u32), ("texels", C.POINTER(f32)), ("texel_count", u64),
         ("camera", Camera), ("film", Film), ("integrator", Integrator), ("environment_medium", Medium),
+        ("environment", Environment),
     ]
 
 

@@ -261,6 +261,29 @@ __global__ void __launch_bounds__(kBlock) trace_query_kernel(DeviceScene sc, con
     });
 }
 
+// ---- escaped rays -----------------------------------------------------------------------------------------
+// Only launched for scenes with an environment light: environment radiance with MIS for every ray of the depth that left the
+// scene (mega_path.cpp:68-75, UniformLightSamplerInstance::evaluate_miss uniform.cpp:67-76).  Without an environment the
+// escaped rays are simply never looked at again (classify_hits_kernel buckets hits only).
+__global__ void __launch_bounds__(kBlock) shade_miss_kernel(DeviceScene sc, PathBuffers pb, uint32_t depth) {
+    const uint32_t n = pb.counts[depth];
+    const int in = depth & 1u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (pb.hit[i].x != ~0u) continue;
+        float4 rd = pb.ray_d[in][i];
+        float4 bp = pb.beta_pdf[in][i];
+        uint2 ir = pb.id_rng[in][i];
+        LightEval e = environment_evaluate(sc, v3(rd.x, rd.y, rd.z));
+        e.pdf *= sc.env_prob;
+        V3 add = v3(bp.x, bp.y, bp.z) * e.L * balance_heuristic(bp.w, e.pdf);
+        float4 li = pb.li[ir.x];
+        li.x += add.x;
+        li.y += add.y;
+        li.z += add.z;
+        pb.li[ir.x] = li;
+    }
+}
+
 // ---- shade ----------------------------------------------------------------------------------------------
 // Closure of the hit's surface node: constants straight from the node, image-textured parameters evaluated at the hit's uv.
 // TEXTURED = false is the instantiation for scenes without image-textured parameters / normal maps: the constants-only code.
@@ -386,7 +409,7 @@ __global__ void __launch_bounds__(kShadeBlock, LRK_SHADE_MIN_BLOCKS) shade_kerne
                     ls.eval.pdf = 0.f;
                     ls.ray_o_tmin = make_float4(0.f, 0.f, 0.f, 0.f);
                     ls.ray_d_tmax = make_float4(0.f, 0.f, 1.f, 0.f);
-                    if (sc.light_count != 0u) ls = sample_light(sc, it, u_sel, ul0, ul1);
+                    if (sc.light_count != 0u || sc.env_prob != 0.f) ls = sample_light(sc, it, u_sel, ul0, ul1);
                     const lrk_surface *surf = sc.surfaces + it.shape.surface_tag;
                     V3 contrib, wi, f;
                     float pdf;

@@ -16,7 +16,7 @@ using namespace lrk;
 namespace {
 
 struct DeviceArrays {
-    void *vertices{}, *triangles{}, *alias{}, *pdf{}, *meshes{}, *inst_handles{}, *inst_kind{}, *inst_o2w{}, *inst_xform{}, *bvh_nodes{}, *textures{}, *texels{},
+    void *vertices{}, *triangles{}, *alias{}, *pdf{}, *meshes{}, *inst_handles{}, *inst_kind{}, *inst_o2w{}, *inst_xform{}, *bvh_nodes{}, *textures{}, *texels{}, *env_alias{}, *env_pdf{},
         *tri_verts{}, *surfaces{}, *lights{}, *light_handles{}, *camera{};
 };
 
@@ -272,10 +272,15 @@ int render_pass(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint32_t spp
         }
         {
             ScopedTimer t{ctx, CAT_SHADE};
+            if (sc.env_present) shade_miss_kernel<<<blocks_for(ctx, n, ctx->grid_classify), kBlock, 0, ctx->stream>>>(sc, pb, depth);
             classify_hits_kernel<<<blocks_for(ctx, n, ctx->grid_classify), kBlock, 0, ctx->stream>>>(sc, pb, depth);
-            shade_kernel<0u><<<blocks_for(ctx, n, ctx->grid_shade[0]), kBlock, 0, ctx->stream>>>(sc, pb, depth);
-            if (ctx->has_kind[1]) shade_kernel<1u><<<blocks_for(ctx, n, ctx->grid_shade[1]), kBlock, 0, ctx->stream>>>(sc, pb, depth);
-            if (ctx->has_kind[2]) shade_kernel<2u><<<blocks_for(ctx, n, ctx->grid_shade[2]), kBlock, 0, ctx->stream>>>(sc, pb, depth);
+            // TEXTURED variants only for scenes with image-textured parameters / normal maps
+            auto launch = [&](auto kernel, int kind) {
+                kernel<<<blocks_for(ctx, n, ctx->grid_shade[kind]), kShadeBlock, 0, ctx->stream>>>(sc, pb, depth);
+            };
+            launch(shade_kernel<0u, false>, 0);
+            if (ctx->has_kind[1]) ctx->textured ? launch(shade_kernel<1u, true>, 1) : launch(shade_kernel<1u, false>, 1);
+            if (ctx->has_kind[2]) ctx->textured ? launch(shade_kernel<2u, true>, 2) : launch(shade_kernel<2u, false>, 2);
         }
         if (bin) {
             ScopedTimer t{ctx, CAT_OTHER};
@@ -466,7 +471,17 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
     if (s->integrator.max_depth > kMaxDepthSlots - 1u) return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: max depth > 63");
     if (s->camera.resolution[0] > 65535u || s->camera.resolution[1] > 65535u)
         return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: film larger than 65535 pixels per side");
-    if (s->light_count == 0u) return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "No lights in scene. Rendering aborted.");// wave_path.cpp:224-228
+    if (s->light_count == 0u && !s->environment.present)// !pipeline().has_lighting(), wave_path.cpp:224-228
+        return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "No lights in scene. Rendering aborted.");
+    if (s->environment.present) {
+        const auto &e = s->environment;
+        if (s->integrator.type == LRK_INTEGRATOR_VOLUME_PATH)
+            return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: environment lights are not supported by the volume path integrator");
+        if (e.emission_tex > s->texture_count || !(e.env_prob > 0.f && e.env_prob <= 1.f) ||
+            (e.emission_tex != 0u && (e.map_width == 0u || e.map_height == 0u || e.alias == nullptr || e.pdf == nullptr)))
+            return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_upload_scene: invalid environment record");
+        if (s->light_count == 0u && e.env_prob != 1.f) return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_upload_scene: env_prob must be 1 without area lights");
+    }
     for (uint32_t i = 0; i < s->surface_count; i++) {
         if (s->surfaces[i].type > LRK_SURFACE_DISNEY) return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: unknown surface type");
         for (uint32_t k = 0; k < 16u; k++)
@@ -497,6 +512,13 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
     if ((rc = upload(ctx, &a.tri_verts, s->tri_verts, s->tri_slot_count * 12u))) return rc;
     if ((rc = upload(ctx, &a.surfaces, s->surfaces, s->surface_count))) return rc;
     if ((rc = upload(ctx, &a.textures, s->textures, s->texture_count))) return rc;
+    {
+        const auto &e = s->environment;
+        const bool mapped = e.present && e.emission_tex != 0u;
+        const size_t cells = mapped ? static_cast<size_t>(e.map_width) * e.map_height : 0u;
+        if ((rc = upload(ctx, &a.env_alias, e.alias, mapped ? cells + e.map_height : 0u))) return rc;
+        if ((rc = upload(ctx, &a.env_pdf, e.pdf, cells))) return rc;
+    }
     if ((rc = upload(ctx, &a.texels, s->texels, s->texel_count * 4u))) return rc;
     if ((rc = upload(ctx, &a.lights, s->lights, s->light_count))) return rc;
     if ((rc = upload(ctx, &a.light_handles, s->light_handles, s->light_count))) return rc;
@@ -545,6 +567,16 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
     sc.tri_verts = static_cast<const float4 *>(a.tri_verts);
     sc.surfaces = static_cast<const lrk_surface *>(a.surfaces);
     sc.textures = static_cast<const lrk_texture *>(a.textures);
+    sc.env_alias = static_cast<const lrk_alias_entry *>(a.env_alias);
+    sc.env_pdf = static_cast<const float *>(a.env_pdf);
+    sc.env_present = s->environment.present ? 1u : 0u;
+    sc.env_emission_tex = s->environment.present ? s->environment.emission_tex : 0u;
+    sc.env_map_width = s->environment.map_width;
+    sc.env_map_height = s->environment.map_height;
+    sc.env_scale = s->environment.scale;
+    sc.env_prob = s->environment.present ? s->environment.env_prob : 0.f;
+    for (int k = 0; k < 3; k++) sc.env_emission[k] = s->environment.emission[k];
+    for (int k = 0; k < 9; k++) sc.env_to_world[k] = s->environment.to_world[k];
     sc.texels = static_cast<const float4 *>(a.texels);
     sc.lights = static_cast<const lrk_light *>(a.lights);
     sc.light_handles = static_cast<const lrk_light_handle *>(a.light_handles);

@@ -25,6 +25,12 @@ struct DeviceScene {
     const lrk_surface *surfaces;
     const lrk_texture *textures;// image textures referenced by lrk_surface::tex
     const float4 *texels;       // RGBA float texels of all textures
+    // environment light (spherical.cpp): importance map tables + parameters; env_prob = 0 <=> no environment
+    const lrk_alias_entry *env_alias;
+    const float *env_pdf;
+    uint32_t env_present, env_emission_tex, env_map_width, env_map_height;
+    float env_emission[3], env_scale, env_prob;
+    float env_to_world[9];
     const lrk_light *lights;
     const lrk_light_handle *light_handles;
     const lrk_camera *camera;

@@ -234,9 +234,13 @@ __device__ __forceinline__ LightEval diffuse_light_evaluate(const DeviceScene &s
 __device__ __forceinline__ LightEval evaluate_hit(const DeviceScene &sc, const Interaction &it, V3 p_from) {
     LightEval e = diffuse_light_evaluate(sc, it, p_from);
     float n = static_cast<float>(sc.light_count);
-    e.pdf *= (1.f - 0.f) / n;
+    e.pdf *= (1.f - sc.env_prob) / n;// uniform.cpp:63 (env_prob = 0 without an environment)
     return e;
 }
+
+// the environment light (defined after the texture code): src/environments/spherical.cpp:83-137
+__device__ LightEval environment_evaluate(const DeviceScene &sc, V3 wi);
+__device__ LightEval environment_sample(const DeviceScene &sc, float u0, float u1, V3 &wi);
 
 struct LightSample {
     LightEval eval;
@@ -246,8 +250,29 @@ struct LightSample {
 __device__ __forceinline__ LightSample sample_light(const DeviceScene &sc, const Interaction &it_from, float u_sel, float u0, float u1) {
     LightSample s;
     float n = static_cast<float>(sc.light_count);
-    uint32_t tag = static_cast<uint32_t>(clampf(u_sel * n, 0.f, n - 1.f));
-    float sel_prob = 1.f / n;
+    // UniformLightSamplerInstance::select, uniform.cpp:78-90
+    const float ep = sc.env_prob;
+    bool is_env = ep == 1.f;
+    uint32_t tag = 0u;
+    float sel_prob = 1.f;
+    if (ep == 0.f) {
+        tag = static_cast<uint32_t>(clampf(u_sel * n, 0.f, n - 1.f));
+        sel_prob = 1.f / n;
+    } else if (ep != 1.f) {
+        float uu = (u_sel - ep) / (1.f - ep);
+        tag = static_cast<uint32_t>(clampf(uu * n, 0.f, n - 1.f));
+        is_env = u_sel < ep;
+        sel_prob = is_env ? ep : (1.f - ep) / n;
+    }
+    if (is_env) {// sample_environment + Sample::from_environment (light_sampler.cpp:84-90,120-123): a ray to infinity
+        V3 wi;
+        s.eval = environment_sample(sc, u0, u1, wi);
+        s.eval.pdf *= sel_prob;
+        V3 o = p_robust(it_from, wi);
+        s.ray_o_tmin = make_float4(o.x, o.y, o.z, 0.f);
+        s.ray_d_tmax = make_float4(wi.x, wi.y, wi.z, kFltMax);
+        return s;
+    }
     const lrk_light_handle handle = sc.light_handles[tag];
     ShapeHandle light_inst = decode_handle(__ldg(sc.inst_handles + handle.instance_id));
     const lrk_mesh mesh = sc.meshes[light_inst.mesh];
@@ -353,6 +378,84 @@ __device__ __forceinline__ void resolve_surface_textures(const DeviceScene &sc, 
             }
         }
     }
+}
+
+// ---- Spherical environment: src/environments/spherical.cpp:42-137 (uv mapping, evaluate, sample); tables built by the host ----
+__device__ __forceinline__ V3 env_mul(const float *m, V3 v, bool transposed) {// float3x3 * float3 = v.x*col0 + v.y*col1 + v.z*col2
+    if (!transposed) return v.x * v3(m[0], m[3], m[6]) + v.y * v3(m[1], m[4], m[7]) + v.z * v3(m[2], m[5], m[8]);
+    return v.x * v3(m[0], m[1], m[2]) + v.y * v3(m[3], m[4], m[5]) + v.z * v3(m[6], m[7], m[8]);
+}
+__device__ __forceinline__ V3 env_radiance(const DeviceScene &sc, float u, float v) {// _evaluate (:70-75) + decode_illuminant
+    V3 rgb = v3(sc.env_emission[0], sc.env_emission[1], sc.env_emission[2]);
+    if (sc.env_emission_tex != 0u) {
+        float4 t = texture_evaluate(sc, sc.env_emission_tex - 1u, u, v);
+        rgb = v3(fmaxf(t.x, 0.f), fmaxf(t.y, 0.f), fmaxf(t.z, 0.f));
+    }
+    return rgb * sc.env_scale;
+}
+__device__ __forceinline__ float env_directional_pdf(float p, float theta) {// :77-81
+    float s = sinf(theta);
+    float inv_s = s > 0.f ? 1.f / s : 0.f;
+    return p * inv_s * (.5f * kInvPi * kInvPi);
+}
+__device__ __noinline__ LightEval environment_evaluate(const DeviceScene &sc, V3 wi) {
+    V3 w = normalize(env_mul(sc.env_to_world, wi, true));
+    float theta = acosf(w.y), phi = atan2f(w.x, w.z);// direction_to_uv, :53-59
+    float u = 1.f - 0.5f * kInvPi * phi, v = theta * kInvPi;
+    u = u - floorf(u);
+    v = v - floorf(v);
+    LightEval out;
+    out.L = env_radiance(sc, u, v);
+    if (sc.env_emission_tex == 0u) {
+        out.pdf = kInvPi * 0.25f;// uniform_sphere_pdf
+    } else {
+        float sx = static_cast<float>(sc.env_map_width), sy = static_cast<float>(sc.env_map_height);
+        uint32_t ix = static_cast<uint32_t>(clampf(u * sx, 0.f, sx - 1.f)), iy = static_cast<uint32_t>(clampf(v * sy, 0.f, sy - 1.f));
+        out.pdf = env_directional_pdf(__ldg(sc.env_pdf + static_cast<size_t>(iy) * sc.env_map_width + ix), theta);
+    }
+    return out;
+}
+__device__ __forceinline__ void sample_alias(const lrk_alias_entry *table, uint32_t n, float u_in, uint32_t &index, float &uu) {
+    float u = u_in * static_cast<float>(n);// sample_alias_table, src/util/sampling.h:38-50
+    uint32_t i = min(max(static_cast<uint32_t>(u), 0u), n - 1u);
+    float u_remapped = u - floorf(u);
+    lrk_alias_entry entry = table[i];
+    bool keep = u_remapped < entry.prob;
+    index = keep ? i : entry.alias;
+    uu = keep ? u_remapped / entry.prob : (u_remapped - entry.prob) / (1.0f - entry.prob);
+}
+__device__ __noinline__ LightEval environment_sample(const DeviceScene &sc, float u0, float u1, V3 &wi) {
+    LightEval e;
+    V3 w;
+    if (sc.env_emission_tex == 0u) {
+        float z = 1.0f - 2.0f * u0;// sample_uniform_sphere, sampling.cpp:100-108
+        float r = sqrtf(fmaxf(1.0f - z * z, 0.0f));
+        float phi = 2.0f * kPi * u1;
+        float sp, cp;
+        sincosf(phi, &sp, &cp);
+        w = v3(r * cp, r * sp, z);
+        float theta = acosf(w.y), ph = atan2f(w.x, w.z);
+        float u = 1.f - 0.5f * kInvPi * ph, v = theta * kInvPi;
+        e.L = env_radiance(sc, u - floorf(u), v - floorf(v));
+        e.pdf = kInvPi * 0.25f;
+    } else {
+        const uint32_t W = sc.env_map_width, H = sc.env_map_height;
+        uint32_t iy, ix;
+        float uy, ux;
+        sample_alias(sc.env_alias, H, u1, iy, uy);
+        sample_alias(sc.env_alias + static_cast<size_t>(H) + static_cast<size_t>(iy) * W, W, u0, ix, ux);
+        float u = (static_cast<float>(ix) + ux) / static_cast<float>(W), v = (static_cast<float>(iy) + uy) / static_cast<float>(H);
+        float p = __ldg(sc.env_pdf + static_cast<size_t>(iy) * W + ix);
+        float phi = 2.f * kPi * (1.f - u), theta = kPi * v;// uv_to_direction, :42-51
+        float sphi, cphi, sth, cth;
+        sincosf(phi, &sphi, &cphi);
+        sincosf(theta, &sth, &cth);
+        w = normalize(v3(sphi * sth, cth, cphi * sth));
+        e.L = env_radiance(sc, u, v);
+        e.pdf = env_directional_pdf(p, theta);
+    }
+    wi = normalize(env_mul(sc.env_to_world, w, false));
+    return e;
 }
 
 // Geometry::_alpha_skip (src/base/geometry.cpp:165-192): whether a traversal candidate (instance, primitive, barycentrics of

@@ -1,5 +1,7 @@
 #include "flatten.h"
 
+#include "envmap.h"
+
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -43,6 +45,9 @@ lrk_scene_desc FlatScene::desc(uint32_t camera_index) const {
     d.film = cameras[camera_index].film;
     d.integrator = integrator;
     d.environment_medium = environment_medium;
+    d.environment = environment;
+    d.environment.alias = env_alias.empty() ? nullptr : env_alias.data();
+    d.environment.pdf = env_pdf.empty() ? nullptr : env_pdf.data();
     return d;
 }
 
@@ -350,6 +355,30 @@ std::unique_ptr<FlatScene> flatten_scene(const Scene &scene) {
     }
     for (auto &s : out->surfaces)
         if (s.type == LRK_SURFACE_DISNEY) s.lobes = disney_lobes;
+    // the environment light: src/environments/spherical.cpp, src/lightsamplers/uniform.cpp:40-47
+    if (auto env = scene.environment(); env != nullptr && !env->is_null() && !env->is_black()) {
+        auto &e = out->environment;
+        e.present = 1u;
+        e.scale = env->scale;
+        e.emission_tex = texture_table.slot(env->emission);
+        if (e.emission_tex == 0u) {
+            auto c = env->emission->value();
+            auto n = env->emission->channels();
+            float rgb[3] = {c.x, n == 1u ? c.x : c.y, n == 1u ? c.x : (n == 2u ? 1.f : c.z)};// extend_color_to_rgb
+            for (int k = 0; k < 3; k++) e.emission[k] = std::max(rgb[k], 0.f);                  // encode/decode_illuminant
+        }
+        auto m = env->transform != nullptr ? env->transform->matrix() : float4x4::identity();// make_float3x3(transform), environment.cpp:18-20
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 3; c++) e.to_world[r * 3 + c] = m.c[c][r];// columns c[], row-major output
+        auto w = scene.integrator()->light_sampler ? scene.integrator()->light_sampler->environment_weight : .5f;
+        e.env_prob = f.light_nodes.empty() ? 1.f : std::min(std::max(w, 0.01f), 0.99f);
+        if (e.emission_tex != 0u) {
+            const auto &rec = texture_table.records[e.emission_tex - 1u];
+            build_environment_map(rec, texture_table.texels.data() + rec.texel_offset * 4u, env->compensate_mis, out->env_alias, out->env_pdf);
+            e.map_width = kEnvMapWidth;
+            e.map_height = kEnvMapHeight;
+        }
+    }
     out->textures = std::move(texture_table.records);
     out->texels = std::move(texture_table.texels);
     for (auto l : f.light_nodes) out->lights.push_back(l->flatten());

@@ -35,6 +35,9 @@ struct FlatScene {
     std::vector<FlatCamera> cameras;
     lrk_integrator integrator{};
     lrk_medium environment_medium{};
+    lrk_environment environment{};           // pointers are filled by desc()
+    std::vector<lrk_alias_entry> env_alias;  // importance map of an image-textured environment (spherical.cpp:140-236)
+    std::vector<float> env_pdf;
     uint32_t tlas_root{0};
     float world_min[3]{}, world_max[3]{};
     uint64_t total_instanced_triangles{0};

@@ -120,7 +120,7 @@ std::unique_ptr<Scene> Scene::create(const SceneDesc *desc) {
     if (!spectrum_desc) spectrum_desc = scene->shared_default(Tag::SPECTRUM, "sRGB");
     scene->_spectrum = scene->load<Spectrum>(Tag::SPECTRUM, spectrum_desc);
     scene->_integrator = scene->load<Integrator>(Tag::INTEGRATOR, root->required_node("integrator"));
-    if (auto env = root->node("environment")) scene->load_node(Tag::ENVIRONMENT, env);// no env plugin -> hard error
+    if (auto env = root->node("environment")) scene->_environment = scene->load<Environment>(Tag::ENVIRONMENT, env);
     scene->_environment_medium = scene->load_medium(root->node("environment_medium"));
     for (auto c : root->required_nodes("cameras")) scene->_cameras.push_back(scene->load<Camera>(Tag::CAMERA, c));
     for (auto s : root->required_nodes("shapes")) scene->_shapes.push_back(scene->load_shape(s));
@@ -611,6 +611,35 @@ LRH_PLUGIN("phasefunction-henyeygreenstein", HenyeyGreenstein)
 LRH_PLUGIN("medium-homogeneous", HomogeneousMedium)
 LRH_PLUGIN("medium-null", NullMedium)
 LRH_PLUGIN("medium-vacuum", VacuumMedium)
+
+// ---------------------------------------------------------------- environments
+
+Environment::Environment(Scene *scene, const NodeDesc *desc) : SceneNode{scene, desc, Tag::ENVIRONMENT} {
+    transform = scene->load_transform(desc->node("transform"));
+}
+
+namespace {
+
+struct SphericalEnvironment final : Environment {
+    SphericalEnvironment(Scene *s, const NodeDesc *d) : Environment{s, d} {
+        emission = s->load_texture(d->required_node("emission"));
+        if (!emission->is_constant() && !emission->is_image())
+            throw Error("Only constant and image textures are supported ('emission'). [" + d->location() + "]");
+        scale = std::max(d->f("scale", 1.0f), 0.0f);
+        compensate_mis = d->b("compensate_mis", true);
+    }
+    bool is_black() const override { return scale == 0.0f || emission->is_black(); }
+};
+
+struct NullEnvironment final : Environment {
+    NullEnvironment(Scene *s, const NodeDesc *d) : Environment{s, d} {}
+    bool is_null() const override { return true; }
+    bool is_black() const override { return true; }
+};
+
+}// namespace
+LRH_PLUGIN("environment-spherical", SphericalEnvironment)
+LRH_PLUGIN("environment-null", NullEnvironment)
 
 // ---------------------------------------------------------------- surfaces / lights
 

@@ -151,6 +151,17 @@ protected:
     void flatten_wrappers(lrk_surface &out, TextureTable &textures) const;
 };
 
+struct Environment : SceneNode {
+    // src/base/environment.cpp:11-13 ; the Spherical plugin: src/environments/spherical.cpp:16-33
+    Environment(Scene *scene, const NodeDesc *desc);
+    virtual bool is_null() const { return false; }
+    virtual bool is_black() const = 0;
+    const Transform *transform{};
+    const Texture *emission{};
+    float scale{1.f};
+    bool compensate_mis{true};
+};
+
 struct Light : SceneNode {
     using SceneNode::SceneNode;
     virtual bool is_null() const { return false; }
@@ -218,6 +229,7 @@ public:
     const Integrator *integrator() const { return _integrator; }
     const Spectrum *spectrum() const { return _spectrum; }
     const Medium *environment_medium() const { return _environment_medium; }
+    const Environment *environment() const { return _environment; }
     const std::vector<const Camera *> &cameras() const { return _cameras; }
     const std::vector<const Shape *> &shapes() const { return _shapes; }
     float shadow_terminator_factor() const { return _shadow_terminator; }
@@ -237,6 +249,7 @@ private:
     const Integrator *_integrator{};
     const Spectrum *_spectrum{};
     const Medium *_environment_medium{};
+    const Environment *_environment{};
     std::vector<const Camera *> _cameras;
     std::vector<const Shape *> _shapes;
     float _shadow_terminator{0.f};

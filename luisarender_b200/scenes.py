@@ -290,3 +290,63 @@ render {{
   shapes {{ @floor, @wall, @cube, @tetra, @lamp{screen_ref} }}
 }}
 """
+
+
+def environment_scene(resolution=(64, 40), spp=8, depth=5, rr_depth=0, rr_threshold=0.95, seed=19980810, assets="tests/golden/assets",
+                      emission="image", area_light=True, environment_weight=0.5, compensate_mis=True, output="env.exr") -> str:
+    """a Spherical environment light (src/environments/spherical.cpp) — image emission with the
+    importance map, or a constant one — next to an optional area light (uniform light sampler, environment_weight), seen by a
+    Matte sphere on a Disney floor."""
+    a = assets.rstrip("/")
+    if emission == "image":
+        em = f'emission : Image {{ file {{ "{a}/sky.pfm" }} encoding {{ "linear" }} address {{ "repeat" }} }}'
+    else:
+        em = f"emission : Constant {{ v {{ {_fmt(emission[0])}, {_fmt(emission[1])}, {_fmt(emission[2])} }} }}"
+    light = lamp = lamp_ref = ""
+    if area_light:
+        light = "Light area_light : Diffuse { emission : Constant { v { 9.0, 8.0, 6.0 } } }"
+        lamp = """Shape lamp : InlineMesh {
+  positions { -0.4, 2.2, 0.4,  -0.4, 2.2, -0.4,  0.4, 2.2, -0.4,  0.4, 2.2, 0.4 }
+  indices { 0, 1, 2, 0, 2, 3 }
+  light { @area_light }
+}"""
+        lamp_ref = ", @lamp"
+    return f"""
+Surface ball_s : Matte {{ Kd : Constant {{ v {{ 0.8, 0.8, 0.8 }} }} }}
+Surface floor_s : Disney {{ color : Constant {{ v {{ 0.5, 0.45, 0.4 }} }} roughness : Constant {{ v {{ 0.6 }} }} }}
+{light}
+Shape ball : Sphere {{ subdivision {{ 3 }} surface {{ @ball_s }} transform : SRT {{ scale {{ 0.7 }} translate {{ 0.0, 0.7, 0.0 }} }} }}
+Shape floor : InlineMesh {{
+  positions {{ -3.0, 0.0, 3.0,  3.0, 0.0, 3.0,  3.0, 0.0, -3.0,  -3.0, 0.0, -3.0 }}
+  indices {{ 0, 1, 2, 0, 2, 3 }}
+  surface {{ @floor_s }}
+}}
+{lamp}
+Camera camera : Pinhole {{
+  position {{ 0.0, 1.2, 4.0 }}
+  front {{ 0.0, -0.12, -1.0 }}
+  up {{ 0.0, 1.0, 0.0 }}
+  fov {{ 42.0 }}
+  spp {{ {int(spp)} }}
+  film : Color {{ resolution {{ {int(resolution[0])}, {int(resolution[1])} }} }}
+  filter : Box {{ radius {{ 0.5 }} }}
+  file {{ "{output}" }}
+}}
+render {{
+  integrator : WavePath {{
+    depth {{ {int(depth)} }}
+    rr_depth {{ {int(rr_depth)} }}
+    rr_threshold {{ {_fmt(rr_threshold)} }}
+    sampler : Independent {{ seed {{ {int(seed)} }} }}
+    light_sampler : Uniform {{ environment_weight {{ {_fmt(environment_weight)} }} }}
+  }}
+  environment : Spherical {{
+    {em}
+    scale {{ 1.0 }}
+    compensate_mis {{ {"true" if compensate_mis else "false"} }}
+    transform : SRT {{ rotate {{ 0.0, 1.0, 0.0, 40.0 }} }}
+  }}
+  cameras {{ @camera }}
+  shapes {{ @ball, @floor{lamp_ref} }}
+}}
+"""

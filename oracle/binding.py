@@ -68,6 +68,10 @@ def lib() -> C.CDLL:
         _lib.oracle_interaction.restype = None
         _lib.oracle_sample_light.argtypes = [vp, vp, vp, C.c_float, f32p, f32p]
         _lib.oracle_sample_light.restype = None
+        _lib.oracle_environment_sample.argtypes = [vp, f32p, f32p]
+        _lib.oracle_environment_sample.restype = None
+        _lib.oracle_environment_evaluate.argtypes = [vp, f32p, f32p]
+        _lib.oracle_environment_evaluate.restype = None
         _lib.oracle_texture_evaluate.argtypes = [vp, C.c_uint32, f32p, f32p]
         _lib.oracle_texture_evaluate.restype = None
         _lib.oracle_resolve_surface.argtypes = [vp, C.c_uint32, f32p, vp]

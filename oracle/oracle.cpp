@@ -567,12 +567,20 @@ LightEval diffuse_light_evaluate(const lrk_scene_desc &sc, const Interaction &it
     return e;
 }
 
+inline float env_prob(const lrk_scene_desc &sc) { return sc.environment.present ? sc.environment.env_prob : 0.f; }
 LightEval evaluate_hit(const lrk_scene_desc &sc, const Interaction &it, V3 p_from) {
     LightEval e = diffuse_light_evaluate(sc, it, p_from);
     float n = static_cast<float>(sc.light_count);
-    e.pdf *= (1.f - 0.f) / n;// env_prob = 0 (no environment)
+    e.pdf *= (1.f - env_prob(sc)) / n;// uniform.cpp:63
     return e;
 }
+// the environment (defined with the texture code below): src/environments/spherical.cpp:83-137
+struct EnvSample {
+    LightEval eval;
+    V3 wi{};
+};
+LightEval environment_evaluate(const lrk_scene_desc &sc, V3 wi);
+EnvSample environment_sample(const lrk_scene_desc &sc, float u0, float u1);
 
 struct LightSample {
     LightEval eval;
@@ -581,10 +589,29 @@ struct LightSample {
 
 LightSample sample_light(const lrk_scene_desc &sc, const Interaction &it_from, float u_sel, float u0, float u1) {
     LightSample s;
-    if (sc.light_count == 0u) return s;
+    const float ep = env_prob(sc);
+    if (sc.light_count == 0u && ep == 0.f) return s;// !has_lighting (light_sampler.cpp:58)
     float n = static_cast<float>(sc.light_count);
-    uint32_t tag = static_cast<uint32_t>(clampf(u_sel * n, 0.f, n - 1.f));
-    float sel_prob = 1.f / n;
+    // UniformLightSamplerInstance::select, uniform.cpp:78-90
+    bool is_env = ep == 1.f;
+    uint32_t tag = 0u;
+    float sel_prob = 1.f;
+    if (ep == 0.f) {
+        tag = static_cast<uint32_t>(clampf(u_sel * n, 0.f, n - 1.f));
+        sel_prob = 1.f / n;
+    } else if (ep != 1.f) {
+        float uu = (u_sel - ep) / (1.f - ep);
+        tag = static_cast<uint32_t>(clampf(uu * n, 0.f, n - 1.f));
+        is_env = u_sel < ep;
+        sel_prob = is_env ? ep : (1.f - ep) / n;
+    }
+    if (is_env) {// sample_environment + Sample::from_environment, light_sampler.cpp:84-90,120-123
+        EnvSample es = environment_sample(sc, u0, u1);
+        s.eval = es.eval;
+        s.eval.pdf *= sel_prob;
+        s.shadow_ray = spawn_ray(it_from, es.wi);
+        return s;
+    }
     const auto &handle = sc.light_handles[tag];
     ShapeHandle light_inst = decode_handle(sc.instances[handle.instance_id].handle);
     const auto &mesh = sc.meshes[light_inst.buffer_base >> 2u];
@@ -1055,6 +1082,77 @@ F4 texture_evaluate(const lrk_scene_desc &sc, uint32_t tex_id, float u, float v)
     F4 s = texture_sample(sc, t, u * t.uv_scale[0] + t.uv_offset[0], v * t.uv_scale[1] + t.uv_offset[1]);
     return {tex_decode(t, s.x), tex_decode(t, s.y), tex_decode(t, s.z), tex_decode(t, s.w)};
 }
+// ------------------------------------------------------------------------------------------------
+// Spherical environment: src/environments/spherical.cpp:42-137 (uv mapping, evaluate, sample); tables built by the host.
+// ------------------------------------------------------------------------------------------------
+inline V3 env_mul(const float m[9], V3 v, bool transposed) {// float3x3 * float3 = v.x*col0 + v.y*col1 + v.z*col2
+    if (!transposed) return v.x * v3(m[0], m[3], m[6]) + v.y * v3(m[1], m[4], m[7]) + v.z * v3(m[2], m[5], m[8]);
+    return v.x * v3(m[0], m[1], m[2]) + v.y * v3(m[3], m[4], m[5]) + v.z * v3(m[6], m[7], m[8]);
+}
+inline V3 env_radiance(const lrk_scene_desc &sc, float u, float v) {// _evaluate (:70-75) + decode_illuminant (srgb.cpp:48-54)
+    const lrk_environment &e = sc.environment;
+    V3 rgb = v3(e.emission[0], e.emission[1], e.emission[2]);
+    if (e.emission_tex != 0u) {
+        F4 t = texture_evaluate(sc, e.emission_tex - 1u, u, v);
+        rgb = v3(std::fmax(t.x, 0.f), std::fmax(t.y, 0.f), std::fmax(t.z, 0.f));
+    }
+    return rgb * e.scale;
+}
+inline float env_directional_pdf(float p, float theta) {// :77-81
+    float s = std::sin(theta);
+    float inv_s = s > 0.f ? 1.f / s : 0.f;
+    return p * inv_s * (.5f * kInvPi * kInvPi);
+}
+LightEval environment_evaluate(const lrk_scene_desc &sc, V3 wi) {
+    const lrk_environment &e = sc.environment;
+    V3 w = normalize(env_mul(e.to_world, wi, true));
+    float theta = std::acos(w.y), phi = std::atan2(w.x, w.z);// direction_to_uv, :53-59
+    float u = 1.f - 0.5f * kInvPi * phi, v = theta * kInvPi;
+    u = u - std::floor(u);
+    v = v - std::floor(v);
+    LightEval out;
+    out.L = env_radiance(sc, u, v);
+    if (e.emission_tex == 0u) {
+        out.pdf = kInvPi * 0.25f;// uniform_sphere_pdf
+    } else {
+        float sx = static_cast<float>(e.map_width), sy = static_cast<float>(e.map_height);
+        uint32_t ix = static_cast<uint32_t>(clampf(u * sx, 0.f, sx - 1.f)), iy = static_cast<uint32_t>(clampf(v * sy, 0.f, sy - 1.f));
+        out.pdf = env_directional_pdf(e.pdf[static_cast<size_t>(iy) * e.map_width + ix], theta);
+    }
+    return out;
+}
+EnvSample environment_sample(const lrk_scene_desc &sc, float u0, float u1) {
+    const lrk_environment &e = sc.environment;
+    EnvSample s;
+    V3 w;
+    if (e.emission_tex == 0u) {
+        float z = 1.0f - 2.0f * u0;// sample_uniform_sphere, sampling.cpp:100-108
+        float r = std::sqrt(std::fmax(1.0f - z * z, 0.0f));
+        float phi = 2.0f * kPi * u1;
+        w = v3(r * std::cos(phi), r * std::sin(phi), z);
+        float theta = std::acos(w.y), ph = std::atan2(w.x, w.z);
+        float u = 1.f - 0.5f * kInvPi * ph, v = theta * kInvPi;
+        s.eval.L = env_radiance(sc, u - std::floor(u), v - std::floor(v));
+        s.eval.pdf = kInvPi * 0.25f;
+    } else {
+        const uint32_t W = e.map_width, H = e.map_height;
+        uint32_t iy, ix;
+        float uy, ux;
+        sample_alias_table([&](uint32_t i) { return e.alias[i].prob; }, [&](uint32_t i) { return e.alias[i].alias; }, H, u1, iy, uy);
+        const size_t offset = static_cast<size_t>(H) + static_cast<size_t>(iy) * W;
+        sample_alias_table([&](uint32_t i) { return e.alias[offset + i].prob; }, [&](uint32_t i) { return e.alias[offset + i].alias; }, W, u0, ix, ux);
+        float u = (static_cast<float>(ix) + ux) / static_cast<float>(W), v = (static_cast<float>(iy) + uy) / static_cast<float>(H);
+        float p = e.pdf[static_cast<size_t>(iy) * W + ix];
+        float phi = 2.f * kPi * (1.f - u), theta = kPi * v;// uv_to_direction, :42-51
+        float y = std::cos(theta), sin_theta = std::sin(theta);
+        w = normalize(v3(std::sin(phi) * sin_theta, y, std::cos(phi) * sin_theta));
+        s.eval.L = env_radiance(sc, u, v);
+        s.eval.pdf = env_directional_pdf(p, theta);
+    }
+    s.wi = normalize(env_mul(e.to_world, w, false));
+    return s;
+}
+
 bool alpha_skip(const lrk_scene_desc &sc, uint32_t inst_id, uint32_t prim_id, float bu, float bv) {
     const auto &inst = sc.instances[inst_id];
     ShapeHandle shape = decode_handle(inst.handle);
@@ -1148,7 +1246,14 @@ V3 path_li(const lrk_scene_desc &sc, uint32_t px, uint32_t py, uint32_t sample_i
         lrk_hit hit = trace_bvh(sc, ray, false, &tc);
         if (cnt) cnt->closest_rays++;
         Interaction it = interaction_from_hit(sc, ray, hit);
-        if (!it.valid()) break;// no environment
+        if (!it.valid()) {// miss: mega_path.cpp:68-75, uniform.cpp:67-76
+            if (sc.environment.present) {
+                LightEval e = environment_evaluate(sc, v3(ray.d[0], ray.d[1], ray.d[2]));
+                e.pdf *= env_prob(sc);
+                Li = Li + beta * e.L * balance_heuristic(pdf_bsdf, e.pdf);
+            }
+            break;
+        }
         if (sc.light_count != 0u && it.shape.has_light()) {
             LightEval e = evaluate_hit(sc, it, v3(ray.o[0], ray.o[1], ray.o[2]));
             Li = Li + beta * e.L * balance_heuristic(pdf_bsdf, e.pdf);
@@ -1656,6 +1761,17 @@ void oracle_sample_light(const lrk_scene_desc *scene, const lrk_ray *ray, const 
     const float vals[12]{s.eval.L.x, s.eval.L.y, s.eval.L.z, s.eval.pdf, s.shadow_ray.o[0], s.shadow_ray.o[1], s.shadow_ray.o[2],
                          s.shadow_ray.tmin, s.shadow_ray.d[0], s.shadow_ray.d[1], s.shadow_ray.d[2], s.shadow_ray.tmax};
     std::memcpy(out, vals, sizeof(vals));
+}
+
+void oracle_environment_sample(const lrk_scene_desc *scene, const float u[2], float out[7]) {
+    EnvSample s = environment_sample(*scene, u[0], u[1]);
+    const float vals[7]{s.eval.L.x, s.eval.L.y, s.eval.L.z, s.eval.pdf, s.wi.x, s.wi.y, s.wi.z};
+    std::memcpy(out, vals, sizeof(vals));
+}
+
+void oracle_environment_evaluate(const lrk_scene_desc *scene, const float wi[3], float out[4]) {
+    LightEval e = environment_evaluate(*scene, v3(wi[0], wi[1], wi[2]));
+    out[0] = e.L.x, out[1] = e.L.y, out[2] = e.L.z, out[3] = e.pdf;
 }
 
 void oracle_texture_evaluate(const lrk_scene_desc *scene, uint32_t texture_id, const float uv[2], float out[4]) {

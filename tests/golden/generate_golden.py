@@ -47,6 +47,8 @@ def golden_scenes():
         "textured": scenes.textured_room(resolution=(48, 32), spp=4),
         # + the surface wrappers: normal map, alpha-tested cut-out (stochastic alpha inside traversal), constant opacity
         "textured_wrappers": scenes.textured_room(resolution=(48, 32), spp=4, wrappers=True),
+        # rows a12 / f3: image-textured Spherical environment (importance map, MIS in the miss stage) next to an area light
+        "environment": scenes.environment_scene(resolution=(48, 30), spp=4),
     }
 
 

@@ -74,6 +74,20 @@ def normal_rgb8(n=32) -> np.ndarray:
     return np.round((np.stack([nx, ny, nz], -1) + 1) * 127.5).astype(np.uint8)
 
 
+def sky_pfm(w=32, h=16) -> np.ndarray:
+    """A small HDR sky (top row = zenith): blue-ish gradient, a warm horizon band and one very bright 'sun' texel."""
+    y, x = np.mgrid[0:h, 0:w]
+    t = (y + 0.5) / h
+    img = np.zeros((h, w, 3), np.float32)
+    img[..., 0] = 0.15 + 0.5 * np.exp(-((t - 0.5) * 6) ** 2)
+    img[..., 1] = 0.25 + 0.4 * np.exp(-((t - 0.5) * 6) ** 2)
+    img[..., 2] = 0.6 * (1 - t) + 0.1
+    img[t > 0.55] *= 0.15  # dark ground half
+    img[4, 22] = (60.0, 52.0, 40.0)
+    img[4, 23] = (30.0, 26.0, 20.0)
+    return img
+
+
 CUBE_OBJ = """# unit cube centred at the origin, quads, per-face uvs, no normals (smooth-normal generation is exercised)
 v -0.5 -0.5 -0.5
 v  0.5 -0.5 -0.5
@@ -126,6 +140,8 @@ def main():
     (OUT / "cube.obj").write_text(CUBE_OBJ)
     write_tetra_ply(OUT / "tetra_ascii.ply", False)
     write_tetra_ply(OUT / "tetra_binary.ply", True)
+    sky = sky_pfm()
+    (OUT / "sky.pfm").write_bytes(b"PF\n%d %d\n-1.0\n" % (sky.shape[1], sky.shape[0]) + sky[::-1].astype("<f4").tobytes())
     # a PFM (bottom-up, little endian) and a P6 PPM of the same 4x2 picture
     pic = np.arange(4 * 2 * 3, dtype=np.float32).reshape(2, 4, 3) / 23.0
     (OUT / "tiny.pfm").write_bytes(b"PF\n4 2\n-1.0\n" + pic[::-1].astype("<f4").tobytes())

@@ -80,7 +80,7 @@ def _image_parity(gpu_raw, cpu_raw):
     return rel, off
 
 
-@pytest.mark.parametrize("name", ["cornell", "cornell_disney", "spheres", "spheres_medium", "textured", "textured_wrappers"])
+@pytest.mark.parametrize("name", ["cornell", "cornell_disney", "spheres", "spheres_medium", "textured", "textured_wrappers", "environment"])
 def test_render_matches_oracle(name, gpu_renderer):
     import importlib.util
     spec = importlib.util.spec_from_file_location("generate_golden", Path(__file__).resolve().parent / "golden" / "generate_golden.py")
@@ -131,6 +131,23 @@ def test_render_matches_oracle(name, gpu_renderer):
         assert st["closest_rays"] == GOLD["scenes"][name]["counters"]["closest_rays"]
     # normalised film = (sum / max(w,1)) * 2^exposure (color.cpp:87-93)
     assert np.allclose(gpu_renderer.film(), O.convert_film(d, gpu_raw), rtol=1e-6, atol=1e-7)
+
+
+def test_constant_environment_furnace(gpu_renderer):
+    """Constant white environment, no area light, a lone convex Matte sphere: radiance 0.8 on the sphere, 1 on the background
+    (miss term + uniform-sphere NEE + MIS), and parity with the oracle on the same samples."""
+    src = scenes.environment_scene(resolution=(40, 40), spp=64, emission=(1.0, 1.0, 1.0), area_light=False, depth=12)
+    src = src.replace("shapes { @ball, @floor }", "shapes { @ball }").replace("position { 0.0, 1.2, 4.0 }", "position { 0.0, 0.7, 4.0 }").replace(
+        "front { 0.0, -0.12, -1.0 }", "front { 0.0, 0.0, -1.0 }")
+    d = Scene.from_source(src, REPO).desc()
+    gpu_renderer.upload(d)
+    gpu_renderer.render(0, 64)
+    img = gpu_renderer.film()[..., :3]
+    assert np.allclose(img[:3], 1.0, atol=1e-5) and img[17:23, 17:23].mean() == pytest.approx(0.8, rel=0.02)
+    cpu_raw, cnt = O.render(d, 0, 64)
+    rel, off = _image_parity(gpu_renderer.film(raw=True), cpu_raw)
+    assert rel <= 1e-3 and off <= 5e-3, (rel, off)
+    assert gpu_renderer.stats()["closest_rays"] == cnt["closest_rays"]
 
 
 def test_alpha_first_bounce_is_exact(gpu_renderer):
