@@ -62,6 +62,10 @@ int lrh_save_image(const char *path, const float *rgba, uint32_t width, uint32_t
 uint32_t lrh_plugin_count(void);
 const char *lrh_plugin_name(uint32_t index);
 
+/* The alias-table builder used for mesh light sampling, filter importance sampling and the environment map: replaces
+ * create_alias_table (src/util/sampling.cpp:38-87).  prob / alias / pdf are caller-allocated arrays of n elements. */
+int lrh_create_alias_table(const float *values, uint32_t n, float *prob, uint32_t *alias, float *pdf);
+
 #ifdef __cplusplus
 }
 #endif

@@ -138,6 +138,16 @@ typedef struct lrk_instance {
 
 #define LRK_SURFACE_MATTE 0u  /* src/surfaces/matte.cpp */
 #define LRK_SURFACE_DISNEY 1u /* src/surfaces/disney.cpp (opaque, non-thin closure "disney") */
+#define LRK_SURFACE_MIRROR 2u  /* src/surfaces/mirror.cpp */
+#define LRK_SURFACE_GLASS 3u   /* src/surfaces/glass.cpp (non-dispersive: fixed sRGB spectrum) */
+#define LRK_SURFACE_PLASTIC 4u /* src/surfaces/plastic.cpp */
+#define LRK_SURFACE_METAL 5u   /* src/surfaces/metal.cpp */
+#define LRK_SURFACE_TYPE_COUNT 6u
+
+/* Surface::event_*: src/base/surface.h:37-40 */
+#define LRK_EVENT_REFLECT 0u
+#define LRK_EVENT_ENTER 1u
+#define LRK_EVENT_EXIT 2u
 
 /* Disney lobe bits: src/surfaces/disney.cpp:326-333 */
 #define LRK_DISNEY_LOBE_DIFFUSE 1u
@@ -160,6 +170,17 @@ typedef struct lrk_instance {
  *           p[15] = diffuse_trans; lobes = union of enabled lobes over ALL disney surface
  *           nodes of the scene (the reference ORs them into one shared closure,
  *           src/surfaces/disney.cpp:869,994-995).
+ *   MIRROR : p[0..2] = reflectance colour, p[3..4] = alpha (roughness after the optional remap; 0 without a roughness
+ *            node: the distribution clamps it to 1e-4) — MirrorClosure::Context, mirror.cpp:84-88,142-162
+ *   GLASS  : p[0..2] = Kr, p[3..5] = Kt, p[6] = eta_t (default 1.5; eta_i is 1), p[7..8] = alpha,
+ *            p[9] = Kr_ratio = lum(Kr) / (lum(Kr) + lum(Kt)) — GlassClosure::Context, glass.cpp:133-142,229-279
+ *   PLASTIC: p[0..2] = Kd / (1 - Kd * fresnel_dielectric_integral(eta)), p[3] = Kd_weight = lum(Kd) * exp(-2 lum(sigma_a)
+ *            thickness), p[4..6] = sigma_a (NOT scaled by thickness, as the reference binds it), p[7] = eta,
+ *            p[8..9] = alpha — PlasticContext, plastic.cpp:107-114,252-291
+ *   METAL  : p[0..2] = n, p[3..5] = k (complex index at the spectrum's three wavelengths), p[6..8] = Kd reflectance tint,
+ *            p[9..10] = alpha (default 0.5) — MetalClosure::Context, metal.cpp:208-215,273-310
+ *   The four closures above take constant parameters only (tex[] must be 0); image-textured Mirror / Glass / Plastic /
+ *   Metal nodes are rejected by the host.
  *
  * Image-textured parameters: tex[k] != 0 means parameter slot k is NOT the constant p[k] but is
  * evaluated per hit from image texture (tex[k] - 1) at the hit's uv, exactly as populate_closure does

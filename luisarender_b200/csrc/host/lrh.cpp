@@ -119,4 +119,21 @@ const char *lrh_plugin_name(uint32_t index) {
     return name.c_str();
 }
 
+int lrh_create_alias_table(const float *values, uint32_t n, float *prob, uint32_t *alias, float *pdf) {
+    if (!values || !prob || !alias || !pdf) return fail("lrh_create_alias_table: null argument.");
+    try {
+        std::vector<lrk_alias_entry> table;
+        std::vector<float> p;
+        lrh::create_alias_table(values, n, table, p);
+        for (uint32_t i = 0u; i < n; i++) {
+            prob[i] = table[i].prob;
+            alias[i] = table[i].alias;
+            pdf[i] = p[i];
+        }
+        return 0;
+    } catch (const std::exception &e) {
+        return fail(e.what());
+    }
+}
+
 }// extern "C"

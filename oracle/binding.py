@@ -130,3 +130,17 @@ def generate_ray(desc, px: int, py: int, sample: int):
     state = C.c_uint32()
     lib().oracle_generate_ray(C.byref(desc), px, py, sample, ray.ctypes.data, _fp(weight), C.byref(state))
     return ray, weight, state.value
+
+
+def unit(name: str, inputs: np.ndarray, n_out: int, buffer: np.ndarray | None = None, buffer_count: int = 0) -> np.ndarray:
+    """oracle_unit: one named numerical unit on packed 32-bit words (same packing as oracle/ref/pins.cpp)."""
+    L = lib()
+    L.oracle_unit.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint64]
+    inputs = np.ascontiguousarray(inputs, dtype=np.uint32)
+    out = np.zeros((inputs.shape[0], n_out), dtype=np.uint32)
+    bptr = buffer.ctypes.data_as(C.c_void_p) if buffer is not None else None
+    rc = L.oracle_unit(name.encode(), inputs.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), inputs.shape[0], bptr,
+                       buffer_count)
+    if rc != 0:
+        raise KeyError(f"oracle_unit('{name}') failed with {rc}")
+    return out

@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -108,6 +109,12 @@ inline V3 sample_uniform_triangle(float ux, float uy) {
     if (ux < uy) { a = 0.5f * ux; b = -0.5f * ux + uy; }
     else { a = -0.5f * uy + ux; b = 0.5f * uy; }
     return {a, b, 1.0f - a - b};
+}
+inline V3 sample_uniform_sphere(float u0, float u1) {// sampling.cpp:99-108
+    float z = 1.0f - 2.0f * u0;
+    float r = std::sqrt(std::fmax(1.0f - z * z, 0.0f));
+    float phi = 2.0f * kPi * u1;
+    return {r * std::cos(phi), r * std::sin(phi), z};
 }
 inline float balance_heuristic(float f_pdf, float g_pdf) {
     float sum_f = 1.0f * f_pdf;// nf = 1
@@ -638,6 +645,7 @@ struct SurfEval {
 struct SurfSample {
     SurfEval eval;
     V3 wi{0.f, 0.f, 1.f};
+    uint32_t event{0u};// Surface::event_*, src/base/surface.h:37-40
 };
 
 inline bool validate_surface_sides(V3 ng, V3 ns, V3 wo, V3 wi) {
@@ -767,6 +775,208 @@ struct TrowbridgeReitz {
         ry = ay * ry;
         V3 wh = normalize(v3(-rx, -ry, 1.f));
         return s * wh;
+    }
+};
+
+// --- BxDF library shared by the Mirror / Glass / Metal / Plastic closures and pinned against the reference's own code
+//     (oracle/ref, tests/test_ref_pins.py): src/util/scattering.cpp:14-125 (refract, Fresnel terms, spherical helpers),
+//     :238-345 (BxDF base, Lambertian, microfacet reflection / transmission), :402-447 (FresnelBlend);
+//     src/util/sampling.cpp:99-175
+inline bool refract(V3 wi, V3 n, float eta, V3 &wt) {// scattering.cpp:14-28
+    float cosThetaI = dot(n, wi);
+    float sin2ThetaI = std::fmax(0.0f, 1.f - sqr(cosThetaI));
+    float sin2ThetaT = sqr(eta) * sin2ThetaI;
+    float cosThetaT = std::sqrt(1.f - sin2ThetaT);
+    wt = (eta * cosThetaI - cosThetaT) * n - eta * wi;
+    return sin2ThetaT < 1.0f;
+}
+inline V3 spherical_direction(float sinTheta, float cosTheta, float phi) {// :81-83
+    return {sinTheta * std::cos(phi), sinTheta * std::sin(phi), cosTheta};
+}
+inline float spherical_theta(V3 v) { return std::acos(clampf(v.z, -1.f, 1.f)); }// :89-91
+inline float spherical_phi(V3 v) {// :93-96
+    float p = std::atan2(v.y, v.x);
+    return p < 0.f ? p + 2.f * kPi : p;
+}
+inline V3 exp3(V3 a) { return {std::exp(a.x), std::exp(a.y), std::exp(a.z)}; }
+inline V3 vdiv(V3 a, V3 b) { return {a.x / b.x, a.y / b.y, a.z / b.z}; }
+inline V3 vsqrt(V3 a) { return {std::sqrt(a.x), std::sqrt(a.y), std::sqrt(a.z)}; }
+inline V3 operator-(float s, V3 a) { return {s - a.x, s - a.y, s - a.z}; }
+inline V3 operator-(V3 a, float s) { return {a.x - s, a.y - s, a.z - s}; }
+inline V3 operator/(V3 a, float s) { return {a.x / s, a.y / s, a.z / s}; }
+V3 fresnel_conductor(float cosThetaI, float etai, V3 etat, V3 k) {// :56-75
+    cosThetaI = clampf(cosThetaI, -1.f, 1.f);
+    V3 eta = etat / etai;
+    V3 etak = k / etai;
+    float cosThetaI2 = cosThetaI * cosThetaI;
+    float sinThetaI2 = 1.f - cosThetaI2;
+    V3 eta2 = eta * eta;
+    V3 etak2 = etak * etak;
+    V3 t0 = eta2 - etak2 - sinThetaI2;
+    V3 a2plusb2 = vsqrt(t0 * t0 + 4.f * eta2 * etak2);
+    V3 t1 = a2plusb2 + cosThetaI2;
+    V3 a = vsqrt(.5f * (a2plusb2 + t0));
+    V3 t2 = 2.f * cosThetaI * a;
+    V3 Rs = vdiv(t1 - t2, t1 + t2);
+    V3 t3 = cosThetaI2 * a2plusb2 + sinThetaI2 * sinThetaI2;
+    V3 t4 = t2 * sinThetaI2;
+    V3 Rp = Rs * vdiv(t3 - t4, t3 + t4);
+    return .5f * (Rp + Rs);
+}
+inline float fresnel_dielectric_integral(float eta) {// :98-108; polynomial() = Horner from the last coefficient, spec.h:45-51
+    float r;
+    if (eta == 1.f) {
+        r = 0.f;
+    } else if (eta < 1.f) {
+        r = eta * (eta * (eta * -0.90663979f + 2.23559031f) + -2.09069066f) + 0.75985009f;
+    } else {
+        float x = 1.f / eta;
+        r = x * (x * -1.18995376f + 0.21762732f) + 0.97945724f;
+    }
+    return saturate(r);
+}
+
+// the Fresnel term of a MicrofacetReflection: dielectric (glass, plastic coat), conductor (metal), Schlick (mirror.cpp:67-79)
+struct FresnelTerm {
+    enum Kind { DIELECTRIC, CONDUCTOR, SCHLICK } kind{DIELECTRIC};
+    float eta_i{1.f}, eta_t{1.5f};
+    V3 eta{}, k{}, r0{};
+    V3 evaluate(float cosI) const {
+        switch (kind) {
+            case DIELECTRIC: return v3(fresnel_dielectric(cosI, eta_i, eta_t));// :243-245
+            case CONDUCTOR: return fresnel_conductor(std::fabs(cosI), eta_i, eta, k);// :239-241
+            default: {
+                float m = saturate(1.f - cosI);
+                float weight = sqr(sqr(m)) * m;
+                return (1.f - weight) * r0 + weight;
+            }
+        }
+    }
+    static FresnelTerm dielectric(float ei, float et) { FresnelTerm f; f.kind = DIELECTRIC; f.eta_i = ei; f.eta_t = et; return f; }
+    static FresnelTerm conductor(float ei, V3 eta, V3 k) { FresnelTerm f; f.kind = CONDUCTOR; f.eta_i = ei; f.eta = eta; f.k = k; return f; }
+    static FresnelTerm schlick(V3 r0) { FresnelTerm f; f.kind = SCHLICK; f.r0 = r0; return f; }
+};
+
+struct BxDFSample {
+    V3 wi{0.f, 0.f, 0.f};
+    bool valid{false};
+};
+inline BxDFSample lambert_sample_wi(V3 wo, float u0, float u1) {// BxDF::sample_wi :260-264
+    V3 wi = sample_cosine_hemisphere(u0, u1);
+    wi.z *= sign(cos_theta(wo));
+    return {wi, true};
+}
+inline V3 lambert_evaluate(V3 r, V3 wo, V3 wi) { return r * (same_hemisphere(wo, wi) ? kInvPi : 0.f); }// :266-269
+
+struct MicrofacetReflection {// :290-329
+    V3 r;
+    TrowbridgeReitz d;
+    FresnelTerm fr;
+    V3 evaluate(V3 wo, V3 wi) const {
+        V3 wh = wi + wo;
+        V3 f = v3(0.f);
+        if (same_hemisphere(wo, wi) && any_nonzero_v(wh)) {
+            wh = normalize(wh);
+            V3 F = fr.evaluate(dot(wi, face_forward(wh, v3(0.f, 0.f, 1.f))));
+            float D = d.D(wh);
+            float G = d.G(wo, wi);
+            float cos_o = cos_theta(wo), cos_i = cos_theta(wi);
+            f = r * F * std::fabs(0.25f * D * G / (cos_i * cos_o));
+        }
+        return f;
+    }
+    BxDFSample sample_wi(V3 wo, float u0, float u1) const {
+        V3 wh = d.sample_wh(wo, u0, u1);
+        V3 wi = reflect(-wo, wh);
+        return {wi, same_hemisphere(wo, wi)};
+    }
+    float pdf(V3 wo, V3 wi) const {
+        float p = 0.f;
+        V3 wh = wi + wo;
+        if (same_hemisphere(wo, wi) && any_nonzero_v(wh)) {
+            wh = normalize(wh);
+            p = d.pdf(wo, wh) / (4.f * dot(wo, wh));
+        }
+        return p;
+    }
+    static bool any_nonzero_v(V3 w) { return w.x != 0.f || w.y != 0.f || w.z != 0.f; }
+};
+
+struct MicrofacetTransmission {// :331-380 (TransportMode::RADIANCE)
+    V3 t;
+    TrowbridgeReitz d;
+    float eta_a, eta_b;
+    V3 evaluate(V3 wo, V3 wi) const {
+        float cosThetaO = cos_theta(wo), cosThetaI = cos_theta(wi);
+        float eta = cosThetaO > 0.f ? eta_b / eta_a : eta_a / eta_b;
+        V3 wh = normalize(wo + wi * eta);
+        wh = sign(cos_theta(wh)) * wh;
+        V3 f = v3(0.f);
+        if (!same_hemisphere(wo, wi) && cosThetaO != 0.f && cosThetaI != 0.f && dot(wo, wh) * dot(wi, wh) < 0.f) {
+            float G = d.G(wo, wi);
+            float sqrtDenom = dot(wo, wh) + eta * dot(wi, wh);
+            float F = fresnel_dielectric(dot(wo, wh), eta_a, eta_b);
+            float D = d.D(wh);
+            f = (1.f - F) * t * D * G * dot(wi, wh) * dot(wo, wh) / (cosThetaI * cosThetaO * sqr(sqrtDenom));
+        }
+        return f;
+    }
+    BxDFSample sample_wi(V3 wo, float u0, float u1) const {
+        float eta = cos_theta(wo) > 0.f ? eta_a / eta_b : eta_b / eta_a;
+        V3 wh = d.sample_wh(wo, u0, u1);
+        V3 wi = v3(0.f);
+        bool refr = refract(wo, wh, eta, wi);
+        return {wi, refr && !same_hemisphere(wo, wi)};
+    }
+    float pdf(V3 wo, V3 wi) const {
+        float p = 0.f;
+        bool entering = cos_theta(wo) > 0.f;
+        float eta = entering ? eta_b / eta_a : eta_a / eta_b;
+        V3 wh = normalize(wo + wi * eta);
+        if (!same_hemisphere(wo, wi) && dot(wo, wh) * dot(wi, wh) < 0.f) {
+            float sqrtDenom = dot(wo, wh) + eta * dot(wi, wh);
+            float dwh_dwi = sqr(eta / sqrtDenom) * abs_dot(wi, wh);
+            p = d.pdf(wo, wh) * dwh_dwi;
+        }
+        return p;
+    }
+};
+
+struct FresnelBlend {// :402-447
+    V3 rd, rs;
+    float rd_ratio;
+    TrowbridgeReitz d;
+    FresnelBlend(V3 Rd, V3 Rs, TrowbridgeReitz dist, float ratio = .5f) : rd{Rd}, rs{Rs}, rd_ratio{clampf(ratio, .05f, .95f)}, d{dist} {}
+    static float pow5(float v) { return sqr(sqr(v)) * v; }
+    V3 schlick(float cosTheta) const { return rs + pow5(1.f - cosTheta) * (1.f - rs); }
+    V3 evaluate(V3 wo, V3 wi) const {
+        V3 wh = wi + wo;
+        bool valid = same_hemisphere(wo, wi) && MicrofacetReflection::any_nonzero_v(wh);
+        wh = normalize(wh);
+        float D = d.D(wh);
+        float absCosThetaI = abs_cos_theta(wi), absCosThetaO = abs_cos_theta(wo);
+        V3 diffuse = (28.f / (23.f * kPi)) * rd * (1.f - rs) * (1.f - pow5(1.f - .5f * absCosThetaI)) * (1.f - pow5(1.f - .5f * absCosThetaO));
+        V3 specular = D / (4.f * abs_dot(wi, wh) * std::fmax(absCosThetaI, absCosThetaO)) * schlick(dot(wi, wh));
+        return valid ? diffuse + specular : v3(0.f);
+    }
+    BxDFSample sample_wi(V3 wo, float u0, float u1) const {
+        V3 wi;
+        if (u0 < rd_ratio) {
+            u0 = u0 / rd_ratio;
+            wi = sample_cosine_hemisphere(u0, u1);
+            wi.z *= sign(cos_theta(wo));
+        } else {
+            u0 = (u0 - rd_ratio) / (1.f - rd_ratio);
+            V3 wh = d.sample_wh(wo, u0, u1);
+            wi = reflect(-wo, wh);
+        }
+        return {wi, same_hemisphere(wo, wi)};
+    }
+    float pdf(V3 wo, V3 wi) const {
+        V3 wh = normalize(wo + wi);
+        float pdf_wh = d.pdf(wo, wh);
+        float p = lerp(pdf_wh / (4.f * dot(wo, wh)), abs_cos_theta(wi) * kInvPi, rd_ratio);
+        return same_hemisphere(wo, wi) ? p : 0.f;
     }
 };
 
@@ -1008,8 +1218,188 @@ SurfSample disney_sample(const lrk_surface &s, const Interaction &it, V3 wo, flo
     return out;
 }
 
+// --- Mirror / Glass / Plastic / Metal.  lrk_surface.p holds each closure's Context as
+//     populate_closure computes it for constant textures (include/lrk.h); pinned against the reference's closures through
+//     Surface::Closure::{evaluate,sample} (oracle/ref/pin_<name>.cpp, tests/test_ref_pins.py).
+inline SurfSample finish_sample(const Interaction &it, V3 wi_local, V3 f, float pdf, uint32_t event) {
+    SurfSample out;
+    out.wi = it.shading.local_to_world(wi_local);
+    out.eval.f = f * abs_cos_theta(wi_local);
+    out.eval.pdf = pdf;
+    out.event = event;
+    return out;
+}
+template<typename B>
+inline void bxdf_sample(const B &bxdf, V3 wo, float u0, float u1, V3 &wi, V3 &f, float &pdf) {// BxDF::sample, scattering.cpp:247-254
+    BxDFSample s = bxdf.sample_wi(wo, u0, u1);
+    wi = s.wi;
+    pdf = s.valid ? bxdf.pdf(wo, wi) : 0.f;
+    f = s.valid ? bxdf.evaluate(wo, wi) : v3(0.f);
+}
+
+// mirror.cpp:81-131: MicrofacetReflection with a Schlick Fresnel term around the reflectance colour
+inline MicrofacetReflection mirror_lobe(const lrk_surface &s) {
+    V3 refl = v3(s.p[0], s.p[1], s.p[2]);
+    return {refl, TrowbridgeReitz{s.p[3], s.p[4]}, FresnelTerm::schlick(refl)};
+}
+SurfEval mirror_evaluate(const lrk_surface &s, const Interaction &it, V3 wo, V3 wi) {
+    MicrofacetReflection refl = mirror_lobe(s);
+    V3 wo_local = it.shading.world_to_local(wo), wi_local = it.shading.world_to_local(wi);
+    SurfEval e;
+    e.f = refl.evaluate(wo_local, wi_local) * abs_cos_theta(wi_local);
+    e.pdf = refl.pdf(wo_local, wi_local);
+    return e;
+}
+SurfSample mirror_sample(const lrk_surface &s, const Interaction &it, V3 wo, float, float u0, float u1) {
+    MicrofacetReflection refl = mirror_lobe(s);
+    V3 wo_local = it.shading.world_to_local(wo), wi_local = v3(0.f, 0.f, 1.f), f;
+    float pdf = 0.f;
+    bxdf_sample(refl, wo_local, u0, u1, wi_local, f, pdf);
+    return finish_sample(it, wi_local, f, pdf, LRK_EVENT_REFLECT);
+}
+
+// metal.cpp:205-266: conductor Fresnel from (n, k), result tinted by the `Kd` reflectance
+inline MicrofacetReflection metal_lobe(const lrk_surface &s) {
+    return {v3(1.f), TrowbridgeReitz{s.p[9], s.p[10]}, FresnelTerm::conductor(1.f, v3(s.p[0], s.p[1], s.p[2]), v3(s.p[3], s.p[4], s.p[5]))};
+}
+SurfEval metal_evaluate(const lrk_surface &s, const Interaction &it, V3 wo, V3 wi) {
+    MicrofacetReflection lobe = metal_lobe(s);
+    V3 wo_local = it.shading.world_to_local(wo), wi_local = it.shading.world_to_local(wi);
+    V3 f = lobe.evaluate(wo_local, wi_local);
+    f = f * v3(s.p[6], s.p[7], s.p[8]);
+    SurfEval e;
+    e.f = f * abs_cos_theta(wi_local);
+    e.pdf = lobe.pdf(wo_local, wi_local);
+    return e;
+}
+SurfSample metal_sample(const lrk_surface &s, const Interaction &it, V3 wo, float, float u0, float u1) {
+    MicrofacetReflection lobe = metal_lobe(s);
+    V3 wo_local = it.shading.world_to_local(wo), wi_local = v3(0.f, 0.f, 1.f), f;
+    float pdf = 0.f;
+    bxdf_sample(lobe, wo_local, u0, u1, wi_local, f, pdf);
+    f = f * v3(s.p[6], s.p[7], s.p[8]);
+    return finish_sample(it, wi_local, f, pdf, LRK_EVENT_REFLECT);
+}
+
+// glass.cpp:129-222: reflection / transmission lobes chosen by Kr_ratio-weighted Fresnel
+struct GlassLobes {
+    MicrofacetReflection refl;
+    MicrofacetTransmission trans;
+    float eta_t, kr_ratio;
+    explicit GlassLobes(const lrk_surface &s)
+        : refl{v3(s.p[0], s.p[1], s.p[2]), TrowbridgeReitz{s.p[7], s.p[8]}, FresnelTerm::dielectric(1.f, s.p[6])},
+          trans{v3(s.p[3], s.p[4], s.p[5]), TrowbridgeReitz{s.p[7], s.p[8]}, 1.f, s.p[6]}, eta_t{s.p[6]}, kr_ratio{s.p[9]} {}
+    float refl_prob(V3 wo_local) const {// :162-167
+        float F = fresnel_dielectric(cos_theta(wo_local), 1.f, eta_t);
+        float r = kr_ratio * F;
+        float t = (1.f - kr_ratio) * (1.f - F);
+        return r == 0.f ? 0.f : r / (r + t);
+    }
+};
+SurfEval glass_evaluate(const lrk_surface &s, const Interaction &it, V3 wo, V3 wi) {
+    GlassLobes g{s};
+    V3 wo_local = it.shading.world_to_local(wo), wi_local = it.shading.world_to_local(wi);
+    float ratio = g.refl_prob(wo_local);
+    V3 f;
+    float pdf;
+    if (same_hemisphere(wo_local, wi_local)) {
+        f = g.refl.evaluate(wo_local, wi_local);
+        pdf = g.refl.pdf(wo_local, wi_local) * ratio;
+    } else {
+        f = g.trans.evaluate(wo_local, wi_local);
+        pdf = g.trans.pdf(wo_local, wi_local) * (1.f - ratio);
+    }
+    SurfEval e;
+    e.f = f * abs_cos_theta(wi_local);
+    e.pdf = pdf;
+    return e;
+}
+SurfSample glass_sample(const lrk_surface &s, const Interaction &it, V3 wo, float u_lobe, float u0, float u1) {
+    GlassLobes g{s};
+    V3 wo_local = it.shading.world_to_local(wo), wi_local = v3(0.f, 0.f, 1.f), f;
+    float pdf = 0.f;
+    uint32_t event = LRK_EVENT_REFLECT;
+    float ratio = g.refl_prob(wo_local);
+    if (u_lobe < ratio) {
+        bxdf_sample(g.refl, wo_local, u0, u1, wi_local, f, pdf);
+        pdf *= ratio;
+    } else {
+        bxdf_sample(g.trans, wo_local, u0, u1, wi_local, f, pdf);
+        pdf *= (1.f - ratio);
+        event = cos_theta(wo_local) > 0.f ? LRK_EVENT_ENTER : LRK_EVENT_EXIT;
+    }
+    return finish_sample(it, wi_local, f, pdf, event);
+}
+
+// plastic.cpp:116-214: dielectric coat over a Lambertian substrate with absorption (Tungsten's rough plastic)
+struct PlasticLobes {
+    V3 kd, sigma_a;
+    float kd_weight, eta;
+    MicrofacetReflection coat;
+    explicit PlasticLobes(const lrk_surface &s)
+        : kd{v3(s.p[0], s.p[1], s.p[2])}, sigma_a{v3(s.p[4], s.p[5], s.p[6])}, kd_weight{s.p[3]}, eta{s.p[7]},
+          coat{v3(1.f), TrowbridgeReitz{s.p[8], s.p[9]}, FresnelTerm::dielectric(1.f, s.p[7])} {}
+    static float substrate_weight(float Fo, float kd_w) {// :125-128
+        float w = kd_w * (1.0f - Fo);
+        return w == 0.f ? 0.f : w / (w + Fo);
+    }
+    V3 diffuse(V3 wo_local, V3 wi_local, float Fo) const {// :155-159
+        float Fi = fresnel_dielectric(abs_cos_theta(wi_local), 1.f, eta);
+        V3 a = exp3(-(1.f / abs_cos_theta(wi_local) + 1.f / abs_cos_theta(wo_local)) * sigma_a);
+        return (1.f - Fi) * (1.f - Fo) * sqr(1.f / eta) * a * lambert_evaluate(kd, wo_local, wi_local);
+    }
+};
+SurfEval plastic_evaluate(const lrk_surface &s, const Interaction &it, V3 wo, V3 wi) {
+    PlasticLobes p{s};
+    V3 wo_local = it.shading.world_to_local(wo);
+    V3 sgn = cos_theta(wo_local) < 0.f ? v3(1.f, 1.f, -1.f) : v3(1.f, 1.f, 1.f);
+    wo_local = wo_local * sgn;
+    V3 wi_local = it.shading.world_to_local(wi) * sgn;
+    SurfEval e;
+    V3 f_coat = p.coat.evaluate(wo_local, wi_local);
+    float pdf_coat = p.coat.pdf(wo_local, wi_local);
+    float Fo = fresnel_dielectric(abs_cos_theta(wo_local), 1.f, p.eta);
+    V3 f_diffuse = p.diffuse(wo_local, wi_local, Fo);
+    float pdf_diffuse = lambert_pdf(wo_local, wi_local);
+    float sw = PlasticLobes::substrate_weight(Fo, p.kd_weight);
+    e.f = (f_coat + f_diffuse) * abs_cos_theta(wi_local);
+    e.pdf = lerp(pdf_coat, pdf_diffuse, sw);
+    return e;
+}
+SurfSample plastic_sample(const lrk_surface &s, const Interaction &it, V3 wo, float u_lobe, float u0, float u1) {
+    PlasticLobes p{s};
+    V3 wo_local = it.shading.world_to_local(wo);
+    V3 sgn = cos_theta(wo_local) < 0.f ? v3(1.f, 1.f, -1.f) : v3(1.f, 1.f, 1.f);
+    wo_local = wo_local * sgn;
+    float Fo = fresnel_dielectric(abs_cos_theta(wo_local), 1.f, p.eta);
+    float sw = PlasticLobes::substrate_weight(Fo, p.kd_weight);
+    BxDFSample ws = u_lobe < sw ? lambert_sample_wi(wo_local, u0, u1) : p.coat.sample_wi(wo_local, u0, u1);
+    SurfSample out;
+    out.wi = v3(0.f, 0.f, 1.f);
+    out.event = LRK_EVENT_REFLECT;
+    if (ws.valid) {
+        V3 wi_local = ws.wi;
+        out.wi = it.shading.local_to_world(ws.wi * sgn);
+        V3 f_coat = p.coat.evaluate(wo_local, wi_local);
+        float pdf_coat = p.coat.pdf(wo_local, wi_local);
+        V3 f_diffuse = p.diffuse(wo_local, wi_local, Fo);
+        float pdf_diffuse = lambert_pdf(wo_local, wi_local);
+        out.eval.f = (f_coat + f_diffuse) * abs_cos_theta(wi_local);
+        out.eval.pdf = lerp(pdf_coat, pdf_diffuse, sw);
+    }
+    return out;
+}
+
 SurfEval surface_evaluate(const lrk_surface &s, const Interaction &it, V3 wo, V3 wi) {
-    SurfEval e = s.type == LRK_SURFACE_MATTE ? matte_evaluate(s, it, wo, wi) : disney_evaluate(s, it, wo, wi);
+    SurfEval e;
+    switch (s.type) {
+        case LRK_SURFACE_MATTE: e = matte_evaluate(s, it, wo, wi); break;
+        case LRK_SURFACE_DISNEY: e = disney_evaluate(s, it, wo, wi); break;
+        case LRK_SURFACE_MIRROR: e = mirror_evaluate(s, it, wo, wi); break;
+        case LRK_SURFACE_GLASS: e = glass_evaluate(s, it, wo, wi); break;
+        case LRK_SURFACE_PLASTIC: e = plastic_evaluate(s, it, wo, wi); break;
+        default: e = metal_evaluate(s, it, wo, wi); break;
+    }
     if (!validate_surface_sides(it.ng, it.shading.n, wo, wi)) {
         e.f = v3(0.f);
         e.pdf = 0.f;
@@ -1017,7 +1407,15 @@ SurfEval surface_evaluate(const lrk_surface &s, const Interaction &it, V3 wo, V3
     return e;
 }
 SurfSample surface_sample(const lrk_surface &s, const Interaction &it, V3 wo, float u_lobe, float u0, float u1) {
-    SurfSample r = s.type == LRK_SURFACE_MATTE ? matte_sample(s, it, wo, u_lobe, u0, u1) : disney_sample(s, it, wo, u_lobe, u0, u1);
+    SurfSample r;
+    switch (s.type) {
+        case LRK_SURFACE_MATTE: r = matte_sample(s, it, wo, u_lobe, u0, u1); break;
+        case LRK_SURFACE_DISNEY: r = disney_sample(s, it, wo, u_lobe, u0, u1); break;
+        case LRK_SURFACE_MIRROR: r = mirror_sample(s, it, wo, u_lobe, u0, u1); break;
+        case LRK_SURFACE_GLASS: r = glass_sample(s, it, wo, u_lobe, u0, u1); break;
+        case LRK_SURFACE_PLASTIC: r = plastic_sample(s, it, wo, u_lobe, u0, u1); break;
+        default: r = metal_sample(s, it, wo, u_lobe, u0, u1); break;
+    }
     if (!validate_surface_sides(it.ng, it.shading.n, wo, r.wi)) {
         r.eval.f = v3(0.f);
         r.eval.pdf = 0.f;
@@ -1126,10 +1524,7 @@ EnvSample environment_sample(const lrk_scene_desc &sc, float u0, float u1) {
     EnvSample s;
     V3 w;
     if (e.emission_tex == 0u) {
-        float z = 1.0f - 2.0f * u0;// sample_uniform_sphere, sampling.cpp:100-108
-        float r = std::sqrt(std::fmax(1.0f - z * z, 0.0f));
-        float phi = 2.0f * kPi * u1;
-        w = v3(r * std::cos(phi), r * std::sin(phi), z);
+        w = sample_uniform_sphere(u0, u1);
         float theta = std::acos(w.y), ph = std::atan2(w.x, w.z);
         float u = 1.f - 0.5f * kInvPi * ph, v = theta * kInvPi;
         s.eval.L = env_radiance(sc, u - std::floor(u), v - std::floor(v));
@@ -1283,7 +1678,12 @@ V3 path_li(const lrk_scene_desc &sc, uint32_t px, uint32_t py, uint32_t sample_i
         pdf_bsdf = ss.eval.pdf;
         float w = ss.eval.pdf > 0.f ? 1.f / ss.eval.pdf : 0.f;
         beta = beta * (w * ss.eval.f);
-        float eta_scale = 1.f;// no transmissive closures
+        float eta_scale = 1.f;// mega_path.cpp:113,133-138
+        if (surface.type == LRK_SURFACE_GLASS) {
+            float eta = surface.p[6];
+            if (ss.event == LRK_EVENT_ENTER) eta_scale = sqr(eta);
+            else if (ss.event == LRK_EVENT_EXIT) eta_scale = sqr(1.f / eta);
+        }
         // zero_if_any_nan: src/util/spec.cpp:404-407
         if (std::isnan(beta.x) || std::isnan(beta.y) || std::isnan(beta.z)) beta = v3(0.f);
         if (beta.x <= 0.f && beta.y <= 0.f && beta.z <= 0.f) break;
@@ -1345,7 +1745,6 @@ struct MediumSample {
     V3 o{}, d{};
     uint32_t event{~0u};// 0 absorb, 1 scatter, 3 hit surface, ~0 invalid (src/base/medium.h:31-36)
 };
-inline V3 exp3(V3 a) { return {std::exp(a.x), std::exp(a.y), std::exp(a.z)}; }
 inline float sum3(V3 a) { return a.x + a.y + a.z; }
 inline float comp(V3 a, uint32_t i) { return i == 0u ? a.x : i == 1u ? a.y : a.z; }
 
@@ -1787,3 +2186,149 @@ void oracle_resolve_surface(const lrk_scene_desc *scene, uint32_t surface_tag, c
 }
 
 }// extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// oracle_unit: one named numerical unit on packed 32-bit words (floats as bit patterns), the same names, argument order
+// and result packing as the reference pins in oracle/ref/pins.cpp, so tests/test_ref_pins.py can compare them 1:1.
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct Words {
+    const uint32_t *in;
+    uint32_t *out;
+    float f() { float v; std::memcpy(&v, in++, 4); return v; }
+    uint32_t u() { return *in++; }
+    V3 v() { float x = f(), y = f(), z = f(); return {x, y, z}; }
+    void put(float v) { std::memcpy(out++, &v, 4); }
+    void put(uint32_t v) { *out++ = v; }
+    void put(V3 v) { put(v.x); put(v.y); put(v.z); }
+    void put(bool b) { put(b ? 1.0f : 0.0f); }
+};
+template<typename B>
+void put_bxdf_sample(Words &w, const B &bxdf, V3 wo, float u0, float u1) {// BxDF::sample, scattering.cpp:247-254
+    BxDFSample s = bxdf.sample_wi(wo, u0, u1);
+    w.put(s.wi);
+    w.put(s.valid ? bxdf.pdf(wo, s.wi) : 0.f);
+    w.put(s.valid ? bxdf.evaluate(wo, s.wi) : v3(0.f));
+}
+struct LambertBxDF {
+    V3 r;
+    BxDFSample sample_wi(V3 wo, float u0, float u1) const { return lambert_sample_wi(wo, u0, u1); }
+    float pdf(V3 wo, V3 wi) const { return lambert_pdf(wo, wi); }
+    V3 evaluate(V3 wo, V3 wi) const { return lambert_evaluate(r, wo, wi); }
+};
+}// namespace
+
+extern "C" int oracle_unit(const char *name_c, const uint32_t *in, uint32_t *out, int count, const void *buffer, uint64_t buffer_count) {
+    const std::string name{name_c};
+    Words w{in, out};
+    for (int n = 0; n < count; n++) {
+        if (name == "xxhash32_4") { uint32_t a = w.u(), b = w.u(), c = w.u(), d = w.u(); w.put(xxhash32_uint4(a, b, c, d)); }
+        else if (name == "uniform_uint_to_float") { w.put(std::fmin(kOneMinusEpsilon, static_cast<float>(w.u()) * 0x1p-32f)); }
+        else if (name == "lcg") { uint32_t st = w.u(); float u = lcg(st); w.put(u); w.put(st); }
+        else if (name == "pcg32_seq") {
+            uint32_t hi = w.u(), lo = w.u();
+            PCG32 rng{};
+            rng.set_sequence((static_cast<uint64_t>(hi) << 32u) | lo);
+            for (int i = 0; i < 4; i++) { w.put(rng.uniform_uint()); }
+            w.put(rng.uniform_float());
+            w.put(rng.uniform_float());
+            w.put(static_cast<uint32_t>(rng.state >> 32u)); w.put(static_cast<uint32_t>(rng.state));
+            w.put(static_cast<uint32_t>(rng.inc >> 32u)); w.put(static_cast<uint32_t>(rng.inc));
+        }
+        else if (name == "sample_uniform_triangle") { float a = w.f(), b = w.f(); w.put(sample_uniform_triangle(a, b)); }
+        else if (name == "sample_uniform_disk_concentric") { float a = w.f(), b = w.f(), x, y; sample_uniform_disk_concentric(a, b, x, y); w.put(x); w.put(y); }
+        else if (name == "sample_cosine_hemisphere") { float a = w.f(), b = w.f(); w.put(sample_cosine_hemisphere(a, b)); }
+        else if (name == "cosine_hemisphere_pdf") { w.put(w.f() * kInvPi); }
+        else if (name == "sample_uniform_sphere") { float a = w.f(), b = w.f(); w.put(sample_uniform_sphere(a, b)); }
+        else if (name == "balance_heuristic") { float a = w.f(), b = w.f(); w.put(balance_heuristic(a, b)); }
+        else if (name == "sample_alias_table") {
+            auto table = static_cast<const lrk_alias_entry *>(buffer);
+            uint32_t cnt = w.u(), index; float u = w.f(), uu;
+            if (cnt > buffer_count) { return -2; }
+            sample_alias_table([&](uint32_t i) { return table[i].prob; }, [&](uint32_t i) { return table[i].alias; }, cnt, u, index, uu);
+            w.put(index); w.put(uu);
+        }
+        else if (name == "frame_make_n") { Frame f = Frame::make(w.v()); w.put(f.s); w.put(f.t); w.put(f.n); }
+        else if (name == "frame_make_ns") { V3 nn = w.v(), ss = w.v(); Frame f = Frame::make(nn, ss); w.put(f.s); w.put(f.t); w.put(f.n); }
+        else if (name == "frame_local_to_world") { V3 s = w.v(), t = w.v(), nn = w.v(), d = w.v(); w.put(Frame{s, t, nn}.local_to_world(d)); }
+        else if (name == "frame_world_to_local") { V3 s = w.v(), t = w.v(), nn = w.v(), d = w.v(); w.put(Frame{s, t, nn}.world_to_local(d)); }
+        else if (name == "clamp_shading_normal") { V3 ns = w.v(), ng = w.v(), d = w.v(); w.put(clamp_shading_normal(ns, ng, d)); }
+        else if (name == "refract") { V3 wi = w.v(), nn = w.v(); float eta = w.f(); V3 wt; bool ok = refract(wi, nn, eta, wt); w.put(ok); w.put(wt); }
+        else if (name == "face_forward") { V3 a = w.v(), b = w.v(); w.put(face_forward(a, b)); }
+        else if (name == "spherical_direction") { float a = w.f(), b = w.f(), c = w.f(); w.put(spherical_direction(a, b, c)); }
+        else if (name == "spherical_theta") { w.put(spherical_theta(w.v())); }
+        else if (name == "spherical_phi") { w.put(spherical_phi(w.v())); }
+        else if (name == "tr_roughness_to_alpha") { w.put(std::fmax(sqr(w.f()), 1e-4f)); }
+        else if (name == "tr_D") { float ax = w.f(), ay = w.f(); w.put(TrowbridgeReitz{ax, ay}.D(w.v())); }
+        else if (name == "tr_Lambda") { float ax = w.f(), ay = w.f(); w.put(TrowbridgeReitz{ax, ay}.Lambda(w.v())); }
+        else if (name == "tr_G1") { float ax = w.f(), ay = w.f(); w.put(TrowbridgeReitz{ax, ay}.G1(w.v())); }
+        else if (name == "tr_G") { float ax = w.f(), ay = w.f(); V3 a = w.v(), b = w.v(); w.put(TrowbridgeReitz{ax, ay}.G(a, b)); }
+        else if (name == "tr_sample_wh") { float ax = w.f(), ay = w.f(); V3 wo = w.v(); float a = w.f(), b = w.f(); w.put(TrowbridgeReitz{ax, ay}.sample_wh(wo, a, b)); }
+        else if (name == "tr_pdf") { float ax = w.f(), ay = w.f(); V3 a = w.v(), b = w.v(); w.put(TrowbridgeReitz{ax, ay}.pdf(a, b)); }
+        else if (name == "fresnel_dielectric") { float a = w.f(), b = w.f(), c = w.f(); w.put(fresnel_dielectric(a, b, c)); }
+        else if (name == "fresnel_conductor") { float a = w.f(), b = w.f(); V3 e = w.v(), k = w.v(); w.put(fresnel_conductor(a, b, e, k)); }
+        else if (name == "fresnel_dielectric_integral") { w.put(fresnel_dielectric_integral(w.f())); }
+        else if (name == "lambert_reflection_evaluate") { V3 r = w.v(), wo = w.v(), wi = w.v(); w.put(lambert_evaluate(r, wo, wi)); }
+        else if (name == "lambert_reflection_sample") { V3 r = w.v(), wo = w.v(); float a = w.f(), b = w.f(); put_bxdf_sample(w, LambertBxDF{r}, wo, a, b); }
+        else if (name == "lambert_reflection_pdf") { w.v(); V3 wo = w.v(), wi = w.v(); w.put(lambert_pdf(wo, wi)); }
+        else if (name == "oren_nayar_evaluate") { V3 r = w.v(); float sg = w.f(); V3 wo = w.v(), wi = w.v(); w.put(OrenNayar{r, sg}.evaluate(wo, wi)); }
+        else if (name == "microfacet_reflection_dielectric_evaluate" || name == "microfacet_reflection_dielectric_pdf" ||
+                 name == "microfacet_reflection_dielectric_sample") {
+            V3 r = w.v(); float ax = w.f(), ay = w.f(), ei = w.f(), et = w.f(); V3 wo = w.v();
+            MicrofacetReflection bxdf{r, TrowbridgeReitz{ax, ay}, FresnelTerm::dielectric(ei, et)};
+            if (name.back() == 'e' && name[name.size() - 2] == 't') { w.put(bxdf.evaluate(wo, w.v())); }
+            else if (name.back() == 'f') { w.put(bxdf.pdf(wo, w.v())); }
+            else { float a = w.f(), b = w.f(); put_bxdf_sample(w, bxdf, wo, a, b); }
+        }
+        else if (name == "microfacet_reflection_conductor_evaluate" || name == "microfacet_reflection_conductor_sample") {
+            V3 r = w.v(); float ax = w.f(), ay = w.f(); V3 eta = w.v(), k = w.v(), wo = w.v();
+            MicrofacetReflection bxdf{r, TrowbridgeReitz{ax, ay}, FresnelTerm::conductor(1.f, eta, k)};
+            if (name.back() == 'e' && name[name.size() - 2] == 't') { w.put(bxdf.evaluate(wo, w.v())); }
+            else { float a = w.f(), b = w.f(); put_bxdf_sample(w, bxdf, wo, a, b); }
+        }
+        else if (name == "microfacet_transmission_evaluate" || name == "microfacet_transmission_pdf" || name == "microfacet_transmission_sample") {
+            V3 t = w.v(); float ax = w.f(), ay = w.f(), ea = w.f(), eb = w.f(); V3 wo = w.v();
+            MicrofacetTransmission bxdf{t, TrowbridgeReitz{ax, ay}, ea, eb};
+            if (name.back() == 'e' && name[name.size() - 2] == 't') { w.put(bxdf.evaluate(wo, w.v())); }
+            else if (name.back() == 'f') { w.put(bxdf.pdf(wo, w.v())); }
+            else { float a = w.f(), b = w.f(); put_bxdf_sample(w, bxdf, wo, a, b); }
+        }
+        else if (name == "fresnel_blend_evaluate" || name == "fresnel_blend_pdf" || name == "fresnel_blend_sample") {
+            V3 rd = w.v(), rs = w.v(); float ax = w.f(), ay = w.f(), ratio = w.f(); V3 wo = w.v();
+            FresnelBlend bxdf{rd, rs, TrowbridgeReitz{ax, ay}, ratio};
+            if (name.back() == 'e' && name[name.size() - 2] == 't') { w.put(bxdf.evaluate(wo, w.v())); }
+            else if (name.back() == 'f') { w.put(bxdf.pdf(wo, w.v())); }
+            else { float a = w.f(), b = w.f(); put_bxdf_sample(w, bxdf, wo, a, b); }
+        }
+        else if (name.rfind("_evaluate") != std::string::npos || name.rfind("_sample") != std::string::npos) {
+            // closure pins (oracle/ref/pin_<surface>.cpp): context words in lrk_surface.p order, then ng, ns, tangent, wo, ...
+            lrk_surface sf{};
+            auto take = [&](int count, int at = 0) { for (int i = 0; i < count; i++) sf.p[at + i] = w.f(); };
+            bool is_eval = name.find("_evaluate") != std::string::npos;
+            if (name.rfind("matte_", 0) == 0) { sf.type = LRK_SURFACE_MATTE; take(4); }
+            else if (name.rfind("disney_", 0) == 0) {
+                sf.type = LRK_SURFACE_DISNEY; take(15);
+                sf.lobes = static_cast<uint32_t>(std::stoul(name.substr(name.rfind('_') + 1)));
+            }
+            else if (name.rfind("mirror_", 0) == 0) { sf.type = LRK_SURFACE_MIRROR; take(5); }
+            else if (name.rfind("glass_", 0) == 0) { sf.type = LRK_SURFACE_GLASS; take(10); }
+            else if (name.rfind("plastic_", 0) == 0) { sf.type = LRK_SURFACE_PLASTIC; take(10); }
+            else if (name.rfind("metal_", 0) == 0) { sf.type = LRK_SURFACE_METAL; take(11); }
+            else { return -1; }
+            V3 ng = w.v(), ns = w.v(), tg = w.v(), wo = w.v();
+            Interaction it;
+            it.ng = ng;
+            it.shading = Frame::make(ns, tg);
+            if (is_eval) {
+                SurfEval e = surface_evaluate(sf, it, wo, w.v());
+                w.put(e.f); w.put(e.pdf);
+            } else {
+                float ul = w.f(), u0 = w.f(), u1 = w.f();
+                SurfSample r = surface_sample(sf, it, wo, ul, u0, u1);
+                w.put(r.wi); w.put(r.eval.f); w.put(r.eval.pdf); w.put(r.event);
+            }
+        }
+        else { return -1; }
+    }
+    return 0;
+}

@@ -1,0 +1,33 @@
+// pin_matte.cpp — the reference's 'matte' surface plugin (src/surfaces/matte.cpp, compiled from where it lies) driven through
+// Surface::Closure::{evaluate,sample}.  TEST INFRASTRUCTURE; see oracle/ref/README.md.
+#include <base/scene_node.h>
+#undef LUISA_RENDER_MAKE_SCENE_NODE_PLUGIN
+#define LUISA_RENDER_MAKE_SCENE_NODE_PLUGIN(cls)
+#define LUISA_RENDER_PLUGIN_NAME "matte"
+#include <surfaces/matte.cpp>
+
+#include "pin_surface.h"
+
+namespace luisa::render {
+namespace {
+using namespace refpins;
+auto make_closure(const SampledWavelengths &swl, Expr<float3> kd, Expr<float> sigma, Expr<float3> ng, Expr<float3> ns, Expr<float3> tangent) {
+    auto closure = luisa::make_unique<MatteClosure>(unused_pipeline(), swl, 0.f);
+    closure->bind(MatteClosure::Context{.it = make_interaction(ng, ns, tangent), .Kd = spec3(kd), .sigma = sigma});
+    return closure;
+}
+void register_pins() {
+    add("matte_evaluate", [](Float3 kd, Float sigma, Float3 ng, Float3 ns, Float3 tangent, Float3 wo, Float3 wi) {
+        SampledWavelengths swl{3u};
+        auto c = make_closure(swl, kd, sigma, ng, ns, tangent);
+        return closure_evaluate(*c, wo, wi);
+    });
+    add("matte_sample", [](Float3 kd, Float sigma, Float3 ng, Float3 ns, Float3 tangent, Float3 wo, Float u_lobe, Float2 u) {
+        SampledWavelengths swl{3u};
+        auto c = make_closure(swl, kd, sigma, ng, ns, tangent);
+        return closure_sample(*c, wo, u_lobe, u);
+    });
+}
+Registrar registrar{register_pins};
+}// namespace
+}// namespace luisa::render
