@@ -5,6 +5,10 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <deque>
+#include <mutex>
+#include <thread>
+#include <atomic>
 #include <unordered_map>
 
 #include <luisa/ast/constant_data.h>
@@ -130,13 +134,19 @@ void store(std::byte *p, const Lane &x) {
 
 /* ---- values ------------------------------------------------------------------------------------------------- */
 
+/* a typed value; up to 64 bytes (any scalar / vector / matrix, small structs) live inline */
 struct Val {
     const Type *t{nullptr};
-    std::vector<std::byte> m;
+    size_t n{0u};
+    alignas(16) std::byte inl[64];
+    std::vector<std::byte> heap;
     Val() = default;
-    explicit Val(const Type *type) : t{type}, m(type == nullptr ? 0u : type->size(), std::byte{0}) {}
-    std::byte *p() { return m.data(); }
-    const std::byte *p() const { return m.data(); }
+    explicit Val(const Type *type) : t{type}, n{type == nullptr ? 0u : type->size()} {
+        if (n <= sizeof(inl)) { std::memset(inl, 0, sizeof(inl)); } else { heap.assign(n, std::byte{0}); }
+    }
+    std::byte *p() { return n <= sizeof(inl) ? inl : heap.data(); }
+    const std::byte *p() const { return n <= sizeof(inl) ? inl : heap.data(); }
+    size_t size() const { return n; }
 };
 
 struct Ptr {
@@ -158,9 +168,26 @@ Shape shape_of(const Type *t) {
     fail("expected a scalar, vector or matrix, got " + std::string{t->description()});
 }
 
-std::vector<Lane> lanes(const Val &v) {
+/* up to 16 lanes (float4x4) without heap traffic */
+struct Lanes {
+    Lane v[16];
+    uint32_t n{0u};
+    Lanes() = default;
+    Lanes(std::initializer_list<Lane> init) { for (auto &x : init) { v[n++] = x; } }
+    Lanes(size_t count, const Lane &x) { for (n = 0u; n < count; n++) { v[n] = x; } }
+    void push_back(const Lane &x) { if (n >= 16u) { fail("more than 16 lanes"); } v[n++] = x; }
+    [[nodiscard]] size_t size() const { return n; }
+    Lane &operator[](size_t i) { return v[i]; }
+    const Lane &operator[](size_t i) const { return v[i]; }
+    Lane *begin() { return v; }
+    Lane *end() { return v + n; }
+    const Lane *begin() const { return v; }
+    const Lane *end() const { return v + n; }
+};
+
+Lanes lanes(const Val &v) {
     auto s = shape_of(v.t);
-    std::vector<Lane> out;
+    Lanes out;
     if (!s.matrix) {
         auto es = scalar_size(s.elem);
         for (auto i = 0u; i < s.n; i++) { out.push_back(load(v.p() + i * es, s.elem)); }
@@ -173,7 +200,7 @@ std::vector<Lane> lanes(const Val &v) {
     return out;
 }
 
-Val from_lanes(const Type *t, const std::vector<Lane> &ls) {
+Val from_lanes(const Type *t, const Lanes &ls) {
     Val v{t};
     auto s = shape_of(t);
     if (!s.matrix) {
@@ -299,7 +326,7 @@ Val binary(BinaryOp op, const Val &a, const Val &b, const Type *rt) {
     auto lb = lanes(b);
     if (sa.matrix || sb.matrix) {
         auto n = sa.matrix ? sa.n : sb.n;
-        std::vector<Lane> out;
+        Lanes out;
         if (sa.matrix && sb.matrix && op == BinaryOp::MUL) {// (A * B)[c] = A * B[c]
             for (auto c = 0u; c < n; c++) {
                 for (auto r = 0u; r < n; r++) {
@@ -340,7 +367,7 @@ Val binary(BinaryOp op, const Val &a, const Val &b, const Type *rt) {
     }
     auto n = std::max(sa.n, sb.n);
     if ((sa.n != 1u && sa.n != n) || (sb.n != 1u && sb.n != n)) { fail("vector size mismatch in binary op"); }
-    std::vector<Lane> out;
+    Lanes out;
     for (auto i = 0u; i < n; i++) { out.push_back(binary_lane(op, la[sa.n == 1u ? 0u : i], lb[sb.n == 1u ? 0u : i])); }
     (void)is_relational;
     return from_lanes(rt, out);
@@ -348,7 +375,7 @@ Val binary(BinaryOp op, const Val &a, const Val &b, const Type *rt) {
 
 Val unary(UnaryOp op, const Val &a, const Type *rt) {
     auto la = lanes(a);
-    std::vector<Lane> out;
+    Lanes out;
     for (auto &x : la) {
         switch (op) {
             case UnaryOp::PLUS: out.push_back(x); break;
@@ -401,10 +428,19 @@ bool isnan_impl(float x) { uint32_t u; std::memcpy(&u, &x, 4u); return (u & 0x7f
 namespace {
 
 struct Slot {
+    enum struct Kind : uint8_t { UNSET, DATA, BUFFER, BINDLESS_ARRAY, ACCEL } kind{Kind::UNSET};
     std::byte *ptr{nullptr};
+    alignas(16) std::byte inl[64];
     std::vector<std::byte> own;
     BufferArg buffer;
+    uint64_t handle{0u};
 };
+
+/* atomics on buffers shared by the host threads of one launch: striped locks are plenty here */
+std::mutex &atomic_lock(const void *address) {
+    static std::mutex locks[256];
+    return locks[(reinterpret_cast<uintptr_t>(address) >> 2u) & 255u];
+}
 
 enum struct Flow { NORMAL, BREAK, CONTINUE, RETURN };
 
@@ -412,36 +448,62 @@ class Machine {
 
 private:
     Function _f;
-    std::unordered_map<uint32_t, Slot> _slots;
+    DeviceResources *_res{nullptr};
+    std::deque<Slot> _slots;// indexed by variable uid (uids are small and dense per function)
     Val _ret;
 
+    Slot &raw_slot(uint32_t uid) {
+        if (uid >= _slots.size()) { _slots.resize(uid + 1u); }
+        return _slots[uid];
+    }
+
 public:
-    explicit Machine(Function f) : _f{f} {}
+    Machine(Function f, DeviceResources *res) : _f{f}, _res{res} {}
     Slot &slot(Variable v) {
-        auto it = _slots.find(v.uid());
-        if (it == _slots.end()) {
-            Slot s;
-            if (!v.is_resource()) {
-                s.own.assign(std::max<size_t>(v.type()->size(), 1u), std::byte{0});// locals are zero-initialised
+        auto &s = raw_slot(v.uid());
+        if (s.kind == Slot::Kind::UNSET) {
+            if (v.is_resource()) { fail("unbound resource variable"); }
+            s.kind = Slot::Kind::DATA;
+            auto n = std::max<size_t>(v.type()->size(), 1u);// locals are zero-initialised
+            if (n <= sizeof(s.inl)) {
+                std::memset(s.inl, 0, sizeof(s.inl));
+                s.ptr = s.inl;
+            } else {
+                s.own.assign(n, std::byte{0});
+                s.ptr = s.own.data();
             }
-            it = _slots.emplace(v.uid(), std::move(s)).first;
-            if (!v.is_resource()) { it->second.ptr = it->second.own.data(); }
         }
-        return it->second;
+        return s;
     }
     void bind_value(Variable v, const std::byte *data) {
         auto &s = slot(v);
         std::memcpy(s.ptr, data, v.type()->size());
     }
     void bind_reference(Variable v, std::byte *target) {
-        Slot s;
+        auto &s = raw_slot(v.uid());
+        s.kind = Slot::Kind::DATA;
         s.ptr = target;
-        _slots[v.uid()] = std::move(s);
     }
     void bind_buffer(Variable v, BufferArg b) {
-        Slot s;
+        auto &s = raw_slot(v.uid());
+        s.kind = Slot::Kind::BUFFER;
         s.buffer = b;
-        _slots[v.uid()] = std::move(s);
+    }
+    void bind_handle(Variable v, Slot::Kind kind, uint64_t handle) {
+        auto &s = raw_slot(v.uid());
+        s.kind = kind;
+        s.handle = handle;
+    }
+    void bind_arg(Variable p, const Arg &a) {
+        switch (a.kind) {
+            case Arg::Kind::BUFFER: bind_buffer(p, a.buffer); break;
+            case Arg::Kind::BINDLESS_ARRAY: bind_handle(p, Slot::Kind::BINDLESS_ARRAY, a.handle); break;
+            case Arg::Kind::ACCEL: bind_handle(p, Slot::Kind::ACCEL, a.handle); break;
+            default:
+                if (a.bytes.size() != p.type()->size()) { fail("argument size mismatch"); }
+                bind_value(p, a.bytes.data());
+                break;
+        }
     }
     Val run() {
         exec(_f.body());
@@ -454,8 +516,9 @@ private:
             case Expression::Tag::REF: {
                 auto v = static_cast<const RefExpr *>(e)->variable();
                 if (v.is_resource()) { return false; }
-                if (v.tag() != Variable::Tag::LOCAL && v.tag() != Variable::Tag::REFERENCE && v.tag() != Variable::Tag::SHARED) {
-                    fail("builtin variables (thread ids) are not available in callables");
+                if (v.tag() != Variable::Tag::LOCAL && v.tag() != Variable::Tag::REFERENCE && v.tag() != Variable::Tag::SHARED &&
+                    raw_slot(v.uid()).kind != Slot::Kind::DATA) {
+                    fail("builtin variable (thread / dispatch id) used outside a kernel launch");
                 }
                 out = {slot(v).ptr, v.type()};
                 return true;
@@ -506,7 +569,7 @@ private:
         Ptr lv;
         if (try_lvalue(e, lv)) {
             Val v{e->type()};
-            std::memcpy(v.p(), lv.p, v.m.size());
+            std::memcpy(v.p(), lv.p, v.size());
             return v;
         }
         switch (e->tag()) {
@@ -528,7 +591,7 @@ private:
                         std::memcpy(out.p() + i * es, self.p() + m->swizzle_index(i) * es, es);
                     }
                 } else {
-                    std::memcpy(out.p(), self.p() + member_offset(self.t, m->member_index()), out.m.size());
+                    std::memcpy(out.p(), self.p() + member_offset(self.t, m->member_index()), out.size());
                 }
                 return out;
             }
@@ -538,7 +601,7 @@ private:
                 if (a->range()->type()->is_buffer()) { return buffer_read(a->range(), idx, e->type()); }
                 auto range = eval(a->range());
                 Val out{e->type()};
-                std::memcpy(out.p(), range.p() + element_offset(range.t, idx), out.m.size());
+                std::memcpy(out.p(), range.p() + element_offset(range.t, idx), out.size());
                 return out;
             }
             case Expression::Tag::LITERAL: {
@@ -546,7 +609,7 @@ private:
                 Val out{e->type()};
                 luisa::visit(
                     [&out](auto v) {
-                        if (sizeof(v) != out.m.size()) { fail("literal size mismatch"); }
+                        if (sizeof(v) != out.size()) { fail("literal size mismatch"); }
                         std::memcpy(out.p(), &v, sizeof(v));
                     },
                     l->value().to_variant());
@@ -555,7 +618,7 @@ private:
             case Expression::Tag::CONSTANT: {
                 auto c = static_cast<const ConstantExpr *>(e);
                 Val out{e->type()};
-                std::memcpy(out.p(), c->data().raw(), out.m.size());
+                std::memcpy(out.p(), c->data().raw(), out.size());
                 return out;
             }
             case Expression::Tag::CAST: {
@@ -563,8 +626,8 @@ private:
                 auto src = eval(c->expression());
                 if (c->op() == CastOp::BITWISE) {
                     Val out{e->type()};
-                    if (out.m.size() != src.m.size()) { fail("bitwise cast between different sizes"); }
-                    std::memcpy(out.p(), src.p(), out.m.size());
+                    if (out.size() != src.size()) { fail("bitwise cast between different sizes"); }
+                    std::memcpy(out.p(), src.p(), out.size());
                     return out;
                 }
                 return from_lanes(e->type(), lanes(src));
@@ -577,16 +640,29 @@ private:
     BufferArg buffer_of(const Expression *e) {
         if (e->tag() != Expression::Tag::REF) { fail("buffer expression is not a variable"); }
         auto v = static_cast<const RefExpr *>(e)->variable();
-        auto it = _slots.find(v.uid());
-        if (it == _slots.end() || it->second.buffer.data == nullptr) { fail("unbound buffer argument"); }
-        return it->second.buffer;
+        auto &s = raw_slot(v.uid());
+        if (s.kind != Slot::Kind::BUFFER || s.buffer.data == nullptr) { fail("unbound buffer argument"); }
+        return s.buffer;
+    }
+    uint64_t handle_of(const Expression *e, Slot::Kind kind) {
+        if (e->tag() != Expression::Tag::REF) { fail("resource expression is not a variable"); }
+        auto &s = raw_slot(static_cast<const RefExpr *>(e)->variable().uid());
+        if (s.kind != kind) { fail("resource variable bound to the wrong kind"); }
+        return s.handle;
+    }
+    DeviceResources &res() {
+        if (_res == nullptr) { fail("device resources used outside a device launch"); }
+        return *_res;
     }
 
     Val buffer_read(const Expression *buffer, size_t idx, const Type *elem) {
-        auto b = buffer_of(buffer);
-        if (idx >= b.count) { fail("buffer read out of range"); }
+        return read_element(buffer_of(buffer), idx, elem);
+    }
+    Val read_element(BufferArg b, size_t idx, const Type *elem) {
+        auto stride = align_up(elem->size(), elem->alignment());
+        if ((idx + 1u) * stride > b.size_bytes) { fail("buffer read out of range"); }
         Val out{elem};
-        std::memcpy(out.p(), b.data + idx * align_up(elem->size(), elem->alignment()), out.m.size());
+        std::memcpy(out.p(), b.data + idx * stride, out.size());
         return out;
     }
 
@@ -594,7 +670,7 @@ private:
     template<typename F>
     Val map_f(const CallExpr *e, F &&fn) {// float -> float, per lane
         auto a = lanes(eval(e->arguments()[0]));
-        std::vector<Lane> out;
+        Lanes out;
         for (auto &x : a) { out.push_back(mk(static_cast<float>(fn(conv(x, Tag::FLOAT32).f)))); }
         return from_lanes(e->type(), out);
     }
@@ -603,7 +679,7 @@ private:
         auto a = lanes(eval(e->arguments()[0]));
         auto b = lanes(eval(e->arguments()[1]));
         auto n = std::max(a.size(), b.size());
-        std::vector<Lane> out;
+        Lanes out;
         for (auto i = 0u; i < n; i++) {
             out.push_back(mk(static_cast<float>(fn(conv(a[a.size() == 1u ? 0u : i], Tag::FLOAT32).f, conv(b[b.size() == 1u ? 0u : i], Tag::FLOAT32).f))));
         }
@@ -615,8 +691,8 @@ private:
         auto b = lanes(eval(e->arguments()[1]));
         auto c = lanes(eval(e->arguments()[2]));
         auto n = std::max({a.size(), b.size(), c.size()});
-        std::vector<Lane> out;
-        auto at = [](const std::vector<Lane> &v, size_t i) { return conv(v[v.size() == 1u ? 0u : i], Tag::FLOAT32).f; };
+        Lanes out;
+        auto at = [](const Lanes &v, size_t i) { return conv(v[v.size() == 1u ? 0u : i], Tag::FLOAT32).f; };
         for (auto i = 0u; i < n; i++) { out.push_back(mk(static_cast<float>(fn(at(a, i), at(b, i), at(c, i))))); }
         return from_lanes(e->type(), out);
     }
@@ -633,25 +709,69 @@ private:
         if (ct == Tag::FLOAT32) { return mk(std::fmax(ca.f, cb.f)); }
         return binary_lane(BinaryOp::GREATER, ca, cb).b ? ca : cb;
     }
-    static float fdot(const std::vector<Lane> &a, const std::vector<Lane> &b) {// a.x*b.x + a.y*b.y + ... (:3483)
+    static float fdot(const Lanes &a, const Lanes &b) {// a.x*b.x + a.y*b.y + ... (:3483)
         auto acc = a[0].f * b[0].f;
         for (auto i = 1u; i < a.size(); i++) { acc = acc + a[i].f * b[i].f; }
         return acc;
     }
 
+    /* atomic ops: arguments = (buffer, index, [member / component indices ...], value[s]) */
+    Val atomic(const CallExpr *e) {
+        auto args = e->arguments();
+        auto n_values = e->op() == CallOp::ATOMIC_COMPARE_EXCHANGE ? 2u : 1u;
+        if (!args[0]->type()->is_buffer()) { fail("atomics are implemented for buffers only"); }
+        auto b = buffer_of(args[0]);
+        auto t = args[0]->type()->element();
+        auto idx = static_cast<size_t>(conv(lanes(eval(args[1]))[0], Tag::UINT32).u);
+        auto stride = align_up(t->size(), t->alignment());
+        if ((idx + 1u) * stride > b.size_bytes) { fail("atomic access out of range"); }
+        auto p = b.data + idx * stride;
+        for (auto i = 2u; i + n_values < args.size(); i++) {
+            auto k = static_cast<size_t>(conv(lanes(eval(args[i]))[0], Tag::UINT32).u);
+            if (t->is_structure()) {
+                p += member_offset(t, static_cast<uint32_t>(k));
+                t = t->members()[k];
+            } else {
+                p += element_offset(t, k);
+                t = t->is_matrix() ? Type::vector(Type::of<float>(), t->dimension()) : t->element();
+            }
+        }
+        if (!t->is_scalar()) { fail("atomic on a non-scalar"); }
+        auto v0 = conv(lanes(eval(args[args.size() - n_values]))[0], t->tag());
+        std::scoped_lock lock{atomic_lock(p)};
+        auto old = load(p, t->tag());
+        Lane next = old;
+        switch (e->op()) {
+            case CallOp::ATOMIC_EXCHANGE: next = v0; break;
+            case CallOp::ATOMIC_COMPARE_EXCHANGE: {
+                auto desired = conv(lanes(eval(args[args.size() - 1u]))[0], t->tag());
+                if (binary_lane(BinaryOp::EQUAL, old, v0).b) { next = desired; }
+                break;
+            }
+            case CallOp::ATOMIC_FETCH_ADD: next = binary_lane(BinaryOp::ADD, old, v0); break;
+            case CallOp::ATOMIC_FETCH_SUB: next = binary_lane(BinaryOp::SUB, old, v0); break;
+            case CallOp::ATOMIC_FETCH_AND: next = binary_lane(BinaryOp::BIT_AND, old, v0); break;
+            case CallOp::ATOMIC_FETCH_OR: next = binary_lane(BinaryOp::BIT_OR, old, v0); break;
+            case CallOp::ATOMIC_FETCH_XOR: next = binary_lane(BinaryOp::BIT_XOR, old, v0); break;
+            case CallOp::ATOMIC_FETCH_MIN: next = lane_min(old, v0); break;
+            default: next = lane_max(old, v0); break;
+        }
+        store(p, conv(next, t->tag()));
+        return from_lanes(e->type(), {old});
+    }
+
     Val make_vector(const CallExpr *e) {
         auto s = shape_of(e->type());
-        std::vector<Lane> all;
+        Lanes all;
         for (auto arg : e->arguments()) {
-            auto ls = lanes(eval(arg));
-            all.insert(all.end(), ls.begin(), ls.end());
+            for (auto &x : lanes(eval(arg))) { all.push_back(x); }
         }
-        std::vector<Lane> out;
+        Lanes out;
         if (all.size() == 1u) {
-            out.assign(s.n, all[0]);
+            out = Lanes(s.n, all[0]);
         } else {
             if (all.size() < s.n) { fail("make_vector: too few components"); }
-            out.assign(all.begin(), all.begin() + s.n);// truncation of a wider vector
+            for (auto i = 0u; i < s.n; i++) { out.push_back(all[i]); }// truncation of a wider vector
         }
         return from_lanes(e->type(), out);
     }
@@ -659,7 +779,7 @@ private:
     Val make_matrix(const CallExpr *e) {
         auto n = e->type()->dimension();
         auto args = e->arguments();
-        std::vector<Lane> out(n * n, mk(0.f));
+        Lanes out(n * n, mk(0.f));
         if (args.size() == 1u && args[0]->type()->is_matrix()) {
             auto src = lanes(eval(args[0]));
             auto m = args[0]->type()->dimension();
@@ -668,10 +788,9 @@ private:
             }
             return from_lanes(e->type(), out);
         }
-        std::vector<Lane> all;
+        Lanes all;
         for (auto arg : args) {
-            auto ls = lanes(eval(arg));
-            all.insert(all.end(), ls.begin(), ls.end());
+            for (auto &x : lanes(eval(arg))) { all.push_back(x); }
         }
         if (all.size() != n * n) { fail("make_matrix: component count"); }
         return from_lanes(e->type(), all);
@@ -679,7 +798,7 @@ private:
 
     Val call_custom(const CallExpr *e) {
         auto callee = e->custom();
-        Machine m{callee};
+        Machine m{callee, _res};
         auto params = callee.arguments();
         auto args = e->arguments();
         if (params.size() != args.size()) { fail("callable argument count mismatch"); }
@@ -688,8 +807,11 @@ private:
         for (auto i = 0u; i < params.size(); i++) {
             auto p = params[i];
             if (p.is_resource()) {
-                if (p.tag() != Variable::Tag::BUFFER) { fail("only buffer resources are supported"); }
-                m.bind_buffer(p, buffer_of(args[i]));
+                if (args[i]->tag() != Expression::Tag::REF) { fail("resource argument is not a variable"); }
+                auto &src = raw_slot(static_cast<const RefExpr *>(args[i])->variable().uid());
+                if (src.kind == Slot::Kind::BUFFER) { m.bind_buffer(p, src.buffer); }
+                else if (src.kind == Slot::Kind::BINDLESS_ARRAY || src.kind == Slot::Kind::ACCEL) { m.bind_handle(p, src.kind, src.handle); }
+                else { fail("unsupported resource argument"); }
             } else if (p.is_reference()) {
                 Ptr lv;
                 if (try_lvalue(args[i], lv)) {
@@ -730,13 +852,13 @@ private:
                 auto p = F(2);
                 if (p.size() == 1u) { return p[0].b ? tv : fv; }
                 auto lf = lanes(fv), lt = lanes(tv);
-                std::vector<Lane> out;
+                Lanes out;
                 for (auto i = 0u; i < p.size(); i++) { out.push_back(p[i].b ? lt[lt.size() == 1u ? 0u : i] : lf[lf.size() == 1u ? 0u : i]); }
                 return from_lanes(e->type(), out);
             }
             case CallOp::CLAMP: {// min(max(v, lo), hi)
                 auto v = F(0), lo = F(1), hi = F(2);
-                std::vector<Lane> out;
+                Lanes out;
                 for (auto i = 0u; i < v.size(); i++) {
                     out.push_back(lane_min(lane_max(v[i], lo[lo.size() == 1u ? 0u : i]), hi[hi.size() == 1u ? 0u : i]));
                 }
@@ -752,7 +874,7 @@ private:
             case CallOp::STEP: return map_ff(e, [](float edge, float x) { return x < edge ? 0.f : 1.f; });
             case CallOp::ABS: {
                 auto a = F(0);
-                std::vector<Lane> out;
+                Lanes out;
                 for (auto &x : a) {
                     out.push_back(visit(x, [](auto v) -> Lane {
                         using T = decltype(v);
@@ -767,7 +889,7 @@ private:
             case CallOp::MAX: {
                 auto a = F(0), b = F(1);
                 auto n = std::max(a.size(), b.size());
-                std::vector<Lane> out;
+                Lanes out;
                 for (auto i = 0u; i < n; i++) {
                     auto &x = a[a.size() == 1u ? 0u : i];
                     auto &y = b[b.size() == 1u ? 0u : i];
@@ -780,7 +902,7 @@ private:
             case CallOp::POPCOUNT:
             case CallOp::REVERSE: {
                 auto a = F(0);
-                std::vector<Lane> out;
+                Lanes out;
                 for (auto &x : a) {
                     auto u = conv(x, Tag::UINT32).u;
                     uint32_t r = 0u;
@@ -797,7 +919,7 @@ private:
             case CallOp::ISINF:
             case CallOp::ISNAN: {
                 auto a = F(0);
-                std::vector<Lane> out;
+                Lanes out;
                 for (auto &x : a) { out.push_back(mk(op == CallOp::ISINF ? isinf_impl(x.f) : isnan_impl(x.f))); }
                 return from_lanes(e->type(), out);
             }
@@ -851,21 +973,21 @@ private:
             case CallOp::NORMALIZE: {// v * rsqrt(dot(v, v))
                 auto a = F(0);
                 auto s = 1.0f / std::sqrt(fdot(a, a));
-                std::vector<Lane> out;
+                Lanes out;
                 for (auto &x : a) { out.push_back(mk(x.f * s)); }
                 return from_lanes(e->type(), out);
             }
             case CallOp::FACEFORWARD: {// select(-n, n, dot(n_ref, i) < 0)
                 auto n = F(0), i = F(1), nref = F(2);
                 auto keep = fdot(nref, i) < 0.f;
-                std::vector<Lane> out;
+                Lanes out;
                 for (auto &x : n) { out.push_back(mk(keep ? x.f : -x.f)); }
                 return from_lanes(e->type(), out);
             }
             case CallOp::REFLECT: {// v - 2 * dot(v, n) * n
                 auto v = F(0), n = F(1);
                 auto s = 2.0f * fdot(v, n);
-                std::vector<Lane> out;
+                Lanes out;
                 for (auto i = 0u; i < v.size(); i++) { out.push_back(mk(v[i].f - s * n[i].f)); }
                 return from_lanes(e->type(), out);
             }
@@ -883,10 +1005,61 @@ private:
                 }
                 return from_lanes(e->type(), {acc});
             }
+            case CallOp::DETERMINANT:
+            case CallOp::INVERSE: {// cofactor expansion as the CUDA backend's lc_determinant / lc_inverse (GLM's), cuda_device_math.h:3554-3680
+                auto a = F(0);
+                auto n = args[0]->type()->dimension();
+                auto M = [&](uint32_t c, uint32_t r) { return a[c * n + r].f; };
+                if (n == 2u) {
+                    auto det = M(0, 0) * M(1, 1) - M(1, 0) * M(0, 1);
+                    if (op == CallOp::DETERMINANT) { return from_lanes(e->type(), {mk(det)}); }
+                    auto inv = 1.0f / det;
+                    return from_lanes(e->type(), {mk(M(1, 1) * inv), mk(-M(0, 1) * inv), mk(-M(1, 0) * inv), mk(M(0, 0) * inv)});
+                }
+                if (n == 3u) {
+                    auto det = M(0, 0) * (M(1, 1) * M(2, 2) - M(2, 1) * M(1, 2)) - M(1, 0) * (M(0, 1) * M(2, 2) - M(2, 1) * M(0, 2)) +
+                               M(2, 0) * (M(0, 1) * M(1, 2) - M(1, 1) * M(0, 2));
+                    if (op == CallOp::DETERMINANT) { return from_lanes(e->type(), {mk(det)}); }
+                    auto inv = 1.0f / det;
+                    return from_lanes(e->type(), {mk((M(1, 1) * M(2, 2) - M(2, 1) * M(1, 2)) * inv), mk((M(2, 1) * M(0, 2) - M(0, 1) * M(2, 2)) * inv),
+                                                  mk((M(0, 1) * M(1, 2) - M(1, 1) * M(0, 2)) * inv), mk((M(2, 0) * M(1, 2) - M(1, 0) * M(2, 2)) * inv),
+                                                  mk((M(0, 0) * M(2, 2) - M(2, 0) * M(0, 2)) * inv), mk((M(1, 0) * M(0, 2) - M(0, 0) * M(1, 2)) * inv),
+                                                  mk((M(1, 0) * M(2, 1) - M(2, 0) * M(1, 1)) * inv), mk((M(2, 0) * M(0, 1) - M(0, 0) * M(2, 1)) * inv),
+                                                  mk((M(0, 0) * M(1, 1) - M(1, 0) * M(0, 1)) * inv)});
+                }
+                // 4x4: 2x2 sub-determinants of rows (2,3), (1,3), (1,2) over column pairs, then the adjugate by columns
+                auto sub = [&](uint32_t r0, uint32_t r1, uint32_t c0, uint32_t c1) { return M(c0, r0) * M(c1, r1) - M(c1, r0) * M(c0, r1); };
+                float c00 = sub(2, 3, 2, 3), c02 = sub(2, 3, 1, 3), c03 = sub(2, 3, 1, 2);
+                float c04 = sub(1, 3, 2, 3), c06 = sub(1, 3, 1, 3), c07 = sub(1, 3, 1, 2);
+                float c08 = sub(1, 2, 2, 3), c10 = sub(1, 2, 1, 3), c11 = sub(1, 2, 1, 2);
+                float c12 = sub(0, 3, 2, 3), c14 = sub(0, 3, 1, 3), c15 = sub(0, 3, 1, 2);
+                float c16 = sub(0, 2, 2, 3), c18 = sub(0, 2, 1, 3), c19 = sub(0, 2, 1, 2);
+                float c20 = sub(0, 1, 2, 3), c22 = sub(0, 1, 1, 3), c23 = sub(0, 1, 1, 2);
+                float fac0[4] = {c00, c00, c02, c03}, fac1[4] = {c04, c04, c06, c07}, fac2[4] = {c08, c08, c10, c11};
+                float fac3[4] = {c12, c12, c14, c15}, fac4[4] = {c16, c16, c18, c19}, fac5[4] = {c20, c20, c22, c23};
+                float v0[4] = {M(1, 0), M(0, 0), M(0, 0), M(0, 0)}, v1[4] = {M(1, 1), M(0, 1), M(0, 1), M(0, 1)};
+                float v2[4] = {M(1, 2), M(0, 2), M(0, 2), M(0, 2)}, v3_[4] = {M(1, 3), M(0, 3), M(0, 3), M(0, 3)};
+                float inv_c[4][4];
+                for (auto i = 0u; i < 4u; i++) {
+                    auto sa = (i % 2u == 0u) ? 1.0f : -1.0f;
+                    inv_c[0][i] = (v1[i] * fac0[i] - v2[i] * fac1[i] + v3_[i] * fac2[i]) * sa;
+                    inv_c[1][i] = (v0[i] * fac0[i] - v2[i] * fac3[i] + v3_[i] * fac4[i]) * -sa;
+                    inv_c[2][i] = (v0[i] * fac1[i] - v1[i] * fac3[i] + v3_[i] * fac5[i]) * sa;
+                    inv_c[3][i] = (v0[i] * fac2[i] - v1[i] * fac4[i] + v2[i] * fac5[i]) * -sa;
+                }
+                auto det = M(0, 0) * inv_c[0][0] + M(0, 1) * inv_c[1][0] + M(0, 2) * inv_c[2][0] + M(0, 3) * inv_c[3][0];
+                if (op == CallOp::DETERMINANT) { return from_lanes(e->type(), {mk(det)}); }
+                auto inv = 1.0f / det;
+                Lanes out;
+                for (auto c = 0u; c < 4u; c++) {
+                    for (auto r = 0u; r < 4u; r++) { out.push_back(mk(inv_c[c][r] * inv)); }
+                }
+                return from_lanes(e->type(), out);
+            }
             case CallOp::TRANSPOSE: {
                 auto a = F(0);
                 auto n = e->type()->dimension();
-                std::vector<Lane> out(n * n);
+                Lanes out(n * n, mk(0.f));
                 for (auto c = 0u; c < n; c++) {
                     for (auto r = 0u; r < n; r++) { out[c * n + r] = a[r * n + c]; }
                 }
@@ -900,11 +1073,53 @@ private:
                 auto b = buffer_of(args[0]);
                 auto idx = static_cast<size_t>(conv(F(1)[0], Tag::UINT32).u);
                 auto v = eval(args[2]);
-                if (idx >= b.count) { fail("buffer write out of range"); }
-                std::memcpy(b.data + idx * align_up(v.t->size(), v.t->alignment()), v.p(), v.m.size());
+                auto stride = align_up(v.t->size(), v.t->alignment());
+                if ((idx + 1u) * stride > b.size_bytes) { fail("buffer write out of range"); }
+                std::memcpy(b.data + idx * stride, v.p(), v.size());
                 return Val{};
             }
-            case CallOp::BUFFER_SIZE: return from_lanes(e->type(), {mk(static_cast<uint64_t>(buffer_of(args[0]).count))});
+            case CallOp::BUFFER_SIZE: {
+                auto elem = args[0]->type()->element();
+                return from_lanes(e->type(), {mk(static_cast<uint64_t>(buffer_of(args[0]).size_bytes / align_up(elem->size(), elem->alignment())))});
+            }
+            case CallOp::BINDLESS_BUFFER_READ: {
+                auto array = handle_of(args[0], Slot::Kind::BINDLESS_ARRAY);
+                auto slot_index = conv(F(1)[0], Tag::UINT32).u;
+                auto idx = static_cast<size_t>(conv(F(2)[0], Tag::UINT32).u);
+                return read_element(res().bindless_buffer(array, slot_index), idx, e->type());
+            }
+            case CallOp::RAY_TRACING_TRACE_CLOSEST:
+            case CallOp::RAY_TRACING_TRACE_ANY: {
+                auto accel = handle_of(args[0], Slot::Kind::ACCEL);
+                auto ray = eval(args[1]);
+                if (ray.size() != sizeof(RayData)) { fail("unexpected Ray layout"); }
+                RayData rd;
+                std::memcpy(&rd, ray.p(), sizeof(rd));
+                auto mask = conv(F(2)[0], Tag::UINT32).u;
+                if (op == CallOp::RAY_TRACING_TRACE_ANY) { return from_lanes(e->type(), {mk(res().trace_any(accel, rd, mask))}); }
+                auto hit = res().trace_closest(accel, rd, mask);
+                Val out{e->type()};
+                if (out.size() > sizeof(HitData)) { fail("unexpected Hit layout"); }
+                std::memcpy(out.p(), &hit, out.size());
+                return out;
+            }
+            case CallOp::RAY_TRACING_INSTANCE_TRANSFORM: {
+                auto accel = handle_of(args[0], Slot::Kind::ACCEL);
+                float m[16];
+                res().instance_transform(accel, conv(F(1)[0], Tag::UINT32).u, m);
+                Lanes out;
+                for (auto x : m) { out.push_back(mk(x)); }
+                return from_lanes(e->type(), out);
+            }
+            case CallOp::ATOMIC_EXCHANGE:
+            case CallOp::ATOMIC_COMPARE_EXCHANGE:
+            case CallOp::ATOMIC_FETCH_ADD:
+            case CallOp::ATOMIC_FETCH_SUB:
+            case CallOp::ATOMIC_FETCH_AND:
+            case CallOp::ATOMIC_FETCH_OR:
+            case CallOp::ATOMIC_FETCH_XOR:
+            case CallOp::ATOMIC_FETCH_MIN:
+            case CallOp::ATOMIC_FETCH_MAX: return atomic(e);
             case CallOp::MAKE_BOOL2:
             case CallOp::MAKE_BOOL3:
             case CallOp::MAKE_BOOL4:
@@ -932,7 +1147,7 @@ private:
             case CallOp::ZERO: return Val{e->type()};
             case CallOp::ONE: {
                 auto s = shape_of(e->type());
-                std::vector<Lane> out(s.matrix ? s.n * s.n : s.n, conv(mk(1), s.elem));
+                Lanes out(s.matrix ? s.n * s.n : s.n, conv(mk(1), s.elem));
                 return from_lanes(e->type(), out);
             }
             default: fail("unsupported builtin call op " + std::to_string(static_cast<uint32_t>(op)));
@@ -943,14 +1158,14 @@ private:
     void assign(const Expression *lhs, const Val &v) {
         Ptr lv;
         if (try_lvalue(lhs, lv)) {
-            if (lv.t->size() != v.m.size()) {// scalar -> vector broadcast etc. never happens in LC; convert by lanes
+            if (lv.t->size() != v.size()) {// scalar -> vector broadcast etc. never happens in LC; convert by lanes
                 auto c = from_lanes(lv.t, lanes(v));
-                std::memcpy(lv.p, c.p(), c.m.size());
+                std::memcpy(lv.p, c.p(), c.size());
             } else if (lv.t != v.t && (lv.t->is_scalar() || lv.t->is_vector())) {
                 auto c = from_lanes(lv.t, lanes(v));
-                std::memcpy(lv.p, c.p(), c.m.size());
+                std::memcpy(lv.p, c.p(), c.size());
             } else {
-                std::memcpy(lv.p, v.p(), v.m.size());
+                std::memcpy(lv.p, v.p(), v.size());
             }
             return;
         }
@@ -1049,23 +1264,68 @@ private:
 
 }// namespace
 
-std::vector<std::byte> call(Function f, std::vector<Arg> &args) {
-    Machine m{f};
+std::vector<std::byte> call(Function f, std::vector<Arg> &args, DeviceResources *resources) {
+    Machine m{f, resources};
     auto params = f.arguments();
     if (params.size() != args.size()) { fail("entry argument count mismatch"); }
     for (auto i = 0u; i < params.size(); i++) {
         auto p = params[i];
-        if (p.is_resource()) {
-            if (p.tag() != Variable::Tag::BUFFER) { fail("only buffer resources are supported"); }
-            m.bind_buffer(p, args[i].buffer);
-        } else {
+        if (!p.is_resource() && p.is_reference()) {
             if (args[i].bytes.size() != p.type()->size()) { fail("entry argument size mismatch"); }
-            if (p.is_reference()) { m.bind_reference(p, args[i].bytes.data()); }
-            else { m.bind_value(p, args[i].bytes.data()); }
+            m.bind_reference(p, args[i].bytes.data());
+        } else {
+            m.bind_arg(p, args[i]);
         }
     }
     auto r = m.run();
-    return r.m;
+    return std::vector<std::byte>(r.p(), r.p() + r.size());
+}
+
+void launch(Function f, const std::vector<Arg> &args, const uint32_t size[3], DeviceResources *resources, unsigned threads) {
+    auto params = f.arguments();
+    if (params.size() != args.size()) { fail("kernel argument count mismatch"); }
+    auto total = static_cast<uint64_t>(size[0]) * size[1] * size[2];
+    auto block = f.block_size();
+    std::atomic<uint64_t> cursor{0u};
+    std::mutex error_mutex;
+    std::string error;
+    auto worker = [&] {
+        try {
+            for (;;) {
+                auto begin = cursor.fetch_add(64u);
+                if (begin >= total) { break; }
+                for (auto id = begin; id < std::min<uint64_t>(begin + 64u, total); id++) {
+                    uint32_t d[4] = {static_cast<uint32_t>(id % size[0]), static_cast<uint32_t>(id / size[0] % size[1]),
+                                     static_cast<uint32_t>(id / size[0] / size[1]), 0u};
+                    uint32_t ds[4] = {size[0], size[1], size[2], 0u};
+                    uint32_t tid[4] = {d[0] % block.x, d[1] % block.y, d[2] % block.z, 0u};
+                    uint32_t bid[4] = {d[0] / block.x, d[1] / block.y, d[2] / block.z, 0u};
+                    uint32_t zero[4] = {0u, 0u, 0u, 0u};
+                    Machine m{f, resources};
+                    for (auto i = 0u; i < params.size(); i++) { m.bind_arg(params[i], args[i]); }
+                    for (auto v : f.builtin_variables()) {
+                        switch (v.tag()) {
+                            case Variable::Tag::DISPATCH_ID: m.bind_value(v, reinterpret_cast<const std::byte *>(d)); break;
+                            case Variable::Tag::DISPATCH_SIZE: m.bind_value(v, reinterpret_cast<const std::byte *>(ds)); break;
+                            case Variable::Tag::THREAD_ID: m.bind_value(v, reinterpret_cast<const std::byte *>(tid)); break;
+                            case Variable::Tag::BLOCK_ID: m.bind_value(v, reinterpret_cast<const std::byte *>(bid)); break;
+                            default: m.bind_value(v, reinterpret_cast<const std::byte *>(zero)); break;
+                        }
+                    }
+                    (void)m.run();
+                }
+            }
+        } catch (const std::exception &e) {
+            std::scoped_lock lock{error_mutex};
+            if (error.empty()) { error = e.what(); }
+            cursor.store(total);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (auto i = 1u; i < std::max(threads, 1u); i++) { pool.emplace_back(worker); }
+    worker();
+    for (auto &t : pool) { t.join(); }
+    if (!error.empty()) { throw std::runtime_error(error); }
 }
 
 }// namespace refinterp

@@ -326,7 +326,9 @@ int refpin_eval(const char *name, const uint32_t *in, uint32_t *out, int count, 
             for (auto a : f.arguments()) {
                 refinterp::Arg arg;
                 if (a.is_resource()) {
-                    arg.buffer = {static_cast<std::byte *>(buffer), static_cast<size_t>(buffer_count)};
+                    auto elem = a.type()->element();
+                    arg.kind = refinterp::Arg::Kind::BUFFER;
+                    arg.buffer = {static_cast<std::byte *>(buffer), static_cast<size_t>(buffer_count) * align_up(elem->size(), elem->alignment())};
                 } else {
                     arg.bytes.assign(a.type()->size(), std::byte{0});
                     words_to_bytes(a.type(), in, arg.bytes.data());

@@ -1,0 +1,425 @@
+// refdevice.cpp — "interp": a LuisaCompute backend that executes kernels with the AST interpreter (interp.cpp).
+// TEST INFRASTRUCTURE; see oracle/ref/README.md.
+//
+// It implements LuisaCompute's DeviceInterface (include/luisa/runtime/rhi/device_interface.h) the way the reference's own
+// backends do (src/compute/src/backends/cuda/cuda_device.cpp is the model for which calls must work): buffers are host
+// memory, shaders keep the recorded AST, a dispatch runs the AST once per dispatch id on the host's cores, bindless
+// arrays / meshes / accels are small host tables.  Built as `liblc-backend-interp.so` next to the reference's own plugins
+// and CLI (oracle/_ref/bin), it is selected like any other backend: `luisa-render-cli -b interp scene.luisa` runs the
+// UNMODIFIED reference renderer end to end.
+//
+// Ray / triangle intersection is the one third-party piece of the reference's path (OptiX / Embree); here it
+// is a brute-force loop over all triangles with the Moeller-Trumbore arithmetic this repository's oracle and CUDA kernels
+// use (oracle/oracle.cpp: trace_brute), so that hits are comparable bit for bit.
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <thread>
+
+#include <luisa/ast/function_builder.h>
+#include <luisa/core/logging.h>
+#include <luisa/runtime/context.h>
+#include <luisa/runtime/device.h>
+#include <luisa/runtime/rhi/command.h>
+#include <luisa/runtime/rhi/device_interface.h>
+#include <luisa/runtime/command_list.h>
+
+#include "interp.h"
+
+namespace luisa::compute::interp {
+
+namespace {
+
+struct BufferObject {
+    luisa::vector<std::byte> data;
+    size_t stride{0u};
+};
+
+struct BindlessObject {
+    struct Slot {
+        uint64_t buffer{0u};
+        size_t offset{0u};
+    };
+    luisa::vector<Slot> slots;
+};
+
+struct MeshObject {
+    uint64_t vertex_buffer{0u};
+    size_t vertex_offset{0u}, vertex_size{0u}, vertex_stride{0u};
+    uint64_t triangle_buffer{0u};
+    size_t triangle_offset{0u}, triangle_size{0u};
+};
+
+struct AccelObject {
+    struct Instance {
+        float affine[12]{1.f, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f};// row-major 3x4, object -> world
+        float inverse[12]{1.f, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f};
+        uint64_t mesh{0u};
+        uint32_t visibility{0xffu};
+        bool opaque{true};
+    };
+    luisa::vector<Instance> instances;
+};
+
+struct ShaderObject {
+    luisa::shared_ptr<const detail::FunctionBuilder> builder;
+    luisa::vector<Argument> bound;
+};
+
+struct StreamObject {};
+struct EventObject {};
+
+template<typename T>
+[[nodiscard]] T *object(uint64_t handle) noexcept { return reinterpret_cast<T *>(handle); }
+
+void invert_affine(const float m[12], float out[12]) noexcept {// rows of the 3x4 matrix [A | t]; out = [A^-1 | -A^-1 t]
+    auto a = [&](int r, int c) { return static_cast<double>(m[r * 4 + c]); };
+    auto det = a(0, 0) * (a(1, 1) * a(2, 2) - a(1, 2) * a(2, 1)) -
+               a(0, 1) * (a(1, 0) * a(2, 2) - a(1, 2) * a(2, 0)) +
+               a(0, 2) * (a(1, 0) * a(2, 1) - a(1, 1) * a(2, 0));
+    auto inv_det = 1.0 / det;
+    double inv[3][3];
+    inv[0][0] = (a(1, 1) * a(2, 2) - a(1, 2) * a(2, 1)) * inv_det;
+    inv[0][1] = (a(0, 2) * a(2, 1) - a(0, 1) * a(2, 2)) * inv_det;
+    inv[0][2] = (a(0, 1) * a(1, 2) - a(0, 2) * a(1, 1)) * inv_det;
+    inv[1][0] = (a(1, 2) * a(2, 0) - a(1, 0) * a(2, 2)) * inv_det;
+    inv[1][1] = (a(0, 0) * a(2, 2) - a(0, 2) * a(2, 0)) * inv_det;
+    inv[1][2] = (a(0, 2) * a(1, 0) - a(0, 0) * a(1, 2)) * inv_det;
+    inv[2][0] = (a(1, 0) * a(2, 1) - a(1, 1) * a(2, 0)) * inv_det;
+    inv[2][1] = (a(0, 1) * a(2, 0) - a(0, 0) * a(2, 1)) * inv_det;
+    inv[2][2] = (a(0, 0) * a(1, 1) - a(0, 1) * a(1, 0)) * inv_det;
+    for (auto r = 0; r < 3; r++) {
+        for (auto c = 0; c < 3; c++) { out[r * 4 + c] = static_cast<float>(inv[r][c]); }
+        out[r * 4 + 3] = static_cast<float>(-(inv[r][0] * a(0, 3) + inv[r][1] * a(1, 3) + inv[r][2] * a(2, 3)));
+    }
+}
+
+}// namespace
+
+class InterpDevice final : public DeviceInterface, public refinterp::DeviceResources {
+
+private:
+    unsigned _threads;
+
+public:
+    explicit InterpDevice(Context &&ctx) noexcept
+        : DeviceInterface{std::move(ctx)}, _threads{std::max(1u, std::thread::hardware_concurrency())} {
+        if (auto env = std::getenv("LUISA_INTERP_THREADS")) { _threads = std::max(1, std::atoi(env)); }
+    }
+
+    void *native_handle() const noexcept override { return const_cast<InterpDevice *>(this); }
+    uint compute_warp_size() const noexcept override { return 1u; }
+
+    // ---- buffers
+    BufferCreationInfo create_buffer(const Type *element, size_t elem_count, void *) noexcept override {
+        auto stride = element == Type::of<void>() ? size_t{1u} : (element->size() + element->alignment() - 1u) / element->alignment() * element->alignment();
+        auto b = new BufferObject;
+        b->stride = stride;
+        b->data.resize(std::max<size_t>(stride * elem_count, 16u), std::byte{0});
+        BufferCreationInfo info{};
+        info.handle = reinterpret_cast<uint64_t>(b);
+        info.native_handle = b->data.data();
+        info.element_stride = stride;
+        info.total_size_bytes = stride * elem_count;
+        return info;
+    }
+    BufferCreationInfo create_buffer(const ir::CArc<ir::Type> *, size_t, void *) noexcept override {
+        LUISA_ERROR_WITH_LOCATION("interp: IR buffers are not supported.");
+    }
+    void destroy_buffer(uint64_t handle) noexcept override { delete object<BufferObject>(handle); }
+
+    // ---- textures: not needed by the paths exercised (constant textures live in a buffer, the film is a buffer)
+    ResourceCreationInfo create_texture(PixelFormat, uint, uint, uint, uint, uint, bool, bool) noexcept override {
+        LUISA_ERROR_WITH_LOCATION("interp: device textures are not implemented.");
+    }
+    void destroy_texture(uint64_t) noexcept override {}
+
+    // ---- bindless arrays
+    ResourceCreationInfo create_bindless_array(size_t size) noexcept override {
+        auto a = new BindlessObject;
+        a->slots.resize(size);
+        return {reinterpret_cast<uint64_t>(a), a};
+    }
+    void destroy_bindless_array(uint64_t handle) noexcept override { delete object<BindlessObject>(handle); }
+
+    // ---- streams / events: everything executes synchronously inside dispatch()
+    ResourceCreationInfo create_stream(StreamTag) noexcept override {
+        auto s = new StreamObject;
+        return {reinterpret_cast<uint64_t>(s), s};
+    }
+    void destroy_stream(uint64_t handle) noexcept override { delete object<StreamObject>(handle); }
+    void synchronize_stream(uint64_t) noexcept override {}
+    void set_stream_log_callback(uint64_t, const StreamLogCallback &) noexcept override {}
+    ResourceCreationInfo create_event() noexcept override {
+        auto e = new EventObject;
+        return {reinterpret_cast<uint64_t>(e), e};
+    }
+    void destroy_event(uint64_t handle) noexcept override { delete object<EventObject>(handle); }
+    void signal_event(uint64_t, uint64_t, uint64_t) noexcept override {}
+    void wait_event(uint64_t, uint64_t, uint64_t) noexcept override {}
+    bool is_event_completed(uint64_t, uint64_t) const noexcept override { return true; }
+    void synchronize_event(uint64_t, uint64_t) noexcept override {}
+
+    // ---- swapchains: none
+    SwapchainCreationInfo create_swapchain(uint64_t, uint64_t, uint, uint, bool, bool, uint) noexcept override {
+        LUISA_ERROR_WITH_LOCATION("interp: no swapchains.");
+    }
+    void destroy_swap_chain(uint64_t) noexcept override {}
+    void present_display_in_stream(uint64_t, uint64_t, uint64_t) noexcept override {}
+
+    // ---- shaders
+    ShaderCreationInfo create_shader(const ShaderOption &, Function kernel) noexcept override {
+        auto s = new ShaderObject;
+        s->builder = kernel.shared_builder();
+        for (auto &&binding : kernel.bound_arguments()) {// as cuda_device.cpp:619-646
+            luisa::visit(
+                [s]<typename T>(T b) noexcept {
+                    Argument a{};
+                    if constexpr (std::is_same_v<T, Function::BufferBinding>) {
+                        a.tag = Argument::Tag::BUFFER;
+                        a.buffer = {b.handle, b.offset, b.size};
+                    } else if constexpr (std::is_same_v<T, Function::BindlessArrayBinding>) {
+                        a.tag = Argument::Tag::BINDLESS_ARRAY;
+                        a.bindless_array.handle = b.handle;
+                    } else if constexpr (std::is_same_v<T, Function::AccelBinding>) {
+                        a.tag = Argument::Tag::ACCEL;
+                        a.accel.handle = b.handle;
+                    } else if constexpr (std::is_same_v<T, Function::TextureBinding>) {
+                        LUISA_ERROR_WITH_LOCATION("interp: texture bindings are not implemented.");
+                    } else {
+                        LUISA_ERROR_WITH_LOCATION("interp: unbound captured argument.");
+                    }
+                    s->bound.emplace_back(a);
+                },
+                binding);
+        }
+        ShaderCreationInfo info{};
+        info.handle = reinterpret_cast<uint64_t>(s);
+        info.native_handle = s;
+        info.block_size = kernel.block_size();
+        return info;
+    }
+    ShaderCreationInfo create_shader(const ShaderOption &, const ir::KernelModule *) noexcept override {
+        LUISA_ERROR_WITH_LOCATION("interp: IR kernels are not supported.");
+    }
+    ShaderCreationInfo load_shader(luisa::string_view, luisa::span<const Type *const>) noexcept override {
+        LUISA_ERROR_WITH_LOCATION("interp: AOT shaders are not supported.");
+    }
+    Usage shader_argument_usage(uint64_t handle, size_t index) noexcept override {
+        Function f{object<ShaderObject>(handle)->builder.get()};
+        return f.variable_usage(f.arguments()[index].uid());
+    }
+    void destroy_shader(uint64_t handle) noexcept override { delete object<ShaderObject>(handle); }
+
+    // ---- ray tracing resources
+    ResourceCreationInfo create_mesh(const AccelOption &) noexcept override {
+        auto m = new MeshObject;
+        return {reinterpret_cast<uint64_t>(m), m};
+    }
+    void destroy_mesh(uint64_t handle) noexcept override { delete object<MeshObject>(handle); }
+    ResourceCreationInfo create_procedural_primitive(const AccelOption &) noexcept override {
+        LUISA_ERROR_WITH_LOCATION("interp: procedural primitives are not implemented.");
+    }
+    void destroy_procedural_primitive(uint64_t) noexcept override {}
+    ResourceCreationInfo create_accel(const AccelOption &) noexcept override {
+        auto a = new AccelObject;
+        return {reinterpret_cast<uint64_t>(a), a};
+    }
+    void destroy_accel(uint64_t handle) noexcept override { delete object<AccelObject>(handle); }
+    void set_name(luisa::compute::Resource::Tag, uint64_t, luisa::string_view) noexcept override {}
+
+    // ---- command execution
+    void dispatch(uint64_t, CommandList &&list) noexcept override {
+        struct Visitor final : CommandVisitor {
+            InterpDevice *device;
+            explicit Visitor(InterpDevice *d) noexcept : device{d} {}
+            void visit(const BufferUploadCommand *c) noexcept override {
+                auto b = object<BufferObject>(c->handle());
+                std::memcpy(b->data.data() + c->offset(), c->data(), c->size());
+            }
+            void visit(const BufferDownloadCommand *c) noexcept override {
+                auto b = object<BufferObject>(c->handle());
+                std::memcpy(c->data(), b->data.data() + c->offset(), c->size());
+            }
+            void visit(const BufferCopyCommand *c) noexcept override {
+                std::memmove(object<BufferObject>(c->dst_handle())->data.data() + c->dst_offset(),
+                             object<BufferObject>(c->src_handle())->data.data() + c->src_offset(), c->size());
+            }
+            void visit(const BufferToTextureCopyCommand *) noexcept override { LUISA_ERROR_WITH_LOCATION("interp: textures."); }
+            void visit(const TextureUploadCommand *) noexcept override { LUISA_ERROR_WITH_LOCATION("interp: textures."); }
+            void visit(const TextureDownloadCommand *) noexcept override { LUISA_ERROR_WITH_LOCATION("interp: textures."); }
+            void visit(const TextureCopyCommand *) noexcept override { LUISA_ERROR_WITH_LOCATION("interp: textures."); }
+            void visit(const TextureToBufferCopyCommand *) noexcept override { LUISA_ERROR_WITH_LOCATION("interp: textures."); }
+            void visit(const CurveBuildCommand *) noexcept override { LUISA_ERROR_WITH_LOCATION("interp: curves."); }
+            void visit(const ProceduralPrimitiveBuildCommand *) noexcept override { LUISA_ERROR_WITH_LOCATION("interp: procedural primitives."); }
+            void visit(const CustomCommand *) noexcept override { LUISA_ERROR_WITH_LOCATION("interp: custom commands."); }
+            void visit(const MeshBuildCommand *c) noexcept override {
+                auto m = object<MeshObject>(c->handle());
+                m->vertex_buffer = c->vertex_buffer();
+                m->vertex_offset = c->vertex_buffer_offset();
+                m->vertex_size = c->vertex_buffer_size();
+                m->vertex_stride = c->vertex_stride();
+                m->triangle_buffer = c->triangle_buffer();
+                m->triangle_offset = c->triangle_buffer_offset();
+                m->triangle_size = c->triangle_buffer_size();
+            }
+            void visit(const AccelBuildCommand *c) noexcept override {
+                auto a = object<AccelObject>(c->handle());
+                a->instances.resize(c->instance_count());
+                using M = AccelBuildCommand::Modification;
+                for (auto &&m : c->modifications()) {
+                    auto &inst = a->instances[m.index];
+                    if (m.flags & M::flag_primitive) { inst.mesh = m.primitive; }
+                    if (m.flags & M::flag_transform) {
+                        std::memcpy(inst.affine, m.affine, sizeof(inst.affine));
+                        invert_affine(inst.affine, inst.inverse);
+                    }
+                    if (m.flags & M::flag_visibility) { inst.visibility = m.vis_mask; }
+                    if (m.flags & M::flag_opaque_on) { inst.opaque = true; }
+                    if (m.flags & M::flag_opaque_off) { inst.opaque = false; }
+                }
+            }
+            void visit(const BindlessArrayUpdateCommand *c) noexcept override {
+                auto a = object<BindlessObject>(c->handle());
+                using Op = BindlessArrayUpdateCommand::Modification::Operation;
+                for (auto &&m : const_cast<BindlessArrayUpdateCommand *>(c)->steal_modifications()) {
+                    if (m.buffer.op == Op::EMPLACE) { a->slots[m.slot] = {m.buffer.handle, m.buffer.offset_bytes}; }
+                    else if (m.buffer.op == Op::REMOVE) { a->slots[m.slot] = {}; }
+                    if (m.tex2d.op == Op::EMPLACE || m.tex3d.op == Op::EMPLACE) { LUISA_ERROR_WITH_LOCATION("interp: bindless textures."); }
+                }
+            }
+            void visit(const ShaderDispatchCommand *c) noexcept override { device->run(c); }
+        } visitor{this};
+        for (auto &&cmd : list.commands()) { cmd->accept(visitor); }
+        for (auto &&callback : list.callbacks()) { callback(); }
+    }
+
+    void run(const ShaderDispatchCommand *c) noexcept {
+        auto shader = object<ShaderObject>(c->handle());
+        Function kernel{shader->builder.get()};
+        if (c->is_indirect() || c->is_multiple_dispatch()) { LUISA_ERROR_WITH_LOCATION("interp: indirect / batched dispatch."); }
+        luisa::vector<Argument> all{shader->bound};
+        for (auto &&a : c->arguments()) { all.emplace_back(a); }
+        auto params = kernel.arguments();
+        LUISA_ASSERT(params.size() == all.size(), "interp: kernel takes {} arguments, {} given.", params.size(), all.size());
+        std::vector<refinterp::Arg> args(all.size());
+        for (auto i = 0u; i < all.size(); i++) {
+            auto &&a = all[i];
+            switch (a.tag) {
+                case Argument::Tag::BUFFER: {
+                    auto b = object<BufferObject>(a.buffer.handle);
+                    args[i].kind = refinterp::Arg::Kind::BUFFER;
+                    args[i].buffer = {b->data.data() + a.buffer.offset, a.buffer.size};
+                    break;
+                }
+                case Argument::Tag::UNIFORM: {
+                    auto u = c->uniform(a.uniform);
+                    args[i].bytes.assign(u.begin(), u.end());
+                    args[i].bytes.resize(params[i].type()->size());
+                    break;
+                }
+                case Argument::Tag::BINDLESS_ARRAY:
+                    args[i].kind = refinterp::Arg::Kind::BINDLESS_ARRAY;
+                    args[i].handle = a.bindless_array.handle;
+                    break;
+                case Argument::Tag::ACCEL:
+                    args[i].kind = refinterp::Arg::Kind::ACCEL;
+                    args[i].handle = a.accel.handle;
+                    break;
+                default: LUISA_ERROR_WITH_LOCATION("interp: texture arguments are not implemented.");
+            }
+        }
+        auto size = c->dispatch_size();
+        uint32_t s[3] = {size.x, size.y, size.z};
+        try {
+            refinterp::launch(kernel, args, s, this, _threads);
+        } catch (const std::exception &e) {
+            LUISA_ERROR_WITH_LOCATION("interp: kernel failed: {}", e.what());
+        }
+    }
+
+    // ---- refinterp::DeviceResources
+    refinterp::BufferArg bindless_buffer(uint64_t array, uint32_t slot) override {
+        auto a = object<BindlessObject>(array);
+        if (slot >= a->slots.size() || a->slots[slot].buffer == 0u) { throw std::runtime_error("empty bindless buffer slot"); }
+        auto b = object<BufferObject>(a->slots[slot].buffer);
+        return {b->data.data() + a->slots[slot].offset, b->data.size() - a->slots[slot].offset};
+    }
+
+    template<bool any_hit>
+    refinterp::HitData trace(uint64_t accel, const refinterp::RayData &ray, uint32_t mask) const {
+        // oracle/oracle.cpp: trace_brute — the same expressions, explicit fma where the oracle / CUDA kernels spell it out
+        auto a = object<AccelObject>(accel);
+        refinterp::HitData best{~0u, ~0u, {0.f, 0.f}, ray.t_max, 0u};
+        auto tbest = ray.t_max;
+        auto fdot = [](const float x[3], const float y[3]) { return std::fmaf(x[0], y[0], std::fmaf(x[1], y[1], x[2] * y[2])); };
+        auto fcross = [](const float x[3], const float y[3], float out[3]) {
+            out[0] = std::fmaf(x[1], y[2], -(x[2] * y[1]));
+            out[1] = std::fmaf(x[2], y[0], -(x[0] * y[2]));
+            out[2] = std::fmaf(x[0], y[1], -(x[1] * y[0]));
+        };
+        for (auto i = 0u; i < a->instances.size(); i++) {
+            auto &inst = a->instances[i];
+            if ((inst.visibility & mask) == 0u || inst.mesh == 0u) { continue; }
+            auto w = inst.inverse;
+            auto o = ray.origin, d = ray.direction;
+            float oo[3] = {std::fmaf(w[0], o[0], std::fmaf(w[1], o[1], std::fmaf(w[2], o[2], w[3]))),
+                           std::fmaf(w[4], o[0], std::fmaf(w[5], o[1], std::fmaf(w[6], o[2], w[7]))),
+                           std::fmaf(w[8], o[0], std::fmaf(w[9], o[1], std::fmaf(w[10], o[2], w[11])))};
+            float dd[3] = {std::fmaf(w[0], d[0], std::fmaf(w[1], d[1], w[2] * d[2])),
+                           std::fmaf(w[4], d[0], std::fmaf(w[5], d[1], w[6] * d[2])),
+                           std::fmaf(w[8], d[0], std::fmaf(w[9], d[1], w[10] * d[2]))};
+            auto mesh = object<MeshObject>(inst.mesh);
+            auto vbuf = object<BufferObject>(mesh->vertex_buffer)->data.data() + mesh->vertex_offset;
+            auto tbuf = reinterpret_cast<const uint32_t *>(object<BufferObject>(mesh->triangle_buffer)->data.data() + mesh->triangle_offset);
+            auto tri_count = mesh->triangle_size / 12u;
+            auto position = [&](uint32_t v) { return reinterpret_cast<const float *>(vbuf + v * mesh->vertex_stride); };
+            for (auto k = 0u; k < tri_count; k++) {
+                auto p0 = position(tbuf[3u * k]), p1 = position(tbuf[3u * k + 1u]), p2 = position(tbuf[3u * k + 2u]);
+                float e1[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]};
+                float e2[3] = {p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2]};
+                float pvec[3], qvec[3];
+                fcross(dd, e2, pvec);
+                auto det = fdot(e1, pvec);
+                if (!(det != 0.0f)) { continue; }
+                auto inv_det = 1.0f / det;
+                float tvec[3] = {oo[0] - p0[0], oo[1] - p0[1], oo[2] - p0[2]};
+                auto u = fdot(tvec, pvec) * inv_det;
+                if (!(u >= 0.0f && u <= 1.0f)) { continue; }
+                fcross(tvec, e1, qvec);
+                auto v = fdot(dd, qvec) * inv_det;
+                if (!(v >= 0.0f && u + v <= 1.0f)) { continue; }
+                auto t = fdot(e2, qvec) * inv_det;
+                if (!(t > ray.t_min && t < tbest)) { continue; }
+                tbest = t;
+                best = {i, k, {u, v}, t, 0u};
+                if constexpr (any_hit) { return best; }
+            }
+        }
+        return best;
+    }
+    refinterp::HitData trace_closest(uint64_t accel, const refinterp::RayData &ray, uint32_t mask) override { return trace<false>(accel, ray, mask); }
+    bool trace_any(uint64_t accel, const refinterp::RayData &ray, uint32_t mask) override { return trace<true>(accel, ray, mask).inst != ~0u; }
+    void instance_transform(uint64_t accel, uint32_t index, float out[16]) override {
+        auto &m = object<AccelObject>(accel)->instances.at(index).affine;
+        for (auto c = 0; c < 4; c++) {
+            for (auto r = 0; r < 3; r++) { out[c * 4 + r] = m[r * 4 + c]; }
+            out[c * 4 + 3] = c == 3 ? 1.f : 0.f;
+        }
+    }
+};
+
+}// namespace luisa::compute::interp
+
+LUISA_EXPORT_API luisa::compute::DeviceInterface *create(luisa::compute::Context &&ctx, const luisa::compute::DeviceConfig *) noexcept {
+    return luisa::new_with_allocator<luisa::compute::interp::InterpDevice>(std::move(ctx));
+}
+
+LUISA_EXPORT_API void destroy(luisa::compute::DeviceInterface *device) noexcept {
+    luisa::delete_with_allocator(device);
+}
+
+LUISA_EXPORT_API void backend_device_names(luisa::vector<luisa::string> &names) noexcept {
+    names.clear();
+    names.emplace_back("host AST interpreter");
+}
