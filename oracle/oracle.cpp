@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -1749,6 +1750,7 @@ inline float sum3(V3 a) { return a.x + a.y + a.z; }
 inline float comp(V3 a, uint32_t i) { return i == 0u ? a.x : i == 1u ? a.y : a.z; }
 
 // HomogeneousMediumClosure::sample, src/media/homogeneous.cpp:48-118
+std::atomic<bool> g_hg_args_right_to_left{false};
 MediumSample homogeneous_sample(const lrk_medium &m, V3 o, V3 d, float t_max, PCG32 &rng) {
     V3 sigma_a = v3(m.sigma_a[0], m.sigma_a[1], m.sigma_a[2]), sigma_s = v3(m.sigma_s[0], m.sigma_s[1], m.sigma_s[2]);
     V3 sigma_t = sigma_a + sigma_s;
@@ -1791,7 +1793,14 @@ MediumSample homogeneous_sample(const lrk_medium &m, V3 o, V3 d, float t_max, PC
             s.event = 1u;
             V3 Tr = exp3(-sigma_t * t);
             // HenyeyGreenstein::sample_p(wo = -d, u), src/phasefunctions/henyey_greenstein.cpp:28-48
-            float u0 = rng.uniform_float(), u1 = rng.uniform_float();
+            // make_float2(rng.uniform_float(), rng.uniform_float()) (homogeneous.cpp:91): the ORDER of the two draws is the C++
+            // compiler's argument evaluation order - unspecified by the language.  clang and MSVC (what the reference's
+            // supported toolchains are: BUILD.md) evaluate left to right: u.x is drawn first; GCC evaluates right to left.
+            // The oracle follows clang/MSVC; oracle_set_hg_args_right_to_left(1) mirrors a GCC build of the reference (the only
+            // one that can be built here, oracle/ref) so that tests/test_ref_render.py can compare like with like.
+            float u0, u1;
+            if (g_hg_args_right_to_left.load(std::memory_order_relaxed)) { u1 = rng.uniform_float(); u0 = rng.uniform_float(); }
+            else { u0 = rng.uniform_float(); u1 = rng.uniform_float(); }
             float g = m.g;
             float cosTheta = std::fabs(g) < 1e-3f ? 1.f - 2.f * u0
                                                   : -1.f / (2.f * g) * (1.f + sqr(g) - sqr((1.f - sqr(g)) / (1.f + g - 2.f * g * u0)));
@@ -2217,6 +2226,8 @@ struct LambertBxDF {
     V3 evaluate(V3 wo, V3 wi) const { return lambert_evaluate(r, wo, wi); }
 };
 }// namespace
+
+extern "C" void oracle_set_hg_args_right_to_left(int enabled) { g_hg_args_right_to_left.store(enabled != 0); }
 
 extern "C" int oracle_unit(const char *name_c, const uint32_t *in, uint32_t *out, int count, const void *buffer, uint64_t buffer_count) {
     const std::string name{name_c};
