@@ -790,6 +790,194 @@ struct DisneySurface final : Surface {
     }
 };
 
+// roughness -> alpha of Mirror / Glass / Plastic / Metal (e.g. mirror.cpp:144-155): one channel is used for both axes,
+// remap_roughness applies TrowbridgeReitzDistribution::roughness_to_alpha = max(r^2, 1e-4) (scattering.cpp:129-135)
+void flatten_alpha(const Texture *roughness, bool remap, float dflt, float out[2]) {
+    out[0] = out[1] = dflt;
+    if (roughness == nullptr) return;
+    auto r = roughness->value();
+    auto r2a = [](float x) { return std::max(x * x, 1e-4f); };
+    if (roughness->channels() == 1u) {
+        out[0] = out[1] = remap ? r2a(r.x) : r.x;
+    } else {
+        out[0] = remap ? r2a(r.x) : r.x;
+        out[1] = remap ? r2a(r.y) : r.y;
+    }
+}
+
+const Texture *constant_surface_texture(Scene *s, const NodeDesc *d, const char *name) {
+    auto t = s->load_texture(d->node(name));
+    if (t && !t->is_constant())
+        throw Error("Only constant textures are supported for '" + std::string{name} + "' of " + std::string{d->impl_type()} +
+                    " surfaces. [" + d->location() + "]");
+    return t;
+}
+
+struct MirrorSurface final : Surface {
+    // src/surfaces/mirror.cpp:13-36,142-162
+    const Texture *color, *roughness;
+    bool remap_roughness;
+    MirrorSurface(Scene *s, const NodeDesc *d) : Surface{s, d, Tag::SURFACE} {
+        color = constant_surface_texture(s, d, d->has_property("color") ? "color" : "Kd");
+        roughness = constant_surface_texture(s, d, "roughness");
+        remap_roughness = d->b("remap_roughness", true);
+    }
+    lrk_surface flatten(TextureTable &textures) const override {
+        lrk_surface out{};
+        out.type = LRK_SURFACE_MIRROR;
+        auto c = decode_albedo(color, nullptr);
+        out.p[0] = c.x; out.p[1] = c.y; out.p[2] = c.z;
+        flatten_alpha(roughness, remap_roughness, 0.f, &out.p[3]);
+        flatten_wrappers(out, textures);
+        return out;
+    }
+};
+
+struct GlassSurface final : Surface {
+    // src/surfaces/glass.cpp:54-91,222-279
+    const Texture *kr, *kt, *roughness, *eta{};
+    float named_eta{0.f};
+    bool remap_roughness;
+    GlassSurface(Scene *s, const NodeDesc *d) : Surface{s, d, Tag::SURFACE} {
+        kr = constant_surface_texture(s, d, "Kr");
+        kt = constant_surface_texture(s, d, "Kt");
+        roughness = constant_surface_texture(s, d, "roughness");
+        remap_roughness = d->b("remap_roughness", true);
+        if (auto name = d->s("eta", ""); !name.empty()) {
+            // built-in glasses (glass.cpp:28-41): refractive index at the Fraunhofer C line (656.27 nm) - with the fixed sRGB
+            // spectrum the closure reads the first component of the (C, d, F) triple only (glass.cpp:262-264)
+            static const std::pair<const char *, float> known[] = {
+                {"bk7", 1.5140814565098806f}, {"baf10", 1.665552211440938f}, {"fk51a", 1.4846524304153899f},
+                {"lasf9", 1.8422161861952726f}, {"sf5", 1.6663001504164476f}, {"sf10", 1.720557014155419f},
+                {"sf11", 1.7754589288508518f}, {"diamond", 2.410486117067883f}, {"ice", 1.3077084260466776f},
+                {"quartz", 1.4562471554155727f}, {"salt", 1.5404463273409252f}, {"sapphire", 1.764706495252994f}};
+            for (auto &c : name) c = static_cast<char>(std::tolower(c));
+            for (auto &&[k, v] : known) if (name == k) named_eta = v;
+            // unknown names: the reference warns and falls back to 1.5 (glass.cpp:65-71)
+        } else {
+            eta = constant_surface_texture(s, d, "eta");
+            if (eta && (eta->channels() == 2u || eta->channels() == 4u))
+                throw Error("Invalid channel count for GlassSurface::eta. [" + d->location() + "]");
+        }
+    }
+    lrk_surface flatten(TextureTable &textures) const override {
+        lrk_surface out{};
+        out.type = LRK_SURFACE_GLASS;
+        float kr_lum = 1.f, kt_lum = 1.f;
+        auto r = kr ? decode_albedo(kr, &kr_lum) : float3{1.f, 1.f, 1.f};
+        auto t = kt ? decode_albedo(kt, &kt_lum) : float3{1.f, 1.f, 1.f};
+        out.p[0] = r.x; out.p[1] = r.y; out.p[2] = r.z;
+        out.p[3] = t.x; out.p[4] = t.y; out.p[5] = t.z;
+        out.p[6] = named_eta != 0.f ? named_eta : (eta ? eta->value().x : 1.5f);
+        flatten_alpha(roughness, remap_roughness, 0.f, &out.p[7]);
+        out.p[9] = kr_lum == 0.f ? 0.f : kr_lum / (kr_lum + kt_lum);
+        flatten_wrappers(out, textures);
+        return out;
+    }
+};
+
+struct PlasticSurface final : Surface {
+    // src/surfaces/plastic.cpp:42-66,252-291
+    const Texture *kd, *roughness, *sigma_a, *eta, *thickness;
+    bool remap_roughness;
+    PlasticSurface(Scene *s, const NodeDesc *d) : Surface{s, d, Tag::SURFACE} {
+        kd = constant_surface_texture(s, d, "Kd");
+        roughness = constant_surface_texture(s, d, "roughness");
+        sigma_a = constant_surface_texture(s, d, "sigma_a");
+        eta = constant_surface_texture(s, d, "eta");
+        thickness = constant_surface_texture(s, d, "thickness");
+        remap_roughness = d->b("remap_roughness", true);
+    }
+    lrk_surface flatten(TextureTable &textures) const override {
+        lrk_surface out{};
+        out.type = LRK_SURFACE_PLASTIC;
+        auto e = (eta ? eta->value().x : 1.5f) / 1.f;// eta_i = 1
+        float kd_lum = 1.f, sa_lum = 0.f;
+        auto c = kd ? decode_albedo(kd, &kd_lum) : float3{1.f, 1.f, 1.f};
+        auto sa = sigma_a ? decode_albedo(sigma_a, &sa_lum) : float3{0.f, 0.f, 0.f};
+        auto th = thickness ? thickness->value().x : 1.f;
+        auto average_transmittance = std::exp(-2.f * sa_lum * th);
+        // fresnel_dielectric_integral (scattering.cpp:98-108): the fitted polynomials, Horner from the last coefficient
+        auto saturate1 = [](float x) { return std::fmin(std::fmax(x, 0.f), 1.f); };
+        float fdr;
+        if (e == 1.f) fdr = 0.f;
+        else if (e < 1.f) fdr = e * (e * (e * -0.90663979f + 2.23559031f) + -2.09069066f) + 0.75985009f;
+        else { auto x = 1.f / e; fdr = x * (x * -1.18995376f + 0.21762732f) + 0.97945724f; }
+        fdr = saturate1(fdr);
+        out.p[0] = c.x / (1.f - c.x * fdr);
+        out.p[1] = c.y / (1.f - c.y * fdr);
+        out.p[2] = c.z / (1.f - c.z * fdr);
+        out.p[3] = kd_lum * average_transmittance;
+        out.p[4] = sa.x; out.p[5] = sa.y; out.p[6] = sa.z;
+        out.p[7] = e;
+        flatten_alpha(roughness, remap_roughness, 0.f, &out.p[8]);
+        flatten_wrappers(out, textures);
+        return out;
+    }
+};
+
+struct MetalSurface final : Surface {
+    // src/surfaces/metal.cpp:52-151,273-310.  The complex index comes from an `eta` list of (wavelength, n, k) triples; the
+    // reference's eleven built-in metals are measured spectra shipped as a data table (metal_ior.inl.h) and are not
+    // reproduced here: a named `eta` fails at load with a message saying so.
+    const Texture *roughness, *kd;
+    bool remap_roughness;
+    float n[3], k[3];
+    MetalSurface(Scene *s, const NodeDesc *d) : Surface{s, d, Tag::SURFACE} {
+        roughness = constant_surface_texture(s, d, "roughness");
+        kd = constant_surface_texture(s, d, "Kd");
+        remap_roughness = d->b("remap_roughness", true);
+        if (auto name = d->s("eta", ""); !name.empty())
+            throw Error("Metal: built-in IOR tables ('" + name + "') are not available; give `eta` as a list of "
+                        "(wavelength, n, k) triples. [" + d->location() + "]");
+        auto eta = d->float_list("eta");
+        if (eta.empty() || eta.size() % 3u != 0u) throw Error("Invalid eta list size. [" + d->location() + "]");
+        auto count = eta.size() / 3u;
+        std::vector<float> lambda(count), nn(count), kk(count);
+        for (size_t i = 0; i < count; i++) { lambda[i] = eta[i * 3u]; nn[i] = eta[i * 3u + 1u]; kk[i] = eta[i * 3u + 2u]; }
+        if (!std::is_sorted(lambda.begin(), lambda.end())) throw Error("Unsorted wavelengths in eta list. [" + d->location() + "]");
+        if (lambda.front() > 360.f || lambda.back() < 830.f) throw Error("Invalid wavelength range in eta list. [" + d->location() + "]");
+        if (count < 2u) throw Error("Invalid eta list size. [" + d->location() + "]");
+        // the 5 nm look-up table over [360, 830] nm (:132-146) ...
+        constexpr uint32_t lut_size = (830u - 360u) / 5u + 1u;
+        std::vector<float> lut_n(lut_size), lut_k(lut_size);
+        for (uint32_t i = 0; i < lut_size; i++) {
+            auto wavelength = static_cast<float>(i * 5u + 360u);
+            auto lb = std::lower_bound(lambda.begin(), lambda.end(), wavelength);
+            auto index = std::clamp(static_cast<size_t>(std::distance(lambda.begin(), lb)), size_t{1u}, lambda.size() - 1u);
+            auto t = (wavelength - lambda[index - 1u]) / (lambda[index] - lambda[index - 1u]);
+            // std::lerp (C++20) as libstdc++ / libc++ implement it: exact at the end points, monotonic
+            auto std_lerp = [](float a, float b, float tt) {
+                if ((a <= 0.f && b >= 0.f) || (a >= 0.f && b <= 0.f)) return tt * b + (1.f - tt) * a;
+                if (tt == 1.f) return b;
+                auto x = a + tt * (b - a);
+                return (tt > 1.f) == (b > a) ? (b < x ? x : b) : (x < b ? x : b);
+            };
+            lut_n[i] = std_lerp(nn[index - 1u], nn[index], t);
+            lut_k[i] = std_lerp(kk[index - 1u], kk[index], t);
+        }
+        // ... sampled at the sRGB spectrum's three wavelengths (srgb.cpp:27-33, spec.h:22-23) by SPD::sample (spd.cpp:91-99)
+        const float peaks[3] = {602.785f, 539.285f, 445.772f};
+        for (int c = 0; c < 3; c++) {
+            auto t = (std::fmin(std::fmax(peaks[c], 360.f), 830.f) - 360.f) / 5.f;
+            auto i = static_cast<uint32_t>(std::fmin(t, static_cast<float>(lut_size - 2u)));
+            auto fr = t - std::floor(t);
+            n[c] = fr * (lut_n[i + 1u] - lut_n[i]) + lut_n[i];// lerp(a, b, t) = t * (b - a) + a
+            k[c] = fr * (lut_k[i + 1u] - lut_k[i]) + lut_k[i];
+        }
+    }
+    lrk_surface flatten(TextureTable &textures) const override {
+        lrk_surface out{};
+        out.type = LRK_SURFACE_METAL;
+        for (int c = 0; c < 3; c++) { out.p[c] = n[c]; out.p[3 + c] = k[c]; }
+        auto r = kd ? decode_albedo(kd, nullptr) : float3{1.f, 1.f, 1.f};
+        out.p[6] = r.x; out.p[7] = r.y; out.p[8] = r.z;
+        flatten_alpha(roughness, remap_roughness, .5f, &out.p[9]);
+        flatten_wrappers(out, textures);
+        return out;
+    }
+};
+
 struct NullSurface final : Surface {
     NullSurface(Scene *s, const NodeDesc *d) : Surface{s, d, Tag::SURFACE} {}
     bool is_null() const override { return true; }
@@ -831,6 +1019,10 @@ struct NullLight final : Light {
 }// namespace
 LRH_PLUGIN("surface-matte", MatteSurface)
 LRH_PLUGIN("surface-disney", DisneySurface)
+LRH_PLUGIN("surface-mirror", MirrorSurface)
+LRH_PLUGIN("surface-glass", GlassSurface)
+LRH_PLUGIN("surface-plastic", PlasticSurface)
+LRH_PLUGIN("surface-metal", MetalSurface)
 LRH_PLUGIN("surface-null", NullSurface)
 LRH_PLUGIN("light-diffuse", DiffuseLight)
 LRH_PLUGIN("light-null", NullLight)

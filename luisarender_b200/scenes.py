@@ -350,3 +350,66 @@ render {{
   shapes {{ @ball, @floor{lamp_ref} }}
 }}
 """
+
+
+def materials_box(resolution=(32, 24), spp=4, depth=8, rr_depth=0, rr_threshold=0.95, seed=19980810, subdivision=2,
+                  integrator="WavePath", output="materials.exr") -> str:
+    """a Cornell-like box with one Loop-subdivision sphere per closure of src/surfaces -
+    Mirror, Glass (built-in bk7), rough Glass, Plastic, Metal (custom eta list) - on a Matte floor, plus a mirror back wall."""
+    out = [
+        "Surface white : Matte { Kd : Constant { v { 0.725, 0.71, 0.68 } } }",
+        "Surface red : Matte { Kd : Constant { v { 0.63, 0.065, 0.05 } } }",
+        "Surface green : Plastic { Kd : Constant { v { 0.14, 0.45, 0.091 } } roughness : Constant { v { 0.3 } } }",
+        "Surface wall_mirror : Mirror { color : Constant { v { 0.9, 0.9, 0.95 } } roughness : Constant { v { 0.05 } } }",
+        "Surface m_mirror : Mirror { Kd : Constant { v { 0.95, 0.8, 0.6 } } }",
+        "Surface m_glass : Glass { eta { \"BK7\" } }",
+        "Surface m_rough_glass : Glass { Kr : Constant { v { 1.0, 0.9, 0.9 } } Kt : Constant { v { 0.7, 0.9, 1.0 } } "
+        "eta : Constant { v { 1.33 } } roughness : Constant { v { 0.4, 0.2 } } }",
+        "Surface m_plastic : Plastic { Kd : Constant { v { 0.2, 0.3, 0.8 } } roughness : Constant { v { 0.15 } } "
+        "sigma_a : Constant { v { 0.3, 0.1, 0.05 } } thickness : Constant { v { 0.5 } } eta : Constant { v { 1.45 } } }",
+        "Surface m_metal : Metal { eta { 350.0, 0.2, 1.9, 500.0, 0.35, 2.4, 600.0, 0.25, 3.0, 850.0, 0.2, 5.0 } "
+        "roughness : Constant { v { 0.25 } } Kd : Constant { v { 1.0, 0.85, 0.6 } } }",
+        "Light area_light : Diffuse { emission : Constant { v { 17.0, 14.0, 10.0 } } }",
+        f"Shape ball : Sphere {{ subdivision {{ {int(subdivision)} }} }}",
+    ]
+    shapes = []
+
+    def quad(name, pts, surface=None, light=None):
+        pos, idx = _mesh_props([pts])
+        attach = f"surface {{ @{surface} }}" if surface else f"light {{ @{light} }}"
+        out.append(f"Shape {name} : InlineMesh {{ positions {{ {pos} }} indices {{ {idx} }} {attach} }}")
+        shapes.append(f"@{name}")
+
+    quad("floor", [(-2.0, 0.0, 1.5), (2.0, 0.0, 1.5), (2.0, 0.0, -1.5), (-2.0, 0.0, -1.5)], "white")
+    quad("ceiling", [(-2.0, 2.5, 1.5), (-2.0, 2.5, -1.5), (2.0, 2.5, -1.5), (2.0, 2.5, 1.5)], "white")
+    quad("back", [(-2.0, 0.0, -1.5), (2.0, 0.0, -1.5), (2.0, 2.5, -1.5), (-2.0, 2.5, -1.5)], "wall_mirror")
+    quad("left", [(-2.0, 0.0, 1.5), (-2.0, 0.0, -1.5), (-2.0, 2.5, -1.5), (-2.0, 2.5, 1.5)], "red")
+    quad("right", [(2.0, 0.0, -1.5), (2.0, 0.0, 1.5), (2.0, 2.5, 1.5), (2.0, 2.5, -1.5)], "green")
+    quad("lamp", [(-0.6, 2.49, 0.4), (-0.6, 2.49, -0.4), (0.6, 2.49, -0.4), (0.6, 2.49, 0.4)], light="area_light")
+    for i, surface in enumerate(["m_mirror", "m_glass", "m_rough_glass", "m_plastic", "m_metal"]):
+        x = -1.5 + 0.75 * i
+        z = 0.3 if i % 2 == 0 else -0.4
+        out.append(f"Shape ball_{i} : Instance {{ shape {{ @ball }} surface {{ @{surface} }} "
+                   f"transform : SRT {{ scale {{ 0.33 }} translate {{ {_fmt(x)}, 0.33, {_fmt(z)} }} }} }}")
+        shapes.append(f"@ball_{i}")
+    out.append(f"""Camera camera : Pinhole {{
+  position {{ 0.0, 1.2, 5.2 }}
+  look_at {{ 0.0, 0.9, 0.0 }}
+  up {{ 0.0, 1.0, 0.0 }}
+  fov {{ 38.0 }}
+  spp {{ {int(spp)} }}
+  film : Color {{ resolution {{ {int(resolution[0])}, {int(resolution[1])} }} }}
+  filter : Box {{ radius {{ 0.5 }} }}
+  file {{ "{output}" }}
+}}""")
+    out.append(f"""render {{
+  integrator : {integrator} {{
+    depth {{ {int(depth)} }}
+    rr_depth {{ {int(rr_depth)} }}
+    rr_threshold {{ {_fmt(rr_threshold)} }}
+    sampler : Independent {{ seed {{ {int(seed)} }} }}
+  }}
+  cameras {{ @camera }}
+  shapes {{ {", ".join(shapes)} }}
+}}""")
+    return "\n".join(out) + "\n"

@@ -821,7 +821,7 @@ V3 fresnel_conductor(float cosThetaI, float etai, V3 etat, V3 k) {// :56-75
     V3 Rs = vdiv(t1 - t2, t1 + t2);
     V3 t3 = cosThetaI2 * a2plusb2 + sinThetaI2 * sinThetaI2;
     V3 t4 = t2 * sinThetaI2;
-    V3 Rp = Rs * vdiv(t3 - t4, t3 + t4);
+    V3 Rp = vdiv(Rs * (t3 - t4), t3 + t4);// Rs * (t3 - t4) / (t3 + t4): left to right
     return .5f * (Rp + Rs);
 }
 inline float fresnel_dielectric_integral(float eta) {// :98-108; polynomial() = Horner from the last coefficient, spec.h:45-51

@@ -32,7 +32,8 @@ from luisarender_b200.api import Scene  # noqa: E402
 from oracle import binding as O  # noqa: E402
 
 GOLDEN = REPO / "tests" / "golden" / "ref_renders.npz"
-CASES = ["cornell_wavepath", "cornell_megapath", "cornell_russian_roulette", "spheres_disney", "spheres_medium"]
+CASES = ["cornell_wavepath", "cornell_megapath", "cornell_russian_roulette", "spheres_disney", "spheres_medium",
+         "materials_wavepath", "materials_megapath_rr"]
 
 
 @pytest.fixture(scope="module")

@@ -37,6 +37,10 @@ def cases() -> dict[str, str]:
     c["spheres_disney"] = scenes.instanced_spheres(resolution=(32, 18), spp=2, depth=6, **spheres)
     # config C4: + homogeneous medium, MegaVPTNaive
     c["spheres_medium"] = scenes.instanced_spheres(resolution=(32, 18), spp=2, depth=6, medium=True, **spheres)
+    # row f3: Mirror, Glass (smooth / rough), Plastic and Metal closures; Russian roulette with the refraction eta scale
+    c["materials_wavepath"] = scenes.materials_box(resolution=(32, 24), spp=4, depth=8)
+    c["materials_megapath_rr"] = scenes.materials_box(resolution=(32, 24), spp=4, depth=10, rr_depth=2, rr_threshold=0.95,
+                                                      integrator="MegaPath")
     return c
 
 
