@@ -37,7 +37,7 @@ struct PathBuffers {
     float4 *beta_pdf[2];
     uint2 *id_rng[2];
     uint4 *hit;// {inst, prim, bary} per ray of the current queue (inst == ~0u: escaped)
-    uint32_t *hit_index[3];// per closure kind: indices (into the current ray queue) of the rays that hit such a surface
+    uint32_t *hit_index[4];// per closure kind: indices (into the current ray queue) of the rays that hit such a surface
     float4 *sray_o;
     float4 *sray_d;
     float4 *scontrib;// rgb + path id bits
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(kBlock) generate_rays_kernel(DeviceScene sc, P
     uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id == 0u) {
         pb.counts[0] = n;
-        for (uint32_t d = 1u; d < 7u * kMaxDepthSlots; d++) pb.counts[d] = 0u;// sizes + the traversal kernels' fetch cursors
+        for (uint32_t d = 1u; d < 8u * kMaxDepthSlots; d++) pb.counts[d] = 0u;// sizes + the traversal kernels' fetch cursors
     }
     if (id >= n) return;
     uint32_t k = id % npix;
@@ -151,7 +151,8 @@ __global__ void __launch_bounds__(kBlock, 4) trace_closest_kernel(DeviceScene sc
 // block-aggregated partition).  Escaped rays are dropped, so the shade kernels only ever see real work; every bucket
 // keeps the ray-queue order inside a block chunk, which keeps the shade kernels' gathers coalesced.
 //   kind 0: hit has no surface (emitter only)   kind 1: Matte closure   kind 2: Disney closure
-constexpr uint32_t kHitKinds = 3u;
+//   kind 3: Mirror / Glass / Plastic / Metal (MicrofacetFamilyClosure)
+constexpr uint32_t kHitKinds = 4u;
 __global__ void __launch_bounds__(kBlock) classify_hits_kernel(DeviceScene sc, PathBuffers pb, uint32_t depth) {
     __shared__ uint32_t s_warp[kHitKinds][kBlock / 32];
     __shared__ uint32_t s_base[kHitKinds];
@@ -413,14 +414,20 @@ __global__ void __launch_bounds__(kShadeBlock, LRK_SHADE_MIN_BLOCKS) shade_kerne
                     const lrk_surface *surf = sc.surfaces + it.shape.surface_tag;
                     V3 contrib, wi, f;
                     float pdf;
+                    float eta_scale = 1.f;// mega_path.cpp:113,133-138
                     if (KIND == 1u) {
                         MatteClosure cl;
                         init_closure<TEXTURED>(sc, cl, surf, it);
                         shade_surface<false>(cl, it, closure_frame<TEXTURED>(sc, surf, it, wo), wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
-                    } else {
+                    } else if (KIND == 2u) {
                         DisneyClosure cl;
                         init_closure<TEXTURED>(sc, cl, surf, it);
                         shade_surface<false>(cl, it, closure_frame<TEXTURED>(sc, surf, it, wo), wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
+                    } else {
+                        MicrofacetFamilyClosure cl;
+                        cl.init(*surf);// constant parameters only (include/lrk.h)
+                        shade_surface<false>(cl, it, closure_frame<TEXTURED>(sc, surf, it, wo), wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
+                        eta_scale = cl.rr_eta_scale;
                     }
                     if (contrib.x != 0.f || contrib.y != 0.f || contrib.z != 0.f) {
                         // a zero (or NaN-free zero) contribution needs no shadow ray; NaNs must reach the film filter
@@ -436,7 +443,7 @@ __global__ void __launch_bounds__(kShadeBlock, LRK_SHADE_MIN_BLOCKS) shade_kerne
                     if (isnan(beta.x) || isnan(beta.y) || isnan(beta.z)) beta = v3(0.f);
                     bool alive = !(beta.x <= 0.f && beta.y <= 0.f && beta.z <= 0.f);
                     if (alive) {
-                        float q = fmaxf(max3(beta) * 1.f, .05f);
+                        float q = fmaxf(max3(beta) * eta_scale, .05f);
                         if (depth + 1u >= sc.rr_depth) {
                             if (q < sc.rr_threshold && u_rr >= q) alive = false;
                             beta = beta * (q < sc.rr_threshold ? 1.0f / q : 1.f);
@@ -551,7 +558,7 @@ __global__ void __launch_bounds__(kBlock) generate_rays_volume_kernel(DeviceScen
     uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id == 0u) {
         pb.counts[0] = n;
-        for (uint32_t d = 1u; d < 7u * kMaxDepthSlots; d++) pb.counts[d] = 0u;
+        for (uint32_t d = 1u; d < 8u * kMaxDepthSlots; d++) pb.counts[d] = 0u;
     }
     if (id >= n) return;
     uint32_t k = id % npix;

@@ -61,8 +61,8 @@ struct lrk_ctx {
     cudaEvent_t ev_begin{}, ev_end{};
     std::vector<TimedLaunch> timed;
     std::vector<cudaEvent_t> event_pool;
-    int grid_trace{0}, grid_shade[3]{0, 0, 0}, grid_shadow{0}, grid_classify{0};
-    bool has_kind[3]{true, false, false};
+    int grid_trace{0}, grid_shade[4]{0, 0, 0, 0}, grid_shadow{0}, grid_classify{0};
+    bool has_kind[4]{true, false, false, false};
     bool volume{false};
     uint64_t volume_capacity{0};
     int grid_vshade[3]{0, 0, 0}, grid_vmedium{0}, grid_vshadow{0};
@@ -132,12 +132,12 @@ int alloc_paths(lrk_ctx *ctx, uint64_t capacity) {
         LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.id_rng[k]), capacity * sizeof(uint2)));
     }
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.hit), capacity * sizeof(uint4)));
-    for (int k = 0; k < 3; k++) LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.hit_index[k]), capacity * sizeof(uint32_t)));
+    for (int k = 0; k < 4; k++) LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.hit_index[k]), capacity * sizeof(uint32_t)));
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.sray_o), capacity * sizeof(float4)));
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.sray_d), capacity * sizeof(float4)));
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.scontrib), capacity * sizeof(float4)));
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.li), capacity * sizeof(float4)));
-    LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.counts), 7u * kMaxDepthSlots * sizeof(uint32_t)));
+    LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.counts), 8u * kMaxDepthSlots * sizeof(uint32_t)));
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.ray_order), capacity * kRayBins * sizeof(uint32_t)));
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.bin_counts), 2u * kMaxDepthSlots * kRayBins * sizeof(uint32_t)));
     pb.capacity = static_cast<uint32_t>(capacity);
@@ -281,6 +281,7 @@ int render_pass(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint32_t spp
             launch(shade_kernel<0u, false>, 0);
             if (ctx->has_kind[1]) ctx->textured ? launch(shade_kernel<1u, true>, 1) : launch(shade_kernel<1u, false>, 1);
             if (ctx->has_kind[2]) ctx->textured ? launch(shade_kernel<2u, true>, 2) : launch(shade_kernel<2u, false>, 2);
+            if (ctx->has_kind[3]) ctx->textured ? launch(shade_kernel<3u, true>, 3) : launch(shade_kernel<3u, false>, 3);
         }
         if (bin) {
             ScopedTimer t{ctx, CAT_OTHER};
@@ -299,7 +300,7 @@ int render_pass(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint32_t spp
             if (ctx->any_non_opaque) ctx->count_traversal ? launch(trace_shadow_kernel<true, true>) : launch(trace_shadow_kernel<false, true>);
             else ctx->count_traversal ? launch(trace_shadow_kernel<true, false>) : launch(trace_shadow_kernel<false, false>);
         }
-        ctx->stats.kernel_launches += 4u + (ctx->has_kind[1] ? 1u : 0u) + (ctx->has_kind[2] ? 1u : 0u);
+        ctx->stats.kernel_launches += 4u + (ctx->has_kind[1] ? 1u : 0u) + (ctx->has_kind[2] ? 1u : 0u) + (ctx->has_kind[3] ? 1u : 0u);
     }
     {
         ScopedTimer t{ctx, CAT_OTHER};
@@ -420,6 +421,7 @@ int lrk_create(const lrk_device_cfg *cfg, lrk_ctx **out) {
     ctx->grid_shade[0] = grid_for(reinterpret_cast<const void *>(shade_kernel<0u, false>));
     ctx->grid_shade[1] = grid_for(reinterpret_cast<const void *>(shade_kernel<1u, false>));
     ctx->grid_shade[2] = grid_for(reinterpret_cast<const void *>(shade_kernel<2u, false>));
+    ctx->grid_shade[3] = grid_for(reinterpret_cast<const void *>(shade_kernel<3u, false>));
     ctx->grid_classify = grid_for(reinterpret_cast<const void *>(classify_hits_kernel));
     ctx->grid_vmedium = grid_for(reinterpret_cast<const void *>(volume_medium_kernel));
     ctx->grid_vshade[0] = grid_for(reinterpret_cast<const void *>(volume_surface_kernel<0u, false>));
@@ -483,7 +485,11 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
         if (s->light_count == 0u && e.env_prob != 1.f) return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_upload_scene: env_prob must be 1 without area lights");
     }
     for (uint32_t i = 0; i < s->surface_count; i++) {
-        if (s->surfaces[i].type > LRK_SURFACE_DISNEY) return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: unknown surface type");
+        if (s->surfaces[i].type >= LRK_SURFACE_TYPE_COUNT) return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: unknown surface type");
+        if (s->surfaces[i].type > LRK_SURFACE_DISNEY && (s->surfaces[i].flags & LRK_SURFACE_HAS_TEXTURES))
+            return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: Mirror / Glass / Plastic / Metal take constant parameters only");
+        if (s->surfaces[i].type > LRK_SURFACE_DISNEY && s->integrator.type == LRK_INTEGRATOR_VOLUME_PATH)
+            return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: the volume path supports Matte and Disney surfaces only");
         for (uint32_t k = 0; k < 16u; k++)
             if (s->surfaces[i].tex[k] > s->texture_count) return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_upload_scene: texture id out of range");
         if (s->surfaces[i].opacity_tex > s->texture_count || s->surfaces[i].normal_tex > s->texture_count)
@@ -524,7 +530,7 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
     if ((rc = upload(ctx, &a.light_handles, s->light_handles, s->light_count))) return rc;
     if ((rc = upload(ctx, &a.camera, &s->camera, 1))) return rc;
     std::vector<uint32_t> handles(static_cast<size_t>(s->instance_count) * 4u), kinds(s->instance_count);
-    ctx->has_kind[1] = ctx->has_kind[2] = false;
+    ctx->has_kind[1] = ctx->has_kind[2] = ctx->has_kind[3] = false;
     ctx->any_non_opaque = false;
     std::vector<float> o2w(static_cast<size_t>(s->instance_count) * 12u), xform(static_cast<size_t>(s->instance_count) * 16u);
     for (uint32_t i = 0; i < s->instance_count; i++) {
@@ -535,7 +541,8 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
             uint32_t kind = 0u;
             if (flags & LRK_SHAPE_HAS_SURFACE) {
                 if (surface_tag >= s->surface_count) return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_upload_scene: surface tag out of range");
-                kind = s->surfaces[surface_tag].type == LRK_SURFACE_MATTE ? 1u : 2u;
+                const uint32_t type = s->surfaces[surface_tag].type;
+                kind = type == LRK_SURFACE_MATTE ? 1u : type == LRK_SURFACE_DISNEY ? 2u : 3u;
             }
             kinds[i] = kind;
             ctx->has_kind[kind] = true;

@@ -845,4 +845,229 @@ struct DisneyClosure {
     }
 };
 
+// Mirror / Glass / Plastic / Metal: src/surfaces/{mirror,glass,plastic,metal}.cpp over the BxDFs of
+// src/util/scattering.cpp:14-125,238-345.  One closure type for the four nodes (hit bucket 3): they are rare next to the
+// Matte / Disney buckets and share the microfacet code.  lrk_surface.p holds each node's closure Context (include/lrk.h).
+// The expressions are the oracle's (oracle/oracle.cpp: MicrofacetReflection, MicrofacetTransmission, PlasticLobes, ...),
+// which are pinned bit for bit against the reference's closures (tests/test_ref_pins.py, tests/test_ref_render.py).
+__device__ __forceinline__ bool refract(V3 wi, V3 n, float eta, V3 &wt) {// scattering.cpp:14-28
+    float cosThetaI = dot(n, wi);
+    float sin2ThetaI = fmaxf(0.0f, 1.f - sqr(cosThetaI));
+    float sin2ThetaT = sqr(eta) * sin2ThetaI;
+    float cosThetaT = sqrtf(1.f - sin2ThetaT);
+    wt = (eta * cosThetaI - cosThetaT) * n - eta * wi;
+    return sin2ThetaT < 1.0f;
+}
+__device__ __forceinline__ V3 vdiv(V3 a, V3 b) { return v3(a.x / b.x, a.y / b.y, a.z / b.z); }
+__device__ __forceinline__ V3 vsqrt(V3 a) { return v3(sqrtf(a.x), sqrtf(a.y), sqrtf(a.z)); }
+__device__ __forceinline__ V3 vsub(V3 a, float s) { return v3(a.x - s, a.y - s, a.z - s); }
+__device__ __forceinline__ V3 vrsub(float s, V3 a) { return v3(s - a.x, s - a.y, s - a.z); }
+__device__ __forceinline__ V3 fresnel_conductor(float cosThetaI, float etai, V3 etat, V3 k) {// scattering.cpp:56-75
+    cosThetaI = clampf(cosThetaI, -1.f, 1.f);
+    V3 eta = v3(etat.x / etai, etat.y / etai, etat.z / etai);
+    V3 etak = v3(k.x / etai, k.y / etai, k.z / etai);
+    float cosThetaI2 = cosThetaI * cosThetaI;
+    float sinThetaI2 = 1.f - cosThetaI2;
+    V3 eta2 = eta * eta;
+    V3 etak2 = etak * etak;
+    V3 t0 = vsub(eta2 - etak2, sinThetaI2);
+    V3 a2plusb2 = vsqrt(t0 * t0 + 4.f * eta2 * etak2);
+    V3 t1 = a2plusb2 + cosThetaI2;
+    V3 a = vsqrt(.5f * (a2plusb2 + t0));
+    V3 t2 = (2.f * cosThetaI) * a;
+    V3 Rs = vdiv(t1 - t2, t1 + t2);
+    V3 t3 = cosThetaI2 * a2plusb2 + sinThetaI2 * sinThetaI2;
+    V3 t4 = t2 * sinThetaI2;
+    V3 Rp = vdiv(Rs * (t3 - t4), t3 + t4);
+    return .5f * (Rp + Rs);
+}
+
+struct MicrofacetFamilyClosure {
+    uint32_t type;
+    V3 c0, c1, c2;     // MIRROR: refl | GLASS: Kr, Kt | PLASTIC: Kd', sigma_a | METAL: n, k, tint
+    float eta, w0;     // GLASS: eta_t, Kr_ratio | PLASTIC: eta, Kd_weight
+    TrowbridgeReitz d;
+    float flip;        // PLASTIC: sign applied to the z components (plastic.cpp:143-147)
+    float rr_eta_scale;// eta scale of the sampled event for Russian roulette (mega_path.cpp:133-138)
+    __device__ __forceinline__ void init(const lrk_surface &s) {
+        type = s.type;
+        rr_eta_scale = 1.f;
+        flip = 1.f;
+        eta = 1.5f;
+        w0 = 0.f;
+        c0 = v3(s.p[0], s.p[1], s.p[2]);
+        c1 = c2 = v3(0.f);
+        float ax = 0.f, ay = 0.f;
+        if (type == LRK_SURFACE_MIRROR) {
+            ax = s.p[3]; ay = s.p[4];
+        } else if (type == LRK_SURFACE_GLASS) {
+            c1 = v3(s.p[3], s.p[4], s.p[5]);
+            eta = s.p[6]; ax = s.p[7]; ay = s.p[8]; w0 = s.p[9];
+        } else if (type == LRK_SURFACE_PLASTIC) {
+            w0 = s.p[3];
+            c1 = v3(s.p[4], s.p[5], s.p[6]);
+            eta = s.p[7]; ax = s.p[8]; ay = s.p[9];
+        } else {
+            c1 = v3(s.p[3], s.p[4], s.p[5]);
+            c2 = v3(s.p[6], s.p[7], s.p[8]);
+            ax = s.p[9]; ay = s.p[10];
+        }
+        d.ax = fmaxf(ax, 1e-4f);// MicrofacetDistribution ctor, scattering.cpp:124-125
+        d.ay = fmaxf(ay, 1e-4f);
+    }
+    __device__ __forceinline__ void prepare(V3 wo_local) { flip = (type == LRK_SURFACE_PLASTIC && cos_theta(wo_local) < 0.f) ? -1.f : 1.f; }
+
+    // Fresnel term of the reflection lobe: Schlick around the colour (mirror.cpp:67-79), dielectric, conductor
+    __device__ __forceinline__ V3 fresnel(float cosI) const {
+        if (type == LRK_SURFACE_MIRROR) {
+            float m = saturate(1.f - cosI);
+            float weight = sqr(sqr(m)) * m;
+            return (1.f - weight) * c0 + weight;
+        }
+        if (type == LRK_SURFACE_METAL) return fresnel_conductor(fabsf(cosI), 1.f, c0, c1);
+        return v3(fresnel_dielectric(cosI, 1.f, eta));
+    }
+    __device__ __forceinline__ V3 reflection_evaluate(V3 r, V3 wo, V3 wi) const {// MicrofacetReflection::evaluate :290-308
+        V3 wh = wi + wo;
+        V3 f = v3(0.f);
+        if (same_hemisphere(wo, wi) && any_nonzero(wh)) {
+            wh = normalize(wh);
+            V3 F = fresnel(dot(wi, face_forward(wh, v3(0.f, 0.f, 1.f))));
+            float D = d.D(wh);
+            float G = d.G(wo, wi);
+            float cos_o = cos_theta(wo), cos_i = cos_theta(wi);
+            f = r * F * fabsf(0.25f * D * G / (cos_i * cos_o));
+        }
+        return f;
+    }
+    __device__ __forceinline__ float reflection_pdf(V3 wo, V3 wi) const {// :316-324
+        float p = 0.f;
+        V3 wh = wi + wo;
+        if (same_hemisphere(wo, wi) && any_nonzero(wh)) {
+            wh = normalize(wh);
+            p = d.pdf(wo, wh) / (4.f * dot(wo, wh));
+        }
+        return p;
+    }
+    __device__ __forceinline__ V3 transmission_evaluate(V3 wo, V3 wi) const {// MicrofacetTransmission::evaluate :326-350, eta_a = 1
+        float cosThetaO = cos_theta(wo), cosThetaI = cos_theta(wi);
+        float e = cosThetaO > 0.f ? eta / 1.f : 1.f / eta;
+        V3 wh = normalize(wo + wi * e);
+        wh = sign(cos_theta(wh)) * wh;
+        V3 f = v3(0.f);
+        if (!same_hemisphere(wo, wi) && cosThetaO != 0.f && cosThetaI != 0.f && dot(wo, wh) * dot(wi, wh) < 0.f) {
+            float G = d.G(wo, wi);
+            float sqrtDenom = dot(wo, wh) + e * dot(wi, wh);
+            float F = fresnel_dielectric(dot(wo, wh), 1.f, eta);
+            float D = d.D(wh);
+            V3 num = (1.f - F) * c1 * D * G * dot(wi, wh) * dot(wo, wh);
+            float den = cosThetaI * cosThetaO * sqr(sqrtDenom);
+            f = v3(num.x / den, num.y / den, num.z / den);
+        }
+        return f;
+    }
+    __device__ __forceinline__ float transmission_pdf(V3 wo, V3 wi) const {// :360-373
+        float p = 0.f;
+        float e = cos_theta(wo) > 0.f ? eta / 1.f : 1.f / eta;
+        V3 wh = normalize(wo + wi * e);
+        if (!same_hemisphere(wo, wi) && dot(wo, wh) * dot(wi, wh) < 0.f) {
+            float sqrtDenom = dot(wo, wh) + e * dot(wi, wh);
+            float dwh_dwi = sqr(e / sqrtDenom) * abs_dot(wi, wh);
+            p = d.pdf(wo, wh) * dwh_dwi;
+        }
+        return p;
+    }
+    __device__ __forceinline__ float glass_refl_prob(V3 wo) const {// glass.cpp:162-167
+        float F = fresnel_dielectric(cos_theta(wo), 1.f, eta);
+        float r = w0 * F;
+        float t = (1.f - w0) * (1.f - F);
+        return r == 0.f ? 0.f : r / (r + t);
+    }
+    __device__ __forceinline__ static float substrate_weight(float Fo, float kd_w) {// plastic.cpp:125-128
+        float w = kd_w * (1.0f - Fo);
+        return w == 0.f ? 0.f : w / (w + Fo);
+    }
+
+    __device__ __forceinline__ SurfEval evaluate_local(V3 wo, V3 wi) const {
+        SurfEval e;
+        if (type == LRK_SURFACE_MIRROR) {
+            e.f = reflection_evaluate(c0, wo, wi) * abs_cos_theta(wi);
+            e.pdf = reflection_pdf(wo, wi);
+        } else if (type == LRK_SURFACE_METAL) {
+            V3 f = reflection_evaluate(v3(1.f), wo, wi);
+            f = f * c2;
+            e.f = f * abs_cos_theta(wi);
+            e.pdf = reflection_pdf(wo, wi);
+        } else if (type == LRK_SURFACE_GLASS) {// glass.cpp:169-191
+            float ratio = glass_refl_prob(wo);
+            V3 f;
+            float pdf;
+            if (same_hemisphere(wo, wi)) {
+                f = reflection_evaluate(c0, wo, wi);
+                pdf = reflection_pdf(wo, wi) * ratio;
+            } else {
+                f = transmission_evaluate(wo, wi);
+                pdf = transmission_pdf(wo, wi) * (1.f - ratio);
+            }
+            e.f = f * abs_cos_theta(wi);
+            e.pdf = pdf;
+        } else {// plastic.cpp:138-165
+            V3 wo_l = v3(wo.x, wo.y, wo.z * flip), wi_l = v3(wi.x, wi.y, wi.z * flip);
+            V3 f_coat = reflection_evaluate(v3(1.f), wo_l, wi_l);
+            float pdf_coat = reflection_pdf(wo_l, wi_l);
+            float Fi = fresnel_dielectric(abs_cos_theta(wi_l), 1.f, eta);
+            float Fo = fresnel_dielectric(abs_cos_theta(wo_l), 1.f, eta);
+            float ex = -(1.f / abs_cos_theta(wi_l) + 1.f / abs_cos_theta(wo_l));
+            V3 a = v3(expf(ex * c1.x), expf(ex * c1.y), expf(ex * c1.z));
+            V3 lam = c0 * (same_hemisphere(wo_l, wi_l) ? kInvPi : 0.f);
+            V3 f_diffuse = (1.f - Fi) * (1.f - Fo) * sqr(1.f / eta) * a * lam;
+            float pdf_diffuse = lambert_pdf(wo_l, wi_l);
+            float sw = substrate_weight(Fo, w0);
+            e.f = (f_coat + f_diffuse) * abs_cos_theta(wi_l);
+            e.pdf = lerp(pdf_coat, pdf_diffuse, sw);
+        }
+        return e;
+    }
+
+    __device__ __forceinline__ bool sample_direction(V3 wo, float u_lobe, float u0, float u1, V3 &wi) {
+        rr_eta_scale = 1.f;
+        if (type == LRK_SURFACE_MIRROR || type == LRK_SURFACE_METAL) {
+            V3 wh = d.sample_wh(wo, u0, u1);
+            wi = reflect(-wo, wh);
+            return same_hemisphere(wo, wi);
+        }
+        if (type == LRK_SURFACE_GLASS) {// glass.cpp:193-221
+            float ratio = glass_refl_prob(wo);
+            if (u_lobe < ratio) {
+                V3 wh = d.sample_wh(wo, u0, u1);
+                wi = reflect(-wo, wh);
+                return same_hemisphere(wo, wi);
+            }
+            float e = cos_theta(wo) > 0.f ? 1.f / eta : eta / 1.f;
+            V3 wh = d.sample_wh(wo, u0, u1);
+            wi = v3(0.f);
+            bool refr = refract(wo, wh, e, wi);
+            rr_eta_scale = cos_theta(wo) > 0.f ? sqr(eta) : sqr(1.f / eta);// event_enter / event_exit
+            return refr && !same_hemisphere(wo, wi);
+        }
+        // plastic.cpp:168-214: sampled above the flipped surface, returned in the original frame
+        V3 wo_l = v3(wo.x, wo.y, wo.z * flip);
+        float Fo = fresnel_dielectric(abs_cos_theta(wo_l), 1.f, eta);
+        float sw = substrate_weight(Fo, w0);
+        V3 w;
+        bool valid;
+        if (u_lobe < sw) {
+            w = sample_cosine_hemisphere(u0, u1);
+            w.z *= sign(cos_theta(wo_l));
+            valid = true;
+        } else {
+            V3 wh = d.sample_wh(wo_l, u0, u1);
+            w = reflect(-wo_l, wh);
+            valid = same_hemisphere(wo_l, w);
+        }
+        wi = valid ? v3(w.x, w.y, w.z * flip) : v3(0.f, 0.f, 1.f);
+        return valid;
+    }
+};
+
 }// namespace lrk

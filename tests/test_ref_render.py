@@ -88,7 +88,8 @@ def test_fixture_is_what_the_reference_renders_now(golden):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["cornell_wavepath", "cornell_russian_roulette", "spheres_disney"])
+@pytest.mark.parametrize("name", ["cornell_wavepath", "cornell_russian_roulette", "spheres_disney", "materials_wavepath",
+                                  "materials_megapath_rr"])
 def test_cuda_film_matches_the_reference_render(golden, name, gpu_renderer):
     source, scene, desc = _scene(golden, name)
     want = golden[f"{name}/image"][..., :3]
@@ -96,7 +97,42 @@ def test_cuda_film_matches_the_reference_render(golden, name, gpu_renderer):
     gpu_renderer.clear()
     gpu_renderer.render(0, _spp(source))
     got = gpu_renderer.film()[..., :3]
+    err = np.abs(got - want)
+    off = (err > 1e-4 * np.maximum(np.abs(want), 1.0)).any(axis=-1)
+    if name.startswith("materials"):
+        # Specular chains (mirror wall, smooth and rough glass) amplify the ulp-level differences between CUDA's and glibc's
+        # sin / cos / pow into different discrete decisions (lobe choice, total internal reflection, Russian roulette) for a
+        # few paths: <= 3 % of the pixels may take another, equally valid, branch; the rest agree to 1e-3 rel-L2 and the
+        # image means to 2 %.  The closures themselves are compared without that chaos in the first-bounce test below.
+        keep = ~off if off.mean() <= 0.03 else np.ones_like(off)
+        assert off.mean() <= 0.03, f"{name}: {off.mean():.4f} of the pixels off"
+        assert np.linalg.norm((got - want)[keep]) / np.linalg.norm(want[keep]) <= 1e-3
+        assert got.mean() == pytest.approx(want.mean(), rel=0.02)
+    else:
+        rel_l2 = float(np.linalg.norm(got - want) / np.linalg.norm(want))
+        assert rel_l2 <= 1e-3, f"{name}: rel-L2 {rel_l2}"
+        assert off.mean() <= 0.005, f"{name}: {off.mean():.4f} of the pixels off"
+
+
+@pytest.mark.gpu
+def test_cuda_materials_first_bounce_matches_oracle(gpu_renderer):
+    """Depth 2 = camera hit + next-event estimation + one sampled bounce that can only ADD an emitter hit: every pixel is a
+    smooth function of the Mirror / Glass / Plastic / Metal closures' evaluate() and sample() at the first hit, with no
+    path-length-dependent branching to flip.  The oracle it is compared with is bit-identical to the reference renderer on
+    this scene (test_oracle_film_is_bit_identical_to_the_reference_render[materials_*])."""
+    from luisarender_b200 import scenes
+
+    source = scenes.materials_box(resolution=(48, 36), spp=16, depth=2)
+    desc = Scene.from_source(source, REPO).desc()
+    raw, counters = O.render(desc, 0, 16)
+    want = O.convert_film(desc, raw)[..., :3]
+    gpu_renderer.upload(desc)
+    gpu_renderer.clear()
+    gpu_renderer.render(0, 16)
+    got = gpu_renderer.film()[..., :3]
+    stats = gpu_renderer.stats()
+    assert stats["closest_rays"] == counters["closest_rays"]
     rel_l2 = float(np.linalg.norm(got - want) / np.linalg.norm(want))
-    off = np.abs(got - want) > 1e-4 * np.maximum(np.abs(want), 1.0)
-    assert rel_l2 <= 1e-3, f"{name}: rel-L2 {rel_l2}"
-    assert off.any(axis=-1).mean() <= 0.005, f"{name}: {off.any(axis=-1).mean():.4f} of the pixels off"
+    off = (np.abs(got - want) > 1e-4 * np.maximum(np.abs(want), 1.0)).any(axis=-1)
+    assert rel_l2 <= 1e-3, rel_l2
+    assert off.mean() <= 0.01, off.mean()
