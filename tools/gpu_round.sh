@@ -20,10 +20,12 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
     -k regex:trace_closest_kernel -c 10 --csv --log-file $OUT/traffic_${TAG}.csv \
     python bench.py --steps 1 --warmup 1 --no-cpu >> $OUT/ncu_bench_${TAG}.log 2>&1
-# (3) full captures, source-correlated
+# (3) full captures, source-correlated (skipped with NO_FULL=1)
+if [ -z "$NO_FULL" ]; then
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:trace_closest_kernel -s 0 -c 2 -f -o $OUT/prof_trace_${TAG} \
     python bench.py --steps 1 --warmup 1 --no-cpu > $OUT/ncu_full_${TAG}.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:shade_kernel -s 0 -c 3 -f -o $OUT/prof_shade_${TAG} \
     python bench.py --steps 1 --warmup 1 --no-cpu >> $OUT/ncu_full_${TAG}.log 2>&1
+fi
 ls -la $OUT | grep ${TAG}
 fi
