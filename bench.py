@@ -166,7 +166,8 @@ def run_reference(args, rank: int):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus),
         "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample_desc,
                          "note": "the reference's Rust/LLVM `cpu` backend + Embree cannot be built in this environment (SURVEY.md §8c); "
-                                 "this is the oracle port of the same estimator on all host cores"},
+                                 "this is the oracle port of the same estimator on all host cores; the port's films are bit-identical to the unmodified "
+                                 "reference renderer run through oracle/ref's interpreter backend (tests/test_ref_render.py)"},
         "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -302,7 +303,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if rank == 0 and world == 1 and not args.no_cpu:
         rate, n, secs, sample_desc, _ = cpu_oracle_rate(desc, 15.0, SPP_PER_STEP)
         cpu = {"value": round(rate, 4), "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": sample_desc,
-               "seconds": round(secs, 2)}
+               "seconds": round(secs, 2),
+               "pinned": "films bit-identical to the unmodified reference renderer on 7 scenes (tests/test_ref_render.py)"}
 
     if rank == 0:
         line = {
