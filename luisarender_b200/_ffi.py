@@ -147,7 +147,7 @@ LRK_SYMBOLS = [
 LRH_SYMBOLS = [
     "lrh_last_error", "lrh_scene_load", "lrh_scene_load_source", "lrh_scene_destroy", "lrh_scene_get_info",
     "lrh_scene_get_desc", "lrh_scene_camera_file", "lrh_save_image", "lrh_plugin_count", "lrh_plugin_name",
-    "lrh_create_alias_table",
+    "lrh_create_alias_table", "lrh_load_image",
 ]
 
 _libs: dict[str, C.CDLL] = {}

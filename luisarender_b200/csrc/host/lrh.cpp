@@ -119,6 +119,23 @@ const char *lrh_plugin_name(uint32_t index) {
     return name.c_str();
 }
 
+int lrh_load_image(const char *path, uint32_t *width, uint32_t *height, uint32_t *channels, float *rgba, uint64_t rgba_capacity) {
+    if (!path || !width || !height || !channels) return fail("lrh_load_image: null argument.");
+    try {
+        auto image = lrh::load_image(path);
+        *width = image.width;
+        *height = image.height;
+        *channels = image.channels;
+        if (rgba != nullptr) {
+            if (rgba_capacity < image.rgba.size()) return fail("lrh_load_image: output buffer too small.");
+            std::copy(image.rgba.begin(), image.rgba.end(), rgba);
+        }
+        return 0;
+    } catch (const std::exception &e) {
+        return fail(e.what());
+    }
+}
+
 int lrh_create_alias_table(const float *values, uint32_t n, float *prob, uint32_t *alias, float *pdf) {
     if (!values || !prob || !alias || !pdf) return fail("lrh_create_alias_table: null argument.");
     try {

@@ -197,7 +197,8 @@ def instanced_spheres(resolution=(1920, 1080), spp=1024, seed=1, depth=10, rr_de
 
 
 def textured_room(resolution=(96, 64), spp=8, depth=6, rr_depth=0, rr_threshold=0.95, seed=19980810,
-                  assets="tests/golden/assets", output="textured.exr", integrator="WavePath", wrappers=False) -> str:
+                  assets="tests/golden/assets", output="textured.exr", integrator="WavePath", wrappers=False,
+                  mesh_files=True) -> str:
     """SURVEY.md §8 row f1 in one small scene: image-textured Matte and Disney parameters (PNG 8/16-bit, grey, palette; all
     four address modes, point + bilinear filters, sRGB + linear encodings, uv scale/offset) on an InlineMesh with uvs and
     on mesh FILES (Wavefront OBJ without normals, binary PLY).  `assets` is relative to the directory the scene is loaded from.
@@ -205,6 +206,15 @@ def textured_room(resolution=(96, 64), spp=8, depth=6, rr_depth=0, rr_threshold=
     alpha texture (stochastic alpha test inside closest-hit and any-hit traversal) and a half-transparent cube (constant opacity)."""
     a = assets.rstrip("/")
     floor_extra = cube_extra = screen = screen_ref = ""
+    # mesh_files=False: the two file meshes become inline panels with uvs (the reference build under oracle/ref has no
+    # `Mesh` plugin: it needs assimp)
+    cube_geometry = f'Mesh {{\n  file {{ "{a}/cube.obj" }}'
+    tetra_geometry = f'Mesh {{\n  file {{ "{a}/tetra_binary.ply" }}\n  flip_uv {{ true }}'
+    if not mesh_files:
+        cube_geometry = ("InlineMesh {\n  positions { -0.5, -0.5, 0.5,  0.5, -0.5, 0.5,  0.5, 0.5, 0.5,  -0.5, 0.5, 0.5,  0.5, -0.5, -0.5,  0.5, 0.5, -0.5 }\n"
+                         "  uvs { 0.0, 0.0,  1.0, 0.0,  1.0, 1.0,  0.0, 1.0,  2.0, 0.0,  2.0, 1.0 }\n  indices { 0, 1, 2, 0, 2, 3, 1, 4, 5, 1, 5, 2 }")
+        tetra_geometry = ("InlineMesh {\n  positions { -0.5, 0.0, 0.4,  0.5, 0.0, 0.4,  0.0, 0.9, 0.0,  0.0, 0.0, -0.5 }\n"
+                          "  uvs { 0.0, 0.0,  1.0, 0.0,  0.5, 1.0,  0.5, -0.3 }\n  indices { 0, 1, 2, 1, 3, 2, 3, 0, 2 }")
     if wrappers:
         floor_extra = f'normal_map : Image {{ file {{ "{a}/normal_rgb8.png" }} encoding {{ "linear" }} uv_scale {{ 4.0 }} }} normal_map_strength {{ 0.8 }}'
         cube_extra = "opacity : Constant { v { 0.5 } }"
@@ -252,14 +262,11 @@ Shape wall : InlineMesh {{
   indices {{ 0, 1, 2, 0, 2, 3 }}
   surface {{ @wall_s }}
 }}
-Shape cube : Mesh {{
-  file {{ "{a}/cube.obj" }}
+Shape cube : {cube_geometry}
   surface {{ @cube_s }}
   transform : SRT {{ scale {{ 0.8 }} rotate {{ 0.0, 1.0, 0.0, 30.0 }} translate {{ -0.6, 0.4, -0.3 }} }}
 }}
-Shape tetra : Mesh {{
-  file {{ "{a}/tetra_binary.ply" }}
-  flip_uv {{ true }}
+Shape tetra : {tetra_geometry}
   surface {{ @tetra_s }}
   transform : SRT {{ scale {{ 1.1 }} translate {{ 0.5, 0.0, -0.2 }} }}
 }}
@@ -293,13 +300,15 @@ render {{
 
 
 def environment_scene(resolution=(64, 40), spp=8, depth=5, rr_depth=0, rr_threshold=0.95, seed=19980810, assets="tests/golden/assets",
-                      emission="image", area_light=True, environment_weight=0.5, compensate_mis=True, output="env.exr") -> str:
+                      emission="image", area_light=True, environment_weight=0.5, compensate_mis=True, output="env.exr",
+                      sky_file="sky.pfm") -> str:
     """a Spherical environment light (src/environments/spherical.cpp) — image emission with the
     importance map, or a constant one — next to an optional area light (uniform light sampler, environment_weight), seen by a
     Matte sphere on a Disney floor."""
     a = assets.rstrip("/")
     if emission == "image":
-        em = f'emission : Image {{ file {{ "{a}/sky.pfm" }} encoding {{ "linear" }} address {{ "repeat" }} }}'
+        # sky.exr holds the same texels as sky.pfm (the reference's image reader has no PFM decoder)
+        em = f'emission : Image {{ file {{ "{a}/{sky_file}" }} encoding {{ "linear" }} address {{ "repeat" }} }}'
     else:
         em = f"emission : Constant {{ v {{ {_fmt(emission[0])}, {_fmt(emission[1])}, {_fmt(emission[2])} }} }}"
     light = lamp = lamp_ref = ""

@@ -451,6 +451,23 @@ private:
     DeviceResources *_res{nullptr};
     std::deque<Slot> _slots;// indexed by variable uid (uids are small and dense per function)
     Val _ret;
+    /* ray queries (RayQueryAll / RayQueryAny variables of this function), keyed by variable uid */
+    struct QueryState {
+        uint64_t accel{0u};
+        RayData ray{};
+        uint32_t mask{0xffu};
+        bool any{false};
+        bool terminated{false};
+        HitData committed{~0u, ~0u, {0.f, 0.f}, 0.f, 0u};
+        HitData candidate{~0u, ~0u, {0.f, 0.f}, 0.f, 0u};
+    };
+    std::unordered_map<uint32_t, QueryState> _queries;
+    QueryState &query_of(const Expression *e) {
+        if (e->tag() != Expression::Tag::REF) { fail("ray query expression is not a variable"); }
+        auto it = _queries.find(static_cast<const RefExpr *>(e)->variable().uid());
+        if (it == _queries.end()) { fail("ray query used before it was created"); }
+        return it->second;
+    }
 
     Slot &raw_slot(uint32_t uid) {
         if (uid >= _slots.size()) { _slots.resize(uid + 1u); }
@@ -1086,7 +1103,32 @@ private:
                 auto array = handle_of(args[0], Slot::Kind::BINDLESS_ARRAY);
                 auto slot_index = conv(F(1)[0], Tag::UINT32).u;
                 auto idx = static_cast<size_t>(conv(F(2)[0], Tag::UINT32).u);
-                return read_element(res().bindless_buffer(array, slot_index), idx, e->type());
+                auto b = res().bindless_buffer(array, slot_index);
+                if (b.data == nullptr) { return Val{e->type()}; }// unpopulated slot: see refdevice.cpp bindless_buffer
+                return read_element(b, idx, e->type());
+            }
+            case CallOp::BINDLESS_TEXTURE2D_SAMPLE:
+            case CallOp::BINDLESS_TEXTURE2D_SAMPLE_LEVEL: {// level 0 only (the image plugin samples without LOD, image.cpp:166)
+                auto array = handle_of(args[0], Slot::Kind::BINDLESS_ARRAY);
+                auto slot_index = conv(F(1)[0], Tag::UINT32).u;
+                auto uv = F(2);
+                float out[4];
+                res().bindless_tex2d_sample(array, slot_index, uv[0].f, uv[1].f, out);
+                return from_lanes(e->type(), {mk(out[0]), mk(out[1]), mk(out[2]), mk(out[3])});
+            }
+            case CallOp::BINDLESS_TEXTURE2D_READ: {
+                auto array = handle_of(args[0], Slot::Kind::BINDLESS_ARRAY);
+                auto slot_index = conv(F(1)[0], Tag::UINT32).u;
+                auto xy = F(2);
+                float out[4];
+                res().bindless_tex2d_read(array, slot_index, conv(xy[0], Tag::UINT32).u, conv(xy[1], Tag::UINT32).u, out);
+                return from_lanes(e->type(), {mk(out[0]), mk(out[1]), mk(out[2]), mk(out[3])});
+            }
+            case CallOp::BINDLESS_TEXTURE2D_SIZE: {
+                auto array = handle_of(args[0], Slot::Kind::BINDLESS_ARRAY);
+                uint32_t size[2];
+                res().bindless_tex2d_size(array, conv(F(1)[0], Tag::UINT32).u, size);
+                return from_lanes(e->type(), {mk(size[0]), mk(size[1])});
             }
             case CallOp::RAY_TRACING_TRACE_CLOSEST:
             case CallOp::RAY_TRACING_TRACE_ANY: {
@@ -1102,6 +1144,40 @@ private:
                 if (out.size() > sizeof(HitData)) { fail("unexpected Hit layout"); }
                 std::memcpy(out.p(), &hit, out.size());
                 return out;
+            }
+            case CallOp::RAY_QUERY_WORLD_SPACE_RAY: {
+                auto &q = query_of(args[0]);
+                Val out{e->type()};
+                if (out.size() != sizeof(RayData)) { fail("unexpected Ray layout"); }
+                std::memcpy(out.p(), &q.ray, sizeof(RayData));
+                return out;
+            }
+            case CallOp::RAY_QUERY_TRIANGLE_CANDIDATE_HIT: {
+                auto &q = query_of(args[0]);
+                Val out{e->type()};
+                std::memcpy(out.p(), &q.candidate, std::min(out.size(), sizeof(HitData)));
+                return out;
+            }
+            case CallOp::RAY_QUERY_COMMITTED_HIT: {// CommittedHit {inst, prim, bary, hit_type, committed_ray_t} (rtx/hit.h:18-24)
+                auto &q = query_of(args[0]);
+                struct { uint32_t inst, prim; float bary[2]; uint32_t hit_type; float t; } c{
+                    q.committed.inst, q.committed.prim, {q.committed.bary[0], q.committed.bary[1]},
+                    q.committed.inst == ~0u ? 0u : 1u, q.committed.committed_ray_t};
+                Val out{e->type()};
+                if (out.size() != sizeof(c)) { fail("unexpected CommittedHit layout"); }
+                std::memcpy(out.p(), &c, sizeof(c));
+                return out;
+            }
+            case CallOp::RAY_QUERY_COMMIT_TRIANGLE: {
+                auto &q = query_of(args[0]);
+                q.committed = q.candidate;
+                q.ray.t_max = q.candidate.committed_ray_t;
+                if (q.any) { q.terminated = true; }
+                return Val{};
+            }
+            case CallOp::RAY_QUERY_TERMINATE: {
+                query_of(args[0]).terminated = true;
+                return Val{};
             }
             case CallOp::RAY_TRACING_INSTANCE_TRANSFORM: {
                 auto accel = handle_of(args[0], Slot::Kind::ACCEL);
@@ -1239,6 +1315,22 @@ private:
             }
             case Statement::Tag::ASSIGN: {
                 auto a = static_cast<const AssignStmt *>(s);
+                if (a->rhs()->tag() == Expression::Tag::CALL) {
+                    auto c = static_cast<const CallExpr *>(a->rhs());
+                    if (c->op() == CallOp::RAY_TRACING_QUERY_ALL || c->op() == CallOp::RAY_TRACING_QUERY_ANY) {
+                        if (a->lhs()->tag() != Expression::Tag::REF) { fail("ray query assigned to a non-variable"); }
+                        QueryState q;
+                        q.accel = handle_of(c->arguments()[0], Slot::Kind::ACCEL);
+                        auto ray = eval(c->arguments()[1]);
+                        if (ray.size() != sizeof(RayData)) { fail("unexpected Ray layout"); }
+                        std::memcpy(&q.ray, ray.p(), sizeof(RayData));
+                        q.mask = conv(lanes(eval(c->arguments()[2]))[0], Tag::UINT32).u;
+                        q.any = c->op() == CallOp::RAY_TRACING_QUERY_ANY;
+                        q.committed.committed_ray_t = q.ray.t_max;
+                        _queries[static_cast<const RefExpr *>(a->lhs())->variable().uid()] = q;
+                        return Flow::NORMAL;
+                    }
+                }
                 assign(a->lhs(), eval(a->rhs()));
                 return Flow::NORMAL;
             }
@@ -1252,6 +1344,24 @@ private:
                     if (flow == Flow::RETURN) { return flow; }
                     auto next = binary(BinaryOp::ADD, eval(f->variable()), eval(f->step()), f->variable()->type());
                     assign(f->variable(), next);
+                }
+                return Flow::NORMAL;
+            }
+            case Statement::Tag::RAY_QUERY: {
+                auto rq = static_cast<const RayQueryStmt *>(s);
+                auto &q = query_of(rq->query());
+                for (auto &&c : res().candidates(q.accel, q.ray, q.mask)) {
+                    if (q.terminated) { break; }
+                    if (!(c.hit.committed_ray_t < q.ray.t_max)) { continue; }// a closer hit has been committed meanwhile
+                    q.candidate = c.hit;
+                    if (c.opaque) {// opaque geometry commits without the callback
+                        q.committed = c.hit;
+                        q.ray.t_max = c.hit.committed_ray_t;
+                        if (q.any) { q.terminated = true; }
+                    } else {
+                        auto flow = exec(rq->on_triangle_candidate());
+                        if (flow == Flow::RETURN) { return flow; }
+                    }
                 }
                 return Flow::NORMAL;
             }
@@ -1321,6 +1431,10 @@ void launch(Function f, const std::vector<Arg> &args, const uint32_t size[3], De
             cursor.store(total);
         }
     };
+    // Small dispatches (the per-pass kernels of a small render, incl. the film's float atomics) run on ONE thread so that
+    // the order of atomic accumulation - and with it the last bit of the film - is reproducible; large dispatches (e.g. the
+    // 2048x1024 importance-map kernels of the Spherical environment) use every thread.
+    if (total <= 32768u) { threads = 1u; }
     std::vector<std::thread> pool;
     for (auto i = 1u; i < std::max(threads, 1u); i++) { pool.emplace_back(worker); }
     worker();

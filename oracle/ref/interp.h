@@ -51,6 +51,17 @@ struct DeviceResources {
     [[nodiscard]] virtual HitData trace_closest(uint64_t accel, const RayData &ray, uint32_t mask) = 0;
     [[nodiscard]] virtual bool trace_any(uint64_t accel, const RayData &ray, uint32_t mask) = 0;
     virtual void instance_transform(uint64_t accel, uint32_t index, float out_column_major[16]) = 0;
+    /* every triangle the ray crosses inside (t_min, t_max), in traversal order, with its instance's opaque flag: the
+     * candidates of a ray query (include/luisa/dsl/rtx/ray_query.h) */
+    struct Candidate {
+        HitData hit;
+        bool opaque;
+    };
+    [[nodiscard]] virtual std::vector<Candidate> candidates(uint64_t accel, const RayData &ray, uint32_t mask) = 0;
+    /* bindless 2D texture `slot` of `array`, sampled at uv with the slot's sampler (level 0), as float4 */
+    virtual void bindless_tex2d_sample(uint64_t array, uint32_t slot, float u, float v, float out[4]) = 0;
+    virtual void bindless_tex2d_size(uint64_t array, uint32_t slot, uint32_t out[2]) = 0;
+    virtual void bindless_tex2d_read(uint64_t array, uint32_t slot, uint32_t x, uint32_t y, float out[4]) = 0;
 };
 
 /* one argument of the entry function */

@@ -39,9 +39,40 @@ struct BindlessObject {
     struct Slot {
         uint64_t buffer{0u};
         size_t offset{0u};
+        uint64_t tex2d{0u};
+        Sampler sampler{};
     };
     luisa::vector<Slot> slots;
 };
+
+struct TextureObject {
+    PixelStorage storage{PixelStorage::FLOAT4};
+    uint32_t width{0u}, height{0u};
+    luisa::vector<std::byte> texels;// level 0, rows tightly packed
+};
+
+float half_bits_to_float(uint16_t h) noexcept {
+    auto sign = static_cast<uint32_t>(h & 0x8000u) << 16u;
+    auto exponent = (h >> 10u) & 0x1fu;
+    auto mantissa = static_cast<uint32_t>(h & 0x3ffu);
+    uint32_t bits;
+    if (exponent == 0u) {
+        if (mantissa == 0u) {
+            bits = sign;
+        } else {// subnormal
+            auto e = 127u - 15u + 1u;
+            while ((mantissa & 0x400u) == 0u) { mantissa <<= 1u; e--; }
+            bits = sign | (e << 23u) | ((mantissa & 0x3ffu) << 13u);
+        }
+    } else if (exponent == 31u) {
+        bits = sign | 0x7f800000u | (mantissa << 13u);
+    } else {
+        bits = sign | ((exponent + 127u - 15u) << 23u) | (mantissa << 13u);
+    }
+    float f;
+    std::memcpy(&f, &bits, 4u);
+    return f;
+}
 
 struct MeshObject {
     uint64_t vertex_buffer{0u};
@@ -129,10 +160,17 @@ public:
     void destroy_buffer(uint64_t handle) noexcept override { delete object<BufferObject>(handle); }
 
     // ---- textures: not needed by the paths exercised (constant textures live in a buffer, the film is a buffer)
-    ResourceCreationInfo create_texture(PixelFormat, uint, uint, uint, uint, uint, bool, bool) noexcept override {
-        LUISA_ERROR_WITH_LOCATION("interp: device textures are not implemented.");
+    // ---- textures: 2D, level 0 (the image-texture plugin samples without LOD, src/textures/image.cpp:166)
+    ResourceCreationInfo create_texture(PixelFormat format, uint dimension, uint width, uint height, uint depth, uint, bool, bool) noexcept override {
+        LUISA_ASSERT(dimension == 2u && depth == 1u, "interp: only 2D textures are implemented.");
+        auto t = new TextureObject;
+        t->storage = pixel_format_to_storage(format);
+        t->width = width;
+        t->height = height;
+        t->texels.resize(pixel_storage_size(t->storage, make_uint3(width, height, 1u)), std::byte{0});
+        return {reinterpret_cast<uint64_t>(t), t};
     }
-    void destroy_texture(uint64_t) noexcept override {}
+    void destroy_texture(uint64_t handle) noexcept override { delete object<TextureObject>(handle); }
 
     // ---- bindless arrays
     ResourceCreationInfo create_bindless_array(size_t size) noexcept override {
@@ -246,7 +284,13 @@ public:
                              object<BufferObject>(c->src_handle())->data.data() + c->src_offset(), c->size());
             }
             void visit(const BufferToTextureCopyCommand *) noexcept override { LUISA_ERROR_WITH_LOCATION("interp: textures."); }
-            void visit(const TextureUploadCommand *) noexcept override { LUISA_ERROR_WITH_LOCATION("interp: textures."); }
+            void visit(const TextureUploadCommand *c) noexcept override {
+                auto t = object<TextureObject>(c->handle());
+                if (c->level() != 0u) { return; }// mip levels are never sampled here
+                auto size = c->size();
+                LUISA_ASSERT(all(c->offset() == make_uint3(0u)) && size.x == t->width && size.y == t->height, "interp: partial texture uploads.");
+                std::memcpy(t->texels.data(), c->data(), t->texels.size());
+            }
             void visit(const TextureDownloadCommand *) noexcept override { LUISA_ERROR_WITH_LOCATION("interp: textures."); }
             void visit(const TextureCopyCommand *) noexcept override { LUISA_ERROR_WITH_LOCATION("interp: textures."); }
             void visit(const TextureToBufferCopyCommand *) noexcept override { LUISA_ERROR_WITH_LOCATION("interp: textures."); }
@@ -285,7 +329,13 @@ public:
                 for (auto &&m : const_cast<BindlessArrayUpdateCommand *>(c)->steal_modifications()) {
                     if (m.buffer.op == Op::EMPLACE) { a->slots[m.slot] = {m.buffer.handle, m.buffer.offset_bytes}; }
                     else if (m.buffer.op == Op::REMOVE) { a->slots[m.slot] = {}; }
-                    if (m.tex2d.op == Op::EMPLACE || m.tex3d.op == Op::EMPLACE) { LUISA_ERROR_WITH_LOCATION("interp: bindless textures."); }
+                    if (m.tex2d.op == Op::EMPLACE) {
+                        a->slots[m.slot].tex2d = m.tex2d.handle;
+                        a->slots[m.slot].sampler = m.tex2d.sampler;
+                    } else if (m.tex2d.op == Op::REMOVE) {
+                        a->slots[m.slot].tex2d = 0u;
+                    }
+                    if (m.tex3d.op == Op::EMPLACE) { LUISA_ERROR_WITH_LOCATION("interp: bindless 3D textures."); }
                 }
             }
             void visit(const ShaderDispatchCommand *c) noexcept override { device->run(c); }
@@ -341,13 +391,99 @@ public:
     // ---- refinterp::DeviceResources
     refinterp::BufferArg bindless_buffer(uint64_t array, uint32_t slot) override {
         auto a = object<BindlessObject>(array);
-        if (slot >= a->slots.size() || a->slots[slot].buffer == 0u) { throw std::runtime_error("empty bindless buffer slot"); }
+        // reads through an unpopulated slot happen in never-taken `ite` operands (both sides are evaluated, as on a GPU, where
+        // such a read returns garbage that is then discarded): give them zeros
+        if (slot >= a->slots.size() || a->slots[slot].buffer == 0u) { return {nullptr, 0u}; }
         auto b = object<BufferObject>(a->slots[slot].buffer);
         return {b->data.data() + a->slots[slot].offset, b->data.size() - a->slots[slot].offset};
     }
 
+    // The reference's software sampler: src/compute/src/rust/luisa_compute_backend_impl/src/cpu/codegen/cpu_texture.h
+    // (:63 unorm conversion, :369-372 out-of-bounds reads return zero, :418-464 coordinates + bilinear, :489-493 point)
+    static void read_texel(const TextureObject *t, uint32_t x, uint32_t y, float out[4]) {
+        out[0] = out[1] = out[2] = out[3] = 0.f;
+        if (!(x < t->width && y < t->height)) { return; }
+        auto channels = pixel_storage_channel_count(t->storage);
+        auto index = static_cast<size_t>(y) * t->width + x;
+        for (auto c = 0u; c < channels; c++) {
+            switch (t->storage) {
+                case PixelStorage::BYTE1:
+                case PixelStorage::BYTE2:
+                case PixelStorage::BYTE4: out[c] = static_cast<float>(reinterpret_cast<const uint8_t *>(t->texels.data())[index * channels + c]) / 255.f; break;
+                case PixelStorage::SHORT1:
+                case PixelStorage::SHORT2:
+                case PixelStorage::SHORT4: out[c] = static_cast<float>(reinterpret_cast<const uint16_t *>(t->texels.data())[index * channels + c]) / 65535.f; break;
+                case PixelStorage::HALF1:
+                case PixelStorage::HALF2:
+                case PixelStorage::HALF4: out[c] = half_bits_to_float(reinterpret_cast<const uint16_t *>(t->texels.data())[index * channels + c]); break;
+                case PixelStorage::FLOAT1:
+                case PixelStorage::FLOAT2:
+                case PixelStorage::FLOAT4: out[c] = reinterpret_cast<const float *>(t->texels.data())[index * channels + c]; break;
+                default: throw std::runtime_error("unsupported texture storage");
+            }
+        }
+    }
+    static float coord(Sampler::Address address, float uv, float s) {
+        constexpr auto one_minus_epsilon = 0x1.fffffep-1f;
+        switch (address) {
+            case Sampler::Address::EDGE: return std::fmin(std::fmax(uv, 0.0f), one_minus_epsilon) * s;
+            case Sampler::Address::REPEAT: return (uv - std::floor(uv)) * s;
+            case Sampler::Address::MIRROR: {
+                uv = std::fmod(std::fabs(uv), 2.0f);
+                uv = uv < 1.f ? uv : 2.f - uv;
+                return std::fmin(uv, one_minus_epsilon) * s;
+            }
+            default: return (uv < 0.f || uv >= 1.f) ? 65536.f : uv * s;
+        }
+    }
+    const BindlessObject::Slot &tex_slot(uint64_t array, uint32_t slot) const {
+        auto a = object<BindlessObject>(array);
+        if (slot >= a->slots.size() || a->slots[slot].tex2d == 0u) { throw std::runtime_error("empty bindless texture slot"); }
+        return a->slots[slot];
+    }
+    void bindless_tex2d_sample(uint64_t array, uint32_t slot, float u, float v, float out[4]) override {
+        auto &s = tex_slot(array, slot);
+        auto t = object<TextureObject>(s.tex2d);
+        auto sx = static_cast<float>(t->width), sy = static_cast<float>(t->height);
+        auto address = s.sampler.address();
+        if (s.sampler.filter() == Sampler::Filter::POINT) {
+            read_texel(t, static_cast<uint32_t>(coord(address, u, sx)), static_cast<uint32_t>(coord(address, v, sy)), out);
+            return;
+        }
+        auto inv_sx = 1.f / sx, inv_sy = 1.f / sy;
+        auto ax = coord(address, u - .5f * inv_sx, sx), bx = coord(address, u + .5f * inv_sx, sx);
+        auto ay = coord(address, v - .5f * inv_sy, sy), by = coord(address, v + .5f * inv_sy, sy);
+        auto x_min = std::fmin(ax, bx), x_max = std::fmax(ax, bx), y_min = std::fmin(ay, by), y_max = std::fmax(ay, by);
+        auto tx = x_max - std::floor(x_max), ty = y_max - std::floor(y_max);
+        auto x0 = static_cast<uint32_t>(x_min), y0 = static_cast<uint32_t>(y_min), x1 = static_cast<uint32_t>(x_max), y1 = static_cast<uint32_t>(y_max);
+        float v00[4], v01[4], v10[4], v11[4];
+        read_texel(t, x0, y0, v00);
+        read_texel(t, x1, y0, v01);
+        read_texel(t, x0, y1, v10);
+        read_texel(t, x1, y1, v11);
+        for (auto c = 0; c < 4; c++) {
+            auto a = tx * (v01[c] - v00[c]) + v00[c];
+            auto b = tx * (v11[c] - v10[c]) + v10[c];
+            out[c] = ty * (b - a) + a;
+        }
+    }
+    void bindless_tex2d_size(uint64_t array, uint32_t slot, uint32_t out[2]) override {
+        auto t = object<TextureObject>(tex_slot(array, slot).tex2d);
+        out[0] = t->width;
+        out[1] = t->height;
+    }
+    void bindless_tex2d_read(uint64_t array, uint32_t slot, uint32_t x, uint32_t y, float out[4]) override {
+        read_texel(object<TextureObject>(tex_slot(array, slot).tex2d), x, y, out);
+    }
+
+    std::vector<Candidate> candidates(uint64_t accel, const refinterp::RayData &ray, uint32_t mask) override {
+        std::vector<Candidate> out;
+        trace<false>(accel, ray, mask, &out);
+        return out;
+    }
+
     template<bool any_hit>
-    refinterp::HitData trace(uint64_t accel, const refinterp::RayData &ray, uint32_t mask) const {
+    refinterp::HitData trace(uint64_t accel, const refinterp::RayData &ray, uint32_t mask, std::vector<Candidate> *all = nullptr) const {
         // oracle/oracle.cpp: trace_brute — the same expressions, explicit fma where the oracle / CUDA kernels spell it out
         auto a = object<AccelObject>(accel);
         refinterp::HitData best{~0u, ~0u, {0.f, 0.f}, ray.t_max, 0u};
@@ -391,6 +527,10 @@ public:
                 if (!(v >= 0.0f && u + v <= 1.0f)) { continue; }
                 auto t = fdot(e2, qvec) * inv_det;
                 if (!(t > ray.t_min && t < tbest)) { continue; }
+                if (all != nullptr) {// ray query: every crossing is a candidate, the query decides what is committed
+                    all->push_back({refinterp::HitData{i, k, {u, v}, t, 0u}, inst.opaque});
+                    continue;
+                }
                 tbest = t;
                 best = {i, k, {u, v}, t, 0u};
                 if constexpr (any_hit) { return best; }

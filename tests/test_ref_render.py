@@ -33,7 +33,7 @@ from oracle import binding as O  # noqa: E402
 
 GOLDEN = REPO / "tests" / "golden" / "ref_renders.npz"
 CASES = ["cornell_wavepath", "cornell_megapath", "cornell_russian_roulette", "spheres_disney", "spheres_medium",
-         "materials_wavepath", "materials_megapath_rr"]
+         "materials_wavepath", "materials_megapath_rr", "textured", "textured_wrappers", "environment_image"]
 
 
 @pytest.fixture(scope="module")
@@ -65,7 +65,7 @@ def test_oracle_film_is_bit_identical_to_the_reference_render(golden, name):
     finally:
         O.lib().oracle_set_hg_args_right_to_left(0)
     assert got.shape == want.shape
-    assert np.isfinite(want).all() and want[..., :3].mean() > 0.05
+    assert np.isfinite(want).all() and want[..., :3].mean() > 0.02
     same = (got.view(np.uint32) == want.view(np.uint32)).all(axis=-1)
     assert same.all(), (f"{name}: {int((~same).sum())} of {same.size} pixels differ from the reference render; first at "
                         f"{np.argwhere(~same)[0].tolist()}: oracle {got[tuple(np.argwhere(~same)[0])]} reference "
@@ -83,13 +83,12 @@ def test_fixture_is_what_the_reference_renders_now(golden):
         for name in ("cornell_wavepath", "spheres_medium"):
             source = bytes(golden[f"{name}/scene"]).decode()
             image = G.render_with_reference(source, Path(tmp), name)
-            # the film is accumulated with float atomics by several host threads: the sum order is not fixed
-            np.testing.assert_allclose(image, golden[f"{name}/image"], rtol=2e-6, atol=1e-7, err_msg=name)
+            np.testing.assert_array_equal(image, golden[f"{name}/image"], err_msg=name)  # single interpreter thread: deterministic
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["cornell_wavepath", "cornell_russian_roulette", "spheres_disney", "materials_wavepath",
-                                  "materials_megapath_rr"])
+                                  "materials_megapath_rr", "textured", "textured_wrappers", "environment_image"])
 def test_cuda_film_matches_the_reference_render(golden, name, gpu_renderer):
     source, scene, desc = _scene(golden, name)
     want = golden[f"{name}/image"][..., :3]
@@ -99,7 +98,11 @@ def test_cuda_film_matches_the_reference_render(golden, name, gpu_renderer):
     got = gpu_renderer.film()[..., :3]
     err = np.abs(got - want)
     off = (err > 1e-4 * np.maximum(np.abs(want), 1.0)).any(axis=-1)
-    if name.startswith("materials"):
+    if name == "textured_wrappers":
+        # the stochastic alpha test hashes barycentric BITS: see tests/test_gpu_parity.py::test_render_matches_oracle
+        assert off.mean() <= 0.04, f"{name}: {off.mean():.4f} of the pixels off"
+        assert got.mean() == pytest.approx(want.mean(), rel=0.03)
+    elif name.startswith("materials"):
         # Specular chains (mirror wall, smooth and rough glass) amplify the ulp-level differences between CUDA's and glibc's
         # sin / cos / pow into different discrete decisions (lobe choice, total internal reflection, Russian roulette) for a
         # few paths: <= 3 % of the pixels may take another, equally valid, branch; the rest agree to 1e-3 rel-L2 and the

@@ -41,27 +41,48 @@ def cases() -> dict[str, str]:
     c["materials_wavepath"] = scenes.materials_box(resolution=(32, 24), spp=4, depth=8)
     c["materials_megapath_rr"] = scenes.materials_box(resolution=(32, 24), spp=4, depth=10, rr_depth=2, rr_threshold=0.95,
                                                       integrator="MegaPath")
+    # row f1: image textures (8 / 16-bit PNG, grey, palette; all address modes, point + bilinear, sRGB / linear / gamma) on
+    # Matte and Disney parameters; with wrappers: normal map, alpha-tested cut-out (ray queries), constant opacity.
+    # mesh_files=False: the `Mesh` plugin of the reference needs assimp, which is not built
+    assets = "tests/golden/assets"
+    c["textured"] = scenes.textured_room(resolution=(32, 24), spp=2, mesh_files=False, assets=assets)
+    c["textured_wrappers"] = scenes.textured_room(resolution=(32, 24), spp=2, mesh_files=False, assets=assets, wrappers=True)
+    # row a12: Spherical environment with an image emission (importance map, MIS compensation) next to an area light
+    c["environment_image"] = scenes.environment_scene(resolution=(32, 20), spp=2, emission="image", assets=assets, sky_file="sky.exr")
     return c
 
 
-def read_f32(path: Path) -> np.ndarray:
-    with open(path, "rb") as f:
-        w, h, ch = map(int, f.readline().split())
-        return np.frombuffer(f.read(), dtype=np.float32).reshape(h, w, ch).copy()
+def read_image(path: Path) -> np.ndarray:
+    """The film the reference wrote (EXR, fp32 ZIP, through its tinyexr) decoded by this repository's own reader."""
+    import ctypes as C
+
+    from luisarender_b200 import _ffi as F
+
+    host = F.host_lib()
+    host.lrh_load_image.argtypes = [C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_void_p, C.c_uint64]
+    w, h, ch = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    if host.lrh_load_image(str(path).encode(), C.byref(w), C.byref(h), C.byref(ch), None, 0) != 0:
+        raise RuntimeError(host.lrh_last_error().decode())
+    out = np.zeros((h.value, w.value, 4), dtype=np.float32)
+    if host.lrh_load_image(str(path).encode(), C.byref(w), C.byref(h), C.byref(ch), out.ctypes.data, out.size) != 0:
+        raise RuntimeError(host.lrh_last_error().decode())
+    return out
 
 
 def render_with_reference(source: str, workdir: Path, name: str = "scene") -> np.ndarray:
-    """Runs the reference CLI on `source`; returns the RGBA film (the camera's `file` + '.f32', oracle/ref/shim.cpp)."""
+    """Runs the reference CLI on `source`; returns the RGBA film it saved (the camera's `file`, an fp32 EXR)."""
     import re
 
     scene_path = workdir / f"{name}.luisa"
-    scene_path.write_text(source)
-    out_name = re.search(r'file\s*\{\s*"([^"]+)"\s*\}', source).group(1)
-    log = subprocess.run([str(CLI), "-b", "interp", scene_path.name], cwd=workdir, capture_output=True, text=True, timeout=3600)
-    out = workdir / (out_name + ".f32")
+    # asset paths in the scene text are relative to the repository root (the product resolves them the same way)
+    scene_path.write_text(source.replace('"tests/golden/assets/', f'"{REPO}/tests/golden/assets/'))
+    out_name = re.search(r'Camera\b.*?\bfile\s*\{\s*"([^"]+)"\s*\}', source, re.S).group(1)  # the camera's output file
+    # (the interp backend runs small dispatches - everything that touches the film - on one thread: reproducible atomics)
+    log = subprocess.run([str(CLI), "-b", "interp", scene_path.name], cwd=workdir, capture_output=True, text=True, timeout=1200)
+    out = workdir / out_name
     if not out.exists():
         raise RuntimeError(f"reference render of '{name}' failed:\n{log.stdout[-2000:]}\n{log.stderr[-2000:]}")
-    return read_f32(out)
+    return read_image(out)
 
 
 def main() -> int:
