@@ -11,8 +11,10 @@
 // Ray / triangle intersection is the one third-party piece of the reference's path (OptiX / Embree); here it
 // is a brute-force loop over all triangles with the Moeller-Trumbore arithmetic this repository's oracle and CUDA kernels
 // use (oracle/oracle.cpp: trace_brute), so that hits are comparable bit for bit.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <limits>
 #include <mutex>
 #include <thread>
 
@@ -79,6 +81,15 @@ struct MeshObject {
     size_t vertex_offset{0u}, vertex_size{0u}, vertex_stride{0u};
     uint64_t triangle_buffer{0u};
     size_t triangle_offset{0u}, triangle_size{0u};
+    // A plain median-split bounding-volume hierarchy over the triangles (object space), only to skip triangles the ray
+    // cannot reach: every triangle whose box the ray enters is still tested with the expressions below, so the set of
+    // crossings - and the closest one - is the brute-force loop's (up to exact ties in t, which keep the first found).
+    struct Node {
+        float lo[3], hi[3];
+        uint32_t left, right;// inner: child indices; leaf: left = first, right = count | 0x80000000
+    };
+    luisa::vector<Node> nodes;
+    luisa::vector<uint32_t> order;// triangle indices in leaf order
 };
 
 struct AccelObject {
@@ -122,6 +133,68 @@ void invert_affine(const float m[12], float out[12]) noexcept {// rows of the 3x
     for (auto r = 0; r < 3; r++) {
         for (auto c = 0; c < 3; c++) { out[r * 4 + c] = static_cast<float>(inv[r][c]); }
         out[r * 4 + 3] = static_cast<float>(-(inv[r][0] * a(0, 3) + inv[r][1] * a(1, 3) + inv[r][2] * a(2, 3)));
+    }
+}
+
+void build_mesh_bvh(MeshObject *m) {
+    auto vbuf = object<BufferObject>(m->vertex_buffer)->data.data() + m->vertex_offset;
+    auto tbuf = reinterpret_cast<const uint32_t *>(object<BufferObject>(m->triangle_buffer)->data.data() + m->triangle_offset);
+    auto count = static_cast<uint32_t>(m->triangle_size / 12u);
+    auto position = [&](uint32_t v) { return reinterpret_cast<const float *>(vbuf + v * m->vertex_stride); };
+    m->order.resize(count);
+    for (auto i = 0u; i < count; i++) { m->order[i] = i; }
+    luisa::vector<float> centroid(static_cast<size_t>(count) * 3u), tlo(static_cast<size_t>(count) * 3u), thi(static_cast<size_t>(count) * 3u);
+    for (auto i = 0u; i < count; i++) {
+        for (auto a = 0; a < 3; a++) {
+            auto x = position(tbuf[3u * i])[a], y = position(tbuf[3u * i + 1u])[a], z = position(tbuf[3u * i + 2u])[a];
+            tlo[3u * i + a] = std::min({x, y, z});
+            thi[3u * i + a] = std::max({x, y, z});
+            centroid[3u * i + a] = (x + y + z) * (1.f / 3.f);
+        }
+    }
+    m->nodes.clear();
+    m->nodes.reserve(2u * count / 4u + 8u);
+    struct Task { uint32_t node, first, count; };
+    luisa::vector<Task> stack;
+    m->nodes.emplace_back();
+    stack.push_back({0u, 0u, count});
+    while (!stack.empty()) {
+        auto task = stack.back();
+        stack.pop_back();
+        MeshObject::Node node{};
+        float clo[3], chi[3];
+        for (auto a = 0; a < 3; a++) { node.lo[a] = clo[a] = std::numeric_limits<float>::max(); node.hi[a] = chi[a] = -std::numeric_limits<float>::max(); }
+        for (auto j = task.first; j < task.first + task.count; j++) {
+            auto tri = m->order[j];
+            for (auto a = 0; a < 3; a++) {
+                node.lo[a] = std::min(node.lo[a], tlo[3u * tri + a]);
+                node.hi[a] = std::max(node.hi[a], thi[3u * tri + a]);
+                clo[a] = std::min(clo[a], centroid[3u * tri + a]);
+                chi[a] = std::max(chi[a], centroid[3u * tri + a]);
+            }
+        }
+        for (auto a = 0; a < 3; a++) {// pad: the box must never reject a triangle the exact test would accept
+            auto pad = 1e-4f * std::max({std::fabs(node.lo[a]), std::fabs(node.hi[a]), 1e-3f});
+            node.lo[a] -= pad;
+            node.hi[a] += pad;
+        }
+        auto axis = 0;
+        for (auto a = 1; a < 3; a++) { if (chi[a] - clo[a] > chi[axis] - clo[axis]) { axis = a; } }
+        if (task.count <= 4u || !(chi[axis] > clo[axis])) {
+            node.left = task.first;
+            node.right = task.count | 0x80000000u;
+        } else {
+            auto mid = task.first + task.count / 2u;
+            std::nth_element(m->order.begin() + task.first, m->order.begin() + mid, m->order.begin() + task.first + task.count,
+                             [&](uint32_t x, uint32_t y) { return centroid[3u * x + axis] < centroid[3u * y + axis]; });
+            node.left = static_cast<uint32_t>(m->nodes.size());
+            node.right = node.left + 1u;
+            m->nodes.emplace_back();
+            m->nodes.emplace_back();
+            stack.push_back({node.left, task.first, mid - task.first});
+            stack.push_back({node.right, mid, task.first + task.count - mid});
+        }
+        m->nodes[task.node] = node;
     }
 }
 
@@ -306,6 +379,7 @@ public:
                 m->triangle_buffer = c->triangle_buffer();
                 m->triangle_offset = c->triangle_buffer_offset();
                 m->triangle_size = c->triangle_buffer_size();
+                build_mesh_bvh(m);
             }
             void visit(const AccelBuildCommand *c) noexcept override {
                 auto a = object<AccelObject>(c->handle());
@@ -510,31 +584,65 @@ public:
             auto tbuf = reinterpret_cast<const uint32_t *>(object<BufferObject>(mesh->triangle_buffer)->data.data() + mesh->triangle_offset);
             auto tri_count = mesh->triangle_size / 12u;
             auto position = [&](uint32_t v) { return reinterpret_cast<const float *>(vbuf + v * mesh->vertex_stride); };
-            for (auto k = 0u; k < tri_count; k++) {
+            // object-space slab test (conservative: padded boxes, NaN-dropping min / max)
+            float inv[3] = {1.f / dd[0], 1.f / dd[1], 1.f / dd[2]};
+            auto enters = [&](const MeshObject::Node &n, float t_far) {
+                auto t0 = ray.t_min, t1 = t_far;
+                for (auto ax = 0; ax < 3; ax++) {
+                    auto a0 = (n.lo[ax] - oo[ax]) * inv[ax], a1 = (n.hi[ax] - oo[ax]) * inv[ax];
+                    if (dd[ax] == 0.f) {// parallel: inside the slab or not at all
+                        if (oo[ax] < n.lo[ax] || oo[ax] > n.hi[ax]) { return false; }
+                        continue;
+                    }
+                    t0 = std::fmax(t0, std::fmin(a0, a1));
+                    t1 = std::fmin(t1, std::fmax(a0, a1));
+                }
+                return t0 <= t1 * 1.0001f + 1e-6f;
+            };
+            auto test = [&](uint32_t k) -> bool {// returns true when the traversal can stop (any-hit)
                 auto p0 = position(tbuf[3u * k]), p1 = position(tbuf[3u * k + 1u]), p2 = position(tbuf[3u * k + 2u]);
                 float e1[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]};
                 float e2[3] = {p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2]};
                 float pvec[3], qvec[3];
                 fcross(dd, e2, pvec);
                 auto det = fdot(e1, pvec);
-                if (!(det != 0.0f)) { continue; }
+                if (!(det != 0.0f)) { return false; }
                 auto inv_det = 1.0f / det;
                 float tvec[3] = {oo[0] - p0[0], oo[1] - p0[1], oo[2] - p0[2]};
                 auto u = fdot(tvec, pvec) * inv_det;
-                if (!(u >= 0.0f && u <= 1.0f)) { continue; }
+                if (!(u >= 0.0f && u <= 1.0f)) { return false; }
                 fcross(tvec, e1, qvec);
                 auto v = fdot(dd, qvec) * inv_det;
-                if (!(v >= 0.0f && u + v <= 1.0f)) { continue; }
+                if (!(v >= 0.0f && u + v <= 1.0f)) { return false; }
                 auto t = fdot(e2, qvec) * inv_det;
-                if (!(t > ray.t_min && t < tbest)) { continue; }
+                // exact ties in t: the lower (instance, primitive) wins, as in an index-ordered brute-force loop
+                auto tie = t == tbest && best.inst != ~0u && (i < best.inst || (i == best.inst && k < best.prim));
+                if (!(t > ray.t_min && (t < tbest || tie))) { return false; }
                 if (all != nullptr) {// ray query: every crossing is a candidate, the query decides what is committed
                     all->push_back({refinterp::HitData{i, k, {u, v}, t, 0u}, inst.opaque});
-                    continue;
+                    return false;
                 }
                 tbest = t;
                 best = {i, k, {u, v}, t, 0u};
-                if constexpr (any_hit) { return best; }
+                return any_hit;
+            };
+            (void)tri_count;
+            uint32_t todo[128];
+            auto top = 0u;
+            todo[top++] = 0u;
+            auto done = false;
+            while (top != 0u && !done) {
+                auto &n = mesh->nodes[todo[--top]];
+                if (!enters(n, tbest)) { continue; }
+                if (n.right & 0x80000000u) {
+                    for (auto j = n.left; j < n.left + (n.right & 0x7fffffffu) && !done; j++) { done = test(mesh->order[j]); }
+                } else {
+                    if (top + 2u > 128u) { throw std::runtime_error("BVH stack overflow"); }
+                    todo[top++] = n.left;
+                    todo[top++] = n.right;
+                }
             }
+            if (done) { return best; }
         }
         return best;
     }

@@ -33,7 +33,8 @@ from oracle import binding as O  # noqa: E402
 
 GOLDEN = REPO / "tests" / "golden" / "ref_renders.npz"
 CASES = ["cornell_wavepath", "cornell_megapath", "cornell_russian_roulette", "spheres_disney", "spheres_medium",
-         "materials_wavepath", "materials_megapath_rr", "textured", "textured_wrappers", "environment_image"]
+         "materials_wavepath", "materials_megapath_rr", "textured", "textured_wrappers", "environment_image",
+         "config_c3_full_scene", "config_c4_full_scene"]
 
 
 @pytest.fixture(scope="module")
@@ -58,7 +59,7 @@ def _spp(source):
 def test_oracle_film_is_bit_identical_to_the_reference_render(golden, name):
     source, scene, desc = _scene(golden, name)
     want = golden[f"{name}/image"]
-    O.lib().oracle_set_hg_args_right_to_left(1 if "medium" in name else 0)
+    O.lib().oracle_set_hg_args_right_to_left(1 if ("medium" in name or "c4" in name) else 0)
     try:
         raw, _ = O.render(desc, 0, _spp(source))
         got = O.convert_film(desc, raw)
@@ -88,7 +89,8 @@ def test_fixture_is_what_the_reference_renders_now(golden):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["cornell_wavepath", "cornell_russian_roulette", "spheres_disney", "materials_wavepath",
-                                  "materials_megapath_rr", "textured", "textured_wrappers", "environment_image"])
+                                  "materials_megapath_rr", "textured", "textured_wrappers", "environment_image",
+                                  "config_c3_full_scene"])
 def test_cuda_film_matches_the_reference_render(golden, name, gpu_renderer):
     source, scene, desc = _scene(golden, name)
     want = golden[f"{name}/image"][..., :3]

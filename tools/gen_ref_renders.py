@@ -49,6 +49,10 @@ def cases() -> dict[str, str]:
     c["textured_wrappers"] = scenes.textured_room(resolution=(32, 24), spp=2, mesh_files=False, assets=assets, wrappers=True)
     # row a12: Spherical environment with an image emission (importance map, MIS compensation) next to an area light
     c["environment_image"] = scenes.environment_scene(resolution=(32, 20), spp=2, emission="image", assets=assets, sky_file="sky.exr")
+    # the headline scenes at full geometric size (1 387 526 instanced triangles: Loop-subdivision spheres at level 7 and 3
+    # built by the reference's own Sphere plugin), low resolution: config C3 (Disney + NEE) and config C4 (+ medium, depth 8)
+    c["config_c3_full_scene"] = scenes.instanced_spheres(resolution=(96, 54), spp=2, output="c3.exr")
+    c["config_c4_full_scene"] = scenes.instanced_spheres(resolution=(96, 54), spp=2, medium=True, depth=8, output="c4.exr")
     return c
 
 
@@ -86,12 +90,17 @@ def render_with_reference(source: str, workdir: Path, name: str = "scene") -> np
 
 
 def main() -> int:
+    """python tools/gen_ref_renders.py [name ...]: without names every case is rendered (the environment case alone takes
+    ~17 min: its 2048x1024 importance-map kernels run on the interpreter); with names only those, merged into the fixture."""
     if not CLI.exists():
         print(f"{CLI} is missing: run `make -C oracle/ref` (needs /root/reference)", file=sys.stderr)
         return 1
-    data = {}
+    only = set(sys.argv[1:])
+    data = dict(np.load(OUT)) if only and OUT.exists() else {}
     with tempfile.TemporaryDirectory() as tmp:
         for name, source in cases().items():
+            if only and name not in only:
+                continue
             image = render_with_reference(source, Path(tmp), name)
             data[f"{name}/scene"] = np.frombuffer(source.encode(), dtype=np.uint8)
             data[f"{name}/image"] = image
