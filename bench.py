@@ -140,6 +140,34 @@ def cpu_oracle_rate(desc, target_seconds: float, spp: int, threads: int = 0):
     return cnt["samples"] / dt * 1e-6, cnt["samples"], dt, desc_s, world
 
 
+def reference_on_interpreter():
+    """The UNMODIFIED reference renderer (oracle/_ref/bin/luisa-render-cli, built from /root/reference by oracle/ref) on its
+    `interp` backend - a host AST interpreter - for a 96x54 @2spp view of the same scene, timed by the reference's own
+    'Rendering finished in ... ms' line (src/base/integrator.cpp:111-112).  Reported for completeness only: an interpreter
+    says nothing about the reference's LLVM `cpu` backend.  Returns None when oracle/_ref is absent."""
+    import re
+    import subprocess
+    import tempfile
+
+    cli = REPO / "oracle" / "_ref" / "bin" / "luisa-render-cli"
+    if not cli.exists():
+        return None
+    try:
+        from luisarender_b200 import scenes
+
+        w, h, spp = 96, 54, 2
+        with tempfile.TemporaryDirectory() as tmp:
+            (Path(tmp) / "scene.luisa").write_text(scenes.instanced_spheres(resolution=(w, h), spp=spp, output="interp.exr"))
+            log = subprocess.run([str(cli), "-b", "interp", "scene.luisa"], cwd=tmp, capture_output=True, text=True, timeout=600)
+        ms = float(re.search(r"Rendering finished in ([0-9.eE+-]+) ms", log.stdout + log.stderr).group(1))
+        return {"value": round(w * h * spp / ms * 1e-3, 6), "unit": UNIT, "kind": "reference",
+                "sample": f"{w}x{h} @{spp} spp of the same scene, the reference's own render timer",
+                "note": "unmodified reference renderer on oracle/ref's AST-interpreter backend (one host thread per small "
+                        "dispatch); bit-identical output to the port, not representative of the reference's LLVM cpu backend"}
+    except Exception as e:  # noqa: BLE001 - a reported extra, never fatal
+        return {"unavailable": str(e)[:200]}
+
+
 def run_reference(args, rank: int):
     """--impl reference: the CPU implementation of the path (oracle port) on the host cores, rank 0 only."""
     if rank != 0:
@@ -171,6 +199,9 @@ def run_reference(args, rank: int):
         "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    interp = reference_on_interpreter()
+    if interp is not None:
+        line["reference_on_interpreter"] = interp
     print(json.dumps(line), flush=True)
 
 
