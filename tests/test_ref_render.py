@@ -34,7 +34,8 @@ from oracle import binding as O  # noqa: E402
 GOLDEN = REPO / "tests" / "golden" / "ref_renders.npz"
 CASES = ["cornell_wavepath", "cornell_megapath", "cornell_russian_roulette", "spheres_disney", "spheres_medium",
          "materials_wavepath", "materials_megapath_rr", "textured", "textured_wrappers", "environment_image",
-         "config_c3_full_scene", "config_c4_full_scene"]
+         "config_c3_full_scene", "config_c4_full_scene", "cornell_filter_gaussian", "cornell_filter_triangle",
+         "cornell_filter_mitchell", "cornell_filter_lanczossinc", "cornell_film_and_light_options"]
 
 
 @pytest.fixture(scope="module")
@@ -90,7 +91,8 @@ def test_fixture_is_what_the_reference_renders_now(golden):
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["cornell_wavepath", "cornell_russian_roulette", "spheres_disney", "materials_wavepath",
                                   "materials_megapath_rr", "textured", "textured_wrappers", "environment_image",
-                                  "config_c3_full_scene"])
+                                  "config_c3_full_scene", "cornell_filter_gaussian", "cornell_filter_mitchell",
+                                  "cornell_film_and_light_options"])
 def test_cuda_film_matches_the_reference_render(golden, name, gpu_renderer):
     source, scene, desc = _scene(golden, name)
     want = golden[f"{name}/image"][..., :3]

@@ -33,6 +33,14 @@ def cases() -> dict[str, str]:
     c["cornell_wavepath"] = scenes.cornell_box(resolution=(24, 24), spp=4)
     c["cornell_megapath"] = scenes.cornell_box(resolution=(24, 24), spp=4).replace("integrator : WavePath", "integrator : MegaPath")
     c["cornell_russian_roulette"] = scenes.cornell_box(resolution=(24, 24), spp=4, depth=12, rr_depth=2, rr_threshold=0.95)
+    # row a2 (filter importance sampling through the 64-tap LUT + alias table) with the four non-trivial reconstruction
+    # filters; rows a19 / a20: film clamp and exposure; a9: a two-sided, scaled area light
+    base = scenes.cornell_box(resolution=(24, 24), spp=4)
+    for filt, radius in (("Gaussian", 1.5), ("Triangle", 1.0), ("Mitchell", 2.0), ("LanczosSinc", 1.5)):
+        c[f"cornell_filter_{filt.lower()}"] = base.replace("filter : Box { radius { 0.5 } }", f"filter : {filt} {{ radius {{ {radius} }} }}")
+    c["cornell_film_and_light_options"] = (
+        base.replace("film : Color { resolution { 24, 24 } }", "film : Color { resolution { 24, 24 } exposure { 1.5 } clamp { 1.25 } }")
+            .replace("emission : Constant { v { 17.0, 12.0, 4.0 } } }", "emission : Constant { v { 17.0, 12.0, 4.0 } } two_sided { true } scale { 0.75 } }"))
     # config C3: instanced Loop-subdivision spheres, Disney closures, two area lights (reduced triangle count)
     c["spheres_disney"] = scenes.instanced_spheres(resolution=(32, 18), spp=2, depth=6, **spheres)
     # config C4: + homogeneous medium, MegaVPTNaive
