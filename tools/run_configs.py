@@ -21,6 +21,9 @@ CONFIGS = {
     "C2": lambda: (scenes.cornell_box(resolution=(1024, 1024), spp=4096), 4096),
     "C3": lambda: (scenes.instanced_spheres(resolution=(1920, 1080), spp=1024), 1024),
     "C4": lambda: (scenes.instanced_spheres(resolution=(3840, 2160), spp=4096, medium=True, depth=8), 4096),
+    # row f3 (not a BASELINE config): Mirror / Glass / rough Glass / Plastic / Metal spheres, mirror wall - the hit bucket of
+    # the MicrofacetFamilyClosure next to the Matte bucket
+    "F3": lambda: (scenes.materials_box(resolution=(1920, 1080), spp=256, depth=10, subdivision=5), 256),
 }
 
 
