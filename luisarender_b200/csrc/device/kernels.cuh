@@ -37,7 +37,7 @@ struct PathBuffers {
     float4 *beta_pdf[2];
     uint2 *id_rng[2];
     uint4 *hit;// {inst, prim, bary} per ray of the current queue (inst == ~0u: escaped)
-    uint32_t *hit_index[4];// per closure kind: indices (into the current ray queue) of the rays that hit such a surface
+    uint32_t *hit_index[7];// per closure kind: indices (into the current ray queue) of the rays that hit such a surface
     float4 *sray_o;
     float4 *sray_d;
     float4 *scontrib;// rgb + path id bits
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(kBlock) generate_rays_kernel(DeviceScene sc, P
     uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id == 0u) {
         pb.counts[0] = n;
-        for (uint32_t d = 1u; d < 8u * kMaxDepthSlots; d++) pb.counts[d] = 0u;// sizes + the traversal kernels' fetch cursors
+        for (uint32_t d = 1u; d < 11u * kMaxDepthSlots; d++) pb.counts[d] = 0u;// sizes + the traversal kernels' fetch cursors
     }
     if (id >= n) return;
     uint32_t k = id % npix;
@@ -151,8 +151,8 @@ __global__ void __launch_bounds__(kBlock, 4) trace_closest_kernel(DeviceScene sc
 // block-aggregated partition).  Escaped rays are dropped, so the shade kernels only ever see real work; every bucket
 // keeps the ray-queue order inside a block chunk, which keeps the shade kernels' gathers coalesced.
 //   kind 0: hit has no surface (emitter only)   kind 1: Matte closure   kind 2: Disney closure
-//   kind 3: Mirror / Glass / Plastic / Metal (MicrofacetFamilyClosure)
-constexpr uint32_t kHitKinds = 4u;
+//   kinds 3..6: Mirror, Glass, Plastic, Metal (MicrofacetFamilyClosure<type>, kind = type + 1)
+constexpr uint32_t kHitKinds = 7u;
 __global__ void __launch_bounds__(kBlock) classify_hits_kernel(DeviceScene sc, PathBuffers pb, uint32_t depth) {
     __shared__ uint32_t s_warp[kHitKinds][kBlock / 32];
     __shared__ uint32_t s_base[kHitKinds];
@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(kShadeBlock, LRK_SHADE_MIN_BLOCKS) shade_kerne
                         init_closure<TEXTURED>(sc, cl, surf, it);
                         shade_surface<false>(cl, it, closure_frame<TEXTURED>(sc, surf, it, wo), wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
                     } else {
-                        MicrofacetFamilyClosure cl;
+                        MicrofacetFamilyClosure<KIND - 1u> cl;// kind = surface type + 1
                         cl.init(*surf);// constant parameters only (include/lrk.h)
                         shade_surface<false>(cl, it, closure_frame<TEXTURED>(sc, surf, it, wo), wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
                         eta_scale = cl.rr_eta_scale;
@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(kBlock) generate_rays_volume_kernel(DeviceScen
     uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id == 0u) {
         pb.counts[0] = n;
-        for (uint32_t d = 1u; d < 8u * kMaxDepthSlots; d++) pb.counts[d] = 0u;
+        for (uint32_t d = 1u; d < 11u * kMaxDepthSlots; d++) pb.counts[d] = 0u;
     }
     if (id >= n) return;
     uint32_t k = id % npix;

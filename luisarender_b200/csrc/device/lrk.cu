@@ -61,8 +61,9 @@ struct lrk_ctx {
     cudaEvent_t ev_begin{}, ev_end{};
     std::vector<TimedLaunch> timed;
     std::vector<cudaEvent_t> event_pool;
-    int grid_trace{0}, grid_shade[4]{0, 0, 0, 0}, grid_shadow{0}, grid_classify{0};
-    bool has_kind[4]{true, false, false, false};
+    int grid_trace{0}, grid_shade[7]{0, 0, 0, 0, 0, 0, 0}, grid_shadow{0}, grid_classify{0};
+    bool has_kind[7]{true, false, false, false, false, false, false};
+    uint32_t allocated_kinds{0u};// bit k: hit_index[k] is allocated
     bool volume{false};
     uint64_t volume_capacity{0};
     int grid_vshade[3]{0, 0, 0}, grid_vmedium{0}, grid_vshadow{0};
@@ -114,10 +115,13 @@ void free_paths(lrk_ctx *ctx) {
     ctx->path_allocs.clear();
     ctx->capacity = 0;
     ctx->volume_capacity = 0;
+    ctx->allocated_kinds = 0u;
 }
 
 int alloc_paths(lrk_ctx *ctx, uint64_t capacity) {
-    if (ctx->capacity >= capacity && (!ctx->volume || ctx->volume_capacity >= capacity)) return LRK_OK;
+    uint32_t kinds = 0u;
+    for (int k = 0; k < 7; k++) if (k < 3 || ctx->has_kind[k]) kinds |= 1u << k;// buckets 3..6 only for scenes that use them
+    if (ctx->capacity >= capacity && (!ctx->volume || ctx->volume_capacity >= capacity) && (ctx->allocated_kinds & kinds) == kinds) return LRK_OK;
     free_paths(ctx);
     auto alloc = [&](void **p, size_t bytes) -> cudaError_t {
         cudaError_t e = cudaMalloc(p, bytes);
@@ -132,12 +136,16 @@ int alloc_paths(lrk_ctx *ctx, uint64_t capacity) {
         LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.id_rng[k]), capacity * sizeof(uint2)));
     }
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.hit), capacity * sizeof(uint4)));
-    for (int k = 0; k < 4; k++) LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.hit_index[k]), capacity * sizeof(uint32_t)));
+    for (int k = 0; k < 7; k++) {
+        pb.hit_index[k] = nullptr;
+        if (kinds & (1u << k)) LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.hit_index[k]), capacity * sizeof(uint32_t)));
+    }
+    ctx->allocated_kinds = kinds;
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.sray_o), capacity * sizeof(float4)));
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.sray_d), capacity * sizeof(float4)));
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.scontrib), capacity * sizeof(float4)));
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.li), capacity * sizeof(float4)));
-    LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.counts), 8u * kMaxDepthSlots * sizeof(uint32_t)));
+    LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.counts), 11u * kMaxDepthSlots * sizeof(uint32_t)));
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.ray_order), capacity * kRayBins * sizeof(uint32_t)));
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.bin_counts), 2u * kMaxDepthSlots * kRayBins * sizeof(uint32_t)));
     pb.capacity = static_cast<uint32_t>(capacity);
@@ -282,6 +290,9 @@ int render_pass(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint32_t spp
             if (ctx->has_kind[1]) ctx->textured ? launch(shade_kernel<1u, true>, 1) : launch(shade_kernel<1u, false>, 1);
             if (ctx->has_kind[2]) ctx->textured ? launch(shade_kernel<2u, true>, 2) : launch(shade_kernel<2u, false>, 2);
             if (ctx->has_kind[3]) ctx->textured ? launch(shade_kernel<3u, true>, 3) : launch(shade_kernel<3u, false>, 3);
+            if (ctx->has_kind[4]) ctx->textured ? launch(shade_kernel<4u, true>, 4) : launch(shade_kernel<4u, false>, 4);
+            if (ctx->has_kind[5]) ctx->textured ? launch(shade_kernel<5u, true>, 5) : launch(shade_kernel<5u, false>, 5);
+            if (ctx->has_kind[6]) ctx->textured ? launch(shade_kernel<6u, true>, 6) : launch(shade_kernel<6u, false>, 6);
         }
         if (bin) {
             ScopedTimer t{ctx, CAT_OTHER};
@@ -300,7 +311,8 @@ int render_pass(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint32_t spp
             if (ctx->any_non_opaque) ctx->count_traversal ? launch(trace_shadow_kernel<true, true>) : launch(trace_shadow_kernel<false, true>);
             else ctx->count_traversal ? launch(trace_shadow_kernel<true, false>) : launch(trace_shadow_kernel<false, false>);
         }
-        ctx->stats.kernel_launches += 4u + (ctx->has_kind[1] ? 1u : 0u) + (ctx->has_kind[2] ? 1u : 0u) + (ctx->has_kind[3] ? 1u : 0u);
+        ctx->stats.kernel_launches += 4u + (ctx->has_kind[1] ? 1u : 0u) + (ctx->has_kind[2] ? 1u : 0u) + (ctx->has_kind[3] ? 1u : 0u) + (ctx->has_kind[4] ? 1u : 0u) +
+                                      (ctx->has_kind[5] ? 1u : 0u) + (ctx->has_kind[6] ? 1u : 0u);
     }
     {
         ScopedTimer t{ctx, CAT_OTHER};
@@ -422,6 +434,9 @@ int lrk_create(const lrk_device_cfg *cfg, lrk_ctx **out) {
     ctx->grid_shade[1] = grid_for(reinterpret_cast<const void *>(shade_kernel<1u, false>));
     ctx->grid_shade[2] = grid_for(reinterpret_cast<const void *>(shade_kernel<2u, false>));
     ctx->grid_shade[3] = grid_for(reinterpret_cast<const void *>(shade_kernel<3u, false>));
+    ctx->grid_shade[4] = grid_for(reinterpret_cast<const void *>(shade_kernel<4u, false>));
+    ctx->grid_shade[5] = grid_for(reinterpret_cast<const void *>(shade_kernel<5u, false>));
+    ctx->grid_shade[6] = grid_for(reinterpret_cast<const void *>(shade_kernel<6u, false>));
     ctx->grid_classify = grid_for(reinterpret_cast<const void *>(classify_hits_kernel));
     ctx->grid_vmedium = grid_for(reinterpret_cast<const void *>(volume_medium_kernel));
     ctx->grid_vshade[0] = grid_for(reinterpret_cast<const void *>(volume_surface_kernel<0u, false>));
@@ -530,7 +545,7 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
     if ((rc = upload(ctx, &a.light_handles, s->light_handles, s->light_count))) return rc;
     if ((rc = upload(ctx, &a.camera, &s->camera, 1))) return rc;
     std::vector<uint32_t> handles(static_cast<size_t>(s->instance_count) * 4u), kinds(s->instance_count);
-    ctx->has_kind[1] = ctx->has_kind[2] = ctx->has_kind[3] = false;
+    for (int k = 1; k < 7; k++) ctx->has_kind[k] = false;
     ctx->any_non_opaque = false;
     std::vector<float> o2w(static_cast<size_t>(s->instance_count) * 12u), xform(static_cast<size_t>(s->instance_count) * 16u);
     for (uint32_t i = 0; i < s->instance_count; i++) {
@@ -542,7 +557,7 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
             if (flags & LRK_SHAPE_HAS_SURFACE) {
                 if (surface_tag >= s->surface_count) return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_upload_scene: surface tag out of range");
                 const uint32_t type = s->surfaces[surface_tag].type;
-                kind = type == LRK_SURFACE_MATTE ? 1u : type == LRK_SURFACE_DISNEY ? 2u : 3u;
+                kind = type + 1u;// Matte 1, Disney 2, Mirror 3, Glass 4, Plastic 5, Metal 6
             }
             kinds[i] = kind;
             ctx->has_kind[kind] = true;

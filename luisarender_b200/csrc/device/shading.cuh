@@ -882,15 +882,19 @@ __device__ __forceinline__ V3 fresnel_conductor(float cosThetaI, float etai, V3 
     return .5f * (Rp + Rs);
 }
 
+// TYPE (LRK_SURFACE_MIRROR .. LRK_SURFACE_METAL) is a template parameter: each node type gets its own hit bucket and shade
+// kernel instantiation (sorted-by-material dispatch), so a warp runs ONE closure's code - the first version switched on a
+// run-time type inside one kernel and was instruction-fetch bound (ncu: 16.8 no-instruction stall cycles per issue, 15.5 of
+// 32 lanes; profiles/README.md).
+template<uint32_t TYPE>
 struct MicrofacetFamilyClosure {
-    uint32_t type;
+    static constexpr uint32_t type = TYPE;
     V3 c0, c1, c2;     // MIRROR: refl | GLASS: Kr, Kt | PLASTIC: Kd', sigma_a | METAL: n, k, tint
     float eta, w0;     // GLASS: eta_t, Kr_ratio | PLASTIC: eta, Kd_weight
     TrowbridgeReitz d;
     float flip;        // PLASTIC: sign applied to the z components (plastic.cpp:143-147)
     float rr_eta_scale;// eta scale of the sampled event for Russian roulette (mega_path.cpp:133-138)
     __device__ __forceinline__ void init(const lrk_surface &s) {
-        type = s.type;
         rr_eta_scale = 1.f;
         flip = 1.f;
         eta = 1.5f;

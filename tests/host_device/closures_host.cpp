@@ -91,12 +91,11 @@ extern "C" int device_closure_unit(const char *name_c, const uint32_t *in, uint3
             sf.lobes = static_cast<uint32_t>(std::stoul(name.substr(name.rfind('_') + 1)));
             DisneyClosure cl; cl.init(sf); run(cl, w, is_eval);
         } else {
-            if (name.rfind("mirror_", 0) == 0) { sf.type = LRK_SURFACE_MIRROR; take(5); }
-            else if (name.rfind("glass_", 0) == 0) { sf.type = LRK_SURFACE_GLASS; take(10); }
-            else if (name.rfind("plastic_", 0) == 0) { sf.type = LRK_SURFACE_PLASTIC; take(10); }
-            else if (name.rfind("metal_", 0) == 0) { sf.type = LRK_SURFACE_METAL; take(11); }
+            if (name.rfind("mirror_", 0) == 0) { take(5); MicrofacetFamilyClosure<LRK_SURFACE_MIRROR> cl; cl.init(sf); run(cl, w, is_eval); }
+            else if (name.rfind("glass_", 0) == 0) { take(10); MicrofacetFamilyClosure<LRK_SURFACE_GLASS> cl; cl.init(sf); run(cl, w, is_eval); }
+            else if (name.rfind("plastic_", 0) == 0) { take(10); MicrofacetFamilyClosure<LRK_SURFACE_PLASTIC> cl; cl.init(sf); run(cl, w, is_eval); }
+            else if (name.rfind("metal_", 0) == 0) { take(11); MicrofacetFamilyClosure<LRK_SURFACE_METAL> cl; cl.init(sf); run(cl, w, is_eval); }
             else return -1;
-            MicrofacetFamilyClosure cl; cl.init(sf); run(cl, w, is_eval);
         }
     }
     return 0;
