@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define LRK_ABI_VERSION 3u
+#define LRK_ABI_VERSION 4u /* 4: surface types Mirror / Glass / Plastic / Metal (row f3) */
 
 typedef enum lrk_status {
     LRK_OK = 0,

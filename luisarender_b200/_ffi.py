@@ -13,7 +13,7 @@ PKG_DIR = Path(__file__).resolve().parent
 REPO_DIR = PKG_DIR.parent
 LIB_DIR = PKG_DIR / "lib"
 
-LRK_ABI_VERSION = 3
+LRK_ABI_VERSION = 4
 TEX_ADDRESS_EDGE, TEX_ADDRESS_REPEAT, TEX_ADDRESS_MIRROR, TEX_ADDRESS_ZERO = 0, 1, 2, 3
 TEX_FILTER_POINT, TEX_FILTER_LINEAR = 0, 1
 TEX_ENCODING_LINEAR, TEX_ENCODING_SRGB, TEX_ENCODING_GAMMA = 0, 1, 2
