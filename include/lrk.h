@@ -142,7 +142,8 @@ typedef struct lrk_instance {
 #define LRK_SURFACE_GLASS 3u   /* src/surfaces/glass.cpp (non-dispersive: fixed sRGB spectrum) */
 #define LRK_SURFACE_PLASTIC 4u /* src/surfaces/plastic.cpp */
 #define LRK_SURFACE_METAL 5u   /* src/surfaces/metal.cpp */
-#define LRK_SURFACE_TYPE_COUNT 6u
+#define LRK_SURFACE_MIX 6u     /* src/surfaces/mix.cpp: two constant, non-Disney surface records mixed by a ratio */
+#define LRK_SURFACE_TYPE_COUNT 7u
 
 /* Surface::event_*: src/base/surface.h:37-40 */
 #define LRK_EVENT_REFLECT 0u
@@ -179,6 +180,11 @@ typedef struct lrk_instance {
  *            p[8..9] = alpha — PlasticContext, plastic.cpp:107-114,252-291
  *   METAL  : p[0..2] = n, p[3..5] = k (complex index at the spectrum's three wavelengths), p[6..8] = Kd reflectance tint,
  *            p[9..10] = alpha (default 0.5) — MetalClosure::Context, metal.cpp:208-215,273-310
+ *   MIX    : p[0] = ratio = clamp(ratio.x, 0, 1) (default 0.5); mix_a / mix_b = indices of the two mixed surface records, which
+ *            the host appends behind the tagged surfaces (surface_count counts them; instance handles never name them) —
+ *            MixSurfaceClosure::Context, mix.cpp:88-91,195-211.  The closure reproduces the reference's arithmetic including
+ *            its second sampling branch, which samples surface `a` again and weights the two evaluations the other way
+ *            round (mix.cpp:170-176).
  *   The four closures above take constant parameters only (tex[] must be 0); image-textured Mirror / Glass / Plastic /
  *   Metal nodes are rejected by the host.
  *
@@ -205,7 +211,7 @@ typedef struct lrk_surface {
     uint32_t type;
     uint32_t lobes;
     uint32_t flags;
-    uint32_t reserved;
+    uint32_t mix_a; /* MIX: record index of surface `a` */
     float p[16];
     uint32_t tex[16];
     uint32_t opacity_tex; /* 0 = constant `opacity` */
@@ -213,7 +219,7 @@ typedef struct lrk_surface {
     uint32_t normal_tex; /* 0 = constant `normal_value` */
     float normal_strength;
     float normal_value[3];
-    uint32_t reserved2;
+    uint32_t mix_b; /* MIX: record index of surface `b` */
 } lrk_surface;
 
 /* One image texture (src/textures/image.cpp:16-151).  Texels are RGBA float (8/16-bit sources converted with x/255,

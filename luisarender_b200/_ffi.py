@@ -60,8 +60,8 @@ class Instance(C.Structure):
 
 
 class Surface(C.Structure):
-    _fields_ = [("type", u32), ("lobes", u32), ("flags", u32), ("reserved", u32), ("p", f32 * 16), ("tex", u32 * 16),
-                ("opacity_tex", u32), ("opacity", f32), ("normal_tex", u32), ("normal_strength", f32), ("normal_value", f32 * 3), ("reserved2", u32)]
+    _fields_ = [("type", u32), ("lobes", u32), ("flags", u32), ("mix_a", u32), ("p", f32 * 16), ("tex", u32 * 16),
+                ("opacity_tex", u32), ("opacity", f32), ("normal_tex", u32), ("normal_strength", f32), ("normal_value", f32 * 3), ("mix_b", u32)]
 
 
 class Texture(C.Structure):

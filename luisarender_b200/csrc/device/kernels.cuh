@@ -37,7 +37,7 @@ struct PathBuffers {
     float4 *beta_pdf[2];
     uint2 *id_rng[2];
     uint4 *hit;// {inst, prim, bary} per ray of the current queue (inst == ~0u: escaped)
-    uint32_t *hit_index[7];// per closure kind: indices (into the current ray queue) of the rays that hit such a surface
+    uint32_t *hit_index[8];// per closure kind: indices (into the current ray queue) of the rays that hit such a surface
     float4 *sray_o;
     float4 *sray_d;
     float4 *scontrib;// rgb + path id bits
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(kBlock) generate_rays_kernel(DeviceScene sc, P
     uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id == 0u) {
         pb.counts[0] = n;
-        for (uint32_t d = 1u; d < 11u * kMaxDepthSlots; d++) pb.counts[d] = 0u;// sizes + the traversal kernels' fetch cursors
+        for (uint32_t d = 1u; d < 12u * kMaxDepthSlots; d++) pb.counts[d] = 0u;// sizes + the traversal kernels' fetch cursors
     }
     if (id >= n) return;
     uint32_t k = id % npix;
@@ -151,8 +151,8 @@ __global__ void __launch_bounds__(kBlock, 4) trace_closest_kernel(DeviceScene sc
 // block-aggregated partition).  Escaped rays are dropped, so the shade kernels only ever see real work; every bucket
 // keeps the ray-queue order inside a block chunk, which keeps the shade kernels' gathers coalesced.
 //   kind 0: hit has no surface (emitter only)   kind 1: Matte closure   kind 2: Disney closure
-//   kinds 3..6: Mirror, Glass, Plastic, Metal (MicrofacetFamilyClosure<type>, kind = type + 1)
-constexpr uint32_t kHitKinds = 7u;
+//   kinds 3..6: Mirror, Glass, Plastic, Metal (MicrofacetFamilyClosure<type>, kind = type + 1)   kind 7: Mix
+constexpr uint32_t kHitKinds = 8u;
 __global__ void __launch_bounds__(kBlock) classify_hits_kernel(DeviceScene sc, PathBuffers pb, uint32_t depth) {
     __shared__ uint32_t s_warp[kHitKinds][kBlock / 32];
     __shared__ uint32_t s_base[kHitKinds];
@@ -311,6 +311,15 @@ __device__ __forceinline__ Frame closure_frame(const DeviceScene &sc, const lrk_
 // closure is several thousand SASS instructions and two inlined copies thrash the instruction cache.
 // VOLUME selects the direct-light weight of the volume integrator: 1 / (pdf_light + pdf_bsdf + pdf_transmittance) with
 // pdf_transmittance = 0 for an unoccluded ray (mega_vpt_naive.cpp:403-407) instead of the balance heuristic (mega_path.cpp:108-113).
+// f / pdf of the closure's own sample: evaluate_local at the sampled direction for every closure (matte.cpp:118-134,
+// disney.cpp:583-586, ...) except Mix, whose sample is not its evaluate (mix.cpp:158-180) and which provides evaluate_sampled
+template<typename Closure>
+__device__ __forceinline__ auto evaluate_sampled(const Closure &cl, V3 wo, V3 wi, int) -> decltype(cl.evaluate_sampled(wo, wi)) {
+    return cl.evaluate_sampled(wo, wi);
+}
+template<typename Closure>
+__device__ __forceinline__ SurfEval evaluate_sampled(const Closure &cl, V3 wo, V3 wi, long) { return cl.evaluate_local(wo, wi); }
+
 template<bool VOLUME, typename Closure>
 __device__ __forceinline__ void shade_surface(Closure &cl, const Interaction &it, const Frame &shading, V3 wo, const LightSample &ls, V3 beta,
                                               float u_lobe, float ub0, float ub1, V3 &contrib, V3 &wi_world, V3 &f_over, float &pdf_bsdf) {
@@ -332,7 +341,7 @@ __device__ __forceinline__ void shade_surface(Closure &cl, const Interaction &it
         e.f = v3(0.f);
         e.pdf = 0.f;
         if (run) {
-            e = cl.evaluate_local(wo_local, wi_l);
+            e = k == 0 ? cl.evaluate_local(wo_local, wi_l) : evaluate_sampled(cl, wo_local, wi_l, 0);
             if (!validate_surface_sides(it.ng, shading.n, wo, wi_w)) {
                 e.f = v3(0.f);
                 e.pdf = 0.f;
@@ -423,8 +432,13 @@ __global__ void __launch_bounds__(kShadeBlock, LRK_SHADE_MIN_BLOCKS) shade_kerne
                         DisneyClosure cl;
                         init_closure<TEXTURED>(sc, cl, surf, it);
                         shade_surface<false>(cl, it, closure_frame<TEXTURED>(sc, surf, it, wo), wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
+                    } else if (KIND == 7u) {
+                        MixClosure cl;
+                        cl.init(*surf, sc.surfaces);
+                        shade_surface<false>(cl, it, closure_frame<TEXTURED>(sc, surf, it, wo), wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
+                        eta_scale = cl.rr_eta_scale;
                     } else {
-                        MicrofacetFamilyClosure<KIND - 1u> cl;// kind = surface type + 1
+                        MicrofacetFamilyClosure<(KIND >= 3u && KIND <= 6u) ? KIND - 1u : LRK_SURFACE_MIRROR> cl;// kind = surface type + 1
                         cl.init(*surf);// constant parameters only (include/lrk.h)
                         shade_surface<false>(cl, it, closure_frame<TEXTURED>(sc, surf, it, wo), wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
                         eta_scale = cl.rr_eta_scale;
@@ -558,7 +572,7 @@ __global__ void __launch_bounds__(kBlock) generate_rays_volume_kernel(DeviceScen
     uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id == 0u) {
         pb.counts[0] = n;
-        for (uint32_t d = 1u; d < 11u * kMaxDepthSlots; d++) pb.counts[d] = 0u;
+        for (uint32_t d = 1u; d < 12u * kMaxDepthSlots; d++) pb.counts[d] = 0u;
     }
     if (id >= n) return;
     uint32_t k = id % npix;

@@ -61,8 +61,8 @@ struct lrk_ctx {
     cudaEvent_t ev_begin{}, ev_end{};
     std::vector<TimedLaunch> timed;
     std::vector<cudaEvent_t> event_pool;
-    int grid_trace{0}, grid_shade[7]{0, 0, 0, 0, 0, 0, 0}, grid_shadow{0}, grid_classify{0};
-    bool has_kind[7]{true, false, false, false, false, false, false};
+    int grid_trace{0}, grid_shade[8]{0, 0, 0, 0, 0, 0, 0, 0}, grid_shadow{0}, grid_classify{0};
+    bool has_kind[8]{true, false, false, false, false, false, false, false};
     uint32_t allocated_kinds{0u};// bit k: hit_index[k] is allocated
     bool volume{false};
     uint64_t volume_capacity{0};
@@ -120,7 +120,7 @@ void free_paths(lrk_ctx *ctx) {
 
 int alloc_paths(lrk_ctx *ctx, uint64_t capacity) {
     uint32_t kinds = 0u;
-    for (int k = 0; k < 7; k++) if (k < 3 || ctx->has_kind[k]) kinds |= 1u << k;// buckets 3..6 only for scenes that use them
+    for (int k = 0; k < 8; k++) if (k < 3 || ctx->has_kind[k]) kinds |= 1u << k;// buckets 3..6 only for scenes that use them
     if (ctx->capacity >= capacity && (!ctx->volume || ctx->volume_capacity >= capacity) && (ctx->allocated_kinds & kinds) == kinds) return LRK_OK;
     free_paths(ctx);
     auto alloc = [&](void **p, size_t bytes) -> cudaError_t {
@@ -136,7 +136,7 @@ int alloc_paths(lrk_ctx *ctx, uint64_t capacity) {
         LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.id_rng[k]), capacity * sizeof(uint2)));
     }
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.hit), capacity * sizeof(uint4)));
-    for (int k = 0; k < 7; k++) {
+    for (int k = 0; k < 8; k++) {
         pb.hit_index[k] = nullptr;
         if (kinds & (1u << k)) LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.hit_index[k]), capacity * sizeof(uint32_t)));
     }
@@ -145,7 +145,7 @@ int alloc_paths(lrk_ctx *ctx, uint64_t capacity) {
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.sray_d), capacity * sizeof(float4)));
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.scontrib), capacity * sizeof(float4)));
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.li), capacity * sizeof(float4)));
-    LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.counts), 11u * kMaxDepthSlots * sizeof(uint32_t)));
+    LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.counts), 12u * kMaxDepthSlots * sizeof(uint32_t)));
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.ray_order), capacity * kRayBins * sizeof(uint32_t)));
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.bin_counts), 2u * kMaxDepthSlots * kRayBins * sizeof(uint32_t)));
     pb.capacity = static_cast<uint32_t>(capacity);
@@ -293,6 +293,7 @@ int render_pass(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint32_t spp
             if (ctx->has_kind[4]) ctx->textured ? launch(shade_kernel<4u, true>, 4) : launch(shade_kernel<4u, false>, 4);
             if (ctx->has_kind[5]) ctx->textured ? launch(shade_kernel<5u, true>, 5) : launch(shade_kernel<5u, false>, 5);
             if (ctx->has_kind[6]) ctx->textured ? launch(shade_kernel<6u, true>, 6) : launch(shade_kernel<6u, false>, 6);
+            if (ctx->has_kind[7]) ctx->textured ? launch(shade_kernel<7u, true>, 7) : launch(shade_kernel<7u, false>, 7);
         }
         if (bin) {
             ScopedTimer t{ctx, CAT_OTHER};
@@ -312,7 +313,7 @@ int render_pass(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint32_t spp
             else ctx->count_traversal ? launch(trace_shadow_kernel<true, false>) : launch(trace_shadow_kernel<false, false>);
         }
         ctx->stats.kernel_launches += 4u + (ctx->has_kind[1] ? 1u : 0u) + (ctx->has_kind[2] ? 1u : 0u) + (ctx->has_kind[3] ? 1u : 0u) + (ctx->has_kind[4] ? 1u : 0u) +
-                                      (ctx->has_kind[5] ? 1u : 0u) + (ctx->has_kind[6] ? 1u : 0u);
+                                      (ctx->has_kind[5] ? 1u : 0u) + (ctx->has_kind[6] ? 1u : 0u) + (ctx->has_kind[7] ? 1u : 0u);
     }
     {
         ScopedTimer t{ctx, CAT_OTHER};
@@ -437,6 +438,7 @@ int lrk_create(const lrk_device_cfg *cfg, lrk_ctx **out) {
     ctx->grid_shade[4] = grid_for(reinterpret_cast<const void *>(shade_kernel<4u, false>));
     ctx->grid_shade[5] = grid_for(reinterpret_cast<const void *>(shade_kernel<5u, false>));
     ctx->grid_shade[6] = grid_for(reinterpret_cast<const void *>(shade_kernel<6u, false>));
+    ctx->grid_shade[7] = grid_for(reinterpret_cast<const void *>(shade_kernel<7u, false>));
     ctx->grid_classify = grid_for(reinterpret_cast<const void *>(classify_hits_kernel));
     ctx->grid_vmedium = grid_for(reinterpret_cast<const void *>(volume_medium_kernel));
     ctx->grid_vshade[0] = grid_for(reinterpret_cast<const void *>(volume_surface_kernel<0u, false>));
@@ -503,6 +505,13 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
         if (s->surfaces[i].type >= LRK_SURFACE_TYPE_COUNT) return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: unknown surface type");
         if (s->surfaces[i].type > LRK_SURFACE_DISNEY && (s->surfaces[i].flags & LRK_SURFACE_HAS_TEXTURES))
             return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: Mirror / Glass / Plastic / Metal take constant parameters only");
+        if (s->surfaces[i].type == LRK_SURFACE_MIX) {
+            for (uint32_t child : {s->surfaces[i].mix_a, s->surfaces[i].mix_b}) {
+                if (child >= s->surface_count || s->surfaces[child].type == LRK_SURFACE_MIX || s->surfaces[child].type == LRK_SURFACE_DISNEY ||
+                    (s->surfaces[child].flags & (LRK_SURFACE_HAS_TEXTURES | LRK_SURFACE_HAS_NORMAL_MAP | LRK_SURFACE_MAYBE_NON_OPAQUE)))
+                    return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: a Mix blends two constant Matte / Mirror / Glass / Plastic / Metal records");
+            }
+        }
         if (s->surfaces[i].type > LRK_SURFACE_DISNEY && s->integrator.type == LRK_INTEGRATOR_VOLUME_PATH)
             return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: the volume path supports Matte and Disney surfaces only");
         for (uint32_t k = 0; k < 16u; k++)
@@ -545,7 +554,7 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
     if ((rc = upload(ctx, &a.light_handles, s->light_handles, s->light_count))) return rc;
     if ((rc = upload(ctx, &a.camera, &s->camera, 1))) return rc;
     std::vector<uint32_t> handles(static_cast<size_t>(s->instance_count) * 4u), kinds(s->instance_count);
-    for (int k = 1; k < 7; k++) ctx->has_kind[k] = false;
+    for (int k = 1; k < 8; k++) ctx->has_kind[k] = false;
     ctx->any_non_opaque = false;
     std::vector<float> o2w(static_cast<size_t>(s->instance_count) * 12u), xform(static_cast<size_t>(s->instance_count) * 16u);
     for (uint32_t i = 0; i < s->instance_count; i++) {

@@ -1074,4 +1074,92 @@ struct MicrofacetFamilyClosure {
     }
 };
 
+// Mix (src/surfaces/mix.cpp:82-193): two constant, non-Disney surface records blended by a ratio; hit bucket 7.
+// The children are evaluated through out-of-line dispatchers (ONE copy of each closure's code in the kernel, called two or
+// three times per shaded hit): a Mix is rare, and inlining every closure several times is what made the first row-f3 kernel
+// instruction-fetch bound.  Expressions and quirks are the oracle's mix_evaluate / mix_sample, bit-identical to the reference
+// render (tests/test_ref_render.py::materials_mix).
+template<typename Closure>
+__device__ __forceinline__ SurfEval child_evaluate(const lrk_surface *s, V3 wo, V3 wi) {
+    Closure c;
+    c.init(*s);
+    c.prepare(wo);
+    return c.evaluate_local(wo, wi);
+}
+__device__ __noinline__ SurfEval any_evaluate_local(const lrk_surface *s, V3 wo, V3 wi) {
+    switch (s->type) {
+        case LRK_SURFACE_MATTE: return child_evaluate<MatteClosure>(s, wo, wi);
+        case LRK_SURFACE_MIRROR: return child_evaluate<MicrofacetFamilyClosure<LRK_SURFACE_MIRROR>>(s, wo, wi);
+        case LRK_SURFACE_GLASS: return child_evaluate<MicrofacetFamilyClosure<LRK_SURFACE_GLASS>>(s, wo, wi);
+        case LRK_SURFACE_PLASTIC: return child_evaluate<MicrofacetFamilyClosure<LRK_SURFACE_PLASTIC>>(s, wo, wi);
+        default: return child_evaluate<MicrofacetFamilyClosure<LRK_SURFACE_METAL>>(s, wo, wi);
+    }
+}
+// returns the sample's validity; `transmitted`: the sampled event is a refraction (Surface::event_enter / event_exit)
+__device__ __noinline__ bool any_sample_direction(const lrk_surface *s, V3 wo, float u_lobe, float u0, float u1, V3 &wi, bool &transmitted) {
+    transmitted = false;
+    switch (s->type) {
+        case LRK_SURFACE_MATTE: { MatteClosure c; c.init(*s); c.prepare(wo); return c.sample_direction(wo, u_lobe, u0, u1, wi); }
+        case LRK_SURFACE_MIRROR: { MicrofacetFamilyClosure<LRK_SURFACE_MIRROR> c; c.init(*s); c.prepare(wo); return c.sample_direction(wo, u_lobe, u0, u1, wi); }
+        case LRK_SURFACE_GLASS: {
+            MicrofacetFamilyClosure<LRK_SURFACE_GLASS> c;
+            c.init(*s);
+            c.prepare(wo);
+            bool valid = c.sample_direction(wo, u_lobe, u0, u1, wi);
+            transmitted = !(u_lobe < c.glass_refl_prob(wo));
+            return valid;
+        }
+        case LRK_SURFACE_PLASTIC: { MicrofacetFamilyClosure<LRK_SURFACE_PLASTIC> c; c.init(*s); c.prepare(wo); return c.sample_direction(wo, u_lobe, u0, u1, wi); }
+        default: { MicrofacetFamilyClosure<LRK_SURFACE_METAL> c; c.init(*s); c.prepare(wo); return c.sample_direction(wo, u_lobe, u0, u1, wi); }
+    }
+}
+
+struct MixClosure {
+    const lrk_surface *a, *b;
+    float ratio, eta;  // eta: MixSurfaceClosure::eta() (mix.cpp:133-141), 0 = none; computed by the host into p[1]
+    float rr_eta_scale;
+    bool first_branch, child_valid;
+    __device__ __forceinline__ void init(const lrk_surface &s, const lrk_surface *records) {
+        a = records + s.mix_a;
+        b = records + s.mix_b;
+        ratio = s.p[0];
+        eta = s.p[1];
+        rr_eta_scale = 1.f;
+        first_branch = true;
+        child_valid = false;
+    }
+    __device__ __forceinline__ void prepare(V3) {}
+    __device__ __forceinline__ static SurfEval mix(const SurfEval &x, const SurfEval &y, float ratio) {// _mix: lerp(x, y, 1 - ratio)
+        float t = 1.f - ratio;
+        SurfEval e;
+        e.f = lerp(x.f, y.f, t);
+        e.pdf = lerp(x.pdf, y.pdf, t);
+        return e;
+    }
+    __device__ __forceinline__ SurfEval evaluate_local(V3 wo, V3 wi) const {
+        SurfEval ea = any_evaluate_local(a, wo, wi);
+        SurfEval eb = any_evaluate_local(b, wo, wi);
+        return mix(ea, eb, ratio);
+    }
+    // mix.cpp:158-180: both branches sample child `a` (the second one with the rescaled lobe number)
+    __device__ __forceinline__ bool sample_direction(V3 wo, float u_lobe, float u0, float u1, V3 &wi) {
+        first_branch = u_lobe < ratio;
+        float ul = first_branch ? u_lobe / ratio : (u_lobe - ratio) / (1.f - ratio);
+        bool transmitted;
+        child_valid = any_sample_direction(a, wo, ul, u0, u1, wi, transmitted);
+        rr_eta_scale = 1.f;
+        if (transmitted && eta != 0.f) rr_eta_scale = cos_theta(wo) > 0.f ? sqr(eta) : sqr(1.f / eta);
+        return true;// the other child is evaluated at wi whether or not a's sample is valid
+    }
+    // f and pdf of the sample: first branch mix(a's sample, b(wi)); second branch mix(b(wi), a's sample) — sic
+    __device__ __forceinline__ SurfEval evaluate_sampled(V3 wo, V3 wi) const {
+        SurfEval sa;
+        sa.f = v3(0.f);
+        sa.pdf = 0.f;
+        if (child_valid) sa = any_evaluate_local(a, wo, wi);
+        SurfEval ob = any_evaluate_local(b, wo, wi);
+        return first_branch ? mix(sa, ob, ratio) : mix(ob, sa, ratio);
+    }
+};
+
 }// namespace lrk

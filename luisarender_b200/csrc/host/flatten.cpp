@@ -353,6 +353,22 @@ std::unique_ptr<FlatScene> flatten_scene(const Scene &scene) {
         out->surfaces.push_back(s->flatten(texture_table));
         if (out->surfaces.back().type == LRK_SURFACE_DISNEY) disney_lobes |= out->surfaces.back().lobes;
     }
+    // Mix nodes: their two surfaces become extra records behind the tagged ones (never referenced by an instance handle)
+    for (size_t tag = 0, tagged = f.surface_nodes.size(); tag < tagged; tag++) {
+        auto [a, b] = f.surface_nodes[tag]->mix_children();
+        if (a == nullptr) continue;
+        for (auto child : {a, b}) {
+            auto rec = child->flatten(texture_table);
+            if (rec.type == LRK_SURFACE_DISNEY || (rec.flags & LRK_SURFACE_HAS_TEXTURES))
+                throw Error("Mix: only constant Matte / Mirror / Glass / Plastic / Metal surfaces can be mixed.");
+            (child == a ? out->surfaces[tag].mix_a : out->surfaces[tag].mix_b) = static_cast<uint32_t>(out->surfaces.size());
+            out->surfaces.push_back(rec);
+        }
+        // MixSurfaceClosure::eta() (mix.cpp:133-141) for the Russian-roulette eta scale: Glass children have one
+        auto eta_of = [&](uint32_t i) { return out->surfaces[i].type == LRK_SURFACE_GLASS ? out->surfaces[i].p[6] : 0.f; };
+        float ea = eta_of(out->surfaces[tag].mix_a), eb = eta_of(out->surfaces[tag].mix_b), ratio = out->surfaces[tag].p[0];
+        out->surfaces[tag].p[1] = ea == 0.f ? eb : eb == 0.f ? ea : ratio * (ea - eb) + eb;// lerp(eta_b, eta_a, ratio)
+    }
     for (auto &s : out->surfaces)
         if (s.type == LRK_SURFACE_DISNEY) s.lobes = disney_lobes;
     // the environment light: src/environments/spherical.cpp, src/lightsamplers/uniform.cpp:40-47

@@ -978,6 +978,31 @@ struct MetalSurface final : Surface {
     }
 };
 
+struct MixSurface final : Surface {
+    // src/surfaces/mix.cpp:22-31,195-211: ratio = clamp(ratio.x, 0, 1), default 0.5
+    const Surface *a, *b;
+    const Texture *ratio;
+    MixSurface(Scene *s, const NodeDesc *d) : Surface{s, d, Tag::SURFACE} {
+        a = s->load_surface(d->required_node("a"));
+        b = s->load_surface(d->required_node("b"));
+        ratio = constant_surface_texture(s, d, "ratio");
+        if (a == nullptr || b == nullptr || a->is_null() || b->is_null()) throw Error("MixSurface: Both surfaces must be valid. [" + d->location() + "]");
+        for (auto c : {a, b}) {
+            if (c->mix_children().first != nullptr) throw Error("Nested Mix surfaces are not supported. [" + d->location() + "]");
+            if (c->opacity != nullptr || c->normal_map != nullptr)
+                throw Error("Mix: surfaces with opacity / normal maps cannot be mixed. [" + d->location() + "]");
+        }
+    }
+    std::pair<const Surface *, const Surface *> mix_children() const override { return {a, b}; }
+    lrk_surface flatten(TextureTable &textures) const override {
+        lrk_surface out{};
+        out.type = LRK_SURFACE_MIX;
+        out.p[0] = ratio ? std::fmin(std::fmax(ratio->value().x, 0.f), 1.f) : .5f;
+        flatten_wrappers(out, textures);
+        return out;// mix_a / mix_b are filled by flatten_scene, which owns the record array
+    }
+};
+
 struct NullSurface final : Surface {
     NullSurface(Scene *s, const NodeDesc *d) : Surface{s, d, Tag::SURFACE} {}
     bool is_null() const override { return true; }
@@ -1023,6 +1048,7 @@ LRH_PLUGIN("surface-mirror", MirrorSurface)
 LRH_PLUGIN("surface-glass", GlassSurface)
 LRH_PLUGIN("surface-plastic", PlasticSurface)
 LRH_PLUGIN("surface-metal", MetalSurface)
+LRH_PLUGIN("surface-mix", MixSurface)
 LRH_PLUGIN("surface-null", NullSurface)
 LRH_PLUGIN("light-diffuse", DiffuseLight)
 LRH_PLUGIN("light-null", NullLight)

@@ -4,6 +4,7 @@
 // create/destroy C signature as LUISA_RENDER_MAKE_SCENE_NODE_PLUGIN (src/base/scene_node.h:58-67).
 // Unknown node implementations are a hard error naming the plugin (reference: dlopen failure abort).
 #pragma once
+#include <utility>
 #include <functional>
 #include <memory>
 #include <mutex>
@@ -141,6 +142,8 @@ struct Surface : SceneNode {
     Surface(Scene *scene, const NodeDesc *desc, Tag tag);
     virtual bool is_null() const { return false; }
     virtual lrk_surface flatten(TextureTable &textures) const = 0;
+    // Mix (src/surfaces/mix.cpp): the two mixed surface nodes, flattened to extra records behind the tagged ones
+    virtual std::pair<const Surface *, const Surface *> mix_children() const { return {nullptr, nullptr}; }
     // OpacitySurfaceWrapper::Instance::maybe_non_opaque (surface.h:177-181)
     bool maybe_non_opaque() const;
     const Texture *opacity{};

@@ -362,7 +362,7 @@ render {{
 
 
 def materials_box(resolution=(32, 24), spp=4, depth=8, rr_depth=0, rr_threshold=0.95, seed=19980810, subdivision=2,
-                  integrator="WavePath", output="materials.exr") -> str:
+                  integrator="WavePath", output="materials.exr", mix=False) -> str:
     """a Cornell-like box with one Loop-subdivision sphere per closure of src/surfaces -
     Mirror, Glass (built-in bk7), rough Glass, Plastic, Metal (custom eta list) - on a Matte floor, plus a mirror back wall."""
     out = [
@@ -381,6 +381,16 @@ def materials_box(resolution=(32, 24), spp=4, depth=8, rr_depth=0, rr_threshold=
         "Light area_light : Diffuse { emission : Constant { v { 17.0, 14.0, 10.0 } } }",
         f"Shape ball : Sphere {{ subdivision {{ {int(subdivision)} }} }}",
     ]
+    ball_surfaces = ["m_mirror", "m_glass", "m_rough_glass", "m_plastic", "m_metal"]
+    floor_surface = "white"
+    if mix:  # src/surfaces/mix.cpp: a matte/mirror blend, a plastic/glass blend (refraction events), the default ratio
+        out += [
+            "Surface mx_matte_mirror : Mix { a { @red } b { @m_mirror } ratio : Constant { v { 0.3 } } }",
+            "Surface mx_glass_plastic : Mix { a { @m_rough_glass } b { @m_plastic } ratio : Constant { v { 0.65 } } }",
+            "Surface mx_floor : Mix { a { @white } b { @m_metal } }",
+        ]
+        ball_surfaces = ["mx_matte_mirror", "m_glass", "mx_glass_plastic", "m_plastic", "mx_matte_mirror"]
+        floor_surface = "mx_floor"
     shapes = []
 
     def quad(name, pts, surface=None, light=None):
@@ -389,13 +399,13 @@ def materials_box(resolution=(32, 24), spp=4, depth=8, rr_depth=0, rr_threshold=
         out.append(f"Shape {name} : InlineMesh {{ positions {{ {pos} }} indices {{ {idx} }} {attach} }}")
         shapes.append(f"@{name}")
 
-    quad("floor", [(-2.0, 0.0, 1.5), (2.0, 0.0, 1.5), (2.0, 0.0, -1.5), (-2.0, 0.0, -1.5)], "white")
+    quad("floor", [(-2.0, 0.0, 1.5), (2.0, 0.0, 1.5), (2.0, 0.0, -1.5), (-2.0, 0.0, -1.5)], floor_surface)
     quad("ceiling", [(-2.0, 2.5, 1.5), (-2.0, 2.5, -1.5), (2.0, 2.5, -1.5), (2.0, 2.5, 1.5)], "white")
     quad("back", [(-2.0, 0.0, -1.5), (2.0, 0.0, -1.5), (2.0, 2.5, -1.5), (-2.0, 2.5, -1.5)], "wall_mirror")
     quad("left", [(-2.0, 0.0, 1.5), (-2.0, 0.0, -1.5), (-2.0, 2.5, -1.5), (-2.0, 2.5, 1.5)], "red")
     quad("right", [(2.0, 0.0, -1.5), (2.0, 0.0, 1.5), (2.0, 2.5, 1.5), (2.0, 2.5, -1.5)], "green")
     quad("lamp", [(-0.6, 2.49, 0.4), (-0.6, 2.49, -0.4), (0.6, 2.49, -0.4), (0.6, 2.49, 0.4)], light="area_light")
-    for i, surface in enumerate(["m_mirror", "m_glass", "m_rough_glass", "m_plastic", "m_metal"]):
+    for i, surface in enumerate(ball_surfaces):
         x = -1.5 + 0.75 * i
         z = 0.3 if i % 2 == 0 else -0.4
         out.append(f"Shape ball_{i} : Instance {{ shape {{ @ball }} surface {{ @{surface} }} "

@@ -1391,7 +1391,57 @@ SurfSample plastic_sample(const lrk_surface &s, const Interaction &it, V3 wo, fl
     return out;
 }
 
-SurfEval surface_evaluate(const lrk_surface &s, const Interaction &it, V3 wo, V3 wi) {
+// `records` = lrk_scene_desc::surfaces (the two mixed surfaces of a Mix node are records of the same array); nullptr where a
+// closure is evaluated on its own (unit tests: no Mix)
+SurfEval surface_evaluate(const lrk_surface &s, const Interaction &it, V3 wo, V3 wi, const lrk_surface *records = nullptr);
+SurfSample surface_sample(const lrk_surface &s, const Interaction &it, V3 wo, float u_lobe, float u0, float u1, const lrk_surface *records = nullptr);
+
+// Mix: src/surfaces/mix.cpp:82-193.  _mix(a, b, ratio) = lerp(a, b, 1 - ratio) on f and pdf.
+inline SurfEval mix_eval(const SurfEval &a, const SurfEval &b, float ratio) {
+    float t = 1.f - ratio;
+    SurfEval e;
+    e.f = lerp(a.f, b.f, t);
+    e.pdf = lerp(a.pdf, b.pdf, t);
+    return e;
+}
+SurfEval mix_evaluate(const lrk_surface &s, const Interaction &it, V3 wo, V3 wi, const lrk_surface *records) {
+    SurfEval eval_a = surface_evaluate(records[s.mix_a], it, wo, wi, records);
+    SurfEval eval_b = surface_evaluate(records[s.mix_b], it, wo, wi, records);
+    return mix_eval(eval_a, eval_b, s.p[0]);
+}
+SurfSample mix_sample(const lrk_surface &s, const Interaction &it, V3 wo, float u_lobe, float u0, float u1, const lrk_surface *records) {
+    const float ratio = s.p[0];
+    const lrk_surface &a = records[s.mix_a], &b = records[s.mix_b];
+    SurfSample out;
+    if (u_lobe < ratio) {// sample a
+        SurfSample sample_a = surface_sample(a, it, wo, u_lobe / ratio, u0, u1, records);
+        SurfEval eval_b = surface_evaluate(b, it, wo, sample_a.wi, records);
+        out.eval = mix_eval(sample_a.eval, eval_b, ratio);
+        out.wi = sample_a.wi;
+        out.event = sample_a.event;
+    } else {// "sample b" — the reference samples `a` again and evaluates `b` in a's place (mix.cpp:170-176); kept as is
+        SurfSample sample_b = surface_sample(a, it, wo, (u_lobe - ratio) / (1.f - ratio), u0, u1, records);
+        SurfEval eval_a = surface_evaluate(b, it, wo, sample_b.wi, records);
+        out.eval = mix_eval(eval_a, sample_b.eval, ratio);
+        out.wi = sample_b.wi;
+        out.event = sample_b.event;
+    }
+    return out;
+}
+// Surface::Closure::eta() for the Russian-roulette eta scale (mega_path.cpp:133): Glass has one, a Mix lerps / forwards them
+// (mix.cpp:133-141); 0 = nullopt
+float surface_eta(const lrk_surface &s, const lrk_surface *records) {
+    if (s.type == LRK_SURFACE_GLASS) return s.p[6];
+    if (s.type == LRK_SURFACE_MIX) {
+        float ea = surface_eta(records[s.mix_a], records), eb = surface_eta(records[s.mix_b], records);
+        if (ea == 0.f) return eb;
+        if (eb == 0.f) return ea;
+        return lerp(eb, ea, s.p[0]);
+    }
+    return 0.f;
+}
+
+SurfEval surface_evaluate(const lrk_surface &s, const Interaction &it, V3 wo, V3 wi, const lrk_surface *records) {
     SurfEval e;
     switch (s.type) {
         case LRK_SURFACE_MATTE: e = matte_evaluate(s, it, wo, wi); break;
@@ -1399,6 +1449,7 @@ SurfEval surface_evaluate(const lrk_surface &s, const Interaction &it, V3 wo, V3
         case LRK_SURFACE_MIRROR: e = mirror_evaluate(s, it, wo, wi); break;
         case LRK_SURFACE_GLASS: e = glass_evaluate(s, it, wo, wi); break;
         case LRK_SURFACE_PLASTIC: e = plastic_evaluate(s, it, wo, wi); break;
+        case LRK_SURFACE_MIX: e = mix_evaluate(s, it, wo, wi, records); break;
         default: e = metal_evaluate(s, it, wo, wi); break;
     }
     if (!validate_surface_sides(it.ng, it.shading.n, wo, wi)) {
@@ -1407,7 +1458,7 @@ SurfEval surface_evaluate(const lrk_surface &s, const Interaction &it, V3 wo, V3
     }
     return e;
 }
-SurfSample surface_sample(const lrk_surface &s, const Interaction &it, V3 wo, float u_lobe, float u0, float u1) {
+SurfSample surface_sample(const lrk_surface &s, const Interaction &it, V3 wo, float u_lobe, float u0, float u1, const lrk_surface *records) {
     SurfSample r;
     switch (s.type) {
         case LRK_SURFACE_MATTE: r = matte_sample(s, it, wo, u_lobe, u0, u1); break;
@@ -1415,6 +1466,7 @@ SurfSample surface_sample(const lrk_surface &s, const Interaction &it, V3 wo, fl
         case LRK_SURFACE_MIRROR: r = mirror_sample(s, it, wo, u_lobe, u0, u1); break;
         case LRK_SURFACE_GLASS: r = glass_sample(s, it, wo, u_lobe, u0, u1); break;
         case LRK_SURFACE_PLASTIC: r = plastic_sample(s, it, wo, u_lobe, u0, u1); break;
+        case LRK_SURFACE_MIX: r = mix_sample(s, it, wo, u_lobe, u0, u1, records); break;
         default: r = metal_sample(s, it, wo, u_lobe, u0, u1); break;
     }
     if (!validate_surface_sides(it.ng, it.shading.n, wo, r.wi)) {
@@ -1670,18 +1722,17 @@ V3 path_li(const lrk_scene_desc &sc, uint32_t px, uint32_t py, uint32_t sample_i
         const Interaction cit = closure_interaction(sc, surface, it, wo);// the closure's (normal-mapped) view of the hit
         if (ls.eval.pdf > 0.0f && !occluded) {
             V3 wi = v3(ls.shadow_ray.d[0], ls.shadow_ray.d[1], ls.shadow_ray.d[2]);
-            SurfEval ev = surface_evaluate(surface, cit, wo, wi);
+            SurfEval ev = surface_evaluate(surface, cit, wo, wi, sc.surfaces);
             float w = balance_heuristic(ls.eval.pdf, ev.pdf) / ls.eval.pdf;
             Li = Li + w * beta * ev.f * ls.eval.L;
         }
-        SurfSample ss = surface_sample(surface, cit, wo, u_lobe, ub0, ub1);
+        SurfSample ss = surface_sample(surface, cit, wo, u_lobe, ub0, ub1, sc.surfaces);
         ray = spawn_ray(it, ss.wi);
         pdf_bsdf = ss.eval.pdf;
         float w = ss.eval.pdf > 0.f ? 1.f / ss.eval.pdf : 0.f;
         beta = beta * (w * ss.eval.f);
         float eta_scale = 1.f;// mega_path.cpp:113,133-138
-        if (surface.type == LRK_SURFACE_GLASS) {
-            float eta = surface.p[6];
+        if (float eta = surface_eta(surface, sc.surfaces); eta != 0.f) {// closure->eta().value_or(1.f)
             if (ss.event == LRK_EVENT_ENTER) eta_scale = sqr(eta);
             else if (ss.event == LRK_EVENT_EXIT) eta_scale = sqr(1.f / eta);
         }
@@ -1822,7 +1873,6 @@ struct Transmittance {
     V3 f{1.f, 1.f, 1.f};
     float pdf{0.f};
 };
-SurfEval surface_evaluate(const lrk_surface &s, const Interaction &it, V3 wo, V3 wi);// defined above
 Transmittance volume_transmittance(const lrk_scene_desc &sc, PCG32 &rng, lrk_ray origin_ray, TraceCounters *tc, oracle_counters *cnt,
                                    bool *occluded_any) {
     const lrk_medium &m = sc.environment_medium;

@@ -35,7 +35,7 @@ GOLDEN = REPO / "tests" / "golden" / "ref_renders.npz"
 CASES = ["cornell_wavepath", "cornell_megapath", "cornell_russian_roulette", "spheres_disney", "spheres_medium",
          "materials_wavepath", "materials_megapath_rr", "textured", "textured_wrappers", "environment_image",
          "config_c3_full_scene", "config_c4_full_scene", "cornell_filter_gaussian", "cornell_filter_triangle",
-         "cornell_filter_mitchell", "cornell_filter_lanczossinc", "cornell_film_and_light_options"]
+         "cornell_filter_mitchell", "cornell_filter_lanczossinc", "cornell_film_and_light_options", "materials_mix"]
 
 
 @pytest.fixture(scope="module")
@@ -92,7 +92,7 @@ def test_fixture_is_what_the_reference_renders_now(golden):
 @pytest.mark.parametrize("name", ["cornell_wavepath", "cornell_russian_roulette", "spheres_disney", "materials_wavepath",
                                   "materials_megapath_rr", "textured", "textured_wrappers", "environment_image",
                                   "config_c3_full_scene", "cornell_filter_gaussian", "cornell_filter_mitchell",
-                                  "cornell_film_and_light_options"])
+                                  "cornell_film_and_light_options", "materials_mix"])
 def test_cuda_film_matches_the_reference_render(golden, name, gpu_renderer):
     source, scene, desc = _scene(golden, name)
     want = golden[f"{name}/image"][..., :3]
@@ -122,14 +122,15 @@ def test_cuda_film_matches_the_reference_render(golden, name, gpu_renderer):
 
 
 @pytest.mark.gpu
-def test_cuda_materials_first_bounce_matches_oracle(gpu_renderer):
+@pytest.mark.parametrize("mix", [False, True])
+def test_cuda_materials_first_bounce_matches_oracle(gpu_renderer, mix):
     """Depth 2 = camera hit + next-event estimation + one sampled bounce that can only ADD an emitter hit: every pixel is a
     smooth function of the Mirror / Glass / Plastic / Metal closures' evaluate() and sample() at the first hit, with no
     path-length-dependent branching to flip.  The oracle it is compared with is bit-identical to the reference renderer on
     this scene (test_oracle_film_is_bit_identical_to_the_reference_render[materials_*])."""
     from luisarender_b200 import scenes
 
-    source = scenes.materials_box(resolution=(48, 36), spp=16, depth=2)
+    source = scenes.materials_box(resolution=(48, 36), spp=16, depth=2, mix=mix)
     desc = Scene.from_source(source, REPO).desc()
     raw, counters = O.render(desc, 0, 16)
     want = O.convert_film(desc, raw)[..., :3]
