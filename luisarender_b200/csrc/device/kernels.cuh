@@ -16,6 +16,8 @@
 // warp ballots + one atomic per block iteration.  Radiance is carried in Li[path_id] (path_id is the
 // generation slot), so film accumulation needs no atomics and is run-to-run deterministic.
 #pragma once
+#include <type_traits>
+#include <utility>
 #include "shading.cuh"
 #include "traverse.cuh"
 
@@ -312,13 +314,12 @@ __device__ __forceinline__ Frame closure_frame(const DeviceScene &sc, const lrk_
 // VOLUME selects the direct-light weight of the volume integrator: 1 / (pdf_light + pdf_bsdf + pdf_transmittance) with
 // pdf_transmittance = 0 for an unoccluded ray (mega_vpt_naive.cpp:403-407) instead of the balance heuristic (mega_path.cpp:108-113).
 // f / pdf of the closure's own sample: evaluate_local at the sampled direction for every closure (matte.cpp:118-134,
-// disney.cpp:583-586, ...) except Mix, whose sample is not its evaluate (mix.cpp:158-180) and which provides evaluate_sampled
+// disney.cpp:583-586, ...) except Mix, whose sample is not its evaluate (mix.cpp:158-180) and which provides evaluate_sampled.
+// The choice is made at compile time so that the other closures keep ONE call site of evaluate_local in the two-trip loop.
+template<typename Closure, typename = void>
+struct has_evaluate_sampled : std::false_type {};
 template<typename Closure>
-__device__ __forceinline__ auto evaluate_sampled(const Closure &cl, V3 wo, V3 wi, int) -> decltype(cl.evaluate_sampled(wo, wi)) {
-    return cl.evaluate_sampled(wo, wi);
-}
-template<typename Closure>
-__device__ __forceinline__ SurfEval evaluate_sampled(const Closure &cl, V3 wo, V3 wi, long) { return cl.evaluate_local(wo, wi); }
+struct has_evaluate_sampled<Closure, std::void_t<decltype(std::declval<const Closure &>().evaluate_sampled(V3{}, V3{}))>> : std::true_type {};
 
 template<bool VOLUME, typename Closure>
 __device__ __forceinline__ void shade_surface(Closure &cl, const Interaction &it, const Frame &shading, V3 wo, const LightSample &ls, V3 beta,
@@ -341,7 +342,11 @@ __device__ __forceinline__ void shade_surface(Closure &cl, const Interaction &it
         e.f = v3(0.f);
         e.pdf = 0.f;
         if (run) {
-            e = k == 0 ? cl.evaluate_local(wo_local, wi_l) : evaluate_sampled(cl, wo_local, wi_l, 0);
+            if constexpr (has_evaluate_sampled<Closure>::value) {
+                e = k == 0 ? cl.evaluate_local(wo_local, wi_l) : cl.evaluate_sampled(wo_local, wi_l);
+            } else {
+                e = cl.evaluate_local(wo_local, wi_l);
+            }
             if (!validate_surface_sides(it.ng, shading.n, wo, wi_w)) {
                 e.f = v3(0.f);
                 e.pdf = 0.f;
