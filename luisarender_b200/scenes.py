@@ -432,3 +432,88 @@ def materials_box(resolution=(32, 24), spp=4, depth=8, rr_depth=0, rr_threshold=
   shapes {{ {", ".join(shapes)} }}
 }}""")
     return "\n".join(out) + "\n"
+
+
+def flatten_stress(resolution=(32, 24), spp=4, depth=6, output="flatten.exr") -> str:
+    """Host-side flattening in one scene: Group / Instance nesting with SRT, Matrix and Stack transforms,
+    surface and light overrides down the hierarchy, an invisible shape that still casts no shadow, vertex normals with a
+    shadow-terminator factor and an intersection-offset factor, a two-sided light as an instanced shape, a render-level
+    shadow_terminator default."""
+    return f"""
+Surface white : Matte {{ Kd : Constant {{ v {{ 0.75, 0.75, 0.75 }} }} }}
+Surface blue : Matte {{ Kd : Constant {{ v {{ 0.15, 0.25, 0.7 }} }} sigma : Constant {{ v {{ 0.4 }} }} }}
+Surface gold : Disney {{ color : Constant {{ v {{ 0.9, 0.7, 0.2 }} }} metallic : Constant {{ v {{ 0.9 }} }} roughness : Constant {{ v {{ 0.35 }} }} }}
+Light lamp_light : Diffuse {{ emission : Constant {{ v {{ 12.0, 11.0, 10.0 }} }} two_sided {{ true }} }}
+Light small_light : Diffuse {{ emission : Constant {{ v {{ 3.0, 6.0, 9.0 }} }} scale {{ 2.0 }} }}
+Transform lamp_tilt : SRT {{ rotate {{ 1.0, 0.0, 0.0, 90.0 }} scale {{ 1.6 }} }}
+Transform lamp_lift : SRT {{ translate {{ 0.0, 2.6, 0.0 }} }}
+Shape floor : InlineMesh {{
+  positions {{ -3.0, 0.0, 3.0,  3.0, 0.0, 3.0,  3.0, 0.0, -3.0,  -3.0, 0.0, -3.0 }}
+  indices {{ 0, 1, 2, 0, 2, 3 }}
+  surface {{ @white }}
+}}
+Shape bump : InlineMesh {{
+  positions {{ -0.6, 0.0, 0.6,  0.6, 0.0, 0.6,  0.6, 0.0, -0.6,  -0.6, 0.0, -0.6,  0.0, 0.7, 0.0 }}
+  normals {{ -0.6, 0.5, 0.6,  0.6, 0.5, 0.6,  0.6, 0.5, -0.6,  -0.6, 0.5, -0.6,  0.0, 1.0, 0.0 }}
+  uvs {{ 0.0, 0.0,  1.0, 0.0,  1.0, 1.0,  0.0, 1.0,  0.5, 0.5 }}
+  indices {{ 0, 1, 4,  1, 2, 4,  2, 3, 4,  3, 0, 4 }}
+  surface {{ @blue }}
+  shadow_terminator {{ 0.6 }}
+  intersection_offset {{ 0.3 }}
+}}
+Shape quad : InlineMesh {{
+  positions {{ -0.5, -0.5, 0.0,  0.5, -0.5, 0.0,  0.5, 0.5, 0.0,  -0.5, 0.5, 0.0 }}
+  indices {{ 0, 1, 2, 0, 2, 3 }}
+}}
+Shape gold_bump : Instance {{
+  shape {{ @bump }}
+  surface {{ @gold }}
+  transform : SRT {{ scale {{ 0.7, 1.3, 0.7 }} rotate {{ 0.0, 1.0, 0.0, 25.0 }} translate {{ 1.4, 0.0, -0.4 }} }}
+}}
+Shape lamp : Instance {{
+  shape {{ @quad }}
+  light {{ @lamp_light }}
+  transform : Stack {{ transforms {{ @lamp_tilt, @lamp_lift }} }}
+}}
+Shape pair : Group {{
+  shapes {{ @bump, @gold_bump }}
+  transform : Matrix {{ m {{ 0.8, 0.0, 0.0, -1.5,   0.0, 0.8, 0.0, 0.0,   0.0, 0.0, 0.8, 0.8,   0.0, 0.0, 0.0, 1.0 }} }}
+}}
+Shape pair_again : Instance {{
+  shape {{ @pair }}
+  surface {{ @white }}
+  transform : SRT {{ translate {{ 2.2, 0.0, -1.6 }} rotate {{ 0.0, 1.0, 0.0, -40.0 }} }}
+}}
+Shape hidden_wall : Instance {{
+  shape {{ @quad }}
+  surface {{ @blue }}
+  visible {{ false }}
+  transform : SRT {{ scale {{ 3.0 }} translate {{ 0.0, 1.0, 1.5 }} }}
+}}
+Shape small_lamp : Instance {{
+  shape {{ @quad }}
+  light {{ @small_light }}
+  surface {{ @white }}
+  transform : SRT {{ scale {{ 0.5 }} rotate {{ 0.0, 1.0, 0.0, 180.0 }} translate {{ -2.0, 1.0, -2.5 }} }}
+}}
+Camera camera : Pinhole {{
+  position {{ 0.5, 2.2, 5.5 }}
+  look_at {{ 0.0, 0.6, 0.0 }}
+  up {{ 0.0, 1.0, 0.0 }}
+  fov {{ 42.0 }}
+  spp {{ {int(spp)} }}
+  film : Color {{ resolution {{ {int(resolution[0])}, {int(resolution[1])} }} }}
+  filter : Box {{ radius {{ 0.5 }} }}
+  file {{ "{output}" }}
+}}
+render {{
+  integrator : WavePath {{
+    depth {{ {int(depth)} }}
+    rr_depth {{ 1 }}
+    sampler : Independent {{ seed {{ 7 }} }}
+  }}
+  shadow_terminator {{ 0.25 }}
+  cameras {{ @camera }}
+  shapes {{ @floor, @pair, @pair_again, @gold_bump, @lamp, @hidden_wall, @small_lamp }}
+}}
+"""

@@ -35,7 +35,7 @@ GOLDEN = REPO / "tests" / "golden" / "ref_renders.npz"
 CASES = ["cornell_wavepath", "cornell_megapath", "cornell_russian_roulette", "spheres_disney", "spheres_medium",
          "materials_wavepath", "materials_megapath_rr", "textured", "textured_wrappers", "environment_image",
          "config_c3_full_scene", "config_c4_full_scene", "cornell_filter_gaussian", "cornell_filter_triangle",
-         "cornell_filter_mitchell", "cornell_filter_lanczossinc", "cornell_film_and_light_options", "materials_mix"]
+         "cornell_filter_mitchell", "cornell_filter_lanczossinc", "cornell_film_and_light_options", "materials_mix", "flatten_stress"]
 
 
 @pytest.fixture(scope="module")
@@ -92,7 +92,7 @@ def test_fixture_is_what_the_reference_renders_now(golden):
 @pytest.mark.parametrize("name", ["cornell_wavepath", "cornell_russian_roulette", "spheres_disney", "materials_wavepath",
                                   "materials_megapath_rr", "textured", "textured_wrappers", "environment_image",
                                   "config_c3_full_scene", "cornell_filter_gaussian", "cornell_filter_mitchell",
-                                  "cornell_film_and_light_options", "materials_mix"])
+                                  "cornell_film_and_light_options", "materials_mix", "flatten_stress"])
 def test_cuda_film_matches_the_reference_render(golden, name, gpu_renderer):
     source, scene, desc = _scene(golden, name)
     want = golden[f"{name}/image"][..., :3]

@@ -50,6 +50,7 @@ def cases() -> dict[str, str]:
     c["materials_megapath_rr"] = scenes.materials_box(resolution=(32, 24), spp=4, depth=10, rr_depth=2, rr_threshold=0.95,
                                                       integrator="MegaPath")
     c["materials_mix"] = scenes.materials_box(resolution=(32, 24), spp=4, depth=10, rr_depth=2, mix=True, output="mix.exr")
+    c["flatten_stress"] = scenes.flatten_stress()
     # row f1: image textures (8 / 16-bit PNG, grey, palette; all address modes, point + bilinear, sRGB / linear / gamma) on
     # Matte and Disney parameters; with wrappers: normal map, alpha-tested cut-out (ray queries), constant opacity.
     # mesh_files=False: the `Mesh` plugin of the reference needs assimp, which is not built
