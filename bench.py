@@ -335,7 +335,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         rate, n, secs, sample_desc, _ = cpu_oracle_rate(desc, 15.0, SPP_PER_STEP)
         cpu = {"value": round(rate, 4), "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": sample_desc,
                "seconds": round(secs, 2),
-               "pinned": "films bit-identical to the unmodified reference renderer on 19 scenes incl. this one at 96x54 (tests/test_ref_render.py)"}
+               "pinned": "films bit-identical to the unmodified reference renderer on 21 scenes incl. this one at 96x54 (tests/test_ref_render.py)"}
 
     if rank == 0:
         line = {

@@ -35,7 +35,8 @@ GOLDEN = REPO / "tests" / "golden" / "ref_renders.npz"
 CASES = ["cornell_wavepath", "cornell_megapath", "cornell_russian_roulette", "spheres_disney", "spheres_medium",
          "materials_wavepath", "materials_megapath_rr", "textured", "textured_wrappers", "environment_image",
          "config_c3_full_scene", "config_c4_full_scene", "cornell_filter_gaussian", "cornell_filter_triangle",
-         "cornell_filter_mitchell", "cornell_filter_lanczossinc", "cornell_film_and_light_options", "materials_mix", "flatten_stress"]
+         "cornell_filter_mitchell", "cornell_filter_lanczossinc", "cornell_film_and_light_options", "materials_mix", "flatten_stress", "spheres_disney_all_lobes",
+         "spheres_medium_isotropic"]
 
 
 @pytest.fixture(scope="module")
@@ -60,7 +61,7 @@ def _spp(source):
 def test_oracle_film_is_bit_identical_to_the_reference_render(golden, name):
     source, scene, desc = _scene(golden, name)
     want = golden[f"{name}/image"]
-    O.lib().oracle_set_hg_args_right_to_left(1 if ("medium" in name or "c4" in name) else 0)
+    O.lib().oracle_set_hg_args_right_to_left(1 if ("medium" in name or "c4" in name) else 0)  # GCC build of the reference
     try:
         raw, _ = O.render(desc, 0, _spp(source))
         got = O.convert_film(desc, raw)
@@ -92,7 +93,7 @@ def test_fixture_is_what_the_reference_renders_now(golden):
 @pytest.mark.parametrize("name", ["cornell_wavepath", "cornell_russian_roulette", "spheres_disney", "materials_wavepath",
                                   "materials_megapath_rr", "textured", "textured_wrappers", "environment_image",
                                   "config_c3_full_scene", "cornell_filter_gaussian", "cornell_filter_mitchell",
-                                  "cornell_film_and_light_options", "materials_mix", "flatten_stress"])
+                                  "cornell_film_and_light_options", "materials_mix", "flatten_stress", "spheres_disney_all_lobes"])
 def test_cuda_film_matches_the_reference_render(golden, name, gpu_renderer):
     source, scene, desc = _scene(golden, name)
     want = golden[f"{name}/image"][..., :3]

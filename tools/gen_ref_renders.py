@@ -51,6 +51,17 @@ def cases() -> dict[str, str]:
                                                       integrator="MegaPath")
     c["materials_mix"] = scenes.materials_box(resolution=(32, 24), spp=4, depth=10, rr_depth=2, mix=True, output="mix.exr")
     c["flatten_stress"] = scenes.flatten_stress()
+    # every Disney parameter (fake subsurface via flatness, anisotropy, sheen tint, clearcoat gloss, eta) on the sphere scene
+    extra = ("  anisotropic : Constant { v { 0.6 } }\n  sheen_tint : Constant { v { 0.7 } }\n  clearcoat_gloss : Constant { v { 0.3 } }\n"
+             "  flatness : Constant { v { 0.4 } }\n  eta : Constant { v { 1.33 } }\n}")
+    c["spheres_disney_all_lobes"] = "\n".join(
+        (line if not (line == "}" and prev.strip().startswith("sheen : Constant")) else extra)
+        for prev, line in zip([""] + c["spheres_disney"].split("\n"), c["spheres_disney"].split("\n"))).replace('"spheres.exr"', '"lobes.exr"')
+    # the medium path with an isotropic phase function (|g| < 1e-3 branch) and per-channel coefficients
+    c["spheres_medium_isotropic"] = (c["spheres_medium"].replace("g { 0.3 }", "g { 0.0 }")
+                                     .replace("sigma_a : Constant { v { 0.01, 0.01, 0.01 } }", "sigma_a : Constant { v { 0.02, 0.01, 0.005 } }")
+                                     .replace("sigma_s : Constant { v { 0.05, 0.05, 0.05 } }", "sigma_s : Constant { v { 0.03, 0.06, 0.12 } }")
+                                     .replace('"spheres.exr"', '"iso.exr"'))
     # row f1: image textures (8 / 16-bit PNG, grey, palette; all address modes, point + bilinear, sRGB / linear / gamma) on
     # Matte and Disney parameters; with wrappers: normal map, alpha-tested cut-out (ray queries), constant opacity.
     # mesh_files=False: the `Mesh` plugin of the reference needs assimp, which is not built
