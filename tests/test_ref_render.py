@@ -145,3 +145,23 @@ def test_cuda_materials_first_bounce_matches_oracle(gpu_renderer, mix):
     off = (np.abs(got - want) > 1e-4 * np.maximum(np.abs(want), 1.0)).any(axis=-1)
     assert rel_l2 <= 1e-3, rel_l2
     assert off.mean() <= 0.01, off.mean()
+
+
+def test_config_c1_at_full_size_is_bit_identical_to_the_reference():
+    """BASELINE.json configs[0] — Cornell 512x512 @16 spp, 4.19 M samples — rendered by the unmodified reference renderer
+    (tools/gen_ref_full_size.py, ~10 min on the interpreter backend): the oracle's film has the same SHA-256."""
+    import json
+
+    import gen_ref_full_size as F
+
+    golden = json.loads((REPO / "tests" / "golden" / "ref_full_size.json").read_text())
+    source = F.c1_scene()
+    import hashlib
+
+    assert hashlib.sha256(source.encode()).hexdigest() == golden["scene_sha256"], "the fixture was rendered from another scene text"
+    desc = Scene.from_source(source, REPO).desc()
+    raw, _ = O.render(desc, 0, 16)
+    film = O.convert_film(desc, raw)
+    digest = F.film_digest(film)
+    np.testing.assert_allclose(np.array(digest["block_means_32x32"]), np.array(golden["block_means_32x32"]), rtol=0, atol=2e-6)
+    assert digest["sha256"] == golden["sha256"], "the oracle's 512x512 @16 spp Cornell film differs from the reference's"

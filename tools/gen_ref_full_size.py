@@ -1,0 +1,66 @@
+#!/usr/bin/env python3
+"""BASELINE.json configs[0] at FULL size by the unmodified reference renderer: Cornell box, 512x512 @16 spp (4.19 M samples).
+
+Runs `oracle/_ref/bin/luisa-render-cli -b interp` (oracle/ref/README.md) on the scene text of scenes.cornell_box(512x512, 16 spp)
+with the MegaPath integrator (the estimator of WavePath, one sample per pixel per dispatch: the film's float atomics then
+have a fixed order even on several interpreter threads) - about 10 minutes on 8 cores - and stores the SHA-256 of the
+film plus 32x32 block means in tests/golden/ref_full_size.json.  tests/test_ref_render.py compares the oracle's film, bit
+for bit, through the hash.
+
+    make -C oracle/ref && python tools/gen_ref_full_size.py
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+REPO = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(REPO))
+sys.path.insert(0, str(REPO / "tools"))
+OUT = REPO / "tests" / "golden" / "ref_full_size.json"
+
+
+def c1_scene() -> str:
+    from luisarender_b200 import scenes
+
+    return scenes.cornell_box(resolution=(512, 512), spp=16).replace("integrator : WavePath", "integrator : MegaPath")
+
+
+def film_digest(film: np.ndarray) -> dict:
+    film = np.ascontiguousarray(film, dtype=np.float32)
+    h, w = film.shape[:2]
+    blocks = film[..., :3].reshape(h // 32, 32, w // 32, 32, 3).mean(axis=(1, 3))
+    return {"sha256": hashlib.sha256(film.tobytes()).hexdigest(), "resolution": [w, h], "mean_rgb": [float(x) for x in film[..., :3].mean(axis=(0, 1))],
+            "block_means_32x32": [[[round(float(c), 6) for c in px] for px in row] for row in blocks]}
+
+
+def main() -> int:
+    import gen_ref_renders as G
+
+    if not G.CLI.exists():
+        print(f"{G.CLI} is missing: run `make -C oracle/ref` (needs /root/reference)", file=sys.stderr)
+        return 1
+    source = c1_scene()
+    t0 = time.time()
+    if len(sys.argv) > 1:  # an already rendered film (EXR written by the reference CLI)
+        film = G.read_image(Path(sys.argv[1]))
+    else:
+        with tempfile.TemporaryDirectory() as tmp:
+            film = G.render_with_reference(source, Path(tmp), "c1")
+    digest = film_digest(film)
+    digest["config"] = "BASELINE.json configs[0]: Cornell box 512x512 @16 spp (MegaPath), rendered by luisa-render-cli -b interp"
+    digest["scene_sha256"] = hashlib.sha256(source.encode()).hexdigest()
+    digest["render_seconds"] = round(time.time() - t0, 1)
+    OUT.write_text(json.dumps(digest, indent=1) + "\n")
+    print(f"wrote {OUT}: sha256 {digest['sha256']}, mean rgb {digest['mean_rgb']}")
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
