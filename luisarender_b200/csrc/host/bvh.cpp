@@ -20,10 +20,16 @@ struct Builder {
     uint32_t max_leaf;
     bool tlas;
 
-    static void set_box(lrk_bvh_node &n, int child, const Aabb &b) {
+    // Stored boxes are padded: the traversal's slab test (fmaf(lo, 1/d, -o/d) per axis, then min / max) rounds, and a ray
+    // that grazes a box edge or lies in the plane of an axis-aligned (zero-thickness) leaf box could otherwise be culled
+    // although the triangle test would accept it.  Found by rendering BASELINE config C1 at full size with the unmodified
+    // reference (tools/gen_ref_full_size.py): 58 of 262 144 pixels differed until the boxes were padded; with the padding the
+    // film is bit-identical.  The pad is a few hundred ulps of the hierarchy's extent - far below any triangle's size.
+    float pad{0.f};
+    void set_box(lrk_bvh_node &n, int child, const Aabb &b) const {
         float *lo = child == 0 ? n.lo0 : n.lo1;
         float *hi = child == 0 ? n.hi0 : n.hi1;
-        for (int a = 0; a < 3; a++) { lo[a] = b.lo[a]; hi[a] = b.hi[a]; }
+        for (int a = 0; a < 3; a++) { lo[a] = b.lo[a] - pad; hi[a] = b.hi[a] + pad; }
     }
     static void set_empty(lrk_bvh_node &n, int child) {
         float *lo = child == 0 ? n.lo0 : n.lo1;
@@ -137,6 +143,11 @@ BvhBuildResult build_bvh(const Aabb *bounds, uint32_t n, uint32_t max_leaf, bool
         b.centroid[i] = (bounds[i].lo + bounds[i].hi) * 0.5f;
         all.grow(bounds[i]);
     }
+    if (n != 0u) {
+        float extent = 0.f;
+        for (int a = 0; a < 3; a++) extent = std::max({extent, std::fabs(all.lo[a]), std::fabs(all.hi[a]), all.hi[a] - all.lo[a]});
+        b.pad = 4e-5f * extent;
+    }
     b.nodes.reserve(n);
     BvhBuildResult out;
     if (n == 0u) {
@@ -151,7 +162,7 @@ BvhBuildResult build_bvh(const Aabb *bounds, uint32_t n, uint32_t max_leaf, bool
     if (ref & LRK_BVH_LEAF) {
         // the whole range became one leaf: wrap it so that the root is always an inner node
         lrk_bvh_node root{};
-        Builder::set_box(root, 0, all);
+        b.set_box(root, 0, all);
         root.ref0 = ref;
         Builder::set_empty(root, 1);
         root.parent = LRK_BVH_EMPTY;

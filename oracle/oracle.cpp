@@ -378,7 +378,10 @@ inline bool slab(const float lo[3], const float hi[3], const RaySetup &r, float 
 // Geometry::_alpha_skip, src/base/geometry.cpp:165-192 (defined with the texture code below)
 bool alpha_skip(const lrk_scene_desc &sc, uint32_t inst_id, uint32_t prim_id, float bu, float bv);
 
+lrk_hit trace_brute(const lrk_scene_desc &sc, const lrk_ray &ray, bool any_hit);
+std::atomic<bool> g_trace_brute_force{false};// diagnostic: every ray through the brute-force loop (oracle_set_trace_brute_force)
 lrk_hit trace_bvh(const lrk_scene_desc &sc, const lrk_ray &ray, bool any_hit, TraceCounters *cnt) {
+    if (g_trace_brute_force.load(std::memory_order_relaxed)) return trace_brute(sc, ray, any_hit);
     lrk_hit best{~0u, ~0u, {0.f, 0.f}};
     float tbest = ray.tmax;
     const float tmin = ray.tmin;
@@ -2277,6 +2280,7 @@ struct LambertBxDF {
 };
 }// namespace
 
+extern "C" void oracle_set_trace_brute_force(int enabled) { g_trace_brute_force.store(enabled != 0); }
 extern "C" void oracle_set_hg_args_right_to_left(int enabled) { g_hg_args_right_to_left.store(enabled != 0); }
 
 extern "C" int oracle_unit(const char *name_c, const uint32_t *in, uint32_t *out, int count, const void *buffer, uint64_t buffer_count) {
