@@ -165,3 +165,26 @@ def test_config_c1_at_full_size_is_bit_identical_to_the_reference():
     digest = F.film_digest(film)
     np.testing.assert_allclose(np.array(digest["block_means_32x32"]), np.array(golden["block_means_32x32"]), rtol=0, atol=2e-6)
     assert digest["sha256"] == golden["sha256"], "the oracle's 512x512 @16 spp Cornell film differs from the reference's"
+
+
+@pytest.mark.gpu
+def test_cuda_config_c1_at_full_size_matches_the_reference(gpu_renderer):
+    """The CUDA film of BASELINE.json configs[0] at its full size against the digest of the reference's own render: the
+    16x16 means of 32x32-pixel blocks (1024 pixels x 16 spp each) agree to 2e-3 relative — the films are the same estimator on the same
+    random streams, so there is no Monte-Carlo term in the difference, only the rare branch flips of CUDA's libm."""
+    import json
+
+    import gen_ref_full_size as F
+
+    golden = json.loads((REPO / "tests" / "golden" / "ref_full_size.json").read_text())
+    desc = Scene.from_source(F.c1_scene(), REPO).desc()
+    gpu_renderer.upload(desc)
+    gpu_renderer.clear()
+    gpu_renderer.render(0, 16)
+    film = gpu_renderer.film()
+    got = np.array(F.film_digest(film)["block_means_32x32"])
+    want = np.array(golden["block_means_32x32"])
+    assert got.shape == want.shape
+    rel = np.abs(got - want) / np.maximum(np.abs(want), 1e-3)
+    assert np.median(rel) <= 1e-4, f"median block difference {np.median(rel)}"
+    assert rel.max() <= 2e-3, f"largest block difference {rel.max()}"
