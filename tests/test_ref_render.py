@@ -147,41 +147,46 @@ def test_cuda_materials_first_bounce_matches_oracle(gpu_renderer, mix):
     assert off.mean() <= 0.01, off.mean()
 
 
-def test_config_c1_at_full_size_is_bit_identical_to_the_reference():
-    """BASELINE.json configs[0] — Cornell 512x512 @16 spp, 4.19 M samples — rendered by the unmodified reference renderer
-    (tools/gen_ref_full_size.py, ~10 min on the interpreter backend): the oracle's film has the same SHA-256."""
+def _full_size(name):
+    import hashlib
     import json
 
     import gen_ref_full_size as F
 
     golden = json.loads((REPO / "tests" / "golden" / "ref_full_size.json").read_text())
-    source = F.c1_scene()
-    import hashlib
-
+    assert name in golden, f"tests/golden/ref_full_size.json has no '{name}': run tools/gen_ref_full_size.py {name}"
+    golden = golden[name]
+    source = F.CASES[name][0]()
     assert hashlib.sha256(source.encode()).hexdigest() == golden["scene_sha256"], "the fixture was rendered from another scene text"
-    desc = Scene.from_source(source, REPO).desc()
-    raw, _ = O.render(desc, 0, 16)
+    return F, golden, Scene.from_source(source, REPO).desc()
+
+
+@pytest.mark.parametrize("name", ["c1", "c3_quarter"])
+def test_large_render_is_bit_identical_to_the_reference(name):
+    """c1: BASELINE.json configs[0] — Cornell 512x512 @16 spp, 4.19 M samples; c3_quarter: the headline scene of configs[1]
+    (1.39 M instanced triangles) at 480x270 @4 spp — rendered by the unmodified reference renderer
+    (tools/gen_ref_full_size.py, minutes on the interpreter backend): the oracle's film has the same SHA-256."""
+    F, golden, desc = _full_size(name)
+    raw, _ = O.render(desc, 0, golden["spp"])
     film = O.convert_film(desc, raw)
     digest = F.film_digest(film)
     np.testing.assert_allclose(np.array(digest["block_means_32x32"]), np.array(golden["block_means_32x32"]), rtol=0, atol=2e-6)
-    assert digest["sha256"] == golden["sha256"], "the oracle's 512x512 @16 spp Cornell film differs from the reference's"
+    assert digest["sha256"] == golden["sha256"], f"the oracle's film of '{name}' differs from the reference's"
 
 
 @pytest.mark.gpu
-def test_cuda_config_c1_at_full_size_matches_the_reference(gpu_renderer):
-    """The CUDA film of BASELINE.json configs[0] at its full size against the digest of the reference's own render: the
-    16x16 means of 32x32-pixel blocks (1024 pixels x 16 spp each) agree to 2e-3 relative — the films are the same estimator on the same
-    random streams, so there is no Monte-Carlo term in the difference, only the rare branch flips of CUDA's libm."""
-    import json
-
-    import gen_ref_full_size as F
-
-    golden = json.loads((REPO / "tests" / "golden" / "ref_full_size.json").read_text())
-    desc = Scene.from_source(F.c1_scene(), REPO).desc()
+@pytest.mark.parametrize("name", ["c1", "c3_quarter"])
+def test_cuda_large_render_matches_the_reference(gpu_renderer, name):
+    """The CUDA film of the large renders against the digest of the reference's own render: the means of 32x32-pixel blocks
+    (1024 pixels x spp each) agree to 2e-3 relative — the films are the same estimator on the same random streams, so there
+    is no Monte-Carlo term in the difference, only the rare branch flips of CUDA's libm."""
+    F, golden, desc = _full_size(name)
     gpu_renderer.upload(desc)
     gpu_renderer.clear()
-    gpu_renderer.render(0, 16)
+    gpu_renderer.render(0, golden["spp"])
     film = gpu_renderer.film()
+    h, w = film.shape[:2]
+    film = film[: h // 32 * 32, : w // 32 * 32]
     got = np.array(F.film_digest(film)["block_means_32x32"])
     want = np.array(golden["block_means_32x32"])
     assert got.shape == want.shape

@@ -1,5 +1,9 @@
 #!/usr/bin/env python3
-"""BASELINE.json configs[0] at FULL size by the unmodified reference renderer: Cornell box, 512x512 @16 spp (4.19 M samples).
+"""Large renders by the unmodified reference renderer, kept as digests (SHA-256 of the film + 32x32-pixel block means):
+
+    c1          BASELINE.json configs[0] at FULL size: Cornell box, 512x512 @16 spp (4.19 M samples; ~7 min)
+    c3_quarter  the headline scene of configs[1] (1 387 526 instanced triangles, Disney + NEE, depth 10) at a quarter of its
+                resolution: 480x270 @4 spp (0.52 M samples)
 
 Runs `oracle/_ref/bin/luisa-render-cli -b interp` (oracle/ref/README.md) on the scene text of scenes.cornell_box(512x512, 16 spp)
 with the MegaPath integrator (the estimator of WavePath, one sample per pixel per dispatch: the film's float atomics then
@@ -7,7 +11,7 @@ have a fixed order even on several interpreter threads) - about 10 minutes on 8 
 film plus 32x32 block means in tests/golden/ref_full_size.json.  tests/test_ref_render.py compares the oracle's film, bit
 for bit, through the hash.
 
-    make -C oracle/ref && python tools/gen_ref_full_size.py
+    make -C oracle/ref && python tools/gen_ref_full_size.py [case [film.exr]]
 """
 from __future__ import annotations
 
@@ -32,10 +36,23 @@ def c1_scene() -> str:
     return scenes.cornell_box(resolution=(512, 512), spp=16).replace("integrator : WavePath", "integrator : MegaPath")
 
 
+def c3_quarter_scene() -> str:
+    from luisarender_b200 import scenes
+
+    return scenes.instanced_spheres(resolution=(480, 270), spp=4, output="c3q.exr").replace("integrator : WavePath", "integrator : MegaPath")
+
+
+CASES = {
+    "c1": (c1_scene, 16, "BASELINE.json configs[0]: Cornell box 512x512 @16 spp (MegaPath), rendered by luisa-render-cli -b interp"),
+    "c3_quarter": (c3_quarter_scene, 4, "BASELINE.json configs[1]'s scene (instanced Disney spheres) at 480x270 @4 spp (MegaPath), rendered by luisa-render-cli -b interp"),
+}
+
+
 def film_digest(film: np.ndarray) -> dict:
     film = np.ascontiguousarray(film, dtype=np.float32)
     h, w = film.shape[:2]
-    blocks = film[..., :3].reshape(h // 32, 32, w // 32, 32, 3).mean(axis=(1, 3))
+    bh, bw = h // 32, w // 32  # whole blocks only (270 rows: 8 blocks, the last 14 rows are covered by the hash alone)
+    blocks = film[: bh * 32, : bw * 32, :3].reshape(bh, 32, bw, 32, 3).mean(axis=(1, 3))
     return {"sha256": hashlib.sha256(film.tobytes()).hexdigest(), "resolution": [w, h], "mean_rgb": [float(x) for x in film[..., :3].mean(axis=(0, 1))],
             "block_means_32x32": [[[round(float(c), 6) for c in px] for px in row] for row in blocks]}
 
@@ -46,19 +63,25 @@ def main() -> int:
     if not G.CLI.exists():
         print(f"{G.CLI} is missing: run `make -C oracle/ref` (needs /root/reference)", file=sys.stderr)
         return 1
-    source = c1_scene()
-    t0 = time.time()
-    if len(sys.argv) > 1:  # an already rendered film (EXR written by the reference CLI)
-        film = G.read_image(Path(sys.argv[1]))
-    else:
-        with tempfile.TemporaryDirectory() as tmp:
-            film = G.render_with_reference(source, Path(tmp), "c1")
-    digest = film_digest(film)
-    digest["config"] = "BASELINE.json configs[0]: Cornell box 512x512 @16 spp (MegaPath), rendered by luisa-render-cli -b interp"
-    digest["scene_sha256"] = hashlib.sha256(source.encode()).hexdigest()
-    digest["render_seconds"] = round(time.time() - t0, 1)
-    OUT.write_text(json.dumps(digest, indent=1) + "\n")
-    print(f"wrote {OUT}: sha256 {digest['sha256']}, mean rgb {digest['mean_rgb']}")
+    names = [sys.argv[1]] if len(sys.argv) > 1 else list(CASES)
+    data = json.loads(OUT.read_text()) if OUT.exists() else {}
+    for name in names:
+        scene, spp, what = CASES[name]
+        source = scene()
+        t0 = time.time()
+        if len(sys.argv) > 2:  # an already rendered film (EXR written by the reference CLI)
+            film = G.read_image(Path(sys.argv[2]))
+        else:
+            with tempfile.TemporaryDirectory() as tmp:
+                film = G.render_with_reference(source, Path(tmp), name, timeout=3600)
+        digest = film_digest(film)
+        digest["config"] = what
+        digest["spp"] = spp
+        digest["scene_sha256"] = hashlib.sha256(source.encode()).hexdigest()
+        digest["render_seconds"] = round(time.time() - t0, 1)
+        data[name] = digest
+        print(f"{name}: sha256 {digest['sha256']}, mean rgb {digest['mean_rgb']}")
+    OUT.write_text(json.dumps(data, indent=1) + "\n")
     return 0
 
 
