@@ -23,8 +23,12 @@ struct Builder {
     // Stored boxes are padded: the traversal's slab test (fmaf(lo, 1/d, -o/d) per axis, then min / max) rounds, and a ray
     // that grazes a box edge or lies in the plane of an axis-aligned (zero-thickness) leaf box could otherwise be culled
     // although the triangle test would accept it.  Found by rendering BASELINE config C1 at full size with the unmodified
-    // reference (tools/gen_ref_full_size.py): 58 of 262 144 pixels differed until the boxes were padded; with the padding the
-    // film is bit-identical.  The pad is a few hundred ulps of the hierarchy's extent - far below any triangle's size.
+    // reference (tools/gen_ref_full_size.py): 58 of 262 144 pixels differed with exact boxes; padded, the film is bit-identical.
+    // Size of the pad: for an origin inside the root box the rounding of o/d, 1/d and the fmaf moves each of tn and tf by at
+    // most ~1.8e-7 x extent in position units, so 5e-7 x extent covers the gap (1e-7 already makes the large renders
+    // bit-identical).  It must also stay BELOW the spawned-ray offset (offset_ray_origin: 1/65536 near the origin planes):
+    // a larger pad (2e-6 was measured) puts every ray that leaves a flat surface inside that surface's own padded leaf box and
+    // costs +32 % triangle tests and +47 % instance transforms on the headline scene; 5e-7 costs +0.01 %.
     float pad{0.f};
     void set_box(lrk_bvh_node &n, int child, const Aabb &b) const {
         float *lo = child == 0 ? n.lo0 : n.lo1;
@@ -146,7 +150,7 @@ BvhBuildResult build_bvh(const Aabb *bounds, uint32_t n, uint32_t max_leaf, bool
     if (n != 0u) {
         float extent = 0.f;
         for (int a = 0; a < 3; a++) extent = std::max({extent, std::fabs(all.lo[a]), std::fabs(all.hi[a]), all.hi[a] - all.lo[a]});
-        b.pad = 4e-5f * extent;
+        b.pad = 5e-7f * extent;
     }
     b.nodes.reserve(n);
     BvhBuildResult out;

@@ -2,6 +2,8 @@
 """Large renders by the unmodified reference renderer, kept as digests (SHA-256 of the film + 32x32-pixel block means):
 
     c1          BASELINE.json configs[0] at FULL size: Cornell box, 512x512 @16 spp (4.19 M samples; ~7 min)
+    c3_full_resolution  configs[1] at its full 1920x1080, 2 spp (4.15 M samples)
+    c4_quarter  configs[3]'s scene (homogeneous medium, MegaVPTNaive, depth 8) at 480x270 @4 spp
     c3_quarter  the headline scene of configs[1] (1 387 526 instanced triangles, Disney + NEE, depth 10) at a quarter of its
                 resolution: 480x270 @4 spp (0.52 M samples)
 
@@ -42,9 +44,23 @@ def c3_quarter_scene() -> str:
     return scenes.instanced_spheres(resolution=(480, 270), spp=4, output="c3q.exr").replace("integrator : WavePath", "integrator : MegaPath")
 
 
+def c3_full_resolution_scene() -> str:
+    from luisarender_b200 import scenes
+
+    return scenes.instanced_spheres(resolution=(1920, 1080), spp=2, output="c3f.exr").replace("integrator : WavePath", "integrator : MegaPath")
+
+
+def c4_quarter_scene() -> str:
+    from luisarender_b200 import scenes
+
+    return scenes.instanced_spheres(resolution=(480, 270), spp=4, medium=True, depth=8, output="c4q.exr")
+
+
 CASES = {
     "c1": (c1_scene, 16, "BASELINE.json configs[0]: Cornell box 512x512 @16 spp (MegaPath), rendered by luisa-render-cli -b interp"),
     "c3_quarter": (c3_quarter_scene, 4, "BASELINE.json configs[1]'s scene (instanced Disney spheres) at 480x270 @4 spp (MegaPath), rendered by luisa-render-cli -b interp"),
+    "c3_full_resolution": (c3_full_resolution_scene, 2, "BASELINE.json configs[1] at its full 1920x1080 resolution, 2 of its spp (4.15 M samples; MegaPath), rendered by luisa-render-cli -b interp"),
+    "c4_quarter": (c4_quarter_scene, 4, "BASELINE.json configs[3]'s scene (the same spheres in a homogeneous medium, MegaVPTNaive, depth 8) at 480x270 @4 spp, rendered by luisa-render-cli -b interp (GCC build: see DESIGN.md section 4 on homogeneous.cpp:91)"),
 }
 
 
