@@ -340,10 +340,10 @@ __device__ __forceinline__ float4 texture_sample(const DeviceScene &sc, const lr
 // ImageTextureInstance::evaluate: uv transform, sample, decode (image.cpp:136-166)
 __device__ __forceinline__ float tex_decode(const lrk_texture &t, float x) {
     if (t.encoding == LRK_TEX_ENCODING_SRGB) {
-        float lin = x <= 0.04045f ? x * (1.0f / 12.92f) : powf((x + 0.055f) * (1.0f / 1.055f), 2.4f);
+        float lin = x <= 0.04045f ? x * (1.0f / 12.92f) : builtin_pow((x + 0.055f) * (1.0f / 1.055f), 2.4f);
         return t.scale * lin;
     }
-    if (t.encoding == LRK_TEX_ENCODING_GAMMA) return t.scale * powf(x, t.gamma);
+    if (t.encoding == LRK_TEX_ENCODING_GAMMA) return t.scale * builtin_pow(x, t.gamma);
     return t.scale * x;
 }
 // Not inlined on purpose: up to a dozen call sites per closure, executed only for textured materials.
@@ -830,7 +830,7 @@ struct DisneyClosure {
         } else {
             if (has_clearcoat) {
                 float alpha2 = gloss * gloss;
-                float cosTheta = sqrtf(fmaxf(0.f, (1.f - powf(alpha2, 1.f - u0)) / (1.f - alpha2)));
+                float cosTheta = sqrtf(fmaxf(0.f, (1.f - builtin_pow(alpha2, 1.f - u0)) / (1.f - alpha2)));
                 float sinTheta = sqrtf(fmaxf(0.f, 1.f - cosTheta * cosTheta));
                 float phi = 2.f * kPi * u1;
                 float s, c;

@@ -35,6 +35,18 @@ __device__ __forceinline__ float saturate(float x) { return fminf(fmaxf(x, 0.f),
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 __device__ __forceinline__ float lerp(float a, float b, float t) { return t * (b - a) + a; }
 __device__ __forceinline__ V3 lerp(V3 a, V3 b, float t) { return t * (b - a) + a; }
+// The reference backends' builtin pow (cuda_device_math.h:21-36): a whole-number exponent (decided at run time) means
+// square-and-multiply with exactly rounded products, anything else powf.  A gamma-2.0 texture decode is x * x, not powf(x, 2).
+__device__ inline float builtin_pow(float x, float y) {
+    const int n = static_cast<int>(y);
+    if (static_cast<float>(n) != y) return powf(x, y);
+    float acc = 1.0f, base = x;
+    for (unsigned bits = n < 0 ? 0u - static_cast<unsigned>(n) : static_cast<unsigned>(n); bits != 0u; bits >>= 1) {
+        if (bits & 1u) acc *= base;
+        base *= base;
+    }
+    return n < 0 ? 1.0f / acc : acc;
+}
 __device__ __forceinline__ float sign(float x) { return copysignf(1.0f, x); }// never 0
 __device__ __forceinline__ V3 reflect(V3 v, V3 n) { return v - 2.0f * dot(v, n) * n; }
 __device__ __forceinline__ V3 face_forward(V3 v, V3 n) { return dot(v, n) < 0.f ? -v : v; }

@@ -45,6 +45,19 @@ inline float sqr(float x) { return x * x; }
 inline float saturate(float x) { return std::fmin(std::fmax(x, 0.f), 1.f); }// lc_clamp = min(max(v,lo),hi)
 inline float clampf(float x, float lo, float hi) { return std::fmin(std::fmax(x, lo), hi); }
 inline float lerp(float a, float b, float t) { return t * (b - a) + a; }// cuda_device_math.h:3353
+// The builtin pow of the reference's backends (src/compute/src/backends/cuda/cuda_builtin/cuda_device_math.h:21-36): an exponent
+// that is a whole number at run time selects square-and-multiply (exactly rounded products) instead of powf - 1 ulp apart
+// from glibc's powf for a few arguments, e.g. a gamma-2.0 texture decode (found by the 320x240 textured reference render).
+inline float builtin_pow(float x, float y) {
+    const int n = static_cast<int>(y);
+    if (static_cast<float>(n) != y) return std::pow(x, y);
+    float acc = 1.0f, base = x;
+    for (unsigned bits = n < 0 ? 0u - static_cast<unsigned>(n) : static_cast<unsigned>(n); bits != 0u; bits >>= 1) {
+        if (bits & 1u) acc *= base;
+        base *= base;
+    }
+    return n < 0 ? 1.0f / acc : acc;
+}
 inline V3 lerp(V3 a, V3 b, float t) { return t * (b - a) + a; }// src/util/spec.h:272
 inline float sign(float x) { return std::copysign(1.0f, x); }// src/compute/include/luisa/dsl/builtin.h:1542-1543
 inline V3 reflect(V3 v, V3 n) { return v - 2.0f * dot(v, n) * n; }// cuda_device_math.h:3680-3682
@@ -1118,7 +1131,7 @@ struct DisneyClosure {
     }
     V3 clearcoat_sample_wi(V3 wo, float u0, float u1, bool &valid) const {
         float alpha2 = gloss * gloss;
-        float cosTheta = std::sqrt(std::fmax(0.f, (1.f - std::pow(alpha2, 1.f - u0)) / (1.f - alpha2)));
+        float cosTheta = std::sqrt(std::fmax(0.f, (1.f - builtin_pow(alpha2, 1.f - u0)) / (1.f - alpha2)));
         float sinTheta = std::sqrt(std::fmax(0.f, 1.f - cosTheta * cosTheta));
         float phi = 2.f * kPi * u1;
         V3 wh = v3(sinTheta * std::cos(phi), sinTheta * std::sin(phi), cosTheta);
@@ -1525,10 +1538,10 @@ F4 texture_sample(const lrk_scene_desc &sc, const lrk_texture &t, float u, float
 }
 inline float tex_decode(const lrk_texture &t, float x) {// image.cpp:143-158
     if (t.encoding == LRK_TEX_ENCODING_SRGB) {
-        float lin = x <= 0.04045f ? x * (1.0f / 12.92f) : std::pow((x + 0.055f) * (1.0f / 1.055f), 2.4f);
+        float lin = x <= 0.04045f ? x * (1.0f / 12.92f) : builtin_pow((x + 0.055f) * (1.0f / 1.055f), 2.4f);
         return t.scale * lin;
     }
-    if (t.encoding == LRK_TEX_ENCODING_GAMMA) return t.scale * std::pow(x, t.gamma);
+    if (t.encoding == LRK_TEX_ENCODING_GAMMA) return t.scale * builtin_pow(x, t.gamma);
     return t.scale * x;
 }
 F4 texture_evaluate(const lrk_scene_desc &sc, uint32_t tex_id, float u, float v) {

@@ -161,10 +161,16 @@ def _full_size(name):
     return F, golden, Scene.from_source(source, REPO).desc()
 
 
-@pytest.mark.parametrize("name", ["c1", "c3_quarter", "c3_full_resolution", "c4_quarter"])
+LARGE = ["c1", "c2_full_resolution", "c3_quarter", "c3_full_resolution", "c3_full_resolution_wavepath", "c4_quarter", "materials_large",
+         "textured_large", "flatten_large"]
+
+
+@pytest.mark.parametrize("name", LARGE)
 def test_large_render_is_bit_identical_to_the_reference(name):
-    """c1: BASELINE.json configs[0] — Cornell 512x512 @16 spp, 4.19 M samples; c3_quarter: the headline scene of configs[1]
-    (1.39 M instanced triangles) at 480x270 @4 spp — rendered by the unmodified reference renderer
+    """c1: BASELINE.json configs[0] — Cornell 512x512 @16 spp, 4.19 M samples; c3_quarter: the headline scene of configs[2]
+    (1.39 M instanced triangles) at 480x270 @4 spp; ... (the list is tools/gen_ref_full_size.py's CASES: configs C2 and C3 at
+    their full resolutions, WavePath itself, the medium scene, and 320x240 versions of the materials / textured / flattening
+    scenes) — rendered by the unmodified reference renderer
     (tools/gen_ref_full_size.py, minutes on the interpreter backend): the oracle's film has the same SHA-256."""
     F, golden, desc = _full_size(name)
     O.lib().oracle_set_hg_args_right_to_left(1 if name.startswith("c4") else 0)  # GCC build of the reference
@@ -179,7 +185,7 @@ def test_large_render_is_bit_identical_to_the_reference(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["c1", "c3_quarter", "c3_full_resolution"])
+@pytest.mark.parametrize("name", ["c1", "c2_full_resolution", "c3_quarter", "c3_full_resolution_wavepath", "flatten_large"])
 def test_cuda_large_render_matches_the_reference(gpu_renderer, name):
     """The CUDA film of the large renders against the digest of the reference's own render: the means of 32x32-pixel blocks
     (1024 pixels x spp each) agree to 2e-3 relative in >= 99 % of the blocks — the films are the same estimator on the same random streams, so there

@@ -2,9 +2,9 @@
 """Large renders by the unmodified reference renderer, kept as digests (SHA-256 of the film + 32x32-pixel block means):
 
     c1          BASELINE.json configs[0] at FULL size: Cornell box, 512x512 @16 spp (4.19 M samples; ~7 min)
-    c3_full_resolution  configs[1] at its full 1920x1080, 2 spp (4.15 M samples)
+    c3_full_resolution  configs[2] at its full 1920x1080, 2 spp (4.15 M samples)
     c4_quarter  configs[3]'s scene (homogeneous medium, MegaVPTNaive, depth 8) at 480x270 @4 spp
-    c3_quarter  the headline scene of configs[1] (1 387 526 instanced triangles, Disney + NEE, depth 10) at a quarter of its
+    c3_quarter  the headline scene of configs[2] (1 387 526 instanced triangles, Disney + NEE, depth 10) at a quarter of its
                 resolution: 480x270 @4 spp (0.52 M samples)
 
 Runs `oracle/_ref/bin/luisa-render-cli -b interp` (oracle/ref/README.md) on the scene text of scenes.cornell_box(512x512, 16 spp)
@@ -56,11 +56,53 @@ def c4_quarter_scene() -> str:
     return scenes.instanced_spheres(resolution=(480, 270), spp=4, medium=True, depth=8, output="c4q.exr")
 
 
+def _megapath(source: str) -> str:
+    assert "integrator : WavePath" in source
+    return source.replace("integrator : WavePath", "integrator : MegaPath")
+
+
+def c3_full_resolution_wavepath_scene() -> str:
+    # WavePath itself at full resolution: with 2 spp the film's two float atomic adds per pixel commute, so the film does
+    # not depend on the interpreter's thread schedule
+    from luisarender_b200 import scenes
+
+    return scenes.instanced_spheres(resolution=(1920, 1080), spp=2, output="c3w.exr")
+
+
+def c2_full_resolution_scene() -> str:
+    from luisarender_b200 import scenes
+
+    return scenes.cornell_box(resolution=(1024, 1024), spp=2, output="c2.exr")
+
+
+def materials_large_scene() -> str:
+    from luisarender_b200 import scenes
+
+    return _megapath(scenes.materials_box(resolution=(320, 240), spp=4, depth=10, rr_depth=2, subdivision=4, mix=True, output="materials_large.exr"))
+
+
+def textured_large_scene() -> str:
+    from luisarender_b200 import scenes
+
+    return _megapath(scenes.textured_room(resolution=(320, 240), spp=4, mesh_files=False, wrappers=True, output="textured_large.exr"))
+
+
+def flatten_large_scene() -> str:
+    from luisarender_b200 import scenes
+
+    return _megapath(scenes.flatten_stress(resolution=(320, 240), spp=4, output="flatten_large.exr"))
+
+
 CASES = {
     "c1": (c1_scene, 16, "BASELINE.json configs[0]: Cornell box 512x512 @16 spp (MegaPath), rendered by luisa-render-cli -b interp"),
-    "c3_quarter": (c3_quarter_scene, 4, "BASELINE.json configs[1]'s scene (instanced Disney spheres) at 480x270 @4 spp (MegaPath), rendered by luisa-render-cli -b interp"),
-    "c3_full_resolution": (c3_full_resolution_scene, 2, "BASELINE.json configs[1] at its full 1920x1080 resolution, 2 of its spp (4.15 M samples; MegaPath), rendered by luisa-render-cli -b interp"),
-    "c4_quarter": (c4_quarter_scene, 4, "BASELINE.json configs[3]'s scene (the same spheres in a homogeneous medium, MegaVPTNaive, depth 8) at 480x270 @4 spp, rendered by luisa-render-cli -b interp (GCC build: see DESIGN.md section 4 on homogeneous.cpp:91)"),
+    "c3_quarter": (c3_quarter_scene, 4, "config C3's scene (BASELINE.json configs[2]: instanced Disney spheres) at 480x270 @4 spp (MegaPath), rendered by luisa-render-cli -b interp"),
+    "c3_full_resolution": (c3_full_resolution_scene, 2, "config C3 (BASELINE.json configs[2]) at its full 1920x1080 resolution, 2 of its spp (4.15 M samples; MegaPath), rendered by luisa-render-cli -b interp"),
+    "c4_quarter": (c4_quarter_scene, 4, "config C4's scene (BASELINE.json configs[3]: the same spheres in a homogeneous medium, MegaVPTNaive, depth 8) at 480x270 @4 spp, rendered by luisa-render-cli -b interp (GCC build: see DESIGN.md section 4 on homogeneous.cpp:91)"),
+    "c3_full_resolution_wavepath": (c3_full_resolution_wavepath_scene, 2, "as c3_full_resolution, but the WavePath integrator itself"),
+    "c2_full_resolution": (c2_full_resolution_scene, 2, "config C2 (BASELINE.json configs[1]): Cornell box at its full 1024x1024, 2 of its spp, WavePath"),
+    "materials_large": (materials_large_scene, 4, "row f3: the materials box (Mirror, Glass, rough Glass, Plastic, Metal, Mix; level-4 spheres) 320x240 @4 spp, depth 10, Russian roulette from depth 2, MegaPath"),
+    "textured_large": (textured_large_scene, 4, "row f1: the image-textured room with the surface wrappers (normal map, alpha cut-out, opacity) 320x240 @4 spp, MegaPath"),
+    "flatten_large": (flatten_large_scene, 4, "row a23: the flattening stress scene 320x240 @4 spp, MegaPath"),
 }
 
 
