@@ -162,7 +162,8 @@ def _full_size(name):
 
 
 LARGE = ["c1", "c2_full_resolution", "c3_quarter", "c3_full_resolution", "c3_full_resolution_wavepath", "c4_quarter", "materials_large",
-         "textured_large", "flatten_large"]
+         "textured_large", "flatten_large", "disney_lobes_large", "cornell_rr_gaussian_large", "cornell_mitchell_large",
+         "cornell_options_large", "medium_channels_large", "medium_hg_large"]
 
 
 @pytest.mark.parametrize("name", LARGE)
@@ -173,7 +174,7 @@ def test_large_render_is_bit_identical_to_the_reference(name):
     scenes) — rendered by the unmodified reference renderer
     (tools/gen_ref_full_size.py, minutes on the interpreter backend): the oracle's film has the same SHA-256."""
     F, golden, desc = _full_size(name)
-    O.lib().oracle_set_hg_args_right_to_left(1 if name.startswith("c4") else 0)  # GCC build of the reference
+    O.lib().oracle_set_hg_args_right_to_left(1 if name.startswith(("c4", "medium")) else 0)  # GCC build of the reference
     try:
         raw, _ = O.render(desc, 0, golden["spp"])
     finally:

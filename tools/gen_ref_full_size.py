@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import hashlib
 import json
+import os
 import sys
 import tempfile
 import time
@@ -93,6 +94,50 @@ def flatten_large_scene() -> str:
     return _megapath(scenes.flatten_stress(resolution=(320, 240), spp=4, output="flatten_large.exr"))
 
 
+def _small_case(name: str, resolution: tuple, new_resolution: tuple, spp: int, new_spp: int, output: str) -> str:
+    """One of tools/gen_ref_renders.py's scenes at a larger film."""
+    import re
+
+    import gen_ref_renders as G
+
+    source = G.cases()[name]
+    old = f"resolution {{ {resolution[0]}, {resolution[1]} }}"
+    assert source.count(old) == 1 and source.count(f"spp {{ {spp} }}") == 1
+    source = source.replace(old, f"resolution {{ {new_resolution[0]}, {new_resolution[1]} }}").replace(f"spp {{ {spp} }}", f"spp {{ {new_spp} }}")
+    source, n = re.subn(r'(Camera\b.*?\bfile\s*\{\s*")[^"]+("\s*\})', rf"\g<1>{output}\g<2>", source, count=1, flags=re.S)
+    assert n == 1
+    return source.replace("integrator : WavePath", "integrator : MegaPath")
+
+
+def disney_lobes_large_scene() -> str:
+    return _small_case("spheres_disney_all_lobes", (32, 18), (480, 270), 2, 4, "lobes_large.exr")
+
+
+def cornell_rr_gaussian_large_scene() -> str:
+    return _small_case("cornell_russian_roulette", (24, 24), (512, 512), 4, 4, "rr_large.exr").replace(
+        "filter : Box { radius { 0.5 } }", "filter : Gaussian { radius { 1.5 } }")
+
+
+def cornell_mitchell_large_scene() -> str:
+    return _small_case("cornell_filter_mitchell", (24, 24), (256, 256), 4, 4, "mitchell_large.exr")
+
+
+def cornell_options_large_scene() -> str:
+    return _small_case("cornell_film_and_light_options", (24, 24), (256, 256), 4, 4, "options_large.exr")
+
+
+def medium_channels_large_scene() -> str:
+    return _small_case("spheres_medium_isotropic", (32, 18), (320, 180), 2, 4, "iso_large.exr")
+
+
+def medium_hg_large_scene() -> str:
+    return _small_case("spheres_medium", (32, 18), (320, 180), 2, 4, "hg_large.exr")
+
+
+def environment_large_scene() -> str:
+    return _small_case("environment_image", (32, 20), (320, 200), 2, 4, "env_large.exr")
+
+
 CASES = {
     "c1": (c1_scene, 16, "BASELINE.json configs[0]: Cornell box 512x512 @16 spp (MegaPath), rendered by luisa-render-cli -b interp"),
     "c3_quarter": (c3_quarter_scene, 4, "config C3's scene (BASELINE.json configs[2]: instanced Disney spheres) at 480x270 @4 spp (MegaPath), rendered by luisa-render-cli -b interp"),
@@ -103,6 +148,13 @@ CASES = {
     "materials_large": (materials_large_scene, 4, "row f3: the materials box (Mirror, Glass, rough Glass, Plastic, Metal, Mix; level-4 spheres) 320x240 @4 spp, depth 10, Russian roulette from depth 2, MegaPath"),
     "textured_large": (textured_large_scene, 4, "row f1: the image-textured room with the surface wrappers (normal map, alpha cut-out, opacity) 320x240 @4 spp, MegaPath"),
     "flatten_large": (flatten_large_scene, 4, "row a23: the flattening stress scene 320x240 @4 spp, MegaPath"),
+    "disney_lobes_large": (disney_lobes_large_scene, 4, "row a15: the Disney sphere scene with EVERY Disney parameter set, 480x270 @4 spp, MegaPath"),
+    "cornell_rr_gaussian_large": (cornell_rr_gaussian_large_scene, 4, "Cornell 512x512 @4 spp, depth 12, Russian roulette from depth 2, Gaussian filter (row a2), MegaPath"),
+    "cornell_mitchell_large": (cornell_mitchell_large_scene, 4, "Cornell 256x256 @4 spp, Mitchell filter (negative lobes), MegaPath"),
+    "cornell_options_large": (cornell_options_large_scene, 4, "Cornell 256x256 @4 spp, film exposure + clamp, two-sided scaled light, MegaPath"),
+    "medium_channels_large": (medium_channels_large_scene, 4, "row a22: isotropic medium with per-channel coefficients, 320x180 @4 spp, MegaVPTNaive (GCC build)"),
+    "medium_hg_large": (medium_hg_large_scene, 4, "row a22: Henyey-Greenstein medium g = 0.3, 320x180 @4 spp, MegaVPTNaive (GCC build)"),
+    "environment_large": (environment_large_scene, 4, "row a12: image-lit Spherical environment (importance map, MIS compensation) + area light, 320x200 @4 spp, MegaPath (~20 min: the 2048x1024 importance-map kernels run on the interpreter)"),
 }
 
 
@@ -130,8 +182,9 @@ def main() -> int:
         if len(sys.argv) > 2:  # an already rendered film (EXR written by the reference CLI)
             film = G.read_image(Path(sys.argv[2]))
         else:
+            keep = os.environ.get("LRK_REF_KEEP")  # a directory to render into and keep the EXR files in (for diffing)
             with tempfile.TemporaryDirectory() as tmp:
-                film = G.render_with_reference(source, Path(tmp), name, timeout=3600)
+                film = G.render_with_reference(source, Path(keep or tmp), name, timeout=3600, quiet=True)
         digest = film_digest(film)
         digest["config"] = what
         digest["spp"] = spp

@@ -94,7 +94,7 @@ def read_image(path: Path) -> np.ndarray:
     return out
 
 
-def render_with_reference(source: str, workdir: Path, name: str = "scene", timeout: int = 1200) -> np.ndarray:
+def render_with_reference(source: str, workdir: Path, name: str = "scene", timeout: int = 1200, quiet: bool = False) -> np.ndarray:
     """Runs the reference CLI on `source`; returns the RGBA film it saved (the camera's `file`, an fp32 EXR)."""
     import re
 
@@ -103,10 +103,12 @@ def render_with_reference(source: str, workdir: Path, name: str = "scene", timeo
     scene_path.write_text(source.replace('"tests/golden/assets/', f'"{REPO}/tests/golden/assets/'))
     out_name = re.search(r'Camera\b.*?\bfile\s*\{\s*"([^"]+)"\s*\}', source, re.S).group(1)  # the camera's output file
     # (the interp backend runs small dispatches - everything that touches the film - on one thread: reproducible atomics)
-    log = subprocess.run([str(CLI), "-b", "interp", scene_path.name], cwd=workdir, capture_output=True, text=True, timeout=timeout)
+    # (large medium renders: MegaVPTNaive logs every path vertex through device_log - do not keep gigabytes of it)
+    log = subprocess.run([str(CLI), "-b", "interp", scene_path.name], cwd=workdir, text=True, timeout=timeout,
+                         **({"stdout": subprocess.DEVNULL, "stderr": subprocess.DEVNULL} if quiet else {"capture_output": True}))
     out = workdir / out_name
     if not out.exists():
-        raise RuntimeError(f"reference render of '{name}' failed:\n{log.stdout[-2000:]}\n{log.stderr[-2000:]}")
+        raise RuntimeError(f"reference render of '{name}' failed:\n{(log.stdout or '')[-2000:]}\n{(log.stderr or '')[-2000:]}")
     return read_image(out)
 
 
