@@ -168,11 +168,11 @@ LARGE = ["c1", "c2_full_resolution", "c3_quarter", "c3_full_resolution", "c3_ful
 
 @pytest.mark.parametrize("name", LARGE)
 def test_large_render_is_bit_identical_to_the_reference(name):
-    """c1: BASELINE.json configs[0] — Cornell 512x512 @16 spp, 4.19 M samples; c3_quarter: the headline scene of configs[2]
-    (1.39 M instanced triangles) at 480x270 @4 spp; ... (the list is tools/gen_ref_full_size.py's CASES: configs C2 and C3 at
-    their full resolutions, WavePath itself, the medium scene, and 320x240 versions of the materials / textured / flattening
-    scenes) — rendered by the unmodified reference renderer
-    (tools/gen_ref_full_size.py, minutes on the interpreter backend): the oracle's film has the same SHA-256."""
+    """Renders by the UNMODIFIED reference renderer that are too large to keep as images (tools/gen_ref_full_size.py: 0.06 - 4.2 M
+    paths each, minutes on the interpreter backend), kept as SHA-256 of the film + block means: BASELINE.json configs[0] at
+    its full size (Cornell 512x512 @16 spp), configs[1] and configs[2] at their full resolutions with 2 spp through WavePath
+    (configs[2] also through MegaPath), the configs[2] / configs[3] scenes at 480x270, and 256² - 512² versions of the small
+    scenes of test_oracle_film_is_bit_identical_to_the_reference_render.  The oracle's film has the same SHA-256."""
     F, golden, desc = _full_size(name)
     O.lib().oracle_set_hg_args_right_to_left(1 if name.startswith(("c4", "medium")) else 0)  # GCC build of the reference
     try:
