@@ -247,6 +247,12 @@ def test_bvh_is_valid(spheres_small):
                 b = child_bounds(ref, True)
                 if b is not None:
                     assert (boxes[n, lo_s] <= b[0] + 1e-6).all() and (boxes[n, hi_s] >= b[1] - 1e-6).all()
+                    if ref & LEAF:
+                        # stored boxes are PADDED (bvh.cpp: the rounded slab test must not cull what the triangle test accepts),
+                        # by less than the spawned-ray offset: 5e-7 x the mesh's extent
+                        extent = np.abs(tv[:, [0, 1, 2, 4, 5, 6, 8, 9, 10]]).max() * 2.0
+                        assert (boxes[n, lo_s] < b[0]).all() and (boxes[n, hi_s] > b[1]).all()
+                        assert (b[0] - boxes[n, lo_s] <= 1e-6 * extent).all() and (boxes[n, hi_s] - b[1] <= 1e-6 * extent).all()
                 if ref != 0xFFFFFFFF and not (ref & LEAF):
                     assert int(nodes[ref, 14]) == n  # parent link
                     stack.append(ref)
