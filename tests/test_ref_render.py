@@ -163,7 +163,8 @@ def _full_size(name):
 
 LARGE = ["c1", "c2_full_resolution", "c3_quarter", "c3_full_resolution", "c3_full_resolution_wavepath", "c4_quarter", "materials_large",
          "textured_large", "flatten_large", "disney_lobes_large", "cornell_rr_gaussian_large", "cornell_mitchell_large",
-         "cornell_options_large", "medium_channels_large", "medium_hg_large", "environment_large"]
+         "cornell_options_large", "medium_channels_large", "medium_hg_large", "environment_large",
+         "materials_wavepath_large", "textured_wavepath_large", "cornell_disney_odd"]
 
 
 @pytest.mark.parametrize("name", LARGE)

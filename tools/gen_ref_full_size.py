@@ -134,6 +134,24 @@ def medium_hg_large_scene() -> str:
     return _small_case("spheres_medium", (32, 18), (320, 180), 2, 4, "hg_large.exr")
 
 
+def materials_wavepath_large_scene() -> str:
+    from luisarender_b200 import scenes
+
+    return scenes.materials_box(resolution=(320, 240), spp=2, depth=10, rr_depth=2, subdivision=4, mix=True, output="materials_wavepath_large.exr")
+
+
+def textured_wavepath_large_scene() -> str:
+    from luisarender_b200 import scenes
+
+    return scenes.textured_room(resolution=(320, 240), spp=2, mesh_files=False, wrappers=True, output="textured_wavepath_large.exr")
+
+
+def cornell_disney_odd_scene() -> str:
+    from luisarender_b200 import scenes
+
+    return _megapath(scenes.cornell_box(resolution=(333, 187), spp=3, surface="Disney", output="cornell_disney_odd.exr"))
+
+
 def environment_large_scene() -> str:
     return _small_case("environment_image", (32, 20), (320, 200), 2, 4, "env_large.exr")
 
@@ -154,6 +172,9 @@ CASES = {
     "cornell_options_large": (cornell_options_large_scene, 4, "Cornell 256x256 @4 spp, film exposure + clamp, two-sided scaled light, MegaPath"),
     "medium_channels_large": (medium_channels_large_scene, 4, "row a22: isotropic medium with per-channel coefficients, 320x180 @4 spp, MegaVPTNaive (GCC build)"),
     "medium_hg_large": (medium_hg_large_scene, 4, "row a22: Henyey-Greenstein medium g = 0.3, 320x180 @4 spp, MegaVPTNaive (GCC build)"),
+    "materials_wavepath_large": (materials_wavepath_large_scene, 2, "row f3 through WavePath: the materials box + Mix, 320x240 @2 spp, depth 10, Russian roulette from depth 2"),
+    "textured_wavepath_large": (textured_wavepath_large_scene, 2, "row f1 through WavePath: textures + wrappers, 320x240 @2 spp"),
+    "cornell_disney_odd": (cornell_disney_odd_scene, 3, "Cornell box with Disney surfaces at an odd film size, 333x187 @3 spp, MegaPath"),
     "environment_large": (environment_large_scene, 4, "row a12: image-lit Spherical environment (importance map, MIS compensation) + area light, 320x200 @4 spp, MegaPath (~20 min: the 2048x1024 importance-map kernels run on the interpreter)"),
 }
 
@@ -192,7 +213,9 @@ def main() -> int:
         digest["render_seconds"] = round(time.time() - t0, 1)
         data[name] = digest
         print(f"{name}: sha256 {digest['sha256']}, mean rgb {digest['mean_rgb']}")
-    OUT.write_text(json.dumps(data, indent=1) + "\n")
+    merged = json.loads(OUT.read_text()) if OUT.exists() else {}  # (another case may have been written meanwhile)
+    merged.update({name: data[name] for name in names})
+    OUT.write_text(json.dumps(merged, indent=1) + "\n")
     return 0
 
 
