@@ -141,7 +141,7 @@ using EdgeKey = std::pair<int32_t, int32_t>;
 inline EdgeKey edge_key(int32_t a, int32_t b) { return {std::min(a, b), std::max(a, b)}; }
 
 void loop_subdivide_positions(const std::vector<float3> &base_p, const std::vector<lrk_triangle> &base_t, uint32_t level,
-                              std::vector<float3> &out_p, std::vector<lrk_triangle> &out_t) {
+                              std::vector<float3> &out_p, std::vector<lrk_triangle> &out_t, std::vector<float3> *out_n = nullptr) {
     if (level == 0u) {
         out_p = base_p;
         out_t = base_t;
@@ -268,6 +268,42 @@ void loop_subdivide_positions(const std::vector<float3> &base_p, const std::vect
         out_p[i] = cur.verts[i].boundary ? cur.weight_boundary(vi, 1.f / 5.f, ring)
                                          : cur.weight_one_ring(vi, loop_gamma(cur.valence(vi)), ring);
     }
+    if (out_n != nullptr) {
+        // limit-surface normals from the one-ring tangents of the LIMIT positions (src/util/loop_subdiv.cpp:320-358)
+        constexpr float pi = 3.14159265358979323846264338327950288f;
+        for (size_t i = 0; i < cur.verts.size(); i++) cur.verts[i].p = out_p[i];
+        out_n->resize(cur.verts.size());
+        for (size_t i = 0; i < cur.verts.size(); i++) {
+            auto vi = static_cast<int32_t>(i);
+            auto val = cur.valence(vi);
+            cur.one_ring(vi, ring);
+            float3 S{0.f, 0.f, 0.f}, T{0.f, 0.f, 0.f};
+            if (!cur.verts[i].boundary) {
+                for (uint32_t j = 0; j < val; j++) {
+                    S += std::cos(2.f * pi * static_cast<float>(j) / static_cast<float>(val)) * ring[j];
+                    T += std::sin(2.f * pi * static_cast<float>(j) / static_cast<float>(val)) * ring[j];
+                }
+            } else {
+                S = ring[val - 1u] - ring[0];
+                if (val == 2u) {
+                    T = ring[0] + ring[1] - 2.f * cur.verts[i].p;
+                } else if (val == 3u) {
+                    T = ring[1] - cur.verts[i].p;
+                } else if (val == 4u) {
+                    T = -1.f * ring[0] + 2.f * ring[1] + 2.f * ring[2] - 1.f * ring[3] - 2.f * cur.verts[i].p;
+                } else {
+                    auto theta = pi / static_cast<float>(val - 1u);
+                    T = std::sin(theta) * (ring[0] + ring[val - 1u]);
+                    for (uint32_t k = 1u; k < val - 1u; k++) {
+                        auto wt = (2.f * std::cos(theta) - 2.f) * std::sin(static_cast<float>(k) * theta);
+                        T += wt * ring[k];
+                    }
+                    T = -T;
+                }
+            }
+            (*out_n)[i] = normalize(cross(T, S));
+        }
+    }
     out_t.resize(cur.faces.size());
     for (size_t i = 0; i < cur.faces.size(); i++) {
         out_t[i] = {static_cast<uint32_t>(cur.faces[i].v[0]), static_cast<uint32_t>(cur.faces[i].v[1]),
@@ -276,6 +312,16 @@ void loop_subdivide_positions(const std::vector<float3> &base_p, const std::vect
 }
 
 }// namespace
+
+void loop_subdivide_mesh(const std::vector<lrk_vertex> &base_v, const std::vector<lrk_triangle> &base_t, uint32_t level,
+                         std::vector<lrk_vertex> &vertices, std::vector<lrk_triangle> &triangles) {
+    // loop_subdivide, src/util/loop_subdiv.cpp:131-377: limit positions, limit normals, uv = 0 ("FIXME: uv" there)
+    std::vector<float3> bp(base_v.size()), p, n;
+    for (size_t i = 0; i < base_v.size(); i++) bp[i] = {base_v[i].p[0], base_v[i].p[1], base_v[i].p[2]};
+    loop_subdivide_positions(bp, base_t, level, p, triangles, &n);
+    vertices.resize(p.size());
+    for (size_t i = 0; i < p.size(); i++) vertices[i] = {{p[i].x, p[i].y, p[i].z}, {n[i].x, n[i].y, n[i].z}, {0.f, 0.f}};
+}
 
 void make_sphere(uint32_t subdivision, std::vector<lrk_vertex> &vertices, std::vector<lrk_triangle> &triangles) {
     // src/shapes/sphere.cpp:15-50

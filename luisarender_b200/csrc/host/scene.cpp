@@ -1181,6 +1181,32 @@ struct SphereShape final : Shape {
     const std::vector<lrk_triangle> &triangles() const override { return geom->t; }
 };
 
+struct LoopSubdivShape final : Shape {
+    // src/shapes/loop_subdiv.cpp:14-62: Loop subdivision (limit surface, limit normals, uvs dropped) of another mesh shape;
+    // only the base shape's geometry is used - surface, light, transform and the wrappers are this node's own
+    const Shape *base;
+    std::vector<lrk_vertex> verts;
+    std::vector<lrk_triangle> tris;
+    bool subdivided{false};
+    LoopSubdivShape(Scene *s, const NodeDesc *d) : Shape{s, d} {
+        read_mesh_wrappers(this, s, d);
+        auto n = d->node("mesh");
+        if (!n) n = d->node("shape");
+        if (!n) n = d->required_node("base");
+        base = s->load_shape(n);
+        if (!base->is_mesh()) throw Error("LoopSubdiv only supports mesh shapes. [" + d->location() + "]");
+        auto level = std::min(d->u("level", 1u), 10u);
+        if (level != 0u) {
+            loop_subdivide_mesh(base->vertices(), base->triangles(), level, verts, tris);
+            subdivided = true;
+        }
+    }
+    bool is_mesh() const override { return true; }
+    uint32_t vertex_properties() const override { return subdivided ? LRK_SHAPE_HAS_VERTEX_NORMAL : base->vertex_properties(); }
+    const std::vector<lrk_vertex> &vertices() const override { return subdivided ? verts : base->vertices(); }
+    const std::vector<lrk_triangle> &triangles() const override { return subdivided ? tris : base->triangles(); }
+};
+
 struct InstanceShape final : Shape {
     const Shape *child;
     InstanceShape(Scene *s, const NodeDesc *d) : Shape{s, d} {
@@ -1203,6 +1229,7 @@ struct GroupShape final : Shape {
 LRH_PLUGIN("shape-inlinemesh", InlineMesh)
 LRH_PLUGIN("shape-mesh", MeshShape)
 LRH_PLUGIN("shape-sphere", SphereShape)
+LRH_PLUGIN("shape-loopsubdiv", LoopSubdivShape)
 LRH_PLUGIN("shape-instance", InstanceShape)
 LRH_PLUGIN("shape-group", GroupShape)
 

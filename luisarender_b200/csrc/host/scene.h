@@ -266,5 +266,7 @@ void create_alias_table(const float *values, size_t n, std::vector<lrk_alias_ent
 
 // icosphere by Loop subdivision, then projection to the unit sphere (src/shapes/sphere.cpp:60-101)
 void make_sphere(uint32_t subdivision, std::vector<lrk_vertex> &vertices, std::vector<lrk_triangle> &triangles);
+void loop_subdivide_mesh(const std::vector<lrk_vertex> &base_v, const std::vector<lrk_triangle> &base_t, uint32_t level,
+                         std::vector<lrk_vertex> &vertices, std::vector<lrk_triangle> &triangles);
 
 }// namespace lrh

@@ -517,3 +517,93 @@ render {{
   shapes {{ @floor, @pair, @pair_again, @gold_bump, @lamp, @hidden_wall, @small_lamp }}
 }}
 """
+
+
+def subdivision_scene(resolution=(64, 48), spp=4, depth=5, output="subdiv.exr", integrator="WavePath") -> str:
+    """The `LoopSubdiv` shape (src/shapes/loop_subdiv.cpp): Loop subdivision to the limit surface with limit normals of
+    a closed cube (valence-4/5 extraordinary vertices), a tetrahedron (valence 3: the 3/16 rule), an OPEN two-triangle sheet
+    (boundary and corner rules, valence-2 corners) and an open fan of five triangles (boundary valence 3, interior valence 5);
+    level 0 passes the base mesh through."""
+    return f"""
+Surface white : Matte {{ Kd : Constant {{ v {{ 0.75, 0.75, 0.75 }} }} }}
+Surface blue : Disney {{ color : Constant {{ v {{ 0.2, 0.35, 0.8 }} }} roughness : Constant {{ v {{ 0.35 }} }} metallic : Constant {{ v {{ 0.1 }} }} }}
+Surface orange : Matte {{ Kd : Constant {{ v {{ 0.85, 0.45, 0.12 }} }} sigma : Constant {{ v {{ 20.0 }} }} }}
+Surface steel : Metal {{ eta {{ 350.0, 0.2, 1.9, 500.0, 0.35, 2.4, 600.0, 0.25, 3.0, 850.0, 0.2, 5.0 }} roughness : Constant {{ v {{ 0.25 }} }} }}
+Light area_light : Diffuse {{ emission : Constant {{ v {{ 15.0, 14.0, 12.0 }} }} }}
+Shape floor : InlineMesh {{
+  positions {{ -3.0, 0.0, 3.0,  3.0, 0.0, 3.0,  3.0, 0.0, -3.0,  -3.0, 0.0, -3.0 }}
+  indices {{ 0, 1, 2, 0, 2, 3 }}
+  surface {{ @white }}
+}}
+Shape lamp : InlineMesh {{
+  positions {{ -0.8, 3.0, 0.8,  -0.8, 3.0, -0.8,  0.8, 3.0, -0.8,  0.8, 3.0, 0.8 }}
+  indices {{ 0, 1, 2, 0, 2, 3 }}
+  light {{ @area_light }}
+}}
+Shape cube : LoopSubdiv {{
+  mesh : InlineMesh {{
+    positions {{ -0.5, -0.5, 0.5,  0.5, -0.5, 0.5,  0.5, 0.5, 0.5,  -0.5, 0.5, 0.5,  -0.5, -0.5, -0.5,  0.5, -0.5, -0.5,  0.5, 0.5, -0.5,  -0.5, 0.5, -0.5 }}
+    indices {{ 0, 1, 2, 0, 2, 3,  1, 5, 6, 1, 6, 2,  5, 4, 7, 5, 7, 6,  4, 0, 3, 4, 3, 7,  3, 2, 6, 3, 6, 7,  4, 5, 1, 4, 1, 0 }}
+  }}
+  level {{ 3 }}
+  surface {{ @blue }}
+  transform : SRT {{ scale {{ 1.2 }} rotate {{ 0.0, 1.0, 0.0, 25.0 }} translate {{ -1.1, 0.62, 0.0 }} }}
+}}
+Shape tetra : LoopSubdiv {{
+  shape : InlineMesh {{
+    positions {{ 0.0, 1.0, 0.0,  -0.9, -0.4, 0.55,  0.9, -0.4, 0.55,  0.0, -0.4, -1.0 }}
+    indices {{ 0, 1, 2,  0, 2, 3,  0, 3, 1,  1, 3, 2 }}
+  }}
+  level {{ 2 }}
+  surface {{ @orange }}
+  transform : SRT {{ scale {{ 0.9 }} translate {{ 0.9, 0.55, -0.4 }} }}
+}}
+Shape sheet : LoopSubdiv {{
+  base : InlineMesh {{
+    positions {{ -0.6, 0.0, 0.5,  0.6, 0.0, 0.5,  0.6, 0.9, 0.1,  -0.6, 0.9, 0.1 }}
+    indices {{ 0, 1, 2, 0, 2, 3 }}
+  }}
+  level {{ 2 }}
+  surface {{ @steel }}
+  transform : SRT {{ rotate {{ 0.0, 1.0, 0.0, -20.0 }} translate {{ 0.2, 0.02, 1.3 }} }}
+}}
+Shape fan : LoopSubdiv {{
+  mesh : InlineMesh {{
+    positions {{ 0.0, 0.5, 0.0,  0.6, 0.0, 0.0,  0.3, 0.0, 0.55,  -0.3, 0.0, 0.55,  -0.6, 0.0, 0.0,  -0.3, 0.0, -0.55,  0.3, 0.0, -0.55 }}
+    indices {{ 0, 1, 2,  0, 2, 3,  0, 3, 4,  0, 4, 5,  0, 5, 6 }}
+  }}
+  level {{ 1 }}
+  shadow_terminator {{ 0.5 }}
+  surface {{ @white }}
+  transform : SRT {{ translate {{ -0.3, 0.01, -1.6 }} }}
+}}
+Shape passthrough : LoopSubdiv {{
+  mesh : InlineMesh {{
+    positions {{ 1.6, 0.0, -1.8,  2.4, 0.0, -1.8,  2.0, 1.2, -1.8 }}
+    normals {{ 0.0, 0.3, 1.0,  0.2, 0.0, 1.0,  -0.2, 0.1, 1.0 }}
+    indices {{ 0, 1, 2 }}
+  }}
+  level {{ 0 }}
+  surface {{ @orange }}
+}}
+Camera camera : Pinhole {{
+  position {{ 0.0, 2.2, 5.2 }}
+  front {{ 0.0, -0.32, -1.0 }}
+  up {{ 0.0, 1.0, 0.0 }}
+  fov {{ 42.0 }}
+  spp {{ {spp} }}
+  film : Color {{ resolution {{ {resolution[0]}, {resolution[1]} }} }}
+  filter : Box {{ radius {{ 0.5 }} }}
+  file {{ "{output}" }}
+}}
+render {{
+  integrator : {integrator} {{
+    depth {{ {depth} }}
+    rr_depth {{ 0 }}
+    rr_threshold {{ 0.95 }}
+    sampler : Independent {{ seed {{ 19980810 }} }}
+  }}
+  cameras {{ @camera }}
+  shapes {{ @floor, @lamp, @cube, @tetra, @sheet, @fan, @passthrough }}
+}}
+"""

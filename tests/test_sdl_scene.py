@@ -290,3 +290,20 @@ def test_scene_generators_match_baseline_configs():
     info = Scene.from_source(scenes.instanced_spheres(big_subdivision=5)).info()  # full size is built by the GPU tests / bench
     assert info["instances"] == 67 and info["surfaces"] == 9 and info["lights"] == 2
     assert info["instanced_triangles"] == 4 * 20 * 4 ** 5 + 60 * 1280 + 2 + 4
+
+
+def test_loop_subdiv_shape():
+    """src/shapes/loop_subdiv.cpp: `mesh` / `shape` / `base` name the base shape, which must be a mesh; the level is clamped
+    to 10, level 0 passes the base mesh (and its vertex properties) through; a subdivided mesh has normals and no uvs."""
+    from luisarender_b200 import scenes
+
+    src = scenes.subdivision_scene(resolution=(8, 6), spp=1)
+    d = Scene.from_source(src).desc()
+    counts = sorted(int(d.meshes[i].triangle_count) for i in range(d.mesh_count))
+    assert counts == sorted([2, 2, 12 * 4 ** 3, 4 * 4 ** 2, 2 * 4 ** 2, 5 * 4, 1])
+    with pytest.raises(RuntimeError, match="LoopSubdiv only supports mesh shapes"):
+        Scene.from_source(src.replace("shape : InlineMesh {\n    positions { 0.0, 1.0, 0.0,  -0.9, -0.4, 0.55,  0.9, -0.4, 0.55,  0.0, -0.4, -1.0 }\n"
+                                      "    indices { 0, 1, 2,  0, 2, 3,  0, 3, 1,  1, 3, 2 }\n  }",
+                                      "shape : Group { shapes { @floor } }"))
+    with pytest.raises(RuntimeError, match="base"):
+        Scene.from_source(src.replace("  level { 0 }", "  level { 0 }").replace("Shape passthrough : LoopSubdiv {\n  mesh : InlineMesh", "Shape passthrough : LoopSubdiv {\n  cage : InlineMesh"))

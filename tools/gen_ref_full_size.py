@@ -152,6 +152,12 @@ def cornell_disney_odd_scene() -> str:
     return _megapath(scenes.cornell_box(resolution=(333, 187), spp=3, surface="Disney", output="cornell_disney_odd.exr"))
 
 
+def subdivision_large_scene() -> str:
+    from luisarender_b200 import scenes
+
+    return _megapath(scenes.subdivision_scene(resolution=(320, 240), spp=4, output="sd.exr"))
+
+
 def environment_large_scene() -> str:
     return _small_case("environment_image", (32, 20), (320, 200), 2, 4, "env_large.exr")
 
@@ -175,6 +181,7 @@ CASES = {
     "materials_wavepath_large": (materials_wavepath_large_scene, 2, "row f3 through WavePath: the materials box + Mix, 320x240 @2 spp, depth 10, Russian roulette from depth 2"),
     "textured_wavepath_large": (textured_wavepath_large_scene, 2, "row f1 through WavePath: textures + wrappers, 320x240 @2 spp"),
     "cornell_disney_odd": (cornell_disney_odd_scene, 3, "Cornell box with Disney surfaces at an odd film size, 333x187 @3 spp, MegaPath"),
+    "subdivision_large": (subdivision_large_scene, 4, "the LoopSubdiv shape (closed / open / valence-3 base meshes, limit normals) 320x240 @4 spp, MegaPath"),
     "environment_large": (environment_large_scene, 4, "row a12: image-lit Spherical environment (importance map, MIS compensation) + area light, 320x200 @4 spp, MegaPath (~20 min: the 2048x1024 importance-map kernels run on the interpreter)"),
 }
 

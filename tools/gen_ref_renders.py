@@ -51,6 +51,8 @@ def cases() -> dict[str, str]:
                                                       integrator="MegaPath")
     c["materials_mix"] = scenes.materials_box(resolution=(32, 24), spp=4, depth=10, rr_depth=2, mix=True, output="mix.exr")
     c["flatten_stress"] = scenes.flatten_stress()
+    # the LoopSubdiv shape: closed, open (boundary / corner rules) and valence-3 base meshes, limit normals, level 0 pass-through
+    c["subdivision"] = scenes.subdivision_scene(resolution=(64, 48), spp=4)
     # every Disney parameter (fake subsurface via flatness, anisotropy, sheen tint, clearcoat gloss, eta) on the sphere scene
     extra = ("  anisotropic : Constant { v { 0.6 } }\n  sheen_tint : Constant { v { 0.7 } }\n  clearcoat_gloss : Constant { v { 0.3 } }\n"
              "  flatness : Constant { v { 0.4 } }\n  eta : Constant { v { 1.33 } }\n}")
