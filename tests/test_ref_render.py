@@ -93,7 +93,8 @@ def test_fixture_is_what_the_reference_renders_now(golden):
 @pytest.mark.parametrize("name", ["cornell_wavepath", "cornell_russian_roulette", "spheres_disney", "materials_wavepath",
                                   "materials_megapath_rr", "textured", "textured_wrappers", "environment_image",
                                   "config_c3_full_scene", "cornell_filter_gaussian", "cornell_filter_mitchell",
-                                  "cornell_film_and_light_options", "materials_mix", "flatten_stress", "spheres_disney_all_lobes"])
+                                  "cornell_film_and_light_options", "materials_mix", "flatten_stress", "spheres_disney_all_lobes",
+                                  "subdivision"])
 def test_cuda_film_matches_the_reference_render(golden, name, gpu_renderer):
     source, scene, desc = _scene(golden, name)
     want = golden[f"{name}/image"][..., :3]
