@@ -303,6 +303,61 @@ struct ImageTexture final : Texture {
     }
 };
 
+struct SwizzleTexture final : Texture {
+    // src/textures/swizzle.cpp:17-104: picks / reorders the channels of another texture.  The decode of an image texture
+    // (encoding, scale) acts per channel, so swizzling an image is a permutation of its texels' channels: host-only.
+    const Texture *base;
+    std::vector<uint32_t> pick;
+    SwizzleTexture(Scene *s, const NodeDesc *d) : Texture{s, d, Tag::TEXTURE} {
+        base = s->load_texture(d->required_node("base"));
+        if (auto numbers = d->numbers("swizzle")) {
+            for (auto x : *numbers) pick.push_back(static_cast<uint32_t>(x));
+        } else {
+            for (auto c : d->s("swizzle", "rgba")) {
+                switch (c) {
+                    case 'r': case 'x': pick.push_back(0u); break;
+                    case 'g': case 'y': pick.push_back(1u); break;
+                    case 'b': case 'z': pick.push_back(2u); break;
+                    case 'a': case 'w': pick.push_back(3u); break;
+                    default: throw Error(std::string{"Invalid swizzle channel '"} + c + "'. [" + d->location() + "]");
+                }
+            }
+        }
+        if (pick.size() > 4u) pick.resize(4u);// the reference warns and discards the rest
+        if (pick.empty()) throw Error("Swizzle channel index out of range. [" + d->location() + "]");
+        for (auto c : pick)
+            if (c >= 4u) throw Error("Swizzle channel '" + std::to_string(c) + "' out of range. [" + d->location() + "]");
+    }
+    // SwizzleTextureInstance::evaluate (:87-94): 1 -> (a,a,a,a), 2 -> (a,b,0,1), 3 -> (a,b,c,1), 4 -> (a,b,c,d)
+    void apply(const float in[4], float out[4]) const {
+        float v[4]{in[0], in[1], in[2], in[3]};
+        switch (pick.size()) {
+            case 1u: out[0] = out[1] = out[2] = out[3] = v[pick[0]]; break;
+            case 2u: out[0] = v[pick[0]]; out[1] = v[pick[1]]; out[2] = 0.f; out[3] = 1.f; break;
+            case 3u: out[0] = v[pick[0]]; out[1] = v[pick[1]]; out[2] = v[pick[2]]; out[3] = 1.f; break;
+            default: out[0] = v[pick[0]]; out[1] = v[pick[1]]; out[2] = v[pick[2]]; out[3] = v[pick[3]]; break;
+        }
+    }
+    bool is_black() const override { return base->is_black(); }
+    bool is_constant() const override { return base->is_constant(); }
+    bool is_image() const override { return base->is_image(); }
+    uint32_t channels() const override { return static_cast<uint32_t>(pick.size()); }
+    float4 value() const override {// evaluate_static (:65-72): unpicked channels stay 0
+        auto b = base->value();
+        float in[4]{b.x, b.y, b.z, b.w};
+        float4 out{0.f, 0.f, 0.f, 0.f};
+        float *o = &out.x;
+        for (size_t i = 0; i < pick.size(); i++) o[i] = in[pick[i]];
+        return out;
+    }
+    void emit(lrk_texture &out, std::vector<float> &texels) const override {
+        auto first = texels.size();
+        base->emit(out, texels);
+        out.channels = channels();
+        for (auto i = first; i + 4u <= texels.size(); i += 4u) apply(&texels[i], &texels[i]);
+    }
+};
+
 struct SRGBSpectrum final : Spectrum {
     SRGBSpectrum(Scene *s, const NodeDesc *d) : Spectrum{s, d, Tag::SPECTRUM} {}
 };
@@ -340,6 +395,7 @@ const Texture *surface_texture(Scene *s, const NodeDesc *d, const char *name) {
 }// namespace
 LRH_PLUGIN("texture-constant", ConstantTexture)
 LRH_PLUGIN("texture-image", ImageTexture)
+LRH_PLUGIN("texture-swizzle", SwizzleTexture)
 LRH_PLUGIN("spectrum-srgb", SRGBSpectrum)
 
 // ---------------------------------------------------------------- transforms

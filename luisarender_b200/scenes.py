@@ -607,3 +607,25 @@ render {{
   shapes {{ @floor, @lamp, @cube, @tetra, @sheet, @fan, @passthrough }}
 }}
 """
+
+
+def swizzle_scene(resolution=(64, 48), spp=4, output="swizzle.exr", assets="tests/golden/assets", integrator="WavePath") -> str:
+    """The `Swizzle` texture (src/textures/swizzle.cpp) on the textured room: reordered image channels ("bgr" of an sRGB PNG,
+    "gbr" of a gamma-decoded palette PNG), one channel of a four-channel 16-bit image as a scalar parameter (index list form),
+    a swizzled constant, and a swizzle of a swizzle."""
+    src = textured_room(resolution=resolution, spp=spp, mesh_files=False, assets=assets, output=output, integrator=integrator)
+    a = assets.rstrip("/")
+
+    def swap(text, old, new):
+        assert text.count(old) == 1, old
+        return text.replace(old, new)
+
+    src = swap(src, f'Kd : Image {{ file {{ "{a}/checker_rgb8.png" }} address {{ "repeat" }} filter {{ "bilinear" }} uv_scale {{ 2.0, 3.0 }} uv_offset {{ 0.25, 0.0 }} }}',
+               f'Kd : Swizzle {{ base : Image {{ file {{ "{a}/checker_rgb8.png" }} address {{ "repeat" }} filter {{ "bilinear" }} uv_scale {{ 2.0, 3.0 }} uv_offset {{ 0.25, 0.0 }} }} swizzle {{ "bgr" }} }}')
+    src = swap(src, f'sigma : Image {{ file {{ "{a}/rough_gray8.png" }} encoding {{ "linear" }} filter {{ "point" }} }}',
+               f'sigma : Swizzle {{ base : Image {{ file {{ "{a}/ramp_rgba16.png" }} encoding {{ "linear" }} scale {{ 40.0 }} }} swizzle {{ 1 }} }}')
+    src = swap(src, 'metallic : Constant { v { 0.2 } }',
+               'metallic : Swizzle { base : Swizzle { base : Constant { v { 0.9, 0.2, 0.5 } } swizzle { 2, 0, 1 } } swizzle { "z" } }')
+    src = swap(src, f'Kd : Image {{ file {{ "{a}/palette4.png" }} address {{ "zero" }} encoding {{ "gamma" }} gamma {{ 2.0 }} }}',
+               f'Kd : Swizzle {{ base : Image {{ file {{ "{a}/palette4.png" }} address {{ "zero" }} encoding {{ "gamma" }} gamma {{ 2.0 }} }} swizzle {{ "gbr" }} }}')
+    return src

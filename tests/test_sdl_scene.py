@@ -307,3 +307,19 @@ def test_loop_subdiv_shape():
                                       "shape : Group { shapes { @floor } }"))
     with pytest.raises(RuntimeError, match="base"):
         Scene.from_source(src.replace("  level { 0 }", "  level { 0 }").replace("Shape passthrough : LoopSubdiv {\n  mesh : InlineMesh", "Shape passthrough : LoopSubdiv {\n  cage : InlineMesh"))
+
+
+def test_swizzle_texture():
+    """src/textures/swizzle.cpp: channel letters or an index list, at most four, each < 4; constants fold (nesting included);
+    an image base stays an image texture with permuted texels and the swizzle's channel count."""
+    from pathlib import Path
+
+    REPO = Path(__file__).resolve().parent.parent
+    src = scenes.swizzle_scene(resolution=(8, 6), spp=1)
+    d = Scene.from_source(src, REPO).desc()
+    channels = sorted(int(d.textures[i].channels) for i in range(d.texture_count))
+    assert 1 in channels and 3 in channels  # sigma <- one channel of the RGBA16 ramp; "bgr" / "gbr" stay three-channel
+    with pytest.raises(RuntimeError, match="Invalid swizzle channel 'q'"):
+        Scene.from_source(src.replace('swizzle { "bgr" }', 'swizzle { "bqr" }'), REPO)
+    with pytest.raises(RuntimeError, match="out of range"):
+        Scene.from_source(src.replace("swizzle { 2, 0, 1 }", "swizzle { 2, 0, 7 }"), REPO)
