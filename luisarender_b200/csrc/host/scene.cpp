@@ -358,6 +358,56 @@ struct SwizzleTexture final : Texture {
     }
 };
 
+struct CheckerboardTexture final : Texture {
+    // src/textures/checkerboard.cpp:19-74 with a CONSTANT on texture and a constant or absent (black) off texture: the selector
+    // (int(floor(u sx)) + int(floor(v sy))) % 2 == 0 is what a point-sampled, repeating 2x2 image gives at uv * (scale / 2)
+    // (halving commutes with every rounding involved), so the checkerboard is baked into four texels: host-only.
+    const Texture *on{}, *off{};
+    float scale[2]{1.f, 1.f};
+    CheckerboardTexture(Scene *s, const NodeDesc *d) : Texture{s, d, Tag::TEXTURE} {
+        if (auto n = d->node("on")) on = s->load_texture(n);
+        if (auto n = d->node("off")) off = s->load_texture(n);
+        // an absent 'on' is 1 through evaluate() (scalar parameters) but a ZERO spectrum through evaluate_albedo_spectrum /
+        // evaluate_illuminant_spectrum (checkerboard.cpp:78-83, 93-98: SampledSpectrum{n} is all zeros): one texture record
+        // cannot be both, so the ambiguous form is refused; an absent 'off' is zero either way
+        if (on == nullptr)
+            throw Error("Checkerboard: 'on' must be given (the reference evaluates an absent 'on' as 1 for scalar parameters and as "
+                        "black for colours). [" + d->location() + "]");
+        if ((on && !on->is_constant()) || (off && !off->is_constant()))
+            throw Error("Checkerboard: only constant 'on' / 'off' textures are supported. [" + d->location() + "]");
+        auto v = d->float_list("scale");
+        if (v.size() >= 2u) { scale[0] = v[0]; scale[1] = v[1]; }
+        else if (v.size() == 1u) { scale[0] = scale[1] = v[0]; }
+    }
+    bool is_black() const override { return (on != nullptr && on->is_black()) && (off == nullptr || off->is_black()); }
+    bool is_constant() const override { return false; }// no static value in the reference either (no evaluate_static)
+    bool is_image() const override { return true; }
+    uint32_t channels() const override { return std::min(on ? on->channels() : 4u, off ? off->channels() : 4u); }
+    float4 value() const override { throw Error("Checkerboard has no constant value."); }
+    void emit(lrk_texture &out, std::vector<float> &texels) const override {
+        auto offset = out.texel_offset;
+        out = lrk_texture{};
+        out.texel_offset = offset;
+        out.width = out.height = 2u;
+        out.channels = channels();
+        out.address = LRK_TEX_ADDRESS_REPEAT;
+        out.filter = LRK_TEX_FILTER_POINT;
+        out.encoding = LRK_TEX_ENCODING_LINEAR;
+        out.gamma = 1.f;
+        out.scale = 1.f;
+        out.uv_scale[0] = scale[0] * 0.5f;
+        out.uv_scale[1] = scale[1] * 0.5f;
+        out.uv_offset[0] = out.uv_offset[1] = 0.f;
+        auto a = on ? on->value() : float4{1.f, 1.f, 1.f, 1.f};
+        auto b = off ? off->value() : float4{0.f, 0.f, 0.f, 0.f};
+        for (int y = 0; y < 2; y++)
+            for (int x = 0; x < 2; x++) {
+                auto c = ((x + y) % 2 == 0) ? a : b;
+                texels.insert(texels.end(), {c.x, c.y, c.z, c.w});
+            }
+    }
+};
+
 struct SRGBSpectrum final : Spectrum {
     SRGBSpectrum(Scene *s, const NodeDesc *d) : Spectrum{s, d, Tag::SPECTRUM} {}
 };
@@ -396,6 +446,7 @@ const Texture *surface_texture(Scene *s, const NodeDesc *d, const char *name) {
 LRH_PLUGIN("texture-constant", ConstantTexture)
 LRH_PLUGIN("texture-image", ImageTexture)
 LRH_PLUGIN("texture-swizzle", SwizzleTexture)
+LRH_PLUGIN("texture-checkerboard", CheckerboardTexture)
 LRH_PLUGIN("spectrum-srgb", SRGBSpectrum)
 
 // ---------------------------------------------------------------- transforms

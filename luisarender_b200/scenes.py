@@ -629,3 +629,22 @@ def swizzle_scene(resolution=(64, 48), spp=4, output="swizzle.exr", assets="test
     src = swap(src, f'Kd : Image {{ file {{ "{a}/palette4.png" }} address {{ "zero" }} encoding {{ "gamma" }} gamma {{ 2.0 }} }}',
                f'Kd : Swizzle {{ base : Image {{ file {{ "{a}/palette4.png" }} address {{ "zero" }} encoding {{ "gamma" }} gamma {{ 2.0 }} }} swizzle {{ "gbr" }} }}')
     return src
+
+
+def checkerboard_scene(resolution=(64, 48), spp=4, output="checker.exr", assets="tests/golden/assets", integrator="WavePath") -> str:
+    """The `Checkerboard` texture (src/textures/checkerboard.cpp) with constant squares on the textured room: RGB squares with
+    an anisotropic scale, a scalar parameter (Oren-Nayar sigma), the default off texture (black)."""
+    src = textured_room(resolution=resolution, spp=spp, mesh_files=False, assets=assets, output=output, integrator=integrator)
+    a = assets.rstrip("/")
+
+    def swap(text, old, new):
+        assert text.count(old) == 1, old
+        return text.replace(old, new)
+
+    src = swap(src, f'Kd : Image {{ file {{ "{a}/checker_rgb8.png" }} address {{ "repeat" }} filter {{ "bilinear" }} uv_scale {{ 2.0, 3.0 }} uv_offset {{ 0.25, 0.0 }} }}',
+               'Kd : Checkerboard { on : Constant { v { 0.8, 0.2, 0.2 } } off : Constant { v { 0.1, 0.1, 0.6 } } scale { 5.0, 7.0 } }')
+    src = swap(src, f'sigma : Image {{ file {{ "{a}/rough_gray8.png" }} encoding {{ "linear" }} filter {{ "point" }} }}',
+               'sigma : Checkerboard { on : Constant { v { 35.0 } } off : Constant { v { 0.0 } } scale { 3.0 } }')
+    src = swap(src, f'Kd : Image {{ file {{ "{a}/palette4.png" }} address {{ "zero" }} encoding {{ "gamma" }} gamma {{ 2.0 }} }}',
+               'Kd : Checkerboard { on : Constant { v { 0.9, 0.85, 0.3 } } scale { 2.5 } }')
+    return src

@@ -36,7 +36,7 @@ CASES = ["cornell_wavepath", "cornell_megapath", "cornell_russian_roulette", "sp
          "materials_wavepath", "materials_megapath_rr", "textured", "textured_wrappers", "environment_image",
          "config_c3_full_scene", "config_c4_full_scene", "cornell_filter_gaussian", "cornell_filter_triangle",
          "cornell_filter_mitchell", "cornell_filter_lanczossinc", "cornell_film_and_light_options", "materials_mix", "flatten_stress", "spheres_disney_all_lobes",
-         "spheres_medium_isotropic", "subdivision", "swizzle"]
+         "spheres_medium_isotropic", "subdivision", "swizzle", "checkerboard"]
 
 
 @pytest.fixture(scope="module")
@@ -165,7 +165,7 @@ def _full_size(name):
 LARGE = ["c1", "c2_full_resolution", "c3_quarter", "c3_full_resolution", "c3_full_resolution_wavepath", "c4_quarter", "materials_large",
          "textured_large", "flatten_large", "disney_lobes_large", "cornell_rr_gaussian_large", "cornell_mitchell_large",
          "cornell_options_large", "medium_channels_large", "medium_hg_large", "environment_large",
-         "materials_wavepath_large", "textured_wavepath_large", "cornell_disney_odd", "subdivision_large", "swizzle_large"]
+         "materials_wavepath_large", "textured_wavepath_large", "cornell_disney_odd", "subdivision_large", "swizzle_large", "checkerboard_large"]
 
 
 @pytest.mark.parametrize("name", LARGE)

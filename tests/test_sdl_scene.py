@@ -323,3 +323,20 @@ def test_swizzle_texture():
         Scene.from_source(src.replace('swizzle { "bgr" }', 'swizzle { "bqr" }'), REPO)
     with pytest.raises(RuntimeError, match="out of range"):
         Scene.from_source(src.replace("swizzle { 2, 0, 1 }", "swizzle { 2, 0, 7 }"), REPO)
+
+
+def test_checkerboard_texture():
+    """src/textures/checkerboard.cpp with constant squares: baked into a 2x2 point-sampled repeating image at uv * scale / 2;
+    image squares and the ambiguous absent 'on' (1 as a scalar, black as a colour in the reference) are refused."""
+    from pathlib import Path
+
+    REPO = Path(__file__).resolve().parent.parent
+    src = scenes.checkerboard_scene(resolution=(8, 6), spp=1)
+    d = Scene.from_source(src, REPO).desc()
+    baked = [d.textures[i] for i in range(d.texture_count) if d.textures[i].width == 2 and d.textures[i].height == 2]
+    assert len(baked) == 3
+    assert sorted((round(t.uv_scale[0], 3), round(t.uv_scale[1], 3), int(t.channels)) for t in baked) == [(1.25, 1.25, 3), (1.5, 1.5, 1), (2.5, 3.5, 3)]
+    with pytest.raises(RuntimeError, match="'on' must be given"):
+        Scene.from_source(src.replace("on : Constant { v { 0.9, 0.85, 0.3 } } scale { 2.5 }", "scale { 2.5 }"), REPO)
+    with pytest.raises(RuntimeError, match="only constant"):
+        Scene.from_source(src.replace("on : Constant { v { 35.0 } }", 'on : Image { file { "tests/golden/assets/rough_gray8.png" } }'), REPO)

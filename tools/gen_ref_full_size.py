@@ -164,6 +164,12 @@ def swizzle_large_scene() -> str:
     return _megapath(scenes.swizzle_scene(resolution=(320, 240), spp=4, output="sw.exr"))
 
 
+def checkerboard_large_scene() -> str:
+    from luisarender_b200 import scenes
+
+    return _megapath(scenes.checkerboard_scene(resolution=(320, 240), spp=4, output="ck.exr"))
+
+
 def environment_large_scene() -> str:
     return _small_case("environment_image", (32, 20), (320, 200), 2, 4, "env_large.exr")
 
@@ -189,6 +195,7 @@ CASES = {
     "cornell_disney_odd": (cornell_disney_odd_scene, 3, "Cornell box with Disney surfaces at an odd film size, 333x187 @3 spp, MegaPath"),
     "subdivision_large": (subdivision_large_scene, 4, "the LoopSubdiv shape (closed / open / valence-3 base meshes, limit normals) 320x240 @4 spp, MegaPath"),
     "swizzle_large": (swizzle_large_scene, 4, "the Swizzle texture (image channels reordered / picked, constants, nesting) on the textured room, 320x240 @4 spp, MegaPath"),
+    "checkerboard_large": (checkerboard_large_scene, 4, "the Checkerboard texture with constant squares on the textured room, 320x240 @4 spp, MegaPath"),
     "environment_large": (environment_large_scene, 4, "row a12: image-lit Spherical environment (importance map, MIS compensation) + area light, 320x200 @4 spp, MegaPath (~20 min: the 2048x1024 importance-map kernels run on the interpreter)"),
 }
 

@@ -72,6 +72,8 @@ def cases() -> dict[str, str]:
     c["textured_wrappers"] = scenes.textured_room(resolution=(32, 24), spp=2, mesh_files=False, assets=assets, wrappers=True)
     # the Swizzle texture: reordered image channels, one channel as a scalar parameter, swizzled constants, nesting
     c["swizzle"] = scenes.swizzle_scene(resolution=(64, 48), spp=4, assets=assets)
+    # the Checkerboard texture with constant squares (baked into a point-sampled, repeating 2x2 image by the host)
+    c["checkerboard"] = scenes.checkerboard_scene(resolution=(64, 48), spp=4, assets=assets)
     # row a12: Spherical environment with an image emission (importance map, MIS compensation) next to an area light
     c["environment_image"] = scenes.environment_scene(resolution=(32, 20), spp=2, emission="image", assets=assets, sky_file="sky.exr")
     # the headline scenes at full geometric size (1 387 526 instanced triangles: Loop-subdivision spheres at level 7 and 3
