@@ -340,3 +340,23 @@ def test_checkerboard_texture():
         Scene.from_source(src.replace("on : Constant { v { 0.9, 0.85, 0.3 } } scale { 2.5 }", "scale { 2.5 }"), REPO)
     with pytest.raises(RuntimeError, match="only constant"):
         Scene.from_source(src.replace("on : Constant { v { 35.0 } }", 'on : Image { file { "tests/golden/assets/rough_gray8.png" } }'), REPO)
+
+
+def test_swizzle_of_checkerboard_composes():
+    """Swizzle { Checkerboard { on : Swizzle { Constant } } }: the baked 2x2 texels carry the composed permutation (this
+    composition was also rendered with the reference once: bit-identical to the oracle)."""
+    from pathlib import Path
+
+    REPO = Path(__file__).resolve().parent.parent
+    src = scenes.checkerboard_scene(resolution=(8, 6), spp=1)
+    old = "Kd : Checkerboard { on : Constant { v { 0.8, 0.2, 0.2 } } off : Constant { v { 0.1, 0.1, 0.6 } } scale { 5.0, 7.0 } }"
+    assert src.count(old) == 1
+    src = src.replace(old, 'Kd : Swizzle { base : Checkerboard { on : Swizzle { base : Constant { v { 0.8, 0.2, 0.2, 0.5 } } swizzle { "xyz" } } '
+                           'off : Constant { v { 0.1, 0.1, 0.6 } } scale { 5.0, 7.0 } } swizzle { "brg" } }')
+    d = Scene.from_source(src, REPO).desc()
+    t = next(d.textures[i] for i in range(d.texture_count) if d.textures[i].width == 2 and round(d.textures[i].uv_scale[1], 3) == 3.5)
+    texels = np.array([d.texels[4 * t.texel_offset + k] for k in range(16)], dtype=np.float32).reshape(4, 4)
+    assert int(t.channels) == 3
+    np.testing.assert_array_equal(texels[0, :3], np.float32([0.2, 0.8, 0.2]))  # on, "brg"
+    np.testing.assert_array_equal(texels[1, :3], np.float32([0.6, 0.1, 0.1]))  # off, "brg"
+    np.testing.assert_array_equal(texels[3, :3], texels[0, :3])
