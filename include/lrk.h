@@ -390,7 +390,7 @@ typedef struct lrk_stats {
     uint64_t kernel_launches;
     uint64_t passes;
     /* filled only when counting is enabled (lrk_set_option("count_traversal", 1)) */
-    uint64_t closest_nodes;  /* N_int of the closest-hit kernel */
+    uint64_t closest_nodes;  /* N_int of the closest-hit kernel: 128-byte 4-wide nodes visited */
     uint64_t closest_tris;   /* N_tri */
     uint64_t closest_xforms; /* N_xform */
     uint64_t shadow_nodes;   /* the same three for the any-hit kernel */
@@ -415,8 +415,15 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *scene);
  * tile_id % world == rank, tiles are tile_size x tile_size pixels in row-major tile order. */
 int lrk_set_shard(lrk_ctx *ctx, uint32_t rank, uint32_t world, uint32_t tile_size);
 
-/* Options: "count_traversal" (0/1), "time_kernels" (0/1), "sort_by_surface" (0/1),
- * "use_graph" (0/1). Unknown name -> LRK_ERR_INVALID_ARGUMENT. */
+/* Options (unknown name -> LRK_ERR_INVALID_ARGUMENT):
+ *   "count_traversal" (0/1)   traversal kernels count wide nodes / triangles / instance entries into lrk_stats
+ *   "time_kernels" (0/1)      CUDA-event time per kernel category into lrk_stats
+ *   "max_paths_per_pass" (n)  path-state capacity of one pass
+ *   "refill_below", "inner_min" (1..32)  warp scheduling of the traversal kernels (results do not depend on them)
+ *   "pin_host_buffers" (0/1)  the caller promises that the host arrays it passes to lrk_upload_scene / lrk_download_film*
+ *                             stay allocated until lrk_destroy (or until the option is cleared); the library page-locks each
+ *                             of them once (cudaHostRegister), so that every later transfer of the same buffer is a
+ *                             full-speed DMA: the per-frame path of an animation, and of bench.py's end-to-end leg */
 int lrk_set_option(lrk_ctx *ctx, const char *name, int64_t value);
 
 int lrk_film_clear(lrk_ctx *ctx);

@@ -185,7 +185,8 @@ def host_lib() -> C.CDLL:
 
 
 def device_lib() -> C.CDLL:
-    lib = _load("libb200pt.so")
+    # LRK_DEVICE_LIB: another build of the same library (kernel experiments: tools/build_variants.sh), never a different backend
+    lib = _load(os.environ.get("LRK_DEVICE_LIB", "libb200pt.so"))
     if not getattr(lib, "_lrk_typed", False):
         lib.lrk_create.argtypes = [C.POINTER(DeviceCfg), C.POINTER(C.c_void_p)]
         lib.lrk_destroy.argtypes = [C.c_void_p]

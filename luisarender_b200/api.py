@@ -122,9 +122,13 @@ class Renderer:
     def render(self, spp_begin: int, spp_end: int):
         self._check(self._lib.lrk_render(self._ctx, spp_begin, spp_end), "lrk_render")
 
-    def film(self, raw: bool = False) -> np.ndarray:
+    def film(self, raw: bool = False, out: np.ndarray | None = None) -> np.ndarray:
+        """The film as [H, W, 4] float32: normalised like the reference's convert_image, or the raw sums (raw=True).
+        `out`: destination to reuse (with the option pin_host_buffers the library page-locks it once)."""
         w, h = self._res
-        out = np.empty((h, w, 4), dtype=np.float32)
+        if out is None:
+            out = np.empty((h, w, 4), dtype=np.float32)
+        assert out.shape == (h, w, 4) and out.dtype == np.float32 and out.flags.c_contiguous
         fn = self._lib.lrk_download_film_raw if raw else self._lib.lrk_download_film
         self._check(fn(self._ctx, out.ctypes.data), "lrk_download_film")
         return out

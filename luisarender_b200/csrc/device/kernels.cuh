@@ -24,6 +24,9 @@
 namespace lrk {
 
 constexpr int kBlock = 256;
+#ifndef LRK_TRACE_MIN_BLOCKS
+#define LRK_TRACE_MIN_BLOCKS 4
+#endif
 #ifndef LRK_SHADE_BLOCK
 #define LRK_SHADE_BLOCK 256
 #endif
@@ -45,10 +48,7 @@ struct PathBuffers {
     float4 *scontrib;// rgb + path id bits
     float4 *li;
     uint32_t *counts;
-    uint32_t *ray_order; // [kRayBins][capacity]: direction-octant bins of the queue about to be traced
-    uint32_t *bin_counts;// [2 kinds][kMaxDepthSlots][kRayBins]: bin sizes (closest queue, shadow queue) per depth
     uint32_t capacity;
-    uint32_t bin_rays;   // 0: trace queues in storage order
     // volume path integrator only (config C4)
     ulonglong2 *pcg[2]; // per-path PCG32 {state, inc}
     float *u_rr[2];     // Russian-roulette number of the coming bounce (drawn at the top of the loop, mega_vpt_naive.cpp:256-257)
@@ -132,15 +132,15 @@ __global__ void __launch_bounds__(kBlock) generate_rays_kernel(DeviceScene sc, P
 //   [0] path-queue sizes  [1] shadow-queue sizes  [2] closest-hit fetch cursors  [3] shadow fetch cursors
 //   [4],[5],[6] hit-bucket sizes: light-only hits, Matte hits, Disney hits
 template<bool COUNT, bool ALPHA = false>
-__global__ void __launch_bounds__(kBlock, 4) trace_closest_kernel(DeviceScene sc, const float4 *__restrict__ ray_o,
+__global__ void __launch_bounds__(kBlock, LRK_TRACE_MIN_BLOCKS) trace_closest_kernel(DeviceScene sc, const float4 *__restrict__ ray_o,
                                                                const float4 *__restrict__ ray_d, uint4 *__restrict__ hits,
                                                                const uint32_t *__restrict__ count, uint32_t *cursor,
-                                                               unsigned long long *stats, RayOrder order) {
+                                                               unsigned long long *stats) {
     const uint32_t n = *count;
     TraversalCounters tc{0u, 0u, 0u};
     trace_queue<false, COUNT, 1, ALPHA>(sc, ray_o, ray_d, n, cursor, tc, [&](bool finished, uint32_t i, uint4 h) {
         if (finished) hits[i] = h;
-    }, order);
+    });
     if (COUNT) {
         atomicAdd(stats + 2, static_cast<unsigned long long>(tc.nodes));
         atomicAdd(stats + 3, static_cast<unsigned long long>(tc.tris));
@@ -191,8 +191,8 @@ __global__ void __launch_bounds__(kBlock) classify_hits_kernel(DeviceScene sc, P
 }
 
 template<bool COUNT, bool ALPHA = false>
-__global__ void __launch_bounds__(kBlock, 4) trace_shadow_kernel(DeviceScene sc, PathBuffers pb, const uint32_t *__restrict__ count,
-                                                              uint32_t *cursor, RayOrder order) {
+__global__ void __launch_bounds__(kBlock, LRK_TRACE_MIN_BLOCKS) trace_shadow_kernel(DeviceScene sc, PathBuffers pb, const uint32_t *__restrict__ count,
+                                                              uint32_t *cursor) {
     const uint32_t n = *count;
     TraversalCounters tc{0u, 0u, 0u};
     trace_queue<true, COUNT, 1, ALPHA>(sc, pb.sray_o, pb.sray_d, n, cursor, tc, [&](bool finished, uint32_t i, uint4 h) {
@@ -205,51 +205,11 @@ __global__ void __launch_bounds__(kBlock, 4) trace_shadow_kernel(DeviceScene sc,
             li.z += c.z;
             pb.li[path] = li;
         }
-    }, order);
+    });
     if (COUNT) {
         atomicAdd(pb.stats + 5, static_cast<unsigned long long>(tc.nodes));
         atomicAdd(pb.stats + 6, static_cast<unsigned long long>(tc.tris));
         atomicAdd(pb.stats + 7, static_cast<unsigned long long>(tc.xforms));
-    }
-}
-
-// Coherence pass for incoherent queues (bounce >= 1 rays, shadow rays): bin the rays by direction octant so that the
-// lanes of a traversal warp visit BVH children in the same order and finish at similar times.  Near-stable
-// block-aggregated partition like classify_hits_kernel; only an index array is written, the rays stay where they are.
-__global__ void __launch_bounds__(kBlock) bin_rays_kernel(const float4 *__restrict__ ray_d, const uint32_t *__restrict__ count,
-                                                          uint32_t *__restrict__ order, uint32_t capacity, uint32_t *bin_counts) {
-    __shared__ uint32_t s_warp[kRayBins][kBlock / 32];
-    __shared__ uint32_t s_base[kRayBins];
-    const uint32_t n = *count;
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5u, lane_lt = (1u << lane) - 1u;
-    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-        const uint32_t i = base + threadIdx.x;
-        uint32_t bin = ~0u;
-        if (i < n) {
-            float4 d = ray_d[i];
-            bin = (d.x < 0.f ? 1u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 4u : 0u);
-        }
-        uint32_t my_mask = 0u;
-#pragma unroll
-        for (uint32_t b = 0; b < kRayBins; b++) {
-            const uint32_t m = __ballot_sync(0xffffffffu, bin == b);
-            if (bin == b) my_mask = m;
-            if (lane == 0u) s_warp[b][warp] = __popc(m);
-        }
-        __syncthreads();
-        if (threadIdx.x < kRayBins) {
-            const uint32_t b = threadIdx.x;
-            uint32_t total = 0u;
-            for (int w = 0; w < kBlock / 32; w++) {
-                uint32_t c = s_warp[b][w];
-                s_warp[b][w] = total;
-                total += c;
-            }
-            s_base[b] = total ? atomicAdd(bin_counts + b, total) : 0u;
-        }
-        __syncthreads();
-        if (bin != ~0u) order[static_cast<size_t>(bin) * capacity + s_base[bin] + s_warp[bin][warp] + __popc(my_mask & lane_lt)] = i;
-        __syncthreads();
     }
 }
 

@@ -16,7 +16,7 @@ using namespace lrk;
 namespace {
 
 struct DeviceArrays {
-    void *vertices{}, *triangles{}, *alias{}, *pdf{}, *meshes{}, *inst_handles{}, *inst_kind{}, *inst_o2w{}, *inst_xform{}, *bvh_nodes{}, *textures{}, *texels{}, *env_alias{}, *env_pdf{},
+    void *vertices{}, *triangles{}, *alias{}, *pdf{}, *meshes{}, *inst_handles{}, *inst_kind{}, *inst_o2w{}, *inst_xform{}, *bvh_nodes{}, *wide_nodes{}, *traversal_overflow{}, *textures{}, *texels{}, *env_alias{}, *env_pdf{},
         *tri_verts{}, *surfaces{}, *lights{}, *light_handles{}, *camera{};
 };
 
@@ -55,7 +55,10 @@ struct lrk_ctx {
     float4 *d_film_out{nullptr};
     uint32_t *d_query_cursor{nullptr};
     // options
-    bool count_traversal{false}, time_kernels{false}, bin_rays{false};
+    bool count_traversal{false}, time_kernels{false};
+    bool pin_host{false};// option pin_host_buffers: page-lock the caller's scene arrays / film buffers on first sight (see pin_range)
+    std::unordered_map<const void *, size_t> pinned;
+    uint32_t h_overflow{0u};// host copy of DeviceScene::traversal_overflow, fetched with every render / trace call
     // stats
     lrk_stats stats{};
     cudaEvent_t ev_begin{}, ev_end{};
@@ -84,6 +87,28 @@ int fail(lrk_ctx *ctx, int code, const std::string &msg) {
         }                                                                                                     \
     } while (0)
 
+// Option `pin_host_buffers`: the caller promises that the host arrays it passes (scene arrays, film destinations) stay allocated
+// until lrk_destroy or until the option is switched off; they are then page-locked once (cudaHostRegister) so that every
+// later upload / download of the same buffer is a full-speed asynchronous DMA instead of a staged pageable copy.  This is
+// the per-frame path of an animation or of bench.py's end-to-end leg, where the same buffers cross the bus every step.
+void pin_range(lrk_ctx *ctx, const void *p, size_t bytes) {
+    if (!ctx->pin_host || p == nullptr || bytes < (256u << 10)) return;
+    auto it = ctx->pinned.find(p);
+    if (it != ctx->pinned.end()) {
+        if (it->second >= bytes) return;
+        cudaHostUnregister(const_cast<void *>(p));
+        ctx->pinned.erase(it);
+    }
+    if (cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterDefault) == cudaSuccess) ctx->pinned[p] = bytes;
+    else cudaGetLastError();// not fatal (e.g. the range overlaps an earlier registration): the copy falls back to pageable
+}
+
+void unpin_all(lrk_ctx *ctx) {
+    for (auto &kv : ctx->pinned) cudaHostUnregister(const_cast<void *>(kv.first));
+    ctx->pinned.clear();
+    cudaGetLastError();
+}
+
 // Host -> device copy of one scene array.  The allocation is kept across uploads when it is large enough, so
 // re-uploading a scene of the same shape (the end-to-end path of bench.py, animation frames) costs only the copy.
 template<typename T>
@@ -98,7 +123,10 @@ int upload(lrk_ctx *ctx, void **dst, const T *src, size_t count) {
         LRK_CUDA(cudaMalloc(dst, bytes));
         have = bytes;
     }
-    if (count) LRK_CUDA(cudaMemcpyAsync(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    if (count) {
+        pin_range(ctx, src, count * sizeof(T));
+        LRK_CUDA(cudaMemcpyAsync(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    }
     return LRK_OK;
 }
 
@@ -113,6 +141,7 @@ void free_arrays(DeviceArrays &a) {
 void free_paths(lrk_ctx *ctx) {
     for (auto p : ctx->path_allocs) cudaFree(p);
     ctx->path_allocs.clear();
+    ctx->pb = PathBuffers{};// no dangling pointers: lrk_film_clear / lrk_get_stats look at pb.stats
     ctx->capacity = 0;
     ctx->volume_capacity = 0;
     ctx->allocated_kinds = 0u;
@@ -146,8 +175,6 @@ int alloc_paths(lrk_ctx *ctx, uint64_t capacity) {
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.scontrib), capacity * sizeof(float4)));
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.li), capacity * sizeof(float4)));
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.counts), 12u * kMaxDepthSlots * sizeof(uint32_t)));
-    LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.ray_order), capacity * kRayBins * sizeof(uint32_t)));
-    LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.bin_counts), 2u * kMaxDepthSlots * kRayBins * sizeof(uint32_t)));
     pb.capacity = static_cast<uint32_t>(capacity);
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.stats), 8u * sizeof(unsigned long long)));
     LRK_CUDA(cudaMemsetAsync(pb.stats, 0, 8u * sizeof(unsigned long long), ctx->stream));
@@ -253,27 +280,16 @@ int render_pass(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint32_t spp
             sc, pb, ctx->d_pixel_list, pixel_offset, npix, spp_begin, static_cast<uint32_t>(n));
     }
     ctx->stats.kernel_launches++;
-    const bool bin = ctx->bin_rays;
-    if (bin) LRK_CUDA(cudaMemsetAsync(pb.bin_counts, 0, 2u * kMaxDepthSlots * kRayBins * sizeof(uint32_t), ctx->stream));
     // upper bound of the live queue at depth d is n; launch persistent-size grids and let kernels read *count
     for (uint32_t depth = 0; depth < sc.max_depth; depth++) {
         const int in = depth & 1u;
-        RayOrder closest_order{nullptr, nullptr, 0u}, shadow_order{nullptr, nullptr, 0u};
-        if (bin && depth > 0u) {// camera rays are coherent as generated
-            ScopedTimer t{ctx, CAT_OTHER};
-            uint32_t *bc = pb.bin_counts + static_cast<size_t>(depth) * kRayBins;
-            bin_rays_kernel<<<blocks_for(ctx, n, ctx->grid_classify), kBlock, 0, ctx->stream>>>(pb.ray_d[in], pb.counts + depth, pb.ray_order,
-                                                                                            pb.capacity, bc);
-            closest_order = RayOrder{pb.ray_order, bc, pb.capacity};
-            ctx->stats.kernel_launches++;
-        }
         {
             ScopedTimer t{ctx, CAT_TRACE_CLOSEST};
             int g = blocks_for(ctx, n, ctx->grid_trace);
             // four instantiations: traversal counters on/off x stochastic alpha test on/off (scenes with non-opaque surfaces)
             auto launch = [&](auto kernel) {
                 kernel<<<g, kBlock, 0, ctx->stream>>>(sc, pb.ray_o[in], pb.ray_d[in], pb.hit, pb.counts + depth,
-                                                      pb.counts + 2u * kMaxDepthSlots + depth, pb.stats, closest_order);
+                                                      pb.counts + 2u * kMaxDepthSlots + depth, pb.stats);
             };
             if (ctx->any_non_opaque) ctx->count_traversal ? launch(trace_closest_kernel<true, true>) : launch(trace_closest_kernel<false, true>);
             else ctx->count_traversal ? launch(trace_closest_kernel<true, false>) : launch(trace_closest_kernel<false, false>);
@@ -295,19 +311,11 @@ int render_pass(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint32_t spp
             if (ctx->has_kind[6]) ctx->textured ? launch(shade_kernel<6u, true>, 6) : launch(shade_kernel<6u, false>, 6);
             if (ctx->has_kind[7]) ctx->textured ? launch(shade_kernel<7u, true>, 7) : launch(shade_kernel<7u, false>, 7);
         }
-        if (bin) {
-            ScopedTimer t{ctx, CAT_OTHER};
-            uint32_t *bc = pb.bin_counts + (static_cast<size_t>(kMaxDepthSlots) + depth) * kRayBins;
-            bin_rays_kernel<<<blocks_for(ctx, n, ctx->grid_classify), kBlock, 0, ctx->stream>>>(pb.sray_d, pb.counts + kMaxDepthSlots + depth,
-                                                                                            pb.ray_order, pb.capacity, bc);
-            shadow_order = RayOrder{pb.ray_order, bc, pb.capacity};
-            ctx->stats.kernel_launches++;
-        }
         {
             ScopedTimer t{ctx, CAT_TRACE_SHADOW};
             int g = blocks_for(ctx, n, ctx->grid_shadow);
             auto launch = [&](auto kernel) {
-                kernel<<<g, kBlock, 0, ctx->stream>>>(sc, pb, pb.counts + kMaxDepthSlots + depth, pb.counts + 3u * kMaxDepthSlots + depth, shadow_order);
+                kernel<<<g, kBlock, 0, ctx->stream>>>(sc, pb, pb.counts + kMaxDepthSlots + depth, pb.counts + 3u * kMaxDepthSlots + depth);
             };
             if (ctx->any_non_opaque) ctx->count_traversal ? launch(trace_shadow_kernel<true, true>) : launch(trace_shadow_kernel<false, true>);
             else ctx->count_traversal ? launch(trace_shadow_kernel<true, false>) : launch(trace_shadow_kernel<false, false>);
@@ -353,10 +361,10 @@ int render_pass_volume(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint3
             int g = blocks_for(ctx, n, ctx->grid_trace);
             if (ctx->count_traversal)
                 trace_closest_kernel<true, false><<<g, kBlock, 0, ctx->stream>>>(sc, pb.ray_o[in], pb.ray_d[in], pb.hit, pb.counts + depth,
-                                                                                 pb.counts + 2u * kMaxDepthSlots + depth, pb.stats, RayOrder{nullptr, nullptr, 0u});
+                                                                                 pb.counts + 2u * kMaxDepthSlots + depth, pb.stats);
             else
                 trace_closest_kernel<false, false><<<g, kBlock, 0, ctx->stream>>>(sc, pb.ray_o[in], pb.ray_d[in], pb.hit, pb.counts + depth,
-                                                                                  pb.counts + 2u * kMaxDepthSlots + depth, pb.stats, RayOrder{nullptr, nullptr, 0u});
+                                                                                  pb.counts + 2u * kMaxDepthSlots + depth, pb.stats);
         }
         {
             ScopedTimer t{ctx, CAT_SHADE};
@@ -453,6 +461,7 @@ void lrk_destroy(lrk_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    unpin_all(ctx);
     free_paths(ctx);
     free_arrays(ctx->arrays);
     if (ctx->d_pixel_list) cudaFree(ctx->d_pixel_list);
@@ -539,6 +548,25 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
     if ((rc = upload(ctx, &a.pdf, s->pdf, s->triangle_count))) return rc;
     if ((rc = upload(ctx, &a.meshes, s->meshes, s->mesh_count))) return rc;
     if ((rc = upload(ctx, &a.bvh_nodes, s->bvh_nodes, s->bvh_node_count))) return rc;
+    {// the 4-wide hierarchy the traversal kernels walk: collapsed on the device from the BVH2 just uploaded (wide_bvh.cuh)
+        static const uint32_t zero = 0u;
+        if ((rc = upload(ctx, &a.wide_nodes, static_cast<const float4 *>(nullptr), 0u))) return rc;
+        const size_t wide_bytes = std::max<size_t>(s->bvh_node_count, 1u) * kWideRows * sizeof(float4);
+        size_t &have = ctx->array_bytes[&a.wide_nodes];
+        if (have < wide_bytes) {
+            cudaFree(a.wide_nodes);
+            a.wide_nodes = nullptr;
+            LRK_CUDA(cudaMalloc(&a.wide_nodes, wide_bytes));
+            have = wide_bytes;
+        }
+        if ((rc = upload(ctx, &a.traversal_overflow, &zero, 1u))) return rc;
+        if (s->bvh_node_count != 0u) {
+            const uint32_t nn = static_cast<uint32_t>(s->bvh_node_count);
+            collapse_wide_kernel<<<(nn + 255u) / 256u, 256, 0, ctx->stream>>>(static_cast<const float4 *>(a.bvh_nodes),
+                                                                             static_cast<float4 *>(a.wide_nodes), nn);
+            LRK_CUDA(cudaGetLastError());
+        }
+    }
     if ((rc = upload(ctx, &a.tri_verts, s->tri_verts, s->tri_slot_count * 12u))) return rc;
     if ((rc = upload(ctx, &a.surfaces, s->surfaces, s->surface_count))) return rc;
     if ((rc = upload(ctx, &a.textures, s->textures, s->texture_count))) return rc;
@@ -595,6 +623,8 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
     sc.inst_o2w = static_cast<const float4 *>(a.inst_o2w);
     sc.inst_xform = static_cast<const float4 *>(a.inst_xform);
     sc.bvh_nodes = static_cast<const float4 *>(a.bvh_nodes);
+    sc.wide_nodes = static_cast<const float4 *>(a.wide_nodes);
+    sc.traversal_overflow = static_cast<uint32_t *>(a.traversal_overflow);
     sc.tri_verts = static_cast<const float4 *>(a.tri_verts);
     sc.surfaces = static_cast<const lrk_surface *>(a.surfaces);
     sc.textures = static_cast<const lrk_texture *>(a.textures);
@@ -667,11 +697,12 @@ int lrk_set_option(lrk_ctx *ctx, const char *name, int64_t value) {
     std::string n{name};
     if (n == "count_traversal") ctx->count_traversal = value != 0;
     else if (n == "time_kernels") ctx->time_kernels = value != 0;
-    else if (n == "max_paths_per_pass") ctx->max_paths = value > 0 ? static_cast<uint64_t>(value) : ctx->max_paths;
-    else if (n == "bin_rays") ctx->bin_rays = value != 0;
+    else if (n == "pin_host_buffers") {
+        ctx->pin_host = value != 0;
+        if (!ctx->pin_host) unpin_all(ctx);
+    } else if (n == "max_paths_per_pass") ctx->max_paths = value > 0 ? static_cast<uint64_t>(value) : ctx->max_paths;
     else if (n == "refill_below") ctx->scene.refill_below = static_cast<uint32_t>(std::min<int64_t>(std::max<int64_t>(value, 1), 32));
     else if (n == "inner_min") ctx->scene.inner_min = static_cast<uint32_t>(std::min<int64_t>(std::max<int64_t>(value, 1), 32));
-    else if (n == "sort_by_surface" || n == "use_graph") { /* accepted; the material sort is always on, graphs not implemented */ }
     else return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_set_option: unknown option '" + n + "'");
     return LRK_OK;
 }
@@ -710,8 +741,10 @@ int lrk_render(lrk_ctx *ctx, uint32_t spp_begin, uint32_t spp_end) {
         }
     }
     LRK_CUDA(cudaEventRecord(ctx->ev_end, ctx->stream));
+    LRK_CUDA(cudaMemcpyAsync(&ctx->h_overflow, ctx->scene.traversal_overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     LRK_CUDA(cudaStreamSynchronize(ctx->stream));
     LRK_CUDA(cudaGetLastError());
+    if (ctx->h_overflow != 0u) return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_render: traversal stack overflow (BVH deeper than the kernels support)");
     float ms = 0.f;
     LRK_CUDA(cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
     ctx->stats.render_ms += ms;
@@ -735,6 +768,7 @@ static int convert_and_copy(lrk_ctx *ctx, const float4 *raw, float *rgba) {
     const uint32_t npix = ctx->scene.width * ctx->scene.height;
     convert_film_kernel<<<(npix + kBlock - 1u) / kBlock, kBlock, 0, ctx->stream>>>(ctx->scene, raw, ctx->d_film_out, npix);
     LRK_CUDA(cudaGetLastError());
+    pin_range(ctx, rgba, static_cast<size_t>(npix) * sizeof(float4));
     LRK_CUDA(cudaMemcpyAsync(rgba, ctx->d_film_out, static_cast<size_t>(npix) * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
     LRK_CUDA(cudaStreamSynchronize(ctx->stream));
     return LRK_OK;
@@ -750,6 +784,7 @@ int lrk_download_film_raw(lrk_ctx *ctx, float *rgba) {
     if (!ctx || !ctx->has_scene || !rgba) return fail(ctx, LRK_ERR_NO_SCENE, "lrk_download_film_raw: no scene / null buffer");
     LRK_CUDA(cudaSetDevice(ctx->device));
     const size_t npix = static_cast<size_t>(ctx->scene.width) * ctx->scene.height;
+    pin_range(ctx, rgba, npix * sizeof(float4));
     LRK_CUDA(cudaMemcpyAsync(rgba, ctx->d_film, npix * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
     LRK_CUDA(cudaStreamSynchronize(ctx->stream));
     return LRK_OK;
@@ -785,11 +820,13 @@ int lrk_trace(lrk_ctx *ctx, const lrk_ray *rays, uint64_t n, int any_hit, lrk_hi
     cudaMemsetAsync(ctx->d_query_cursor, 0, sizeof(uint32_t), ctx->stream);
     launch_query(ctx, g, any_hit != 0, d_rays, d_hits, static_cast<uint32_t>(n));
     cudaMemcpyAsync(hits, d_hits, n * sizeof(lrk_hit), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(&ctx->h_overflow, ctx->scene.traversal_overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (e == cudaSuccess) e = cudaGetLastError();
     cudaFree(d_rays);
     cudaFree(d_hits);
     if (e != cudaSuccess) return fail(ctx, LRK_ERR_CUDA, std::string("lrk_trace: ") + cudaGetErrorString(e));
+    if (ctx->h_overflow != 0u) return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_trace: traversal stack overflow (BVH deeper than the kernels support)");
     return LRK_OK;
 }
 

@@ -10,6 +10,11 @@ namespace lrh {
 namespace {
 
 constexpr int kBins = 32;
+// Depth cap of the SAH recursion: binned SAH can peel one bin at a time on geometrically graded input (a huge ground plane next to
+// tiny detail, instance scales spanning decades), giving trees as deep as the primitive count.  Below this depth every split is
+// a median split by count, so a hierarchy is never deeper than kSahDepth + ceil(log2(n)): the traversal stacks (oracle: 512
+// entries, device: keyed stack with an overflow flag) and this function's own recursion stay bounded.
+constexpr uint32_t kSahDepth = 48;
 constexpr float kTraversalCost = 1.0f;// cost of visiting a two-box node relative to one triangle test
 
 struct Builder {
@@ -110,17 +115,23 @@ struct Builder {
     }
 
     // builds [begin,end) and returns the reference to put into the parent (inner node index or leaf ref)
-    uint32_t build(uint32_t begin, uint32_t end, const Aabb &range_box, uint32_t parent) {
+    uint32_t build(uint32_t begin, uint32_t end, const Aabb &range_box, uint32_t parent, uint32_t depth = 0u) {
         auto n = end - begin;
         if (n == 1u) return leaf_ref(begin, end);
-        auto mid = split(begin, end, range_box);
-        if (mid == begin) return leaf_ref(begin, end);
+        uint32_t mid;
+        if (depth < kSahDepth) {
+            mid = split(begin, end, range_box);
+            if (mid == begin) return leaf_ref(begin, end);
+        } else {
+            if (n <= max_leaf) return leaf_ref(begin, end);
+            mid = begin + n / 2u;// too deep for SAH: halve by count (order within the range is whatever the splits above left)
+        }
         auto node_index = static_cast<uint32_t>(nodes.size());
         nodes.emplace_back();
         auto lb = range_bounds(begin, mid);
         auto rb = range_bounds(mid, end);
-        auto r0 = build(begin, mid, lb, node_index);
-        auto r1 = build(mid, end, rb, node_index);
+        auto r0 = build(begin, mid, lb, node_index, depth + 1u);
+        auto r1 = build(mid, end, rb, node_index, depth + 1u);
         auto &node = nodes[node_index];
         set_box(node, 0, lb);
         set_box(node, 1, rb);

@@ -355,18 +355,22 @@ LoadedImage load_exr(const std::filesystem::path &path, const std::vector<uint8_
         std::memcpy(&size, &d[pos], 4);
         pos += 4;
         size_t start = pos;
-        if (start + static_cast<size_t>(size) > d.size()) fail(path, "truncated EXR attribute");
+        if (size < 0 || start + static_cast<size_t>(size) > d.size()) fail(path, "truncated EXR attribute");
+        const size_t end = start + static_cast<size_t>(size);
         if (name == "channels") {
-            while (pos < start + static_cast<size_t>(size) && d[pos] != 0) {
+            while (pos < end && d[pos] != 0) {
                 Channel c;
                 c.name = cstr();
+                if (pos + 16 > end) fail(path, "truncated EXR channel list");
                 std::memcpy(&c.type, &d[pos], 4);
                 pos += 16;// pixel type, pLinear + reserved, xSampling, ySampling
                 channels.push_back(c);
             }
         } else if (name == "compression") {
+            if (size < 1) fail(path, "truncated EXR compression attribute");
             compression = d[pos];
         } else if (name == "dataWindow") {
+            if (size < 16) fail(path, "truncated EXR dataWindow attribute");
             std::memcpy(dw, &d[pos], 16);
         }
         pos = start + static_cast<size_t>(size);
@@ -375,7 +379,10 @@ LoadedImage load_exr(const std::filesystem::path &path, const std::vector<uint8_
     if (compression != 0 && compression != 2 && compression != 3) fail(path, "only uncompressed / ZIPS / ZIP EXR files are supported");
     for (auto &c : channels)
         if (c.type != 1 && c.type != 2) fail(path, "only HALF / FLOAT EXR channels are supported");
-    const uint32_t w = static_cast<uint32_t>(dw[2] - dw[0] + 1), h = static_cast<uint32_t>(dw[3] - dw[1] + 1);
+    // window extents in 64 bits: a hostile header must not wrap the int32 subtraction or the w * h * channels products below
+    const int64_t w64 = static_cast<int64_t>(dw[2]) - dw[0] + 1, h64 = static_cast<int64_t>(dw[3]) - dw[1] + 1;
+    if (w64 > 65536 || h64 > 65536 || w64 * h64 > (int64_t{1} << 28)) fail(path, "EXR data window too large");
+    const uint32_t w = static_cast<uint32_t>(w64), h = static_cast<uint32_t>(h64);
     const uint32_t lines_per_block = compression == 3 ? 16u : 1u;
     const uint32_t blocks = (h + lines_per_block - 1u) / lines_per_block;
     if (pos + static_cast<size_t>(blocks) * 8u > d.size()) fail(path, "truncated EXR offset table");
@@ -409,10 +416,14 @@ LoadedImage load_exr(const std::filesystem::path &path, const std::vector<uint8_
         std::memcpy(&data_size, &d[p + 4], 4);
         p += 8;
         if (data_size < 0 || p + static_cast<size_t>(data_size) > d.size()) fail(path, "truncated EXR block");
-        uint32_t lines = std::min(lines_per_block, h - static_cast<uint32_t>(y0 - dw[1]));
+        // the block's first scan line comes from the file: it has to lie inside the data window, on a block boundary
+        const int64_t row0 = static_cast<int64_t>(y0) - dw[1];
+        if (row0 < 0 || row0 >= static_cast<int64_t>(h) || row0 % lines_per_block != 0) fail(path, "EXR block outside the data window");
+        uint32_t lines = std::min(lines_per_block, h - static_cast<uint32_t>(row0));
         size_t expect = line_bytes * lines;
         block.resize(expect);
         if (compression == 0 || static_cast<size_t>(data_size) == expect) {
+            if (static_cast<size_t>(data_size) < expect) fail(path, "truncated EXR block");
             std::memcpy(block.data(), &d[p], expect);
         } else {
             tmp.resize(expect);
@@ -424,7 +435,7 @@ LoadedImage load_exr(const std::filesystem::path &path, const std::vector<uint8_
         }
         const uint8_t *q = block.data();
         for (uint32_t l = 0; l < lines; l++) {
-            uint32_t y = static_cast<uint32_t>(y0 - dw[1]) + l;
+            uint32_t y = static_cast<uint32_t>(row0) + l;
             for (uint32_t c = 0; c < nfile; c++) {
                 int slot = slot_of(c);
                 for (uint32_t x = 0; x < w; x++) {

@@ -303,6 +303,8 @@ struct ImageTexture final : Texture {
     }
 };
 
+float3 extend_color_to_rgb(float4 c, uint32_t n);
+
 struct SwizzleTexture final : Texture {
     // src/textures/swizzle.cpp:17-104: picks / reorders the channels of another texture.  The decode of an image texture
     // (encoding, scale) acts per channel, so swizzling an image is a permutation of its texels' channels: host-only.
@@ -310,8 +312,8 @@ struct SwizzleTexture final : Texture {
     std::vector<uint32_t> pick;
     SwizzleTexture(Scene *s, const NodeDesc *d) : Texture{s, d, Tag::TEXTURE} {
         base = s->load_texture(d->required_node("base"));
-        if (auto numbers = d->numbers("swizzle")) {
-            for (auto x : *numbers) pick.push_back(static_cast<uint32_t>(x));
+        if (d->numbers("swizzle")) {
+            pick = d->uint_list("swizzle");// throws on negative / fractional entries, like the reference's property_uint_list
         } else {
             for (auto c : d->s("swizzle", "rgba")) {
                 switch (c) {
@@ -382,7 +384,10 @@ struct CheckerboardTexture final : Texture {
     bool is_black() const override { return (on != nullptr && on->is_black()) && (off == nullptr || off->is_black()); }
     bool is_constant() const override { return false; }// no static value in the reference either (no evaluate_static)
     bool is_image() const override { return true; }
-    uint32_t channels() const override { return std::min(on ? on->channels() : 4u, off ? off->channels() : 4u); }
+    // The reference decodes each square by ITS OWN channel count (checkerboard.cpp:76-105: extend_color_to_rgb per child), so a
+    // grey `on` next to an RGB `off` stays grey and RGB.  The baked texels are therefore extended per child, and the record
+    // reports at least three channels; scalar consumers read .x, which the extension keeps.
+    uint32_t channels() const override { return std::max(3u, std::min(on ? on->channels() : 4u, off ? off->channels() : 4u)); }
     float4 value() const override { throw Error("Checkerboard has no constant value."); }
     void emit(lrk_texture &out, std::vector<float> &texels) const override {
         auto offset = out.texel_offset;
@@ -398,8 +403,17 @@ struct CheckerboardTexture final : Texture {
         out.uv_scale[0] = scale[0] * 0.5f;
         out.uv_scale[1] = scale[1] * 0.5f;
         out.uv_offset[0] = out.uv_offset[1] = 0.f;
-        auto a = on ? on->value() : float4{1.f, 1.f, 1.f, 1.f};
-        auto b = off ? off->value() : float4{0.f, 0.f, 0.f, 0.f};
+        auto square = [](const Texture *t, float4 absent) {
+            if (t == nullptr) return absent;
+            auto v = t->value();
+            if (t->channels() < 3u) {
+                auto rgb = extend_color_to_rgb(v, t->channels());
+                v = float4{rgb.x, rgb.y, rgb.z, v.w};
+            }
+            return v;
+        };
+        auto a = square(on, float4{1.f, 1.f, 1.f, 1.f});
+        auto b = square(off, float4{0.f, 0.f, 0.f, 0.f});
         for (int y = 0; y < 2; y++)
             for (int x = 0; x < 2; x++) {
                 auto c = ((x + y) % 2 == 0) ? a : b;
@@ -668,6 +682,9 @@ struct RegisterPathAliases {
     RegisterPathAliases() {
         register_plugin("integrator-wavepath_v2", Plugin{create_path_alias, destroy_path_alias});
         register_plugin("integrator-megapath", Plugin{create_path_alias, destroy_path_alias});
+        // the name under which the reference loads this repository's integrator plugin (integration/b200_path.cpp): a scene
+        // written for it parses here as the path integrator it is
+        register_plugin("integrator-b200path", Plugin{create_path_alias, destroy_path_alias});
     }
 } register_path_aliases_instance;
 }// namespace

@@ -38,6 +38,8 @@ def lib() -> C.CDLL:
         _lib = C.CDLL(str(LIB_PATH))
         f32p, vp = C.POINTER(C.c_float), C.c_void_p
         _lib.oracle_render.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp, C.POINTER(Counters)]
+        _lib.oracle_last_render_stats.argtypes = [C.POINTER(C.c_double)]
+        _lib.oracle_last_render_stats.restype = None
         _lib.oracle_convert_film.argtypes = [vp, vp, vp]
         _lib.oracle_convert_film.restype = None
         _lib.oracle_li.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, f32p]
@@ -95,6 +97,13 @@ def render(desc, spp_begin: int, spp_end: int, threads: int = 0, rank: int = 0, 
     if rc != 0:
         raise RuntimeError(f"oracle_render failed: {rc}")
     return film_raw, c.as_dict()
+
+
+def last_render_stats() -> dict:
+    """How the last render() used the host: threads, their busy fraction, work items, seconds."""
+    out = (C.c_double * 4)()
+    lib().oracle_last_render_stats(out)
+    return {"threads": int(out[0]), "threads_busy": round(float(out[1]), 4), "work_items": int(out[2]), "seconds": float(out[3])}
 
 
 def convert_film(desc, film_raw: np.ndarray) -> np.ndarray:

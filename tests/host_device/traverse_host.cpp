@@ -1,0 +1,153 @@
+// traverse_host.cpp — the DEVICE traversal code (luisarender_b200/csrc/device/{wide_bvh,traverse}.cuh: the BVH2 -> 4-wide collapse,
+// the inner-node step with its sorting network and stack rules, the leaf step with instance entry / exit and the triangle test)
+// compiled for the host, so that the per-ray logic the sm_100a kernels run can be checked against the oracle's BVH2 traversal
+// without a GPU (tests/test_device_traversal_on_host.py).  TEST INFRASTRUCTURE: nothing here is part of the product.  What the
+// GPU adds on top is warp scheduling only (ray refill, descent / leaf phases), which does not touch per-ray results.
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+template<typename T>
+static inline T __ldg(const T *p) { return *p; }
+static inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+static inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
+static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
+#ifndef __noinline__
+#define __noinline__
+#endif
+#include <algorithm>
+using std::isinf;
+using std::isnan;
+using std::max;
+using std::min;
+
+#include "../../luisarender_b200/csrc/device/traverse.cuh"
+#include "../../luisarender_b200/csrc/device/shading.cuh"// alpha_skip (stochastic alpha test of traversal candidates)
+
+namespace {
+using namespace lrk;
+
+struct HostMem {
+    std::vector<uint2> e;
+    size_t max_depth{0};
+    uint2 ring[kListSize];
+    V3 wo, wd;
+    void reset() { e.clear(); }
+    int depth() const { return static_cast<int>(e.size()); }
+    void push_if(bool valid, uint32_t ref, uint32_t key) {
+        if (!valid) return;
+        e.push_back(make_uint2(ref, key));
+        max_depth = std::max(max_depth, e.size());
+    }
+    void push4_if(bool pa, uint32_t ra, uint32_t ka, bool pb, uint32_t rb, uint32_t kb, bool pc, uint32_t rc, uint32_t kc, bool pd,
+                  uint32_t rd, uint32_t kd) {
+        push_if(pa, ra, ka);
+        push_if(pb, rb, kb);
+        push_if(pc, rc, kc);
+        push_if(pd, rd, kd);
+    }
+    uint2 peek() const { return e.back(); }
+    void drop() { e.pop_back(); }
+    uint2 pop() {
+        uint2 v = e.back();
+        e.pop_back();
+        return v;
+    }
+    void list_store(uint32_t slot, uint32_t inst, uint32_t key) { ring[slot] = make_uint2(inst, key); }
+    uint2 list_load(uint32_t slot) const { return ring[slot]; }
+    void world_save(V3 o, V3 d) { wo = o; wd = d; }
+    void world_load(V3 &o, V3 &d) const { o = wo; d = wd; }
+};
+
+// the device's control flow for ONE lane: TLAS steps (suspending when the candidate queue is nearly full), then inner / leaf steps
+template<bool ANY_HIT, bool ALPHA>
+void trace_one(const DeviceScene &sc, const float *ray, uint32_t *hit, TraversalCounters &cnt, size_t &max_stack, uint64_t &suspensions) {
+    RayState r;
+    HostMem mem;
+    start_ray(sc, r, mem, make_float4(ray[0], ray[1], ray[2], ray[3]), make_float4(ray[4], ray[5], ray[6], ray[7]));
+    for (;;) {
+#ifdef LRK_TRACE_DEBUG
+        std::printf("node %08x cur_inst %d tbest %g best (%d,%d) stack %zu list %x\n", r.node, (int)r.cur_inst, r.tbest, (int)r.best_inst, (int)r.best_prim, mem.e.size(), r.list);
+#endif
+        if (!(r.node & LRK_BVH_LEAF)) {
+            if (r.cur_inst == ~0u) {
+                if (tlas_suspend_if_full(r, mem)) suspensions++;
+                else inner_step<!ANY_HIT, true, true>(sc, r, mem, cnt);
+            } else {
+                inner_step<!ANY_HIT, true, false>(sc, r, mem, cnt);
+            }
+        } else if (leaf_step<ANY_HIT, true, ALPHA>(sc, r, mem, cnt)) {
+            break;
+        }
+    }
+    max_stack = std::max(max_stack, mem.max_depth);
+    hit[0] = r.best_inst;
+    hit[1] = r.best_prim;
+    hit[2] = __float_as_uint(r.best_u);
+    hit[3] = __float_as_uint(r.best_v);
+}
+
+}// namespace
+
+// rays: n x {o.xyz, tmin, d.xyz, tmax}; hits: n x {inst, prim, bary.u bits, bary.v bits}; counters: {wide nodes, triangles, instance
+// entries, deepest stack, TLAS suspensions}
+extern "C" int wide_trace_host(const lrk_scene_desc *s, const float *rays, uint64_t n, int any_hit, uint32_t *hits, uint64_t *counters) {
+    std::vector<float4> wide(static_cast<size_t>(s->bvh_node_count) * kWideRows);
+    for (uint64_t i = 0; i < s->bvh_node_count; i++)
+        collapse_wide_node(reinterpret_cast<const float4 *>(s->bvh_nodes), static_cast<uint32_t>(i), wide.data() + i * kWideRows);
+    std::vector<float4> xform(static_cast<size_t>(s->instance_count) * 4u);
+    for (uint32_t i = 0; i < s->instance_count; i++) {// as lrk_upload_scene lays the traversal instance records out
+        const auto &inst = s->instances[i];
+        std::memcpy(&xform[i * 4u], inst.world_to_object, 48);
+        xform[i * 4u + 3u] = make_float4(__uint_as_float(s->meshes[inst.mesh].bvh_root), 0.f, 0.f, 0.f);
+    }
+    std::vector<uint4> handles(s->instance_count);
+    bool alpha = false;
+    for (uint32_t i = 0; i < s->instance_count; i++) {
+        std::memcpy(&handles[i], s->instances[i].handle, 16);
+        const uint32_t flags = s->instances[i].handle[0] & 1023u;
+        if ((flags & LRK_SHAPE_MAYBE_NON_OPAQUE) && (flags & LRK_SHAPE_HAS_SURFACE)) alpha = true;// lrk_upload_scene's rule
+    }
+    DeviceScene sc{};
+    sc.inst_handles = handles.data();
+    sc.surfaces = s->surfaces;
+    sc.meshes = s->meshes;
+    sc.triangles = s->triangles;
+    sc.vertices = s->vertices;
+    sc.textures = s->textures;
+    sc.texels = reinterpret_cast<const float4 *>(s->texels);
+    sc.wide_nodes = wide.data();
+    sc.tri_verts = reinterpret_cast<const float4 *>(s->tri_verts);
+    sc.inst_xform = xform.data();
+    sc.tlas_root = s->tlas_root;
+    TraversalCounters cnt{0u, 0u, 0u};
+    uint64_t totals[3]{0u, 0u, 0u};
+    size_t max_stack = 0;
+    uint64_t suspensions = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        cnt = TraversalCounters{0u, 0u, 0u};
+        if (alpha) {
+            if (any_hit) trace_one<true, true>(sc, rays + i * 8u, hits + i * 4u, cnt, max_stack, suspensions);
+            else trace_one<false, true>(sc, rays + i * 8u, hits + i * 4u, cnt, max_stack, suspensions);
+        } else {
+            if (any_hit) trace_one<true, false>(sc, rays + i * 8u, hits + i * 4u, cnt, max_stack, suspensions);
+            else trace_one<false, false>(sc, rays + i * 8u, hits + i * 4u, cnt, max_stack, suspensions);
+        }
+        totals[0] += cnt.nodes;
+        totals[1] += cnt.tris;
+        totals[2] += cnt.xforms;
+    }
+    if (counters) {
+        counters[0] = totals[0];
+        counters[1] = totals[1];
+        counters[2] = totals[2];
+        counters[3] = max_stack;
+        counters[4] = suspensions;
+    }
+    return 0;
+}

@@ -1,0 +1,149 @@
+"""The DEVICE traversal logic, compiled for the host, against the oracle's BVH2 traversal.
+
+tests/host_device/traverse_host.cpp includes luisarender_b200/csrc/device/{wide_bvh,traverse}.cuh — the files the sm_100a
+traversal kernels are built from — and is compiled with g++ (-ffp-contract=off: explicit fmaf only, as nvcc's -fmad=false).
+It collapses the host's BVH2 into the 4-wide hierarchy exactly as collapse_wide_kernel does and walks it with the kernels' own
+inner_step / leaf_step functions (sorting network, keyed stack with culling on pop, instance entry / exit, Moeller-Trumbore).
+The oracle (oracle/oracle.cpp) walks the BVH2.  Both must return the same instance, primitive and barycentric BITS for every
+ray; what is left for the GPU tests is the warp scheduling around these functions.  No GPU, no /root/reference needed.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from luisarender_b200 import scenes
+from luisarender_b200.api import Scene
+from oracle import binding as O
+
+REPO = Path(__file__).resolve().parent.parent
+SRC = REPO / "tests" / "host_device" / "traverse_host.cpp"
+OUT = REPO / "tests" / "host_device" / "_build" / "libtraverse_host.so"
+DEV = REPO / "luisarender_b200" / "csrc" / "device"
+
+
+@pytest.fixture(scope="module")
+def lib():
+    cuda_include = Path("/usr/local/cuda/include")
+    if not (cuda_include / "cuda_runtime.h").exists():
+        pytest.skip("CUDA headers not found")
+    deps = [SRC, DEV / "traverse.cuh", DEV / "wide_bvh.cuh", DEV / "scene.cuh", DEV / "vecmath.cuh", DEV / "shading.cuh", REPO / "include" / "lrk.h"]
+    if not OUT.exists() or OUT.stat().st_mtime < max(d.stat().st_mtime for d in deps):
+        OUT.parent.mkdir(parents=True, exist_ok=True)
+        subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-w", "-ffp-contract=off", f"-I{cuda_include}", "-shared", str(SRC), "-o", str(OUT)],
+                       check=True)
+    handle = C.CDLL(str(OUT))
+    handle.wide_trace_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
+    return handle
+
+
+def wide_trace(lib, desc, rays, any_hit=False):
+    rays = np.ascontiguousarray(rays, dtype=np.float32)
+    hits = np.zeros((rays.shape[0], 4), np.uint32)
+    counters = np.zeros(5, np.uint64)
+    assert lib.wide_trace_host(C.byref(desc), rays.ctypes.data, rays.shape[0], int(any_hit), hits.ctypes.data, counters.ctypes.data) == 0
+    return hits, counters
+
+
+def random_rays(scene, n, seed):
+    rng = np.random.default_rng(seed)
+    info = scene.info()
+    lo, hi = np.array(info["world_min"]), np.array(info["world_max"])
+    o = rng.uniform(lo - 0.5, hi + 0.5, size=(n, 3))
+    t = rng.uniform(lo, hi, size=(n, 3))
+    d = t - o
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.zeros((n, 8), np.float32)
+    rays[:, :3], rays[:, 4:7], rays[:, 7] = o, d, np.finfo(np.float32).max
+    rays[::3, 7] = rng.uniform(0.5, 6.0, size=len(rays[::3]))
+    return rays
+
+
+def bounce_rays(rays, ref, seed):
+    """Rays that START on surfaces (inside the padded leaf boxes), like spawned bounce and shadow rays."""
+    rng = np.random.default_rng(seed)
+    hit = ref["inst"] != 0xFFFFFFFF
+    # the hit distance is not part of the hit record: re-derive a point near the surface by marching the oracle's ray
+    # against a brute-force distance is unnecessary here - any origin within the scene serves; use points along the ray
+    o = rays[hit, :3] + rays[hit, 4:7] * rng.uniform(0.0, 3.0, size=(int(hit.sum()), 1)).astype(np.float32)
+    d = rng.normal(size=o.shape)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    # a share of exactly axis-aligned and of negative-zero directions: the clamped reciprocal and the sign-selected near planes
+    d[::7, 0] = 0.0
+    d[::11, 1] = -0.0
+    d[::13] = np.eye(3)[rng.integers(0, 3, size=len(d[::13]))] * rng.choice([-1.0, 1.0], size=(len(d[::13]), 1))
+    out = np.zeros((o.shape[0], 8), np.float32)
+    out[:, :3], out[:, 4:7], out[:, 7] = o, d, np.finfo(np.float32).max
+    return out
+
+
+def check(lib, scene, rays):
+    d = scene.desc()
+    ref, ref_cnt = O.trace(d, rays)
+    got, cnt = wide_trace(lib, d, rays)
+    assert np.array_equal(got[:, 0], ref["inst"])
+    assert np.array_equal(got[:, 1], ref["prim"])
+    assert np.array_equal(got[:, 2:4], ref["bary"].view(np.uint32))
+    occ_ref, _ = O.trace(d, rays, any_hit=True)
+    occ, _ = wide_trace(lib, d, rays, any_hit=True)
+    assert np.array_equal(occ[:, 0] != 0xFFFFFFFF, occ_ref["inst"] != 0)
+    return ref, ref_cnt, cnt
+
+
+@pytest.mark.parametrize("fixture", ["cornell_small", "spheres_small", "textured_wrappers_small"])
+def test_wide_traversal_matches_oracle_bit_exactly(lib, fixture, request):
+    scene = request.getfixturevalue(fixture)
+    rays = random_rays(scene, 100_000, seed=11)
+    ref, ref_cnt, cnt = check(lib, scene, rays)
+    assert (ref["inst"] != 0xFFFFFFFF).mean() > 0.1
+    check(lib, scene, bounce_rays(rays, ref, seed=5))
+    # a wide step replaces about two BVH2 steps; the keyed stack never grows beyond what the kernels hold in shared + local memory
+    assert cnt[0] < 0.75 * ref_cnt["nodes_visited"]
+    assert cnt[3] <= 8 + 56
+
+
+def test_wide_traversal_edge_cases(lib, cornell_small):
+    fmax = np.finfo(np.float32).max
+    rays = np.array([
+        [0, 1, 0, 0, 0, 0, -1, fmax],
+        [0, 1, 0, 0, 0, -1, 0, fmax],
+        [0, 1, 0, 0, 1, 0, 0, 0.5],
+        [0, 1, 0, 0, 1, 0, 0, 2.0],
+        [0, 1, 10, 0, 0, 0, 1, fmax],
+        [0, 1, 0, 0, 0, 0, -1, 0.0],
+        [0, 1, 0, 0, 0, 0, -1, -1.0],        # tmax < tmin: nothing can be hit, and the culling pop must still find the sentinel
+        [0, 1, 0, 0, 0, 0, -1, np.nan],
+        [-0.005, 1.98, -0.03, 0, 0, 1, 0, fmax],
+    ], dtype=np.float32)
+    d = cornell_small.desc()
+    ref, _ = O.trace(d, rays)
+    got, _ = wide_trace(lib, d, rays)
+    assert np.array_equal(got[:, 0], ref["inst"]) and np.array_equal(got[:, 1], ref["prim"])
+
+
+def test_wide_traversal_full_size_scene(lib):
+    """BASELINE config C3's 1.39 M-triangle instanced scene: camera rays + incoherent rays, every hit bit-identical."""
+    scene = Scene.from_source(scenes.instanced_spheres(resolution=(96, 54), spp=1), REPO)
+    d = scene.desc()
+    cam = np.stack([O.generate_ray(d, x, y, 0)[0] for y in range(0, 54, 2) for x in range(0, 96, 2)])
+    rays = np.concatenate([cam, random_rays(scene, 30_000, seed=3)])
+    ref, ref_cnt, cnt = check(lib, scene, rays)
+    check(lib, scene, bounce_rays(rays, ref, seed=9))
+    assert cnt[3] <= 8 + 56
+
+
+def test_wide_traversal_many_overlapping_instances(lib):
+    """900 instances in an 8x8x8 box: rays cross more instance boxes than the candidate queue holds, so the TLAS walk is suspended and
+    resumed (with a shortened ray) - results still identical to the oracle's nested BVH2 walk."""
+    scene = Scene.from_source(scenes.instanced_spheres(resolution=(32, 18), spp=1, big_subdivision=2, big_count=100, small_subdivision=1,
+                                                       small_count=800), REPO)
+    rays = random_rays(scene, 20_000, seed=21)
+    ref, ref_cnt, cnt = check(lib, scene, rays)
+    assert cnt[4] > 100          # suspensions happened
+    d = scene.desc()
+    _, occ_cnt = wide_trace(lib, d, rays, any_hit=True)
+    assert occ_cnt[4] > 10

@@ -335,11 +335,31 @@ def test_checkerboard_texture():
     d = Scene.from_source(src, REPO).desc()
     baked = [d.textures[i] for i in range(d.texture_count) if d.textures[i].width == 2 and d.textures[i].height == 2]
     assert len(baked) == 3
-    assert sorted((round(t.uv_scale[0], 3), round(t.uv_scale[1], 3), int(t.channels)) for t in baked) == [(1.25, 1.25, 3), (1.5, 1.5, 1), (2.5, 3.5, 3)]
+    assert sorted((round(t.uv_scale[0], 3), round(t.uv_scale[1], 3), int(t.channels)) for t in baked) == [(1.25, 1.25, 3), (1.5, 1.5, 3), (2.5, 3.5, 3)]
     with pytest.raises(RuntimeError, match="'on' must be given"):
         Scene.from_source(src.replace("on : Constant { v { 0.9, 0.85, 0.3 } } scale { 2.5 }", "scale { 2.5 }"), REPO)
     with pytest.raises(RuntimeError, match="only constant"):
         Scene.from_source(src.replace("on : Constant { v { 35.0 } }", 'on : Image { file { "tests/golden/assets/rough_gray8.png" } }'), REPO)
+
+
+def test_checkerboard_extends_each_square_by_its_own_channel_count():
+    """checkerboard.cpp:76-105 decodes `on` and `off` separately (extend_color_to_rgb per child): a grey square next to an RGB
+    square stays grey, and a one-channel square used as a colour is (a, a, a) - not (a, 0, 0)."""
+    from pathlib import Path
+
+    REPO = Path(__file__).resolve().parent.parent
+    src = scenes.checkerboard_scene(resolution=(8, 6), spp=1)
+    old = "Kd : Checkerboard { on : Constant { v { 0.8, 0.2, 0.2 } } off : Constant { v { 0.1, 0.1, 0.6 } } scale { 5.0, 7.0 } }"
+    assert src.count(old) == 1
+    d = Scene.from_source(src.replace(old, "Kd : Checkerboard { on : Constant { v { 0.8, 0.2, 0.2 } } off : Constant { v { 0.3 } } scale { 5.0, 7.0 } }"),
+                          REPO).desc()
+    t = next(d.textures[i] for i in range(d.texture_count) if d.textures[i].width == 2 and round(d.textures[i].uv_scale[1], 3) == 3.5)
+    texels = np.array([d.texels[4 * t.texel_offset + k] for k in range(16)], dtype=np.float32).reshape(4, 4)
+    assert int(t.channels) == 3
+    np.testing.assert_array_equal(texels[0, :3], np.float32([0.8, 0.2, 0.2]))
+    np.testing.assert_array_equal(texels[1, :3], np.float32([0.3, 0.3, 0.3]))
+    with pytest.raises(RuntimeError, match="Cannot convert property 'swizzle'"):
+        Scene.from_source(src.replace(old, "Kd : Swizzle { base : Constant { v { 0.8, 0.2, 0.2 } } swizzle { 0, 1.7, 2 } }"), REPO)
 
 
 def test_swizzle_of_checkerboard_composes():
