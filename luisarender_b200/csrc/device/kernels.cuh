@@ -25,7 +25,7 @@ namespace lrk {
 
 constexpr int kBlock = 256;
 #ifndef LRK_TRACE_MIN_BLOCKS
-#define LRK_TRACE_MIN_BLOCKS 4
+#define LRK_TRACE_MIN_BLOCKS 5// blocks of kTraceBlock threads per SM the traversal kernels are compiled for (register budget)
 #endif
 #ifndef LRK_SHADE_BLOCK
 #define LRK_SHADE_BLOCK 256
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(kBlock) generate_rays_kernel(DeviceScene sc, P
 //   [0] path-queue sizes  [1] shadow-queue sizes  [2] closest-hit fetch cursors  [3] shadow fetch cursors
 //   [4],[5],[6] hit-bucket sizes: light-only hits, Matte hits, Disney hits
 template<bool COUNT, bool ALPHA = false>
-__global__ void __launch_bounds__(kBlock, LRK_TRACE_MIN_BLOCKS) trace_closest_kernel(DeviceScene sc, const float4 *__restrict__ ray_o,
+__global__ void __launch_bounds__(kTraceBlock, LRK_TRACE_MIN_BLOCKS) trace_closest_kernel(DeviceScene sc, const float4 *__restrict__ ray_o,
                                                                const float4 *__restrict__ ray_d, uint4 *__restrict__ hits,
                                                                const uint32_t *__restrict__ count, uint32_t *cursor,
                                                                unsigned long long *stats) {
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(kBlock) classify_hits_kernel(DeviceScene sc, P
 }
 
 template<bool COUNT, bool ALPHA = false>
-__global__ void __launch_bounds__(kBlock, LRK_TRACE_MIN_BLOCKS) trace_shadow_kernel(DeviceScene sc, PathBuffers pb, const uint32_t *__restrict__ count,
+__global__ void __launch_bounds__(kTraceBlock, LRK_TRACE_MIN_BLOCKS) trace_shadow_kernel(DeviceScene sc, PathBuffers pb, const uint32_t *__restrict__ count,
                                                               uint32_t *cursor) {
     const uint32_t n = *count;
     TraversalCounters tc{0u, 0u, 0u};
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(kBlock, LRK_TRACE_MIN_BLOCKS) trace_shadow_ker
 
 // stand-alone queries (lrk_trace) on interleaved lrk_ray records: any-hit result is written as inst = 1 (occluded) / 0 (free)
 template<bool ANY_HIT, bool ALPHA = false>
-__global__ void __launch_bounds__(kBlock) trace_query_kernel(DeviceScene sc, const float4 *__restrict__ rays, uint4 *__restrict__ hits,
+__global__ void __launch_bounds__(kTraceBlock) trace_query_kernel(DeviceScene sc, const float4 *__restrict__ rays, uint4 *__restrict__ hits,
                                                              uint32_t n, uint32_t *cursor) {
     TraversalCounters tc{0u, 0u, 0u};
     trace_queue<ANY_HIT, false, 2, ALPHA>(sc, rays, rays + 1, n, cursor, tc, [&](bool finished, uint32_t i, uint4 h) {
@@ -573,7 +573,7 @@ __global__ void __launch_bounds__(kBlock) generate_rays_volume_kernel(DeviceScen
 
 // T1 / T2: any-hit queries that record occlusion.  T2 also applies the pending surface NEE contribution.
 template<bool COUNT>
-__global__ void __launch_bounds__(kBlock) trace_medium_shadow_kernel(DeviceScene sc, PathBuffers pb, const uint32_t *__restrict__ count,
+__global__ void __launch_bounds__(kTraceBlock) trace_medium_shadow_kernel(DeviceScene sc, PathBuffers pb, const uint32_t *__restrict__ count,
                                                                      uint32_t *cursor) {
     const uint32_t n = *count;
     TraversalCounters tc{0u, 0u, 0u};
@@ -588,7 +588,7 @@ __global__ void __launch_bounds__(kBlock) trace_medium_shadow_kernel(DeviceScene
 }
 
 template<bool COUNT>
-__global__ void __launch_bounds__(kBlock) trace_volume_nee_kernel(DeviceScene sc, PathBuffers pb, const uint32_t *__restrict__ count,
+__global__ void __launch_bounds__(kTraceBlock) trace_volume_nee_kernel(DeviceScene sc, PathBuffers pb, const uint32_t *__restrict__ count,
                                                                   uint32_t *cursor, uint32_t *__restrict__ occl_out) {
     const uint32_t n = *count;
     TraversalCounters tc{0u, 0u, 0u};

@@ -265,7 +265,7 @@ int blocks_for(lrk_ctx *ctx, uint64_t n, int persistent_grid) {
 }
 
 void launch_query(lrk_ctx *ctx, int g, bool any_hit, const float4 *d_rays, uint4 *d_hits, uint32_t n) {
-    auto launch = [&](auto kernel) { kernel<<<g, kBlock, 0, ctx->stream>>>(ctx->scene, d_rays, d_hits, n, ctx->d_query_cursor); };
+    auto launch = [&](auto kernel) { kernel<<<g, kTraceBlock, 0, ctx->stream>>>(ctx->scene, d_rays, d_hits, n, ctx->d_query_cursor); };
     if (ctx->any_non_opaque) any_hit ? launch(trace_query_kernel<true, true>) : launch(trace_query_kernel<false, true>);
     else any_hit ? launch(trace_query_kernel<true, false>) : launch(trace_query_kernel<false, false>);
 }
@@ -288,7 +288,7 @@ int render_pass(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint32_t spp
             int g = blocks_for(ctx, n, ctx->grid_trace);
             // four instantiations: traversal counters on/off x stochastic alpha test on/off (scenes with non-opaque surfaces)
             auto launch = [&](auto kernel) {
-                kernel<<<g, kBlock, 0, ctx->stream>>>(sc, pb.ray_o[in], pb.ray_d[in], pb.hit, pb.counts + depth,
+                kernel<<<g, kTraceBlock, 0, ctx->stream>>>(sc, pb.ray_o[in], pb.ray_d[in], pb.hit, pb.counts + depth,
                                                       pb.counts + 2u * kMaxDepthSlots + depth, pb.stats);
             };
             if (ctx->any_non_opaque) ctx->count_traversal ? launch(trace_closest_kernel<true, true>) : launch(trace_closest_kernel<false, true>);
@@ -315,7 +315,7 @@ int render_pass(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint32_t spp
             ScopedTimer t{ctx, CAT_TRACE_SHADOW};
             int g = blocks_for(ctx, n, ctx->grid_shadow);
             auto launch = [&](auto kernel) {
-                kernel<<<g, kBlock, 0, ctx->stream>>>(sc, pb, pb.counts + kMaxDepthSlots + depth, pb.counts + 3u * kMaxDepthSlots + depth);
+                kernel<<<g, kTraceBlock, 0, ctx->stream>>>(sc, pb, pb.counts + kMaxDepthSlots + depth, pb.counts + 3u * kMaxDepthSlots + depth);
             };
             if (ctx->any_non_opaque) ctx->count_traversal ? launch(trace_shadow_kernel<true, true>) : launch(trace_shadow_kernel<false, true>);
             else ctx->count_traversal ? launch(trace_shadow_kernel<true, false>) : launch(trace_shadow_kernel<false, false>);
@@ -352,18 +352,18 @@ int render_pass_volume(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint3
             int g = blocks_for(ctx, n, ctx->grid_vshadow);
             // the in-medium shadow rays share the depth's path-queue size; their cursor lives in the shadow-cursor region + 32
             if (ctx->count_traversal)
-                trace_medium_shadow_kernel<true><<<g, kBlock, 0, ctx->stream>>>(sc, pb, pb.counts + depth, pb.counts + 3u * kMaxDepthSlots + 32u + depth);
+                trace_medium_shadow_kernel<true><<<g, kTraceBlock, 0, ctx->stream>>>(sc, pb, pb.counts + depth, pb.counts + 3u * kMaxDepthSlots + 32u + depth);
             else
-                trace_medium_shadow_kernel<false><<<g, kBlock, 0, ctx->stream>>>(sc, pb, pb.counts + depth, pb.counts + 3u * kMaxDepthSlots + 32u + depth);
+                trace_medium_shadow_kernel<false><<<g, kTraceBlock, 0, ctx->stream>>>(sc, pb, pb.counts + depth, pb.counts + 3u * kMaxDepthSlots + 32u + depth);
         }
         {
             ScopedTimer t{ctx, CAT_TRACE_CLOSEST};
             int g = blocks_for(ctx, n, ctx->grid_trace);
             if (ctx->count_traversal)
-                trace_closest_kernel<true, false><<<g, kBlock, 0, ctx->stream>>>(sc, pb.ray_o[in], pb.ray_d[in], pb.hit, pb.counts + depth,
+                trace_closest_kernel<true, false><<<g, kTraceBlock, 0, ctx->stream>>>(sc, pb.ray_o[in], pb.ray_d[in], pb.hit, pb.counts + depth,
                                                                                  pb.counts + 2u * kMaxDepthSlots + depth, pb.stats);
             else
-                trace_closest_kernel<false, false><<<g, kBlock, 0, ctx->stream>>>(sc, pb.ray_o[in], pb.ray_d[in], pb.hit, pb.counts + depth,
+                trace_closest_kernel<false, false><<<g, kTraceBlock, 0, ctx->stream>>>(sc, pb.ray_o[in], pb.ray_d[in], pb.hit, pb.counts + depth,
                                                                                   pb.counts + 2u * kMaxDepthSlots + depth, pb.stats);
         }
         {
@@ -378,10 +378,10 @@ int render_pass_volume(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint3
             ScopedTimer t{ctx, CAT_TRACE_SHADOW};
             int g = blocks_for(ctx, n, ctx->grid_vshadow);
             if (ctx->count_traversal)
-                trace_volume_nee_kernel<true><<<g, kBlock, 0, ctx->stream>>>(sc, pb, pb.counts + kMaxDepthSlots + depth,
+                trace_volume_nee_kernel<true><<<g, kTraceBlock, 0, ctx->stream>>>(sc, pb, pb.counts + kMaxDepthSlots + depth,
                                                                              pb.counts + 3u * kMaxDepthSlots + depth, pb.occl2[out]);
             else
-                trace_volume_nee_kernel<false><<<g, kBlock, 0, ctx->stream>>>(sc, pb, pb.counts + kMaxDepthSlots + depth,
+                trace_volume_nee_kernel<false><<<g, kTraceBlock, 0, ctx->stream>>>(sc, pb, pb.counts + kMaxDepthSlots + depth,
                                                                               pb.counts + 3u * kMaxDepthSlots + depth, pb.occl2[out]);
         }
         ctx->stats.kernel_launches += 5u + (ctx->has_kind[1] ? 1u : 0u) + (ctx->has_kind[2] ? 1u : 0u);
@@ -432,13 +432,13 @@ int lrk_create(const lrk_device_cfg *cfg, lrk_ctx **out) {
         delete ctx;
         return LRK_ERR_OUT_OF_MEMORY;
     }
-    auto grid_for = [&](const void *fn) {
+    auto grid_for = [&](const void *fn, int block = kBlock) {
         int per_sm = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kBlock, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, block, 0);
         return std::max(1, per_sm) * ctx->sm_count;
     };
-    ctx->grid_trace = grid_for(reinterpret_cast<const void *>(trace_closest_kernel<false, false>));
-    ctx->grid_shadow = grid_for(reinterpret_cast<const void *>(trace_shadow_kernel<false, false>));
+    ctx->grid_trace = grid_for(reinterpret_cast<const void *>(trace_closest_kernel<false, false>), kTraceBlock);
+    ctx->grid_shadow = grid_for(reinterpret_cast<const void *>(trace_shadow_kernel<false, false>), kTraceBlock);
     ctx->grid_shade[0] = grid_for(reinterpret_cast<const void *>(shade_kernel<0u, false>));
     ctx->grid_shade[1] = grid_for(reinterpret_cast<const void *>(shade_kernel<1u, false>));
     ctx->grid_shade[2] = grid_for(reinterpret_cast<const void *>(shade_kernel<2u, false>));
@@ -452,7 +452,7 @@ int lrk_create(const lrk_device_cfg *cfg, lrk_ctx **out) {
     ctx->grid_vshade[0] = grid_for(reinterpret_cast<const void *>(volume_surface_kernel<0u, false>));
     ctx->grid_vshade[1] = grid_for(reinterpret_cast<const void *>(volume_surface_kernel<1u, false>));
     ctx->grid_vshade[2] = grid_for(reinterpret_cast<const void *>(volume_surface_kernel<2u, false>));
-    ctx->grid_vshadow = grid_for(reinterpret_cast<const void *>(trace_volume_nee_kernel<false>));
+    ctx->grid_vshadow = grid_for(reinterpret_cast<const void *>(trace_volume_nee_kernel<false>), kTraceBlock);
     *out = ctx;
     return LRK_OK;
 }

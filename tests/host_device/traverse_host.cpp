@@ -32,70 +32,67 @@ using std::min;
 namespace {
 using namespace lrk;
 
-struct HostMem {
-    std::vector<uint2> e;
+// host stand-ins for the device's Slot (shared-memory stack + parked world ray)
+struct HostStack {
+    std::vector<uint32_t> e;
     size_t max_depth{0};
-    uint2 ring[kListSize];
-    V3 wo, wd;
-    void reset() { e.clear(); }
-    int depth() const { return static_cast<int>(e.size()); }
-    void push_if(bool valid, uint32_t ref, uint32_t key) {
-        if (!valid) return;
-        e.push_back(make_uint2(ref, key));
+    void push(int &sp, uint32_t ref) {
+        e.resize(static_cast<size_t>(sp));
+        e.push_back(ref);
+        sp++;
         max_depth = std::max(max_depth, e.size());
     }
-    void push4_if(bool pa, uint32_t ra, uint32_t ka, bool pb, uint32_t rb, uint32_t kb, bool pc, uint32_t rc, uint32_t kc, bool pd,
-                  uint32_t rd, uint32_t kd) {
-        push_if(pa, ra, ka);
-        push_if(pb, rb, kb);
-        push_if(pc, rc, kc);
-        push_if(pd, rd, kd);
+    void push4_if(int &sp, bool pa, uint32_t ra, bool pb, uint32_t rb, bool pc, uint32_t rc, bool pd, uint32_t rd) {
+        if (pa) push(sp, ra);
+        if (pb) push(sp, rb);
+        if (pc) push(sp, rc);
+        if (pd) push(sp, rd);
     }
-    uint2 peek() const { return e.back(); }
-    void drop() { e.pop_back(); }
-    uint2 pop() {
-        uint2 v = e.back();
-        e.pop_back();
-        return v;
-    }
-    void list_store(uint32_t slot, uint32_t inst, uint32_t key) { ring[slot] = make_uint2(inst, key); }
-    uint2 list_load(uint32_t slot) const { return ring[slot]; }
-    void world_save(V3 o, V3 d) { wo = o; wd = d; }
-    void world_load(V3 &o, V3 &d) const { o = wo; d = wd; }
+    uint32_t pop(int &sp) { return e[static_cast<size_t>(--sp)]; }
 };
 
-// the device's control flow for ONE lane: TLAS steps (suspending when the candidate queue is nearly full), then inner / leaf steps
+struct HostWorld {
+    RayHot hot;
+    V3 o, d;
+    void save(const RayHot &r, const RayCold &c) { hot = r; o = c.o; d = c.d; }
+    void load(RayHot &r, RayCold &c) const {
+        r.ix = hot.ix; r.iy = hot.iy; r.iz = hot.iz;
+        r.ox = hot.ox; r.oy = hot.oy; r.oz = hot.oz;
+        c.o = o;
+        c.d = d;
+        r.near = near_offsets(d);// as the device does: the offsets come back from the signs of d
+    }
+};
+
+// the device's per-ray control flow: inner steps while the ray stands on an inner node, leaf steps otherwise
 template<bool ANY_HIT, bool ALPHA>
-void trace_one(const DeviceScene &sc, const float *ray, uint32_t *hit, TraversalCounters &cnt, size_t &max_stack, uint64_t &suspensions) {
-    RayState r;
-    HostMem mem;
-    start_ray(sc, r, mem, make_float4(ray[0], ray[1], ray[2], ray[3]), make_float4(ray[4], ray[5], ray[6], ray[7]));
+void trace_one(const DeviceScene &sc, const float *ray, uint32_t *hit, TraversalCounters &cnt, size_t &max_stack) {
+    RayHot r;
+    RayCold c;
+    HostStack stack;
+    HostWorld world;
+    start_ray(sc, r, c, stack, make_float4(ray[0], ray[1], ray[2], ray[3]), make_float4(ray[4], ray[5], ray[6], ray[7]), 0u);
     for (;;) {
 #ifdef LRK_TRACE_DEBUG
-        std::printf("node %08x cur_inst %d tbest %g best (%d,%d) stack %zu list %x\n", r.node, (int)r.cur_inst, r.tbest, (int)r.best_inst, (int)r.best_prim, mem.e.size(), r.list);
+        std::printf("node %08x cur_inst %d tbest %g best (%d,%d) sp %d\n", r.node, (int)r.cur_inst, r.tbest, (int)c.best_inst, (int)c.best_prim, r.sp);
 #endif
         if (!(r.node & LRK_BVH_LEAF)) {
-            if (r.cur_inst == ~0u) {
-                if (tlas_suspend_if_full(r, mem)) suspensions++;
-                else inner_step<!ANY_HIT, true, true>(sc, r, mem, cnt);
-            } else {
-                inner_step<!ANY_HIT, true, false>(sc, r, mem, cnt);
-            }
-        } else if (leaf_step<ANY_HIT, true, ALPHA>(sc, r, mem, cnt)) {
+            inner_step<!ANY_HIT, true>(sc, r, stack, cnt);
+        } else if (leaf_step<ANY_HIT, true, ALPHA>(sc, r, c, stack, world, cnt)) {
             break;
         }
     }
-    max_stack = std::max(max_stack, mem.max_depth);
-    hit[0] = r.best_inst;
-    hit[1] = r.best_prim;
-    hit[2] = __float_as_uint(r.best_u);
-    hit[3] = __float_as_uint(r.best_v);
+    max_stack = std::max(max_stack, stack.max_depth);
+    hit[0] = c.best_inst;
+    hit[1] = c.best_prim;
+    hit[2] = __float_as_uint(c.best_u);
+    hit[3] = __float_as_uint(c.best_v);
 }
 
 }// namespace
 
 // rays: n x {o.xyz, tmin, d.xyz, tmax}; hits: n x {inst, prim, bary.u bits, bary.v bits}; counters: {wide nodes, triangles, instance
-// entries, deepest stack, TLAS suspensions}
+// entries, deepest stack}
 extern "C" int wide_trace_host(const lrk_scene_desc *s, const float *rays, uint64_t n, int any_hit, uint32_t *hits, uint64_t *counters) {
     std::vector<float4> wide(static_cast<size_t>(s->bvh_node_count) * kWideRows);
     for (uint64_t i = 0; i < s->bvh_node_count; i++)
@@ -128,15 +125,14 @@ extern "C" int wide_trace_host(const lrk_scene_desc *s, const float *rays, uint6
     TraversalCounters cnt{0u, 0u, 0u};
     uint64_t totals[3]{0u, 0u, 0u};
     size_t max_stack = 0;
-    uint64_t suspensions = 0;
     for (uint64_t i = 0; i < n; i++) {
         cnt = TraversalCounters{0u, 0u, 0u};
         if (alpha) {
-            if (any_hit) trace_one<true, true>(sc, rays + i * 8u, hits + i * 4u, cnt, max_stack, suspensions);
-            else trace_one<false, true>(sc, rays + i * 8u, hits + i * 4u, cnt, max_stack, suspensions);
+            if (any_hit) trace_one<true, true>(sc, rays + i * 8u, hits + i * 4u, cnt, max_stack);
+            else trace_one<false, true>(sc, rays + i * 8u, hits + i * 4u, cnt, max_stack);
         } else {
-            if (any_hit) trace_one<true, false>(sc, rays + i * 8u, hits + i * 4u, cnt, max_stack, suspensions);
-            else trace_one<false, false>(sc, rays + i * 8u, hits + i * 4u, cnt, max_stack, suspensions);
+            if (any_hit) trace_one<true, false>(sc, rays + i * 8u, hits + i * 4u, cnt, max_stack);
+            else trace_one<false, false>(sc, rays + i * 8u, hits + i * 4u, cnt, max_stack);
         }
         totals[0] += cnt.nodes;
         totals[1] += cnt.tris;
@@ -147,7 +143,6 @@ extern "C" int wide_trace_host(const lrk_scene_desc *s, const float *rays, uint6
         counters[1] = totals[1];
         counters[2] = totals[2];
         counters[3] = max_stack;
-        counters[4] = suspensions;
     }
     return 0;
 }

@@ -3,7 +3,7 @@
 tests/host_device/traverse_host.cpp includes luisarender_b200/csrc/device/{wide_bvh,traverse}.cuh — the files the sm_100a
 traversal kernels are built from — and is compiled with g++ (-ffp-contract=off: explicit fmaf only, as nvcc's -fmad=false).
 It collapses the host's BVH2 into the 4-wide hierarchy exactly as collapse_wide_kernel does and walks it with the kernels' own
-inner_step / leaf_step functions (sorting network, keyed stack with culling on pop, instance entry / exit, Moeller-Trumbore).
+inner_step / leaf_step functions (nearest-first ordering, deferred children, instance entry / exit, Moeller-Trumbore with the tie rule).
 The oracle (oracle/oracle.cpp) walks the BVH2.  Both must return the same instance, primitive and barycentric BITS for every
 ray; what is left for the GPU tests is the warp scheduling around these functions.  No GPU, no /root/reference needed.
 """
@@ -101,7 +101,7 @@ def test_wide_traversal_matches_oracle_bit_exactly(lib, fixture, request):
     ref, ref_cnt, cnt = check(lib, scene, rays)
     assert (ref["inst"] != 0xFFFFFFFF).mean() > 0.1
     check(lib, scene, bounce_rays(rays, ref, seed=5))
-    # a wide step replaces about two BVH2 steps; the keyed stack never grows beyond what the kernels hold in shared + local memory
+    # a wide step replaces about two BVH2 steps; the stack never grows beyond what the kernels hold in shared + local memory
     assert cnt[0] < 0.75 * ref_cnt["nodes_visited"]
     assert cnt[3] <= 8 + 56
 
@@ -137,13 +137,10 @@ def test_wide_traversal_full_size_scene(lib):
 
 
 def test_wide_traversal_many_overlapping_instances(lib):
-    """900 instances in an 8x8x8 box: rays cross more instance boxes than the candidate queue holds, so the TLAS walk is suspended and
-    resumed (with a shortened ray) - results still identical to the oracle's nested BVH2 walk."""
+    """900 instances in an 8x8x8 box: rays cross many instance boxes, entering and leaving instances dozens of times (exit
+    sentinel, world-ray restore) with a deep stack - results still identical to the oracle's BVH2 walk."""
     scene = Scene.from_source(scenes.instanced_spheres(resolution=(32, 18), spp=1, big_subdivision=2, big_count=100, small_subdivision=1,
                                                        small_count=800), REPO)
     rays = random_rays(scene, 20_000, seed=21)
     ref, ref_cnt, cnt = check(lib, scene, rays)
-    assert cnt[4] > 100          # suspensions happened
-    d = scene.desc()
-    _, occ_cnt = wide_trace(lib, d, rays, any_hit=True)
-    assert occ_cnt[4] > 10
+    assert cnt[2] > len(rays) and cnt[3] >= 8  # more than one instance entry per ray, a stack deeper than the shared part
