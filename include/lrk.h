@@ -168,9 +168,9 @@ typedef struct lrk_instance {
  *           (already remapped to alpha when remap_roughness), p[7] = specular_tint,
  *           p[8] = anisotropic, p[9] = sheen, p[10] = sheen_tint, p[11] = clearcoat,
  *           p[12] = clearcoat_gloss, p[13] = specular_trans, p[14] = flatness,
- *           p[15] = diffuse_trans; lobes = union of enabled lobes over ALL disney surface
- *           nodes of the scene (the reference ORs them into one shared closure,
- *           src/surfaces/disney.cpp:869,994-995).
+ *           p[15] = diffuse_trans; lobes = union of enabled lobes over all disney surface nodes of the scene
+ *           that share the record's closure class (opaque / LRK_SURFACE_DISNEY_TRANSMISSIVE; the reference ORs them
+ *           into one shared closure per class, src/surfaces/disney.cpp:869,994-995).
  *   MIRROR : p[0..2] = reflectance colour, p[3..4] = alpha (roughness after the optional remap; 0 without a roughness
  *            node: the distribution clamps it to 1e-4) — MirrorClosure::Context, mirror.cpp:84-88,142-162
  *   GLASS  : p[0..2] = Kr, p[3..5] = Kt, p[6] = eta_t (default 1.5; eta_i is 1), p[7..8] = alpha,
@@ -207,6 +207,12 @@ typedef struct lrk_instance {
 #define LRK_SURFACE_REMAP_ROUGHNESS 2u
 #define LRK_SURFACE_MAYBE_NON_OPAQUE 4u
 #define LRK_SURFACE_HAS_NORMAL_MAP 8u
+/* DISNEY only: the node is transmissive (`specular_trans` given and not black, not `thin`): the reference builds the closure
+ * class "disney_trans" for it (src/surfaces/disney.cpp:61-75,925-930,1001-1007) - a fourth sampling technique with a
+ * MicrofacetTransmission lobe (:452-464), a one-sided DisneyFresnel (:425), eta() = eta_t for the Russian-roulette scale
+ * (:531-533).  `lobes` of such records is the union over the TRANSMISSIVE Disney nodes of the scene (each closure class
+ * collects its own, :994-995). */
+#define LRK_SURFACE_DISNEY_TRANSMISSIVE 16u
 typedef struct lrk_surface {
     uint32_t type;
     uint32_t lobes;

@@ -25,7 +25,7 @@ namespace lrk {
 
 constexpr int kBlock = 256;
 #ifndef LRK_TRACE_MIN_BLOCKS
-#define LRK_TRACE_MIN_BLOCKS 5// blocks of kTraceBlock threads per SM the traversal kernels are compiled for (register budget)
+#define LRK_TRACE_MIN_BLOCKS 4// blocks of kTraceBlock threads per SM the traversal kernels are compiled for (register budget)
 #endif
 #ifndef LRK_SHADE_BLOCK
 #define LRK_SHADE_BLOCK 256
@@ -34,6 +34,7 @@ constexpr int kBlock = 256;
 #define LRK_SHADE_MIN_BLOCKS 2
 #endif
 constexpr int kShadeBlock = LRK_SHADE_BLOCK;// threads per block of the surface shade kernels (register-bound: see DESIGN.md)
+constexpr uint32_t kCountSlots = 16u;   // rows of 64 counters in PathBuffers::counts: 4 queue / cursor rows + one per hit bucket
 constexpr uint32_t kMaxDepthSlots = 64u;// counts[0..63]: path queue size per depth, counts[64..127]: shadow queue size
 
 struct PathBuffers {
@@ -42,7 +43,7 @@ struct PathBuffers {
     float4 *beta_pdf[2];
     uint2 *id_rng[2];
     uint4 *hit;// {inst, prim, bary} per ray of the current queue (inst == ~0u: escaped)
-    uint32_t *hit_index[8];// per closure kind: indices (into the current ray queue) of the rays that hit such a surface
+    uint32_t *hit_index[9];// per closure kind: indices (into the current ray queue) of the rays that hit such a surface
     float4 *sray_o;
     float4 *sray_d;
     float4 *scontrib;// rgb + path id bits
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(kBlock) generate_rays_kernel(DeviceScene sc, P
     uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id == 0u) {
         pb.counts[0] = n;
-        for (uint32_t d = 1u; d < 12u * kMaxDepthSlots; d++) pb.counts[d] = 0u;// sizes + the traversal kernels' fetch cursors
+        for (uint32_t d = 1u; d < kCountSlots * kMaxDepthSlots; d++) pb.counts[d] = 0u;// sizes + the traversal kernels' fetch cursors
     }
     if (id >= n) return;
     uint32_t k = id % npix;
@@ -154,7 +155,8 @@ __global__ void __launch_bounds__(kTraceBlock, LRK_TRACE_MIN_BLOCKS) trace_close
 // keeps the ray-queue order inside a block chunk, which keeps the shade kernels' gathers coalesced.
 //   kind 0: hit has no surface (emitter only)   kind 1: Matte closure   kind 2: Disney closure
 //   kinds 3..6: Mirror, Glass, Plastic, Metal (MicrofacetFamilyClosure<type>, kind = type + 1)   kind 7: Mix
-constexpr uint32_t kHitKinds = 8u;
+//   kind 8: transmissive Disney closure ("disney_trans": LRK_SURFACE_DISNEY_TRANSMISSIVE records)
+constexpr uint32_t kHitKinds = 9u;
 __global__ void __launch_bounds__(kBlock) classify_hits_kernel(DeviceScene sc, PathBuffers pb, uint32_t depth) {
     __shared__ uint32_t s_warp[kHitKinds][kBlock / 32];
     __shared__ uint32_t s_base[kHitKinds];
@@ -397,6 +399,11 @@ __global__ void __launch_bounds__(kShadeBlock, LRK_SHADE_MIN_BLOCKS) shade_kerne
                         DisneyClosure cl;
                         init_closure<TEXTURED>(sc, cl, surf, it);
                         shade_surface<false>(cl, it, closure_frame<TEXTURED>(sc, surf, it, wo), wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
+                    } else if (KIND == 8u) {
+                        DisneyTransClosure cl;
+                        init_closure<TEXTURED>(sc, cl, surf, it);
+                        shade_surface<false>(cl, it, closure_frame<TEXTURED>(sc, surf, it, wo), wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
+                        if (surf->lobes & LRK_DISNEY_LOBE_SPEC_TRANS) eta_scale = cl.rr_eta_scale;// closure->eta() (disney.cpp:531-533)
                     } else if (KIND == 7u) {
                         MixClosure cl;
                         cl.init(*surf, sc.surfaces);
@@ -537,7 +544,7 @@ __global__ void __launch_bounds__(kBlock) generate_rays_volume_kernel(DeviceScen
     uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id == 0u) {
         pb.counts[0] = n;
-        for (uint32_t d = 1u; d < 12u * kMaxDepthSlots; d++) pb.counts[d] = 0u;
+        for (uint32_t d = 1u; d < kCountSlots * kMaxDepthSlots; d++) pb.counts[d] = 0u;
     }
     if (id >= n) return;
     uint32_t k = id % npix;

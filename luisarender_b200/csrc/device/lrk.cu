@@ -16,7 +16,7 @@ using namespace lrk;
 namespace {
 
 struct DeviceArrays {
-    void *vertices{}, *triangles{}, *alias{}, *pdf{}, *meshes{}, *inst_handles{}, *inst_kind{}, *inst_o2w{}, *inst_xform{}, *bvh_nodes{}, *wide_nodes{}, *traversal_overflow{}, *textures{}, *texels{}, *env_alias{}, *env_pdf{},
+    void *vertices{}, *triangles{}, *alias{}, *pdf{}, *meshes{}, *inst_handles{}, *inst_kind{}, *inst_o2w{}, *inst_xform{}, *bvh_nodes{}, *traversal_overflow{}, *textures{}, *texels{}, *env_alias{}, *env_pdf{},
         *tri_verts{}, *surfaces{}, *lights{}, *light_handles{}, *camera{};
 };
 
@@ -64,8 +64,8 @@ struct lrk_ctx {
     cudaEvent_t ev_begin{}, ev_end{};
     std::vector<TimedLaunch> timed;
     std::vector<cudaEvent_t> event_pool;
-    int grid_trace{0}, grid_shade[8]{0, 0, 0, 0, 0, 0, 0, 0}, grid_shadow{0}, grid_classify{0};
-    bool has_kind[8]{true, false, false, false, false, false, false, false};
+    int grid_trace{0}, grid_shade[9]{0, 0, 0, 0, 0, 0, 0, 0, 0}, grid_shadow{0}, grid_classify{0};
+    bool has_kind[9]{true, false, false, false, false, false, false, false, false};
     uint32_t allocated_kinds{0u};// bit k: hit_index[k] is allocated
     bool volume{false};
     uint64_t volume_capacity{0};
@@ -149,7 +149,7 @@ void free_paths(lrk_ctx *ctx) {
 
 int alloc_paths(lrk_ctx *ctx, uint64_t capacity) {
     uint32_t kinds = 0u;
-    for (int k = 0; k < 8; k++) if (k < 3 || ctx->has_kind[k]) kinds |= 1u << k;// buckets 3..6 only for scenes that use them
+    for (int k = 0; k < 9; k++) if (k < 3 || ctx->has_kind[k]) kinds |= 1u << k;// buckets 3..8 only for scenes that use them
     if (ctx->capacity >= capacity && (!ctx->volume || ctx->volume_capacity >= capacity) && (ctx->allocated_kinds & kinds) == kinds) return LRK_OK;
     free_paths(ctx);
     auto alloc = [&](void **p, size_t bytes) -> cudaError_t {
@@ -165,7 +165,7 @@ int alloc_paths(lrk_ctx *ctx, uint64_t capacity) {
         LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.id_rng[k]), capacity * sizeof(uint2)));
     }
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.hit), capacity * sizeof(uint4)));
-    for (int k = 0; k < 8; k++) {
+    for (int k = 0; k < 9; k++) {
         pb.hit_index[k] = nullptr;
         if (kinds & (1u << k)) LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.hit_index[k]), capacity * sizeof(uint32_t)));
     }
@@ -174,7 +174,7 @@ int alloc_paths(lrk_ctx *ctx, uint64_t capacity) {
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.sray_d), capacity * sizeof(float4)));
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.scontrib), capacity * sizeof(float4)));
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.li), capacity * sizeof(float4)));
-    LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.counts), 12u * kMaxDepthSlots * sizeof(uint32_t)));
+    LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.counts), kCountSlots * kMaxDepthSlots * sizeof(uint32_t)));
     pb.capacity = static_cast<uint32_t>(capacity);
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.stats), 8u * sizeof(unsigned long long)));
     LRK_CUDA(cudaMemsetAsync(pb.stats, 0, 8u * sizeof(unsigned long long), ctx->stream));
@@ -310,6 +310,7 @@ int render_pass(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint32_t spp
             if (ctx->has_kind[5]) ctx->textured ? launch(shade_kernel<5u, true>, 5) : launch(shade_kernel<5u, false>, 5);
             if (ctx->has_kind[6]) ctx->textured ? launch(shade_kernel<6u, true>, 6) : launch(shade_kernel<6u, false>, 6);
             if (ctx->has_kind[7]) ctx->textured ? launch(shade_kernel<7u, true>, 7) : launch(shade_kernel<7u, false>, 7);
+            if (ctx->has_kind[8]) ctx->textured ? launch(shade_kernel<8u, true>, 8) : launch(shade_kernel<8u, false>, 8);
         }
         {
             ScopedTimer t{ctx, CAT_TRACE_SHADOW};
@@ -321,7 +322,7 @@ int render_pass(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint32_t spp
             else ctx->count_traversal ? launch(trace_shadow_kernel<true, false>) : launch(trace_shadow_kernel<false, false>);
         }
         ctx->stats.kernel_launches += 4u + (ctx->has_kind[1] ? 1u : 0u) + (ctx->has_kind[2] ? 1u : 0u) + (ctx->has_kind[3] ? 1u : 0u) + (ctx->has_kind[4] ? 1u : 0u) +
-                                      (ctx->has_kind[5] ? 1u : 0u) + (ctx->has_kind[6] ? 1u : 0u) + (ctx->has_kind[7] ? 1u : 0u);
+                                      (ctx->has_kind[5] ? 1u : 0u) + (ctx->has_kind[6] ? 1u : 0u) + (ctx->has_kind[7] ? 1u : 0u) + (ctx->has_kind[8] ? 1u : 0u);
     }
     {
         ScopedTimer t{ctx, CAT_OTHER};
@@ -447,6 +448,7 @@ int lrk_create(const lrk_device_cfg *cfg, lrk_ctx **out) {
     ctx->grid_shade[5] = grid_for(reinterpret_cast<const void *>(shade_kernel<5u, false>));
     ctx->grid_shade[6] = grid_for(reinterpret_cast<const void *>(shade_kernel<6u, false>));
     ctx->grid_shade[7] = grid_for(reinterpret_cast<const void *>(shade_kernel<7u, false>));
+    ctx->grid_shade[8] = grid_for(reinterpret_cast<const void *>(shade_kernel<8u, false>));
     ctx->grid_classify = grid_for(reinterpret_cast<const void *>(classify_hits_kernel));
     ctx->grid_vmedium = grid_for(reinterpret_cast<const void *>(volume_medium_kernel));
     ctx->grid_vshade[0] = grid_for(reinterpret_cast<const void *>(volume_surface_kernel<0u, false>));
@@ -521,8 +523,9 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
                     return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: a Mix blends two constant Matte / Mirror / Glass / Plastic / Metal records");
             }
         }
-        if (s->surfaces[i].type > LRK_SURFACE_DISNEY && s->integrator.type == LRK_INTEGRATOR_VOLUME_PATH)
-            return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: the volume path supports Matte and Disney surfaces only");
+        if ((s->surfaces[i].type > LRK_SURFACE_DISNEY || (s->surfaces[i].flags & LRK_SURFACE_DISNEY_TRANSMISSIVE)) &&
+            s->integrator.type == LRK_INTEGRATOR_VOLUME_PATH)
+            return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: the volume path supports Matte and opaque Disney surfaces only");
         for (uint32_t k = 0; k < 16u; k++)
             if (s->surfaces[i].tex[k] > s->texture_count) return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_upload_scene: texture id out of range");
         if (s->surfaces[i].opacity_tex > s->texture_count || s->surfaces[i].normal_tex > s->texture_count)
@@ -548,24 +551,9 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
     if ((rc = upload(ctx, &a.pdf, s->pdf, s->triangle_count))) return rc;
     if ((rc = upload(ctx, &a.meshes, s->meshes, s->mesh_count))) return rc;
     if ((rc = upload(ctx, &a.bvh_nodes, s->bvh_nodes, s->bvh_node_count))) return rc;
-    {// the 4-wide hierarchy the traversal kernels walk: collapsed on the device from the BVH2 just uploaded (wide_bvh.cuh)
+    {
         static const uint32_t zero = 0u;
-        if ((rc = upload(ctx, &a.wide_nodes, static_cast<const float4 *>(nullptr), 0u))) return rc;
-        const size_t wide_bytes = std::max<size_t>(s->bvh_node_count, 1u) * kWideRows * sizeof(float4);
-        size_t &have = ctx->array_bytes[&a.wide_nodes];
-        if (have < wide_bytes) {
-            cudaFree(a.wide_nodes);
-            a.wide_nodes = nullptr;
-            LRK_CUDA(cudaMalloc(&a.wide_nodes, wide_bytes));
-            have = wide_bytes;
-        }
         if ((rc = upload(ctx, &a.traversal_overflow, &zero, 1u))) return rc;
-        if (s->bvh_node_count != 0u) {
-            const uint32_t nn = static_cast<uint32_t>(s->bvh_node_count);
-            collapse_wide_kernel<<<(nn + 255u) / 256u, 256, 0, ctx->stream>>>(static_cast<const float4 *>(a.bvh_nodes),
-                                                                             static_cast<float4 *>(a.wide_nodes), nn);
-            LRK_CUDA(cudaGetLastError());
-        }
     }
     if ((rc = upload(ctx, &a.tri_verts, s->tri_verts, s->tri_slot_count * 12u))) return rc;
     if ((rc = upload(ctx, &a.surfaces, s->surfaces, s->surface_count))) return rc;
@@ -582,7 +570,7 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
     if ((rc = upload(ctx, &a.light_handles, s->light_handles, s->light_count))) return rc;
     if ((rc = upload(ctx, &a.camera, &s->camera, 1))) return rc;
     std::vector<uint32_t> handles(static_cast<size_t>(s->instance_count) * 4u), kinds(s->instance_count);
-    for (int k = 1; k < 8; k++) ctx->has_kind[k] = false;
+    for (int k = 1; k < 9; k++) ctx->has_kind[k] = false;
     ctx->any_non_opaque = false;
     std::vector<float> o2w(static_cast<size_t>(s->instance_count) * 12u), xform(static_cast<size_t>(s->instance_count) * 16u);
     for (uint32_t i = 0; i < s->instance_count; i++) {
@@ -594,7 +582,8 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
             if (flags & LRK_SHAPE_HAS_SURFACE) {
                 if (surface_tag >= s->surface_count) return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_upload_scene: surface tag out of range");
                 const uint32_t type = s->surfaces[surface_tag].type;
-                kind = type + 1u;// Matte 1, Disney 2, Mirror 3, Glass 4, Plastic 5, Metal 6
+                kind = type + 1u;// Matte 1, Disney 2, Mirror 3, Glass 4, Plastic 5, Metal 6, Mix 7
+                if (type == LRK_SURFACE_DISNEY && (s->surfaces[surface_tag].flags & LRK_SURFACE_DISNEY_TRANSMISSIVE)) kind = 8u;
             }
             kinds[i] = kind;
             ctx->has_kind[kind] = true;
@@ -623,7 +612,6 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
     sc.inst_o2w = static_cast<const float4 *>(a.inst_o2w);
     sc.inst_xform = static_cast<const float4 *>(a.inst_xform);
     sc.bvh_nodes = static_cast<const float4 *>(a.bvh_nodes);
-    sc.wide_nodes = static_cast<const float4 *>(a.wide_nodes);
     sc.traversal_overflow = static_cast<uint32_t *>(a.traversal_overflow);
     sc.tri_verts = static_cast<const float4 *>(a.tri_verts);
     sc.surfaces = static_cast<const lrk_surface *>(a.surfaces);

@@ -21,7 +21,6 @@ struct DeviceScene {
     const float4 *inst_o2w;
     const float4 *inst_xform;
     const float4 *bvh_nodes;// 4 x float4 per node: {lo0.xyz,hi0.x} {hi0.yz,lo1.xy} {lo1.z,hi1.xyz} {ref0,ref1,parent,-}
-    const float4 *wide_nodes;// 8 x float4 per node: the 4-wide collapse of bvh_nodes, built on the device at upload (wide_bvh.cuh)
     uint32_t *traversal_overflow;// set by a traversal kernel whose stack ran out (hierarchy deeper than the kernels support)
     const float4 *tri_verts;// 3 x float4 per BVH-ordered triangle slot, v0.w = prim id bits
     const lrk_surface *surfaces;

@@ -645,14 +645,59 @@ __device__ __forceinline__ float smithG_GGX(float cosTheta, float alpha) {
     return 1.f / (cosTheta + sqrtf(alpha2 + cosTheta2 - alpha2 * cosTheta2));
 }
 
-struct DisneyClosure {
+// MicrofacetTransmission (src/util/scattering.cpp:326-373) with eta_a = 1, as free functions over (t, distribution, eta_b):
+// the Glass closure below and the transmissive Disney closure share them.
+__device__ __forceinline__ bool refract(V3 wi, V3 n, float eta, V3 &wt);
+__device__ __forceinline__ V3 microfacet_transmission_evaluate(V3 t, const TrowbridgeReitz &d, float eta, V3 wo, V3 wi) {
+    float cosThetaO = cos_theta(wo), cosThetaI = cos_theta(wi);
+    float e = cosThetaO > 0.f ? eta / 1.f : 1.f / eta;
+    V3 wh = normalize(wo + wi * e);
+    wh = sign(cos_theta(wh)) * wh;
+    V3 f = v3(0.f);
+    if (!same_hemisphere(wo, wi) && cosThetaO != 0.f && cosThetaI != 0.f && dot(wo, wh) * dot(wi, wh) < 0.f) {
+        float G = d.G(wo, wi);
+        float sqrtDenom = dot(wo, wh) + e * dot(wi, wh);
+        float F = fresnel_dielectric(dot(wo, wh), 1.f, eta);
+        float D = d.D(wh);
+        V3 num = (1.f - F) * t * D * G * dot(wi, wh) * dot(wo, wh);
+        float den = cosThetaI * cosThetaO * sqr(sqrtDenom);
+        f = v3(num.x / den, num.y / den, num.z / den);
+    }
+    return f;
+}
+__device__ __forceinline__ float microfacet_transmission_pdf(const TrowbridgeReitz &d, float eta, V3 wo, V3 wi) {
+    float p = 0.f;
+    float e = cos_theta(wo) > 0.f ? eta / 1.f : 1.f / eta;
+    V3 wh = normalize(wo + wi * e);
+    if (!same_hemisphere(wo, wi) && dot(wo, wh) * dot(wi, wh) < 0.f) {
+        float sqrtDenom = dot(wo, wh) + e * dot(wi, wh);
+        float dwh_dwi = sqr(e / sqrtDenom) * abs_dot(wi, wh);
+        p = d.pdf(wo, wh) * dwh_dwi;
+    }
+    return p;
+}
+
+// TRANS: the closure class "disney_trans" of a transmissive node (LRK_SURFACE_DISNEY_TRANSMISSIVE, src/surfaces/disney.cpp:376-383,
+// 425,452-464,514-522,571-576): a fourth technique with a MicrofacetTransmission lobe, a one-sided Fresnel term, eta() = eta_t.
+template<bool TRANS>
+struct DisneyClosureT {
     V3 Cdiff, Css, Csheen, Cspec0;
     float metallic, roughness, clearcoat, fresnel_eta, gloss;
     TrowbridgeReitz distrib;
     float w0, w1, w2;
     bool has_diffuse, has_fake_ss, has_sheen, has_clearcoat;
+    // transmissive closure only
+    V3 Cst;
+    float w3, eta_t_;
+    bool has_spec_trans;
+    float rr_eta_scale;// eta scale of the sampled event for Russian roulette (mega_path.cpp:133-138)
 
     __device__ __forceinline__ void init(const lrk_surface &s) {
+        rr_eta_scale = 1.f;
+        Cst = v3(0.f);
+        w3 = 0.f;
+        has_spec_trans = false;
+        eta_t_ = s.p[5];
         V3 color = v3(s.p[0], s.p[1], s.p[2]);
         float color_lum = s.p[3];
         metallic = s.p[4];
@@ -709,14 +754,23 @@ struct DisneyClosure {
             w2 = saturate(clearcoat * FrSchlick(.04f, 1.f));
             en2 = true;
         }
+        if (TRANS && (lobes & LRK_DISNEY_LOBE_SPEC_TRANS)) {
+            float Cst_weight = (1.f - metallic) * specular_trans;
+            Cst = Cst_weight * v3(sqrtf(color.x), sqrtf(color.y), sqrtf(color.z));
+            has_spec_trans = true;
+            float Cst_lum = Cst_weight * sqrtf(color_lum);
+            w3 = saturate(Cst_lum);
+        }
         float sum_weights = 0.f;
         if (en0) sum_weights += w0;
         sum_weights += w1;
         if (en2) sum_weights += w2;
+        if (TRANS && has_spec_trans) sum_weights += w3;
         float inv_sum_weights = sum_weights == 0.f ? 0.f : 1.f / sum_weights;
         if (en0) w0 *= inv_sum_weights;
         w1 *= inv_sum_weights;
         if (en2) w2 *= inv_sum_weights;
+        if (TRANS && has_spec_trans) w3 *= inv_sum_weights;
         enabled0 = en0;
         enabled2 = en2;
     }
@@ -736,7 +790,7 @@ struct DisneyClosure {
         gtr1_pi_log_a2 = kPi * logf(alpha2);
     }
     __device__ __forceinline__ V3 disney_fresnel(float cosI_in) const {
-        float cosI = fabsf(cosI_in);
+        float cosI = TRANS ? cosI_in : fabsf(cosI_in);// DisneyFresnel: two_sided = !is_transmissive (disney.cpp:287-292,425)
         float fr = fresnel_dielectric(cosI, 1.f, fresnel_eta);
         V3 f0 = v3(FrSchlick(Cspec0.x, cosI), FrSchlick(Cspec0.y, cosI), FrSchlick(Cspec0.z, cosI));
         return lerp(v3(fr), f0, metallic);
@@ -774,8 +828,8 @@ struct DisneyClosure {
                 V3 fs = v3(0.f);
                 float ps = 0.f;
                 if (valid) {
-                    // dot(wi, face_forward(wh, +z)) = +-dot(wi, wh) and the Fresnel term takes its absolute value
-                    V3 F = disney_fresnel(cosThetaD);
+                    // dot(wi, face_forward(wh, +z)) = +-dot(wi, wh); the opaque closure's Fresnel term takes its absolute value
+                    V3 F = disney_fresnel(TRANS ? (cos_theta(wh) < 0.f ? -cosThetaD : cosThetaD) : cosThetaD);
                     float D = distrib.D(wh);
                     float G = 1.0f / (1.0f + lambda_o + distrib.Lambda(wi));
                     float cos_o = cos_theta(wo), cos_i = cos_theta(wi);
@@ -795,13 +849,18 @@ struct DisneyClosure {
                     pdf += w2 * (valid ? Dr * cos_h / (4.f * wo_dot_wh) : 0.f);
                 }
             }
+        } else if (TRANS && has_spec_trans) {// transmission, disney.cpp:514-522
+            if (w3 > 0.f) {
+                f = f + microfacet_transmission_evaluate(Cst, distrib, eta_t_, wo, wi);
+                pdf += w3 * microfacet_transmission_pdf(distrib, eta_t_, wo, wi);
+            }
         }
         SurfEval e;
         e.f = f * abs_cos_theta(wi);
         e.pdf = pdf;
         return e;
     }
-    __device__ __forceinline__ bool sample_direction(V3 wo, float u_lobe, float u0, float u1, V3 &wi) const {
+    __device__ __forceinline__ bool sample_direction(V3 wo, float u_lobe, float u0, float u1, V3 &wi) {
         // technique selection: src/surfaces/disney.cpp:544-551 (strict '>' against the running sum)
         uint32_t tech = 0u;
         float sum_weights = 0.f;
@@ -815,9 +874,20 @@ struct DisneyClosure {
             tech = u_lobe > sum_weights ? 2u : tech;
             sum_weights += w2;
         }
+        if (TRANS && has_spec_trans) {
+            tech = u_lobe > sum_weights ? 3u : tech;
+            sum_weights += w3;
+        }
         wi = v3(0.f);
         bool valid = false;
-        if (tech == 0u) {
+        rr_eta_scale = 1.f;
+        if (TRANS && tech == 3u) {// MicrofacetTransmission::sample_wi (scattering.cpp:352-358), event enter / exit (disney.cpp:571-576)
+            float e = cos_theta(wo) > 0.f ? 1.f / eta_t_ : eta_t_ / 1.f;
+            V3 wh = distrib.sample_wh(wo, u0, u1);
+            bool refr = refract(wo, wh, e, wi);
+            valid = refr && !same_hemisphere(wo, wi);
+            rr_eta_scale = cos_theta(wo) > 0.f ? sqr(eta_t_) : sqr(1.f / eta_t_);
+        } else if (tech == 0u) {
             if (has_diffuse) {
                 wi = sample_cosine_hemisphere(u0, u1);
                 wi.z *= sign(cos_theta(wo));
@@ -848,6 +918,8 @@ struct DisneyClosure {
         return valid;// f and pdf of the sample are evaluate_local(wo, wi) (disney.cpp:583-586)
     }
 };
+using DisneyClosure = DisneyClosureT<false>;
+using DisneyTransClosure = DisneyClosureT<true>;
 
 // Mirror / Glass / Plastic / Metal: src/surfaces/{mirror,glass,plastic,metal}.cpp over the BxDFs of
 // src/util/scattering.cpp:14-125,238-345.  One closure type for the four nodes (hit bucket 3): they are rare next to the

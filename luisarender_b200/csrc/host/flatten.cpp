@@ -346,12 +346,14 @@ std::unique_ptr<FlatScene> flatten_scene(const Scene &scene) {
     f.build_tlas();
     out->bvh_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 
-    // surfaces; Disney lobes are OR-ed over all disney nodes (one shared closure, src/surfaces/disney.cpp:869,994)
-    uint32_t disney_lobes = 0u;
+    // surfaces; Disney lobes are OR-ed over all disney nodes of one closure class - opaque "disney", transmissive "disney_trans"
+    // (one shared closure per class, src/surfaces/disney.cpp:869,925-930,994)
+    uint32_t disney_lobes[2] = {0u, 0u};
+    auto disney_class = [](const lrk_surface &s) { return (s.flags & LRK_SURFACE_DISNEY_TRANSMISSIVE) ? 1 : 0; };
     TextureTable texture_table;
     for (auto s : f.surface_nodes) {
         out->surfaces.push_back(s->flatten(texture_table));
-        if (out->surfaces.back().type == LRK_SURFACE_DISNEY) disney_lobes |= out->surfaces.back().lobes;
+        if (out->surfaces.back().type == LRK_SURFACE_DISNEY) disney_lobes[disney_class(out->surfaces.back())] |= out->surfaces.back().lobes;
     }
     // Mix nodes: their two surfaces become extra records behind the tagged ones (never referenced by an instance handle)
     for (size_t tag = 0, tagged = f.surface_nodes.size(); tag < tagged; tag++) {
@@ -370,7 +372,7 @@ std::unique_ptr<FlatScene> flatten_scene(const Scene &scene) {
         out->surfaces[tag].p[1] = ea == 0.f ? eb : eb == 0.f ? ea : ratio * (ea - eb) + eb;// lerp(eta_b, eta_a, ratio)
     }
     for (auto &s : out->surfaces)
-        if (s.type == LRK_SURFACE_DISNEY) s.lobes = disney_lobes;
+        if (s.type == LRK_SURFACE_DISNEY) s.lobes = disney_lobes[disney_class(s)];
     // the environment light: src/environments/spherical.cpp, src/lightsamplers/uniform.cpp:40-47
     if (auto env = scene.environment(); env != nullptr && !env->is_null() && !env->is_black()) {
         auto &e = out->environment;

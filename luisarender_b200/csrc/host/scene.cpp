@@ -854,13 +854,13 @@ struct DisneySurface final : Surface {
         sheen_tint = surface_texture(s, d, "sheen_tint");
         clearcoat = surface_texture(s, d, "clearcoat");
         clearcoat_gloss = surface_texture(s, d, "clearcoat_gloss");
-        specular_trans = constant_or_null(s, d, "specular_trans");
+        specular_trans = surface_texture(s, d, "specular_trans");
         flatness = surface_texture(s, d, "flatness");
         diffuse_trans = constant_or_null(s, d, "diffuse_trans");
         if (thin) throw Error("Thin Disney surfaces are not supported. [" + d->location() + "]");
-        if (specular_trans && !specular_trans->is_black())
-            throw Error("Transmissive Disney surfaces (specular_trans != 0) are not supported. [" + d->location() + "]");
     }
+    // src/surfaces/disney.cpp:61-75: the closure class "disney_trans" (a specular-transmission lobe exists)
+    bool is_transmissive() const { return specular_trans != nullptr && !specular_trans->is_black(); }
     uint32_t lobes() const {
         // src/surfaces/disney.cpp:966-990
         uint32_t l = 0u;
@@ -871,6 +871,7 @@ struct DisneySurface final : Surface {
         }
         l |= LRK_DISNEY_LOBE_SPECULAR;
         if (clearcoat && !clearcoat->is_black()) l |= LRK_DISNEY_LOBE_CLEARCOAT;
+        if (is_transmissive()) l |= LRK_DISNEY_LOBE_SPEC_TRANS;
         return l;
     }
     lrk_surface flatten(TextureTable &textures) const override {
@@ -878,6 +879,7 @@ struct DisneySurface final : Surface {
         out.type = LRK_SURFACE_DISNEY;
         out.lobes = lobes();
         if (remap_roughness) out.flags |= LRK_SURFACE_REMAP_ROUGHNESS;
+        if (is_transmissive()) out.flags |= LRK_SURFACE_DISNEY_TRANSMISSIVE;
         // a parameter is either the node's constant (p[k]) or an image texture evaluated per hit (tex[k])
         auto x = [&](const Texture *t, float dflt, uint32_t slot) {
             if (t && t->is_image()) {
@@ -906,7 +908,7 @@ struct DisneySurface final : Surface {
         out.p[10] = x(sheen_tint, 0.f, 10);
         out.p[11] = x(clearcoat, 0.f, 11);
         out.p[12] = x(clearcoat_gloss, 1.f, 12);
-        out.p[13] = specular_trans ? specular_trans->value().x : 0.f;
+        out.p[13] = x(specular_trans, 0.f, 13);
         out.p[14] = x(flatness, 0.f, 14);
         out.p[15] = 0.f;// diffuse_trans is only built for thin surfaces (src/surfaces/disney.cpp:1017)
         flatten_wrappers(out, textures);

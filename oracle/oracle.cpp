@@ -1031,10 +1031,16 @@ struct DisneyClosure {
     V3 Cdiff{}, Css{}, Csheen{}, Cspec0{};
     float fresnel_eta{}, gloss{};
     TrowbridgeReitz distrib{1.f, 1.f};
-    float w[3]{0.f, 0.f, 0.f};
-    bool enabled[3]{false, false, false};
+    // techniques: diffuse-like, specular, clearcoat and - transmissive closure ("disney_trans", disney.cpp:376-383,452-464) only -
+    // specular transmission
+    float w[4]{0.f, 0.f, 0.f, 0.f};
+    bool enabled[4]{false, false, false, false};
+    bool transmissive{false};
+    bool has_spec_trans{false};
+    MicrofacetTransmission spec_trans{v3(0.f), TrowbridgeReitz{1.f, 1.f}, 1.f, 1.f};
 
     explicit DisneyClosure(const lrk_surface &s) {
+        transmissive = (s.flags & LRK_SURFACE_DISNEY_TRANSMISSIVE) != 0u;
         color = v3(s.p[0], s.p[1], s.p[2]);
         color_lum = s.p[3]; metallic = s.p[4]; eta_t = s.p[5]; roughness = s.p[6]; specular_tint = s.p[7];
         anisotropic = s.p[8]; sheen = s.p[9]; sheen_tint = s.p[10]; clearcoat = s.p[11]; clearcoat_gloss = s.p[12];
@@ -1083,14 +1089,24 @@ struct DisneyClosure {
             w[2] = saturate(clearcoat * FrSchlick(.04f, 1.f));
             enabled[2] = true;
         }
+        if (transmissive && (lobes & LRK_DISNEY_LOBE_SPEC_TRANS)) {// disney.cpp:452-464
+            float Cst_weight = (1.f - metallic) * specular_trans;
+            V3 Cst = Cst_weight * v3(std::sqrt(color.x), std::sqrt(color.y), std::sqrt(color.z));
+            spec_trans = MicrofacetTransmission{Cst, distrib, eta_i, eta_t};
+            has_spec_trans = true;
+            float Cst_lum = Cst_weight * std::sqrt(color_lum);
+            w[3] = saturate(Cst_lum);
+            enabled[3] = true;
+        }
+        const int techniques = transmissive ? 4 : 3;
         float sum_weights = 0.f;
-        for (int i = 0; i < 3; i++) if (enabled[i]) sum_weights += w[i];
+        for (int i = 0; i < techniques; i++) if (enabled[i]) sum_weights += w[i];
         float inv_sum_weights = sum_weights == 0.f ? 0.f : 1.f / sum_weights;
-        for (int i = 0; i < 3; i++) if (enabled[i]) w[i] *= inv_sum_weights;
+        for (int i = 0; i < techniques; i++) if (enabled[i]) w[i] *= inv_sum_weights;
     }
 
-    V3 disney_fresnel(float cosI_in) const {// DisneyFresnel::evaluate, two_sided = true (opaque closure)
-        float cosI = std::fabs(cosI_in);
+    V3 disney_fresnel(float cosI_in) const {// DisneyFresnel::evaluate, two_sided = !is_transmissive (disney.cpp:287-292,425)
+        float cosI = transmissive ? cosI_in : std::fabs(cosI_in);
         float fr = fresnel_dielectric(cosI, 1.f, fresnel_eta);
         V3 f0 = v3(FrSchlick(Cspec0.x, cosI), FrSchlick(Cspec0.y, cosI), FrSchlick(Cspec0.z, cosI));
         return lerp(v3(fr), f0, metallic);
@@ -1195,6 +1211,11 @@ struct DisneyClosure {
                     pdf += w[2] * clearcoat_pdf(wo, wi);
                 }
             }
+        } else if (has_spec_trans) {// transmission, disney.cpp:514-522
+            if (w[3] > 0.f) {
+                f = f + spec_trans.evaluate(wo, wi);
+                pdf += w[3] * spec_trans.pdf(wo, wi);
+            }
         }
         SurfEval e;
         e.f = f * abs_cos_theta(wi);
@@ -1211,7 +1232,7 @@ SurfSample disney_sample(const lrk_surface &s, const Interaction &it, V3 wo, flo
     DisneyClosure c{s};
     uint32_t tech = 0u;
     float sum_weights = 0.f;
-    for (uint32_t i = 0; i < 3u; i++) {
+    for (uint32_t i = 0; i < (c.transmissive ? 4u : 3u); i++) {
         if (c.enabled[i]) {
             tech = u_lobe > sum_weights ? i : tech;
             sum_weights += c.w[i];
@@ -1220,6 +1241,7 @@ SurfSample disney_sample(const lrk_surface &s, const Interaction &it, V3 wo, flo
     V3 wo_local = it.shading.world_to_local(wo);
     V3 wi_local = v3(0.f);
     bool valid = false;
+    uint32_t event = LRK_EVENT_REFLECT;
     if (tech == 0u) {
         if (c.has_diffuse) {// BxDF::sample_wi, scattering.cpp:274-278
             wi_local = sample_cosine_hemisphere(u0, u1);
@@ -1232,10 +1254,16 @@ SurfSample disney_sample(const lrk_surface &s, const Interaction &it, V3 wo, flo
         valid = same_hemisphere(wo_local, wi_local);
     } else if (tech == 2u) {
         if (c.has_clearcoat) wi_local = c.clearcoat_sample_wi(wo_local, u0, u1, valid);
+    } else if (c.has_spec_trans) {// disney.cpp:571-576
+        BxDFSample bs = c.spec_trans.sample_wi(wo_local, u0, u1);
+        wi_local = bs.wi;
+        valid = bs.valid;
+        event = cos_theta(wo_local) > 0.f ? LRK_EVENT_ENTER : LRK_EVENT_EXIT;
     }
     SurfSample out;
     out.wi = it.shading.local_to_world(wi_local);
     if (valid) out.eval = c.evaluate_local(wo_local, wi_local);
+    out.event = event;
     return out;
 }
 
@@ -1452,6 +1480,8 @@ SurfSample mix_sample(const lrk_surface &s, const Interaction &it, V3 wo, float 
 // (mix.cpp:133-141); 0 = nullopt
 float surface_eta(const lrk_surface &s, const lrk_surface *records) {
     if (s.type == LRK_SURFACE_GLASS) return s.p[6];
+    // DisneyClosureImpl::eta(): eta_t when the specular-transmission lobe exists (disney.cpp:531-533)
+    if (s.type == LRK_SURFACE_DISNEY && (s.flags & LRK_SURFACE_DISNEY_TRANSMISSIVE) && (s.lobes & LRK_DISNEY_LOBE_SPEC_TRANS)) return s.p[5];
     if (s.type == LRK_SURFACE_MIX) {
         float ea = surface_eta(records[s.mix_a], records), eb = surface_eta(records[s.mix_b], records);
         if (ea == 0.f) return eb;
@@ -2421,9 +2451,10 @@ extern "C" int oracle_unit(const char *name_c, const uint32_t *in, uint32_t *out
             auto take = [&](int count, int at = 0) { for (int i = 0; i < count; i++) sf.p[at + i] = w.f(); };
             bool is_eval = name.find("_evaluate") != std::string::npos;
             if (name.rfind("matte_", 0) == 0) { sf.type = LRK_SURFACE_MATTE; take(4); }
-            else if (name.rfind("disney_", 0) == 0) {
+            else if (name.rfind("disney_", 0) == 0 || name.rfind("disneytrans_", 0) == 0) {
                 sf.type = LRK_SURFACE_DISNEY; take(15);
                 sf.lobes = static_cast<uint32_t>(std::stoul(name.substr(name.rfind('_') + 1)));
+                if (name.rfind("disneytrans_", 0) == 0) sf.flags |= LRK_SURFACE_DISNEY_TRANSMISSIVE;// closure class "disney_trans"
             }
             else if (name.rfind("mirror_", 0) == 0) { sf.type = LRK_SURFACE_MIRROR; take(5); }
             else if (name.rfind("glass_", 0) == 0) { sf.type = LRK_SURFACE_GLASS; take(10); }

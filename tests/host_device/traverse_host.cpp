@@ -1,5 +1,5 @@
-// traverse_host.cpp — the DEVICE traversal code (luisarender_b200/csrc/device/{wide_bvh,traverse}.cuh: the BVH2 -> 4-wide collapse,
-// the inner-node step with its sorting network and stack rules, the leaf step with instance entry / exit and the triangle test)
+// traverse_host.cpp — the DEVICE traversal code (luisarender_b200/csrc/device/traverse.cuh: the inner-node step with its
+// ordering and stack rules, the leaf step with instance entry / exit, the triangle test and its tie rule)
 // compiled for the host, so that the per-ray logic the sm_100a kernels run can be checked against the oracle's BVH2 traversal
 // without a GPU (tests/test_device_traversal_on_host.py).  TEST INFRASTRUCTURE: nothing here is part of the product.  What the
 // GPU adds on top is warp scheduling only (ray refill, descent / leaf phases), which does not touch per-ray results.
@@ -32,61 +32,54 @@ using std::min;
 namespace {
 using namespace lrk;
 
-// host stand-ins for the device's Slot (shared-memory stack + parked world ray)
+// host stand-ins for the device's LaneStack / LaneWorld
 struct HostStack {
     std::vector<uint32_t> e;
     size_t max_depth{0};
-    void push(int &sp, uint32_t ref) {
-        e.resize(static_cast<size_t>(sp));
+    void reset() { e.clear(); }
+    void push(uint32_t ref) {
         e.push_back(ref);
-        sp++;
         max_depth = std::max(max_depth, e.size());
     }
-    void push4_if(int &sp, bool pa, uint32_t ra, bool pb, uint32_t rb, bool pc, uint32_t rc, bool pd, uint32_t rd) {
-        if (pa) push(sp, ra);
-        if (pb) push(sp, rb);
-        if (pc) push(sp, rc);
-        if (pd) push(sp, rd);
+    uint32_t pop() {
+        uint32_t v = e.back();
+        e.pop_back();
+        return v;
     }
-    uint32_t pop(int &sp) { return e[static_cast<size_t>(--sp)]; }
+    void push_if(bool p, uint32_t ref) {
+        if (p) push(ref);
+    }
+    uint32_t top() const { return e.back(); }
+    void drop_if(bool p) {
+        if (p) e.pop_back();
+    }
 };
 
 struct HostWorld {
-    RayHot hot;
-    V3 o, d;
-    void save(const RayHot &r, const RayCold &c) { hot = r; o = c.o; d = c.d; }
-    void load(RayHot &r, RayCold &c) const {
-        r.ix = hot.ix; r.iy = hot.iy; r.iz = hot.iz;
-        r.ox = hot.ox; r.oy = hot.oy; r.oz = hot.oz;
-        c.o = o;
-        c.d = d;
-        r.near = near_offsets(d);// as the device does: the offsets come back from the signs of d
-    }
+    RaySetup saved;
+    void save(const RaySetup &c) { saved = c; }
+    void load(RaySetup &c) const { c = saved; }
 };
 
 // the device's per-ray control flow: inner steps while the ray stands on an inner node, leaf steps otherwise
 template<bool ANY_HIT, bool ALPHA>
 void trace_one(const DeviceScene &sc, const float *ray, uint32_t *hit, TraversalCounters &cnt, size_t &max_stack) {
-    RayHot r;
-    RayCold c;
+    RayState r;
     HostStack stack;
     HostWorld world;
-    start_ray(sc, r, c, stack, make_float4(ray[0], ray[1], ray[2], ray[3]), make_float4(ray[4], ray[5], ray[6], ray[7]), 0u);
+    start_ray(sc, r, stack, make_float4(ray[0], ray[1], ray[2], ray[3]), make_float4(ray[4], ray[5], ray[6], ray[7]));
     for (;;) {
-#ifdef LRK_TRACE_DEBUG
-        std::printf("node %08x cur_inst %d tbest %g best (%d,%d) sp %d\n", r.node, (int)r.cur_inst, r.tbest, (int)c.best_inst, (int)c.best_prim, r.sp);
-#endif
         if (!(r.node & LRK_BVH_LEAF)) {
-            inner_step<!ANY_HIT, true>(sc, r, stack, cnt);
-        } else if (leaf_step<ANY_HIT, true, ALPHA>(sc, r, c, stack, world, cnt)) {
+            inner_step<true>(sc, r, stack, cnt);
+        } else if (leaf_step<ANY_HIT, true, ALPHA>(sc, r, stack, world, cnt)) {
             break;
         }
     }
     max_stack = std::max(max_stack, stack.max_depth);
-    hit[0] = c.best_inst;
-    hit[1] = c.best_prim;
-    hit[2] = __float_as_uint(c.best_u);
-    hit[3] = __float_as_uint(c.best_v);
+    hit[0] = r.best_inst;
+    hit[1] = r.best_prim;
+    hit[2] = __float_as_uint(r.best_u);
+    hit[3] = __float_as_uint(r.best_v);
 }
 
 }// namespace
@@ -94,9 +87,6 @@ void trace_one(const DeviceScene &sc, const float *ray, uint32_t *hit, Traversal
 // rays: n x {o.xyz, tmin, d.xyz, tmax}; hits: n x {inst, prim, bary.u bits, bary.v bits}; counters: {wide nodes, triangles, instance
 // entries, deepest stack}
 extern "C" int wide_trace_host(const lrk_scene_desc *s, const float *rays, uint64_t n, int any_hit, uint32_t *hits, uint64_t *counters) {
-    std::vector<float4> wide(static_cast<size_t>(s->bvh_node_count) * kWideRows);
-    for (uint64_t i = 0; i < s->bvh_node_count; i++)
-        collapse_wide_node(reinterpret_cast<const float4 *>(s->bvh_nodes), static_cast<uint32_t>(i), wide.data() + i * kWideRows);
     std::vector<float4> xform(static_cast<size_t>(s->instance_count) * 4u);
     for (uint32_t i = 0; i < s->instance_count; i++) {// as lrk_upload_scene lays the traversal instance records out
         const auto &inst = s->instances[i];
@@ -118,7 +108,7 @@ extern "C" int wide_trace_host(const lrk_scene_desc *s, const float *rays, uint6
     sc.vertices = s->vertices;
     sc.textures = s->textures;
     sc.texels = reinterpret_cast<const float4 *>(s->texels);
-    sc.wide_nodes = wide.data();
+    sc.bvh_nodes = reinterpret_cast<const float4 *>(s->bvh_nodes);
     sc.tri_verts = reinterpret_cast<const float4 *>(s->tri_verts);
     sc.inst_xform = xform.data();
     sc.tlas_root = s->tlas_root;

@@ -23,7 +23,7 @@ import gen_ref_pins as G  # noqa: E402
 
 SRC = REPO / "tests" / "host_device" / "closures_host.cpp"
 OUT = REPO / "tests" / "host_device" / "_build" / "libclosures_host.so"
-CLOSURE_PINS = sorted(n for n in G.PINS if n.split("_")[0] in ("matte", "disney", "mirror", "glass", "plastic", "metal"))
+CLOSURE_PINS = sorted(n for n in G.PINS if n.split("_")[0] in ("matte", "disney", "disneytrans", "mirror", "glass", "plastic", "metal"))
 
 
 @pytest.fixture(scope="module")
@@ -34,7 +34,7 @@ def lib():
     deps = [SRC, REPO / "luisarender_b200" / "csrc" / "device" / "shading.cuh", REPO / "luisarender_b200" / "csrc" / "device" / "vecmath.cuh"]
     if not OUT.exists() or OUT.stat().st_mtime < max(d.stat().st_mtime for d in deps):
         OUT.parent.mkdir(parents=True, exist_ok=True)
-        subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-w", "-ffp-contract=off", f"-I{cuda_include}", "-shared", str(SRC), "-o", str(OUT)],
+        subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-w", "-ffp-contract=off", f"-I{cuda_include}", "-shared", "-Wl,-Bsymbolic", str(SRC), "-o", str(OUT)],
                        check=True)
     handle = C.CDLL(str(OUT))
     handle.device_closure_unit.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_int]

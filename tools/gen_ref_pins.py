@@ -125,6 +125,14 @@ def _disney_ctx(r, n):  # lrk_surface.p[0..14] of a Disney node (include/lrk.h)
     return c.astype(np.float32)
 
 
+def _disney_trans_ctx(r, n):  # a transmissive Disney node: specular_trans in [0, 1], with pure-transmission and opaque-like rows
+    c = _disney_ctx(r, n)
+    c[:, 13] = r.random(n, dtype=np.float32)
+    c[: n // 6, 13] = 1.0
+    c[n // 6: n // 4, 4] = 0.0  # non-metallic rows keep the transmission lobe alive
+    return c.astype(np.float32)
+
+
 def _sigma_a(r, n):
     a = (2.0 * r.random((n, 3), dtype=np.float32)).astype(np.float32)
     a[: n // 3] = 0.0
@@ -201,6 +209,11 @@ PINS = {
 for _mask in (35, 59, 63, 32):  # lobe masks: diffuse+retro+specular, + sheen + clearcoat, + fake subsurface, specular only
     PINS[f"disney_evaluate_{_mask}"] = ([_disney_ctx, _frame, _dir, _dir], _EVAL_OUT)
     PINS[f"disney_sample_{_mask}"] = ([_disney_ctx, _frame, _dir, _u, _u2], _SAMPLE_OUT)
+
+
+for _mask in (163, 191):  # transmissive closure: diffuse+retro+specular+spec_trans, and every lobe + spec_trans
+    PINS[f"disneytrans_evaluate_{_mask}"] = ([_disney_trans_ctx, _frame, _dir, _dir], _EVAL_OUT)
+    PINS[f"disneytrans_sample_{_mask}"] = ([_disney_trans_ctx, _frame, _dir, _u, _u2], _SAMPLE_OUT)
 
 
 def alias_table_values(seed: int = 7, n: int = 37) -> np.ndarray:

@@ -59,6 +59,20 @@ def cases() -> dict[str, str]:
     c["spheres_disney_all_lobes"] = "\n".join(
         (line if not (line == "}" and prev.strip().startswith("sheen : Constant")) else extra)
         for prev, line in zip([""] + c["spheres_disney"].split("\n"), c["spheres_disney"].split("\n"))).replace('"spheres.exr"', '"lobes.exr"')
+    # transmissive Disney surfaces (closure class "disney_trans": specular-transmission lobe, enter / exit events and the
+    # Russian-roulette eta scale) next to opaque ones: every other Disney node of the sphere scene gets specular_trans
+    def _transmissive(src):
+        out, k = [], 0
+        for line in src.split("\n"):
+            out.append(line)
+            if line.strip().startswith("sheen : Constant"):
+                if k % 2 == 0:
+                    out.append("  specular_trans : Constant { v { %s } }" % ("0.85" if k % 4 == 0 else "1.0"))
+                    out.append("  eta : Constant { v { 1.45 } }")
+                k += 1
+        return "\n".join(out)
+    c["spheres_disney_transmissive"] = _transmissive(
+        scenes.instanced_spheres(resolution=(32, 18), spp=4, depth=8, rr_depth=2, **spheres)).replace('"spheres.exr"', '"trans.exr"')
     # the medium path with an isotropic phase function (|g| < 1e-3 branch) and per-channel coefficients
     c["spheres_medium_isotropic"] = (c["spheres_medium"].replace("g { 0.3 }", "g { 0.0 }")
                                      .replace("sigma_a : Constant { v { 0.01, 0.01, 0.01 } }", "sigma_a : Constant { v { 0.02, 0.01, 0.005 } }")
