@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define LRK_ABI_VERSION 4u /* 4: surface types Mirror / Glass / Plastic / Metal (row f3) */
+#define LRK_ABI_VERSION 5u /* 5: lrk_sampler (row f2), LRK_SURFACE_DISNEY_TRANSMISSIVE */
 
 typedef enum lrk_status {
     LRK_OK = 0,
@@ -338,6 +338,42 @@ typedef struct lrk_environment {
     const float *pdf;             /* map_height * map_width */
 } lrk_environment;
 
+/* The sampler: src/base/sampler.h:42-48 as implemented by src/samplers/{independent,pmj02bn,sobol,
+ * padded_sobol,zsobol}.cpp.  INDEPENDENT needs nothing but integrator.sampler_seed.  The quasi-Monte-Carlo samplers are
+ * table driven; the host passes the tables (luisarender_b200/data/sampler_tables.bin, tools/extract_sampler_tables.py) and
+ * what Sampler::Instance::reset(resolution, spp) derives from them on the host:
+ *   PMJ02BN      pmj_samples u32[5][65536][2], blue_noise u16[48][128][128]; spp (<= 65536), w = the bit mask covering spp - 1,
+ *                tile = pixel_tile_size, pmj_pixel_samples float2[tile * tile * spp] (the sorted first set, pmj02bn.cpp:132-162)
+ *   SOBOL        sobol_matrices u32[1024][52]; scale = next_pow2(max(resolution)), vdc / vdc_inv u64[52] = the rows m - 1 of the
+ *                van-der-Corput matrices for m = log2(scale) (sobol.cpp:112-131)
+ *   PADDED_SOBOL sobol_matrices (the first two dimensions are read); spp
+ *   ZSOBOL       sobol_matrices (first two dimensions); log2_spp, num_base4_digits (zsobol.cpp:96-103),
+ *                zsobol_hash uint2[1024] = hash_value((seed << 32) | i) (zsobol.cpp:71-79)
+ * Every sampler draws in the order the integrator asks (generate_pixel_2d for the filter, then 1D / 2D per bounce, App. A). */
+#define LRK_SAMPLER_INDEPENDENT 0u
+#define LRK_SAMPLER_PMJ02BN 1u
+#define LRK_SAMPLER_SOBOL 2u
+#define LRK_SAMPLER_PADDED_SOBOL 3u
+#define LRK_SAMPLER_ZSOBOL 4u
+typedef struct lrk_sampler {
+    uint32_t type;
+    uint32_t spp;
+    uint32_t w;                /* PMJ02BN */
+    uint32_t tile;             /* PMJ02BN: pixel_tile_size */
+    uint32_t scale;            /* SOBOL */
+    uint32_t log2_spp;         /* ZSOBOL */
+    uint32_t num_base4_digits; /* ZSOBOL */
+    uint32_t reserved;
+    const uint32_t *sobol_matrices;
+    const uint64_t *vdc;
+    const uint64_t *vdc_inv;
+    const uint32_t *pmj_samples;
+    const uint16_t *blue_noise;
+    const float *pmj_pixel_samples;
+    uint64_t pmj_pixel_sample_count; /* float2 entries */
+    const uint32_t *zsobol_hash;
+} lrk_sampler;
+
 typedef struct lrk_scene_desc {
     uint32_t abi_version; /* LRK_ABI_VERSION */
     uint32_t reserved0;
@@ -378,6 +414,7 @@ typedef struct lrk_scene_desc {
     lrk_integrator integrator;
     lrk_medium environment_medium;
     lrk_environment environment;
+    lrk_sampler sampler;
 } lrk_scene_desc;
 
 /* ---- device control ----------------------------------------------------------------- */

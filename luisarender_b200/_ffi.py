@@ -13,11 +13,11 @@ PKG_DIR = Path(__file__).resolve().parent
 REPO_DIR = PKG_DIR.parent
 LIB_DIR = PKG_DIR / "lib"
 
-LRK_ABI_VERSION = 4
+LRK_ABI_VERSION = 5
 TEX_ADDRESS_EDGE, TEX_ADDRESS_REPEAT, TEX_ADDRESS_MIRROR, TEX_ADDRESS_ZERO = 0, 1, 2, 3
 TEX_FILTER_POINT, TEX_FILTER_LINEAR = 0, 1
 TEX_ENCODING_LINEAR, TEX_ENCODING_SRGB, TEX_ENCODING_GAMMA = 0, 1, 2
-SURFACE_HAS_TEXTURES, SURFACE_REMAP_ROUGHNESS, SURFACE_MAYBE_NON_OPAQUE, SURFACE_HAS_NORMAL_MAP = 1, 2, 4, 8
+SURFACE_HAS_TEXTURES, SURFACE_REMAP_ROUGHNESS, SURFACE_MAYBE_NON_OPAQUE, SURFACE_HAS_NORMAL_MAP, SURFACE_DISNEY_TRANSMISSIVE = 1, 2, 4, 8, 16
 SHAPE_HAS_VERTEX_NORMAL, SHAPE_HAS_VERTEX_UV, SHAPE_HAS_SURFACE, SHAPE_HAS_LIGHT, SHAPE_MAYBE_NON_OPAQUE = 1, 2, 4, 8, 32
 LRK_FILTER_LUT_SIZE = 64
 
@@ -103,6 +103,16 @@ class Environment(C.Structure):
                 ("map_width", u32), ("map_height", u32), ("reserved", u32), ("alias", C.POINTER(AliasEntry)), ("pdf", C.POINTER(f32))]
 
 
+SAMPLER_INDEPENDENT, SAMPLER_PMJ02BN, SAMPLER_SOBOL, SAMPLER_PADDED_SOBOL, SAMPLER_ZSOBOL = 0, 1, 2, 3, 4
+
+
+class Sampler(C.Structure):
+    _fields_ = [("type", u32), ("spp", u32), ("w", u32), ("tile", u32), ("scale", u32), ("log2_spp", u32), ("num_base4_digits", u32),
+                ("reserved", u32), ("sobol_matrices", C.POINTER(u32)), ("vdc", C.POINTER(u64)), ("vdc_inv", C.POINTER(u64)),
+                ("pmj_samples", C.POINTER(u32)), ("blue_noise", C.POINTER(C.c_uint16)), ("pmj_pixel_samples", C.POINTER(f32)),
+                ("pmj_pixel_sample_count", u64), ("zsobol_hash", C.POINTER(u32))]
+
+
 class SceneDesc(C.Structure):
     _fields_ = [
         ("abi_version", u32), ("reserved0", u32),
@@ -117,7 +127,7 @@ class SceneDesc(C.Structure):
         ("lights", C.POINTER(Light)), ("light_handles", C.POINTER(LightHandle)),
         ("textures", C.POINTER(Texture)), ("texture_count", u32), ("reserved2", u32), ("texels", C.POINTER(f32)), ("texel_count", u64),
         ("camera", Camera), ("film", Film), ("integrator", Integrator), ("environment_medium", Medium),
-        ("environment", Environment),
+        ("environment", Environment), ("sampler", Sampler),
     ]
 
 

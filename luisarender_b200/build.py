@@ -54,7 +54,7 @@ def build_host(force=False, verbose=False) -> Path:
     if not force and _newer(out, deps):
         return out
     LIB.mkdir(exist_ok=True)
-    _run(["g++", *HOST_FLAGS, "-shared", *[src_dir / s for s in HOST_SRC], "-o", out, "-lpthread", "-lz"], verbose)
+    _run(["g++", *HOST_FLAGS, "-shared", *[src_dir / s for s in HOST_SRC], "-o", out, "-lpthread", "-lz", "-ldl"], verbose)
     return out
 
 

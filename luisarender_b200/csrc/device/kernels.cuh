@@ -18,6 +18,7 @@
 #pragma once
 #include <type_traits>
 #include <utility>
+#include "samplers.cuh"
 #include "shading.cuh"
 #include "traverse.cuh"
 
@@ -50,6 +51,9 @@ struct PathBuffers {
     float4 *li;
     uint32_t *counts;
     uint32_t capacity;
+    // the pass being rendered: generation slot id -> (pixel, sample index) for the table-driven samplers (samplers.cuh)
+    const uint32_t *pass_pixel_list;
+    uint32_t pass_pixel_offset, pass_npix, pass_spp_begin;
     // volume path integrator only (config C4)
     ulonglong2 *pcg[2]; // per-path PCG32 {state, inc}
     float *u_rr[2];     // Russian-roulette number of the coming bounce (drawn at the top of the loop, mega_vpt_naive.cpp:256-257)
@@ -115,16 +119,16 @@ __global__ void __launch_bounds__(kBlock) generate_rays_kernel(DeviceScene sc, P
     uint32_t s = id / npix;
     uint32_t pixel = __ldg(pixel_list + pixel_offset + k);
     uint32_t px = pixel & 0xffffu, py = pixel >> 16u;
-    uint32_t state = xxhash32_uint4(px, py, sc.sampler_seed, spp_begin + s);
-    float ux = lcg(state);
-    float uy = lcg(state);
+    PathSampler smp;
+    smp.start(sc, px, py, spp_begin + s);
+    const float2 uf = smp.pixel2d(sc);
     float4 ro, rd;
     float weight;
-    camera_ray(sc.camera, px, py, ux, uy, ro, rd, weight);
+    camera_ray(sc.camera, px, py, uf.x, uf.y, ro, rd, weight);
     pb.ray_o[0][id] = ro;
     pb.ray_d[0][id] = rd;
     pb.beta_pdf[0][id] = make_float4(weight, weight, weight, 1e16f);
-    pb.id_rng[0][id] = make_uint2(id, state);
+    pb.id_rng[0][id] = make_uint2(id, smp.state);
     pb.li[id] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
@@ -375,12 +379,26 @@ __global__ void __launch_bounds__(kShadeBlock, LRK_SHADE_MIN_BLOCKS) shade_kerne
                 }
                 if (KIND != 0u) {// kind 0 = emitter-only hit (no surface): the path ends here (mega_path.cpp:89)
                     // draw order is normative: mega_path.cpp:91-98
-                    float u_sel = lcg(state);
-                    float ul0 = lcg(state), ul1 = lcg(state);
-                    float u_lobe = lcg(state);
-                    float ub0 = lcg(state), ub1 = lcg(state);
+                    PathSampler smp;
+                    {
+                        uint32_t spx = 0u, spy = 0u, ssi = 0u;
+                        if (sc.sampler_type != LRK_SAMPLER_INDEPENDENT) {// the path's pixel and sample index from its generation slot
+                            const uint32_t pixel = __ldg(pb.pass_pixel_list + pb.pass_pixel_offset + ir.x % pb.pass_npix);
+                            spx = pixel & 0xffffu;
+                            spy = pixel >> 16u;
+                            ssi = pb.pass_spp_begin + ir.x / pb.pass_npix;
+                        }
+                        smp.resume(sc, state, spx, spy, ssi);
+                    }
+                    float u_sel = smp.next1d(sc);
+                    const float2 ul = smp.next2d(sc);
+                    float ul0 = ul.x, ul1 = ul.y;
+                    float u_lobe = smp.next1d(sc);
+                    const float2 ub = smp.next2d(sc);
+                    float ub0 = ub.x, ub1 = ub.y;
                     float u_rr = 0.f;
-                    if (depth + 1u >= sc.rr_depth) u_rr = lcg(state);
+                    if (depth + 1u >= sc.rr_depth) u_rr = smp.next1d(sc);
+                    state = smp.state;
                     LightSample ls;
                     ls.eval.L = v3(0.f);
                     ls.eval.pdf = 0.f;

@@ -16,7 +16,7 @@ using namespace lrk;
 namespace {
 
 struct DeviceArrays {
-    void *vertices{}, *triangles{}, *alias{}, *pdf{}, *meshes{}, *inst_handles{}, *inst_kind{}, *inst_o2w{}, *inst_xform{}, *bvh_nodes{}, *traversal_overflow{}, *textures{}, *texels{}, *env_alias{}, *env_pdf{},
+    void *vertices{}, *triangles{}, *alias{}, *pdf{}, *meshes{}, *inst_handles{}, *inst_kind{}, *inst_o2w{}, *inst_xform{}, *bvh_nodes{}, *traversal_overflow{}, *sobol{}, *vdc{}, *vdc_inv{}, *pmj{}, *blue_noise{}, *pmj_pixels{}, *zsobol_hash{}, *sampler{}, *textures{}, *texels{}, *env_alias{}, *env_pdf{},
         *tri_verts{}, *surfaces{}, *lights{}, *light_handles{}, *camera{};
 };
 
@@ -56,6 +56,7 @@ struct lrk_ctx {
     uint32_t *d_query_cursor{nullptr};
     // options
     bool count_traversal{false}, time_kernels{false};
+    const void *sampler_table_src[3]{nullptr, nullptr, nullptr};// host addresses of the static sampler tables already on the device
     bool pin_host{false};// option pin_host_buffers: page-lock the caller's scene arrays / film buffers on first sight (see pin_range)
     std::unordered_map<const void *, size_t> pinned;
     uint32_t h_overflow{0u};// host copy of DeviceScene::traversal_overflow, fetched with every render / trace call
@@ -273,6 +274,10 @@ void launch_query(lrk_ctx *ctx, int g, bool any_hit, const float4 *d_rays, uint4
 int render_pass(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint32_t spp_begin, uint32_t spp) {
     const uint64_t n = static_cast<uint64_t>(npix) * spp;
     auto &pb = ctx->pb;
+    pb.pass_pixel_list = ctx->d_pixel_list;
+    pb.pass_pixel_offset = pixel_offset;
+    pb.pass_npix = npix;
+    pb.pass_spp_begin = spp_begin;
     const auto &sc = ctx->scene;
     {
         ScopedTimer t{ctx, CAT_OTHER};
@@ -533,6 +538,18 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
         if ((s->surfaces[i].flags & LRK_SURFACE_MAYBE_NON_OPAQUE) && s->integrator.type == LRK_INTEGRATOR_VOLUME_PATH)
             return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: non-opaque surfaces are not supported by the volume path integrator");
     }
+    if (s->sampler.type > LRK_SAMPLER_ZSOBOL) return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: unknown sampler type");
+    if (s->sampler.type != LRK_SAMPLER_INDEPENDENT) {
+        const auto &q = s->sampler;
+        if (s->integrator.type == LRK_INTEGRATOR_VOLUME_PATH)
+            return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: the volume path integrator supports the Independent sampler only");
+        const bool ok = q.spp != 0u && q.sobol_matrices != nullptr &&
+                        (q.type != LRK_SAMPLER_PMJ02BN || (q.pmj_samples && q.blue_noise && q.pmj_pixel_samples && q.tile != 0u && q.spp <= 65536u &&
+                                                           q.pmj_pixel_sample_count == static_cast<uint64_t>(q.tile) * q.tile * q.spp)) &&
+                        (q.type != LRK_SAMPLER_SOBOL || (q.vdc && q.vdc_inv && q.scale != 0u && q.scale <= 0xffffu)) &&
+                        (q.type != LRK_SAMPLER_ZSOBOL || (q.zsobol_hash != nullptr && q.num_base4_digits <= 32u));
+        if (!ok) return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_upload_scene: incomplete sampler record");
+    }
     ctx->textured = false;
     for (uint32_t i = 0; i < s->surface_count; i++)
         if (s->surfaces[i].flags & (LRK_SURFACE_HAS_TEXTURES | LRK_SURFACE_HAS_NORMAL_MAP)) ctx->textured = true;
@@ -569,6 +586,31 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
     if ((rc = upload(ctx, &a.lights, s->lights, s->light_count))) return rc;
     if ((rc = upload(ctx, &a.light_handles, s->light_handles, s->light_count))) return rc;
     if ((rc = upload(ctx, &a.camera, &s->camera, 1))) return rc;
+    if (s->sampler.type != LRK_SAMPLER_INDEPENDENT) {
+        // the static tables (213 KB / 2.6 MB / 1.5 MB) cross the bus once per context: same host address = same table
+        const auto &q = s->sampler;
+        if (ctx->sampler_table_src[0] != q.sobol_matrices) {
+            if ((rc = upload(ctx, &a.sobol, q.sobol_matrices, 1024u * 52u))) return rc;
+            ctx->sampler_table_src[0] = q.sobol_matrices;
+        }
+        if (q.type == LRK_SAMPLER_PMJ02BN) {
+            if (ctx->sampler_table_src[1] != q.pmj_samples) {
+                if ((rc = upload(ctx, &a.pmj, q.pmj_samples, 5u * 65536u * 2u))) return rc;
+                ctx->sampler_table_src[1] = q.pmj_samples;
+            }
+            if (ctx->sampler_table_src[2] != q.blue_noise) {
+                if ((rc = upload(ctx, &a.blue_noise, q.blue_noise, 48u * 128u * 128u))) return rc;
+                ctx->sampler_table_src[2] = q.blue_noise;
+            }
+            if ((rc = upload(ctx, &a.pmj_pixels, q.pmj_pixel_samples, q.pmj_pixel_sample_count * 2u))) return rc;
+        }
+        if (q.type == LRK_SAMPLER_SOBOL) {
+            if ((rc = upload(ctx, &a.vdc, q.vdc, 52u))) return rc;
+            if ((rc = upload(ctx, &a.vdc_inv, q.vdc_inv, 52u))) return rc;
+        }
+        if (q.type == LRK_SAMPLER_ZSOBOL)
+            if ((rc = upload(ctx, &a.zsobol_hash, q.zsobol_hash, 2048u))) return rc;
+    }
     std::vector<uint32_t> handles(static_cast<size_t>(s->instance_count) * 4u), kinds(s->instance_count);
     for (int k = 1; k < 9; k++) ctx->has_kind[k] = false;
     ctx->any_non_opaque = false;
@@ -638,6 +680,20 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
     sc.rr_depth = s->integrator.rr_depth;
     sc.rr_threshold = s->integrator.rr_threshold;
     sc.sampler_seed = s->integrator.sampler_seed;
+    {// the sampler record in device memory, its table pointers replaced by the device copies
+        lrk_sampler rec = s->sampler;
+        rec.sobol_matrices = static_cast<const uint32_t *>(a.sobol);
+        rec.vdc = static_cast<const uint64_t *>(a.vdc);
+        rec.vdc_inv = static_cast<const uint64_t *>(a.vdc_inv);
+        rec.pmj_samples = static_cast<const uint32_t *>(a.pmj);
+        rec.blue_noise = static_cast<const uint16_t *>(a.blue_noise);
+        rec.pmj_pixel_samples = static_cast<const float *>(a.pmj_pixels);
+        rec.zsobol_hash = static_cast<const uint32_t *>(a.zsobol_hash);
+        if ((rc = upload(ctx, &a.sampler, &rec, 1))) return rc;
+        LRK_CUDA(cudaStreamSynchronize(ctx->stream));// `rec` is a stack object
+        sc.sampler_type = rec.type;
+        sc.sampler = static_cast<const lrk_sampler *>(a.sampler);
+    }
     sc.film_clamp = s->film.clamp;
     for (int i = 0; i < 3; i++) sc.film_scale[i] = s->film.scale[i];
     sc.width = s->camera.resolution[0];

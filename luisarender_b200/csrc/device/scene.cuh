@@ -44,6 +44,9 @@ struct DeviceScene {
     uint32_t rr_depth;
     float rr_threshold;
     uint32_t sampler_seed;
+    uint32_t sampler_type;     // LRK_SAMPLER_*: uniform over a launch
+    const lrk_sampler *sampler;// the record in device memory, its table pointers DEVICE copies (a kernel PARAMETER whose address is
+                               // taken would be copied to every thread's local memory)
     // film
     float film_clamp;
     float film_scale[3];

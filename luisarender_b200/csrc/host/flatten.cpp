@@ -2,10 +2,15 @@
 
 #include "envmap.h"
 
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <filesystem>
+#include <fstream>
 #include <map>
 #include <unordered_map>
 
@@ -48,10 +53,173 @@ lrk_scene_desc FlatScene::desc(uint32_t camera_index) const {
     d.environment = environment;
     d.environment.alias = env_alias.empty() ? nullptr : env_alias.data();
     d.environment.pdf = env_pdf.empty() ? nullptr : env_pdf.data();
+    const auto &cam = cameras[camera_index];
+    d.sampler = cam.sampler;
+    if (d.sampler.type != LRK_SAMPLER_INDEPENDENT) {
+        const auto &t = sampler_tables();
+        d.sampler.sobol_matrices = t.sobol_matrices.data();
+        d.sampler.pmj_samples = t.pmj_samples.data();
+        d.sampler.blue_noise = t.blue_noise.data();
+        d.sampler.vdc = cam.vdc.empty() ? nullptr : cam.vdc.data();
+        d.sampler.vdc_inv = cam.vdc_inv.empty() ? nullptr : cam.vdc_inv.data();
+        d.sampler.pmj_pixel_samples = cam.pmj_pixel_samples.empty() ? nullptr : cam.pmj_pixel_samples.data();
+        d.sampler.pmj_pixel_sample_count = cam.pmj_pixel_samples.size() / 2u;
+        d.sampler.zsobol_hash = cam.zsobol_hash.empty() ? nullptr : cam.zsobol_hash.data();
+    }
     return d;
 }
 
+// ---- quasi-Monte-Carlo sampler tables (row f2) --------------------------------------------------------------------------------
+// luisarender_b200/data/sampler_tables.bin (tools/extract_sampler_tables.py): Sobol' generator matrices, van-der-Corput matrices,
+// pmj02bn sets, blue-noise textures - the data of pbrt-v4's samplers that the reference's samplers are built on.  Located next
+// to this library (<lib dir>/../data/) or through LRH_DATA_DIR; loaded once, on first use.
+const SamplerTables &sampler_tables() {
+    static const SamplerTables tables = [] {
+        std::filesystem::path dir;
+        if (auto env = std::getenv("LRH_DATA_DIR")) {
+            dir = env;
+        } else {
+            Dl_info info{};
+            if (dladdr(reinterpret_cast<const void *>(&sampler_tables), &info) == 0 || info.dli_fname == nullptr)
+                throw Error("Cannot locate the host library to find its data directory (set LRH_DATA_DIR).");
+            dir = std::filesystem::path{info.dli_fname}.parent_path().parent_path() / "data";
+        }
+        auto path = dir / "sampler_tables.bin";
+        std::ifstream f{path, std::ios::binary};
+        if (!f) throw Error("Cannot open the sampler tables '" + path.string() + "' (tools/extract_sampler_tables.py writes them).");
+        char magic[4];
+        uint32_t version = 0u;
+        f.read(magic, 4);
+        f.read(reinterpret_cast<char *>(&version), 4);
+        if (!f || std::memcmp(magic, "LRST", 4) != 0 || version != 1u) throw Error("'" + path.string() + "' is not a sampler table file.");
+        SamplerTables t;
+        for (int section = 0; section < 5; section++) {
+            uint32_t tag = 0u, elem = 0u;
+            uint64_t count = 0u;
+            f.read(reinterpret_cast<char *>(&tag), 4);
+            f.read(reinterpret_cast<char *>(&elem), 4);
+            f.read(reinterpret_cast<char *>(&count), 8);
+            auto read_into = [&](auto &vec, uint32_t want_elem, uint64_t want_count) {
+                if (elem != want_elem || count != want_count) throw Error("Unexpected section in '" + path.string() + "'.");
+                vec.resize(count);
+                f.read(reinterpret_cast<char *>(vec.data()), static_cast<std::streamsize>(count * elem));
+            };
+            switch (tag) {
+                case 1u: read_into(t.sobol_matrices, 4u, 1024u * 52u); break;
+                case 2u: read_into(t.vdc, 8u, 25u * 52u); break;
+                case 3u: read_into(t.vdc_inv, 8u, 26u * 52u); break;
+                case 4u: read_into(t.pmj_samples, 4u, 5u * 65536u * 2u); break;
+                case 5u: read_into(t.blue_noise, 2u, 48u * 128u * 128u); break;
+                default: throw Error("Unknown section in '" + path.string() + "'.");
+            }
+            if (!f) throw Error("'" + path.string() + "' is truncated.");
+        }
+        return t;
+    }();
+    return tables;
+}
+
 namespace {
+
+// XXH3_64bits_withSeed for an 8-byte input: what luisa::hash_value(uint64_t) computes (src/compute/src/core/stl/hash.cpp:10-12,
+// seed = hash64_default_seed = 2^61 - 1, hash_fwd.h:10) - ZSobol's per-dimension hashes (zsobol.cpp:71-79).  Published
+// algorithm (xxHash, XXH3_len_4to8_64b + XXH3_rrmxmx); the secret words are bytes 8..23 of its default secret.
+uint64_t xxh3_64_of_u64(uint64_t value, uint64_t seed) {
+    auto rotl64 = [](uint64_t x, int r) { return (x << r) | (x >> (64 - r)); };
+    auto swap32 = [](uint32_t x) { return (x << 24) | ((x << 8) & 0x00ff0000u) | ((x >> 8) & 0x0000ff00u) | (x >> 24); };
+    constexpr uint64_t secret8 = 0x1cad21f72c81017cull, secret16 = 0xdb979083e96dd4deull;// little-endian reads of the secret
+    seed ^= static_cast<uint64_t>(swap32(static_cast<uint32_t>(seed))) << 32;
+    const uint32_t input1 = static_cast<uint32_t>(value), input2 = static_cast<uint32_t>(value >> 32);
+    const uint64_t bitflip = (secret8 ^ secret16) - seed;
+    const uint64_t input64 = input2 + (static_cast<uint64_t>(input1) << 32);
+    uint64_t h = input64 ^ bitflip;
+    h ^= rotl64(h, 49) ^ rotl64(h, 24);
+    h *= 0x9FB21C651E98DF25ull;
+    h ^= (h >> 35) + 8u;
+    h *= 0x9FB21C651E98DF25ull;
+    return h ^ (h >> 28);
+}
+
+uint32_t next_pow2_u32(uint32_t x) {
+    uint32_t p = 1u;
+    while (p < x) p <<= 1u;
+    return p;
+}
+
+// Sampler::Instance::reset(resolution, state_count, spp) of the node's sampler, for one camera
+void flatten_sampler(const Sampler *node, FlatCamera &cam) {
+    auto &s = cam.sampler;
+    s = lrk_sampler{};
+    s.type = node ? node->type : LRK_SAMPLER_INDEPENDENT;
+    s.spp = cam.camera.spp;
+    const uint32_t w = cam.camera.resolution[0], h = cam.camera.resolution[1], spp = cam.camera.spp;
+    if (s.type == LRK_SAMPLER_INDEPENDENT) return;
+    if (spp == 0u) throw Error("The camera's spp must be positive for a table-driven sampler.");
+    const auto &t = sampler_tables();
+    auto log2u = [](uint32_t x) { uint32_t l = 0u; while ((2u << l) <= x) l++; return l; };// bit_width(x) - 1
+    switch (s.type) {
+        case LRK_SAMPLER_PMJ02BN: {// pmj02bn.cpp:103-162
+            auto log4 = [&](uint32_t x) { return log2u(x) / 2u; };
+            auto is_pow4 = [&](uint32_t x) { return x == (1u << (2u * log4(x))); };
+            auto next_pow4 = [&](uint32_t x) { return is_pow4(x) ? x : 1u << (2u * (log4(x) + 1u)); };
+            if (spp > 65536u) throw Error("PMJ02BNSampler only supports up to 65536 samples per pixel (" + std::to_string(spp) + " requested).");
+            uint32_t mask = spp - 1u;
+            mask |= mask >> 1u; mask |= mask >> 2u; mask |= mask >> 4u; mask |= mask >> 8u; mask |= mask >> 16u;
+            s.w = mask;
+            s.tile = 1u << (log4(65536u) - log4(next_pow4(spp)));
+            const size_t count = static_cast<size_t>(s.tile) * s.tile * spp;
+            cam.pmj_pixel_samples.assign(count * 2u, 0.f);
+            std::vector<uint32_t> stored(static_cast<size_t>(s.tile) * s.tile, 0u);
+            for (uint32_t i = 0u; i < 65536u; i++) {
+                // pmj02bn_sample(0, i): the doubles are narrowed to float BEFORE the scaling (make_float2(static_cast<float>(...)))
+                const float sx = static_cast<float>(t.pmj_samples[static_cast<size_t>(i) * 2u] * 0x1p-32);
+                const float sy = static_cast<float>(t.pmj_samples[static_cast<size_t>(i) * 2u + 1u] * 0x1p-32);
+                const float px = sx * static_cast<float>(s.tile), py = sy * static_cast<float>(s.tile);
+                const uint32_t pixel_offset = static_cast<uint32_t>(py) * s.tile + static_cast<uint32_t>(px);
+                if (stored[pixel_offset] == spp) {
+                    if (is_pow4(spp)) throw Error("Invalid pmj02bn pixel sorting state.");
+                    continue;
+                }
+                const size_t at = static_cast<size_t>(pixel_offset) * spp + stored[pixel_offset];
+                cam.pmj_pixel_samples[at * 2u] = px - std::floor(px);
+                cam.pmj_pixel_samples[at * 2u + 1u] = py - std::floor(py);
+                stored[pixel_offset]++;
+            }
+            for (auto c : stored)
+                if (c != spp) throw Error("Invalid pmj02bn pixel sorting state.");
+            break;
+        }
+        case LRK_SAMPLER_SOBOL: {// sobol.cpp:112-131
+            s.scale = next_pow2_u32(std::max(w, h));
+            if (s.scale > 0xffffu) throw Error("Sobol sampler scale is too large.");
+            const uint32_t m = log2u(s.scale);
+            cam.vdc.assign(52u, 0u);
+            cam.vdc_inv.assign(52u, 0u);
+            if (m >= 1u) {
+                for (uint32_t i = 0u; i < 52u; i++) {
+                    cam.vdc[i] = t.vdc[static_cast<size_t>(m - 1u) * 52u + i];
+                    cam.vdc_inv[i] = t.vdc_inv[static_cast<size_t>(m - 1u) * 52u + i];
+                }
+            }
+            break;
+        }
+        case LRK_SAMPLER_PADDED_SOBOL: break;// spp only (padded_sobol.cpp:99-111)
+        case LRK_SAMPLER_ZSOBOL: {// zsobol.cpp:69-103
+            auto log2_ceil = [&](uint32_t x) { return log2u(next_pow2_u32(x)); };// bit_width(next_pow2(x)) - 1
+            s.log2_spp = log2_ceil(spp);
+            const uint32_t log4_spp = (s.log2_spp + 1u) / 2u;
+            s.num_base4_digits = log2_ceil(std::max(w, h)) + log4_spp;
+            cam.zsobol_hash.resize(2048u);
+            for (uint32_t i = 0u; i < 1024u; i++) {
+                const uint64_t hsh = xxh3_64_of_u64((static_cast<uint64_t>(node->seed) << 32u) | i, (1ull << 61u) - 1ull);
+                cam.zsobol_hash[i * 2u] = static_cast<uint32_t>(hsh & 0xffffffffull);
+                cam.zsobol_hash[i * 2u + 1u] = static_cast<uint32_t>(hsh >> 32u);
+            }
+            break;
+        }
+        default: throw Error("Unknown sampler type.");
+    }
+}
 
 uint64_t fnv1a(const void *data, size_t bytes, uint64_t h = 1469598103934665603ull) {
     auto p = static_cast<const unsigned char *>(data);
@@ -405,6 +573,7 @@ std::unique_ptr<FlatScene> flatten_scene(const Scene &scene) {
     if (out->cameras.empty()) throw Error("The scene has no camera.");
 
     auto integ = scene.integrator();
+    for (auto &cam : out->cameras) flatten_sampler(integ->sampler, cam);
     out->integrator.type = integ->kind;
     out->integrator.max_depth = integ->max_depth;
     out->integrator.rr_depth = integ->rr_depth;

@@ -16,6 +16,11 @@ struct FlatCamera {
     lrk_camera camera;
     lrk_film film;
     std::filesystem::path file;
+    // what Sampler::Instance::reset(resolution, spp) prepares for this camera (pointers of `sampler` are filled by desc())
+    lrk_sampler sampler{};
+    std::vector<float> pmj_pixel_samples;       // PMJ02BN: float2[tile * tile * spp]
+    std::vector<uint64_t> vdc, vdc_inv;         // SOBOL: the rows of the van-der-Corput matrices for this resolution
+    std::vector<uint32_t> zsobol_hash;          // ZSOBOL: uint2[1024]
 };
 
 struct FlatScene {
@@ -48,5 +53,14 @@ struct FlatScene {
 };
 
 std::unique_ptr<FlatScene> flatten_scene(const Scene &scene);
+
+// the tables of the quasi-Monte-Carlo samplers (luisarender_b200/data/sampler_tables.bin), loaded on first use
+struct SamplerTables {
+    std::vector<uint32_t> sobol_matrices;// [1024][52]
+    std::vector<uint64_t> vdc, vdc_inv;  // [25][52], [26][52]
+    std::vector<uint32_t> pmj_samples;   // [5][65536][2]
+    std::vector<uint16_t> blue_noise;    // [48][128][128]
+};
+const SamplerTables &sampler_tables();
 
 }// namespace lrh

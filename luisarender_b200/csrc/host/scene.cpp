@@ -640,6 +640,16 @@ struct ColorFilm final : Film {
 struct IndependentSampler final : Sampler {
     IndependentSampler(Scene *s, const NodeDesc *d) : Sampler{s, d} {}
 };
+// the table-driven samplers of row f2: nothing but `seed` in their descriptions (src/samplers/*.cpp); tables and the values
+// Sampler::Instance::reset derives from resolution / spp are attached per camera by flatten_sampler (flatten.cpp)
+template<uint32_t TYPE>
+struct TableSampler final : Sampler {
+    TableSampler(Scene *s, const NodeDesc *d) : Sampler{s, d} { type = TYPE; }
+};
+using PMJ02BNSampler = TableSampler<LRK_SAMPLER_PMJ02BN>;
+using SobolSampler = TableSampler<LRK_SAMPLER_SOBOL>;
+using PaddedSobolSampler = TableSampler<LRK_SAMPLER_PADDED_SOBOL>;
+using ZSobolSampler = TableSampler<LRK_SAMPLER_ZSOBOL>;
 
 struct UniformLightSampler final : LightSampler {
     UniformLightSampler(Scene *s, const NodeDesc *d) : LightSampler{s, d, Tag::LIGHT_SAMPLER} {
@@ -673,6 +683,10 @@ struct VolumePathIntegrator final : Integrator {
 }// namespace
 LRH_PLUGIN("film-color", ColorFilm)
 LRH_PLUGIN("sampler-independent", IndependentSampler)
+LRH_PLUGIN("sampler-pmj02bn", PMJ02BNSampler)
+LRH_PLUGIN("sampler-sobol", SobolSampler)
+LRH_PLUGIN("sampler-paddedsobol", PaddedSobolSampler)
+LRH_PLUGIN("sampler-zsobol", ZSobolSampler)
 LRH_PLUGIN("lightsampler-uniform", UniformLightSampler)
 LRH_PLUGIN("integrator-wavepath", PathIntegrator)
 namespace {

@@ -106,6 +106,7 @@ struct Film : SceneNode {
 struct Sampler : SceneNode {
     Sampler(const Scene *s, const NodeDesc *d);
     uint32_t seed;
+    uint32_t type{LRK_SAMPLER_INDEPENDENT};// LRK_SAMPLER_*: src/samplers/{independent,pmj02bn,sobol,padded_sobol,zsobol}.cpp
 };
 
 struct LightSampler : SceneNode {

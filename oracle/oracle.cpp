@@ -95,10 +95,258 @@ inline float lcg(uint32_t &state) {
     return std::fmin(kOneMinusEpsilon, static_cast<float>(state) * 0x1p-32f);
 }
 
+inline uint32_t xxhash32_uint2(uint32_t px, uint32_t py) {// src/util/rng.cpp (xxhash32(uint2))
+    constexpr uint32_t PRIME32_2 = 2246822519u, PRIME32_3 = 3266489917u, PRIME32_4 = 668265263u, PRIME32_5 = 374761393u;
+    uint32_t h32 = py + PRIME32_5 + px * PRIME32_3;
+    h32 = PRIME32_4 * rotl(h32, 17u);
+    h32 = PRIME32_2 * (h32 ^ (h32 >> 15u));
+    h32 = PRIME32_3 * (h32 ^ (h32 >> 13u));
+    return h32 ^ (h32 >> 16u);
+}
+
+inline uint32_t reverse_bits32(uint32_t v) {
+    v = ((v >> 1u) & 0x55555555u) | ((v & 0x55555555u) << 1u);
+    v = ((v >> 2u) & 0x33333333u) | ((v & 0x33333333u) << 2u);
+    v = ((v >> 4u) & 0x0f0f0f0fu) | ((v & 0x0f0f0f0fu) << 4u);
+    v = ((v >> 8u) & 0x00ff00ffu) | ((v & 0x00ff00ffu) << 8u);
+    return (v >> 16u) | (v << 16u);
+}
+
+// The samplers: src/base/sampler.h:42-48 implemented by src/samplers/independent.cpp:57-82,
+// pmj02bn.cpp:46-207, sobol.cpp:38-166, padded_sobol.cpp:34-146, zsobol.cpp:40-177.  One struct, switched by lrk_sampler::type.
 struct Sampler {
-    uint32_t state;
-    void start(uint32_t px, uint32_t py, uint32_t seed, uint32_t index) { state = xxhash32_uint4(px, py, seed, index); }
-    float generate_1d() { return lcg(state); }
+    const lrk_sampler *cfg{nullptr};
+    uint32_t seed{0u};
+    uint32_t state{0u};      // INDEPENDENT: LCG state
+    uint32_t px{0u}, py{0u}, sample_index{0u}, dimension{0u};
+    uint64_t sobol_index{0u};// SOBOL: index of the sample in the global sequence; ZSOBOL: Morton index
+
+    static uint32_t permutation_element(uint32_t i, uint32_t l, uint32_t w, uint32_t p) {// pmj02bn.cpp:60-86, padded_sobol.cpp:57-90
+        do {
+            i ^= p;
+            i *= 0xe170893du;
+            i ^= p >> 16u;
+            i ^= (i & w) >> 4u;
+            i ^= p >> 8u;
+            i *= 0x0929eb3fu;
+            i ^= p >> 23u;
+            i ^= (i & w) >> 1u;
+            i *= 1u | p >> 27u;
+            i *= 0x6935fa69u;
+            i ^= (i & w) >> 11u;
+            i *= 0x74dcb303u;
+            i ^= (i & w) >> 2u;
+            i *= 0x9e501cc3u;
+            i ^= (i & w) >> 2u;
+            i *= 0xc860a3dfu;
+            i &= w;
+            i ^= i >> 5u;
+        } while (i >= l);
+        return (i + p) % l;
+    }
+    static uint32_t fast_owen_scramble(uint32_t seed, uint32_t v) {// sobol.cpp:40-48
+        v = reverse_bits32(v);
+        v ^= v * 0x3d20adeau;
+        v += seed;
+        v *= (seed >> 16u) | 1u;
+        v ^= v * 0x05526c56u;
+        v ^= v * 0x53a22864u;
+        return reverse_bits32(v);
+    }
+    uint32_t sobol_bits(uint64_t a, uint32_t dim) const {// sobol.cpp:52-62: the generator matrix of `dim` applied to the index
+        uint32_t v = 0u;
+        for (uint32_t i = dim * 52u; a != 0u; a >>= 1u, i++)
+            if (a & 1u) v ^= cfg->sobol_matrices[i];
+        return v;
+    }
+    float blue_noise(uint32_t tex_index, uint32_t x, uint32_t y) const {// pmj02bn.cpp:46-51: p.yx % 128, SHORT1 storage = u16 / 65535
+        const uint32_t u = y % 128u, v = x % 128u, wv = tex_index % 48u;
+        return static_cast<float>(cfg->blue_noise[(static_cast<size_t>(wv) * 128u + v) * 128u + u]) / 65535.f;
+    }
+    void pmj_sample(uint32_t set_id, uint32_t sample_id, float &x, float &y) const {// pmj02bn.cpp:53-58
+        const uint32_t *e = cfg->pmj_samples + (static_cast<size_t>(set_id % 5u) * 65536u + sample_id) * 2u;
+        x = static_cast<float>(e[0]) * 0x1p-32f;
+        y = static_cast<float>(e[1]) * 0x1p-32f;
+    }
+    static uint64_t mix_bits(uint64_t v) {// zsobol.cpp:112-119 (the last xor uses the HIGH word: v.hi() >> 1)
+        v ^= v >> 31u;
+        v *= 0x7fb5d329728ea185ull;
+        v ^= v >> 27u;
+        v *= 0x81dadef4bc2dd44dull;
+        v ^= (v >> 32u) >> 1u;
+        return v;
+    }
+    uint64_t zsobol_sample_index() const {// zsobol.cpp:104-140
+        static const uint8_t permutations[24][4] = {
+            {0, 1, 2, 3}, {0, 1, 3, 2}, {0, 2, 1, 3}, {0, 2, 3, 1}, {0, 3, 2, 1}, {0, 3, 1, 2}, {1, 0, 2, 3}, {1, 0, 3, 2},
+            {1, 2, 0, 3}, {1, 2, 3, 0}, {1, 3, 2, 0}, {1, 3, 0, 2}, {2, 1, 0, 3}, {2, 1, 3, 0}, {2, 0, 1, 3}, {2, 0, 3, 1},
+            {2, 3, 0, 1}, {2, 3, 1, 0}, {3, 1, 2, 0}, {3, 1, 0, 2}, {3, 2, 1, 0}, {3, 2, 0, 1}, {3, 0, 2, 1}, {3, 0, 1, 2}};
+        uint64_t sample = 0u;
+        const bool pow2_samples = (cfg->log2_spp & 1u) != 0u;
+        const int last_digit = pow2_samples ? 1 : 0;
+        const uint64_t morton = sobol_index;
+        for (int i = static_cast<int>(cfg->num_base4_digits) - 1; i >= last_digit; i--) {
+            const uint32_t digit_shift = 2u * static_cast<uint32_t>(i) - (pow2_samples ? 1u : 0u);
+            const uint32_t digit = static_cast<uint32_t>(morton >> digit_shift) & 3u;
+            const uint64_t higher = morton >> (digit_shift + 2u);
+            const uint32_t p = static_cast<uint32_t>((mix_bits(higher ^ (static_cast<uint64_t>(dimension * 0x55555555u))) >> 24u) % 24u);
+            sample |= static_cast<uint64_t>(permutations[p][digit]) << digit_shift;
+        }
+        if (pow2_samples) {
+            const uint64_t digit = (morton & 1u) ^ (mix_bits((morton >> 1u) ^ static_cast<uint64_t>(dimension * 0x55555555u)) & 1u);
+            sample |= digit;
+        }
+        return sample;
+    }
+    static uint64_t left_shift2(uint64_t x) {// zsobol.cpp:144-152
+        x = (x ^ (x << 16u)) & 0x0000ffff0000ffffull;
+        x = (x ^ (x << 8u)) & 0x00ff00ff00ff00ffull;
+        x = (x ^ (x << 4u)) & 0x0f0f0f0f0f0f0f0full;
+        x = (x ^ (x << 2u)) & 0x3333333333333333ull;
+        x = (x ^ (x << 1u)) & 0x5555555555555555ull;
+        return x;
+    }
+
+    void start(const lrk_scene_desc &sc, uint32_t x, uint32_t y, uint32_t index) {
+        cfg = &sc.sampler;
+        seed = sc.integrator.sampler_seed;
+        px = x;
+        py = y;
+        sample_index = index;
+        switch (cfg->type) {
+            case LRK_SAMPLER_PMJ02BN: dimension = 2u; break;
+            case LRK_SAMPLER_SOBOL: {// sobol.cpp:64-96,132-137: the index whose first two dimensions fall into this pixel
+                dimension = 2u;
+                const uint32_t scale = cfg->scale;
+                uint32_t m = 0u;
+                while ((1u << m) < scale) m++;
+                if (m == 0u) { sobol_index = index; break; }
+                uint64_t idx = static_cast<uint64_t>(index) << (2u * m);
+                uint64_t delta = 0u;
+                uint32_t frame = index;
+                for (uint32_t c = 0u; frame != 0u; frame >>= 1u, c++)
+                    if (frame & 1u) delta ^= cfg->vdc[c];
+                uint64_t b = delta ^ ((static_cast<uint64_t>(x) << m) | y);
+                for (uint32_t d = 0u; b != 0u; b >>= 1u, d++)
+                    if (b & 1u) idx ^= cfg->vdc_inv[d];
+                sobol_index = idx;
+                break;
+            }
+            case LRK_SAMPLER_PADDED_SOBOL: dimension = 0u; break;
+            case LRK_SAMPLER_ZSOBOL:
+                dimension = 0u;
+                sobol_index = (((left_shift2(y) << 1u) | left_shift2(x)) << cfg->log2_spp) | index;
+                break;
+            default: state = xxhash32_uint4(x, y, seed, index); break;
+        }
+    }
+    float generate_1d() {
+        switch (cfg->type) {
+            case LRK_SAMPLER_PMJ02BN: {// pmj02bn.cpp:179-191
+                const uint32_t hash = xxhash32_uint4(px, py, dimension, seed);
+                const uint32_t index = permutation_element(sample_index, cfg->spp, cfg->w, hash);
+                const float delta = blue_noise(dimension, px, py);
+                const float u = (static_cast<float>(index) + delta) * (1.f / static_cast<float>(cfg->spp));
+                dimension += 1u;
+                return std::fmin(std::fmax(u, 0.f), kOneMinusEpsilon);
+            }
+            case LRK_SAMPLER_SOBOL: {// sobol.cpp:148-154
+                if (dimension >= 1024u) dimension = 2u;
+                const uint32_t hash = xxhash32_uint2(dimension, seed);
+                const float u = static_cast<float>(fast_owen_scramble(hash, sobol_bits(sobol_index, dimension))) * 0x1p-32f;
+                dimension += 1u;
+                return std::fmin(std::fmax(u, 0.f), kOneMinusEpsilon);
+            }
+            case LRK_SAMPLER_PADDED_SOBOL: {// padded_sobol.cpp:124-133
+                const uint32_t hash = xxhash32_uint4(px, py, sample_index ^ seed, dimension);
+                uint32_t w = cfg->spp - 1u;
+                w |= w >> 1u; w |= w >> 2u; w |= w >> 4u; w |= w >> 8u; w |= w >> 16u;
+                const uint32_t index = permutation_element(sample_index, cfg->spp, w, hash);
+                const float u = std::fmin(static_cast<float>(fast_owen_scramble(hash, sobol_bits(index, 0u))) * 0x1p-32f, kOneMinusEpsilon);
+                dimension += 1u;
+                return u;
+            }
+            case LRK_SAMPLER_ZSOBOL: {// zsobol.cpp:164-169
+                const uint64_t si = zsobol_sample_index();
+                const uint32_t hash = cfg->zsobol_hash[dimension * 2u];
+                dimension = (dimension + 1u) % 1024u;
+                return std::fmin(static_cast<float>(fast_owen_scramble(hash, sobol_bits(si, 0u))) * 0x1p-32f, kOneMinusEpsilon);
+            }
+            default: return lcg(state);
+        }
+    }
+    void generate_2d(float &ux, float &uy) {
+        switch (cfg->type) {
+            case LRK_SAMPLER_PMJ02BN: {// pmj02bn.cpp:192-207
+                uint32_t index = sample_index;
+                const uint32_t pmj_instance = dimension / 2u;
+                if (pmj_instance >= 5u) {
+                    const uint32_t hash = xxhash32_uint4(px, py, dimension, seed);
+                    index = permutation_element(sample_index, cfg->spp, cfg->w, hash);
+                }
+                float sx, sy;
+                pmj_sample(pmj_instance, index, sx, sy);
+                const float u0 = sx + blue_noise(dimension, px, py), u1 = sy + blue_noise(dimension + 1u, px, py);
+                ux = u0 - std::floor(u0);
+                uy = u1 - std::floor(u1);
+                dimension += 2u;
+                return;
+            }
+            case LRK_SAMPLER_SOBOL: {// sobol.cpp:155-163
+                if (dimension + 1u >= 1024u) dimension = 2u;
+                const uint32_t hx = xxhash32_uint2(dimension, seed), hy = xxhash32_uint2(dimension + 1u, seed);
+                const float x = static_cast<float>(fast_owen_scramble(hx, sobol_bits(sobol_index, dimension))) * 0x1p-32f;
+                const float y = static_cast<float>(fast_owen_scramble(hy, sobol_bits(sobol_index, dimension + 1u))) * 0x1p-32f;
+                dimension += 2u;
+                ux = std::fmin(std::fmax(x, 0.f), kOneMinusEpsilon);
+                uy = std::fmin(std::fmax(y, 0.f), kOneMinusEpsilon);
+                return;
+            }
+            case LRK_SAMPLER_PADDED_SOBOL: {// padded_sobol.cpp:134-146
+                const uint32_t hx = xxhash32_uint4(px, py, sample_index ^ seed, dimension);
+                const uint32_t hy = xxhash32_uint4(px, py, sample_index ^ seed, dimension + 1u);
+                uint32_t w = cfg->spp - 1u;
+                w |= w >> 1u; w |= w >> 2u; w |= w >> 4u; w |= w >> 8u; w |= w >> 16u;
+                const uint32_t index = permutation_element(sample_index, cfg->spp, w, hx);
+                ux = std::fmin(static_cast<float>(fast_owen_scramble(hx, sobol_bits(index, 0u))) * 0x1p-32f, kOneMinusEpsilon);
+                uy = std::fmin(static_cast<float>(fast_owen_scramble(hy, sobol_bits(index, 1u))) * 0x1p-32f, kOneMinusEpsilon);
+                dimension += 2u;
+                return;
+            }
+            case LRK_SAMPLER_ZSOBOL: {// zsobol.cpp:170-177
+                const uint64_t si = zsobol_sample_index();
+                const uint32_t hx = cfg->zsobol_hash[dimension * 2u], hy = cfg->zsobol_hash[dimension * 2u + 1u];
+                dimension = (dimension + 2u) % 1024u;
+                ux = std::fmin(static_cast<float>(fast_owen_scramble(hx, sobol_bits(si, 0u))) * 0x1p-32f, kOneMinusEpsilon);
+                uy = std::fmin(static_cast<float>(fast_owen_scramble(hy, sobol_bits(si, 1u))) * 0x1p-32f, kOneMinusEpsilon);
+                return;
+            }
+            default:
+                ux = lcg(state);
+                uy = lcg(state);
+                return;
+        }
+    }
+    void generate_pixel_2d(float &ux, float &uy) {// sampler.h:48: generate_2d unless the sampler stratifies the pixel itself
+        switch (cfg->type) {
+            case LRK_SAMPLER_PMJ02BN: {// pmj02bn.cpp:209-213
+                const uint32_t tx = px % cfg->tile, ty = py % cfg->tile;
+                const size_t offset = static_cast<size_t>(tx + ty * cfg->tile) * cfg->spp + sample_index;
+                ux = cfg->pmj_pixel_samples[offset * 2u];
+                uy = cfg->pmj_pixel_samples[offset * 2u + 1u];
+                return;
+            }
+            case LRK_SAMPLER_SOBOL: {// sobol.cpp:164-170: the unscrambled first two dimensions, relative to the pixel
+                const float x = static_cast<float>(sobol_bits(sobol_index, 0u)) * 0x1p-32f;
+                const float y = static_cast<float>(sobol_bits(sobol_index, 1u)) * 0x1p-32f;
+                const float s = static_cast<float>(cfg->scale);
+                ux = std::fmin(std::fmax(x * s - static_cast<float>(px), 0.f), kOneMinusEpsilon);
+                uy = std::fmin(std::fmax(y * s - static_cast<float>(py), 0.f), kOneMinusEpsilon);
+                return;
+            }
+            default: generate_2d(ux, uy); return;
+        }
+    }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -1731,8 +1979,9 @@ lrk_surface resolve_surface(const lrk_scene_desc &sc, const lrk_surface &node, c
 // ------------------------------------------------------------------------------------------------
 V3 path_li(const lrk_scene_desc &sc, uint32_t px, uint32_t py, uint32_t sample_index, oracle_counters *cnt) {
     Sampler sampler;
-    sampler.start(px, py, sc.integrator.sampler_seed, sample_index);
-    float uf0 = sampler.generate_1d(), uf1 = sampler.generate_1d();
+    sampler.start(sc, px, py, sample_index);
+    float uf0, uf1;
+    sampler.generate_pixel_2d(uf0, uf1);
     float camera_weight;
     lrk_ray ray = generate_camera_ray(sc.camera, px, py, uf0, uf1, camera_weight);
     V3 beta = v3(camera_weight);
@@ -1759,9 +2008,11 @@ V3 path_li(const lrk_scene_desc &sc, uint32_t px, uint32_t py, uint32_t sample_i
         if (!it.shape.has_surface()) break;
         if (cnt) cnt->path_vertices++;
         float u_light_selection = sampler.generate_1d();
-        float ul0 = sampler.generate_1d(), ul1 = sampler.generate_1d();
+        float ul0, ul1;
+        sampler.generate_2d(ul0, ul1);
         float u_lobe = sampler.generate_1d();
-        float ub0 = sampler.generate_1d(), ub1 = sampler.generate_1d();
+        float ub0, ub1;
+        sampler.generate_2d(ub0, ub1);
         float u_rr = 0.f;
         if (depth + 1u >= sc.integrator.rr_depth) u_rr = sampler.generate_1d();
         LightSample ls = sample_light(sc, it, u_light_selection, ul0, ul1);
@@ -1965,14 +2216,16 @@ Transmittance volume_transmittance(const lrk_scene_desc &sc, PCG32 &rng, lrk_ray
 V3 volume_path_li(const lrk_scene_desc &sc, uint32_t px, uint32_t py, uint32_t sample_index, oracle_counters *cnt) {
     const lrk_medium &medium = sc.environment_medium;
     Sampler sampler;
-    sampler.start(px, py, sc.integrator.sampler_seed, sample_index);
-    float uf0 = sampler.generate_1d(), uf1 = sampler.generate_1d();
+    sampler.start(sc, px, py, sample_index);
+    float uf0, uf1;
+    sampler.generate_pixel_2d(uf0, uf1);
     float camera_weight;
     lrk_ray ray = generate_camera_ray(sc.camera, px, py, uf0, uf1, camera_weight);
     V3 beta = v3(camera_weight);
     V3 Li = v3(0.f);
     // PCG32 rng(U64(as<UInt2>(sampler()->generate_2d()))): x = high word, y = low word (src/util/u64.h:48,58-59)
-    float s0 = sampler.generate_1d(), s1 = sampler.generate_1d();
+    float s0, s1;
+    sampler.generate_2d(s0, s1);
     uint32_t hi, lo;
     std::memcpy(&hi, &s0, 4);
     std::memcpy(&lo, &s1, 4);
@@ -1992,7 +2245,8 @@ V3 volume_path_li(const lrk_scene_desc &sc, uint32_t px, uint32_t py, uint32_t s
         MediumSample ms;
         {// the tracker is never vacuum: direct light at the ray origin, then distance sampling
             float u_sel = sampler.generate_1d();
-            float ul0 = sampler.generate_1d(), ul1 = sampler.generate_1d();
+            float ul0, ul1;
+        sampler.generate_2d(ul0, ul1);
             Interaction it_medium;// Interaction{ray->origin()}: pg = ng = origin, default frame, zero offset factor
             it_medium.pg = ro;
             it_medium.ng = ro;
@@ -2020,9 +2274,11 @@ V3 volume_path_li(const lrk_scene_desc &sc, uint32_t px, uint32_t py, uint32_t s
             if (!it.shape.has_surface()) break;
             if (cnt) cnt->path_vertices++;
             float u_light_selection = sampler.generate_1d();
-            float ul0 = sampler.generate_1d(), ul1 = sampler.generate_1d();
+            float ul0, ul1;
+        sampler.generate_2d(ul0, ul1);
             float u_lobe = sampler.generate_1d();
-            float ub0 = sampler.generate_1d(), ub1 = sampler.generate_1d();
+            float ub0, ub1;
+        sampler.generate_2d(ub0, ub1);
             LightSample ls = sample_light(sc, it, u_light_selection, ul0, ul1);
             Transmittance T = volume_transmittance(sc, rng, ls.shadow_ray, &tc, cnt, nullptr);
             V3 wo = -v3(ray.d[0], ray.d[1], ray.d[2]);
@@ -2231,8 +2487,9 @@ void oracle_sample_filter(const lrk_scene_desc *scene, const float u[2], float o
 void oracle_generate_ray(const lrk_scene_desc *scene, uint32_t px, uint32_t py, uint32_t sample_index, lrk_ray *ray,
                          float weight[3], uint32_t *rng_state) {
     Sampler s;
-    s.start(px, py, scene->integrator.sampler_seed, sample_index);
-    float u0 = s.generate_1d(), u1 = s.generate_1d();
+    s.start(*scene, px, py, sample_index);
+    float u0, u1;
+    s.generate_pixel_2d(u0, u1);
     float w;
     *ray = generate_camera_ray(scene->camera, px, py, u0, u1, w);
     weight[0] = weight[1] = weight[2] = w;

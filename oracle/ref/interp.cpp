@@ -1124,6 +1124,14 @@ private:
                 res().bindless_tex2d_read(array, slot_index, conv(xy[0], Tag::UINT32).u, conv(xy[1], Tag::UINT32).u, out);
                 return from_lanes(e->type(), {mk(out[0]), mk(out[1]), mk(out[2]), mk(out[3])});
             }
+            case CallOp::BINDLESS_TEXTURE3D_READ: {// point reads of a volume: the PMJ02BN sampler's blue-noise textures
+                auto array = handle_of(args[0], Slot::Kind::BINDLESS_ARRAY);
+                auto slot_index = conv(F(1)[0], Tag::UINT32).u;
+                auto xyz = F(2);
+                float out[4];
+                res().bindless_tex3d_read(array, slot_index, conv(xyz[0], Tag::UINT32).u, conv(xyz[1], Tag::UINT32).u, conv(xyz[2], Tag::UINT32).u, out);
+                return from_lanes(e->type(), {mk(out[0]), mk(out[1]), mk(out[2]), mk(out[3])});
+            }
             case CallOp::BINDLESS_TEXTURE2D_SIZE: {
                 auto array = handle_of(args[0], Slot::Kind::BINDLESS_ARRAY);
                 uint32_t size[2];

@@ -62,6 +62,7 @@ struct DeviceResources {
     virtual void bindless_tex2d_sample(uint64_t array, uint32_t slot, float u, float v, float out[4]) = 0;
     virtual void bindless_tex2d_size(uint64_t array, uint32_t slot, uint32_t out[2]) = 0;
     virtual void bindless_tex2d_read(uint64_t array, uint32_t slot, uint32_t x, uint32_t y, float out[4]) = 0;
+    virtual void bindless_tex3d_read(uint64_t array, uint32_t slot, uint32_t x, uint32_t y, uint32_t z, float out[4]) = 0;
 };
 
 /* one argument of the entry function */

@@ -43,14 +43,15 @@ struct BindlessObject {
         size_t offset{0u};
         uint64_t tex2d{0u};
         Sampler sampler{};
+        uint64_t tex3d{0u};
     };
     luisa::vector<Slot> slots;
 };
 
 struct TextureObject {
     PixelStorage storage{PixelStorage::FLOAT4};
-    uint32_t width{0u}, height{0u};
-    luisa::vector<std::byte> texels;// level 0, rows tightly packed
+    uint32_t width{0u}, height{0u}, depth{1u};
+    luisa::vector<std::byte> texels;// level 0, rows tightly packed (slices back to back for a volume)
 };
 
 float half_bits_to_float(uint16_t h) noexcept {
@@ -235,12 +236,14 @@ public:
     // ---- textures: not needed by the paths exercised (constant textures live in a buffer, the film is a buffer)
     // ---- textures: 2D, level 0 (the image-texture plugin samples without LOD, src/textures/image.cpp:166)
     ResourceCreationInfo create_texture(PixelFormat format, uint dimension, uint width, uint height, uint depth, uint, bool, bool) noexcept override {
-        LUISA_ASSERT(dimension == 2u && depth == 1u, "interp: only 2D textures are implemented.");
+        // 2D images, and 3D volumes for point reads (the blue-noise volume of the PMJ02BN sampler, pmj02bn.cpp:91-101)
+        LUISA_ASSERT(dimension == 2u || dimension == 3u, "interp: only 2D / 3D textures are implemented.");
         auto t = new TextureObject;
         t->storage = pixel_format_to_storage(format);
         t->width = width;
         t->height = height;
-        t->texels.resize(pixel_storage_size(t->storage, make_uint3(width, height, 1u)), std::byte{0});
+        t->depth = dimension == 3u ? depth : 1u;
+        t->texels.resize(pixel_storage_size(t->storage, make_uint3(width, height, t->depth)), std::byte{0});
         return {reinterpret_cast<uint64_t>(t), t};
     }
     void destroy_texture(uint64_t handle) noexcept override { delete object<TextureObject>(handle); }
@@ -361,7 +364,8 @@ public:
                 auto t = object<TextureObject>(c->handle());
                 if (c->level() != 0u) { return; }// mip levels are never sampled here
                 auto size = c->size();
-                LUISA_ASSERT(all(c->offset() == make_uint3(0u)) && size.x == t->width && size.y == t->height, "interp: partial texture uploads.");
+                LUISA_ASSERT(all(c->offset() == make_uint3(0u)) && size.x == t->width && size.y == t->height && size.z == t->depth,
+                             "interp: partial texture uploads.");
                 std::memcpy(t->texels.data(), c->data(), t->texels.size());
             }
             void visit(const TextureDownloadCommand *) noexcept override { LUISA_ERROR_WITH_LOCATION("interp: textures."); }
@@ -409,7 +413,8 @@ public:
                     } else if (m.tex2d.op == Op::REMOVE) {
                         a->slots[m.slot].tex2d = 0u;
                     }
-                    if (m.tex3d.op == Op::EMPLACE) { LUISA_ERROR_WITH_LOCATION("interp: bindless 3D textures."); }
+                    if (m.tex3d.op == Op::EMPLACE) { a->slots[m.slot].tex3d = m.tex3d.handle; }
+                    else if (m.tex3d.op == Op::REMOVE) { a->slots[m.slot].tex3d = 0u; }
                 }
             }
             void visit(const ShaderDispatchCommand *c) noexcept override { device->run(c); }
@@ -474,11 +479,11 @@ public:
 
     // The reference's software sampler: src/compute/src/rust/luisa_compute_backend_impl/src/cpu/codegen/cpu_texture.h
     // (:63 unorm conversion, :369-372 out-of-bounds reads return zero, :418-464 coordinates + bilinear, :489-493 point)
-    static void read_texel(const TextureObject *t, uint32_t x, uint32_t y, float out[4]) {
+    static void read_texel(const TextureObject *t, uint32_t x, uint32_t y, float out[4], uint32_t z = 0u) {
         out[0] = out[1] = out[2] = out[3] = 0.f;
-        if (!(x < t->width && y < t->height)) { return; }
+        if (!(x < t->width && y < t->height && z < t->depth)) { return; }
         auto channels = pixel_storage_channel_count(t->storage);
-        auto index = static_cast<size_t>(y) * t->width + x;
+        auto index = (static_cast<size_t>(z) * t->height + y) * t->width + x;
         for (auto c = 0u; c < channels; c++) {
             switch (t->storage) {
                 case PixelStorage::BYTE1:
@@ -548,6 +553,11 @@ public:
     }
     void bindless_tex2d_read(uint64_t array, uint32_t slot, uint32_t x, uint32_t y, float out[4]) override {
         read_texel(object<TextureObject>(tex_slot(array, slot).tex2d), x, y, out);
+    }
+    void bindless_tex3d_read(uint64_t array, uint32_t slot, uint32_t x, uint32_t y, uint32_t z, float out[4]) override {
+        auto a = object<BindlessObject>(array);
+        if (slot >= a->slots.size() || a->slots[slot].tex3d == 0u) { throw std::runtime_error("empty bindless 3D texture slot"); }
+        read_texel(object<TextureObject>(a->slots[slot].tex3d), x, y, out, z);
     }
 
     std::vector<Candidate> candidates(uint64_t accel, const refinterp::RayData &ray, uint32_t mask) override {

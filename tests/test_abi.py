@@ -40,11 +40,11 @@ def test_struct_layouts_match_c(tmp_path):
         "lrk_vertex": F.Vertex, "lrk_triangle": F.Triangle, "lrk_alias_entry": F.AliasEntry, "lrk_ray": F.Ray,
         "lrk_hit": F.Hit, "lrk_mesh": F.Mesh, "lrk_bvh_node": F.BvhNode, "lrk_instance": F.Instance,
         "lrk_surface": F.Surface, "lrk_texture": F.Texture, "lrk_light": F.Light, "lrk_light_handle": F.LightHandle, "lrk_camera": F.Camera,
-        "lrk_film": F.Film, "lrk_integrator": F.Integrator, "lrk_medium": F.Medium, "lrk_environment": F.Environment, "lrk_scene_desc": F.SceneDesc,
+        "lrk_film": F.Film, "lrk_integrator": F.Integrator, "lrk_medium": F.Medium, "lrk_environment": F.Environment, "lrk_sampler": F.Sampler, "lrk_scene_desc": F.SceneDesc,
         "lrk_device_cfg": F.DeviceCfg, "lrk_stats": F.Stats, "lrh_scene_info": F.SceneInfo,
     }
     offsets = [("lrk_scene_desc", "camera"), ("lrk_scene_desc", "integrator"), ("lrk_scene_desc", "environment_medium"),
-               ("lrk_scene_desc", "light_handles"), ("lrk_scene_desc", "texels"), ("lrk_scene_desc", "environment"), ("lrk_environment", "alias"), ("lrk_surface", "tex"), ("lrk_stats", "trace_closest_ms"), ("lrk_camera", "filter_alias_indices")]
+               ("lrk_scene_desc", "light_handles"), ("lrk_scene_desc", "texels"), ("lrk_scene_desc", "environment"), ("lrk_scene_desc", "sampler"), ("lrk_sampler", "zsobol_hash"), ("lrk_environment", "alias"), ("lrk_surface", "tex"), ("lrk_stats", "trace_closest_ms"), ("lrk_camera", "filter_alias_indices")]
     src = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{REPO / "include" / "lrh.h"}"', "int main(void){"]
     for name in structs:
         src.append(f'printf("{name} %zu\\n", sizeof({name}));')

@@ -36,7 +36,9 @@ CASES = ["cornell_wavepath", "cornell_megapath", "cornell_russian_roulette", "sp
          "materials_wavepath", "materials_megapath_rr", "textured", "textured_wrappers", "environment_image",
          "config_c3_full_scene", "config_c4_full_scene", "cornell_filter_gaussian", "cornell_filter_triangle",
          "cornell_filter_mitchell", "cornell_filter_lanczossinc", "cornell_film_and_light_options", "materials_mix", "flatten_stress", "spheres_disney_all_lobes",
-         "spheres_medium_isotropic", "subdivision", "swizzle", "checkerboard", "spheres_disney_transmissive"]
+         "spheres_medium_isotropic", "subdivision", "swizzle", "checkerboard", "spheres_disney_transmissive",
+         "cornell_sampler_pmj02bn", "cornell_sampler_sobol", "cornell_sampler_paddedsobol", "cornell_sampler_zsobol",
+         "spheres_sampler_pmj02bn", "spheres_sampler_sobol", "spheres_sampler_paddedsobol", "spheres_sampler_zsobol"]
 
 
 @pytest.fixture(scope="module")
@@ -94,7 +96,9 @@ def test_fixture_is_what_the_reference_renders_now(golden):
                                   "materials_megapath_rr", "textured", "textured_wrappers", "environment_image",
                                   "config_c3_full_scene", "cornell_filter_gaussian", "cornell_filter_mitchell",
                                   "cornell_film_and_light_options", "materials_mix", "flatten_stress", "spheres_disney_all_lobes",
-                                  "subdivision", "spheres_disney_transmissive"])
+                                  "subdivision", "spheres_disney_transmissive",
+                                  "cornell_sampler_pmj02bn", "cornell_sampler_sobol", "cornell_sampler_paddedsobol", "cornell_sampler_zsobol",
+                                  "spheres_sampler_pmj02bn", "spheres_sampler_sobol", "spheres_sampler_paddedsobol", "spheres_sampler_zsobol"])
 def test_cuda_film_matches_the_reference_render(golden, name, gpu_renderer):
     source, scene, desc = _scene(golden, name)
     want = golden[f"{name}/image"][..., :3]

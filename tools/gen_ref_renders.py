@@ -73,6 +73,14 @@ def cases() -> dict[str, str]:
         return "\n".join(out)
     c["spheres_disney_transmissive"] = _transmissive(
         scenes.instanced_spheres(resolution=(32, 18), spp=4, depth=8, rr_depth=2, **spheres)).replace('"spheres.exr"', '"trans.exr"')
+    # row f2: the table-driven samplers.  Cornell @4 spp with each; the sphere scene with sample counts that are NOT the samplers'
+    # favourite powers (pmj02bn: 8 is no power of 4 -> its pixel-sample sorting skips entries; Sobol' / PaddedSobol: 3 is no power of
+    # 2; ZSobol: log2(2) is odd -> the half-digit branch), depth 6 = 30 dimensions per path
+    for smp in ("PMJ02BN", "Sobol", "PaddedSobol", "ZSobol"):
+        c[f"cornell_sampler_{smp.lower()}"] = base.replace("sampler : Independent", f"sampler : {smp}").replace('"cornell.exr"', f'"{smp.lower()}.exr"')
+    for smp, n in (("PMJ02BN", 8), ("Sobol", 3), ("PaddedSobol", 3), ("ZSobol", 2)):
+        c[f"spheres_sampler_{smp.lower()}"] = (scenes.instanced_spheres(resolution=(32, 18), spp=n, depth=6, **spheres)
+                                               .replace("sampler : Independent", f"sampler : {smp}").replace('"spheres.exr"', f'"s{smp.lower()}.exr"'))
     # the medium path with an isotropic phase function (|g| < 1e-3 branch) and per-channel coefficients
     c["spheres_medium_isotropic"] = (c["spheres_medium"].replace("g { 0.3 }", "g { 0.0 }")
                                      .replace("sigma_a : Constant { v { 0.01, 0.01, 0.01 } }", "sigma_a : Constant { v { 0.02, 0.01, 0.005 } }")
