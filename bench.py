@@ -15,7 +15,9 @@ e2e    : Msamples/s through the C-ABI with HOST buffers — every step uploads t
          (lrk_upload_scene), renders, and downloads the normalised film (lrk_download_film).
 roofline: the closest-hit traversal kernel: algorithmic bytes (48 B per ray + 64 B per BVH node visited
          + 48 B per triangle tested + 64 B per instance entered, counted by the kernel's counting variant on the same
-         deterministic workload) / CUDA-event time of its launches inside the timed region, against the measured HBM peak.
+         deterministic workload) / CUDA-event time of its launches inside the timed region, against the measured HBM peak;
+         next to it dram_frac (bytes that really reached DRAM, from the committed ncu capture) and the issue-side figures
+         (issue-slot utilisation x active lanes per instruction): the hierarchy is cache resident, issue bounds the kernel.
 cpu_baseline: the CPU oracle (a port of the reference estimator; the reference's own `cpu` backend cannot be built here)
          on all host cores, on a bounded tile sample of the same frame.
 --impl reference: times that CPU implementation as its own arm (rank 0 only).
@@ -150,6 +152,16 @@ def cpu_oracle_rate(desc, target_seconds: float, spp: int, threads: int = 0):
     return cnt["samples"] / dt * 1e-6, cnt["samples"], dt, desc_s, world, st
 
 
+def cpu_quota() -> str | None:
+    """The cgroup CPU limit of this process, if any ('max 100000' = none)."""
+    for p in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            return Path(p).read_text().strip()
+        except OSError:
+            continue
+    return None
+
+
 def cpu_thread_scaling(desc, spp: int) -> list[dict]:
     """The same CPU implementation at 1, 1/4, 1/2 and all of the host's threads, each on its own bounded sample (~2 s):
     shows whether the all-threads figure is a fed-thread figure."""
@@ -199,16 +211,21 @@ def run_reference(args, rank: int):
     cores = os.cpu_count() or 1
     scene = build_scene()
     desc = scene.desc()
+    # "all the host threads it can use": the box may expose more logical CPUs than it lets a process run (SMT siblings, a cgroup
+    # quota) - 128 threads were SLOWER than 64 on one benchmark box - so the arm first measures the port at 1, 1/4, 1/2 and all of
+    # the logical CPUs (~2 s each) and then runs its timed steps with the fastest count
+    scaling = cpu_thread_scaling(desc, SPP_PER_STEP)
+    threads = max(scaling, key=lambda r: r["value"])["threads"]
     # every step renders the same share of the frame's tiles: about 2 s of work, and never fewer than MIN_ITEMS_PER_THREAD
     # work items per host thread (the calibration inside cpu_oracle_rate is the first warm-up)
-    _, _, _, _, world, _ = cpu_oracle_rate(desc, 2.0, SPP_PER_STEP)
+    _, _, _, _, world, _ = cpu_oracle_rate(desc, 2.0, SPP_PER_STEP, threads=threads)
     for w in range(args.warmup):
-        O.render(desc, w * SPP_PER_STEP, (w + 1) * SPP_PER_STEP, rank=0, world=world, tile_size=32)
+        O.render(desc, w * SPP_PER_STEP, (w + 1) * SPP_PER_STEP, threads=threads, rank=0, world=world, tile_size=32)
     samples = 0
     busy = []
     t0 = time.perf_counter()
     for s in range(args.steps):
-        _, cnt = O.render(desc, s * SPP_PER_STEP, (s + 1) * SPP_PER_STEP, rank=0, world=world, tile_size=32)
+        _, cnt = O.render(desc, s * SPP_PER_STEP, (s + 1) * SPP_PER_STEP, threads=threads, rank=0, world=world, tile_size=32)
         samples += cnt["samples"]
         busy.append(O.last_render_stats())
     dt = time.perf_counter() - t0
@@ -219,9 +236,10 @@ def run_reference(args, rank: int):
         "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample_desc,
+        "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": threads, "logical_cpus": cores, "cpu_quota": cpu_quota(),
+                         "kind": "port", "sample": sample_desc,
                          "threads_busy": round(float(np.mean([b["threads_busy"] for b in busy])), 4),
-                         "thread_scaling": cpu_thread_scaling(desc, SPP_PER_STEP),
+                         "thread_scaling": scaling,
                          "note": "the reference's Rust/LLVM `cpu` backend + Embree cannot be built in this environment (SURVEY.md §8c); "
                                  "this is the oracle port of the same estimator on all host cores - a scalar BVH2 walk, one ray at a time: the "
                                  "reference's real backend (LLVM-vectorised kernels over Embree's SIMD BVH) would be several times faster than "
@@ -398,10 +416,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         step(s)
     r.set_option("count_traversal", 0)
     cst = r.stats()
-    # algorithmic bytes (SURVEY.md §8d's per-ray formula with the node size of the hierarchy the kernel walks - 128-byte 4-wide
-    # nodes since round 2): 32 B ray + 16 B hit per ray, 128 B per wide node visited, 48 B per triangle tested, 64 B per
-    # instance entered; the visit counts come from the kernel's counting variant on the same deterministic samples
-    alg_bytes = 48 * cst["closest_rays"] + 128 * cst["closest_nodes"] + 48 * cst["closest_tris"] + 64 * cst["closest_xforms"]
+    # algorithmic bytes (SURVEY.md §8d's per-ray formula): 32 B ray + 16 B hit per ray, 64 B per BVH2 node visited, 48 B per triangle
+    # tested, 64 B per instance entered; the visit counts come from the kernel's counting variant on the same deterministic samples
+    alg_bytes = 48 * cst["closest_rays"] + 64 * cst["closest_nodes"] + 48 * cst["closest_tris"] + 64 * cst["closest_xforms"]
     trace_launches = st["passes"] * desc.integrator.max_depth  # one closest-hit launch per bounce per pass
     peak, peak_src = measured_hbm_peak()
     achieved = alg_bytes / max(st["trace_closest_ms"] * 1e-3, 1e-9) * 1e-9
@@ -417,11 +434,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     traffic = prof.get("dram_bytes_per_launch")
     launch_ms = st["trace_closest_ms"] / max(trace_launches, 1)
     roofline = {
-        "kernel": "trace_closest_kernel<false, false> (two-level 4-wide BVH closest-hit traversal)", "bound": "hbm",
+        "kernel": "trace_closest_kernel<false, false> (two-level BVH2 closest-hit traversal)", "bound": "hbm",
         "achieved": round(achieved, 1), "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": round(achieved / peak, 4),
         "traffic": traffic, "algorithmic_bytes": int(alg_bytes), "launches": int(trace_launches),
         "kernel_ms_total": round(st["trace_closest_ms"], 3),
-        "per_ray": {"wide_nodes": round(cst["closest_nodes"] / max(cst["closest_rays"], 1), 2),
+        "per_ray": {"nodes": round(cst["closest_nodes"] / max(cst["closest_rays"], 1), 2),
                     "tris": round(cst["closest_tris"] / max(cst["closest_rays"], 1), 2),
                     "xforms": round(cst["closest_xforms"] / max(cst["closest_rays"], 1), 2)},
         "share_of_step": round(st["trace_closest_ms"] / max(st["render_ms"], 1e-9), 4),
@@ -473,8 +490,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     # ---- CPU baseline (rank 0, single GPU run only) ------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        rate, n, secs, sample_desc, _, cst_cpu = cpu_oracle_rate(desc, 15.0, SPP_PER_STEP)
-        cpu = {"value": round(rate, 4), "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": sample_desc,
+        scaling = cpu_thread_scaling(desc, SPP_PER_STEP)
+        threads = max(scaling, key=lambda r: r["value"])["threads"]
+        rate, n, secs, sample_desc, _, cst_cpu = cpu_oracle_rate(desc, 10.0, SPP_PER_STEP, threads=threads)
+        cpu = {"value": round(rate, 4), "unit": UNIT, "cores": threads, "logical_cpus": os.cpu_count() or 1, "cpu_quota": cpu_quota(),
+               "thread_scaling": scaling, "kind": "port", "sample": sample_desc,
                "seconds": round(secs, 2), "threads_busy": cst_cpu["threads_busy"],
                "note": "oracle port (scalar BVH2 walk) of the reference estimator: the reference's own LLVM + Embree cpu backend cannot "
                        "be built here and would be several times faster than this port",

@@ -120,8 +120,8 @@ __global__ void __launch_bounds__(kBlock) generate_rays_kernel(DeviceScene sc, P
     uint32_t pixel = __ldg(pixel_list + pixel_offset + k);
     uint32_t px = pixel & 0xffffu, py = pixel >> 16u;
     PathSampler smp;
-    smp.start(sc, px, py, spp_begin + s);
-    const float2 uf = smp.pixel2d(sc);
+    smp.start(sampler_ref(sc), px, py, spp_begin + s);
+    const float2 uf = smp.pixel2d(sampler_ref(sc));
     float4 ro, rd;
     float weight;
     camera_ray(sc.camera, px, py, uf.x, uf.y, ro, rd, weight);
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(kBlock) shade_miss_kernel(DeviceScene sc, Path
         float4 rd = pb.ray_d[in][i];
         float4 bp = pb.beta_pdf[in][i];
         uint2 ir = pb.id_rng[in][i];
-        LightEval e = environment_evaluate(sc, v3(rd.x, rd.y, rd.z));
+        LightEval e = environment_evaluate(*sc.self, v3(rd.x, rd.y, rd.z));
         e.pdf *= sc.env_prob;
         V3 add = v3(bp.x, bp.y, bp.z) * e.L * balance_heuristic(bp.w, e.pdf);
         float4 li = pb.li[ir.x];
@@ -340,6 +340,32 @@ __device__ __forceinline__ void shade_surface(Closure &cl, const Interaction &it
     }
 }
 
+// The numbers one bounce consumes, drawn from a table-driven sampler (row f2) for the path with generation slot `id`: pixel and
+// sample index follow from the slot (PathBuffers::pass_*), `word` is the dimension counter the path carries.  Out of line, so
+// that the Independent sampler's path through shade_kernel is the code it was before the table-driven samplers existed.
+struct BounceDraws {
+    float u_sel, ul0, ul1, u_lobe, ub0, ub1, u_rr;
+    uint32_t state;
+};
+__device__ __noinline__ BounceDraws draw_bounce_from_tables(SamplerRef sc, const uint32_t *pixel_list, uint32_t pixel_offset, uint32_t npix,
+                                                            uint32_t spp_begin, uint32_t id, uint32_t word, bool draw_rr) {
+    const uint32_t pixel = __ldg(pixel_list + pixel_offset + id % npix);
+    PathSampler smp;
+    smp.resume(sc, word, pixel & 0xffffu, pixel >> 16u, spp_begin + id / npix);
+    BounceDraws d;
+    d.u_sel = smp.next1d(sc);
+    const float2 ul = smp.next2d(sc);
+    d.ul0 = ul.x;
+    d.ul1 = ul.y;
+    d.u_lobe = smp.next1d(sc);
+    const float2 ub = smp.next2d(sc);
+    d.ub0 = ub.x;
+    d.ub1 = ub.y;
+    d.u_rr = draw_rr ? smp.next1d(sc) : 0.f;
+    d.state = smp.state;
+    return d;
+}
+
 // Sorted-by-material dispatch, step 2: one shade kernel per closure kind, each over its own hit bucket.
 template<uint32_t KIND, bool TEXTURED = false>
 __global__ void __launch_bounds__(kShadeBlock, LRK_SHADE_MIN_BLOCKS) shade_kernel(DeviceScene sc, PathBuffers pb, uint32_t depth) {
@@ -379,26 +405,21 @@ __global__ void __launch_bounds__(kShadeBlock, LRK_SHADE_MIN_BLOCKS) shade_kerne
                 }
                 if (KIND != 0u) {// kind 0 = emitter-only hit (no surface): the path ends here (mega_path.cpp:89)
                     // draw order is normative: mega_path.cpp:91-98
-                    PathSampler smp;
-                    {
-                        uint32_t spx = 0u, spy = 0u, ssi = 0u;
-                        if (sc.sampler_type != LRK_SAMPLER_INDEPENDENT) {// the path's pixel and sample index from its generation slot
-                            const uint32_t pixel = __ldg(pb.pass_pixel_list + pb.pass_pixel_offset + ir.x % pb.pass_npix);
-                            spx = pixel & 0xffffu;
-                            spy = pixel >> 16u;
-                            ssi = pb.pass_spp_begin + ir.x / pb.pass_npix;
-                        }
-                        smp.resume(sc, state, spx, spy, ssi);
+                    float u_sel, ul0, ul1, u_lobe, ub0, ub1, u_rr = 0.f;
+                    if (sc.sampler_type == LRK_SAMPLER_INDEPENDENT) {// the headline path: an LCG word in a register
+                        u_sel = lcg(state);
+                        ul0 = lcg(state);
+                        ul1 = lcg(state);
+                        u_lobe = lcg(state);
+                        ub0 = lcg(state);
+                        ub1 = lcg(state);
+                        if (depth + 1u >= sc.rr_depth) u_rr = lcg(state);
+                    } else {// table-driven samplers: all of the bounce's numbers from one out-of-line call
+                        BounceDraws dr = draw_bounce_from_tables(sampler_ref(sc), pb.pass_pixel_list, pb.pass_pixel_offset, pb.pass_npix, pb.pass_spp_begin,
+                                                                 ir.x, state, depth + 1u >= sc.rr_depth);
+                        u_sel = dr.u_sel; ul0 = dr.ul0; ul1 = dr.ul1; u_lobe = dr.u_lobe; ub0 = dr.ub0; ub1 = dr.ub1; u_rr = dr.u_rr;
+                        state = dr.state;
                     }
-                    float u_sel = smp.next1d(sc);
-                    const float2 ul = smp.next2d(sc);
-                    float ul0 = ul.x, ul1 = ul.y;
-                    float u_lobe = smp.next1d(sc);
-                    const float2 ub = smp.next2d(sc);
-                    float ub0 = ub.x, ub1 = ub.y;
-                    float u_rr = 0.f;
-                    if (depth + 1u >= sc.rr_depth) u_rr = smp.next1d(sc);
-                    state = smp.state;
                     LightSample ls;
                     ls.eval.L = v3(0.f);
                     ls.eval.pdf = 0.f;

@@ -5,18 +5,20 @@
 #include <chrono>
 #include <cstdio>
 #include <cstring>
+#include <limits>
 #include <string>
 #include <unordered_map>
 #include <vector>
 
 #include "kernels.cuh"
+#include "bvh_build.cuh"
 
 using namespace lrk;
 
 namespace {
 
 struct DeviceArrays {
-    void *vertices{}, *triangles{}, *alias{}, *pdf{}, *meshes{}, *inst_handles{}, *inst_kind{}, *inst_o2w{}, *inst_xform{}, *bvh_nodes{}, *traversal_overflow{}, *sobol{}, *vdc{}, *vdc_inv{}, *pmj{}, *blue_noise{}, *pmj_pixels{}, *zsobol_hash{}, *sampler{}, *textures{}, *texels{}, *env_alias{}, *env_pdf{},
+    void *vertices{}, *triangles{}, *alias{}, *pdf{}, *meshes{}, *inst_handles{}, *inst_kind{}, *inst_o2w{}, *inst_xform{}, *bvh_nodes{}, *traversal_overflow{}, *sobol{}, *vdc{}, *vdc_inv{}, *pmj{}, *blue_noise{}, *pmj_pixels{}, *zsobol_hash{}, *sampler{}, *build_scratch{}, *mesh_bounds{}, *inst_mesh{}, *visible_ids{}, *scene_copy{}, *textures{}, *texels{}, *env_alias{}, *env_pdf{},
         *tri_verts{}, *surfaces{}, *lights{}, *light_handles{}, *camera{};
 };
 
@@ -56,6 +58,8 @@ struct lrk_ctx {
     uint32_t *d_query_cursor{nullptr};
     // options
     bool count_traversal{false}, time_kernels{false};
+    bool device_bvh{false};// option device_bvh: build the hierarchy on the GPU (bvh_build.cuh) instead of uploading the host's
+    double bvh_build_ms{0.0};
     const void *sampler_table_src[3]{nullptr, nullptr, nullptr};// host addresses of the static sampler tables already on the device
     bool pin_host{false};// option pin_host_buffers: page-lock the caller's scene arrays / film buffers on first sight (see pin_range)
     std::unordered_map<const void *, size_t> pinned;
@@ -403,6 +407,119 @@ int render_pass_volume(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint3
     return LRK_OK;
 }
 
+// Hierarchy build on the device (bvh_build.cuh): fills a.bvh_nodes / a.tri_verts from the uploaded geometry, returns the root of
+// every mesh's BLAS and of the TLAS.  One round of kernels per unique mesh, one for the instances.
+int build_bvh_on_device(lrk_ctx *ctx, const lrk_scene_desc *s, std::vector<uint32_t> &mesh_root, uint32_t &tlas_root) {
+    auto &a = ctx->arrays;
+    std::vector<uint32_t> visible, inst_mesh(s->instance_count);
+    for (uint32_t i = 0; i < s->instance_count; i++) {
+        inst_mesh[i] = s->instances[i].mesh;
+        if (s->instances[i].visible) visible.push_back(i);
+    }
+    // node layout: per mesh max(n - 1, 1) nodes, then the TLAS
+    mesh_root.resize(s->mesh_count);
+    uint64_t nodes = 0u, max_n = std::max<uint64_t>(visible.size(), 2u);
+    for (uint32_t m = 0; m < s->mesh_count; m++) {
+        mesh_root[m] = static_cast<uint32_t>(nodes);
+        const uint64_t n = s->meshes[m].triangle_count;
+        if (n == 0u) return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_upload_scene: mesh without triangles");
+        nodes += std::max<uint64_t>(n - 1u, 1u);
+        max_n = std::max(max_n, n);
+    }
+    tlas_root = static_cast<uint32_t>(nodes);
+    nodes += std::max<uint64_t>(visible.size(), 2u) - 1u;
+    if (nodes >= 0x7fffffffull || s->triangle_count >= (1ull << 28)) return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: scene too large for the BVH encoding");
+    int rc;
+    if ((rc = upload(ctx, &a.bvh_nodes, static_cast<const lrk_bvh_node *>(nullptr), 0u))) return rc;
+    auto ensure = [&](void **p, size_t bytes) -> int {
+        size_t &have = ctx->array_bytes[p];
+        if (*p == nullptr || have < bytes) {
+            if (*p) cudaFree(*p);
+            *p = nullptr;
+            LRK_CUDA(cudaMalloc(p, bytes));
+            have = bytes;
+        }
+        return LRK_OK;
+    };
+    if ((rc = ensure(&a.bvh_nodes, nodes * 64u))) return rc;
+    if ((rc = ensure(&a.tri_verts, std::max<uint64_t>(s->triangle_count, 1u) * 48u))) return rc;
+    if ((rc = ensure(&a.mesh_bounds, std::max<uint64_t>(s->mesh_count, 1u) * sizeof(BuildBox)))) return rc;
+    if ((rc = upload(ctx, &a.inst_mesh, inst_mesh.data(), inst_mesh.size()))) return rc;
+    if ((rc = upload(ctx, &a.visible_ids, visible.data(), visible.size()))) return rc;
+    // scratch: boxes, node boxes, keys / values (double buffered), radix nodes, leaf parents, visit counters, whole-set bounds, cub
+    size_t cub_bytes = 0u;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, static_cast<const uint32_t *>(nullptr), static_cast<uint32_t *>(nullptr),
+                                    static_cast<const uint32_t *>(nullptr), static_cast<uint32_t *>(nullptr), static_cast<int>(max_n), 0, 30, ctx->stream);
+    const size_t n8 = (max_n + 7u) & ~size_t{7u};
+    const size_t off_boxes = 0u, off_node_boxes = off_boxes + n8 * sizeof(BuildBox), off_keys = off_node_boxes + n8 * sizeof(BuildBox),
+                 off_keys2 = off_keys + n8 * 4u, off_vals = off_keys2 + n8 * 4u, off_vals2 = off_vals + n8 * 4u, off_radix = off_vals2 + n8 * 4u,
+                 off_leaf_parent = off_radix + n8 * sizeof(RadixNode), off_visits = off_leaf_parent + n8 * 4u, off_whole = off_visits + n8 * 4u,
+                 off_cub = off_whole + 64u, total = off_cub + cub_bytes;
+    if ((rc = ensure(&a.build_scratch, total))) return rc;
+    auto base = static_cast<char *>(a.build_scratch);
+    auto boxes = reinterpret_cast<BuildBox *>(base + off_boxes), node_boxes = reinterpret_cast<BuildBox *>(base + off_node_boxes);
+    auto keys = reinterpret_cast<uint32_t *>(base + off_keys), keys2 = reinterpret_cast<uint32_t *>(base + off_keys2);
+    auto vals = reinterpret_cast<uint32_t *>(base + off_vals), vals2 = reinterpret_cast<uint32_t *>(base + off_vals2);
+    auto radix = reinterpret_cast<RadixNode *>(base + off_radix);
+    auto leaf_parent = reinterpret_cast<uint32_t *>(base + off_leaf_parent), visits = reinterpret_cast<uint32_t *>(base + off_visits);
+    auto whole = reinterpret_cast<uint32_t *>(base + off_whole);
+    auto out_nodes = static_cast<float4 *>(a.bvh_nodes);
+    auto stream = ctx->stream;
+    static const uint32_t whole_init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+    auto blocks = [](uint64_t n) { return static_cast<unsigned>((n + 255u) / 256u); };
+    // common tail: sort, radix tree, fit, emit
+    auto hierarchy = [&](uint32_t n, bool tlas, uint32_t node_base, uint32_t slot_base) -> int {
+        if (n == 1u) {
+            if (tlas) build_single_kernel<true><<<1, 1, 0, stream>>>(boxes, whole, static_cast<const uint32_t *>(a.visible_ids), node_base, slot_base, out_nodes);
+            else build_single_kernel<false><<<1, 1, 0, stream>>>(boxes, whole, nullptr, node_base, slot_base, out_nodes);
+            LRK_CUDA(cudaMemsetAsync(vals2, 0, 4u, stream));// sorted order of one primitive
+            return LRK_OK;
+        }
+        build_morton_kernel<<<blocks(n), 256, 0, stream>>>(boxes, n, whole, keys, vals);
+        size_t bytes = cub_bytes;
+        LRK_CUDA(cub::DeviceRadixSort::SortPairs(base + off_cub, bytes, keys, keys2, vals, vals2, static_cast<int>(n), 0, 30, stream));
+        LRK_CUDA(cudaMemsetAsync(visits, 0, static_cast<size_t>(n) * 4u, stream));
+        build_radix_tree_kernel<<<blocks(n - 1u), 256, 0, stream>>>(keys2, static_cast<int>(n), radix, leaf_parent);
+        build_fit_kernel<<<blocks(n), 256, 0, stream>>>(radix, leaf_parent, vals2, boxes, static_cast<int>(n), node_boxes, visits);
+        if (tlas) build_emit_kernel<true><<<blocks(n - 1u), 256, 0, stream>>>(radix, vals2, boxes, node_boxes, static_cast<int>(n), whole,
+                                                                               static_cast<const uint32_t *>(a.visible_ids), node_base, slot_base, out_nodes);
+        else build_emit_kernel<false><<<blocks(n - 1u), 256, 0, stream>>>(radix, vals2, boxes, node_boxes, static_cast<int>(n), whole, nullptr, node_base,
+                                                                          slot_base, out_nodes);
+        LRK_CUDA(cudaGetLastError());
+        return LRK_OK;
+    };
+    uint32_t slot_base = 0u;
+    for (uint32_t m = 0; m < s->mesh_count; m++) {
+        const auto &mesh = s->meshes[m];
+        const uint32_t n = mesh.triangle_count;
+        auto verts = static_cast<const lrk_vertex *>(a.vertices) + mesh.vertex_offset;
+        auto tris = static_cast<const lrk_triangle *>(a.triangles) + mesh.triangle_offset;
+        LRK_CUDA(cudaMemcpyAsync(whole, whole_init, sizeof(whole_init), cudaMemcpyHostToDevice, stream));
+        build_triangle_bounds_kernel<<<blocks(n), 256, 0, stream>>>(verts, tris, n, boxes, whole);
+        build_store_mesh_bounds_kernel<<<1, 1, 0, stream>>>(whole, static_cast<BuildBox *>(a.mesh_bounds), m);
+        if ((rc = hierarchy(n, false, mesh_root[m], slot_base))) return rc;
+        build_tri_verts_kernel<<<blocks(n), 256, 0, stream>>>(verts, tris, vals2, n, static_cast<float4 *>(a.tri_verts) + static_cast<size_t>(slot_base) * 3u);
+        slot_base += n;
+    }
+    const uint32_t nv = static_cast<uint32_t>(visible.size());
+    if (nv == 0u) {// nothing to hit: a root with two empty children
+        const float inf = std::numeric_limits<float>::infinity();
+        lrk_bvh_node root{};
+        for (int k = 0; k < 3; k++) { root.lo0[k] = root.lo1[k] = inf; root.hi0[k] = root.hi1[k] = -inf; }
+        root.ref0 = root.ref1 = root.parent = LRK_BVH_EMPTY;
+        LRK_CUDA(cudaMemcpyAsync(out_nodes + static_cast<size_t>(tlas_root) * 4u, &root, sizeof(root), cudaMemcpyHostToDevice, stream));
+    } else {
+        LRK_CUDA(cudaMemcpyAsync(whole, whole_init, sizeof(whole_init), cudaMemcpyHostToDevice, stream));
+        build_instance_bounds_kernel<<<blocks(nv), 256, 0, stream>>>(static_cast<const float4 *>(a.inst_o2w), static_cast<const uint32_t *>(a.inst_mesh),
+                                                                    static_cast<const uint32_t *>(a.visible_ids), nv,
+                                                                    static_cast<const BuildBox *>(a.mesh_bounds), boxes, whole);
+        if ((rc = hierarchy(nv, true, tlas_root, 0u))) return rc;
+    }
+    LRK_CUDA(cudaStreamSynchronize(stream));// host vectors (visible, inst_mesh) and the static init block are done with
+    LRK_CUDA(cudaGetLastError());
+    return LRK_OK;
+}
+
 }// namespace
 
 extern "C" {
@@ -567,12 +684,14 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
     if ((rc = upload(ctx, &a.alias, s->alias, s->triangle_count))) return rc;
     if ((rc = upload(ctx, &a.pdf, s->pdf, s->triangle_count))) return rc;
     if ((rc = upload(ctx, &a.meshes, s->meshes, s->mesh_count))) return rc;
-    if ((rc = upload(ctx, &a.bvh_nodes, s->bvh_nodes, s->bvh_node_count))) return rc;
+    if (!ctx->device_bvh)
+        if ((rc = upload(ctx, &a.bvh_nodes, s->bvh_nodes, s->bvh_node_count))) return rc;
     {
         static const uint32_t zero = 0u;
         if ((rc = upload(ctx, &a.traversal_overflow, &zero, 1u))) return rc;
     }
-    if ((rc = upload(ctx, &a.tri_verts, s->tri_verts, s->tri_slot_count * 12u))) return rc;
+    if (!ctx->device_bvh)
+        if ((rc = upload(ctx, &a.tri_verts, s->tri_verts, s->tri_slot_count * 12u))) return rc;
     if ((rc = upload(ctx, &a.surfaces, s->surfaces, s->surface_count))) return rc;
     if ((rc = upload(ctx, &a.textures, s->textures, s->texture_count))) return rc;
     {
@@ -631,15 +750,25 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
             ctx->has_kind[kind] = true;
             if ((flags & LRK_SHAPE_MAYBE_NON_OPAQUE) && (flags & LRK_SHAPE_HAS_SURFACE)) ctx->any_non_opaque = true;
         }
+        if (inst.mesh >= s->mesh_count) return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_upload_scene: mesh index out of range");
         std::memcpy(&o2w[i * 12u], inst.object_to_world, 48);
         std::memcpy(&xform[i * 16u], inst.world_to_object, 48);
-        uint32_t root = s->meshes[inst.mesh].bvh_root;
-        std::memcpy(&xform[i * 16u + 12u], &root, 4);
-        xform[i * 16u + 13u] = xform[i * 16u + 14u] = xform[i * 16u + 15u] = 0.f;
+        xform[i * 16u + 12u] = xform[i * 16u + 13u] = xform[i * 16u + 14u] = xform[i * 16u + 15u] = 0.f;
     }
     if ((rc = upload(ctx, &a.inst_handles, handles.data(), handles.size()))) return rc;
     if ((rc = upload(ctx, &a.inst_kind, kinds.data(), kinds.size()))) return rc;
     if ((rc = upload(ctx, &a.inst_o2w, o2w.data(), o2w.size()))) return rc;
+    // the hierarchy: the host's (the parity path: the oracle walks the same nodes) or one built here on the device
+    std::vector<uint32_t> mesh_root(s->mesh_count);
+    uint32_t tlas_root = s->tlas_root;
+    if (ctx->device_bvh) {
+        const auto t0 = std::chrono::steady_clock::now();
+        if ((rc = build_bvh_on_device(ctx, s, mesh_root, tlas_root))) return rc;
+        ctx->bvh_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    } else {
+        for (uint32_t m = 0; m < s->mesh_count; m++) mesh_root[m] = s->meshes[m].bvh_root;
+    }
+    for (uint32_t i = 0; i < s->instance_count; i++) std::memcpy(&xform[i * 16u + 12u], &mesh_root[s->instances[i].mesh], 4);
     if ((rc = upload(ctx, &a.inst_xform, xform.data(), xform.size()))) return rc;
     LRK_CUDA(cudaStreamSynchronize(ctx->stream));
 
@@ -672,7 +801,7 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
     sc.lights = static_cast<const lrk_light *>(a.lights);
     sc.light_handles = static_cast<const lrk_light_handle *>(a.light_handles);
     sc.camera = static_cast<const lrk_camera *>(a.camera);
-    sc.tlas_root = s->tlas_root;
+    sc.tlas_root = tlas_root;
     sc.light_count = s->light_count;
     sc.instance_count = s->instance_count;
     sc.surface_count = s->surface_count;
@@ -719,6 +848,19 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
         LRK_CUDA(cudaMalloc(reinterpret_cast<void **>(&ctx->d_film_out), npix * sizeof(float4)));
         ctx->film_pixels = npix;
     }
+    {// the scene record itself in device memory, for the out-of-line device functions (DeviceScene::self)
+        if ((rc = upload(ctx, &a.scene_copy, static_cast<const DeviceScene *>(nullptr), 0u))) return rc;
+        size_t &have = ctx->array_bytes[&a.scene_copy];
+        if (have < sizeof(DeviceScene)) {
+            cudaFree(a.scene_copy);
+            a.scene_copy = nullptr;
+            LRK_CUDA(cudaMalloc(&a.scene_copy, sizeof(DeviceScene)));
+            have = sizeof(DeviceScene);
+        }
+        sc.self = static_cast<const DeviceScene *>(a.scene_copy);
+        LRK_CUDA(cudaMemcpyAsync(a.scene_copy, &sc, sizeof(DeviceScene), cudaMemcpyHostToDevice, ctx->stream));
+        LRK_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
     ctx->has_scene = true;
     if ((rc = build_pixel_list(ctx))) return rc;
     return lrk_film_clear(ctx);
@@ -741,12 +883,18 @@ int lrk_set_option(lrk_ctx *ctx, const char *name, int64_t value) {
     std::string n{name};
     if (n == "count_traversal") ctx->count_traversal = value != 0;
     else if (n == "time_kernels") ctx->time_kernels = value != 0;
+    else if (n == "device_bvh") ctx->device_bvh = value != 0;
     else if (n == "pin_host_buffers") {
         ctx->pin_host = value != 0;
         if (!ctx->pin_host) unpin_all(ctx);
     } else if (n == "max_paths_per_pass") ctx->max_paths = value > 0 ? static_cast<uint64_t>(value) : ctx->max_paths;
-    else if (n == "refill_below") ctx->scene.refill_below = static_cast<uint32_t>(std::min<int64_t>(std::max<int64_t>(value, 1), 32));
-    else if (n == "inner_min") ctx->scene.inner_min = static_cast<uint32_t>(std::min<int64_t>(std::max<int64_t>(value, 1), 32));
+    else if (n == "refill_below" || n == "inner_min") {
+        (n == "refill_below" ? ctx->scene.refill_below : ctx->scene.inner_min) = static_cast<uint32_t>(std::min<int64_t>(std::max<int64_t>(value, 1), 32));
+        if (ctx->has_scene && ctx->arrays.scene_copy) {// keep DeviceScene::self in step
+            LRK_CUDA(cudaMemcpyAsync(ctx->arrays.scene_copy, &ctx->scene, sizeof(DeviceScene), cudaMemcpyHostToDevice, ctx->stream));
+            LRK_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+    }
     else return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_set_option: unknown option '" + n + "'");
     return LRK_OK;
 }

@@ -61,6 +61,14 @@ __device__ __forceinline__ uint32_t mask_covering(uint32_t x) {// the bit mask c
     return x;
 }
 
+// What a kernel hands to the sampler: three scalars out of its DeviceScene parameter (never a reference to the parameter itself -
+// a kernel parameter whose address is taken is copied to every thread's local memory).
+struct SamplerRef {
+    uint32_t type, seed;
+    const lrk_sampler *rec;
+};
+__device__ __forceinline__ SamplerRef sampler_ref(const DeviceScene &sc) { return SamplerRef{sc.sampler_type, sc.sampler_seed, sc.sampler}; }
+
 struct PathSampler {
     uint32_t state;// Independent: LCG state; table-driven samplers: the dimension counter
     uint32_t px, py, sample_index;
@@ -239,46 +247,46 @@ struct PathSampler {
 
     // ---- the interface the kernels use -------------------------------------------------------------------------------------------
     // Sampler::Instance::start(pixel, sample_index)
-    __device__ __forceinline__ void start(const DeviceScene &sc, uint32_t x, uint32_t y, uint32_t s) {
+    __device__ __forceinline__ void start(SamplerRef sc, uint32_t x, uint32_t y, uint32_t s) {
         px = x;
         py = y;
         sample_index = s;
-        if (sc.sampler_type == LRK_SAMPLER_INDEPENDENT) {
-            state = xxhash32_uint4(x, y, sc.sampler_seed, s);
+        if (sc.type == LRK_SAMPLER_INDEPENDENT) {
+            state = xxhash32_uint4(x, y, sc.seed, s);
         } else {
-            state = (sc.sampler_type == LRK_SAMPLER_PMJ02BN || sc.sampler_type == LRK_SAMPLER_SOBOL) ? 2u : 0u;
-            index = derive(*sc.sampler, x, y, s);
+            state = (sc.type == LRK_SAMPLER_PMJ02BN || sc.type == LRK_SAMPLER_SOBOL) ? 2u : 0u;
+            index = derive(*sc.rec, x, y, s);
         }
     }
     // Sampler::Instance::load_state: the word the path carried + what follows from its generation slot
-    __device__ __forceinline__ void resume(const DeviceScene &sc, uint32_t word, uint32_t x, uint32_t y, uint32_t s) {
+    __device__ __forceinline__ void resume(SamplerRef sc, uint32_t word, uint32_t x, uint32_t y, uint32_t s) {
         state = word;
-        if (sc.sampler_type != LRK_SAMPLER_INDEPENDENT) {
+        if (sc.type != LRK_SAMPLER_INDEPENDENT) {
             px = x;
             py = y;
             sample_index = s;
-            index = derive(*sc.sampler, x, y, s);
+            index = derive(*sc.rec, x, y, s);
         }
     }
-    __device__ __forceinline__ float next1d(const DeviceScene &sc) {
-        if (sc.sampler_type == LRK_SAMPLER_INDEPENDENT) return lcg(state);
-        const Draw d = table_1d(*sc.sampler, sc.sampler_seed, state, px, py, sample_index, index);
+    __device__ __forceinline__ float next1d(SamplerRef sc) {
+        if (sc.type == LRK_SAMPLER_INDEPENDENT) return lcg(state);
+        const Draw d = table_1d(*sc.rec, sc.seed, state, px, py, sample_index, index);
         state = d.dimension;
         return d.x;
     }
-    __device__ __forceinline__ float2 next2d(const DeviceScene &sc) {
-        if (sc.sampler_type == LRK_SAMPLER_INDEPENDENT) {
+    __device__ __forceinline__ float2 next2d(SamplerRef sc) {
+        if (sc.type == LRK_SAMPLER_INDEPENDENT) {
             const float a = lcg(state);
             const float b = lcg(state);
             return make_float2(a, b);
         }
-        const Draw d = table_2d(*sc.sampler, sc.sampler_seed, state, px, py, sample_index, index);
+        const Draw d = table_2d(*sc.rec, sc.seed, state, px, py, sample_index, index);
         state = d.dimension;
         return make_float2(d.x, d.y);
     }
-    __device__ __forceinline__ float2 pixel2d(const DeviceScene &sc) {// generate_pixel_2d, sampler.h:48
-        if (sc.sampler_type == LRK_SAMPLER_INDEPENDENT) return next2d(sc);
-        const Draw d = table_pixel_2d(*sc.sampler, sc.sampler_seed, state, px, py, sample_index, index);
+    __device__ __forceinline__ float2 pixel2d(SamplerRef sc) {// generate_pixel_2d, sampler.h:48
+        if (sc.type == LRK_SAMPLER_INDEPENDENT) return next2d(sc);
+        const Draw d = table_pixel_2d(*sc.rec, sc.seed, state, px, py, sample_index, index);
         state = d.dimension;
         return make_float2(d.x, d.y);
     }

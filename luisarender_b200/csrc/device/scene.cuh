@@ -11,6 +11,10 @@ namespace lrk {
 //   rows 0..2 : world_to_object 3x4, row 3 : {as_float(blas_root), 0, 0, 0}
 // One shading instance record: handle (uint4, 16 B) + object_to_world 3x4 (3 x float4, 48 B).
 struct DeviceScene {
+    // A copy of this very record in device memory (lrk_upload_scene).  Out-of-line device functions take the scene by reference;
+    // handing them the kernel PARAMETER would make the compiler copy all of it into every thread's local memory (416 bytes of
+    // stack and ~200 instructions per thread in the shade kernels before this pointer existed) - they get *self instead.
+    const DeviceScene *self;
     const lrk_vertex *vertices;
     const lrk_triangle *triangles;
     const lrk_alias_entry *alias;

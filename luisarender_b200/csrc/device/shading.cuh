@@ -266,7 +266,7 @@ __device__ __forceinline__ LightSample sample_light(const DeviceScene &sc, const
     }
     if (is_env) {// sample_environment + Sample::from_environment (light_sampler.cpp:84-90,120-123): a ray to infinity
         V3 wi;
-        s.eval = environment_sample(sc, u0, u1, wi);
+        s.eval = environment_sample(*sc.self, u0, u1, wi);
         s.eval.pdf *= sel_prob;
         V3 o = p_robust(it_from, wi);
         s.ray_o_tmin = make_float4(o.x, o.y, o.z, 0.f);
@@ -357,7 +357,7 @@ __device__ __noinline__ float4 texture_evaluate(const DeviceScene &sc, uint32_t 
 // colours through Texture::Instance::evaluate_albedo_spectrum texture.cpp:20-31 + srgb.cpp:34-40,70-72).
 __device__ __forceinline__ void resolve_surface_textures(const DeviceScene &sc, lrk_surface &s, float u, float v) {
     if (s.tex[0] != 0u) {
-        float4 val = texture_evaluate(sc, s.tex[0] - 1u, u, v);
+        float4 val = texture_evaluate(*sc.self, s.tex[0] - 1u, u, v);
         const uint32_t ch = sc.textures[s.tex[0] - 1u].channels;
         V3 rgb = ch == 1u ? v3(val.x, val.x, val.x) : ch == 2u ? v3(val.x, val.y, 1.f) : v3(val.x, val.y, val.z);
         rgb = v3(saturate(rgb.x), saturate(rgb.y), saturate(rgb.z));// encode_srgb_albedo's clamp, decode_albedo's saturate
@@ -367,12 +367,12 @@ __device__ __forceinline__ void resolve_surface_textures(const DeviceScene &sc, 
         if (s.type == LRK_SURFACE_DISNEY) s.p[3] = 0.212671f * rgb.x + 0.715160f * rgb.y + 0.072169f * rgb.z;
     }
     if (s.type == LRK_SURFACE_MATTE) {
-        if (s.tex[3] != 0u) s.p[3] = saturate(texture_evaluate(sc, s.tex[3] - 1u, u, v).x) * 90.f;
+        if (s.tex[3] != 0u) s.p[3] = saturate(texture_evaluate(*sc.self, s.tex[3] - 1u, u, v).x) * 90.f;
     } else {
 #pragma unroll
         for (uint32_t k = 4u; k < 15u; k++) {
             if (s.tex[k] != 0u) {
-                float x = texture_evaluate(sc, s.tex[k] - 1u, u, v).x;
+                float x = texture_evaluate(*sc.self, s.tex[k] - 1u, u, v).x;
                 if (k == 6u && (s.flags & LRK_SURFACE_REMAP_ROUGHNESS)) x = fmaxf(x * x, 1e-4f);// roughness_to_alpha
                 s.p[k] = x;
             }
@@ -388,7 +388,7 @@ __device__ __forceinline__ V3 env_mul(const float *m, V3 v, bool transposed) {//
 __device__ __forceinline__ V3 env_radiance(const DeviceScene &sc, float u, float v) {// _evaluate (:70-75) + decode_illuminant
     V3 rgb = v3(sc.env_emission[0], sc.env_emission[1], sc.env_emission[2]);
     if (sc.env_emission_tex != 0u) {
-        float4 t = texture_evaluate(sc, sc.env_emission_tex - 1u, u, v);
+        float4 t = texture_evaluate(*sc.self, sc.env_emission_tex - 1u, u, v);
         rgb = v3(fmaxf(t.x, 0.f), fmaxf(t.y, 0.f), fmaxf(t.z, 0.f));
     }
     return rgb * sc.env_scale;
@@ -475,7 +475,7 @@ __device__ __noinline__ bool alpha_skip(const DeviceScene &sc, uint32_t inst_id,
         float4 a1 = __ldg(vb + tri.i0 * 2u + 1u), b1 = __ldg(vb + tri.i1 * 2u + 1u), c1 = __ldg(vb + tri.i2 * 2u + 1u);
         const float b0 = 1.f - bu - bv;
         float tu = b0 * a1.z + bu * b1.z + bv * c1.z, tv = b0 * a1.w + bu * b1.w + bv * c1.w;// geometry.cpp:372
-        alpha = texture_evaluate(sc, surf->opacity_tex - 1u, tu, tv).x;
+        alpha = texture_evaluate(*sc.self, surf->opacity_tex - 1u, tu, tv).x;
     }
     return u > alpha;
 }
@@ -490,7 +490,7 @@ __device__ __forceinline__ V3 clamp_shading_normal(V3 ns, V3 ng, V3 w) {
 __device__ __forceinline__ Frame normal_mapped_frame(const DeviceScene &sc, const lrk_surface *surf, const Interaction &it, V3 wo) {
     V3 rgb = v3(surf->normal_value[0], surf->normal_value[1], surf->normal_value[2]);
     if (surf->normal_tex != 0u) {
-        float4 t = texture_evaluate(sc, surf->normal_tex - 1u, it.u, it.v);
+        float4 t = texture_evaluate(*sc.self, surf->normal_tex - 1u, it.u, it.v);
         rgb = v3(t.x, t.y, t.z);
     }
     V3 nl = 2.f * rgb + (-1.f);

@@ -158,7 +158,7 @@ __device__ __forceinline__ bool leaf_step(const DeviceScene &sc, RayState &r, St
             const bool tie = t == r.tbest && r.best_inst != ~0u && (r.cur_inst < r.best_inst || (r.cur_inst == r.best_inst && prim < r.best_prim));
             if (!(t > r.tmin && (t < r.tbest || tie))) continue;
             if (ALPHA) {// on_surface_candidate: commit only if not skipped (geometry.cpp:248-279)
-                if (alpha_skip(sc, r.cur_inst, prim, u, v)) continue;
+                if (alpha_skip(*sc.self, r.cur_inst, prim, u, v)) continue;
             }
             r.tbest = t;
             r.best_inst = r.cur_inst;

@@ -101,6 +101,7 @@ extern "C" int wide_trace_host(const lrk_scene_desc *s, const float *rays, uint6
         if ((flags & LRK_SHAPE_MAYBE_NON_OPAQUE) && (flags & LRK_SHAPE_HAS_SURFACE)) alpha = true;// lrk_upload_scene's rule
     }
     DeviceScene sc{};
+    sc.self = &sc;
     sc.inst_handles = handles.data();
     sc.surfaces = s->surfaces;
     sc.meshes = s->meshes;

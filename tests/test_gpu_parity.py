@@ -313,3 +313,56 @@ def test_full_size_properties_c4_medium(gpu_renderer):
     assert (err > 1e-4 * np.maximum(np.abs(c).max(axis=-1), 1.0)).mean() <= 1e-2
     keep = err <= np.quantile(err, 0.99)
     assert np.linalg.norm((g - c)[keep]) / np.linalg.norm(c[keep]) <= 1e-3
+
+
+@pytest.mark.parametrize("fixture", ["cornell_small", "spheres_small", "textured_wrappers_small"])
+def test_device_built_bvh_gives_bit_identical_hits_and_films(fixture, request, gpu_renderer):
+    """Row f4: the LBVH built on the GPU (csrc/device/bvh_build.cuh, option device_bvh) instead of the host's binned-SAH hierarchy.
+    Closest hits do not depend on the hierarchy (boxes contain their triangles, ties in t go to the lower (instance, primitive)),
+    so hit records equal the oracle's bit for bit and the film equals the film rendered with the host's hierarchy exactly."""
+    scene = request.getfixturevalue(fixture)
+    d = scene.desc()
+    rays = _random_rays(scene, 100_000, seed=5)
+    ref, _ = O.trace(d, rays)
+    occ_ref, _ = O.trace(d, rays, any_hit=True)
+    gpu_renderer.upload(d)
+    gpu_renderer.clear()
+    gpu_renderer.render(0, 4)
+    film_host = gpu_renderer.film(raw=True).copy()
+    try:
+        gpu_renderer.set_option("device_bvh", 1)
+        gpu_renderer.upload(d)
+        got = gpu_renderer.trace(rays)
+        assert np.array_equal(got["inst"], ref["inst"]) and np.array_equal(got["prim"], ref["prim"])
+        assert np.array_equal(got["bary"].view(np.uint32), ref["bary"].view(np.uint32))
+        occ = gpu_renderer.trace(rays, any_hit=True)
+        assert np.array_equal(occ["inst"], occ_ref["inst"])
+        gpu_renderer.clear()
+        gpu_renderer.render(0, 4)
+        assert np.array_equal(gpu_renderer.film(raw=True), film_host)
+    finally:
+        gpu_renderer.set_option("device_bvh", 0)
+
+
+def test_device_built_bvh_full_size_scene(gpu_renderer):
+    """BASELINE config C3's 1.39 M-triangle scene: the device build (five meshes, one of 327 680 triangles, 67 instances) against
+    the oracle on random rays, and a 2-spp 480x270 film against the host-hierarchy film."""
+    scene = Scene.from_source(scenes.instanced_spheres(resolution=(480, 270), spp=2), REPO)
+    d = scene.desc()
+    rays = _random_rays(scene, 50_000, seed=8)
+    ref, _ = O.trace(d, rays)
+    gpu_renderer.upload(d)
+    gpu_renderer.clear()
+    gpu_renderer.render(0, 2)
+    film_host = gpu_renderer.film(raw=True).copy()
+    try:
+        gpu_renderer.set_option("device_bvh", 1)
+        gpu_renderer.upload(d)
+        got = gpu_renderer.trace(rays)
+        assert np.array_equal(got["inst"], ref["inst"]) and np.array_equal(got["prim"], ref["prim"])
+        assert np.array_equal(got["bary"].view(np.uint32), ref["bary"].view(np.uint32))
+        gpu_renderer.clear()
+        gpu_renderer.render(0, 2)
+        assert np.array_equal(gpu_renderer.film(raw=True), film_host)
+    finally:
+        gpu_renderer.set_option("device_bvh", 0)
