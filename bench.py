@@ -288,7 +288,7 @@ def other_configs(r, rank: int, world: int, dist, barrier) -> dict | None:
         r.render(0, spp)
         red_ms = 0.0
         if shard and world > 1:
-            D.reduce_film(D.device_film_tensor(r, h, w))
+            r.reduce_film(0)
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3
         ms = r.stats()["render_ms"]
@@ -338,7 +338,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     r = Renderer(device_index=local_rank)
     r.upload(desc)
     r.set_shard(rank, world, D.TILE_SIZE)
-    film_t = D.device_film_tensor(r, HEIGHT, WIDTH) if world > 1 else None
+    if world > 1:
+        D.init_film_comm(r, rank, world)  # the library's own NCCL communicator: lrk_reduce_film is the path's one collective
     K, W, S = args.steps, args.warmup, SPP_PER_STEP
 
     def step(s):
@@ -347,8 +348,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     # ---- device-resident timing -------------------------------------------------------------------------
     for w in range(W):
         step(w)
-    if film_t is not None:
-        D.reduce_film(film_t)  # warm the NCCL communicator
+    if world > 1:
+        r.reduce_film(0)  # warm the NCCL communicator
     r.clear()
     r.set_option("time_kernels", 1)
     clocks = ClockSampler(local_rank)
@@ -358,18 +359,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     t0 = time.perf_counter()
     for s in range(K):
         step(s)
-    reduce_ms = 0.0
-    if film_t is not None:
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        D.reduce_film(film_t)
-        ev1.record()
+    if world > 1:
+        r.reduce_film(0)  # lrk_reduce_film: ncclReduce on the renderer's stream, CUDA-event timed inside (lrk_stats.reduce_ms)
     barrier()
     dt = time.perf_counter() - t0
-    if film_t is not None:
-        reduce_ms = ev0.elapsed_time(ev1)
     clock_info = clocks.stop() if rank == 0 else None
     st = r.stats()
+    reduce_ms = st["reduce_ms"]
     r.set_option("time_kernels", 0)
     per_rank = None
     if dist is not None:
@@ -469,8 +465,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         r.upload(desc)  # host -> device copy of the step's inputs (flattened scene, camera, integrator)
         r.render(s * S, (s + 1) * S)
         if world > 1:
-            D.reduce_film(D.device_film_tensor(r, HEIGHT, WIDTH))
-            torch.cuda.synchronize()
+            r.reduce_film(0)
         if rank == 0:
             r.film(out=img)  # device -> host read of the step's result (normalised film)
     barrier()

@@ -14,6 +14,8 @@
  *   lrk_upload_scene    <- Pipeline::create (Geometry::build, register_surface/light,
  *                          Integrator::build)                                    src/base/pipeline.cpp:44-99
  *   lrk_set_shard       <- (none: the reference is single device)               SURVEY.md §8e
+ *   lrk_comm_unique_id / lrk_comm_init / lrk_reduce_film
+ *                       <- (none; sums the film of src/films/color.cpp:107-130 over ranks)  SURVEY.md §8e
  *   lrk_film_clear      <- Film::Instance::prepare / clear                      src/films/color.cpp:132-144
  *   lrk_render          <- ProgressiveIntegrator::Instance::_render_one_camera  src/integrators/wave_path.cpp:220-567
  *   lrk_download_film   <- Film::Instance::download (convert_image + copy)      src/films/color.cpp:87-105
@@ -37,7 +39,7 @@
 extern "C" {
 #endif
 
-#define LRK_ABI_VERSION 5u /* 5: lrk_sampler (row f2), LRK_SURFACE_DISNEY_TRANSMISSIVE */
+#define LRK_ABI_VERSION 6u /* 6: lrk_comm_* / lrk_reduce_film, lrk_stats::reduce_ms, hashed lrk_tile_owner */
 
 typedef enum lrk_status {
     LRK_OK = 0,
@@ -443,6 +445,7 @@ typedef struct lrk_stats {
     double trace_shadow_ms;
     double shade_ms;
     double other_ms;
+    double reduce_ms; /* CUDA-event time of the lrk_reduce_film calls */
 } lrk_stats;
 
 typedef struct lrk_ctx lrk_ctx;
@@ -455,8 +458,31 @@ const char *lrk_last_error(const lrk_ctx *ctx);
 int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *scene);
 
 /* Pixel-tile sharding for multi-GPU: this ctx renders the tiles with
- * tile_id % world == rank, tiles are tile_size x tile_size pixels in row-major tile order. */
+ * lrk_tile_owner(tile_id, world) == rank, tiles are tile_size x tile_size pixels in row-major tile order.
+ *
+ * Every run of `world` consecutive tiles hands one tile to each rank (exact balance of the tile COUNT), and the order inside
+ * a run is rotated by a hash of the run's index: a plain tile_id % world makes every rank own fixed columns or diagonals of
+ * the image whenever world and the number of tile columns share a factor (60 columns, 8 ranks: two column stripes per rank),
+ * and the cost of a tile follows the image's structure. */
+static inline uint32_t lrk_tile_owner(uint32_t tile_id, uint32_t world) {
+    uint32_t run = tile_id / world, h = run * 0x9E3779B1u;
+    h ^= h >> 15;
+    h *= 0x85EBCA77u;
+    h ^= h >> 13;
+    return (tile_id % world + h % world) % world;
+}
 int lrk_set_shard(lrk_ctx *ctx, uint32_t rank, uint32_t world, uint32_t tile_size);
+
+/* The film reduce of the multi-GPU path (the reference is single-device, its film is src/films/color.cpp:107-130).
+ * One process per GPU.  One rank calls lrk_comm_unique_id and hands the LRK_COMM_ID_BYTES to the others by any means (a file,
+ * MPI, torch.distributed); every rank then calls lrk_comm_init (collective) once, renders its tiles (lrk_set_shard), and calls
+ * lrk_reduce_film (collective): the raw film of rank `root` becomes the sum over ranks - bit-identical to a single-GPU render,
+ * since every pixel has exactly one owner - and the other ranks' films are left as they were.  NCCL is opened at run time
+ * (libnccl.so.2; the copy already loaded into the process, if any); without it these calls return LRK_ERR_UNSUPPORTED. */
+#define LRK_COMM_ID_BYTES 128
+int lrk_comm_unique_id(uint8_t *id);
+int lrk_comm_init(lrk_ctx *ctx, const uint8_t *id, uint32_t rank, uint32_t world);
+int lrk_reduce_film(lrk_ctx *ctx, uint32_t root);
 
 /* Options (unknown name -> LRK_ERR_INVALID_ARGUMENT):
  *   "count_traversal" (0/1)   traversal kernels count wide nodes / triangles / instance entries into lrk_stats

@@ -13,7 +13,7 @@ PKG_DIR = Path(__file__).resolve().parent
 REPO_DIR = PKG_DIR.parent
 LIB_DIR = PKG_DIR / "lib"
 
-LRK_ABI_VERSION = 5
+LRK_ABI_VERSION = 6
 TEX_ADDRESS_EDGE, TEX_ADDRESS_REPEAT, TEX_ADDRESS_MIRROR, TEX_ADDRESS_ZERO = 0, 1, 2, 3
 TEX_FILTER_POINT, TEX_FILTER_LINEAR = 0, 1
 TEX_ENCODING_LINEAR, TEX_ENCODING_SRGB, TEX_ENCODING_GAMMA = 0, 1, 2
@@ -139,7 +139,7 @@ class Stats(C.Structure):
     _fields_ = [("render_ms", f64), ("samples", u64), ("closest_rays", u64), ("shadow_rays", u64),
                 ("kernel_launches", u64), ("passes", u64), ("closest_nodes", u64), ("closest_tris", u64),
                 ("closest_xforms", u64), ("shadow_nodes", u64), ("shadow_tris", u64), ("shadow_xforms", u64), ("trace_closest_ms", f64), ("trace_shadow_ms", f64), ("shade_ms", f64),
-                ("other_ms", f64)]
+                ("other_ms", f64), ("reduce_ms", f64)]
 
 
 class SceneInfo(C.Structure):
@@ -152,7 +152,7 @@ LRK_SYMBOLS = [
     "lrk_abi_version", "lrk_create", "lrk_destroy", "lrk_last_error", "lrk_upload_scene", "lrk_set_shard",
     "lrk_set_option", "lrk_film_clear", "lrk_render", "lrk_download_film", "lrk_download_film_raw",
     "lrk_film_device_ptr", "lrk_film_normalize_to_host", "lrk_trace", "lrk_trace_device", "lrk_get_stats",
-    "lrk_stream",
+    "lrk_stream", "lrk_comm_unique_id", "lrk_comm_init", "lrk_reduce_film",
 ]
 LRH_SYMBOLS = [
     "lrh_last_error", "lrh_scene_load", "lrh_scene_load_source", "lrh_scene_destroy", "lrh_scene_get_info",
@@ -217,5 +217,8 @@ def device_lib() -> C.CDLL:
         lib.lrk_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         lib.lrk_stream.argtypes = [C.c_void_p]
         lib.lrk_stream.restype = C.c_void_p
+        lib.lrk_comm_unique_id.argtypes = [C.c_void_p]
+        lib.lrk_comm_init.argtypes = [C.c_void_p, C.c_void_p, u32, u32]
+        lib.lrk_reduce_film.argtypes = [C.c_void_p, u32]
         lib._lrk_typed = True
     return lib

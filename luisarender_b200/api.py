@@ -113,6 +113,24 @@ class Renderer:
     def set_shard(self, rank: int, world: int, tile_size: int = 32):
         self._check(self._lib.lrk_set_shard(self._ctx, rank, world, tile_size), "lrk_set_shard")
 
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """lrk_comm_unique_id: the 128 bytes one rank creates and every rank passes to comm_init."""
+        buf = C.create_string_buffer(128)
+        rc = F.device_lib().lrk_comm_unique_id(buf)
+        if rc != 0:
+            raise RuntimeError(f"lrk_comm_unique_id failed ({rc}): NCCL (libnccl.so.2) is not available")
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        """lrk_comm_init (collective): join the film-reduce communicator."""
+        assert len(unique_id) == 128
+        self._check(self._lib.lrk_comm_init(self._ctx, C.c_char_p(unique_id), rank, world), "lrk_comm_init")
+
+    def reduce_film(self, root: int = 0):
+        """lrk_reduce_film (collective): rank `root`'s raw film becomes the sum over ranks."""
+        self._check(self._lib.lrk_reduce_film(self._ctx, root), "lrk_reduce_film")
+
     def set_option(self, name: str, value: int):
         self._check(self._lib.lrk_set_option(self._ctx, name.encode(), value), f"lrk_set_option({name})")
 

@@ -12,6 +12,7 @@
 
 #include "kernels.cuh"
 #include "bvh_build.cuh"
+#include "comm.cuh"
 
 using namespace lrk;
 
@@ -63,6 +64,10 @@ struct lrk_ctx {
     const void *sampler_table_src[3]{nullptr, nullptr, nullptr};// host addresses of the static sampler tables already on the device
     bool pin_host{false};// option pin_host_buffers: page-lock the caller's scene arrays / film buffers on first sight (see pin_range)
     std::unordered_map<const void *, size_t> pinned;
+    // multi-GPU film reduce (comm.cuh)
+    ncclComm_t comm{nullptr};
+    uint32_t comm_rank{0}, comm_world{1};
+    cudaEvent_t ev_reduce_begin{}, ev_reduce_end{};
     uint32_t h_overflow{0u};// host copy of DeviceScene::traversal_overflow, fetched with every render / trace call
     // stats
     lrk_stats stats{};
@@ -200,7 +205,7 @@ int alloc_paths(lrk_ctx *ctx, uint64_t capacity) {
     return LRK_OK;
 }
 
-// Pixel order of a shard: tiles in row-major tile order (tile_id % world == rank), inside a tile 8x4
+// Pixel order of a shard: tiles in row-major tile order (lrk_tile_owner(tile_id, world) == rank), inside a tile 8x4
 // pixel blocks so that a warp's 32 consecutive paths cover a compact screen region.
 int build_pixel_list(lrk_ctx *ctx) {
     const uint32_t W = ctx->scene.width, H = ctx->scene.height, ts = ctx->tile_size;
@@ -213,7 +218,7 @@ int build_pixel_list(lrk_ctx *ctx) {
     for (uint32_t ty = 0; ty < tiles_y; ty++) {
         for (uint32_t tx = 0; tx < tiles_x; tx++) {
             uint32_t tile_id = ty * tiles_x + tx;
-            if (tile_id % ctx->world != ctx->rank) continue;
+            if (lrk_tile_owner(tile_id, ctx->world) != ctx->rank) continue;
             uint32_t x0 = tx * ts, y0 = ty * ts;
             uint32_t x1 = std::min(W, x0 + ts), y1 = std::min(H, y0 + ts);
             for (uint32_t by = y0; by < y1; by += 4u)
@@ -597,6 +602,11 @@ void lrk_destroy(lrk_ctx *ctx) {
         cudaEventDestroy(t.stop);
     }
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
+    if (ctx->comm != nullptr) {
+        lrk::nccl_api().comm_destroy(ctx->comm);
+        cudaEventDestroy(ctx->ev_reduce_begin);
+        cudaEventDestroy(ctx->ev_reduce_end);
+    }
     cudaEventDestroy(ctx->ev_begin);
     cudaEventDestroy(ctx->ev_end);
     cudaStreamDestroy(ctx->stream);
@@ -1038,6 +1048,61 @@ int lrk_trace_device(lrk_ctx *ctx, const void *d_rays, uint64_t n, int any_hit, 
     float ms = 0.f;
     LRK_CUDA(cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
     if (avg_ms) *avg_ms = ms / static_cast<float>(repeat);
+    return LRK_OK;
+}
+
+int lrk_comm_unique_id(uint8_t *id) {
+    if (id == nullptr) return LRK_ERR_INVALID_ARGUMENT;
+    static_assert(sizeof(ncclUniqueId) == LRK_COMM_ID_BYTES, "LRK_COMM_ID_BYTES must be NCCL's unique id size");
+    auto &api = lrk::nccl_api();
+    if (!api.error.empty()) return LRK_ERR_UNSUPPORTED;
+    ncclUniqueId uid;
+    if (api.get_unique_id(&uid) != ncclSuccess) return LRK_ERR_CUDA;
+    std::memcpy(id, &uid, sizeof(uid));
+    return LRK_OK;
+}
+
+int lrk_comm_init(lrk_ctx *ctx, const uint8_t *id, uint32_t rank, uint32_t world) {
+    if (!ctx || !id || world == 0u || rank >= world) return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_comm_init: bad arguments");
+    auto &api = lrk::nccl_api();
+    if (!api.error.empty()) return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_comm_init: " + api.error);
+    LRK_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->comm != nullptr) {
+        api.comm_destroy(ctx->comm);
+        ctx->comm = nullptr;
+    } else {
+        LRK_CUDA(cudaEventCreate(&ctx->ev_reduce_begin));
+        LRK_CUDA(cudaEventCreate(&ctx->ev_reduce_end));
+    }
+    ncclUniqueId uid;
+    std::memcpy(&uid, id, sizeof(uid));
+    ncclResult_t r = api.comm_init_rank(&ctx->comm, static_cast<int>(world), uid, static_cast<int>(rank));
+    if (r != ncclSuccess) {
+        ctx->comm = nullptr;
+        cudaEventDestroy(ctx->ev_reduce_begin);
+        cudaEventDestroy(ctx->ev_reduce_end);
+        return fail(ctx, LRK_ERR_CUDA, std::string("lrk_comm_init: ncclCommInitRank: ") + api.error_string(r));
+    }
+    ctx->comm_rank = rank;
+    ctx->comm_world = world;
+    return LRK_OK;
+}
+
+int lrk_reduce_film(lrk_ctx *ctx, uint32_t root) {
+    if (!ctx || !ctx->has_scene) return fail(ctx, LRK_ERR_NO_SCENE, "lrk_reduce_film: no scene");
+    if (ctx->comm == nullptr) return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_reduce_film: lrk_comm_init was not called");
+    if (root >= ctx->comm_world) return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_reduce_film: root outside the communicator");
+    LRK_CUDA(cudaSetDevice(ctx->device));
+    auto &api = lrk::nccl_api();
+    const size_t count = static_cast<size_t>(ctx->scene.width) * ctx->scene.height * 4u;
+    LRK_CUDA(cudaEventRecord(ctx->ev_reduce_begin, ctx->stream));
+    ncclResult_t r = api.reduce(ctx->d_film, ctx->d_film, count, ncclFloat, ncclSum, static_cast<int>(root), ctx->comm, ctx->stream);
+    if (r != ncclSuccess) return fail(ctx, LRK_ERR_CUDA, std::string("lrk_reduce_film: ncclReduce: ") + api.error_string(r));
+    LRK_CUDA(cudaEventRecord(ctx->ev_reduce_end, ctx->stream));
+    LRK_CUDA(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    LRK_CUDA(cudaEventElapsedTime(&ms, ctx->ev_reduce_begin, ctx->ev_reduce_end));
+    ctx->stats.reduce_ms += ms;
     return LRK_OK;
 }
 

@@ -2370,7 +2370,7 @@ int oracle_render(const lrk_scene_desc *scene, uint32_t spp_begin, uint32_t spp_
         if (tile_size == 0u || world <= 1u) return true;
         uint32_t shard_tiles_x = (W + tile_size - 1u) / tile_size;
         uint32_t tile_id = (y / tile_size) * shard_tiles_x + (x / tile_size);
-        return tile_id % world == rank;
+        return lrk_tile_owner(tile_id, world) == rank;
     };
     std::vector<uint32_t> items;
     for (uint32_t t = 0; t < tiles_x * tiles_y; t++) {

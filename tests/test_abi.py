@@ -15,6 +15,7 @@ REPO = Path(__file__).resolve().parents[1]
 def _declared(header: str, prefix: str) -> set[str]:
     text = (REPO / "include" / header).read_text()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"static inline[^{]*\{.*?\n\}", "", text, flags=re.S)  # header-only helpers are not exports
     return set(re.findall(rf"\b({prefix}_[a-z_0-9]+)\s*\(", text))
 
 

@@ -63,3 +63,20 @@ def test_owned_pixel_mask_partitions_the_film():
     for rank in range(4):
         total += owned_pixel_mask(100, 70, rank, 4, 32)
     assert (total == 1).all()
+
+
+def test_tile_owner_is_balanced_and_not_striped():
+    """60 tile columns and 8 ranks: tile_id % world gave every rank fixed diagonals; the hashed rotation must keep the tile
+    count exact (+-1) and spread every rank over all tile columns and rows."""
+    from luisarender_b200.distributed import tile_owner
+
+    tiles_x, tiles_y = 60, 34
+    for world in (2, 3, 4, 8):
+        owner = tile_owner(np.arange(tiles_x * tiles_y), world).reshape(tiles_y, tiles_x)
+        counts = np.bincount(owner.ravel(), minlength=world)
+        assert counts.max() - counts.min() <= 1
+        for rank in range(world):
+            mine = owner == rank
+            assert mine.any(axis=0).mean() >= 0.9 and mine.any(axis=1).all()
+            # no rank owns a vertical run longer than a plain stripe pattern would make impossible to balance
+            assert mine.sum(axis=0).max() <= 3 * tiles_y // world + 3
