@@ -567,15 +567,15 @@ int lrk_create(const lrk_device_cfg *cfg, lrk_ctx **out) {
     };
     ctx->grid_trace = grid_for(reinterpret_cast<const void *>(trace_closest_kernel<false, false>), kTraceBlock);
     ctx->grid_shadow = grid_for(reinterpret_cast<const void *>(trace_shadow_kernel<false, false>), kTraceBlock);
-    ctx->grid_shade[0] = grid_for(reinterpret_cast<const void *>(shade_kernel<0u, false>));
-    ctx->grid_shade[1] = grid_for(reinterpret_cast<const void *>(shade_kernel<1u, false>));
-    ctx->grid_shade[2] = grid_for(reinterpret_cast<const void *>(shade_kernel<2u, false>));
-    ctx->grid_shade[3] = grid_for(reinterpret_cast<const void *>(shade_kernel<3u, false>));
-    ctx->grid_shade[4] = grid_for(reinterpret_cast<const void *>(shade_kernel<4u, false>));
-    ctx->grid_shade[5] = grid_for(reinterpret_cast<const void *>(shade_kernel<5u, false>));
-    ctx->grid_shade[6] = grid_for(reinterpret_cast<const void *>(shade_kernel<6u, false>));
-    ctx->grid_shade[7] = grid_for(reinterpret_cast<const void *>(shade_kernel<7u, false>));
-    ctx->grid_shade[8] = grid_for(reinterpret_cast<const void *>(shade_kernel<8u, false>));
+    ctx->grid_shade[0] = grid_for(reinterpret_cast<const void *>(shade_kernel<0u, false>), kShadeBlock);
+    ctx->grid_shade[1] = grid_for(reinterpret_cast<const void *>(shade_kernel<1u, false>), kShadeBlock);
+    ctx->grid_shade[2] = grid_for(reinterpret_cast<const void *>(shade_kernel<2u, false>), kShadeBlock);
+    ctx->grid_shade[3] = grid_for(reinterpret_cast<const void *>(shade_kernel<3u, false>), kShadeBlock);
+    ctx->grid_shade[4] = grid_for(reinterpret_cast<const void *>(shade_kernel<4u, false>), kShadeBlock);
+    ctx->grid_shade[5] = grid_for(reinterpret_cast<const void *>(shade_kernel<5u, false>), kShadeBlock);
+    ctx->grid_shade[6] = grid_for(reinterpret_cast<const void *>(shade_kernel<6u, false>), kShadeBlock);
+    ctx->grid_shade[7] = grid_for(reinterpret_cast<const void *>(shade_kernel<7u, false>), kShadeBlock);
+    ctx->grid_shade[8] = grid_for(reinterpret_cast<const void *>(shade_kernel<8u, false>), kShadeBlock);
     ctx->grid_classify = grid_for(reinterpret_cast<const void *>(classify_hits_kernel));
     ctx->grid_vmedium = grid_for(reinterpret_cast<const void *>(volume_medium_kernel));
     ctx->grid_vshade[0] = grid_for(reinterpret_cast<const void *>(volume_surface_kernel<0u, false>));

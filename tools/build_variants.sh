@@ -5,7 +5,7 @@ set -e
 cd "$(dirname "$0")/.."
 for spec in "$@"; do
   tag="${spec%%=*}"; flags="${spec#*=}"
-  ( nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false --shared -Xcompiler -fPIC $flags \
+  ( nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=${MAD:-false} --shared -Xcompiler -fPIC $flags \
       luisarender_b200/csrc/device/lrk.cu -o luisarender_b200/lib/libb200pt_${tag}.so && echo "built $tag ($flags)" ) &
 done
 wait
