@@ -304,7 +304,13 @@ typedef struct lrk_integrator {
     uint32_t reserved[2];
 } lrk_integrator;
 
-/* Homogeneous environment medium (config C4): src/media/homogeneous.cpp */
+/* A participating medium (row a22): src/media/homogeneous.cpp, src/media/vacuum.cpp.  `present` is the kind: a vacuum medium has
+ * priority LRK_MEDIUM_VACUUM_PRIORITY and never becomes the current medium of a path (src/util/medium_tracker.cpp:23-43). */
+#define LRK_MEDIUM_NONE 0u
+#define LRK_MEDIUM_HOMOGENEOUS 1u
+#define LRK_MEDIUM_VACUUM 2u
+#define LRK_MEDIUM_VACUUM_PRIORITY 0xffffffffu /* Medium::VACUUM_PRIORITY, src/base/medium.h:29 */
+#define LRK_MEDIUM_INVALID_TAG 0xffffffffu     /* Medium::INVALID_TAG, src/base/medium.h:28 */
 typedef struct lrk_medium {
     uint32_t present;
     uint32_t priority;
@@ -414,9 +420,15 @@ typedef struct lrk_scene_desc {
     lrk_camera camera;
     lrk_film film;
     lrk_integrator integrator;
-    lrk_medium environment_medium;
+    lrk_medium environment_medium; /* copy of media[environment_medium_tag]; present = 0 when the scene has none */
     lrk_environment environment;
     lrk_sampler sampler;
+    /* every medium of the scene, indexed by the medium tag of the shape handles: shape media in the order Geometry::build meets
+     * them (src/base/geometry.cpp:134-142), then the environment medium (src/base/pipeline.cpp:72-79).  The order is part of the
+     * result: MediumTracker::true_hit is called with a TAG where it expects a priority (src/integrators/mega_vpt_naive.cpp:387). */
+    const lrk_medium *media;
+    uint32_t medium_count;
+    uint32_t environment_medium_tag; /* LRK_MEDIUM_INVALID_TAG: none */
 } lrk_scene_desc;
 
 /* ---- device control ----------------------------------------------------------------- */

@@ -128,6 +128,7 @@ class SceneDesc(C.Structure):
         ("textures", C.POINTER(Texture)), ("texture_count", u32), ("reserved2", u32), ("texels", C.POINTER(f32)), ("texel_count", u64),
         ("camera", Camera), ("film", Film), ("integrator", Integrator), ("environment_medium", Medium),
         ("environment", Environment), ("sampler", Sampler),
+        ("media", C.POINTER(Medium)), ("medium_count", u32), ("environment_medium_tag", u32),
     ]
 
 

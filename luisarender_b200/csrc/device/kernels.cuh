@@ -713,6 +713,64 @@ __device__ __forceinline__ void volume_store_next(const PathBuffers &pb, int out
     pb.occl2[out][slot] = 0u;
 }
 
+// HomogeneousMediumClosure::sample (src/media/homogeneous.cpp:48-118) with HenyeyGreenstein::sample_p (henyey_greenstein.cpp:28-48):
+// event 0 absorb, 1 scatter, 3 hit surface (src/base/medium.h:31-36); f and pdf of the event, the ray that continues the path
+__device__ __forceinline__ void homogeneous_medium_sample(V3 sigma_a, V3 sigma_s, float g, V3 o, V3 d, float t_max, PCG32 &rng, uint32_t &event,
+                                                          V3 &mf, float &mpdf, V3 &no, V3 &nd) {
+    const V3 sigma_t = sigma_a + sigma_s;
+    V3 pch;
+    pch.x = rng.uniform_float();
+    pch.y = rng.uniform_float();
+    pch.z = rng.uniform_float();
+    float psum = pch.x + pch.y + pch.z;
+    pch = v3(pch.x / psum, pch.y / psum, pch.z / psum);
+    float u_rescaled = rng.uniform_float() * (pch.x + pch.y + pch.z);
+    uint32_t channel = ~0u;
+    float accum = 0.f;
+#pragma unroll
+    for (uint32_t c = 0; c < 3u; c++) {
+        accum += comp3(pch, c);
+        if (channel == ~0u && u_rescaled <= accum) channel = c;
+    }
+    float u = rng.uniform_float();
+    float st = channel < 3u ? comp3(sigma_t, channel) : __int_as_float(0x7fc00000);
+    float t = -logf(fmaxf(1.f - u, 1.17549435e-38f)) / st;
+    no = o;
+    nd = d;
+    if (t > t_max) {
+        event = 3u;
+        t = t_max;
+        V3 Tr = exp3(-sigma_t * t);
+        no = o + d * t;
+        mf = Tr;
+        mpdf = (pch * Tr).x + (pch * Tr).y + (pch * Tr).z;
+    } else {
+        float p_absorb = comp3(sigma_a, channel) / st, p_scatter = comp3(sigma_s, channel) / st;
+        float ur = rng.uniform_float() * (p_absorb + p_scatter);
+        if (ur <= p_absorb) {
+            event = 0u;
+            mf = v3(0.f);
+            V3 pp = pch * sigma_t;
+            mpdf = pp.x + pp.y + pp.z;
+        } else {
+            event = 1u;
+            V3 Tr = exp3(-sigma_t * t);
+            float u0 = rng.uniform_float(), u1 = rng.uniform_float();
+            float cosTheta = fabsf(g) < 1e-3f ? 1.f - 2.f * u0
+                                              : -1.f / (2.f * g) * (1.f + sqr(g) - sqr((1.f - sqr(g)) / (1.f + g - 2.f * g * u0)));
+            float sinTheta = sqrtf(fmaxf(0.f, 1.f - sqr(cosTheta)));
+            float phi = 2.f * kPi * u1;
+            float sphi, cphi;
+            sincosf(phi, &sphi, &cphi);
+            no = o + d * t;
+            nd = v3(sinTheta * cphi, cosTheta, sinTheta * sphi);
+            mf = Tr * sigma_s;
+            V3 pp = pch * (sigma_t * Tr);
+            mpdf = pp.x + pp.y + pp.z;
+        }
+    }
+}
+
 // Volume wave, step 1 (every path of the depth): advance the PCG32 stream by the occlusion results, sample the medium
 // along the ray (homogeneous.cpp:48-118).  Absorption / scattering events finish here; paths that reach their surface hit
 // (event 3) write their updated throughput, pdf, PCG state and the MOVED ray origin back in place and are appended to the
@@ -725,7 +783,6 @@ __global__ void __launch_bounds__(kBlock) volume_medium_kernel(DeviceScene sc, P
     const int in = depth & 1u, out = in ^ 1;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5u, lane_lt = (1u << lane) - 1u;
     const V3 sigma_a = v3(sc.sigma_a[0], sc.sigma_a[1], sc.sigma_a[2]), sigma_s = v3(sc.sigma_s[0], sc.sigma_s[1], sc.sigma_s[2]);
-    const V3 sigma_t = sigma_a + sigma_s;
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
         const uint32_t i = base + threadIdx.x;
         uint32_t list = ~0u;// which list this item is appended to, if any
@@ -748,60 +805,10 @@ __global__ void __launch_bounds__(kBlock) volume_medium_kernel(DeviceScene sc, P
             const float bu = __uint_as_float(hit.z), bv = __uint_as_float(hit.w);
             float t_max = kFltMax;
             if (valid) t_max = length(hit_position(sc, hit.x, hit.y, v3(1.f - bu - bv, bu, bv)) - o);
-            // HomogeneousMediumClosure::sample, homogeneous.cpp:48-118
-            V3 pch;
-            pch.x = rng.uniform_float();
-            pch.y = rng.uniform_float();
-            pch.z = rng.uniform_float();
-            float psum = pch.x + pch.y + pch.z;
-            pch = v3(pch.x / psum, pch.y / psum, pch.z / psum);
-            float u_rescaled = rng.uniform_float() * (pch.x + pch.y + pch.z);
-            uint32_t channel = ~0u;
-            float accum = 0.f;
-#pragma unroll
-            for (uint32_t c = 0; c < 3u; c++) {
-                accum += comp3(pch, c);
-                if (channel == ~0u && u_rescaled <= accum) channel = c;
-            }
-            float u = rng.uniform_float();
-            float st = channel < 3u ? comp3(sigma_t, channel) : __int_as_float(0x7fc00000);
-            float t = -logf(fmaxf(1.f - u, 1.17549435e-38f)) / st;
             uint32_t event;
-            V3 mf, no = o, nd = d;
+            V3 mf, no, nd;
             float mpdf;
-            if (t > t_max) {
-                event = 3u;
-                t = t_max;
-                V3 Tr = exp3(-sigma_t * t);
-                no = o + d * t;
-                mf = Tr;
-                mpdf = (pch * Tr).x + (pch * Tr).y + (pch * Tr).z;
-            } else {
-                float p_absorb = comp3(sigma_a, channel) / st, p_scatter = comp3(sigma_s, channel) / st;
-                float ur = rng.uniform_float() * (p_absorb + p_scatter);
-                if (ur <= p_absorb) {
-                    event = 0u;
-                    mf = v3(0.f);
-                    V3 pp = pch * sigma_t;
-                    mpdf = pp.x + pp.y + pp.z;
-                } else {
-                    event = 1u;
-                    V3 Tr = exp3(-sigma_t * t);
-                    float u0 = rng.uniform_float(), u1 = rng.uniform_float();
-                    float g = sc.medium_g;
-                    float cosTheta = fabsf(g) < 1e-3f ? 1.f - 2.f * u0
-                                                      : -1.f / (2.f * g) * (1.f + sqr(g) - sqr((1.f - sqr(g)) / (1.f + g - 2.f * g * u0)));
-                    float sinTheta = sqrtf(fmaxf(0.f, 1.f - sqr(cosTheta)));
-                    float phi = 2.f * kPi * u1;
-                    float sphi, cphi;
-                    sincosf(phi, &sphi, &cphi);
-                    no = o + d * t;
-                    nd = v3(sinTheta * cphi, cosTheta, sinTheta * sphi);
-                    mf = Tr * sigma_s;
-                    V3 pp = pch * (sigma_t * Tr);
-                    mpdf = pp.x + pp.y + pp.z;
-                }
-            }
+            homogeneous_medium_sample(sigma_a, sigma_s, sc.medium_g, o, d, t_max, rng, event, mf, mpdf, no, nd);
             {
                 float w = mpdf > 0.f ? 1.f / mpdf : 0.f;
                 beta = beta * (mf * w);

@@ -691,9 +691,11 @@ struct DisneyClosureT {
     float w3, eta_t_;
     bool has_spec_trans;
     float rr_eta_scale;// eta scale of the sampled event for Russian roulette (mega_path.cpp:133-138)
+    uint32_t event;    // Surface::event_* of the sampled direction (what the volume integrator's medium tracker follows)
 
     __device__ __forceinline__ void init(const lrk_surface &s) {
         rr_eta_scale = 1.f;
+        event = LRK_EVENT_REFLECT;
         Cst = v3(0.f);
         w3 = 0.f;
         has_spec_trans = false;
@@ -881,12 +883,14 @@ struct DisneyClosureT {
         wi = v3(0.f);
         bool valid = false;
         rr_eta_scale = 1.f;
+        event = LRK_EVENT_REFLECT;
         if (TRANS && tech == 3u) {// MicrofacetTransmission::sample_wi (scattering.cpp:352-358), event enter / exit (disney.cpp:571-576)
             float e = cos_theta(wo) > 0.f ? 1.f / eta_t_ : eta_t_ / 1.f;
             V3 wh = distrib.sample_wh(wo, u0, u1);
             bool refr = refract(wo, wh, e, wi);
             valid = refr && !same_hemisphere(wo, wi);
             rr_eta_scale = cos_theta(wo) > 0.f ? sqr(eta_t_) : sqr(1.f / eta_t_);
+            event = cos_theta(wo) > 0.f ? LRK_EVENT_ENTER : LRK_EVENT_EXIT;
         } else if (tech == 0u) {
             if (has_diffuse) {
                 wi = sample_cosine_hemisphere(u0, u1);
@@ -970,8 +974,10 @@ struct MicrofacetFamilyClosure {
     TrowbridgeReitz d;
     float flip;        // PLASTIC: sign applied to the z components (plastic.cpp:143-147)
     float rr_eta_scale;// eta scale of the sampled event for Russian roulette (mega_path.cpp:133-138)
+    uint32_t event;    // Surface::event_* of the sampled direction
     __device__ __forceinline__ void init(const lrk_surface &s) {
         rr_eta_scale = 1.f;
+        event = LRK_EVENT_REFLECT;
         flip = 1.f;
         eta = 1.5f;
         w0 = 0.f;
@@ -1111,6 +1117,7 @@ struct MicrofacetFamilyClosure {
 
     __device__ __forceinline__ bool sample_direction(V3 wo, float u_lobe, float u0, float u1, V3 &wi) {
         rr_eta_scale = 1.f;
+        event = LRK_EVENT_REFLECT;
         if (type == LRK_SURFACE_MIRROR || type == LRK_SURFACE_METAL) {
             V3 wh = d.sample_wh(wo, u0, u1);
             wi = reflect(-wo, wh);
@@ -1128,6 +1135,7 @@ struct MicrofacetFamilyClosure {
             wi = v3(0.f);
             bool refr = refract(wo, wh, e, wi);
             rr_eta_scale = cos_theta(wo) > 0.f ? sqr(eta) : sqr(1.f / eta);// event_enter / event_exit
+            event = cos_theta(wo) > 0.f ? LRK_EVENT_ENTER : LRK_EVENT_EXIT;
             return refr && !same_hemisphere(wo, wi);
         }
         // plastic.cpp:168-214: sampled above the flipped surface, returned in the original frame
@@ -1194,6 +1202,7 @@ struct MixClosure {
     const lrk_surface *a, *b;
     float ratio, eta;  // eta: MixSurfaceClosure::eta() (mix.cpp:133-141), 0 = none; computed by the host into p[1]
     float rr_eta_scale;
+    uint32_t event;
     bool first_branch, child_valid;
     __device__ __forceinline__ void init(const lrk_surface &s, const lrk_surface *records) {
         a = records + s.mix_a;
@@ -1201,6 +1210,7 @@ struct MixClosure {
         ratio = s.p[0];
         eta = s.p[1];
         rr_eta_scale = 1.f;
+        event = LRK_EVENT_REFLECT;
         first_branch = true;
         child_valid = false;
     }
@@ -1225,6 +1235,7 @@ struct MixClosure {
         child_valid = any_sample_direction(a, wo, ul, u0, u1, wi, transmitted);
         rr_eta_scale = 1.f;
         if (transmitted && eta != 0.f) rr_eta_scale = cos_theta(wo) > 0.f ? sqr(eta) : sqr(1.f / eta);
+        event = transmitted ? (cos_theta(wo) > 0.f ? LRK_EVENT_ENTER : LRK_EVENT_EXIT) : LRK_EVENT_REFLECT;// sample_a.event (mix.cpp:158-180)
         return true;// the other child is evaluated at wi whether or not a's sample is valid
     }
     // f and pdf of the sample: first branch mix(a's sample, b(wi)); second branch mix(b(wi), a's sample) — sic

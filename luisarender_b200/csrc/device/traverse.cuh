@@ -339,6 +339,57 @@ __device__ __forceinline__ void trace_queue(const DeviceScene &sc, const float4 
     }
 }
 
+// ---- one ray per thread ---------------------------------------------------------------------------------------------------
+// The same step functions driven by a plain per-thread loop with a local-memory stack: for code that traces from inside a
+// longer per-thread computation (the general volume integrator walks its transmittance rays surface by surface).  Results are
+// those of trace_queue bit for bit; only the scheduling differs.
+struct ThreadStack {
+    uint32_t *e;
+    int sp;
+    uint32_t *overflow;
+    static constexpr int kCapacity = kSmemStack + kLocalStack;
+    __device__ __forceinline__ void reset() { sp = 0; }
+    __device__ __forceinline__ void push(uint32_t ref) {
+        if (sp < kCapacity) e[sp] = ref;
+        else *overflow = 1u;
+        sp++;
+    }
+    __device__ __forceinline__ uint32_t at(int i) const { return e[min(i, kCapacity - 1)]; }
+    __device__ __forceinline__ uint32_t pop() {
+        --sp;
+        return at(sp);
+    }
+    __device__ __forceinline__ void push_if(bool p, uint32_t ref) {
+        if (p) push(ref);
+    }
+    __device__ __forceinline__ uint32_t top() const { return at(sp - 1); }
+    __device__ __forceinline__ void drop_if(bool p) { sp -= p ? 1 : 0; }
+};
+
+struct ThreadWorld {
+    RaySetup saved;
+    __device__ __forceinline__ void save(const RaySetup &c) { saved = c; }
+    __device__ __forceinline__ void load(RaySetup &c) const { c = saved; }
+};
+
+// hit = {inst, prim, bary.u bits, bary.v bits}; miss <=> inst == ~0u
+template<bool ANY_HIT, bool ALPHA>
+__device__ __noinline__ uint4 trace_single(const DeviceScene &sc, float4 o, float4 d) {
+    uint32_t entries[ThreadStack::kCapacity];
+    ThreadStack stack;
+    stack.e = entries;
+    stack.overflow = sc.traversal_overflow;
+    ThreadWorld world;
+    TraversalCounters cnt{0u, 0u, 0u};
+    RayState r;
+    start_ray(sc, r, stack, o, d);
+    for (;;) {
+        if (!(r.node & LRK_BVH_LEAF)) inner_step<false>(sc, r, stack, cnt);
+        else if (leaf_step<ANY_HIT, false, ALPHA>(sc, r, stack, world, cnt)) break;
+    }
+    return make_uint4(r.best_inst, r.best_prim, __float_as_uint(r.best_u), __float_as_uint(r.best_v));
+}
+
 #endif// __CUDACC__
 
 }// namespace lrk

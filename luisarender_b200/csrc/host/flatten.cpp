@@ -50,6 +50,9 @@ lrk_scene_desc FlatScene::desc(uint32_t camera_index) const {
     d.film = cameras[camera_index].film;
     d.integrator = integrator;
     d.environment_medium = environment_medium;
+    d.media = media.empty() ? nullptr : media.data();
+    d.medium_count = static_cast<uint32_t>(media.size());
+    d.environment_medium_tag = environment_medium_tag;
     d.environment = environment;
     d.environment.alias = env_alias.empty() ? nullptr : env_alias.data();
     d.environment.pdf = env_pdf.empty() ? nullptr : env_pdf.data();
@@ -255,6 +258,7 @@ struct Flattener {
     std::multimap<uint64_t, uint32_t> mesh_by_hash;
     std::unordered_map<const Surface *, uint32_t> surface_tags;
     std::unordered_map<const Light *, uint32_t> light_tags;
+    std::unordered_map<const Medium *, uint32_t> medium_tags;
     std::vector<const Surface *> surface_nodes;
     std::vector<const Light *> light_nodes;
     std::vector<float4x4> xform_stack;
@@ -342,6 +346,24 @@ struct Flattener {
         surface_tags.emplace(s, tag);
         return tag;
     }
+    // Pipeline::register_medium (src/base/pipeline.cpp:36-42): one record per medium node, in first-use order
+    uint32_t register_medium(const Medium *m) {
+        if (auto it = medium_tags.find(m); it != medium_tags.end()) return it->second;
+        auto tag = static_cast<uint32_t>(out.media.size());
+        lrk_medium rec{};
+        rec.present = m->is_vacuum() ? LRK_MEDIUM_VACUUM : LRK_MEDIUM_HOMOGENEOUS;
+        rec.priority = m->is_vacuum() ? LRK_MEDIUM_VACUUM_PRIORITY : m->priority;
+        rec.eta = m->eta;
+        rec.g = m->phase ? m->phase->g : 0.f;
+        for (int i = 0; i < 3; i++) {
+            rec.sigma_a[i] = m->sigma_a[i];
+            rec.sigma_s[i] = m->sigma_s[i];
+            rec.le[i] = m->le[i];
+        }
+        out.media.push_back(rec);
+        medium_tags.emplace(m, tag);
+        return tag;
+    }
     uint32_t register_light(const Light *l) {
         if (auto it = light_tags.find(l); it != light_tags.end()) return it->second;
         auto tag = static_cast<uint32_t>(light_nodes.size());
@@ -390,8 +412,9 @@ struct Flattener {
                 light_tag = register_light(light);
                 properties |= LRK_SHAPE_HAS_LIGHT;
             }
-            if (medium != nullptr && !medium->is_null()) {
-                throw Error("Per-shape media are not supported (only environment_medium). [" + shape->desc()->location() + "]");
+            if (medium != nullptr && !medium->is_null()) {// geometry.cpp:139-142
+                medium_tag = register_medium(medium);
+                properties |= LRK_SHAPE_HAS_MEDIUM;
             }
             auto fixed16 = [](float x) {
                 return static_cast<float>(static_cast<uint16_t>(std::min(std::max(std::round(x * 65535.f), 0.f), 65535.f))) / 65535.f;
@@ -581,17 +604,11 @@ std::unique_ptr<FlatScene> flatten_scene(const Scene &scene) {
     out->integrator.samples_per_pass = integ->samples_per_pass;
     out->integrator.sampler_seed = integ->sampler->seed;
 
+    // the environment medium is registered after the shapes' media (src/base/pipeline.cpp:72-79); a vacuum one never enters a
+    // path's medium tracker (its priority is VACUUM_PRIORITY, medium_tracker.cpp:29-41) and counts as none
     if (auto m = scene.environment_medium(); m != nullptr && !m->is_null() && !m->is_vacuum()) {
-        auto &em = out->environment_medium;
-        em.present = 1u;
-        em.priority = m->priority;
-        em.eta = m->eta;
-        em.g = m->phase ? m->phase->g : 0.f;
-        for (int i = 0; i < 3; i++) {
-            em.sigma_a[i] = m->sigma_a[i];
-            em.sigma_s[i] = m->sigma_s[i];
-            em.le[i] = m->le[i];
-        }
+        out->environment_medium_tag = f.register_medium(m);
+        out->environment_medium = out->media[out->environment_medium_tag];
     }
     return out;
 }

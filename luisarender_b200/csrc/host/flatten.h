@@ -40,6 +40,8 @@ struct FlatScene {
     std::vector<FlatCamera> cameras;
     lrk_integrator integrator{};
     lrk_medium environment_medium{};
+    std::vector<lrk_medium> media;             // indexed by the handles' medium tags; the environment medium is registered last
+    uint32_t environment_medium_tag{LRK_MEDIUM_INVALID_TAG};
     lrk_environment environment{};           // pointers are filled by desc()
     std::vector<lrk_alias_entry> env_alias;  // importance map of an image-textured environment (spherical.cpp:140-236)
     std::vector<float> env_pdf;

@@ -196,6 +196,70 @@ def instanced_spheres(resolution=(1920, 1080), spp=1024, seed=1, depth=10, rr_de
     return "\n".join(out) + "\n"
 
 
+def media_box(resolution=(64, 64), spp=4, depth=8, rr_depth=0, rr_threshold=0.95, seed=19980810, output="media.exr",
+              environment_medium=False, skip_quirk=False) -> str:
+    """Row a22 beyond config C4: media bound to shapes (MegaVPTNaive's medium tracker).  The Cornell box whose short box is a
+    smooth Glass shell around a dense, coloured medium and whose tall box is a rough Glass shell around a second medium; with
+    ``environment_medium`` the room itself is filled with a thin third medium (registered last: highest medium tag), otherwise
+    the environment medium is a Vacuum node.
+    ``skip_quirk`` gives the tall box's medium priority 0 and tag 1: inside it `true_hit(tag)` (mega_vpt_naive.cpp:387 compares
+    the TAG with the current priority) is false for its own boundary and the path leaves straight through, without refraction."""
+    out = []
+    for name, rgb in _CORNELL_COLORS.items():
+        out.append(f"Surface {name} : Matte {{ Kd : Constant {{ v {{ {_fmt(rgb[0])}, {_fmt(rgb[1])}, {_fmt(rgb[2])} }} }} }}")
+    out.append('Surface shell_smooth : Glass { eta { "BK7" } }')
+    out.append("Surface shell_rough : Glass { Kr : Constant { v { 1.0, 0.95, 0.9 } } Kt : Constant { v { 0.9, 0.95, 1.0 } } "
+               "roughness : Constant { v { 0.25 } } eta { 1.33 } }")
+    out.append("Medium fog_dense : Homogeneous {\n  priority { 2 }\n  sigma_a : Constant { v { 0.4, 0.8, 2.5 } }\n"
+               "  sigma_s : Constant { v { 2.0, 3.0, 1.5 } }\n  phasefunction : HenyeyGreenstein { g { 0.5 } }\n}")
+    out.append(f"Medium fog_light : Homogeneous {{\n  priority {{ {0 if skip_quirk else 1} }}\n  sigma_a : Constant {{ v {{ 0.3, 0.1, 0.1 }} }}\n"
+               "  sigma_s : Constant { v { 0.8, 0.9, 1.2 } }\n  phasefunction : HenyeyGreenstein { g { 0.0 } }\n}")
+    out.append("Light area_light : Diffuse { emission : Constant { v { 17.0, 12.0, 4.0 } } }")
+    shape_names = []
+    for name, quads in _CORNELL_QUADS.items():
+        positions, indices = _mesh_props(quads)
+        if name == "light":
+            binding = "light { @area_light }"
+        elif name == "short_box":
+            binding = "surface { @shell_smooth }\n  medium { @fog_dense }"
+        elif name == "tall_box":
+            binding = "surface { @shell_rough }\n  medium { @fog_light }"
+        else:
+            binding = f"surface {{ @{_CORNELL_SURFACE_OF[name]} }}"
+        out.append(f"Shape {name} : InlineMesh {{\n  positions {{ {positions} }}\n  indices {{ {indices} }}\n  {binding}\n}}")
+        shape_names.append(f"@{name}")
+    out.append(f"""Camera camera : Pinhole {{
+  position {{ -0.01, 0.995, 5.0 }}
+  front {{ 0.0, 0.0, -1.0 }}
+  up {{ 0.0, 1.0, 0.0 }}
+  fov {{ 27.8 }}
+  spp {{ {int(spp)} }}
+  film : Color {{ resolution {{ {int(resolution[0])}, {int(resolution[1])} }} }}
+  filter : Box {{ radius {{ 0.5 }} }}
+  file {{ "{output}" }}
+}}""")
+    # the reference needs SOME environment medium as soon as two media are registered: the tracker's initialisation dispatches on
+    # the environment medium's tag and an invalid tag runs into the dispatch's unreachable() (mega_vpt_naive.cpp:184-190)
+    medium_line = "  environment_medium : Vacuum {}\n"
+    if environment_medium:
+        medium_line = ("  environment_medium : Homogeneous {\n    priority { 1 }\n"
+                       "    sigma_a : Constant { v { 0.02, 0.02, 0.02 } }\n"
+                       "    sigma_s : Constant { v { 0.08, 0.08, 0.1 } }\n"
+                       "    phasefunction : HenyeyGreenstein { g { 0.3 } }\n"
+                       "  }\n")
+    out.append(f"""render {{
+  integrator : MegaVPTNaive {{
+    depth {{ {int(depth)} }}
+    rr_depth {{ {int(rr_depth)} }}
+    rr_threshold {{ {_fmt(rr_threshold)} }}
+    sampler : Independent {{ seed {{ {int(seed)} }} }}
+  }}
+{medium_line}  cameras {{ @camera }}
+  shapes {{ {", ".join(shape_names)} }}
+}}""")
+    return "\n".join(out) + "\n"
+
+
 def textured_room(resolution=(96, 64), spp=8, depth=6, rr_depth=0, rr_threshold=0.95, seed=19980810,
                   assets="tests/golden/assets", output="textured.exr", integrator="WavePath", wrappers=False,
                   mesh_files=True) -> str:

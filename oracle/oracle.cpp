@@ -450,6 +450,7 @@ struct ShapeHandle {
     bool has_vertex_uv() const { return flags & LRK_SHAPE_HAS_VERTEX_UV; }
     bool has_surface() const { return flags & LRK_SHAPE_HAS_SURFACE; }
     bool has_light() const { return flags & LRK_SHAPE_HAS_LIGHT; }
+    bool has_medium() const { return flags & LRK_SHAPE_HAS_MEDIUM; }
 };
 ShapeHandle decode_handle(const uint32_t c[4]) {
     ShapeHandle h;
@@ -2058,8 +2059,8 @@ V3 path_li(const lrk_scene_desc &sc, uint32_t px, uint32_t py, uint32_t sample_i
 // ------------------------------------------------------------------------------------------------
 // Volumetric estimator (config C4): src/integrators/mega_vpt_naive.cpp:170-485 with
 // VPT_NAIVE_ENABLE_DIRECT_LIGHTING defined (:16) and VPT_NAIVE_ENABLE_MEDIUM_STACK_INIT not (:15).
-// Scope: ONE homogeneous environment medium, no per-shape media, opaque surfaces — so the medium tracker
-// (src/util/medium_tracker.cpp) always holds exactly the environment medium and never becomes vacuum.
+// Scope: homogeneous and vacuum media with eta = 1 (the closures are built with eta_i = 1), as the environment medium and on
+// shapes; the medium tracker, the surface events and the transmittance walk through transmissive surfaces are restated in full.
 // The reference's quirks are kept on purpose (they define its output):
 //   * `_transmittance` (:96-168) only accumulates medium transmittance up to a surface it HITS; an unoccluded
 //     shadow ray returns f = 1, pdf = 0 — light reaches surfaces unattenuated, and the in-medium direct light
@@ -2168,31 +2169,86 @@ MediumSample homogeneous_sample(const lrk_medium &m, V3 o, V3 d, float t_max, PC
     return s;
 }
 
-// _transmittance (mega_vpt_naive.cpp:96-168) for the supported scope. Returns f and pdf; draws from rng when a
-// surface is hit.  `occluded_any` reports whether any surface was hit (what the wavefront kernels track).
+// MediumTracker (src/util/medium_tracker.{h,cpp}): the media a path is inside of, sorted by priority (lowest value first;
+// equal priorities keep their order of entry).  Restated with its quirks: `size` also counts entries that were never stored
+// (VACUUM_PRIORITY never sorts in front of anything), exit() scans capacity - 1 slots and clears slot `size` after removing.
+struct MediumTracker {
+    static constexpr uint32_t capacity = 32u;
+    uint32_t priority[capacity], tag[capacity];
+    uint32_t size{0u};
+    MediumTracker() {
+        for (uint32_t i = 0; i < capacity; i++) {
+            priority[i] = LRK_MEDIUM_VACUUM_PRIORITY;
+            tag[i] = LRK_MEDIUM_INVALID_TAG;
+        }
+    }
+    bool vacuum() const { return priority[0] == LRK_MEDIUM_VACUUM_PRIORITY; }
+    bool true_hit(uint32_t p) const { return p <= priority[0]; }
+    uint32_t current_tag() const { return vacuum() ? LRK_MEDIUM_INVALID_TAG : tag[0]; }
+    void enter(uint32_t p, uint32_t t) {
+        if (size == capacity) return;// the reference logs "Medium stack overflow" and carries on
+        size += 1u;
+        uint32_t x = p, v = t;
+        for (uint32_t i = 0; i < capacity; i++) {
+            const uint32_t pi = priority[i], ti = tag[i];
+            const bool swap = pi > x;
+            priority[i] = swap ? x : pi;
+            tag[i] = swap ? v : ti;
+            x = swap ? pi : x;
+            v = swap ? ti : v;
+        }
+    }
+    void exit(uint32_t p, uint32_t t) {
+        uint32_t removed = 0u;
+        for (uint32_t i = 0; i < capacity - 1u; i++) {
+            const bool should_remove = priority[i] == p && tag[i] == t && removed == 0u;
+            removed += should_remove ? 1u : 0u;
+            priority[i] = priority[i + removed];
+            tag[i] = tag[i + removed];
+        }
+        if (removed != 0u) {
+            size -= 1u;
+            priority[size] = LRK_MEDIUM_VACUUM_PRIORITY;
+            tag[size] = LRK_MEDIUM_INVALID_TAG;
+        }// else: "trying to exit nonexistent" is logged, nothing changes
+    }
+};
+
+// _event (mega_vpt_naive.cpp:68-94): which side of the surface wo and wi are on, in the closure's shading frame
+uint32_t volume_surface_event(const lrk_scene_desc &sc, const Interaction &it, V3 wo, V3 wi) {
+    Frame shading = it.shading;
+    if (it.shape.has_surface()) {
+        const lrk_surface surface = resolve_surface(sc, sc.surfaces[it.shape.surface_tag], it);
+        shading = closure_interaction(sc, surface, it, wo).shading;
+    }
+    const V3 wo_local = shading.world_to_local(wo), wi_local = shading.world_to_local(wi);
+    return wo_local.z * wi_local.z > 0.f ? LRK_EVENT_REFLECT : wi_local.z > 0.f ? LRK_EVENT_EXIT : LRK_EVENT_ENTER;
+}
+
+// _transmittance (mega_vpt_naive.cpp:96-168).  The tracker is taken BY VALUE, as the reference does: what the shadow ray enters
+// and leaves does not change the path's own tracker.  Draws three numbers from rng for every surface reached inside a medium.
 struct Transmittance {
     V3 f{1.f, 1.f, 1.f};
     float pdf{0.f};
 };
-Transmittance volume_transmittance(const lrk_scene_desc &sc, PCG32 &rng, lrk_ray origin_ray, TraceCounters *tc, oracle_counters *cnt,
-                                   bool *occluded_any) {
-    const lrk_medium &m = sc.environment_medium;
-    V3 sigma_t = v3(m.sigma_a[0] + m.sigma_s[0], m.sigma_a[1] + m.sigma_s[1], m.sigma_a[2] + m.sigma_s[2]);
+Transmittance volume_transmittance(const lrk_scene_desc &sc, PCG32 &rng, MediumTracker tracker, lrk_ray origin_ray, TraceCounters *tc,
+                                   oracle_counters *cnt) {
     float t_max = origin_ray.tmax;
     V3 dir = v3(origin_ray.d[0], origin_ray.d[1], origin_ray.d[2]);
     lrk_ray ray = origin_ray;
     V3 light_p = v3(origin_ray.o[0], origin_ray.o[1], origin_ray.o[2]) + dir * t_max;
     Transmittance T;
-    if (occluded_any) *occluded_any = false;
     while (T.f.x > 0.f || T.f.y > 0.f || T.f.z > 0.f) {
         lrk_hit hit = trace_bvh(sc, ray, false, tc);
         if (cnt) cnt->shadow_rays++;
         Interaction it = interaction_from_hit(sc, ray, hit);
         if (!it.valid()) break;
-        if (occluded_any) *occluded_any = true;
         float t2surface = length(it.pg - v3(ray.o[0], ray.o[1], ray.o[2]));
         V3 wo = -dir, wi = dir;
-        {// HomogeneousMediumClosure::transmittance, homogeneous.cpp:119-133
+        const uint32_t surface_event = volume_surface_event(sc, it, wo, wi);
+        if (!tracker.vacuum()) {// HomogeneousMediumClosure::transmittance, homogeneous.cpp:119-133
+            const lrk_medium &m = sc.media[tracker.current_tag()];
+            V3 sigma_t = v3(m.sigma_a[0] + m.sigma_s[0], m.sigma_a[1] + m.sigma_s[1], m.sigma_a[2] + m.sigma_s[2]);
             V3 pc;
             pc.x = rng.uniform_float();
             pc.y = rng.uniform_float();
@@ -2203,8 +2259,14 @@ Transmittance volume_transmittance(const lrk_scene_desc &sc, PCG32 &rng, lrk_ray
             T.f = T.f * Tr;
             T.pdf += sum3(pc * Tr);
         }
-        if (it.shape.has_surface()) {
-            SurfEval ev = surface_evaluate(sc.surfaces[it.shape.surface_tag], it, wo, wi);
+        if (it.shape.has_medium()) {// :134-146 (a reflect event enters, like the reference's $else)
+            const uint32_t tag = it.shape.medium_tag, priority = sc.media[tag].priority;
+            if (surface_event == LRK_EVENT_EXIT) tracker.exit(priority, tag);
+            else tracker.enter(priority, tag);
+        }
+        if (it.shape.has_surface()) {// :149-160: the closure is built with eta_i = 1 and evaluated straight through
+            const lrk_surface surface = resolve_surface(sc, sc.surfaces[it.shape.surface_tag], it);
+            SurfEval ev = surface_evaluate(surface, closure_interaction(sc, surface, it, wo), wo, wi);
             T.f = T.f * ev.f;
             T.pdf += ev.pdf;
         }
@@ -2214,7 +2276,6 @@ Transmittance volume_transmittance(const lrk_scene_desc &sc, PCG32 &rng, lrk_ray
 }
 
 V3 volume_path_li(const lrk_scene_desc &sc, uint32_t px, uint32_t py, uint32_t sample_index, oracle_counters *cnt) {
-    const lrk_medium &medium = sc.environment_medium;
     Sampler sampler;
     sampler.start(sc, px, py, sample_index);
     float uf0, uf1;
@@ -2231,22 +2292,28 @@ V3 volume_path_li(const lrk_scene_desc &sc, uint32_t px, uint32_t py, uint32_t s
     std::memcpy(&lo, &s1, 4);
     PCG32 rng;
     rng.set_sequence((static_cast<uint64_t>(hi) << 32u) | lo);
+    // the path starts inside the environment medium (:184-190); VPT_NAIVE_ENABLE_MEDIUM_STACK_INIT is off (:15)
+    MediumTracker tracker;
+    if (sc.environment_medium_tag != LRK_MEDIUM_INVALID_TAG)
+        tracker.enter(sc.media[sc.environment_medium_tag].priority, sc.environment_medium_tag);
     float pdf_bsdf = 1e16f;
-    const float eta_scale = 1.f;// no refractive interfaces in scope
+    float eta_scale = 1.f;
     TraceCounters tc;
     for (uint32_t depth = 0; depth < sc.integrator.max_depth; depth++) {
+        float eta = 1.f;
         float u_rr = 0.f;
         if (depth + 1u >= sc.integrator.rr_depth) u_rr = sampler.generate_1d();
         lrk_hit hit = trace_bvh(sc, ray, false, &tc);
         if (cnt) cnt->closest_rays++;
         Interaction it = interaction_from_hit(sc, ray, hit);
+        const bool has_medium = it.valid() && it.shape.has_medium();
         V3 ro = v3(ray.o[0], ray.o[1], ray.o[2]), rd = v3(ray.d[0], ray.d[1], ray.d[2]);
         float t_max = it.valid() ? length(it.pg - ro) : std::numeric_limits<float>::max();
         MediumSample ms;
-        {// the tracker is never vacuum: direct light at the ray origin, then distance sampling
+        if (!tracker.vacuum()) {// :275-311: direct light at the ray origin, then distance sampling in the current medium
             float u_sel = sampler.generate_1d();
             float ul0, ul1;
-        sampler.generate_2d(ul0, ul1);
+            sampler.generate_2d(ul0, ul1);
             Interaction it_medium;// Interaction{ray->origin()}: pg = ng = origin, default frame, zero offset factor
             it_medium.pg = ro;
             it_medium.ng = ro;
@@ -2254,11 +2321,13 @@ V3 volume_path_li(const lrk_scene_desc &sc, uint32_t px, uint32_t py, uint32_t s
             it_medium.shading = Frame{v3(1.f, 0.f, 0.f), v3(0.f, 1.f, 0.f), v3(0.f, 0.f, 1.f)};
             it_medium.shape.intersection_offset = 0.f;
             LightSample ls = sample_light(sc, it_medium, u_sel, ul0, ul1);
-            Transmittance T = volume_transmittance(sc, rng, ls.shadow_ray, &tc, cnt, nullptr);
+            Transmittance T = volume_transmittance(sc, rng, tracker, ls.shadow_ray, &tc, cnt);
             if (T.pdf > 0.f) {
                 float w = 1.f / (pdf_bsdf + T.pdf + ls.eval.pdf);
                 Li = Li + w * beta * T.f * ls.eval.L;
             }
+            const lrk_medium &medium = sc.media[tracker.current_tag()];
+            eta = medium.eta;
             ms = homogeneous_sample(medium, ro, rd, t_max, rng);
             ray = make_ray(ms.o, ms.d, 0.f, std::numeric_limits<float>::max());
             float w = ms.pdf > 0.f ? 1.f / ms.pdf : 0.f;
@@ -2266,7 +2335,14 @@ V3 volume_path_li(const lrk_scene_desc &sc, uint32_t px, uint32_t py, uint32_t s
             pdf_bsdf = ms.pdf;
         }
         if (ms.event == ~0u || ms.event == 3u) {
-            if (!it.valid()) break;
+            if (!it.valid()) {// :315-321
+                if (sc.environment.present) {
+                    LightEval e = environment_evaluate(sc, v3(ray.d[0], ray.d[1], ray.d[2]));// uniform.cpp:67-76
+                    e.pdf *= env_prob(sc);
+                    Li = Li + beta * e.L * balance_heuristic(pdf_bsdf, e.pdf);
+                }
+                break;
+            }
             if (sc.light_count != 0u && it.shape.has_light()) {
                 LightEval e = evaluate_hit(sc, it, v3(ray.o[0], ray.o[1], ray.o[2]));
                 Li = Li + beta * e.L * balance_heuristic(pdf_bsdf, e.pdf);
@@ -2275,18 +2351,30 @@ V3 volume_path_li(const lrk_scene_desc &sc, uint32_t px, uint32_t py, uint32_t s
             if (cnt) cnt->path_vertices++;
             float u_light_selection = sampler.generate_1d();
             float ul0, ul1;
-        sampler.generate_2d(ul0, ul1);
+            sampler.generate_2d(ul0, ul1);
             float u_lobe = sampler.generate_1d();
             float ub0, ub1;
-        sampler.generate_2d(ub0, ub1);
+            sampler.generate_2d(ub0, ub1);
             LightSample ls = sample_light(sc, it, u_light_selection, ul0, ul1);
-            Transmittance T = volume_transmittance(sc, rng, ls.shadow_ray, &tc, cnt, nullptr);
-            V3 wo = -v3(ray.d[0], ray.d[1], ray.d[2]);
+            Transmittance T = volume_transmittance(sc, rng, tracker, ls.shadow_ray, &tc, cnt);
+            const uint32_t medium_tag = it.shape.medium_tag;// 0 for a shape without a medium (geometry.cpp:134)
+            uint32_t medium_priority = LRK_MEDIUM_VACUUM_PRIORITY;
+            float eta_next = 1.f;
+            if (has_medium) {
+                medium_priority = sc.media[medium_tag].priority;
+                eta_next = sc.media[medium_tag].eta;
+            }
+            const V3 dir = v3(ray.d[0], ray.d[1], ray.d[2]);
+            const uint32_t surface_event_skip = volume_surface_event(sc, it, -dir, dir);
+            V3 wo = -dir;
             const lrk_surface surface = resolve_surface(sc, sc.surfaces[it.shape.surface_tag], it);
             const Interaction cit = closure_interaction(sc, surface, it, wo);
-            // true_hit(medium_tag = 0) is `0 <= priority of the environment medium` (medium_tracker.cpp:19-21)
-            if (!(0u <= medium.priority)) {
-                ray = spawn_ray(it, v3(ray.d[0], ray.d[1], ray.d[2]));
+            uint32_t surface_event;
+            // true_hit is given the medium TAG where it expects a priority (:387, medium_tracker.cpp:19-21): `tag <= priority of
+            // the current medium`.  A shape without a medium has tag 0 and is always a true hit.
+            if (!tracker.true_hit(medium_tag)) {
+                surface_event = surface_event_skip;
+                ray = spawn_ray(it, dir);
                 pdf_bsdf = 1e16f;
             } else {
                 if (ls.eval.pdf > 0.0f) {
@@ -2296,10 +2384,19 @@ V3 volume_path_li(const lrk_scene_desc &sc, uint32_t px, uint32_t py, uint32_t s
                     Li = Li + w * beta * ev.f * ls.eval.L * T.f;
                 }
                 SurfSample ss = surface_sample(surface, cit, wo, u_lobe, ub0, ub1);
+                surface_event = ss.event;
                 float w = ss.eval.pdf > 0.f ? 1.f / ss.eval.pdf : 0.f;
                 pdf_bsdf = ss.eval.pdf;
                 ray = spawn_ray(it, ss.wi);
                 beta = beta * (w * ss.eval.f);
+                if (has_medium) {// :436-446
+                    if (surface_event == LRK_EVENT_ENTER) eta_scale = sqr(eta_next / eta);
+                    else if (surface_event == LRK_EVENT_EXIT) eta_scale = sqr(eta / eta_next);
+                }
+            }
+            if (has_medium) {// :449-458
+                if (surface_event == LRK_EVENT_ENTER) tracker.enter(medium_priority, medium_tag);
+                else if (surface_event == LRK_EVENT_EXIT) tracker.exit(medium_priority, medium_tag);
             }
         }
         if (std::isnan(beta.x) || std::isnan(beta.y) || std::isnan(beta.z)) beta = v3(0.f);
@@ -2354,8 +2451,9 @@ int oracle_render(const lrk_scene_desc *scene, uint32_t spp_begin, uint32_t spp_
                   uint32_t world, uint32_t tile_size, float *film_raw, oracle_counters *counters) {
     if (!scene || !film_raw || scene->abi_version != LRK_ABI_VERSION) return -1;
     if (scene->integrator.type == LRK_INTEGRATOR_VOLUME_PATH) {
-        // supported volume scope: one homogeneous environment medium with eta = 1 (see volume_path_li)
-        if (!scene->environment_medium.present || scene->environment_medium.eta != 1.f) return -5;
+        // supported volume scope: homogeneous / vacuum media with eta = 1 (see volume_path_li)
+        for (uint32_t m = 0; m < scene->medium_count; m++)
+            if (scene->media[m].present == LRK_MEDIUM_HOMOGENEOUS && scene->media[m].eta != 1.f) return -5;
     } else if (scene->integrator.type != LRK_INTEGRATOR_PATH || scene->environment_medium.present) {
         return -5;
     }

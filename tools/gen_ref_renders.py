@@ -86,6 +86,11 @@ def cases() -> dict[str, str]:
                                      .replace("sigma_a : Constant { v { 0.01, 0.01, 0.01 } }", "sigma_a : Constant { v { 0.02, 0.01, 0.005 } }")
                                      .replace("sigma_s : Constant { v { 0.05, 0.05, 0.05 } }", "sigma_s : Constant { v { 0.03, 0.06, 0.12 } }")
                                      .replace('"spheres.exr"', '"iso.exr"'))
+    # row a22 beyond config C4: media bound to shapes - the medium tracker, enter / exit events at Glass shells, the transmittance
+    # walk through them; with an environment medium around (three media, nested); the true_hit(tag) quirk of the reference
+    c["media_shapes"] = scenes.media_box(resolution=(32, 32), spp=4)
+    c["media_nested_in_environment_medium"] = scenes.media_box(resolution=(32, 32), spp=4, environment_medium=True, rr_depth=2, output="nested.exr")
+    c["media_true_hit_quirk"] = scenes.media_box(resolution=(32, 32), spp=4, skip_quirk=True, output="quirk.exr")
     # row f1: image textures (8 / 16-bit PNG, grey, palette; all address modes, point + bilinear, sRGB / linear / gamma) on
     # Matte and Disney parameters; with wrappers: normal map, alpha-tested cut-out (ray queries), constant opacity.
     # mesh_files=False: the `Mesh` plugin of the reference needs assimp, which is not built
