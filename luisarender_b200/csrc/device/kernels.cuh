@@ -287,9 +287,9 @@ struct has_evaluate_sampled : std::false_type {};
 template<typename Closure>
 struct has_evaluate_sampled<Closure, std::void_t<decltype(std::declval<const Closure &>().evaluate_sampled(V3{}, V3{}))>> : std::true_type {};
 
-template<bool VOLUME, typename Closure>
-__device__ __forceinline__ void shade_surface(Closure &cl, const Interaction &it, const Frame &shading, V3 wo, const LightSample &ls, V3 beta,
-                                              float u_lobe, float ub0, float ub1, V3 &contrib, V3 &wi_world, V3 &f_over, float &pdf_bsdf) {
+template<typename Closure>
+__device__ __forceinline__ void shade_surface_eval(Closure &cl, const Interaction &it, const Frame &shading, V3 wo, const LightSample &ls,
+                                                   float u_lobe, float ub0, float ub1, SurfEval &e_light, V3 &wi_world, V3 &f_over, float &pdf_bsdf) {
     V3 wo_local = shading.world_to_local(wo);
     cl.prepare(wo_local);
     V3 wi_sampled_local;
@@ -299,7 +299,6 @@ __device__ __forceinline__ void shade_surface(Closure &cl, const Interaction &it
     V3 wi_w = v3(ls.ray_d_tmax.x, ls.ray_d_tmax.y, ls.ray_d_tmax.z);
     V3 wi_l = shading.world_to_local(wi_w);
     bool run = run_light;
-    SurfEval e_light;
     e_light.f = f_over = v3(0.f);
     e_light.pdf = pdf_bsdf = 0.f;
 #pragma unroll 1
@@ -328,6 +327,14 @@ __device__ __forceinline__ void shade_surface(Closure &cl, const Interaction &it
             pdf_bsdf = e.pdf;
         }
     }
+}
+
+template<bool VOLUME, typename Closure>
+__device__ __forceinline__ void shade_surface(Closure &cl, const Interaction &it, const Frame &shading, V3 wo, const LightSample &ls, V3 beta,
+                                              float u_lobe, float ub0, float ub1, V3 &contrib, V3 &wi_world, V3 &f_over, float &pdf_bsdf) {
+    SurfEval e_light;
+    shade_surface_eval(cl, it, shading, wo, ls, u_lobe, ub0, ub1, e_light, wi_world, f_over, pdf_bsdf);
+    const bool run_light = ls.eval.pdf > 0.0f;
     contrib = v3(0.f);
     if (run_light) {
         if (VOLUME) {
@@ -1013,3 +1020,5 @@ __global__ void __launch_bounds__(kBlock) convert_film_kernel(DeviceScene sc, co
 }
 
 }// namespace lrk
+
+#include "volume_general.cuh"

@@ -19,7 +19,7 @@ using namespace lrk;
 namespace {
 
 struct DeviceArrays {
-    void *vertices{}, *triangles{}, *alias{}, *pdf{}, *meshes{}, *inst_handles{}, *inst_kind{}, *inst_o2w{}, *inst_xform{}, *bvh_nodes{}, *traversal_overflow{}, *sobol{}, *vdc{}, *vdc_inv{}, *pmj{}, *blue_noise{}, *pmj_pixels{}, *zsobol_hash{}, *sampler{}, *build_scratch{}, *mesh_bounds{}, *inst_mesh{}, *visible_ids{}, *scene_copy{}, *textures{}, *texels{}, *env_alias{}, *env_pdf{},
+    void *vertices{}, *triangles{}, *alias{}, *pdf{}, *meshes{}, *inst_handles{}, *inst_kind{}, *inst_o2w{}, *inst_xform{}, *bvh_nodes{}, *traversal_overflow{}, *sobol{}, *vdc{}, *vdc_inv{}, *pmj{}, *blue_noise{}, *pmj_pixels{}, *zsobol_hash{}, *sampler{}, *build_scratch{}, *mesh_bounds{}, *inst_mesh{}, *visible_ids{}, *scene_copy{}, *media{}, *textures{}, *texels{}, *env_alias{}, *env_pdf{},
         *tri_verts{}, *surfaces{}, *lights{}, *light_handles{}, *camera{};
 };
 
@@ -78,6 +78,8 @@ struct lrk_ctx {
     bool has_kind[9]{true, false, false, false, false, false, false, false, false};
     uint32_t allocated_kinds{0u};// bit k: hit_index[k] is allocated
     bool volume{false};
+    bool volume_general{false};// the volume integrator's per-thread kernel (volume_general.cuh) instead of the wavefront one
+    int grid_vgeneral{0};
     uint64_t volume_capacity{0};
     int grid_vshade[3]{0, 0, 0}, grid_vmedium{0}, grid_vshadow{0};
 };
@@ -350,7 +352,32 @@ int render_pass(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint32_t spp
 }
 
 // One pass of the volume path integrator (config C4); schedule described in kernels.cuh.
+// the general volume path: one thread per camera sample (volume_general.cuh), then the common film accumulation
+int render_pass_volume_general(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint32_t spp_begin, uint32_t spp) {
+    const uint64_t n = static_cast<uint64_t>(npix) * spp;
+    auto &pb = ctx->pb;
+    const auto &sc = ctx->scene;
+    {
+        ScopedTimer t{ctx, CAT_SHADE};
+        const unsigned blocks = static_cast<unsigned>((n + kGeneralBlock - 1u) / kGeneralBlock);
+        auto launch = [&](auto kernel) {
+            kernel<<<blocks, kGeneralBlock, 0, ctx->stream>>>(sc, pb, ctx->d_pixel_list, pixel_offset, npix, spp_begin, static_cast<uint32_t>(n));
+        };
+        ctx->any_non_opaque ? launch(volume_general_kernel<true>) : launch(volume_general_kernel<false>);
+    }
+    {
+        ScopedTimer t{ctx, CAT_OTHER};
+        accumulate_kernel<<<(npix + kBlock - 1u) / kBlock, kBlock, 0, ctx->stream>>>(sc, pb.li, ctx->d_film, ctx->d_pixel_list, pixel_offset,
+                                                                                  npix, spp, pb.counts, pb.stats);
+    }
+    ctx->stats.kernel_launches += 2u;
+    ctx->stats.passes++;
+    LRK_CUDA(cudaGetLastError());
+    return LRK_OK;
+}
+
 int render_pass_volume(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint32_t spp_begin, uint32_t spp) {
+    if (ctx->volume_general) return render_pass_volume_general(ctx, pixel_offset, npix, spp_begin, spp);
     const uint64_t n = static_cast<uint64_t>(npix) * spp;
     auto &pb = ctx->pb;
     const auto &sc = ctx->scene;
@@ -618,12 +645,33 @@ const char *lrk_last_error(const lrk_ctx *ctx) { return ctx ? ctx->error.c_str()
 int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
     if (!ctx || !s) return LRK_ERR_INVALID_ARGUMENT;
     if (s->abi_version != LRK_ABI_VERSION) return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_upload_scene: ABI version mismatch");
+    // The volume integrator has two implementations.  The wavefront kernels (kernels.cuh) cover config C4's shape: ONE homogeneous
+    // environment medium around opaque Matte / Disney closures, nothing else.  Everything beyond that - media bound to shapes,
+    // transmissive surfaces, no environment medium, an environment light - runs the per-thread kernel of volume_general.cuh.
+    bool volume_general = false;
     if (s->integrator.type == LRK_INTEGRATOR_VOLUME_PATH) {
-        // supported volume scope: one homogeneous environment medium with eta = 1, opaque surfaces (see kernels.cuh)
-        if (!s->environment_medium.present)
-            return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: the volume path integrator needs an environment medium");
-        if (s->environment_medium.eta != 1.f)
-            return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: environment media with eta != 1 are not supported");
+        if (s->medium_count > 256u || (s->medium_count != 0u && s->media == nullptr))
+            return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_upload_scene: invalid media table");
+        if (s->environment_medium_tag != LRK_MEDIUM_INVALID_TAG && s->environment_medium_tag >= s->medium_count)
+            return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_upload_scene: environment medium tag outside the media table");
+        for (uint32_t m = 0; m < s->medium_count; m++) {
+            if (s->media[m].present != LRK_MEDIUM_HOMOGENEOUS && s->media[m].present != LRK_MEDIUM_VACUUM)
+                return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: unknown medium kind");
+            if (s->media[m].present == LRK_MEDIUM_HOMOGENEOUS && s->media[m].eta != 1.f)
+                return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: media with eta != 1 are not supported");
+        }
+        volume_general = !s->environment_medium.present || s->medium_count != 1u || s->environment.present;
+        for (uint32_t i = 0; i < s->instance_count && !volume_general; i++)
+            if (s->instances[i].handle[0] & LRK_SHAPE_HAS_MEDIUM) volume_general = true;
+        for (uint32_t i = 0; i < s->surface_count && !volume_general; i++)
+            if (s->surfaces[i].type > LRK_SURFACE_DISNEY || (s->surfaces[i].flags & LRK_SURFACE_DISNEY_TRANSMISSIVE)) volume_general = true;
+        for (uint32_t i = 0; i < s->instance_count; i++) {
+            const uint32_t flags = s->instances[i].handle[0] & 1023u, tag = (s->instances[i].handle[1] >> 24u) & 255u;
+            if ((flags & LRK_SHAPE_HAS_MEDIUM) && tag >= s->medium_count)
+                return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_upload_scene: a shape's medium tag is outside the media table");
+        }
+        if (volume_general && s->sampler.type != LRK_SAMPLER_INDEPENDENT)
+            return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: the volume path with shape media / transmissive surfaces takes the Independent sampler");
         if (s->integrator.max_depth > 31u) return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: volume path depth > 31");
     } else if (s->integrator.type != LRK_INTEGRATOR_PATH) {
         return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: unknown integrator type");
@@ -637,8 +685,6 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
         return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "No lights in scene. Rendering aborted.");
     if (s->environment.present) {
         const auto &e = s->environment;
-        if (s->integrator.type == LRK_INTEGRATOR_VOLUME_PATH)
-            return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: environment lights are not supported by the volume path integrator");
         if (e.emission_tex > s->texture_count || !(e.env_prob > 0.f && e.env_prob <= 1.f) ||
             (e.emission_tex != 0u && (e.map_width == 0u || e.map_height == 0u || e.alias == nullptr || e.pdf == nullptr)))
             return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_upload_scene: invalid environment record");
@@ -655,9 +701,6 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
                     return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: a Mix blends two constant Matte / Mirror / Glass / Plastic / Metal records");
             }
         }
-        if ((s->surfaces[i].type > LRK_SURFACE_DISNEY || (s->surfaces[i].flags & LRK_SURFACE_DISNEY_TRANSMISSIVE)) &&
-            s->integrator.type == LRK_INTEGRATOR_VOLUME_PATH)
-            return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: the volume path supports Matte and opaque Disney surfaces only");
         for (uint32_t k = 0; k < 16u; k++)
             if (s->surfaces[i].tex[k] > s->texture_count) return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_upload_scene: texture id out of range");
         if (s->surfaces[i].opacity_tex > s->texture_count || s->surfaces[i].normal_tex > s->texture_count)
@@ -847,6 +890,11 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
     }
     sc.medium_g = s->environment_medium.g;
     sc.medium_priority = s->environment_medium.priority;
+    ctx->volume_general = volume_general;
+    if ((rc = upload(ctx, &a.media, s->media, s->medium_count))) return rc;
+    sc.media = static_cast<const lrk_medium *>(a.media);
+    sc.medium_count = s->medium_count;
+    sc.env_medium_tag = s->environment_medium_tag;
 
     const size_t npix = static_cast<size_t>(sc.width) * sc.height;
     if (ctx->film_pixels != npix) {
@@ -946,6 +994,7 @@ int lrk_render(lrk_ctx *ctx, uint32_t spp_begin, uint32_t spp_end) {
     LRK_CUDA(cudaMemcpyAsync(&ctx->h_overflow, ctx->scene.traversal_overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     LRK_CUDA(cudaStreamSynchronize(ctx->stream));
     LRK_CUDA(cudaGetLastError());
+    if (ctx->h_overflow & 2u) return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_render: a path was inside more than 8 media at once (medium tracker overflow)");
     if (ctx->h_overflow != 0u) return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_render: traversal stack overflow (BVH deeper than the kernels support)");
     float ms = 0.f;
     LRK_CUDA(cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));

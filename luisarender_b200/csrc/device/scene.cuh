@@ -62,6 +62,10 @@ struct DeviceScene {
     float sigma_a[3], sigma_s[3];
     float medium_g;
     uint32_t medium_priority;
+    // every medium of the scene, indexed by the shape handles' medium tags (general volume path, volume_general.cuh)
+    const lrk_medium *media;
+    uint32_t medium_count;
+    uint32_t env_medium_tag;// LRK_MEDIUM_INVALID_TAG: none
 };
 
 }// namespace lrk

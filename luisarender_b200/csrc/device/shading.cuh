@@ -78,12 +78,13 @@ __device__ __forceinline__ float abs_dot(V3 a, V3 b) { return fabsf(dot(a, b)); 
 
 // ---- Shape::Handle::decode: src/base/shape.cpp:72-93 ----------------------------------------------
 struct ShapeHandle {
-    uint32_t mesh, flags, surface_tag, light_tag, tri_count;
+    uint32_t mesh, flags, surface_tag, light_tag, medium_tag, tri_count;
     float intersection_offset;
     __device__ __forceinline__ bool has_vertex_normal() const { return flags & LRK_SHAPE_HAS_VERTEX_NORMAL; }
     __device__ __forceinline__ bool has_vertex_uv() const { return flags & LRK_SHAPE_HAS_VERTEX_UV; }
     __device__ __forceinline__ bool has_surface() const { return flags & LRK_SHAPE_HAS_SURFACE; }
     __device__ __forceinline__ bool has_light() const { return flags & LRK_SHAPE_HAS_LIGHT; }
+    __device__ __forceinline__ bool has_medium() const { return flags & LRK_SHAPE_HAS_MEDIUM; }
 };
 __device__ __forceinline__ ShapeHandle decode_handle(uint4 c) {
     ShapeHandle h;
@@ -91,6 +92,7 @@ __device__ __forceinline__ ShapeHandle decode_handle(uint4 c) {
     h.flags = c.x & 1023u;
     h.surface_tag = (c.y >> 12u) & 4095u;
     h.light_tag = c.y & 4095u;
+    h.medium_tag = (c.y >> 24u) & 255u;
     h.tri_count = c.z;
     float off = static_cast<float>(c.w & 0xffffu) * (1.0f / 65536.f);
     h.intersection_offset = clampf(off * 255.f + 1.f, 1.f, 256.f);
