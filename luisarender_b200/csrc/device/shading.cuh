@@ -249,7 +249,10 @@ struct LightSample {
     float4 ray_o_tmin, ray_d_tmax;
 };
 
-__device__ __forceinline__ LightSample sample_light(const DeviceScene &sc, const Interaction &it_from, float u_sel, float u0, float u1) {
+// `p_shading`: it_from.p_shading(), the point the light's emission and pdf are evaluated from (diffuse.cpp:62-86) - the hit point
+// for a surface interaction, but the WORLD ORIGIN for the volume integrator's Interaction{ray->origin()}, whose shading point is
+// never set (mega_vpt_naive.cpp:283-285; the reference's renders carry that, so this library does too)
+__device__ __forceinline__ LightSample sample_light_from(const DeviceScene &sc, const Interaction &it_from, V3 p_shading, float u_sel, float u0, float u1) {
     LightSample s;
     float n = static_cast<float>(sc.light_count);
     // UniformLightSamplerInstance::select, uniform.cpp:78-90
@@ -289,7 +292,7 @@ __device__ __forceinline__ LightSample sample_light(const DeviceScene &sc, const
     V3 uvw = sample_uniform_triangle(ux, u1);
     Interaction it_light = make_interaction(sc, handle.instance_id, triangle_id, uvw);
     it_light.back_facing = dot(it_light.ng, it_from.pg - it_light.pg) < 0.f;
-    s.eval = diffuse_light_evaluate(sc, it_light, it_from.pg);
+    s.eval = diffuse_light_evaluate(sc, it_light, p_shading);
     s.eval.pdf *= sel_prob;
     // Interaction::spawn_ray_to, src/base/interaction.cpp:25-30
     V3 p_from = p_robust(it_from, it_light.pg - it_from.pg);
@@ -299,6 +302,10 @@ __device__ __forceinline__ LightSample sample_light(const DeviceScene &sc, const
     s.ray_o_tmin = make_float4(p_from.x, p_from.y, p_from.z, 0.f);
     s.ray_d_tmax = make_float4(dir.x, dir.y, dir.z, d * .9999f);
     return s;
+}
+
+__device__ __forceinline__ LightSample sample_light(const DeviceScene &sc, const Interaction &it_from, float u_sel, float u0, float u1) {
+    return sample_light_from(sc, it_from, it_from.pg, u_sel, u0, u1);
 }
 
 // ---- image textures: src/textures/image.cpp:132-166, sampled like the reference's software sampler

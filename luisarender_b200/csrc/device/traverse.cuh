@@ -339,6 +339,8 @@ __device__ __forceinline__ void trace_queue(const DeviceScene &sc, const float4 
     }
 }
 
+#endif// __CUDACC__
+
 // ---- one ray per thread ---------------------------------------------------------------------------------------------------
 // The same step functions driven by a plain per-thread loop with a local-memory stack: for code that traces from inside a
 // longer per-thread computation (the general volume integrator walks its transmittance rays surface by surface).  Results are
@@ -389,7 +391,5 @@ __device__ __noinline__ uint4 trace_single(const DeviceScene &sc, float4 o, floa
     }
     return make_uint4(r.best_inst, r.best_prim, __float_as_uint(r.best_u), __float_as_uint(r.best_v));
 }
-
-#endif// __CUDACC__
 
 }// namespace lrk

@@ -12,6 +12,8 @@
 // closure kind of the surface integrator, the Independent sampler.  The reference's quirks are restated next to the oracle's
 // volume_path_li (oracle/oracle.cpp), which this kernel follows statement by statement.
 #pragma once
+#include "pathcommon.cuh"
+#include "traverse.cuh"
 
 namespace lrk {
 
@@ -246,6 +248,140 @@ __device__ __noinline__ DeviceTransmittance general_transmittance(const DeviceSc
     return T;
 }
 
+// One camera sample of the volume integrator: pixel (px, py), sample `sample_index`.  Returns Li; adds the rays it traced to the
+// two counters and reports a medium-tracker overflow.
+template<bool ALPHA>
+__device__ __forceinline__ V3 volume_general_li(const DeviceScene &sc, uint32_t px, uint32_t py, uint32_t sample_index, uint32_t &closest_rays,
+                                                uint32_t &shadow_rays, bool &tracker_overflow) {
+    uint32_t state = xxhash32_uint4(px, py, sc.sampler_seed, sample_index);
+    const float ux = lcg(state);
+    const float uy = lcg(state);
+    float4 ro, rd;
+    float weight;
+    camera_ray(sc.camera, px, py, ux, uy, ro, rd, weight);
+    // PCG32 rng(U64(as<UInt2>(generate_2d()))): first float = high word (src/util/u64.h:48,58-59)
+    const float s0 = lcg(state), s1 = lcg(state);
+    PCG32 rng;
+    rng.set_sequence((static_cast<unsigned long long>(__float_as_uint(s0)) << 32u) | __float_as_uint(s1));
+    DeviceMediumTracker tracker;
+    tracker.init();
+    if (sc.env_medium_tag != LRK_MEDIUM_INVALID_TAG) tracker.enter(sc.media[sc.env_medium_tag].priority, sc.env_medium_tag);
+    V3 beta = v3(weight), Li = v3(0.f);
+    float pdf_bsdf = 1e16f, eta_scale = 1.f;
+    for (uint32_t depth = 0; depth < sc.max_depth; depth++) {
+        float eta = 1.f;
+        float u_rr = 0.f;
+        if (depth + 1u >= sc.rr_depth) u_rr = lcg(state);
+        const uint4 hit = trace_single<false, ALPHA>(sc, ro, rd);
+        closest_rays++;
+        const bool valid = hit.x != ~0u;
+        V3 o = v3(ro.x, ro.y, ro.z), d = v3(rd.x, rd.y, rd.z);
+        Interaction it{};
+        if (valid) it = interaction_of_hit(sc, hit, d);
+        const bool has_medium = valid && it.shape.has_medium();
+        const float t_max = valid ? length(it.pg - o) : kFltMax;
+        uint32_t medium_event = ~0u;
+        if (!tracker.vacuum()) {// :275-311
+            const float u_sel = lcg(state), ul0 = lcg(state), ul1 = lcg(state);
+            Interaction it_medium{};// Interaction{ray->origin()}: pg = ng = origin, default frame, zero offset factor
+            it_medium.pg = o;
+            it_medium.ng = o;
+            it_medium.shading = Frame{v3(1.f, 0.f, 0.f), v3(0.f, 1.f, 0.f), v3(0.f, 0.f, 1.f)};
+            it_medium.shape.intersection_offset = 0.f;
+            const LightSample ls = sample_light_from(sc, it_medium, v3(0.f), u_sel, ul0, ul1);// p_shading of Interaction{origin} is the world origin
+            const DeviceTransmittance T = general_transmittance<ALPHA>(sc, rng, tracker, ls.ray_o_tmin, ls.ray_d_tmax, shadow_rays, tracker_overflow);
+            if (T.pdf > 0.f) {
+                const float w = 1.f / (pdf_bsdf + T.pdf + ls.eval.pdf);
+                Li = Li + w * beta * T.f * ls.eval.L;
+            }
+            const lrk_medium m = sc.media[tracker.current_tag()];
+            eta = m.eta;
+            V3 mf, no, nd;
+            float mpdf;
+            homogeneous_medium_sample(v3(m.sigma_a[0], m.sigma_a[1], m.sigma_a[2]), v3(m.sigma_s[0], m.sigma_s[1], m.sigma_s[2]), m.g, o, d, t_max, rng,
+                                      medium_event, mf, mpdf, no, nd);
+            ro = make_float4(no.x, no.y, no.z, 0.f);
+            rd = make_float4(nd.x, nd.y, nd.z, kFltMax);
+            o = no;
+            d = nd;
+            const float w = mpdf > 0.f ? 1.f / mpdf : 0.f;
+            beta = beta * (mf * w);
+            pdf_bsdf = mpdf;
+        }
+        if (medium_event == ~0u || medium_event == 3u) {
+            if (!valid) {// :315-321
+                if (sc.env_present) {
+                    LightEval e = environment_evaluate(sc, d);
+                    e.pdf *= sc.env_prob;
+                    Li = Li + beta * e.L * balance_heuristic(pdf_bsdf, e.pdf);
+                }
+                break;
+            }
+            if (sc.light_count != 0u && it.shape.has_light()) {
+                const LightEval e = evaluate_hit(sc, it, o);
+                Li = Li + beta * e.L * balance_heuristic(pdf_bsdf, e.pdf);
+            }
+            if (!it.shape.has_surface()) break;
+            const float u_sel = lcg(state), ul0 = lcg(state), ul1 = lcg(state);
+            const float u_lobe = lcg(state), ub0 = lcg(state), ub1 = lcg(state);
+            const LightSample ls = sample_light(sc, it, u_sel, ul0, ul1);
+            const DeviceTransmittance T = general_transmittance<ALPHA>(sc, rng, tracker, ls.ray_o_tmin, ls.ray_d_tmax, shadow_rays, tracker_overflow);
+            const uint32_t medium_tag = it.shape.medium_tag;// 0 for a shape without a medium (geometry.cpp:134)
+            uint32_t medium_priority = LRK_MEDIUM_VACUUM_PRIORITY;
+            float eta_next = 1.f;
+            if (has_medium) {
+                medium_priority = sc.media[medium_tag].priority;
+                eta_next = sc.media[medium_tag].eta;
+            }
+            const V3 wo = -d;
+            const uint32_t kind = __ldg(sc.inst_kind + hit.x);
+            const lrk_surface *surf = sc.surfaces + it.shape.surface_tag;
+            const Frame shading = closure_frame<true>(sc, surf, it, wo);
+            const uint32_t surface_event_skip = surface_event_of(shading, wo, d);
+            uint32_t surface_event;
+            // true_hit gets the medium TAG where it expects a priority (:387, medium_tracker.cpp:19-21)
+            if (!tracker.true_hit(medium_tag)) {
+                surface_event = surface_event_skip;
+                const V3 po = p_robust(it, d);
+                ro = make_float4(po.x, po.y, po.z, 0.f);
+                rd = make_float4(d.x, d.y, d.z, kFltMax);
+                pdf_bsdf = 1e16f;
+            } else {
+                const GeneralSurfaceSample ss = general_surface_shade(sc, kind, surf, it, shading, wo, ls, u_lobe, ub0, ub1);
+                if (ls.eval.pdf > 0.0f) {
+                    const float w = 1.f / (ls.eval.pdf + ss.light.pdf + T.pdf);
+                    Li = Li + w * beta * ss.light.f * ls.eval.L * T.f;
+                }
+                surface_event = ss.event;
+                const float w = ss.pdf > 0.f ? 1.f / ss.pdf : 0.f;
+                pdf_bsdf = ss.pdf;
+                const V3 po = p_robust(it, ss.wi);
+                ro = make_float4(po.x, po.y, po.z, 0.f);
+                rd = make_float4(ss.wi.x, ss.wi.y, ss.wi.z, kFltMax);
+                beta = beta * (w * ss.f);
+                if (has_medium) {// :436-446
+                    if (surface_event == LRK_EVENT_ENTER) eta_scale = sqr(eta_next / eta);
+                    else if (surface_event == LRK_EVENT_EXIT) eta_scale = sqr(eta / eta_next);
+                }
+            }
+            if (has_medium) {// :449-458
+                if (surface_event == LRK_EVENT_ENTER) tracker.enter(medium_priority, medium_tag);
+                else if (surface_event == LRK_EVENT_EXIT) tracker.exit(medium_priority, medium_tag);
+            }
+        }
+        if (isnan(beta.x) || isnan(beta.y) || isnan(beta.z)) beta = v3(0.f);
+        if (beta.x <= 0.f && beta.y <= 0.f && beta.z <= 0.f) break;
+        const float q = fmaxf(max3(beta) * eta_scale, .05f);
+        if (depth + 1u >= sc.rr_depth) {
+            if (q < sc.rr_threshold && u_rr >= q) break;
+            beta = beta * (q < sc.rr_threshold ? 1.0f / q : 1.f);
+        }
+    }
+    tracker_overflow = tracker_overflow || tracker.overflow;
+    return Li;
+}
+
+#ifdef __CUDACC__
 constexpr int kGeneralBlock = 128;
 
 template<bool ALPHA>
@@ -256,134 +392,10 @@ __global__ void __launch_bounds__(kGeneralBlock) volume_general_kernel(DeviceSce
     uint32_t closest_rays = 0u, shadow_rays = 0u;
     if (id < n) {
         const uint32_t pixel = __ldg(pixel_list + pixel_offset + id % npix);
-        const uint32_t px = pixel & 0xffffu, py = pixel >> 16u;
-        uint32_t state = xxhash32_uint4(px, py, sc.sampler_seed, spp_begin + id / npix);
-        const float ux = lcg(state);
-        const float uy = lcg(state);
-        float4 ro, rd;
-        float weight;
-        camera_ray(sc.camera, px, py, ux, uy, ro, rd, weight);
-        // PCG32 rng(U64(as<UInt2>(generate_2d()))): first float = high word (src/util/u64.h:48,58-59)
-        const float s0 = lcg(state), s1 = lcg(state);
-        PCG32 rng;
-        rng.set_sequence((static_cast<unsigned long long>(__float_as_uint(s0)) << 32u) | __float_as_uint(s1));
-        DeviceMediumTracker tracker;
-        tracker.init();
         bool tracker_overflow = false;
-        if (sc.env_medium_tag != LRK_MEDIUM_INVALID_TAG) tracker.enter(sc.media[sc.env_medium_tag].priority, sc.env_medium_tag);
-        V3 beta = v3(weight), Li = v3(0.f);
-        float pdf_bsdf = 1e16f, eta_scale = 1.f;
-        for (uint32_t depth = 0; depth < sc.max_depth; depth++) {
-            float eta = 1.f;
-            float u_rr = 0.f;
-            if (depth + 1u >= sc.rr_depth) u_rr = lcg(state);
-            const uint4 hit = trace_single<false, ALPHA>(sc, ro, rd);
-            closest_rays++;
-            const bool valid = hit.x != ~0u;
-            V3 o = v3(ro.x, ro.y, ro.z), d = v3(rd.x, rd.y, rd.z);
-            Interaction it{};
-            if (valid) it = interaction_of_hit(sc, hit, d);
-            const bool has_medium = valid && it.shape.has_medium();
-            const float t_max = valid ? length(it.pg - o) : kFltMax;
-            uint32_t medium_event = ~0u;
-            if (!tracker.vacuum()) {// :275-311
-                const float u_sel = lcg(state), ul0 = lcg(state), ul1 = lcg(state);
-                Interaction it_medium{};// Interaction{ray->origin()}: pg = ng = origin, default frame, zero offset factor
-                it_medium.pg = o;
-                it_medium.ng = o;
-                it_medium.shading = Frame{v3(1.f, 0.f, 0.f), v3(0.f, 1.f, 0.f), v3(0.f, 0.f, 1.f)};
-                it_medium.shape.intersection_offset = 0.f;
-                const LightSample ls = sample_light(sc, it_medium, u_sel, ul0, ul1);
-                const DeviceTransmittance T = general_transmittance<ALPHA>(sc, rng, tracker, ls.ray_o_tmin, ls.ray_d_tmax, shadow_rays, tracker_overflow);
-                if (T.pdf > 0.f) {
-                    const float w = 1.f / (pdf_bsdf + T.pdf + ls.eval.pdf);
-                    Li = Li + w * beta * T.f * ls.eval.L;
-                }
-                const lrk_medium m = sc.media[tracker.current_tag()];
-                eta = m.eta;
-                V3 mf, no, nd;
-                float mpdf;
-                homogeneous_medium_sample(v3(m.sigma_a[0], m.sigma_a[1], m.sigma_a[2]), v3(m.sigma_s[0], m.sigma_s[1], m.sigma_s[2]), m.g, o, d, t_max, rng,
-                                          medium_event, mf, mpdf, no, nd);
-                ro = make_float4(no.x, no.y, no.z, 0.f);
-                rd = make_float4(nd.x, nd.y, nd.z, kFltMax);
-                o = no;
-                d = nd;
-                const float w = mpdf > 0.f ? 1.f / mpdf : 0.f;
-                beta = beta * (mf * w);
-                pdf_bsdf = mpdf;
-            }
-            if (medium_event == ~0u || medium_event == 3u) {
-                if (!valid) {// :315-321
-                    if (sc.env_present) {
-                        LightEval e = environment_evaluate(sc, d);
-                        e.pdf *= sc.env_prob;
-                        Li = Li + beta * e.L * balance_heuristic(pdf_bsdf, e.pdf);
-                    }
-                    break;
-                }
-                if (sc.light_count != 0u && it.shape.has_light()) {
-                    const LightEval e = evaluate_hit(sc, it, o);
-                    Li = Li + beta * e.L * balance_heuristic(pdf_bsdf, e.pdf);
-                }
-                if (!it.shape.has_surface()) break;
-                const float u_sel = lcg(state), ul0 = lcg(state), ul1 = lcg(state);
-                const float u_lobe = lcg(state), ub0 = lcg(state), ub1 = lcg(state);
-                const LightSample ls = sample_light(sc, it, u_sel, ul0, ul1);
-                const DeviceTransmittance T = general_transmittance<ALPHA>(sc, rng, tracker, ls.ray_o_tmin, ls.ray_d_tmax, shadow_rays, tracker_overflow);
-                const uint32_t medium_tag = it.shape.medium_tag;// 0 for a shape without a medium (geometry.cpp:134)
-                uint32_t medium_priority = LRK_MEDIUM_VACUUM_PRIORITY;
-                float eta_next = 1.f;
-                if (has_medium) {
-                    medium_priority = sc.media[medium_tag].priority;
-                    eta_next = sc.media[medium_tag].eta;
-                }
-                const V3 wo = -d;
-                const uint32_t kind = __ldg(sc.inst_kind + hit.x);
-                const lrk_surface *surf = sc.surfaces + it.shape.surface_tag;
-                const Frame shading = closure_frame<true>(sc, surf, it, wo);
-                const uint32_t surface_event_skip = surface_event_of(shading, wo, d);
-                uint32_t surface_event;
-                // true_hit gets the medium TAG where it expects a priority (:387, medium_tracker.cpp:19-21)
-                if (!tracker.true_hit(medium_tag)) {
-                    surface_event = surface_event_skip;
-                    const V3 po = p_robust(it, d);
-                    ro = make_float4(po.x, po.y, po.z, 0.f);
-                    rd = make_float4(d.x, d.y, d.z, kFltMax);
-                    pdf_bsdf = 1e16f;
-                } else {
-                    const GeneralSurfaceSample ss = general_surface_shade(sc, kind, surf, it, shading, wo, ls, u_lobe, ub0, ub1);
-                    if (ls.eval.pdf > 0.0f) {
-                        const float w = 1.f / (ls.eval.pdf + ss.light.pdf + T.pdf);
-                        Li = Li + w * beta * ss.light.f * ls.eval.L * T.f;
-                    }
-                    surface_event = ss.event;
-                    const float w = ss.pdf > 0.f ? 1.f / ss.pdf : 0.f;
-                    pdf_bsdf = ss.pdf;
-                    const V3 po = p_robust(it, ss.wi);
-                    ro = make_float4(po.x, po.y, po.z, 0.f);
-                    rd = make_float4(ss.wi.x, ss.wi.y, ss.wi.z, kFltMax);
-                    beta = beta * (w * ss.f);
-                    if (has_medium) {// :436-446
-                        if (surface_event == LRK_EVENT_ENTER) eta_scale = sqr(eta_next / eta);
-                        else if (surface_event == LRK_EVENT_EXIT) eta_scale = sqr(eta / eta_next);
-                    }
-                }
-                if (has_medium) {// :449-458
-                    if (surface_event == LRK_EVENT_ENTER) tracker.enter(medium_priority, medium_tag);
-                    else if (surface_event == LRK_EVENT_EXIT) tracker.exit(medium_priority, medium_tag);
-                }
-            }
-            if (isnan(beta.x) || isnan(beta.y) || isnan(beta.z)) beta = v3(0.f);
-            if (beta.x <= 0.f && beta.y <= 0.f && beta.z <= 0.f) break;
-            const float q = fmaxf(max3(beta) * eta_scale, .05f);
-            if (depth + 1u >= sc.rr_depth) {
-                if (q < sc.rr_threshold && u_rr >= q) break;
-                beta = beta * (q < sc.rr_threshold ? 1.0f / q : 1.f);
-            }
-        }
+        const V3 Li = volume_general_li<ALPHA>(sc, pixel & 0xffffu, pixel >> 16u, spp_begin + id / npix, closest_rays, shadow_rays, tracker_overflow);
         pb.li[id] = make_float4(Li.x, Li.y, Li.z, 0.f);
-        if (tracker_overflow || tracker.overflow) atomicOr(sc.traversal_overflow, 2u);
+        if (tracker_overflow) atomicOr(sc.traversal_overflow, 2u);
     }
     // ray totals of the pass (the wavefront kernels derive them from their queue sizes)
     for (int off = 16; off > 0; off >>= 1) {
@@ -398,5 +410,7 @@ __global__ void __launch_bounds__(kGeneralBlock) volume_general_kernel(DeviceSce
         for (uint32_t k = 0; k < kCountSlots * kMaxDepthSlots; k++) pb.counts[k] = 0u;// accumulate_kernel adds the queue sizes: none here
     }
 }
+
+#endif// __CUDACC__
 
 }// namespace lrk
