@@ -58,14 +58,34 @@ def build_host(force=False, verbose=False) -> Path:
     return out
 
 
-def build_device(force=False, verbose=False) -> Path:
-    out = LIB / "libb200pt.so"
+def build_device(force=False, verbose=False, name="libb200pt.so", extra_flags=()) -> Path:
+    """libb200pt.so = lrk.cu + shade.cu.  lrk.cu (ray generation, traversal, classification, film, the host API) is compiled with
+    IEEE arithmetic and no FMA contraction: bit-exact with the oracle.  shade.cu (the closure kernels) is compiled with nvcc's
+    fast-math arithmetic, as the reference's CUDA backend compiles all of its kernels (see the header of shade.cu);
+    LRK_SHADE_STRICT=1 in the environment builds it like lrk.cu."""
+    out = LIB / name
     src_dir = PKG / "csrc" / "device"
-    deps = list(src_dir.glob("*.cu")) + list(src_dir.glob("*.cuh")) + list((REPO / "include").glob("*.h"))
+    deps = list(src_dir.glob("*.cu")) + list(src_dir.glob("*.cuh")) + list(src_dir.glob("*.h")) + list((REPO / "include").glob("*.h"))
     if not force and _newer(out, deps):
         return out
     LIB.mkdir(exist_ok=True)
-    _run([_nvcc(), *NVCC_ARCH, *NVCC_FLAGS, src_dir / "lrk.cu", "-o", out], verbose)
+    obj = LIB / ("_obj_" + Path(name).stem)
+    obj.mkdir(exist_ok=True)
+    common = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", *extra_flags]
+    shade_math = ["-fmad=false"] if os.environ.get("LRK_SHADE_STRICT") == "1" else ["--use_fast_math"]
+    steps = [([_nvcc(), *NVCC_ARCH, *common, "-fmad=false", "-c", src_dir / "lrk.cu", "-o", obj / "lrk.o"], None),
+             ([_nvcc(), *NVCC_ARCH, *common, *shade_math, "-c", src_dir / "shade.cu", "-o", obj / "shade.o"], None)]
+    procs = []
+    for cmd, _ in steps:  # the two translation units compile side by side
+        if verbose:
+            print("+", " ".join(str(c) for c in cmd), flush=True)
+        procs.append((cmd, subprocess.Popen([str(c) for c in cmd], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for cmd, proc in procs:
+        text, _ = proc.communicate()
+        if proc.returncode != 0:
+            sys.stderr.write(text)
+            raise RuntimeError(f"build step failed: {' '.join(str(c) for c in cmd[:3])} ...")
+    _run([_nvcc(), *NVCC_ARCH, "--shared", obj / "lrk.o", obj / "shade.o", "-o", out], verbose)
     return out
 
 

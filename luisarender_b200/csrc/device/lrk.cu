@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "shade_launch.h"
 #include "bvh_build.cuh"
 #include "comm.cuh"
 
@@ -314,19 +315,11 @@ int render_pass(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint32_t spp
             ScopedTimer t{ctx, CAT_SHADE};
             if (sc.env_present) shade_miss_kernel<<<blocks_for(ctx, n, ctx->grid_classify), kBlock, 0, ctx->stream>>>(sc, pb, depth);
             classify_hits_kernel<<<blocks_for(ctx, n, ctx->grid_classify), kBlock, 0, ctx->stream>>>(sc, pb, depth);
-            // TEXTURED variants only for scenes with image-textured parameters / normal maps
-            auto launch = [&](auto kernel, int kind) {
-                kernel<<<blocks_for(ctx, n, ctx->grid_shade[kind]), kShadeBlock, 0, ctx->stream>>>(sc, pb, depth);
-            };
-            launch(shade_kernel<0u, false>, 0);
-            if (ctx->has_kind[1]) ctx->textured ? launch(shade_kernel<1u, true>, 1) : launch(shade_kernel<1u, false>, 1);
-            if (ctx->has_kind[2]) ctx->textured ? launch(shade_kernel<2u, true>, 2) : launch(shade_kernel<2u, false>, 2);
-            if (ctx->has_kind[3]) ctx->textured ? launch(shade_kernel<3u, true>, 3) : launch(shade_kernel<3u, false>, 3);
-            if (ctx->has_kind[4]) ctx->textured ? launch(shade_kernel<4u, true>, 4) : launch(shade_kernel<4u, false>, 4);
-            if (ctx->has_kind[5]) ctx->textured ? launch(shade_kernel<5u, true>, 5) : launch(shade_kernel<5u, false>, 5);
-            if (ctx->has_kind[6]) ctx->textured ? launch(shade_kernel<6u, true>, 6) : launch(shade_kernel<6u, false>, 6);
-            if (ctx->has_kind[7]) ctx->textured ? launch(shade_kernel<7u, true>, 7) : launch(shade_kernel<7u, false>, 7);
-            if (ctx->has_kind[8]) ctx->textured ? launch(shade_kernel<8u, true>, 8) : launch(shade_kernel<8u, false>, 8);
+            // one kernel per closure kind over its own hit bucket (shade.cu); TEXTURED variants only for scenes with image-textured
+            // parameters / normal maps
+            for (uint32_t kind = 0; kind < kHitKinds; kind++)
+                if (kind == 0u || ctx->has_kind[kind])
+                    launch_shade(kind, ctx->textured, blocks_for(ctx, n, ctx->grid_shade[kind]), ctx->stream, sc, pb, depth);
         }
         {
             ScopedTimer t{ctx, CAT_TRACE_SHADOW};
@@ -410,11 +403,10 @@ int render_pass_volume(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint3
         }
         {
             ScopedTimer t{ctx, CAT_SHADE};
-            volume_medium_kernel<<<blocks_for(ctx, n, ctx->grid_vmedium), kBlock, 0, ctx->stream>>>(sc, pb, depth);
-            auto launch = [&](auto kernel, int kind) { kernel<<<blocks_for(ctx, n, ctx->grid_vshade[kind]), kBlock, 0, ctx->stream>>>(sc, pb, depth); };
-            launch(volume_surface_kernel<0u, false>, 0);
-            if (ctx->has_kind[1]) ctx->textured ? launch(volume_surface_kernel<1u, true>, 1) : launch(volume_surface_kernel<1u, false>, 1);
-            if (ctx->has_kind[2]) ctx->textured ? launch(volume_surface_kernel<2u, true>, 2) : launch(volume_surface_kernel<2u, false>, 2);
+            launch_volume_medium(blocks_for(ctx, n, ctx->grid_vmedium), ctx->stream, sc, pb, depth);
+            for (uint32_t kind = 0; kind < 3u; kind++)
+                if (kind == 0u || ctx->has_kind[kind])
+                    launch_volume_surface(kind, ctx->textured, blocks_for(ctx, n, ctx->grid_vshade[kind]), ctx->stream, sc, pb, depth);
         }
         {
             ScopedTimer t{ctx, CAT_TRACE_SHADOW};
@@ -594,20 +586,10 @@ int lrk_create(const lrk_device_cfg *cfg, lrk_ctx **out) {
     };
     ctx->grid_trace = grid_for(reinterpret_cast<const void *>(trace_closest_kernel<false, false>), kTraceBlock);
     ctx->grid_shadow = grid_for(reinterpret_cast<const void *>(trace_shadow_kernel<false, false>), kTraceBlock);
-    ctx->grid_shade[0] = grid_for(reinterpret_cast<const void *>(shade_kernel<0u, false>), kShadeBlock);
-    ctx->grid_shade[1] = grid_for(reinterpret_cast<const void *>(shade_kernel<1u, false>), kShadeBlock);
-    ctx->grid_shade[2] = grid_for(reinterpret_cast<const void *>(shade_kernel<2u, false>), kShadeBlock);
-    ctx->grid_shade[3] = grid_for(reinterpret_cast<const void *>(shade_kernel<3u, false>), kShadeBlock);
-    ctx->grid_shade[4] = grid_for(reinterpret_cast<const void *>(shade_kernel<4u, false>), kShadeBlock);
-    ctx->grid_shade[5] = grid_for(reinterpret_cast<const void *>(shade_kernel<5u, false>), kShadeBlock);
-    ctx->grid_shade[6] = grid_for(reinterpret_cast<const void *>(shade_kernel<6u, false>), kShadeBlock);
-    ctx->grid_shade[7] = grid_for(reinterpret_cast<const void *>(shade_kernel<7u, false>), kShadeBlock);
-    ctx->grid_shade[8] = grid_for(reinterpret_cast<const void *>(shade_kernel<8u, false>), kShadeBlock);
+    for (uint32_t kind = 0; kind < kHitKinds; kind++) ctx->grid_shade[kind] = shade_grid(kind, ctx->sm_count);
     ctx->grid_classify = grid_for(reinterpret_cast<const void *>(classify_hits_kernel));
-    ctx->grid_vmedium = grid_for(reinterpret_cast<const void *>(volume_medium_kernel));
-    ctx->grid_vshade[0] = grid_for(reinterpret_cast<const void *>(volume_surface_kernel<0u, false>));
-    ctx->grid_vshade[1] = grid_for(reinterpret_cast<const void *>(volume_surface_kernel<1u, false>));
-    ctx->grid_vshade[2] = grid_for(reinterpret_cast<const void *>(volume_surface_kernel<2u, false>));
+    ctx->grid_vmedium = volume_medium_grid(ctx->sm_count);
+    for (uint32_t kind = 0; kind < 3u; kind++) ctx->grid_vshade[kind] = volume_surface_grid(kind, ctx->sm_count);
     ctx->grid_vshadow = grid_for(reinterpret_cast<const void *>(trace_volume_nee_kernel<false>), kTraceBlock);
     *out = ctx;
     return LRK_OK;

@@ -225,4 +225,28 @@ __device__ __forceinline__ void homogeneous_medium_sample(V3 sigma_a, V3 sigma_s
     }
 }
 
+// shadow ray from a point in the medium towards a sampled light point: LightSampler::sample with
+// Interaction{ray->origin()} (mega_vpt_naive.cpp:270-273): zero offset factor, so the origin is the point itself
+__device__ __forceinline__ void medium_light_shadow_ray(const DeviceScene &sc, V3 p_from, float u_sel, float u0, float u1,
+                                                        float4 &ro, float4 &rd) {
+    float n = static_cast<float>(sc.light_count);
+    uint32_t tag = static_cast<uint32_t>(clampf(u_sel * n, 0.f, n - 1.f));
+    const lrk_light_handle handle = sc.light_handles[tag];
+    ShapeHandle light_inst = decode_handle(__ldg(sc.inst_handles + handle.instance_id));
+    const lrk_mesh mesh = sc.meshes[light_inst.mesh];
+    float u = u0 * static_cast<float>(light_inst.tri_count);
+    uint32_t i = min(max(static_cast<uint32_t>(u), 0u), light_inst.tri_count - 1u);
+    float u_remapped = u - floorf(u);
+    lrk_alias_entry entry = sc.alias[mesh.triangle_offset + i];
+    bool keep = u_remapped < entry.prob;
+    uint32_t triangle_id = keep ? i : entry.alias;
+    float ux = keep ? u_remapped / entry.prob : (u_remapped - entry.prob) / (1.0f - entry.prob);
+    V3 uvw = sample_uniform_triangle(ux, u1);
+    V3 Lv = hit_position(sc, handle.instance_id, triangle_id, uvw) - p_from;
+    float d = length(Lv);
+    V3 dir = Lv * (1.f / d);
+    ro = make_float4(p_from.x, p_from.y, p_from.z, 0.f);
+    rd = make_float4(dir.x, dir.y, dir.z, d * .9999f);
+}
+
 }// namespace lrk

@@ -241,8 +241,8 @@ __device__ __forceinline__ LightEval evaluate_hit(const DeviceScene &sc, const I
 }
 
 // the environment light (defined after the texture code): src/environments/spherical.cpp:83-137
-__device__ LightEval environment_evaluate(const DeviceScene &sc, V3 wi);
-__device__ LightEval environment_sample(const DeviceScene &sc, float u0, float u1, V3 &wi);
+__device__ inline LightEval environment_evaluate(const DeviceScene &sc, V3 wi);
+__device__ inline LightEval environment_sample(const DeviceScene &sc, float u0, float u1, V3 &wi);
 
 struct LightSample {
     LightEval eval;
@@ -356,7 +356,7 @@ __device__ __forceinline__ float tex_decode(const lrk_texture &t, float x) {
     return t.scale * x;
 }
 // Not inlined on purpose: up to a dozen call sites per closure, executed only for textured materials.
-__device__ __noinline__ float4 texture_evaluate(const DeviceScene &sc, uint32_t tex_id, float u, float v) {
+__device__ __noinline__ inline float4 texture_evaluate(const DeviceScene &sc, uint32_t tex_id, float u, float v) {
     const lrk_texture t = sc.textures[tex_id];
     float4 s = texture_sample(sc, t, u * t.uv_scale[0] + t.uv_offset[0], v * t.uv_scale[1] + t.uv_offset[1]);
     return make_float4(tex_decode(t, s.x), tex_decode(t, s.y), tex_decode(t, s.z), tex_decode(t, s.w));
@@ -407,7 +407,7 @@ __device__ __forceinline__ float env_directional_pdf(float p, float theta) {// :
     float inv_s = s > 0.f ? 1.f / s : 0.f;
     return p * inv_s * (.5f * kInvPi * kInvPi);
 }
-__device__ __noinline__ LightEval environment_evaluate(const DeviceScene &sc, V3 wi) {
+__device__ __noinline__ inline LightEval environment_evaluate(const DeviceScene &sc, V3 wi) {
     V3 w = normalize(env_mul(sc.env_to_world, wi, true));
     float theta = acosf(w.y), phi = atan2f(w.x, w.z);// direction_to_uv, :53-59
     float u = 1.f - 0.5f * kInvPi * phi, v = theta * kInvPi;
@@ -433,7 +433,7 @@ __device__ __forceinline__ void sample_alias(const lrk_alias_entry *table, uint3
     index = keep ? i : entry.alias;
     uu = keep ? u_remapped / entry.prob : (u_remapped - entry.prob) / (1.0f - entry.prob);
 }
-__device__ __noinline__ LightEval environment_sample(const DeviceScene &sc, float u0, float u1, V3 &wi) {
+__device__ __noinline__ inline LightEval environment_sample(const DeviceScene &sc, float u0, float u1, V3 &wi) {
     LightEval e;
     V3 w;
     if (sc.env_emission_tex == 0u) {
@@ -470,7 +470,7 @@ __device__ __noinline__ LightEval environment_sample(const DeviceScene &sc, floa
 // Geometry::_alpha_skip (src/base/geometry.cpp:165-192): whether a traversal candidate (instance, primitive, barycentrics of
 // the triangle test) is stochastically transparent.  The random number is a hash of the hit, so the decision is the same
 // in every traversal that meets this candidate.
-__device__ __noinline__ bool alpha_skip(const DeviceScene &sc, uint32_t inst_id, uint32_t prim_id, float bu, float bv) {
+__device__ __noinline__ inline bool alpha_skip(const DeviceScene &sc, uint32_t inst_id, uint32_t prim_id, float bu, float bv) {
     const ShapeHandle shape = decode_handle(__ldg(sc.inst_handles + inst_id));
     if (!((shape.flags & LRK_SHAPE_MAYBE_NON_OPAQUE) && shape.has_surface())) return false;
     const lrk_surface *surf = sc.surfaces + shape.surface_tag;
@@ -1179,7 +1179,7 @@ __device__ __forceinline__ SurfEval child_evaluate(const lrk_surface *s, V3 wo, 
     c.prepare(wo);
     return c.evaluate_local(wo, wi);
 }
-__device__ __noinline__ SurfEval any_evaluate_local(const lrk_surface *s, V3 wo, V3 wi) {
+__device__ __noinline__ inline SurfEval any_evaluate_local(const lrk_surface *s, V3 wo, V3 wi) {
     switch (s->type) {
         case LRK_SURFACE_MATTE: return child_evaluate<MatteClosure>(s, wo, wi);
         case LRK_SURFACE_MIRROR: return child_evaluate<MicrofacetFamilyClosure<LRK_SURFACE_MIRROR>>(s, wo, wi);
@@ -1189,7 +1189,7 @@ __device__ __noinline__ SurfEval any_evaluate_local(const lrk_surface *s, V3 wo,
     }
 }
 // returns the sample's validity; `transmitted`: the sampled event is a refraction (Surface::event_enter / event_exit)
-__device__ __noinline__ bool any_sample_direction(const lrk_surface *s, V3 wo, float u_lobe, float u0, float u1, V3 &wi, bool &transmitted) {
+__device__ __noinline__ inline bool any_sample_direction(const lrk_surface *s, V3 wo, float u_lobe, float u0, float u1, V3 &wi, bool &transmitted) {
     transmitted = false;
     switch (s->type) {
         case LRK_SURFACE_MATTE: { MatteClosure c; c.init(*s); c.prepare(wo); return c.sample_direction(wo, u_lobe, u0, u1, wi); }

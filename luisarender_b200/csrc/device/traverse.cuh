@@ -114,7 +114,7 @@ __device__ __forceinline__ void inner_step(const DeviceScene &sc, RayState &r, S
 }
 
 // ALPHA: stochastic alpha test of every accepted candidate (scenes with non-opaque surfaces only; alpha_skip is in shading.cuh)
-__device__ bool alpha_skip(const DeviceScene &sc, uint32_t inst_id, uint32_t prim_id, float bu, float bv);
+__device__ inline bool alpha_skip(const DeviceScene &sc, uint32_t inst_id, uint32_t prim_id, float bu, float bv);
 
 // One step on a leaf-like reference (bit 31 set): sentinel, instance (TLAS leaf) or triangle range (BLAS leaf).
 // `world` parks the world-space ray while the lane is inside an instance.  Returns true when the ray is finished.
@@ -376,7 +376,7 @@ struct ThreadWorld {
 
 // hit = {inst, prim, bary.u bits, bary.v bits}; miss <=> inst == ~0u
 template<bool ANY_HIT, bool ALPHA>
-__device__ __noinline__ uint4 trace_single(const DeviceScene &sc, float4 o, float4 d) {
+__device__ __noinline__ inline uint4 trace_single(const DeviceScene &sc, float4 o, float4 d) {
     uint32_t entries[ThreadStack::kCapacity];
     ThreadStack stack;
     stack.e = entries;

@@ -141,7 +141,7 @@ template<typename Closure>
 struct has_event_member<Closure, std::void_t<decltype(std::declval<const Closure &>().event)>> : std::true_type {};
 
 // Surface::Closure::evaluate (src/base/surface.cpp:35-68) of the hit's closure
-__device__ __noinline__ SurfEval general_surface_evaluate(const DeviceScene &sc, uint32_t kind, const lrk_surface *surf, const Interaction &it,
+__device__ __noinline__ inline SurfEval general_surface_evaluate(const DeviceScene &sc, uint32_t kind, const lrk_surface *surf, const Interaction &it,
                                                           Frame shading, V3 wo, V3 wi) {
     SurfEval e;
     e.f = v3(0.f);
@@ -164,7 +164,7 @@ struct GeneralSurfaceSample {
     float pdf;
     uint32_t event;
 };
-__device__ __noinline__ GeneralSurfaceSample general_surface_shade(const DeviceScene &sc, uint32_t kind, const lrk_surface *surf, const Interaction &it,
+__device__ __noinline__ inline GeneralSurfaceSample general_surface_shade(const DeviceScene &sc, uint32_t kind, const lrk_surface *surf, const Interaction &it,
                                                                    Frame shading, V3 wo, LightSample ls, float u_lobe, float ub0, float ub1) {
     GeneralSurfaceSample out;
     out.light.f = out.f = v3(0.f);
@@ -192,7 +192,7 @@ __device__ __forceinline__ Interaction interaction_of_hit(const DeviceScene &sc,
 
 // _transmittance (mega_vpt_naive.cpp:96-168); the tracker is a copy (taken by value)
 template<bool ALPHA>
-__device__ __noinline__ DeviceTransmittance general_transmittance(const DeviceScene &sc, PCG32 &rng, DeviceMediumTracker tracker, float4 ray_o, float4 ray_d,
+__device__ __noinline__ inline DeviceTransmittance general_transmittance(const DeviceScene &sc, PCG32 &rng, DeviceMediumTracker tracker, float4 ray_o, float4 ray_d,
                                                                  uint32_t &rays, bool &tracker_overflow) {
     const float t_max = ray_d.w;
     const V3 dir = v3(ray_d.x, ray_d.y, ray_d.z);

@@ -22,13 +22,19 @@ def main():
     ap.add_argument("--spp", type=int, default=64)
     ap.add_argument("--repeat", type=int, default=2)
     ap.add_argument("--count", action="store_true")
+    ap.add_argument("--device-bvh", action="store_true", help="build the hierarchy on the GPU (option device_bvh) instead of uploading the host's")
     ap.add_argument("opts", nargs="*")
     a = ap.parse_args()
     sweep = [(o.split("=")[0], [int(v) for v in o.split("=")[1].split(",")]) for o in a.opts]
     sc = Scene.from_source(SCENES[a.scene](), REPO)
     d = sc.desc()
     r = Renderer(0)
+    if a.device_bvh:
+        r.set_option("device_bvh", 1)
+    import time
+    t0 = time.perf_counter()
     r.upload(d)
+    upload_ms = (time.perf_counter() - t0) * 1e3
     w, h = d.camera.resolution[0], d.camera.resolution[1]
     r.render(0, min(a.spp, 8))
     for combo in itertools.product(*[vals for _, vals in sweep]) if sweep else [()]:
@@ -42,7 +48,8 @@ def main():
             st = r.stats()
             if best is None or st["render_ms"] < best["render_ms"]:
                 best = st
-        out = {"lib": os.environ.get("LRK_DEVICE_LIB", "libb200pt.so"), "scene": a.scene, "spp": a.spp,
+        out = {"lib": os.environ.get("LRK_DEVICE_LIB", "libb200pt.so"), "scene": a.scene, "spp": a.spp, "device_bvh": bool(a.device_bvh),
+               "upload_ms": round(upload_ms, 1), "host_bvh_build_ms": round(sc.info()["bvh_build_ms"], 1),
                **{name: v for (name, _), v in zip(sweep, combo)},
                "ms": round(best["render_ms"], 2), "Msamples_s": round(w * h * a.spp / best["render_ms"] * 1e-3, 1),
                "closest_ms": round(best["trace_closest_ms"], 2), "shadow_ms": round(best["trace_shadow_ms"], 2),
