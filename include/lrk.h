@@ -501,6 +501,11 @@ int lrk_reduce_film(lrk_ctx *ctx, uint32_t root);
  *   "time_kernels" (0/1)      CUDA-event time per kernel category into lrk_stats
  *   "max_paths_per_pass" (n)  path-state capacity of one pass
  *   "refill_below", "inner_min" (1..32)  warp scheduling of the traversal kernels (results do not depend on them)
+ *   "strict_math" (0/1)       closure kernels in IEEE arithmetic without FMA contraction (films then equal the CPU oracle's to
+ *                             rel-L2 ~ 1e-7) instead of the fast-math arithmetic the reference's own CUDA backend compiles its
+ *                             kernels with (the default; ~15 % faster on the headline scene).  Traversal, ray generation and the
+ *                             film are IEEE either way; the near-specular closures (Mirror .. Mix) too
+ *   "device_bvh" (0/1)        build the hierarchy on the GPU at the next lrk_upload_scene instead of taking the caller's
  *   "pin_host_buffers" (0/1)  the caller promises that the host arrays it passes to lrk_upload_scene / lrk_download_film*
  *                             stay allocated until lrk_destroy (or until the option is cleared); the library page-locks each
  *                             of them once (cudaHostRegister), so that every later transfer of the same buffer is a

@@ -19,6 +19,7 @@ HOST_SRC = ["sdl.cpp", "scene.cpp", "geomutil.cpp", "bvh.cpp", "flatten.cpp", "i
 NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # -fmad=false: expressions evaluate as written (see csrc/device/vecmath.cuh); FMAs are explicit fmaf().
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-fmad=false", "--shared", "-Xcompiler", "-fPIC"]
+SHADE_MATH = ["--use_fast_math"]  # arithmetic of shade.cu (see its header)
 HOST_FLAGS = ["-std=c++17", "-O2", "-fPIC", "-march=x86-64-v3", "-ffp-contract=off", "-Wall", "-Wextra",
               "-Wno-unused-parameter", "-Wno-missing-field-initializers"]
 
@@ -59,10 +60,10 @@ def build_host(force=False, verbose=False) -> Path:
 
 
 def build_device(force=False, verbose=False, name="libb200pt.so", extra_flags=()) -> Path:
-    """libb200pt.so = lrk.cu + shade.cu.  lrk.cu (ray generation, traversal, classification, film, the host API) is compiled with
-    IEEE arithmetic and no FMA contraction: bit-exact with the oracle.  shade.cu (the closure kernels) is compiled with nvcc's
-    fast-math arithmetic, as the reference's CUDA backend compiles all of its kernels (see the header of shade.cu);
-    LRK_SHADE_STRICT=1 in the environment builds it like lrk.cu."""
+    """libb200pt.so = lrk.cu + shade.cu (twice).  lrk.cu (ray generation, traversal, classification, film, the host API) is compiled
+    with IEEE arithmetic and no FMA contraction: bit-exact with the oracle.  shade.cu (the closure kernels) is compiled once with
+    nvcc's fast-math arithmetic, as the reference's CUDA backend compiles all of its kernels, and once like lrk.cu (see the
+    header of shade.cu; lrk_set_option("strict_math") selects at run time)."""
     out = LIB / name
     src_dir = PKG / "csrc" / "device"
     deps = list(src_dir.glob("*.cu")) + list(src_dir.glob("*.cuh")) + list(src_dir.glob("*.h")) + list((REPO / "include").glob("*.h"))
@@ -72,11 +73,15 @@ def build_device(force=False, verbose=False, name="libb200pt.so", extra_flags=()
     obj = LIB / ("_obj_" + Path(name).stem)
     obj.mkdir(exist_ok=True)
     common = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", *extra_flags]
-    shade_math = ["-fmad=false"] if os.environ.get("LRK_SHADE_STRICT") == "1" else ["--use_fast_math"]
-    steps = [([_nvcc(), *NVCC_ARCH, *common, "-fmad=false", "-c", src_dir / "lrk.cu", "-o", obj / "lrk.o"], None),
-             ([_nvcc(), *NVCC_ARCH, *common, *shade_math, "-c", src_dir / "shade.cu", "-o", obj / "shade.o"], None)]
+    shade_math = ["-fmad=false"] if os.environ.get("LRK_SHADE_STRICT") == "1" else SHADE_MATH
+    if os.environ.get("LRK_SHADE_FLAGS"):  # experiments (tools/build_variants.sh)
+        shade_math = os.environ["LRK_SHADE_FLAGS"].split()
+    objects = [obj / "lrk.o", obj / "shade_fast.o", obj / "shade_strict.o"]
+    steps = [([_nvcc(), *NVCC_ARCH, *common, "-fmad=false", "-c", src_dir / "lrk.cu", "-o", objects[0]], None),
+             ([_nvcc(), *NVCC_ARCH, *common, *shade_math, "-DLRK_SHADE_VARIANT=fast", "-c", src_dir / "shade.cu", "-o", objects[1]], None),
+             ([_nvcc(), *NVCC_ARCH, *common, "-fmad=false", "-DLRK_SHADE_VARIANT=strict", "-c", src_dir / "shade.cu", "-o", objects[2]], None)]
     procs = []
-    for cmd, _ in steps:  # the two translation units compile side by side
+    for cmd, _ in steps:  # the three objects compile side by side
         if verbose:
             print("+", " ".join(str(c) for c in cmd), flush=True)
         procs.append((cmd, subprocess.Popen([str(c) for c in cmd], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -85,7 +90,7 @@ def build_device(force=False, verbose=False, name="libb200pt.so", extra_flags=()
         if proc.returncode != 0:
             sys.stderr.write(text)
             raise RuntimeError(f"build step failed: {' '.join(str(c) for c in cmd[:3])} ...")
-    _run([_nvcc(), *NVCC_ARCH, "--shared", obj / "lrk.o", obj / "shade.o", "-o", out], verbose)
+    _run([_nvcc(), *NVCC_ARCH, "--shared", *objects, "-o", out], verbose)
     return out
 
 

@@ -75,14 +75,15 @@ struct lrk_ctx {
     cudaEvent_t ev_begin{}, ev_end{};
     std::vector<TimedLaunch> timed;
     std::vector<cudaEvent_t> event_pool;
-    int grid_trace{0}, grid_shade[9]{0, 0, 0, 0, 0, 0, 0, 0, 0}, grid_shadow{0}, grid_classify{0};
+    int grid_trace{0}, grid_shade[2][9]{}, grid_shadow{0}, grid_classify{0};// grid_shade[variant]: 0 = fast, 1 = strict arithmetic
     bool has_kind[9]{true, false, false, false, false, false, false, false, false};
     uint32_t allocated_kinds{0u};// bit k: hit_index[k] is allocated
     bool volume{false};
+    bool strict_math{false};// option strict_math: every closure kernel from shade.cu's IEEE-arithmetic compilation
     bool volume_general{false};// the volume integrator's per-thread kernel (volume_general.cuh) instead of the wavefront one
     int grid_vgeneral{0};
     uint64_t volume_capacity{0};
-    int grid_vshade[3]{0, 0, 0}, grid_vmedium{0}, grid_vshadow{0};
+    int grid_vshade[2][3]{}, grid_vmedium[2]{0, 0}, grid_vshadow{0};
 };
 
 namespace {
@@ -317,9 +318,14 @@ int render_pass(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint32_t spp
             classify_hits_kernel<<<blocks_for(ctx, n, ctx->grid_classify), kBlock, 0, ctx->stream>>>(sc, pb, depth);
             // one kernel per closure kind over its own hit bucket (shade.cu); TEXTURED variants only for scenes with image-textured
             // parameters / normal maps
-            for (uint32_t kind = 0; kind < kHitKinds; kind++)
-                if (kind == 0u || ctx->has_kind[kind])
-                    launch_shade(kind, ctx->textured, blocks_for(ctx, n, ctx->grid_shade[kind]), ctx->stream, sc, pb, depth);
+            for (uint32_t kind = 0; kind < kHitKinds; kind++) {
+                if (kind != 0u && !ctx->has_kind[kind]) continue;
+                // the near-specular closures (Mirror, Glass, Plastic, Metal, Mix: buckets 3..7) always run in IEEE arithmetic
+                const bool strict = ctx->strict_math || (kind >= 3u && kind <= 7u);
+                const int blocks = blocks_for(ctx, n, ctx->grid_shade[strict ? 1 : 0][kind]);
+                if (strict) strict::launch_shade(kind, ctx->textured, blocks, ctx->stream, sc, pb, depth);
+                else fast::launch_shade(kind, ctx->textured, blocks, ctx->stream, sc, pb, depth);
+            }
         }
         {
             ScopedTimer t{ctx, CAT_TRACE_SHADOW};
@@ -403,10 +409,15 @@ int render_pass_volume(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint3
         }
         {
             ScopedTimer t{ctx, CAT_SHADE};
-            launch_volume_medium(blocks_for(ctx, n, ctx->grid_vmedium), ctx->stream, sc, pb, depth);
-            for (uint32_t kind = 0; kind < 3u; kind++)
-                if (kind == 0u || ctx->has_kind[kind])
-                    launch_volume_surface(kind, ctx->textured, blocks_for(ctx, n, ctx->grid_vshade[kind]), ctx->stream, sc, pb, depth);
+            const int v = ctx->strict_math ? 1 : 0;
+            if (v) strict::launch_volume_medium(blocks_for(ctx, n, ctx->grid_vmedium[v]), ctx->stream, sc, pb, depth);
+            else fast::launch_volume_medium(blocks_for(ctx, n, ctx->grid_vmedium[v]), ctx->stream, sc, pb, depth);
+            for (uint32_t kind = 0; kind < 3u; kind++) {
+                if (kind != 0u && !ctx->has_kind[kind]) continue;
+                const int blocks = blocks_for(ctx, n, ctx->grid_vshade[v][kind]);
+                if (v) strict::launch_volume_surface(kind, ctx->textured, blocks, ctx->stream, sc, pb, depth);
+                else fast::launch_volume_surface(kind, ctx->textured, blocks, ctx->stream, sc, pb, depth);
+            }
         }
         {
             ScopedTimer t{ctx, CAT_TRACE_SHADOW};
@@ -586,10 +597,17 @@ int lrk_create(const lrk_device_cfg *cfg, lrk_ctx **out) {
     };
     ctx->grid_trace = grid_for(reinterpret_cast<const void *>(trace_closest_kernel<false, false>), kTraceBlock);
     ctx->grid_shadow = grid_for(reinterpret_cast<const void *>(trace_shadow_kernel<false, false>), kTraceBlock);
-    for (uint32_t kind = 0; kind < kHitKinds; kind++) ctx->grid_shade[kind] = shade_grid(kind, ctx->sm_count);
+    for (uint32_t kind = 0; kind < kHitKinds; kind++) {
+        ctx->grid_shade[0][kind] = fast::shade_grid(kind, ctx->sm_count);
+        ctx->grid_shade[1][kind] = strict::shade_grid(kind, ctx->sm_count);
+    }
     ctx->grid_classify = grid_for(reinterpret_cast<const void *>(classify_hits_kernel));
-    ctx->grid_vmedium = volume_medium_grid(ctx->sm_count);
-    for (uint32_t kind = 0; kind < 3u; kind++) ctx->grid_vshade[kind] = volume_surface_grid(kind, ctx->sm_count);
+    ctx->grid_vmedium[0] = fast::volume_medium_grid(ctx->sm_count);
+    ctx->grid_vmedium[1] = strict::volume_medium_grid(ctx->sm_count);
+    for (uint32_t kind = 0; kind < 3u; kind++) {
+        ctx->grid_vshade[0][kind] = fast::volume_surface_grid(kind, ctx->sm_count);
+        ctx->grid_vshade[1][kind] = strict::volume_surface_grid(kind, ctx->sm_count);
+    }
     ctx->grid_vshadow = grid_for(reinterpret_cast<const void *>(trace_volume_nee_kernel<false>), kTraceBlock);
     *out = ctx;
     return LRK_OK;
@@ -924,6 +942,7 @@ int lrk_set_option(lrk_ctx *ctx, const char *name, int64_t value) {
     if (n == "count_traversal") ctx->count_traversal = value != 0;
     else if (n == "time_kernels") ctx->time_kernels = value != 0;
     else if (n == "device_bvh") ctx->device_bvh = value != 0;
+    else if (n == "strict_math") ctx->strict_math = value != 0;
     else if (n == "pin_host_buffers") {
         ctx->pin_host = value != 0;
         if (!ctx->pin_host) unpin_all(ctx);

@@ -1,18 +1,25 @@
-// shade.cu - the closure kernels of the device library, as their own translation unit.
+// shade.cu - the closure kernels of the device library, as their own translation unit, compiled TWICE.
 //
 // lrk.cu (ray generation, BVH traversal, hit classification, film) is compiled with IEEE arithmetic and no FMA contraction: its
 // results are compared with the oracle bit for bit.  The kernels in THIS file evaluate closures, lights and media - thousands of
-// fp32 operations per path vertex whose exact rounding no interface depends on - and are compiled the way the reference's own
-// CUDA backend compiles every kernel: with nvcc's fast-math arithmetic (the reference passes -use_fast_math to NVRTC by default:
-// src/compute/src/backends/cuda/cuda_device.cpp:697-698, ShaderOption::enable_fast_math{true} in
-// src/compute/include/luisa/runtime/rhi/resource.h:109).  Measured on the 1.39 M-triangle scene: shade 18.3 -> 11.0 ms per
-// 64-spp pass (profiles/r02k_shade_arithmetic.jsonl).  Parity is the stated film tolerance (tests/test_gpu_parity.py,
-// tests/test_ref_render.py); the closures' source is still checked against the reference's closures bit for bit when compiled
-// for the host (tests/test_device_closures_on_host.py).  build.py passes the flags; LRK_SHADE_STRICT=1 builds this file like lrk.cu.
+// fp32 operations per path vertex whose exact rounding no interface depends on.
+//   -DLRK_SHADE_VARIANT=fast   --use_fast_math: the arithmetic the reference's own CUDA backend uses for every kernel (it passes
+//                              -use_fast_math to NVRTC by default: src/compute/src/backends/cuda/cuda_device.cpp:697-698,
+//                              ShaderOption::enable_fast_math{true} in src/compute/include/luisa/runtime/rhi/resource.h:109).
+//                              The default for the emitter / Matte / Disney buckets and the volume integrator's steps.  Measured on
+//                              the 1.39 M-triangle scene: shade 18.3 -> 11.0 ms per 64-spp pass (profiles/r02k_shade_arithmetic.jsonl).
+//   -DLRK_SHADE_VARIANT=strict -fmad=false, IEEE div / sqrt: bit-compatible with lrk.cu and the oracle.  Always used for the
+//                              Mirror / Glass / Plastic / Metal / Mix buckets (near-specular lobes amplify a 1e-6 error in the half
+//                              vector into percents of the lobe value), and for everything with lrk_set_option("strict_math", 1) -
+//                              the configuration the tight parity tests run (films equal the oracle's to rel-L2 ~ 1e-7).
+// The closures' source is the same in both, and is checked against the reference's closures bit for bit when compiled for the host
+// (tests/test_device_closures_on_host.py).  build.py compiles the two objects; cross products and the uv determinant are written so
+// that contraction cannot turn their exact zeros into rounding residue (vecmath.cuh: mul_exact).
 #include "shade_launch.h"
 #include "shade_kernels.cuh"
 
 namespace lrk {
+namespace LRK_SHADE_VARIANT {
 
 namespace {
 
@@ -76,4 +83,5 @@ void launch_volume_surface(uint32_t kind, bool textured, int blocks, cudaStream_
     with_volume_surface_kernel(kind, textured, [&](auto kernel) { kernel<<<blocks, kBlock, 0, stream>>>(sc, pb, depth); });
 }
 
+}// namespace LRK_SHADE_VARIANT
 }// namespace lrk

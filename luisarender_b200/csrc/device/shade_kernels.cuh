@@ -1,12 +1,17 @@
 // The closure kernels of the wavefront integrators: shade_kernel<KIND> (surface integrator: emitter MIS, light sample + shadow
 // record, closure evaluate / sample, Russian roulette, compaction) and the volume integrator's medium / surface steps.
-// Included by shade.cu ONLY (these kernels are compiled with the reference CUDA backend's arithmetic, not with lrk.cu's).
+// Included by shade.cu ONLY.  shade.cu is compiled twice, with different arithmetic (see its header); LRK_SHADE_VARIANT names the
+// namespace the kernels of each compilation live in, so that the two sets of __global__ functions stay distinct symbols.
 #pragma once
+#ifndef LRK_SHADE_VARIANT
+#error "shade_kernels.cuh is compiled through shade.cu with -DLRK_SHADE_VARIANT=fast|strict"
+#endif
 #include "pathcommon.cuh"
 #include "pathstate.cuh"
 #include "samplers.cuh"
 
 namespace lrk {
+namespace LRK_SHADE_VARIANT {
 
 // The numbers one bounce consumes, drawn from a table-driven sampler (row f2) for the path with generation slot `id`: pixel and
 // sample index follow from the slot (PathBuffers::pass_*), `word` is the dimension counter the path carries.  Out of line, so
@@ -434,4 +439,5 @@ __global__ void __launch_bounds__(kBlock, 2) volume_surface_kernel(DeviceScene s
     }
 }
 
+}// namespace LRK_SHADE_VARIANT
 }// namespace lrk

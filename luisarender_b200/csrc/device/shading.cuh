@@ -162,7 +162,7 @@ __device__ __forceinline__ Interaction make_interaction(const DeviceScene &sc, u
     V3 ns_local = bary.x * n0 + bary.y * n1 + bary.z * n2;
     float duv0x = b1.z - a1.z, duv0y = b1.w - a1.w;
     float duv1x = c1.z - a1.z, duv1y = c1.w - a1.w;
-    float det = duv0x * duv1y - duv0y * duv1x;
+    float det = mul_exact(duv0x, duv1y) - mul_exact(duv0y, duv1x);// exactly 0 for degenerate uv: selects the fallback frame below
     float inv_det = 1.f / det;
     V3 dp0 = p1 - p0, dp1 = p2 - p0;
     V3 dpdu_local = (dp0 * duv1y - dp1 * duv0y) * inv_det;

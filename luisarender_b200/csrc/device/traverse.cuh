@@ -37,6 +37,9 @@ constexpr uint32_t kSentinelExit = 0xfffffffeu;
 #ifndef LRK_SMEM_STACK
 #define LRK_SMEM_STACK 16
 #endif
+#ifndef LRK_INNER_UNROLL
+#define LRK_INNER_UNROLL 2// inner-node steps per warp vote of the descent phase (trace_queue)
+#endif
 constexpr int kSmemStack = LRK_SMEM_STACK;// stack entries per thread kept in shared memory (0: all in local memory)
 constexpr int kLocalStack = 160;// further entries in local memory: the host builder caps a hierarchy's depth at 48 + log2(n)
 constexpr int kRefillBelow = 16;// refill when fewer than this many lanes of the warp hold a live ray (swept on B200: 13-19 is a plateau)
@@ -324,7 +327,12 @@ __device__ __forceinline__ void trace_queue(const DeviceScene &sc, const float4 
                 const uint32_t n_inner = __popc(__ballot_sync(0xffffffffu, inner));
                 if (n_inner == 0u) break;
                 if (n_inner < sc.inner_min && __any_sync(0xffffffffu, active && !inner)) break;
-                if (inner) inner_step<COUNT>(sc, r, stack, cnt);
+                if (inner) {
+                    inner_step<COUNT>(sc, r, stack, cnt);
+#pragma unroll
+                    for (int extra = 1; extra < LRK_INNER_UNROLL; extra++)// further steps without a new warp vote
+                        if (!(r.node & LRK_BVH_LEAF)) inner_step<COUNT>(sc, r, stack, cnt);
+                }
             }
             bool finished = false;
             if (active && (r.node & LRK_BVH_LEAF)) finished = leaf_step<ANY_HIT, COUNT, ALPHA>(sc, r, stack, world, cnt);

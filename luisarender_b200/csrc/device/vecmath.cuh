@@ -25,8 +25,21 @@ __device__ __forceinline__ V3 operator*(float s, V3 a) { return {s * a.x, s * a.
 __device__ __forceinline__ V3 operator+(V3 a, float s) { return {a.x + s, a.y + s, a.z + s}; }
 __device__ __forceinline__ V3 operator-(V3 a) { return {-a.x, -a.y, -a.z}; }
 __device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+// A product that the compiler must not fuse into a neighbouring add (shade.cu is compiled with FMA contraction): where a
+// difference of two products is EXACTLY zero in IEEE arithmetic - every cross product of axis-aligned edges is - a fused
+// multiply-add leaves the rounding error of one product instead, and the sign of that residue then picks a branch (the
+// orthonormal-basis construction of a shading frame switches on the sign of n.z: a wall whose normal has n.z = 0 exactly would
+// get another - equally valid, but different - frame than the oracle's, and with it other sampled directions).
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ float mul_exact(float a, float b) { return __fmul_rn(a, b); }
+#else
+#if defined(__GNUC__) && !defined(__clang__)
+__attribute__((optimize("fp-contract=off")))
+#endif
+inline float mul_exact(float a, float b) { return a * b; }
+#endif
 __device__ __forceinline__ V3 cross(V3 a, V3 b) {
-    return {a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y};
+    return {mul_exact(a.y, b.z) - mul_exact(b.y, a.z), mul_exact(a.z, b.x) - mul_exact(b.z, a.x), mul_exact(a.x, b.y) - mul_exact(b.x, a.y)};
 }
 __device__ __forceinline__ float length(V3 a) { return sqrtf(dot(a, a)); }
 __device__ __forceinline__ V3 normalize(V3 a) { return a * (1.0f / sqrtf(dot(a, a))); }

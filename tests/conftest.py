@@ -63,10 +63,17 @@ def textured_wrappers_small():
     return Scene.from_source(scenes.textured_room(resolution=(48, 32), spp=4, wrappers=True), REPO)
 
 
-@pytest.fixture(scope="session")
-def gpu_renderer():
+@pytest.fixture(scope="session", params=["strict_math", "fast_math"])
+def gpu_renderer(request):
+    """The device library in its two arithmetic configurations (csrc/device/shade.cu): `fast_math` is the product default - the
+    Matte / Disney / volume closure kernels compiled with the fast-math arithmetic the reference's own CUDA backend uses - and
+    `strict_math` (lrk_set_option("strict_math", 1)) runs every closure kernel in IEEE arithmetic like the oracle.  Every GPU test
+    that takes this fixture runs in both; `gpu_renderer.fast` tells a test which tolerance to state.  Traversal, ray generation
+    and the film are the same IEEE code in both."""
     from luisarender_b200.api import Renderer
 
     r = Renderer(device_index=0)  # raises when there is no CUDA device: GPU tests must not silently fall back
+    r.fast = request.param == "fast_math"
+    r.set_option("strict_math", 0 if r.fast else 1)
     yield r
     r.close()

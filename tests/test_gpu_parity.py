@@ -96,6 +96,7 @@ def test_render_matches_oracle(name, gpu_renderer):
     cpu_raw, cnt = O.render(d, 0, spp)
     assert np.array_equal(gpu_raw[..., 3], cpu_raw[..., 3])  # weights: exact
     rel, off = _image_parity(gpu_raw, cpu_raw)
+    fast = gpu_renderer.fast
     if name == "spheres_medium":
         # The reference's volume estimator evaluates an emitter hit from a ray origin that was moved ONTO the hit point
         # (mega_vpt_naive.cpp:308,319): cos_wo is the direction of a rounding-noise vector, so whether such a hit counts
@@ -112,23 +113,35 @@ def test_render_matches_oracle(name, gpu_renderer):
         # a few per cent of the paths that meet a non-opaque surface after their first bounce take another, equally valid,
         # branch.  Parity is therefore exact for everything up to the first bounce (test_alpha_first_bounce_is_exact) and
         # statistical afterwards: <= 4 % of the pixels differ, the rest agree to 1e-3 rel-L2, and the image means agree.
-        assert off <= 4e-2, off
+        # fast_math: the shadow rays' origins differ in the last bit too, so the decisions of the alpha tests THEY meet flip as well
+        limit = 0.12 if fast else 4e-2
+        assert off <= limit, off
         err = np.abs(gpu_raw[..., :3] - cpu_raw[..., :3]).max(axis=-1)
-        keep = err <= np.quantile(err, 0.96)
+        keep = err <= np.quantile(err, 1.0 - limit)
         assert np.linalg.norm((gpu_raw[..., :3] - cpu_raw[..., :3])[keep]) / np.linalg.norm(cpu_raw[..., :3][keep]) <= 1e-3
         assert gpu_raw[..., :3].mean() == pytest.approx(cpu_raw[..., :3].mean(), rel=0.03)
+    elif fast:
+        # fast_math closures differ from the oracle's in the last bits; a discrete decision (light triangle, lobe, Russian roulette)
+        # flips for about one path in 10^4, and at 4 - 8 spp one such path that ends on a light moves the rel-L2 of the whole
+        # image by percents.  Stated tolerance: <= 1 % of the pixels off by more than 1e-4, the other 99 % agree to 1e-4 rel-L2,
+        # image means to 0.5 %.
+        assert off <= 1e-2, off
+        err = np.abs(gpu_raw[..., :3] - cpu_raw[..., :3]).max(axis=-1)
+        keep = err <= np.quantile(err, 0.99)
+        assert np.linalg.norm((gpu_raw[..., :3] - cpu_raw[..., :3])[keep]) / np.linalg.norm(cpu_raw[..., :3][keep]) <= 1e-4
+        assert gpu_raw[..., :3].mean() == pytest.approx(cpu_raw[..., :3].mean(), rel=5e-3)
     else:
         assert rel <= 1e-3, rel
         assert off <= 5e-3, off
     if name != "textured_wrappers":
-        assert st["closest_rays"] == cnt["closest_rays"]  # same paths, ray for ray
+        assert st["closest_rays"] == pytest.approx(cnt["closest_rays"], rel=2e-3 if fast else 0)  # same paths, ray for ray (strict)
     assert st["shadow_rays"] <= cnt["shadow_rays"]    # zero-contribution shadow rays are not traced on the GPU
     # and against the committed golden film row (generated by the oracle, tests/golden/generate_golden.py)
     gold = np.array(GOLD["scenes"][name]["film_row0"], np.float32).reshape(-1, 3)
     row_ok = np.isclose(gpu_raw[0, :, :3], gold, rtol=1e-3, atol=1e-4).all(axis=-1)
-    assert row_ok.all() if name not in ("spheres_medium", "textured_wrappers") else row_ok.mean() >= 0.9
+    assert row_ok.all() if name not in ("spheres_medium", "textured_wrappers") and not fast else row_ok.mean() >= (0.85 if fast else 0.9)
     if name != "textured_wrappers":
-        assert st["closest_rays"] == GOLD["scenes"][name]["counters"]["closest_rays"]
+        assert st["closest_rays"] == pytest.approx(GOLD["scenes"][name]["counters"]["closest_rays"], rel=2e-3 if fast else 0)
     # normalised film = (sum / max(w,1)) * 2^exposure (color.cpp:87-93)
     assert np.allclose(gpu_renderer.film(), O.convert_film(d, gpu_raw), rtol=1e-6, atol=1e-7)
 
@@ -162,8 +175,13 @@ def test_alpha_first_bounce_is_exact(gpu_renderer):
     st = gpu_renderer.stats()
     cpu_raw, cnt = O.render(d, 0, 8)
     rel, off = _image_parity(gpu_raw, cpu_raw)
-    assert rel <= 1e-5 and off == 0.0, (rel, off)
     assert st["closest_rays"] == cnt["closest_rays"] and np.array_equal(gpu_raw[..., 3], cpu_raw[..., 3])
+    if gpu_renderer.fast:
+        # the shadow ray's origin and direction come out of the fast-math shade kernel: one ulp there changes the barycentric BITS
+        # the alpha test of every surface it crosses is hashed from - only the statistics survive
+        assert off <= 0.12 and gpu_raw[..., :3].mean() == pytest.approx(cpu_raw[..., :3].mean(), rel=0.03), (rel, off)
+    else:
+        assert rel <= 1e-5 and off == 0.0, (rel, off)
 
 
 def test_render_is_deterministic_and_independent_of_scheduling(cornell_small, gpu_renderer):
@@ -278,8 +296,16 @@ def test_full_size_properties_c3_spheres(gpu_renderer):
     cpu_part, _ = O.render(d, 0, 4, rank=7, world=64, tile_size=32)
     mask = cpu_part[..., 3] > 0
     assert mask.sum() > 20000
-    rel = np.linalg.norm(raw[mask][:, :3] - cpu_part[mask][:, :3]) / np.linalg.norm(cpu_part[mask][:, :3])
-    assert rel <= 1e-3, rel
+    g, c = raw[mask][:, :3], cpu_part[mask][:, :3]
+    rel = np.linalg.norm(g - c) / np.linalg.norm(c)
+    if gpu_renderer.fast:  # see test_render_matches_oracle: a handful of diverged paths dominate rel-L2 at 4 spp
+        err = np.abs(g - c).max(axis=-1)
+        keep = err <= np.quantile(err, 0.99)
+        assert (err > 1e-4 * np.maximum(np.abs(c).max(axis=-1), 1.0)).mean() <= 1e-2
+        assert np.linalg.norm((g - c)[keep]) / np.linalg.norm(c[keep]) <= 1e-4
+        assert g.mean() == pytest.approx(c.mean(), rel=2e-3)
+    else:
+        assert rel <= 1e-3, rel
 
 
 def test_full_size_properties_c4_medium(gpu_renderer):
@@ -306,7 +332,7 @@ def test_full_size_properties_c4_medium(gpu_renderer):
     assert mask.sum() > 20000 and not (mask & ~tiles).any()
     # dropped samples are the emitter hits whose moved ray origin lands EXACTLY on the hit point (normalize(0) = NaN in
     # diffuse.cpp:78-82) - the same last-bit decision as the chaotic cos_wo test above, so a few per 10^4 pixels differ
-    assert (raw[tiles][:, 3] != cpu_part[tiles][:, 3]).mean() <= 1e-3
+    assert (raw[tiles][:, 3] != cpu_part[tiles][:, 3]).mean() <= (4e-3 if gpu_renderer.fast else 1e-3)
     mask &= raw[..., 3] == cpu_part[..., 3]
     g, c = raw[mask][:, :3], cpu_part[mask][:, :3]
     err = np.abs(g - c).max(axis=-1)

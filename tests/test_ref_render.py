@@ -109,17 +109,28 @@ def test_cuda_film_matches_the_reference_render(golden, name, gpu_renderer):
     got = gpu_renderer.film()[..., :3]
     err = np.abs(got - want)
     off = (err > 1e-4 * np.maximum(np.abs(want), 1.0)).any(axis=-1)
+    fast = gpu_renderer.fast  # product default: fast-math closure kernels (conftest.py: gpu_renderer)
     if name == "textured_wrappers":
         # the stochastic alpha test hashes barycentric BITS: see tests/test_gpu_parity.py::test_render_matches_oracle
-        assert off.mean() <= 0.04, f"{name}: {off.mean():.4f} of the pixels off"
+        assert off.mean() <= (0.12 if fast else 0.04), f"{name}: {off.mean():.4f} of the pixels off"
         assert got.mean() == pytest.approx(want.mean(), rel=0.03)
+    elif fast and not (name.startswith("materials") or name == "spheres_disney_transmissive"):
+        # fast_math: about one path in 10^4 takes another branch of a discrete decision; at the 2 - 8 spp of these fixtures one such
+        # path that finds the light moves the whole image's rel-L2 by percents.  Stated: <= 1 % of the pixels off by > 1e-4 relative,
+        # the other 99 % agree to 1e-4 rel-L2, image means to 1 %.
+        assert off.mean() <= 0.01, f"{name}: {off.mean():.4f} of the pixels off"
+        e = err.max(axis=-1)
+        keep = e <= np.quantile(e, 0.99)
+        assert np.linalg.norm((got - want)[keep]) / np.linalg.norm(want[keep]) <= 1e-4
+        assert got.mean() == pytest.approx(want.mean(), rel=0.01)
     elif name.startswith("materials") or name == "spheres_disney_transmissive":
         # Specular chains (mirror wall, smooth and rough glass) amplify the ulp-level differences between CUDA's and glibc's
         # sin / cos / pow into different discrete decisions (lobe choice, total internal reflection, Russian roulette) for a
         # few paths: <= 3 % of the pixels may take another, equally valid, branch; the rest agree to 1e-3 rel-L2 and the
         # image means to 2 %.  The closures themselves are compared without that chaos in the first-bounce test below.
-        keep = ~off if off.mean() <= 0.03 else np.ones_like(off)
-        assert off.mean() <= 0.03, f"{name}: {off.mean():.4f} of the pixels off"
+        limit = 0.08 if fast else 0.03  # fast_math: the Matte / Disney surfaces between the specular ones add their share of flips
+        keep = ~off if off.mean() <= limit else np.ones_like(off)
+        assert off.mean() <= limit, f"{name}: {off.mean():.4f} of the pixels off"
         assert np.linalg.norm((got - want)[keep]) / np.linalg.norm(want[keep]) <= 1e-3
         assert got.mean() == pytest.approx(want.mean(), rel=0.02)
     else:
@@ -146,7 +157,7 @@ def test_cuda_materials_first_bounce_matches_oracle(gpu_renderer, mix):
     gpu_renderer.render(0, 16)
     got = gpu_renderer.film()[..., :3]
     stats = gpu_renderer.stats()
-    assert stats["closest_rays"] == counters["closest_rays"]
+    assert stats["closest_rays"] == pytest.approx(counters["closest_rays"], rel=1e-3 if gpu_renderer.fast else 0)
     rel_l2 = float(np.linalg.norm(got - want) / np.linalg.norm(want))
     off = (np.abs(got - want) > 1e-4 * np.maximum(np.abs(want), 1.0)).any(axis=-1)
     assert rel_l2 <= 1e-3, rel_l2
@@ -212,5 +223,6 @@ def test_cuda_large_render_matches_the_reference(gpu_renderer, name):
     # (measured on B200: medians ~1e-6; at 1920x1080 one of the 1 980 blocks was off by 1.4 % - ONE path of its 2 048 that took
     # another branch of a discrete decision and found the light)
     assert np.median(rel) <= 1e-4, f"median block difference {np.median(rel)}"
-    assert (rel > 2e-3).mean() <= 0.01, f"{(rel > 2e-3).mean():.4f} of the blocks differ by more than 2e-3"
-    assert rel.max() <= 0.1, f"largest block difference {rel.max()}"
+    # fast_math closure kernels: a few times as many flipped paths (see test_cuda_film_matches_the_reference_render)
+    assert (rel > 2e-3).mean() <= (0.03 if gpu_renderer.fast else 0.01), f"{(rel > 2e-3).mean():.4f} of the blocks differ by more than 2e-3"
+    assert rel.max() <= (0.25 if gpu_renderer.fast else 0.1), f"largest block difference {rel.max()}"
