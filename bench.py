@@ -479,6 +479,28 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         assert np.isfinite(img).all()
     r.set_option("pin_host_buffers", 0)
 
+    # ---- the same workload with every closure kernel in IEEE arithmetic (option strict_math): what the default's fast-math closure
+    # kernels (the reference CUDA backend's arithmetic, csrc/device/shade.cu) buy; two steps, device time of lrk_render -------------
+    strict = None
+    if not args.no_configs:
+        r.set_option("strict_math", 1)
+        r.upload(desc)
+        r.set_shard(rank, world, D.TILE_SIZE)
+        r.render(0, S)  # warm-up
+        r.clear()
+        barrier()
+        for s in range(2):
+            r.render(s * S, (s + 1) * S)
+        ms = r.stats()["render_ms"] / 2.0
+        if dist is not None:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        strict = {"value": round(WIDTH * HEIGHT * S / ms * 1e-3, 2), "unit": UNIT, "device_ms_per_step": round(ms, 3),
+                  "what": "option strict_math = 1: films then equal the CPU oracle's to rel-L2 ~ 1e-7 (tests/conftest.py: gpu_renderer)"}
+        r.set_option("strict_math", 0)
+        r.upload(desc)
+
     # ---- the other BASELINE.json configurations, one short step each (device time of lrk_render) ---------------------
     configs = None if args.no_configs else other_configs(r, rank, world, dist, barrier)
 
@@ -505,6 +527,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
             "gpu_launches": int(total_launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clock_info,
             "device_ms_per_step": round(st["render_ms"] / K, 3), "per_rank": per_rank, "film_check": film_check, "configs": configs,
+            "arithmetic": {"default": "closure kernels of the emitter / Matte / Disney / volume buckets in nvcc fast math (what the reference's CUDA "
+                                      "backend compiles its kernels with), traversal / generation / film / near-specular closures in IEEE arithmetic",
+                           "strict_math": strict},
         }
         print(json.dumps(line), flush=True)
     if dist is not None:

@@ -76,17 +76,46 @@ lrk_scene_desc FlatScene::desc(uint32_t camera_index) const {
 // luisarender_b200/data/sampler_tables.bin (tools/extract_sampler_tables.py): Sobol' generator matrices, van-der-Corput matrices,
 // pmj02bn sets, blue-noise textures - the data of pbrt-v4's samplers that the reference's samplers are built on.  Located next
 // to this library (<lib dir>/../data/) or through LRH_DATA_DIR; loaded once, on first use.
+std::filesystem::path data_directory() {
+    if (auto env = std::getenv("LRH_DATA_DIR")) return env;
+    Dl_info info{};
+    if (dladdr(reinterpret_cast<const void *>(&data_directory), &info) == 0 || info.dli_fname == nullptr)
+        throw Error("Cannot locate the host library to find its data directory (set LRH_DATA_DIR).");
+    return std::filesystem::path{info.dli_fname}.parent_path().parent_path() / "data";
+}
+
+const MetalIor &metal_ior_table(const std::string &name) {
+    static const std::map<std::string, MetalIor> tables = [] {
+        auto path = data_directory() / "metal_ior.bin";
+        std::ifstream f{path, std::ios::binary};
+        if (!f) throw Error("Cannot open the metal IOR tables '" + path.string() + "' (tools/extract_metal_ior.py writes them).");
+        char magic[4];
+        uint32_t header[3]{};
+        f.read(magic, 4);
+        f.read(reinterpret_cast<char *>(header), 12);
+        if (!f || std::memcmp(magic, "LRMI", 4) != 0 || header[0] != 1u || header[2] != 95u) throw Error("'" + path.string() + "' is not a metal IOR table file.");
+        std::map<std::string, MetalIor> out;
+        for (uint32_t m = 0; m < header[1]; m++) {
+            char nm[9]{};
+            MetalIor ior;
+            ior.n.resize(header[2]);
+            ior.k.resize(header[2]);
+            f.read(nm, 8);
+            f.read(reinterpret_cast<char *>(ior.n.data()), header[2] * 4u);
+            f.read(reinterpret_cast<char *>(ior.k.data()), header[2] * 4u);
+            if (!f) throw Error("'" + path.string() + "' is truncated.");
+            out.emplace(nm, std::move(ior));
+        }
+        return out;
+    }();
+    auto it = tables.find(name);
+    if (it == tables.end()) throw Error("No IOR table for metal '" + name + "'.");
+    return it->second;
+}
+
 const SamplerTables &sampler_tables() {
     static const SamplerTables tables = [] {
-        std::filesystem::path dir;
-        if (auto env = std::getenv("LRH_DATA_DIR")) {
-            dir = env;
-        } else {
-            Dl_info info{};
-            if (dladdr(reinterpret_cast<const void *>(&sampler_tables), &info) == 0 || info.dli_fname == nullptr)
-                throw Error("Cannot locate the host library to find its data directory (set LRH_DATA_DIR).");
-            dir = std::filesystem::path{info.dli_fname}.parent_path().parent_path() / "data";
-        }
+        auto dir = data_directory();
         auto path = dir / "sampler_tables.bin";
         std::ifstream f{path, std::ios::binary};
         if (!f) throw Error("Cannot open the sampler tables '" + path.string() + "' (tools/extract_sampler_tables.py writes them).");

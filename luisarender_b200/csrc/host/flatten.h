@@ -65,4 +65,12 @@ struct SamplerTables {
 };
 const SamplerTables &sampler_tables();
 
+// the Metal surface's named metals (luisarender_b200/data/metal_ior.bin, tools/extract_metal_ior.py): measured complex refractive
+// index at 360 .. 830 nm in 5 nm steps; `name` as the reference calls its tables (Ag Al Au Cu CuZn Fe Ti V VN Li Cr)
+struct MetalIor {
+    std::vector<float> n, k;// 95 samples each
+};
+const MetalIor &metal_ior_table(const std::string &name);
+std::filesystem::path data_directory();// <library dir>/../data or $LRH_DATA_DIR
+
 }// namespace lrh

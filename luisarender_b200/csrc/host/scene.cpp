@@ -1,4 +1,5 @@
 #include "scene.h"
+#include "flatten.h"
 
 #include "imageio.h"
 #include "meshload.h"
@@ -1057,9 +1058,8 @@ struct PlasticSurface final : Surface {
 };
 
 struct MetalSurface final : Surface {
-    // src/surfaces/metal.cpp:52-151,273-310.  The complex index comes from an `eta` list of (wavelength, n, k) triples; the
-    // reference's eleven built-in metals are measured spectra shipped as a data table (metal_ior.inl.h) and are not
-    // reproduced here: a named `eta` fails at load with a message saying so.
+    // src/surfaces/metal.cpp:52-151,273-310.  The complex index comes from an `eta` list of (wavelength, n, k) triples or from
+    // the name of one of the reference's eleven built-in metals (measured spectra: luisarender_b200/data/metal_ior.bin).
     const Texture *roughness, *kd;
     bool remap_roughness;
     float n[3], k[3];
@@ -1067,34 +1067,47 @@ struct MetalSurface final : Surface {
         roughness = constant_surface_texture(s, d, "roughness");
         kd = constant_surface_texture(s, d, "Kd");
         remap_roughness = d->b("remap_roughness", true);
-        if (auto name = d->s("eta", ""); !name.empty())
-            throw Error("Metal: built-in IOR tables ('" + name + "') are not available; give `eta` as a list of "
-                        "(wavelength, n, k) triples. [" + d->location() + "]");
-        auto eta = d->float_list("eta");
-        if (eta.empty() || eta.size() % 3u != 0u) throw Error("Invalid eta list size. [" + d->location() + "]");
-        auto count = eta.size() / 3u;
-        std::vector<float> lambda(count), nn(count), kk(count);
-        for (size_t i = 0; i < count; i++) { lambda[i] = eta[i * 3u]; nn[i] = eta[i * 3u + 1u]; kk[i] = eta[i * 3u + 2u]; }
-        if (!std::is_sorted(lambda.begin(), lambda.end())) throw Error("Unsorted wavelengths in eta list. [" + d->location() + "]");
-        if (lambda.front() > 360.f || lambda.back() < 830.f) throw Error("Invalid wavelength range in eta list. [" + d->location() + "]");
-        if (count < 2u) throw Error("Invalid eta list size. [" + d->location() + "]");
-        // the 5 nm look-up table over [360, 830] nm (:132-146) ...
         constexpr uint32_t lut_size = (830u - 360u) / 5u + 1u;
         std::vector<float> lut_n(lut_size), lut_k(lut_size);
-        for (uint32_t i = 0; i < lut_size; i++) {
-            auto wavelength = static_cast<float>(i * 5u + 360u);
-            auto lb = std::lower_bound(lambda.begin(), lambda.end(), wavelength);
-            auto index = std::clamp(static_cast<size_t>(std::distance(lambda.begin(), lb)), size_t{1u}, lambda.size() - 1u);
-            auto t = (wavelength - lambda[index - 1u]) / (lambda[index] - lambda[index - 1u]);
-            // std::lerp (C++20) as libstdc++ / libc++ implement it: exact at the end points, monotonic
-            auto std_lerp = [](float a, float b, float tt) {
-                if ((a <= 0.f && b >= 0.f) || (a >= 0.f && b <= 0.f)) return tt * b + (1.f - tt) * a;
-                if (tt == 1.f) return b;
-                auto x = a + tt * (b - a);
-                return (tt > 1.f) == (b > a) ? (b < x ? x : b) : (x < b ? x : b);
-            };
-            lut_n[i] = std_lerp(nn[index - 1u], nn[index], t);
-            lut_k[i] = std_lerp(kk[index - 1u], kk[index], t);
+        if (auto name = d->s("eta", ""); !name.empty()) {
+            // a named metal (:73-104): measured (n, k) on the same 5 nm grid, luisarender_b200/data/metal_ior.bin
+            for (auto &c : name) c = static_cast<char>(std::tolower(static_cast<unsigned char>(c)));
+            static const std::pair<const char *, const char *> names[] = {
+                {"ag", "Ag"}, {"silver", "Ag"}, {"al", "Al"}, {"aluminium", "Al"}, {"au", "Au"}, {"gold", "Au"}, {"cu", "Cu"}, {"copper", "Cu"},
+                {"cuzn", "CuZn"}, {"cu-zn", "CuZn"}, {"brass", "CuZn"}, {"fe", "Fe"}, {"iron", "Fe"}, {"ti", "Ti"}, {"titanium", "Ti"},
+                {"v", "V"}, {"vanadium", "V"}, {"vn", "VN"}, {"li", "Li"}, {"lithium", "Li"}, {"cr", "Cr"}, {"chromium", "Cr"}};
+            std::string table = "Al";// "Unknown metal ... Fallback to Aluminium" (:98-103)
+            bool known = false;
+            for (auto &[alias, t] : names) if (name == alias) { table = t; known = true; }
+            if (!known) std::fprintf(stderr, "[warning] Unknown metal '%s'. Fallback to Aluminium. [%s]\n", name.c_str(), d->location().c_str());
+            const auto &ior = metal_ior_table(table);
+            std::copy(ior.n.begin(), ior.n.end(), lut_n.begin());
+            std::copy(ior.k.begin(), ior.k.end(), lut_k.begin());
+        } else {
+            auto eta = d->float_list("eta");
+            if (eta.empty() || eta.size() % 3u != 0u) throw Error("Invalid eta list size. [" + d->location() + "]");
+            auto count = eta.size() / 3u;
+            std::vector<float> lambda(count), nn(count), kk(count);
+            for (size_t i = 0; i < count; i++) { lambda[i] = eta[i * 3u]; nn[i] = eta[i * 3u + 1u]; kk[i] = eta[i * 3u + 2u]; }
+            if (!std::is_sorted(lambda.begin(), lambda.end())) throw Error("Unsorted wavelengths in eta list. [" + d->location() + "]");
+            if (lambda.front() > 360.f || lambda.back() < 830.f) throw Error("Invalid wavelength range in eta list. [" + d->location() + "]");
+            if (count < 2u) throw Error("Invalid eta list size. [" + d->location() + "]");
+            // the 5 nm look-up table over [360, 830] nm (:132-146) ...
+            for (uint32_t i = 0; i < lut_size; i++) {
+                auto wavelength = static_cast<float>(i * 5u + 360u);
+                auto lb = std::lower_bound(lambda.begin(), lambda.end(), wavelength);
+                auto index = std::clamp(static_cast<size_t>(std::distance(lambda.begin(), lb)), size_t{1u}, lambda.size() - 1u);
+                auto t = (wavelength - lambda[index - 1u]) / (lambda[index] - lambda[index - 1u]);
+                // std::lerp (C++20) as libstdc++ / libc++ implement it: exact at the end points, monotonic
+                auto std_lerp = [](float a, float b, float tt) {
+                    if ((a <= 0.f && b >= 0.f) || (a >= 0.f && b <= 0.f)) return tt * b + (1.f - tt) * a;
+                    if (tt == 1.f) return b;
+                    auto x = a + tt * (b - a);
+                    return (tt > 1.f) == (b > a) ? (b < x ? x : b) : (x < b ? x : b);
+                };
+                lut_n[i] = std_lerp(nn[index - 1u], nn[index], t);
+                lut_k[i] = std_lerp(kk[index - 1u], kk[index], t);
+            }
         }
         // ... sampled at the sRGB spectrum's three wavelengths (srgb.cpp:27-33, spec.h:22-23) by SPD::sample (spd.cpp:91-99)
         const float peaks[3] = {602.785f, 539.285f, 445.772f};

@@ -50,6 +50,15 @@ def cases() -> dict[str, str]:
     c["materials_megapath_rr"] = scenes.materials_box(resolution=(32, 24), spp=4, depth=10, rr_depth=2, rr_threshold=0.95,
                                                       integrator="MegaPath")
     c["materials_mix"] = scenes.materials_box(resolution=(32, 24), spp=4, depth=10, rr_depth=2, mix=True, output="mix.exr")
+    # Metal with the reference's built-in measured spectra: gold, copper (on the mirror ball's place) and an unknown name (-> aluminium)
+    named = (scenes.materials_box(resolution=(32, 24), spp=4, depth=6, output="metals.exr")
+             .replace('Surface m_mirror : Mirror { Kd : Constant { v { 0.95, 0.8, 0.6 } } }',
+                      'Surface m_mirror : Metal { eta { "Cu" } roughness : Constant { v { 0.15 } } }')
+             .replace('Surface m_glass : Glass { eta { "BK7" } }', 'Surface m_glass : Metal { eta { "unobtainium" } roughness : Constant { v { 0.3 } } }'))
+    import re as _re
+    named = _re.sub(r'Surface m_metal : Metal \{ eta \{ [0-9., ]+\} ', 'Surface m_metal : Metal { eta { "Gold" } ', named)
+    assert named.count('eta { "Gold" }') == 1 and named.count('eta { "Cu" }') == 1
+    c["materials_named_metals"] = named
     c["flatten_stress"] = scenes.flatten_stress()
     # the LoopSubdiv shape: closed, open (boundary / corner rules) and valence-3 base meshes, limit normals, level 0 pass-through
     c["subdivision"] = scenes.subdivision_scene(resolution=(64, 48), spp=4)
