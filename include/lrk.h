@@ -187,8 +187,7 @@ typedef struct lrk_instance {
  *            MixSurfaceClosure::Context, mix.cpp:88-91,195-211.  The closure reproduces the reference's arithmetic including
  *            its second sampling branch, which samples surface `a` again and weights the two evaluations the other way
  *            round (mix.cpp:170-176).
- *   The four closures above take constant parameters only (tex[] must be 0); image-textured Mirror / Glass / Plastic /
- *   Metal nodes are rejected by the host.
+ *   With image-textured parameters the four records use the raw layouts of LRK_SURFACE_RAW_PARAMS below.
  *
  * Image-textured parameters: tex[k] != 0 means parameter slot k is NOT the constant p[k] but is
  * evaluated per hit from image texture (tex[k] - 1) at the hit's uv, exactly as populate_closure does
@@ -215,6 +214,16 @@ typedef struct lrk_instance {
  * (:531-533).  `lobes` of such records is the union over the TRANSMISSIVE Disney nodes of the scene (each closure class
  * collects its own, :994-995). */
 #define LRK_SURFACE_DISNEY_TRANSMISSIVE 16u
+/* MIRROR / GLASS / PLASTIC / METAL with an image-textured parameter: p[] holds the node's RAW parameters and the closure context
+ * above is derived per hit (colour slots: saturate(extend_color_to_rgb(texel)), as populate_closure's evaluate_albedo_spectrum;
+ * alpha slots: a 1-channel roughness texture feeds both axes, a 2-channel one x and y, remapped max(r^2, 1e-4) when
+ * LRK_SURFACE_REMAP_ROUGHNESS is set - a slot WITHOUT a texture already holds the final alpha):
+ *   MIRROR : p[0..2] colour (tex[0]), p[3..4] alpha (tex[3])                                          mirror.cpp:142-162
+ *   GLASS  : p[0..2] Kr (tex[0]), p[3..5] Kt (tex[3]), p[6] eta_t, p[7..8] alpha (tex[7]); p[9] = Kr_ratio from the luminances  glass.cpp:236-279
+ *   PLASTIC: p[0..2] Kd (tex[0]), p[4..6] sigma_a (tex[4]), p[7] eta, p[8..9] alpha (tex[8]), p[10] thickness (tex[10]);
+ *            p[0..2] <- Kd / (1 - Kd Fdr(eta)), p[3] <- lum(Kd) exp(-2 lum(sigma_a) thickness)        plastic.cpp:252-291
+ *   METAL  : p[0..5] n, k (never textured), p[6..8] Kd (tex[6]), p[9..10] alpha (tex[9])               metal.cpp:273-310 */
+#define LRK_SURFACE_RAW_PARAMS 32u
 typedef struct lrk_surface {
     uint32_t type;
     uint32_t lobes;

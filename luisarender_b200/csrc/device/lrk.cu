@@ -692,8 +692,10 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
     }
     for (uint32_t i = 0; i < s->surface_count; i++) {
         if (s->surfaces[i].type >= LRK_SURFACE_TYPE_COUNT) return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: unknown surface type");
-        if (s->surfaces[i].type > LRK_SURFACE_DISNEY && (s->surfaces[i].flags & LRK_SURFACE_HAS_TEXTURES))
-            return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: Mirror / Glass / Plastic / Metal take constant parameters only");
+        if (s->surfaces[i].type == LRK_SURFACE_MIX && (s->surfaces[i].flags & LRK_SURFACE_HAS_TEXTURES) && s->surfaces[i].tex[0] != 0u)
+            return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: the ratio of a Mix is a constant");
+        if ((s->surfaces[i].flags & LRK_SURFACE_RAW_PARAMS) && (s->surfaces[i].type < LRK_SURFACE_MIRROR || s->surfaces[i].type > LRK_SURFACE_METAL))
+            return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_upload_scene: LRK_SURFACE_RAW_PARAMS is for Mirror / Glass / Plastic / Metal records");
         if (s->surfaces[i].type == LRK_SURFACE_MIX) {
             for (uint32_t child : {s->surfaces[i].mix_a, s->surfaces[i].mix_b}) {
                 if (child >= s->surface_count || s->surfaces[child].type == LRK_SURFACE_MIX || s->surfaces[child].type == LRK_SURFACE_DISNEY ||

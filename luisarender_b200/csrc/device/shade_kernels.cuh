@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(kShadeBlock, LRK_SHADE_MIN_BLOCKS) shade_kerne
                         eta_scale = cl.rr_eta_scale;
                     } else {
                         MicrofacetFamilyClosure<(KIND >= 3u && KIND <= 6u) ? KIND - 1u : LRK_SURFACE_MIRROR> cl;// kind = surface type + 1
-                        cl.init(*surf);// constant parameters only (include/lrk.h)
+                        init_closure<TEXTURED>(sc, cl, surf, it);
                         shade_surface<false>(cl, it, closure_frame<TEXTURED>(sc, surf, it, wo), wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
                         eta_scale = cl.rr_eta_scale;
                     }

@@ -364,7 +364,83 @@ __device__ __noinline__ inline float4 texture_evaluate(const DeviceScene &sc, ui
 // Surface parameters at a hit: the node's constants with the image-textured slots evaluated at the hit's uv
 // (MatteInstance::populate_closure matte.cpp:117-131, DisneySurfaceInstance::populate_closure disney.cpp:932-956;
 // colours through Texture::Instance::evaluate_albedo_spectrum texture.cpp:20-31 + srgb.cpp:34-40,70-72).
+// fresnel_dielectric_integral (src/util/scattering.cpp:98-108): the fitted polynomials, Horner from the last coefficient
+__device__ __forceinline__ float fresnel_dielectric_integral(float eta) {
+    float r;
+    if (eta == 1.f) {
+        r = 0.f;
+    } else if (eta < 1.f) {
+        r = eta * (eta * (eta * -0.90663979f + 2.23559031f) + -2.09069066f) + 0.75985009f;
+    } else {
+        float x = 1.f / eta;
+        r = x * (x * -1.18995376f + 0.21762732f) + 0.97945724f;
+    }
+    return saturate(r);
+}
+
+// Mirror / Glass / Plastic / Metal with image-textured parameters (LRK_SURFACE_RAW_PARAMS, include/lrk.h): evaluates the textured
+// raw parameters at the hit and derives the closure context as the surfaces' populate_closure do (mirror.cpp:142-162,
+// glass.cpp:236-279, plastic.cpp:252-291, metal.cpp:273-310).  Out of line: these kernels are not the headline's.
+__device__ __noinline__ inline void resolve_raw_surface(const DeviceScene &sc, lrk_surface &s, float u, float v) {
+    auto colour = [&](uint32_t slot) {// evaluate_albedo_spectrum with the sRGB spectrum: saturate(extend_color_to_rgb(v))
+        if (s.tex[slot] == 0u) return;
+        const float4 val = texture_evaluate(sc, s.tex[slot] - 1u, u, v);
+        const uint32_t ch = sc.textures[s.tex[slot] - 1u].channels;
+        const V3 rgb = ch == 1u ? v3(val.x, val.x, val.x) : ch == 2u ? v3(val.x, val.y, 1.f) : v3(val.x, val.y, val.z);
+        s.p[slot] = saturate(rgb.x);
+        s.p[slot + 1u] = saturate(rgb.y);
+        s.p[slot + 2u] = saturate(rgb.z);
+    };
+    auto alpha = [&](uint32_t slot) {// one channel feeds both axes; roughness_to_alpha = max(r^2, 1e-4) (scattering.cpp:129-135)
+        if (s.tex[slot] == 0u) return;
+        const float4 r = texture_evaluate(sc, s.tex[slot] - 1u, u, v);
+        const bool one = sc.textures[s.tex[slot] - 1u].channels == 1u;
+        float ax = r.x, ay = one ? r.x : r.y;
+        if (s.flags & LRK_SURFACE_REMAP_ROUGHNESS) {
+            ax = fmaxf(ax * ax, 1e-4f);
+            ay = fmaxf(ay * ay, 1e-4f);
+        }
+        s.p[slot] = ax;
+        s.p[slot + 1u] = ay;
+    };
+    auto lum = [](const float *c) { return 0.212671f * c[0] + 0.715160f * c[1] + 0.072169f * c[2]; };// src/util/colorspace.h:21-25
+    switch (s.type) {
+        case LRK_SURFACE_MIRROR:
+            colour(0u);
+            alpha(3u);
+            break;
+        case LRK_SURFACE_GLASS: {
+            colour(0u);
+            colour(3u);
+            alpha(7u);
+            const float kr_lum = lum(&s.p[0]), kt_lum = lum(&s.p[3]);
+            s.p[9] = kr_lum == 0.f ? 0.f : kr_lum / (kr_lum + kt_lum);
+            break;
+        }
+        case LRK_SURFACE_PLASTIC: {
+            colour(0u);
+            colour(4u);
+            alpha(8u);
+            if (s.tex[10] != 0u) s.p[10] = texture_evaluate(sc, s.tex[10] - 1u, u, v).x;
+            const float kd_lum = lum(&s.p[0]), sa_lum = lum(&s.p[4]);
+            const float average_transmittance = expf(-2.f * sa_lum * s.p[10]);
+            const float fdr = fresnel_dielectric_integral(s.p[7]);
+            for (int c = 0; c < 3; c++) s.p[c] = s.p[c] / (1.f - s.p[c] * fdr);
+            s.p[3] = kd_lum * average_transmittance;
+            break;
+        }
+        default:// METAL
+            colour(6u);
+            alpha(9u);
+            break;
+    }
+}
+
 __device__ __forceinline__ void resolve_surface_textures(const DeviceScene &sc, lrk_surface &s, float u, float v) {
+    if (s.flags & LRK_SURFACE_RAW_PARAMS) {
+        resolve_raw_surface(*sc.self, s, u, v);
+        return;
+    }
     if (s.tex[0] != 0u) {
         float4 val = texture_evaluate(*sc.self, s.tex[0] - 1u, u, v);
         const uint32_t ch = sc.textures[s.tex[0] - 1u].channels;

@@ -109,25 +109,25 @@ __device__ __forceinline__ void with_closure(const DeviceScene &sc, uint32_t kin
         }
         case 3u: {
             MicrofacetFamilyClosure<2u> cl;
-            cl.init(*surf);
+            init_closure<true>(sc, cl, surf, it);
             f(cl);
             break;
         }
         case 4u: {
             MicrofacetFamilyClosure<3u> cl;
-            cl.init(*surf);
+            init_closure<true>(sc, cl, surf, it);
             f(cl);
             break;
         }
         case 5u: {
             MicrofacetFamilyClosure<4u> cl;
-            cl.init(*surf);
+            init_closure<true>(sc, cl, surf, it);
             f(cl);
             break;
         }
         case 6u: {
             MicrofacetFamilyClosure<5u> cl;
-            cl.init(*surf);
+            init_closure<true>(sc, cl, surf, it);
             f(cl);
             break;
         }

@@ -946,6 +946,38 @@ void flatten_alpha(const Texture *roughness, bool remap, float dflt, float out[2
     }
 }
 
+// Mirror / Glass / Plastic / Metal with an image-textured parameter: the record carries the node's RAW
+// parameters (LRK_SURFACE_RAW_PARAMS) and the closure context is derived per hit, on the device, from the raw values and the
+// textures (include/lrk.h gives the layouts).  These helpers fill one raw slot.
+bool any_image(std::initializer_list<const Texture *> list) {
+    for (auto t : list) if (t != nullptr && t->is_image()) return true;
+    return false;
+}
+void raw_colour(lrk_surface &out, TextureTable &textures, const Texture *t, uint32_t slot, float3 dflt) {
+    if (t != nullptr && t->is_image()) {
+        out.tex[slot] = textures.slot(t);
+    } else {
+        auto c = t != nullptr ? decode_albedo(t, nullptr) : dflt;
+        out.p[slot] = c.x; out.p[slot + 1u] = c.y; out.p[slot + 2u] = c.z;
+    }
+}
+// constant / absent roughness: the final alpha (as flatten_alpha); image roughness: remapped on the device when the flag is set
+void raw_alpha(lrk_surface &out, TextureTable &textures, const Texture *roughness, bool remap, float dflt, uint32_t slot) {
+    if (roughness != nullptr && roughness->is_image()) {
+        out.tex[slot] = textures.slot(roughness);
+        if (remap) out.flags |= LRK_SURFACE_REMAP_ROUGHNESS;
+    } else {
+        flatten_alpha(roughness, remap, dflt, &out.p[slot]);
+    }
+}
+float raw_scalar(lrk_surface &out, TextureTable &textures, const Texture *t, uint32_t slot, float dflt) {
+    if (t != nullptr && t->is_image()) {
+        out.tex[slot] = textures.slot(t);
+        return dflt;
+    }
+    return t != nullptr ? t->value().x : dflt;
+}
+
 const Texture *constant_surface_texture(Scene *s, const NodeDesc *d, const char *name) {
     auto t = s->load_texture(d->node(name));
     if (t && !t->is_constant())
@@ -959,13 +991,20 @@ struct MirrorSurface final : Surface {
     const Texture *color, *roughness;
     bool remap_roughness;
     MirrorSurface(Scene *s, const NodeDesc *d) : Surface{s, d, Tag::SURFACE} {
-        color = constant_surface_texture(s, d, d->has_property("color") ? "color" : "Kd");
-        roughness = constant_surface_texture(s, d, "roughness");
+        color = surface_texture(s, d, d->has_property("color") ? "color" : "Kd");
+        roughness = surface_texture(s, d, "roughness");
         remap_roughness = d->b("remap_roughness", true);
     }
     lrk_surface flatten(TextureTable &textures) const override {
         lrk_surface out{};
         out.type = LRK_SURFACE_MIRROR;
+        if (any_image({color, roughness})) {// raw layout: p[0..2] colour, p[3..4] alpha / roughness
+            out.flags |= LRK_SURFACE_HAS_TEXTURES | LRK_SURFACE_RAW_PARAMS;
+            raw_colour(out, textures, color, 0u, float3{1.f, 1.f, 1.f});
+            raw_alpha(out, textures, roughness, remap_roughness, 0.f, 3u);
+            flatten_wrappers(out, textures);
+            return out;
+        }
         auto c = decode_albedo(color, nullptr);
         out.p[0] = c.x; out.p[1] = c.y; out.p[2] = c.z;
         flatten_alpha(roughness, remap_roughness, 0.f, &out.p[3]);
@@ -980,9 +1019,9 @@ struct GlassSurface final : Surface {
     float named_eta{0.f};
     bool remap_roughness;
     GlassSurface(Scene *s, const NodeDesc *d) : Surface{s, d, Tag::SURFACE} {
-        kr = constant_surface_texture(s, d, "Kr");
-        kt = constant_surface_texture(s, d, "Kt");
-        roughness = constant_surface_texture(s, d, "roughness");
+        kr = surface_texture(s, d, "Kr");
+        kt = surface_texture(s, d, "Kt");
+        roughness = surface_texture(s, d, "roughness");
         remap_roughness = d->b("remap_roughness", true);
         if (auto name = d->s("eta", ""); !name.empty()) {
             // built-in glasses (glass.cpp:28-41): refractive index at the Fraunhofer C line (656.27 nm) - with the fixed sRGB
@@ -1004,6 +1043,15 @@ struct GlassSurface final : Surface {
     lrk_surface flatten(TextureTable &textures) const override {
         lrk_surface out{};
         out.type = LRK_SURFACE_GLASS;
+        if (any_image({kr, kt, roughness})) {// raw layout: p[0..2] Kr, p[3..5] Kt, p[6] eta, p[7..8] alpha / roughness; p[9] derived per hit
+            out.flags |= LRK_SURFACE_HAS_TEXTURES | LRK_SURFACE_RAW_PARAMS;
+            raw_colour(out, textures, kr, 0u, float3{1.f, 1.f, 1.f});
+            raw_colour(out, textures, kt, 3u, float3{1.f, 1.f, 1.f});
+            out.p[6] = named_eta != 0.f ? named_eta : (eta ? eta->value().x : 1.5f);
+            raw_alpha(out, textures, roughness, remap_roughness, 0.f, 7u);
+            flatten_wrappers(out, textures);
+            return out;
+        }
         float kr_lum = 1.f, kt_lum = 1.f;
         auto r = kr ? decode_albedo(kr, &kr_lum) : float3{1.f, 1.f, 1.f};
         auto t = kt ? decode_albedo(kt, &kt_lum) : float3{1.f, 1.f, 1.f};
@@ -1022,17 +1070,28 @@ struct PlasticSurface final : Surface {
     const Texture *kd, *roughness, *sigma_a, *eta, *thickness;
     bool remap_roughness;
     PlasticSurface(Scene *s, const NodeDesc *d) : Surface{s, d, Tag::SURFACE} {
-        kd = constant_surface_texture(s, d, "Kd");
-        roughness = constant_surface_texture(s, d, "roughness");
-        sigma_a = constant_surface_texture(s, d, "sigma_a");
+        kd = surface_texture(s, d, "Kd");
+        roughness = surface_texture(s, d, "roughness");
+        sigma_a = surface_texture(s, d, "sigma_a");
         eta = constant_surface_texture(s, d, "eta");
-        thickness = constant_surface_texture(s, d, "thickness");
+        thickness = surface_texture(s, d, "thickness");
         remap_roughness = d->b("remap_roughness", true);
     }
     lrk_surface flatten(TextureTable &textures) const override {
         lrk_surface out{};
         out.type = LRK_SURFACE_PLASTIC;
         auto e = (eta ? eta->value().x : 1.5f) / 1.f;// eta_i = 1
+        if (any_image({kd, roughness, sigma_a, thickness})) {
+            // raw layout: p[0..2] Kd, p[4..6] sigma_a, p[7] eta, p[8..9] alpha / roughness, p[10] thickness; p[0..3] derived per hit
+            out.flags |= LRK_SURFACE_HAS_TEXTURES | LRK_SURFACE_RAW_PARAMS;
+            raw_colour(out, textures, kd, 0u, float3{1.f, 1.f, 1.f});
+            raw_colour(out, textures, sigma_a, 4u, float3{0.f, 0.f, 0.f});
+            out.p[7] = e;
+            raw_alpha(out, textures, roughness, remap_roughness, 0.f, 8u);
+            out.p[10] = raw_scalar(out, textures, thickness, 10u, 1.f);
+            flatten_wrappers(out, textures);
+            return out;
+        }
         float kd_lum = 1.f, sa_lum = 0.f;
         auto c = kd ? decode_albedo(kd, &kd_lum) : float3{1.f, 1.f, 1.f};
         auto sa = sigma_a ? decode_albedo(sigma_a, &sa_lum) : float3{0.f, 0.f, 0.f};
@@ -1064,8 +1123,8 @@ struct MetalSurface final : Surface {
     bool remap_roughness;
     float n[3], k[3];
     MetalSurface(Scene *s, const NodeDesc *d) : Surface{s, d, Tag::SURFACE} {
-        roughness = constant_surface_texture(s, d, "roughness");
-        kd = constant_surface_texture(s, d, "Kd");
+        roughness = surface_texture(s, d, "roughness");
+        kd = surface_texture(s, d, "Kd");
         remap_roughness = d->b("remap_roughness", true);
         constexpr uint32_t lut_size = (830u - 360u) / 5u + 1u;
         std::vector<float> lut_n(lut_size), lut_k(lut_size);
@@ -1123,6 +1182,13 @@ struct MetalSurface final : Surface {
         lrk_surface out{};
         out.type = LRK_SURFACE_METAL;
         for (int c = 0; c < 3; c++) { out.p[c] = n[c]; out.p[3 + c] = k[c]; }
+        if (any_image({kd, roughness})) {// raw layout = the context layout: p[6..8] Kd, p[9..10] alpha / roughness
+            out.flags |= LRK_SURFACE_HAS_TEXTURES | LRK_SURFACE_RAW_PARAMS;
+            raw_colour(out, textures, kd, 6u, float3{1.f, 1.f, 1.f});
+            raw_alpha(out, textures, roughness, remap_roughness, .5f, 9u);
+            flatten_wrappers(out, textures);
+            return out;
+        }
         auto r = kd ? decode_albedo(kd, nullptr) : float3{1.f, 1.f, 1.f};
         out.p[6] = r.x; out.p[7] = r.y; out.p[8] = r.z;
         flatten_alpha(roughness, remap_roughness, .5f, &out.p[9]);

@@ -196,6 +196,67 @@ def instanced_spheres(resolution=(1920, 1080), spp=1024, seed=1, depth=10, rr_de
     return "\n".join(out) + "\n"
 
 
+def textured_materials(resolution=(64, 40), spp=4, depth=6, rr_depth=0, rr_threshold=0.95, seed=19980810, assets="tests/golden/assets",
+                       output="texmat.exr", integrator="WavePath") -> str:
+    """SURVEY.md §8 row f3 with image-textured parameters: four uv-mapped panels - Mirror (colour + roughness images), Glass (Kr, Kt
+    and roughness images), Plastic (Kd, sigma_a, thickness and roughness images) and Metal (named copper, Kd + roughness images) -
+    in a Matte room, so that the closure context of each is derived per hit from texels (mirror.cpp:142-162, glass.cpp:236-279,
+    plastic.cpp:252-291, metal.cpp:273-310)."""
+    a = assets
+    img = lambda f, enc="sRGB", extra="": f'Image {{ file {{ "{a}/{f}" }} encoding {{ "{enc}" }} {extra}}}'  # noqa: E731
+    out = [
+        "Surface white : Matte { Kd : Constant { v { 0.725, 0.71, 0.68 } } }",
+        "Surface blue : Matte { Kd : Constant { v { 0.15, 0.25, 0.65 } } }",
+        f"Surface t_mirror : Mirror {{ color : {img('checker_rgb8.png')} roughness : {img('rough_gray8.png', 'linear', 'uv_scale { 2.0 } ')} }}",
+        f"Surface t_glass : Glass {{ Kr : {img('palette4.png')} Kt : {img('checker_rgb8.png', 'sRGB', 'uv_scale { 3.0 } ')} "
+        f"roughness : {img('rough_gray8.png', 'linear')} remap_roughness {{ false }} eta : Constant {{ v {{ 1.4 }} }} }}",
+        f"Surface t_plastic : Plastic {{ Kd : {img('ramp_rgba16.png', 'linear')} sigma_a : {img('palette4.png', 'linear', 'uv_scale { 2.0 } ')} "
+        f"thickness : {img('rough_gray8.png', 'linear', 'uv_offset { 0.25, 0.1 } ')} roughness : {img('rough_gray8.png', 'linear')} eta : Constant {{ v {{ 1.5 }} }} }}",
+        f"Surface t_metal : Metal {{ eta {{ \"Cu\" }} Kd : {img('checker_rgb8.png', 'sRGB', 'uv_scale { 2.0 } ')} roughness : {img('rough_gray8.png', 'linear', 'uv_scale { 1.5 } ')} }}",
+        "Light area_light : Diffuse { emission : Constant { v { 17.0, 14.0, 10.0 } } }",
+    ]
+    shapes = []
+
+    def quad(name, pts, surface=None, light=None, uvs=False):
+        pos, idx = _mesh_props([pts])
+        attach = f"surface {{ @{surface} }}" if surface else f"light {{ @{light} }}"
+        uv = " uvs { 0.0, 0.0,  1.0, 0.0,  1.0, 1.0,  0.0, 1.0 }" if uvs else ""
+        out.append(f"Shape {name} : InlineMesh {{ positions {{ {pos} }}{uv} indices {{ {idx} }} {attach} }}")
+        shapes.append(f"@{name}")
+
+    quad("floor", [(-2.0, 0.0, 1.5), (2.0, 0.0, 1.5), (2.0, 0.0, -1.5), (-2.0, 0.0, -1.5)], "white")
+    quad("ceiling", [(-2.0, 2.5, 1.5), (-2.0, 2.5, -1.5), (2.0, 2.5, -1.5), (2.0, 2.5, 1.5)], "white")
+    quad("back", [(-2.0, 0.0, -1.5), (2.0, 0.0, -1.5), (2.0, 2.5, -1.5), (-2.0, 2.5, -1.5)], "blue")
+    quad("left", [(-2.0, 0.0, 1.5), (-2.0, 0.0, -1.5), (-2.0, 2.5, -1.5), (-2.0, 2.5, 1.5)], "white")
+    quad("right", [(2.0, 0.0, -1.5), (2.0, 0.0, 1.5), (2.0, 2.5, 1.5), (2.0, 2.5, -1.5)], "white")
+    quad("lamp", [(-0.6, 2.49, 0.4), (-0.6, 2.49, -0.4), (0.6, 2.49, -0.4), (0.6, 2.49, 0.4)], light="area_light")
+    for i, surface in enumerate(["t_mirror", "t_glass", "t_plastic", "t_metal"]):
+        x0 = -1.8 + 0.92 * i
+        z0, z1 = (-0.2, -0.5) if i % 2 == 0 else (-0.6, -0.3)  # slightly turned panels
+        quad(f"panel_{i}", [(x0, 0.15, z0), (x0 + 0.8, 0.15, z1), (x0 + 0.8, 1.55, z1 - 0.25), (x0, 1.55, z0 - 0.25)], surface, uvs=True)
+    out.append(f"""Camera camera : Pinhole {{
+  position {{ 0.0, 1.1, 4.6 }}
+  look_at {{ 0.0, 0.85, 0.0 }}
+  up {{ 0.0, 1.0, 0.0 }}
+  fov {{ 40.0 }}
+  spp {{ {int(spp)} }}
+  film : Color {{ resolution {{ {int(resolution[0])}, {int(resolution[1])} }} }}
+  filter : Box {{ radius {{ 0.5 }} }}
+  file {{ "{output}" }}
+}}""")
+    out.append(f"""render {{
+  integrator : {integrator} {{
+    depth {{ {int(depth)} }}
+    rr_depth {{ {int(rr_depth)} }}
+    rr_threshold {{ {_fmt(rr_threshold)} }}
+    sampler : Independent {{ seed {{ {int(seed)} }} }}
+  }}
+  cameras {{ @camera }}
+  shapes {{ {", ".join(shapes)} }}
+}}""")
+    return "\n".join(out) + "\n"
+
+
 def media_box(resolution=(64, 64), spp=4, depth=8, rr_depth=0, rr_threshold=0.95, seed=19980810, output="media.exr",
               environment_medium=False, skip_quirk=False) -> str:
     """Row a22 beyond config C4: media bound to shapes (MegaVPTNaive's medium tracker).  The Cornell box whose short box is a

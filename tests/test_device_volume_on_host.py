@@ -45,6 +45,9 @@ CASES = {
     "shape_media_deep_rr": lambda: scenes.media_box(resolution=(32, 32), spp=3, depth=16, rr_depth=3, rr_threshold=0.9),
     "nested_in_environment_medium": lambda: scenes.media_box(resolution=(40, 40), spp=3, environment_medium=True, rr_depth=2),
     "true_hit_quirk": lambda: scenes.media_box(resolution=(40, 40), spp=3, skip_quirk=True),
+    # image-textured Mirror / Glass / Plastic / Metal parameters: closure contexts derived per hit (run through the volume integrator
+    # with no medium at all: the tracker stays empty)
+    "textured_materials": lambda: scenes.textured_materials(resolution=(48, 30), spp=3, depth=6, integrator="MegaVPTNaive"),
     # config C4's shape (one environment medium, opaque closures): the wavefront kernels' territory, but the general code must agree
     "environment_medium_only": lambda: scenes.instanced_spheres(resolution=(32, 18), spp=2, depth=6, medium=True, big_subdivision=2,
                                                                 small_subdivision=1, small_count=12),

@@ -28,6 +28,7 @@ def cases() -> dict[str, str]:
     from luisarender_b200 import scenes
 
     spheres = dict(big_subdivision=2, small_subdivision=1, small_count=12)
+    assets_early = "tests/golden/assets"
     c = {}
     # config C1 / C2: Cornell box, matte + area light; the wavefront integrator and the megakernel one
     c["cornell_wavepath"] = scenes.cornell_box(resolution=(24, 24), spp=4)
@@ -59,6 +60,8 @@ def cases() -> dict[str, str]:
     named = _re.sub(r'Surface m_metal : Metal \{ eta \{ [0-9., ]+\} ', 'Surface m_metal : Metal { eta { "Gold" } ', named)
     assert named.count('eta { "Gold" }') == 1 and named.count('eta { "Cu" }') == 1
     c["materials_named_metals"] = named
+    # row f3 with image-textured parameters of Mirror / Glass / Plastic / Metal: the closure contexts are derived per hit
+    c["materials_textured"] = scenes.textured_materials(resolution=(48, 30), spp=4, depth=6, assets=assets_early)
     c["flatten_stress"] = scenes.flatten_stress()
     # the LoopSubdiv shape: closed, open (boundary / corner rules) and valence-3 base meshes, limit normals, level 0 pass-through
     c["subdivision"] = scenes.subdivision_scene(resolution=(64, 48), spp=4)
