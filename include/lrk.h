@@ -145,7 +145,8 @@ typedef struct lrk_instance {
 #define LRK_SURFACE_PLASTIC 4u /* src/surfaces/plastic.cpp */
 #define LRK_SURFACE_METAL 5u   /* src/surfaces/metal.cpp */
 #define LRK_SURFACE_MIX 6u     /* src/surfaces/mix.cpp: two constant, non-Disney surface records mixed by a ratio */
-#define LRK_SURFACE_TYPE_COUNT 7u
+#define LRK_SURFACE_LAYERED 7u /* src/surfaces/layered.cpp: two constant, non-Disney interfaces around a scattering slab */
+#define LRK_SURFACE_TYPE_COUNT 8u
 
 /* Surface::event_*: src/base/surface.h:37-40 */
 #define LRK_EVENT_REFLECT 0u

@@ -579,12 +579,22 @@ std::unique_ptr<FlatScene> flatten_scene(const Scene &scene) {
     for (size_t tag = 0, tagged = f.surface_nodes.size(); tag < tagged; tag++) {
         auto [a, b] = f.surface_nodes[tag]->mix_children();
         if (a == nullptr) continue;
+        const bool layered = out->surfaces[tag].type == LRK_SURFACE_LAYERED;
         for (auto child : {a, b}) {
             auto rec = child->flatten(texture_table);
             if (rec.type == LRK_SURFACE_DISNEY || (rec.flags & LRK_SURFACE_HAS_TEXTURES))
-                throw Error("Mix: only constant Matte / Mirror / Glass / Plastic / Metal surfaces can be mixed.");
+                throw Error(std::string{layered ? "Layered" : "Mix"} + ": only constant Matte / Mirror / Glass / Plastic / Metal surfaces can be " +
+                            (layered ? "layered." : "mixed."));
             (child == a ? out->surfaces[tag].mix_a : out->surfaces[tag].mix_b) = static_cast<uint32_t>(out->surfaces.size());
             out->surfaces.push_back(rec);
+        }
+        if (layered) {
+            // the bottom closure is built with eta_i = top->eta().value_or(1) (layered.cpp:500-502); every closure here takes eta_i = 1,
+            // so under a Glass top only interfaces that never look at eta_i are accepted
+            const auto &top = out->surfaces[out->surfaces[tag].mix_a], &bottom = out->surfaces[out->surfaces[tag].mix_b];
+            if (top.type == LRK_SURFACE_GLASS && top.p[6] != 1.f && bottom.type != LRK_SURFACE_MATTE && bottom.type != LRK_SURFACE_MIRROR)
+                throw Error("Layered: under a Glass top (eta != 1) the bottom interface must be Matte or Mirror.");
+            continue;
         }
         // MixSurfaceClosure::eta() (mix.cpp:133-141) for the Russian-roulette eta scale: Glass children have one
         auto eta_of = [&](uint32_t i) { return out->surfaces[i].type == LRK_SURFACE_GLASS ? out->surfaces[i].p[6] : 0.f; };

@@ -1222,6 +1222,43 @@ struct MixSurface final : Surface {
     }
 };
 
+struct LayeredSurface final : Surface {
+    // src/surfaces/layered.cpp:110-141,478-503: two interfaces around a scattering slab; thickness = max(t.x, FLT_MIN) (default 1e-2),
+    // g (default 0), albedo (default 1), max_depth (10), samples (1).  The interfaces become two extra records, like a Mix's.
+    const Surface *top, *bottom;
+    const Texture *thickness, *g, *albedo;
+    uint32_t max_depth, samples;
+    LayeredSurface(Scene *s, const NodeDesc *d) : Surface{s, d, Tag::SURFACE} {
+        top = s->load_surface(d->required_node("top"));
+        bottom = s->load_surface(d->required_node("bottom"));
+        thickness = constant_surface_texture(s, d, "thickness");
+        g = constant_surface_texture(s, d, "g");
+        albedo = constant_surface_texture(s, d, "albedo");
+        max_depth = d->u("max_depth", 10u);
+        samples = d->u("samples", 1u);
+        if (top == nullptr || bottom == nullptr || top->is_null() || bottom->is_null())
+            throw Error("Creating closure for null LayeredSurface. [" + d->location() + "]");
+        if (max_depth > 0xffffu || samples == 0u || samples > 0xffffu) throw Error("Layered: max_depth / samples out of range. [" + d->location() + "]");
+        for (auto c : {top, bottom}) {
+            if (c->mix_children().first != nullptr) throw Error("Layered: Mix / Layered interfaces are not supported. [" + d->location() + "]");
+            if (c->opacity != nullptr || c->normal_map != nullptr)
+                throw Error("Layered: interfaces with opacity / normal maps are not supported. [" + d->location() + "]");
+        }
+    }
+    std::pair<const Surface *, const Surface *> mix_children() const override { return {top, bottom}; }
+    lrk_surface flatten(TextureTable &textures) const override {
+        lrk_surface out{};
+        out.type = LRK_SURFACE_LAYERED;
+        out.p[0] = thickness ? std::max(thickness->value().x, std::numeric_limits<float>::min()) : 1e-2f;
+        out.p[1] = g ? g->value().x : 0.f;
+        auto a = albedo ? decode_albedo(albedo, nullptr) : float3{1.f, 1.f, 1.f};
+        out.p[2] = a.x; out.p[3] = a.y; out.p[4] = a.z;
+        out.lobes = max_depth | (samples << 16u);
+        flatten_wrappers(out, textures);
+        return out;// mix_a (top) / mix_b (bottom) are filled by flatten_scene
+    }
+};
+
 struct NullSurface final : Surface {
     NullSurface(Scene *s, const NodeDesc *d) : Surface{s, d, Tag::SURFACE} {}
     bool is_null() const override { return true; }
@@ -1267,6 +1304,7 @@ LRH_PLUGIN("surface-mirror", MirrorSurface)
 LRH_PLUGIN("surface-glass", GlassSurface)
 LRH_PLUGIN("surface-plastic", PlasticSurface)
 LRH_PLUGIN("surface-metal", MetalSurface)
+LRH_PLUGIN("surface-layered", LayeredSurface)
 LRH_PLUGIN("surface-mix", MixSurface)
 LRH_PLUGIN("surface-null", NullSurface)
 LRH_PLUGIN("light-diffuse", DiffuseLight)

@@ -486,6 +486,37 @@ render {{
 """
 
 
+def layered_box(**kw) -> str:
+    """Row f3's Layered surface (src/surfaces/layered.cpp) on three of the materials box's balls: a rough Glass coat over a Matte base
+    with a tinted, forward-scattering slab between them (two evaluate samples); a Glass coat over a Mirror base with a black albedo
+    (the slab only attenuates: the reference's `albedo.is_zero()` branch); a Plastic coat over Matte with the node's defaults."""
+    src = materials_box(**kw)
+    layered = [
+        "Surface l_coat : Glass { roughness : Constant { v { 0.2 } } eta : Constant { v { 1.5 } } }",
+        "Surface l_base : Matte { Kd : Constant { v { 0.8, 0.3, 0.2 } } }",
+        "Surface l_base_mirror : Mirror { color : Constant { v { 0.9, 0.85, 0.6 } } roughness : Constant { v { 0.3 } } }",
+        "Surface l_coat_plastic : Plastic { Kd : Constant { v { 0.3, 0.6, 0.3 } } roughness : Constant { v { 0.25 } } }",
+        "Surface m_mirror : Layered { top { @l_coat } bottom { @l_base } thickness : Constant { v { 0.05 } } g : Constant { v { 0.3 } } "
+        "albedo : Constant { v { 0.6, 0.7, 0.9 } } max_depth { 8 } samples { 2 } }",
+        "Surface m_glass : Layered { top { @l_coat } bottom { @l_base_mirror } thickness : Constant { v { 0.02 } } "
+        "albedo : Constant { v { 0.0, 0.0, 0.0 } } max_depth { 6 } }",
+        "Surface m_plastic : Layered { top { @l_coat_plastic } bottom { @l_base } }",
+    ]
+    out = []
+    for line in src.split("\n"):
+        if line.startswith("Surface m_mirror :"):
+            out += layered
+        elif line.startswith("Surface m_glass :"):
+            continue
+        elif line.startswith("Surface m_plastic :"):
+            continue
+        elif line.startswith("sigma_a : Constant") and out and out[-1].startswith("Surface m_plastic : Layered"):
+            continue
+        else:
+            out.append(line)
+    return "\n".join(out)
+
+
 def materials_box(resolution=(32, 24), spp=4, depth=8, rr_depth=0, rr_threshold=0.95, seed=19980810, subdivision=2,
                   integrator="WavePath", output="materials.exr", mix=False) -> str:
     """a Cornell-like box with one Loop-subdivision sphere per closure of src/surfaces -

@@ -90,6 +90,23 @@ uint32_t xxhash32_uint4(uint32_t px, uint32_t py, uint32_t pz, uint32_t pw) {
     return h32 ^ (h32 >> 16u);
 }
 
+// The reference draws several random numbers inside ONE C++ argument list in a few places (homogeneous.cpp:91,
+// layered.cpp: sample(w, lcg(seed), make_float2(lcg(seed), lcg(seed)), mode)); the DSL records in C++ evaluation order, which the
+// language leaves unspecified: clang / MSVC go left to right (the oracle's default, and the CUDA kernels'), GCC right to left -
+// what the reference built under oracle/ref does.  oracle_set_hg_args_right_to_left(1) mirrors the GCC build for the comparisons.
+std::atomic<bool> g_hg_args_right_to_left{false};
+
+inline uint32_t xxhash32_uint3(uint32_t px, uint32_t py, uint32_t pz) {// src/util/rng.cpp:38-51
+    constexpr uint32_t PRIME32_2 = 2246822519u, PRIME32_3 = 3266489917u, PRIME32_4 = 668265263u, PRIME32_5 = 374761393u;
+    uint32_t h32 = pz + PRIME32_5 + px * PRIME32_3;
+    h32 = PRIME32_4 * rotl(h32, 17u);
+    h32 += py * PRIME32_3;
+    h32 = PRIME32_4 * rotl(h32, 17u);
+    h32 = PRIME32_2 * (h32 ^ (h32 >> 15u));
+    h32 = PRIME32_3 * (h32 ^ (h32 >> 13u));
+    return h32 ^ (h32 >> 16u);
+}
+
 inline float lcg(uint32_t &state) {
     state = 1664525u * state + 1013904223u;
     return std::fmin(kOneMinusEpsilon, static_cast<float>(state) * 0x1p-32f);
@@ -1172,10 +1189,11 @@ struct MicrofacetReflection {// :290-329
     static bool any_nonzero_v(V3 w) { return w.x != 0.f || w.y != 0.f || w.z != 0.f; }
 };
 
-struct MicrofacetTransmission {// :331-380 (TransportMode::RADIANCE)
+struct MicrofacetTransmission {// :331-380
     V3 t;
     TrowbridgeReitz d;
     float eta_a, eta_b;
+    bool importance{false};// TransportMode::IMPORTANCE: f *= eta^2 (:340-342); only the Layered surface asks for it
     V3 evaluate(V3 wo, V3 wi) const {
         float cosThetaO = cos_theta(wo), cosThetaI = cos_theta(wi);
         float eta = cosThetaO > 0.f ? eta_b / eta_a : eta_a / eta_b;
@@ -1188,6 +1206,7 @@ struct MicrofacetTransmission {// :331-380 (TransportMode::RADIANCE)
             float F = fresnel_dielectric(dot(wo, wh), eta_a, eta_b);
             float D = d.D(wh);
             f = (1.f - F) * t * D * G * dot(wi, wh) * dot(wo, wh) / (cosThetaI * cosThetaO * sqr(sqrtDenom));
+            if (importance) f = f * sqr(eta);
         }
         return f;
     }
@@ -1584,9 +1603,9 @@ struct GlassLobes {
     MicrofacetReflection refl;
     MicrofacetTransmission trans;
     float eta_t, kr_ratio;
-    explicit GlassLobes(const lrk_surface &s)
+    explicit GlassLobes(const lrk_surface &s, bool importance = false)
         : refl{v3(s.p[0], s.p[1], s.p[2]), TrowbridgeReitz{s.p[7], s.p[8]}, FresnelTerm::dielectric(1.f, s.p[6])},
-          trans{v3(s.p[3], s.p[4], s.p[5]), TrowbridgeReitz{s.p[7], s.p[8]}, 1.f, s.p[6]}, eta_t{s.p[6]}, kr_ratio{s.p[9]} {}
+          trans{v3(s.p[3], s.p[4], s.p[5]), TrowbridgeReitz{s.p[7], s.p[8]}, 1.f, s.p[6], importance}, eta_t{s.p[6]}, kr_ratio{s.p[9]} {}
     float refl_prob(V3 wo_local) const {// :162-167
         float F = fresnel_dielectric(cos_theta(wo_local), 1.f, eta_t);
         float r = kr_ratio * F;
@@ -1594,8 +1613,8 @@ struct GlassLobes {
         return r == 0.f ? 0.f : r / (r + t);
     }
 };
-SurfEval glass_evaluate(const lrk_surface &s, const Interaction &it, V3 wo, V3 wi) {
-    GlassLobes g{s};
+SurfEval glass_evaluate(const lrk_surface &s, const Interaction &it, V3 wo, V3 wi, bool importance = false) {
+    GlassLobes g{s, importance};
     V3 wo_local = it.shading.world_to_local(wo), wi_local = it.shading.world_to_local(wi);
     float ratio = g.refl_prob(wo_local);
     V3 f;
@@ -1612,8 +1631,8 @@ SurfEval glass_evaluate(const lrk_surface &s, const Interaction &it, V3 wo, V3 w
     e.pdf = pdf;
     return e;
 }
-SurfSample glass_sample(const lrk_surface &s, const Interaction &it, V3 wo, float u_lobe, float u0, float u1) {
-    GlassLobes g{s};
+SurfSample glass_sample(const lrk_surface &s, const Interaction &it, V3 wo, float u_lobe, float u0, float u1, bool importance = false) {
+    GlassLobes g{s, importance};
     V3 wo_local = it.shading.world_to_local(wo), wi_local = v3(0.f, 0.f, 1.f), f;
     float pdf = 0.f;
     uint32_t event = LRK_EVENT_REFLECT;
@@ -1690,8 +1709,10 @@ SurfSample plastic_sample(const lrk_surface &s, const Interaction &it, V3 wo, fl
 
 // `records` = lrk_scene_desc::surfaces (the two mixed surfaces of a Mix node are records of the same array); nullptr where a
 // closure is evaluated on its own (unit tests: no Mix)
-SurfEval surface_evaluate(const lrk_surface &s, const Interaction &it, V3 wo, V3 wi, const lrk_surface *records = nullptr);
-SurfSample surface_sample(const lrk_surface &s, const Interaction &it, V3 wo, float u_lobe, float u0, float u1, const lrk_surface *records = nullptr);
+// `importance`: TransportMode::IMPORTANCE (the Layered surface samples its exit interface in the reverse mode); RADIANCE everywhere else
+SurfEval surface_evaluate(const lrk_surface &s, const Interaction &it, V3 wo, V3 wi, const lrk_surface *records = nullptr, bool importance = false);
+SurfSample surface_sample(const lrk_surface &s, const Interaction &it, V3 wo, float u_lobe, float u0, float u1, const lrk_surface *records = nullptr,
+                          bool importance = false);
 
 // Mix: src/surfaces/mix.cpp:82-193.  _mix(a, b, ratio) = lerp(a, b, 1 - ratio) on f and pdf.
 inline SurfEval mix_eval(const SurfEval &a, const SurfEval &b, float ratio) {
@@ -1725,6 +1746,271 @@ SurfSample mix_sample(const lrk_surface &s, const Interaction &it, V3 wo, float 
     }
     return out;
 }
+// ------------------------------------------------------------------------------------------------
+// Layered: src/surfaces/layered.cpp (pbrt-v4's LayeredBxDF as the reference restates it): two interfaces (`top`, `bottom`: records
+// mix_a / mix_b) around a homogeneous slab (thickness p[0], Henyey-Greenstein g p[1], albedo p[2..4]); evaluate() is a stochastic
+// random walk with its own LCG stream seeded from the hit position and wi (:277), sample() from the sample numbers and wo (:427).
+// lobes = max_depth | samples << 16.  Both children are bound to the SAME interaction (:500-502), so to_local / to_world of the
+// reference's TopOrBottom are the Layered closure's own frame.
+// ------------------------------------------------------------------------------------------------
+inline bool is_zero3(V3 a) { return a.x == 0.f && a.y == 0.f && a.z == 0.f; }
+inline uint32_t float_bits(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+inline float power_heuristic(float f_pdf, float g_pdf) {// src/util/sampling.cpp:142-151 with nf = ng = 1
+    float f = 1.f * f_pdf, g = 1.f * g_pdf;
+    float ff = f * f, gg = g * g, sum = ff + gg;
+    return std::isinf(ff) ? 1.f : (sum == 0.f ? 0.f : ff / sum);
+}
+struct LayeredPhase {// HGPhaseFunction, layered.cpp:14-61
+    float g;
+    static float hg(float cosTheta, float g) {
+        float denom = 1.f + sqr(g) + 2.f * g * cosTheta;
+        return kInvPi / 4.0f * (1.f - sqr(g)) / (denom * std::sqrt(denom));
+    }
+    float p(V3 wo, V3 wi) const { return hg(dot(wo, wi), g); }
+    struct Sample {
+        float p;
+        V3 wi;
+        float pdf;
+    };
+    Sample sample_p(V3 wo, float ux, float uy) const {
+        float cosTheta = std::fabs(g) < 1e-3f ? 1.f - 2.f * ux : -1.f / (2.f * g) * (1.f + sqr(g) - sqr((1.f - sqr(g)) / (1.f + g - 2.f * g * ux)));
+        float sinTheta = std::sqrt(1.f - sqr(cosTheta));
+        float phi = 2.f * kPi * uy;
+        Frame wFrame = Frame::make(wo);
+        V3 wi = wFrame.local_to_world(spherical_direction(sinTheta, cosTheta, phi));
+        float pdf = hg(cosTheta, g);
+        return {pdf, wi, pdf};
+    }
+};
+struct LayeredCtx {
+    const lrk_surface *top, *bottom, *records;
+    float thickness, g;
+    V3 albedo;
+    uint32_t max_depth, samples;
+    LayeredCtx(const lrk_surface &s, const lrk_surface *rec)
+        : top{rec + s.mix_a}, bottom{rec + s.mix_b}, records{rec}, thickness{s.p[0]}, g{s.p[1]}, albedo{v3(s.p[2], s.p[3], s.p[4])},
+          max_depth{s.lobes & 0xffffu}, samples{s.lobes >> 16u} {}
+    static float Tr(float dz, V3 w) { return std::fabs(dz) <= std::numeric_limits<float>::min() ? 1.f : std::exp(-std::fabs(dz / w.z)); }
+};
+// lcg draws of `f(x, lcg(seed), make_float2(lcg(seed), lcg(seed)))` and of `make_float2(lcg(seed), lcg(seed))` in the compiler's order
+inline void layered_draw3(uint32_t &seed, float &uc, float &u0, float &u1) {
+    if (g_hg_args_right_to_left.load(std::memory_order_relaxed)) { u1 = lcg(seed); u0 = lcg(seed); uc = lcg(seed); }
+    else { uc = lcg(seed); u0 = lcg(seed); u1 = lcg(seed); }
+}
+inline void layered_draw2(uint32_t &seed, float &u0, float &u1) {
+    if (g_hg_args_right_to_left.load(std::memory_order_relaxed)) { u1 = lcg(seed); u0 = lcg(seed); }
+    else { u0 = lcg(seed); u1 = lcg(seed); }
+}
+
+SurfEval layered_evaluate(const lrk_surface &s, const Interaction &it, V3 wo, V3 wi, const lrk_surface *records, bool mode) {// :251-404
+    const LayeredCtx ctx{s, records};
+    auto eval = [&](const lrk_surface *c, V3 a, V3 b, bool m) { return surface_evaluate(*c, it, a, b, records, m); };
+    auto sample = [&](const lrk_surface *c, V3 a, float uc, float u0, float u1, bool m) { return surface_sample(*c, it, a, uc, u0, u1, records, m); };
+    const V3 wi_local = it.shading.world_to_local(wi), wo_local = it.shading.world_to_local(wo);
+    const bool entered_top = wo_local.z > 0.f;
+    const bool exit_is_bottom = same_hemisphere(wo_local, wi_local) != entered_top;// same_hemisphere ^ entered_top
+    const lrk_surface *enter_interface = entered_top ? ctx.top : ctx.bottom;
+    const lrk_surface *exit_interface = exit_is_bottom ? ctx.bottom : ctx.top;
+    const lrk_surface *nonexit_interface = exit_is_bottom ? ctx.top : ctx.bottom;
+    const float exitZ = exit_is_bottom ? 0.f : ctx.thickness;
+    const float n_samples = static_cast<float>(ctx.samples);
+    V3 f = same_hemisphere(wi_local, wo_local) ? n_samples * eval(enter_interface, wo, wi, mode).f : v3(0.f);
+    uint32_t seed = xxhash32_uint4(float_bits(it.pg.x), float_bits(it.pg.y), float_bits(it.pg.z),
+                                   xxhash32_uint3(float_bits(wi.x), float_bits(wi.y), float_bits(wi.z)));
+    float pdf_sum = same_hemisphere(wi_local, wo_local)
+                        ? (entered_top ? n_samples * eval(ctx.top, wo, wi, mode).pdf : n_samples * eval(ctx.bottom, wo, wi, mode).pdf)
+                        : 0.f;
+    const LayeredPhase phase{ctx.g};
+    for (uint32_t i = 0; i < ctx.samples; i++) {
+        float uc, u0, u1;
+        layered_draw3(seed, uc, u0, u1);
+        const SurfSample wos = sample(enter_interface, wo, uc, u0, u1, mode);
+        if (is_zero3(wos.eval.f) || wos.eval.pdf <= 0.f) continue;
+        layered_draw3(seed, uc, u0, u1);
+        const SurfSample wis = sample(exit_interface, wi, uc, u0, u1, !mode);
+        const V3 wis_wi_local = it.shading.world_to_local(wis.wi);
+        if (is_zero3(wis.eval.f) || wis.eval.pdf <= 0.f) continue;
+        V3 beta = wos.eval.f / wos.eval.pdf;
+        float z = entered_top ? ctx.thickness : 0.f;
+        V3 w = wos.wi;
+        V3 w_local = it.shading.world_to_local(w);
+        for (uint32_t depth = 0; depth < ctx.max_depth; depth++) {
+            if (depth > 3u && max3(beta) < 0.25f) {
+                float q = std::fmax(0.f, 1.f - max3(beta));
+                if (lcg(seed) < q) break;
+                beta = beta / (1.f - q);
+            }
+            if (is_zero3(ctx.albedo)) {
+                z = z == ctx.thickness ? 0.f : ctx.thickness;
+                beta = beta * LayeredCtx::Tr(ctx.thickness, w_local);
+            } else {
+                const float sigma_t = 1.f;
+                float dz = -std::log(1.f - lcg(seed)) / (sigma_t / std::fabs(w_local.z));
+                float zp = w_local.z > 0.f ? z + dz : z - dz;
+                if (z == zp) continue;
+                if (zp > 0.f && zp < ctx.thickness) {
+                    float wt = power_heuristic(wis.eval.pdf, eval(nonexit_interface, -w, -wis.wi, mode).pdf);
+                    f = f + beta * ctx.albedo * phase.p(-w_local, -wis_wi_local) * wt * LayeredCtx::Tr(zp - exitZ, wis_wi_local) * wis.eval.f / wis.eval.pdf;
+                    float ux, uy;
+                    layered_draw2(seed, ux, uy);
+                    LayeredPhase::Sample ps = phase.sample_p(-w_local, ux, uy);
+                    if (ps.pdf <= 0.f || ps.wi.z == 0.f) continue;
+                    beta = beta * (ctx.albedo * ps.p / ps.pdf);
+                    w_local = ps.wi;
+                    w = it.shading.local_to_world(w_local);
+                    z = zp;
+                    if ((z < exitZ && w_local.z > 0.f) || (z > exitZ && w_local.z < 0.f)) {
+                        V3 fExit = eval(exit_interface, -w, wi, mode).f;
+                        if (!is_zero3(fExit)) {
+                            float exitPDF = eval(exit_interface, -w, wi, mode).pdf;
+                            float wt2 = power_heuristic(ps.pdf, exitPDF);
+                            f = f + beta * LayeredCtx::Tr(zp - exitZ, w_local) * fExit * wt2;
+                        }
+                    }
+                    continue;
+                }
+                z = clampf(zp, 0.f, ctx.thickness);
+            }
+            if (z == exitZ) {
+                float uc2 = lcg(seed), ua, ub;
+                layered_draw2(seed, ua, ub);
+                SurfSample bs = sample(exit_interface, -w, uc2, ua, ub, mode);
+                if (is_zero3(bs.eval.f) || bs.eval.pdf <= 0.f) break;
+                beta = beta * (bs.eval.f / bs.eval.pdf);
+                w = bs.wi;
+                w_local = it.shading.world_to_local(w);
+            } else {
+                SurfEval wns = eval(nonexit_interface, -w, -wis.wi, mode);
+                float wt = power_heuristic(wis.eval.pdf, wns.pdf);
+                f = f + beta * wns.f * wt * LayeredCtx::Tr(ctx.thickness, wis_wi_local) * wis.eval.f / wis.eval.pdf;
+                float uc2 = lcg(seed), ua, ub;
+                layered_draw2(seed, ua, ub);
+                SurfSample bs = sample(nonexit_interface, -w, uc2, ua, ub, mode);
+                if (is_zero3(bs.eval.f) || bs.eval.pdf <= 0.f) break;
+                beta = beta * (bs.eval.f / bs.eval.pdf);
+                w = bs.wi;
+                w_local = it.shading.world_to_local(w);
+                SurfEval wes = eval(exit_interface, -w, wi, mode);
+                V3 fExit = wes.f;
+                if (!is_zero3(fExit)) {
+                    float wt2 = power_heuristic(bs.eval.pdf, wes.pdf);
+                    f = f + beta * LayeredCtx::Tr(ctx.thickness, it.shading.world_to_local(bs.wi)) * fExit * wt2;
+                }
+            }
+        }
+    }
+    for (uint32_t k = 0; k < ctx.samples; k++) {// pdf: :361-400
+        if (same_hemisphere(wo_local, wi_local)) {
+            const lrk_surface *r_interface = entered_top ? ctx.bottom : ctx.top;
+            const lrk_surface *t_interface = entered_top ? ctx.top : ctx.bottom;
+            float uc, u0, u1;
+            layered_draw3(seed, uc, u0, u1);
+            SurfSample wos = sample(t_interface, wo, uc, u0, u1, mode);
+            layered_draw3(seed, uc, u0, u1);
+            SurfSample wis = sample(t_interface, wi, uc, u0, u1, !mode);
+            if (!is_zero3(wos.eval.f) && wos.eval.pdf > 0.f && !is_zero3(wis.eval.f) && wis.eval.pdf > 0.f) {
+                layered_draw3(seed, uc, u0, u1);
+                SurfSample rs = sample(r_interface, -wos.wi, uc, u0, u1, mode);
+                if (!is_zero3(rs.eval.f) && rs.eval.pdf > 0.f) {
+                    float r_pdf = eval(r_interface, -wos.wi, -wis.wi, mode).pdf;
+                    float wt = power_heuristic(wis.eval.pdf, r_pdf);
+                    pdf_sum += wt * r_pdf;
+                    float t_pdf = eval(t_interface, -rs.wi, wi, mode).pdf;
+                    wt = power_heuristic(rs.eval.pdf, t_pdf);
+                    pdf_sum += wt * t_pdf;
+                }
+            }
+        } else {
+            const lrk_surface *ti_interface = entered_top ? ctx.bottom : ctx.top;
+            const lrk_surface *to_interface = entered_top ? ctx.top : ctx.bottom;
+            float uc, u0, u1;
+            layered_draw3(seed, uc, u0, u1);
+            SurfSample wos = sample(to_interface, wo, uc, u0, u1, mode);
+            layered_draw3(seed, uc, u0, u1);
+            SurfSample wis = sample(ti_interface, wi, uc, u0, u1, !mode);
+            if (is_zero3(wos.eval.f) || wos.eval.pdf <= 0.f || is_zero3(wis.eval.f) || wis.eval.pdf <= 0.f) continue;
+            pdf_sum += .5f * (eval(to_interface, wo, -wis.wi, mode).pdf + eval(ti_interface, -wos.wi, wi, mode).pdf);
+        }
+    }
+    SurfEval e;
+    e.f = f / n_samples;
+    e.pdf = lerp(1.f / (4.f * kPi), pdf_sum / n_samples, 0.9f);
+    return e;
+}
+
+SurfSample layered_sample(const lrk_surface &s, const Interaction &it, V3 wo, float u_lobe, float u0, float u1, const lrk_surface *records, bool mode) {// :405-472
+    const LayeredCtx ctx{s, records};
+    auto sample = [&](const lrk_surface *c, V3 a, float uc, float ua, float ub, bool m) { return surface_sample(*c, it, a, uc, ua, ub, records, m); };
+    const V3 wo_local = it.shading.world_to_local(wo);
+    const bool entered_top = wo_local.z > 0.f;
+    SurfSample bs = sample(entered_top ? ctx.top : ctx.bottom, wo, u_lobe, u0, u1, mode);
+    SurfSample out;// Surface::Sample::zero: f = 0, pdf = 0, wi = (0, 0, 1), event_reflect
+    out.wi = v3(0.f, 0.f, 1.f);
+    out.event = LRK_EVENT_REFLECT;
+    if (!is_zero3(bs.eval.f) && bs.eval.pdf != 0.f) {
+        V3 wi_local = it.shading.world_to_local(bs.wi);
+        if (same_hemisphere(wi_local, wo_local)) {
+            out = bs;
+        } else {
+            V3 w = bs.wi;
+            V3 w_local = it.shading.world_to_local(bs.wi);
+            uint32_t seed = xxhash32_uint4(float_bits(u0), float_bits(u1), float_bits(u_lobe), xxhash32_uint3(float_bits(wo.x), float_bits(wo.y), float_bits(wo.z)));
+            V3 f = bs.eval.f;
+            float pdf = bs.eval.pdf;
+            float z = entered_top ? ctx.thickness : 0.f;
+            const LayeredPhase phase{ctx.g};
+            for (uint32_t depth = 0; depth < ctx.max_depth; depth++) {
+                float rr_beta = max3(f) / pdf;
+                if (depth > 3u && rr_beta < 0.25f) {
+                    float q = std::fmax(0.f, 1.f - rr_beta);
+                    if (lcg(seed) < q) break;
+                    pdf *= 1.f - q;
+                }
+                if (w_local.z == 0.f) break;
+                if (!is_zero3(ctx.albedo)) {
+                    const float sigma_t = 1.f;
+                    float dz = -std::log(1.f - lcg(seed)) / (sigma_t / std::fabs(w_local.z));
+                    float zp = w_local.z > 0.f ? z + dz : z - dz;
+                    if (z == zp) break;
+                    if (0.f < zp && zp < ctx.thickness) {
+                        float ux, uy;
+                        layered_draw2(seed, ux, uy);
+                        LayeredPhase::Sample ps = phase.sample_p(-w_local, ux, uy);
+                        if (ps.pdf <= 0.f) break;
+                        f = f * (ctx.albedo * ps.p);
+                        pdf *= ps.pdf;
+                        w = ps.wi;// sic: the phase function's LOCAL direction is taken as the world direction (:449-450)
+                        w_local = it.shading.world_to_local(w);
+                        z = zp;
+                        continue;
+                    }
+                    z = clampf(zp, 0.f, ctx.thickness);
+                } else {
+                    z = z == ctx.thickness ? 0.f : ctx.thickness;
+                    f = f * LayeredCtx::Tr(ctx.thickness, w_local);
+                }
+                const lrk_surface *interface = z == 0.f ? ctx.bottom : ctx.top;
+                float uc = lcg(seed), ua, ub;
+                layered_draw2(seed, ua, ub);
+                SurfSample is = sample(interface, -w, uc, ua, ub, mode);
+                if (is_zero3(is.eval.f) || is.eval.pdf <= 0.f) break;
+                f = f * is.eval.f;
+                pdf *= is.eval.pdf;
+                w = is.wi;
+                w_local = it.shading.world_to_local(w);
+                if ((is.event & 3u) != 0u) {// Surface::event_transmit = enter | exit
+                    out.eval.f = f;
+                    out.eval.pdf = pdf;
+                    out.wi = w;
+                    out.event = same_hemisphere(w_local, wo_local) ? LRK_EVENT_REFLECT : (w_local.z > 0.f ? LRK_EVENT_EXIT : LRK_EVENT_ENTER);
+                    break;
+                }
+            }
+        }
+    }
+    return out;
+}
+
 // Surface::Closure::eta() for the Russian-roulette eta scale (mega_path.cpp:133): Glass has one, a Mix lerps / forwards them
 // (mix.cpp:133-141); 0 = nullopt
 float surface_eta(const lrk_surface &s, const lrk_surface *records) {
@@ -1737,18 +2023,20 @@ float surface_eta(const lrk_surface &s, const lrk_surface *records) {
         if (eb == 0.f) return ea;
         return lerp(eb, ea, s.p[0]);
     }
+    if (s.type == LRK_SURFACE_LAYERED) return surface_eta(records[s.mix_b], records);// _bottom->eta(), layered.cpp:248
     return 0.f;
 }
 
-SurfEval surface_evaluate(const lrk_surface &s, const Interaction &it, V3 wo, V3 wi, const lrk_surface *records) {
+SurfEval surface_evaluate(const lrk_surface &s, const Interaction &it, V3 wo, V3 wi, const lrk_surface *records, bool importance) {
     SurfEval e;
     switch (s.type) {
         case LRK_SURFACE_MATTE: e = matte_evaluate(s, it, wo, wi); break;
         case LRK_SURFACE_DISNEY: e = disney_evaluate(s, it, wo, wi); break;
         case LRK_SURFACE_MIRROR: e = mirror_evaluate(s, it, wo, wi); break;
-        case LRK_SURFACE_GLASS: e = glass_evaluate(s, it, wo, wi); break;
+        case LRK_SURFACE_GLASS: e = glass_evaluate(s, it, wo, wi, importance); break;
         case LRK_SURFACE_PLASTIC: e = plastic_evaluate(s, it, wo, wi); break;
         case LRK_SURFACE_MIX: e = mix_evaluate(s, it, wo, wi, records); break;
+        case LRK_SURFACE_LAYERED: e = layered_evaluate(s, it, wo, wi, records, importance); break;
         default: e = metal_evaluate(s, it, wo, wi); break;
     }
     if (!validate_surface_sides(it.ng, it.shading.n, wo, wi)) {
@@ -1757,15 +2045,17 @@ SurfEval surface_evaluate(const lrk_surface &s, const Interaction &it, V3 wo, V3
     }
     return e;
 }
-SurfSample surface_sample(const lrk_surface &s, const Interaction &it, V3 wo, float u_lobe, float u0, float u1, const lrk_surface *records) {
+SurfSample surface_sample(const lrk_surface &s, const Interaction &it, V3 wo, float u_lobe, float u0, float u1, const lrk_surface *records,
+                          bool importance) {
     SurfSample r;
     switch (s.type) {
         case LRK_SURFACE_MATTE: r = matte_sample(s, it, wo, u_lobe, u0, u1); break;
         case LRK_SURFACE_DISNEY: r = disney_sample(s, it, wo, u_lobe, u0, u1); break;
         case LRK_SURFACE_MIRROR: r = mirror_sample(s, it, wo, u_lobe, u0, u1); break;
-        case LRK_SURFACE_GLASS: r = glass_sample(s, it, wo, u_lobe, u0, u1); break;
+        case LRK_SURFACE_GLASS: r = glass_sample(s, it, wo, u_lobe, u0, u1, importance); break;
         case LRK_SURFACE_PLASTIC: r = plastic_sample(s, it, wo, u_lobe, u0, u1); break;
         case LRK_SURFACE_MIX: r = mix_sample(s, it, wo, u_lobe, u0, u1, records); break;
+        case LRK_SURFACE_LAYERED: r = layered_sample(s, it, wo, u_lobe, u0, u1, records, importance); break;
         default: r = metal_sample(s, it, wo, u_lobe, u0, u1); break;
     }
     if (!validate_surface_sides(it.ng, it.shading.n, wo, r.wi)) {
@@ -2163,7 +2453,6 @@ inline float sum3(V3 a) { return a.x + a.y + a.z; }
 inline float comp(V3 a, uint32_t i) { return i == 0u ? a.x : i == 1u ? a.y : a.z; }
 
 // HomogeneousMediumClosure::sample, src/media/homogeneous.cpp:48-118
-std::atomic<bool> g_hg_args_right_to_left{false};
 MediumSample homogeneous_sample(const lrk_medium &m, V3 o, V3 d, float t_max, PCG32 &rng) {
     V3 sigma_a = v3(m.sigma_a[0], m.sigma_a[1], m.sigma_a[2]), sigma_s = v3(m.sigma_s[0], m.sigma_s[1], m.sigma_s[2]);
     V3 sigma_t = sigma_a + sigma_s;

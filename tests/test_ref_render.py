@@ -39,7 +39,7 @@ CASES = ["cornell_wavepath", "cornell_megapath", "cornell_russian_roulette", "sp
          "spheres_medium_isotropic", "subdivision", "swizzle", "checkerboard", "spheres_disney_transmissive",
          "cornell_sampler_pmj02bn", "cornell_sampler_sobol", "cornell_sampler_paddedsobol", "cornell_sampler_zsobol",
          "spheres_sampler_pmj02bn", "spheres_sampler_sobol", "spheres_sampler_paddedsobol", "spheres_sampler_zsobol",
-         "media_shapes", "media_nested_in_environment_medium", "media_true_hit_quirk", "materials_named_metals", "materials_textured"]
+         "media_shapes", "media_nested_in_environment_medium", "media_true_hit_quirk", "materials_named_metals", "materials_textured", "materials_layered", "materials_layered_rr"]
 
 
 @pytest.fixture(scope="module")
@@ -64,7 +64,7 @@ def _spp(source):
 def test_oracle_film_is_bit_identical_to_the_reference_render(golden, name):
     source, scene, desc = _scene(golden, name)
     want = golden[f"{name}/image"]
-    O.lib().oracle_set_hg_args_right_to_left(1 if ("medium" in name or "media" in name or "c4" in name) else 0)  # GCC build of the reference
+    O.lib().oracle_set_hg_args_right_to_left(1 if ("medium" in name or "media" in name or "c4" in name or "layered" in name) else 0)  # GCC build of the reference
     try:
         raw, _ = O.render(desc, 0, _spp(source))
         got = O.convert_film(desc, raw)
@@ -96,7 +96,7 @@ def test_fixture_is_what_the_reference_renders_now(golden):
 @pytest.mark.parametrize("name", ["cornell_wavepath", "cornell_russian_roulette", "spheres_disney", "materials_wavepath",
                                   "materials_megapath_rr", "textured", "textured_wrappers", "environment_image",
                                   "config_c3_full_scene", "cornell_filter_gaussian", "cornell_filter_mitchell",
-                                  "cornell_film_and_light_options", "materials_mix", "materials_named_metals", "materials_textured", "flatten_stress", "spheres_disney_all_lobes",
+                                  "cornell_film_and_light_options", "materials_mix", "materials_named_metals", "materials_textured", "materials_layered", "flatten_stress", "spheres_disney_all_lobes",
                                   "subdivision", "spheres_disney_transmissive",
                                   "cornell_sampler_pmj02bn", "cornell_sampler_sobol", "cornell_sampler_paddedsobol", "cornell_sampler_zsobol",
                                   "spheres_sampler_pmj02bn", "spheres_sampler_sobol", "spheres_sampler_paddedsobol", "spheres_sampler_zsobol"])

@@ -62,6 +62,10 @@ def cases() -> dict[str, str]:
     c["materials_named_metals"] = named
     # row f3 with image-textured parameters of Mirror / Glass / Plastic / Metal: the closure contexts are derived per hit
     c["materials_textured"] = scenes.textured_materials(resolution=(48, 30), spp=4, depth=6, assets=assets_early)
+    # row f3's Layered surface: Glass over Matte with a scattering slab, Glass over Mirror with a black (attenuating) slab, Plastic over
+    # Matte with the node's defaults; with Russian roulette in the second case
+    c["materials_layered"] = scenes.layered_box(resolution=(32, 24), spp=4, depth=6, output="layered.exr")
+    c["materials_layered_rr"] = scenes.layered_box(resolution=(32, 24), spp=4, depth=10, rr_depth=2, rr_threshold=0.95, integrator="MegaPath", output="layered_rr.exr")
     c["flatten_stress"] = scenes.flatten_stress()
     # the LoopSubdiv shape: closed, open (boundary / corner rules) and valence-3 base meshes, limit normals, level 0 pass-through
     c["subdivision"] = scenes.subdivision_scene(resolution=(64, 48), spp=4)
