@@ -188,6 +188,9 @@ typedef struct lrk_instance {
  *            MixSurfaceClosure::Context, mix.cpp:88-91,195-211.  The closure reproduces the reference's arithmetic including
  *            its second sampling branch, which samples surface `a` again and weights the two evaluations the other way
  *            round (mix.cpp:170-176).
+ *   LAYERED: p[0] = thickness (>= FLT_MIN), p[1] = g, p[2..4] = albedo, lobes = max_depth | samples << 16; mix_a / mix_b = record
+ *            indices of the top / bottom interface (constant Matte / Mirror / Glass / Plastic / Metal records appended like a Mix's) —
+ *            LayeredSurfaceClosure::Context, layered.cpp:205-212,478-503
  *   With image-textured parameters the four records use the raw layouts of LRK_SURFACE_RAW_PARAMS below.
  *
  * Image-textured parameters: tex[k] != 0 means parameter slot k is NOT the constant p[k] but is

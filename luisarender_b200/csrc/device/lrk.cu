@@ -75,8 +75,8 @@ struct lrk_ctx {
     cudaEvent_t ev_begin{}, ev_end{};
     std::vector<TimedLaunch> timed;
     std::vector<cudaEvent_t> event_pool;
-    int grid_trace{0}, grid_shade[2][9]{}, grid_shadow{0}, grid_classify{0};// grid_shade[variant]: 0 = fast, 1 = strict arithmetic
-    bool has_kind[9]{true, false, false, false, false, false, false, false, false};
+    int grid_trace{0}, grid_shade[2][10]{}, grid_shadow{0}, grid_classify{0};// grid_shade[variant]: 0 = fast, 1 = strict arithmetic
+    bool has_kind[10]{true, false, false, false, false, false, false, false, false, false};
     uint32_t allocated_kinds{0u};// bit k: hit_index[k] is allocated
     bool volume{false};
     bool strict_math{false};// option strict_math: every closure kernel from shade.cu's IEEE-arithmetic compilation
@@ -163,7 +163,7 @@ void free_paths(lrk_ctx *ctx) {
 
 int alloc_paths(lrk_ctx *ctx, uint64_t capacity) {
     uint32_t kinds = 0u;
-    for (int k = 0; k < 9; k++) if (k < 3 || ctx->has_kind[k]) kinds |= 1u << k;// buckets 3..8 only for scenes that use them
+    for (int k = 0; k < 10; k++) if (k < 3 || ctx->has_kind[k]) kinds |= 1u << k;// buckets 3..9 only for scenes that use them
     if (ctx->capacity >= capacity && (!ctx->volume || ctx->volume_capacity >= capacity) && (ctx->allocated_kinds & kinds) == kinds) return LRK_OK;
     free_paths(ctx);
     auto alloc = [&](void **p, size_t bytes) -> cudaError_t {
@@ -179,7 +179,7 @@ int alloc_paths(lrk_ctx *ctx, uint64_t capacity) {
         LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.id_rng[k]), capacity * sizeof(uint2)));
     }
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.hit), capacity * sizeof(uint4)));
-    for (int k = 0; k < 9; k++) {
+    for (int k = 0; k < 10; k++) {
         pb.hit_index[k] = nullptr;
         if (kinds & (1u << k)) LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.hit_index[k]), capacity * sizeof(uint32_t)));
     }
@@ -321,7 +321,7 @@ int render_pass(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint32_t spp
             for (uint32_t kind = 0; kind < kHitKinds; kind++) {
                 if (kind != 0u && !ctx->has_kind[kind]) continue;
                 // the near-specular closures (Mirror, Glass, Plastic, Metal, Mix: buckets 3..7) always run in IEEE arithmetic
-                const bool strict = ctx->strict_math || (kind >= 3u && kind <= 7u);
+                const bool strict = ctx->strict_math || (kind >= 3u && kind <= 7u) || kind == 9u;
                 const int blocks = blocks_for(ctx, n, ctx->grid_shade[strict ? 1 : 0][kind]);
                 if (strict) strict::launch_shade(kind, ctx->textured, blocks, ctx->stream, sc, pb, depth);
                 else fast::launch_shade(kind, ctx->textured, blocks, ctx->stream, sc, pb, depth);
@@ -696,11 +696,16 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
             return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: the ratio of a Mix is a constant");
         if ((s->surfaces[i].flags & LRK_SURFACE_RAW_PARAMS) && (s->surfaces[i].type < LRK_SURFACE_MIRROR || s->surfaces[i].type > LRK_SURFACE_METAL))
             return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_upload_scene: LRK_SURFACE_RAW_PARAMS is for Mirror / Glass / Plastic / Metal records");
-        if (s->surfaces[i].type == LRK_SURFACE_MIX) {
+        if (s->surfaces[i].type == LRK_SURFACE_LAYERED) {
+            if (s->integrator.type == LRK_INTEGRATOR_VOLUME_PATH)
+                return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: Layered surfaces are not supported by the volume path integrator");
+            if ((s->surfaces[i].lobes >> 16u) == 0u) return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_upload_scene: a Layered surface needs samples >= 1");
+        }
+        if (s->surfaces[i].type == LRK_SURFACE_MIX || s->surfaces[i].type == LRK_SURFACE_LAYERED) {
             for (uint32_t child : {s->surfaces[i].mix_a, s->surfaces[i].mix_b}) {
-                if (child >= s->surface_count || s->surfaces[child].type == LRK_SURFACE_MIX || s->surfaces[child].type == LRK_SURFACE_DISNEY ||
+                if (child >= s->surface_count || s->surfaces[child].type >= LRK_SURFACE_MIX || s->surfaces[child].type == LRK_SURFACE_DISNEY ||
                     (s->surfaces[child].flags & (LRK_SURFACE_HAS_TEXTURES | LRK_SURFACE_HAS_NORMAL_MAP | LRK_SURFACE_MAYBE_NON_OPAQUE)))
-                    return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: a Mix blends two constant Matte / Mirror / Glass / Plastic / Metal records");
+                    return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_upload_scene: a Mix / Layered surface combines two constant Matte / Mirror / Glass / Plastic / Metal records");
             }
         }
         for (uint32_t k = 0; k < 16u; k++)
@@ -786,7 +791,7 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
             if ((rc = upload(ctx, &a.zsobol_hash, q.zsobol_hash, 2048u))) return rc;
     }
     std::vector<uint32_t> handles(static_cast<size_t>(s->instance_count) * 4u), kinds(s->instance_count);
-    for (int k = 1; k < 9; k++) ctx->has_kind[k] = false;
+    for (int k = 1; k < 10; k++) ctx->has_kind[k] = false;
     ctx->any_non_opaque = false;
     std::vector<float> o2w(static_cast<size_t>(s->instance_count) * 12u), xform(static_cast<size_t>(s->instance_count) * 16u);
     for (uint32_t i = 0; i < s->instance_count; i++) {
@@ -800,6 +805,7 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
                 const uint32_t type = s->surfaces[surface_tag].type;
                 kind = type + 1u;// Matte 1, Disney 2, Mirror 3, Glass 4, Plastic 5, Metal 6, Mix 7
                 if (type == LRK_SURFACE_DISNEY && (s->surfaces[surface_tag].flags & LRK_SURFACE_DISNEY_TRANSMISSIVE)) kind = 8u;
+                if (type == LRK_SURFACE_LAYERED) kind = 9u;
             }
             kinds[i] = kind;
             ctx->has_kind[kind] = true;

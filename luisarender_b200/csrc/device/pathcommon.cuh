@@ -85,14 +85,28 @@ struct has_evaluate_sampled : std::false_type {};
 template<typename Closure>
 struct has_evaluate_sampled<Closure, std::void_t<decltype(std::declval<const Closure &>().evaluate_sampled(V3{}, V3{}))>> : std::true_type {};
 
+// Closures that work on world-space directions and return the sample's f / pdf themselves (Layered: its random walks are seeded
+// from the bits of the world-space vectors): evaluate_world(wi), sample_world(u_lobe, u0, u1) -> sampled_wi, sampled.
+template<typename Closure, typename = void>
+struct has_world_api : std::false_type {};
+template<typename Closure>
+struct has_world_api<Closure, std::void_t<decltype(std::declval<Closure &>().sample_world(0.f, 0.f, 0.f))>> : std::true_type {};
+
 template<typename Closure>
 __device__ __forceinline__ void shade_surface_eval(Closure &cl, const Interaction &it, const Frame &shading, V3 wo, const LightSample &ls,
                                                    float u_lobe, float ub0, float ub1, SurfEval &e_light, V3 &wi_world, V3 &f_over, float &pdf_bsdf) {
     V3 wo_local = shading.world_to_local(wo);
     cl.prepare(wo_local);
     V3 wi_sampled_local;
-    const bool run_sampled = cl.sample_direction(wo_local, u_lobe, ub0, ub1, wi_sampled_local);
-    wi_world = shading.local_to_world(wi_sampled_local);
+    bool run_sampled;
+    if constexpr (has_world_api<Closure>::value) {
+        run_sampled = cl.sample_world(u_lobe, ub0, ub1);
+        wi_world = cl.sampled_wi;
+        wi_sampled_local = shading.world_to_local(wi_world);
+    } else {
+        run_sampled = cl.sample_direction(wo_local, u_lobe, ub0, ub1, wi_sampled_local);
+        wi_world = shading.local_to_world(wi_sampled_local);
+    }
     const bool run_light = ls.eval.pdf > 0.0f;
     V3 wi_w = v3(ls.ray_d_tmax.x, ls.ray_d_tmax.y, ls.ray_d_tmax.z);
     V3 wi_l = shading.world_to_local(wi_w);
@@ -105,7 +119,14 @@ __device__ __forceinline__ void shade_surface_eval(Closure &cl, const Interactio
         e.f = v3(0.f);
         e.pdf = 0.f;
         if (run) {
-            if constexpr (has_evaluate_sampled<Closure>::value) {
+            if constexpr (has_world_api<Closure>::value) {
+                if (k == 0) {
+                    e = cl.evaluate_world(wi_w);
+                } else {
+                    e.f = cl.sampled.f;
+                    e.pdf = cl.sampled.pdf;
+                }
+            } else if constexpr (has_evaluate_sampled<Closure>::value) {
                 e = k == 0 ? cl.evaluate_local(wo_local, wi_l) : cl.evaluate_sampled(wo_local, wi_l);
             } else {
                 e = cl.evaluate_local(wo_local, wi_l);

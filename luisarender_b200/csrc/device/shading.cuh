@@ -1060,9 +1060,11 @@ struct MicrofacetFamilyClosure {
     float flip;        // PLASTIC: sign applied to the z components (plastic.cpp:143-147)
     float rr_eta_scale;// eta scale of the sampled event for Russian roulette (mega_path.cpp:133-138)
     uint32_t event;    // Surface::event_* of the sampled direction
+    bool importance;   // TransportMode::IMPORTANCE: the transmission lobe is scaled by eta^2 (scattering.cpp:340-342); Layered only
     __device__ __forceinline__ void init(const lrk_surface &s) {
         rr_eta_scale = 1.f;
         event = LRK_EVENT_REFLECT;
+        importance = false;
         flip = 1.f;
         eta = 1.5f;
         w0 = 0.f;
@@ -1134,6 +1136,7 @@ struct MicrofacetFamilyClosure {
             V3 num = (1.f - F) * c1 * D * G * dot(wi, wh) * dot(wo, wh);
             float den = cosThetaI * cosThetaO * sqr(sqrtDenom);
             f = v3(num.x / den, num.y / den, num.z / den);
+            if (importance) f = f * sqr(e);
         }
         return f;
     }
@@ -1255,11 +1258,18 @@ __device__ __forceinline__ SurfEval child_evaluate(const lrk_surface *s, V3 wo, 
     c.prepare(wo);
     return c.evaluate_local(wo, wi);
 }
-__device__ __noinline__ inline SurfEval any_evaluate_local(const lrk_surface *s, V3 wo, V3 wi) {
+// `importance`: TransportMode::IMPORTANCE, which only the Glass transmission lobe looks at (the Layered surface asks for it)
+__device__ __noinline__ inline SurfEval any_evaluate_local(const lrk_surface *s, V3 wo, V3 wi, bool importance = false) {
     switch (s->type) {
         case LRK_SURFACE_MATTE: return child_evaluate<MatteClosure>(s, wo, wi);
         case LRK_SURFACE_MIRROR: return child_evaluate<MicrofacetFamilyClosure<LRK_SURFACE_MIRROR>>(s, wo, wi);
-        case LRK_SURFACE_GLASS: return child_evaluate<MicrofacetFamilyClosure<LRK_SURFACE_GLASS>>(s, wo, wi);
+        case LRK_SURFACE_GLASS: {
+            MicrofacetFamilyClosure<LRK_SURFACE_GLASS> c;
+            c.init(*s);
+            c.importance = importance;
+            c.prepare(wo);
+            return c.evaluate_local(wo, wi);
+        }
         case LRK_SURFACE_PLASTIC: return child_evaluate<MicrofacetFamilyClosure<LRK_SURFACE_PLASTIC>>(s, wo, wi);
         default: return child_evaluate<MicrofacetFamilyClosure<LRK_SURFACE_METAL>>(s, wo, wi);
     }
@@ -1331,6 +1341,360 @@ struct MixClosure {
         if (child_valid) sa = any_evaluate_local(a, wo, wi);
         SurfEval ob = any_evaluate_local(b, wo, wi);
         return first_branch ? mix(sa, ob, ratio) : mix(ob, sa, ratio);
+    }
+};
+
+
+// ---- Layered (src/surfaces/layered.cpp; pbrt-v4's LayeredBxDF as the reference restates it): hit bucket 9 ---------------------------
+// Two interfaces - constant, non-Disney surface records `top` (mix_a) and `bottom` (mix_b) - around a homogeneous slab (thickness
+// p[0], Henyey-Greenstein g p[1], albedo p[2..4]; lobes = max_depth | samples << 16).  evaluate() is a stochastic random walk with
+// its own LCG stream seeded from the BITS of the hit position and of the world-space wi, sample() from the sample numbers and wo:
+// the closure therefore works on world-space directions (LayeredHit carries the frame, the geometric normal and the position) and
+// hands the kernel its sampled direction and f / pdf directly.  The interfaces are evaluated through the out-of-line dispatchers
+// of the Mix closure, with the reference's per-call side validation (surface.cpp:35-68).  The code below is the oracle's
+// layered_evaluate / layered_sample (bit-identical to the reference's renders, tests/test_ref_render.py::materials_layered*) with
+// the device's types; where the reference draws several numbers inside one argument list the draws go left to right (clang's
+// order, see oracle.cpp).
+struct LayeredHit {
+    Frame shading;
+    V3 ng, pg;
+};
+struct LayeredSampleEval {
+    V3 f;
+    float pdf;
+};
+struct LayeredSample {
+    LayeredSampleEval eval;
+    V3 wi;
+    uint32_t event;
+};
+__device__ __forceinline__ bool is_zero3(V3 a) { return a.x == 0.f && a.y == 0.f && a.z == 0.f; }
+__device__ __forceinline__ V3 spherical_direction(float sinTheta, float cosTheta, float phi) {// src/util/scattering.h:81-83
+    return v3(sinTheta * cosf(phi), sinTheta * sinf(phi), cosTheta);
+}
+// Surface::Closure::evaluate of an interface: the closure in the shared frame + validate_surface_sides
+__device__ __forceinline__ SurfEval layered_child_evaluate(const lrk_surface *c, const LayeredHit &it, V3 wo, V3 wi, bool importance) {
+    SurfEval e = any_evaluate_local(c, it.shading.world_to_local(wo), it.shading.world_to_local(wi), importance);
+    if (!validate_surface_sides(it.ng, it.shading.n, wo, wi)) {
+        e.f = v3(0.f);
+        e.pdf = 0.f;
+    }
+    return e;
+}
+// Surface::Closure::sample of an interface: direction from the closure's sampler, f and pdf from its evaluate at that direction
+__device__ __forceinline__ LayeredSample layered_child_sample(const lrk_surface *c, const LayeredHit &it, V3 wo, float u_lobe, float u0, float u1, bool importance) {
+    const V3 wo_local = it.shading.world_to_local(wo);
+    V3 wi_local;
+    bool transmitted;
+    const bool valid = any_sample_direction(c, wo_local, u_lobe, u0, u1, wi_local, transmitted);
+    LayeredSample out;
+    out.eval.f = v3(0.f);
+    out.eval.pdf = 0.f;
+    if (valid) {
+        const SurfEval e = any_evaluate_local(c, wo_local, wi_local, importance);
+        out.eval.f = e.f;
+        out.eval.pdf = e.pdf;
+    }
+    out.wi = it.shading.local_to_world(wi_local);
+    out.event = transmitted ? (cos_theta(wo_local) > 0.f ? LRK_EVENT_ENTER : LRK_EVENT_EXIT) : LRK_EVENT_REFLECT;
+    if (!validate_surface_sides(it.ng, it.shading.n, wo, out.wi)) {
+        out.eval.f = v3(0.f);
+        out.eval.pdf = 0.f;
+    }
+    return out;
+}
+__device__ __forceinline__ float power_heuristic(float f_pdf, float g_pdf) {// src/util/sampling.cpp:142-151 with nf = ng = 1
+    float f = 1.f * f_pdf, g = 1.f * g_pdf;
+    float ff = f * f, gg = g * g, sum = ff + gg;
+    return isinf(ff) ? 1.f : (sum == 0.f ? 0.f : ff / sum);
+}
+struct LayeredPhase {// HGPhaseFunction, layered.cpp:14-61
+    float g;
+    __device__ __forceinline__ static float hg(float cosTheta, float g) {
+        float denom = 1.f + sqr(g) + 2.f * g * cosTheta;
+        return kInvPi / 4.0f * (1.f - sqr(g)) / (denom * sqrtf(denom));
+    }
+    __device__ __forceinline__ float p(V3 wo, V3 wi) const { return hg(dot(wo, wi), g); }
+    struct Sample {
+        float p;
+        V3 wi;
+        float pdf;
+    };
+    __device__ __forceinline__ Sample sample_p(V3 wo, float ux, float uy) const {
+        float cosTheta = fabsf(g) < 1e-3f ? 1.f - 2.f * ux : -1.f / (2.f * g) * (1.f + sqr(g) - sqr((1.f - sqr(g)) / (1.f + g - 2.f * g * ux)));
+        float sinTheta = sqrtf(1.f - sqr(cosTheta));
+        float phi = 2.f * kPi * uy;
+        Frame wFrame = Frame::make(wo);
+        V3 wi = wFrame.local_to_world(spherical_direction(sinTheta, cosTheta, phi));
+        float pdf = hg(cosTheta, g);
+        return {pdf, wi, pdf};
+    }
+};
+struct LayeredCtx {
+    const lrk_surface *top, *bottom, *records;
+    float thickness, g;
+    V3 albedo;
+    uint32_t max_depth, samples;
+    __device__ __forceinline__ LayeredCtx(const lrk_surface &s, const lrk_surface *rec)
+        : top{rec + s.mix_a}, bottom{rec + s.mix_b}, records{rec}, thickness{s.p[0]}, g{s.p[1]}, albedo{v3(s.p[2], s.p[3], s.p[4])},
+          max_depth{s.lobes & 0xffffu}, samples{s.lobes >> 16u} {}
+    __device__ __forceinline__ static float Tr(float dz, V3 w) { return fabsf(dz) <= 1.17549435e-38f ? 1.f : expf(-fabsf(dz / w.z)); }
+};
+
+__device__ __noinline__ inline SurfEval layered_evaluate(const lrk_surface &s, const LayeredHit &it, V3 wo, V3 wi, const lrk_surface *records, bool mode) {// layered.cpp:251-404
+    const LayeredCtx ctx{s, records};
+    auto eval = [&](const lrk_surface *c, V3 a, V3 b, bool m) { return layered_child_evaluate(c, it, a, b, m); };
+    auto sample = [&](const lrk_surface *c, V3 a, float uc, float u0, float u1, bool m) { return layered_child_sample(c, it, a, uc, u0, u1, m); };
+    const V3 wi_local = it.shading.world_to_local(wi), wo_local = it.shading.world_to_local(wo);
+    const bool entered_top = wo_local.z > 0.f;
+    const bool exit_is_bottom = same_hemisphere(wo_local, wi_local) != entered_top;// same_hemisphere ^ entered_top
+    const lrk_surface *enter_interface = entered_top ? ctx.top : ctx.bottom;
+    const lrk_surface *exit_interface = exit_is_bottom ? ctx.bottom : ctx.top;
+    const lrk_surface *nonexit_interface = exit_is_bottom ? ctx.top : ctx.bottom;
+    const float exitZ = exit_is_bottom ? 0.f : ctx.thickness;
+    const float n_samples = static_cast<float>(ctx.samples);
+    V3 f = same_hemisphere(wi_local, wo_local) ? n_samples * eval(enter_interface, wo, wi, mode).f : v3(0.f);
+    uint32_t seed = xxhash32_uint4(__float_as_uint(it.pg.x), __float_as_uint(it.pg.y), __float_as_uint(it.pg.z),
+                                   xxhash32_uint3(__float_as_uint(wi.x), __float_as_uint(wi.y), __float_as_uint(wi.z)));
+    float pdf_sum = same_hemisphere(wi_local, wo_local)
+                        ? (entered_top ? n_samples * eval(ctx.top, wo, wi, mode).pdf : n_samples * eval(ctx.bottom, wo, wi, mode).pdf)
+                        : 0.f;
+    const LayeredPhase phase{ctx.g};
+    for (uint32_t i = 0; i < ctx.samples; i++) {
+        float uc, u0, u1;
+        uc = lcg(seed); u0 = lcg(seed); u1 = lcg(seed);
+        const LayeredSample wos = sample(enter_interface, wo, uc, u0, u1, mode);
+        if (is_zero3(wos.eval.f) || wos.eval.pdf <= 0.f) continue;
+        uc = lcg(seed); u0 = lcg(seed); u1 = lcg(seed);
+        const LayeredSample wis = sample(exit_interface, wi, uc, u0, u1, !mode);
+        const V3 wis_wi_local = it.shading.world_to_local(wis.wi);
+        if (is_zero3(wis.eval.f) || wis.eval.pdf <= 0.f) continue;
+        V3 beta = wos.eval.f / wos.eval.pdf;
+        float z = entered_top ? ctx.thickness : 0.f;
+        V3 w = wos.wi;
+        V3 w_local = it.shading.world_to_local(w);
+        for (uint32_t depth = 0; depth < ctx.max_depth; depth++) {
+            if (depth > 3u && max3(beta) < 0.25f) {
+                float q = fmaxf(0.f, 1.f - max3(beta));
+                if (lcg(seed) < q) break;
+                beta = beta / (1.f - q);
+            }
+            if (is_zero3(ctx.albedo)) {
+                z = z == ctx.thickness ? 0.f : ctx.thickness;
+                beta = beta * LayeredCtx::Tr(ctx.thickness, w_local);
+            } else {
+                const float sigma_t = 1.f;
+                float dz = -logf(1.f - lcg(seed)) / (sigma_t / fabsf(w_local.z));
+                float zp = w_local.z > 0.f ? z + dz : z - dz;
+                if (z == zp) continue;
+                if (zp > 0.f && zp < ctx.thickness) {
+                    float wt = power_heuristic(wis.eval.pdf, eval(nonexit_interface, -w, -wis.wi, mode).pdf);
+                    f = f + beta * ctx.albedo * phase.p(-w_local, -wis_wi_local) * wt * LayeredCtx::Tr(zp - exitZ, wis_wi_local) * wis.eval.f / wis.eval.pdf;
+                    float ux, uy;
+                    ux = lcg(seed); uy = lcg(seed);
+                    LayeredPhase::Sample ps = phase.sample_p(-w_local, ux, uy);
+                    if (ps.pdf <= 0.f || ps.wi.z == 0.f) continue;
+                    beta = beta * (ctx.albedo * ps.p / ps.pdf);
+                    w_local = ps.wi;
+                    w = it.shading.local_to_world(w_local);
+                    z = zp;
+                    if ((z < exitZ && w_local.z > 0.f) || (z > exitZ && w_local.z < 0.f)) {
+                        V3 fExit = eval(exit_interface, -w, wi, mode).f;
+                        if (!is_zero3(fExit)) {
+                            float exitPDF = eval(exit_interface, -w, wi, mode).pdf;
+                            float wt2 = power_heuristic(ps.pdf, exitPDF);
+                            f = f + beta * LayeredCtx::Tr(zp - exitZ, w_local) * fExit * wt2;
+                        }
+                    }
+                    continue;
+                }
+                z = clampf(zp, 0.f, ctx.thickness);
+            }
+            if (z == exitZ) {
+                float uc2 = lcg(seed), ua, ub;
+                ua = lcg(seed); ub = lcg(seed);
+                LayeredSample bs = sample(exit_interface, -w, uc2, ua, ub, mode);
+                if (is_zero3(bs.eval.f) || bs.eval.pdf <= 0.f) break;
+                beta = beta * (bs.eval.f / bs.eval.pdf);
+                w = bs.wi;
+                w_local = it.shading.world_to_local(w);
+            } else {
+                SurfEval wns = eval(nonexit_interface, -w, -wis.wi, mode);
+                float wt = power_heuristic(wis.eval.pdf, wns.pdf);
+                f = f + beta * wns.f * wt * LayeredCtx::Tr(ctx.thickness, wis_wi_local) * wis.eval.f / wis.eval.pdf;
+                float uc2 = lcg(seed), ua, ub;
+                ua = lcg(seed); ub = lcg(seed);
+                LayeredSample bs = sample(nonexit_interface, -w, uc2, ua, ub, mode);
+                if (is_zero3(bs.eval.f) || bs.eval.pdf <= 0.f) break;
+                beta = beta * (bs.eval.f / bs.eval.pdf);
+                w = bs.wi;
+                w_local = it.shading.world_to_local(w);
+                SurfEval wes = eval(exit_interface, -w, wi, mode);
+                V3 fExit = wes.f;
+                if (!is_zero3(fExit)) {
+                    float wt2 = power_heuristic(bs.eval.pdf, wes.pdf);
+                    f = f + beta * LayeredCtx::Tr(ctx.thickness, it.shading.world_to_local(bs.wi)) * fExit * wt2;
+                }
+            }
+        }
+    }
+    for (uint32_t k = 0; k < ctx.samples; k++) {// pdf: :361-400
+        if (same_hemisphere(wo_local, wi_local)) {
+            const lrk_surface *r_interface = entered_top ? ctx.bottom : ctx.top;
+            const lrk_surface *t_interface = entered_top ? ctx.top : ctx.bottom;
+            float uc, u0, u1;
+            uc = lcg(seed); u0 = lcg(seed); u1 = lcg(seed);
+            LayeredSample wos = sample(t_interface, wo, uc, u0, u1, mode);
+            uc = lcg(seed); u0 = lcg(seed); u1 = lcg(seed);
+            LayeredSample wis = sample(t_interface, wi, uc, u0, u1, !mode);
+            if (!is_zero3(wos.eval.f) && wos.eval.pdf > 0.f && !is_zero3(wis.eval.f) && wis.eval.pdf > 0.f) {
+                uc = lcg(seed); u0 = lcg(seed); u1 = lcg(seed);
+                LayeredSample rs = sample(r_interface, -wos.wi, uc, u0, u1, mode);
+                if (!is_zero3(rs.eval.f) && rs.eval.pdf > 0.f) {
+                    float r_pdf = eval(r_interface, -wos.wi, -wis.wi, mode).pdf;
+                    float wt = power_heuristic(wis.eval.pdf, r_pdf);
+                    pdf_sum += wt * r_pdf;
+                    float t_pdf = eval(t_interface, -rs.wi, wi, mode).pdf;
+                    wt = power_heuristic(rs.eval.pdf, t_pdf);
+                    pdf_sum += wt * t_pdf;
+                }
+            }
+        } else {
+            const lrk_surface *ti_interface = entered_top ? ctx.bottom : ctx.top;
+            const lrk_surface *to_interface = entered_top ? ctx.top : ctx.bottom;
+            float uc, u0, u1;
+            uc = lcg(seed); u0 = lcg(seed); u1 = lcg(seed);
+            LayeredSample wos = sample(to_interface, wo, uc, u0, u1, mode);
+            uc = lcg(seed); u0 = lcg(seed); u1 = lcg(seed);
+            LayeredSample wis = sample(ti_interface, wi, uc, u0, u1, !mode);
+            if (is_zero3(wos.eval.f) || wos.eval.pdf <= 0.f || is_zero3(wis.eval.f) || wis.eval.pdf <= 0.f) continue;
+            pdf_sum += .5f * (eval(to_interface, wo, -wis.wi, mode).pdf + eval(ti_interface, -wos.wi, wi, mode).pdf);
+        }
+    }
+    SurfEval e;
+    e.f = f / n_samples;
+    e.pdf = lerp(1.f / (4.f * kPi), pdf_sum / n_samples, 0.9f);
+    return e;
+}
+
+__device__ __noinline__ inline LayeredSample layered_sample(const lrk_surface &s, const LayeredHit &it, V3 wo, float u_lobe, float u0, float u1, const lrk_surface *records, bool mode) {// layered.cpp:405-472
+    const LayeredCtx ctx{s, records};
+    auto sample = [&](const lrk_surface *c, V3 a, float uc, float ua, float ub, bool m) { return layered_child_sample(c, it, a, uc, ua, ub, m); };
+    const V3 wo_local = it.shading.world_to_local(wo);
+    const bool entered_top = wo_local.z > 0.f;
+    LayeredSample bs = sample(entered_top ? ctx.top : ctx.bottom, wo, u_lobe, u0, u1, mode);
+    LayeredSample out;// Surface::Sample::zero: f = 0, pdf = 0, wi = (0, 0, 1), event_reflect
+    out.eval.f = v3(0.f);
+    out.eval.pdf = 0.f;
+    out.wi = v3(0.f, 0.f, 1.f);
+    out.event = LRK_EVENT_REFLECT;
+    if (!is_zero3(bs.eval.f) && bs.eval.pdf != 0.f) {
+        V3 wi_local = it.shading.world_to_local(bs.wi);
+        if (same_hemisphere(wi_local, wo_local)) {
+            out = bs;
+        } else {
+            V3 w = bs.wi;
+            V3 w_local = it.shading.world_to_local(bs.wi);
+            uint32_t seed = xxhash32_uint4(__float_as_uint(u0), __float_as_uint(u1), __float_as_uint(u_lobe), xxhash32_uint3(__float_as_uint(wo.x), __float_as_uint(wo.y), __float_as_uint(wo.z)));
+            V3 f = bs.eval.f;
+            float pdf = bs.eval.pdf;
+            float z = entered_top ? ctx.thickness : 0.f;
+            const LayeredPhase phase{ctx.g};
+            for (uint32_t depth = 0; depth < ctx.max_depth; depth++) {
+                float rr_beta = max3(f) / pdf;
+                if (depth > 3u && rr_beta < 0.25f) {
+                    float q = fmaxf(0.f, 1.f - rr_beta);
+                    if (lcg(seed) < q) break;
+                    pdf *= 1.f - q;
+                }
+                if (w_local.z == 0.f) break;
+                if (!is_zero3(ctx.albedo)) {
+                    const float sigma_t = 1.f;
+                    float dz = -logf(1.f - lcg(seed)) / (sigma_t / fabsf(w_local.z));
+                    float zp = w_local.z > 0.f ? z + dz : z - dz;
+                    if (z == zp) break;
+                    if (0.f < zp && zp < ctx.thickness) {
+                        float ux, uy;
+                        ux = lcg(seed); uy = lcg(seed);
+                        LayeredPhase::Sample ps = phase.sample_p(-w_local, ux, uy);
+                        if (ps.pdf <= 0.f) break;
+                        f = f * (ctx.albedo * ps.p);
+                        pdf *= ps.pdf;
+                        w = ps.wi;// sic: the phase function's LOCAL direction is taken as the world direction (:449-450)
+                        w_local = it.shading.world_to_local(w);
+                        z = zp;
+                        continue;
+                    }
+                    z = clampf(zp, 0.f, ctx.thickness);
+                } else {
+                    z = z == ctx.thickness ? 0.f : ctx.thickness;
+                    f = f * LayeredCtx::Tr(ctx.thickness, w_local);
+                }
+                const lrk_surface *interface = z == 0.f ? ctx.bottom : ctx.top;
+                float uc = lcg(seed), ua, ub;
+                ua = lcg(seed); ub = lcg(seed);
+                LayeredSample is = sample(interface, -w, uc, ua, ub, mode);
+                if (is_zero3(is.eval.f) || is.eval.pdf <= 0.f) break;
+                f = f * is.eval.f;
+                pdf *= is.eval.pdf;
+                w = is.wi;
+                w_local = it.shading.world_to_local(w);
+                if ((is.event & 3u) != 0u) {// Surface::event_transmit = enter | exit
+                    out.eval.f = f;
+                    out.eval.pdf = pdf;
+                    out.wi = w;
+                    out.event = same_hemisphere(w_local, wo_local) ? LRK_EVENT_REFLECT : (w_local.z > 0.f ? LRK_EVENT_EXIT : LRK_EVENT_ENTER);
+                    break;
+                }
+            }
+        }
+    }
+    return out;
+}
+
+
+struct LayeredClosure {
+    const lrk_surface *node, *records;
+    LayeredHit hit;
+    V3 wo_world, sampled_wi;
+    LayeredSampleEval sampled;
+    float rr_eta_scale;
+    uint32_t event;
+    __device__ __forceinline__ void init(const lrk_surface &s, const lrk_surface *rec, const Interaction &it, const Frame &shading, V3 wo) {
+        node = &s;
+        records = rec;
+        hit.shading = shading;
+        hit.ng = it.ng;
+        hit.pg = it.pg;
+        wo_world = wo;
+        rr_eta_scale = 1.f;
+        event = LRK_EVENT_REFLECT;
+    }
+    __device__ __forceinline__ void prepare(V3) {}
+    // evaluate(wo, wi) for a WORLD-space wi (the light sample's direction)
+    __device__ __forceinline__ SurfEval evaluate_world(V3 wi) const {
+        SurfEval e = layered_evaluate(*node, hit, wo_world, wi, records, false);
+        if (!validate_surface_sides(hit.ng, hit.shading.n, wo_world, wi)) {
+            e.f = v3(0.f);
+            e.pdf = 0.f;
+        }
+        return e;
+    }
+    // sample(wo, u_lobe, u): the walk's direction, f and pdf; eta() = the bottom interface's (layered.cpp:248)
+    __device__ __forceinline__ bool sample_world(float u_lobe, float u0, float u1) {
+        const LayeredSample s = layered_sample(*node, hit, wo_world, u_lobe, u0, u1, records, false);
+        sampled = s.eval;
+        sampled_wi = s.wi;
+        event = s.event;
+        if (!validate_surface_sides(hit.ng, hit.shading.n, wo_world, s.wi)) {
+            sampled.f = v3(0.f);
+            sampled.pdf = 0.f;
+        }
+        const lrk_surface *bottom = records + node->mix_b;
+        const float eta = bottom->type == LRK_SURFACE_GLASS ? bottom->p[6] : 0.f;
+        rr_eta_scale = 1.f;
+        if (eta != 0.f) rr_eta_scale = event == LRK_EVENT_ENTER ? sqr(eta) : event == LRK_EVENT_EXIT ? sqr(1.f / eta) : 1.f;
+        return true;
     }
 };
 

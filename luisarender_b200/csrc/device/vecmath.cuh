@@ -24,6 +24,7 @@ __device__ __forceinline__ V3 operator*(V3 a, float s) { return {a.x * s, a.y * 
 __device__ __forceinline__ V3 operator*(float s, V3 a) { return {s * a.x, s * a.y, s * a.z}; }
 __device__ __forceinline__ V3 operator+(V3 a, float s) { return {a.x + s, a.y + s, a.z + s}; }
 __device__ __forceinline__ V3 operator-(V3 a) { return {-a.x, -a.y, -a.z}; }
+__device__ __forceinline__ V3 operator/(V3 a, float s) { return {a.x / s, a.y / s, a.z / s}; }// true divisions, as the oracle's
 __device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 // A product that the compiler must not fuse into a neighbouring add (shade.cu is compiled with FMA contraction): where a
 // difference of two products is EXACTLY zero in IEEE arithmetic - every cross product of axis-aligned edges is - a fused
@@ -96,6 +97,16 @@ __device__ __forceinline__ uint32_t xxhash32_uint4(uint32_t px, uint32_t py, uin
     return h32 ^ (h32 >> 16u);
 }
 
+__device__ __forceinline__ uint32_t xxhash32_uint3(uint32_t px, uint32_t py, uint32_t pz) {// src/util/rng.cpp:38-51
+    constexpr uint32_t PRIME32_2 = 2246822519u, PRIME32_3 = 3266489917u, PRIME32_4 = 668265263u, PRIME32_5 = 374761393u;
+    uint32_t h32 = pz + PRIME32_5 + px * PRIME32_3;
+    h32 = PRIME32_4 * ((h32 << 17u) | (h32 >> 15u));
+    h32 += py * PRIME32_3;
+    h32 = PRIME32_4 * ((h32 << 17u) | (h32 >> 15u));
+    h32 = PRIME32_2 * (h32 ^ (h32 >> 15u));
+    h32 = PRIME32_3 * (h32 ^ (h32 >> 13u));
+    return h32 ^ (h32 >> 16u);
+}
 __device__ __forceinline__ float lcg(uint32_t &state) {
     state = 1664525u * state + 1013904223u;
     return fminf(kOneMinusEpsilon, static_cast<float>(state) * 0x1p-32f);

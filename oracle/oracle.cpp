@@ -3067,6 +3067,24 @@ struct LambertBxDF {
 extern "C" void oracle_set_trace_brute_force(int enabled) { g_trace_brute_force.store(enabled != 0); }
 extern "C" void oracle_set_hg_args_right_to_left(int enabled) { g_hg_args_right_to_left.store(enabled != 0); }
 
+// the Layered surface on the records of a flattened scene: same row layout as tests/host_device/closures_host.cpp device_layered_unit
+extern "C" int oracle_layered_unit(const lrk_surface *records, uint32_t index, const float *in, float *out, int count) {
+    for (int i = 0; i < count; i++, in += 16, out += 12) {
+        Interaction it{};
+        it.pg = v3(in[0], in[1], in[2]);
+        it.ng = normalize(v3(in[3], in[4], in[5]));
+        it.shading = Frame::make(it.ng);
+        const V3 wo = normalize(v3(in[6], in[7], in[8])), wi = normalize(v3(in[9], in[10], in[11]));
+        const SurfEval e = surface_evaluate(records[index], it, wo, wi, records);
+        const SurfSample s = surface_sample(records[index], it, wo, in[12], in[13], in[14], records);
+        out[0] = e.f.x; out[1] = e.f.y; out[2] = e.f.z; out[3] = e.pdf;
+        out[4] = s.wi.x; out[5] = s.wi.y; out[6] = s.wi.z;
+        out[7] = s.eval.f.x; out[8] = s.eval.f.y; out[9] = s.eval.f.z; out[10] = s.eval.pdf;
+        out[11] = static_cast<float>(s.event);
+    }
+    return 0;
+}
+
 extern "C" int oracle_unit(const char *name_c, const uint32_t *in, uint32_t *out, int count, const void *buffer, uint64_t buffer_count) {
     const std::string name{name_c};
     Words w{in, out};

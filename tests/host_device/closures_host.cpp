@@ -105,3 +105,25 @@ extern "C" int device_closure_unit(const char *name_c, const uint32_t *in, uint3
     }
     return 0;
 }
+
+// The Layered closure (hit bucket 9) against the oracle's restatement, on the records of a flattened scene.
+// rows of 16 floats in: pg(3), shading normal n(3) (= ng), wo(3), wi(3), u_lobe, u0, u1, unused;
+// rows of 12 floats out: evaluate f(3), pdf, sample wi(3), sample f(3), sample pdf, event
+extern "C" int device_layered_unit(const lrk_surface *records, uint32_t index, const float *in, float *out, int count) {
+    for (int i = 0; i < count; i++, in += 16, out += 12) {
+        Interaction it{};
+        it.pg = v3(in[0], in[1], in[2]);
+        it.ng = normalize(v3(in[3], in[4], in[5]));
+        const Frame fr = Frame::make(it.ng);
+        const V3 wo = normalize(v3(in[6], in[7], in[8])), wi = normalize(v3(in[9], in[10], in[11]));
+        LayeredClosure cl;
+        cl.init(records[index], records, it, fr, wo);
+        const SurfEval e = cl.evaluate_world(wi);
+        cl.sample_world(in[12], in[13], in[14]);
+        out[0] = e.f.x; out[1] = e.f.y; out[2] = e.f.z; out[3] = e.pdf;
+        out[4] = cl.sampled_wi.x; out[5] = cl.sampled_wi.y; out[6] = cl.sampled_wi.z;
+        out[7] = cl.sampled.f.x; out[8] = cl.sampled.f.y; out[9] = cl.sampled.f.z; out[10] = cl.sampled.pdf;
+        out[11] = static_cast<float>(cl.event);
+    }
+    return 0;
+}

@@ -63,3 +63,33 @@ def test_device_closure_matches_reference_closure(lib, name):
     bad = ~close.all(axis=1)
     assert not bad.any(), (f"{name}: {int(bad.sum())} of {len(bad)} cases differ; first: in={inp[np.flatnonzero(bad)[0]].view(np.float32)} "
                            f"device={got[np.flatnonzero(bad)[0]].view(np.float32)} reference={want[np.flatnonzero(bad)[0]].view(np.float32)}")
+
+
+def test_device_layered_closure_matches_the_oracle(lib):
+    """The Layered closure (stochastic random walks between two interfaces, seeded from the bits of the hit position and the
+    directions) as the device code evaluates and samples it, against the oracle's restatement - which is bit-identical to the
+    reference's renders (tests/test_ref_render.py::materials_layered*).  Three Layered nodes (scattering slab, attenuating slab,
+    defaults), 4000 random (position, normal, wo, wi, u) rows each; same libm on both sides => identical bits."""
+    from luisarender_b200 import scenes
+    from luisarender_b200.api import Scene
+    from oracle import binding as O
+
+    d = Scene.from_source(scenes.layered_box(resolution=(16, 12), spp=1), REPO).desc()
+    layered = [i for i in range(d.surface_count) if d.surfaces[i].type == 7]
+    assert len(layered) == 3
+    rng = np.random.default_rng(11)
+    rows = np.zeros((4000, 16), np.float32)
+    rows[:, 0:3] = rng.uniform(-2, 2, (4000, 3))
+    rows[:, 3:12] = rng.normal(size=(4000, 9))
+    rows[:, 12:15] = rng.uniform(0, 1, (4000, 3))
+    lib.device_layered_unit.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
+    olib = O.lib()
+    olib.oracle_layered_unit.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
+    for index in layered:
+        got, want = np.zeros((4000, 12), np.float32), np.zeros((4000, 12), np.float32)
+        assert lib.device_layered_unit(d.surfaces, index, rows.ctypes.data, got.ctypes.data, 4000) == 0
+        assert olib.oracle_layered_unit(d.surfaces, index, rows.ctypes.data, want.ctypes.data, 4000) == 0
+        assert (want[:, 3] > 0).mean() > 0.5 and (want[:, 10] > 0).mean() > 0.3  # the cases exercise both calls
+        same = (got.view(np.uint32) == want.view(np.uint32)) | (np.isnan(got) & np.isnan(want))
+        bad = ~same.all(axis=1)
+        assert not bad.any(), f"surface {index}: {int(bad.sum())} of 4000 rows differ; first: device {got[np.flatnonzero(bad)[0]]} oracle {want[np.flatnonzero(bad)[0]]}"

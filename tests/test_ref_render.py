@@ -140,7 +140,7 @@ def test_cuda_film_matches_the_reference_render(golden, name, gpu_renderer):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mix", [False, True])
+@pytest.mark.parametrize("mix", [False, True, "layered"])
 def test_cuda_materials_first_bounce_matches_oracle(gpu_renderer, mix):
     """Depth 2 = camera hit + next-event estimation + one sampled bounce that can only ADD an emitter hit: every pixel is a
     smooth function of the Mirror / Glass / Plastic / Metal closures' evaluate() and sample() at the first hit, with no
@@ -148,7 +148,8 @@ def test_cuda_materials_first_bounce_matches_oracle(gpu_renderer, mix):
     this scene (test_oracle_film_is_bit_identical_to_the_reference_render[materials_*])."""
     from luisarender_b200 import scenes
 
-    source = scenes.materials_box(resolution=(48, 36), spp=16, depth=2, mix=mix)
+    source = (scenes.layered_box(resolution=(48, 36), spp=16, depth=2) if mix == "layered"
+              else scenes.materials_box(resolution=(48, 36), spp=16, depth=2, mix=mix))
     desc = Scene.from_source(source, REPO).desc()
     raw, counters = O.render(desc, 0, 16)
     want = O.convert_film(desc, raw)[..., :3]
