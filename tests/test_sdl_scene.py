@@ -65,8 +65,8 @@ def test_text_scene_with_macros_and_defaults():
 def test_undefined_macro_and_unknown_plugin_are_hard_errors():
     with pytest.raises(RuntimeError, match="Undefined macro"):
         Scene.from_source(MINIMAL)
-    bad = MINIMAL.replace("#SPP", "1").replace("Matte {", "Layered {")
-    with pytest.raises(RuntimeError, match="luisa-render-surface-layered"):
+    bad = MINIMAL.replace("#SPP", "1").replace("Matte {", "Hair {")  # a surface implementation this library does not have
+    with pytest.raises(RuntimeError, match="luisa-render-surface-hair"):
         Scene.from_source(bad)
     with pytest.raises(RuntimeError, match="Redefinition of property"):
         Scene.from_source(MINIMAL.replace("#SPP", "1").replace("fov { 40 }", "fov { 40 } fov { 41 }"))
