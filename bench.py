@@ -58,7 +58,8 @@ def workload_config(n_gpus: int) -> dict:
                     f"{WIDTH}x{HEIGHT}, depth 10, rr_depth 0; step = {SPP_PER_STEP} spp of the 1024-spp render",
         "samples_per_step": WIDTH * HEIGHT * SPP_PER_STEP,
         "spp_per_step": SPP_PER_STEP,
-        "sharding": "single GPU" if n_gpus == 1 else f"interleaved 32x32 pixel tiles over {n_gpus} GPUs + one NCCL film reduce",
+        "sharding": "single GPU" if n_gpus == 1 else (f"32x32 pixel tiles over {n_gpus} GPUs, assigned by probed cost (lrk_balance_shards: a 1-spp probe of the "
+                                                              f"frame on every rank before the timed region, then LPT) + one NCCL film reduce (lrk_reduce_film)"),
         "l2_policy": "per-pass path state (~25 GB for the 132.7 M paths of a 64-spp pass, four passes per step on one GPU) is far larger "
                      "than the 126 MB L2; no explicit flush",
         "host_buffers": "e2e: the host library's scene arrays and a reused film buffer, page-locked once by lrk (option pin_host_buffers)",
@@ -280,7 +281,10 @@ def other_configs(r, rank: int, world: int, dist, barrier) -> dict | None:
         d = sc.desc()
         w, h = d.camera.resolution[0], d.camera.resolution[1]
         r.upload(d)
-        r.set_shard(rank if shard else 0, world if shard else 1, D.TILE_SIZE)
+        if shard and world > 1:
+            r.balance_shards(rank, world, D.TILE_SIZE, 1)
+        else:
+            r.set_shard(0, 1, D.TILE_SIZE)
         r.render(0, min(spp, 4))  # warm-up: allocations
         r.clear()
         barrier()
@@ -337,7 +341,16 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     desc = scene.desc()
     r = Renderer(device_index=local_rank)
     r.upload(desc)
-    r.set_shard(rank, world, D.TILE_SIZE)
+
+    def shard():
+        # N > 1: tiles assigned by probed cost (lrk_balance_shards: one sample per pixel of the whole frame on every rank, then
+        # longest-processing-time-first; deterministic, no communication) instead of the static hashed map
+        if world > 1:
+            r.balance_shards(rank, world, D.TILE_SIZE, 1)
+        else:
+            r.set_shard(rank, world, D.TILE_SIZE)
+
+    shard()
     if world > 1:
         D.init_film_comm(r, rank, world)  # the library's own NCCL communicator: lrk_reduce_film is the path's one collective
     K, W, S = args.steps, args.warmup, SPP_PER_STEP
@@ -402,7 +415,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             same = bool(np.array_equal(reduced, single))
             film_check = {"bit_identical": same, "max_abs_diff": float(np.abs(reduced - single).max()), "spp": K * S,
                           "what": f"NCCL-reduced film of {world} ranks vs rank 0 alone rendering the whole frame, same sample indices"}
-            r.set_shard(rank, world, D.TILE_SIZE)
+            shard()
         barrier()
 
     # ---- roofline of the dominant kernel (closest-hit traversal), rank 0's launches ------------------------
@@ -456,7 +469,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     r.set_option("pin_host_buffers", 1)
     img = np.empty((HEIGHT, WIDTH, 4), np.float32)
     r.upload(desc)  # untimed: first sight of the buffers (cudaHostRegister), as a frame loop pays once
-    r.set_shard(rank, world, D.TILE_SIZE)
+    shard()          # untimed: a frame loop probes once and keeps the table over the per-frame uploads (same film size)
     if rank == 0:
         r.film(out=img)
     barrier()
@@ -485,7 +498,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if not args.no_configs:
         r.set_option("strict_math", 1)
         r.upload(desc)
-        r.set_shard(rank, world, D.TILE_SIZE)
+        shard()
         r.render(0, S)  # warm-up
         r.clear()
         barrier()

@@ -498,6 +498,18 @@ static inline uint32_t lrk_tile_owner(uint32_t tile_id, uint32_t world) {
 }
 int lrk_set_shard(lrk_ctx *ctx, uint32_t rank, uint32_t world, uint32_t tile_size);
 
+/* Cost-balanced sharding.  The static map above balances the tile COUNT; the cost of a tile follows the image (sky vs. geometry),
+ * and at 8 ranks the slowest rank of the benchmark frame was 9 % over the mean.  lrk_balance_shards renders `probe_spp` samples of
+ * the WHOLE frame on this context (every rank does the same, independently: the probe is deterministic, so all ranks arrive at the
+ * same table without talking to each other), counts the rays traced for the pixels of every tile, assigns the tiles to ranks with
+ * lrk_assign_tiles, and makes this context render rank `rank`'s tiles from then on (until the next lrk_set_shard /
+ * lrk_upload_scene); the film is cleared.  The probe costs probe_spp / spp of a frame; the reduced film is bit-identical to a
+ * single-GPU render whatever the assignment.
+ * lrk_assign_tiles (host only, no GPU): longest-processing-time-first - tiles in order of decreasing cost (ties: lower tile id)
+ * each go to the rank with the smallest load so far (ties: lower rank); owner[t] = rank of tile t. */
+int lrk_balance_shards(lrk_ctx *ctx, uint32_t rank, uint32_t world, uint32_t tile_size, uint32_t probe_spp);
+int lrk_assign_tiles(const uint32_t *cost, uint32_t tile_count, uint32_t world, uint32_t *owner);
+
 /* The film reduce of the multi-GPU path (the reference is single-device, its film is src/films/color.cpp:107-130).
  * One process per GPU.  One rank calls lrk_comm_unique_id and hands the LRK_COMM_ID_BYTES to the others by any means (a file,
  * MPI, torch.distributed); every rank then calls lrk_comm_init (collective) once, renders its tiles (lrk_set_shard), and calls

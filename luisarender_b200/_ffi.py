@@ -153,7 +153,7 @@ LRK_SYMBOLS = [
     "lrk_abi_version", "lrk_create", "lrk_destroy", "lrk_last_error", "lrk_upload_scene", "lrk_set_shard",
     "lrk_set_option", "lrk_film_clear", "lrk_render", "lrk_download_film", "lrk_download_film_raw",
     "lrk_film_device_ptr", "lrk_film_normalize_to_host", "lrk_trace", "lrk_trace_device", "lrk_get_stats",
-    "lrk_stream", "lrk_comm_unique_id", "lrk_comm_init", "lrk_reduce_film",
+    "lrk_stream", "lrk_comm_unique_id", "lrk_comm_init", "lrk_reduce_film", "lrk_balance_shards", "lrk_assign_tiles",
 ]
 LRH_SYMBOLS = [
     "lrh_last_error", "lrh_scene_load", "lrh_scene_load_source", "lrh_scene_destroy", "lrh_scene_get_info",
@@ -221,5 +221,7 @@ def device_lib() -> C.CDLL:
         lib.lrk_comm_unique_id.argtypes = [C.c_void_p]
         lib.lrk_comm_init.argtypes = [C.c_void_p, C.c_void_p, u32, u32]
         lib.lrk_reduce_film.argtypes = [C.c_void_p, u32]
+        lib.lrk_balance_shards.argtypes = [C.c_void_p, u32, u32, u32, u32]
+        lib.lrk_assign_tiles.argtypes = [C.c_void_p, u32, u32, C.c_void_p]
         lib._lrk_typed = True
     return lib

@@ -131,6 +131,10 @@ class Renderer:
         """lrk_reduce_film (collective): rank `root`'s raw film becomes the sum over ranks."""
         self._check(self._lib.lrk_reduce_film(self._ctx, root), "lrk_reduce_film")
 
+    def balance_shards(self, rank: int, world: int, tile_size: int = 32, probe_spp: int = 1):
+        """lrk_balance_shards: probe the frame's cost per tile and take rank `rank`'s share of a cost-balanced tile assignment."""
+        self._check(self._lib.lrk_balance_shards(self._ctx, rank, world, tile_size, probe_spp), "lrk_balance_shards")
+
     def set_option(self, name: str, value: int):
         self._check(self._lib.lrk_set_option(self._ctx, name.encode(), value), f"lrk_set_option({name})")
 

@@ -90,6 +90,12 @@ __global__ void __launch_bounds__(kBlock) classify_hits_kernel(DeviceScene sc, P
         if (i < n) {
             const uint32_t inst = pb.hit[i].x;
             if (inst != ~0u) kind = __ldg(sc.inst_kind + inst);
+            if (pb.tile_cost != nullptr) {// lrk_balance_shards' probe: one unit per traced ray, two more per hit that gets shaded
+                const uint32_t id = pb.id_rng[depth & 1u][i].x;
+                const uint32_t pixel = __ldg(pb.pass_pixel_list + pb.pass_pixel_offset + id % pb.pass_npix);
+                const uint32_t tile = ((pixel >> 16u) / pb.tile_cost_size) * pb.tile_cost_tiles_x + (pixel & 0xffffu) / pb.tile_cost_size;
+                atomicAdd(pb.tile_cost + tile, inst != ~0u ? 3u : 1u);
+            }
         }
         uint32_t masks[kHitKinds];
 #pragma unroll

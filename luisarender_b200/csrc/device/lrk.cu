@@ -47,6 +47,7 @@ struct lrk_ctx {
     uint32_t *d_pixel_list{nullptr};
     uint32_t npix_owned{0};
     uint32_t pixel_list_key[5]{0, 0, 0, 0, 0};// width, height, rank, world, tile size of the cached list
+    std::vector<uint32_t> tile_owner;// lrk_balance_shards: owner of every tile (empty: the static lrk_tile_owner map)
     std::unordered_map<void **, size_t> array_bytes;// capacity of each scene array allocation
     bool textured{false};// some surface has image-textured parameters or a normal map: the shade kernels' TEXTURED variants run
     bool any_non_opaque{false};// some instance carries LRK_SHAPE_MAYBE_NON_OPAQUE: traversal runs its alpha-testing variants
@@ -214,7 +215,7 @@ int alloc_paths(lrk_ctx *ctx, uint64_t capacity) {
 int build_pixel_list(lrk_ctx *ctx) {
     const uint32_t W = ctx->scene.width, H = ctx->scene.height, ts = ctx->tile_size;
     const uint32_t key[5]{W, H, ctx->rank, ctx->world, ts};
-    if (ctx->d_pixel_list != nullptr && std::memcmp(key, ctx->pixel_list_key, sizeof(key)) == 0) return LRK_OK;
+    if (ctx->d_pixel_list != nullptr && ctx->tile_owner.empty() && std::memcmp(key, ctx->pixel_list_key, sizeof(key)) == 0) return LRK_OK;
     std::memcpy(ctx->pixel_list_key, key, sizeof(key));
     const uint32_t tiles_x = (W + ts - 1u) / ts, tiles_y = (H + ts - 1u) / ts;
     std::vector<uint32_t> list;
@@ -222,7 +223,8 @@ int build_pixel_list(lrk_ctx *ctx) {
     for (uint32_t ty = 0; ty < tiles_y; ty++) {
         for (uint32_t tx = 0; tx < tiles_x; tx++) {
             uint32_t tile_id = ty * tiles_x + tx;
-            if (lrk_tile_owner(tile_id, ctx->world) != ctx->rank) continue;
+            const uint32_t owner = ctx->tile_owner.empty() ? lrk_tile_owner(tile_id, ctx->world) : ctx->tile_owner[tile_id];
+            if (owner != ctx->rank) continue;
             uint32_t x0 = tx * ts, y0 = ty * ts;
             uint32_t x1 = std::min(W, x0 + ts), y1 = std::min(H, y0 + ts);
             for (uint32_t by = y0; by < y1; by += 4u)
@@ -928,12 +930,72 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
         LRK_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     ctx->has_scene = true;
+    // a balanced assignment stays a valid partition for any scene of the same film size (a frame loop re-uploads per frame and
+    // keeps the table of the frame it probed); another film size drops it
+    {
+        const uint32_t ts = ctx->tile_size, tiles = ((sc.width + ts - 1u) / ts) * ((sc.height + ts - 1u) / ts);
+        if (ctx->tile_owner.size() != tiles) ctx->tile_owner.clear();
+    }
+    if ((rc = build_pixel_list(ctx))) return rc;
+    return lrk_film_clear(ctx);
+}
+
+int lrk_assign_tiles(const uint32_t *cost, uint32_t tile_count, uint32_t world, uint32_t *owner) {
+    if (!cost || !owner || world == 0u) return LRK_ERR_INVALID_ARGUMENT;
+    std::vector<uint32_t> order(tile_count);
+    for (uint32_t t = 0; t < tile_count; t++) order[t] = t;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return cost[a] > cost[b]; });// ties keep the lower tile id first
+    std::vector<uint64_t> load(world, 0u);
+    for (uint32_t t : order) {
+        uint32_t best = 0u;
+        for (uint32_t r = 1u; r < world; r++) if (load[r] < load[best]) best = r;
+        owner[t] = best;
+        load[best] += cost[t];
+    }
+    return LRK_OK;
+}
+
+int lrk_balance_shards(lrk_ctx *ctx, uint32_t rank, uint32_t world, uint32_t tile_size, uint32_t probe_spp) {
+    if (!ctx || world == 0u || rank >= world || tile_size == 0u || probe_spp == 0u)
+        return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_balance_shards: invalid arguments");
+    if (!ctx->has_scene) return fail(ctx, LRK_ERR_NO_SCENE, "lrk_balance_shards: no scene");
+    if (ctx->volume) return fail(ctx, LRK_ERR_UNSUPPORTED, "lrk_balance_shards: the cost probe runs the surface integrator's kernels");
+    LRK_CUDA(cudaSetDevice(ctx->device));
+    // the probe: the whole frame on this context
+    ctx->tile_owner.clear();
+    int rc = lrk_set_shard(ctx, 0u, 1u, tile_size);
+    if (rc) return rc;
+    const uint32_t tiles_x = (ctx->scene.width + tile_size - 1u) / tile_size, tiles_y = (ctx->scene.height + tile_size - 1u) / tile_size;
+    const uint32_t tile_count = tiles_x * tiles_y;
+    uint32_t *d_cost = nullptr;
+    LRK_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_cost), static_cast<size_t>(tile_count) * sizeof(uint32_t)));
+    cudaMemsetAsync(d_cost, 0, static_cast<size_t>(tile_count) * sizeof(uint32_t), ctx->stream);
+    const uint64_t max_paths = std::max<uint64_t>(ctx->max_paths, 1024u);
+    rc = alloc_paths(ctx, std::min<uint64_t>(max_paths, static_cast<uint64_t>(ctx->npix_owned) * probe_spp));
+    if (rc == LRK_OK) {
+        ctx->pb.tile_cost = d_cost;
+        ctx->pb.tile_cost_size = tile_size;
+        ctx->pb.tile_cost_tiles_x = tiles_x;
+        rc = lrk_render(ctx, 0u, probe_spp);
+        ctx->pb.tile_cost = nullptr;
+    }
+    std::vector<uint32_t> cost(tile_count);
+    if (rc == LRK_OK && cudaMemcpy(cost.data(), d_cost, static_cast<size_t>(tile_count) * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess) rc = LRK_ERR_CUDA;
+    cudaFree(d_cost);
+    if (rc) return rc;
+    std::vector<uint32_t> owner(tile_count);
+    lrk_assign_tiles(cost.data(), tile_count, world, owner.data());
+    ctx->tile_owner = std::move(owner);
+    ctx->rank = rank;
+    ctx->world = world;
+    ctx->tile_size = tile_size;
     if ((rc = build_pixel_list(ctx))) return rc;
     return lrk_film_clear(ctx);
 }
 
 int lrk_set_shard(lrk_ctx *ctx, uint32_t rank, uint32_t world, uint32_t tile_size) {
     if (!ctx || world == 0u || rank >= world || tile_size == 0u) return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_set_shard: invalid shard");
+    ctx->tile_owner.clear();
     ctx->rank = rank;
     ctx->world = world;
     ctx->tile_size = tile_size;

@@ -48,6 +48,9 @@ struct PathBuffers {
     uint32_t *occl1;    // ... and whether it hit a surface (advances the PCG32 stream by three draws)
     uint32_t *occl2[2]; // same for the surface NEE shadow ray of the previous bounce
     uint32_t *s2_target;// queue slot (next bounce) that receives occl2 for each shadow record, ~0u if the path ended
+    // cost probe of lrk_balance_shards: live rays per pixel tile, counted by classify_hits_kernel (nullptr outside the probe)
+    uint32_t *tile_cost;
+    uint32_t tile_cost_size, tile_cost_tiles_x;
     unsigned long long *stats;// [0] closest rays, [1] shadow rays, [2..4] closest nodes/tris/xforms, [5..7] shadow nodes/tris/xforms
 };
 constexpr uint32_t kHitKinds = 10u;// hit buckets: emitter-only, Matte, Disney, Mirror, Glass, Plastic, Metal, Mix, transmissive Disney, Layered

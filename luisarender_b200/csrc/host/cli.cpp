@@ -7,7 +7,7 @@
 // Multi-GPU (the reference is single-device): one PROCESS per GPU.  `--gpus N` makes this process a launcher
 // that starts N copies of itself (RANK / WORLD_SIZE / LOCAL_RANK in the environment, as torchrun would set them — a torchrun
 // or mpirun launch of the plain command works too) and waits for them.  Every rank parses the scene, renders the tiles it owns
-// (lrk_set_shard), and one lrk_reduce_film (NCCL) sums the raw films on rank 0, which writes the image.  The NCCL unique id
+// (lrk_balance_shards), and one lrk_reduce_film (NCCL) sums the raw films on rank 0, which writes the image.  The NCCL unique id
 // travels through a file (LRK_COMM_ID_FILE, default /tmp/lrk_comm_<MASTER_PORT>.id): rank 0 writes it, the others wait for it.
 #include <sys/stat.h>
 #include <sys/wait.h>
@@ -207,7 +207,6 @@ int main(int argc, char *argv[]) {
         uint8_t id[LRK_COMM_ID_BYTES];
         exchange_comm_id(rank, id);
         if (lrk_comm_init(ctx, id, rank, world) != 0) die(lrk_last_error(ctx));
-        if (lrk_set_shard(ctx, rank, world, 32u) != 0) die(lrk_last_error(ctx));
         std::printf("[info] Rank %u of %u on device %d.\n", rank, world, device);
     }
     for (uint32_t cam = 0; cam < info.cameras; cam++) {
@@ -221,6 +220,9 @@ int main(int argc, char *argv[]) {
             }
             die(msg);
         }
+        // N ranks: each takes its share of a cost-balanced tile assignment (a one-sample probe of the frame on every rank, no
+        // communication); the volume integrator has no probe and takes the static tile map
+        if (world > 1u && lrk_balance_shards(ctx, rank, world, 32u, 1u) != 0 && lrk_set_shard(ctx, rank, world, 32u) != 0) die(lrk_last_error(ctx));
         const uint32_t w = desc.camera.resolution[0], h = desc.camera.resolution[1], spp = desc.camera.spp;
         std::printf("[info] Wavefront path tracing configurations: resolution = %ux%u, spp = %u.\n", w, h, spp);
         std::printf("[info] Rendering started.\n");

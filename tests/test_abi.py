@@ -86,3 +86,30 @@ def test_cli_help_and_backend_policy():
     assert r.returncode == 0 and "--backend" in r.stdout and "--define" in r.stdout
     r = subprocess.run([str(cli)], capture_output=True, text=True)
     assert r.returncode != 0  # scene file not specified
+
+
+def test_assign_tiles_is_longest_processing_time_first():
+    """lrk_assign_tiles (host only): every tile gets exactly one owner, loads are balanced to within one tile's cost, the result is
+    deterministic, and a uniform cost degenerates to equal counts."""
+    import ctypes as C
+
+    import numpy as np
+
+    lib = F.device_lib()
+    rng = np.random.default_rng(5)
+    cost = (rng.pareto(1.5, 2040) * 1000 + 500).astype(np.uint32)  # heavy-tailed like a frame with sky and geometry
+    for world in (1, 2, 3, 8):
+        owner = np.full(2040, 99, np.uint32)
+        assert lib.lrk_assign_tiles(cost.ctypes.data, 2040, world, owner.ctypes.data) == 0
+        assert owner.max() < world
+        load = np.bincount(owner, weights=cost.astype(np.float64), minlength=world)
+        assert load.max() - load.min() <= cost.max()
+        assert load.max() / load.mean() <= 1.002 or world == 1 or cost.max() > 0.002 * load.mean()
+        again = np.zeros(2040, np.uint32)
+        lib.lrk_assign_tiles(cost.ctypes.data, 2040, world, again.ctypes.data)
+        assert np.array_equal(owner, again)
+    flat = np.full(64, 7, np.uint32)
+    owner = np.zeros(64, np.uint32)
+    lib.lrk_assign_tiles(flat.ctypes.data, 64, 8, owner.ctypes.data)
+    assert (np.bincount(owner, minlength=8) == 8).all()
+    assert lib.lrk_assign_tiles(None, 4, 2, owner.ctypes.data) != 0

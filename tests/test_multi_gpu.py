@@ -54,6 +54,16 @@ if rank == 0:
     single = r.film(raw=True)
     assert np.array_equal(reduced, single), float(np.abs(reduced - single).max())
     assert r.stats()["reduce_ms"] == 0.0  # clear() reset the stats; the reduce above was timed before it
+# cost-balanced shards (lrk_balance_shards): every rank probes the frame on its own and must arrive at the same table
+r.balance_shards(rank, world, D.TILE_SIZE, 1)
+r.render(0, 8)
+mine = r.film(raw=True).copy()
+owned = torch.from_numpy((mine[..., 3] > 0).astype(np.int32)).cuda()
+dist.all_reduce(owned)
+assert (owned.cpu().numpy() == 1).all()           # a partition of the film: no tile rendered twice, none missing
+r.reduce_film(0)
+if rank == 0:
+    assert np.array_equal(r.film(raw=True), single)  # and the same film, bit for bit
 dist.barrier()
 dist.destroy_process_group()
 """
