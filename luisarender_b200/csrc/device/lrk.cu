@@ -46,7 +46,8 @@ struct lrk_ctx {
     uint32_t rank{0}, world{1}, tile_size{32};
     uint32_t *d_pixel_list{nullptr};
     uint32_t npix_owned{0};
-    uint32_t pixel_list_key[5]{0, 0, 0, 0, 0};// width, height, rank, world, tile size of the cached list
+    uint32_t pixel_list_key[6]{0, 0, 0, 0, 0, 0};// width, height, rank, world, tile size, owner-table version of the cached list
+    uint32_t tile_owner_version{0};// bumped whenever tile_owner changes
     std::vector<uint32_t> tile_owner;// lrk_balance_shards: owner of every tile (empty: the static lrk_tile_owner map)
     std::unordered_map<void **, size_t> array_bytes;// capacity of each scene array allocation
     bool textured{false};// some surface has image-textured parameters or a normal map: the shade kernels' TEXTURED variants run
@@ -214,8 +215,8 @@ int alloc_paths(lrk_ctx *ctx, uint64_t capacity) {
 // pixel blocks so that a warp's 32 consecutive paths cover a compact screen region.
 int build_pixel_list(lrk_ctx *ctx) {
     const uint32_t W = ctx->scene.width, H = ctx->scene.height, ts = ctx->tile_size;
-    const uint32_t key[5]{W, H, ctx->rank, ctx->world, ts};
-    if (ctx->d_pixel_list != nullptr && ctx->tile_owner.empty() && std::memcmp(key, ctx->pixel_list_key, sizeof(key)) == 0) return LRK_OK;
+    const uint32_t key[6]{W, H, ctx->rank, ctx->world, ts, ctx->tile_owner.empty() ? 0u : ctx->tile_owner_version};
+    if (ctx->d_pixel_list != nullptr && std::memcmp(key, ctx->pixel_list_key, sizeof(key)) == 0) return LRK_OK;
     std::memcpy(ctx->pixel_list_key, key, sizeof(key));
     const uint32_t tiles_x = (W + ts - 1u) / ts, tiles_y = (H + ts - 1u) / ts;
     std::vector<uint32_t> list;
@@ -986,6 +987,7 @@ int lrk_balance_shards(lrk_ctx *ctx, uint32_t rank, uint32_t world, uint32_t til
     std::vector<uint32_t> owner(tile_count);
     lrk_assign_tiles(cost.data(), tile_count, world, owner.data());
     ctx->tile_owner = std::move(owner);
+    ctx->tile_owner_version++;
     ctx->rank = rank;
     ctx->world = world;
     ctx->tile_size = tile_size;
