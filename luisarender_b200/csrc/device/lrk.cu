@@ -48,6 +48,7 @@ struct lrk_ctx {
     uint32_t npix_owned{0};
     uint32_t pixel_list_key[6]{0, 0, 0, 0, 0, 0};// width, height, rank, world, tile size, owner-table version of the cached list
     uint32_t tile_owner_version{0};// bumped whenever tile_owner changes
+    uint32_t *probe_cost{nullptr};// device counters of a running lrk_balance_shards probe
     std::vector<uint32_t> tile_owner;// lrk_balance_shards: owner of every tile (empty: the static lrk_tile_owner map)
     std::unordered_map<void **, size_t> array_bytes;// capacity of each scene array allocation
     bool textured{false};// some surface has image-textured parameters or a normal map: the shade kernels' TEXTURED variants run
@@ -294,6 +295,9 @@ int render_pass(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint32_t spp
     pb.pass_pixel_offset = pixel_offset;
     pb.pass_npix = npix;
     pb.pass_spp_begin = spp_begin;
+    pb.tile_cost = ctx->probe_cost;// lrk_balance_shards' cost probe (nullptr otherwise); survives a reallocation of the path state
+    pb.tile_cost_size = ctx->tile_size;
+    pb.tile_cost_tiles_x = (ctx->scene.width + ctx->tile_size - 1u) / ctx->tile_size;
     const auto &sc = ctx->scene;
     {
         ScopedTimer t{ctx, CAT_OTHER};
@@ -971,15 +975,9 @@ int lrk_balance_shards(lrk_ctx *ctx, uint32_t rank, uint32_t world, uint32_t til
     uint32_t *d_cost = nullptr;
     LRK_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_cost), static_cast<size_t>(tile_count) * sizeof(uint32_t)));
     cudaMemsetAsync(d_cost, 0, static_cast<size_t>(tile_count) * sizeof(uint32_t), ctx->stream);
-    const uint64_t max_paths = std::max<uint64_t>(ctx->max_paths, 1024u);
-    rc = alloc_paths(ctx, std::min<uint64_t>(max_paths, static_cast<uint64_t>(ctx->npix_owned) * probe_spp));
-    if (rc == LRK_OK) {
-        ctx->pb.tile_cost = d_cost;
-        ctx->pb.tile_cost_size = tile_size;
-        ctx->pb.tile_cost_tiles_x = tiles_x;
-        rc = lrk_render(ctx, 0u, probe_spp);
-        ctx->pb.tile_cost = nullptr;
-    }
+    ctx->probe_cost = d_cost;
+    rc = lrk_render(ctx, 0u, probe_spp);
+    ctx->probe_cost = nullptr;
     std::vector<uint32_t> cost(tile_count);
     if (rc == LRK_OK && cudaMemcpy(cost.data(), d_cost, static_cast<size_t>(tile_count) * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess) rc = LRK_ERR_CUDA;
     cudaFree(d_cost);
