@@ -148,10 +148,11 @@ typedef struct lrk_instance {
 #define LRK_SURFACE_LAYERED 7u /* src/surfaces/layered.cpp: two constant, non-Disney interfaces around a scattering slab */
 #define LRK_SURFACE_TYPE_COUNT 8u
 
-/* Surface::event_*: src/base/surface.h:37-40 */
+/* Surface::event_*: src/base/surface.h:37-41 */
 #define LRK_EVENT_REFLECT 0u
 #define LRK_EVENT_ENTER 1u
 #define LRK_EVENT_EXIT 2u
+#define LRK_EVENT_THROUGH 4u /* transmission through a thin surface: the path stays in its medium, no eta scale */
 
 /* Disney lobe bits: src/surfaces/disney.cpp:326-333 */
 #define LRK_DISNEY_LOBE_DIFFUSE 1u
@@ -172,7 +173,7 @@ typedef struct lrk_instance {
  *           p[8] = anisotropic, p[9] = sheen, p[10] = sheen_tint, p[11] = clearcoat,
  *           p[12] = clearcoat_gloss, p[13] = specular_trans, p[14] = flatness,
  *           p[15] = diffuse_trans; lobes = union of enabled lobes over all disney surface nodes of the scene
- *           that share the record's closure class (opaque / LRK_SURFACE_DISNEY_TRANSMISSIVE; the reference ORs them
+ *           that share the record's closure class (opaque / LRK_SURFACE_DISNEY_TRANSMISSIVE / LRK_SURFACE_DISNEY_THIN; the reference ORs them
  *           into one shared closure per class, src/surfaces/disney.cpp:869,994-995).
  *   MIRROR : p[0..2] = reflectance colour, p[3..4] = alpha (roughness after the optional remap; 0 without a roughness
  *            node: the distribution clamps it to 1e-4) — MirrorClosure::Context, mirror.cpp:84-88,142-162
@@ -197,7 +198,7 @@ typedef struct lrk_instance {
  * evaluated per hit from image texture (tex[k] - 1) at the hit's uv, exactly as populate_closure does
  * (src/surfaces/matte.cpp:117-131, src/surfaces/disney.cpp:932-956):
  *   colour slots (MATTE 0, DISNEY 0): rgb = saturate(extend_color_to_rgb(v.xyz, channels)) -> p[0..2] (+ luminance ->
- *   p[3] for DISNEY); MATTE slot 3: saturate(v.x) * 90; DISNEY scalar slots 4..14: v.x, slot 6 additionally remapped
+ *   p[3] for DISNEY); MATTE slot 3: saturate(v.x) * 90; DISNEY scalar slots 4..15: v.x, slot 6 additionally remapped
  *   max(v.x^2, 1e-4) when LRK_SURFACE_REMAP_ROUGHNESS is set in flags.
  *
  * Wrappers every surface node carries (NormalMapWrapper<OpacitySurfaceWrapper<...>>, src/base/surface.h:160-275):
@@ -228,6 +229,13 @@ typedef struct lrk_instance {
  *            p[0..2] <- Kd / (1 - Kd Fdr(eta)), p[3] <- lum(Kd) exp(-2 lum(sigma_a) thickness)        plastic.cpp:252-291
  *   METAL  : p[0..5] n, k (never textured), p[6..8] Kd (tex[6]), p[9..10] alpha (tex[9])               metal.cpp:273-310 */
 #define LRK_SURFACE_RAW_PARAMS 32u
+/* DISNEY only: a `thin` node with a non-black `specular_trans` or `diffuse_trans` (src/surfaces/disney.cpp:61-69): the closure class
+ * "disney_thin" (ThinDisneyClosureImpl, :590-845) - five sampling techniques: the diffuse-like lobes weighted by
+ * (1 - diffuse_trans), specular, clearcoat, a MicrofacetTransmission lobe through a distribution rescaled by
+ * (0.65 eta - 0.35) (:686-701) and a Lambertian diffuse-transmission lobe weighted by p[15] = diffuse_trans (:703-710); both
+ * transmissions report LRK_EVENT_THROUGH, and the closure has no eta().  `lobes` is the union over the THIN Disney nodes.
+ * A `thin` node with neither transmission is an ordinary opaque Disney record. */
+#define LRK_SURFACE_DISNEY_THIN 64u
 typedef struct lrk_surface {
     uint32_t type;
     uint32_t lobes;

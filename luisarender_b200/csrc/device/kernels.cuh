@@ -78,7 +78,8 @@ __global__ void __launch_bounds__(kTraceBlock, LRK_TRACE_MIN_BLOCKS) trace_close
 // keeps the ray-queue order inside a block chunk, which keeps the shade kernels' gathers coalesced.
 //   kind 0: hit has no surface (emitter only)   kind 1: Matte closure   kind 2: Disney closure
 //   kinds 3..6: Mirror, Glass, Plastic, Metal (MicrofacetFamilyClosure<type>, kind = type + 1)   kind 7: Mix
-//   kind 8: transmissive Disney closure ("disney_trans": LRK_SURFACE_DISNEY_TRANSMISSIVE records)
+//   kind 8: transmissive Disney closure ("disney_trans": LRK_SURFACE_DISNEY_TRANSMISSIVE records)   kind 9: Layered
+//   kind 10: thin Disney closure ("disney_thin": LRK_SURFACE_DISNEY_THIN records)
 __global__ void __launch_bounds__(kBlock) classify_hits_kernel(DeviceScene sc, PathBuffers pb, uint32_t depth) {
     __shared__ uint32_t s_warp[kHitKinds][kBlock / 32];
     __shared__ uint32_t s_base[kHitKinds];

@@ -78,8 +78,8 @@ struct lrk_ctx {
     cudaEvent_t ev_begin{}, ev_end{};
     std::vector<TimedLaunch> timed;
     std::vector<cudaEvent_t> event_pool;
-    int grid_trace{0}, grid_shade[2][10]{}, grid_shadow{0}, grid_classify{0};// grid_shade[variant]: 0 = fast, 1 = strict arithmetic
-    bool has_kind[10]{true, false, false, false, false, false, false, false, false, false};
+    int grid_trace{0}, grid_shade[2][11]{}, grid_shadow{0}, grid_classify{0};// grid_shade[variant]: 0 = fast, 1 = strict arithmetic
+    bool has_kind[11]{true, false, false, false, false, false, false, false, false, false, false};
     uint32_t allocated_kinds{0u};// bit k: hit_index[k] is allocated
     bool volume{false};
     bool strict_math{false};// option strict_math: every closure kernel from shade.cu's IEEE-arithmetic compilation
@@ -327,8 +327,9 @@ int render_pass(lrk_ctx *ctx, uint32_t pixel_offset, uint32_t npix, uint32_t spp
             // parameters / normal maps
             for (uint32_t kind = 0; kind < kHitKinds; kind++) {
                 if (kind != 0u && !ctx->has_kind[kind]) continue;
-                // the near-specular closures (Mirror, Glass, Plastic, Metal, Mix: buckets 3..7) always run in IEEE arithmetic
-                const bool strict = ctx->strict_math || (kind >= 3u && kind <= 7u) || kind == 9u;
+                // the near-specular closures (Mirror, Glass, Plastic, Metal, Mix: buckets 3..7), Layered and thin Disney always run in
+                // IEEE arithmetic
+                const bool strict = ctx->strict_math || (kind >= 3u && kind <= 7u) || kind >= 9u;
                 const int blocks = blocks_for(ctx, n, ctx->grid_shade[strict ? 1 : 0][kind]);
                 if (strict) strict::launch_shade(kind, ctx->textured, blocks, ctx->stream, sc, pb, depth);
                 else fast::launch_shade(kind, ctx->textured, blocks, ctx->stream, sc, pb, depth);
@@ -671,7 +672,7 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
         for (uint32_t i = 0; i < s->instance_count && !volume_general; i++)
             if (s->instances[i].handle[0] & LRK_SHAPE_HAS_MEDIUM) volume_general = true;
         for (uint32_t i = 0; i < s->surface_count && !volume_general; i++)
-            if (s->surfaces[i].type > LRK_SURFACE_DISNEY || (s->surfaces[i].flags & LRK_SURFACE_DISNEY_TRANSMISSIVE)) volume_general = true;
+            if (s->surfaces[i].type > LRK_SURFACE_DISNEY || (s->surfaces[i].flags & (LRK_SURFACE_DISNEY_TRANSMISSIVE | LRK_SURFACE_DISNEY_THIN))) volume_general = true;
         for (uint32_t i = 0; i < s->instance_count; i++) {
             const uint32_t flags = s->instances[i].handle[0] & 1023u, tag = (s->instances[i].handle[1] >> 24u) & 255u;
             if ((flags & LRK_SHAPE_HAS_MEDIUM) && tag >= s->medium_count)
@@ -813,6 +814,7 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
                 kind = type + 1u;// Matte 1, Disney 2, Mirror 3, Glass 4, Plastic 5, Metal 6, Mix 7
                 if (type == LRK_SURFACE_DISNEY && (s->surfaces[surface_tag].flags & LRK_SURFACE_DISNEY_TRANSMISSIVE)) kind = 8u;
                 if (type == LRK_SURFACE_LAYERED) kind = 9u;
+                if (type == LRK_SURFACE_DISNEY && (s->surfaces[surface_tag].flags & LRK_SURFACE_DISNEY_THIN)) kind = 10u;
             }
             kinds[i] = kind;
             ctx->has_kind[kind] = true;

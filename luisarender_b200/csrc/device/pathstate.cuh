@@ -30,7 +30,7 @@ struct PathBuffers {
     float4 *beta_pdf[2];
     uint2 *id_rng[2];
     uint4 *hit;// {inst, prim, bary} per ray of the current queue (inst == ~0u: escaped)
-    uint32_t *hit_index[10];// per closure kind: indices (into the current ray queue) of the rays that hit such a surface
+    uint32_t *hit_index[11];// per closure kind: indices (into the current ray queue) of the rays that hit such a surface
     float4 *sray_o;
     float4 *sray_d;
     float4 *scontrib;// rgb + path id bits
@@ -53,6 +53,6 @@ struct PathBuffers {
     uint32_t tile_cost_size, tile_cost_tiles_x;
     unsigned long long *stats;// [0] closest rays, [1] shadow rays, [2..4] closest nodes/tris/xforms, [5..7] shadow nodes/tris/xforms
 };
-constexpr uint32_t kHitKinds = 10u;// hit buckets: emitter-only, Matte, Disney, Mirror, Glass, Plastic, Metal, Mix, transmissive Disney, Layered
+constexpr uint32_t kHitKinds = 11u;// hit buckets: emitter-only, Matte, Disney, Mirror, Glass, Plastic, Metal, Mix, transmissive Disney, Layered, thin Disney
 
 }// namespace lrk

@@ -43,7 +43,8 @@ void with_shade_kernel(uint32_t kind, bool textured, F &&f) {
         case 6u: textured ? f(shade_kernel<6u, true>) : f(shade_kernel<6u, false>); break;
         case 7u: textured ? f(shade_kernel<7u, true>) : f(shade_kernel<7u, false>); break;
         case 8u: textured ? f(shade_kernel<8u, true>) : f(shade_kernel<8u, false>); break;
-        default: textured ? f(shade_kernel<9u, true>) : f(shade_kernel<9u, false>); break;
+        case 9u: textured ? f(shade_kernel<9u, true>) : f(shade_kernel<9u, false>); break;
+        default: textured ? f(shade_kernel<10u, true>) : f(shade_kernel<10u, false>); break;
     }
 }
 

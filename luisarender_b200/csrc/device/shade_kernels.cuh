@@ -116,6 +116,10 @@ __global__ void __launch_bounds__(kShadeBlock, LRK_SHADE_MIN_BLOCKS) shade_kerne
                         init_closure<TEXTURED>(sc, cl, surf, it);
                         shade_surface<false>(cl, it, closure_frame<TEXTURED>(sc, surf, it, wo), wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
                         if (surf->lobes & LRK_DISNEY_LOBE_SPEC_TRANS) eta_scale = cl.rr_eta_scale;// closure->eta() (disney.cpp:531-533)
+                    } else if (KIND == 10u) {// closure->eta() is empty (disney.cpp:779): no Russian-roulette eta scale
+                        DisneyThinClosure cl;
+                        init_closure<TEXTURED>(sc, cl, surf, it);
+                        shade_surface<false>(cl, it, closure_frame<TEXTURED>(sc, surf, it, wo), wo, ls, beta, u_lobe, ub0, ub1, contrib, wi, f, pdf);
                     } else if (KIND == 9u) {
                         LayeredClosure cl;
                         const Frame fr = closure_frame<TEXTURED>(sc, surf, it, wo);

@@ -455,7 +455,7 @@ __device__ __forceinline__ void resolve_surface_textures(const DeviceScene &sc, 
         if (s.tex[3] != 0u) s.p[3] = saturate(texture_evaluate(*sc.self, s.tex[3] - 1u, u, v).x) * 90.f;
     } else {
 #pragma unroll
-        for (uint32_t k = 4u; k < 15u; k++) {
+        for (uint32_t k = 4u; k < 16u; k++) {
             if (s.tex[k] != 0u) {
                 float x = texture_evaluate(*sc.self, s.tex[k] - 1u, u, v).x;
                 if (k == 6u && (s.flags & LRK_SURFACE_REMAP_ROUGHNESS)) x = fmaxf(x * x, 1e-4f);// roughness_to_alpha
@@ -764,17 +764,28 @@ __device__ __forceinline__ float microfacet_transmission_pdf(const TrowbridgeRei
 
 // TRANS: the closure class "disney_trans" of a transmissive node (LRK_SURFACE_DISNEY_TRANSMISSIVE, src/surfaces/disney.cpp:376-383,
 // 425,452-464,514-522,571-576): a fourth technique with a MicrofacetTransmission lobe, a one-sided Fresnel term, eta() = eta_t.
-template<bool TRANS>
+// THIN: the closure class "disney_thin" (LRK_SURFACE_DISNEY_THIN, ThinDisneyClosureImpl disney.cpp:590-845): the diffuse-like lobes
+// keep (1 - diffuse_trans) of the diffuse weight, the transmission lobe runs through a rescaled distribution with the colour itself,
+// a fifth technique is Lambertian diffuse transmission; both transmissions are "through" events (no medium change, no eta).
+enum DisneyMode : int { kDisneyOpaque = 0, kDisneyTransmissive = 1, kDisneyThin = 2 };
+template<int MODE>
 struct DisneyClosureT {
+    static constexpr bool TRANS = MODE == kDisneyTransmissive;
+    static constexpr bool THIN = MODE == kDisneyThin;
     V3 Cdiff, Css, Csheen, Cspec0;
     float metallic, roughness, clearcoat, fresnel_eta, gloss;
     TrowbridgeReitz distrib;
     float w0, w1, w2;
     bool has_diffuse, has_fake_ss, has_sheen, has_clearcoat;
-    // transmissive closure only
+    // transmissive and thin closures only
     V3 Cst;
     float w3, eta_t_;
     bool has_spec_trans;
+    // thin closure only
+    TrowbridgeReitz thin_distrib;
+    V3 Cdt;
+    float w4;
+    bool has_diff_trans;
     float rr_eta_scale;// eta scale of the sampled event for Russian roulette (mega_path.cpp:133-138)
     uint32_t event;    // Surface::event_* of the sampled direction (what the volume integrator's medium tracker follows)
 
@@ -784,6 +795,9 @@ struct DisneyClosureT {
         Cst = v3(0.f);
         w3 = 0.f;
         has_spec_trans = false;
+        Cdt = v3(0.f);
+        w4 = 0.f;
+        has_diff_trans = false;
         eta_t_ = s.p[5];
         V3 color = v3(s.p[0], s.p[1], s.p[2]);
         float color_lum = s.p[3];
@@ -804,26 +818,28 @@ struct DisneyClosureT {
         V3 tc = color * tint_weight;
         V3 tint = v3(saturate(tc.x), saturate(tc.y), saturate(tc.z));
         float tint_lum = color_lum * tint_weight;
-        float diffuse_like_sampling_weight = diffuse_weight * color_lum;
+        const float diffuse_trans = THIN ? s.p[15] : 0.f;
+        const float diff_refl_weight = THIN ? diffuse_weight * (1.f - diffuse_trans) : diffuse_weight;// disney.cpp:620-622
+        float diffuse_like_sampling_weight = diff_refl_weight * color_lum;
         if ((lobes & LRK_DISNEY_LOBE_DIFFUSE) || (lobes & LRK_DISNEY_LOBE_RETRO)) {
-            float Cdiff_weight = diffuse_weight * (1.f - flatness);
+            float Cdiff_weight = diff_refl_weight * (1.f - flatness);
             Cdiff = color * Cdiff_weight;
             has_diffuse = true;
             en0 = true;
         }
         if (lobes & LRK_DISNEY_LOBE_FAKE_SS) {
-            float Css_weight = diffuse_weight * flatness;
+            float Css_weight = THIN ? diff_refl_weight * flatness * (1.f - diffuse_trans) : diffuse_weight * flatness;// :643
             Css = Css_weight * color;
             has_fake_ss = true;
             en0 = true;
         }
         if (lobes & LRK_DISNEY_LOBE_SHEEN) {
-            float Csheen_weight = diffuse_weight * sheen;
+            float Csheen_weight = THIN ? diff_refl_weight * sheen * (1.f - diffuse_trans) : diffuse_weight * sheen;// :651
             Csheen = Csheen_weight * lerp(v3(1.f), tint, sheen_tint);
             has_sheen = true;
             float sheen_lum = Csheen_weight * lerp(1.f, tint_lum, sheen_tint);
             diffuse_like_sampling_weight += sheen_lum * .1f;
-            en0 = true;
+            if (!THIN) en0 = true;// the thin closure's sheen block does not enable the technique (:650-657)
         }
         w0 = saturate(diffuse_like_sampling_weight);
         float eta = eta_t / 1.f;
@@ -848,16 +864,35 @@ struct DisneyClosureT {
             float Cst_lum = Cst_weight * sqrtf(color_lum);
             w3 = saturate(Cst_lum);
         }
+        if (THIN && (lobes & LRK_DISNEY_LOBE_SPEC_TRANS)) {// disney.cpp:686-701
+            float rscaled = (.65f * eta - .35f) * roughness;
+            thin_distrib.ax = fmaxf(fmaxf(.001f, rscaled / aspect), 1e-4f);
+            thin_distrib.ay = fmaxf(fmaxf(.001f, rscaled * aspect), 1e-4f);
+            float Cst_weight = (1.f - metallic) * specular_trans;
+            Cst = Cst_weight * color;
+            has_spec_trans = true;
+            float Cst_lum = Cst_weight * color_lum;
+            w3 = saturate(Cst_lum);
+        }
+        if (THIN && (lobes & LRK_DISNEY_LOBE_DIFF_TRANS)) {// disney.cpp:703-710
+            float diff_trans_weight = diffuse_weight * diffuse_trans;
+            Cdt = diff_trans_weight * color;
+            float Cdt_lum = diff_trans_weight * color_lum;
+            has_diff_trans = true;
+            w4 = saturate(Cdt_lum);
+        }
         float sum_weights = 0.f;
         if (en0) sum_weights += w0;
         sum_weights += w1;
         if (en2) sum_weights += w2;
-        if (TRANS && has_spec_trans) sum_weights += w3;
+        if ((TRANS || THIN) && has_spec_trans) sum_weights += w3;
+        if (THIN && has_diff_trans) sum_weights += w4;
         float inv_sum_weights = sum_weights == 0.f ? 0.f : 1.f / sum_weights;
         if (en0) w0 *= inv_sum_weights;
         w1 *= inv_sum_weights;
         if (en2) w2 *= inv_sum_weights;
-        if (TRANS && has_spec_trans) w3 *= inv_sum_weights;
+        if ((TRANS || THIN) && has_spec_trans) w3 *= inv_sum_weights;
+        if (THIN && has_diff_trans) w4 *= inv_sum_weights;
         enabled0 = en0;
         enabled2 = en2;
     }
@@ -877,7 +912,7 @@ struct DisneyClosureT {
         gtr1_pi_log_a2 = kPi * logf(alpha2);
     }
     __device__ __forceinline__ V3 disney_fresnel(float cosI_in) const {
-        float cosI = TRANS ? cosI_in : fabsf(cosI_in);// DisneyFresnel: two_sided = !is_transmissive (disney.cpp:287-292,425)
+        float cosI = (TRANS || THIN) ? cosI_in : fabsf(cosI_in);// DisneyFresnel: two_sided = !is_transmissive, false when thin (disney.cpp:287-292,425,666)
         float fr = fresnel_dielectric(cosI, 1.f, fresnel_eta);
         V3 f0 = v3(FrSchlick(Cspec0.x, cosI), FrSchlick(Cspec0.y, cosI), FrSchlick(Cspec0.z, cosI));
         return lerp(v3(fr), f0, metallic);
@@ -916,7 +951,7 @@ struct DisneyClosureT {
                 float ps = 0.f;
                 if (valid) {
                     // dot(wi, face_forward(wh, +z)) = +-dot(wi, wh); the opaque closure's Fresnel term takes its absolute value
-                    V3 F = disney_fresnel(TRANS ? (cos_theta(wh) < 0.f ? -cosThetaD : cosThetaD) : cosThetaD);
+                    V3 F = disney_fresnel((TRANS || THIN) ? (cos_theta(wh) < 0.f ? -cosThetaD : cosThetaD) : cosThetaD);
                     float D = distrib.D(wh);
                     float G = 1.0f / (1.0f + lambda_o + distrib.Lambda(wi));
                     float cos_o = cos_theta(wo), cos_i = cos_theta(wi);
@@ -941,6 +976,19 @@ struct DisneyClosureT {
                 f = f + microfacet_transmission_evaluate(Cst, distrib, eta_t_, wo, wi);
                 pdf += w3 * microfacet_transmission_pdf(distrib, eta_t_, wo, wi);
             }
+        } else if (THIN) {// disney.cpp:755-774
+            if (has_spec_trans) {
+                if (w3 > 0.f) {
+                    f = f + microfacet_transmission_evaluate(Cst, thin_distrib, eta_t_, wo, wi);
+                    pdf += w3 * microfacet_transmission_pdf(thin_distrib, eta_t_, wo, wi);
+                }
+            }
+            if (has_diff_trans) {
+                if (w4 > 0.f) {// LambertianTransmission (scattering.cpp:271-284): wo and wi lie in opposite hemispheres here
+                    f = f + Cdt * kInvPi;
+                    pdf += w4 * (abs_cos_theta(wi) * kInvPi);
+                }
+            }
         }
         SurfEval e;
         e.f = f * abs_cos_theta(wi);
@@ -961,9 +1009,13 @@ struct DisneyClosureT {
             tech = u_lobe > sum_weights ? 2u : tech;
             sum_weights += w2;
         }
-        if (TRANS && has_spec_trans) {
+        if ((TRANS || THIN) && has_spec_trans) {
             tech = u_lobe > sum_weights ? 3u : tech;
             sum_weights += w3;
+        }
+        if (THIN && has_diff_trans) {
+            tech = u_lobe > sum_weights ? 4u : tech;
+            sum_weights += w4;
         }
         wi = v3(0.f);
         bool valid = false;
@@ -976,6 +1028,17 @@ struct DisneyClosureT {
             valid = refr && !same_hemisphere(wo, wi);
             rr_eta_scale = cos_theta(wo) > 0.f ? sqr(eta_t_) : sqr(1.f / eta_t_);
             event = cos_theta(wo) > 0.f ? LRK_EVENT_ENTER : LRK_EVENT_EXIT;
+        } else if (THIN && tech == 3u) {// the same lobe through the rescaled distribution; a "through" event (disney.cpp:820-825)
+            float e = cos_theta(wo) > 0.f ? 1.f / eta_t_ : eta_t_ / 1.f;
+            V3 wh = thin_distrib.sample_wh(wo, u0, u1);
+            bool refr = refract(wo, wh, e, wi);
+            valid = refr && !same_hemisphere(wo, wi);
+            event = LRK_EVENT_THROUGH;
+        } else if (THIN && tech == 4u) {// LambertianTransmission::sample_wi (scattering.cpp:276-280, disney.cpp:827-832)
+            wi = sample_cosine_hemisphere(u0, u1);
+            wi.z *= -sign(cos_theta(wo));
+            valid = true;
+            event = LRK_EVENT_THROUGH;
         } else if (tech == 0u) {
             if (has_diffuse) {
                 wi = sample_cosine_hemisphere(u0, u1);
@@ -1007,8 +1070,9 @@ struct DisneyClosureT {
         return valid;// f and pdf of the sample are evaluate_local(wo, wi) (disney.cpp:583-586)
     }
 };
-using DisneyClosure = DisneyClosureT<false>;
-using DisneyTransClosure = DisneyClosureT<true>;
+using DisneyClosure = DisneyClosureT<kDisneyOpaque>;
+using DisneyTransClosure = DisneyClosureT<kDisneyTransmissive>;
+using DisneyThinClosure = DisneyClosureT<kDisneyThin>;
 
 // Mirror / Glass / Plastic / Metal: src/surfaces/{mirror,glass,plastic,metal}.cpp over the BxDFs of
 // src/util/scattering.cpp:14-125,238-345.  One closure type for the four nodes (hit bucket 3): they are rare next to the

@@ -101,6 +101,12 @@ __device__ __forceinline__ void with_closure(const DeviceScene &sc, uint32_t kin
             f(cl);
             break;
         }
+        case 10u: {
+            DisneyThinClosure cl;
+            init_closure<true>(sc, cl, surf, it);
+            f(cl);
+            break;
+        }
         case 7u: {
             MixClosure cl;
             cl.init(*surf, sc.surfaces);

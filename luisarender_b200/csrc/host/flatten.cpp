@@ -566,10 +566,10 @@ std::unique_ptr<FlatScene> flatten_scene(const Scene &scene) {
     f.build_tlas();
     out->bvh_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 
-    // surfaces; Disney lobes are OR-ed over all disney nodes of one closure class - opaque "disney", transmissive "disney_trans"
-    // (one shared closure per class, src/surfaces/disney.cpp:869,925-930,994)
-    uint32_t disney_lobes[2] = {0u, 0u};
-    auto disney_class = [](const lrk_surface &s) { return (s.flags & LRK_SURFACE_DISNEY_TRANSMISSIVE) ? 1 : 0; };
+    // surfaces; Disney lobes are OR-ed over all disney nodes of one closure class - opaque "disney", transmissive "disney_trans",
+    // thin "disney_thin" (one shared closure per class, src/surfaces/disney.cpp:869,925-930,994)
+    uint32_t disney_lobes[3] = {0u, 0u, 0u};
+    auto disney_class = [](const lrk_surface &s) { return (s.flags & LRK_SURFACE_DISNEY_THIN) ? 2 : (s.flags & LRK_SURFACE_DISNEY_TRANSMISSIVE) ? 1 : 0; };
     TextureTable texture_table;
     for (auto s : f.surface_nodes) {
         out->surfaces.push_back(s->flatten(texture_table));

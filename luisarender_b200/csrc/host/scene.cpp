@@ -871,11 +871,14 @@ struct DisneySurface final : Surface {
         clearcoat_gloss = surface_texture(s, d, "clearcoat_gloss");
         specular_trans = surface_texture(s, d, "specular_trans");
         flatness = surface_texture(s, d, "flatness");
-        diffuse_trans = constant_or_null(s, d, "diffuse_trans");
-        if (thin) throw Error("Thin Disney surfaces are not supported. [" + d->location() + "]");
+        diffuse_trans = surface_texture(s, d, "diffuse_trans");
     }
-    // src/surfaces/disney.cpp:61-75: the closure class "disney_trans" (a specular-transmission lobe exists)
-    bool is_transmissive() const { return specular_trans != nullptr && !specular_trans->is_black(); }
+    // src/surfaces/disney.cpp:61-75: the closure classes "disney_thin" (a thin node with either transmission) and "disney_trans"
+    // (a specular-transmission lobe exists); a thin node without transmission is an ordinary opaque one
+    bool is_thin() const {
+        return thin && ((specular_trans != nullptr && !specular_trans->is_black()) || (diffuse_trans != nullptr && !diffuse_trans->is_black()));
+    }
+    bool is_transmissive() const { return !thin && specular_trans != nullptr && !specular_trans->is_black(); }
     uint32_t lobes() const {
         // src/surfaces/disney.cpp:966-990
         uint32_t l = 0u;
@@ -886,7 +889,8 @@ struct DisneySurface final : Surface {
         }
         l |= LRK_DISNEY_LOBE_SPECULAR;
         if (clearcoat && !clearcoat->is_black()) l |= LRK_DISNEY_LOBE_CLEARCOAT;
-        if (is_transmissive()) l |= LRK_DISNEY_LOBE_SPEC_TRANS;
+        if (specular_trans && !specular_trans->is_black()) l |= LRK_DISNEY_LOBE_SPEC_TRANS;
+        if (diffuse_trans && !diffuse_trans->is_black()) l |= LRK_DISNEY_LOBE_DIFF_TRANS;// the opaque closures never look at these two bits
         return l;
     }
     lrk_surface flatten(TextureTable &textures) const override {
@@ -895,6 +899,7 @@ struct DisneySurface final : Surface {
         out.lobes = lobes();
         if (remap_roughness) out.flags |= LRK_SURFACE_REMAP_ROUGHNESS;
         if (is_transmissive()) out.flags |= LRK_SURFACE_DISNEY_TRANSMISSIVE;
+        if (is_thin()) out.flags |= LRK_SURFACE_DISNEY_THIN;
         // a parameter is either the node's constant (p[k]) or an image texture evaluated per hit (tex[k])
         auto x = [&](const Texture *t, float dflt, uint32_t slot) {
             if (t && t->is_image()) {
@@ -925,7 +930,7 @@ struct DisneySurface final : Surface {
         out.p[12] = x(clearcoat_gloss, 1.f, 12);
         out.p[13] = x(specular_trans, 0.f, 13);
         out.p[14] = x(flatness, 0.f, 14);
-        out.p[15] = 0.f;// diffuse_trans is only built for thin surfaces (src/surfaces/disney.cpp:1017)
+        out.p[15] = thin ? x(diffuse_trans, 0.f, 15) : 0.f;// diffuse_trans is only built for thin surfaces (src/surfaces/disney.cpp:1024)
         flatten_wrappers(out, textures);
         return out;
     }

@@ -1300,15 +1300,23 @@ struct DisneyClosure {
     float fresnel_eta{}, gloss{};
     TrowbridgeReitz distrib{1.f, 1.f};
     // techniques: diffuse-like, specular, clearcoat and - transmissive closure ("disney_trans", disney.cpp:376-383,452-464) only -
-    // specular transmission
-    float w[4]{0.f, 0.f, 0.f, 0.f};
-    bool enabled[4]{false, false, false, false};
+    // specular transmission; the thin closure ("disney_thin", disney.cpp:590-845) has specular transmission through a rescaled
+    // distribution and a fifth technique, Lambertian diffuse transmission
+    float w[5]{0.f, 0.f, 0.f, 0.f, 0.f};
+    bool enabled[5]{false, false, false, false, false};
     bool transmissive{false};
+    bool thin{false};
     bool has_spec_trans{false};
+    bool has_diff_trans{false};
+    V3 Cdt{};
+    float diffuse_trans{0.f};
     MicrofacetTransmission spec_trans{v3(0.f), TrowbridgeReitz{1.f, 1.f}, 1.f, 1.f};
+    int techniques() const { return thin ? 5 : transmissive ? 4 : 3; }
 
     explicit DisneyClosure(const lrk_surface &s) {
-        transmissive = (s.flags & LRK_SURFACE_DISNEY_TRANSMISSIVE) != 0u;
+        thin = (s.flags & LRK_SURFACE_DISNEY_THIN) != 0u;
+        transmissive = !thin && (s.flags & LRK_SURFACE_DISNEY_TRANSMISSIVE) != 0u;
+        diffuse_trans = thin ? s.p[15] : 0.f;
         color = v3(s.p[0], s.p[1], s.p[2]);
         color_lum = s.p[3]; metallic = s.p[4]; eta_t = s.p[5]; roughness = s.p[6]; specular_tint = s.p[7];
         anisotropic = s.p[8]; sheen = s.p[9]; sheen_tint = s.p[10]; clearcoat = s.p[11]; clearcoat_gloss = s.p[12];
@@ -1320,26 +1328,30 @@ struct DisneyClosure {
         V3 tc = color * tint_weight;
         V3 tint = v3(saturate(tc.x), saturate(tc.y), saturate(tc.z));
         float tint_lum = color_lum * tint_weight;
-        float diffuse_like_sampling_weight = diffuse_weight * color_lum;
+        // thin closure (disney.cpp:620-622,633,643,651): the diffuse-like lobes keep the reflected share of the diffuse weight, and
+        // fake subsurface / sheen are scaled by (1 - diffuse_trans) once more
+        const float diff_refl_weight = thin ? diffuse_weight * (1.f - diffuse_trans) : diffuse_weight;
+        const float diff_trans_weight = diffuse_weight * diffuse_trans;
+        float diffuse_like_sampling_weight = diff_refl_weight * color_lum;
         if ((lobes & LRK_DISNEY_LOBE_DIFFUSE) || (lobes & LRK_DISNEY_LOBE_RETRO)) {
-            float Cdiff_weight = diffuse_weight * (1.f - flatness);
+            float Cdiff_weight = diff_refl_weight * (1.f - flatness);
             Cdiff = color * Cdiff_weight;
             has_diffuse = true;
             enabled[0] = true;
         }
         if (lobes & LRK_DISNEY_LOBE_FAKE_SS) {
-            float Css_weight = diffuse_weight * flatness;
+            float Css_weight = thin ? diff_refl_weight * flatness * (1.f - diffuse_trans) : diffuse_weight * flatness;
             Css = Css_weight * color;
             has_fake_ss = true;
             enabled[0] = true;
         }
         if (lobes & LRK_DISNEY_LOBE_SHEEN) {
-            float Csheen_weight = diffuse_weight * sheen;
+            float Csheen_weight = thin ? diff_refl_weight * sheen * (1.f - diffuse_trans) : diffuse_weight * sheen;
             Csheen = Csheen_weight * lerp(v3(1.f), tint, sheen_tint);
             has_sheen = true;
             float sheen_lum = Csheen_weight * lerp(1.f, tint_lum, sheen_tint);
             diffuse_like_sampling_weight += sheen_lum * .1f;
-            enabled[0] = true;
+            if (!thin) enabled[0] = true;// the thin closure's sheen block does not enable the technique (disney.cpp:650-657)
         }
         w[0] = saturate(diffuse_like_sampling_weight);
         float eta = eta_t / eta_i;
@@ -1366,15 +1378,32 @@ struct DisneyClosure {
             w[3] = saturate(Cst_lum);
             enabled[3] = true;
         }
-        const int techniques = transmissive ? 4 : 3;
+        if (thin && (lobes & LRK_DISNEY_LOBE_SPEC_TRANS)) {// disney.cpp:686-701: a rescaled distribution, the colour itself (no sqrt)
+            float rscaled = (.65f * eta - .35f) * roughness;
+            TrowbridgeReitz thin_distrib{std::fmax(.001f, rscaled / aspect), std::fmax(.001f, rscaled * aspect)};
+            float Cst_weight = (1.f - metallic) * specular_trans;
+            V3 Cst = Cst_weight * color;
+            spec_trans = MicrofacetTransmission{Cst, thin_distrib, eta_i, eta_t};
+            has_spec_trans = true;
+            float Cst_lum = Cst_weight * color_lum;
+            w[3] = saturate(Cst_lum);
+            enabled[3] = true;
+        }
+        if (thin && (lobes & LRK_DISNEY_LOBE_DIFF_TRANS)) {// disney.cpp:703-710
+            Cdt = diff_trans_weight * color;
+            float Cdt_lum = diff_trans_weight * color_lum;
+            has_diff_trans = true;
+            w[4] = saturate(Cdt_lum);
+            enabled[4] = true;
+        }
         float sum_weights = 0.f;
-        for (int i = 0; i < techniques; i++) if (enabled[i]) sum_weights += w[i];
+        for (int i = 0; i < techniques(); i++) if (enabled[i]) sum_weights += w[i];
         float inv_sum_weights = sum_weights == 0.f ? 0.f : 1.f / sum_weights;
-        for (int i = 0; i < techniques; i++) if (enabled[i]) w[i] *= inv_sum_weights;
+        for (int i = 0; i < techniques(); i++) if (enabled[i]) w[i] *= inv_sum_weights;
     }
 
     V3 disney_fresnel(float cosI_in) const {// DisneyFresnel::evaluate, two_sided = !is_transmissive (disney.cpp:287-292,425)
-        float cosI = transmissive ? cosI_in : std::fabs(cosI_in);
+        float cosI = (transmissive || thin) ? cosI_in : std::fabs(cosI_in);// the thin closure's term is one-sided too (disney.cpp:666)
         float fr = fresnel_dielectric(cosI, 1.f, fresnel_eta);
         V3 f0 = v3(FrSchlick(Cspec0.x, cosI), FrSchlick(Cspec0.y, cosI), FrSchlick(Cspec0.z, cosI));
         return lerp(v3(fr), f0, metallic);
@@ -1479,10 +1508,18 @@ struct DisneyClosure {
                     pdf += w[2] * clearcoat_pdf(wo, wi);
                 }
             }
-        } else if (has_spec_trans) {// transmission, disney.cpp:514-522
-            if (w[3] > 0.f) {
-                f = f + spec_trans.evaluate(wo, wi);
-                pdf += w[3] * spec_trans.pdf(wo, wi);
+        } else {// transmission, disney.cpp:514-522 (transmissive), :755-774 (thin)
+            if (has_spec_trans) {
+                if (w[3] > 0.f) {
+                    f = f + spec_trans.evaluate(wo, wi);
+                    pdf += w[3] * spec_trans.pdf(wo, wi);
+                }
+            }
+            if (has_diff_trans) {
+                if (w[4] > 0.f) {// LambertianTransmission, scattering.cpp:271-284 (wo and wi are in opposite hemispheres here)
+                    f = f + Cdt * kInvPi;
+                    pdf += w[4] * (abs_cos_theta(wi) * kInvPi);
+                }
             }
         }
         SurfEval e;
@@ -1500,7 +1537,7 @@ SurfSample disney_sample(const lrk_surface &s, const Interaction &it, V3 wo, flo
     DisneyClosure c{s};
     uint32_t tech = 0u;
     float sum_weights = 0.f;
-    for (uint32_t i = 0; i < (c.transmissive ? 4u : 3u); i++) {
+    for (uint32_t i = 0; i < static_cast<uint32_t>(c.techniques()); i++) {
         if (c.enabled[i]) {
             tech = u_lobe > sum_weights ? i : tech;
             sum_weights += c.w[i];
@@ -1522,11 +1559,18 @@ SurfSample disney_sample(const lrk_surface &s, const Interaction &it, V3 wo, flo
         valid = same_hemisphere(wo_local, wi_local);
     } else if (tech == 2u) {
         if (c.has_clearcoat) wi_local = c.clearcoat_sample_wi(wo_local, u0, u1, valid);
-    } else if (c.has_spec_trans) {// disney.cpp:571-576
-        BxDFSample bs = c.spec_trans.sample_wi(wo_local, u0, u1);
-        wi_local = bs.wi;
-        valid = bs.valid;
-        event = cos_theta(wo_local) > 0.f ? LRK_EVENT_ENTER : LRK_EVENT_EXIT;
+    } else if (tech == 3u) {
+        if (c.has_spec_trans) {// disney.cpp:571-576; the thin closure's event is "through" (:820-825): the ray stays in its medium
+            BxDFSample bs = c.spec_trans.sample_wi(wo_local, u0, u1);
+            wi_local = bs.wi;
+            valid = bs.valid;
+            event = c.thin ? LRK_EVENT_THROUGH : cos_theta(wo_local) > 0.f ? LRK_EVENT_ENTER : LRK_EVENT_EXIT;
+        }
+    } else if (c.has_diff_trans) {// LambertianTransmission::sample_wi, scattering.cpp:276-280 (disney.cpp:827-832)
+        wi_local = sample_cosine_hemisphere(u0, u1);
+        wi_local.z *= -sign(cos_theta(wo_local));
+        valid = true;
+        event = LRK_EVENT_THROUGH;
     }
     SurfSample out;
     out.wi = it.shading.local_to_world(wi_local);
@@ -2314,7 +2358,7 @@ lrk_surface resolve_surface(const lrk_scene_desc &sc, const lrk_surface &node, c
     if (s.type == LRK_SURFACE_MATTE) {
         if (s.tex[3] != 0u) s.p[3] = saturate(texture_evaluate(sc, s.tex[3] - 1u, it.u, it.v).x) * 90.f;
     } else {
-        for (uint32_t k = 4u; k < 15u; k++) {
+        for (uint32_t k = 4u; k < 16u; k++) {
             if (s.tex[k] == 0u) continue;
             float x = texture_evaluate(sc, s.tex[k] - 1u, it.u, it.v).x;
             if (k == 6u && (s.flags & LRK_SURFACE_REMAP_ROUGHNESS)) x = std::fmax(x * x, 1e-4f);// scattering.cpp:137-139
@@ -3173,10 +3217,12 @@ extern "C" int oracle_unit(const char *name_c, const uint32_t *in, uint32_t *out
             auto take = [&](int count, int at = 0) { for (int i = 0; i < count; i++) sf.p[at + i] = w.f(); };
             bool is_eval = name.find("_evaluate") != std::string::npos;
             if (name.rfind("matte_", 0) == 0) { sf.type = LRK_SURFACE_MATTE; take(4); }
-            else if (name.rfind("disney_", 0) == 0 || name.rfind("disneytrans_", 0) == 0) {
-                sf.type = LRK_SURFACE_DISNEY; take(15);
+            else if (name.rfind("disney_", 0) == 0 || name.rfind("disneytrans_", 0) == 0 || name.rfind("disneythin_", 0) == 0) {
+                const bool thin = name.rfind("disneythin_", 0) == 0;
+                sf.type = LRK_SURFACE_DISNEY; take(thin ? 16 : 15);
                 sf.lobes = static_cast<uint32_t>(std::stoul(name.substr(name.rfind('_') + 1)));
                 if (name.rfind("disneytrans_", 0) == 0) sf.flags |= LRK_SURFACE_DISNEY_TRANSMISSIVE;// closure class "disney_trans"
+                if (thin) sf.flags |= LRK_SURFACE_DISNEY_THIN;                                       // closure class "disney_thin"
             }
             else if (name.rfind("mirror_", 0) == 0) { sf.type = LRK_SURFACE_MIRROR; take(5); }
             else if (name.rfind("glass_", 0) == 0) { sf.type = LRK_SURFACE_GLASS; take(10); }

@@ -95,6 +95,11 @@ extern "C" int device_closure_unit(const char *name_c, const uint32_t *in, uint3
             sf.flags |= LRK_SURFACE_DISNEY_TRANSMISSIVE;
             sf.lobes = static_cast<uint32_t>(std::stoul(name.substr(name.rfind('_') + 1)));
             DisneyTransClosure cl; cl.init(sf); run(cl, w, is_eval);
+        } else if (name.rfind("disneythin_", 0) == 0) {// the thin closure class (hit bucket 10)
+            sf.type = LRK_SURFACE_DISNEY; take(16);
+            sf.flags |= LRK_SURFACE_DISNEY_THIN;
+            sf.lobes = static_cast<uint32_t>(std::stoul(name.substr(name.rfind('_') + 1)));
+            DisneyThinClosure cl; cl.init(sf); run(cl, w, is_eval);
         } else {
             if (name.rfind("mirror_", 0) == 0) { take(5); MicrofacetFamilyClosure<LRK_SURFACE_MIRROR> cl; cl.init(sf); run(cl, w, is_eval); }
             else if (name.rfind("glass_", 0) == 0) { take(10); MicrofacetFamilyClosure<LRK_SURFACE_GLASS> cl; cl.init(sf); run(cl, w, is_eval); }

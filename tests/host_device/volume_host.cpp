@@ -50,6 +50,7 @@ extern "C" int volume_general_host(const lrk_scene_desc *s, uint32_t spp_begin, 
             const uint32_t type = s->surfaces[surface_tag].type;
             kind = type + 1u;
             if (type == LRK_SURFACE_DISNEY && (s->surfaces[surface_tag].flags & LRK_SURFACE_DISNEY_TRANSMISSIVE)) kind = 8u;
+            if (type == LRK_SURFACE_DISNEY && (s->surfaces[surface_tag].flags & LRK_SURFACE_DISNEY_THIN)) kind = 10u;
         }
         kinds[i] = kind;
         if ((flags & LRK_SHAPE_MAYBE_NON_OPAQUE) && (flags & LRK_SHAPE_HAS_SURFACE)) alpha = true;

@@ -23,7 +23,7 @@ import gen_ref_pins as G  # noqa: E402
 
 SRC = REPO / "tests" / "host_device" / "closures_host.cpp"
 OUT = REPO / "tests" / "host_device" / "_build" / "libclosures_host.so"
-CLOSURE_PINS = sorted(n for n in G.PINS if n.split("_")[0] in ("matte", "disney", "disneytrans", "mirror", "glass", "plastic", "metal"))
+CLOSURE_PINS = sorted(n for n in G.PINS if n.split("_")[0] in ("matte", "disney", "disneytrans", "disneythin", "mirror", "glass", "plastic", "metal"))
 
 
 @pytest.fixture(scope="module")

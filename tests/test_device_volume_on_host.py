@@ -40,6 +40,15 @@ def lib():
     return handle
 
 
+def _golden_case(name):
+    import sys
+
+    sys.path.insert(0, str(REPO / "tools"))
+    import gen_ref_renders as G
+
+    return G.cases()[name]
+
+
 CASES = {
     "shape_media": lambda: scenes.media_box(resolution=(40, 40), spp=3),
     "shape_media_deep_rr": lambda: scenes.media_box(resolution=(32, 32), spp=3, depth=16, rr_depth=3, rr_threshold=0.9),
@@ -51,6 +60,9 @@ CASES = {
     # config C4's shape (one environment medium, opaque closures): the wavefront kernels' territory, but the general code must agree
     "environment_medium_only": lambda: scenes.instanced_spheres(resolution=(32, 18), spp=2, depth=6, medium=True, big_subdivision=2,
                                                                 small_subdivision=1, small_count=12),
+    # the three Disney closure classes - thin ("through" events: the tracker must not move), transmissive (enter / exit), opaque -
+    # inside an environment medium: the scene of tests/golden/ref_renders.npz: spheres_medium_disney_thin
+    "disney_thin_and_transmissive": lambda: _golden_case("spheres_medium_disney_thin"),
 }
 
 

@@ -39,7 +39,11 @@ CASES = ["cornell_wavepath", "cornell_megapath", "cornell_russian_roulette", "sp
          "spheres_medium_isotropic", "subdivision", "swizzle", "checkerboard", "spheres_disney_transmissive",
          "cornell_sampler_pmj02bn", "cornell_sampler_sobol", "cornell_sampler_paddedsobol", "cornell_sampler_zsobol",
          "spheres_sampler_pmj02bn", "spheres_sampler_sobol", "spheres_sampler_paddedsobol", "spheres_sampler_zsobol",
-         "media_shapes", "media_nested_in_environment_medium", "media_true_hit_quirk", "materials_named_metals", "materials_textured", "materials_layered", "materials_layered_rr"]
+         "media_shapes", "media_nested_in_environment_medium", "media_true_hit_quirk", "materials_named_metals", "materials_textured", "materials_layered", "materials_layered_rr",
+         "spheres_disney_thin", "spheres_medium_disney_thin"]
+
+
+TRANSMISSIVE_SPHERES = ("spheres_disney_transmissive", "spheres_disney_thin", "spheres_medium_disney_thin")
 
 
 @pytest.fixture(scope="module")
@@ -97,7 +101,7 @@ def test_fixture_is_what_the_reference_renders_now(golden):
                                   "materials_megapath_rr", "textured", "textured_wrappers", "environment_image",
                                   "config_c3_full_scene", "cornell_filter_gaussian", "cornell_filter_mitchell",
                                   "cornell_film_and_light_options", "materials_mix", "materials_named_metals", "materials_textured", "materials_layered", "flatten_stress", "spheres_disney_all_lobes",
-                                  "subdivision", "spheres_disney_transmissive",
+                                  "subdivision", "spheres_disney_transmissive", "spheres_disney_thin", "spheres_medium_disney_thin",
                                   "cornell_sampler_pmj02bn", "cornell_sampler_sobol", "cornell_sampler_paddedsobol", "cornell_sampler_zsobol",
                                   "spheres_sampler_pmj02bn", "spheres_sampler_sobol", "spheres_sampler_paddedsobol", "spheres_sampler_zsobol"])
 def test_cuda_film_matches_the_reference_render(golden, name, gpu_renderer):
@@ -114,7 +118,7 @@ def test_cuda_film_matches_the_reference_render(golden, name, gpu_renderer):
         # the stochastic alpha test hashes barycentric BITS: see tests/test_gpu_parity.py::test_render_matches_oracle
         assert off.mean() <= (0.12 if fast else 0.04), f"{name}: {off.mean():.4f} of the pixels off"
         assert got.mean() == pytest.approx(want.mean(), rel=0.03)
-    elif fast and not (name.startswith("materials") or name == "spheres_disney_transmissive"):
+    elif fast and not (name.startswith("materials") or name in TRANSMISSIVE_SPHERES):
         # fast_math: about one path in 10^4 takes another branch of a discrete decision; at the 2 - 8 spp of these fixtures one such
         # path that finds the light moves the whole image's rel-L2 by percents.  Stated: <= 1 % of the pixels off by > 1e-4 relative,
         # the other 99 % agree to 1e-4 rel-L2, image means to 1 %.
@@ -133,7 +137,7 @@ def test_cuda_film_matches_the_reference_render(golden, name, gpu_renderer):
         keep = e <= np.quantile(e, 0.7)
         assert np.linalg.norm((got - want)[keep]) / np.linalg.norm(want[keep]) <= 1e-3
         assert got.mean() == pytest.approx(want.mean(), rel=0.05)
-    elif name.startswith("materials") or name == "spheres_disney_transmissive":
+    elif name.startswith("materials") or name in TRANSMISSIVE_SPHERES:
         # Specular chains (mirror wall, smooth and rough glass) amplify the ulp-level differences between CUDA's and glibc's
         # sin / cos / pow into different discrete decisions (lobe choice, total internal reflection, Russian roulette) for a
         # few paths: <= 3 % of the pixels may take another, equally valid, branch; the rest agree to 1e-3 rel-L2 and the

@@ -380,3 +380,32 @@ def test_swizzle_of_checkerboard_composes():
     np.testing.assert_array_equal(texels[0, :3], np.float32([0.2, 0.8, 0.2]))  # on, "brg"
     np.testing.assert_array_equal(texels[1, :3], np.float32([0.6, 0.1, 0.1]))  # off, "brg"
     np.testing.assert_array_equal(texels[3, :3], texels[0, :3])
+
+
+def test_disney_closure_classes_and_their_lobe_unions():
+    """src/surfaces/disney.cpp:61-75,925-930,966-995: a node is "disney_thin" when `thin` is set AND one of the two transmissions is
+    not black, "disney_trans" when not thin with a non-black specular_trans, else "disney"; each class ORs the lobes of its own
+    nodes only.  The scene is the fixture tests/golden/ref_renders.npz: spheres_disney_thin, which the reference itself rendered."""
+    import sys
+    from pathlib import Path
+
+    REPO = Path(__file__).resolve().parent.parent
+    sys.path.insert(0, str(REPO / "tools"))
+    import gen_ref_renders as G
+
+    source = G.cases()["spheres_disney_thin"]
+    d = Scene.from_source(source, REPO).desc()
+    recs = [d.surfaces[i] for i in range(d.surface_count) if d.surfaces[i].type == 1]  # LRK_SURFACE_DISNEY
+    thin = [s for s in recs if s.flags & 64]
+    trans = [s for s in recs if s.flags & 16]
+    opaque = [s for s in recs if not s.flags & (16 | 64)]
+    assert thin and trans and opaque and not any(s.flags & 16 for s in thin)
+    assert {s.lobes for s in thin} == {1 | 2 | 4 | 8 | 16 | 32 | 64 | 128}  # flatness (4), spec_trans and diff_trans come from thin nodes only
+    assert {s.lobes for s in trans} == {1 | 2 | 8 | 16 | 32 | 128}
+    assert {s.lobes for s in opaque} == {1 | 2 | 8 | 16 | 32}
+    assert sorted({round(s.p[15], 3) for s in thin}) == [0.5, 0.7] and all(s.p[15] == 0.0 for s in trans + opaque)
+    # `thin` without any transmission: an ordinary opaque record (diffuse_trans is built but black)
+    plain = source.replace("diffuse_trans : Constant { v { 0.7 } }", "diffuse_trans : Constant { v { 0.0 } }")
+    d2 = Scene.from_source(plain, REPO).desc()
+    assert sum(1 for i in range(d2.surface_count) if d2.surfaces[i].flags & 64) == len(thin) // 2
+    assert {d2.surfaces[i].lobes for i in range(d2.surface_count) if d2.surfaces[i].flags & 64} == {255}  # the remaining thin nodes still carry both transmissions

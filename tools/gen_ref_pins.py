@@ -133,6 +133,14 @@ def _disney_trans_ctx(r, n):  # a transmissive Disney node: specular_trans in [0
     return c.astype(np.float32)
 
 
+def _disney_thin_ctx(r, n):  # a thin Disney node: 16 context values, the last one diffuse_trans (lrk_surface.p[15])
+    c = np.concatenate([_disney_trans_ctx(r, n), r.random((n, 1), dtype=np.float32)], axis=1)
+    c[n // 3: n // 2, 15] = 0.0  # no diffuse transmission
+    c[n // 2: 2 * n // 3, 13] = 0.0  # no specular transmission
+    c[-n // 8:, 15] = 1.0  # everything diffuse goes through
+    return c.astype(np.float32)
+
+
 def _sigma_a(r, n):
     a = (2.0 * r.random((n, 3), dtype=np.float32)).astype(np.float32)
     a[: n // 3] = 0.0
@@ -214,6 +222,11 @@ for _mask in (35, 59, 63, 32):  # lobe masks: diffuse+retro+specular, + sheen + 
 for _mask in (163, 191):  # transmissive closure: diffuse+retro+specular+spec_trans, and every lobe + spec_trans
     PINS[f"disneytrans_evaluate_{_mask}"] = ([_disney_trans_ctx, _frame, _dir, _dir], _EVAL_OUT)
     PINS[f"disneytrans_sample_{_mask}"] = ([_disney_trans_ctx, _frame, _dir, _u, _u2], _SAMPLE_OUT)
+
+
+for _mask in (227, 255, 108):  # thin closure: base + both transmissions, every lobe, and a mask without the diffuse bits
+    PINS[f"disneythin_evaluate_{_mask}"] = ([_disney_thin_ctx, _frame, _dir, _dir], _EVAL_OUT)
+    PINS[f"disneythin_sample_{_mask}"] = ([_disney_thin_ctx, _frame, _dir, _u, _u2], _SAMPLE_OUT)
 
 
 def alias_table_values(seed: int = 7, n: int = 37) -> np.ndarray:

@@ -89,6 +89,28 @@ def cases() -> dict[str, str]:
         return "\n".join(out)
     c["spheres_disney_transmissive"] = _transmissive(
         scenes.instanced_spheres(resolution=(32, 18), spp=4, depth=8, rr_depth=2, **spheres)).replace('"spheres.exr"', '"trans.exr"')
+    # thin Disney surfaces (closure class "disney_thin": five techniques, rescaled transmission distribution, Lambertian diffuse
+    # transmission, "through" events) next to transmissive and opaque ones - all three closure classes, each with its own lobe union;
+    # under the wavefront integrator with Russian roulette, and under the volume integrator (a through event keeps the medium)
+    def _thin(src):
+        out, k = [], 0
+        for line in src.split("\n"):
+            out.append(line)
+            if line.strip().startswith("sheen : Constant"):
+                if k % 4 == 0:
+                    out += ["  thin { true }", "  specular_trans : Constant { v { 0.8 } }", "  diffuse_trans : Constant { v { 0.5 } }",
+                            "  flatness : Constant { v { 0.3 } }", "  eta : Constant { v { 1.45 } }"]
+                elif k % 4 == 1:
+                    out += ["  thin { true }", "  diffuse_trans : Constant { v { 0.7 } }"]
+                elif k % 4 == 2:
+                    out += ["  specular_trans : Constant { v { 0.9 } }", "  eta : Constant { v { 1.33 } }"]
+                k += 1
+        assert k >= 4
+        return "\n".join(out)
+    c["spheres_disney_thin"] = _thin(
+        scenes.instanced_spheres(resolution=(32, 18), spp=4, depth=8, rr_depth=2, **spheres)).replace('"spheres.exr"', '"thin.exr"')
+    c["spheres_medium_disney_thin"] = _thin(
+        scenes.instanced_spheres(resolution=(32, 18), spp=4, depth=6, medium=True, **spheres)).replace('"spheres.exr"', '"thinvpt.exr"')
     # row f2: the table-driven samplers.  Cornell @4 spp with each; the sphere scene with sample counts that are NOT the samplers'
     # favourite powers (pmj02bn: 8 is no power of 4 -> its pixel-sample sorting skips entries; Sobol' / PaddedSobol: 3 is no power of
     # 2; ZSobol: log2(2) is odd -> the half-digit branch), depth 6 = 30 dimensions per path
