@@ -139,7 +139,7 @@ typedef struct lrk_instance {
 /* ---- materials, lights ---------------------------------------------------------------- */
 
 #define LRK_SURFACE_MATTE 0u  /* src/surfaces/matte.cpp */
-#define LRK_SURFACE_DISNEY 1u /* src/surfaces/disney.cpp (opaque, non-thin closure "disney") */
+#define LRK_SURFACE_DISNEY 1u /* src/surfaces/disney.cpp: closure class "disney", or "disney_trans" / "disney_thin" by the flags below */
 #define LRK_SURFACE_MIRROR 2u  /* src/surfaces/mirror.cpp */
 #define LRK_SURFACE_GLASS 3u   /* src/surfaces/glass.cpp (non-dispersive: fixed sRGB spectrum) */
 #define LRK_SURFACE_PLASTIC 4u /* src/surfaces/plastic.cpp */
@@ -275,12 +275,17 @@ typedef struct lrk_texture {
 } lrk_texture;
 
 /* One light node (tag = index): src/lights/diffuse.cpp:23-26. emission is the decoded
- * illuminant (max(rgb,0)), L = emission * scale. */
+ * illuminant (max(rgb,0)), L = emission * scale.
+ * emission_tex != 0: the emission is image texture (emission_tex - 1), L = max(texel.xyz, 0) * scale
+ * (Texture::Instance::evaluate_illuminant_spectrum, src/base/texture.cpp:47-57: no channel extension on this path), looked up
+ * at the uv of the emitter hit or of the sampled light point (the light sampler builds that interaction with the full shading
+ * attributes, src/lightsamplers/uniform.cpp:108-123). */
 typedef struct lrk_light {
     float emission[3];
     float scale;
     uint32_t two_sided;
-    uint32_t reserved[3];
+    uint32_t emission_tex;
+    uint32_t reserved[2];
 } lrk_light;
 
 /* Light::Handle, 8 B: src/base/light.h:26-29 */

@@ -70,7 +70,7 @@ class Texture(C.Structure):
 
 
 class Light(C.Structure):
-    _fields_ = [("emission", f32 * 3), ("scale", f32), ("two_sided", u32), ("reserved", u32 * 3)]
+    _fields_ = [("emission", f32 * 3), ("scale", f32), ("two_sided", u32), ("emission_tex", u32), ("reserved", u32 * 2)]
 
 
 class LightHandle(C.Structure):

@@ -166,7 +166,7 @@ void free_paths(lrk_ctx *ctx) {
 
 int alloc_paths(lrk_ctx *ctx, uint64_t capacity) {
     uint32_t kinds = 0u;
-    for (int k = 0; k < 10; k++) if (k < 3 || ctx->has_kind[k]) kinds |= 1u << k;// buckets 3..9 only for scenes that use them
+    for (int k = 0; k < static_cast<int>(kHitKinds); k++) if (k < 3 || ctx->has_kind[k]) kinds |= 1u << k;// buckets 3..10 only for scenes that use them
     if (ctx->capacity >= capacity && (!ctx->volume || ctx->volume_capacity >= capacity) && (ctx->allocated_kinds & kinds) == kinds) return LRK_OK;
     free_paths(ctx);
     auto alloc = [&](void **p, size_t bytes) -> cudaError_t {
@@ -182,7 +182,7 @@ int alloc_paths(lrk_ctx *ctx, uint64_t capacity) {
         LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.id_rng[k]), capacity * sizeof(uint2)));
     }
     LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.hit), capacity * sizeof(uint4)));
-    for (int k = 0; k < 10; k++) {
+    for (int k = 0; k < static_cast<int>(kHitKinds); k++) {
         pb.hit_index[k] = nullptr;
         if (kinds & (1u << k)) LRK_CUDA(alloc(reinterpret_cast<void **>(&pb.hit_index[k]), capacity * sizeof(uint32_t)));
     }
@@ -738,12 +738,16 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
     ctx->textured = false;
     for (uint32_t i = 0; i < s->surface_count; i++)
         if (s->surfaces[i].flags & (LRK_SURFACE_HAS_TEXTURES | LRK_SURFACE_HAS_NORMAL_MAP)) ctx->textured = true;
+    for (uint32_t i = 0; i < s->light_count; i++)
+        if (s->lights[i].emission_tex != 0u) ctx->textured = true;// image emission: looked up by the TEXTURED kernel variants only
     for (uint32_t i = 0; i < s->texture_count; i++) {
         const auto &t = s->textures[i];
         if (t.width == 0u || t.height == 0u || t.texel_offset + static_cast<uint64_t>(t.width) * t.height > s->texel_count ||
             t.address > LRK_TEX_ADDRESS_ZERO || t.filter > LRK_TEX_FILTER_LINEAR || t.encoding > LRK_TEX_ENCODING_GAMMA)
             return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_upload_scene: invalid image texture record");
     }
+    for (uint32_t i = 0; i < s->light_count; i++)
+        if (s->lights[i].emission_tex > s->texture_count) return fail(ctx, LRK_ERR_INVALID_ARGUMENT, "lrk_upload_scene: a light's emission texture id is out of range");
     LRK_CUDA(cudaSetDevice(ctx->device));
     auto &a = ctx->arrays;
     int rc;
@@ -799,7 +803,7 @@ int lrk_upload_scene(lrk_ctx *ctx, const lrk_scene_desc *s) {
             if ((rc = upload(ctx, &a.zsobol_hash, q.zsobol_hash, 2048u))) return rc;
     }
     std::vector<uint32_t> handles(static_cast<size_t>(s->instance_count) * 4u), kinds(s->instance_count);
-    for (int k = 1; k < 10; k++) ctx->has_kind[k] = false;
+    for (int k = 1; k < static_cast<int>(kHitKinds); k++) ctx->has_kind[k] = false;
     ctx->any_non_opaque = false;
     std::vector<float> o2w(static_cast<size_t>(s->instance_count) * 12u), xform(static_cast<size_t>(s->instance_count) * 16u);
     for (uint32_t i = 0; i < s->instance_count; i++) {

@@ -54,5 +54,6 @@ struct PathBuffers {
     unsigned long long *stats;// [0] closest rays, [1] shadow rays, [2..4] closest nodes/tris/xforms, [5..7] shadow nodes/tris/xforms
 };
 constexpr uint32_t kHitKinds = 11u;// hit buckets: emitter-only, Matte, Disney, Mirror, Glass, Plastic, Metal, Mix, transmissive Disney, Layered, thin Disney
+static_assert(4u + kHitKinds <= kCountSlots, "PathBuffers::counts has one row of counters per hit bucket behind the four queue rows");
 
 }// namespace lrk

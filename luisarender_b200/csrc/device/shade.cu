@@ -34,7 +34,7 @@ int grid_of(Kernel kernel, int block, int sm_count) {
 template<typename F>
 void with_shade_kernel(uint32_t kind, bool textured, F &&f) {
     switch (kind) {
-        case 0u: f(shade_kernel<0u, false>); break;// emitter-only hits: nothing to texture
+        case 0u: textured ? f(shade_kernel<0u, true>) : f(shade_kernel<0u, false>); break;// emitter-only hits: a light's image emission
         case 1u: textured ? f(shade_kernel<1u, true>) : f(shade_kernel<1u, false>); break;
         case 2u: textured ? f(shade_kernel<2u, true>) : f(shade_kernel<2u, false>); break;
         case 3u: textured ? f(shade_kernel<3u, true>) : f(shade_kernel<3u, false>); break;
@@ -51,7 +51,7 @@ void with_shade_kernel(uint32_t kind, bool textured, F &&f) {
 template<typename F>
 void with_volume_surface_kernel(uint32_t kind, bool textured, F &&f) {
     switch (kind) {
-        case 0u: f(volume_surface_kernel<0u, false>); break;
+        case 0u: textured ? f(volume_surface_kernel<0u, true>) : f(volume_surface_kernel<0u, false>); break;
         case 1u: textured ? f(volume_surface_kernel<1u, true>) : f(volume_surface_kernel<1u, false>); break;
         default: textured ? f(volume_surface_kernel<2u, true>) : f(volume_surface_kernel<2u, false>); break;
     }

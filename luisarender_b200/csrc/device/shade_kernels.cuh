@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(kShadeBlock, LRK_SHADE_MIN_BLOCKS) shade_kerne
                 it.back_facing = dot(wo, it.ng) < 0.0f;
                 // emitter hit with MIS: mega_path.cpp:80-87, uniform.cpp:50-65
                 if (sc.light_count != 0u && it.shape.has_light()) {
-                    LightEval e = evaluate_hit(sc, it, v3(ro.x, ro.y, ro.z));
+                    LightEval e = evaluate_hit<TEXTURED>(sc, it, v3(ro.x, ro.y, ro.z));
                     V3 add = beta * e.L * balance_heuristic(pdf_bsdf, e.pdf);
                     float4 li = pb.li[ir.x];
                     li.x += add.x;
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(kShadeBlock, LRK_SHADE_MIN_BLOCKS) shade_kerne
                     ls.eval.pdf = 0.f;
                     ls.ray_o_tmin = make_float4(0.f, 0.f, 0.f, 0.f);
                     ls.ray_d_tmax = make_float4(0.f, 0.f, 1.f, 0.f);
-                    if (sc.light_count != 0u || sc.env_prob != 0.f) ls = sample_light(sc, it, u_sel, ul0, ul1);
+                    if (sc.light_count != 0u || sc.env_prob != 0.f) ls = sample_light<TEXTURED>(sc, it, u_sel, ul0, ul1);
                     const lrk_surface *surf = sc.surfaces + it.shape.surface_tag;
                     V3 contrib, wi, f;
                     float pdf;
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(kBlock, 2) volume_surface_kernel(DeviceScene s
             Interaction it = make_interaction(sc, hit.x, hit.y, v3(1.f - bu - bv, bu, bv));
             it.back_facing = dot(-d, it.ng) < 0.0f;
             if (it.shape.has_light()) {// evaluate_hit from the MOVED ray origin (mega_vpt_naive.cpp:308,319)
-                LightEval e = evaluate_hit(sc, it, no);
+                LightEval e = evaluate_hit<TEXTURED>(sc, it, no);
                 V3 add = beta * e.L * balance_heuristic(pdf_bsdf, e.pdf);
                 float4 li = pb.li[ir.x];
                 li.x += add.x;
@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(kBlock, 2) volume_surface_kernel(DeviceScene s
                 float ul0 = lcg(state), ul1 = lcg(state);
                 float u_lobe = lcg(state);
                 float ub0 = lcg(state), ub1 = lcg(state);
-                LightSample ls = sample_light(sc, it, u_sel, ul0, ul1);
+                LightSample ls = sample_light<TEXTURED>(sc, it, u_sel, ul0, ul1);
                 const lrk_surface *surf = sc.surfaces + it.shape.surface_tag;
                 V3 wo = -d;
                 V3 contrib = v3(0.f), wi, f;

@@ -217,13 +217,19 @@ struct LightEval {
     float pdf;
 };
 
+// image emission: max(texel.xyz, 0) at the interaction's uv (texture.cpp:47-57, srgb.cpp:48-54).  TEX: only the TEXTURED kernel
+// variants contain the lookup (lrk_upload_scene selects them when a light has an emission texture); the others keep the constant
+__device__ __noinline__ inline V3 light_emission_texel(const DeviceScene &sc, uint32_t emission_tex, float u, float v);
+template<bool TEX = true>
 __device__ __forceinline__ LightEval diffuse_light_evaluate(const DeviceScene &sc, const Interaction &it_light, V3 p_from) {
     const lrk_light light = sc.lights[it_light.shape.light_tag];
     const lrk_mesh mesh = sc.meshes[it_light.shape.mesh];
     float pdf_triangle = __ldg(sc.pdf + mesh.triangle_offset + it_light.prim);
     float pdf_area = pdf_triangle / it_light.prim_area;
     float cos_wo = abs_dot(normalize(p_from - it_light.pg), it_light.ng);
-    V3 L = v3(light.emission[0], light.emission[1], light.emission[2]) * light.scale;
+    V3 L = v3(light.emission[0], light.emission[1], light.emission[2]);
+    if (TEX && light.emission_tex != 0u) L = light_emission_texel(sc, light.emission_tex, it_light.u, it_light.v);
+    L = L * light.scale;
     V3 diff = it_light.pg - p_from;
     float pdf = dot(diff, diff) * pdf_area * (1.0f / cos_wo);
     bool invalid = fabsf(cos_wo) < 1e-6f || (!light.two_sided && it_light.back_facing);
@@ -233,8 +239,9 @@ __device__ __forceinline__ LightEval diffuse_light_evaluate(const DeviceScene &s
     return e;
 }
 
+template<bool TEX = true>
 __device__ __forceinline__ LightEval evaluate_hit(const DeviceScene &sc, const Interaction &it, V3 p_from) {
-    LightEval e = diffuse_light_evaluate(sc, it, p_from);
+    LightEval e = diffuse_light_evaluate<TEX>(sc, it, p_from);
     float n = static_cast<float>(sc.light_count);
     e.pdf *= (1.f - sc.env_prob) / n;// uniform.cpp:63 (env_prob = 0 without an environment)
     return e;
@@ -252,6 +259,7 @@ struct LightSample {
 // `p_shading`: it_from.p_shading(), the point the light's emission and pdf are evaluated from (diffuse.cpp:62-86) - the hit point
 // for a surface interaction, but the WORLD ORIGIN for the volume integrator's Interaction{ray->origin()}, whose shading point is
 // never set (mega_vpt_naive.cpp:283-285; the reference's renders carry that, so this library does too)
+template<bool TEX = true>
 __device__ __forceinline__ LightSample sample_light_from(const DeviceScene &sc, const Interaction &it_from, V3 p_shading, float u_sel, float u0, float u1) {
     LightSample s;
     float n = static_cast<float>(sc.light_count);
@@ -292,7 +300,7 @@ __device__ __forceinline__ LightSample sample_light_from(const DeviceScene &sc, 
     V3 uvw = sample_uniform_triangle(ux, u1);
     Interaction it_light = make_interaction(sc, handle.instance_id, triangle_id, uvw);
     it_light.back_facing = dot(it_light.ng, it_from.pg - it_light.pg) < 0.f;
-    s.eval = diffuse_light_evaluate(sc, it_light, p_shading);
+    s.eval = diffuse_light_evaluate<TEX>(sc, it_light, p_shading);
     s.eval.pdf *= sel_prob;
     // Interaction::spawn_ray_to, src/base/interaction.cpp:25-30
     V3 p_from = p_robust(it_from, it_light.pg - it_from.pg);
@@ -304,8 +312,9 @@ __device__ __forceinline__ LightSample sample_light_from(const DeviceScene &sc, 
     return s;
 }
 
+template<bool TEX = true>
 __device__ __forceinline__ LightSample sample_light(const DeviceScene &sc, const Interaction &it_from, float u_sel, float u0, float u1) {
-    return sample_light_from(sc, it_from, it_from.pg, u_sel, u0, u1);
+    return sample_light_from<TEX>(sc, it_from, it_from.pg, u_sel, u0, u1);
 }
 
 // ---- image textures: src/textures/image.cpp:132-166, sampled like the reference's software sampler
@@ -360,6 +369,10 @@ __device__ __noinline__ inline float4 texture_evaluate(const DeviceScene &sc, ui
     const lrk_texture t = sc.textures[tex_id];
     float4 s = texture_sample(sc, t, u * t.uv_scale[0] + t.uv_offset[0], v * t.uv_scale[1] + t.uv_offset[1]);
     return make_float4(tex_decode(t, s.x), tex_decode(t, s.y), tex_decode(t, s.z), tex_decode(t, s.w));
+}
+__device__ __noinline__ inline V3 light_emission_texel(const DeviceScene &sc, uint32_t emission_tex, float u, float v) {
+    const float4 t = texture_evaluate(sc, emission_tex - 1u, u, v);
+    return v3(fmaxf(t.x, 0.f), fmaxf(t.y, 0.f), fmaxf(t.z, 0.f));
 }
 // Surface parameters at a hit: the node's constants with the image-textured slots evaluated at the hit's uv
 // (MatteInstance::populate_closure matte.cpp:117-131, DisneySurfaceInstance::populate_closure disney.cpp:932-956;

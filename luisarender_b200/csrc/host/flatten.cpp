@@ -627,9 +627,9 @@ std::unique_ptr<FlatScene> flatten_scene(const Scene &scene) {
             e.map_height = kEnvMapHeight;
         }
     }
+    for (auto l : f.light_nodes) out->lights.push_back(l->flatten(texture_table));
     out->textures = std::move(texture_table.records);
     out->texels = std::move(texture_table.texels);
-    for (auto l : f.light_nodes) out->lights.push_back(l->flatten());
 
     for (auto cam : scene.cameras()) out->cameras.push_back(flatten_camera(cam));
     if (out->cameras.empty()) throw Error("The scene has no camera.");

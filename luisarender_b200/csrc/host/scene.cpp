@@ -1279,17 +1279,21 @@ struct DiffuseLight final : Light {
         auto e = d->node("emission");
         if (!e) e = s->shared_default(Tag::TEXTURE, "Constant");
         emission = s->load_texture(e);
-        if (!emission->is_constant()) throw Error("Only constant emission textures are supported.");
+        if (!emission->is_constant() && !emission->is_image()) throw Error("Only constant and image emission textures are supported.");
         scale = std::max(d->f("scale", 1.0f), 0.0f);
         two_sided = d->b("two_sided", false);
     }
     bool is_null() const override { return scale == 0.0f || emission->is_black(); }
-    lrk_light flatten() const override {
+    lrk_light flatten(TextureTable &textures) const override {
         lrk_light out{};
-        auto c = extend_color_to_rgb(emission->value(), emission->channels());
-        out.emission[0] = std::max(c.x, 0.f);
-        out.emission[1] = std::max(c.y, 0.f);
-        out.emission[2] = std::max(c.z, 0.f);
+        if (emission->is_image()) {
+            out.emission_tex = textures.slot(emission);// evaluated per point (texture.cpp:47-57)
+        } else {
+            auto c = extend_color_to_rgb(emission->value(), emission->channels());
+            out.emission[0] = std::max(c.x, 0.f);
+            out.emission[1] = std::max(c.y, 0.f);
+            out.emission[2] = std::max(c.z, 0.f);
+        }
         out.scale = scale;
         out.two_sided = two_sided ? 1u : 0u;
         return out;
@@ -1299,7 +1303,7 @@ struct DiffuseLight final : Light {
 struct NullLight final : Light {
     NullLight(Scene *s, const NodeDesc *d) : Light{s, d, Tag::LIGHT} {}
     bool is_null() const override { return true; }
-    lrk_light flatten() const override { throw Error("NullLight cannot be instantiated."); }
+    lrk_light flatten(TextureTable &) const override { throw Error("NullLight cannot be instantiated."); }
 };
 
 }// namespace

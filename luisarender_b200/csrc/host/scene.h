@@ -169,7 +169,7 @@ struct Environment : SceneNode {
 struct Light : SceneNode {
     using SceneNode::SceneNode;
     virtual bool is_null() const { return false; }
-    virtual lrk_light flatten() const = 0;
+    virtual lrk_light flatten(TextureTable &textures) const = 0;
 };
 
 struct Camera : SceneNode {

@@ -323,13 +323,20 @@ def media_box(resolution=(64, 64), spp=4, depth=8, rr_depth=0, rr_threshold=0.95
 
 def textured_room(resolution=(96, 64), spp=8, depth=6, rr_depth=0, rr_threshold=0.95, seed=19980810,
                   assets="tests/golden/assets", output="textured.exr", integrator="WavePath", wrappers=False,
-                  mesh_files=True) -> str:
+                  mesh_files=True, textured_light=False) -> str:
     """SURVEY.md §8 row f1 in one small scene: image-textured Matte and Disney parameters (PNG 8/16-bit, grey, palette; all
     four address modes, point + bilinear filters, sRGB + linear encodings, uv scale/offset) on an InlineMesh with uvs and
     on mesh FILES (Wavefront OBJ without normals, binary PLY).  `assets` is relative to the directory the scene is loaded from.
     ``wrappers=True`` adds the surface wrappers of src/base/surface.h:160-275: a normal-mapped floor, a cut-out screen with an
-    alpha texture (stochastic alpha test inside closest-hit and any-hit traversal) and a half-transparent cube (constant opacity)."""
+    alpha texture (stochastic alpha test inside closest-hit and any-hit traversal) and a half-transparent cube (constant opacity).
+    ``textured_light=True`` gives the lamp an image emission (src/lights/diffuse.cpp:74: evaluated at the uv of the emitter hit or of
+    the sampled light point, src/lightsamplers/uniform.cpp:108-123)."""
     a = assets.rstrip("/")
+    emission = "Constant { v { 14.0, 13.0, 11.0 } }"
+    lamp_uvs = ""
+    if textured_light:
+        emission = f'Image {{ file {{ "{a}/checker_rgb8.png" }} address {{ "repeat" }} filter {{ "bilinear" }} uv_scale {{ 2.0 }} uv_offset {{ 0.3, 0.1 }} scale {{ 20.0 }} }}'
+        lamp_uvs = "\n  uvs { 0.0, 0.0,  0.0, 1.0,  1.0, 1.0,  1.0, 0.0 }"
     floor_extra = cube_extra = screen = screen_ref = ""
     # mesh_files=False: the two file meshes become inline panels with uvs (the reference build under oracle/ref has no
     # `Mesh` plugin: it needs assimp)
@@ -374,7 +381,7 @@ Surface cube_s : Disney {{
 Surface tetra_s : Matte {{
   Kd : Image {{ file {{ "{a}/palette4.png" }} address {{ "zero" }} encoding {{ "gamma" }} gamma {{ 2.0 }} }}
 }}
-Light area_light : Diffuse {{ emission : Constant {{ v {{ 14.0, 13.0, 11.0 }} }} }}
+Light area_light : Diffuse {{ emission : {emission} }}
 Shape floor : InlineMesh {{
   positions {{ -2.0, 0.0, 2.0,  2.0, 0.0, 2.0,  2.0, 0.0, -2.0,  -2.0, 0.0, -2.0 }}
   uvs {{ 0.0, 0.0,  1.0, 0.0,  1.0, 1.0,  0.0, 1.0 }}
@@ -397,7 +404,7 @@ Shape tetra : {tetra_geometry}
 }}
 {screen}
 Shape lamp : InlineMesh {{
-  positions {{ -0.6, 2.4, 0.4,  -0.6, 2.4, -0.4,  0.6, 2.4, -0.4,  0.6, 2.4, 0.4 }}
+  positions {{ -0.6, 2.4, 0.4,  -0.6, 2.4, -0.4,  0.6, 2.4, -0.4,  0.6, 2.4, 0.4 }}{lamp_uvs}
   indices {{ 0, 1, 2, 0, 2, 3 }}
   light {{ @area_light }}
 }}

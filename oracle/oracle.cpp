@@ -845,13 +845,16 @@ struct LightEval {
     float pdf{0.f};
 };
 
+// image emission: max(texel.xyz, 0) at the interaction's uv (Texture::Instance::evaluate_illuminant_spectrum, texture.cpp:47-57 -
+// no extend_color_to_rgb on the non-static path; decode_illuminant, srgb.cpp:48-54).  Defined with the texture code below.
+V3 light_emission(const lrk_scene_desc &sc, const lrk_light &light, float u, float v);
 LightEval diffuse_light_evaluate(const lrk_scene_desc &sc, const Interaction &it_light, V3 p_from) {
     const auto &light = sc.lights[it_light.shape.light_tag];
     const auto &mesh = sc.meshes[it_light.shape.buffer_base >> 2u];
     float pdf_triangle = sc.pdf[mesh.triangle_offset + it_light.prim];
     float pdf_area = pdf_triangle / it_light.prim_area;
     float cos_wo = abs_dot(normalize(p_from - it_light.pg), it_light.ng);
-    V3 L = v3(light.emission[0], light.emission[1], light.emission[2]) * light.scale;
+    V3 L = light_emission(sc, light, it_light.u, it_light.v) * light.scale;
     V3 diff = it_light.pg - p_from;
     float pdf = dot(diff, diff) * pdf_area * (1.0f / cos_wo);
     bool invalid = std::fabs(cos_wo) < 1e-6f || (!light.two_sided && it_light.back_facing);
@@ -916,6 +919,8 @@ LightSample sample_light(const lrk_scene_desc &sc, const Interaction &it_from, f
                        light_inst.tri_count, u0, triangle_id, ux);
     V3 uvw = sample_uniform_triangle(ux, u1);
     Interaction it_light = make_interaction(sc, handle.instance_id, triangle_id, uvw, false, v3(0.f), it_from.pg);
+    // the light sampler builds this interaction itself with the full shading attributes (uniform.cpp:108-123: shading_point, so
+    // the uv is the sampled point's) and asks the light's closure to evaluate() it; DiffuseLightClosure::sample is not on this path
     s.eval = diffuse_light_evaluate(sc, it_light, it_from.ps);
     s.eval.pdf *= sel_prob;
     s.shadow_ray = spawn_ray_to(it_from, it_light.pg);
@@ -2169,6 +2174,11 @@ F4 texture_evaluate(const lrk_scene_desc &sc, uint32_t tex_id, float u, float v)
 // ------------------------------------------------------------------------------------------------
 // Spherical environment: src/environments/spherical.cpp:42-137 (uv mapping, evaluate, sample); tables built by the host.
 // ------------------------------------------------------------------------------------------------
+V3 light_emission(const lrk_scene_desc &sc, const lrk_light &light, float u, float v) {
+    if (light.emission_tex == 0u) return v3(light.emission[0], light.emission[1], light.emission[2]);
+    F4 t = texture_evaluate(sc, light.emission_tex - 1u, u, v);
+    return v3(std::fmax(t.x, 0.f), std::fmax(t.y, 0.f), std::fmax(t.z, 0.f));
+}
 inline V3 env_mul(const float m[9], V3 v, bool transposed) {// float3x3 * float3 = v.x*col0 + v.y*col1 + v.z*col2
     if (!transposed) return v.x * v3(m[0], m[3], m[6]) + v.y * v3(m[1], m[4], m[7]) + v.z * v3(m[2], m[5], m[8]);
     return v.x * v3(m[0], m[1], m[2]) + v.y * v3(m[3], m[4], m[5]) + v.z * v3(m[6], m[7], m[8]);

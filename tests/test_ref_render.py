@@ -40,7 +40,7 @@ CASES = ["cornell_wavepath", "cornell_megapath", "cornell_russian_roulette", "sp
          "cornell_sampler_pmj02bn", "cornell_sampler_sobol", "cornell_sampler_paddedsobol", "cornell_sampler_zsobol",
          "spheres_sampler_pmj02bn", "spheres_sampler_sobol", "spheres_sampler_paddedsobol", "spheres_sampler_zsobol",
          "media_shapes", "media_nested_in_environment_medium", "media_true_hit_quirk", "materials_named_metals", "materials_textured", "materials_layered", "materials_layered_rr",
-         "spheres_disney_thin", "spheres_medium_disney_thin"]
+         "spheres_disney_thin", "spheres_medium_disney_thin", "textured_light"]
 
 
 TRANSMISSIVE_SPHERES = ("spheres_disney_transmissive", "spheres_disney_thin", "spheres_medium_disney_thin")
@@ -98,7 +98,7 @@ def test_fixture_is_what_the_reference_renders_now(golden):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["cornell_wavepath", "cornell_russian_roulette", "spheres_disney", "materials_wavepath",
-                                  "materials_megapath_rr", "textured", "textured_wrappers", "environment_image",
+                                  "materials_megapath_rr", "textured", "textured_wrappers", "textured_light", "environment_image",
                                   "config_c3_full_scene", "cornell_filter_gaussian", "cornell_filter_mitchell",
                                   "cornell_film_and_light_options", "materials_mix", "materials_named_metals", "materials_textured", "materials_layered", "flatten_stress", "spheres_disney_all_lobes",
                                   "subdivision", "spheres_disney_transmissive", "spheres_disney_thin", "spheres_medium_disney_thin",

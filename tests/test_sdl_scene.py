@@ -409,3 +409,17 @@ def test_disney_closure_classes_and_their_lobe_unions():
     d2 = Scene.from_source(plain, REPO).desc()
     assert sum(1 for i in range(d2.surface_count) if d2.surfaces[i].flags & 64) == len(thin) // 2
     assert {d2.surfaces[i].lobes for i in range(d2.surface_count) if d2.surfaces[i].flags & 64} == {255}  # the remaining thin nodes still carry both transmissions
+
+
+def test_light_with_image_emission_flattens_to_a_texture_slot():
+    """src/lights/diffuse.cpp:23-26,74: `emission` is any texture; an image is evaluated per point (lrk_light.emission_tex), a
+    constant is folded into lrk_light.emission."""
+    from pathlib import Path
+
+    repo = Path(__file__).resolve().parent.parent
+    d = Scene.from_source(scenes.textured_room(resolution=(16, 12), spp=1, mesh_files=False, textured_light=True), repo).desc()
+    assert d.light_count == 1 and 1 <= d.lights[0].emission_tex <= d.texture_count and list(d.lights[0].emission) == [0.0, 0.0, 0.0]
+    tex = d.textures[d.lights[0].emission_tex - 1]
+    assert tex.scale == 20.0 and list(tex.uv_scale) == [2.0, 2.0] and tex.address == 1  # repeat
+    d = Scene.from_source(scenes.textured_room(resolution=(16, 12), spp=1, mesh_files=False), repo).desc()
+    assert d.lights[0].emission_tex == 0 and list(d.lights[0].emission) == [14.0, 13.0, 11.0]
