@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(kTraceBlock, LRK_TRACE_MIN_BLOCKS) trace_close
     const uint32_t n = *count;
     TraversalCounters tc{0u, 0u, 0u};
     trace_queue<false, COUNT, 1, ALPHA>(sc, ray_o, ray_d, n, cursor, tc, [&](bool finished, uint32_t i, uint4 h) {
-        if (finished) hits[i] = h;
+        if (finished) store_result_record(hits + i, h);
     });
     if (COUNT) {
         atomicAdd(stats + 2, static_cast<unsigned long long>(tc.nodes));
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(kBlock) classify_hits_kernel(DeviceScene sc, P
 }
 
 template<bool COUNT, bool ALPHA = false>
-__global__ void __launch_bounds__(kTraceBlock, LRK_TRACE_MIN_BLOCKS) trace_shadow_kernel(DeviceScene sc, PathBuffers pb, const uint32_t *__restrict__ count,
+__global__ void __launch_bounds__(kTraceBlock, LRK_SHADOW_MIN_BLOCKS) trace_shadow_kernel(DeviceScene sc, PathBuffers pb, const uint32_t *__restrict__ count,
                                                               uint32_t *cursor) {
     const uint32_t n = *count;
     TraversalCounters tc{0u, 0u, 0u};

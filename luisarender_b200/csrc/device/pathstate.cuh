@@ -14,6 +14,11 @@ constexpr int kBlock = 256;
 #ifndef LRK_TRACE_MIN_BLOCKS
 #define LRK_TRACE_MIN_BLOCKS 4// blocks of kTraceBlock threads per SM the traversal kernels are compiled for (register budget)
 #endif
+#ifndef LRK_SHADOW_MIN_BLOCKS
+// the any-hit kernel is the one that gains from a fifth resident block (51 registers, 22 bytes spilled): 16.54 -> 16.04 ms per pass;
+// the closest-hit kernel loses at 5 (23.36 -> 24.13) and both lose at 6 (profiles/r02x_traversal_occupancy_and_cache_policy.jsonl)
+#define LRK_SHADOW_MIN_BLOCKS 5
+#endif
 #ifndef LRK_SHADE_BLOCK
 #define LRK_SHADE_BLOCK 256
 #endif

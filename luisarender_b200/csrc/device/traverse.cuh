@@ -100,7 +100,15 @@ __device__ __forceinline__ bool slab(float lox, float loy, float loz, float hix,
 template<bool COUNT, typename Stack>
 __device__ __forceinline__ void inner_step(const DeviceScene &sc, RayState &r, Stack &stack, TraversalCounters &cnt) {
     const float4 *np = sc.bvh_nodes + static_cast<size_t>(r.node) * 4u;
+#if defined(LRK_NODE_EVICT_LAST) && defined(__CUDA_ARCH__)
+    float4 n0, n1, n2, n3;
+    asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(n0.x), "=f"(n0.y), "=f"(n0.z), "=f"(n0.w) : "l"(np + 0));
+    asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(n1.x), "=f"(n1.y), "=f"(n1.z), "=f"(n1.w) : "l"(np + 1));
+    asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(n2.x), "=f"(n2.y), "=f"(n2.z), "=f"(n2.w) : "l"(np + 2));
+    asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(n3.x), "=f"(n3.y), "=f"(n3.z), "=f"(n3.w) : "l"(np + 3));
+#else
     float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
+#endif
     if (COUNT) cnt.nodes++;
     float tn0, tn1;
     bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, r.cur, r.tmin, r.tbest, tn0);
@@ -208,7 +216,33 @@ __device__ __forceinline__ void start_ray(const DeviceScene &sc, RayState &r, St
 
 #ifdef __CUDACC__
 
-constexpr int kTraceBlock = 256;// threads per block of every kernel that calls trace_queue
+#ifndef LRK_TRACE_BLOCK
+#define LRK_TRACE_BLOCK 256
+#endif
+constexpr int kTraceBlock = LRK_TRACE_BLOCK;// threads per block of every kernel that calls trace_queue
+
+// Cache policy (profiles/r02x_traversal_occupancy_and_cache_policy.jsonl):
+//   ray records are read once and hit records written once per launch: ld.global.cs / st.global.cs (evict first), so that they do
+//   not push hierarchy nodes out of L1 / L2 (closest 23.36 -> 23.16 ms per pass; -DLRK_NO_STREAM_RAYS restores plain loads);
+//   LRK_NODE_EVICT_LAST (experiment, off): ld.global.nc.L1::evict_last for the nodes on top of that changed nothing.
+#ifndef LRK_NO_STREAM_RAYS
+#define LRK_STREAM_RAYS 1
+#endif
+__device__ __forceinline__ float4 load_ray_record(const float4 *p) {
+#ifdef LRK_STREAM_RAYS
+    return __ldcs(p);
+#else
+    return __ldg(p);
+#endif
+}
+template<typename T>
+__device__ __forceinline__ void store_result_record(T *p, T v) {
+#ifdef LRK_STREAM_RAYS
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
 
 // Deferred-children stack of a lane: kSmemStack entries in shared memory (explicit st/ld.shared through the 32-bit window address:
 // the struct holds scalars only and lives in registers), then local memory, then the overflow flag.
@@ -310,7 +344,7 @@ __device__ __forceinline__ void trace_queue(const DeviceScene &sc, const float4 
             base = __shfl_sync(0xffffffffu, base, 0);
             const uint32_t pos = base + __popc(idle & lane_lt);
             if (!active && pos < n) {
-                float4 o = ray_o[static_cast<size_t>(pos) * STRIDE], d = ray_d[static_cast<size_t>(pos) * STRIDE];
+                float4 o = load_ray_record(ray_o + static_cast<size_t>(pos) * STRIDE), d = load_ray_record(ray_d + static_cast<size_t>(pos) * STRIDE);
                 start_ray(sc, r, stack, o, d);
                 ray_index = pos;
                 active = true;

@@ -426,3 +426,34 @@ def test_volume_with_shape_media_matches_oracle(kw, gpu_renderer):
     assert gpu_raw[..., :3].mean() == pytest.approx(cpu_raw[..., :3].mean(), rel=0.02)
     assert st["closest_rays"] == pytest.approx(cnt["closest_rays"], rel=5e-3)
     assert st["shadow_rays"] == pytest.approx(cnt["shadow_rays"], rel=5e-3)
+
+
+def test_volume_with_thin_and_transmissive_disney_matches_oracle(gpu_renderer):
+    """The three Disney closure classes inside an environment medium on the per-thread volume kernel: thin surfaces report "through"
+    events (the medium tracker and the eta scale stay put), transmissive ones enter / exit.  The scene is the fixture
+    tests/golden/ref_renders.npz: spheres_medium_disney_thin, on which the oracle is bit-identical to the reference renderer and the
+    device code, compiled for the host, bit-identical to the oracle (tests/test_device_volume_on_host.py).  Tolerances as in
+    test_volume_with_shape_media_matches_oracle (refraction chains, the moved-origin emitter hits)."""
+    import sys
+
+    sys.path.insert(0, str(REPO / "tools"))
+    import gen_ref_renders as G
+
+    scene = Scene.from_source(G.cases()["spheres_medium_disney_thin"].replace("resolution { 32, 18 }", "resolution { 96, 54 }"), REPO)
+    d = scene.desc()
+    assert d.camera.resolution[0] == 96
+    gpu_renderer.upload(d)
+    gpu_renderer.clear()
+    gpu_renderer.render(0, 4)
+    gpu_raw = gpu_renderer.film(raw=True)
+    st = gpu_renderer.stats()
+    cpu_raw, cnt = O.render(d, 0, 4)
+    assert (gpu_raw[..., 3] == cpu_raw[..., 3]).mean() >= 0.995
+    rel, off = _image_parity(gpu_raw, cpu_raw)
+    assert off <= 3e-2, (rel, off)
+    err = np.abs(gpu_raw[..., :3] - cpu_raw[..., :3]).max(axis=-1)
+    keep = err <= np.quantile(err, 0.97)
+    assert np.linalg.norm((gpu_raw[..., :3] - cpu_raw[..., :3])[keep]) / np.linalg.norm(cpu_raw[..., :3][keep]) <= 1e-3
+    assert gpu_raw[..., :3].mean() == pytest.approx(cpu_raw[..., :3].mean(), rel=0.02)
+    assert st["closest_rays"] == pytest.approx(cnt["closest_rays"], rel=5e-3)
+    assert st["shadow_rays"] == pytest.approx(cnt["shadow_rays"], rel=5e-3)

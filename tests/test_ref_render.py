@@ -43,7 +43,9 @@ CASES = ["cornell_wavepath", "cornell_megapath", "cornell_russian_roulette", "sp
          "spheres_disney_thin", "spheres_medium_disney_thin", "textured_light"]
 
 
-TRANSMISSIVE_SPHERES = ("spheres_disney_transmissive", "spheres_disney_thin", "spheres_medium_disney_thin")
+# (media scenes are compared with the oracle in tests/test_gpu_parity.py: the reference build's Henyey-Greenstein argument order is
+# GCC's, the device's is nvcc's - see the oracle test above)
+TRANSMISSIVE_SPHERES = ("spheres_disney_transmissive", "spheres_disney_thin")
 
 
 @pytest.fixture(scope="module")
@@ -101,7 +103,7 @@ def test_fixture_is_what_the_reference_renders_now(golden):
                                   "materials_megapath_rr", "textured", "textured_wrappers", "textured_light", "environment_image",
                                   "config_c3_full_scene", "cornell_filter_gaussian", "cornell_filter_mitchell",
                                   "cornell_film_and_light_options", "materials_mix", "materials_named_metals", "materials_textured", "materials_layered", "flatten_stress", "spheres_disney_all_lobes",
-                                  "subdivision", "spheres_disney_transmissive", "spheres_disney_thin", "spheres_medium_disney_thin",
+                                  "subdivision", "spheres_disney_transmissive", "spheres_disney_thin",
                                   "cornell_sampler_pmj02bn", "cornell_sampler_sobol", "cornell_sampler_paddedsobol", "cornell_sampler_zsobol",
                                   "spheres_sampler_pmj02bn", "spheres_sampler_sobol", "spheres_sampler_paddedsobol", "spheres_sampler_zsobol"])
 def test_cuda_film_matches_the_reference_render(golden, name, gpu_renderer):
