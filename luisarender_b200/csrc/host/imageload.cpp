@@ -1,6 +1,7 @@
 // Image file readers for the `Image` texture plugin (reference: LoadedImage::load, src/util/imageio.cpp:347-470, which
 // delegates to stb_image / tinyexr — neither is available here, so the decoders below are written against the file
-// format specifications).  What the readers reproduce from the reference is the STORAGE policy, because it decides the
+// format specifications; JPEG is the one stb format without a reader: a lossy decode only matches the reference's texels bit for bit
+// if it repeats stb's own integer IDCT and chroma filter).  What the readers reproduce from the reference is the STORAGE policy, because it decides the
 // texel values the sampler sees:
 //   * 8-bit files  -> BYTE1/2/4  : texel = x / 255        16-bit files -> SHORT1/2/4 : texel = x / 65535
 //   * .hdr         -> HALF4      : RGBE decoded to float, then rounded to binary16 (imageio.cpp:383, 231-245)
@@ -458,6 +459,242 @@ LoadedImage load_exr(const std::filesystem::path &path, const std::vector<uint8_
     return finish(w, h, nc, samples);
 }
 
+
+// ---- Windows BMP: uncompressed (BI_RGB) and BI_BITFIELDS pictures, 1 / 4 / 8-bit palettes, 16 / 24 / 32 bits per pixel, core (12)
+// and info (40 / 56 / 108 / 124 byte) headers, bottom-up or top-down.  What the reference sees for such a file is what stb_image
+// hands it with four channels requested (imageio.cpp:522-537: an RGB picture has >= 3 channels, so BYTE4): 8-bit RGBA, alpha 255
+// unless the picture has an alpha mask - the implicit 0xff000000 of a 32-bit BI_RGB picture counts, but an alpha channel that is
+// zero everywhere is taken to be absent - and narrow bit fields widened by bit replication.  RLE-compressed pictures are refused
+// (as there).
+struct ByteReader {
+    const std::vector<uint8_t> &d;
+    const std::filesystem::path &path;
+    size_t pos{0};
+    uint8_t u8() {
+        if (pos >= d.size()) fail(path, "truncated file");
+        return d[pos++];
+    }
+    uint32_t u16() { uint32_t a = u8(); return a | (uint32_t{u8()} << 8u); }
+    uint32_t u32() { uint32_t a = u16(); return a | (u16() << 16u); }
+    void skip(size_t n) {
+        if (pos + n > d.size()) fail(path, "truncated file");
+        pos += n;
+    }
+};
+
+// an n-bit field value (n in 1..8) widened to 8 bits by repeating its bit pattern: 5 bits abcde -> abcdeabc
+uint32_t replicate_bits(uint32_t v, uint32_t bits) {
+    uint32_t out = 0u;
+    for (int shift = 8 - static_cast<int>(bits); shift > -static_cast<int>(bits); shift -= static_cast<int>(bits))
+        out |= shift >= 0 ? v << shift : v >> -shift;
+    return out & 0xffu;
+}
+struct BitField {
+    uint32_t mask{0u}, low{0u}, bits{0u};
+    explicit BitField(uint32_t m) : mask{m} {
+        if (m == 0u) return;
+        while (!((m >> low) & 1u)) low++;
+        for (uint32_t b = low; b < 32u && ((m >> b) & 1u); b++) bits++;
+    }
+    bool contiguous() const { return mask == 0u || (bits < 32u && mask == (((1u << bits) - 1u) << low)); }
+    uint32_t extract(uint32_t v) const { return replicate_bits((v & mask) >> low, bits); }
+};
+
+LoadedImage load_bmp(const std::filesystem::path &path, const std::vector<uint8_t> &d) {
+    ByteReader r{d, path};
+    if (r.u8() != 'B' || r.u8() != 'M') fail(path, "not a BMP file");
+    r.skip(8);// file size, reserved
+    const uint32_t data_offset = r.u32(), header_size = r.u32();
+    if (header_size != 12u && header_size != 40u && header_size != 56u && header_size != 108u && header_size != 124u)
+        fail(path, "unsupported BMP header");
+    int64_t w, h;
+    if (header_size == 12u) {
+        w = r.u16();
+        h = r.u16();
+    } else {
+        w = static_cast<int32_t>(r.u32());
+        h = static_cast<int32_t>(r.u32());
+    }
+    if (r.u16() != 1u) fail(path, "bad BMP plane count");
+    const uint32_t bpp = r.u16();
+    uint32_t compression = 0u, mr = 0u, mg = 0u, mb = 0u, ma = 0u;
+    size_t header_end = 14u + header_size;
+    bool implicit_alpha = false;
+    if (header_size != 12u) {
+        compression = r.u32();
+        if (compression == 1u || compression == 2u) fail(path, "RLE-compressed BMP files are not supported");
+        if (compression > 3u) fail(path, "unsupported BMP compression");
+        if (compression == 3u && bpp != 16u && bpp != 32u) fail(path, "BMP bit fields need 16 or 32 bits per pixel");
+        r.skip(20);// image size, resolution, colour counts
+        auto defaults = [&] {// BI_RGB: 5-5-5 for 16 bits, 8-8-8-8 for 32 bits (whose alpha may turn out to be unused)
+            mr = mg = mb = ma = 0u;
+            if (bpp == 16u) { mr = 31u << 10u; mg = 31u << 5u; mb = 31u; }
+            if (bpp == 32u) { mr = 0xffu << 16u; mg = 0xffu << 8u; mb = 0xffu; ma = 0xffu << 24u; implicit_alpha = true; }
+        };
+        if (header_size == 40u || header_size == 56u) {
+            if (header_size == 56u) r.skip(16);
+            if (bpp == 16u || bpp == 32u) {
+                if (compression == 0u) {
+                    defaults();
+                } else {// the three masks follow a 40-byte header
+                    mr = r.u32(); mg = r.u32(); mb = r.u32();
+                    header_end += 12u;
+                    if (mr == mg && mg == mb) fail(path, "bad BMP bit masks");
+                }
+            }
+        } else {
+            mr = r.u32(); mg = r.u32(); mb = r.u32(); ma = r.u32();
+            if (compression != 3u) defaults();
+            r.skip(header_size == 124u ? 68u : 52u);// colour space, and the profile fields of the V5 header
+        }
+    }
+    const bool flip = h > 0;
+    if (h < 0) h = -h;
+    if (w <= 0 || h == 0 || w > (1 << 24) || h > (1 << 24)) fail(path, "bad BMP size");
+    const uint32_t width = static_cast<uint32_t>(w), height = static_cast<uint32_t>(h);
+    std::vector<float> samples(static_cast<size_t>(width) * height * 4u);
+    auto put = [&](uint32_t x, uint32_t y, uint32_t red, uint32_t green, uint32_t blue, uint32_t alpha) {
+        float *px = &samples[(static_cast<size_t>(flip ? height - 1u - y : y) * width + x) * 4u];
+        px[0] = static_cast<float>(red) / 255.f;
+        px[1] = static_cast<float>(green) / 255.f;
+        px[2] = static_cast<float>(blue) / 255.f;
+        px[3] = static_cast<float>(alpha) / 255.f;
+    };
+    if (bpp < 16u) {
+        if (bpp != 1u && bpp != 4u && bpp != 8u) fail(path, "unsupported BMP bit depth");
+        const size_t entry = header_size == 12u ? 3u : 4u;
+        if (data_offset < header_end) fail(path, "bad BMP data offset");
+        const size_t entries = (data_offset - header_end) / entry;
+        if (entries == 0u || entries > 256u) fail(path, "bad BMP palette");
+        uint8_t palette[256][3] = {};
+        for (size_t i = 0; i < entries; i++) {
+            palette[i][2] = r.u8(); palette[i][1] = r.u8(); palette[i][0] = r.u8();
+            if (entry == 4u) r.u8();
+        }
+        r.pos = data_offset;
+        const size_t row_bytes = (static_cast<size_t>(width) * bpp + 7u) / 8u, padding = (4u - row_bytes % 4u) % 4u;
+        for (uint32_t y = 0; y < height; y++) {
+            const size_t row = r.pos;
+            r.skip(row_bytes + padding);
+            for (uint32_t x = 0; x < width; x++) {
+                const uint8_t byte = d[row + static_cast<size_t>(x) * bpp / 8u];
+                const uint32_t index = bpp == 8u ? byte : bpp == 4u ? (x & 1u ? byte & 15u : byte >> 4u) : (byte >> (7u - (x & 7u))) & 1u;
+                put(x, y, palette[index][0], palette[index][1], palette[index][2], 255u);
+            }
+        }
+        return finish(width, height, 4u, samples);
+    }
+    if (bpp != 16u && bpp != 24u && bpp != 32u) fail(path, "unsupported BMP bit depth");
+    if (data_offset < header_end || data_offset - header_end > 1024u) fail(path, "bad BMP data offset");
+    r.pos = data_offset;
+    const BitField fr{mr}, fg{mg}, fb{mb}, fa{ma};
+    if (bpp != 24u) {
+        if (!mr || !mg || !mb || fr.bits > 8u || fg.bits > 8u || fb.bits > 8u || fa.bits > 8u ||
+            !fr.contiguous() || !fg.contiguous() || !fb.contiguous() || !fa.contiguous())
+            fail(path, "bad BMP bit masks");
+    }
+    const size_t row_bytes = static_cast<size_t>(width) * (bpp / 8u), padding = (4u - row_bytes % 4u) % 4u;
+    uint32_t alpha_seen = implicit_alpha ? 0u : 255u;
+    for (uint32_t y = 0; y < height; y++) {
+        for (uint32_t x = 0; x < width; x++) {
+            if (bpp == 24u) {
+                const uint32_t blue = r.u8(), green = r.u8(), red = r.u8();
+                put(x, y, red, green, blue, 255u);
+            } else {
+                const uint32_t v = bpp == 16u ? r.u16() : r.u32();
+                const uint32_t alpha = ma ? fa.extract(v) : 255u;
+                alpha_seen |= alpha;
+                put(x, y, fr.extract(v), fg.extract(v), fb.extract(v), alpha);
+            }
+        }
+        r.skip(padding);
+    }
+    if (alpha_seen == 0u)// a 32-bit BI_RGB picture whose fourth byte is zero everywhere has no alpha channel
+        for (size_t i = 3; i < samples.size(); i += 4u) samples[i] = 1.f;
+    return finish(width, height, 4u, samples);
+}
+
+// ---- Truevision TGA: colour-mapped (1 / 9), true-colour (2 / 10) and grey (3 / 11) pictures, raw or run-length encoded, 8 / 15 /
+// 16 / 24 / 32 bits; the origin bit of the descriptor decides the row order.  Channel count as stb_image reports it - which picks
+// the reference's storage (imageio.cpp:522-530): 8-bit grey -> 1 channel, 16-bit grey -> grey + alpha, 15 / 16-bit colour -> RGB with
+// each 5-bit field scaled as v * 255 / 31, 24 / 32 bits -> RGB(A) stored blue first; for colour-mapped files the palette's entry size
+// decides.  Run-length packets may run across rows.
+LoadedImage load_tga(const std::filesystem::path &path, const std::vector<uint8_t> &d) {
+    ByteReader r{d, path};
+    const uint32_t id_length = r.u8(), map_type = r.u8(), image_type = r.u8();
+    const uint32_t map_start = r.u16(), map_length = r.u16(), map_bits = r.u8();
+    r.skip(4);// x / y origin
+    const uint32_t width = r.u16(), height = r.u16(), pixel_bits = r.u8(), descriptor = r.u8();
+    const bool rle = image_type >= 8u, grey = (image_type & 7u) == 3u, mapped = map_type == 1u;
+    if (map_type > 1u || (mapped ? (image_type & 7u) != 1u : ((image_type & 7u) != 2u && !grey)) || (image_type & ~15u) != 0u)
+        fail(path, "unsupported TGA image type");
+    if (width == 0u || height == 0u) fail(path, "bad TGA size");
+    if (mapped && pixel_bits != 8u && pixel_bits != 16u) fail(path, "unsupported TGA index size");
+    const uint32_t colour_bits = mapped ? map_bits : pixel_bits;
+    uint32_t nc = 0u;
+    bool packed16 = false;
+    switch (colour_bits) {
+        case 8: nc = 1u; break;
+        case 16: if (grey) { nc = 2u; break; } [[fallthrough]];
+        case 15: nc = 3u; packed16 = true; break;
+        case 24: nc = 3u; break;
+        case 32: nc = 4u; break;
+        default: fail(path, "unsupported TGA bit depth");
+    }
+    r.skip(id_length);
+    // one colour as it is stored -> nc 8-bit channels (red first)
+    auto read_colour = [&](uint8_t *out) {
+        if (packed16) {
+            const uint32_t v = r.u16();
+            out[0] = static_cast<uint8_t>(((v >> 10u) & 31u) * 255u / 31u);
+            out[1] = static_cast<uint8_t>(((v >> 5u) & 31u) * 255u / 31u);
+            out[2] = static_cast<uint8_t>((v & 31u) * 255u / 31u);
+            return;
+        }
+        for (uint32_t c = 0; c < nc; c++) out[c] = r.u8();
+        if (nc >= 3u) std::swap(out[0], out[2]);
+    };
+    std::vector<uint8_t> palette;
+    if (mapped) {
+        if (map_length == 0u) fail(path, "bad TGA palette");
+        r.skip(map_start);
+        palette.resize(static_cast<size_t>(map_length) * nc);
+        for (uint32_t i = 0; i < map_length; i++) read_colour(&palette[static_cast<size_t>(i) * nc]);
+    } else if (map_type == 0u && map_length != 0u) {
+        fail(path, "TGA file with a colour map but no colour-mapped picture");
+    }
+    auto read_pixel = [&](uint8_t *out) {
+        if (!mapped) return read_colour(out);
+        uint32_t index = pixel_bits == 8u ? r.u8() : r.u16();
+        if (index >= map_length) index = 0u;
+        std::memcpy(out, &palette[static_cast<size_t>(index) * nc], nc);
+    };
+    const size_t count = static_cast<size_t>(width) * height;
+    std::vector<uint8_t> pixels(count * nc);
+    uint8_t px[4] = {};
+    for (size_t i = 0; i < count;) {
+        size_t run = 1u;
+        bool repeat = false;
+        if (rle) {
+            const uint32_t packet = r.u8();
+            run = (packet & 127u) + 1u;
+            repeat = (packet & 128u) != 0u;
+        }
+        if (repeat) read_pixel(px);
+        for (size_t k = 0; k < run && i < count; k++, i++) {
+            if (!repeat) read_pixel(px);
+            std::memcpy(&pixels[i * nc], px, nc);
+        }
+    }
+    const bool bottom_up = !((descriptor >> 5u) & 1u);
+    std::vector<float> samples(count * nc);
+    for (uint32_t y = 0; y < height; y++) {
+        const uint8_t *row = &pixels[static_cast<size_t>(bottom_up ? height - 1u - y : y) * width * nc];
+        for (size_t i = 0; i < static_cast<size_t>(width) * nc; i++) samples[static_cast<size_t>(y) * width * nc + i] = static_cast<float>(row[i]) / 255.f;
+    }
+    return finish(width, height, nc, samples);
+}
+
 }// namespace
 
 LoadedImage load_image(const std::filesystem::path &path) {
@@ -468,7 +705,9 @@ LoadedImage load_image(const std::filesystem::path &path) {
     if (ext == ".ppm" || ext == ".pgm" || ext == ".pnm" || ext == ".pfm") return load_pnm(path, data);
     if (ext == ".hdr") return load_hdr(path, data);
     if (ext == ".exr") return load_exr(path, data);
-    fail(path, "unsupported image format '" + ext + "' (supported: .png .ppm .pgm .pfm .hdr .exr)");
+    if (ext == ".bmp") return load_bmp(path, data);
+    if (ext == ".tga") return load_tga(path, data);
+    fail(path, "unsupported image format '" + ext + "' (supported: .png .bmp .tga .ppm .pgm .pfm .hdr .exr)");
 }
 
 }// namespace lrh

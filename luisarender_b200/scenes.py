@@ -811,3 +811,56 @@ def checkerboard_scene(resolution=(64, 48), spp=4, output="checker.exr", assets=
     src = swap(src, f'Kd : Image {{ file {{ "{a}/palette4.png" }} address {{ "zero" }} encoding {{ "gamma" }} gamma {{ 2.0 }} }}',
                'Kd : Checkerboard { on : Constant { v { 0.9, 0.85, 0.3 } } scale { 2.5 } }')
     return src
+
+
+IMAGE_FORMAT_FILES = ("bmp_rgb24.bmp", "bmp_pal8.bmp", "bmp_pal4.bmp", "bmp_pal1.bmp", "bmp_rgba32_topdown.bmp", "bmp_rgbx32.bmp", "bmp_rgb565.bmp",
+                      "bmp_rgb555.bmp", "tga_rgb24.tga", "tga_rgba32_rle_topdown.tga", "tga_grey8.tga", "tga_grey_alpha16.tga", "tga_mapped8.tga",
+                      "tga_rgb15.tga")
+
+
+def image_formats_scene(resolution=(80, 48), spp=2, output="formats.exr", assets="tests/golden/assets", integrator="WavePath") -> str:
+    """One point-sampled Matte panel per BMP / TGA storage variant of tests/golden/assets (5 x 3 panels facing the camera, lit by an
+    area light behind it): the film is a function of every texel the readers of csrc/host/imageload.cpp produce, next to what
+    stb_image hands the reference for the same files."""
+    a = assets.rstrip("/")
+    parts, names = [], []
+    for k, name in enumerate(IMAGE_FORMAT_FILES):
+        col, row = k % 5, k // 5
+        x0, y0 = -2.5 + col * 1.0 + 0.05, 1.9 - row * 1.0 + 0.05
+        x1, y1 = x0 + 0.9, y0 - 0.9
+        encoding = ("linear", "sRGB")[k % 2]
+        parts.append(f'''
+Surface s{k} : Matte {{ Kd : Image {{ file {{ "{a}/{name}" }} filter {{ "point" }} address {{ "edge" }} encoding {{ "{encoding}" }} }} }}
+Shape p{k} : InlineMesh {{
+  positions {{ {_fmt(x0)}, {_fmt(y1)}, 0.0,  {_fmt(x1)}, {_fmt(y1)}, 0.0,  {_fmt(x1)}, {_fmt(y0)}, 0.0,  {_fmt(x0)}, {_fmt(y0)}, 0.0 }}
+  uvs {{ 0.0, 1.0,  1.0, 1.0,  1.0, 0.0,  0.0, 0.0 }}
+  indices {{ 0, 1, 2, 0, 2, 3 }}
+  surface {{ @s{k} }}
+}}''')
+        names.append(f"@p{k}")
+    return "".join(parts) + f'''
+Light area_light : Diffuse {{ emission : Constant {{ v {{ 30.0 }} }} }}
+Shape lamp : InlineMesh {{
+  positions {{ -1.5, 3.5, 4.0,  1.5, 3.5, 4.0,  1.5, 2.5, 5.0,  -1.5, 2.5, 5.0 }}
+  indices {{ 0, 1, 2, 0, 2, 3 }}
+  light {{ @area_light }}
+}}
+Camera camera : Pinhole {{
+  position {{ 0.0, 0.4, 5.2 }}
+  front {{ 0.0, 0.0, -1.0 }}
+  up {{ 0.0, 1.0, 0.0 }}
+  fov {{ 38.0 }}
+  spp {{ {int(spp)} }}
+  film : Color {{ resolution {{ {int(resolution[0])}, {int(resolution[1])} }} }}
+  filter : Box {{ radius {{ 0.5 }} }}
+  file {{ "{output}" }}
+}}
+render {{
+  integrator : {integrator} {{
+    depth {{ 3 }}
+    sampler : Independent {{ seed {{ 7 }} }}
+  }}
+  cameras {{ @camera }}
+  shapes {{ {", ".join(names)}, @lamp }}
+}}
+'''

@@ -127,8 +127,100 @@ def write_tetra_ply(path: Path, binary: bool) -> None:
     path.write_bytes(data)
 
 
+# ---- BMP / TGA fixtures: every storage variant the readers of luisarender_b200/csrc/host/imageload.cpp accept ----------------------
+def bmp_tga_pictures() -> dict[str, np.ndarray]:
+    """name -> the (H, W, C) uint8 picture a reader must return (row 0 = top), C as the reference stores it (1, 2 or 4)."""
+    r = np.random.default_rng(20240923)
+    rgb = checker_rgb8(32, 4)[:17, :30]  # 30 pixels x 3 bytes: rows need 2 padding bytes in a BMP
+    opaque = lambda a: np.concatenate([a, np.full(a.shape[:2] + (1,), 255, np.uint8)], axis=2)
+    pal16 = r.integers(0, 256, (16, 3), dtype=np.uint8)
+    idx8 = r.integers(0, 16, (9, 10), dtype=np.uint8)
+    idx4 = r.integers(0, 16, (6, 7), dtype=np.uint8)
+    idx1 = r.integers(0, 2, (5, 13), dtype=np.uint8)
+    rgba = r.integers(0, 256, (7, 5, 4), dtype=np.uint8)
+    rgba[..., 3] = np.maximum(rgba[..., 3], 1)
+    f565 = np.stack([r.integers(0, 32, (6, 9)), r.integers(0, 64, (6, 9)), r.integers(0, 32, (6, 9))], axis=2).astype(np.uint16)
+    f555 = r.integers(0, 32, (5, 6, 3)).astype(np.uint16)
+    rep = lambda v, bits: ((v << (8 - bits)) | (v >> (2 * bits - 8))).astype(np.uint8)  # bit replication, bits in {5, 6}
+    runs = np.repeat(r.integers(0, 256, (12, 4), dtype=np.uint8), r.integers(1, 9, 12), axis=0)[:48].reshape(6, 8, 4)  # runs across rows
+    grey = rough_gray8(12)[:7]
+    grey_alpha = r.integers(0, 256, (4, 6, 2), dtype=np.uint8)
+    return {
+        "bmp_rgb24": opaque(rgb), "bmp_pal8": opaque(pal16[idx8]), "bmp_pal4": opaque(pal16[idx4]), "bmp_pal1": opaque(pal16[idx1]),
+        "bmp_rgba32_topdown": rgba, "bmp_rgbx32": opaque(rgba[..., :3]),
+        "bmp_rgb565": opaque(np.stack([rep(f565[..., 0], 5), rep(f565[..., 1], 6), rep(f565[..., 2], 5)], axis=2)),
+        "bmp_rgb555": opaque(rep(f555, 5)),
+        "tga_rgb24": opaque(rgb), "tga_rgba32_rle_topdown": runs, "tga_grey8": grey[..., None], "tga_grey_alpha16": grey_alpha,
+        "tga_mapped8": opaque(pal16[idx8]), "tga_rgb15": opaque((f555 * 255 // 31).astype(np.uint8)),
+        "_pal16": pal16, "_idx8": idx8, "_idx4": idx4, "_idx1": idx1, "_f565": f565, "_f555": f555,
+    }
+
+
+def write_bmp_tga(out: Path) -> None:
+    pic = bmp_tga_pictures()
+    pal16, idx8, idx4, idx1, f565, f555 = (pic[k] for k in ("_pal16", "_idx8", "_idx4", "_idx1", "_f565", "_f555"))
+
+    def bmp(name, w, h, bpp, rows, *, palette=b"", compression=0, masks=b"", top_down=False, core=False):
+        body = b"".join(row + b"\0" * (-len(row) % 4) for row in (rows if top_down else rows[::-1]))
+        if core:
+            header = struct.pack("<IHHHH", 12, w, h, 1, bpp)
+        else:
+            header = struct.pack("<IiiHHIIiiII", 40, w, -h if top_down else h, 1, bpp, compression, len(body), 2835, 2835, 0, 0) + masks
+        offset = 14 + len(header) + len(palette)
+        (out / f"{name}.bmp").write_bytes(b"BM" + struct.pack("<IHHI", offset + len(body), 0, 0, offset) + header + palette + body)
+
+    bgr = lambda a: a[..., ::-1].astype(np.uint8)
+    rgb = pic["bmp_rgb24"][..., :3]
+    h, w = rgb.shape[:2]
+    bmp("bmp_rgb24", w, h, 24, [bgr(rgb)[y].tobytes() for y in range(h)])
+    pal4 = b"".join(bytes([c[2], c[1], c[0], 0]) for c in pal16)
+    bmp("bmp_pal8", idx8.shape[1], idx8.shape[0], 8, [idx8[y].tobytes() for y in range(idx8.shape[0])], palette=pal4)
+    nib = lambda row: bytes((int(row[i]) << 4) | (int(row[i + 1]) if i + 1 < len(row) else 0) for i in range(0, len(row), 2))
+    bmp("bmp_pal4", idx4.shape[1], idx4.shape[0], 4, [nib(idx4[y]) for y in range(idx4.shape[0])],
+        palette=b"".join(bytes([c[2], c[1], c[0]]) for c in pal16), core=True)  # OS/2 core header: 3-byte palette entries
+    bmp("bmp_pal1", idx1.shape[1], idx1.shape[0], 1, [np.packbits(idx1[y]).tobytes() for y in range(idx1.shape[0])], palette=pal4[:8])
+    rgba = pic["bmp_rgba32_topdown"]
+    bgra = lambda a: a[..., [2, 1, 0, 3]].astype(np.uint8)
+    bmp("bmp_rgba32_topdown", rgba.shape[1], rgba.shape[0], 32, [bgra(rgba)[y].tobytes() for y in range(rgba.shape[0])], top_down=True)
+    rgbx = rgba.copy()
+    rgbx[..., 3] = 0  # alpha zero everywhere: "no alpha channel"
+    bmp("bmp_rgbx32", rgbx.shape[1], rgbx.shape[0], 32, [bgra(rgbx)[y].tobytes() for y in range(rgbx.shape[0])])
+    v565 = ((f565[..., 0] << 11) | (f565[..., 1] << 5) | f565[..., 2]).astype("<u2")
+    bmp("bmp_rgb565", v565.shape[1], v565.shape[0], 16, [v565[y].tobytes() for y in range(v565.shape[0])], compression=3,
+        masks=struct.pack("<III", 0xF800, 0x07E0, 0x001F))
+    v555 = ((f555[..., 0] << 10) | (f555[..., 1] << 5) | f555[..., 2]).astype("<u2")
+    bmp("bmp_rgb555", v555.shape[1], v555.shape[0], 16, [v555[y].tobytes() for y in range(v555.shape[0])])
+
+    def tga(name, image_type, w, h, bits, body, *, descriptor=0, palette=b"", map_len=0, map_bits=0, ident=b""):
+        head = struct.pack("<BBBHHBHHHHBB", len(ident), 1 if palette else 0, image_type, 0, map_len, map_bits, 0, 0, w, h, bits, descriptor)
+        (out / f"{name}.tga").write_bytes(head + ident + palette + body)
+
+    tga("tga_rgb24", 2, w, h, 24, bgr(rgb)[::-1].tobytes(), ident=b"lrk")  # bottom-up, with an image id to skip
+    runs = pic["tga_rgba32_rle_topdown"]
+    flat = bgra(runs).reshape(-1, 4)
+    body, i = b"", 0
+    while i < len(flat):  # run-length packets for repeats (they cross row ends), raw packets otherwise
+        j = i
+        while j + 1 < len(flat) and j - i < 127 and (flat[j + 1] == flat[i]).all():
+            j += 1
+        if j > i:
+            body += bytes([0x80 | (j - i)]) + flat[i].tobytes()
+            i = j + 1
+        else:
+            body += bytes([0]) + flat[i].tobytes()
+            i += 1
+    tga("tga_rgba32_rle_topdown", 10, runs.shape[1], runs.shape[0], 32, body, descriptor=0x28)
+    grey = pic["tga_grey8"][..., 0]
+    tga("tga_grey8", 3, grey.shape[1], grey.shape[0], 8, grey[::-1].tobytes())
+    ga = pic["tga_grey_alpha16"]
+    tga("tga_grey_alpha16", 3, ga.shape[1], ga.shape[0], 16, ga.tobytes(), descriptor=0x28)
+    tga("tga_mapped8", 1, idx8.shape[1], idx8.shape[0], 8, idx8[::-1].tobytes(), palette=bgr(pal16).tobytes(), map_len=16, map_bits=24)
+    tga("tga_rgb15", 2, v555.shape[1], v555.shape[0], 16, v555[::-1].tobytes())
+
+
 def main():
     OUT.mkdir(exist_ok=True)
+    write_bmp_tga(OUT)
     write_png(OUT / "checker_rgb8.png", checker_rgb8())
     write_png(OUT / "rough_gray8.png", rough_gray8())
     write_png(OUT / "ramp_rgba16.png", ramp_rgba16())

@@ -75,6 +75,41 @@ def test_png_loader_matches_source_arrays():
     assert np.array_equal(pal[..., :3], colours[idx])
 
 
+def test_bmp_and_tga_loaders_match_source_arrays():
+    """Every BMP / TGA storage variant the readers accept (tests/golden/make_assets.py: palettes of 1 / 4 / 8 bits, core header, 16-bit
+    5-5-5 and 5-6-5 bit fields, 24 / 32 bits, top-down, an all-zero alpha byte; TGA raw / run-length with runs across rows, grey,
+    grey + alpha, colour-mapped, 15-bit) against the picture it was written from; channel counts as the reference's storage policy
+    has them (stb_image's component count: 1, 2, or RGBA).  The renders of tests/golden/ref_renders.npz: image_formats pin the
+    same files against the reference's own loader."""
+    pictures = make_assets.bmp_tga_pictures()
+    for name, want in pictures.items():
+        if name.startswith("_"):
+            continue
+        ext = name.split("_")[0]
+        d = Scene.from_source(_matte_scene(f'file {{ "{ASSETS / (name + "." + ext)}" }} encoding {{ "linear" }}'), REPO).desc()
+        tex = _texels(d)
+        c = want.shape[2]
+        assert d.textures[0].channels == c and tex.shape[:2] == want.shape[:2], name
+        assert np.array_equal(tex[..., :c] if c != 2 else tex[..., :2], want.astype(f32) / f32(255)), name
+        if c < 4:
+            assert (tex[..., 3] == 1).all(), name
+
+
+def test_bmp_and_tga_readers_refuse_what_the_reference_refuses(tmp_path):
+    rle = bytearray((ASSETS / "bmp_pal8.bmp").read_bytes())
+    rle[30] = 1  # BI_RLE8
+    (tmp_path / "rle.bmp").write_bytes(rle)
+    with pytest.raises(RuntimeError, match="RLE"):
+        Scene.from_source(_matte_scene(f'file {{ "{tmp_path / "rle.bmp"}" }}'), REPO)
+    cut = (ASSETS / "tga_rgb24.tga").read_bytes()[:200]
+    (tmp_path / "cut.tga").write_bytes(cut)
+    with pytest.raises(RuntimeError, match="truncated"):
+        Scene.from_source(_matte_scene(f'file {{ "{tmp_path / "cut.tga"}" }}'), REPO)
+    (tmp_path / "x.jpg").write_bytes(b"\xff\xd8\xff")
+    with pytest.raises(RuntimeError, match="unsupported image format"):
+        Scene.from_source(_matte_scene(f'file {{ "{tmp_path / "x.jpg"}" }}'), REPO)
+
+
 def test_png_filters_and_low_bit_depths(tmp_path):
     """Sub / Up / Average / Paeth scanline filters and a 1-bit greyscale file, written by hand."""
     rng = np.random.default_rng(3)

@@ -139,6 +139,8 @@ def cases() -> dict[str, str]:
     # lamp so that primary rays hit it too
     c["textured_light"] = (scenes.textured_room(resolution=(32, 24), spp=4, mesh_files=False, assets=assets, textured_light=True, output="texlight.exr")
                            .replace("position { 0.0, 1.4, 4.2 }", "position { 0.0, 0.6, 4.2 }").replace("front { 0.0, -0.2, -1.0 }", "front { 0.0, 0.25, -1.0 }"))
+    # BMP and TGA textures in every storage variant the host readers accept, against what stb_image hands the reference for them
+    c["image_formats"] = scenes.image_formats_scene(resolution=(80, 48), spp=2, assets=assets)
     # the Swizzle texture: reordered image channels, one channel as a scalar parameter, swizzled constants, nesting
     c["swizzle"] = scenes.swizzle_scene(resolution=(64, 48), spp=4, assets=assets)
     # the Checkerboard texture with constant squares (baked into a point-sampled, repeating 2x2 image by the host)
