@@ -100,7 +100,7 @@ def test_fixture_is_what_the_reference_renders_now(golden):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["cornell_wavepath", "cornell_russian_roulette", "spheres_disney", "materials_wavepath",
-                                  "materials_megapath_rr", "textured", "textured_wrappers", "textured_light", "environment_image",
+                                  "materials_megapath_rr", "textured", "textured_wrappers", "textured_light", "image_formats", "environment_image",
                                   "config_c3_full_scene", "cornell_filter_gaussian", "cornell_filter_mitchell",
                                   "cornell_film_and_light_options", "materials_mix", "materials_named_metals", "materials_textured", "materials_layered", "flatten_stress", "spheres_disney_all_lobes",
                                   "subdivision", "spheres_disney_transmissive", "spheres_disney_thin",
