@@ -480,6 +480,7 @@ struct ByteReader {
         if (pos + n > d.size()) fail(path, "truncated file");
         pos += n;
     }
+    void skip_padding(size_t n) { pos = std::min(pos + n, d.size()); }// row padding: the last row's may be missing
 };
 
 // an n-bit field value (n in 1..8) widened to 8 bits by repeating its bit pattern: 5 bits abcde -> abcdeabc
@@ -575,7 +576,8 @@ LoadedImage load_bmp(const std::filesystem::path &path, const std::vector<uint8_
         const size_t row_bytes = (static_cast<size_t>(width) * bpp + 7u) / 8u, padding = (4u - row_bytes % 4u) % 4u;
         for (uint32_t y = 0; y < height; y++) {
             const size_t row = r.pos;
-            r.skip(row_bytes + padding);
+            r.skip(row_bytes);
+            r.skip_padding(padding);
             for (uint32_t x = 0; x < width; x++) {
                 const uint8_t byte = d[row + static_cast<size_t>(x) * bpp / 8u];
                 const uint32_t index = bpp == 8u ? byte : bpp == 4u ? (x & 1u ? byte & 15u : byte >> 4u) : (byte >> (7u - (x & 7u))) & 1u;
@@ -607,7 +609,7 @@ LoadedImage load_bmp(const std::filesystem::path &path, const std::vector<uint8_
                 put(x, y, fr.extract(v), fg.extract(v), fb.extract(v), alpha);
             }
         }
-        r.skip(padding);
+        r.skip_padding(padding);
     }
     if (alpha_seen == 0u)// a 32-bit BI_RGB picture whose fourth byte is zero everywhere has no alpha channel
         for (size_t i = 3; i < samples.size(); i += 4u) samples[i] = 1.f;

@@ -63,6 +63,8 @@ CASES = {
     # the three Disney closure classes - thin ("through" events: the tracker must not move), transmissive (enter / exit), opaque -
     # inside an environment medium: the scene of tests/golden/ref_renders.npz: spheres_medium_disney_thin
     "disney_thin_and_transmissive": lambda: _golden_case("spheres_medium_disney_thin"),
+    # a thin Disney surface with image-textured colour and diffuse_trans (slot 15 of the per-hit parameter resolution)
+    "textured_disney_thin": lambda: _golden_case("textured_disney_thin").replace("integrator : WavePath", "integrator : MegaVPTNaive"),
     # an area light with an image emission (texture lookups at emitter hits and at sampled light points), no medium at all
     "textured_light": lambda: scenes.textured_room(resolution=(40, 30), spp=3, mesh_files=False, textured_light=True, integrator="MegaVPTNaive"),
 }

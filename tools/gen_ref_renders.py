@@ -141,6 +141,15 @@ def cases() -> dict[str, str]:
                            .replace("position { 0.0, 1.4, 4.2 }", "position { 0.0, 0.6, 4.2 }").replace("front { 0.0, -0.2, -1.0 }", "front { 0.0, 0.25, -1.0 }"))
     # BMP and TGA textures in every storage variant the host readers accept, against what stb_image hands the reference for them
     c["image_formats"] = scenes.image_formats_scene(resolution=(80, 48), spp=2, assets=assets)
+    # a thin Disney surface whose diffuse_trans (slot 15) and colour are image textures, next to a constant specular_trans
+    def _textured_thin(src):
+        old = "  metallic : Constant { v { 0.2 } }"
+        assert src.count(old) == 1
+        return src.replace(old, old + f'''
+  thin {{ true }}
+  diffuse_trans : Image {{ file {{ "{assets}/rough_gray8.png" }} encoding {{ "linear" }} address {{ "mirror" }} uv_scale {{ 1.5 }} }}
+  specular_trans : Constant {{ v {{ 0.4 }} }}''')
+    c["textured_disney_thin"] = _textured_thin(scenes.textured_room(resolution=(32, 24), spp=4, mesh_files=False, assets=assets, output="texthin.exr"))
     # the Swizzle texture: reordered image channels, one channel as a scalar parameter, swizzled constants, nesting
     c["swizzle"] = scenes.swizzle_scene(resolution=(64, 48), spp=4, assets=assets)
     # the Checkerboard texture with constant squares (baked into a point-sampled, repeating 2x2 image by the host)
