@@ -542,7 +542,7 @@ int lrk_reduce_film(lrk_ctx *ctx, uint32_t root);
  *   "strict_math" (0/1)       closure kernels in IEEE arithmetic without FMA contraction (films then equal the CPU oracle's to
  *                             rel-L2 ~ 1e-7) instead of the fast-math arithmetic the reference's own CUDA backend compiles its
  *                             kernels with (the default; ~15 % faster on the headline scene).  Traversal, ray generation and the
- *                             film are IEEE either way; the near-specular closures (Mirror .. Mix) too
+ *                             film are IEEE either way; the near-specular closures (Mirror .. Mix), Layered and thin Disney too
  *   "device_bvh" (0/1)        build the hierarchy on the GPU at the next lrk_upload_scene instead of taking the caller's
  *   "pin_host_buffers" (0/1)  the caller promises that the host arrays it passes to lrk_upload_scene / lrk_download_film*
  *                             stay allocated until lrk_destroy (or until the option is cleared); the library page-locks each

@@ -10,7 +10,7 @@
 //                              the 1.39 M-triangle scene: shade 18.3 -> 11.0 ms per 64-spp pass (profiles/r02k_shade_arithmetic.jsonl).
 //   -DLRK_SHADE_VARIANT=strict -fmad=false, IEEE div / sqrt: bit-compatible with lrk.cu and the oracle.  Always used for the
 //                              Mirror / Glass / Plastic / Metal / Mix buckets (near-specular lobes amplify a 1e-6 error in the half
-//                              vector into percents of the lobe value), and for everything with lrk_set_option("strict_math", 1) -
+//                              vector into percents of the lobe value), for the Layered and thin Disney buckets, and for everything with lrk_set_option("strict_math", 1) -
 //                              the configuration the tight parity tests run (films equal the oracle's to rel-L2 ~ 1e-7).
 // The closures' source is the same in both, and is checked against the reference's closures bit for bit when compiled for the host
 // (tests/test_device_closures_on_host.py).  build.py compiles the two objects; cross products and the uv determinant are written so
