@@ -150,6 +150,13 @@ def cases() -> dict[str, str]:
   diffuse_trans : Image {{ file {{ "{assets}/rough_gray8.png" }} encoding {{ "linear" }} address {{ "mirror" }} uv_scale {{ 1.5 }} }}
   specular_trans : Constant {{ v {{ 0.4 }} }}''')
     c["textured_disney_thin"] = _textured_thin(scenes.textured_room(resolution=(32, 24), spp=4, mesh_files=False, assets=assets, output="texthin.exr"))
+    # feature crossings: the table-driven samplers under closures that draw a different number of dimensions per bounce
+    c["materials_mix_sobol"] = (scenes.materials_box(resolution=(32, 24), spp=3, depth=6, rr_depth=2, mix=True, output="mixsobol.exr")
+                                .replace("sampler : Independent", "sampler : Sobol"))
+    c["materials_layered_pmj02bn"] = (scenes.layered_box(resolution=(32, 24), spp=4, depth=6, output="layeredpmj.exr")
+                                      .replace("sampler : Independent", "sampler : PMJ02BN"))
+    c["textured_materials_zsobol"] = (scenes.textured_materials(resolution=(48, 30), spp=2, depth=6, assets=assets_early, output="texzsobol.exr")
+                                      .replace("sampler : Independent", "sampler : ZSobol"))
     # the Swizzle texture: reordered image channels, one channel as a scalar parameter, swizzled constants, nesting
     c["swizzle"] = scenes.swizzle_scene(resolution=(64, 48), spp=4, assets=assets)
     # the Checkerboard texture with constant squares (baked into a point-sampled, repeating 2x2 image by the host)
