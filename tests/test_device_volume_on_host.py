@@ -65,6 +65,8 @@ CASES = {
     "disney_thin_and_transmissive": lambda: _golden_case("spheres_medium_disney_thin"),
     # a thin Disney surface with image-textured colour and diffuse_trans (slot 15 of the per-hit parameter resolution)
     "textured_disney_thin": lambda: _golden_case("textured_disney_thin").replace("integrator : WavePath", "integrator : MegaVPTNaive"),
+    # media bound to shapes behind Disney shells: a thin one (through events) and a transmissive one (enter / exit), in an environment medium
+    "media_disney_shells": lambda: _golden_case("media_disney_shells"),
     # an area light with an image emission (texture lookups at emitter hits and at sampled light points), no medium at all
     "textured_light": lambda: scenes.textured_room(resolution=(40, 30), spp=3, mesh_files=False, textured_light=True, integrator="MegaVPTNaive"),
 }

@@ -111,6 +111,8 @@ def cases() -> dict[str, str]:
         scenes.instanced_spheres(resolution=(32, 18), spp=4, depth=8, rr_depth=2, **spheres)).replace('"spheres.exr"', '"thin.exr"')
     c["spheres_medium_disney_thin"] = _thin(
         scenes.instanced_spheres(resolution=(32, 18), spp=4, depth=6, medium=True, **spheres)).replace('"spheres.exr"', '"thinvpt.exr"')
+    c["spheres_disney_thin_paddedsobol"] = (c["spheres_disney_thin"].replace("sampler : Independent", "sampler : PaddedSobol")
+                                            .replace("spp { 4 }", "spp { 3 }").replace('"thin.exr"', '"thinps.exr"'))
     # row f2: the table-driven samplers.  Cornell @4 spp with each; the sphere scene with sample counts that are NOT the samplers'
     # favourite powers (pmj02bn: 8 is no power of 4 -> its pixel-sample sorting skips entries; Sobol' / PaddedSobol: 3 is no power of
     # 2; ZSobol: log2(2) is odd -> the half-digit branch), depth 6 = 30 dimensions per path
@@ -157,6 +159,17 @@ def cases() -> dict[str, str]:
                                       .replace("sampler : Independent", "sampler : PMJ02BN"))
     c["textured_materials_zsobol"] = (scenes.textured_materials(resolution=(48, 30), spp=2, depth=6, assets=assets_early, output="texzsobol.exr")
                                       .replace("sampler : Independent", "sampler : ZSobol"))
+    # media bound to shapes whose shells are Disney surfaces: a thin one (its "through" events never enter the medium behind it) and
+    # a transmissive one (enter / exit with the eta scale), inside an environment medium
+    c["media_disney_shells"] = (scenes.media_box(resolution=(32, 32), spp=4, environment_medium=True, rr_depth=2, output="shells.exr")
+                                .replace('Surface shell_smooth : Glass { eta { "BK7" } }',
+                                         'Surface shell_smooth : Disney { color : Constant { v { 0.9, 0.8, 0.6 } } thin { true } specular_trans : Constant { v { 0.7 } } '
+                                         'diffuse_trans : Constant { v { 0.6 } } roughness : Constant { v { 0.3 } } }')
+                                .replace('Surface shell_rough : Glass { Kr : Constant { v { 1.0, 0.95, 0.9 } } Kt : Constant { v { 0.9, 0.95, 1.0 } } '
+                                         'roughness : Constant { v { 0.25 } } eta { 1.33 } }',
+                                         'Surface shell_rough : Disney { color : Constant { v { 0.6, 0.8, 0.9 } } specular_trans : Constant { v { 0.9 } } '
+                                         'roughness : Constant { v { 0.25 } } eta : Constant { v { 1.33 } } }'))
+    assert "thin { true }" in c["media_disney_shells"] and c["media_disney_shells"].count("Glass") == 0
     # the Swizzle texture: reordered image channels, one channel as a scalar parameter, swizzled constants, nesting
     c["swizzle"] = scenes.swizzle_scene(resolution=(64, 48), spp=4, assets=assets)
     # the Checkerboard texture with constant squares (baked into a point-sampled, repeating 2x2 image by the host)
