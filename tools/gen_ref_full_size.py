@@ -109,6 +109,26 @@ def _small_case(name: str, resolution: tuple, new_resolution: tuple, spp: int, n
     return source.replace("integrator : WavePath", "integrator : MegaPath")
 
 
+def disney_thin_large_scene() -> str:
+    return _small_case("spheres_disney_thin", (32, 18), (480, 270), 4, 4, "thin_large.exr")
+
+
+def disney_thin_medium_large_scene() -> str:
+    return _small_case("spheres_medium_disney_thin", (32, 18), (320, 180), 4, 4, "thin_medium_large.exr")
+
+
+def media_disney_shells_large_scene() -> str:
+    return _small_case("media_disney_shells", (32, 32), (192, 192), 4, 4, "shells_large.exr")
+
+
+def textured_light_large_scene() -> str:
+    return _small_case("textured_light", (32, 24), (320, 240), 4, 4, "texlight_large.exr")
+
+
+def image_formats_large_scene() -> str:
+    return _small_case("image_formats", (80, 48), (400, 240), 2, 2, "formats_large.exr")
+
+
 def disney_lobes_large_scene() -> str:
     return _small_case("spheres_disney_all_lobes", (32, 18), (480, 270), 2, 4, "lobes_large.exr")
 
@@ -184,6 +204,11 @@ CASES = {
     "materials_large": (materials_large_scene, 4, "row f3: the materials box (Mirror, Glass, rough Glass, Plastic, Metal, Mix; level-4 spheres) 320x240 @4 spp, depth 10, Russian roulette from depth 2, MegaPath"),
     "textured_large": (textured_large_scene, 4, "row f1: the image-textured room with the surface wrappers (normal map, alpha cut-out, opacity) 320x240 @4 spp, MegaPath"),
     "flatten_large": (flatten_large_scene, 4, "row a23: the flattening stress scene 320x240 @4 spp, MegaPath"),
+    "disney_thin_large": (disney_thin_large_scene, 4, "row a15: the sphere scene with thin, transmissive and opaque Disney nodes, 480x270 @4 spp, depth 8, Russian roulette from depth 2, MegaPath"),
+    "disney_thin_medium_large": (disney_thin_medium_large_scene, 4, "rows a15 / a22: the same three Disney classes inside a homogeneous medium, 320x180 @4 spp, MegaVPTNaive (GCC build)"),
+    "media_disney_shells_large": (media_disney_shells_large_scene, 4, "row a22: media bound to shapes behind thin / transmissive Disney shells in an environment medium, 192x192 @4 spp, MegaVPTNaive (GCC build)"),
+    "textured_light_large": (textured_light_large_scene, 4, "row f1: an area light with an image emission in the textured room, 320x240 @4 spp, MegaPath"),
+    "image_formats_large": (image_formats_large_scene, 2, "row f1: one panel per BMP / TGA storage variant, 400x240 @2 spp, MegaPath"),
     "disney_lobes_large": (disney_lobes_large_scene, 4, "row a15: the Disney sphere scene with EVERY Disney parameter set, 480x270 @4 spp, MegaPath"),
     "cornell_rr_gaussian_large": (cornell_rr_gaussian_large_scene, 4, "Cornell 512x512 @4 spp, depth 12, Russian roulette from depth 2, Gaussian filter (row a2), MegaPath"),
     "cornell_mitchell_large": (cornell_mitchell_large_scene, 4, "Cornell 256x256 @4 spp, Mitchell filter (negative lobes), MegaPath"),
