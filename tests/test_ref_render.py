@@ -205,7 +205,10 @@ LARGE = ["c1", "c2_full_resolution", "c3_quarter", "c3_full_resolution", "c3_ful
          "textured_large", "flatten_large", "disney_lobes_large", "cornell_rr_gaussian_large", "cornell_mitchell_large",
          "cornell_options_large", "medium_channels_large", "medium_hg_large", "environment_large",
          "materials_wavepath_large", "textured_wavepath_large", "cornell_disney_odd", "subdivision_large", "swizzle_large", "checkerboard_large",
-         "disney_thin_large", "disney_thin_medium_large", "media_disney_shells_large", "textured_light_large", "image_formats_large"]
+         "disney_thin_large", "disney_thin_medium_large", "media_disney_shells_large", "textured_light_large", "image_formats_large",
+         "materials_textured_large", "named_metals_large", "layered_large", "sampler_pmj02bn_large", "sampler_sobol_large",
+         "sampler_paddedsobol_large", "sampler_zsobol_large", "disney_transmissive_large", "media_shapes_large", "media_nested_large",
+         "media_quirk_large"]
 
 
 @pytest.mark.parametrize("name", LARGE)
@@ -216,7 +219,7 @@ def test_large_render_is_bit_identical_to_the_reference(name):
     (configs[2] also through MegaPath), the configs[2] / configs[3] scenes at 480x270, and 256² - 512² versions of the small
     scenes of test_oracle_film_is_bit_identical_to_the_reference_render.  The oracle's film has the same SHA-256."""
     F, golden, desc = _full_size(name)
-    O.lib().oracle_set_hg_args_right_to_left(1 if (name.startswith("c4") or "medium" in name or "media" in name) else 0)  # GCC build of the reference
+    O.lib().oracle_set_hg_args_right_to_left(1 if (name.startswith("c4") or "medium" in name or "media" in name or "layered" in name) else 0)  # GCC build of the reference
     try:
         raw, _ = O.render(desc, 0, golden["spp"])
     finally:

@@ -109,6 +109,50 @@ def _small_case(name: str, resolution: tuple, new_resolution: tuple, spp: int, n
     return source.replace("integrator : WavePath", "integrator : MegaPath")
 
 
+def materials_textured_large_scene() -> str:
+    return _small_case("materials_textured", (48, 30), (320, 200), 4, 4, "materials_textured_large.exr")
+
+
+def named_metals_large_scene() -> str:
+    return _small_case("materials_named_metals", (32, 24), (320, 240), 4, 4, "named_metals_large.exr")
+
+
+def layered_large_scene() -> str:
+    return _small_case("materials_layered", (32, 24), (192, 144), 4, 4, "layered_large.exr")
+
+
+def sampler_pmj02bn_large_scene() -> str:
+    return _small_case("spheres_sampler_pmj02bn", (32, 18), (333, 187), 8, 8, "sampler_pmj02bn_large.exr")
+
+
+def sampler_sobol_large_scene() -> str:
+    return _small_case("spheres_sampler_sobol", (32, 18), (333, 187), 3, 3, "sampler_sobol_large.exr")
+
+
+def sampler_paddedsobol_large_scene() -> str:
+    return _small_case("spheres_sampler_paddedsobol", (32, 18), (333, 187), 3, 3, "sampler_paddedsobol_large.exr")
+
+
+def sampler_zsobol_large_scene() -> str:
+    return _small_case("spheres_sampler_zsobol", (32, 18), (333, 187), 2, 2, "sampler_zsobol_large.exr")
+
+
+def disney_transmissive_large_scene() -> str:
+    return _small_case("spheres_disney_transmissive", (32, 18), (480, 270), 4, 4, "disney_transmissive_large.exr")
+
+
+def media_shapes_large_scene() -> str:
+    return _small_case("media_shapes", (32, 32), (160, 160), 4, 4, "media_shapes_large.exr")
+
+
+def media_nested_large_scene() -> str:
+    return _small_case("media_nested_in_environment_medium", (32, 32), (160, 160), 4, 4, "media_nested_large.exr")
+
+
+def media_quirk_large_scene() -> str:
+    return _small_case("media_true_hit_quirk", (32, 32), (160, 160), 4, 4, "media_quirk_large.exr")
+
+
 def disney_thin_large_scene() -> str:
     return _small_case("spheres_disney_thin", (32, 18), (480, 270), 4, 4, "thin_large.exr")
 
@@ -204,6 +248,17 @@ CASES = {
     "materials_large": (materials_large_scene, 4, "row f3: the materials box (Mirror, Glass, rough Glass, Plastic, Metal, Mix; level-4 spheres) 320x240 @4 spp, depth 10, Russian roulette from depth 2, MegaPath"),
     "textured_large": (textured_large_scene, 4, "row f1: the image-textured room with the surface wrappers (normal map, alpha cut-out, opacity) 320x240 @4 spp, MegaPath"),
     "flatten_large": (flatten_large_scene, 4, "row a23: the flattening stress scene 320x240 @4 spp, MegaPath"),
+    "materials_textured_large": (materials_textured_large_scene, 4, "row f3: image-textured Mirror / Glass / Plastic / Metal parameters, 320x200 @4 spp, MegaPath"),
+    "named_metals_large": (named_metals_large_scene, 4, "row f3: Metal with the reference's measured spectra (Cu, Gold, aluminium fallback), 320x240 @4 spp, MegaPath"),
+    "layered_large": (layered_large_scene, 4, "row f3: the Layered surface (Glass over Matte / Mirror, Plastic over Matte), 192x144 @4 spp, MegaPath (GCC build)"),
+    "sampler_pmj02bn_large": (sampler_pmj02bn_large_scene, 8, "row f2: PMJ02BN at an odd film size, 333x187 @8 spp, MegaPath"),
+    "sampler_sobol_large": (sampler_sobol_large_scene, 3, "row f2: Sobol at an odd film size, 333x187 @3 spp, MegaPath"),
+    "sampler_paddedsobol_large": (sampler_paddedsobol_large_scene, 3, "row f2: PaddedSobol at an odd film size, 333x187 @3 spp, MegaPath"),
+    "sampler_zsobol_large": (sampler_zsobol_large_scene, 2, "row f2: ZSobol at an odd film size (more base-4 digits), 333x187 @2 spp, MegaPath"),
+    "disney_transmissive_large": (disney_transmissive_large_scene, 4, "row a15: transmissive next to opaque Disney nodes, 480x270 @4 spp, MegaPath"),
+    "media_shapes_large": (media_shapes_large_scene, 4, "row a22: media bound to Glass shells, 160x160 @4 spp, MegaVPTNaive (GCC build)"),
+    "media_nested_large": (media_nested_large_scene, 4, "row a22: the same inside an environment medium, Russian roulette, 160x160 @4 spp, MegaVPTNaive (GCC build)"),
+    "media_quirk_large": (media_quirk_large_scene, 4, "row a22: the true_hit(tag) quirk, 160x160 @4 spp, MegaVPTNaive (GCC build)"),
     "disney_thin_large": (disney_thin_large_scene, 4, "row a15: the sphere scene with thin, transmissive and opaque Disney nodes, 480x270 @4 spp, depth 8, Russian roulette from depth 2, MegaPath"),
     "disney_thin_medium_large": (disney_thin_medium_large_scene, 4, "rows a15 / a22: the same three Disney classes inside a homogeneous medium, 320x180 @4 spp, MegaVPTNaive (GCC build)"),
     "media_disney_shells_large": (media_disney_shells_large_scene, 4, "row a22: media bound to shapes behind thin / transmissive Disney shells in an environment medium, 192x192 @4 spp, MegaVPTNaive (GCC build)"),
