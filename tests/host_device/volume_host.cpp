@@ -93,7 +93,18 @@ extern "C" int volume_general_host(const lrk_scene_desc *s, uint32_t spp_begin, 
     sc.media = s->media;
     sc.medium_count = s->medium_count;
     sc.env_medium_tag = s->environment_medium_tag;
-    if (s->environment.present || s->sampler.type != LRK_SAMPLER_INDEPENDENT) return -1;
+    // the environment light, as lrk_upload_scene hands it to the kernels (lrk.cu)
+    sc.env_alias = s->environment.alias;
+    sc.env_pdf = s->environment.pdf;
+    sc.env_present = s->environment.present ? 1u : 0u;
+    sc.env_emission_tex = s->environment.present ? s->environment.emission_tex : 0u;
+    sc.env_map_width = s->environment.map_width;
+    sc.env_map_height = s->environment.map_height;
+    sc.env_scale = s->environment.scale;
+    sc.env_prob = s->environment.present ? s->environment.env_prob : 0.f;
+    for (int k = 0; k < 3; k++) sc.env_emission[k] = s->environment.emission[k];
+    for (int k = 0; k < 9; k++) sc.env_to_world[k] = s->environment.to_world[k];
+    if (s->sampler.type != LRK_SAMPLER_INDEPENDENT) return -1;
     uint64_t closest = 0u, shadow = 0u;
     bool tracker_overflow = false;
     const float threshold = sc.film_clamp * std::fmax(1.f, 1.f);

@@ -67,6 +67,9 @@ CASES = {
     "textured_disney_thin": lambda: _golden_case("textured_disney_thin").replace("integrator : WavePath", "integrator : MegaVPTNaive"),
     # media bound to shapes behind Disney shells: a thin one (through events) and a transmissive one (enter / exit), in an environment medium
     "media_disney_shells": lambda: _golden_case("media_disney_shells"),
+    # an image-lit environment seen from inside an environment medium (environment misses and environment NEE in the volume loop),
+    # next to an area light, with a thin Disney ball
+    "environment_medium_thin": lambda: _golden_case("environment_medium_thin"),
     # an area light with an image emission (texture lookups at emitter hits and at sampled light points), no medium at all
     "textured_light": lambda: scenes.textured_room(resolution=(40, 30), spp=3, mesh_files=False, textured_light=True, integrator="MegaVPTNaive"),
 }

@@ -176,6 +176,16 @@ def cases() -> dict[str, str]:
     c["checkerboard"] = scenes.checkerboard_scene(resolution=(64, 48), spp=4, assets=assets)
     # row a12: Spherical environment with an image emission (importance map, MIS compensation) next to an area light
     c["environment_image"] = scenes.environment_scene(resolution=(32, 20), spp=2, emission="image", assets=assets, sky_file="sky.exr")
+    # the volume integrator under an image-lit environment: environment misses / environment NEE from inside a homogeneous
+    # environment medium, next to an area light, with a thin Disney ball (through events)
+    c["environment_medium_thin"] = (
+        scenes.environment_scene(resolution=(32, 20), spp=2, emission="image", assets=assets, sky_file="sky.exr", output="envvpt.exr")
+        .replace("integrator : WavePath {", "integrator : MegaVPTNaive {")
+        .replace("  cameras { @camera }", "  environment_medium : Homogeneous {\n    sigma_a : Constant { v { 0.02, 0.03, 0.05 } }\n    sigma_s : Constant { v { 0.15, 0.12, 0.1 } }\n"
+                 "    phasefunction : HenyeyGreenstein { g { 0.4 } }\n  }\n  cameras { @camera }")
+        .replace("Surface ball_s : Matte { Kd : Constant { v { 0.8, 0.8, 0.8 } } }",
+                 "Surface ball_s : Disney { color : Constant { v { 0.8, 0.7, 0.5 } } thin { true } diffuse_trans : Constant { v { 0.8 } } specular_trans : Constant { v { 0.3 } } }"))
+    assert "MegaVPTNaive" in c["environment_medium_thin"] and "thin { true }" in c["environment_medium_thin"] and "environment_medium" in c["environment_medium_thin"]
     # the headline scenes at full geometric size (1 387 526 instanced triangles: Loop-subdivision spheres at level 7 and 3
     # built by the reference's own Sphere plugin), low resolution: config C3 (Disney + NEE) and config C4 (+ medium, depth 8)
     c["config_c3_full_scene"] = scenes.instanced_spheres(resolution=(96, 54), spp=2, output="c3.exr")
