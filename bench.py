@@ -528,7 +528,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                "seconds": round(secs, 2), "threads_busy": cst_cpu["threads_busy"],
                "note": "oracle port (scalar BVH2 walk) of the reference estimator: the reference's own LLVM + Embree cpu backend cannot "
                        "be built here and would be several times faster than this port",
-               "pinned": "films bit-identical to the unmodified reference renderer on 50 scenes incl. this one at 96x54 (tests/test_ref_render.py)"}
+               "pinned": "films bit-identical to the unmodified reference renderer on 52 scenes incl. this one at 96x54 (tests/test_ref_render.py)"}
 
     if rank == 0:
         line = {

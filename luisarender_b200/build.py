@@ -15,7 +15,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 REPO = PKG.parent
 LIB = PKG / "lib"
-HOST_SRC = ["sdl.cpp", "scene.cpp", "geomutil.cpp", "bvh.cpp", "flatten.cpp", "imageio.cpp", "imageload.cpp", "meshload.cpp", "envmap.cpp", "lrh.cpp"]
+HOST_SRC = ["sdl.cpp", "scene.cpp", "geomutil.cpp", "bvh.cpp", "flatten.cpp", "imageio.cpp", "imageload.cpp", "jpegload.cpp", "meshload.cpp", "envmap.cpp", "lrh.cpp"]
 NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # -fmad=false: expressions evaluate as written (see csrc/device/vecmath.cuh); FMAs are explicit fmaf().
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-fmad=false", "--shared", "-Xcompiler", "-fPIC"]

@@ -15,4 +15,7 @@ struct LoadedImage {
     std::vector<float> rgba;
 };
 LoadedImage load_image(const std::filesystem::path &path);// throws std::runtime_error
+// jpegload.cpp: nc = 1 (grey) or 3 (RGB) interleaved bytes, row 0 on top; throws std::runtime_error
+void decode_jpeg(const std::filesystem::path &path, const std::vector<uint8_t> &data, uint32_t &w, uint32_t &h, uint32_t &nc,
+                 std::vector<uint8_t> &pixels);
 }// namespace lrh

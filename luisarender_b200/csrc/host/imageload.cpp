@@ -1,7 +1,7 @@
 // Image file readers for the `Image` texture plugin (reference: LoadedImage::load, src/util/imageio.cpp:347-470, which
 // delegates to stb_image / tinyexr — neither is available here, so the decoders below are written against the file
-// format specifications; JPEG is the one stb format without a reader: a lossy decode only matches the reference's texels bit for bit
-// if it repeats stb's own integer IDCT and chroma filter).  What the readers reproduce from the reference is the STORAGE policy, because it decides the
+// format specifications; JPEG, whose lossy decode only matches the reference's texels if it repeats stb's own integer IDCT and chroma
+// filter, has its own file: jpegload.cpp).  What the readers reproduce from the reference is the STORAGE policy, because it decides the
 // texel values the sampler sees:
 //   * 8-bit files  -> BYTE1/2/4  : texel = x / 255        16-bit files -> SHORT1/2/4 : texel = x / 65535
 //   * .hdr         -> HALF4      : RGBE decoded to float, then rounded to binary16 (imageio.cpp:383, 231-245)
@@ -700,6 +700,16 @@ LoadedImage load_tga(const std::filesystem::path &path, const std::vector<uint8_
     return finish(width, height, nc, samples);
 }
 
+// ---- JPEG: decoded by jpegload.cpp (stb_image's arithmetic), stored like every other 8-bit file: grey -> BYTE1, colour -> BYTE4 ----
+LoadedImage load_jpeg(const std::filesystem::path &path, const std::vector<uint8_t> &d) {
+    uint32_t w = 0, h = 0, nc = 0;
+    std::vector<uint8_t> pixels;
+    decode_jpeg(path, d, w, h, nc, pixels);
+    std::vector<float> samples(pixels.size());
+    for (size_t i = 0; i < pixels.size(); i++) samples[i] = static_cast<float>(pixels[i]) / 255.f;
+    return finish(w, h, nc, samples);
+}
+
 }// namespace
 
 LoadedImage load_image(const std::filesystem::path &path) {
@@ -712,7 +722,8 @@ LoadedImage load_image(const std::filesystem::path &path) {
     if (ext == ".exr") return load_exr(path, data);
     if (ext == ".bmp") return load_bmp(path, data);
     if (ext == ".tga") return load_tga(path, data);
-    fail(path, "unsupported image format '" + ext + "' (supported: .png .bmp .tga .ppm .pgm .pfm .hdr .exr)");
+    if (ext == ".jpg" || ext == ".jpeg") return load_jpeg(path, data);
+    fail(path, "unsupported image format '" + ext + "' (supported: .png .jpg .jpeg .bmp .tga .ppm .pgm .pfm .hdr .exr)");
 }
 
 }// namespace lrh

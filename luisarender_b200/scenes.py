@@ -816,15 +816,20 @@ def checkerboard_scene(resolution=(64, 48), spp=4, output="checker.exr", assets=
 IMAGE_FORMAT_FILES = ("bmp_rgb24.bmp", "bmp_pal8.bmp", "bmp_pal4.bmp", "bmp_pal1.bmp", "bmp_rgba32_topdown.bmp", "bmp_rgbx32.bmp", "bmp_rgb565.bmp",
                       "bmp_rgb555.bmp", "tga_rgb24.tga", "tga_rgba32_rle_topdown.tga", "tga_grey8.tga", "tga_grey_alpha16.tga", "tga_mapped8.tga",
                       "tga_rgb15.tga")
+# the JPEG decoding paths of csrc/host/jpegload.cpp (grey, each chroma layout and its upsampling filter, progressive, RGB stored as such)
+JPEG_FORMAT_FILES = ("jpg_grey.jpg", "jpg_444.jpg", "jpg_422.jpg", "jpg_420.jpg", "jpg_440.jpg", "jpg_411.jpg", "jpg_420_restart_optimized.jpg",
+                     "jpg_420_low_quality.jpg", "jpg_progressive_420.jpg", "jpg_progressive_444_restart.jpg", "jpg_progressive_grey.jpg",
+                     "jpg_progressive_440_restart.jpg", "jpg_rgb_by_ids.jpg", "jpg_rgb_by_adobe_marker.jpg", "jpg_444_q100_noise.jpg")
 
 
-def image_formats_scene(resolution=(80, 48), spp=2, output="formats.exr", assets="tests/golden/assets", integrator="WavePath") -> str:
+def image_formats_scene(resolution=(80, 48), spp=2, output="formats.exr", assets="tests/golden/assets", integrator="WavePath",
+                        files=IMAGE_FORMAT_FILES) -> str:
     """One point-sampled Matte panel per BMP / TGA storage variant of tests/golden/assets (5 x 3 panels facing the camera, lit by an
     area light behind it): the film is a function of every texel the readers of csrc/host/imageload.cpp produce, next to what
     stb_image hands the reference for the same files."""
     a = assets.rstrip("/")
     parts, names = [], []
-    for k, name in enumerate(IMAGE_FORMAT_FILES):
+    for k, name in enumerate(files):
         col, row = k % 5, k // 5
         x0, y0 = -2.5 + col * 1.0 + 0.05, 1.9 - row * 1.0 + 0.05
         x1, y1 = x0 + 0.9, y0 - 0.9

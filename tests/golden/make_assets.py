@@ -218,9 +218,80 @@ def write_bmp_tga(out: Path) -> None:
     tga("tga_rgb15", 2, v555.shape[1], v555.shape[0], 16, v555[::-1].tobytes())
 
 
+# ---- JPEG fixtures: every decoding path of luisarender_b200/csrc/host/jpegload.cpp -------------------------------------------------
+# Written with Pillow / OpenCV (libjpeg-turbo) - present in this image; the files are committed, and what a reader must return for
+# them is what the reference's stb_image decodes (tests/golden/jpeg_texels.npz, tools/gen_jpeg_pins.py).
+def jpeg_picture(w: int, h: int, channels: int = 3, noise: int = 40) -> np.ndarray:
+    """smooth colour gradients with edges and some noise: chroma upsampling, the IDCT's rounding and the clamps all matter"""
+    r = np.random.default_rng(w * 1000 + h * 10 + channels)
+    y, x = np.mgrid[0:h, 0:w].astype(np.float64)
+    base = np.stack([127 + 120 * np.sin(x / 3.1 + y / 7.0), 127 + 120 * np.cos(x / 5.3 - y / 2.9), 255.0 * ((x // 4 + y // 3) % 2)], axis=2)
+    pic = np.clip(base + r.integers(-noise, noise + 1, (h, w, 3)), 0, 255).astype(np.uint8)
+    return pic if channels == 3 else pic[..., 0]
+
+
+def write_jpegs(out: Path) -> None:
+    import io
+
+    import cv2
+    from PIL import Image
+
+    def pil(name, a, **kw):
+        b = io.BytesIO()
+        Image.fromarray(a).save(b, "JPEG", **kw)
+        (out / f"{name}.jpg").write_bytes(b.getvalue())
+        return b.getvalue()
+
+    def cv(name, a, *flags):
+        ok, b = cv2.imencode(".jpg", a[..., ::-1].copy(), [int(f) for f in flags])
+        assert ok
+        (out / f"{name}.jpg").write_bytes(b.tobytes())
+
+    pil("jpg_grey", jpeg_picture(21, 13, 1), quality=85)
+    pil("jpg_444", jpeg_picture(19, 13), quality=90, subsampling=0)
+    pil("jpg_422", jpeg_picture(35, 11), quality=88, subsampling=1)
+    pil("jpg_420", jpeg_picture(37, 23), quality=90, subsampling=2)
+    pil("jpg_420_restart_optimized", jpeg_picture(41, 35), quality=80, subsampling=2, restart_marker_blocks=2, optimize=True)
+    pil("jpg_420_low_quality", jpeg_picture(40, 24, noise=90), quality=12, subsampling=2)
+    pil("jpg_444_q100_noise", jpeg_picture(16, 16, noise=127), quality=100, subsampling=0)
+    pil("jpg_420_one_pixel_wide", jpeg_picture(1, 9), quality=90, subsampling=2)
+    pil("jpg_422_one_pixel_wide", jpeg_picture(1, 5), quality=90, subsampling=1)
+    pil("jpg_progressive_420", jpeg_picture(45, 27), quality=85, subsampling=2, progressive=True)
+    pil("jpg_progressive_444_restart", jpeg_picture(26, 18), quality=92, subsampling=0, progressive=True, restart_marker_blocks=3)
+    pil("jpg_progressive_grey", jpeg_picture(30, 17, 1), quality=75, progressive=True)
+    cv("jpg_440", jpeg_picture(18, 29), cv2.IMWRITE_JPEG_QUALITY, 90, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440)
+    cv("jpg_411", jpeg_picture(43, 10), cv2.IMWRITE_JPEG_QUALITY, 90, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_411)
+    cv("jpg_progressive_440_restart", jpeg_picture(22, 33), cv2.IMWRITE_JPEG_QUALITY, 80, cv2.IMWRITE_JPEG_SAMPLING_FACTOR,
+       cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440, cv2.IMWRITE_JPEG_PROGRESSIVE, 1, cv2.IMWRITE_JPEG_RST_INTERVAL, 2)
+
+    # three components stored as RGB: by their ids 'R','G','B', or by an Adobe marker with transform 0 and no JFIF marker
+    def segments(data):
+        pos, found = 2, {}
+        while data[pos + 1] != 0xDA:
+            length = int.from_bytes(data[pos + 2:pos + 4], "big")
+            found.setdefault(data[pos + 1], []).append((pos, length + 2))
+            pos += length + 2
+        found[0xDA] = [(pos, int.from_bytes(data[pos + 2:pos + 4], "big") + 2)]
+        return found
+
+    src = bytearray(pil("jpg_rgb_by_ids", jpeg_picture(20, 12), quality=90, subsampling=0))
+    seg = segments(src)
+    sof, sos = seg[0xC0][0][0], seg[0xDA][0][0]
+    for k, letter in enumerate(b"RGB"):
+        assert src[sof + 10 + 3 * k] == k + 1 and src[sos + 5 + 2 * k] == k + 1
+        src[sof + 10 + 3 * k] = letter
+        src[sos + 5 + 2 * k] = letter
+    (out / "jpg_rgb_by_ids.jpg").write_bytes(bytes(src))
+    src = pil("jpg_rgb_by_adobe_marker", jpeg_picture(17, 14), quality=90, subsampling=0)
+    app0, n0 = segments(src)[0xE0][0]
+    adobe = b"\xff\xee\x00\x0eAdobe\x00\x64\x00\x00\x00\x00\x00"
+    (out / "jpg_rgb_by_adobe_marker.jpg").write_bytes(src[:app0] + adobe + src[app0 + n0:])
+
+
 def main():
     OUT.mkdir(exist_ok=True)
     write_bmp_tga(OUT)
+    write_jpegs(OUT)
     write_png(OUT / "checker_rgb8.png", checker_rgb8())
     write_png(OUT / "rough_gray8.png", rough_gray8())
     write_png(OUT / "ramp_rgba16.png", ramp_rgba16())

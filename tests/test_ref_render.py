@@ -41,7 +41,7 @@ CASES = ["cornell_wavepath", "cornell_megapath", "cornell_russian_roulette", "sp
          "spheres_sampler_pmj02bn", "spheres_sampler_sobol", "spheres_sampler_paddedsobol", "spheres_sampler_zsobol",
          "media_shapes", "media_nested_in_environment_medium", "media_true_hit_quirk", "materials_named_metals", "materials_textured", "materials_layered", "materials_layered_rr",
          "spheres_disney_thin", "spheres_medium_disney_thin", "textured_light", "image_formats", "textured_disney_thin",
-         "materials_mix_sobol", "materials_layered_pmj02bn", "textured_materials_zsobol", "media_disney_shells", "spheres_disney_thin_paddedsobol", "environment_medium_thin"]
+         "materials_mix_sobol", "materials_layered_pmj02bn", "textured_materials_zsobol", "media_disney_shells", "spheres_disney_thin_paddedsobol", "environment_medium_thin", "jpeg_formats"]
 
 
 # (media scenes are compared with the oracle in tests/test_gpu_parity.py: the reference build's Henyey-Greenstein argument order is

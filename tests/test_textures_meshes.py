@@ -95,6 +95,53 @@ def test_bmp_and_tga_loaders_match_source_arrays():
             assert (tex[..., 3] == 1).all(), name
 
 
+def test_jpeg_reader_matches_the_references_decoder_byte_for_byte():
+    """A JPEG decode is lossy: the texels only equal the reference's if the arithmetic after the entropy decoder is stb_image's (csrc/host/
+    jpegload.cpp).  tests/golden/jpeg_texels.npz is what the reference's own stb_image returns (tools/gen_jpeg_pins.py) for the fixtures of
+    tests/golden/make_assets.py: write_jpegs - grey, 4:4:4, 4:2:2, 4:2:0, 4:4:0, 4:1:1, one-pixel-wide pictures, restart intervals, optimised
+    tables, quality 12 and 100, progressive (interleaved DC, refinement scans, restarts), RGB stored as such (by ids / by Adobe marker)."""
+    want_all = np.load(REPO / "tests" / "golden" / "jpeg_texels.npz")
+    assert len(want_all.files) >= 17
+    for name in want_all.files:
+        want = want_all[name]
+        d = Scene.from_source(_matte_scene(f'file {{ "{ASSETS / (name + ".jpg")}" }} encoding {{ "linear" }}'), REPO).desc()
+        tex = _texels(d)
+        c = want.shape[2]
+        assert c in (1, 4) and d.textures[0].channels == c and tex.shape[:2] == want.shape[:2], name
+        assert np.array_equal(tex[..., :c], want.astype(f32) / f32(255)), (name, int((tex[..., :c] != want.astype(f32) / f32(255)).sum()))
+        if c == 1:
+            assert (tex[..., 3] == 1).all(), name
+
+
+def test_jpeg_pins_are_what_the_reference_decodes_now():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_jpeg_pins", REPO / "tools" / "gen_jpeg_pins.py")
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    if not gen.LIB.exists():
+        pytest.skip("oracle/_ref is not built here (the reference's sources are not on this machine)")
+    now, kept = gen.decode_all(), np.load(REPO / "tests" / "golden" / "jpeg_texels.npz")
+    assert sorted(now) == sorted(kept.files)
+    for name, a in now.items():
+        assert np.array_equal(a, kept[name]), name
+
+
+def test_jpeg_reader_refuses_what_it_does_not_read(tmp_path):
+    src = bytearray((ASSETS / "jpg_444.jpg").read_bytes())
+    sof = src.index(b"\xff\xc0")
+    arithmetic = bytearray(src)
+    arithmetic[sof + 1] = 0xC9
+    (tmp_path / "arithmetic.jpg").write_bytes(arithmetic)
+    with pytest.raises(Exception, match="unsupported JPEG process"):
+        Scene.from_source(_matte_scene(f'file {{ "{tmp_path / "arithmetic.jpg"}" }}'), REPO)
+    (tmp_path / "cut.jpg").write_bytes(src[:sof + 6])
+    with pytest.raises(Exception, match="truncated JPEG"):
+        Scene.from_source(_matte_scene(f'file {{ "{tmp_path / "cut.jpg"}" }}'), REPO)
+    (tmp_path / "not.jpg").write_bytes(b"\x89PNG\r\n\x1a\n")
+    with pytest.raises(Exception, match="not a JPEG"):
+        Scene.from_source(_matte_scene(f'file {{ "{tmp_path / "not.jpg"}" }}'), REPO)
+
+
 def test_bmp_and_tga_readers_refuse_what_the_reference_refuses(tmp_path):
     rle = bytearray((ASSETS / "bmp_pal8.bmp").read_bytes())
     rle[30] = 1  # BI_RLE8
@@ -105,9 +152,9 @@ def test_bmp_and_tga_readers_refuse_what_the_reference_refuses(tmp_path):
     (tmp_path / "cut.tga").write_bytes(cut)
     with pytest.raises(RuntimeError, match="truncated"):
         Scene.from_source(_matte_scene(f'file {{ "{tmp_path / "cut.tga"}" }}'), REPO)
-    (tmp_path / "x.jpg").write_bytes(b"\xff\xd8\xff")
+    (tmp_path / "x.gif").write_bytes(b"GIF89a")
     with pytest.raises(RuntimeError, match="unsupported image format"):
-        Scene.from_source(_matte_scene(f'file {{ "{tmp_path / "x.jpg"}" }}'), REPO)
+        Scene.from_source(_matte_scene(f'file {{ "{tmp_path / "x.gif"}" }}'), REPO)
 
 
 def test_png_filters_and_low_bit_depths(tmp_path):
@@ -169,9 +216,9 @@ def test_float_image_formats(tmp_path):
     # RGBE: 8-bit mantissas under the pixel's shared exponent
     assert (np.abs(hdr[..., :3] - rgba[..., :3]) <= rgba[..., :3].max(axis=-1, keepdims=True) / 100).all()
     assert np.array_equal(hdr[..., :3], hdr[..., :3].astype(np.float16).astype(f32))  # stored as HALF4 (imageio.cpp:383)
-    (tmp_path / "nothing.jpg").write_bytes(b"\xff\xd8\xff")
+    (tmp_path / "nothing.gif").write_bytes(b"GIF89a")
     with pytest.raises(RuntimeError, match="unsupported image format"):
-        Scene.from_source(_matte_scene('file { "nothing.jpg" }'), tmp_path)
+        Scene.from_source(_matte_scene('file { "nothing.gif" }'), tmp_path)
     with pytest.raises(RuntimeError, match="cannot open"):
         Scene.from_source(_matte_scene('file { "missing.png" }'), tmp_path)
 

@@ -143,6 +143,8 @@ def cases() -> dict[str, str]:
                            .replace("position { 0.0, 1.4, 4.2 }", "position { 0.0, 0.6, 4.2 }").replace("front { 0.0, -0.2, -1.0 }", "front { 0.0, 0.25, -1.0 }"))
     # BMP and TGA textures in every storage variant the host readers accept, against what stb_image hands the reference for them
     c["image_formats"] = scenes.image_formats_scene(resolution=(80, 48), spp=2, assets=assets)
+    # JPEG textures (lossy: the texels are the reference's only if the decoder's arithmetic is stb_image's - csrc/host/jpegload.cpp)
+    c["jpeg_formats"] = scenes.image_formats_scene(resolution=(120, 72), spp=2, assets=assets, files=scenes.JPEG_FORMAT_FILES, output="jpegs.exr")
     # a thin Disney surface whose diffuse_trans (slot 15) and colour are image textures, next to a constant specular_trans
     def _textured_thin(src):
         old = "  metallic : Constant { v { 0.2 } }"
