@@ -635,6 +635,9 @@ struct ColorFilm final : Film {
         for (int i = 0; i < 3; i++) scale[i] = std::pow(2.0f, e[i]);
         clamp = std::max(1.f, d->f("clamp", 256.f));
         if (resolution[0] == 0 || resolution[1] == 0) throw Error("Invalid film resolution. [" + d->location() + "]");
+        // color.cpp:32,124-129: a debugging aid that overwrites a pixel with (inf, 0, 0, 1) when a NaN / infinite sample arrives; the
+        // accumulate kernel drops such samples like the default does and has no marking pass - refuse rather than differ silently
+        if (d->b("warn_nan", false)) throw Error("Film 'Color': warn_nan { true } is not supported (NaN / infinite samples are dropped, not marked). [" + d->location() + "]");
     }
 };
 

@@ -72,6 +72,17 @@ def test_undefined_macro_and_unknown_plugin_are_hard_errors():
         Scene.from_source(MINIMAL.replace("#SPP", "1").replace("fov { 40 }", "fov { 40 } fov { 41 }"))
 
 
+def test_film_option_that_would_change_the_film_is_refused_not_ignored():
+    """color.cpp:124-129: warn_nan { true } makes the reference overwrite a pixel with (inf, 0, 0, 1) on a NaN / infinite sample; the
+    accumulate kernel has no such pass, so the option is a load error (its default, false, loads)."""
+    from luisarender_b200 import scenes as S
+    src = S.cornell_box(resolution=(16, 16), spp=1)
+    assert "film : Color {" in src
+    Scene.from_source(src.replace("film : Color {", "film : Color { warn_nan { false }"))
+    with pytest.raises(RuntimeError, match="warn_nan"):
+        Scene.from_source(src.replace("film : Color {", "film : Color { warn_nan { true }"))
+
+
 def test_base_node_inheritance_and_tag_aliases():
     src = MINIMAL.replace("#SPP", "1") + """
     """
