@@ -72,6 +72,27 @@ def test_undefined_macro_and_unknown_plugin_are_hard_errors():
         Scene.from_source(MINIMAL.replace("#SPP", "1").replace("fov { 40 }", "fov { 40 } fov { 41 }"))
 
 
+def test_import_pulls_in_text_and_json_files_relative_to_the_importing_file(tmp_path):
+    """scene_parser.cpp:76-82: `import "file"` parses another scene file (by its extension: text or JSON) into the same description,
+    paths relative to the directory of the file that imports; the result equals the scene written in one piece."""
+    whole = MINIMAL.replace("#SPP", "2")
+    head, rest = whole.split("Shape lamp_quad", 1)
+    assert "Surface white" in head and "Light lamp" in head
+    (tmp_path / "parts").mkdir()
+    (tmp_path / "parts" / "materials.luisa").write_text(head + 'import "lamp.json"\n')
+    lamp_body, tail = rest.split("Camera cam", 1)
+    (tmp_path / "parts" / "lamp.json").write_text(json.dumps({"lamp_quad": {"type": "Shape", "impl": "InlineMesh", "prop": {
+        "positions": [-1, 2, -1, -1, 2, 1, 1, 2, 1, 1, 2, -1], "indices": [0, 1, 2, 0, 2, 3], "light": "@lamp"}}}))
+    (tmp_path / "main.luisa").write_text('import "parts/materials.luisa"\nCamera cam' + tail)
+    a, b = Scene.from_file(tmp_path / "main.luisa").desc(), Scene.from_source(whole).desc()
+    assert a.triangle_count == b.triangle_count and a.instance_count == b.instance_count and a.light_count == b.light_count == 1
+    n = a.triangle_count * 3
+    assert np.array_equal(_arr(a.triangles, n, np.uint32), _arr(b.triangles, n, np.uint32))
+    with pytest.raises(RuntimeError):
+        (tmp_path / "broken.luisa").write_text('import "parts/missing.luisa"\nCamera cam' + tail)
+        Scene.from_file(tmp_path / "broken.luisa")
+
+
 def test_film_option_that_would_change_the_film_is_refused_not_ignored():
     """color.cpp:124-129: warn_nan { true } makes the reference overwrite a pixel with (inf, 0, 0, 1) on a NaN / infinite sample; the
     accumulate kernel has no such pass, so the option is a load error (its default, false, loads)."""
