@@ -263,6 +263,7 @@ class JpegReader {
         image_w = be16();
         uint32_t n = byte();
         if (image_w == 0u || image_h == 0u) fail("JPEG file without a size in its frame header");
+        if (static_cast<uint64_t>(image_w) * image_h > (1ull << 28u)) fail("JPEG picture larger than 2^28 pixels");// a header must not buy 25 GB
         if (n == 4u) fail("four-component (CMYK / YCCK) JPEG files are not supported");
         if (n != 1u && n != 3u) fail("bad JPEG component count");
         if (length != 8u + 3u * n) fail("bad JPEG frame header length");

@@ -137,6 +137,11 @@ def test_jpeg_reader_refuses_what_it_does_not_read(tmp_path):
     (tmp_path / "cut.jpg").write_bytes(src[:sof + 6])
     with pytest.raises(Exception, match="truncated JPEG"):
         Scene.from_source(_matte_scene(f'file {{ "{tmp_path / "cut.jpg"}" }}'), REPO)
+    huge = bytearray(src)
+    huge[sof + 5:sof + 9] = b"\xff\xff\xff\xff"  # a 65535 x 65535 frame header must not allocate its 25 GB of coefficients
+    (tmp_path / "huge.jpg").write_bytes(huge)
+    with pytest.raises(Exception, match="larger than"):
+        Scene.from_source(_matte_scene(f'file {{ "{tmp_path / "huge.jpg"}" }}'), REPO)
     (tmp_path / "not.jpg").write_bytes(b"\x89PNG\r\n\x1a\n")
     with pytest.raises(Exception, match="not a JPEG"):
         Scene.from_source(_matte_scene(f'file {{ "{tmp_path / "not.jpg"}" }}'), REPO)
