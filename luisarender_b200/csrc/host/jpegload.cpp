@@ -1,5 +1,5 @@
 // JPEG reader for the `Image` texture plugin (ITU-T T.81: Huffman-coded baseline / extended-sequential / progressive DCT,
-// 8-bit samples, one (grey) or three (YCbCr or RGB) components, restart intervals, interleaved and single-component scans).
+// 8-bit samples, one (grey), three (YCbCr or RGB) or four (CMYK / YCCK) components, restart intervals, interleaved and single-component scans).
 //
 // The reference reads .jpg / .jpeg through stb_image (LoadedImage::load, src/util/imageio.cpp:347-470 -> stbi_load).  Entropy
 // decoding is exact by the standard; everything after it is lossy, so the texels only equal the reference's if the arithmetic
@@ -13,7 +13,8 @@
 //     "no transform" and there is no JFIF marker                                                   (:3877)
 // The pins: tests/golden/jpeg_texels.npz holds what the reference's own stb_image (compiled into oracle/_ref/bin/libluisa-ref.so)
 // decodes for every fixture file (tools/gen_jpeg_pins.py); tests/test_textures_meshes.py compares this reader with it byte for byte.
-// Not read: four-component (CMYK / YCCK) files, arithmetic coding, lossless and hierarchical processes, 12-bit samples, DNL.
+// Four-component files (CMYK / YCCK by the Adobe marker) come out as RGB like stb's (:3858-3862, :3950-3975).
+// Not read: arithmetic coding, lossless and hierarchical processes, 12-bit samples, DNL.
 #include <array>
 #include <cstdint>
 #include <cstring>
@@ -264,8 +265,7 @@ class JpegReader {
         uint32_t n = byte();
         if (image_w == 0u || image_h == 0u) fail("JPEG file without a size in its frame header");
         if (static_cast<uint64_t>(image_w) * image_h > (1ull << 28u)) fail("JPEG picture larger than 2^28 pixels");// a header must not buy 25 GB
-        if (n == 4u) fail("four-component (CMYK / YCCK) JPEG files are not supported");
-        if (n != 1u && n != 3u) fail("bad JPEG component count");
+        if (n != 1u && n != 3u && n != 4u) fail("bad JPEG component count");
         if (length != 8u + 3u * n) fail("bad JPEG frame header length");
         components.resize(n);
         for (auto &c : components) {
@@ -553,8 +553,10 @@ public:
         const bool as_rgb = n == 3u && ((components[0].id == 'R' && components[1].id == 'G' && components[2].id == 'B') || (adobe_transform == 0 && !jfif));
         w = image_w;
         h = image_h;
-        nc = n;
-        pixels.assign(static_cast<size_t>(w) * h * n, 0);
+        nc = n == 1u ? 1u : 3u;// four components (CMYK / YCCK, told apart by the Adobe marker) come out as RGB (:3950-3975)
+        pixels.assign(static_cast<size_t>(w) * h * nc, 0);
+        // stb_image.h:3858-3862: x * y / 255, rounded
+        auto scale8 = [](uint32_t x, uint32_t y) { uint32_t t = x * y + 128u; return static_cast<uint8_t>((t + (t >> 8u)) >> 8u); };
         struct Rows {
             uint32_t hs, vs, step, row, width;
             const uint8_t *line0, *line1;
@@ -591,9 +593,12 @@ public:
                     if (++r.row < c.height) r.line1 += static_cast<size_t>(c.blocks_x) * 8u;
                 }
             }
-            uint8_t *out = pixels.data() + static_cast<size_t>(y) * w * n;
+            uint8_t *out = pixels.data() + static_cast<size_t>(y) * w * nc;
             if (n == 1u) {
                 std::memcpy(out, line[0], w);
+            } else if (n == 4u && adobe_transform == 0) {// CMYK, stored inverted: every colour scaled by the black channel
+                for (uint32_t x = 0; x < w; x++, out += 3)
+                    for (uint32_t k = 0; k < 3u; k++) out[k] = scale8(line[k][x], line[3][x]);
             } else if (as_rgb) {
                 for (uint32_t x = 0; x < w; x++, out += 3)
                     for (uint32_t k = 0; k < 3u; k++) out[k] = line[k][x];
@@ -610,6 +615,8 @@ public:
                     out[0] = clamp8(red >> 20);
                     out[1] = clamp8(green >> 20);
                     out[2] = clamp8(blue >> 20);
+                    if (n == 4u && adobe_transform == 2)// YCCK: the converted colours are the inverted CMY
+                        for (uint32_t k = 0; k < 3u; k++) out[k] = scale8(255u - out[k], line[3][x]);
                 }
             }
         }

@@ -264,6 +264,20 @@ def write_jpegs(out: Path) -> None:
     cv("jpg_progressive_440_restart", jpeg_picture(22, 33), cv2.IMWRITE_JPEG_QUALITY, 80, cv2.IMWRITE_JPEG_SAMPLING_FACTOR,
        cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440, cv2.IMWRITE_JPEG_PROGRESSIVE, 1, cv2.IMWRITE_JPEG_RST_INTERVAL, 2)
 
+    # four components: Pillow writes CMYK pictures with an Adobe marker (transform 0: CMYK as such, inverted); the same scan data under
+    # transform 2 reads as YCCK
+    cmyk = np.concatenate([jpeg_picture(23, 15), jpeg_picture(23, 15, noise=10)[..., :1]], axis=2)
+    b = io.BytesIO()
+    Image.fromarray(cmyk, "CMYK").save(b, "JPEG", quality=90)
+    data = b.getvalue()
+    (out / "jpg_cmyk.jpg").write_bytes(data)
+    at = data.index(b"Adobe") + 11
+    assert data[at] in (0, 2)
+    (out / "jpg_cmyk_other_transform.jpg").write_bytes(data[:at] + bytes([2 - data[at]]) + data[at + 1:])
+    b = io.BytesIO()
+    Image.fromarray(cmyk, "CMYK").save(b, "JPEG", quality=85, progressive=True, subsampling=2)
+    (out / "jpg_cmyk_progressive_subsampled.jpg").write_bytes(b.getvalue())
+
     # three components stored as RGB: by their ids 'R','G','B', or by an Adobe marker with transform 0 and no JFIF marker
     def segments(data):
         pos, found = 2, {}

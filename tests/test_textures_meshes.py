@@ -99,9 +99,9 @@ def test_jpeg_reader_matches_the_references_decoder_byte_for_byte():
     """A JPEG decode is lossy: the texels only equal the reference's if the arithmetic after the entropy decoder is stb_image's (csrc/host/
     jpegload.cpp).  tests/golden/jpeg_texels.npz is what the reference's own stb_image returns (tools/gen_jpeg_pins.py) for the fixtures of
     tests/golden/make_assets.py: write_jpegs - grey, 4:4:4, 4:2:2, 4:2:0, 4:4:0, 4:1:1, one-pixel-wide pictures, restart intervals, optimised
-    tables, quality 12 and 100, progressive (interleaved DC, refinement scans, restarts), RGB stored as such (by ids / by Adobe marker)."""
+    tables, quality 12 and 100, progressive (interleaved DC, refinement scans, restarts), RGB stored as such (by ids / by Adobe marker), CMYK and YCCK."""
     want_all = np.load(REPO / "tests" / "golden" / "jpeg_texels.npz")
-    assert len(want_all.files) >= 17
+    assert len(want_all.files) >= 20
     for name in want_all.files:
         want = want_all[name]
         d = Scene.from_source(_matte_scene(f'file {{ "{ASSETS / (name + ".jpg")}" }} encoding {{ "linear" }}'), REPO).desc()
