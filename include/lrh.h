@@ -58,7 +58,7 @@ const char *lrh_scene_camera_file(const lrh_scene *scene, uint32_t camera);
 /* RGBA float image writer (.exr / .hdr / .pfm; other extensions fall back to .exr). */
 int lrh_save_image(const char *path, const float *rgba, uint32_t width, uint32_t height);
 
-/* Image file reader of the `Image` texture plugin (PNG / PPM / PGM / PFM / HDR / EXR): replaces LoadedImage::load
+/* Image file reader of the `Image` texture plugin (PNG / JPEG / BMP / TGA / PPM / PGM / PFM / HDR / EXR): replaces LoadedImage::load
  * (src/util/imageio.cpp:480-560).  Writes the decoded RGBA float texels (row 0 = top row) into `rgba` when it is non-null
  * and holds at least width * height * 4 floats; call once with rgba = NULL to query the size. */
 int lrh_load_image(const char *path, uint32_t *width, uint32_t *height, uint32_t *channels, float *rgba, uint64_t rgba_capacity);
